@@ -1,0 +1,217 @@
+/*
+ * nerfpp_b200 — C ABI of the B200-native NeRFpp ray-batch hot path (libnerfpp_b200.so).
+ *
+ * The reference (DeliriumV01D/NeRFpp) has no FFI: its boundary is C++ template duck-typing
+ * (src/NeRFRenderer.h:88-159, src/NeRFExecutor.h:299-301).  The C++ drop-in modules in
+ * nerfpp_b200/csrc/host/ keep torch::Tensor at that boundary and call ONLY the functions declared here.
+ * Each entry cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns every buffer;
+ *   - tensors are dense row-major fp32 unless stated; `stream` is a cudaStream_t (NULL = legacy default);
+ *   - functions only enqueue work on `stream` (no host sync) and return 0 (NRF_OK) or a negative nrf_status;
+ *     nrf_last_error() gives the text for the calling thread;  nothing throws across this ABI;
+ *   - no hidden global state besides one-time cudaFuncSetAttribute calls: safe across streams / devices.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns NRF_ERR_CUDA.
+ */
+#ifndef NERFPP_B200_H
+#define NERFPP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRF_ABI_VERSION 1
+
+typedef void* nrf_stream; /* cudaStream_t */
+
+typedef enum nrf_status {
+	NRF_OK = 0,
+	NRF_ERR_INVALID = -1,     /* bad argument (null pointer, unsupported shape) */
+	NRF_ERR_CUDA = -2,        /* CUDA runtime / launch error; text in nrf_last_error() */
+	NRF_ERR_UNSUPPORTED = -3  /* configuration outside what the sm_100a kernels were built for */
+} nrf_status;
+
+int nrf_abi_version(void);
+const char* nrf_last_error(void);
+/* number of kernel launches issued through this library by the calling process (bench.py "gpu_launches") */
+int64_t nrf_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Multiresolution hash grid — replaces CuHashEmbedderFunction::forward/backward and their kernels
+ * (src/CuHashEmbedder.cu:9-102, 106-216, 221-325) and the clamp/keep-mask prologue of
+ * CuHashEmbedderImpl::forward (src/CuHashEmbedder.cpp:85-103).
+ *
+ * The descriptor mirrors the module's public members (src/CuHashEmbedder.h:12-27).  primes / biases /
+ * feat_local_idx / feat_local_size are the module's registered buffers, passed as they are (they are saved in
+ * checkpoints and pin the hash function).  NOTE feat_local_idx is an offset in SCALARS, not rows
+ * (src/CuHashEmbedder.cu:55,150): with F=2 consecutive levels overlap by half — reproduced bit-exactly.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define NRF_MAX_LEVELS 32
+
+typedef struct nrf_hash_grid {
+	int32_t n_levels;           /* NLevels                 (<= NRF_MAX_LEVELS) */
+	int32_t n_features;         /* NFeaturesPerLevel       (2, 4 or 8)         */
+	int32_t n_volumes;          /* NVolumes                (1)                 */
+	int32_t base_resolution;    /* BaseResolution                              */
+	int32_t finest_resolution;  /* FinestResolution                            */
+	float box_min[3];           /* BoundingBox[0:3]                            */
+	float box_max[3];           /* BoundingBox[3:6]                            */
+	const int32_t* primes;          /* [n_levels, n_volumes, 3] int32          */
+	const float* biases;            /* [n_levels * n_volumes, 3]               */
+	const int32_t* feat_local_idx;  /* [n_levels] scalar offsets               */
+	const int32_t* feat_local_size; /* [n_levels] entries per level            */
+	const float* level_scale;       /* [n_levels] from nrf_hash_level_scales   */
+	int64_t table_scalars;          /* numel(Embeddings), for bounds checking  */
+} nrf_hash_grid;
+
+/* Per-level scale exp2f((log2f(finest)-log2f(base))*l/(L-1)+log2f(base)), evaluated ON THE DEVICE with the
+ * reference's exact expression (src/CuHashEmbedder.cu:40) so floorf() lands on the same cell. */
+int nrf_hash_level_scales(int32_t base_resolution, int32_t finest_resolution, int32_t n_levels,
+                          float* level_scale, nrf_stream stream);
+
+/* fp32 master table -> fp16 shadow, round-to-nearest-even (src/CuHashEmbedder.cu:257). */
+int nrf_table_to_half(const float* table_f32, void* table_f16, int64_t n_scalars, nrf_stream stream);
+
+typedef enum nrf_enc_layout {
+	NRF_ENC_F32 = 0, /* [N, L*F] fp32 holding fp16-rounded values — what the reference returns (.cu:274) */
+	NRF_ENC_F16 = 1  /* [N, L*F] fp16 — same values, fed straight to nrf_mlp_small_* */
+} nrf_enc_layout;
+
+/* points [N,3].  clamp_points!=0: clamp into the box and write keep[N] (1 = inside, src/CuHashEmbedder.cpp:92-101;
+ * keep may be NULL).  clamp_points==0: points are taken as already clamped. */
+int nrf_hash_encode_fwd(const nrf_hash_grid* grid, const void* table_f16, const float* points, int64_t n_points,
+                        int clamp_points, uint8_t* keep, void* enc_out, nrf_enc_layout layout, nrf_stream stream);
+
+typedef enum nrf_grad_layout {
+	NRF_GRAD_F32 = 0,  /* [N, L*F] fp32 */
+	NRF_GRAD_BF16 = 1  /* [N, L*F] bf16 (produced by nrf_mlp_small_bwd) */
+} nrf_grad_layout;
+
+/* grad_table[table_scalars] fp32 is ACCUMULATED into (caller zeroes it, or lets nrf_adam_step do so).
+ * fp32 accumulation replaces the reference's x128-scaled fp16 atomics (src/CuHashEmbedder.cu:197-198,303,323). */
+int nrf_hash_encode_bwd(const nrf_hash_grid* grid, const float* points, int64_t n_points, int clamp_points,
+                        const void* grad_enc, nrf_grad_layout layout, float* grad_table, nrf_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Direction / position encoders
+ * ---------------------------------------------------------------------------------------------------------- */
+/* CuSHKernel (src/CuSHEncoder.cu:4-107): dirs [N,3] -> [N, degree^2], degree 1..8. */
+int nrf_sh_encode_fwd(const float* dirs, int64_t n, int32_t degree, float* out, nrf_stream stream);
+
+/* EmbedderImpl::forward (src/NeRF.cpp:22-39): x [N,D] -> [N, D*(include_input + 2*num_freqs)],
+ * channel order x, sin(f0 x), cos(f0 x), sin(f1 x) ...; freq_bands_host[num_freqs] as built at src/NeRF.cpp:11-19. */
+int nrf_posenc_fwd(const float* x, int64_t n, int32_t input_dims, int32_t num_freqs, const float* freq_bands_host,
+                   int32_t include_input, float* out, nrf_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * NeRFSmall (HashNeRF MLP) — NeRFSmallImpl::forward (src/NeRF.cpp:363-412) and its autograd backward.
+ * Built for the BASELINE shape: sigma net in->64->(1+15), colour net (views+15)->64->64->3, bias-free, ReLU
+ * between layers only, output [rgb(3), sigma].  Other shapes return NRF_ERR_UNSUPPORTED.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct nrf_mlp_small_shape {
+	int32_t input_ch;          /* 32  (hash L*F)             */
+	int32_t input_ch_views;    /* 16  (SH degree 4)          */
+	int32_t hidden_dim;        /* 64                          */
+	int32_t geo_feat_dim;      /* 15                          */
+	int32_t hidden_dim_color;  /* 64                          */
+	int32_t num_layers;        /* 2                           */
+	int32_t num_layers_color;  /* 3                           */
+} nrf_mlp_small_shape;
+
+/* bytes of the packed (tensor-core fragment ordered, bf16/fp16) weight blob */
+int64_t nrf_mlp_small_packed_bytes(const nrf_mlp_small_shape* shape);
+/* number of fp32 scalars in the flat parameter / gradient vector, order sigma_net_0, sigma_net_1,
+ * color_net_0, color_net_1, color_net_2, each [out, in] row-major (= torch Linear.weight, src/NeRF.cpp:338-342) */
+int64_t nrf_mlp_small_param_count(const nrf_mlp_small_shape* shape);
+int nrf_mlp_small_pack(const nrf_mlp_small_shape* shape, const float* params_flat, void* packed, nrf_stream stream);
+
+typedef enum nrf_mlp_input {
+	NRF_MLP_IN_ENC16_RAYDIRS = 0, /* enc: fp16 [N,32]; views: per-ray SH table fp32 [R,16]; row n uses ray n / samples_per_ray */
+	NRF_MLP_IN_F32_CAT = 1        /* enc: fp32 [N, input_ch + input_ch_views] = cat(embedded, embedded_dirs) (src/NeRFRenderer.h:182) */
+} nrf_mlp_input;
+
+/* keep (nullable): sigma := 0 where keep==0 (src/NeRFRenderer.h:187-188).  raw_out [N,4] = [r,g,b,sigma]. */
+int nrf_mlp_small_fwd(const nrf_mlp_small_shape* shape, const void* packed, nrf_mlp_input in_kind, const void* enc,
+                      const float* ray_sh, int32_t samples_per_ray, const uint8_t* keep, int64_t n,
+                      float* raw_out, nrf_stream stream);
+
+/* grad_raw [N,4].  grad_in: bf16 [N,32] (NRF_MLP_IN_ENC16_RAYDIRS) or fp32 [N,48] (NRF_MLP_IN_F32_CAT), may be NULL.
+ * grad_params_flat[param_count] fp32 is ACCUMULATED into.  Activations are recomputed, nothing was saved. */
+int nrf_mlp_small_bwd(const nrf_mlp_small_shape* shape, const void* packed, nrf_mlp_input in_kind, const void* enc,
+                      const float* ray_sh, int32_t samples_per_ray, const uint8_t* keep, int64_t n,
+                      const float* grad_raw, void* grad_in, float* grad_params_flat, nrf_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Volume rendering — NeRFRenderer::RawToOutputs (src/NeRFRenderer.h:199-282) with TruncExp
+ * (src/CustomOps.cpp:5-16) folded in, and its backward.
+ * raw [R,S,raw_stride] (channels 0..2 rgb logits, 3 density), z [R,S], rays_d [R,3],
+ * noise (nullable) [R,S] standard normal scaled by raw_noise_std (src/NeRFRenderer.h:253-254).
+ * ---------------------------------------------------------------------------------------------------------- */
+int nrf_composite_fwd(const float* raw, int32_t raw_stride, const float* z, const float* rays_d, const float* noise,
+                      float raw_noise_std, int32_t white_bkgr, int64_t n_rays, int32_t n_samples,
+                      float* rgb /*[R,3]*/, float* depth /*[R]*/, float* disp /*[R]*/, float* acc /*[R]*/,
+                      float* weights /*[R,S] nullable*/, nrf_stream stream);
+
+/* g_* are the upstream gradients of the five outputs (each nullable = zero).  d_raw [R,S,4]. */
+int nrf_composite_bwd(const float* raw, int32_t raw_stride, const float* z, const float* rays_d, const float* noise,
+                      float raw_noise_std, int32_t white_bkgr, int64_t n_rays, int32_t n_samples,
+                      const float* g_rgb, const float* g_depth, const float* g_disp, const float* g_acc,
+                      const float* g_weights, float* d_raw, nrf_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Hierarchical resampling — SamplePDF (src/Sampler.h:6-43).
+ * bins [R,B], weights [R,B-1], u: [n_samples] shared (det: linspace(0,1,n), src/Sampler.h:20) when u_per_ray==0,
+ * else [R,n_samples].  samples_out [R,n_samples].
+ * ---------------------------------------------------------------------------------------------------------- */
+int nrf_sample_pdf(const float* bins, const float* weights, int32_t n_bins, const float* u, int32_t u_per_ray,
+                   int64_t n_rays, int32_t n_samples, float* samples_out, nrf_stream stream);
+
+/* The fused call site in RenderRays (src/NeRFRenderer.h:427-431): z_mid, SamplePDF(z_mid, w[:,1:-1]), then
+ * sort(cat(z, z_samples)).  Both lists are already sorted, so the sort is a rank merge.
+ * z_coarse [R,S], weights [R,S] -> z_merged [R,S+n_importance]; z_samples (nullable) [R,n_importance]. */
+int nrf_sample_pdf_merge(const float* z_coarse, const float* weights, const float* u, int32_t u_per_ray,
+                         int64_t n_rays, int32_t n_samples, int32_t n_importance, float* z_samples,
+                         float* z_merged, nrf_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Rays — RayUtils / Render prologue
+ * ---------------------------------------------------------------------------------------------------------- */
+/* GetRays (src/RayUtils.h:5-46) for image rows [row_begin,row_end): K_host[9] row-major 3x3, c2w_host[12] = c2w[:3,:4].
+ * rays_o, rays_d [(row_end-row_begin)*w, 3]. */
+int nrf_get_rays(int32_t h, int32_t w, const float* K_host, const float* c2w_host, int32_t row_begin, int32_t row_end,
+                 float* rays_o, float* rays_d, nrf_stream stream);
+
+/* Render prologue (src/NeRFRenderer.h:549-583): viewdirs = d/|d|, near/far = IntersectWithAABB(o,d,bbox,near_plane)
+ * (src/RayUtils.h:87-126), ray_batch [R, 8 or 11] = [o, d, near, far (, viewdirs)]. */
+int nrf_rays_prepare(const float* rays_o, const float* rays_d, int64_t n_rays, const float* bbox_host /*[6]*/,
+                     float near_plane, int32_t use_viewdirs, float* ray_batch, nrf_stream stream);
+
+/* z = near*(1-t)+far*t (or the lin_disp variant), src/NeRFRenderer.h:393-402.  t_vals [S] device. */
+int nrf_z_sample(const float* ray_batch, int32_t ray_stride, const float* t_vals, int64_t n_rays, int32_t n_samples,
+                 int32_t lin_disp, float* z, nrf_stream stream);
+
+/* pts = o + d*z, src/NeRFRenderer.h:419,432.  pts [R,S,3]. */
+int nrf_sample_points(const float* ray_batch, int32_t ray_stride, const float* z, int64_t n_rays, int32_t n_samples,
+                      float* pts, nrf_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Training glue restated from NeRFExecutor::Train (src/NeRFExecutor.h:883-890, 539, 986)
+ * ---------------------------------------------------------------------------------------------------------- */
+/* huber_loss(pred, target, delta=1, mean): loss_out[0] += mean loss (caller zeroes), grad[n] = dLoss/dpred * grad_scale */
+int nrf_huber_fwd_bwd(const float* pred, const float* target, int64_t n, float delta, float grad_scale,
+                      float* loss_out, float* grad, nrf_stream stream);
+
+/* torch::optim::Adam step (no amsgrad, no weight decay): g = grad*grad_scale; m,v updated; bias-corrected update.
+ * step is 1-based.  zero_grad!=0 clears grad afterwards.  shadow_f16 (nullable): fp16 copy of the new params
+ * (replaces the per-forward full-table cast, src/CuHashEmbedder.cu:257). */
+int nrf_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int32_t step, float grad_scale, int32_t zero_grad, void* shadow_f16,
+                  nrf_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERFPP_B200_H */

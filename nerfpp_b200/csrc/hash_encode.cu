@@ -1,0 +1,399 @@
+// Multiresolution hash-grid encode, forward and backward, for sm_100a.
+//
+// Replaces CuHashEmbedderForwardKernel / CuHashEmbedderBackwardKernel and their host wrappers
+// (reference src/CuHashEmbedder.cu:9-102, 106-216, 221-325) plus the clamp / keep-mask prologue of
+// CuHashEmbedderImpl::forward (src/CuHashEmbedder.cpp:85-103).
+//
+// Index arithmetic is bit-exact with the reference: same device expression for the per-level scale
+// (precomputed once by nrf_hash_level_scales), IEEE division for the box normalisation, uint32 wrap-around
+// multiply/xor, `% size`, and the reference's scalar (not row) level offsets.
+//
+// B200 layout choices (vs the reference's one thread per (point, level), grid.y = level):
+//   * one thread per POINT walks all levels: the point is read and normalised once, the 8 gathers of a level
+//     are issued back to back (8..32 loads in flight per thread), and the L*F outputs of a point leave as
+//     16-byte vector stores instead of 4-byte stores at 64-byte stride;
+//   * the table is the persistent fp16 shadow (17 MiB used at the BASELINE shape, L2 resident) kept up to date
+//     by nrf_adam_step, not a per-call cast of the fp32 master;
+//   * level metadata (scale, primes, offsets) is staged once per CTA in shared memory;
+//   * the backward accumulates in fp32 with vector RED (red.global.add.v2.f32), no x128 loss scale.
+#include "common.cuh"
+
+namespace nrf {
+
+struct HashMeta {
+	float scale[NRF_MAX_LEVELS];
+	float bx[NRF_MAX_LEVELS], by[NRF_MAX_LEVELS], bz[NRF_MAX_LEVELS];
+	uint32_t pa[NRF_MAX_LEVELS], pb[NRF_MAX_LEVELS], pc[NRF_MAX_LEVELS];
+	uint32_t offset[NRF_MAX_LEVELS], size[NRF_MAX_LEVELS], mask[NRF_MAX_LEVELS];
+};
+
+struct HashArgs {
+	int n_levels, n_volumes;
+	float min_x, min_y, min_z, max_x, max_y, max_z;
+	const int32_t* primes;
+	const float* biases;
+	const int32_t* feat_local_idx;
+	const int32_t* feat_local_size;
+	const float* level_scale;
+};
+
+__device__ __forceinline__ void stage_meta(HashMeta& m, const HashArgs& a)
+{
+	for (int l = threadIdx.x; l < a.n_levels; l += blockDim.x) {
+		const int t = l * a.n_volumes;  // volume index is always 0 (src/CuHashEmbedder.cpp:97)
+		m.scale[l] = a.level_scale[l];
+		m.pa[l] = static_cast<uint32_t>(a.primes[t * 3 + 0]);
+		m.pb[l] = static_cast<uint32_t>(a.primes[t * 3 + 1]);
+		m.pc[l] = static_cast<uint32_t>(a.primes[t * 3 + 2]);
+		m.bx[l] = a.biases[t * 3 + 0];
+		m.by[l] = a.biases[t * 3 + 1];
+		m.bz[l] = a.biases[t * 3 + 2];
+		m.offset[l] = static_cast<uint32_t>(a.feat_local_idx[l]);
+		const uint32_t sz = static_cast<uint32_t>(a.feat_local_size[l]);
+		m.size[l] = sz;
+		m.mask[l] = (sz & (sz - 1u)) == 0u ? sz - 1u : 0u;  // power of two -> and-mask, else generic %
+	}
+	__syncthreads();
+}
+
+// Same expression as src/CuHashEmbedder.cu:40, evaluated on the device so that the rounding is the device's.
+__global__ void level_scale_kernel(int base_resolution, int finest_resolution, int n_levels, float* out)
+{
+	const int level_idx = threadIdx.x;
+	if (level_idx >= n_levels) return;
+	out[level_idx] = exp2f((log2f(finest_resolution) - log2f(base_resolution)) * float(level_idx) / float(n_levels - 1) + log2f(base_resolution));
+}
+
+struct Cell {
+	uint32_t pos[8];
+	float w[8];
+};
+
+// src/CuHashEmbedder.cu:44-90 for one level.  q = (pt - box_min) / (box_max - box_min) is level independent.
+__device__ __forceinline__ void locate(const HashMeta& m, int l, float qx, float qy, float qz, Cell& c)
+{
+	float px = qx * m.scale[l];
+	float py = qy * m.scale[l];
+	float pz = qz * m.scale[l];
+	px += m.bx[l];
+	py += m.by[l];
+	pz += m.bz[l];
+	const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+	const uint32_t pos_x = static_cast<uint32_t>(fx);
+	const uint32_t pos_y = static_cast<uint32_t>(fy);
+	const uint32_t pos_z = static_cast<uint32_t>(fz);
+	const uint32_t pa = m.pa[l], pb = m.pb[l], pc = m.pc[l];
+	const uint32_t x0 = pos_x * pa, x1 = (pos_x + 1u) * pa;
+	const uint32_t y0 = pos_y * pb, y1 = (pos_y + 1u) * pb;
+	const uint32_t z0 = pos_z * pc, z1 = (pos_z + 1u) * pc;
+	c.pos[0] = x0 ^ y0 ^ z0;
+	c.pos[1] = x0 ^ y0 ^ z1;
+	c.pos[2] = x0 ^ y1 ^ z0;
+	c.pos[3] = x0 ^ y1 ^ z1;
+	c.pos[4] = x1 ^ y0 ^ z0;
+	c.pos[5] = x1 ^ y0 ^ z1;
+	c.pos[6] = x1 ^ y1 ^ z0;
+	c.pos[7] = x1 ^ y1 ^ z1;
+	const uint32_t mask = m.mask[l];
+	if (mask) {
+#pragma unroll
+		for (int d = 0; d < 8; d++) c.pos[d] &= mask;
+	} else {
+		const uint32_t sz = m.size[l];
+#pragma unroll
+		for (int d = 0; d < 8; d++) c.pos[d] %= sz;
+	}
+	const float a = px - fx, b = py - fy, cc = pz - fz;
+	c.w[0] = (1.f - a) * (1.f - b) * (1.f - cc);
+	c.w[1] = (1.f - a) * (1.f - b) * cc;
+	c.w[2] = (1.f - a) * b * (1.f - cc);
+	c.w[3] = (1.f - a) * b * cc;
+	c.w[4] = a * (1.f - b) * (1.f - cc);
+	c.w[5] = a * (1.f - b) * cc;
+	c.w[6] = a * b * (1.f - cc);
+	c.w[7] = a * b * cc;
+}
+
+// Clamp into the box and report whether the point was inside (src/CuHashEmbedder.cpp:92-94,101).
+__device__ __forceinline__ bool clamp_point(const HashArgs& a, float& x, float& y, float& z)
+{
+	const float cx = fmaxf(fminf(x, a.max_x), a.min_x);
+	const float cy = fmaxf(fminf(y, a.max_y), a.min_y);
+	const float cz = fmaxf(fminf(z, a.max_z), a.min_z);
+	const bool keep = (x == cx) && (y == cy) && (z == cz);
+	x = cx; y = cy; z = cz;
+	return keep;
+}
+
+template <int F> struct FeatVec;
+template <> struct FeatVec<2> { using type = uint32_t; };
+template <> struct FeatVec<4> { using type = uint2; };
+template <> struct FeatVec<8> { using type = uint4; };
+
+template <int F>
+__device__ __forceinline__ void unpack(const typename FeatVec<F>::type& v, float (&f)[F])
+{
+	const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+	for (int k = 0; k < F / 2; k++) {
+		const float2 t = __half22float2(h[k]);
+		f[2 * k] = t.x;
+		f[2 * k + 1] = t.y;
+	}
+}
+
+// F features per level; CH = levels handled per 16-byte output chunk (8 halves).
+template <int F, bool OUT_F32>
+__global__ void __launch_bounds__(256) hash_fwd_kernel(HashArgs a, const __half* __restrict__ table,
+	const float* __restrict__ points, int64_t n_points, int clamp_points, uint8_t* __restrict__ keep, void* __restrict__ out)
+{
+	constexpr int CH = 8 / F;
+	using V = typename FeatVec<F>::type;
+	__shared__ HashMeta m;
+	stage_meta(m, a);
+
+	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= n_points) return;
+
+	float x = points[i * 3 + 0], y = points[i * 3 + 1], z = points[i * 3 + 2];
+	if (clamp_points) {
+		const bool k = clamp_point(a, x, y, z);
+		if (keep) keep[i] = k ? 1 : 0;
+	}
+	const float qx = (x - a.min_x) / (a.max_x - a.min_x);
+	const float qy = (y - a.min_y) / (a.max_y - a.min_y);
+	const float qz = (z - a.min_z) / (a.max_z - a.min_z);
+
+	const int L = a.n_levels;
+	const int64_t row = i * (static_cast<int64_t>(L) * F);
+	for (int l0 = 0; l0 < L; l0 += CH) {
+		__half2 acc[4];
+#pragma unroll
+		for (int j = 0; j < CH; j++) {
+			const int l = l0 + j;
+			if (l < L) {
+				Cell c;
+				locate(m, l, qx, qy, qz, c);
+				const __half* base = table + m.offset[l];
+				V v[8];
+#pragma unroll
+				for (int d = 0; d < 8; d++) v[d] = __ldg(reinterpret_cast<const V*>(base + static_cast<size_t>(c.pos[d]) * F));
+				float f[8][F];
+#pragma unroll
+				for (int d = 0; d < 8; d++) unpack<F>(v[d], f[d]);
+#pragma unroll
+				for (int k = 0; k < F; k += 2) {
+					// same summation order as src/CuHashEmbedder.cu:96-100
+					const float r0 = c.w[0] * f[0][k] + c.w[1] * f[1][k] + c.w[2] * f[2][k] + c.w[3] * f[3][k] +
+					                 c.w[4] * f[4][k] + c.w[5] * f[5][k] + c.w[6] * f[6][k] + c.w[7] * f[7][k];
+					const float r1 = c.w[0] * f[0][k + 1] + c.w[1] * f[1][k + 1] + c.w[2] * f[2][k + 1] + c.w[3] * f[3][k + 1] +
+					                 c.w[4] * f[4][k + 1] + c.w[5] * f[5][k + 1] + c.w[6] * f[6][k + 1] + c.w[7] * f[7][k + 1];
+					acc[(j * F + k) / 2] = __halves2half2(__float2half_rn(r0), __float2half_rn(r1));
+				}
+			} else {
+#pragma unroll
+				for (int k = 0; k < F; k += 2) acc[(j * F + k) / 2] = __halves2half2(__half(0), __half(0));
+			}
+		}
+		const int n_valid = min(CH, L - l0) * F;  // scalars of this chunk that exist
+		if (OUT_F32) {
+			float* o = reinterpret_cast<float*>(out) + row + static_cast<int64_t>(l0) * F;
+			float v8[8];
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				const float2 t = __half22float2(acc[k]);
+				v8[2 * k] = t.x;
+				v8[2 * k + 1] = t.y;
+			}
+			if (n_valid == 8 && ((L * F) % 4 == 0)) {
+				reinterpret_cast<float4*>(o)[0] = make_float4(v8[0], v8[1], v8[2], v8[3]);
+				reinterpret_cast<float4*>(o)[1] = make_float4(v8[4], v8[5], v8[6], v8[7]);
+			} else {
+				for (int k = 0; k < n_valid; k++) o[k] = v8[k];
+			}
+		} else {
+			__half* o = reinterpret_cast<__half*>(out) + row + static_cast<int64_t>(l0) * F;
+			if (n_valid == 8 && ((L * F) % 8 == 0)) {
+				*reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(acc);
+			} else {
+				const __half* hs = reinterpret_cast<const __half*>(acc);
+				for (int k = 0; k < n_valid; k++) o[k] = hs[k];
+			}
+		}
+	}
+}
+
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b)
+{
+	asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+template <int F, bool GRAD_BF16>
+__global__ void __launch_bounds__(256) hash_bwd_kernel(HashArgs a, const float* __restrict__ points, int64_t n_points,
+	int clamp_points, const void* __restrict__ grad_enc, float* __restrict__ grad_table)
+{
+	__shared__ HashMeta m;
+	stage_meta(m, a);
+
+	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= n_points) return;
+
+	float x = points[i * 3 + 0], y = points[i * 3 + 1], z = points[i * 3 + 2];
+	if (clamp_points) clamp_point(a, x, y, z);
+	const float qx = (x - a.min_x) / (a.max_x - a.min_x);
+	const float qy = (y - a.min_y) / (a.max_y - a.min_y);
+	const float qz = (z - a.min_z) / (a.max_z - a.min_z);
+
+	const int L = a.n_levels;
+	const int64_t row = i * (static_cast<int64_t>(L) * F);
+	for (int l = 0; l < L; l++) {
+		float g[F];
+		if (GRAD_BF16) {
+			const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(grad_enc) + row + static_cast<int64_t>(l) * F;
+#pragma unroll
+			for (int k = 0; k < F; k += 2) {
+				const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gp + k));
+				g[k] = t.x;
+				g[k + 1] = t.y;
+			}
+		} else {
+			const float* gp = reinterpret_cast<const float*>(grad_enc) + row + static_cast<int64_t>(l) * F;
+#pragma unroll
+			for (int k = 0; k < F; k += 2) {
+				const float2 t = *reinterpret_cast<const float2*>(gp + k);
+				g[k] = t.x;
+				g[k + 1] = t.y;
+			}
+		}
+		bool any = false;
+#pragma unroll
+		for (int k = 0; k < F; k++) any |= (g[k] != 0.f);
+		if (!any) continue;  // src/CuHashEmbedder.cu:195 skips all-zero pairs
+		Cell c;
+		locate(m, l, qx, qy, qz, c);
+		float* base = grad_table + m.offset[l];
+#pragma unroll
+		for (int d = 0; d < 8; d++) {
+			float* p = base + static_cast<size_t>(c.pos[d]) * F;
+#pragma unroll
+			for (int k = 0; k < F; k += 2) {
+				if (g[k] != 0.f || g[k + 1] != 0.f) red_add_v2(p + k, g[k] * c.w[d], g[k + 1] * c.w[d]);
+			}
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256) table_to_half_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n)
+{
+	const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 4;
+	for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+		if (i + 3 < n) {
+			const float4 v = *reinterpret_cast<const float4*>(src + i);
+			__half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+			uint2 o;
+			o.x = *reinterpret_cast<uint32_t*>(&lo);
+			o.y = *reinterpret_cast<uint32_t*>(&hi);
+			*reinterpret_cast<uint2*>(dst + i) = o;
+		} else {
+			for (int64_t j = i; j < n; j++) dst[j] = __float2half_rn(src[j]);
+		}
+	}
+}
+
+static int fill_args(const nrf_hash_grid* g, HashArgs& a)
+{
+	NRF_REQUIRE(g != nullptr, "grid is null");
+	NRF_REQUIRE(g->n_levels >= 1 && g->n_levels <= NRF_MAX_LEVELS, "n_levels out of range");
+	NRF_REQUIRE(g->n_volumes >= 1, "n_volumes must be >= 1");
+	NRF_REQUIRE(g->primes && g->biases && g->feat_local_idx && g->feat_local_size && g->level_scale, "grid buffer is null");
+	a.n_levels = g->n_levels;
+	a.n_volumes = g->n_volumes;
+	a.min_x = g->box_min[0]; a.min_y = g->box_min[1]; a.min_z = g->box_min[2];
+	a.max_x = g->box_max[0]; a.max_y = g->box_max[1]; a.max_z = g->box_max[2];
+	a.primes = g->primes;
+	a.biases = g->biases;
+	a.feat_local_idx = g->feat_local_idx;
+	a.feat_local_size = g->feat_local_size;
+	a.level_scale = g->level_scale;
+	return NRF_OK;
+}
+
+}  // namespace nrf
+
+using namespace nrf;
+
+extern "C" {
+
+int nrf_hash_level_scales(int32_t base_resolution, int32_t finest_resolution, int32_t n_levels, float* level_scale, nrf_stream stream)
+{
+	NRF_REQUIRE(level_scale != nullptr, "level_scale is null");
+	NRF_REQUIRE(n_levels >= 1 && n_levels <= NRF_MAX_LEVELS, "n_levels out of range");
+	level_scale_kernel<<<1, NRF_MAX_LEVELS, 0, as_stream(stream)>>>(base_resolution, finest_resolution, n_levels, level_scale);
+	NRF_CHECK_LAUNCH("level_scale_kernel");
+	return NRF_OK;
+}
+
+int nrf_table_to_half(const float* table_f32, void* table_f16, int64_t n_scalars, nrf_stream stream)
+{
+	NRF_REQUIRE(table_f32 && table_f16, "null table");
+	if (n_scalars <= 0) return NRF_OK;
+	NRF_REQUIRE((reinterpret_cast<uintptr_t>(table_f32) & 15) == 0 && (reinterpret_cast<uintptr_t>(table_f16) & 7) == 0, "tables must be 16-byte aligned");
+	const int64_t quads = (n_scalars + 3) / 4;
+	const int blocks = static_cast<int>(std::min<int64_t>((quads + 255) / 256, kNumSMs * 8));
+	table_to_half_kernel<<<blocks, 256, 0, as_stream(stream)>>>(table_f32, reinterpret_cast<__half*>(table_f16), n_scalars);
+	NRF_CHECK_LAUNCH("table_to_half_kernel");
+	return NRF_OK;
+}
+
+int nrf_hash_encode_fwd(const nrf_hash_grid* grid, const void* table_f16, const float* points, int64_t n_points,
+	int clamp_points, uint8_t* keep, void* enc_out, nrf_enc_layout layout, nrf_stream stream)
+{
+	HashArgs a;
+	if (int rc = fill_args(grid, a)) return rc;
+	NRF_REQUIRE(table_f16 && enc_out, "null table / output");
+	NRF_REQUIRE(n_points >= 0, "negative n_points");
+	if (n_points == 0) return NRF_OK;
+	NRF_REQUIRE(points != nullptr, "null points");
+	NRF_REQUIRE(layout == NRF_ENC_F32 || layout == NRF_ENC_F16, "bad layout");
+	const int F = grid->n_features;
+	const unsigned blocks = static_cast<unsigned>((n_points + 255) / 256);
+	const __half* t = reinterpret_cast<const __half*>(table_f16);
+	cudaStream_t s = as_stream(stream);
+#define NRF_LAUNCH_FWD(FF)                                                                                               \
+	if (layout == NRF_ENC_F32) hash_fwd_kernel<FF, true><<<blocks, 256, 0, s>>>(a, t, points, n_points, clamp_points, keep, enc_out); \
+	else hash_fwd_kernel<FF, false><<<blocks, 256, 0, s>>>(a, t, points, n_points, clamp_points, keep, enc_out)
+	if (F == 2) { NRF_LAUNCH_FWD(2); }
+	else if (F == 4) { NRF_LAUNCH_FWD(4); }
+	else if (F == 8) { NRF_LAUNCH_FWD(8); }
+	else { set_error("nrf_hash_encode_fwd: n_features must be 2, 4 or 8"); return NRF_ERR_UNSUPPORTED; }
+#undef NRF_LAUNCH_FWD
+	NRF_CHECK_LAUNCH("hash_fwd_kernel");
+	return NRF_OK;
+}
+
+int nrf_hash_encode_bwd(const nrf_hash_grid* grid, const float* points, int64_t n_points, int clamp_points,
+	const void* grad_enc, nrf_grad_layout layout, float* grad_table, nrf_stream stream)
+{
+	HashArgs a;
+	if (int rc = fill_args(grid, a)) return rc;
+	NRF_REQUIRE(grad_table != nullptr, "null grad_table");
+	NRF_REQUIRE(n_points >= 0, "negative n_points");
+	if (n_points == 0) return NRF_OK;
+	NRF_REQUIRE(points && grad_enc, "null points / grad");
+	NRF_REQUIRE(layout == NRF_GRAD_F32 || layout == NRF_GRAD_BF16, "bad layout");
+	const int F = grid->n_features;
+	const unsigned blocks = static_cast<unsigned>((n_points + 255) / 256);
+	cudaStream_t s = as_stream(stream);
+#define NRF_LAUNCH_BWD(FF)                                                                                          \
+	if (layout == NRF_GRAD_BF16) hash_bwd_kernel<FF, true><<<blocks, 256, 0, s>>>(a, points, n_points, clamp_points, grad_enc, grad_table); \
+	else hash_bwd_kernel<FF, false><<<blocks, 256, 0, s>>>(a, points, n_points, clamp_points, grad_enc, grad_table)
+	if (F == 2) { NRF_LAUNCH_BWD(2); }
+	else if (F == 4) { NRF_LAUNCH_BWD(4); }
+	else if (F == 8) { NRF_LAUNCH_BWD(8); }
+	else { set_error("nrf_hash_encode_bwd: n_features must be 2, 4 or 8"); return NRF_ERR_UNSUPPORTED; }
+#undef NRF_LAUNCH_BWD
+	NRF_CHECK_LAUNCH("hash_bwd_kernel");
+	return NRF_OK;
+}
+
+}

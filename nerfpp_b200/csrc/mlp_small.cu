@@ -1,0 +1,584 @@
+// Fused NeRFSmall (HashNeRF tiny MLP) forward and backward for sm_100a — register-chained tensor-core version.
+//
+// Replaces NeRFSmallImpl::forward (reference src/NeRF.cpp:363-412: 5 cuBLAS SGEMMs + relu/slice/cat kernels, every
+// [N,64] fp32 activation round-tripping HBM) and its autograd backward, plus the keep-mask write of RunNetwork
+// (src/NeRFRenderer.h:187-188) and the per-sample direction expansion + SH + cat (:179-182).
+//
+//   sigma net : h0 = relu(enc32 · W0^T) ; d1 = h0 · W1^T          -> sigma = d1[:,0], geo = d1[:,1:16]
+//   colour net: c  = relu(relu([sh16 | geo15] · W2^T) · W3^T) · W4^T
+//   out [N,4] = [c0,c1,c2, sigma]                                   (src/NeRF.cpp:408; views first: :383)
+//
+// One warp owns 16 (backward) or 32 (forward) rows and chains all five layers in registers: the fp32 accumulator
+// fragment of one m16n8k16 MMA is re-packed (ReLU fused into the convert) as the A fragment of the next layer, so
+// activations never touch shared or global memory.  Weights live in shared memory pre-arranged in B-fragment order
+// (nrf_mlp_small_pack), one conflict-free LDS.64 per MMA.  Layer 0 runs fp16 x fp16 (the encodings ARE fp16 values,
+// src/CuHashEmbedder.cu:253), all other layers bf16 x bf16; accumulation is fp32 throughout.
+//
+// Backward: activations are recomputed (nothing saved by the forward).  The dX chain runs in registers like the
+// forward.  For dW = dY^T X, each warp drops its X_l / dY_l slabs into padded shared-memory tiles; after one CTA
+// barrier the 8 warps split the 80 output 16x8 tiles between them, read the tiles with ldmatrix.trans (both
+// operands are "K = rows"-major) and keep their share of dW in registers across the whole persistent loop; one
+// fp32 atomicAdd per weight per CTA at the end.
+//
+// The A2 operand is laid out [sh(16) | d1(16)] instead of [sh(16) | geo(15) | pad]: column 16 is the sigma slot,
+// whose weight column is zero (and whose value is zeroed), which avoids a cross-lane shift of the accumulators.
+#include "common.cuh"
+
+namespace nrf {
+
+// ---------------------------------------------------------------------------------------------- packed layout
+constexpr int kW0 = 0, kW1 = 2048, kW2 = 3072, kW3 = 5056, kW4 = 9152, kParamCount = 9344;  // flat fp32 offsets
+// fragment blob, offsets in 32-bit words.  fwd: [ks][nt][lane][2]
+constexpr int kF0 = 0, kF1 = 1024, kF2 = 1536, kF3 = 2560, kF4 = 4608, kFwdWords = 4864;
+constexpr int kB4 = 4864, kB3 = 5376, kB2 = 7424, kB1 = 8448, kB0 = 8960, kBlobWords = 9984;
+
+// padded logical weight matrices Wp_l(n, k)
+__device__ __forceinline__ float wp(const float* __restrict__ p, int layer, int n, int k)
+{
+	switch (layer) {
+		case 0: return p[kW0 + n * 32 + k];
+		case 1: return p[kW1 + n * 64 + k];
+		case 2: return k < 16 ? p[kW2 + n * 31 + k] : (k == 16 ? 0.f : p[kW2 + n * 31 + k - 1]);
+		case 3: return p[kW3 + n * 64 + k];
+		default: return n < 3 ? p[kW4 + n * 64 + k] : 0.f;
+	}
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
+{
+	__nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+	return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi)
+{
+	__half2 v = __floats2half2_rn(lo, hi);
+	return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi)
+{
+	uint32_t r;
+	asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+	return r;
+}
+
+__global__ void __launch_bounds__(256) mlp_pack_kernel(const float* __restrict__ p, uint32_t* __restrict__ blob)
+{
+	const int w = blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= kBlobWords) return;
+	int layer, base, NT;
+	bool bwd = w >= kFwdWords;
+	if (!bwd) {
+		if (w < kF1) { layer = 0; base = kF0; NT = 8; }
+		else if (w < kF2) { layer = 1; base = kF1; NT = 2; }
+		else if (w < kF3) { layer = 2; base = kF2; NT = 8; }
+		else if (w < kF4) { layer = 3; base = kF3; NT = 8; }
+		else { layer = 4; base = kF4; NT = 1; }
+	} else {
+		if (w < kB3) { layer = 4; base = kB4; NT = 8; }
+		else if (w < kB2) { layer = 3; base = kB3; NT = 8; }
+		else if (w < kB1) { layer = 2; base = kB2; NT = 4; }
+		else if (w < kB0) { layer = 1; base = kB1; NT = 8; }
+		else { layer = 0; base = kB0; NT = 4; }
+	}
+	const int r = w - base;
+	const int j = r & 1, lane = (r >> 1) & 31, tile = r >> 6;
+	const int nt = tile % NT, ks = tile / NT;
+	const int g = lane >> 2, t = lane & 3;
+	const int nn = nt * 8 + g, kk = ks * 16 + 2 * t + 8 * j;
+	float lo, hi;
+	if (!bwd) {
+		lo = wp(p, layer, nn, kk);
+		hi = wp(p, layer, nn, kk + 1);
+	} else {
+		// B'[k'][n'] = Wp(k', n'): k' = output channel (padded with zero rows), n' = input channel
+		const int n_out = layer == 1 ? 16 : (layer == 4 ? 8 : 64);
+		lo = kk < n_out ? wp(p, layer, kk, nn) : 0.f;
+		hi = kk + 1 < n_out ? wp(p, layer, kk + 1, nn) : 0.f;
+	}
+	blob[w] = (!bwd && layer == 0) ? pack_f16(lo, hi) : pack_bf16(lo, hi);
+}
+
+// ---------------------------------------------------------------------------------------------- MMA helpers
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+	asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+	             : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+	             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+	asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+	             : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+	             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// acc[NT][4] = A[KS] x frag  (frag: [ks][nt][lane] uint2 in shared memory)
+template <int KS, int NT, bool F16>
+__device__ __forceinline__ void layer_mma(const uint32_t (&a)[KS][4], const uint32_t* __restrict__ frag, int lane, float (&acc)[NT][4])
+{
+#pragma unroll
+	for (int nt = 0; nt < NT; nt++) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+	const uint2* f = reinterpret_cast<const uint2*>(frag);
+#pragma unroll
+	for (int ks = 0; ks < KS; ks++) {
+#pragma unroll
+		for (int nt = 0; nt < NT; nt++) {
+			const uint2 b = f[(ks * NT + nt) * 32 + lane];
+			if (F16) mma_f16(acc[nt], a[ks], b.x, b.y);
+			else mma_bf16(acc[nt], a[ks], b.x, b.y);
+		}
+	}
+}
+
+// accumulator fragment of 2*KS n-tiles -> bf16 A fragment of KS k-steps
+template <int KS, bool RELU>
+__device__ __forceinline__ void repack(const float (&acc)[2 * KS][4], uint32_t (&a)[KS][4])
+{
+#pragma unroll
+	for (int ks = 0; ks < KS; ks++) {
+		if (RELU) {
+			a[ks][0] = pack_bf16_relu(acc[2 * ks][0], acc[2 * ks][1]);
+			a[ks][1] = pack_bf16_relu(acc[2 * ks][2], acc[2 * ks][3]);
+			a[ks][2] = pack_bf16_relu(acc[2 * ks + 1][0], acc[2 * ks + 1][1]);
+			a[ks][3] = pack_bf16_relu(acc[2 * ks + 1][2], acc[2 * ks + 1][3]);
+		} else {
+			a[ks][0] = pack_bf16(acc[2 * ks][0], acc[2 * ks][1]);
+			a[ks][1] = pack_bf16(acc[2 * ks][2], acc[2 * ks][3]);
+			a[ks][2] = pack_bf16(acc[2 * ks + 1][0], acc[2 * ks + 1][1]);
+			a[ks][3] = pack_bf16(acc[2 * ks + 1][2], acc[2 * ks + 1][3]);
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------- input loaders
+// A fragment (fp16) of the 32 encoding channels for rows r_lo = row0+g, r_hi = row0+g+8.
+template <int IN_KIND>
+__device__ __forceinline__ void load_enc(const void* __restrict__ enc, int64_t r_lo, int64_t r_hi, int64_t n, int t, uint32_t (&a)[2][4])
+{
+	if (IN_KIND == NRF_MLP_IN_ENC16_RAYDIRS) {
+		const uint32_t* e = reinterpret_cast<const uint32_t*>(enc);  // 16 words per row
+#pragma unroll
+		for (int ks = 0; ks < 2; ks++) {
+			a[ks][0] = r_lo < n ? __ldg(e + r_lo * 16 + ks * 8 + t) : 0u;
+			a[ks][1] = r_hi < n ? __ldg(e + r_hi * 16 + ks * 8 + t) : 0u;
+			a[ks][2] = r_lo < n ? __ldg(e + r_lo * 16 + ks * 8 + 4 + t) : 0u;
+			a[ks][3] = r_hi < n ? __ldg(e + r_hi * 16 + ks * 8 + 4 + t) : 0u;
+		}
+	} else {
+		const float* x = reinterpret_cast<const float*>(enc);  // 48 floats per row
+#pragma unroll
+		for (int ks = 0; ks < 2; ks++) {
+			float2 v;
+			v = r_lo < n ? __ldg(reinterpret_cast<const float2*>(x + r_lo * 48 + ks * 16 + 2 * t)) : make_float2(0.f, 0.f);
+			a[ks][0] = pack_f16(v.x, v.y);
+			v = r_hi < n ? __ldg(reinterpret_cast<const float2*>(x + r_hi * 48 + ks * 16 + 2 * t)) : make_float2(0.f, 0.f);
+			a[ks][1] = pack_f16(v.x, v.y);
+			v = r_lo < n ? __ldg(reinterpret_cast<const float2*>(x + r_lo * 48 + ks * 16 + 8 + 2 * t)) : make_float2(0.f, 0.f);
+			a[ks][2] = pack_f16(v.x, v.y);
+			v = r_hi < n ? __ldg(reinterpret_cast<const float2*>(x + r_hi * 48 + ks * 16 + 8 + 2 * t)) : make_float2(0.f, 0.f);
+			a[ks][3] = pack_f16(v.x, v.y);
+		}
+	}
+}
+
+// A fragment (bf16) of the 16 view channels (k-step 0 of the colour net input)
+template <int IN_KIND>
+__device__ __forceinline__ void load_views(const void* __restrict__ enc, const float* __restrict__ ray_sh, int S, int64_t r_lo, int64_t r_hi,
+	int64_t n, int t, uint32_t (&a)[4])
+{
+	const float* lo;
+	const float* hi;
+	if (IN_KIND == NRF_MLP_IN_ENC16_RAYDIRS) {
+		lo = ray_sh + (r_lo < n ? r_lo / S : 0) * 16;
+		hi = ray_sh + (r_hi < n ? r_hi / S : 0) * 16;
+	} else {
+		const float* x = reinterpret_cast<const float*>(enc);
+		lo = x + (r_lo < n ? r_lo : 0) * 48 + 32;
+		hi = x + (r_hi < n ? r_hi : 0) * 48 + 32;
+	}
+	float2 v;
+	v = __ldg(reinterpret_cast<const float2*>(lo + 2 * t));      a[0] = pack_bf16(v.x, v.y);
+	v = __ldg(reinterpret_cast<const float2*>(hi + 2 * t));      a[1] = pack_bf16(v.x, v.y);
+	v = __ldg(reinterpret_cast<const float2*>(lo + 8 + 2 * t));  a[2] = pack_bf16(v.x, v.y);
+	v = __ldg(reinterpret_cast<const float2*>(hi + 8 + 2 * t));  a[3] = pack_bf16(v.x, v.y);
+}
+
+__device__ __forceinline__ void copy_blob(uint32_t* dst, const uint32_t* __restrict__ src, int words)
+{
+	const uint4* s = reinterpret_cast<const uint4*>(src);
+	uint4* d = reinterpret_cast<uint4*>(dst);
+	for (int i = threadIdx.x; i < words / 4; i += blockDim.x) d[i] = __ldg(s + i);
+}
+
+// ---------------------------------------------------------------------------------------------- forward
+constexpr int kFwdWarps = 8;
+
+template <int IN_KIND>
+__global__ void __launch_bounds__(kFwdWarps * 32) mlp_small_fwd_kernel(const uint32_t* __restrict__ blob, const void* __restrict__ enc,
+	const float* __restrict__ ray_sh, int S, const uint8_t* __restrict__ keep, int64_t n, float* __restrict__ raw_out)
+{
+	__shared__ __align__(16) uint32_t wf[kFwdWords];
+	copy_blob(wf, blob, kFwdWords);
+	__syncthreads();
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+	const int64_t n_slabs = (n + 15) / 16;
+	for (int64_t slab = static_cast<int64_t>(blockIdx.x) * kFwdWarps + warp; slab < n_slabs; slab += static_cast<int64_t>(gridDim.x) * kFwdWarps) {
+		const int64_t r_lo = slab * 16 + g, r_hi = r_lo + 8;
+		uint32_t a0[2][4];
+		load_enc<IN_KIND>(enc, r_lo, r_hi, n, t, a0);
+		float acc[8][4];
+		layer_mma<2, 8, true>(a0, wf + kF0, lane, acc);
+		uint32_t a1[4][4];
+		repack<4, true>(acc, a1);
+		float d1[2][4];
+		layer_mma<4, 2, false>(a1, wf + kF1, lane, d1);
+		const float sig_lo = d1[0][0], sig_hi = d1[0][2];  // column 0 lives in lanes with t == 0
+		uint32_t a2[2][4];
+		load_views<IN_KIND>(enc, ray_sh, S, r_lo, r_hi, n, t, a2[0]);
+		if (t == 0) { d1[0][0] = 0.f; d1[0][2] = 0.f; }     // sigma slot of the colour input
+		repack<1, false>(d1, reinterpret_cast<uint32_t(&)[1][4]>(a2[1]));
+		layer_mma<2, 8, false>(a2, wf + kF2, lane, acc);
+		uint32_t a3[4][4];
+		repack<4, true>(acc, a3);
+		layer_mma<4, 8, false>(a3, wf + kF3, lane, acc);
+		repack<4, true>(acc, a3);
+		float c[1][4];
+		layer_mma<4, 1, false>(a3, wf + kF4, lane, c);
+		// rgb: cols 0,1 in t==0 (c0,c1 / c2,c3), col 2 in t==1
+		const float b_lo = __shfl_down_sync(0xffffffffu, c[0][0], 1);
+		const float b_hi = __shfl_down_sync(0xffffffffu, c[0][2], 1);
+		if (t == 0) {
+			if (r_lo < n) {
+				const float s = (keep && !keep[r_lo]) ? 0.f : sig_lo;
+				*reinterpret_cast<float4*>(raw_out + r_lo * 4) = make_float4(c[0][0], c[0][1], b_lo, s);
+			}
+			if (r_hi < n) {
+				const float s = (keep && !keep[r_hi]) ? 0.f : sig_hi;
+				*reinterpret_cast<float4*>(raw_out + r_hi * 4) = make_float4(c[0][2], c[0][3], b_hi, s);
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------- backward
+constexpr int kBwdWarps = 8;
+constexpr int kTileRows = kBwdWarps * 16;  // 128
+// padded tile pitches (bf16 elements)
+constexpr int kP32 = 40, kP64 = 72, kP16 = 24, kP8 = 16;
+// tile offsets in bf16 elements
+constexpr int kTX0 = 0;
+constexpr int kTD0 = kTX0 + kTileRows * kP32;
+constexpr int kTX1 = kTD0 + kTileRows * kP64;
+constexpr int kTD1 = kTX1 + kTileRows * kP64;
+constexpr int kTX2 = kTD1 + kTileRows * kP16;
+constexpr int kTD2 = kTX2 + kTileRows * kP32;
+constexpr int kTX3 = kTD2 + kTileRows * kP64;
+constexpr int kTD3 = kTX3 + kTileRows * kP64;
+constexpr int kTX4 = kTD3 + kTileRows * kP64;
+constexpr int kTD4 = kTX4 + kTileRows * kP64;
+constexpr int kTileElems = kTD4 + kTileRows * kP8;
+constexpr size_t kBwdSmem = static_cast<size_t>(kBlobWords) * 4 + static_cast<size_t>(kTileElems) * 2;
+
+// store an A-fragment-shaped register set (KS k-steps) for rows (g, g+8) of this warp's slab
+template <int KS>
+__device__ __forceinline__ void store_frag(__nv_bfloat16* tile, int pitch, int row_g, int t, const uint32_t (&a)[KS][4])
+{
+	uint32_t* lo = reinterpret_cast<uint32_t*>(tile + row_g * pitch);
+	uint32_t* hi = reinterpret_cast<uint32_t*>(tile + (row_g + 8) * pitch);
+#pragma unroll
+	for (int ks = 0; ks < KS; ks++) {
+		lo[ks * 8 + t] = a[ks][0];
+		hi[ks * 8 + t] = a[ks][1];
+		lo[ks * 8 + 4 + t] = a[ks][2];
+		hi[ks * 8 + 4 + t] = a[ks][3];
+	}
+}
+
+// dD = dA where the stored activation (bf16 pair words in `tile`) is > 0
+template <int NT>
+__device__ __forceinline__ void relu_mask(float (&acc)[NT][4], const __nv_bfloat16* tile, int pitch, int row_g, int t)
+{
+	const uint32_t* lo = reinterpret_cast<const uint32_t*>(tile + row_g * pitch);
+	const uint32_t* hi = reinterpret_cast<const uint32_t*>(tile + (row_g + 8) * pitch);
+#pragma unroll
+	for (int nt = 0; nt < NT; nt++) {
+		const uint32_t wl = lo[nt * 4 + t], wh = hi[nt * 4 + t];
+		// bf16 > 0  <=>  sign clear and magnitude non-zero
+		if (!((wl & 0x7fffu) != 0u && (wl & 0x8000u) == 0u)) acc[nt][0] = 0.f;
+		if (!((wl & 0x7fff0000u) != 0u && (wl & 0x80000000u) == 0u)) acc[nt][1] = 0.f;
+		if (!((wh & 0x7fffu) != 0u && (wh & 0x8000u) == 0u)) acc[nt][2] = 0.f;
+		if (!((wh & 0x7fff0000u) != 0u && (wh & 0x80000000u) == 0u)) acc[nt][3] = 0.f;
+	}
+}
+
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p)
+{
+	const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+	asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+// acc[NT][4] += D[:, m0:m0+16]^T · X[:, n0:n0+8*NT] over the 128 tile rows.  NT must be even.
+template <int NT>
+__device__ __forceinline__ void dw_accumulate(const __nv_bfloat16* D, int dp, int m0, const __nv_bfloat16* X, int xp, int n0, int lane, float (*acc)[4])
+{
+	const int mi = lane >> 3, r = lane & 7;
+#pragma unroll
+	for (int ks = 0; ks < kTileRows / 16; ks++) {
+		const int k0 = ks * 16;
+		uint32_t a[4];
+		ldsm_x4_trans(a, D + (k0 + (mi >> 1) * 8 + r) * dp + m0 + (mi & 1) * 8);
+#pragma unroll
+		for (int np = 0; np < NT / 2; np++) {
+			uint32_t b[4];
+			ldsm_x4_trans(b, X + (k0 + (mi & 1) * 8 + r) * xp + n0 + np * 16 + (mi >> 1) * 8);
+			mma_bf16(*reinterpret_cast<float(*)[4]>(acc[2 * np]), a, b[0], b[1]);
+			mma_bf16(*reinterpret_cast<float(*)[4]>(acc[2 * np + 1]), a, b[2], b[3]);
+		}
+	}
+}
+
+// flush one 16x8 accumulator tile of layer `layer` (m = out channel, n = in channel, padded indexing) to the flat gradient
+__device__ __forceinline__ void dw_flush(float* __restrict__ gp, int layer, int m0, int n0, int g, int t, const float (&acc)[4])
+{
+#pragma unroll
+	for (int e = 0; e < 4; e++) {
+		const int m = m0 + g + (e >> 1) * 8, k = n0 + 2 * t + (e & 1);
+		int idx = -1;
+		switch (layer) {
+			case 0: idx = kW0 + m * 32 + k; break;
+			case 1: idx = kW1 + m * 64 + k; break;
+			case 2: idx = k < 16 ? kW2 + m * 31 + k : (k == 16 ? -1 : kW2 + m * 31 + k - 1); break;
+			case 3: idx = kW3 + m * 64 + k; break;
+			default: idx = m < 3 ? kW4 + m * 64 + k : -1; break;
+		}
+		if (idx >= 0 && acc[e] != 0.f) atomicAdd(gp + idx, acc[e]);
+	}
+}
+
+template <int IN_KIND>
+__global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const uint32_t* __restrict__ blob, const void* __restrict__ enc,
+	const float* __restrict__ ray_sh, int S, const uint8_t* __restrict__ keep, int64_t n, const float* __restrict__ grad_raw,
+	void* __restrict__ grad_in, float* __restrict__ grad_params)
+{
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	uint32_t* wf = reinterpret_cast<uint32_t*>(smem_raw);
+	__nv_bfloat16* tiles = reinterpret_cast<__nv_bfloat16*>(smem_raw + static_cast<size_t>(kBlobWords) * 4);
+	copy_blob(wf, blob, kBlobWords);
+	__syncthreads();
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+	const int row_g = warp * 16 + g;  // row inside the CTA tile
+
+	float dw[10][4];
+#pragma unroll
+	for (int i = 0; i < 10; i++) dw[i][0] = dw[i][1] = dw[i][2] = dw[i][3] = 0.f;
+
+	const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
+	for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		const int64_t r_lo = tile * kTileRows + row_g, r_hi = r_lo + 8;
+		// ---- forward recompute; every layer input is dropped into its X tile
+		{
+			uint32_t a0[2][4];
+			load_enc<IN_KIND>(enc, r_lo, r_hi, n, t, a0);
+			float acc[8][4];
+			layer_mma<2, 8, true>(a0, wf + kF0, lane, acc);
+			{   // X0 as bf16
+				uint32_t x0[2][4];
+#pragma unroll
+				for (int ks = 0; ks < 2; ks++)
+#pragma unroll
+					for (int e = 0; e < 4; e++) {
+						const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&a0[ks][e]));
+						x0[ks][e] = pack_bf16(v.x, v.y);
+					}
+				store_frag<2>(tiles + kTX0, kP32, row_g, t, x0);
+			}
+			uint32_t a1[4][4];
+			repack<4, true>(acc, a1);
+			store_frag<4>(tiles + kTX1, kP64, row_g, t, a1);
+			float d1[2][4];
+			layer_mma<4, 2, false>(a1, wf + kF1, lane, d1);
+			uint32_t a2[2][4];
+			load_views<IN_KIND>(enc, ray_sh, S, r_lo, r_hi, n, t, a2[0]);
+			if (t == 0) { d1[0][0] = 0.f; d1[0][2] = 0.f; }
+			repack<1, false>(d1, reinterpret_cast<uint32_t(&)[1][4]>(a2[1]));
+			store_frag<2>(tiles + kTX2, kP32, row_g, t, a2);
+			layer_mma<2, 8, false>(a2, wf + kF2, lane, acc);
+			uint32_t a3[4][4];
+			repack<4, true>(acc, a3);
+			store_frag<4>(tiles + kTX3, kP64, row_g, t, a3);
+			layer_mma<4, 8, false>(a3, wf + kF3, lane, acc);
+			repack<4, true>(acc, a3);
+			store_frag<4>(tiles + kTX4, kP64, row_g, t, a3);
+		}
+		__syncwarp();
+		// ---- backward chain
+		{
+			float4 g_lo = make_float4(0.f, 0.f, 0.f, 0.f), g_hi = g_lo;
+			if (r_lo < n) g_lo = __ldg(reinterpret_cast<const float4*>(grad_raw + r_lo * 4));
+			if (r_hi < n) g_hi = __ldg(reinterpret_cast<const float4*>(grad_raw + r_hi * 4));
+			if (keep) {
+				if (r_lo < n && !keep[r_lo]) g_lo.w = 0.f;
+				if (r_hi < n && !keep[r_hi]) g_hi.w = 0.f;
+			}
+			uint32_t d4[1][4];
+			d4[0][0] = t == 0 ? pack_bf16(g_lo.x, g_lo.y) : (t == 1 ? pack_bf16(g_lo.z, 0.f) : 0u);
+			d4[0][1] = t == 0 ? pack_bf16(g_hi.x, g_hi.y) : (t == 1 ? pack_bf16(g_hi.z, 0.f) : 0u);
+			d4[0][2] = 0u;
+			d4[0][3] = 0u;
+			store_frag<1>(tiles + kTD4, kP8, row_g, t, d4);   // 8 real + 8 zero columns
+			float acc[8][4];
+			layer_mma<1, 8, false>(d4, wf + kB4, lane, acc);                 // dA4 = dD4 · W4
+			relu_mask<8>(acc, tiles + kTX4, kP64, row_g, t);
+			uint32_t d3[4][4];
+			repack<4, false>(acc, d3);
+			store_frag<4>(tiles + kTD3, kP64, row_g, t, d3);
+			layer_mma<4, 8, false>(d3, wf + kB3, lane, acc);                 // dA3 = dD3 · W3
+			relu_mask<8>(acc, tiles + kTX3, kP64, row_g, t);
+			repack<4, false>(acc, d3);
+			store_frag<4>(tiles + kTD2, kP64, row_g, t, d3);
+			float da2[4][4];
+			layer_mma<4, 4, false>(d3, wf + kB2, lane, da2);                 // dA2 = dD2 · W2p  (cols 0..15 views, 16..31 d1)
+			if (t == 0) { da2[2][0] += g_lo.w; da2[2][2] += g_hi.w; }        // + d(sigma)
+			uint32_t dd1[1][4];
+			dd1[0][0] = pack_bf16(da2[2][0], da2[2][1]);
+			dd1[0][1] = pack_bf16(da2[2][2], da2[2][3]);
+			dd1[0][2] = pack_bf16(da2[3][0], da2[3][1]);
+			dd1[0][3] = pack_bf16(da2[3][2], da2[3][3]);
+			store_frag<1>(tiles + kTD1, kP16, row_g, t, dd1);
+			layer_mma<1, 8, false>(dd1, wf + kB1, lane, acc);                // dA1 = dD1 · W1
+			relu_mask<8>(acc, tiles + kTX1, kP64, row_g, t);
+			repack<4, false>(acc, d3);
+			store_frag<4>(tiles + kTD0, kP64, row_g, t, d3);
+			if (grad_in) {
+				float de[4][4];
+				layer_mma<4, 4, false>(d3, wf + kB0, lane, de);             // dEnc = dD0 · W0
+				if (IN_KIND == NRF_MLP_IN_ENC16_RAYDIRS) {
+					uint32_t* o = reinterpret_cast<uint32_t*>(grad_in);      // bf16 [N,32] = 16 words per row
+#pragma unroll
+					for (int nt = 0; nt < 4; nt++) {
+						if (r_lo < n) o[r_lo * 16 + nt * 4 + t] = pack_bf16(de[nt][0], de[nt][1]);
+						if (r_hi < n) o[r_hi * 16 + nt * 4 + t] = pack_bf16(de[nt][2], de[nt][3]);
+					}
+				} else {
+					float* o = reinterpret_cast<float*>(grad_in);            // fp32 [N,48]
+#pragma unroll
+					for (int nt = 0; nt < 4; nt++) {
+						if (r_lo < n) *reinterpret_cast<float2*>(o + r_lo * 48 + nt * 8 + 2 * t) = make_float2(de[nt][0], de[nt][1]);
+						if (r_hi < n) *reinterpret_cast<float2*>(o + r_hi * 48 + nt * 8 + 2 * t) = make_float2(de[nt][2], de[nt][3]);
+					}
+#pragma unroll
+					for (int nt = 0; nt < 2; nt++) {
+						if (r_lo < n) *reinterpret_cast<float2*>(o + r_lo * 48 + 32 + nt * 8 + 2 * t) = make_float2(da2[nt][0], da2[nt][1]);
+						if (r_hi < n) *reinterpret_cast<float2*>(o + r_hi * 48 + 32 + nt * 8 + 2 * t) = make_float2(da2[nt][2], da2[nt][3]);
+					}
+				}
+			}
+		}
+		__syncthreads();
+		// ---- dW: 80 output tiles split over the 8 warps, 10 each
+		if (warp < 4) {
+			dw_accumulate<8>(tiles + kTD3, kP64, warp * 16, tiles + kTX3, kP64, 0, lane, dw);            // dW3 rows 16w..16w+15
+			dw_accumulate<2>(tiles + kTD1, kP16, 0, tiles + kTX1, kP64, warp * 16, lane, dw + 8);        // dW1 cols 16w..16w+15
+		} else {
+			const int h = (warp - 4) & 1;
+			const __nv_bfloat16* D = warp < 6 ? tiles + kTD0 : tiles + kTD2;
+			const __nv_bfloat16* X = warp < 6 ? tiles + kTX0 : tiles + kTX2;
+			dw_accumulate<4>(D, kP64, h * 32, X, kP32, 0, lane, dw);                                     // dW0 / dW2 rows 32h..32h+15
+			dw_accumulate<4>(D, kP64, h * 32 + 16, X, kP32, 0, lane, dw + 4);                            //            rows 32h+16..32h+31
+			dw_accumulate<2>(tiles + kTD4, kP8, 0, tiles + kTX4, kP64, (warp - 4) * 16, lane, dw + 8);   // dW4 cols 16(w-4)..
+		}
+		__syncthreads();
+	}
+
+	// ---- flush dW
+	if (warp < 4) {
+#pragma unroll
+		for (int nt = 0; nt < 8; nt++) dw_flush(grad_params, 3, warp * 16, nt * 8, g, t, dw[nt]);
+#pragma unroll
+		for (int nt = 0; nt < 2; nt++) dw_flush(grad_params, 1, 0, warp * 16 + nt * 8, g, t, dw[8 + nt]);
+	} else {
+		const int h = (warp - 4) & 1;
+		const int layer = warp < 6 ? 0 : 2;
+#pragma unroll
+		for (int nt = 0; nt < 4; nt++) dw_flush(grad_params, layer, h * 32, nt * 8, g, t, dw[nt]);
+#pragma unroll
+		for (int nt = 0; nt < 4; nt++) dw_flush(grad_params, layer, h * 32 + 16, nt * 8, g, t, dw[4 + nt]);
+#pragma unroll
+		for (int nt = 0; nt < 2; nt++) dw_flush(grad_params, 4, 0, (warp - 4) * 16 + nt * 8, g, t, dw[8 + nt]);
+	}
+}
+
+static int check_shape(const nrf_mlp_small_shape* s)
+{
+	NRF_REQUIRE(s != nullptr, "shape is null");
+	if (!(s->input_ch == 32 && s->input_ch_views == 16 && s->hidden_dim == 64 && s->geo_feat_dim == 15 &&
+	      s->hidden_dim_color == 64 && s->num_layers == 2 && s->num_layers_color == 3)) {
+		set_error("nrf_mlp_small: only the BASELINE shape 32+16 -> 64 -> 16 | 31 -> 64 -> 64 -> 3 is built");
+		return NRF_ERR_UNSUPPORTED;
+	}
+	return NRF_OK;
+}
+
+}  // namespace nrf
+
+using namespace nrf;
+
+extern "C" {
+
+int64_t nrf_mlp_small_packed_bytes(const nrf_mlp_small_shape* shape) { return check_shape(shape) ? -1 : static_cast<int64_t>(kBlobWords) * 4; }
+int64_t nrf_mlp_small_param_count(const nrf_mlp_small_shape* shape) { return check_shape(shape) ? -1 : kParamCount; }
+
+int nrf_mlp_small_pack(const nrf_mlp_small_shape* shape, const float* params_flat, void* packed, nrf_stream stream)
+{
+	if (int rc = check_shape(shape)) return rc;
+	NRF_REQUIRE(params_flat && packed, "null pointer");
+	NRF_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "packed blob must be 16-byte aligned");
+	mlp_pack_kernel<<<(kBlobWords + 255) / 256, 256, 0, as_stream(stream)>>>(params_flat, reinterpret_cast<uint32_t*>(packed));
+	NRF_CHECK_LAUNCH("mlp_pack_kernel");
+	return NRF_OK;
+}
+
+int nrf_mlp_small_fwd(const nrf_mlp_small_shape* shape, const void* packed, nrf_mlp_input in_kind, const void* enc,
+	const float* ray_sh, int32_t samples_per_ray, const uint8_t* keep, int64_t n, float* raw_out, nrf_stream stream)
+{
+	if (int rc = check_shape(shape)) return rc;
+	NRF_REQUIRE(n >= 0, "negative n");
+	if (n == 0) return NRF_OK;
+	NRF_REQUIRE(packed && enc && raw_out, "null pointer");
+	NRF_REQUIRE(in_kind == NRF_MLP_IN_F32_CAT || (ray_sh && samples_per_ray >= 1), "ray_sh / samples_per_ray missing");
+	const int64_t slabs = (n + 15) / 16;
+	const int blocks = static_cast<int>(std::min<int64_t>((slabs + kFwdWarps - 1) / kFwdWarps, kNumSMs * 4));
+	const uint32_t* blob = reinterpret_cast<const uint32_t*>(packed);
+	if (in_kind == NRF_MLP_IN_ENC16_RAYDIRS)
+		mlp_small_fwd_kernel<NRF_MLP_IN_ENC16_RAYDIRS><<<blocks, kFwdWarps * 32, 0, as_stream(stream)>>>(blob, enc, ray_sh, samples_per_ray, keep, n, raw_out);
+	else
+		mlp_small_fwd_kernel<NRF_MLP_IN_F32_CAT><<<blocks, kFwdWarps * 32, 0, as_stream(stream)>>>(blob, enc, ray_sh, samples_per_ray, keep, n, raw_out);
+	NRF_CHECK_LAUNCH("mlp_small_fwd_kernel");
+	return NRF_OK;
+}
+
+int nrf_mlp_small_bwd(const nrf_mlp_small_shape* shape, const void* packed, nrf_mlp_input in_kind, const void* enc,
+	const float* ray_sh, int32_t samples_per_ray, const uint8_t* keep, int64_t n, const float* grad_raw, void* grad_in,
+	float* grad_params_flat, nrf_stream stream)
+{
+	if (int rc = check_shape(shape)) return rc;
+	NRF_REQUIRE(n >= 0, "negative n");
+	if (n == 0) return NRF_OK;
+	NRF_REQUIRE(packed && enc && grad_raw && grad_params_flat, "null pointer");
+	NRF_REQUIRE(in_kind == NRF_MLP_IN_F32_CAT || (ray_sh && samples_per_ray >= 1), "ray_sh / samples_per_ray missing");
+	const int64_t tiles = (n + kTileRows - 1) / kTileRows;
+	const int blocks = static_cast<int>(std::min<int64_t>(tiles, kNumSMs));
+	const uint32_t* blob = reinterpret_cast<const uint32_t*>(packed);
+	cudaStream_t s = as_stream(stream);
+	if (in_kind == NRF_MLP_IN_ENC16_RAYDIRS) {
+		NRF_CUDA(cudaFuncSetAttribute(mlp_small_bwd_kernel<NRF_MLP_IN_ENC16_RAYDIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBwdSmem)));
+		mlp_small_bwd_kernel<NRF_MLP_IN_ENC16_RAYDIRS><<<blocks, kBwdWarps * 32, kBwdSmem, s>>>(blob, enc, ray_sh, samples_per_ray, keep, n, grad_raw, grad_in, grad_params_flat);
+	} else {
+		NRF_CUDA(cudaFuncSetAttribute(mlp_small_bwd_kernel<NRF_MLP_IN_F32_CAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBwdSmem)));
+		mlp_small_bwd_kernel<NRF_MLP_IN_F32_CAT><<<blocks, kBwdWarps * 32, kBwdSmem, s>>>(blob, enc, ray_sh, samples_per_ray, keep, n, grad_raw, grad_in, grad_params_flat);
+	}
+	NRF_CHECK_LAUNCH("mlp_small_bwd_kernel");
+	return NRF_OK;
+}
+
+}

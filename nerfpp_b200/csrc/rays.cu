@@ -1,0 +1,163 @@
+// Ray generation, AABB clipping, depth sampling and point generation for sm_100a.
+//
+// Replaces the ~40 tiny ATen launches of GetRays / IntersectWithAABB (reference src/RayUtils.h:5-46, 87-126), the
+// Render prologue (src/NeRFRenderer.h:549-583) and the z / point construction of RenderRays (:384-419, :432).
+// Arithmetic keeps ATen's un-fused order (__fmul_rn / __fadd_rn, no FMA contraction) so that z values, and through
+// them the sample points and hash cells, are the same floats the reference produces.
+#include "common.cuh"
+
+namespace nrf {
+
+struct Cam {
+	float fx, fy, cx, cy;
+	float m[12];  // c2w[:3,:4] row-major
+};
+
+__global__ void __launch_bounds__(256) get_rays_kernel(Cam c, int w, int row_begin, int64_t n, float* __restrict__ rays_o, float* __restrict__ rays_d)
+{
+	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const int py = row_begin + static_cast<int>(i / w), px = static_cast<int>(i % w);
+	// GetDirections (src/RayUtils.h:5-21)
+	const float dx = __fdiv_rn(__fsub_rn(static_cast<float>(px), c.cx), c.fx);
+	const float dy = -__fdiv_rn(__fsub_rn(static_cast<float>(py), c.cy), c.fy);
+	const float dz = -1.f;
+	// rays_d = sum(dirs[..., None, :] * c2w[:3,:3], -1) (src/RayUtils.h:28-32)
+#pragma unroll
+	for (int r = 0; r < 3; r++) {
+		const float v = __fadd_rn(__fadd_rn(__fmul_rn(dx, c.m[r * 4 + 0]), __fmul_rn(dy, c.m[r * 4 + 1])), __fmul_rn(dz, c.m[r * 4 + 2]));
+		rays_d[i * 3 + r] = v;
+		rays_o[i * 3 + r] = c.m[r * 4 + 3];
+	}
+}
+
+struct Box {
+	float lo[3], hi[3];
+};
+
+__global__ void __launch_bounds__(256) rays_prepare_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+	int64_t n, Box box, float near_plane, int use_viewdirs, float* __restrict__ ray_batch)
+{
+	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float o[3], d[3];
+#pragma unroll
+	for (int k = 0; k < 3; k++) { o[k] = rays_o[i * 3 + k]; d[k] = rays_d[i * 3 + k]; }
+	// IntersectWithAABB (src/RayUtils.h:87-126)
+	float tnear = -INFINITY, tfar = INFINITY;
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		const float frac = __fdiv_rn(1.0f, __fadd_rn(d[k], 1e-6f));
+		const float t1 = __fmul_rn(__fsub_rn(box.lo[k], o[k]), frac);
+		const float t2 = __fmul_rn(__fsub_rn(box.hi[k], o[k]), frac);
+		tnear = fmaxf(tnear, fminf(t1, t2));
+		tfar = fminf(tfar, fmaxf(t1, t2));
+	}
+	tnear = fmaxf(tnear, near_plane);
+	tfar = fmaxf(tfar, __fadd_rn(tnear, 1e-6f));
+	const int stride = use_viewdirs ? 11 : 8;
+	float* out = ray_batch + i * stride;
+#pragma unroll
+	for (int k = 0; k < 3; k++) { out[k] = o[k]; out[3 + k] = d[k]; }
+	out[6] = tnear;
+	out[7] = tfar;
+	if (use_viewdirs) {
+		// viewdirs = rays_d / norm(rays_d) (src/NeRFRenderer.h:559)
+		const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+#pragma unroll
+		for (int k = 0; k < 3; k++) out[8 + k] = __fdiv_rn(d[k], nrm);
+	}
+}
+
+__device__ __forceinline__ float safe_inv(float x) { return fabsf(x) < 1e-8f ? __fdiv_rn(1.0f, 1e-8f) : __fdiv_rn(1.0f, x); }
+
+__global__ void __launch_bounds__(256) z_sample_kernel(const float* __restrict__ ray_batch, int ray_stride, const float* __restrict__ t_vals,
+	int64_t R, int S, int lin_disp, float* __restrict__ z)
+{
+	const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (e >= R * S) return;
+	const int64_t ray = e / S;
+	const int s = static_cast<int>(e % S);
+	const float nr = ray_batch[ray * ray_stride + 6], fr = ray_batch[ray * ray_stride + 7];
+	const float t = t_vals[s];
+	const float omt = __fsub_rn(1.f, t);
+	float v;
+	if (!lin_disp) v = __fadd_rn(__fmul_rn(nr, omt), __fmul_rn(fr, t));                                   // src/NeRFRenderer.h:397
+	else v = safe_inv(__fadd_rn(__fmul_rn(safe_inv(nr), omt), __fmul_rn(safe_inv(fr), t)));              // :400-401
+	z[e] = v;
+}
+
+__global__ void __launch_bounds__(256) sample_points_kernel(const float* __restrict__ ray_batch, int ray_stride, const float* __restrict__ z,
+	int64_t R, int S, float* __restrict__ pts)
+{
+	// one thread per output scalar: stores are contiguous
+	const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (e >= R * S * 3) return;
+	const int64_t smp = e / 3;
+	const int k = static_cast<int>(e % 3);
+	const int64_t ray = smp / S;
+	const float* rb = ray_batch + ray * ray_stride;
+	pts[e] = __fadd_rn(rb[k], __fmul_rn(rb[3 + k], z[smp]));  // src/NeRFRenderer.h:419
+}
+
+}  // namespace nrf
+
+using namespace nrf;
+
+extern "C" {
+
+int nrf_get_rays(int32_t h, int32_t w, const float* K_host, const float* c2w_host, int32_t row_begin, int32_t row_end,
+	float* rays_o, float* rays_d, nrf_stream stream)
+{
+	NRF_REQUIRE(h > 0 && w > 0 && row_begin >= 0 && row_end <= h && row_begin <= row_end, "bad image / tile size");
+	NRF_REQUIRE(K_host && c2w_host, "null camera");
+	const int64_t n = static_cast<int64_t>(row_end - row_begin) * w;
+	if (n == 0) return NRF_OK;
+	NRF_REQUIRE(rays_o && rays_d, "null output");
+	Cam c;
+	c.fx = K_host[0]; c.cx = K_host[2]; c.fy = K_host[4]; c.cy = K_host[5];
+	for (int i = 0; i < 12; i++) c.m[i] = c2w_host[i];
+	get_rays_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(c, w, row_begin, n, rays_o, rays_d);
+	NRF_CHECK_LAUNCH("get_rays_kernel");
+	return NRF_OK;
+}
+
+int nrf_rays_prepare(const float* rays_o, const float* rays_d, int64_t n_rays, const float* bbox_host, float near_plane,
+	int32_t use_viewdirs, float* ray_batch, nrf_stream stream)
+{
+	NRF_REQUIRE(n_rays >= 0, "bad sizes");
+	NRF_REQUIRE(bbox_host != nullptr, "null bbox");
+	if (n_rays == 0) return NRF_OK;
+	NRF_REQUIRE(rays_o && rays_d && ray_batch, "null pointer");
+	Box b;
+	for (int k = 0; k < 3; k++) { b.lo[k] = bbox_host[k]; b.hi[k] = bbox_host[3 + k]; }
+	rays_prepare_kernel<<<static_cast<unsigned>((n_rays + 255) / 256), 256, 0, as_stream(stream)>>>(rays_o, rays_d, n_rays, b, near_plane, use_viewdirs, ray_batch);
+	NRF_CHECK_LAUNCH("rays_prepare_kernel");
+	return NRF_OK;
+}
+
+int nrf_z_sample(const float* ray_batch, int32_t ray_stride, const float* t_vals, int64_t n_rays, int32_t n_samples,
+	int32_t lin_disp, float* z, nrf_stream stream)
+{
+	NRF_REQUIRE(n_rays >= 0 && n_samples >= 1 && ray_stride >= 8, "bad sizes");
+	if (n_rays == 0) return NRF_OK;
+	NRF_REQUIRE(ray_batch && t_vals && z, "null pointer");
+	const int64_t n = n_rays * n_samples;
+	z_sample_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(ray_batch, ray_stride, t_vals, n_rays, n_samples, lin_disp, z);
+	NRF_CHECK_LAUNCH("z_sample_kernel");
+	return NRF_OK;
+}
+
+int nrf_sample_points(const float* ray_batch, int32_t ray_stride, const float* z, int64_t n_rays, int32_t n_samples,
+	float* pts, nrf_stream stream)
+{
+	NRF_REQUIRE(n_rays >= 0 && n_samples >= 1 && ray_stride >= 8, "bad sizes");
+	if (n_rays == 0) return NRF_OK;
+	NRF_REQUIRE(ray_batch && z && pts, "null pointer");
+	const int64_t n = n_rays * n_samples * 3;
+	sample_points_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(ray_batch, ray_stride, z, n_rays, n_samples, pts);
+	NRF_CHECK_LAUNCH("sample_points_kernel");
+	return NRF_OK;
+}
+
+}

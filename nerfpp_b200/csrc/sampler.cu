@@ -1,0 +1,188 @@
+// Inverse-CDF importance sampling (+ merge with the coarse samples) for sm_100a.
+//
+// Replaces SamplePDF (reference src/Sampler.h:6-43: ~20 ATen launches, gathers through expanded
+// [R,N,63] views, an H2D copy of `u` per call) and the torch::sort of cat(z, z_samples) at
+// src/NeRFRenderer.h:427-431.  One warp per ray:
+//   pdf/cdf  : weights+1e-8, sum by warp reduction, cdf = [0, cumsum(pdf)] by warp prefix scan (shared memory);
+//   invert   : searchsorted(cdf, u, right=true) as a branch-free binary search per sample, then the
+//              reference's below/above gather, `denom < 1e-5 -> 1` guard and lerp;
+//   merge    : both lists are sorted when u is, so the sort is a rank merge (two binary searches per element);
+//              for per-ray random u the S+N values are sorted with an in-warp bitonic network instead.
+// Traffic: (2S + N + S+N) floats per ray, about 1.3 KB/ray at S=64, N=128.
+#include "common.cuh"
+
+namespace nrf {
+
+constexpr int kSamplerWarps = 4;
+
+// number of entries of the ascending array a[0..n) that are <= v  (searchsorted right=true)
+__device__ __forceinline__ int upper_bound(const float* a, int n, float v)
+{
+	int lo = 0, hi = n;
+	while (lo < hi) {
+		const int mid = (lo + hi) >> 1;
+		if (a[mid] <= v) lo = mid + 1;
+		else hi = mid;
+	}
+	return lo;
+}
+
+// number of entries that are < v
+__device__ __forceinline__ int lower_bound(const float* a, int n, float v)
+{
+	int lo = 0, hi = n;
+	while (lo < hi) {
+		const int mid = (lo + hi) >> 1;
+		if (a[mid] < v) lo = mid + 1;
+		else hi = mid;
+	}
+	return lo;
+}
+
+// cdf[0..B) from weights[0..B-1) — src/Sampler.h:10-13.  All lanes of the warp call this.
+__device__ __forceinline__ void build_cdf(const float* __restrict__ w, int nw, float* cdf, int lane)
+{
+	float part = 0.f;
+	for (int k = lane; k < nw; k += 32) part += __fadd_rn(w[k], 1e-8f);
+	const float total = warp_sum(part);
+	float carry = 0.f;
+	if (lane == 0) cdf[0] = 0.f;
+	for (int k0 = 0; k0 < nw; k0 += 32) {
+		const int k = k0 + lane;
+		const float pdf = k < nw ? __fdiv_rn(__fadd_rn(w[k], 1e-8f), total) : 0.f;
+		const float incl = warp_scan_incl(pdf, lane);
+		if (k < nw) cdf[k + 1] = carry + incl;
+		carry += __shfl_sync(0xffffffffu, incl, 31);
+	}
+	__syncwarp();
+}
+
+// src/Sampler.h:28-40 for one u
+__device__ __forceinline__ float invert_cdf(const float* cdf, const float* bins, int B, float u)
+{
+	const int inds = upper_bound(cdf, B, u);
+	const int below = max(0, inds - 1);
+	const int above = min(B - 1, inds);
+	const float c0 = cdf[below], c1 = cdf[above];
+	const float b0 = bins[below], b1 = bins[above];
+	float denom = __fsub_rn(c1, c0);
+	if (denom < 1e-5f) denom = 1.f;
+	const float t = __fdiv_rn(__fsub_rn(u, c0), denom);
+	return __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+}
+
+__device__ __forceinline__ void bitonic_sort(float* a, int n_pow2, int lane)
+{
+	for (int k = 2; k <= n_pow2; k <<= 1) {
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			for (int i = lane; i < n_pow2; i += 32) {
+				const int p = i ^ j;
+				if (p > i) {
+					const float x = a[i], y = a[p];
+					const bool up = (i & k) == 0;
+					if ((x > y) == up) { a[i] = y; a[p] = x; }
+				}
+			}
+			__syncwarp();
+		}
+	}
+}
+
+// shared memory per warp: cdf[B] bins[B] zs[N] zc[S] (+ sort scratch when u is per-ray)
+__global__ void __launch_bounds__(kSamplerWarps * 32) sample_pdf_merge_kernel(const float* __restrict__ z_coarse,
+	const float* __restrict__ weights, const float* __restrict__ u, int u_per_ray, int64_t R, int S, int N,
+	float* __restrict__ z_samples, float* __restrict__ z_merged, int per_warp_floats, int sort_pow2)
+{
+	extern __shared__ float smem[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int64_t ray = static_cast<int64_t>(blockIdx.x) * kSamplerWarps + warp;
+	if (ray >= R) return;
+	const int B = S - 1;
+	float* cdf = smem + static_cast<size_t>(warp) * per_warp_floats;
+	float* bins = cdf + B;
+	float* zs = bins + B;
+	float* zc = zs + N;
+	const float* zrow = z_coarse + ray * S;
+	for (int k = lane; k < S; k += 32) zc[k] = zrow[k];
+	__syncwarp();
+	for (int k = lane; k < B; k += 32) bins[k] = 0.5f * __fadd_rn(zc[k + 1], zc[k]);  // z_vals_mid, src/NeRFRenderer.h:427
+	build_cdf(weights + ray * S + 1, S - 2, cdf, lane);                                // Weights[:, 1:-1], src/NeRFRenderer.h:428
+	const float* urow = u_per_ray ? u + ray * N : u;
+	for (int j = lane; j < N; j += 32) {
+		const float s = invert_cdf(cdf, bins, B, urow[j]);
+		zs[j] = s;
+		if (z_samples) z_samples[ray * N + j] = s;
+	}
+	__syncwarp();
+	float* out = z_merged + ray * (S + N);
+	if (!u_per_ray) {
+		// rank merge; ties: coarse samples first
+		for (int k = lane; k < S; k += 32) out[k + lower_bound(zs, N, zc[k])] = zc[k];
+		for (int j = lane; j < N; j += 32) out[j + upper_bound(zc, S, zs[j])] = zs[j];
+	} else {
+		float* scratch = zc + S;
+		for (int i = lane; i < sort_pow2; i += 32) scratch[i] = i < S ? zc[i] : (i < S + N ? zs[i - S] : __int_as_float(0x7f800000));
+		__syncwarp();
+		bitonic_sort(scratch, sort_pow2, lane);
+		for (int i = lane; i < S + N; i += 32) out[i] = scratch[i];
+	}
+}
+
+__global__ void __launch_bounds__(kSamplerWarps * 32) sample_pdf_kernel(const float* __restrict__ bins_g,
+	const float* __restrict__ weights, int B, const float* __restrict__ u, int u_per_ray, int64_t R, int N,
+	float* __restrict__ out)
+{
+	extern __shared__ float smem[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int64_t ray = static_cast<int64_t>(blockIdx.x) * kSamplerWarps + warp;
+	if (ray >= R) return;
+	float* cdf = smem + static_cast<size_t>(warp) * (2 * B);
+	float* bins = cdf + B;
+	for (int k = lane; k < B; k += 32) bins[k] = bins_g[ray * B + k];
+	build_cdf(weights + ray * (B - 1), B - 1, cdf, lane);
+	const float* urow = u_per_ray ? u + ray * N : u;
+	for (int j = lane; j < N; j += 32) out[ray * N + j] = invert_cdf(cdf, bins, B, urow[j]);
+}
+
+}  // namespace nrf
+
+using namespace nrf;
+
+extern "C" {
+
+int nrf_sample_pdf(const float* bins, const float* weights, int32_t n_bins, const float* u, int32_t u_per_ray,
+	int64_t n_rays, int32_t n_samples, float* samples_out, nrf_stream stream)
+{
+	NRF_REQUIRE(n_bins >= 2 && n_bins <= 1024, "n_bins out of range");
+	NRF_REQUIRE(n_rays >= 0 && n_samples >= 0, "bad sizes");
+	if (n_rays == 0 || n_samples == 0) return NRF_OK;
+	NRF_REQUIRE(bins && weights && u && samples_out, "null pointer");
+	const unsigned blocks = static_cast<unsigned>((n_rays + kSamplerWarps - 1) / kSamplerWarps);
+	const size_t smem = static_cast<size_t>(kSamplerWarps) * 2 * n_bins * sizeof(float);
+	sample_pdf_kernel<<<blocks, kSamplerWarps * 32, smem, as_stream(stream)>>>(bins, weights, n_bins, u, u_per_ray, n_rays, n_samples, samples_out);
+	NRF_CHECK_LAUNCH("sample_pdf_kernel");
+	return NRF_OK;
+}
+
+int nrf_sample_pdf_merge(const float* z_coarse, const float* weights, const float* u, int32_t u_per_ray, int64_t n_rays,
+	int32_t n_samples, int32_t n_importance, float* z_samples, float* z_merged, nrf_stream stream)
+{
+	NRF_REQUIRE(n_samples >= 3, "n_samples must be >= 3");
+	NRF_REQUIRE(n_importance >= 1, "n_importance must be >= 1");
+	NRF_REQUIRE(n_samples + n_importance <= 1024, "n_samples + n_importance > 1024");
+	NRF_REQUIRE(n_rays >= 0, "bad sizes");
+	if (n_rays == 0) return NRF_OK;
+	NRF_REQUIRE(z_coarse && weights && u && z_merged, "null pointer");
+	int pow2 = 1;
+	while (pow2 < n_samples + n_importance) pow2 <<= 1;
+	const int per_warp = 2 * (n_samples - 1) + n_importance + n_samples + (u_per_ray ? pow2 : 0);
+	const size_t smem = static_cast<size_t>(kSamplerWarps) * per_warp * sizeof(float);
+	NRF_REQUIRE(smem <= 48 * 1024, "shared memory budget exceeded");
+	const unsigned blocks = static_cast<unsigned>((n_rays + kSamplerWarps - 1) / kSamplerWarps);
+	sample_pdf_merge_kernel<<<blocks, kSamplerWarps * 32, smem, as_stream(stream)>>>(z_coarse, weights, u, u_per_ray, n_rays,
+		n_samples, n_importance, z_samples, z_merged, per_warp, pow2);
+	NRF_CHECK_LAUNCH("sample_pdf_merge_kernel");
+	return NRF_OK;
+}
+
+}

@@ -1,0 +1,239 @@
+// TEST INFRASTRUCTURE ONLY — never imported by the product path (nerfpp_b200/).
+//
+// pybind11 front-end over the UNMODIFIED reference sources, compiled in place from /root/reference/src by
+// oracle/Makefile into oracle/_ref/nerfpp_ref*.so.  It lets tests/ pin the numpy/torch restatement
+// (oracle/restate.py) against the reference's own code, generates the golden fixtures under tests/golden/
+// (tests/golden/make_golden.py), and is the `--impl reference` / cpu_baseline arm of bench.py.
+//
+// Nothing here restates reference code: every function forwards to a reference symbol, cited beside it.
+#include <torch/extension.h>
+#include <chrono>
+
+#include "NeRF.h"          // Embedder, NeRF, NeRFSmall, HashEmbedder, SHEncoder  (src/NeRF.h)
+#include "CustomOps.h"     // TruncExp                                             (src/CustomOps.h)
+#include "Sampler.h"       // SamplePDF                                            (src/Sampler.h:6)
+#include "RayUtils.h"      // GetRays, IntersectWithAABB                           (src/RayUtils.h:23,87)
+#include "NeRFRenderer.h"  // NeRFRenderer<>                                       (src/NeRFRenderer.h:88)
+#ifdef NRF_REF_CUDA
+#include "CuHashEmbedder.h"  // src/CuHashEmbedder.h
+#include "CuSHEncoder.h"     // src/CuSHEncoder.h
+#endif
+
+namespace py = pybind11;
+using torch::Tensor;
+
+// Exposes the protected virtual stages of the reference renderer (src/NeRFRenderer.h:96,99).
+template <class E, class D, class N>
+struct OpenRenderer : public NeRFRenderer<E, D, N> {
+	using Base = NeRFRenderer<E, D, N>;
+	using Base::Base;
+	using Base::RunNetwork;
+	using Base::RawToOutputs;
+	using Base::NeRF;
+	using Base::EmbedFn;
+	using Base::EmbeddirsFn;
+};
+
+static py::dict OutputsToDict(const NeRFRendererOutputs& o)
+{
+	py::dict d;
+	d["rgb"] = o.RGBMap; d["disp"] = o.DispMap; d["acc"] = o.AccMap; d["weights"] = o.Weights; d["depth"] = o.DepthMap;
+	return d;
+}
+
+static NeRFRenderParams MakeParams(int n_samples, int n_importance, int chunk, bool white_bkgr, bool use_viewdirs,
+	Tensor bbox, bool return_raw, bool lin_disp)
+{
+	NeRFRenderParams p;
+	p.NSamples = n_samples; p.NImportance = n_importance; p.Chunk = chunk; p.ReturnRaw = return_raw;
+	p.LinDisp = lin_disp; p.Perturb = 0.f; p.WhiteBkgr = white_bkgr; p.RawNoiseStd = 0.f; p.Ndc = false;
+	p.UseViewdirs = use_viewdirs; p.ReturnWeights = true; p.ThinRay = true;   // parity config, SURVEY §9-Q4
+	p.BoundingBox = bbox; p.StochasticPreconditioningAlpha = 0.f;
+	return p;
+}
+
+// One wrapper for every <embedder, dir-embedder, model> triple the reference instantiates on this path.
+template <class E, class D, class N>
+struct RefPipeline {
+	E embed{nullptr};
+	D embeddirs{nullptr};
+	N model{nullptr};
+	std::unique_ptr<OpenRenderer<E, D, N>> renderer;
+	std::unique_ptr<torch::optim::Adam> opt;
+	Tensor bbox;
+
+	void Finish(torch::Device dev)
+	{
+		embed->to(dev); embeddirs->to(dev); model->to(dev);
+		renderer = std::make_unique<OpenRenderer<E, D, N>>(embed, embeddirs, model);
+	}
+	std::vector<Tensor> EmbedParams() { return embed->parameters(); }
+	std::vector<Tensor> ModelParams() { return model->parameters(); }
+	std::vector<std::string> ModelParamNames()
+	{
+		std::vector<std::string> r;
+		for (auto& p : model->named_parameters()) r.push_back(p.key());
+		return r;
+	}
+	std::vector<std::string> EmbedBufferNames()
+	{
+		std::vector<std::string> r;
+		for (auto& p : embed->named_buffers()) r.push_back(p.key());
+		return r;
+	}
+	std::vector<Tensor> EmbedBuffers() { return embed->buffers(); }
+	void InitModel() { Trainable::Initialize(model); }                    // src/LibTorchTraining/Trainable.h:32
+	std::pair<Tensor, Tensor> Embed(Tensor x) { return embed->forward(x); }
+	Tensor EmbedDirs(Tensor d) { return embeddirs->forward(d).first; }
+	Tensor Model(Tensor x) { return model->forward(x); }
+	Tensor RunNetwork(Tensor pts, Tensor viewdirs)                       // src/NeRFRenderer.h:164
+	{
+		return renderer->RunNetwork(pts, viewdirs, renderer->NeRF, renderer->EmbedFn, renderer->EmbeddirsFn);
+	}
+	py::dict RawToOutputs(Tensor raw, Tensor z, Tensor rays_d, float noise, bool white)   // src/NeRFRenderer.h:199
+	{
+		return OutputsToDict(renderer->RawToOutputs(raw, Tensor(), z, rays_d, noise, white));
+	}
+	// src/NeRFRenderer.h:366; ray_batch = [o(3) d(3) near far viewdirs(3)]
+	py::dict RenderRays(Tensor ray_batch, int n_samples, int n_importance, bool white, bool return_raw)
+	{
+		auto r = renderer->RenderRays(ray_batch, Tensor(), n_samples, return_raw, false, 0.f, n_importance, white, 0.f, 0.f, bbox, true);
+		py::dict d = OutputsToDict(r.Outputs);
+		if (return_raw) d["raw"] = r.Raw;
+		return d;
+	}
+	// src/NeRFRenderer.h:530 with a ray batch (training call, src/NeRFExecutor.h:876)
+	py::dict Render(Tensor rays_o, Tensor rays_d, int n_samples, int n_importance, int chunk, bool white, bool use_viewdirs)
+	{
+		auto p = MakeParams(n_samples, n_importance, chunk, white, use_viewdirs, bbox, false, false);
+		auto r = renderer->Render(0, 0, Tensor(), p, {rays_o, rays_d, Tensor()}, Tensor(), Tensor());
+		py::dict d = OutputsToDict(r.Outputs);
+		d["near"] = r.Near; d["far"] = r.Far;
+		return d;
+	}
+	// src/NeRFRenderer.h:530 with a camera pose (full-image call, src/NeRFExecutor.h:684)
+	py::dict RenderImage(int h, int w, Tensor k, Tensor c2w, int n_samples, int n_importance, int chunk, bool white, bool use_viewdirs)
+	{
+		torch::NoGradGuard ng;
+		auto p = MakeParams(n_samples, n_importance, chunk, white, use_viewdirs, bbox, false, false);
+		auto r = renderer->Render(h, w, k, p, {Tensor(), Tensor(), Tensor()}, c2w, Tensor());
+		py::dict d = OutputsToDict(r.Outputs);
+		d["near"] = r.Near; d["far"] = r.Far;
+		return d;
+	}
+	// The training lines of NeRFExecutor::Train that touch this path (src/NeRFExecutor.h:539,868,876-890,923,986,
+	// 992-996) driven verbatim: Adam(lr, betas (0.9,0.99), eps 1e-15), zero_grad, Render, huber, backward, step,
+	// lr decay.  Returns (per-step seconds, per-step loss).
+	std::pair<std::vector<double>, std::vector<float>> TrainSteps(Tensor rays_o, Tensor rays_d, Tensor target,
+		int n_steps, int n_samples, int n_importance, int chunk, bool use_viewdirs, float lr, int lrate_decay)
+	{
+		if (!opt)
+		{
+			std::vector<Tensor> gv;
+			for (auto& p : embed->parameters()) gv.push_back(p);
+			for (auto& p : model->parameters()) gv.push_back(p);
+			opt = std::make_unique<torch::optim::Adam>(gv, torch::optim::AdamOptions(lr).eps(1e-15).betas(std::make_tuple(0.9, 0.99)));
+			global_step = 0;
+		}
+		std::vector<double> secs; std::vector<float> losses;
+		auto p = MakeParams(n_samples, n_importance, chunk, false, use_viewdirs, bbox, false, false);
+		for (int i = 0; i < n_steps; i++)
+		{
+			auto t0 = std::chrono::steady_clock::now();
+			opt->zero_grad();
+			auto r = renderer->Render(0, 0, Tensor(), p, {rays_o, rays_d, Tensor()}, Tensor(), Tensor());
+			auto loss = torch::nn::functional::huber_loss(r.Outputs.RGBMap, target.detach());
+			loss.backward();
+			opt->step();
+			float new_lr = lr * powf(0.1f, (float)global_step / (lrate_decay * 1000));
+			for (auto& g : opt->param_groups()) g.options().set_lr(new_lr);
+			global_step++;   // src/NeRFExecutor.h:1047 (after the lr update)
+			float lv = loss.template item<float>();   // forces completion on CUDA as well
+			secs.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+			losses.push_back(lv);
+		}
+		return {secs, losses};
+	}
+	int global_step = 0;
+};
+
+using HashCpuPipe = RefPipeline<HashEmbedder, SHEncoder, NeRFSmall>;
+using ClassicPipe = RefPipeline<Embedder, Embedder, NeRF>;
+#ifdef NRF_REF_CUDA
+using CuHashPipe = RefPipeline<CuHashEmbedder, CuSHEncoder, NeRFSmall>;
+#endif
+
+template <class P>
+static void BindPipe(py::module_& m, const char* name)
+{
+	py::class_<P>(m, name)
+		.def("embed_params", &P::EmbedParams).def("model_params", &P::ModelParams)
+		.def("model_param_names", &P::ModelParamNames)
+		.def("embed_buffers", &P::EmbedBuffers).def("embed_buffer_names", &P::EmbedBufferNames)
+		.def("init_model", &P::InitModel)
+		.def("embed", &P::Embed).def("embed_dirs", &P::EmbedDirs).def("model", &P::Model)
+		.def("run_network", &P::RunNetwork).def("raw_to_outputs", &P::RawToOutputs)
+		.def("render_rays", &P::RenderRays).def("render", &P::Render).def("render_image", &P::RenderImage)
+		.def("train_steps", &P::TrainSteps);
+}
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
+{
+	m.doc() = "reference (DeliriumV01D/NeRFpp) hot-path symbols, unmodified — test oracle only";
+#ifdef NRF_REF_CUDA
+	m.attr("has_cuda") = true;
+#else
+	m.attr("has_cuda") = false;
+#endif
+	m.def("manual_seed", [](int64_t s) { torch::manual_seed(s); });   // src/main.cpp:174
+	m.def("set_num_threads", [](int n) { at::set_num_threads(n); });
+	m.def("get_num_threads", []() { return at::get_num_threads(); });
+	m.def("trunc_exp", [](Tensor x) { return torch::autograd::TruncExp::apply(x)[0]; });   // src/CustomOps.cpp:5
+	m.def("sample_pdf", &SamplePDF);                                                          // src/Sampler.h:6
+	m.def("intersect_aabb", [](Tensor o, Tensor d, Tensor bbox, float near_plane) { return IntersectWithAABB(o, d, bbox, near_plane); });   // src/RayUtils.h:87
+	m.def("get_rays", [](int h, int w, Tensor k, Tensor c2w) { return GetRays(h, w, k, c2w); });   // src/RayUtils.h:23
+	m.def("embedder", [](Tensor x, int multires) { Embedder e("embedder", multires); return e->forward(x).first; });   // src/NeRF.cpp:22
+	m.def("sh_encoder", [](Tensor x, int degree) { SHEncoder e("embeddirs", 3, degree); return e->forward(x).first; }); // src/NeRF.cpp:131
+	m.def("sort_merge", [](Tensor z, Tensor zs) { return std::get<0>(torch::sort(torch::cat({z, zs}, -1), -1)); });      // src/NeRFRenderer.h:431
+
+	BindPipe<HashCpuPipe>(m, "HashCpuPipe");
+	BindPipe<ClassicPipe>(m, "ClassicPipe");
+	// src/NeRFExecutor.h:430-432,451-452,480-493 (HashEmbedder branch; CPU-capable LibTorch embedders)
+	m.def("make_hash_cpu", [](Tensor bbox, int n_levels, int n_feat, int log2_t, int base_res, int finest_res, int sh_degree,
+		int num_layers, int hidden, int geo_feat, int num_layers_color, int hidden_color) {
+		auto p = std::make_unique<HashCpuPipe>();
+		p->bbox = bbox;
+		p->embed = HashEmbedder("embedder", bbox, n_levels, n_feat, log2_t, base_res, finest_res);
+		p->embeddirs = SHEncoder("embeddirs", 3, sh_degree);
+		p->model = NeRFSmall(num_layers, hidden, geo_feat, num_layers_color, hidden_color, false, 3, 64,
+			p->embed->GetOutputDims(), p->embeddirs->GetOutputDims(), "model");
+		p->Finish(torch::kCPU);
+		return p;
+	});
+	// src/NeRFExecutor.h:428,446,478 (classic NeRF branch)
+	m.def("make_classic", [](Tensor bbox, int multires, int multires_views, int depth, int width, bool use_viewdirs, bool cuda) {
+		auto p = std::make_unique<ClassicPipe>();
+		p->bbox = bbox;
+		p->embed = Embedder("embedder", multires);
+		p->embeddirs = Embedder("embeddirs", multires_views);
+		p->model = NeRF(depth, width, p->embed->GetOutputDims(), p->embeddirs->GetOutputDims(), 5, std::set<int>{4}, use_viewdirs, "model");
+		p->Finish(cuda ? torch::kCUDA : torch::kCPU);
+		return p;
+	});
+#ifdef NRF_REF_CUDA
+	BindPipe<CuHashPipe>(m, "CuHashPipe");
+	// src/NeRFExecutor.h:432,452,481-493 (CuHashEmbedder branch) — CUDA only (src/CuHashEmbedder.cpp:24)
+	m.def("make_cuhash", [](Tensor bbox, int n_levels, int n_feat, int log2_t, int base_res, int finest_res, int sh_degree,
+		int num_layers, int hidden, int geo_feat, int num_layers_color, int hidden_color) {
+		auto p = std::make_unique<CuHashPipe>();
+		p->bbox = bbox;
+		p->embed = CuHashEmbedder("embedder", bbox, n_levels, n_feat, log2_t, base_res, finest_res);
+		p->embeddirs = CuSHEncoder("embeddirs", 3, sh_degree);
+		p->model = NeRFSmall(num_layers, hidden, geo_feat, num_layers_color, hidden_color, false, 3, 64,
+			p->embed->GetOutputDims(), p->embeddirs->GetOutputDims(), "model");
+		p->Finish(torch::kCUDA);
+		return p;
+	});
+	m.def("cu_sh_encoder", [](Tensor x, int degree) { CuSHEncoder e("embeddirs", 3, degree); return e->forward(x).first; });   // src/CuSHEncoder.cu:109
+#endif
+}
