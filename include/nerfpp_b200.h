@@ -98,8 +98,9 @@ int nrf_hash_encode_bwd(const nrf_hash_grid* grid, const float* points, int64_t 
 /* ------------------------------------------------------------------------------------------------------------
  * Direction / position encoders
  * ---------------------------------------------------------------------------------------------------------- */
-/* CuSHKernel (src/CuSHEncoder.cu:4-107): dirs [N,3] -> [N, degree^2], degree 1..8. */
-int nrf_sh_encode_fwd(const float* dirs, int64_t n, int32_t degree, float* out, nrf_stream stream);
+/* CuSHKernel (src/CuSHEncoder.cu:4-107): dirs -> [N, degree^2], degree 1..8.  Direction i is read at
+ * dirs + i*dir_stride (3 for the reference's contiguous [N,3]; 11 reads the viewdirs straight out of a ray_batch). */
+int nrf_sh_encode_fwd(const float* dirs, int32_t dir_stride, int64_t n, int32_t degree, float* out, nrf_stream stream);
 
 /* EmbedderImpl::forward (src/NeRF.cpp:22-39): x [N,D] -> [N, D*(include_input + 2*num_freqs)],
  * channel order x, sin(f0 x), cos(f0 x), sin(f1 x) ...; freq_bands_host[num_freqs] as built at src/NeRF.cpp:11-19. */

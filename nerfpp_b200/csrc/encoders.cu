@@ -95,7 +95,7 @@ constexpr int kEncThreads = 128;
 // One thread evaluates one direction into registers; the CTA's [128, DEG^2] block is transposed through shared
 // memory (row pitch DEG^2+1 words: conflict-free) and leaves as contiguous, fully coalesced stores.
 template <int DEG>
-__global__ void __launch_bounds__(kEncThreads) sh_kernel(const float* __restrict__ dirs, int64_t n, float* __restrict__ out)
+__global__ void __launch_bounds__(kEncThreads) sh_kernel(const float* __restrict__ dirs, int stride, int64_t n, float* __restrict__ out)
 {
 	constexpr int D2 = DEG * DEG;
 	__shared__ float tile[kEncThreads * (D2 + 1)];
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kEncThreads) sh_kernel(const float* __restrict
 	const int64_t i = base + threadIdx.x;
 	if (i < n) {
 		float o[D2];
-		sh_basis<DEG>(dirs[i * 3], dirs[i * 3 + 1], dirs[i * 3 + 2], o);
+		sh_basis<DEG>(dirs[i * stride], dirs[i * stride + 1], dirs[i * stride + 2], o);
 #pragma unroll
 		for (int k = 0; k < D2; k++) tile[threadIdx.x * (D2 + 1) + k] = o[k];
 	}
@@ -158,23 +158,24 @@ using namespace nrf;
 
 extern "C" {
 
-int nrf_sh_encode_fwd(const float* dirs, int64_t n, int32_t degree, float* out, nrf_stream stream)
+int nrf_sh_encode_fwd(const float* dirs, int32_t dir_stride, int64_t n, int32_t degree, float* out, nrf_stream stream)
 {
 	NRF_REQUIRE(degree >= 1 && degree <= 8, "degree must be 1..8");
+	NRF_REQUIRE(dir_stride >= 3, "dir_stride must be >= 3");
 	NRF_REQUIRE(n >= 0, "negative n");
 	if (n == 0) return NRF_OK;
 	NRF_REQUIRE(dirs && out, "null pointer");
 	const unsigned blocks = static_cast<unsigned>((n + kEncThreads - 1) / kEncThreads);
 	cudaStream_t s = as_stream(stream);
 	switch (degree) {
-		case 1: sh_kernel<1><<<blocks, kEncThreads, 0, s>>>(dirs, n, out); break;
-		case 2: sh_kernel<2><<<blocks, kEncThreads, 0, s>>>(dirs, n, out); break;
-		case 3: sh_kernel<3><<<blocks, kEncThreads, 0, s>>>(dirs, n, out); break;
-		case 4: sh_kernel<4><<<blocks, kEncThreads, 0, s>>>(dirs, n, out); break;
-		case 5: sh_kernel<5><<<blocks, kEncThreads, 0, s>>>(dirs, n, out); break;
-		case 6: sh_kernel<6><<<blocks, kEncThreads, 0, s>>>(dirs, n, out); break;
-		case 7: sh_kernel<7><<<blocks, kEncThreads, 0, s>>>(dirs, n, out); break;
-		default: sh_kernel<8><<<blocks, kEncThreads, 0, s>>>(dirs, n, out); break;
+		case 1: sh_kernel<1><<<blocks, kEncThreads, 0, s>>>(dirs, dir_stride, n, out); break;
+		case 2: sh_kernel<2><<<blocks, kEncThreads, 0, s>>>(dirs, dir_stride, n, out); break;
+		case 3: sh_kernel<3><<<blocks, kEncThreads, 0, s>>>(dirs, dir_stride, n, out); break;
+		case 4: sh_kernel<4><<<blocks, kEncThreads, 0, s>>>(dirs, dir_stride, n, out); break;
+		case 5: sh_kernel<5><<<blocks, kEncThreads, 0, s>>>(dirs, dir_stride, n, out); break;
+		case 6: sh_kernel<6><<<blocks, kEncThreads, 0, s>>>(dirs, dir_stride, n, out); break;
+		case 7: sh_kernel<7><<<blocks, kEncThreads, 0, s>>>(dirs, dir_stride, n, out); break;
+		default: sh_kernel<8><<<blocks, kEncThreads, 0, s>>>(dirs, dir_stride, n, out); break;
 	}
 	NRF_CHECK_LAUNCH("sh_kernel");
 	return NRF_OK;

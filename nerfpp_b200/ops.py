@@ -1,0 +1,283 @@
+"""Thin functional wrappers: torch tensors in, one C-ABI call each (include/nerfpp_b200.h), torch tensors out.
+
+Used by tests/, bench.py and the Python pipeline (nerfpp_b200/pipeline.py).  Nothing is computed in Python/torch
+here: allocation + pointer plumbing only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import cabi
+from .cabi import check, lib, ptr, stream
+
+f32, f16, bf16, i32, u8 = torch.float32, torch.float16, torch.bfloat16, torch.int32, torch.uint8
+
+
+class KernelTimer:
+    """Optional per-kernel CUDA-event timing on the launching stream (bench.py roofline / breakdown).
+    `only`: restrict to these entry names (without the nrf_ prefix) so the timed region carries two events per step."""
+
+    def __init__(self, only=None):
+        self.only = set(only) if only else None
+        self.records: dict[str, list] = {}
+
+    def summary(self) -> dict:
+        """name -> (launches, total_ms); call after a stream synchronize."""
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.records.items()}
+
+
+_timer: KernelTimer | None = None
+
+
+def set_timer(t: KernelTimer | None) -> None:
+    global _timer
+    _timer = t
+
+
+def _run(name: str, call) -> None:
+    t = _timer
+    if t is not None and (t.only is None or name in t.only):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        status = call()
+        e1.record()
+        t.records.setdefault(name, []).append((e0, e1))
+    else:
+        status = call()
+    check(status)
+
+
+@dataclass
+class HashGridSpec:
+    """Mirror of the public members of CuHashEmbedderImpl (reference src/CuHashEmbedder.h:12-27)."""
+    bounding_box: tuple  # 6 floats
+    primes: torch.Tensor           # int32 [L, V, 3]      ("<name>_primes")
+    biases: torch.Tensor           # f32  [L*V, 3]        ("<name>_biases")
+    feat_local_idx: torch.Tensor   # int32 [L]            ("<name>_feat_local_idx")
+    feat_local_size: torch.Tensor  # int32 [L]            ("<name>_feat_local_size")
+    n_levels: int = 16
+    n_features: int = 2
+    log2_hashmap_size: int = 19
+    base_resolution: int = 16
+    finest_resolution: int = 512
+    n_volumes: int = 1
+    level_scale: torch.Tensor | None = None
+
+    def table_scalars(self) -> int:
+        return (1 << self.log2_hashmap_size) * self.n_levels * self.n_features
+
+    def used_scalars(self) -> int:
+        """Scalars the kernels can touch: level offsets are in scalars (reference quirk), so levels overlap."""
+        idx = self.feat_local_idx.cpu().tolist()
+        size = self.feat_local_size.cpu().tolist()
+        return max(o + s * self.n_features for o, s in zip(idx, size))
+
+    def c_struct(self) -> cabi.HashGrid:
+        if self.level_scale is None:
+            self.level_scale = hash_level_scales(self.base_resolution, self.finest_resolution, self.n_levels, self.primes.device)
+        g = cabi.HashGrid()
+        g.n_levels, g.n_features, g.n_volumes = self.n_levels, self.n_features, self.n_volumes
+        g.base_resolution, g.finest_resolution = self.base_resolution, self.finest_resolution
+        for k in range(3):
+            g.box_min[k] = float(self.bounding_box[k])
+            g.box_max[k] = float(self.bounding_box[3 + k])
+        g.primes = ptr(self.primes, i32)
+        g.biases = ptr(self.biases, f32)
+        g.feat_local_idx = ptr(self.feat_local_idx, i32)
+        g.feat_local_size = ptr(self.feat_local_size, i32)
+        g.level_scale = ptr(self.level_scale, f32)
+        g.table_scalars = self.table_scalars()
+        return g
+
+
+def hash_level_scales(base_res: int, finest_res: int, n_levels: int, device) -> torch.Tensor:
+    out = torch.empty(n_levels, dtype=f32, device=device)
+    _run("hash_level_scales", lambda: lib().nrf_hash_level_scales(base_res, finest_res, n_levels, ptr(out), stream()))
+    return out
+
+
+def table_to_half(table: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty(table.shape, dtype=f16, device=table.device)
+    _run("table_to_half", lambda: lib().nrf_table_to_half(ptr(table, f32), ptr(out, f16), table.numel(), stream()))
+    return out
+
+
+def hash_encode_fwd(grid: HashGridSpec, table_f16: torch.Tensor, points: torch.Tensor, clamp: bool = True,
+                    out_f16: bool = False, want_keep: bool = True):
+    n = points.shape[0]
+    d = grid.n_levels * grid.n_features
+    out = torch.empty((n, d), dtype=f16 if out_f16 else f32, device=points.device)
+    keep = torch.empty(n, dtype=u8, device=points.device) if (clamp and want_keep) else None
+    g = grid.c_struct()
+    _run("hash_encode_fwd", lambda: lib().nrf_hash_encode_fwd(C.byref(g), ptr(table_f16, f16), ptr(points, f32), n, int(clamp), ptr(keep),
+                                    ptr(out), cabi.ENC_F16 if out_f16 else cabi.ENC_F32, stream()))
+    return out, keep
+
+
+def hash_encode_bwd(grid: HashGridSpec, points: torch.Tensor, grad_enc: torch.Tensor, grad_table: torch.Tensor,
+                    clamp: bool = True) -> torch.Tensor:
+    n = points.shape[0]
+    layout = {f32: cabi.GRAD_F32, bf16: cabi.GRAD_BF16}[grad_enc.dtype]
+    g = grid.c_struct()
+    _run("hash_encode_bwd", lambda: lib().nrf_hash_encode_bwd(C.byref(g), ptr(points, f32), n, int(clamp), ptr(grad_enc), layout,
+                                    ptr(grad_table, f32), stream()))
+    return grad_table
+
+
+def sh_encode(dirs: torch.Tensor, degree: int) -> torch.Tensor:
+    """dirs: contiguous [N,3], or a column slice [:, a:a+3] of a contiguous [N,K] matrix (read in place, strided)."""
+    n = dirs.shape[0]
+    if dirs.dim() != 2 or dirs.shape[1] != 3 or dirs.stride(1) != 1 or dirs.dtype != f32 or not dirs.is_cuda:
+        raise cabi.NrfError("sh_encode needs a CUDA fp32 [N,3] tensor with unit inner stride")
+    out = torch.empty((n, degree * degree), dtype=f32, device=dirs.device)
+    _run("sh_encode_fwd", lambda: lib().nrf_sh_encode_fwd(dirs.data_ptr(), dirs.stride(0) if n > 1 else 3, n, degree, ptr(out), stream()))
+    return out
+
+
+def posenc(x: torch.Tensor, freq_bands, include_input: bool = True) -> torch.Tensor:
+    n, d = x.shape
+    nf = len(freq_bands)
+    out = torch.empty((n, d * (int(include_input) + 2 * nf)), dtype=f32, device=x.device)
+    _run("posenc_fwd", lambda: lib().nrf_posenc_fwd(ptr(x, f32), n, d, nf, cabi.host_floats(freq_bands), int(include_input), ptr(out), stream()))
+    return out
+
+
+def mlp_shape(input_ch=32, input_ch_views=16, hidden=64, geo=15, hidden_color=64, num_layers=2, num_layers_color=3):
+    return cabi.MlpSmallShape(input_ch, input_ch_views, hidden, geo, hidden_color, num_layers, num_layers_color)
+
+
+def mlp_small_pack(params_flat: torch.Tensor, shape=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    shape = shape or mlp_shape()
+    nbytes = lib().nrf_mlp_small_packed_bytes(C.byref(shape))
+    if nbytes < 0:
+        check(-3)
+    if out is None:
+        out = torch.empty(nbytes, dtype=u8, device=params_flat.device)
+    _run("mlp_small_pack", lambda: lib().nrf_mlp_small_pack(C.byref(shape), ptr(params_flat, f32), ptr(out), stream()))
+    return out
+
+
+def mlp_small_fwd(packed: torch.Tensor, enc: torch.Tensor, ray_sh: torch.Tensor | None, samples_per_ray: int,
+                  keep: torch.Tensor | None, shape=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    shape = shape or mlp_shape()
+    n = enc.shape[0]
+    kind = cabi.MLP_IN_ENC16_RAYDIRS if enc.dtype == f16 else cabi.MLP_IN_F32_CAT
+    if out is None:
+        out = torch.empty((n, 4), dtype=f32, device=enc.device)
+    _run("mlp_small_fwd", lambda: lib().nrf_mlp_small_fwd(C.byref(shape), ptr(packed), kind, ptr(enc), ptr(ray_sh), samples_per_ray, ptr(keep),
+                                  n, ptr(out, f32), stream()))
+    return out
+
+
+def mlp_small_bwd(packed: torch.Tensor, enc: torch.Tensor, ray_sh: torch.Tensor | None, samples_per_ray: int,
+                  keep: torch.Tensor | None, grad_raw: torch.Tensor, grad_params: torch.Tensor, want_grad_in: bool = True,
+                  shape=None, grad_in: torch.Tensor | None = None):
+    shape = shape or mlp_shape()
+    n = enc.shape[0]
+    if enc.dtype == f16:
+        kind = cabi.MLP_IN_ENC16_RAYDIRS
+        if want_grad_in and grad_in is None:
+            grad_in = torch.empty((n, 32), dtype=bf16, device=enc.device)
+    else:
+        kind = cabi.MLP_IN_F32_CAT
+        if want_grad_in and grad_in is None:
+            grad_in = torch.empty((n, 48), dtype=f32, device=enc.device)
+    _run("mlp_small_bwd", lambda: lib().nrf_mlp_small_bwd(C.byref(shape), ptr(packed), kind, ptr(enc), ptr(ray_sh), samples_per_ray, ptr(keep), n,
+                                  ptr(grad_raw, f32), ptr(grad_in) if want_grad_in else None, ptr(grad_params, f32), stream()))
+    return grad_in
+
+
+def composite_fwd(raw: torch.Tensor, z: torch.Tensor, rays_d: torch.Tensor, white_bkgr: bool = False,
+                  noise: torch.Tensor | None = None, raw_noise_std: float = 0.0, want_weights: bool = True):
+    r, s, c = raw.shape
+    dev = raw.device
+    rgb = torch.empty((r, 3), dtype=f32, device=dev)
+    depth = torch.empty(r, dtype=f32, device=dev)
+    disp = torch.empty(r, dtype=f32, device=dev)
+    acc = torch.empty(r, dtype=f32, device=dev)
+    weights = torch.empty((r, s), dtype=f32, device=dev) if want_weights else None
+    _run("composite_fwd", lambda: lib().nrf_composite_fwd(ptr(raw, f32), c, ptr(z, f32), ptr(rays_d, f32), ptr(noise), raw_noise_std, int(white_bkgr),
+                                  r, s, ptr(rgb), ptr(depth), ptr(disp), ptr(acc), ptr(weights), stream()))
+    return {"rgb": rgb, "depth": depth, "disp": disp, "acc": acc, "weights": weights}
+
+
+def composite_bwd(raw, z, rays_d, white_bkgr=False, noise=None, raw_noise_std=0.0, g_rgb=None, g_depth=None, g_disp=None,
+                  g_acc=None, g_weights=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    r, s, c = raw.shape
+    if out is None:
+        out = torch.empty((r, s, 4), dtype=f32, device=raw.device)
+    _run("composite_bwd", lambda: lib().nrf_composite_bwd(ptr(raw, f32), c, ptr(z, f32), ptr(rays_d, f32), ptr(noise), raw_noise_std, int(white_bkgr),
+                                  r, s, ptr(g_rgb), ptr(g_depth), ptr(g_disp), ptr(g_acc), ptr(g_weights), ptr(out), stream()))
+    return out
+
+
+def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
+    r, b = bins.shape
+    per_ray = u.dim() == 2
+    n = u.shape[-1]
+    out = torch.empty((r, n), dtype=f32, device=bins.device)
+    _run("sample_pdf", lambda: lib().nrf_sample_pdf(ptr(bins, f32), ptr(weights, f32), b, ptr(u, f32), int(per_ray), r, n, ptr(out), stream()))
+    return out
+
+
+def sample_pdf_merge(z_coarse: torch.Tensor, weights: torch.Tensor, u: torch.Tensor, want_samples: bool = False):
+    r, s = z_coarse.shape
+    per_ray = u.dim() == 2
+    n = u.shape[-1]
+    merged = torch.empty((r, s + n), dtype=f32, device=z_coarse.device)
+    samples = torch.empty((r, n), dtype=f32, device=z_coarse.device) if want_samples else None
+    _run("sample_pdf_merge", lambda: lib().nrf_sample_pdf_merge(ptr(z_coarse, f32), ptr(weights, f32), ptr(u, f32), int(per_ray), r, s, n, ptr(samples),
+                                     ptr(merged), stream()))
+    return (merged, samples) if want_samples else merged
+
+
+def get_rays(h: int, w: int, K, c2w, row_begin: int = 0, row_end: int | None = None, device="cuda"):
+    row_end = h if row_end is None else row_end
+    n = (row_end - row_begin) * w
+    rays_o = torch.empty((n, 3), dtype=f32, device=device)
+    rays_d = torch.empty((n, 3), dtype=f32, device=device)
+    kh = cabi.host_floats(torch.as_tensor(K, dtype=f32).reshape(-1).tolist())
+    ch = cabi.host_floats(torch.as_tensor(c2w, dtype=f32)[:3, :4].reshape(-1).tolist())
+    _run("get_rays", lambda: lib().nrf_get_rays(h, w, kh, ch, row_begin, row_end, ptr(rays_o), ptr(rays_d), stream()))
+    return rays_o, rays_d
+
+
+def rays_prepare(rays_o: torch.Tensor, rays_d: torch.Tensor, bbox, near_plane: float = 0.0, use_viewdirs: bool = True) -> torch.Tensor:
+    n = rays_o.shape[0]
+    out = torch.empty((n, 11 if use_viewdirs else 8), dtype=f32, device=rays_o.device)
+    _run("rays_prepare", lambda: lib().nrf_rays_prepare(ptr(rays_o, f32), ptr(rays_d, f32), n, cabi.host_floats(bbox), near_plane, int(use_viewdirs),
+                                 ptr(out), stream()))
+    return out
+
+
+def z_sample(ray_batch: torch.Tensor, t_vals: torch.Tensor, lin_disp: bool = False) -> torch.Tensor:
+    r, stride = ray_batch.shape
+    s = t_vals.shape[0]
+    z = torch.empty((r, s), dtype=f32, device=ray_batch.device)
+    _run("z_sample", lambda: lib().nrf_z_sample(ptr(ray_batch, f32), stride, ptr(t_vals, f32), r, s, int(lin_disp), ptr(z), stream()))
+    return z
+
+
+def sample_points(ray_batch: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+    r, stride = ray_batch.shape
+    s = z.shape[1]
+    pts = torch.empty((r, s, 3), dtype=f32, device=z.device)
+    _run("sample_points", lambda: lib().nrf_sample_points(ptr(ray_batch, f32), stride, ptr(z, f32), r, s, ptr(pts), stream()))
+    return pts
+
+
+def huber_fwd_bwd(pred: torch.Tensor, target: torch.Tensor, loss_out: torch.Tensor, grad: torch.Tensor | None,
+                  delta: float = 1.0, grad_scale: float = 1.0) -> None:
+    _run("huber_fwd_bwd", lambda: lib().nrf_huber_fwd_bwd(ptr(pred, f32), ptr(target, f32), pred.numel(), delta, grad_scale, ptr(loss_out, f32),
+                                  ptr(grad), stream()))
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.99, eps=1e-15, grad_scale=1.0,
+              zero_grad=True, shadow_f16: torch.Tensor | None = None, n: int | None = None) -> None:
+    n = param.numel() if n is None else n
+    _run("adam_step", lambda: lib().nrf_adam_step(ptr(param, f32), ptr(grad, f32), ptr(exp_avg, f32), ptr(exp_avg_sq, f32), n, lr, beta1, beta2, eps,
+                              step, grad_scale, int(zero_grad), ptr(shadow_f16), stream()))

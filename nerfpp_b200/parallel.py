@@ -1,0 +1,73 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink on the box, gloo in CPU tests).
+
+The reference has no multi-GPU code at all; this is the sharding the hot path admits:
+  * training  — rays are independent, so the global ray batch is split contiguously by rank, every rank runs
+    forward/backward on its shard, and the ONE exchange step is an all-reduce(sum) of the flat gradient vector
+    [reachable hash-table scalars | NeRFSmall weights] (34 MiB + 37 KiB fp32 at the BASELINE shape), scaled by 1/world
+    inside the Adam kernel (the loss is a mean over rays, src/NeRFExecutor.h:883-886).  Replicas stay identical
+    because they start identical (same seed) and apply the same reduced gradient.
+  * rendering — image rows are split into contiguous tiles, no communication until a final gather of the maps.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
+    """(rank, world, local_rank) from the torchrun environment; initialises the default process group if world > 1."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local_rank
+
+
+def shard_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced partition of n units (rays or image rows): the first n % world ranks get one extra."""
+    base, extra = divmod(n, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def allreduce_gradients(flat_grad: torch.Tensor, world: int) -> float:
+    """Sum the flat gradient over ranks in place; returns the scale (1/world) the optimiser must apply."""
+    if world > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+    return 1.0 / world
+
+
+def broadcast_parameters(flat_params: torch.Tensor, world: int, src: int = 0) -> None:
+    """Rank 0's table / primes / weights become everyone's (the reference draws them at random)."""
+    if world > 1:
+        dist.broadcast(flat_params, src=src)
+
+
+def gather_rows(local: torch.Tensor, n_total: int, rank: int, world: int, dst: int = 0) -> torch.Tensor | None:
+    """Final gather of a row-sharded map ([rows_local, ...]) onto `dst`; shards follow shard_bounds."""
+    if world == 1:
+        return local
+    shapes = [shard_bounds(n_total, r, world) for r in range(world)]
+    if rank == dst:
+        parts = [torch.empty((e - b,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) for b, e in shapes]
+        dist.gather(local.contiguous(), parts, dst=dst)
+        return torch.cat(parts, 0)
+    dist.gather(local.contiguous(), None, dst=dst)
+    return None
+
+
+def max_over_ranks(value: float, world: int, device) -> float:
+    if world == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

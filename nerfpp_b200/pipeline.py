@@ -1,0 +1,195 @@
+"""HashNeRF ray-batch pipeline on the C ABI: RenderRays (inference) and one training step.
+
+Host-side mirror, in Python, of what the reference does in NeRFRenderer::Render/RenderRays
+(src/NeRFRenderer.h:366-459, 530-604) and the ~20 training lines of NeRFExecutor::Train
+(src/NeRFExecutor.h:868-890, 923, 986-996) for the <CuHashEmbedder, CuSHEncoder, NeRFSmall> instantiation
+(src/main.cpp:220-221).  Every arithmetic step is one call into libnerfpp_b200.so; torch only owns the buffers,
+the stream and (for data-parallel training) the NCCL all-reduce.
+
+Divergences from the reference, all deliberate:
+  * Q3  the coarse pass never receives a gradient, so it runs as inference (nothing recorded);
+  * Q5  table reads go through a persistent fp16 shadow refreshed by the Adam kernel, gradients accumulate in fp32;
+  * Q1  sample points are kept per call (the reference back-propagates with the last forward's points);
+  * the SH basis is evaluated once per ray, not once per sample.
+Configuration is the parity one: ThinRay, Perturb 0, no raw noise, no stochastic preconditioning.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .ops import HashGridSpec, f16, f32, i32
+
+MLP_PARAMS = 9344  # 64*32 + 16*64 + 64*31 + 64*64 + 3*64  (src/NeRF.cpp:338-342 at the BASELINE shape)
+MLP_LAYERS = [(64, 32), (16, 64), (64, 31), (64, 64), (3, 64)]
+
+
+def _is_prime(x: int) -> bool:
+    i = 2
+    while i * i <= x:
+        if x % i == 0:
+            return False
+        i += 1
+    return True
+
+
+def random_primes(n: int, rng: np.random.Generator) -> np.ndarray:
+    """Rejection-sampled primes in [2^28, 2^30) (src/CuHashEmbedder.cpp:28-47)."""
+    out = []
+    while len(out) < n:
+        v = int(rng.integers(1 << 28, 1 << 30))
+        if _is_prime(v):
+            out.append(v)
+    return np.asarray(out, dtype=np.int32)
+
+
+def make_grid(bbox, n_levels=16, n_features=2, log2_hashmap_size=19, base_resolution=16, finest_resolution=512,
+              device="cuda", seed=42, primes: np.ndarray | None = None) -> HashGridSpec:
+    """Buffers of CuHashEmbedderImpl's constructor (src/CuHashEmbedder.cpp:37-76); Primes are an input when given."""
+    rng = np.random.default_rng(seed)
+    if primes is None:
+        primes = random_primes(3 * n_levels, rng)
+    local = ((1 << log2_hashmap_size) >> 4) << 4
+    size = torch.full((n_levels,), local, dtype=i32)
+    idx = (torch.cumsum(size, 0) - local).to(i32)
+    return HashGridSpec(
+        bounding_box=tuple(float(v) for v in bbox),
+        primes=torch.as_tensor(np.asarray(primes, dtype=np.int32).reshape(n_levels, 1, 3)).to(device),
+        biases=torch.zeros((n_levels, 3), dtype=f32, device=device),
+        feat_local_idx=idx.to(device), feat_local_size=size.to(device),
+        n_levels=n_levels, n_features=n_features, log2_hashmap_size=log2_hashmap_size,
+        base_resolution=base_resolution, finest_resolution=finest_resolution)
+
+
+class HashNeRF:
+    """Parameters + optimiser state of one HashNeRF replica, as flat device buffers.
+
+    params = [table scalars the kernels can reach | NeRFSmall weights], one fp32 vector, so the data-parallel
+    gradient exchange is ONE all-reduce and the optimiser is ONE kernel.  The reachable table prefix is
+    (L+1) * 2^T scalars: level offsets are in scalars (reference quirk), the rest of the [L*2^T, F] parameter is
+    never read or written by the reference either (its gradient is identically zero, and Adam with eps=1e-15 leaves
+    a zero-gradient entry with zero moments untouched)."""
+
+    def __init__(self, bbox=(-1.5, -1.5, -1.5, 1.5, 1.5, 1.5), n_levels=16, n_features=2, log2_hashmap_size=19,
+                 base_resolution=16, finest_resolution=512, sh_degree=4, n_samples=64, n_importance=128,
+                 device="cuda", seed=42, lr=1e-2, lrate_decay=250, primes=None):
+        assert n_levels * n_features == 32 and sh_degree == 4, "the fused MLP is built for 32 + 16 inputs"
+        self.device = torch.device(device)
+        self.bbox = tuple(float(v) for v in bbox)
+        self.grid = make_grid(bbox, n_levels, n_features, log2_hashmap_size, base_resolution, finest_resolution, device, seed, primes)
+        self.sh_degree, self.S, self.N = sh_degree, n_samples, n_importance
+        self.n_table = self.grid.used_scalars()
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        self.params = torch.empty(self.n_table + MLP_PARAMS, dtype=f32, device=device)
+        self.params[:self.n_table] = (torch.rand(self.n_table, generator=g) * 1e-4).to(device)   # src/CuHashEmbedder.cpp:24
+        off = self.n_table
+        for fo, fi in MLP_LAYERS:                                                                 # Trainable.h:43 Xavier normal, gain 0.1
+            std = 0.1 * math.sqrt(2.0 / (fi + fo))
+            self.params[off:off + fo * fi] = (torch.randn(fo * fi, generator=g) * std).to(device)
+            off += fo * fi
+        self.grads = torch.zeros_like(self.params)
+        self.exp_avg = torch.zeros_like(self.params)
+        self.exp_avg_sq = torch.zeros_like(self.params)
+        self.shadow = torch.empty(self.params.shape, dtype=f16, device=device)                   # fp16 copy; table part is what the gathers read
+        self.packed = None
+        self.lr0, self.lrate_decay, self.step = lr, lrate_decay, 0
+        self.t_vals = torch.linspace(0.0, 1.0, n_samples, dtype=f32).to(device)                  # src/NeRFRenderer.h:393
+        self.u = torch.linspace(0.0, 1.0, n_importance, dtype=f32).to(device)                    # src/Sampler.h:20
+        self.loss = torch.zeros(1, dtype=f32, device=device)
+        self.refresh()
+
+    # -- views into the flat buffers
+    @property
+    def table(self): return self.params[:self.n_table]
+    @property
+    def mlp_params(self): return self.params[self.n_table:]
+    @property
+    def table_f16(self): return self.shadow[:self.n_table]
+
+    def mlp_weights(self):
+        out, off = [], 0
+        for fo, fi in MLP_LAYERS:
+            out.append(self.mlp_params[off:off + fo * fi].view(fo, fi))
+            off += fo * fi
+        return out
+
+    def refresh(self):
+        """Re-derive the fp16 table shadow and the packed MLP weights from the fp32 masters."""
+        ops.table_to_half(self.table, self.table_f16)
+        self.packed = ops.mlp_small_pack(self.mlp_params, out=self.packed)
+
+    # -- RenderRays (src/NeRFRenderer.h:366-459)
+    def _network(self, ray_batch, z, ray_sh):
+        s = z.shape[1]
+        pts = ops.sample_points(ray_batch, z)
+        enc, keep = ops.hash_encode_fwd(self.grid, self.table_f16, pts.view(-1, 3), clamp=True, out_f16=True)
+        raw = ops.mlp_small_fwd(self.packed, enc, ray_sh, s, keep)
+        return pts, enc, keep, raw.view(-1, s, 4)
+
+    def render_rays(self, rays_o, rays_d, white_bkgr=False, keep_for_backward=False):
+        ray_batch = ops.rays_prepare(rays_o, rays_d, self.bbox, 0.0, True)
+        ray_sh = ops.sh_encode(ray_batch[:, 8:11], self.sh_degree)
+        z = ops.z_sample(ray_batch, self.t_vals)
+        _, _, _, raw = self._network(ray_batch, z, ray_sh)
+        coarse = ops.composite_fwd(raw, z, rays_d, white_bkgr)
+        z_fine = ops.sample_pdf_merge(z, coarse["weights"], self.u)
+        pts, enc, keep, raw = self._network(ray_batch, z_fine, ray_sh)
+        out = ops.composite_fwd(raw, z_fine, rays_d, white_bkgr)
+        out["z"] = z_fine
+        if keep_for_backward:
+            out["_saved"] = (pts, enc, keep, raw, ray_sh)
+        return out
+
+    def render_image(self, h, w, K, c2w, chunk=1 << 18, row_begin=0, row_end=None, white_bkgr=False):
+        """Render(h,w,K,c2w) for image rows [row_begin,row_end) (src/NeRFRenderer.h:540-547, RenderPath :684)."""
+        rays_o, rays_d = ops.get_rays(h, w, K, c2w, row_begin, row_end, self.device)
+        outs = [self.render_rays(rays_o[i:i + chunk], rays_d[i:i + chunk], white_bkgr) for i in range(0, rays_o.shape[0], chunk)]
+        return {k: torch.cat([o[k] for o in outs], 0) for k in ("rgb", "depth", "disp", "acc")}
+
+    # -- one optimisation step (src/NeRFExecutor.h:868-890, 923, 986-996)
+    def forward_backward(self, rays_o, rays_d, target, grad_scale=1.0):
+        """Render + huber + backward into self.grads (accumulating).  self.loss holds the mean huber loss."""
+        out = self.render_rays(rays_o, rays_d, keep_for_backward=True)
+        pts, enc, keep, raw, ray_sh = out.pop("_saved")
+        self.loss.zero_()
+        g_rgb = torch.empty_like(out["rgb"])
+        ops.huber_fwd_bwd(out["rgb"], target, self.loss, g_rgb, 1.0, grad_scale)
+        d_raw = ops.composite_bwd(raw, out["z"], rays_d, g_rgb=g_rgb)
+        g_enc = ops.mlp_small_bwd(self.packed, enc, ray_sh, raw.shape[1], keep, d_raw.view(-1, 4), self.grads[self.n_table:])
+        ops.hash_encode_bwd(self.grid, pts.view(-1, 3), g_enc, self.grads[:self.n_table], clamp=True)
+        return out
+
+    def optimizer_step(self, grad_scale=1.0):
+        self.step += 1
+        # src/NeRFExecutor.h:986-996: step() runs with the rate set at the END of the previous iteration,
+        # lr0 * 0.1^(global_step / decay_steps) with global_step counted from 0 and incremented after the update
+        lr = self.lr0 * (0.1 ** (max(self.step - 2, 0) / (self.lrate_decay * 1000)))
+        ops.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, lr, self.step, 0.9, 0.99, 1e-15,
+                      grad_scale, True, self.shadow)
+        self.packed = ops.mlp_small_pack(self.mlp_params, out=self.packed)
+
+    def train_step(self, rays_o, rays_d, target):
+        self.forward_backward(rays_o, rays_d, target)
+        self.optimizer_step()
+        return self.loss
+
+
+def synthetic_rays(n, h=800, w=800, device="cuda", seed=0, radius=4.0):
+    """Random pixels of an h x w pinhole view on a radius-4 sphere pose (BASELINE C2): pixel sampling as
+    NeRFDataset::get_batch (src/NeRFDataset.cpp:154-157), ray maths as GetRayBatch (:109-144), targets U[0,1]^3."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    focal = 0.5 * w / math.tan(0.5 * 0.6911)
+    py = torch.randint(0, h, (n,), generator=g).float()
+    px = torch.randint(0, w, (n,), generator=g).float()
+    dirs = torch.stack([(px - 0.5 * w) / focal, -(py - 0.5 * h) / focal, -torch.ones(n)], -1)
+    th, ph = math.radians(30.0), math.radians(-30.0)
+    rot_phi = torch.tensor([[1, 0, 0], [0, math.cos(ph), -math.sin(ph)], [0, math.sin(ph), math.cos(ph)]], dtype=f32)
+    rot_th = torch.tensor([[math.cos(th), 0, -math.sin(th)], [0, 1, 0], [math.sin(th), 0, math.cos(th)]], dtype=f32)
+    R = rot_th @ rot_phi
+    rays_d = dirs @ R.t()
+    rays_o = (R @ torch.tensor([0.0, 0.0, radius])).expand(n, 3).contiguous()
+    target = torch.rand(n, 3, generator=g)
+    return rays_o.to(device), rays_d.contiguous().to(device), target.to(device)

@@ -174,7 +174,7 @@ static void BindPipe(py::module_& m, const char* name)
 		.def("embed", &P::Embed).def("embed_dirs", &P::EmbedDirs).def("model", &P::Model)
 		.def("run_network", &P::RunNetwork).def("raw_to_outputs", &P::RawToOutputs)
 		.def("render_rays", &P::RenderRays).def("render", &P::Render).def("render_image", &P::RenderImage)
-		.def("train_steps", &P::TrainSteps);
+		.def("train_steps", &P::TrainSteps, py::call_guard<py::gil_scoped_release>());
 }
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)

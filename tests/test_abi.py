@@ -1,0 +1,63 @@
+"""CPU checks of the drop-in boundary: libnerfpp_b200.so builds, loads, and exports exactly what include/nerfpp_b200.h
+declares (no compute calls — there is no GPU here), and argument validation fails loudly."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "nerfpp_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nrf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    from nerfpp_b200 import cabi
+    lib = cabi.lib()
+    names = declared_symbols()
+    assert len(names) >= 24
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert sorted(cabi.SIGNATURES) == names, "ctypes table and header disagree"
+    assert lib.nrf_abi_version() == 1
+
+
+def test_no_torch_in_the_abi_library():
+    """The boundary is plain C: the shared library must not link torch / c10 / python."""
+    import subprocess
+    from nerfpp_b200 import build
+    out = subprocess.run(["ldd", str(build.build())], capture_output=True, text=True).stdout
+    assert "libtorch" not in out and "libc10" not in out and "libpython" not in out
+    assert "libcudart" in out
+
+
+def test_argument_validation_without_gpu():
+    from nerfpp_b200 import cabi, ops
+    lib = cabi.lib()
+    assert lib.nrf_sh_encode_fwd(None, 3, 8, 9, None, None) == -1          # degree out of range
+    assert b"degree" in lib.nrf_last_error()
+    assert lib.nrf_sh_encode_fwd(None, 3, 0, 4, None, None) == 0           # empty input is a no-op
+    shape = ops.mlp_shape(hidden=128)
+    assert lib.nrf_mlp_small_param_count(ctypes.byref(shape)) == -1        # unsupported shape: loud, no fallback
+    assert lib.nrf_mlp_small_param_count(ctypes.byref(ops.mlp_shape())) == 9344
+    assert lib.nrf_composite_fwd(None, 3, None, None, None, 0.0, 0, 4, 8, None, None, None, None, None, None) == -1
+
+
+def test_product_path_refuses_cpu_tensors():
+    import torch
+    from nerfpp_b200 import cabi, ops
+    with pytest.raises(cabi.NrfError):
+        ops.sh_encode(torch.zeros(4, 3), 4)
+    with pytest.raises(cabi.NrfError):
+        ops.composite_fwd(torch.zeros(2, 4, 4), torch.zeros(2, 4), torch.zeros(2, 3))
+
+
+def test_product_never_imports_the_oracle():
+    for p in (ROOT / "nerfpp_b200").rglob("*"):
+        if p.suffix in (".py", ".cu", ".cuh", ".cpp", ".h") and p.is_file():
+            text = p.read_text()
+            assert not re.search(r"(import|from)\s+(oracle|restate)\b|oracle/_ref|nerfpp_ref|#include\s+\"[^\"]*oracle", text), p

@@ -1,0 +1,209 @@
+"""GPU parity of the hash-grid kernels through the C ABI (nrf_hash_encode_fwd / _bwd) against oracle/restate.py,
+the committed CUDA golden fixtures, and — when oracle/_ref/nerfpp_ref_cuda.so is loadable — the reference's own
+CuHashEmbedder kernels run live on the same device."""
+import numpy as np
+import pytest
+import torch
+
+import restate as O
+
+pytestmark = pytest.mark.gpu
+
+BBOX = (-1.5, -1.5, -1.5, 1.5, 1.5, 1.5)
+
+
+def _grid(L=16, F=2, T=19, base=16, finest=512, seed=1):
+    from nerfpp_b200 import pipeline
+    return pipeline.make_grid(BBOX, L, F, T, base, finest, "cuda", seed)
+
+
+def _np(grid):
+    grid.c_struct()  # materialises the device-computed level scales
+    return dict(box_min=BBOX[:3], box_max=BBOX[3:], scales=grid.level_scale.cpu().numpy(),
+                primes=grid.primes.cpu().numpy(), biases=grid.biases.cpu().numpy(),
+                offsets=grid.feat_local_idx.cpu().numpy(), sizes=grid.feat_local_size.cpu().numpy())
+
+
+def _points(n, seed=0, with_edges=True):
+    g = torch.Generator().manual_seed(seed)
+    p = torch.rand(n, 3, generator=g) * 3 - 1.5
+    if with_edges:
+        p[0] = -1.5                                   # exact box_min
+        p[1] = 1.5                                    # exact box_max
+        p[2] = torch.tensor([0.0, 0.0, 0.0])          # cell boundary on the power-of-two levels
+        p[3] = torch.tensor([1.5, -1.5, 0.75])
+        p[4] = torch.tensor([1.7, 0.1, 0.2])          # outside: clamped, keep = 0
+        p[5] = torch.tensor([0.1, -9.0, 0.2])
+    return p.cuda()
+
+
+def test_level_scales_match_expression():
+    from nerfpp_b200 import ops
+    s = ops.hash_level_scales(16, 512, 16, "cuda").cpu().numpy()
+    assert [float(s[i]) for i in (0, 3, 6, 9, 12, 15)] == [16.0, 32.0, 64.0, 128.0, 256.0, 512.0]
+    np.testing.assert_allclose(s, O.level_scales(16, 512, 16), rtol=3e-7)   # device exp2f vs numpy: <= 2 ulp
+    assert np.all(np.diff(s) > 0)
+
+
+def test_indices_bit_exact_at_vertices():
+    """Points placed exactly on grid vertices of the power-of-two levels get weight 1 on corner 000, so the output IS
+    the table entry; a table that stores bit-slices of its own scalar address reveals the hashed address exactly."""
+    from nerfpp_b200 import ops
+    grid = _grid()
+    meta = _np(grid)
+    n_sc = grid.used_scalars()
+    rng = np.random.default_rng(3)
+    idx = np.arange(grid.table_scalars(), dtype=np.int64)
+    tables = [torch.from_numpy(((idx >> (11 * j)) & 2047).astype(np.float16)).cuda() for j in range(3)]  # 3 x 11 address bits
+    for level, res in ((0, 16), (3, 32), (6, 64), (9, 128), (12, 256), (15, 512)):
+        v = rng.integers(0, res + 1, size=(4096, 3))
+        pts_np = (v.astype(np.float64) / res * 3.0 - 1.5).astype(np.float32)
+        # keep only points whose normalised coordinate is exactly the vertex in fp32 (always true for these res)
+        pos, w = O.hash_cells(pts_np, scales=meta["scales"], box_min=meta["box_min"], box_max=meta["box_max"],
+                              primes=meta["primes"], biases=meta["biases"], sizes=meta["sizes"])
+        assert np.all(w[:, level, 0] == 1.0)
+        addr = np.zeros(len(pts_np), dtype=np.int64)
+        for j in range(3):
+            enc, _ = ops.hash_encode_fwd(grid, tables[j], torch.from_numpy(pts_np).cuda(), clamp=True)
+            addr |= enc[:, level * 2].cpu().numpy().astype(np.int64) << (11 * j)
+        expect = meta["offsets"][level].astype(np.int64) + pos[:, level, 0].astype(np.int64) * 2
+        assert np.array_equal(addr, expect), f"hashed address mismatch at level {level}"
+        assert expect.max() < n_sc
+
+
+@pytest.mark.parametrize("table_kind", ["init", "unit"])
+def test_forward_matches_oracle(table_kind):
+    from nerfpp_b200 import ops
+    grid = _grid()
+    meta = _np(grid)
+    g = torch.Generator().manual_seed(5)
+    n_sc = grid.table_scalars()
+    table = torch.rand(n_sc, generator=g) * 1e-4 if table_kind == "init" else torch.rand(n_sc, generator=g) * 2 - 1
+    t16 = ops.table_to_half(table.cuda())
+    assert torch.equal(t16.cpu(), table.half())               # round-to-nearest-even like .to(kFloat16)
+    pts = _points(3000)
+    enc, keep = ops.hash_encode_fwd(grid, t16, pts, clamp=True)
+    enc16, _ = ops.hash_encode_fwd(grid, t16, pts, clamp=True, out_f16=True)
+    assert torch.equal(enc16.float(), enc)                    # both layouts carry the same fp16 values
+    cl, keep_ref = O.clamp_keep(pts.cpu().numpy(), BBOX[:3], BBOX[3:])
+    assert np.array_equal(keep.cpu().numpy().astype(bool), keep_ref)
+    assert keep_ref[:4].all() and not keep_ref[4] and not keep_ref[5]
+    ref = O.hash_encode(cl, table_f16=t16.cpu().numpy(), n_features=2, **meta)
+    scale = 1e-4 if table_kind == "init" else 1.0
+    # rel 1e-3 of the value plus one fp16 ulp at the table's scale (fp16 output rounding dominates)
+    np.testing.assert_allclose(enc.cpu().numpy(), ref, rtol=1e-3, atol=scale * 2 ** -10)
+    exact = (enc.cpu().numpy() == ref).mean()
+    assert exact > 0.9, f"only {exact:.3f} of outputs bit-equal the sequential-fp32 restatement"
+
+
+def test_backward_matches_fp64_adjoint():
+    from nerfpp_b200 import ops
+    grid = _grid()
+    meta = _np(grid)
+    pts = _points(4000, seed=9)
+    g = torch.Generator().manual_seed(11)
+    grad = torch.randn(4000, 32, generator=g)
+    grad[7] = 0.0                                             # all-zero rows take the skip path (.cu:195)
+    grad[8, ::2] = 0.0
+    gt = torch.zeros(grid.table_scalars(), device="cuda")
+    ops.hash_encode_bwd(grid, pts, grad.cuda(), gt, clamp=True)
+    cl, _ = O.clamp_keep(pts.cpu().numpy(), BBOX[:3], BBOX[3:])
+    ref = O.hash_encode_bwd_f64(cl, grad_enc=grad.numpy(), n_features=2, table_scalars=grid.table_scalars(), **meta)
+    got = gt.cpu().numpy().astype(np.float64)
+    assert np.array_equal(got != 0, ref != 0)                 # exactly the same set of touched scalars
+    assert np.all(got[grid.used_scalars():] == 0)
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < 2e-6, err                                    # fp32 accumulation
+    # bf16 gradient input (what nrf_mlp_small_bwd hands over)
+    gt2 = torch.zeros_like(gt)
+    gb = grad.cuda().bfloat16()
+    ops.hash_encode_bwd(grid, pts, gb, gt2, clamp=True)
+    ref2 = O.hash_encode_bwd_f64(cl, grad_enc=gb.float().cpu().numpy(), n_features=2, table_scalars=grid.table_scalars(), **meta)
+    assert np.abs(gt2.cpu().numpy() - ref2).max() / np.abs(ref2).max() < 2e-6
+
+
+def test_f8_grid_lerf_shape():
+    """F=8 (the LeRF grid, src/main.cpp:203-207) through the same kernels."""
+    from nerfpp_b200 import ops, pipeline
+    grid = pipeline.make_grid(BBOX, 8, 8, 12, 8, 128, "cuda", 4)
+    meta = _np(grid)
+    g = torch.Generator().manual_seed(2)
+    table = (torch.rand(grid.table_scalars(), generator=g) * 2 - 1).cuda()
+    t16 = ops.table_to_half(table)
+    pts = _points(1000, seed=4)
+    enc, _ = ops.hash_encode_fwd(grid, t16, pts, clamp=True)
+    cl, _ = O.clamp_keep(pts.cpu().numpy(), BBOX[:3], BBOX[3:])
+    ref = O.hash_encode(cl, table_f16=t16.cpu().numpy(), n_features=8, **meta)
+    np.testing.assert_allclose(enc.cpu().numpy(), ref, rtol=1e-3, atol=2 ** -10)
+    grad = torch.randn(1000, 64, generator=g)
+    gt = torch.zeros(grid.table_scalars(), device="cuda")
+    ops.hash_encode_bwd(grid, pts, grad.cuda(), gt, clamp=True)
+    refg = O.hash_encode_bwd_f64(cl, grad_enc=grad.numpy(), n_features=8, table_scalars=grid.table_scalars(), **meta)
+    assert np.abs(gt.cpu().numpy() - refg).max() / np.abs(refg).max() < 2e-6
+
+
+def test_empty_and_ragged():
+    from nerfpp_b200 import ops
+    grid = _grid()
+    t16 = torch.zeros(grid.table_scalars(), dtype=torch.float16, device="cuda")
+    enc, keep = ops.hash_encode_fwd(grid, t16, torch.empty(0, 3, device="cuda"))
+    assert enc.shape == (0, 32) and keep.shape == (0,)
+    for n in (1, 31, 257):
+        enc, _ = ops.hash_encode_fwd(grid, t16, _points(n, with_edges=False))
+        assert enc.shape == (n, 32) and float(enc.abs().max()) == 0.0
+
+
+def test_full_size_adjoint_identity():
+    """BASELINE fine-pass size (786 432 points): <enc(T), G> == <T, bwd(G)> — the forward and backward kernels are
+    adjoint maps over the same hashed addresses (size-independent property; tolerance = fp16 output rounding)."""
+    from nerfpp_b200 import ops
+    grid = _grid()
+    n = 4096 * 192
+    g = torch.Generator(device="cuda").manual_seed(1)
+    table = torch.rand(grid.table_scalars(), generator=g, device="cuda") * 2 - 1
+    t16 = ops.table_to_half(table)
+    pts = torch.rand(n, 3, generator=g, device="cuda") * 3 - 1.5
+    G = torch.randn(n, 32, generator=g, device="cuda")
+    enc, _ = ops.hash_encode_fwd(grid, t16, pts)
+    gt = torch.zeros(grid.table_scalars(), device="cuda")
+    ops.hash_encode_bwd(grid, pts, G, gt)
+    lhs = (enc.double() * G.double()).sum().item()
+    rhs = (t16.double() * gt.double()).sum().item()
+    assert abs(lhs - rhs) / (enc.double().abs() * G.double().abs()).sum().item() < 1e-4
+
+
+def test_against_reference_cuda_kernels(ref_cuda):
+    """Live: the reference's CuHashEmbedder forward/backward kernels on the same table, primes and points."""
+    if ref_cuda is None:
+        pytest.skip("oracle/_ref/nerfpp_ref_cuda.so not loadable")
+    from nerfpp_b200 import ops
+    from nerfpp_b200.ops import HashGridSpec
+    ref_cuda.manual_seed(42)
+    pipe = ref_cuda.make_cuhash(torch.tensor(BBOX), 16, 2, 19, 16, 512, 4, 2, 64, 15, 3, 64)
+    bufs = dict(zip(pipe.embed_buffer_names(), pipe.embed_buffers()))
+    table = pipe.embed_params()[0]
+    with torch.no_grad():
+        table.copy_(torch.rand_like(table) * 2 - 1)
+    grid = HashGridSpec(BBOX, bufs["embedder_primes"].contiguous(), bufs["embedder_biases"].contiguous(),
+                        bufs["embedder_feat_local_idx"].contiguous(), bufs["embedder_feat_local_size"].contiguous())
+    pts = _points(20000, seed=21)
+    ref_enc, ref_keep = pipe.embed(pts)
+    t16 = ops.table_to_half(table.detach().reshape(-1))
+    enc, keep = ops.hash_encode_fwd(grid, t16, pts)
+    assert torch.equal(keep.bool(), ref_keep)
+    # identical hashed cells => outputs agree to fp16 rounding of differently-ordered fp32 sums
+    assert (enc - ref_enc).abs().max().item() <= 2 ** -9
+    assert (enc == ref_enc).float().mean().item() > 0.95
+    # gradient: ours (fp32 atomics) vs the reference's (x128 fp16 atomics), both judged against the fp64 adjoint
+    gout = torch.randn(20000, 32, device="cuda") * 1e-3
+    ref_enc.backward(gout)
+    ref_grad = table.grad.reshape(-1).double().cpu().numpy()
+    gt = torch.zeros(grid.table_scalars(), device="cuda")
+    ops.hash_encode_bwd(grid, pts, gout, gt)
+    meta = _np(grid)
+    cl, _ = O.clamp_keep(pts.cpu().numpy(), BBOX[:3], BBOX[3:])
+    exact = O.hash_encode_bwd_f64(cl, grad_enc=gout.cpu().numpy(), n_features=2, table_scalars=grid.table_scalars(), **meta)
+    ours_err = np.abs(gt.double().cpu().numpy() - exact).max()
+    ref_err = np.abs(ref_grad - exact).max()
+    assert ours_err <= ref_err, (ours_err, ref_err)
+    assert np.abs(gt.double().cpu().numpy() - ref_grad).max() <= 1e-2 * np.abs(exact).max() + 2 * ref_err

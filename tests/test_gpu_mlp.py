@@ -1,0 +1,141 @@
+"""GPU parity of the fused NeRFSmall kernels (nrf_mlp_small_fwd / _bwd) against the reference's NeRFSmallImpl
+(golden fixture generated from src/NeRF.cpp:363-412 through autograd) and oracle/restate.py.
+
+Tolerance class: the reference MLP is true fp32 SGEMM; the fused kernels run bf16 x bf16 (layer 0: fp16 x fp16) with fp32
+accumulation, so outputs / gradients are held to rel 1e-2 of the tensor's scale (BASELINE north star: "1e-2 bf16")."""
+import numpy as np
+import pytest
+import torch
+
+import restate as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def flat(ws):
+    return torch.cat([w.reshape(-1) for w in ws]).contiguous()
+
+
+def run_fwd_bwd_f32cat(ws, x, g):
+    from nerfpp_b200 import ops
+    params = flat(ws).cuda()
+    packed = ops.mlp_small_pack(params)
+    xc = x.cuda().contiguous()
+    out = ops.mlp_small_fwd(packed, xc, None, 1, None)
+    gp = torch.zeros_like(params)
+    gx = ops.mlp_small_bwd(packed, xc, None, 1, None, g.cuda().contiguous(), gp)
+    return out, gx, gp
+
+
+@pytest.mark.parametrize("which", ["xavier", "unit"])
+def test_against_reference_fixture(golden, which):
+    g = golden("nerf_small.npz")
+    wk, xk, ok, gxk, gwk = ("w", "x", "out", "gx", "gw") if which == "xavier" else ("v", "x2", "out2", "gx2", "gv")
+    ws = [torch.from_numpy(g[f"{wk}{i}"]) for i in range(5)]
+    x = torch.from_numpy(g[xk])
+    x = torch.cat([x[:, :32].half().float(), x[:, 32:]], -1)      # the kernel consumes the encodings as fp16 values
+    gout = torch.from_numpy(g["g"])
+    out, gx, gp = run_fwd_bwd_f32cat(ws, x, gout)
+    # fp32 re-evaluation on the fp16-rounded encodings (the fixture's x is not fp16-exact for the xavier case)
+    wr = [w.clone().requires_grad_(True) for w in ws]
+    xr = x.clone().requires_grad_(True)
+    ref = O.nerf_small_forward(xr, (wr[:2], wr[2:]))
+    ref.backward(gout)
+    if which == "unit":
+        assert rel_err(ref.detach(), torch.from_numpy(g[ok])) < 1e-5   # the restatement IS the reference here
+    assert rel_err(out, ref.detach()) < 1e-2
+    assert rel_err(gx[:, :32], xr.grad[:, :32]) < 1.5e-2
+    assert rel_err(gx[:, 32:], xr.grad[:, 32:]) < 1.5e-2
+    gref = flat([w.grad for w in wr])
+    off = 0
+    for i, w in enumerate(ws):
+        n = w.numel()
+        assert rel_err(gp[off:off + n], gref[off:off + n]) < 1.5e-2, f"dW{i}"
+        off += n
+
+
+def test_fused_input_path_matches_cat_path():
+    """ENC16 + per-ray SH input (the pipeline path) == fp32 cat input (the drop-in NeRFSmall::forward path)."""
+    from nerfpp_b200 import ops
+    torch.manual_seed(3)
+    rays, s = 37, 5                                            # 185 rows: ragged vs the 16-row slabs and 128-row tiles
+    n = rays * s
+    ws = [torch.randn(o, i) * (2.0 / i) ** 0.5 for o, i in ((64, 32), (16, 64), (64, 31), (64, 64), (3, 64))]
+    params = flat(ws).cuda()
+    packed = ops.mlp_small_pack(params)
+    enc = torch.randn(n, 32).half().cuda()
+    dirs = torch.nn.functional.normalize(torch.randn(rays, 3), dim=-1).cuda()
+    ray_sh = ops.sh_encode(dirs, 4)
+    keep = (torch.rand(n) > 0.2).to(torch.uint8).cuda()
+    x = torch.cat([enc.float(), ray_sh.repeat_interleave(s, 0)], -1).contiguous()
+    out_a = ops.mlp_small_fwd(packed, enc, ray_sh, s, keep)
+    out_b = ops.mlp_small_fwd(packed, x, None, 1, keep)
+    assert torch.equal(out_a, out_b)
+    assert float(out_a[keep == 0, 3].abs().max()) == 0.0       # sigma := 0 outside the box (NeRFRenderer.h:188)
+    g = torch.randn(n, 4).cuda()
+    gp_a, gp_b = torch.zeros_like(params), torch.zeros_like(params)
+    gx_a = ops.mlp_small_bwd(packed, enc, ray_sh, s, keep, g, gp_a)
+    gx_b = ops.mlp_small_bwd(packed, x, None, 1, keep, g, gp_b)
+    assert rel_err(gx_a.float(), gx_b[:, :32]) < 1e-2          # bf16 vs fp32 output of the same values
+    assert rel_err(gp_a, gp_b) < 1e-5
+    # reference semantics of the mask: gradient of sigma is dropped where keep == 0
+    wr = [w.clone().requires_grad_(True) for w in ws]
+    xr = x.cpu().clone().requires_grad_(True)
+    ref = O.nerf_small_forward(xr, (wr[:2], wr[2:]))
+    ref = torch.cat([ref[:, :3], ref[:, 3:] * keep.cpu().float()[:, None]], -1)
+    ref.backward(g.cpu())
+    assert rel_err(out_a, ref.detach()) < 1e-2
+    assert rel_err(gp_a, flat([w.grad for w in wr])) < 1.5e-2
+
+
+def test_sizes_and_accumulation():
+    from nerfpp_b200 import ops
+    torch.manual_seed(0)
+    ws = [torch.randn(o, i) * (2.0 / i) ** 0.5 for o, i in ((64, 32), (16, 64), (64, 31), (64, 64), (3, 64))]
+    params = flat(ws).cuda()
+    packed = ops.mlp_small_pack(params)
+    for n in (0, 1, 15, 16, 17, 127, 128, 129, 1000):
+        x = torch.cat([torch.randn(n, 32).half().float(), torch.randn(n, 16)], -1).cuda()
+        out = ops.mlp_small_fwd(packed, x, None, 1, None)
+        assert out.shape == (n, 4)
+        if n:
+            ref = O.nerf_small_forward(x.cpu(), (ws[:2], ws[2:]))
+            assert rel_err(out, ref) < 1e-2, n
+    # the parameter gradient ACCUMULATES across calls (the coarse/fine passes of one step share it)
+    x = torch.cat([torch.randn(300, 32).half().float(), torch.randn(300, 16)], -1).cuda()
+    g = torch.randn(300, 4).cuda()
+    gp1 = torch.zeros_like(params)
+    ops.mlp_small_bwd(packed, x, None, 1, None, g, gp1)
+    gp2 = gp1.clone()
+    ops.mlp_small_bwd(packed, x, None, 1, None, g, gp2)
+    assert rel_err(gp2, 2 * gp1) < 1e-5
+
+
+def test_unsupported_shape_fails_loudly():
+    from nerfpp_b200 import cabi, ops
+    with pytest.raises(cabi.NrfError):
+        ops.mlp_small_pack(torch.zeros(9344, device="cuda"), shape=ops.mlp_shape(hidden=128))
+
+
+def test_full_size_linearity():
+    """BASELINE size (786 432 rows): the backward is linear in grad_raw — bwd(a*g1 + g2) == a*bwd(g1) + bwd(g2)."""
+    from nerfpp_b200 import ops
+    torch.manual_seed(1)
+    n = 4096 * 192
+    ws = [torch.randn(o, i) * (2.0 / i) ** 0.5 for o, i in ((64, 32), (16, 64), (64, 31), (64, 64), (3, 64))]
+    params = flat(ws).cuda()
+    packed = ops.mlp_small_pack(params)
+    enc = torch.randn(n, 32, device="cuda").half()
+    ray_sh = ops.sh_encode(torch.nn.functional.normalize(torch.randn(4096, 3, device="cuda"), dim=-1), 4)
+    g1, g2 = torch.randn(n, 4, device="cuda"), torch.randn(n, 4, device="cuda")
+    outs = []
+    for g in (g1, g2, 0.5 * g1 + g2):
+        gp = torch.zeros_like(params)
+        ops.mlp_small_bwd(packed, enc, ray_sh, 192, None, g, gp, want_grad_in=False)
+        outs.append(gp)
+    assert rel_err(outs[2], 0.5 * outs[0] + outs[1]) < 2e-2

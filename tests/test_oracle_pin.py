@@ -1,0 +1,145 @@
+"""Pins oracle/restate.py (the CPU restatement) against the reference: the committed golden fixtures generated from
+the unmodified reference sources (tests/golden/make_golden.py), and the compiled reference itself when present."""
+import numpy as np
+import pytest
+import torch
+
+import restate as O
+
+T = torch.from_numpy
+
+
+def close(a, b, rtol=1e-5, atol=1e-6):
+    a = a.detach().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+def test_trunc_exp(golden):
+    g = golden("trunc_exp.npz")
+    x = T(g["x"]).requires_grad_(True)
+    y = O.TruncExp.apply(x)
+    y.backward(torch.ones_like(y))
+    close(y, g["y"], rtol=1e-6)
+    close(x.grad, g["gx"], rtol=1e-6)
+    assert abs(float(x.grad[7]) - np.exp(5.0)) < 1e-3  # grad at x=7 is e^5: backward is truncated, forward is not
+
+
+def test_sample_pdf(golden):
+    g = golden("sample_pdf.npz")
+    samples, _ = O.sample_pdf(T(g["bins"]), T(g["weights"]), 128, True)
+    close(samples, g["samples"], rtol=1e-6, atol=1e-6)
+    merged = torch.sort(torch.cat([T(g["z"]), samples], -1), -1).values
+    close(merged, g["merged"], rtol=1e-6, atol=1e-6)
+    assert merged.shape[1] == 192
+
+
+@pytest.mark.parametrize("white", [False, True])
+def test_raw_to_outputs(golden, white):
+    g = golden("raw_to_outputs.npz")
+    tag = "w" if white else "b"
+    raw = T(g["raw"]).requires_grad_(True)
+    res = O.raw_to_outputs(raw, T(g["z"]), T(g["rays_d"]), 0.0, white)
+    for k in ("rgb", "depth", "disp", "acc", "weights"):
+        close(res[k], g[f"{tag}_{k}"], rtol=1e-5, atol=1e-6)
+    sum((res[k] * T(g[f"{tag}_g_{k}"])).sum() for k in res).backward()
+    close(raw.grad, g[f"{tag}_d_raw"], rtol=1e-4, atol=1e-5)
+
+
+def test_nerf_small(golden):
+    g = golden("nerf_small.npz")
+    for xk, ok, gxk, wk, gwk in (("x", "out", "gx", "w", "gw"), ("x2", "out2", "gx2", "v", "gv")):
+        ws = [T(g[f"{wk}{i}"]).requires_grad_(True) for i in range(5)]
+        x = T(g[xk]).requires_grad_(True)
+        out = O.nerf_small_forward(x, (ws[:2], ws[2:]))
+        close(out, g[ok], rtol=1e-5, atol=1e-7)
+        out.backward(T(g["g"]))
+        close(x.grad, g[gxk], rtol=1e-4, atol=1e-6)
+        for i in range(5):
+            close(ws[i].grad, g[f"{gwk}{i}"], rtol=1e-4, atol=1e-5)
+
+
+def test_nerf_classic(golden):
+    g = golden("nerf_classic.npz")
+    p = {k.replace("__", "."): T(g[k]) for k in g.files if k.startswith("model_")}
+    out = O.nerf_forward(T(g["x"]), p)
+    close(out, g["out"], rtol=1e-4, atol=1e-5)
+
+
+def test_encoders(golden):
+    g = golden("encoders.npz")
+    x = T(g["x"])
+    close(O.posenc(x, 10), g["emb10"], rtol=1e-6, atol=1e-6)
+    close(O.posenc(x, 4), g["emb4"], rtol=1e-6, atol=1e-6)
+    assert O.posenc(x, 10).shape[1] == 63 and O.posenc(x, 4).shape[1] == 27
+    # closed-form real SH == the reference's polynomial table on unit vectors (LibTorch SHEncoder, degree <= 5)
+    for deg in (2, 3, 4, 5):
+        close(O.sh_encode_closed_form(g["dirs"], deg), g[f"sh{deg}"], rtol=1e-4, atol=2e-6)
+
+
+def test_ray_utils(golden):
+    g = golden("ray_utils.npz")
+    ro, rd = O.get_rays(int(g["h"]), int(g["w"]), T(g["K"]), T(g["c2w"]))
+    close(ro, g["rays_o_img"], rtol=0, atol=0)
+    close(rd, g["rays_d_img"], rtol=1e-7, atol=1e-7)
+    near, far = O.intersect_aabb(T(g["o"]), T(g["d"]), T(g["bbox"]))
+    close(near, g["near"], rtol=1e-6, atol=1e-6)
+    close(far, g["far"], rtol=1e-6, atol=1e-6)
+
+
+def test_render_rays_classic(golden):
+    """Whole RenderRays (coarse -> SamplePDF -> sort -> fine) against the reference template instantiation."""
+    g = golden("render_rays_classic.npz")
+    p = {k.replace("__", "."): T(g[k]) for k in g.files if k.startswith("model_")}
+
+    def run_network(pts, viewdirs):
+        r, s, _ = pts.shape
+        e = O.posenc(pts.reshape(-1, 3), 10)
+        ed = O.posenc(viewdirs[:, None, :].expand(r, s, 3).reshape(-1, 3), 4)
+        return O.nerf_forward(torch.cat([e, ed], -1), p).reshape(r, s, 4)
+
+    rb = O.ray_batch(T(g["o"]), T(g["d"]), T(g["bbox"]))
+    for white, key in ((False, "rgb"), (True, "rgb_white")):
+        out, _, z = O.render_rays(rb, 64, 128, run_network, white)
+        assert z.shape[1] == 192
+        close(out["rgb"], g[key], rtol=1e-4, atol=1e-5)
+    close(out["depth"], g["depth"], rtol=1e-4, atol=1e-5)
+    close(out["acc"], g["acc"], rtol=1e-4, atol=1e-5)
+    close(out["weights"], g["weights"], rtol=1e-3, atol=1e-5)
+
+
+def test_hash_cells_properties():
+    """Index arithmetic sanity that needs no GPU: weights are a partition of unity, indices in range, corner order
+    z-fastest, and the level scales are the exact powers of two where the exponent is an integer."""
+    rng = np.random.default_rng(0)
+    L, T_ = 16, 19
+    scales = O.level_scales(16, 512, L)
+    assert [float(scales[i]) for i in (0, 3, 6, 9, 12, 15)] == [16.0, 32.0, 64.0, 128.0, 256.0, 512.0]
+    primes = rng.integers(1 << 28, 1 << 30, size=(L, 1, 3)).astype(np.int32)
+    pts = rng.uniform(-1.5, 1.5, size=(257, 3)).astype(np.float32)
+    pts[0] = -1.5
+    pts[1] = 1.5
+    sizes = np.full(L, 1 << T_, dtype=np.int32)
+    pos, w = O.hash_cells(pts, [-1.5] * 3, [1.5] * 3, scales, primes, np.zeros((L, 3), np.float32), sizes)
+    assert pos.max() < (1 << T_)
+    np.testing.assert_allclose(w.sum(-1), 1.0, atol=1e-6)
+    # the box_max corner sits exactly on vertex (res,res,res): weight 1 on corner 000, hashed coords (16,16,16) at level 0
+    assert w[1, 0, 0] == 1.0
+    pr = primes[0, 0].astype(np.int64).astype(np.uint32)
+    with np.errstate(over="ignore"):
+        expect = ((np.uint32(16) * pr[0]) ^ (np.uint32(16) * pr[1]) ^ (np.uint32(16) * pr[2])) % np.uint32(1 << T_)
+    assert pos[1, 0, 0] == expect
+
+
+def test_against_compiled_reference(ref_cpu):
+    """Live check against oracle/_ref (skipped where the reference was not compiled)."""
+    if ref_cpu is None:
+        pytest.skip("oracle/_ref/nerfpp_ref_cpu.so not built")
+    torch.manual_seed(7)
+    bins = torch.sort(torch.rand(5, 63) * 4 + 2, -1).values
+    w = torch.rand(5, 62) ** 3
+    close(O.sample_pdf(bins, w, 128, True)[0], ref_cpu.sample_pdf(bins, w, 128, True), rtol=1e-6, atol=1e-6)
+    x = torch.randn(9, requires_grad=True)
+    close(O.TruncExp.apply(x), ref_cpu.trunc_exp(x), rtol=1e-7)
+    pts = torch.rand(17, 3)
+    close(O.posenc(pts, 10), ref_cpu.embedder(pts, 10), rtol=1e-6, atol=1e-6)
