@@ -52,7 +52,9 @@ __device__ __forceinline__ SampleEval eval_sample(const float* __restrict__ raw,
 	if (noise_row) sig = __fadd_rn(sig, __fmul_rn(noise_row[i], noise_std));
 	e.sig = sig;
 	e.x = -__fmul_rn(fmaxf(sig, 0.f), e.dist);
-	e.alpha = 1.f - expf(e.x);
+	// S == 1 reproduces a reference quirk: `dists` is built from z[...,1:]-z[...,:-1] ([R,0]) and the 1e10 tail is
+	// expanded to that EMPTY shape (src/NeRFRenderer.h:239-240), so every [R,S] tensor is empty and all maps are zero.
+	e.alpha = (S == 1) ? 0.f : 1.f - expf(e.x);
 	e.ell = logf(fmaxf(1.f - e.alpha, 1e-10f));
 	return e;
 }
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(kRaysPerCta * 32) composite_bwd_kernel(const f
 			const float om = 1.f - e[b].alpha;
 			if (om >= 1e-10f) dalpha -= dell / om;
 			const float dx = -dalpha * expf(fminf(fmaxf(e[b].x, -100.f), 5.f));
-			const float dsig = e[b].sig > 0.f ? -e[b].dist * dx : 0.f;
+			const float dsig = (e[b].sig > 0.f && S > 1) ? -e[b].dist * dx : 0.f;
 			const float w = e[b].alpha * T;
 			float4 o;
 			o.x = w * gr * e[b].r * (1.f - e[b].r);

@@ -350,9 +350,9 @@ int nrf_hash_encode_fwd(const nrf_hash_grid* grid, const void* table_f16, const 
 {
 	HashArgs a;
 	if (int rc = fill_args(grid, a)) return rc;
-	NRF_REQUIRE(table_f16 && enc_out, "null table / output");
 	NRF_REQUIRE(n_points >= 0, "negative n_points");
 	if (n_points == 0) return NRF_OK;
+	NRF_REQUIRE(table_f16 && enc_out, "null table / output");
 	NRF_REQUIRE(points != nullptr, "null points");
 	NRF_REQUIRE(layout == NRF_ENC_F32 || layout == NRF_ENC_F16, "bad layout");
 	const int F = grid->n_features;
@@ -376,9 +376,9 @@ int nrf_hash_encode_bwd(const nrf_hash_grid* grid, const float* points, int64_t 
 {
 	HashArgs a;
 	if (int rc = fill_args(grid, a)) return rc;
-	NRF_REQUIRE(grad_table != nullptr, "null grad_table");
 	NRF_REQUIRE(n_points >= 0, "negative n_points");
 	if (n_points == 0) return NRF_OK;
+	NRF_REQUIRE(grad_table != nullptr, "null grad_table");
 	NRF_REQUIRE(points && grad_enc, "null points / grad");
 	NRF_REQUIRE(layout == NRF_GRAD_F32 || layout == NRF_GRAD_BF16, "bad layout");
 	const int F = grid->n_features;

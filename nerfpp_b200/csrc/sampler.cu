@@ -39,20 +39,49 @@ __device__ __forceinline__ int lower_bound(const float* a, int n, float v)
 	return lo;
 }
 
+// inclusive prefix sum / max across the warp
+__device__ __forceinline__ double warp_scan_incl_f64(double v, int lane)
+{
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const double n = __shfl_up_sync(0xffffffffu, v, o);
+		if (lane >= o) v += n;
+	}
+	return v;
+}
+__device__ __forceinline__ float warp_scan_max(float v, int lane)
+{
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const float n = __shfl_up_sync(0xffffffffu, v, o);
+		if (lane >= o) v = fmaxf(v, n);
+	}
+	return v;
+}
+
 // cdf[0..B) from weights[0..B-1) — src/Sampler.h:10-13.  All lanes of the warp call this.
+// Summation order of sum()/cumsum() is implementation-defined in LibTorch (CPU cumsum accumulates in double,
+// at::acc_type<float,false>; the CUDA one is a blocked fp32 scan).  Here both run in fp64 and are rounded to fp32
+// once, i.e. each cdf knot is the correctly rounded prefix sum: equal to the CPU result and order independent.
+// A prefix max then makes the knots monotone by construction, which the binary search and the rank merge rely on.
 __device__ __forceinline__ void build_cdf(const float* __restrict__ w, int nw, float* cdf, int lane)
 {
-	float part = 0.f;
-	for (int k = lane; k < nw; k += 32) part += __fadd_rn(w[k], 1e-8f);
-	const float total = warp_sum(part);
-	float carry = 0.f;
+	double part = 0.0;
+	for (int k = lane; k < nw; k += 32) part += static_cast<double>(__fadd_rn(w[k], 1e-8f));
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+	const float total = static_cast<float>(part);
+	double carry = 0.0;
+	float carry_max = 0.f;
 	if (lane == 0) cdf[0] = 0.f;
 	for (int k0 = 0; k0 < nw; k0 += 32) {
 		const int k = k0 + lane;
 		const float pdf = k < nw ? __fdiv_rn(__fadd_rn(w[k], 1e-8f), total) : 0.f;
-		const float incl = warp_scan_incl(pdf, lane);
-		if (k < nw) cdf[k + 1] = carry + incl;
+		const double incl = warp_scan_incl_f64(static_cast<double>(pdf), lane);
+		const float knot = fmaxf(warp_scan_max(static_cast<float>(carry + incl), lane), carry_max);
+		if (k < nw) cdf[k + 1] = knot;
 		carry += __shfl_sync(0xffffffffu, incl, 31);
+		carry_max = __shfl_sync(0xffffffffu, knot, 31);
 	}
 	__syncwarp();
 }
@@ -88,6 +117,23 @@ __device__ __forceinline__ void bitonic_sort(float* a, int n_pow2, int lane)
 	}
 }
 
+// a[0..n) in shared memory, sorted except for rounding-level inversions -> sorted (odd-even transposition, whole warp)
+__device__ __forceinline__ void restore_order(float* a, int n, int lane)
+{
+	for (;;) {
+		bool swapped = false;
+#pragma unroll
+		for (int phase = 0; phase < 2; phase++) {
+			for (int j = 2 * lane + phase; j + 1 < n; j += 64) {
+				const float x = a[j], y = a[j + 1];
+				if (x > y) { a[j] = y; a[j + 1] = x; swapped = true; }
+			}
+			__syncwarp();
+		}
+		if (!__any_sync(0xffffffffu, swapped)) break;
+	}
+}
+
 // shared memory per warp: cdf[B] bins[B] zs[N] zc[S] (+ sort scratch when u is per-ray)
 __global__ void __launch_bounds__(kSamplerWarps * 32) sample_pdf_merge_kernel(const float* __restrict__ z_coarse,
 	const float* __restrict__ weights, const float* __restrict__ u, int u_per_ray, int64_t R, int S, int N,
@@ -116,6 +162,11 @@ __global__ void __launch_bounds__(kSamplerWarps * 32) sample_pdf_merge_kernel(co
 	__syncwarp();
 	float* out = z_merged + ray * (S + N);
 	if (!u_per_ray) {
+		// Both lists are sorted only up to rounding: the lerp b0 + t*(b1-b0) may pass b1 by an ulp while the next sample
+		// starts at b1, and for a ray that misses the box (far = near + 1e-6) near*(1-t)+far*t is not monotone in fp32.
+		// Odd-even passes until clean (normally zero swaps) make the rank merge equal to torch::sort on any input.
+		restore_order(zs, N, lane);
+		restore_order(zc, S, lane);
 		// rank merge; ties: coarse samples first
 		for (int k = lane; k < S; k += 32) out[k + lower_bound(zs, N, zc[k])] = zc[k];
 		for (int j = lane; j < N; j += 32) out[j + upper_bound(zc, S, zs[j])] = zs[j];

@@ -260,11 +260,23 @@ def raw_to_outputs(raw: torch.Tensor, z: torch.Tensor, rays_d: torch.Tensor, raw
     return {"rgb": rgb_map, "depth": depth, "disp": disp, "acc": acc, "weights": weights}
 
 
-def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, det: bool = True, u: torch.Tensor | None = None):
-    """src/Sampler.h:6-43.  Returns (samples, inds) — inds are the searchsorted indices (int64) for exactness checks."""
+def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, det: bool = True, u: torch.Tensor | None = None,
+               sums: str = "torch"):
+    """src/Sampler.h:6-43.  Returns (samples, inds) — inds are the searchsorted indices (int64) for exactness checks.
+
+    sums: the summation ORDER of torch::sum / torch::cumsum (:11-12) is implementation-defined in LibTorch (CPU: vectorised
+    cascade fp32 sum, cumsum accumulating in double; CUDA: blocked fp32 reduce / scan).  "torch" uses this process's
+    torch (what the compiled reference does on CPU); "exact" fixes the order-dependence by making every sum the correctly
+    rounded one (fp64 accumulate, one rounding to fp32, knots made monotone) — the variant the CUDA kernel implements.
+    The two differ only in the last ulp of a knot, i.e. in `inds` only where u ties a knot within that ulp."""
     weights = weights + 1e-8                                                                # :10
-    pdf = weights / torch.sum(weights, -1, True)                                            # :11
-    cdf = torch.cumsum(pdf, -1)                                                             # :12
+    if sums == "exact":
+        total = weights.double().sum(-1, True).to(weights.dtype)
+        pdf = weights / total
+        cdf = torch.cummax(torch.cumsum(pdf.double(), -1).to(weights.dtype), -1).values
+    else:
+        pdf = weights / torch.sum(weights, -1, True)                                        # :11
+        cdf = torch.cumsum(pdf, -1)                                                         # :12
     cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)                              # :13
     if u is None:
         assert det

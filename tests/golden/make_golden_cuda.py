@@ -19,7 +19,7 @@ import nerfpp_ref_cuda as R  # noqa: E402
 
 out_dir = Path(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/golden")
 out_dir.mkdir(parents=True, exist_ok=True)
-BBOX = torch.tensor([-1.5, -1.5, -1.5, 1.5, 1.5, 1.5])
+BBOX = torch.tensor([-1.5, -1.5, -1.5, 1.5, 1.5, 1.5]).cuda()   # BoundingBox is a plain member: ->to(device) does not move it
 
 
 def npz(name, **kw):

@@ -179,7 +179,8 @@ def test_against_reference_cuda_kernels(ref_cuda):
     from nerfpp_b200 import ops
     from nerfpp_b200.ops import HashGridSpec
     ref_cuda.manual_seed(42)
-    pipe = ref_cuda.make_cuhash(torch.tensor(BBOX), 16, 2, 19, 16, 512, 4, 2, 64, 15, 3, 64)
+    # BoundingBox is a plain member of the reference module, not a buffer: ->to(device) does not move it
+    pipe = ref_cuda.make_cuhash(torch.tensor(BBOX).cuda(), 16, 2, 19, 16, 512, 4, 2, 64, 15, 3, 64)
     bufs = dict(zip(pipe.embed_buffer_names(), pipe.embed_buffers()))
     table = pipe.embed_params()[0]
     with torch.no_grad():

@@ -48,8 +48,11 @@ def test_composite_random(S):
     ref = O.raw_to_outputs(x, z, d)
     (ref["rgb"] * g_rgb).sum().backward()
     out = ops.composite_fwd(raw.cuda(), z.cuda(), d.cuda())
-    for k in ("rgb", "depth", "disp", "acc", "weights"):
+    # S == 1: the reference's dists/weights degenerate to EMPTY [R,0] tensors (NeRFRenderer.h:239-240) and every map is 0
+    for k in ("rgb", "depth", "disp", "acc") + (("weights",) if S > 1 else ()):
         close(out[k], ref[k], rtol=1e-3, atol=1e-6)
+    if S == 1:
+        assert float(out["weights"].abs().max()) == 0.0
     d_raw = ops.composite_bwd(raw.cuda(), z.cuda(), d.cuda(), g_rgb=g_rgb.cuda())
     close(d_raw, x.grad, rtol=1e-3, atol=1e-5 * float(x.grad.abs().max()))
 
@@ -69,39 +72,60 @@ def test_composite_noise_and_stride():
 
 
 # ------------------------------------------------------------------------------------------------ sampler
+def assert_samples_match(got, bins, w, n, ref=None):
+    """got == the restatement with correctly rounded sums (tight), and that restatement == the torch-summed reference
+    except at ulp ties between u and a cdf knot (count reported and bounded; see oracle/restate.py sample_pdf)."""
+    exact, inds_e = O.sample_pdf(bins, w, n, True, sums="exact")
+    torch_ref, inds_t = O.sample_pdf(bins, w, n, True)
+    if ref is not None:                                                      # the committed fixture IS the torch-summed result
+        close(torch_ref, ref, rtol=1e-6, atol=1e-6)
+    close(got, exact, rtol=2e-6, atol=2e-6)
+    moved = inds_e != inds_t
+    wp = w + 1e-8
+    cdf = torch.cat([torch.zeros_like(wp[:, :1]), torch.cumsum(wp / wp.sum(-1, keepdim=True), -1)], -1)
+    u = torch.linspace(0.0, 1.0, n).expand(bins.shape[0], n)
+    lo, hi = torch.minimum(inds_e, inds_t), torch.maximum(inds_e, inds_t)
+    # every knot the index moved across lies within a few ulp of u: cdf[lo] and cdf[hi-1] bracket them (cdf is sorted)
+    k_lo = torch.gather(cdf, -1, lo.clamp(0, cdf.shape[-1] - 1))
+    k_hi = torch.gather(cdf, -1, (hi - 1).clamp(0, cdf.shape[-1] - 1))
+    assert bool((((u - k_lo).abs() <= 5e-7) & ((u - k_hi).abs() <= 5e-7))[moved].all())
+    same = ~moved
+    # t = (u - c0) / denom amplifies the last-ulp difference of a knot by 1/denom (down to the 1e-5 guard): up to ~1e-2 of a bin
+    close(got[same], torch_ref[same], rtol=1e-4, atol=2e-4)
+    assert float((got[same] - torch_ref[same]).abs().median()) <= 1e-6
+    print(f"searchsorted index moved at an ulp tie for {int(moved.sum())} of {moved.numel()} samples")
+    assert int(moved.sum()) <= max(bins.shape[0], int(moved.numel() * 2e-3))   # at most ~the u == 1.0 sample of each ray
+    assert bool((got[:, 1:] >= got[:, :-1]).all())                           # monotone: the rank merge relies on it
+
+
 def test_sample_pdf_against_reference_fixture(golden):
     from nerfpp_b200 import ops
     g = golden("sample_pdf.npz")
     u = torch.linspace(0.0, 1.0, 128).cuda()
-    s = ops.sample_pdf(T(g["bins"]).cuda(), T(g["weights"]).cuda(), u)
-    close(s, g["samples"], rtol=1e-5, atol=1e-5)
+    bins, w = T(g["bins"]), T(g["weights"])
+    s = ops.sample_pdf(bins.cuda(), w.cuda(), u)
+    assert_samples_match(s.cpu(), bins, w, 128, T(g["samples"]))
     # the fused call site: weights[:,1:-1] and z_mid are taken inside the kernel
-    w_full = torch.cat([torch.zeros(8, 1), T(g["weights"]), torch.zeros(8, 1)], -1).cuda()
+    w_full = torch.cat([torch.zeros(8, 1), w, torch.zeros(8, 1)], -1).cuda()
     merged, zs = ops.sample_pdf_merge(T(g["z"]).cuda(), w_full, u, want_samples=True)
     assert merged.shape == (8, 192)                                           # sample count exact
-    close(zs, g["samples"], rtol=1e-5, atol=1e-5)
-    close(merged, g["merged"], rtol=1e-5, atol=1e-5)
-    assert bool((merged[:, 1:] >= merged[:, :-1]).all())
+    assert torch.equal(zs, s)
+    # merge == torch::sort(cat(z, z_samples)) (NeRFRenderer.h:431), bit for bit on the same samples
+    assert torch.equal(merged.cpu(), torch.sort(torch.cat([T(g["z"]), zs.cpu()], -1), -1).values)
+    tie_free = (zs.cpu() - T(g["samples"])).abs().max(-1).values < 1e-4
+    close(merged.cpu()[tie_free], T(g["merged"])[tie_free], rtol=1e-5, atol=1e-5)
+    assert int(tie_free.sum()) >= 4
 
 
 def test_sample_pdf_indices_and_ties():
-    """Index exactness: samples fall in the same cdf interval as the oracle's searchsorted, except where u is within
-    an ulp of a cdf knot (the cdf is a warp scan here, a sequential/ blocked cumsum in LibTorch); the count is reported."""
+    """Index exactness on spiky pdfs (most bins below the denom < 1e-5 guard, where a moved index is visible)."""
     from nerfpp_b200 import ops
     torch.manual_seed(11)
     R, B, N = 512, 63, 128
     bins = torch.sort(torch.rand(R, B) * 4 + 2, -1).values
     w = torch.rand(R, B - 1) ** 6
-    ref, inds = O.sample_pdf(bins, w, N, True)
     got = ops.sample_pdf(bins.cuda(), w.cuda(), torch.linspace(0.0, 1.0, N).cuda()).cpu()
-    below = torch.clamp_min(inds - 1, 0)
-    above = torch.clamp_max(inds, B - 1)
-    lo, hi = torch.gather(bins, -1, below), torch.gather(bins, -1, above)
-    inside = (got >= lo - 1e-6) & (got <= hi + 1e-6)
-    n_off = int((~inside).sum())
-    print(f"samples outside the oracle's interval (ulp ties): {n_off} of {R * N}")
-    assert n_off <= R * N * 1e-3
-    assert float((got - ref).abs().max()) < 1e-4
+    assert_samples_match(got, bins, w, N)
     # per-ray random u: bitonic path
     u = torch.rand(R, N)
     ref_r, _ = O.sample_pdf(bins, w, N, False, u)
@@ -112,6 +136,23 @@ def test_sample_pdf_indices_and_ties():
     ref_s, _ = O.sample_pdf(zmid, wfull[:, 1:-1], N, False, u)
     close(zs, ref_s, rtol=1e-4, atol=1e-4)
     close(merged, torch.sort(torch.cat([z, zs.cpu()], -1), -1).values, rtol=0, atol=0)
+
+
+def test_merge_equals_sort_on_degenerate_rays():
+    """A ray that misses the box gets far = near + 1e-6 (RayUtils.h:123): near*(1-t)+far*t is then NOT monotone in fp32 and
+    every weight is 0.  The reference sorts (NeRFRenderer.h:431); the rank merge must give the same floats in the same order."""
+    from nerfpp_b200 import ops
+    near = torch.tensor([3.396746873855591, 2.0, 7.123456, 0.5])
+    rb = torch.zeros(4, 11)
+    rb[:, 6], rb[:, 7] = near, near + 1e-6
+    rb[3, 7] = 2.5                                                           # one ordinary ray alongside
+    t = torch.linspace(0.0, 1.0, 64)
+    z = ops.z_sample(rb.cuda(), t.cuda())
+    assert not bool((z[0, 1:] >= z[0, :-1]).all())                           # the case under test exists
+    w = torch.zeros(4, 64)
+    w[3] = torch.rand(64)
+    merged, zs = ops.sample_pdf_merge(z, w.cuda(), torch.linspace(0.0, 1.0, 128).cuda(), want_samples=True)
+    assert torch.equal(merged, torch.sort(torch.cat([z, zs], -1), -1).values)
 
 
 # ------------------------------------------------------------------------------------------------ rays
