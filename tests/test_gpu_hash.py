@@ -208,3 +208,32 @@ def test_against_reference_cuda_kernels(ref_cuda):
     ref_err = np.abs(ref_grad - exact).max()
     assert ours_err <= ref_err, (ours_err, ref_err)
     assert np.abs(gt.double().cpu().numpy() - ref_grad).max() <= 1e-2 * np.abs(exact).max() + 2 * ref_err
+
+
+def test_against_reference_cuda_fixture(golden):
+    """The committed outputs of the reference's CuHashEmbedder forward/backward kernels (tests/golden/cuhash.npz)."""
+    from nerfpp_b200 import ops
+    from nerfpp_b200.ops import HashGridSpec
+    g = golden("cuhash.npz")
+    T = lambda k: torch.from_numpy(g[k]).cuda().contiguous()   # noqa: E731
+    grid = HashGridSpec(BBOX, T("primes"), T("biases"), T("feat_local_idx"), T("feat_local_size"), log2_hashmap_size=10)
+    t16 = T("table_f16").reshape(-1)
+    pts = T("points")
+    enc, keep = ops.hash_encode_fwd(grid, t16, pts)
+    assert np.array_equal(keep.cpu().numpy().astype(bool), g["keep"])
+    assert (enc.cpu().numpy() == g["enc"]).mean() > 0.97                     # same cells; fp16 rounding of re-ordered fp32 sums
+    np.testing.assert_allclose(enc.cpu().numpy(), g["enc"], rtol=2 ** -10, atol=2 ** -24)
+    enc16, _ = ops.hash_encode_fwd(grid, t16, pts, out_f16=True)
+    assert torch.equal(enc16.float(), enc)
+    gt = torch.zeros(g["grad_table"].size, device="cuda")
+    ops.hash_encode_bwd(grid, pts, T("grad_enc"), gt)
+    meta = _np(grid)
+    cl, _ = O.clamp_keep(g["points"], BBOX[:3], BBOX[3:])
+    exact = O.hash_encode_bwd_f64(cl, grad_enc=g["grad_enc"], n_features=2, table_scalars=gt.numel(), **meta)
+    ours_err = np.abs(gt.double().cpu().numpy() - exact).max()
+    ref_err = np.abs(g["grad_table"].reshape(-1).astype(np.float64) - exact).max()
+    print(f"max |dTable - fp64 adjoint|: ours {ours_err:.3e}, reference (x128 fp16 atomics) {ref_err:.3e}")
+    assert ours_err <= ref_err
+    assert ours_err <= 1e-5 * np.abs(exact).max()
+    # the device-evaluated level scales are the fixture's
+    assert np.array_equal(grid.level_scale.cpu().numpy(), golden("level_scales.npz")["s_16_512_16"])

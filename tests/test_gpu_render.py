@@ -195,6 +195,10 @@ def test_encoders(golden):
         close(ops.sh_encode(d, deg), g[f"sh{deg}"], rtol=1e-4, atol=2e-6)
     for deg in range(1, 9):                            # degrees 6..8 exist only in the CUDA encoder: closed form
         close(ops.sh_encode(d, deg), O.sh_encode_closed_form(g["dirs"], deg), rtol=1e-4, atol=5e-6)
+    # the reference's CUDA kernel outputs (tests/golden/cush.npz), unit and non-unit directions, degrees 1..8
+    c = golden("cush.npz")
+    for deg in range(1, 9):
+        close(ops.sh_encode(T(c["dirs"]).cuda(), deg), c[f"sh{deg}"], rtol=2e-6, atol=1e-6)
     # strided read straight out of a ray batch
     rb = torch.zeros(32, 11, device="cuda")
     rb[:, 8:11] = d
