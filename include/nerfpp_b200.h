@@ -198,6 +198,14 @@ int nrf_z_sample(const float* ray_batch, int32_t ray_stride, const float* t_vals
 int nrf_sample_points(const float* ray_batch, int32_t ray_stride, const float* z, int64_t n_rays, int32_t n_samples,
                       float* pts, nrf_stream stream);
 
+/* TangentScatter (src/NeRFRenderer.h:307-362): pts [R,S,3] += (tangent*r*cos(theta) + bitangent*r*sin(theta)) * cone_angle*z,
+ * then clamp into bbox_host[6] (nullable = no clamp).  rand_r / rand_theta [R,S] are the two torch::rand draws of :342-343
+ * (drawn by the host so the RNG stream matches the reference's).  cone_angle: one scalar (cone_stride 0) or one per ray
+ * at cone_angle[ray*cone_stride].  Directions are read at rays_d + ray*dir_stride. */
+int nrf_tangent_scatter(float* pts, const float* z, const float* cone_angle, int32_t cone_stride, const float* rays_d,
+                        int32_t dir_stride, const float* rand_r, const float* rand_theta, const float* bbox_host,
+                        int64_t n_rays, int32_t n_samples, nrf_stream stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Training glue restated from NeRFExecutor::Train (src/NeRFExecutor.h:883-890, 539, 986)
  * ---------------------------------------------------------------------------------------------------------- */

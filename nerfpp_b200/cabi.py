@@ -68,6 +68,7 @@ SIGNATURES = {
     "nrf_rays_prepare": (c_int32, [_P, _P, c_int64, POINTER(c_float), c_float, c_int32, _P, _P]),
     "nrf_z_sample": (c_int32, [_P, c_int32, _P, c_int64, c_int32, c_int32, _P, _P]),
     "nrf_sample_points": (c_int32, [_P, c_int32, _P, c_int64, c_int32, _P, _P]),
+    "nrf_tangent_scatter": (c_int32, [_P, _P, _P, c_int32, _P, c_int32, _P, _P, POINTER(c_float), c_int64, c_int32, _P]),
     "nrf_huber_fwd_bwd": (c_int32, [_P, _P, c_int64, c_float, c_float, _P, _P, _P]),
     "nrf_adam_step": (c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int32, c_float, c_int32, _P, _P]),
 }

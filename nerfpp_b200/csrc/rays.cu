@@ -100,6 +100,57 @@ __global__ void __launch_bounds__(256) sample_points_kernel(const float* __restr
 	pts[e] = __fadd_rn(rb[k], __fmul_rn(rb[3 + k], z[smp]));  // src/NeRFRenderer.h:419
 }
 
+// TangentScatter (src/NeRFRenderer.h:307-362): in-cone jitter of the sample points.  The two uniform variates per sample are
+// INPUTS (the host draws them with the same two torch::rand calls as the reference, :342-343, so the Philox stream stays
+// in lock-step with it); this kernel fuses the ~40 ATen launches that build the tangent frame and apply the offset.
+__device__ __forceinline__ void safe_normalize3(float& x, float& y, float& z)
+{
+	const float n = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))), 1e-8f);
+	x = __fdiv_rn(x, n); y = __fdiv_rn(y, n); z = __fdiv_rn(z, n);
+}
+
+__global__ void __launch_bounds__(256) tangent_scatter_kernel(float* __restrict__ pts, const float* __restrict__ z,
+	const float* __restrict__ cone_angle, int cone_stride, const float* __restrict__ rays_d, int d_stride,
+	const float* __restrict__ rand_r, const float* __restrict__ rand_theta, Box box, int clamp_box, int64_t R, int S)
+{
+	const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (e >= R * S) return;
+	const int64_t ray = e / S;
+	float dx = rays_d[ray * d_stride], dy = rays_d[ray * d_stride + 1], dz = rays_d[ray * d_stride + 2];
+	safe_normalize3(dx, dy, dz);
+	// helper axis: the coordinate axis along which |d| is strictly smallest, z otherwise (:321-331)
+	const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+	float ux = 0.f, uy = 0.f, uz = 0.f;
+	if (ax < ay && ax < az) ux = 1.f;
+	else if (ay < ax && ay < az) uy = 1.f;
+	else uz = 1.f;
+	// tangent = normalize(d x up), bitangent = normalize(d x tangent) (:333-336)
+	float tx = __fsub_rn(__fmul_rn(dy, uz), __fmul_rn(dz, uy));
+	float ty = __fsub_rn(__fmul_rn(dz, ux), __fmul_rn(dx, uz));
+	float tz = __fsub_rn(__fmul_rn(dx, uy), __fmul_rn(dy, ux));
+	safe_normalize3(tx, ty, tz);
+	float bx = __fsub_rn(__fmul_rn(dy, tz), __fmul_rn(dz, ty));
+	float by = __fsub_rn(__fmul_rn(dz, tx), __fmul_rn(dx, tz));
+	float bz = __fsub_rn(__fmul_rn(dx, ty), __fmul_rn(dy, tx));
+	safe_normalize3(bx, by, bz);
+	// uniform over the disc: r = sqrt(clamp(u1)), theta = fmod(u2 * 2 pi, 2 pi) (:342-345)
+	const float r = sqrtf(fminf(fmaxf(rand_r[e], 1e-8f), 1.0f - 1e-8f));
+	const float two_pi = 6.283185307179586f;
+	const float theta = fmodf(__fmul_rn(__fmul_rn(rand_theta[e], 2.0f), 3.14159265358979323846f), two_pi);
+	const float ox = __fmul_rn(r, cosf(theta)), oy = __fmul_rn(r, sinf(theta));
+	const float radius = __fmul_rn(cone_angle[cone_stride ? ray * cone_stride : 0], z[e]);   // cone_radii = cone_angle * z (:313)
+	float* p = pts + e * 3;
+	float px = __fadd_rn(p[0], __fmul_rn(__fadd_rn(__fmul_rn(tx, ox), __fmul_rn(bx, oy)), radius));
+	float py = __fadd_rn(p[1], __fmul_rn(__fadd_rn(__fmul_rn(ty, ox), __fmul_rn(by, oy)), radius));
+	float pz = __fadd_rn(p[2], __fmul_rn(__fadd_rn(__fmul_rn(tz, ox), __fmul_rn(bz, oy)), radius));
+	if (clamp_box) {
+		px = fminf(fmaxf(px, box.lo[0]), box.hi[0]);
+		py = fminf(fmaxf(py, box.lo[1]), box.hi[1]);
+		pz = fminf(fmaxf(pz, box.lo[2]), box.hi[2]);
+	}
+	p[0] = px; p[1] = py; p[2] = pz;
+}
+
 }  // namespace nrf
 
 using namespace nrf;
@@ -157,6 +208,22 @@ int nrf_sample_points(const float* ray_batch, int32_t ray_stride, const float* z
 	const int64_t n = n_rays * n_samples * 3;
 	sample_points_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(ray_batch, ray_stride, z, n_rays, n_samples, pts);
 	NRF_CHECK_LAUNCH("sample_points_kernel");
+	return NRF_OK;
+}
+
+int nrf_tangent_scatter(float* pts, const float* z, const float* cone_angle, int32_t cone_stride, const float* rays_d,
+	int32_t dir_stride, const float* rand_r, const float* rand_theta, const float* bbox_host, int64_t n_rays, int32_t n_samples,
+	nrf_stream stream)
+{
+	NRF_REQUIRE(n_rays >= 0 && n_samples >= 1 && dir_stride >= 3 && cone_stride >= 0, "bad sizes");
+	if (n_rays == 0) return NRF_OK;
+	NRF_REQUIRE(pts && z && cone_angle && rays_d && rand_r && rand_theta, "null pointer");
+	Box b{};
+	if (bbox_host) for (int k = 0; k < 3; k++) { b.lo[k] = bbox_host[k]; b.hi[k] = bbox_host[3 + k]; }
+	const int64_t n = n_rays * n_samples;
+	tangent_scatter_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(pts, z, cone_angle, cone_stride, rays_d,
+		dir_stride, rand_r, rand_theta, b, bbox_host != nullptr, n_rays, n_samples);
+	NRF_CHECK_LAUNCH("tangent_scatter_kernel");
 	return NRF_OK;
 }
 

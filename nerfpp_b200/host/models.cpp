@@ -1,0 +1,245 @@
+// Host side of the drop-in models (see models.h).
+#include "models.h"
+#include "embedders.h"
+
+using torch::Tensor;
+using torch::autograd::AutogradContext;
+using torch::autograd::variable_list;
+namespace nn = torch::nn;
+
+// ------------------------------------------------------------------------------------------------ NeRF (classic)
+NeRFImpl::NeRFImpl(const int d, const int w, const int input_ch, const int input_ch_views, const int output_ch,
+	const std::set<int>& skips, const bool use_viewdirs, const std::string module_name)
+	: BaseNeRFImpl(module_name), D(d), W(w), InputCh(input_ch), InputChViews(input_ch_views), OutputCh(output_ch), Skips(skips),
+	  UseViewDirs(use_viewdirs)
+{
+	// layer i+1 takes [x | h] when layer i is a skip layer (src/NeRF.cpp:52-57)
+	for (int i = 0; i < d; i++) {
+		const int in = i == 0 ? input_ch : (skips.count(i - 1) ? w + input_ch : w);
+		PtsLinears->push_back(nn::Linear(in, w));
+	}
+	if (use_viewdirs) {
+		ViewsLinears->push_back(nn::Linear(input_ch_views + w, w / 2));
+		FeatureLinear = nn::Linear(w, w);
+		AlphaLinear = nn::Linear(w, 1);
+		RGBLinear = nn::Linear(w / 2, 3);
+	} else {
+		OutputLinear = nn::Linear(w + input_ch, output_ch);
+	}
+	for (size_t i = 0; i < PtsLinears->size(); i++) register_module(module_name + "_pts_linears_" + std::to_string(i), PtsLinears[i]);
+	if (use_viewdirs) {
+		for (size_t i = 0; i < ViewsLinears->size(); i++) register_module(module_name + "_views_linears_" + std::to_string(i), ViewsLinears[i]);
+		register_module(module_name + "_feature_linear", FeatureLinear);
+		register_module(module_name + "_alpha_linear", AlphaLinear);
+		register_module(module_name + "_rgb_linear", RGBLinear);
+	} else {
+		register_module(module_name + "_output_linear", OutputLinear);
+	}
+}
+
+Tensor NeRFImpl::forward(Tensor x)
+{
+	Tensor pts = x.narrow(-1, 0, InputCh), views = x.narrow(-1, InputCh, InputChViews);
+	Tensor h = pts;
+	for (size_t i = 0; i < PtsLinears->size(); i++) {
+		h = torch::relu(PtsLinears[i]->as<nn::Linear>()->forward(h));
+		if (Skips.count(int(i))) h = torch::cat({pts, h}, -1);             // src/NeRF.cpp:103-104
+	}
+	if (!UseViewDirs) return OutputLinear(torch::cat({h, pts}, -1));        // :122-123
+	Tensor alpha = AlphaLinear(h);                                          // :110
+	h = torch::cat({FeatureLinear(h), views}, -1);                          // :111-112
+	for (size_t i = 0; i < ViewsLinears->size(); i++) h = torch::relu(ViewsLinears[i]->as<nn::Linear>()->forward(h));
+	return torch::cat({RGBLinear(h), alpha}, -1);                           // :119-120
+}
+
+// ------------------------------------------------------------------------------------------------ NeRFSmall
+NeRFSmallImpl::NeRFSmallImpl(const int num_layers, const int hidden_dim, const int geo_feat_dim, const int num_layers_color,
+	const int hidden_dim_color, const bool use_pred_normal, const int num_layers_normals, const int hidden_dim_normals,
+	const int input_ch, const int input_ch_views, const std::string module_name)
+	: BaseNeRFImpl(module_name), InputCh(input_ch), InputChViews(input_ch_views), NumLayers(num_layers), HiddenDim(hidden_dim),
+	  GeoFeatDim(geo_feat_dim), NumLayersColor(num_layers_color), HiddenDimColor(hidden_dim_color),
+	  NumLayersNormals(num_layers_normals), HiddenDimNormals(hidden_dim_normals), UsePredNormal(use_pred_normal)
+{
+	auto chain = [](nn::ModuleList& list, int n, int first_in, int hidden, int last_out) {
+		for (int l = 0; l < n; l++)
+			list->push_back(nn::Linear(nn::LinearOptions(l == 0 ? first_in : hidden, l == n - 1 ? last_out : hidden).bias(false)));
+	};
+	chain(SigmaNet, NumLayers, InputCh, HiddenDim, 1 + GeoFeatDim);                       // src/NeRF.cpp:338-339
+	chain(ColorNet, NumLayersColor, InputChViews + GeoFeatDim, HiddenDimColor, 3);        // :341-342
+	if (UsePredNormal) chain(NormalsNet, NumLayersNormals, 1 + GeoFeatDim + InputCh, HiddenDimNormals, 3);   // :344-348
+	for (size_t i = 0; i < SigmaNet->size(); i++) register_module(module_name + "_sigma_net_" + std::to_string(i), SigmaNet[i]);
+	for (size_t i = 0; i < ColorNet->size(); i++) register_module(module_name + "_color_net_" + std::to_string(i), ColorNet[i]);
+	for (size_t i = 0; i < NormalsNet->size(); i++) register_module(module_name + "_normals_net_" + std::to_string(i), NormalsNet[i]);
+}
+
+nrf_mlp_small_shape NeRFSmallImpl::Shape() const
+{
+	nrf_mlp_small_shape s{};
+	s.input_ch = InputCh; s.input_ch_views = InputChViews; s.hidden_dim = HiddenDim; s.geo_feat_dim = GeoFeatDim;
+	s.hidden_dim_color = HiddenDimColor; s.num_layers = NumLayers; s.num_layers_color = NumLayersColor;
+	return s;
+}
+
+bool NeRFSmallImpl::Fused() const
+{
+	if (UsePredNormal) return false;
+	const nrf_mlp_small_shape s = Shape();
+	return nrf_mlp_small_param_count(&s) > 0;   // the library answers -1 for shapes it was not built for
+}
+
+std::vector<Tensor> NeRFSmallImpl::Weights()
+{
+	std::vector<Tensor> w;
+	for (size_t i = 0; i < SigmaNet->size(); i++) w.push_back(SigmaNet[i]->as<nn::Linear>()->weight);
+	for (size_t i = 0; i < ColorNet->size(); i++) w.push_back(ColorNet[i]->as<nn::Linear>()->weight);
+	return w;
+}
+
+Tensor NeRFSmallImpl::Packed()
+{
+	std::vector<Tensor> w = Weights();
+	std::vector<std::pair<const void*, uint32_t>> key;
+	for (const Tensor& t : w) key.emplace_back(t.data_ptr(), t._version());
+	if (!PackedBlob.defined() || key != PackedKey) {
+		torch::NoGradGuard no_grad;
+		std::vector<Tensor> flat;
+		for (const Tensor& t : w) flat.push_back(nrfhost::Dense(t, torch::kFloat32, "NeRFSmall weight").reshape({-1}));
+		FlatParams = torch::cat(flat).contiguous();
+		const nrf_mlp_small_shape s = Shape();
+		// a NEW blob per re-pack: a blob saved for a pending backward stays valid while the optimizer moves on
+		PackedBlob = torch::empty({nrf_mlp_small_packed_bytes(&s)}, torch::TensorOptions().dtype(torch::kUInt8).device(FlatParams.device()));
+		nrfhost::Check(nrf_mlp_small_pack(&s, FlatParams.data_ptr<float>(), PackedBlob.data_ptr(), nrfhost::Stream()), "nrf_mlp_small_pack");
+		PackedKey = key;
+	}
+	return PackedBlob;
+}
+
+namespace {
+
+variable_list SplitFlatGrad(const Tensor& flat, const std::vector<Tensor>& weights)
+{
+	variable_list out;
+	int64_t off = 0;
+	for (const Tensor& w : weights) {
+		out.push_back(flat.narrow(0, off, w.numel()).view(w.sizes()));
+		off += w.numel();
+	}
+	return out;
+}
+
+// NeRFSmall::forward on a dense [N, in+views] fp32 input
+struct MlpSmallFn : public torch::autograd::Function<MlpSmallFn> {
+	static Tensor forward(AutogradContext* ctx, Tensor x, Tensor w0, Tensor w1, Tensor w2, Tensor w3, Tensor w4, int64_t module)
+	{
+		auto* model = reinterpret_cast<NeRFSmallImpl*>(module);
+		Tensor in = nrfhost::Dense(x, torch::kFloat32, "NeRFSmall input");
+		Tensor packed = model->Packed();
+		const nrf_mlp_small_shape s = model->Shape();
+		Tensor out = torch::empty({in.size(0), 4}, nrfhost::F32Like(in));
+		nrfhost::Check(nrf_mlp_small_fwd(&s, packed.data_ptr(), NRF_MLP_IN_F32_CAT, in.data_ptr(), nullptr, 1, nullptr, in.size(0),
+			nrfhost::Ptr<float>(out), nrfhost::Stream()), "nrf_mlp_small_fwd");
+		ctx->save_for_backward({in, packed});
+		ctx->saved_data["module"] = module;
+		ctx->saved_data["need_dx"] = x.requires_grad();
+		return out;
+	}
+
+	static variable_list backward(AutogradContext* ctx, variable_list grad_out)
+	{
+		auto* model = reinterpret_cast<NeRFSmallImpl*>(ctx->saved_data["module"].toInt());
+		auto saved = ctx->get_saved_variables();
+		Tensor in = saved[0], packed = saved[1];
+		const nrf_mlp_small_shape s = model->Shape();
+		Tensor g = nrfhost::Dense(grad_out[0], torch::kFloat32, "grad of NeRFSmall output");
+		Tensor flat = torch::zeros({nrf_mlp_small_param_count(&s)}, nrfhost::F32Like(in));
+		Tensor gx = ctx->saved_data["need_dx"].toBool() ? torch::empty_like(in) : Tensor();
+		nrfhost::Check(nrf_mlp_small_bwd(&s, packed.data_ptr(), NRF_MLP_IN_F32_CAT, in.data_ptr(), nullptr, 1, nullptr, in.size(0),
+			nrfhost::CPtr<float>(g), gx.defined() ? gx.data_ptr() : nullptr, flat.data_ptr<float>(), nrfhost::Stream()), "nrf_mlp_small_bwd");
+		variable_list grads = {gx};
+		for (Tensor& t : SplitFlatGrad(flat, model->Weights())) grads.push_back(t);
+		grads.push_back(Tensor());
+		return grads;
+	}
+};
+
+// hash encode (fp16 rows) -> fused MLP with per-ray SH and keep mask: what RunNetwork computes (src/NeRFRenderer.h:164-194)
+struct HashNeRFNetworkFn : public torch::autograd::Function<HashNeRFNetworkFn> {
+	static Tensor forward(AutogradContext* ctx, Tensor embeddings, Tensor w0, Tensor w1, Tensor w2, Tensor w3, Tensor w4,
+		Tensor points, Tensor ray_sh, int64_t samples_per_ray, int64_t hash_module, int64_t mlp_module)
+	{
+		auto* hash = reinterpret_cast<CuHashEmbedderImpl*>(hash_module);
+		auto* model = reinterpret_cast<NeRFSmallImpl*>(mlp_module);
+		Tensor pts = nrfhost::Dense(points, torch::kFloat32, "points");
+		Tensor sh = nrfhost::Dense(ray_sh, torch::kFloat32, "per-ray SH");
+		auto [enc, keep] = hash->EncodeF16(pts);
+		Tensor packed = model->Packed();
+		const nrf_mlp_small_shape s = model->Shape();
+		Tensor raw = torch::empty({pts.size(0), 4}, nrfhost::F32Like(pts));
+		nrfhost::Check(nrf_mlp_small_fwd(&s, packed.data_ptr(), NRF_MLP_IN_ENC16_RAYDIRS, enc.data_ptr(), nrfhost::CPtr<float>(sh),
+			int32_t(samples_per_ray), reinterpret_cast<const uint8_t*>(keep.data_ptr()), pts.size(0), nrfhost::Ptr<float>(raw),
+			nrfhost::Stream()), "nrf_mlp_small_fwd");
+		ctx->save_for_backward({pts, enc, keep, sh, packed});
+		ctx->saved_data["spr"] = samples_per_ray;
+		ctx->saved_data["hash"] = hash_module;
+		ctx->saved_data["mlp"] = mlp_module;
+		return raw;
+	}
+
+	static variable_list backward(AutogradContext* ctx, variable_list grad_out)
+	{
+		auto* hash = reinterpret_cast<CuHashEmbedderImpl*>(ctx->saved_data["hash"].toInt());
+		auto* model = reinterpret_cast<NeRFSmallImpl*>(ctx->saved_data["mlp"].toInt());
+		auto saved = ctx->get_saved_variables();
+		Tensor pts = saved[0], enc = saved[1], keep = saved[2], sh = saved[3], packed = saved[4];
+		const nrf_mlp_small_shape s = model->Shape();
+		Tensor g = nrfhost::Dense(grad_out[0], torch::kFloat32, "grad of raw").reshape({-1, 4});
+		Tensor flat = torch::zeros({nrf_mlp_small_param_count(&s)}, nrfhost::F32Like(pts));
+		Tensor g_enc = torch::empty({pts.size(0), enc.size(1)}, torch::TensorOptions().dtype(torch::kBFloat16).device(pts.device()));
+		nrfhost::Check(nrf_mlp_small_bwd(&s, packed.data_ptr(), NRF_MLP_IN_ENC16_RAYDIRS, enc.data_ptr(), nrfhost::CPtr<float>(sh),
+			int32_t(ctx->saved_data["spr"].toInt()), reinterpret_cast<const uint8_t*>(keep.data_ptr()), pts.size(0),
+			nrfhost::CPtr<float>(g), g_enc.data_ptr(), flat.data_ptr<float>(), nrfhost::Stream()), "nrf_mlp_small_bwd");
+		Tensor grad_table = torch::zeros_like(hash->Embeddings);
+		hash->Backward(pts, g_enc, grad_table);
+		variable_list grads = {grad_table};
+		for (Tensor& t : SplitFlatGrad(flat, model->Weights())) grads.push_back(t);
+		for (int i = 0; i < 5; i++) grads.push_back(Tensor());
+		return grads;
+	}
+};
+
+}  // namespace
+
+Tensor nrfhost::MlpSmallF32(NeRFSmallImpl& model, const Tensor& x)
+{
+	std::vector<Tensor> w = model.Weights();
+	return MlpSmallFn::apply(x, w[0], w[1], w[2], w[3], w[4], reinterpret_cast<int64_t>(&model));
+}
+
+Tensor nrfhost::HashNeRFNetwork(CuHashEmbedderImpl& hash, NeRFSmallImpl& model, const Tensor& points, const Tensor& ray_sh,
+	int samples_per_ray)
+{
+	std::vector<Tensor> w = model.Weights();
+	return HashNeRFNetworkFn::apply(hash.Embeddings, w[0], w[1], w[2], w[3], w[4], points, ray_sh, int64_t(samples_per_ray),
+		reinterpret_cast<int64_t>(&hash), reinterpret_cast<int64_t>(&model));
+}
+
+Tensor NeRFSmallImpl::forward(Tensor x)
+{
+	TORCH_CHECK(x.dim() == 2 && x.size(1) == InputCh + InputChViews, "NeRFSmall: input must be [N,", InputCh + InputChViews, "]");
+	if (Fused()) return nrfhost::MlpSmallF32(*this, x);
+	// other shapes (normals head, different widths): same maths through torch::linear (src/NeRF.cpp:363-412)
+	Tensor pts = x.narrow(-1, 0, InputCh), views = x.narrow(-1, InputCh, InputChViews);
+	auto run = [](nn::ModuleList& net, Tensor h) {
+		for (size_t i = 0; i < net->size(); i++) {
+			h = net[i]->as<nn::Linear>()->forward(h);
+			if (i + 1 != net->size()) h = torch::relu(h);                  // final activations live in RawToOutputs
+		}
+		return h;
+	};
+	Tensor h = run(SigmaNet, pts);
+	Tensor sigma = h.narrow(-1, 0, 1), geo = h.narrow(-1, 1, h.size(-1) - 1);
+	Tensor color = run(ColorNet, torch::cat({views, geo}, -1));             // views first (:383)
+	if (!UsePredNormal) return torch::cat({color, sigma}, -1);              // :408
+	Tensor normals = run(NormalsNet, torch::cat({sigma, geo, pts}, -1));    // :394
+	return torch::cat({color, sigma, normals}, -1);
+}

@@ -61,3 +61,24 @@ def test_product_never_imports_the_oracle():
         if p.suffix in (".py", ".cu", ".cuh", ".cpp", ".h") and p.is_file():
             text = p.read_text()
             assert not re.search(r"(import|from)\s+(oracle|restate)\b|oracle/_ref|nerfpp_ref|#include\s+\"[^\"]*oracle", text), p
+
+
+def test_cpp_host_layer_loads_and_refuses_cpu_tensors():
+    """nerfpp_b200_torch.so (the torch::Tensor drop-in layer) builds, imports and exposes the reference's class surface; like
+    the C ABI it has no CPU path."""
+    import sys
+    import torch
+    from nerfpp_b200 import build
+    sys.path.insert(0, str(build.build_host().parent))
+    import nerfpp_b200_torch as H
+    for name in ("make_cuhash", "make_classic", "sample_pdf", "get_rays", "intersect_aabb", "trunc_exp", "cu_sh_encoder", "embedder"):
+        assert hasattr(H, name)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        H.embedder(torch.rand(4, 3), 10)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        H.sample_pdf(torch.rand(2, 5), torch.rand(2, 4), 8, True)
+    x = torch.randn(5, requires_grad=True)                       # TruncExp is plain ATen (src/CustomOps.cpp:5-16)
+    y = H.trunc_exp(x * 4)
+    y.sum().backward()
+    assert torch.allclose(y, torch.exp(x.detach() * 4))
+    assert torch.allclose(x.grad, 4 * torch.exp(torch.clamp(x.detach() * 4, -100, 5)))
