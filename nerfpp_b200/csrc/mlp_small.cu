@@ -22,49 +22,28 @@
 //
 // The A2 operand is laid out [sh(16) | d1(16)] instead of [sh(16) | geo(15) | pad]: column 16 is the sigma slot,
 // whose weight column is zero (and whose value is zeroed), which avoids a cross-lane shift of the accumulators.
-#include "common.cuh"
+#include "mlp_small_layout.cuh"
 
 namespace nrf {
 
-// ---------------------------------------------------------------------------------------------- packed layout
-constexpr int kW0 = 0, kW1 = 2048, kW2 = 3072, kW3 = 5056, kW4 = 9152, kParamCount = 9344;  // flat fp32 offsets
-// fragment blob, offsets in 32-bit words.  fwd: [ks][nt][lane][2]
-constexpr int kF0 = 0, kF1 = 1024, kF2 = 1536, kF3 = 2560, kF4 = 4608, kFwdWords = 4864;
-constexpr int kB4 = 4864, kB3 = 5376, kB2 = 7424, kB1 = 8448, kB0 = 8960, kBlobWords = 9984;
-
-// padded logical weight matrices Wp_l(n, k)
-__device__ __forceinline__ float wp(const float* __restrict__ p, int layer, int n, int k)
-{
-	switch (layer) {
-		case 0: return p[kW0 + n * 32 + k];
-		case 1: return p[kW1 + n * 64 + k];
-		case 2: return k < 16 ? p[kW2 + n * 31 + k] : (k == 16 ? 0.f : p[kW2 + n * 31 + k - 1]);
-		case 3: return p[kW3 + n * 64 + k];
-		default: return n < 3 ? p[kW4 + n * 64 + k] : 0.f;
-	}
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
-{
-	__nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-	return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ uint32_t pack_f16(float lo, float hi)
-{
-	__half2 v = __floats2half2_rn(lo, hi);
-	return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi)
-{
-	uint32_t r;
-	asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-	return r;
-}
 
 __global__ void __launch_bounds__(256) mlp_pack_kernel(const float* __restrict__ p, uint32_t* __restrict__ blob)
 {
 	const int w = blockIdx.x * blockDim.x + threadIdx.x;
-	if (w >= kBlobWords) return;
+	if (w >= kTotalWords) return;
+	if (w >= kUmmaBase) {
+		// UMMA K-major core-matrix layout (mlp_small_layout.cuh): word q of layer l holds (n, k) and (n, k+1)
+		int layer, base, N;
+		if (w < kU1) { layer = 0; base = kU0; N = 64; }
+		else if (w < kU2) { layer = 1; base = kU1; N = 16; }
+		else if (w < kU3) { layer = 2; base = kU2; N = 64; }
+		else if (w < kU4) { layer = 3; base = kU3; N = 64; }
+		else { layer = 4; base = kU4; N = 16; }
+		const int q = w - base;
+		const int kc = q / (4 * N), n = (q >> 2) % N, k = 8 * kc + 2 * (q & 3);
+		blob[w] = pack_f16(wp(p, layer, n, k), wp(p, layer, n, k + 1));
+		return;
+	}
 	int layer, base, NT;
 	bool bwd = w >= kFwdWords;
 	if (!bwd) {
@@ -95,7 +74,9 @@ __global__ void __launch_bounds__(256) mlp_pack_kernel(const float* __restrict__
 		lo = kk < n_out ? wp(p, layer, kk, nn) : 0.f;
 		hi = kk + 1 < n_out ? wp(p, layer, kk + 1, nn) : 0.f;
 	}
-	blob[w] = (!bwd && layer == 0) ? pack_f16(lo, hi) : pack_bf16(lo, hi);
+	// forward operands (activations AND weights) are fp16 on every layer: 10-bit mantissa, 8x fewer ReLU sign flips against
+	// the fp32 reference than bf16; the gradient chain stays bf16 (fp32 range, no loss scale)
+	blob[w] = !bwd ? pack_f16(lo, hi) : pack_bf16(lo, hi);
 }
 
 // ---------------------------------------------------------------------------------------------- MMA helpers
@@ -130,24 +111,33 @@ __device__ __forceinline__ void layer_mma(const uint32_t (&a)[KS][4], const uint
 	}
 }
 
-// accumulator fragment of 2*KS n-tiles -> bf16 A fragment of KS k-steps
-template <int KS, bool RELU>
+// accumulator fragment of 2*KS n-tiles -> 16-bit A fragment of KS k-steps (F16: forward activations, else bf16 gradients)
+template <int KS, bool RELU, bool F16>
 __device__ __forceinline__ void repack(const float (&acc)[2 * KS][4], uint32_t (&a)[KS][4])
 {
 #pragma unroll
 	for (int ks = 0; ks < KS; ks++) {
-		if (RELU) {
-			a[ks][0] = pack_bf16_relu(acc[2 * ks][0], acc[2 * ks][1]);
-			a[ks][1] = pack_bf16_relu(acc[2 * ks][2], acc[2 * ks][3]);
-			a[ks][2] = pack_bf16_relu(acc[2 * ks + 1][0], acc[2 * ks + 1][1]);
-			a[ks][3] = pack_bf16_relu(acc[2 * ks + 1][2], acc[2 * ks + 1][3]);
-		} else {
-			a[ks][0] = pack_bf16(acc[2 * ks][0], acc[2 * ks][1]);
-			a[ks][1] = pack_bf16(acc[2 * ks][2], acc[2 * ks][3]);
-			a[ks][2] = pack_bf16(acc[2 * ks + 1][0], acc[2 * ks + 1][1]);
-			a[ks][3] = pack_bf16(acc[2 * ks + 1][2], acc[2 * ks + 1][3]);
+#pragma unroll
+		for (int e = 0; e < 4; e++) {
+			const float lo = acc[2 * ks + (e >> 1)][2 * (e & 1)], hi = acc[2 * ks + (e >> 1)][2 * (e & 1) + 1];
+			a[ks][e] = F16 ? (RELU ? pack_f16_relu(lo, hi) : pack_f16(lo, hi)) : (RELU ? pack_bf16_relu(lo, hi) : pack_bf16(lo, hi));
 		}
 	}
+}
+
+// fp16 pair word -> bf16 pair word (the dW MMAs take bf16 x bf16: activations are re-quantised for that product only)
+__device__ __forceinline__ uint32_t f16x2_to_bf16x2(uint32_t w)
+{
+	const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w));
+	return pack_bf16(v.x, v.y);
+}
+template <int KS>
+__device__ __forceinline__ void to_bf16(const uint32_t (&a)[KS][4], uint32_t (&b)[KS][4])
+{
+#pragma unroll
+	for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+		for (int e = 0; e < 4; e++) b[ks][e] = f16x2_to_bf16x2(a[ks][e]);
 }
 
 // ---------------------------------------------------------------------------------------------- input loaders
@@ -181,7 +171,7 @@ __device__ __forceinline__ void load_enc(const void* __restrict__ enc, int64_t r
 	}
 }
 
-// A fragment (bf16) of the 16 view channels (k-step 0 of the colour net input)
+// A fragment (fp16) of the 16 view channels (k-step 0 of the colour net input)
 template <int IN_KIND>
 __device__ __forceinline__ void load_views(const void* __restrict__ enc, const float* __restrict__ ray_sh, int S, int64_t r_lo, int64_t r_hi,
 	int64_t n, int t, uint32_t (&a)[4])
@@ -197,10 +187,10 @@ __device__ __forceinline__ void load_views(const void* __restrict__ enc, const f
 		hi = x + (r_hi < n ? r_hi : 0) * 48 + 32;
 	}
 	float2 v;
-	v = __ldg(reinterpret_cast<const float2*>(lo + 2 * t));      a[0] = pack_bf16(v.x, v.y);
-	v = __ldg(reinterpret_cast<const float2*>(hi + 2 * t));      a[1] = pack_bf16(v.x, v.y);
-	v = __ldg(reinterpret_cast<const float2*>(lo + 8 + 2 * t));  a[2] = pack_bf16(v.x, v.y);
-	v = __ldg(reinterpret_cast<const float2*>(hi + 8 + 2 * t));  a[3] = pack_bf16(v.x, v.y);
+	v = __ldg(reinterpret_cast<const float2*>(lo + 2 * t));      a[0] = pack_f16(v.x, v.y);
+	v = __ldg(reinterpret_cast<const float2*>(hi + 2 * t));      a[1] = pack_f16(v.x, v.y);
+	v = __ldg(reinterpret_cast<const float2*>(lo + 8 + 2 * t));  a[2] = pack_f16(v.x, v.y);
+	v = __ldg(reinterpret_cast<const float2*>(hi + 8 + 2 * t));  a[3] = pack_f16(v.x, v.y);
 }
 
 __device__ __forceinline__ void copy_blob(uint32_t* dst, const uint32_t* __restrict__ src, int words)
@@ -229,21 +219,21 @@ __global__ void __launch_bounds__(kFwdWarps * 32) mlp_small_fwd_kernel(const uin
 		float acc[8][4];
 		layer_mma<2, 8, true>(a0, wf + kF0, lane, acc);
 		uint32_t a1[4][4];
-		repack<4, true>(acc, a1);
+		repack<4, true, true>(acc, a1);
 		float d1[2][4];
-		layer_mma<4, 2, false>(a1, wf + kF1, lane, d1);
+		layer_mma<4, 2, true>(a1, wf + kF1, lane, d1);
 		const float sig_lo = d1[0][0], sig_hi = d1[0][2];  // column 0 lives in lanes with t == 0
 		uint32_t a2[2][4];
 		load_views<IN_KIND>(enc, ray_sh, S, r_lo, r_hi, n, t, a2[0]);
 		if (t == 0) { d1[0][0] = 0.f; d1[0][2] = 0.f; }     // sigma slot of the colour input
-		repack<1, false>(d1, reinterpret_cast<uint32_t(&)[1][4]>(a2[1]));
-		layer_mma<2, 8, false>(a2, wf + kF2, lane, acc);
+		repack<1, false, true>(d1, reinterpret_cast<uint32_t(&)[1][4]>(a2[1]));
+		layer_mma<2, 8, true>(a2, wf + kF2, lane, acc);
 		uint32_t a3[4][4];
-		repack<4, true>(acc, a3);
-		layer_mma<4, 8, false>(a3, wf + kF3, lane, acc);
-		repack<4, true>(acc, a3);
+		repack<4, true, true>(acc, a3);
+		layer_mma<4, 8, true>(a3, wf + kF3, lane, acc);
+		repack<4, true, true>(acc, a3);
 		float c[1][4];
-		layer_mma<4, 1, false>(a3, wf + kF4, lane, c);
+		layer_mma<4, 1, true>(a3, wf + kF4, lane, c);
 		// rgb: cols 0,1 in t==0 (c0,c1 / c2,c3), col 2 in t==1
 		const float b_lo = __shfl_down_sync(0xffffffffu, c[0][0], 1);
 		const float b_hi = __shfl_down_sync(0xffffffffu, c[0][2], 1);
@@ -381,34 +371,30 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			load_enc<IN_KIND>(enc, r_lo, r_hi, n, t, a0);
 			float acc[8][4];
 			layer_mma<2, 8, true>(a0, wf + kF0, lane, acc);
-			{   // X0 as bf16
-				uint32_t x0[2][4];
-#pragma unroll
-				for (int ks = 0; ks < 2; ks++)
-#pragma unroll
-					for (int e = 0; e < 4; e++) {
-						const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&a0[ks][e]));
-						x0[ks][e] = pack_bf16(v.x, v.y);
-					}
-				store_frag<2>(tiles + kTX0, kP32, row_g, t, x0);
-			}
+			uint32_t xb2[2][4], xb4[4][4];                               // bf16 copies for the dW products
+			to_bf16<2>(a0, xb2);
+			store_frag<2>(tiles + kTX0, kP32, row_g, t, xb2);
 			uint32_t a1[4][4];
-			repack<4, true>(acc, a1);
-			store_frag<4>(tiles + kTX1, kP64, row_g, t, a1);
+			repack<4, true, true>(acc, a1);
+			to_bf16<4>(a1, xb4);
+			store_frag<4>(tiles + kTX1, kP64, row_g, t, xb4);
 			float d1[2][4];
-			layer_mma<4, 2, false>(a1, wf + kF1, lane, d1);
+			layer_mma<4, 2, true>(a1, wf + kF1, lane, d1);
 			uint32_t a2[2][4];
 			load_views<IN_KIND>(enc, ray_sh, S, r_lo, r_hi, n, t, a2[0]);
 			if (t == 0) { d1[0][0] = 0.f; d1[0][2] = 0.f; }
-			repack<1, false>(d1, reinterpret_cast<uint32_t(&)[1][4]>(a2[1]));
-			store_frag<2>(tiles + kTX2, kP32, row_g, t, a2);
-			layer_mma<2, 8, false>(a2, wf + kF2, lane, acc);
+			repack<1, false, true>(d1, reinterpret_cast<uint32_t(&)[1][4]>(a2[1]));
+			to_bf16<2>(a2, xb2);
+			store_frag<2>(tiles + kTX2, kP32, row_g, t, xb2);
+			layer_mma<2, 8, true>(a2, wf + kF2, lane, acc);
 			uint32_t a3[4][4];
-			repack<4, true>(acc, a3);
-			store_frag<4>(tiles + kTX3, kP64, row_g, t, a3);
-			layer_mma<4, 8, false>(a3, wf + kF3, lane, acc);
-			repack<4, true>(acc, a3);
-			store_frag<4>(tiles + kTX4, kP64, row_g, t, a3);
+			repack<4, true, true>(acc, a3);
+			to_bf16<4>(a3, xb4);
+			store_frag<4>(tiles + kTX3, kP64, row_g, t, xb4);
+			layer_mma<4, 8, true>(a3, wf + kF3, lane, acc);
+			repack<4, true, true>(acc, a3);
+			to_bf16<4>(a3, xb4);
+			store_frag<4>(tiles + kTX4, kP64, row_g, t, xb4);
 		}
 		__syncwarp();
 		// ---- backward chain
@@ -430,11 +416,11 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			layer_mma<1, 8, false>(d4, wf + kB4, lane, acc);                 // dA4 = dD4 · W4
 			relu_mask<8>(acc, tiles + kTX4, kP64, row_g, t);
 			uint32_t d3[4][4];
-			repack<4, false>(acc, d3);
+			repack<4, false, false>(acc, d3);
 			store_frag<4>(tiles + kTD3, kP64, row_g, t, d3);
 			layer_mma<4, 8, false>(d3, wf + kB3, lane, acc);                 // dA3 = dD3 · W3
 			relu_mask<8>(acc, tiles + kTX3, kP64, row_g, t);
-			repack<4, false>(acc, d3);
+			repack<4, false, false>(acc, d3);
 			store_frag<4>(tiles + kTD2, kP64, row_g, t, d3);
 			float da2[4][4];
 			layer_mma<4, 4, false>(d3, wf + kB2, lane, da2);                 // dA2 = dD2 · W2p  (cols 0..15 views, 16..31 d1)
@@ -447,7 +433,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			store_frag<1>(tiles + kTD1, kP16, row_g, t, dd1);
 			layer_mma<1, 8, false>(dd1, wf + kB1, lane, acc);                // dA1 = dD1 · W1
 			relu_mask<8>(acc, tiles + kTX1, kP64, row_g, t);
-			repack<4, false>(acc, d3);
+			repack<4, false, false>(acc, d3);
 			store_frag<4>(tiles + kTD0, kP64, row_g, t, d3);
 			if (grad_in) {
 				float de[4][4];
@@ -508,6 +494,17 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 	}
 }
 
+// mlp_small_tc.cu
+cudaError_t launch_mlp_small_fwd_tc(const uint32_t* blob, int in_kind, const void* enc, const float* ray_sh, int S, const uint8_t* keep, int64_t n,
+	float* raw_out, cudaStream_t stream);
+
+// NRF_MLP_FWD=mma selects the mma.sync forward (kept as the A/B baseline of the tcgen05 kernel); read once
+static bool use_tcgen05_fwd()
+{
+	static const bool v = [] { const char* e = getenv("NRF_MLP_FWD"); return !(e && e[0] == 'm'); }();
+	return v;
+}
+
 static int check_shape(const nrf_mlp_small_shape* s)
 {
 	NRF_REQUIRE(s != nullptr, "shape is null");
@@ -525,7 +522,7 @@ using namespace nrf;
 
 extern "C" {
 
-int64_t nrf_mlp_small_packed_bytes(const nrf_mlp_small_shape* shape) { return check_shape(shape) ? -1 : static_cast<int64_t>(kBlobWords) * 4; }
+int64_t nrf_mlp_small_packed_bytes(const nrf_mlp_small_shape* shape) { return check_shape(shape) ? -1 : static_cast<int64_t>(kTotalWords) * 4; }
 int64_t nrf_mlp_small_param_count(const nrf_mlp_small_shape* shape) { return check_shape(shape) ? -1 : kParamCount; }
 
 int nrf_mlp_small_pack(const nrf_mlp_small_shape* shape, const float* params_flat, void* packed, nrf_stream stream)
@@ -533,7 +530,7 @@ int nrf_mlp_small_pack(const nrf_mlp_small_shape* shape, const float* params_fla
 	if (int rc = check_shape(shape)) return rc;
 	NRF_REQUIRE(params_flat && packed, "null pointer");
 	NRF_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "packed blob must be 16-byte aligned");
-	mlp_pack_kernel<<<(kBlobWords + 255) / 256, 256, 0, as_stream(stream)>>>(params_flat, reinterpret_cast<uint32_t*>(packed));
+	mlp_pack_kernel<<<(kTotalWords + 255) / 256, 256, 0, as_stream(stream)>>>(params_flat, reinterpret_cast<uint32_t*>(packed));
 	NRF_CHECK_LAUNCH("mlp_pack_kernel");
 	return NRF_OK;
 }
@@ -546,9 +543,16 @@ int nrf_mlp_small_fwd(const nrf_mlp_small_shape* shape, const void* packed, nrf_
 	if (n == 0) return NRF_OK;
 	NRF_REQUIRE(packed && enc && raw_out, "null pointer");
 	NRF_REQUIRE(in_kind == NRF_MLP_IN_F32_CAT || (ray_sh && samples_per_ray >= 1), "ray_sh / samples_per_ray missing");
+	const uint32_t* blob = reinterpret_cast<const uint32_t*>(packed);
+	if (use_tcgen05_fwd()) {
+		NRF_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "packed blob must be 16-byte aligned");
+		NRF_REQUIRE(in_kind != NRF_MLP_IN_ENC16_RAYDIRS || (reinterpret_cast<uintptr_t>(enc) & 15) == 0, "enc must be 16-byte aligned");
+		NRF_CUDA(launch_mlp_small_fwd_tc(blob, in_kind, enc, ray_sh, samples_per_ray, keep, n, raw_out, as_stream(stream)));
+		count_launch();
+		return NRF_OK;
+	}
 	const int64_t slabs = (n + 15) / 16;
 	const int blocks = static_cast<int>(std::min<int64_t>((slabs + kFwdWarps - 1) / kFwdWarps, kNumSMs * 4));
-	const uint32_t* blob = reinterpret_cast<const uint32_t*>(packed);
 	if (in_kind == NRF_MLP_IN_ENC16_RAYDIRS)
 		mlp_small_fwd_kernel<NRF_MLP_IN_ENC16_RAYDIRS><<<blocks, kFwdWarps * 32, 0, as_stream(stream)>>>(blob, enc, ray_sh, samples_per_ray, keep, n, raw_out);
 	else

@@ -1,0 +1,347 @@
+// Fused NeRFSmall forward on the 5th-generation tensor cores (tcgen05 / TMEM / TMA) for sm_100a.
+//
+// Same function as mlp_small_fwd_kernel (mlp_small.cu; reference src/NeRF.cpp:363-412 + src/NeRFRenderer.h:179-188), other
+// machine mapping:
+//   * a CTA owns the SM (persistent, 1 CTA/SM) and all 512 TMEM columns, split into kSlots independent tile pipelines;
+//   * each pipeline processes 128 sample points at a time: M = 128 rows = the 128 TMEM lanes, one epilogue thread per row;
+//   * every layer is tcgen05.mma.cta_group::1.kind::f16 with M=128, N=64 (or 16), K=16 per instruction:
+//         A  (activations)  lives in TENSOR MEMORY  (written by the epilogue threads with tcgen05.st, fp16 pairs per column)
+//         B  (weights)      lives in SHARED MEMORY  (K-major core matrices, staged once per CTA by one TMA bulk copy)
+//         D  (accumulator)  lives in TENSOR MEMORY  (fp32, read back with tcgen05.ld)
+//     so the chain enc -> h0 -> [sigma|geo] -> colour net never touches shared or global memory between layers;
+//   * one thread (warp 0, lane 0) issues all MMAs; it polls the per-pipeline "A ready" mbarriers and signals "D ready"
+//     with tcgen05.commit, so the tensor pipe works on one pipeline while the other pipelines run their epilogues
+//     (ReLU + fp16 pack + tcgen05.st) — the epilogue, not the MMA, is the long pole of a 64-wide MLP.
+//
+// TMEM columns of pipeline s (base = 128 s):  [0,64) D of the 64-wide layers | [64,80) D of the 16-wide layers |
+//                                             [96,128) A operand of the next layer (K <= 64 fp16 = 32 columns)
+#include "mlp_small_layout.cuh"
+
+namespace nrf {
+
+namespace tc {
+
+constexpr int kSlots = 4;                    // tile pipelines per CTA (4 x 128 TMEM columns)
+constexpr int kThreads = 32 * (1 + 4 * kSlots);
+constexpr uint32_t kColD = 0, kColD16 = 64, kColA = 96, kSlotCols = 128;
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity)
+{
+	uint32_t ok;
+	asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+	             : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+	asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+	             ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc_all(uint32_t* dst_smem)
+{
+	asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(dst_smem)) : "memory");
+	asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free_all(uint32_t base)
+{
+	asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(base) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, one K=16 step
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+	             ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// tcgen05.ld / st, shape 32x32b: thread i of the warp owns TMEM lane (32*(warp%4) + i) and gets / gives consecutive columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+	asm volatile(
+		"tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+		"{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+		: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+		  "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+		  "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+		  "=r"(r[31])
+		: "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+	asm volatile(
+		"tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+		: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+		  "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+		: "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4])
+{
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16])
+{
+	asm volatile(
+		"tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+		::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+		  "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+		: "memory");
+}
+
+// ---- descriptors ---------------------------------------------------------------------------------------------------
+// instruction descriptor, kind::f16: D fp32 (bits 4-5 = 1), A/B fp16 (bits 7-9, 10-12 = 0), both K-major (bits 15,16 = 0),
+// N>>3 at bit 17, M>>4 at bit 24 (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) { return (1u << 4) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24); }
+// shared-memory matrix descriptor, no swizzle, K-major: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+	return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(lbo_bytes >> 4) << 16) | (uint64_t(sbo_bytes >> 4) << 32) | (uint64_t(1) << 46);
+}
+
+struct LayerDesc {
+	int word_off, N, KS;      // offset in the staged blob, padded out channels, K/16
+	uint32_t d_col;           // accumulator column inside the slot
+};
+__device__ __forceinline__ LayerDesc layer_desc(int l)
+{
+	switch (l) {
+		case 0: return {kU0 - kUmmaBase, 64, 2, kColD};
+		case 1: return {kU1 - kUmmaBase, 16, 4, kColD16};
+		case 2: return {kU2 - kUmmaBase, 64, 2, kColD};
+		case 3: return {kU3 - kUmmaBase, 64, 4, kColD};
+		default: return {kU4 - kUmmaBase, 16, 4, kColD16};
+	}
+}
+
+struct __align__(16) Smem {
+	uint32_t w[kUmmaWords];            // 20 KiB of UMMA B operands
+	uint64_t w_ready;
+	uint64_t a_ready[kSlots];          // 128 epilogue threads -> MMA thread
+	uint64_t d_ready[kSlots];          // tcgen05.commit -> epilogue threads
+	uint32_t tmem_base;
+};
+
+// 32 fp32 accumulator columns -> 16 fp16-pair words, ReLU fused into the convert
+__device__ __forceinline__ void relu_pack(const uint32_t (&acc)[32], uint32_t (&out)[16])
+{
+#pragma unroll
+	for (int i = 0; i < 16; i++) out[i] = pack_f16_relu(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+}
+
+template <int IN_KIND>
+__global__ void __launch_bounds__(kThreads, 1) mlp_small_fwd_tc_kernel(const uint32_t* __restrict__ blob, const void* __restrict__ enc,
+	const float* __restrict__ ray_sh, int S, const uint8_t* __restrict__ keep, int64_t n, float* __restrict__ raw_out)
+{
+	__shared__ Smem sm;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int64_t n_tiles = (n + 127) / 128;
+
+	if (warp == 0) {
+		if (lane == 0) {
+			mbar_init(&sm.w_ready, 1);
+			for (int s = 0; s < kSlots; s++) { mbar_init(&sm.a_ready[s], 128); mbar_init(&sm.d_ready[s], 1); }
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncwarp();
+		tmem_alloc_all(&sm.tmem_base);
+	}
+	fence_before();
+	__syncthreads();
+	fence_after();
+	const uint32_t tmem = sm.tmem_base;
+
+	if (warp == 0) {
+		if (lane == 0) {
+			// ===== weights: one TMA bulk copy, then the MMA issue loop =====
+			mbar_expect_tx(&sm.w_ready, kUmmaWords * 4);
+			tma_bulk_g2s(sm.w, blob + kUmmaBase, kUmmaWords * 4, &sm.w_ready);
+			mbar_wait(&sm.w_ready, 0);
+			const uint32_t w_saddr = smem_u32(sm.w);
+			int64_t steps_left[kSlots];
+			uint32_t step[kSlots];
+			int64_t remaining = 0;
+			for (int s = 0; s < kSlots; s++) {
+				// pipeline s of CTA b handles tiles b + gridDim.x * (s + kSlots * i)
+				const int64_t first = blockIdx.x + static_cast<int64_t>(gridDim.x) * s;
+				const int64_t stride = static_cast<int64_t>(gridDim.x) * kSlots;
+				const int64_t cnt = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+				steps_left[s] = cnt * 5;
+				step[s] = 0;
+				remaining += steps_left[s];
+			}
+			while (remaining > 0) {
+#pragma unroll
+				for (int s = 0; s < kSlots; s++) {
+					if (steps_left[s] == 0 || !mbar_test(&sm.a_ready[s], step[s] & 1)) continue;
+					fence_after();
+					const LayerDesc L = layer_desc(static_cast<int>(step[s] % 5));
+					const uint32_t col = tmem + s * kSlotCols;
+					const uint32_t idesc = idesc_f16(128, L.N);
+					const uint32_t lbo = L.N * 16;   // bytes between the two 8-wide K chunks of one instruction
+#pragma unroll 4
+					for (int j = 0; j < L.KS; j++) {
+						const uint64_t bd = smem_desc(w_saddr + L.word_off * 4 + j * 2 * lbo, lbo, 128);
+						umma_ts(col + L.d_col, col + kColA + j * 8, bd, idesc, j > 0);
+					}
+					umma_commit(&sm.d_ready[s]);
+					step[s]++;
+					steps_left[s]--;
+					remaining--;
+				}
+			}
+		}
+	} else {
+		// ===== epilogue / load / store threads: one per row of the slot's 128-row tile =====
+		const int s = (warp - 1) >> 2;
+		const int row = ((warp & 3) << 5) | lane;                       // TMEM lane == row inside the tile
+		const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) << 5) << 16) + s * kSlotCols;
+		uint32_t ph = 0;                                                // completed uses of d_ready[s]
+		const int64_t stride = static_cast<int64_t>(gridDim.x) * kSlots;
+		for (int64_t tile = blockIdx.x + static_cast<int64_t>(gridDim.x) * s; tile < n_tiles; tile += stride) {
+			const int64_t r = tile * 128 + row;
+			const bool ok = r < n;
+			uint32_t a16[16];
+			// ---- layer 0 operand: the 32 fp16 encodings of this row
+			if (IN_KIND == NRF_MLP_IN_ENC16_RAYDIRS) {
+				const uint4* e = reinterpret_cast<const uint4*>(enc) + r * 4;
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					const uint4 v = ok ? __ldg(e + q) : make_uint4(0u, 0u, 0u, 0u);
+					a16[4 * q] = v.x; a16[4 * q + 1] = v.y; a16[4 * q + 2] = v.z; a16[4 * q + 3] = v.w;
+				}
+			} else {
+				const float4* x = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(enc) + r * 48);
+#pragma unroll
+				for (int q = 0; q < 8; q++) {
+					const float4 v = ok ? __ldg(x + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+					a16[2 * q] = pack_f16(v.x, v.y);
+					a16[2 * q + 1] = pack_f16(v.z, v.w);
+				}
+			}
+			tmem_st16(t_lane + kColA, a16);
+			// the 16 view channels of this row (per-ray SH table or the tail of the cat input), kept for layer 2
+			uint32_t v16[8];
+			{
+				const float4* vp = IN_KIND == NRF_MLP_IN_ENC16_RAYDIRS ? reinterpret_cast<const float4*>(ray_sh + (ok ? r / S : 0) * 16)
+				                                                       : reinterpret_cast<const float4*>(reinterpret_cast<const float*>(enc) + (ok ? r : 0) * 48 + 32);
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					const float4 v = __ldg(vp + q);
+					v16[2 * q] = pack_f16(v.x, v.y);
+					v16[2 * q + 1] = pack_f16(v.z, v.w);
+				}
+			}
+			const bool kept = !(keep && ok && !keep[r]);
+			tmem_st_wait();
+			fence_before();
+			mbar_arrive(&sm.a_ready[s]);
+
+			uint32_t acc[32];
+			// ---- layer 0 -> h0 = relu(.) as the K=64 operand of layer 1
+			mbar_wait(&sm.d_ready[s], ph++ & 1);
+			fence_after();
+#pragma unroll
+			for (int h = 0; h < 2; h++) {
+				tmem_ld32(t_lane + kColD + 32 * h, acc);
+				tmem_ld_wait();
+				relu_pack(acc, a16);
+				tmem_st16(t_lane + kColA + 16 * h, a16);
+			}
+			tmem_st_wait();
+			fence_before();
+			mbar_arrive(&sm.a_ready[s]);
+
+			// ---- layer 1 -> [sigma | geo(15)]; colour input = [views(16) | 0 | geo(15)]
+			mbar_wait(&sm.d_ready[s], ph++ & 1);
+			fence_after();
+			uint32_t d1[16];
+			tmem_ld16(t_lane + kColD16, d1);
+			tmem_ld_wait();
+			const float sigma = __uint_as_float(d1[0]);
+			d1[0] = 0u;                                                  // sigma slot of the colour input (its weight column is zero too)
+#pragma unroll
+			for (int i = 0; i < 8; i++) { a16[i] = v16[i]; a16[8 + i] = pack_f16(__uint_as_float(d1[2 * i]), __uint_as_float(d1[2 * i + 1])); }
+			tmem_st16(t_lane + kColA, a16);
+			tmem_st_wait();
+			fence_before();
+			mbar_arrive(&sm.a_ready[s]);
+
+			// ---- layers 2 and 3 -> relu -> K=64 operand of the next layer
+#pragma unroll
+			for (int l = 2; l <= 3; l++) {
+				mbar_wait(&sm.d_ready[s], ph++ & 1);
+				fence_after();
+#pragma unroll
+				for (int h = 0; h < 2; h++) {
+					tmem_ld32(t_lane + kColD + 32 * h, acc);
+					tmem_ld_wait();
+					relu_pack(acc, a16);
+					tmem_st16(t_lane + kColA + 16 * h, a16);
+				}
+				tmem_st_wait();
+				fence_before();
+				mbar_arrive(&sm.a_ready[s]);
+			}
+
+			// ---- layer 4 -> rgb; out = [r, g, b, sigma (0 outside the box, src/NeRFRenderer.h:188)]
+			mbar_wait(&sm.d_ready[s], ph++ & 1);
+			fence_after();
+			uint32_t c[4];
+			tmem_ld4(t_lane + kColD16, c);
+			tmem_ld_wait();
+			if (ok) *reinterpret_cast<float4*>(raw_out + r * 4) = make_float4(__uint_as_float(c[0]), __uint_as_float(c[1]), __uint_as_float(c[2]), kept ? sigma : 0.f);
+		}
+	}
+
+	fence_before();
+	__syncthreads();
+	if (warp == 0) {
+		fence_after();
+		tmem_free_all(tmem);
+	}
+}
+
+}  // namespace tc
+
+// called by nrf_mlp_small_fwd (mlp_small.cu)
+cudaError_t launch_mlp_small_fwd_tc(const uint32_t* blob, int in_kind, const void* enc, const float* ray_sh, int S, const uint8_t* keep, int64_t n,
+	float* raw_out, cudaStream_t stream)
+{
+	const int64_t tiles = (n + 127) / 128;
+	const int blocks = static_cast<int>(std::min<int64_t>((tiles + tc::kSlots - 1) / tc::kSlots, kNumSMs));
+	if (in_kind == NRF_MLP_IN_ENC16_RAYDIRS)
+		tc::mlp_small_fwd_tc_kernel<NRF_MLP_IN_ENC16_RAYDIRS><<<blocks, tc::kThreads, 0, stream>>>(blob, enc, ray_sh, S, keep, n, raw_out);
+	else
+		tc::mlp_small_fwd_tc_kernel<NRF_MLP_IN_F32_CAT><<<blocks, tc::kThreads, 0, stream>>>(blob, enc, ray_sh, S, keep, n, raw_out);
+	return cudaGetLastError();
+}
+
+}  // namespace nrf

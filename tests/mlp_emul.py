@@ -1,10 +1,11 @@
 """Quantisation-point-exact emulation of the fused NeRFSmall kernels (test infrastructure).
 
-The reference MLP (src/NeRF.cpp:363-412) is fp32 SGEMM.  The sm_100a kernels run layer 0 in fp16 x fp16 and layers 1-4
-in bf16 x bf16 with fp32 accumulation, re-quantising each activation / gradient where it becomes a tensor-core operand.
-Against the fp32 reference such a chain is only comparable in a norm sense: a pre-activation within one bf16 ulp of zero
+The reference MLP (src/NeRF.cpp:363-412) is fp32 SGEMM.  The sm_100a kernels run the forward chain (and its recompute in
+the backward) in fp16 x fp16 and the gradient chain in bf16 x bf16, all with fp32 accumulation, re-quantising each
+activation / gradient where it becomes a tensor-core operand (activations are re-quantised to bf16 for the dW products).
+Against the fp32 reference such a chain is only comparable in a norm sense: a pre-activation within rounding error of zero
 takes the other ReLU branch and changes that row's gradient by a whole term, which a max-norm bound cannot absorb.  So
-parity is established in two steps (tests/test_gpu_mlp.py):
+parity is established in four steps (tests/test_gpu_mlp.py):
     kernel == this emulation                      tight, max-norm (catches every indexing / layout / masking bug)
     kernel ~  fp32 reference, forward             max-norm rel <= 1e-2 (the bf16 tolerance class of the north star)
     kernel ~  fp32 arithmetic on the SAME active sets (fp32_with_masks), gradients: max-norm rel <= 1.5e-2
@@ -32,19 +33,19 @@ def forward_backward(ws, x, g, keep=None):
     w0, w1, w2, w3, w4 = [w.float() for w in ws]
     w2p = pad_w2(w2)
     x0 = hf(x[:, :32])
-    views = bf(x[:, 32:])
+    views = hf(x[:, 32:])
     acc0 = x0 @ hf(w0).t()
-    a1 = bf(torch.relu(acc0))
-    d1 = a1 @ bf(w1).t()
+    a1 = hf(torch.relu(acc0))
+    d1 = a1 @ hf(w1).t()
     sigma = d1[:, 0].clone()
     d1z = d1.clone()
     d1z[:, 0] = 0.0
-    a2 = torch.cat([views, bf(d1z)], -1)
-    acc2 = a2 @ bf(w2p).t()
-    a3 = bf(torch.relu(acc2))
-    acc3 = a3 @ bf(w3).t()
-    a4 = bf(torch.relu(acc3))
-    c = a4 @ bf(w4).t()
+    a2 = torch.cat([views, hf(d1z)], -1)
+    acc2 = a2 @ hf(w2p).t()
+    a3 = hf(torch.relu(acc2))
+    acc3 = a3 @ hf(w3).t()
+    a4 = hf(torch.relu(acc3))
+    c = a4 @ hf(w4).t()
     if keep is not None:
         sigma = sigma * keep.float()
     out = torch.cat([c, sigma[:, None]], -1)
@@ -67,11 +68,11 @@ def forward_backward(ws, x, g, keep=None):
     denc = dD0 @ bf(w0)
     gx = torch.cat([denc, dviews], -1)
     dW0 = dD0.t() @ bf(x0)
-    dW1 = dd1.t() @ a1
-    dW2p = dD2.t() @ a2
+    dW1 = dd1.t() @ bf(a1)
+    dW2p = dD2.t() @ bf(a2)
     dW2 = torch.cat([dW2p[:, :16], dW2p[:, 17:]], -1)
-    dW3 = dD3.t() @ a3
-    dW4 = d4.t() @ a4
+    dW3 = dD3.t() @ bf(a3)
+    dW4 = d4.t() @ bf(a4)
     return out, gx, [dW0, dW1, dW2, dW3, dW4], (a1 > 0, a3 > 0, a4 > 0)
 
 
