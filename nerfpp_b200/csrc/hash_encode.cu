@@ -67,6 +67,7 @@ __global__ void level_scale_kernel(int base_resolution, int finest_resolution, i
 struct Cell {
 	uint32_t pos[8];
 	float w[8];
+	uint32_t cx, cy, cz;   // integer cell of the point at this level (identifies the 8 corners; the backward's run key)
 };
 
 // src/CuHashEmbedder.cu:44-90 for one level.  q = (pt - box_min) / (box_max - box_min) is level independent.
@@ -82,6 +83,7 @@ __device__ __forceinline__ void locate(const HashMeta& m, int l, float qx, float
 	const uint32_t pos_x = static_cast<uint32_t>(fx);
 	const uint32_t pos_y = static_cast<uint32_t>(fy);
 	const uint32_t pos_z = static_cast<uint32_t>(fz);
+	c.cx = pos_x; c.cy = pos_y; c.cz = pos_z;
 	const uint32_t pa = m.pa[l], pb = m.pb[l], pc = m.pc[l];
 	const uint32_t x0 = pos_x * pa, x1 = (pos_x + 1u) * pa;
 	const uint32_t y0 = pos_y * pb, y1 = (pos_y + 1u) * pb;
@@ -228,56 +230,126 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b)
 	asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 
+// Backward: dTable[corner] += w_corner * dEnc, fp32 RED (src/CuHashEmbedder.cu:106-216).
+//
+// Warp-aggregated scatter.  Points arrive in ray-major order (samples of a ray are consecutive), so on the coarse levels
+// neighbouring lanes of a warp sit in the SAME grid cell and would hit the same 8 table entries.  Per level the warp
+//   1. flags lanes whose cell equals the previous lane's cell (3 SHFL + 1 ballot) -> contiguous runs of equal cells,
+//   2. sums the 8 x F corner contributions over each run with a segmented shuffle reduction whose depth is chosen from the
+//      longest run in the warp (warp-uniform; zero steps on the fine levels where every lane is alone in its cell),
+//   3. lets only the first lane of a run issue the vector REDs.
+// Any point order is handled correctly (a run is defined by adjacency, not by key equality); ray-major order is what
+// makes it pay.  The reference issues N*L*8 half2 atomics regardless.
 template <int F, bool GRAD_BF16>
 __global__ void __launch_bounds__(256) hash_bwd_kernel(HashArgs a, const float* __restrict__ points, int64_t n_points,
 	int clamp_points, const void* __restrict__ grad_enc, float* __restrict__ grad_table)
 {
+	constexpr int CH = 8 / F;   // levels per 8-value gradient chunk (16 B of bf16 / 32 B of fp32)
+	constexpr uint32_t FULL = 0xffffffffu;
 	__shared__ HashMeta m;
 	stage_meta(m, a);
 
+	const int lane = threadIdx.x & 31;
 	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-	if (i >= n_points) return;
+	const bool valid = i < n_points;   // no early return: the whole warp takes part in the shuffles
 
-	float x = points[i * 3 + 0], y = points[i * 3 + 1], z = points[i * 3 + 2];
+	float x = 0.f, y = 0.f, z = 0.f;
+	if (valid) { x = points[i * 3 + 0]; y = points[i * 3 + 1]; z = points[i * 3 + 2]; }
 	if (clamp_points) clamp_point(a, x, y, z);
 	const float qx = (x - a.min_x) / (a.max_x - a.min_x);
 	const float qy = (y - a.min_y) / (a.max_y - a.min_y);
 	const float qz = (z - a.min_z) / (a.max_z - a.min_z);
 
 	const int L = a.n_levels;
-	const int64_t row = i * (static_cast<int64_t>(L) * F);
-	for (int l = 0; l < L; l++) {
-		float g[F];
-		if (GRAD_BF16) {
-			const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(grad_enc) + row + static_cast<int64_t>(l) * F;
+	const int D = L * F;
+	const int64_t row = i * static_cast<int64_t>(D);
+	const bool vec_ok = (D % 8) == 0;   // rows are 16-byte (bf16) / 32-byte (fp32) aligned
+	for (int l0 = 0; l0 < L; l0 += CH) {
+		float g8[8];
 #pragma unroll
-			for (int k = 0; k < F; k += 2) {
-				const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gp + k));
-				g[k] = t.x;
-				g[k + 1] = t.y;
-			}
-		} else {
-			const float* gp = reinterpret_cast<const float*>(grad_enc) + row + static_cast<int64_t>(l) * F;
+		for (int k = 0; k < 8; k++) g8[k] = 0.f;
+		if (valid) {
+			const int n_valid = min(CH, L - l0) * F;
+			if (GRAD_BF16) {
+				const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(grad_enc) + row + static_cast<int64_t>(l0) * F;
+				if (vec_ok) {
+					const uint4 v = __ldg(reinterpret_cast<const uint4*>(gp));
+					const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
-			for (int k = 0; k < F; k += 2) {
-				const float2 t = *reinterpret_cast<const float2*>(gp + k);
-				g[k] = t.x;
-				g[k + 1] = t.y;
+					for (int k = 0; k < 4; k++) {
+						const float2 t = __bfloat1622float2(h[k]);
+						g8[2 * k] = t.x;
+						g8[2 * k + 1] = t.y;
+					}
+				} else {
+#pragma unroll
+					for (int k = 0; k < 8; k++) if (k < n_valid) g8[k] = __bfloat162float(gp[k]);
+				}
+			} else {
+				const float* gp = reinterpret_cast<const float*>(grad_enc) + row + static_cast<int64_t>(l0) * F;
+				if (vec_ok) {
+					const float4 v0 = __ldg(reinterpret_cast<const float4*>(gp)), v1 = __ldg(reinterpret_cast<const float4*>(gp) + 1);
+					g8[0] = v0.x; g8[1] = v0.y; g8[2] = v0.z; g8[3] = v0.w;
+					g8[4] = v1.x; g8[5] = v1.y; g8[6] = v1.z; g8[7] = v1.w;
+				} else {
+#pragma unroll
+					for (int k = 0; k < 8; k++) if (k < n_valid) g8[k] = gp[k];
+				}
 			}
 		}
-		bool any = false;
+		for (int j = 0; j < CH; j++) {
+			const int l = l0 + j;
+			if (l >= L) break;   // warp-uniform
+			float g[F];
+			bool any = false;
 #pragma unroll
-		for (int k = 0; k < F; k++) any |= (g[k] != 0.f);
-		if (!any) continue;  // src/CuHashEmbedder.cu:195 skips all-zero pairs
-		Cell c;
-		locate(m, l, qx, qy, qz, c);
-		float* base = grad_table + m.offset[l];
+			for (int k = 0; k < F; k++) {
+				g[k] = g8[k];
+				any |= (g[k] != 0.f);
+			}
 #pragma unroll
-		for (int d = 0; d < 8; d++) {
-			float* p = base + static_cast<size_t>(c.pos[d]) * F;
+			for (int k = 0; k + F < 8; k++) g8[k] = g8[k + F];   // next level's values move to the front (static indices only)
+			const bool active = valid && any;   // src/CuHashEmbedder.cu:195 skips all-zero gradients
+			Cell c;
+			locate(m, l, qx, qy, qz, c);
+			// ---- runs of equal cells among neighbouring active lanes
+			const uint32_t px_ = __shfl_up_sync(FULL, c.cx, 1), py_ = __shfl_up_sync(FULL, c.cy, 1), pz_ = __shfl_up_sync(FULL, c.cz, 1);
+			const bool prev_active = __shfl_up_sync(FULL, static_cast<int>(active), 1) != 0;
+			const bool cont = lane > 0 && active && prev_active && px_ == c.cx && py_ == c.cy && pz_ == c.cz;
+			const uint32_t nh = __ballot_sync(FULL, cont);   // bit j: lane j continues lane j-1's run
+			if (__ballot_sync(FULL, active) == 0u) continue;  // warp-uniform
+			float v[8][F];
 #pragma unroll
-			for (int k = 0; k < F; k += 2) {
-				if (g[k] != 0.f || g[k + 1] != 0.f) red_add_v2(p + k, g[k] * c.w[d], g[k + 1] * c.w[d]);
+			for (int d = 0; d < 8; d++)
+#pragma unroll
+				for (int k = 0; k < F; k++) v[d][k] = g[k] * c.w[d];
+			if (nh != 0u) {
+				// depth of the segmented reduction from the longest run: > 2^s lanes <=> 2^s consecutive continuation bits
+				const uint32_t t2 = nh & (nh >> 1), t4 = t2 & (t2 >> 2), t8 = t4 & (t4 >> 4), t16 = t8 & (t8 >> 8);
+				const int steps = 1 + (t2 != 0u) + (t4 != 0u) + (t8 != 0u) + (t16 != 0u);
+				const uint32_t above = lane < 31 ? (nh >> (lane + 1)) : 0u;   // bit b: lane+1+b continues its predecessor
+				for (int s = 0; s < steps; s++) {   // warp-uniform trip count
+					const int off = 1 << s;
+					// lane+off is in my run  <=>  lanes lane+1 .. lane+off all continue their predecessor
+					const uint32_t need = (off == 32) ? FULL : ((1u << off) - 1u);
+					const bool take = (lane + off < 32) && ((above & need) == need);
+#pragma unroll
+					for (int d = 0; d < 8; d++)
+#pragma unroll
+						for (int k = 0; k < F; k++) {
+							const float o = __shfl_down_sync(FULL, v[d][k], off);
+							if (take) v[d][k] += o;
+						}
+				}
+			}
+			if (active && !cont) {   // first lane of a run owns the run's sum
+				float* base = grad_table + m.offset[l];
+#pragma unroll
+				for (int d = 0; d < 8; d++) {
+					float* p = base + static_cast<size_t>(c.pos[d]) * F;
+#pragma unroll
+					for (int k = 0; k < F; k += 2) red_add_v2(p + k, v[d][k], v[d][k + 1]);
+				}
 			}
 		}
 	}

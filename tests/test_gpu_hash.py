@@ -172,6 +172,62 @@ def test_full_size_adjoint_identity():
     assert abs(lhs - rhs) / (enc.double().abs() * G.double().abs()).sum().item() < 1e-4
 
 
+def _ray_ordered_points(n_rays, n_samples, seed=0):
+    """Samples of a ray are consecutive rows (the order RenderRays produces): on the coarse levels neighbouring points
+    share a grid cell, which is the case the warp-aggregated scatter reduces before issuing its REDs."""
+    g = torch.Generator().manual_seed(seed)
+    o = torch.randn(n_rays, 1, 3, generator=g)
+    o = 4.0 * o / o.norm(dim=-1, keepdim=True)
+    d = -o / 4.0 + 0.15 * torch.randn(n_rays, 1, 3, generator=g)
+    t = torch.sort(2.0 + 4.0 * torch.rand(n_rays, n_samples, 1, generator=g), dim=1).values
+    return (o + d * t).reshape(-1, 3)
+
+
+@pytest.mark.parametrize("n_rays,n_samples,dtype", [(40, 100, "f32"), (33, 192, "bf16"), (7, 61, "f32")])
+def test_backward_warp_aggregation_on_ray_ordered_points(n_rays, n_samples, dtype):
+    """Runs of equal cells (incl. runs cut by zero-gradient rows, warp boundaries, out-of-box points and a ragged tail)
+    must scatter exactly what the per-point fp64 adjoint does."""
+    from nerfpp_b200 import ops
+    grid = _grid()
+    meta = _np(grid)
+    pts = _ray_ordered_points(n_rays, n_samples, seed=n_rays)
+    n = pts.shape[0]
+    pts[5:9] = pts[5]                                         # identical points: one run, four members
+    g = torch.Generator().manual_seed(3)
+    grad = torch.randn(n, 32, generator=g)
+    grad[10:14] = 0.0                                         # inactive lanes inside a run
+    grad[20, 4:6] = 0.0                                       # one level of one point inactive
+    grad[64:96, :8] = 0.0                                     # a whole warp inactive on the first four levels
+    if dtype == "bf16":
+        grad = grad.bfloat16()
+    gt = torch.zeros(grid.table_scalars(), device="cuda")
+    ops.hash_encode_bwd(grid, pts.cuda(), grad.cuda(), gt, clamp=True)
+    cl, keep = O.clamp_keep(pts.numpy(), BBOX[:3], BBOX[3:])
+    assert (~keep).any() and keep.any()
+    ref = O.hash_encode_bwd_f64(cl, grad_enc=grad.float().numpy(), n_features=2, table_scalars=grid.table_scalars(), **meta)
+    got = gt.cpu().numpy().astype(np.float64)
+    assert np.all(got[ref == 0] == 0)                         # nothing outside the touched entries (sums may cancel to 0 inside)
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < 2e-6, err
+
+
+def test_backward_full_size_ray_ordered_adjoint():
+    """786 432 ray-ordered points (4096 rays x 192 samples): <enc(T), G> == <T, bwd(G)> with the aggregation active."""
+    from nerfpp_b200 import ops
+    grid = _grid()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    table = torch.rand(grid.table_scalars(), generator=g, device="cuda") * 2 - 1
+    t16 = ops.table_to_half(table)
+    pts = _ray_ordered_points(4096, 192, seed=8).cuda()
+    G = torch.randn(pts.shape[0], 32, generator=g, device="cuda")
+    enc, _ = ops.hash_encode_fwd(grid, t16, pts)
+    gt = torch.zeros(grid.table_scalars(), device="cuda")
+    ops.hash_encode_bwd(grid, pts, G, gt)
+    lhs = (enc.double() * G.double()).sum().item()
+    rhs = (t16.double() * gt.double()).sum().item()
+    assert abs(lhs - rhs) / (enc.double().abs() * G.double().abs()).sum().item() < 1e-4
+
+
 def test_against_reference_cuda_kernels(ref_cuda):
     """Live: the reference's CuHashEmbedder forward/backward kernels on the same table, primes and points."""
     if ref_cuda is None:
