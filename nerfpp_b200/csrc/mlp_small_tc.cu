@@ -9,9 +9,13 @@
 //         B  (weights)      lives in SHARED MEMORY  (K-major core matrices, staged once per CTA by one TMA bulk copy)
 //         D  (accumulator)  lives in TENSOR MEMORY  (fp32, read back with tcgen05.ld)
 //     so the chain enc -> h0 -> [sigma|geo] -> colour net never touches shared or global memory between layers;
-//   * one thread (warp 0, lane 0) issues all MMAs; it polls the per-pipeline "A ready" mbarriers and signals "D ready"
-//     with tcgen05.commit, so the tensor pipe works on one pipeline while the other pipelines run their epilogues
-//     (ReLU + fp16 pack + tcgen05.st) — the epilogue, not the MMA, is the long pole of a 64-wide MLP.
+//   * every pipeline has its own issuing thread (lane 0 of its first epilogue warp): it waits for the pipeline's "A ready"
+//     mbarrier (one arrival per epilogue warp), issues the layer's 2-4 MMAs with compile-time descriptors and signals
+//     "D ready" with tcgen05.commit.  The tensor pipe works on one pipeline while the others run their epilogues
+//     (ReLU + fp16 pack + tcgen05.st) — the epilogue round trip, not the MMA, is the long pole of a 64-wide MLP.
+//     (r1c profile: ONE thread issuing for all four pipelines spent ~730 cycles of dependent scalar work per layer step
+//     and capped the tensor pipe at 10 %; profiles/r1_mlp_small_fwd_tc_v1_ncu.txt.)
+//   * the next tile's encodings are loaded while the current tile runs its last two layers.
 //
 // TMEM columns of pipeline s (base = 128 s):  [0,64) D of the 64-wide layers | [64,80) D of the 16-wide layers |
 //                                             [96,128) A operand of the next layer (K <= 64 fp16 = 32 columns)
@@ -22,7 +26,7 @@ namespace nrf {
 namespace tc {
 
 constexpr int kSlots = 4;                    // tile pipelines per CTA (4 x 128 TMEM columns)
-constexpr int kThreads = 32 * (1 + 4 * kSlots);
+constexpr int kThreads = 128 * kSlots;     // 4 epilogue warps per pipeline; lane 0 of each pipeline's first warp issues its MMAs
 constexpr uint32_t kColD = 0, kColD16 = 64, kColA = 96, kSlotCols = 128;
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------------
@@ -126,25 +130,18 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 	return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(lbo_bytes >> 4) << 16) | (uint64_t(sbo_bytes >> 4) << 32) | (uint64_t(1) << 46);
 }
 
-struct LayerDesc {
-	int word_off, N, KS;      // offset in the staged blob, padded out channels, K/16
-	uint32_t d_col;           // accumulator column inside the slot
-};
-__device__ __forceinline__ LayerDesc layer_desc(int l)
-{
-	switch (l) {
-		case 0: return {kU0 - kUmmaBase, 64, 2, kColD};
-		case 1: return {kU1 - kUmmaBase, 16, 4, kColD16};
-		case 2: return {kU2 - kUmmaBase, 64, 2, kColD};
-		case 3: return {kU3 - kUmmaBase, 64, 4, kColD};
-		default: return {kU4 - kUmmaBase, 16, 4, kColD16};
-	}
-}
+// compile-time description of layer L: offset in the staged blob (words), padded out channels N, K/16, accumulator column
+template <int L> struct Layer;
+template <> struct Layer<0> { static constexpr int off = kU0 - kUmmaBase, N = 64, KS = 2; static constexpr uint32_t d_col = kColD; };
+template <> struct Layer<1> { static constexpr int off = kU1 - kUmmaBase, N = 16, KS = 4; static constexpr uint32_t d_col = kColD16; };
+template <> struct Layer<2> { static constexpr int off = kU2 - kUmmaBase, N = 64, KS = 2; static constexpr uint32_t d_col = kColD; };
+template <> struct Layer<3> { static constexpr int off = kU3 - kUmmaBase, N = 64, KS = 4; static constexpr uint32_t d_col = kColD; };
+template <> struct Layer<4> { static constexpr int off = kU4 - kUmmaBase, N = 16, KS = 4; static constexpr uint32_t d_col = kColD16; };
 
 struct __align__(16) Smem {
 	uint32_t w[kUmmaWords];            // 20 KiB of UMMA B operands
 	uint64_t w_ready;
-	uint64_t a_ready[kSlots];          // 128 epilogue threads -> MMA thread
+	uint64_t a_ready[kSlots];          // 4 epilogue warps -> the slot's issuing thread
 	uint64_t d_ready[kSlots];          // tcgen05.commit -> epilogue threads
 	uint32_t tmem_base;
 };
@@ -154,6 +151,78 @@ __device__ __forceinline__ void relu_pack(const uint32_t (&acc)[32], uint32_t (&
 {
 #pragma unroll
 	for (int i = 0; i < 16; i++) out[i] = pack_f16_relu(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+}
+
+// The slot's issuing thread: wait until the four epilogue warps have published the A operand, issue the K/16 MMAs of
+// layer L (every descriptor field is a compile-time constant but the two base addresses), commit to d_ready.
+template <int L>
+__device__ __forceinline__ void issue_layer(uint64_t* a_ready, uint64_t* d_ready, uint32_t& pa, uint32_t col, uint32_t w_saddr)
+{
+	using LY = Layer<L>;
+	constexpr uint32_t idesc = idesc_f16(128, LY::N);
+	constexpr uint32_t lbo = LY::N * 16;   // bytes between the two 8-wide K chunks of one instruction
+	mbar_wait(a_ready, pa);
+	pa ^= 1u;
+	fence_after();
+#pragma unroll
+	for (int j = 0; j < LY::KS; j++) {
+		const uint64_t bd = smem_desc(w_saddr + LY::off * 4 + j * 2 * lbo, lbo, 128);
+		umma_ts(col + LY::d_col, col + kColA + j * 8, bd, idesc, j > 0);
+	}
+	umma_commit(d_ready);
+}
+
+struct RowInputs {
+	uint32_t e[16];   // layer-0 operand: the row's 32 fp16 encodings
+	uint32_t v[8];    // the row's 16 view channels as fp16 pairs (layer-2 operand, K chunk 0)
+	bool kept;
+};
+
+template <int IN_KIND>
+__device__ __forceinline__ void load_enc_row(RowInputs& in, const void* __restrict__ enc, int64_t r, int64_t n)
+{
+	const bool ok = r < n;
+	if (IN_KIND == NRF_MLP_IN_ENC16_RAYDIRS) {
+		const uint4* e = reinterpret_cast<const uint4*>(enc) + r * 4;
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			const uint4 v = ok ? __ldg(e + q) : make_uint4(0u, 0u, 0u, 0u);
+			in.e[4 * q] = v.x; in.e[4 * q + 1] = v.y; in.e[4 * q + 2] = v.z; in.e[4 * q + 3] = v.w;
+		}
+	} else {
+		const float4* x = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(enc) + r * 48);
+#pragma unroll
+		for (int q = 0; q < 8; q++) {
+			const float4 v = ok ? __ldg(x + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+			in.e[2 * q] = pack_f16(v.x, v.y);
+			in.e[2 * q + 1] = pack_f16(v.z, v.w);
+		}
+	}
+}
+
+template <int IN_KIND>
+__device__ __forceinline__ void load_view_row(RowInputs& in, const void* __restrict__ enc, const float* __restrict__ ray_sh, int S,
+	const uint8_t* __restrict__ keep, int64_t r, int64_t n)
+{
+	const bool ok = r < n;
+	const float4* vp = IN_KIND == NRF_MLP_IN_ENC16_RAYDIRS ? reinterpret_cast<const float4*>(ray_sh + (ok ? r / S : 0) * 16)
+	                                                       : reinterpret_cast<const float4*>(reinterpret_cast<const float*>(enc) + (ok ? r : 0) * 48 + 32);
+#pragma unroll
+	for (int q = 0; q < 4; q++) {
+		const float4 v = __ldg(vp + q);
+		in.v[2 * q] = pack_f16(v.x, v.y);
+		in.v[2 * q + 1] = pack_f16(v.z, v.w);
+	}
+	in.kept = !(keep && ok && !keep[r]);
+}
+
+// publish the A operand this warp just wrote to TMEM: one mbarrier arrival per warp
+__device__ __forceinline__ void publish_a(uint64_t* a_ready, int lane)
+{
+	tmem_st_wait();
+	fence_before();
+	__syncwarp();
+	if (lane == 0) mbar_arrive(a_ready);
 }
 
 template <int IN_KIND>
@@ -167,8 +236,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_small_fwd_tc_kernel(const uin
 	if (warp == 0) {
 		if (lane == 0) {
 			mbar_init(&sm.w_ready, 1);
-			for (int s = 0; s < kSlots; s++) { mbar_init(&sm.a_ready[s], 128); mbar_init(&sm.d_ready[s], 1); }
+			for (int s = 0; s < kSlots; s++) { mbar_init(&sm.a_ready[s], 4); mbar_init(&sm.d_ready[s], 1); }
 			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			// weights: one TMA bulk copy per CTA
+			mbar_expect_tx(&sm.w_ready, kUmmaWords * 4);
+			tma_bulk_g2s(sm.w, blob + kUmmaBase, kUmmaWords * 4, &sm.w_ready);
 		}
 		__syncwarp();
 		tmem_alloc_all(&sm.tmem_base);
@@ -178,147 +250,89 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_small_fwd_tc_kernel(const uin
 	fence_after();
 	const uint32_t tmem = sm.tmem_base;
 
-	if (warp == 0) {
-		if (lane == 0) {
-			// ===== weights: one TMA bulk copy, then the MMA issue loop =====
-			mbar_expect_tx(&sm.w_ready, kUmmaWords * 4);
-			tma_bulk_g2s(sm.w, blob + kUmmaBase, kUmmaWords * 4, &sm.w_ready);
-			mbar_wait(&sm.w_ready, 0);
-			const uint32_t w_saddr = smem_u32(sm.w);
-			int64_t steps_left[kSlots];
-			uint32_t step[kSlots];
-			int64_t remaining = 0;
-			for (int s = 0; s < kSlots; s++) {
-				// pipeline s of CTA b handles tiles b + gridDim.x * (s + kSlots * i)
-				const int64_t first = blockIdx.x + static_cast<int64_t>(gridDim.x) * s;
-				const int64_t stride = static_cast<int64_t>(gridDim.x) * kSlots;
-				const int64_t cnt = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
-				steps_left[s] = cnt * 5;
-				step[s] = 0;
-				remaining += steps_left[s];
-			}
-			while (remaining > 0) {
-#pragma unroll
-				for (int s = 0; s < kSlots; s++) {
-					if (steps_left[s] == 0 || !mbar_test(&sm.a_ready[s], step[s] & 1)) continue;
-					fence_after();
-					const LayerDesc L = layer_desc(static_cast<int>(step[s] % 5));
-					const uint32_t col = tmem + s * kSlotCols;
-					const uint32_t idesc = idesc_f16(128, L.N);
-					const uint32_t lbo = L.N * 16;   // bytes between the two 8-wide K chunks of one instruction
-#pragma unroll 4
-					for (int j = 0; j < L.KS; j++) {
-						const uint64_t bd = smem_desc(w_saddr + L.word_off * 4 + j * 2 * lbo, lbo, 128);
-						umma_ts(col + L.d_col, col + kColA + j * 8, bd, idesc, j > 0);
-					}
-					umma_commit(&sm.d_ready[s]);
-					step[s]++;
-					steps_left[s]--;
-					remaining--;
-				}
-			}
-		}
-	} else {
-		// ===== epilogue / load / store threads: one per row of the slot's 128-row tile =====
-		const int s = (warp - 1) >> 2;
-		const int row = ((warp & 3) << 5) | lane;                       // TMEM lane == row inside the tile
-		const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) << 5) << 16) + s * kSlotCols;
-		uint32_t ph = 0;                                                // completed uses of d_ready[s]
-		const int64_t stride = static_cast<int64_t>(gridDim.x) * kSlots;
-		for (int64_t tile = blockIdx.x + static_cast<int64_t>(gridDim.x) * s; tile < n_tiles; tile += stride) {
-			const int64_t r = tile * 128 + row;
-			const bool ok = r < n;
-			uint32_t a16[16];
-			// ---- layer 0 operand: the 32 fp16 encodings of this row
-			if (IN_KIND == NRF_MLP_IN_ENC16_RAYDIRS) {
-				const uint4* e = reinterpret_cast<const uint4*>(enc) + r * 4;
-#pragma unroll
-				for (int q = 0; q < 4; q++) {
-					const uint4 v = ok ? __ldg(e + q) : make_uint4(0u, 0u, 0u, 0u);
-					a16[4 * q] = v.x; a16[4 * q + 1] = v.y; a16[4 * q + 2] = v.z; a16[4 * q + 3] = v.w;
-				}
-			} else {
-				const float4* x = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(enc) + r * 48);
-#pragma unroll
-				for (int q = 0; q < 8; q++) {
-					const float4 v = ok ? __ldg(x + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-					a16[2 * q] = pack_f16(v.x, v.y);
-					a16[2 * q + 1] = pack_f16(v.z, v.w);
-				}
-			}
-			tmem_st16(t_lane + kColA, a16);
-			// the 16 view channels of this row (per-ray SH table or the tail of the cat input), kept for layer 2
-			uint32_t v16[8];
-			{
-				const float4* vp = IN_KIND == NRF_MLP_IN_ENC16_RAYDIRS ? reinterpret_cast<const float4*>(ray_sh + (ok ? r / S : 0) * 16)
-				                                                       : reinterpret_cast<const float4*>(reinterpret_cast<const float*>(enc) + (ok ? r : 0) * 48 + 32);
-#pragma unroll
-				for (int q = 0; q < 4; q++) {
-					const float4 v = __ldg(vp + q);
-					v16[2 * q] = pack_f16(v.x, v.y);
-					v16[2 * q + 1] = pack_f16(v.z, v.w);
-				}
-			}
-			const bool kept = !(keep && ok && !keep[r]);
-			tmem_st_wait();
-			fence_before();
-			mbar_arrive(&sm.a_ready[s]);
+	// ===== slot s = warps 4s..4s+3: one thread per row of the slot's 128-row tile; lane 0 of the slot's first warp also issues =====
+	const int s = warp >> 2;
+	const int row = ((warp & 3) << 5) | lane;                       // TMEM lane == row inside the tile
+	const uint32_t col = tmem + s * kSlotCols;
+	const uint32_t t_lane = col + (static_cast<uint32_t>((warp & 3) << 5) << 16);
+	const bool issuer = (warp & 3) == 0 && lane == 0;
+	uint64_t* const a_ready = &sm.a_ready[s];
+	uint64_t* const d_ready = &sm.d_ready[s];
+	const uint32_t w_saddr = smem_u32(sm.w);
+	uint32_t pa = 0, pd = 0;                                        // phase parities of a_ready (issuer) / d_ready (everyone)
+	const int64_t stride = static_cast<int64_t>(gridDim.x) * kSlots;
+	int64_t tile = blockIdx.x + static_cast<int64_t>(gridDim.x) * s;
 
-			uint32_t acc[32];
-			// ---- layer 0 -> h0 = relu(.) as the K=64 operand of layer 1
-			mbar_wait(&sm.d_ready[s], ph++ & 1);
-			fence_after();
-#pragma unroll
-			for (int h = 0; h < 2; h++) {
-				tmem_ld32(t_lane + kColD + 32 * h, acc);
-				tmem_ld_wait();
-				relu_pack(acc, a16);
-				tmem_st16(t_lane + kColA + 16 * h, a16);
-			}
-			tmem_st_wait();
-			fence_before();
-			mbar_arrive(&sm.a_ready[s]);
+	RowInputs in;
+	if (tile < n_tiles) load_enc_row<IN_KIND>(in, enc, tile * 128 + row, n);
+	if (issuer) mbar_wait(&sm.w_ready, 0);
 
-			// ---- layer 1 -> [sigma | geo(15)]; colour input = [views(16) | 0 | geo(15)]
-			mbar_wait(&sm.d_ready[s], ph++ & 1);
+	for (; tile < n_tiles; tile += stride) {
+		const int64_t r = tile * 128 + row;
+		// ---- layer 0 operand
+		tmem_st16(t_lane + kColA, in.e);
+		publish_a(a_ready, lane);
+		if (issuer) issue_layer<0>(a_ready, d_ready, pa, col, w_saddr);
+
+		uint32_t acc0[32], acc1[32], a16[16];
+		// ---- layer 0 -> h0 = relu(.) as the K=64 operand of layer 1
+		mbar_wait(d_ready, pd); pd ^= 1u;
+		fence_after();
+		tmem_ld32(t_lane + kColD, acc0);
+		tmem_ld32(t_lane + kColD + 32, acc1);
+		tmem_ld_wait();
+		relu_pack(acc0, a16);
+		tmem_st16(t_lane + kColA, a16);
+		relu_pack(acc1, a16);
+		tmem_st16(t_lane + kColA + 16, a16);
+		publish_a(a_ready, lane);
+		if (issuer) issue_layer<1>(a_ready, d_ready, pa, col, w_saddr);
+		// this row's view channels (per-ray SH table: cache hits) arrive while layer 1 runs
+		load_view_row<IN_KIND>(in, enc, ray_sh, S, keep, r, n);
+
+		// ---- layer 1 -> [sigma | geo(15)]; colour input = [views(16) | 0 | geo(15)]
+		mbar_wait(d_ready, pd); pd ^= 1u;
+		fence_after();
+		uint32_t d1[16];
+		tmem_ld16(t_lane + kColD16, d1);
+		tmem_ld_wait();
+		const float sigma = __uint_as_float(d1[0]);
+		d1[0] = 0u;                                                  // sigma slot of the colour input (its weight column is zero too)
+#pragma unroll
+		for (int i = 0; i < 8; i++) { a16[i] = in.v[i]; a16[8 + i] = pack_f16(__uint_as_float(d1[2 * i]), __uint_as_float(d1[2 * i + 1])); }
+		tmem_st16(t_lane + kColA, a16);
+		publish_a(a_ready, lane);
+		const bool kept = in.kept;
+		if (issuer) issue_layer<2>(a_ready, d_ready, pa, col, w_saddr);
+
+		// ---- layers 2 and 3 -> relu -> K=64 operand of the next layer
+#pragma unroll
+		for (int l = 2; l <= 3; l++) {
+			mbar_wait(d_ready, pd); pd ^= 1u;
 			fence_after();
-			uint32_t d1[16];
-			tmem_ld16(t_lane + kColD16, d1);
+			tmem_ld32(t_lane + kColD, acc0);
+			tmem_ld32(t_lane + kColD + 32, acc1);
 			tmem_ld_wait();
-			const float sigma = __uint_as_float(d1[0]);
-			d1[0] = 0u;                                                  // sigma slot of the colour input (its weight column is zero too)
-#pragma unroll
-			for (int i = 0; i < 8; i++) { a16[i] = v16[i]; a16[8 + i] = pack_f16(__uint_as_float(d1[2 * i]), __uint_as_float(d1[2 * i + 1])); }
+			relu_pack(acc0, a16);
 			tmem_st16(t_lane + kColA, a16);
-			tmem_st_wait();
-			fence_before();
-			mbar_arrive(&sm.a_ready[s]);
-
-			// ---- layers 2 and 3 -> relu -> K=64 operand of the next layer
-#pragma unroll
-			for (int l = 2; l <= 3; l++) {
-				mbar_wait(&sm.d_ready[s], ph++ & 1);
-				fence_after();
-#pragma unroll
-				for (int h = 0; h < 2; h++) {
-					tmem_ld32(t_lane + kColD + 32 * h, acc);
-					tmem_ld_wait();
-					relu_pack(acc, a16);
-					tmem_st16(t_lane + kColA + 16 * h, a16);
-				}
-				tmem_st_wait();
-				fence_before();
-				mbar_arrive(&sm.a_ready[s]);
+			relu_pack(acc1, a16);
+			tmem_st16(t_lane + kColA + 16, a16);
+			publish_a(a_ready, lane);
+			if (issuer) {
+				if (l == 2) issue_layer<3>(a_ready, d_ready, pa, col, w_saddr);
+				else issue_layer<4>(a_ready, d_ready, pa, col, w_saddr);
 			}
-
-			// ---- layer 4 -> rgb; out = [r, g, b, sigma (0 outside the box, src/NeRFRenderer.h:188)]
-			mbar_wait(&sm.d_ready[s], ph++ & 1);
-			fence_after();
-			uint32_t c[4];
-			tmem_ld4(t_lane + kColD16, c);
-			tmem_ld_wait();
-			if (ok) *reinterpret_cast<float4*>(raw_out + r * 4) = make_float4(__uint_as_float(c[0]), __uint_as_float(c[1]), __uint_as_float(c[2]), kept ? sigma : 0.f);
+			// next tile's encodings: in flight while this tile finishes its last two layers
+			if (l == 2 && tile + stride < n_tiles) load_enc_row<IN_KIND>(in, enc, (tile + stride) * 128 + row, n);
 		}
+
+		// ---- layer 4 -> rgb; out = [r, g, b, sigma (0 outside the box, src/NeRFRenderer.h:188)]
+		mbar_wait(d_ready, pd); pd ^= 1u;
+		fence_after();
+		uint32_t c[4];
+		tmem_ld4(t_lane + kColD16, c);
+		tmem_ld_wait();
+		if (r < n) *reinterpret_cast<float4*>(raw_out + r * 4) = make_float4(__uint_as_float(c[0]), __uint_as_float(c[1]), __uint_as_float(c[2]), kept ? sigma : 0.f);
 	}
 
 	fence_before();
