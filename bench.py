@@ -30,6 +30,11 @@ N_SAMPLES, N_IMPORTANCE = 64, 128
 BBOX = (-1.5, -1.5, -1.5, 1.5, 1.5, 1.5)
 CPU_SAMPLE_RAYS = 256   # bounded sample of the 4096-ray step for the CPU arms
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/), largest launch
+NCU_TRAFFIC_BYTES = {
+    "hash_encode_fwd": 25.85e6 + 6.95e6,    # profiles/r1_hash_fwd_ncu.txt, 786 432-point launch
+    "hash_encode_bwd": 89.12e6 + 2.39e6,    # profiles/r1_hash_bwd_v2_ncu.txt
+}
 # algorithmic bytes per unit (SURVEY §8d with this repo's fp16 encoding output)
 BYTES_PER_POINT = {
     "hash_encode_fwd": 12 + 512 + 64 + 1,   # xyz in, 16 lvl x 8 corners x 2 feat x fp16 gathered, fp16 [32] out, keep byte
@@ -123,6 +128,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the captured step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -149,7 +155,7 @@ def main() -> None:
     host_batches = [tuple(t.cpu().pin_memory() for t in b) for b in dev_batches]
     stage = tuple(torch.empty_like(t) for t in dev_batches[0])
 
-    def step(batch):
+    def eager_step(batch):
         model.forward_backward(*batch)
         scale = parallel.allreduce_gradients(model.grads, world)
         model.optimizer_step(grad_scale=scale)
@@ -163,17 +169,28 @@ def main() -> None:
     timer = ops.KernelTimer()
     ops.set_timer(timer)
     for i in range(warmup):
-        step(dev_batches[i % pool])
+        eager_step(dev_batches[i % pool])
     torch.cuda.synchronize()
     ops.set_timer(None)
     breakdown = {k: {"launches_per_step": n / warmup, "ms_per_step": ms / warmup} for k, (n, ms) in timer.summary().items()}
     dominant = max(("hash_encode_fwd", "hash_encode_bwd"), key=lambda k: breakdown.get(k, {"ms_per_step": 0})["ms_per_step"])
 
-    # ---- timed region A: K steps, inputs resident in HBM; only the dominant kernel carries an event pair
-    timer = ops.KernelTimer(only=[dominant])
-    ops.set_timer(timer)
+    # ---- the step as the public API runs it: one CUDA-graph replay (two around the all-reduce when world > 1)
+    use_graph = not args.no_graph
+    if use_graph:
+        model.capture_train_step(R, world, lambda g: parallel.allreduce_gradients(g, world))
+        step = lambda batch: model.train_step_graph(*batch)   # noqa: E731
+        for i in range(3):
+            step(dev_batches[i % pool])
+        launches_per_step = model.graph_kernels_per_step
+    else:
+        step = eager_step
+        l0 = cabi.launch_count()
+        step(dev_batches[0])
+        launches_per_step = cabi.launch_count() - l0 + 1
+
+    # ---- timed region A: K steps, inputs resident in HBM
     sampler = ClockSampler(local_rank)
-    launches0 = cabi.launch_count()
     sync_all()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -183,11 +200,24 @@ def main() -> None:
     e1.record()
     sync_all()
     clocks = sampler.stop()
-    ops.set_timer(None)
-    launches = cabi.launch_count() - launches0
     ms_total = parallel.max_over_ranks(e0.elapsed_time(e1), world, dev)
-    n_launch, ms_kernel = timer.summary()[dominant]
     loss_resident = float(model.loss)
+
+    # ---- roofline leg: the same steps launched eagerly so the dominant kernel can carry a CUDA-event pair on its stream
+    # (a graph replay cannot); same buffers, same sizes, run back to back with the timed region
+    roof_steps = min(args.steps, 50)
+    timer = ops.KernelTimer(only=[dominant])
+    ops.set_timer(timer)
+    sync_all()
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record()
+    for i in range(roof_steps):
+        eager_step(dev_batches[i % pool])
+    e5.record()
+    sync_all()
+    ops.set_timer(None)
+    ms_eager = e4.elapsed_time(e5) / roof_steps
+    n_launch, ms_kernel = timer.summary()[dominant]
 
     # ---- timed region B (e2e): the public API with HOST buffers — pinned H2D of the step's rays/targets and a D2H read
     # of the loss inside the timed region, every step
@@ -197,13 +227,17 @@ def main() -> None:
     loss_host = 0.0
     for i in range(args.steps):
         hb = host_batches[i % pool]
-        for dst, src in zip(stage, hb):
-            dst.copy_(src, non_blocking=True)
-        step(stage)
+        if use_graph:
+            step(hb)                    # train_step_graph copies the pinned host rays/targets into its static inputs
+        else:
+            for dst, src in zip(stage, hb):
+                dst.copy_(src, non_blocking=True)
+            step(stage)
         loss_host = float(model.loss)   # device -> host read of the step's result
     e3.record()
     sync_all()
     ms_e2e = parallel.max_over_ranks(e2.elapsed_time(e3), world, dev)
+    launches = launches_per_step * args.steps   # kernels inside timed region A (graph: kernel nodes per replay x replays)
 
     if rank != 0:
         return
@@ -215,11 +249,15 @@ def main() -> None:
         peak_gbs, peak_src = 6650.0, "fallback B200_PROFILING.md"
     pts_per_step = R * (N_SAMPLES + N_SAMPLES + N_IMPORTANCE) if dominant == "hash_encode_fwd" else R * (N_SAMPLES + N_IMPORTANCE)
     bytes_per_step = BYTES_PER_POINT[dominant] * pts_per_step
-    launches_per_step = n_launch / args.steps
-    achieved = (bytes_per_step * args.steps / 1e9) / (ms_kernel / 1e3)
+    kl_per_step = n_launch / roof_steps
+    achieved = (bytes_per_step * roof_steps / 1e9) / (ms_kernel / 1e3)
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": None, "peak_source": peak_src, "bytes_per_launch": bytes_per_step / launches_per_step,
-                "ms_per_launch": ms_kernel / n_launch, "share_of_step": ms_kernel / ms_total}
+                "traffic": NCU_TRAFFIC_BYTES.get(dominant), "peak_source": peak_src, "bytes_per_launch": bytes_per_step / kl_per_step,
+                "ms_per_launch": ms_kernel / n_launch, "share_of_step": (ms_kernel / roof_steps) / ms_eager,
+                "timing": f"CUDA-event pair around every launch over {roof_steps} eagerly launched steps run right after the timed region "
+                          f"({ms_eager:.3f} ms/step eager)",
+                "l2_note": "the table shadow (17 MiB) is L2-resident: the kernel is bound by L2 sector throughput (one 32 B sector per 4 B gather / 8 B "
+                           "RED), not by HBM; see DESIGN.md"}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -243,7 +281,7 @@ def main() -> None:
                    "precision": "fp16 hash table reads / encodings, bf16 tensor-core MLP with fp32 accumulate, fp32 everything else"},
         "e2e": {"value": rays_total / (ms_e2e / 1e3), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches * world, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "gpu_launches": launches * world, "graph_replay": use_graph, "kernels_per_step": launches_per_step, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms_per_step"])},
         "final_loss": {"resident": loss_resident, "e2e": loss_host},
     }))

@@ -220,6 +220,17 @@ int nrf_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
                   float beta2, float eps, int32_t step, float grad_scale, int32_t zero_grad, void* shadow_f16,
                   nrf_stream stream);
 
+/* CUDA-graph replay of the optimiser: the step count, Adam bias corrections and the decayed learning rate
+ * lr0 * decay_rate^(max(step-2,0) / decay_steps) (src/NeRFExecutor.h:992-996, evaluated in the order of :986-996) live in a
+ * 16-byte device record {int32 step; float lr/(1-b1^step); float 1/sqrt(1-b2^step); float lr}, zero-initialised by the caller.
+ * nrf_adam_schedule_advance increments it ON THE DEVICE (fp64 arithmetic); nrf_adam_step_scheduled is nrf_adam_step reading it.
+ * Both only enqueue work, so one captured graph replays every training step. */
+int nrf_adam_schedule_advance(void* sched_state, float lr0, float decay_rate, float decay_steps, float beta1, float beta2,
+                              nrf_stream stream);
+int nrf_adam_step_scheduled(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const void* sched_state,
+                            float beta1, float beta2, float eps, float grad_scale, int32_t zero_grad, void* shadow_f16,
+                            nrf_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

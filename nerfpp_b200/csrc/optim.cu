@@ -48,9 +48,38 @@ __device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, 
 	return p - a.lr_over_bc1 * (m / denom);
 }
 
-__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restrict__ m,
-	float* __restrict__ v, int64_t n, AdamArgs a, int zero_grad, __half* __restrict__ shadow)
+// Device-resident schedule (nrf_adam_schedule_advance): lets a captured CUDA graph replay the optimiser with a step count,
+// bias corrections and decayed learning rate that advance on the device.
+struct AdamSchedState {
+	int32_t step;         // completed optimiser steps
+	float lr_over_bc1;    // lr / (1 - beta1^step)
+	float inv_sqrt_bc2;   // 1 / sqrt(1 - beta2^step)
+	float lr;             // decayed rate used by this step
+};
+
+__global__ void adam_schedule_kernel(AdamSchedState* st, double lr0, double decay_rate, double decay_steps, double beta1, double beta2)
 {
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	const int step = st->step + 1;
+	// src/NeRFExecutor.h:986-996: step() runs with the rate set at the END of the previous iteration, lr0 * rate^(global_step / decay_steps)
+	// with global_step counted from 0 and incremented after the update  =>  exponent (step - 2) / decay_steps, clamped at 0
+	const int e = step - 2 > 0 ? step - 2 : 0;
+	const double lr = decay_steps > 0.0 ? lr0 * pow(decay_rate, static_cast<double>(e) / decay_steps) : lr0;
+	const double bc1 = 1.0 - pow(beta1, static_cast<double>(step));
+	const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
+	st->step = step;
+	st->lr = static_cast<float>(lr);
+	st->lr_over_bc1 = static_cast<float>(lr / bc1);
+	st->inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restrict__ m,
+	float* __restrict__ v, int64_t n, AdamArgs a, int zero_grad, __half* __restrict__ shadow, const AdamSchedState* __restrict__ sched)
+{
+	if (sched) {
+		a.lr_over_bc1 = sched->lr_over_bc1;
+		a.inv_sqrt_bc2 = sched->inv_sqrt_bc2;
+	}
 	const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 4;
 	for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
 		if (i + 3 < n) {
@@ -120,7 +149,36 @@ int nrf_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
 	a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_scale = grad_scale;
 	const int64_t quads = (n + 3) / 4;
 	const int blocks = static_cast<int>(std::min<int64_t>((quads + 255) / 256, kNumSMs * 8));
-	adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, a, zero_grad, reinterpret_cast<__half*>(shadow_f16));
+	adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, a, zero_grad, reinterpret_cast<__half*>(shadow_f16), nullptr);
+	NRF_CHECK_LAUNCH("adam_kernel");
+	return NRF_OK;
+}
+
+int nrf_adam_schedule_advance(void* sched_state, float lr0, float decay_rate, float decay_steps, float beta1, float beta2, nrf_stream stream)
+{
+	NRF_REQUIRE(sched_state != nullptr, "null schedule state");
+	NRF_REQUIRE((reinterpret_cast<uintptr_t>(sched_state) & 15) == 0, "schedule state must be 16-byte aligned");
+	adam_schedule_kernel<<<1, 32, 0, as_stream(stream)>>>(reinterpret_cast<AdamSchedState*>(sched_state), lr0, decay_rate, decay_steps, beta1, beta2);
+	NRF_CHECK_LAUNCH("adam_schedule_kernel");
+	return NRF_OK;
+}
+
+int nrf_adam_step_scheduled(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const void* sched_state, float beta1,
+	float beta2, float eps, float grad_scale, int32_t zero_grad, void* shadow_f16, nrf_stream stream)
+{
+	NRF_REQUIRE(n >= 0, "bad size");
+	if (n == 0) return NRF_OK;
+	NRF_REQUIRE(param && grad && exp_avg && exp_avg_sq && sched_state, "null pointer");
+	NRF_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
+	              reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0, "buffers must be 16-byte aligned");
+	NRF_REQUIRE(!shadow_f16 || (reinterpret_cast<uintptr_t>(shadow_f16) & 7) == 0, "shadow must be 8-byte aligned");
+	AdamArgs a;
+	a.lr_over_bc1 = 0.f; a.inv_sqrt_bc2 = 0.f;   // taken from sched_state on the device
+	a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_scale = grad_scale;
+	const int64_t quads = (n + 3) / 4;
+	const int blocks = static_cast<int>(std::min<int64_t>((quads + 255) / 256, kNumSMs * 8));
+	adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, a, zero_grad, reinterpret_cast<__half*>(shadow_f16),
+		reinterpret_cast<const AdamSchedState*>(sched_state));
 	NRF_CHECK_LAUNCH("adam_kernel");
 	return NRF_OK;
 }

@@ -281,3 +281,14 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.99,
     n = param.numel() if n is None else n
     _run("adam_step", lambda: lib().nrf_adam_step(ptr(param, f32), ptr(grad, f32), ptr(exp_avg, f32), ptr(exp_avg_sq, f32), n, lr, beta1, beta2, eps,
                               step, grad_scale, int(zero_grad), ptr(shadow_f16), stream()))
+
+
+def adam_schedule_advance(sched_state: torch.Tensor, lr0: float, decay_rate: float, decay_steps: float, beta1=0.9, beta2=0.99) -> None:
+    """sched_state: 16-byte device record (4 x 32-bit, zero-initialised) — see nrf_adam_schedule_advance."""
+    _run("adam_schedule_advance", lambda: lib().nrf_adam_schedule_advance(ptr(sched_state), lr0, decay_rate, decay_steps, beta1, beta2, stream()))
+
+
+def adam_step_scheduled(param, grad, exp_avg, exp_avg_sq, sched_state: torch.Tensor, beta1=0.9, beta2=0.99, eps=1e-15, grad_scale=1.0,
+                        zero_grad=True, shadow_f16: torch.Tensor | None = None) -> None:
+    _run("adam_step", lambda: lib().nrf_adam_step_scheduled(ptr(param, f32), ptr(grad, f32), ptr(exp_avg, f32), ptr(exp_avg_sq, f32), param.numel(),
+                              ptr(sched_state), beta1, beta2, eps, grad_scale, int(zero_grad), ptr(shadow_f16), stream()))

@@ -176,6 +176,59 @@ class HashNeRF:
         self.optimizer_step()
         return self.loss
 
+    # -- the same step as ONE CUDA-graph replay (launch-bound otherwise: ~20 kernels of 3..300 us behind ~20 ctypes calls)
+    def capture_train_step(self, n_rays: int, world: int = 1, allreduce=None):
+        """Captures forward_backward and the optimiser for a fixed ray count.  world == 1: one graph per step;
+        world > 1: graph(render + loss + backward) -> allreduce(self.grads) (eager NCCL call) -> graph(Adam + repack).
+        The step count / bias corrections / decayed rate advance on the device (nrf_adam_schedule_advance)."""
+        dev = self.device
+        self._g_in = (torch.tensor([[0.0, 0.0, 4.0]], device=dev).repeat(n_rays, 1), torch.tensor([[0.0, 0.0, -1.0]], device=dev).repeat(n_rays, 1),
+                      torch.full((n_rays, 3), 0.5, dtype=f32, device=dev))
+        self._g_world, self._g_allreduce = world, allreduce
+        self.sched = torch.zeros(4, dtype=i32, device=dev)
+        self._sched_step = -1
+        # warm-up outside the capture (one-time function attributes, level scales, allocator pools); its gradient is discarded
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self.forward_backward(*self._g_in)
+            self.grads.zero_()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from . import cabi
+        l0 = cabi.launch_count()
+        self._g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g_fb):
+            self._g_out = self.forward_backward(*self._g_in)
+            if world == 1:
+                self._optimizer_step_scheduled(1.0)
+        self._g_opt = None
+        if world > 1:
+            self._g_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._g_opt):
+                self._optimizer_step_scheduled(1.0 / world)
+        self.graph_kernels_per_step = cabi.launch_count() - l0 + 1   # + the loss memset
+        return self
+
+    def _optimizer_step_scheduled(self, grad_scale):
+        ops.adam_schedule_advance(self.sched, self.lr0, 0.1, float(self.lrate_decay * 1000))
+        ops.adam_step_scheduled(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.sched, 0.9, 0.99, 1e-15, grad_scale, True, self.shadow)
+        self.packed = ops.mlp_small_pack(self.mlp_params, out=self.packed)
+
+    def train_step_graph(self, rays_o, rays_d, target):
+        """Replay of the captured step.  Inputs may be device tensors or pinned host tensors (copied on the current stream)."""
+        if self._sched_step != self.step:          # eager steps ran in between: re-seed the device-side step counter
+            self.sched[0:1].copy_(torch.tensor([self.step], dtype=i32), non_blocking=False)
+        for dst, src in zip(self._g_in, (rays_o, rays_d, target)):
+            dst.copy_(src, non_blocking=True)
+        self._g_fb.replay()
+        if self._g_opt is not None:
+            self._g_allreduce(self.grads)
+            self._g_opt.replay()
+        self.step += 1
+        self._sched_step = self.step
+        return self.loss
+
 
 def synthetic_rays(n, h=800, w=800, device="cuda", seed=0, radius=4.0):
     """Random pixels of an h x w pinhole view on a radius-4 sphere pose (BASELINE C2): pixel sampling as
