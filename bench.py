@@ -239,6 +239,35 @@ def main() -> None:
     ms_e2e = parallel.max_over_ranks(e2.elapsed_time(e3), world, dev)
     launches = launches_per_step * args.steps   # kernels inside timed region A (graph: kernel nodes per replay x replays)
 
+    # ---- render leg (BASELINE C4): one 1920x1080 frame, image rows sharded over the ranks, 64 coarse + 64 importance samples
+    # (the fine pass evaluates 128 samples/ray), no communication until the final gather of the maps to rank 0
+    import math
+    H, W = 1080, 1920
+    focal = 0.5 * W / math.tan(0.5 * 0.6911)
+    K = [[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]]
+    c2w = torch.eye(4)
+    c2w[2, 3] = 4.0
+    r0, r1 = parallel.shard_bounds(H, rank, world)
+    frames = 3
+
+    def render_frame():
+        maps = model.render_image(H, W, K, c2w, chunk=32768, row_begin=r0, row_end=r1, n_importance=64)
+        return parallel.gather_rows(maps["rgb"], H * W, rank, world, unit=W) if world > 1 else maps["rgb"]
+
+    render_frame()
+    sync_all()
+    e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e6.record()
+    for _ in range(frames):
+        img = render_frame()
+    e7.record()
+    sync_all()
+    ms_render = parallel.max_over_ranks(e6.elapsed_time(e7), world, dev) / frames
+    render = {"metric": "render_msamples_per_s", "value": H * W * (N_SAMPLES + N_SAMPLES + 64) / (ms_render * 1e3), "unit": "Msamples/s",
+              "frames_per_s": 1e3 / ms_render, "ms_per_frame": ms_render, "frames": frames,
+              "config": "1920x1080 frame, image rows sharded over the GPUs, 64 coarse + 64 importance samples (192 network evaluations/ray), "
+                        "32768-ray chunks, rgb gathered on rank 0; untrained (random-init) model"}
+
     if rank != 0:
         return
 
@@ -283,7 +312,7 @@ def main() -> None:
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches * world, "graph_replay": use_graph, "kernels_per_step": launches_per_step, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms_per_step"])},
-        "final_loss": {"resident": loss_resident, "e2e": loss_host},
+        "final_loss": {"resident": loss_resident, "e2e": loss_host}, "render": render,
     }))
 
 

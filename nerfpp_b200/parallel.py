@@ -52,11 +52,12 @@ def broadcast_parameters(flat_params: torch.Tensor, world: int, src: int = 0) ->
         dist.broadcast(flat_params, src=src)
 
 
-def gather_rows(local: torch.Tensor, n_total: int, rank: int, world: int, dst: int = 0) -> torch.Tensor | None:
-    """Final gather of a row-sharded map ([rows_local, ...]) onto `dst`; shards follow shard_bounds."""
+def gather_rows(local: torch.Tensor, n_total: int, rank: int, world: int, dst: int = 0, unit: int = 1) -> torch.Tensor | None:
+    """Final gather of a row-sharded map ([rows_local, ...]) onto `dst`; shards follow shard_bounds over n_total // unit
+    units of `unit` tensor rows each (unit = image width when image rows are the sharded unit)."""
     if world == 1:
         return local
-    shapes = [shard_bounds(n_total, r, world) for r in range(world)]
+    shapes = [tuple(unit * v for v in shard_bounds(n_total // unit, r, world)) for r in range(world)]
     if rank == dst:
         parts = [torch.empty((e - b,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) for b, e in shapes]
         dist.gather(local.contiguous(), parts, dst=dst)

@@ -99,6 +99,7 @@ class HashNeRF:
         self.t_vals = torch.linspace(0.0, 1.0, n_samples, dtype=f32).to(device)                  # src/NeRFRenderer.h:393
         self.u = torch.linspace(0.0, 1.0, n_importance, dtype=f32).to(device)                    # src/Sampler.h:20
         self.loss = torch.zeros(1, dtype=f32, device=device)
+        self._u_cache = {}
         self.refresh()
 
     # -- views into the flat buffers
@@ -129,13 +130,18 @@ class HashNeRF:
         raw = ops.mlp_small_fwd(self.packed, enc, ray_sh, s, keep)
         return pts, enc, keep, raw.view(-1, s, 4)
 
-    def render_rays(self, rays_o, rays_d, white_bkgr=False, keep_for_backward=False):
+    def render_rays(self, rays_o, rays_d, white_bkgr=False, keep_for_backward=False, n_importance=None):
         ray_batch = ops.rays_prepare(rays_o, rays_d, self.bbox, 0.0, True)
         ray_sh = ops.sh_encode(ray_batch[:, 8:11], self.sh_degree)
         z = ops.z_sample(ray_batch, self.t_vals)
         _, _, _, raw = self._network(ray_batch, z, ray_sh)
         coarse = ops.composite_fwd(raw, z, rays_d, white_bkgr)
-        z_fine = ops.sample_pdf_merge(z, coarse["weights"], self.u)
+        u = self.u
+        if n_importance is not None and n_importance != self.N:
+            u = self._u_cache.get(n_importance)
+            if u is None:
+                u = self._u_cache[n_importance] = torch.linspace(0.0, 1.0, n_importance, dtype=f32).to(self.device)
+        z_fine = ops.sample_pdf_merge(z, coarse["weights"], u)
         pts, enc, keep, raw = self._network(ray_batch, z_fine, ray_sh)
         out = ops.composite_fwd(raw, z_fine, rays_d, white_bkgr)
         out["z"] = z_fine
@@ -143,10 +149,11 @@ class HashNeRF:
             out["_saved"] = (pts, enc, keep, raw, ray_sh)
         return out
 
-    def render_image(self, h, w, K, c2w, chunk=1 << 18, row_begin=0, row_end=None, white_bkgr=False):
+    def render_image(self, h, w, K, c2w, chunk=1 << 18, row_begin=0, row_end=None, white_bkgr=False, n_importance=None):
         """Render(h,w,K,c2w) for image rows [row_begin,row_end) (src/NeRFRenderer.h:540-547, RenderPath :684)."""
         rays_o, rays_d = ops.get_rays(h, w, K, c2w, row_begin, row_end, self.device)
-        outs = [self.render_rays(rays_o[i:i + chunk], rays_d[i:i + chunk], white_bkgr) for i in range(0, rays_o.shape[0], chunk)]
+        outs = [self.render_rays(rays_o[i:i + chunk], rays_d[i:i + chunk], white_bkgr, n_importance=n_importance)
+                for i in range(0, rays_o.shape[0], chunk)]
         return {k: torch.cat([o[k] for o in outs], 0) for k in ("rgb", "depth", "disp", "acc")}
 
     # -- one optimisation step (src/NeRFExecutor.h:868-890, 923, 986-996)

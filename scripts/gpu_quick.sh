@@ -21,4 +21,4 @@ for what in "$@"; do
              python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_$K.log 2>&1; echo "ncu $K exit $?";;
   esac
 done
-[ -f $OUT/pytest_gpu.log ] && tail -25 $OUT/pytest_gpu.log
+if [ -f $OUT/pytest_gpu.log ]; then tail -25 $OUT/pytest_gpu.log; fi
