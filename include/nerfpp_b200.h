@@ -95,6 +95,22 @@ typedef enum nrf_grad_layout {
 int nrf_hash_encode_bwd(const nrf_hash_grid* grid, const float* points, int64_t n_points, int clamp_points,
                         const void* grad_enc, nrf_grad_layout layout, float* grad_table, nrf_stream stream);
 
+/* Fused point generation (src/NeRFRenderer.h:419,432 + the two entries above): sample i of ray r is the point
+ * o_r + d_r * z[r,i], evaluated inside the kernel with ATen's un-fused rounding (mul, then add) from ray_batch [R, ray_stride]
+ * (o at columns 0..2, d at 3..5) and z [R,S]; the [R,S,3] point array is never materialised.  n_rays * n_samples < 2^31.
+ *
+ * Row reuse (forward only; reuse_perm NULL to disable): reuse_perm [R, S] int16 is nrf_sample_pdf_merge_perm's output for this
+ * merged z (S = n_importance + reuse_samples).  The reuse_samples coarse samples whose z it reports as bit-identical are not
+ * gathered again: their rows (and keep flags) are copied from the coarse call's output reuse_enc [R, reuse_samples, L*F] (same
+ * layout) / reuse_keep [R, reuse_samples] — same point, same table, same bits; all other samples are encoded as usual. */
+int nrf_hash_encode_rays_fwd(const nrf_hash_grid* grid, const void* table_f16, const float* ray_batch, int32_t ray_stride,
+                             const float* z, int64_t n_rays, int32_t n_samples, int clamp_points, uint8_t* keep, void* enc_out,
+                             nrf_enc_layout layout, const int16_t* reuse_perm, const void* reuse_enc, const uint8_t* reuse_keep,
+                             int32_t reuse_samples, nrf_stream stream);
+int nrf_hash_encode_rays_bwd(const nrf_hash_grid* grid, const float* ray_batch, int32_t ray_stride, const float* z,
+                             int64_t n_rays, int32_t n_samples, int clamp_points, const void* grad_enc, nrf_grad_layout layout,
+                             float* grad_table, nrf_stream stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Direction / position encoders
  * ---------------------------------------------------------------------------------------------------------- */
@@ -176,6 +192,13 @@ int nrf_sample_pdf(const float* bins, const float* weights, int32_t n_bins, cons
 int nrf_sample_pdf_merge(const float* z_coarse, const float* weights, const float* u, int32_t u_per_ray,
                          int64_t n_rays, int32_t n_samples, int32_t n_importance, float* z_samples,
                          float* z_merged, nrf_stream stream);
+
+/* Same, and perm_out [R, n_importance + S] int16 (nullable): entry j < n_importance is the merged position of the j-th
+ * importance sample; entry n_importance + k is the merged position p of coarse sample k if z_merged[r,p] is bit-identical to
+ * z_coarse[r,k], else -(p+1) (only on degenerate rays, e.g. ones that miss the box, where fp32 z is not monotone). */
+int nrf_sample_pdf_merge_perm(const float* z_coarse, const float* weights, const float* u, int32_t u_per_ray,
+                              int64_t n_rays, int32_t n_samples, int32_t n_importance, float* z_samples,
+                              float* z_merged, int16_t* perm_out, nrf_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Rays — RayUtils / Render prologue

@@ -53,6 +53,9 @@ SIGNATURES = {
     "nrf_table_to_half": (c_int32, [_P, _P, c_int64, _P]),
     "nrf_hash_encode_fwd": (c_int32, [POINTER(HashGrid), _P, _P, c_int64, c_int32, _P, _P, c_int32, _P]),
     "nrf_hash_encode_bwd": (c_int32, [POINTER(HashGrid), _P, c_int64, c_int32, _P, c_int32, _P, _P]),
+    "nrf_hash_encode_rays_fwd": (c_int32, [POINTER(HashGrid), _P, _P, c_int32, _P, c_int64, c_int32, c_int32, _P, _P, c_int32, _P, _P, _P, c_int32, _P]),
+    "nrf_hash_encode_rays_bwd": (c_int32, [POINTER(HashGrid), _P, c_int32, _P, c_int64, c_int32, c_int32, _P, c_int32, _P, _P]),
+    "nrf_sample_pdf_merge_perm": (c_int32, [_P, _P, _P, c_int32, c_int64, c_int32, c_int32, _P, _P, _P, _P]),
     "nrf_sh_encode_fwd": (c_int32, [_P, c_int32, c_int64, c_int32, _P, _P]),
     "nrf_posenc_fwd": (c_int32, [_P, c_int64, c_int32, c_int32, POINTER(c_float), c_int32, _P, _P]),
     "nrf_mlp_small_packed_bytes": (c_int64, [POINTER(MlpSmallShape)]),

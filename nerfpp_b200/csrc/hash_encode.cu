@@ -64,6 +64,43 @@ __global__ void level_scale_kernel(int base_resolution, int finest_resolution, i
 	out[level_idx] = exp2f((log2f(finest_resolution) - log2f(base_resolution)) * float(level_idx) / float(n_levels - 1) + log2f(base_resolution));
 }
 
+// Where the sample points come from: an explicit [N,3] array, or — fused point generation, src/NeRFRenderer.h:419,432 —
+// pts = o + d * z evaluated here from the ray batch and the z values with ATen's un-fused rounding (mul, then add), so the
+// cells are those of the reference's materialised points and the [R,S,3] array never exists.
+struct PointSrc {
+	const float* points;      // [N,3] or nullptr
+	const float* ray_batch;   // [R, ray_stride]: o at 0..2, d at 3..5
+	const float* z;           // [R,S]
+	int ray_stride, S;
+};
+
+__device__ __forceinline__ void load_point(const PointSrc& ps, int64_t i, float& x, float& y, float& z)
+{
+	if (ps.points) {
+		x = ps.points[i * 3 + 0]; y = ps.points[i * 3 + 1]; z = ps.points[i * 3 + 2];
+	} else {
+		const uint32_t ray = static_cast<uint32_t>(i) / static_cast<uint32_t>(ps.S);   // N < 2^31 checked by the host
+		const float* rb = ps.ray_batch + static_cast<int64_t>(ray) * ps.ray_stride;
+		const float zi = ps.z[i];
+		x = __fadd_rn(__ldg(rb + 0), __fmul_rn(__ldg(rb + 3), zi));
+		y = __fadd_rn(__ldg(rb + 1), __fmul_rn(__ldg(rb + 4), zi));
+		z = __fadd_rn(__ldg(rb + 2), __fmul_rn(__ldg(rb + 5), zi));
+	}
+}
+
+// Rows of the fine pass that are bit-identical to rows the coarse pass already encoded (same z => same point => same
+// cells, same table).  perm [R, N+S_prev] is nrf_sample_pdf_merge_perm's output: thread t of a ray handles
+//   t <  N          the t-th importance sample: encode it, write row perm[t]
+//   t >= N, p >= 0  coarse sample t-N, found unchanged at merged position p: COPY its row (and keep flag) from the coarse pass
+//   t >= N, p <  0  coarse sample whose z moved: encode the merged position -(p+1) like any other
+// so that warps are homogeneous (all-encode or all-copy) instead of one lane in three idling through every gather.
+struct Reuse {
+	const int16_t* perm;      // [R, S] (S = N + S_prev) or nullptr
+	const void* enc;          // [R, S_prev, L*F] in the output layout
+	const uint8_t* keep;      // [R, S_prev] or nullptr
+	int S_prev;
+};
+
 struct Cell {
 	uint32_t pos[8];
 	float w[8];
@@ -147,17 +184,36 @@ __device__ __forceinline__ void unpack(const typename FeatVec<F>::type& v, float
 // F features per level; CH = levels handled per 16-byte output chunk (8 halves).
 template <int F, bool OUT_F32>
 __global__ void __launch_bounds__(256) hash_fwd_kernel(HashArgs a, const __half* __restrict__ table,
-	const float* __restrict__ points, int64_t n_points, int clamp_points, uint8_t* __restrict__ keep, void* __restrict__ out)
+	PointSrc ps, Reuse ru, int64_t n_points, int clamp_points, uint8_t* __restrict__ keep, void* __restrict__ out)
 {
 	constexpr int CH = 8 / F;
 	using V = typename FeatVec<F>::type;
 	__shared__ HashMeta m;
 	stage_meta(m, a);
 
-	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
 	if (i >= n_points) return;
 
-	float x = points[i * 3 + 0], y = points[i * 3 + 1], z = points[i * 3 + 2];
+	if (ru.perm) {
+		const uint32_t ray = static_cast<uint32_t>(i) / static_cast<uint32_t>(ps.S);
+		const int t = static_cast<int>(static_cast<uint32_t>(i) - ray * static_cast<uint32_t>(ps.S));
+		const int p = ru.perm[i];
+		const int64_t row0 = static_cast<int64_t>(ray) * ps.S;
+		if (p >= 0 && t >= ps.S - ru.S_prev) {
+			// copy the row the coarse pass produced for this very point (16-byte vectors; rows are 16-byte aligned, host-checked)
+			const int64_t from = static_cast<int64_t>(ray) * ru.S_prev + (t - (ps.S - ru.S_prev));
+			const int row_bytes = a.n_levels * F * (OUT_F32 ? 4 : 2);
+			const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(ru.enc) + from * row_bytes);
+			uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + (row0 + p) * row_bytes);
+			for (int q = 0; q < row_bytes / 16; q++) d4[q] = __ldg(s4 + q);
+			if (keep) keep[row0 + p] = ru.keep ? ru.keep[from] : 1;
+			return;
+		}
+		i = row0 + (p >= 0 ? p : -(p + 1));   // the merged position this thread encodes
+	}
+
+	float x, y, z;
+	load_point(ps, i, x, y, z);
 	if (clamp_points) {
 		const bool k = clamp_point(a, x, y, z);
 		if (keep) keep[i] = k ? 1 : 0;
@@ -241,7 +297,7 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b)
 // Any point order is handled correctly (a run is defined by adjacency, not by key equality); ray-major order is what
 // makes it pay.  The reference issues N*L*8 half2 atomics regardless.
 template <int F, bool GRAD_BF16>
-__global__ void __launch_bounds__(256) hash_bwd_kernel(HashArgs a, const float* __restrict__ points, int64_t n_points,
+__global__ void __launch_bounds__(256) hash_bwd_kernel(HashArgs a, PointSrc ps, int64_t n_points,
 	int clamp_points, const void* __restrict__ grad_enc, float* __restrict__ grad_table)
 {
 	constexpr int CH = 8 / F;   // levels per 8-value gradient chunk (16 B of bf16 / 32 B of fp32)
@@ -254,7 +310,7 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(HashArgs a, const float* 
 	const bool valid = i < n_points;   // no early return: the whole warp takes part in the shuffles
 
 	float x = 0.f, y = 0.f, z = 0.f;
-	if (valid) { x = points[i * 3 + 0]; y = points[i * 3 + 1]; z = points[i * 3 + 2]; }
+	if (valid) load_point(ps, i, x, y, z);
 	if (clamp_points) clamp_point(a, x, y, z);
 	const float qx = (x - a.min_x) / (a.max_x - a.min_x);
 	const float qy = (y - a.min_y) / (a.max_y - a.min_y);
@@ -417,23 +473,20 @@ int nrf_table_to_half(const float* table_f32, void* table_f16, int64_t n_scalars
 	return NRF_OK;
 }
 
-int nrf_hash_encode_fwd(const nrf_hash_grid* grid, const void* table_f16, const float* points, int64_t n_points,
+static int launch_hash_fwd(const nrf_hash_grid* grid, const void* table_f16, const PointSrc& ps, const Reuse& ru, int64_t n_points,
 	int clamp_points, uint8_t* keep, void* enc_out, nrf_enc_layout layout, nrf_stream stream)
 {
 	HashArgs a;
 	if (int rc = fill_args(grid, a)) return rc;
-	NRF_REQUIRE(n_points >= 0, "negative n_points");
-	if (n_points == 0) return NRF_OK;
 	NRF_REQUIRE(table_f16 && enc_out, "null table / output");
-	NRF_REQUIRE(points != nullptr, "null points");
 	NRF_REQUIRE(layout == NRF_ENC_F32 || layout == NRF_ENC_F16, "bad layout");
 	const int F = grid->n_features;
 	const unsigned blocks = static_cast<unsigned>((n_points + 255) / 256);
 	const __half* t = reinterpret_cast<const __half*>(table_f16);
 	cudaStream_t s = as_stream(stream);
 #define NRF_LAUNCH_FWD(FF)                                                                                               \
-	if (layout == NRF_ENC_F32) hash_fwd_kernel<FF, true><<<blocks, 256, 0, s>>>(a, t, points, n_points, clamp_points, keep, enc_out); \
-	else hash_fwd_kernel<FF, false><<<blocks, 256, 0, s>>>(a, t, points, n_points, clamp_points, keep, enc_out)
+	if (layout == NRF_ENC_F32) hash_fwd_kernel<FF, true><<<blocks, 256, 0, s>>>(a, t, ps, ru, n_points, clamp_points, keep, enc_out); \
+	else hash_fwd_kernel<FF, false><<<blocks, 256, 0, s>>>(a, t, ps, ru, n_points, clamp_points, keep, enc_out)
 	if (F == 2) { NRF_LAUNCH_FWD(2); }
 	else if (F == 4) { NRF_LAUNCH_FWD(4); }
 	else if (F == 8) { NRF_LAUNCH_FWD(8); }
@@ -443,22 +496,19 @@ int nrf_hash_encode_fwd(const nrf_hash_grid* grid, const void* table_f16, const 
 	return NRF_OK;
 }
 
-int nrf_hash_encode_bwd(const nrf_hash_grid* grid, const float* points, int64_t n_points, int clamp_points,
-	const void* grad_enc, nrf_grad_layout layout, float* grad_table, nrf_stream stream)
+static int launch_hash_bwd(const nrf_hash_grid* grid, const PointSrc& ps, int64_t n_points, int clamp_points, const void* grad_enc,
+	nrf_grad_layout layout, float* grad_table, nrf_stream stream)
 {
 	HashArgs a;
 	if (int rc = fill_args(grid, a)) return rc;
-	NRF_REQUIRE(n_points >= 0, "negative n_points");
-	if (n_points == 0) return NRF_OK;
-	NRF_REQUIRE(grad_table != nullptr, "null grad_table");
-	NRF_REQUIRE(points && grad_enc, "null points / grad");
+	NRF_REQUIRE(grad_table != nullptr && grad_enc != nullptr, "null grad_table / grad");
 	NRF_REQUIRE(layout == NRF_GRAD_F32 || layout == NRF_GRAD_BF16, "bad layout");
 	const int F = grid->n_features;
 	const unsigned blocks = static_cast<unsigned>((n_points + 255) / 256);
 	cudaStream_t s = as_stream(stream);
 #define NRF_LAUNCH_BWD(FF)                                                                                          \
-	if (layout == NRF_GRAD_BF16) hash_bwd_kernel<FF, true><<<blocks, 256, 0, s>>>(a, points, n_points, clamp_points, grad_enc, grad_table); \
-	else hash_bwd_kernel<FF, false><<<blocks, 256, 0, s>>>(a, points, n_points, clamp_points, grad_enc, grad_table)
+	if (layout == NRF_GRAD_BF16) hash_bwd_kernel<FF, true><<<blocks, 256, 0, s>>>(a, ps, n_points, clamp_points, grad_enc, grad_table); \
+	else hash_bwd_kernel<FF, false><<<blocks, 256, 0, s>>>(a, ps, n_points, clamp_points, grad_enc, grad_table)
 	if (F == 2) { NRF_LAUNCH_BWD(2); }
 	else if (F == 4) { NRF_LAUNCH_BWD(4); }
 	else if (F == 8) { NRF_LAUNCH_BWD(8); }
@@ -466,6 +516,60 @@ int nrf_hash_encode_bwd(const nrf_hash_grid* grid, const float* points, int64_t 
 #undef NRF_LAUNCH_BWD
 	NRF_CHECK_LAUNCH("hash_bwd_kernel");
 	return NRF_OK;
+}
+
+int nrf_hash_encode_fwd(const nrf_hash_grid* grid, const void* table_f16, const float* points, int64_t n_points,
+	int clamp_points, uint8_t* keep, void* enc_out, nrf_enc_layout layout, nrf_stream stream)
+{
+	NRF_REQUIRE(n_points >= 0, "negative n_points");
+	if (n_points == 0) { HashArgs a; return fill_args(grid, a); }
+	NRF_REQUIRE(points != nullptr, "null points");
+	const PointSrc ps{points, nullptr, nullptr, 0, 1};
+	const Reuse ru{nullptr, nullptr, nullptr, 0};
+	return launch_hash_fwd(grid, table_f16, ps, ru, n_points, clamp_points, keep, enc_out, layout, stream);
+}
+
+int nrf_hash_encode_bwd(const nrf_hash_grid* grid, const float* points, int64_t n_points, int clamp_points,
+	const void* grad_enc, nrf_grad_layout layout, float* grad_table, nrf_stream stream)
+{
+	NRF_REQUIRE(n_points >= 0, "negative n_points");
+	if (n_points == 0) { HashArgs a; return fill_args(grid, a); }
+	NRF_REQUIRE(points != nullptr, "null points");
+	const PointSrc ps{points, nullptr, nullptr, 0, 1};
+	return launch_hash_bwd(grid, ps, n_points, clamp_points, grad_enc, layout, grad_table, stream);
+}
+
+int nrf_hash_encode_rays_fwd(const nrf_hash_grid* grid, const void* table_f16, const float* ray_batch, int32_t ray_stride, const float* z,
+	int64_t n_rays, int32_t n_samples, int clamp_points, uint8_t* keep, void* enc_out, nrf_enc_layout layout, const int16_t* reuse_perm,
+	const void* reuse_enc, const uint8_t* reuse_keep, int32_t reuse_samples, nrf_stream stream)
+{
+	NRF_REQUIRE(n_rays >= 0 && n_samples >= 1 && ray_stride >= 6, "bad sizes");
+	if (n_rays == 0) { HashArgs a; return fill_args(grid, a); }
+	NRF_REQUIRE(ray_batch && z, "null ray_batch / z");
+	const int64_t n_points = n_rays * n_samples;
+	NRF_REQUIRE(n_points < (int64_t(1) << 31), "n_rays * n_samples must be < 2^31 per call");
+	Reuse ru{nullptr, nullptr, nullptr, 0};
+	if (reuse_perm) {
+		NRF_REQUIRE(grid != nullptr && reuse_enc && reuse_samples >= 1 && reuse_samples <= n_samples && n_samples < 32768, "bad reuse arguments");
+		const int row_bytes = grid->n_levels * grid->n_features * (layout == NRF_ENC_F32 ? 4 : 2);
+		NRF_REQUIRE(row_bytes % 16 == 0 && ((reinterpret_cast<uintptr_t>(reuse_enc) | reinterpret_cast<uintptr_t>(enc_out)) & 15) == 0,
+			"row reuse needs 16-byte aligned rows");
+		ru = Reuse{reuse_perm, reuse_enc, reuse_keep, reuse_samples};
+	}
+	const PointSrc ps{nullptr, ray_batch, z, ray_stride, n_samples};
+	return launch_hash_fwd(grid, table_f16, ps, ru, n_points, clamp_points, keep, enc_out, layout, stream);
+}
+
+int nrf_hash_encode_rays_bwd(const nrf_hash_grid* grid, const float* ray_batch, int32_t ray_stride, const float* z, int64_t n_rays,
+	int32_t n_samples, int clamp_points, const void* grad_enc, nrf_grad_layout layout, float* grad_table, nrf_stream stream)
+{
+	NRF_REQUIRE(n_rays >= 0 && n_samples >= 1 && ray_stride >= 6, "bad sizes");
+	if (n_rays == 0) { HashArgs a; return fill_args(grid, a); }
+	NRF_REQUIRE(ray_batch && z, "null ray_batch / z");
+	const int64_t n_points = n_rays * n_samples;
+	NRF_REQUIRE(n_points < (int64_t(1) << 31), "n_rays * n_samples must be < 2^31 per call");
+	const PointSrc ps{nullptr, ray_batch, z, ray_stride, n_samples};
+	return launch_hash_bwd(grid, ps, n_points, clamp_points, grad_enc, layout, grad_table, stream);
 }
 
 }

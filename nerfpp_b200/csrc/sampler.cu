@@ -137,7 +137,7 @@ __device__ __forceinline__ void restore_order(float* a, int n, int lane)
 // shared memory per warp: cdf[B] bins[B] zs[N] zc[S] (+ sort scratch when u is per-ray)
 __global__ void __launch_bounds__(kSamplerWarps * 32) sample_pdf_merge_kernel(const float* __restrict__ z_coarse,
 	const float* __restrict__ weights, const float* __restrict__ u, int u_per_ray, int64_t R, int S, int N,
-	float* __restrict__ z_samples, float* __restrict__ z_merged, int per_warp_floats, int sort_pow2)
+	float* __restrict__ z_samples, float* __restrict__ z_merged, int16_t* __restrict__ perm_out, int per_warp_floats, int sort_pow2)
 {
 	extern __shared__ float smem[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -168,14 +168,28 @@ __global__ void __launch_bounds__(kSamplerWarps * 32) sample_pdf_merge_kernel(co
 		restore_order(zs, N, lane);
 		restore_order(zc, S, lane);
 		// rank merge; ties: coarse samples first
-		for (int k = lane; k < S; k += 32) out[k + lower_bound(zs, N, zc[k])] = zc[k];
-		for (int j = lane; j < N; j += 32) out[j + upper_bound(zc, S, zs[j])] = zs[j];
+		// perm_out (optional) [R, N+S]: entry j < N is the merged position of the j-th importance sample; entry N+k is the merged
+		// position p of coarse sample k when its z is still bit-identical to z_coarse[r,k] (restore_order did not move another
+		// value there), else -(p+1).  "perm >= 0 at N+k" therefore always means "same z, hence same point" — the contract the
+		// row reuse of nrf_hash_encode_rays_fwd relies on.
+		int16_t* po = perm_out ? perm_out + ray * (S + N) : nullptr;
+		for (int k = lane; k < S; k += 32) {
+			const int pos = k + lower_bound(zs, N, zc[k]);
+			out[pos] = zc[k];
+			if (po) po[N + k] = static_cast<int16_t>(zc[k] == zrow[k] ? pos : -(pos + 1));
+		}
+		for (int j = lane; j < N; j += 32) {
+			const int pos = j + upper_bound(zc, S, zs[j]);
+			out[pos] = zs[j];
+			if (po) po[j] = static_cast<int16_t>(pos);
+		}
 	} else {
 		float* scratch = zc + S;
 		for (int i = lane; i < sort_pow2; i += 32) scratch[i] = i < S ? zc[i] : (i < S + N ? zs[i - S] : __int_as_float(0x7f800000));
 		__syncwarp();
 		bitonic_sort(scratch, sort_pow2, lane);
 		for (int i = lane; i < S + N; i += 32) out[i] = scratch[i];
+		if (perm_out) for (int i = lane; i < S + N; i += 32) perm_out[ray * (S + N) + i] = static_cast<int16_t>(i < N ? i : -(i + 1));
 	}
 }
 
@@ -218,6 +232,12 @@ int nrf_sample_pdf(const float* bins, const float* weights, int32_t n_bins, cons
 int nrf_sample_pdf_merge(const float* z_coarse, const float* weights, const float* u, int32_t u_per_ray, int64_t n_rays,
 	int32_t n_samples, int32_t n_importance, float* z_samples, float* z_merged, nrf_stream stream)
 {
+	return nrf_sample_pdf_merge_perm(z_coarse, weights, u, u_per_ray, n_rays, n_samples, n_importance, z_samples, z_merged, nullptr, stream);
+}
+
+int nrf_sample_pdf_merge_perm(const float* z_coarse, const float* weights, const float* u, int32_t u_per_ray, int64_t n_rays,
+	int32_t n_samples, int32_t n_importance, float* z_samples, float* z_merged, int16_t* perm_out, nrf_stream stream)
+{
 	NRF_REQUIRE(n_samples >= 3, "n_samples must be >= 3");
 	NRF_REQUIRE(n_importance >= 1, "n_importance must be >= 1");
 	NRF_REQUIRE(n_samples + n_importance <= 1024, "n_samples + n_importance > 1024");
@@ -231,7 +251,7 @@ int nrf_sample_pdf_merge(const float* z_coarse, const float* weights, const floa
 	NRF_REQUIRE(smem <= 48 * 1024, "shared memory budget exceeded");
 	const unsigned blocks = static_cast<unsigned>((n_rays + kSamplerWarps - 1) / kSamplerWarps);
 	sample_pdf_merge_kernel<<<blocks, kSamplerWarps * 32, smem, as_stream(stream)>>>(z_coarse, weights, u, u_per_ray, n_rays,
-		n_samples, n_importance, z_samples, z_merged, per_warp, pow2);
+		n_samples, n_importance, z_samples, z_merged, perm_out, per_warp, pow2);
 	NRF_CHECK_LAUNCH("sample_pdf_merge_kernel");
 	return NRF_OK;
 }

@@ -128,6 +128,31 @@ def hash_encode_bwd(grid: HashGridSpec, points: torch.Tensor, grad_enc: torch.Te
     return grad_table
 
 
+def hash_encode_rays_fwd(grid: HashGridSpec, table_f16: torch.Tensor, ray_batch: torch.Tensor, z: torch.Tensor, clamp: bool = True,
+                         out_f16: bool = True, reuse=None):
+    """Fused point generation + encode.  reuse = (perm [R,S] int16, enc_prev [R*S_prev, D], keep_prev [R*S_prev] | None, S_prev)."""
+    r, s = z.shape
+    d = grid.n_levels * grid.n_features
+    out = torch.empty((r * s, d), dtype=f16 if out_f16 else f32, device=z.device)
+    keep = torch.empty(r * s, dtype=u8, device=z.device) if clamp else None
+    g = grid.c_struct()
+    src, enc_prev, keep_prev, s_prev = reuse if reuse is not None else (None, None, None, 0)
+    _run("hash_encode_fwd", lambda: lib().nrf_hash_encode_rays_fwd(C.byref(g), ptr(table_f16, f16), ptr(ray_batch, f32), ray_batch.shape[1], ptr(z, f32),
+                                    r, s, int(clamp), ptr(keep), ptr(out), cabi.ENC_F16 if out_f16 else cabi.ENC_F32, ptr(src, torch.int16) if src is not None else None,
+                                    ptr(enc_prev), ptr(keep_prev), s_prev, stream()))
+    return out, keep
+
+
+def hash_encode_rays_bwd(grid: HashGridSpec, ray_batch: torch.Tensor, z: torch.Tensor, grad_enc: torch.Tensor, grad_table: torch.Tensor,
+                         clamp: bool = True) -> torch.Tensor:
+    r, s = z.shape
+    layout = {f32: cabi.GRAD_F32, bf16: cabi.GRAD_BF16}[grad_enc.dtype]
+    g = grid.c_struct()
+    _run("hash_encode_bwd", lambda: lib().nrf_hash_encode_rays_bwd(C.byref(g), ptr(ray_batch, f32), ray_batch.shape[1], ptr(z, f32), r, s, int(clamp),
+                                    ptr(grad_enc), layout, ptr(grad_table, f32), stream()))
+    return grad_table
+
+
 def sh_encode(dirs: torch.Tensor, degree: int) -> torch.Tensor:
     """dirs: contiguous [N,3], or a column slice [:, a:a+3] of a contiguous [N,K] matrix (read in place, strided)."""
     n = dirs.shape[0]
@@ -224,15 +249,17 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, u: torch.Tensor) -> to
     return out
 
 
-def sample_pdf_merge(z_coarse: torch.Tensor, weights: torch.Tensor, u: torch.Tensor, want_samples: bool = False):
+def sample_pdf_merge(z_coarse: torch.Tensor, weights: torch.Tensor, u: torch.Tensor, want_samples: bool = False, want_perm: bool = False):
     r, s = z_coarse.shape
     per_ray = u.dim() == 2
     n = u.shape[-1]
     merged = torch.empty((r, s + n), dtype=f32, device=z_coarse.device)
     samples = torch.empty((r, n), dtype=f32, device=z_coarse.device) if want_samples else None
-    _run("sample_pdf_merge", lambda: lib().nrf_sample_pdf_merge(ptr(z_coarse, f32), ptr(weights, f32), ptr(u, f32), int(per_ray), r, s, n, ptr(samples),
-                                     ptr(merged), stream()))
-    return (merged, samples) if want_samples else merged
+    src = torch.empty((r, s + n), dtype=torch.int16, device=z_coarse.device) if want_perm else None
+    _run("sample_pdf_merge", lambda: lib().nrf_sample_pdf_merge_perm(ptr(z_coarse, f32), ptr(weights, f32), ptr(u, f32), int(per_ray), r, s, n, ptr(samples),
+                                     ptr(merged), ptr(src), stream()))
+    out = (merged,) + ((samples,) if want_samples else ()) + ((src,) if want_perm else ())
+    return out if len(out) > 1 else merged
 
 
 def get_rays(h: int, w: int, K, c2w, row_begin: int = 0, row_end: int | None = None, device="cuda"):

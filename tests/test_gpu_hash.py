@@ -228,6 +228,72 @@ def test_backward_full_size_ray_ordered_adjoint():
     assert abs(lhs - rhs) / (enc.double().abs() * G.double().abs()).sum().item() < 1e-4
 
 
+def _ray_batch(n_rays, seed=0):
+    from nerfpp_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    o = torch.randn(n_rays, 3, generator=g)
+    o = (4.0 * o / o.norm(dim=-1, keepdim=True)).cuda()
+    d = (-o / 4.0 + 0.2 * torch.randn(n_rays, 3, generator=g).cuda()).contiguous()
+    return ops.rays_prepare(o, d, BBOX, 0.0, True)
+
+
+def test_fused_point_generation_is_bit_identical():
+    """nrf_hash_encode_rays_fwd/_bwd (points built in-kernel from ray_batch and z) == nrf_sample_points followed by the
+    point-array entries, bit for bit (forward) / to accumulation order (backward), incl. rays that miss the box."""
+    from nerfpp_b200 import ops
+    grid = _grid()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    t16 = ops.table_to_half(torch.rand(grid.table_scalars(), generator=g, device="cuda") * 2 - 1)
+    rb = _ray_batch(300, seed=2)
+    z = ops.z_sample(rb, torch.linspace(0, 1, 77).cuda())
+    pts = ops.sample_points(rb, z)
+    e0, k0 = ops.hash_encode_fwd(grid, t16, pts.view(-1, 3), clamp=True, out_f16=True)
+    e1, k1 = ops.hash_encode_rays_fwd(grid, t16, rb, z, clamp=True, out_f16=True)
+    assert torch.equal(e0, e1) and torch.equal(k0, k1)
+    e2, _ = ops.hash_encode_rays_fwd(grid, t16, rb, z, clamp=True, out_f16=False)
+    assert torch.equal(e2, ops.hash_encode_fwd(grid, t16, pts.view(-1, 3), clamp=True)[0])
+    G = torch.randn(300 * 77, 32, generator=g, device="cuda").bfloat16()
+    g0 = torch.zeros(grid.table_scalars(), device="cuda")
+    g1 = torch.zeros_like(g0)
+    ops.hash_encode_bwd(grid, pts.view(-1, 3), G, g0)
+    ops.hash_encode_rays_bwd(grid, rb, z, G, g1)
+    assert torch.equal(g0 != 0, g1 != 0)
+    assert (g0 - g1).abs().max().item() <= 2e-6 * g0.abs().max().item()
+
+
+def test_coarse_row_reuse_is_bit_identical():
+    """The fine pass copies the encoding rows of the coarse samples it contains (same z => same point): the result must
+    equal a full re-encode bit for bit, src must name only bit-identical z, and every coarse sample must be found."""
+    from nerfpp_b200 import ops
+    grid = _grid()
+    g = torch.Generator(device="cuda").manual_seed(6)
+    t16 = ops.table_to_half(torch.rand(grid.table_scalars(), generator=g, device="cuda") * 2 - 1)
+    R, S, N = 257, 64, 128
+    rb = _ray_batch(R, seed=5)
+    rb[7, 3:6] = torch.tensor([0.0, 1.0, 0.0], device="cuda")        # a ray that misses the box: far = near + 1e-6, z not monotone in fp32
+    rb[7, 0:3] = torch.tensor([9.0, 9.0, 9.0], device="cuda")
+    rb2 = ops.rays_prepare(rb[:, 0:3].contiguous(), rb[:, 3:6].contiguous(), BBOX, 0.0, True)
+    z = ops.z_sample(rb2, torch.linspace(0, 1, S).cuda())
+    w = torch.rand(R, S, generator=g, device="cuda")
+    w[3] = 0.0
+    zf, perm = ops.sample_pdf_merge(z, w, torch.linspace(0, 1, N).cuda(), want_perm=True)
+    assert torch.equal(zf, ops.sample_pdf_merge(z, w, torch.linspace(0, 1, N).cuda()))
+    pl = perm.long()
+    pos = torch.where(pl >= 0, pl, -(pl + 1))
+    assert torch.equal(torch.sort(pos, dim=1).values, torch.arange(S + N, device="cuda").expand(R, -1))   # a permutation of the merged row
+    claimed = pl[:, N:] >= 0
+    z_at = torch.gather(zf, 1, pos[:, N:])
+    assert torch.equal(z_at[claimed], z[claimed])                      # a claimed position holds the coarse z bit for bit
+    assert bool((pl[:, :N] >= 0).all())
+    regular = (z[:, 1:] > z[:, :-1]).all(dim=1)                        # strictly increasing coarse z (rays that really cross the box)
+    assert int(regular.sum()) > R // 2 and bool(claimed[regular].all()) and not bool(claimed.all())
+    src = perm
+    enc_c, keep_c = ops.hash_encode_rays_fwd(grid, t16, rb2, z)
+    full, keep_full = ops.hash_encode_rays_fwd(grid, t16, rb2, zf)
+    fast, keep_fast = ops.hash_encode_rays_fwd(grid, t16, rb2, zf, reuse=(src, enc_c, keep_c, S))
+    assert torch.equal(full, fast) and torch.equal(keep_full, keep_fast)
+
+
 def test_against_reference_cuda_kernels(ref_cuda):
     """Live: the reference's CuHashEmbedder forward/backward kernels on the same table, primes and points."""
     if ref_cuda is None:

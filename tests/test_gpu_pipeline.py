@@ -164,6 +164,7 @@ def test_graph_replay_matches_eager_steps():
     from nerfpp_b200.pipeline import HashNeRF, synthetic_rays
     a = HashNeRF(BBOX, log2_hashmap_size=15, seed=3, lrate_decay=1)     # fast decay: the schedule matters within a few steps
     b = HashNeRF(BBOX, log2_hashmap_size=15, seed=3, lrate_decay=1)
+    c = HashNeRF(BBOX, log2_hashmap_size=15, seed=3, lrate_decay=1)     # second eager replica: the atomic-order noise floor
     assert torch.equal(a.params, b.params)
     batches = [synthetic_rays(512, seed=20 + i) for i in range(3)]
     b.capture_train_step(512)
@@ -172,19 +173,22 @@ def test_graph_replay_matches_eager_steps():
     for i in range(6):
         la.append(float(a.train_step(*batches[i % 3])))
         lb.append(float(b.train_step_graph(*batches[i % 3])))
+        c.train_step(*batches[i % 3])
     assert b.step == a.step == 6 and int(b.sched[0]) == 6
     np.testing.assert_allclose(lb, la, rtol=2e-3)
     # same arithmetic, different atomic orders.  Adam with eps = 1e-15 is sign-like, so the few entries whose gradient is a
     # cancelling sum (order-dependent sign) may move by up to 2 lr per step in either run; everything else must agree
     diff = (a.params - b.params).abs()
-    assert (diff > 1e-4).float().mean().item() < 2e-3, (diff > 1e-4).float().mean().item()
+    noise = ((a.params - c.params).abs() > 1e-4).float().mean().item()
+    frac = (diff > 1e-4).float().mean().item()
+    assert frac < max(2.0 * noise, 2e-3), (frac, noise)
     assert diff.median().item() < 1e-6
     assert torch.equal(b.shadow[:b.n_table], b.params[:b.n_table].half())
     # eager steps in between re-seed the device-side step counter
     a.train_step(*batches[0]); b.train_step(*batches[0])
     a.train_step(*batches[1]); b.train_step_graph(*batches[1])
     assert int(b.sched[0]) == 8 and b.step == 8
-    assert ((a.params - b.params).abs() > 1e-4).float().mean().item() < 4e-3
+    assert ((a.params - b.params).abs() > 1e-4).float().mean().item() < max(3.0 * noise, 4e-3)
 
 
 def test_scheduled_adam_matches_host_schedule():
@@ -204,3 +208,13 @@ def test_scheduled_adam_matches_host_schedule():
         assert int(sched[0]) == step
         np.testing.assert_allclose(sched[3:4].view(torch.float32).item(), lr, rtol=1e-6)
     np.testing.assert_allclose(pb.cpu().numpy(), pa.cpu().numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_coarse_row_reuse_leaves_the_render_unchanged():
+    m = _model()
+    o, d, _ = synthetic_rays(300, seed=4)
+    a = m.render_rays(o, d)
+    m.reuse_coarse_rows = True
+    b = m.render_rays(o, d)
+    for k in ("rgb", "depth", "acc", "weights", "z"):
+        assert torch.equal(a[k], b[k]), k
