@@ -211,6 +211,7 @@ def test_scheduled_adam_matches_host_schedule():
 
 
 def test_coarse_row_reuse_leaves_the_render_unchanged():
+    from nerfpp_b200.pipeline import synthetic_rays
     m = _model()
     o, d, _ = synthetic_rays(300, seed=4)
     a = m.render_rays(o, d)
