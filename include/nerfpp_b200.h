@@ -230,6 +230,30 @@ int nrf_tangent_scatter(float* pts, const float* z, const float* cone_angle, int
                         int64_t n_rays, int32_t n_samples, nrf_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * RenderRays for inference in one call — NeRFRenderer::RenderRays (src/NeRFRenderer.h:366-459) behind the Render prologue
+ * (:549-583) for <CuHashEmbedder, CuSHEncoder, NeRFSmall>, parity configuration (ThinRay, Perturb 0, no raw noise): ray prologue,
+ * SH per ray, z sampling, [hash encode + fused MLP], RawToOutputs, SamplePDF + merge, second network pass, RawToOutputs.
+ * Enqueues this library's kernels on `stream` into a caller-owned workspace; no allocation, no host sync (graph-capturable).
+ * t_vals [n_samples] = linspace(0,1) (src/NeRFRenderer.h:393) and u [n_importance] = linspace(0,1) (src/Sampler.h:20) are device
+ * arrays.  Outputs: rgb [R,3], depth/disp/acc [R], weights / z_out [R, n_samples+n_importance] (each nullable).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct nrf_render_config {
+	int32_t n_samples;      /* NSamples                        */
+	int32_t n_importance;   /* NImportance (>= 1)  */
+	int32_t white_bkgr;     /* WhiteBkgr                       */
+	int32_t lin_disp;       /* LinDisp                         */
+	int32_t sh_degree;      /* CuSHEncoder degree (4)          */
+	float near_plane;       /* IntersectWithAABB near clamp    */
+	float bbox[6];          /* BoundingBox (host)              */
+} nrf_render_config;
+
+int64_t nrf_render_rays_workspace_bytes(const nrf_render_config* cfg, const nrf_hash_grid* grid, int64_t n_rays);
+int nrf_render_rays_fwd(const nrf_render_config* cfg, const nrf_hash_grid* grid, const void* table_f16,
+                        const nrf_mlp_small_shape* shape, const void* packed, const float* rays_o, const float* rays_d,
+                        int64_t n_rays, const float* t_vals, const float* u, void* workspace, int64_t workspace_bytes,
+                        float* rgb, float* depth, float* disp, float* acc, float* weights, float* z_out, nrf_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Training glue restated from NeRFExecutor::Train (src/NeRFExecutor.h:883-890, 539, 986)
  * ---------------------------------------------------------------------------------------------------------- */
 /* huber_loss(pred, target, delta=1, mean): loss_out[0] += mean loss (caller zeroes), grad[n] = dLoss/dpred * grad_scale */
@@ -253,6 +277,32 @@ int nrf_adam_schedule_advance(void* sched_state, float lr0, float decay_rate, fl
 int nrf_adam_step_scheduled(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const void* sched_state,
                             float beta1, float beta2, float eps, float grad_scale, int32_t zero_grad, void* shadow_f16,
                             nrf_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Data-parallel optimiser step fused with its collectives over NVLink peer memory (no counterpart in the reference, which
+ * is single-GPU): reduce-scatter of the flat gradient + Adam on this rank's 1/world shard + all-gather of the fp16 shadow,
+ * ONE kernel per rank.  All pointer arrays hold addresses valid on THIS device for every rank's buffer (peer-mapped, e.g.
+ * torch.distributed._symmetric_memory buffer_ptrs); entry [rank] is the local one.
+ *   grads[p]       fp32 [n_total]  rank p's local gradient (summed in rank order, cleared locally at the end)
+ *   shadow_f16[p]  fp16 [n_total]  rank p's parameter shadow (the owner of a scalar writes its new value to every rank)
+ *   flags[p]       nrf_peer_flags_bytes(world) bytes, zero-initialised once (system-scope barrier words and epoch)
+ * The first n_sharded scalars (the hash table) are owned in contiguous shards of floor/ceil(n_sharded/4/world) quads; the
+ * tail [n_sharded, n_total) (the MLP weights) is updated identically on every rank.  param/exp_avg/exp_avg_sq are local
+ * fp32 [n_total]; only the owned shard and the tail are touched (non-owned table entries of `param` go stale by design:
+ * the forward reads the shadow).  Every rank must call this once per step; a missing peer releases the others after ~2 s.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define NRF_MAX_PEERS 8
+typedef struct nrf_peer_group {
+	int32_t world, rank;
+	const float* grads[NRF_MAX_PEERS];
+	void* shadow_f16[NRF_MAX_PEERS];
+	uint32_t* flags[NRF_MAX_PEERS];
+} nrf_peer_group;
+
+int64_t nrf_peer_flags_bytes(int32_t world);
+int nrf_adam_step_sharded(const nrf_peer_group* pg, float* param, float* exp_avg, float* exp_avg_sq, int64_t n_sharded,
+                          int64_t n_total, const void* sched_state, float beta1, float beta2, float eps, float grad_scale,
+                          nrf_stream stream);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,21 @@ class MlpSmallShape(Structure):
     ]
 
 
+class RenderConfig(Structure):
+    """struct nrf_render_config"""
+    _fields_ = [("n_samples", c_int32), ("n_importance", c_int32), ("white_bkgr", c_int32), ("lin_disp", c_int32), ("sh_degree", c_int32),
+                ("near_plane", c_float), ("bbox", c_float * 6)]
+
+
+NRF_MAX_PEERS = 8
+
+
+class PeerGroup(Structure):
+    """struct nrf_peer_group"""
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("grads", c_void_p * NRF_MAX_PEERS), ("shadow_f16", c_void_p * NRF_MAX_PEERS),
+                ("flags", c_void_p * NRF_MAX_PEERS)]
+
+
 # name -> (restype, argtypes); must list every symbol include/nerfpp_b200.h declares (tests/test_abi.py checks)
 _P = c_void_p
 SIGNATURES = {
@@ -74,6 +89,11 @@ SIGNATURES = {
     "nrf_tangent_scatter": (c_int32, [_P, _P, _P, c_int32, _P, c_int32, _P, _P, POINTER(c_float), c_int64, c_int32, _P]),
     "nrf_huber_fwd_bwd": (c_int32, [_P, _P, c_int64, c_float, c_float, _P, _P, _P]),
     "nrf_adam_step": (c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int32, c_float, c_int32, _P, _P]),
+    "nrf_render_rays_workspace_bytes": (c_int64, [POINTER(RenderConfig), POINTER(HashGrid), c_int64]),
+    "nrf_render_rays_fwd": (c_int32, [POINTER(RenderConfig), POINTER(HashGrid), _P, POINTER(MlpSmallShape), _P, _P, _P, c_int64, _P, _P, _P, c_int64,
+                                      _P, _P, _P, _P, _P, _P, _P]),
+    "nrf_peer_flags_bytes": (c_int64, [c_int32]),
+    "nrf_adam_step_sharded": (c_int32, [POINTER(PeerGroup), _P, _P, _P, c_int64, c_int64, _P, c_float, c_float, c_float, c_float, _P]),
     "nrf_adam_schedule_advance": (c_int32, [_P, c_float, c_float, c_float, c_float, c_float, _P]),
     "nrf_adam_step_scheduled": (c_int32, [_P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float, c_int32, _P, _P]),
 }

@@ -1,0 +1,188 @@
+// Data-parallel optimiser step as ONE kernel over NVLink peer memory: reduce-scatter of the gradient + Adam on the owned
+// shard + all-gather of the fp16 table shadow, fused (nrf_adam_step_sharded).
+//
+// The reference has no multi-GPU code; the plain data-parallel step is all-reduce(grad) [NCCL] -> dense Adam on every rank
+// (nerfpp_b200/parallel.py).  Every rank then spends the full 48 us streaming ALL 8.9 M parameters and moments, and the
+// all-reduce moves 2 (G-1)/G x 35.6 MB per GPU.  Here each rank OWNS a contiguous 1/G shard of the hash table:
+//   phase 0   system-scope barrier: every peer's gradient is complete (flags in peer memory, monotone epochs);
+//   phase 1   for the owned shard: g = sum over ranks (fixed rank order: bit-identical on every run) of the peers' gradient
+//             slices, read straight from their HBM over NVLink (ld.global on mapped peer pointers); Adam on the local fp32
+//             master / moments; the new value is rounded to fp16 and STORED INTO EVERY PEER'S SHADOW TABLE (st.global on
+//             mapped peer pointers) — the forward pass only ever reads the fp16 shadow, so fp32 never crosses the link again;
+//             the 9 344 MLP weights are not sharded: every rank reduces their gradients in the same order and keeps a replica;
+//   phase 2   system-scope barrier: all shadows written, all gradients consumed; then the local gradient is cleared.
+// Per GPU and step: (G-1)/G x 35.6 MB in, (G-1)/G x 17.8 MB out, Adam traffic / G.  Pointers come from
+// torch.distributed._symmetric_memory (plumbing); the kernel itself is plain loads/stores on peer addresses.
+#include "common.cuh"
+
+namespace nrf {
+
+struct AdamSchedState {   // optim.cu
+	int32_t step;
+	float lr_over_bc1, inv_sqrt_bc2, lr;
+};
+
+struct PeerArgs {
+	int world, rank;
+	const float* grads[NRF_MAX_PEERS];   // every rank's flat gradient (mapped peer memory; [rank] is local)
+	__half* shadow[NRF_MAX_PEERS];       // every rank's fp16 parameter shadow
+	uint32_t* flags[NRF_MAX_PEERS];      // every rank's flag block: [0,world) entry barrier, [world,2 world) exit barrier,
+	                                     // [2 world] local epoch, [2 world + 1] local release word, [2 world + 2] timeout marker
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+	uint32_t v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p)
+{
+	uint32_t v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
+// All CTAs of all ranks meet here.  CTA 0 / thread 0 raises this rank's slot in every peer's flag block to `epoch` and waits for
+// every peer's slot in the local block; the other CTAs wait for the local release word.  Needs all CTAs co-resident (grid <= SMs).
+// A rank that never arrives (crashed peer) releases the others after ~2 s with the timeout marker set instead of hanging the box.
+__device__ __forceinline__ void peer_barrier(const PeerArgs& a, int which, uint32_t epoch, uint32_t* done_counter)
+{
+	uint32_t* mine = a.flags[a.rank];
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence_system();   // this CTA's peer stores / loads are ordered before its arrival
+		const uint32_t arrived = atomicAdd(done_counter, 1u) + 1u;
+		if (arrived == gridDim.x * (2u * (epoch - 1u) + which + 1u)) {
+			// last CTA of this rank to arrive: tell the peers, wait for them, release the local CTAs
+			for (int p = 0; p < a.world; p++) st_release_sys(a.flags[p] + which * a.world + a.rank, epoch);
+			const long long t0 = clock64();
+			for (int p = 0; p < a.world; p++) {
+				while (ld_acquire_sys(mine + which * a.world + p) < epoch) {
+					if (clock64() - t0 > 4000000000LL) { mine[2 * a.world + 2] = 1u; break; }
+				}
+			}
+			st_release_sys(mine + 2 * a.world + 1, 2u * (epoch - 1u) + which + 1u);
+		} else {
+			const long long t0 = clock64();
+			while (ld_acquire_gpu(mine + 2 * a.world + 1) < 2u * (epoch - 1u) + which + 1u) {
+				if (clock64() - t0 > 6000000000LL) break;
+			}
+		}
+		__threadfence_system();
+	}
+	__syncthreads();
+}
+
+__device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, float beta1, float beta2, float eps, float lr_over_bc1,
+	float inv_sqrt_bc2)
+{
+	m = m * beta1 + g * (1.f - beta1);
+	v = v * beta2 + g * g * (1.f - beta2);
+	const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
+	return p - lr_over_bc1 * (m / denom);
+}
+
+// n_sharded: leading scalars partitioned over the ranks in contiguous shards (multiple of 4 per shard boundary);
+// [n_sharded, n_total): replicated tail (every rank reduces and updates it identically).
+__global__ void __launch_bounds__(512, 1) adam_sharded_kernel(PeerArgs a, float* __restrict__ param, float* __restrict__ m, float* __restrict__ v,
+	float* __restrict__ grad_local, int64_t n_sharded, int64_t n_total, const AdamSchedState* __restrict__ sched, float beta1, float beta2, float eps,
+	float grad_scale)
+{
+	uint32_t* mine = a.flags[a.rank];
+	__shared__ uint32_t s_epoch;
+	if (threadIdx.x == 0) s_epoch = mine[2 * a.world] + 1u;   // every CTA reads the epoch before anyone bumps it (bumped after barrier 1)
+	__syncthreads();
+	const uint32_t epoch = s_epoch;
+	uint32_t* done_counter = mine + 2 * a.world + 3;
+
+	peer_barrier(a, 0, epoch, done_counter);
+
+	const float lr_over_bc1 = sched->lr_over_bc1, inv_sqrt_bc2 = sched->inv_sqrt_bc2;
+	// shard bounds in units of 4 scalars
+	const int64_t quads = n_sharded / 4;
+	const int64_t base = quads / a.world, extra = quads % a.world;
+	const int64_t q_lo = a.rank * base + (a.rank < extra ? a.rank : extra);
+	const int64_t q_hi = q_lo + base + (a.rank < extra ? 1 : 0);
+	const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
+	for (int64_t q = q_lo + tid; q < q_hi; q += nthreads) {
+		const int64_t i = q * 4;
+		float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+		for (int p = 0; p < a.world; p++) {   // fixed order: the sum is the same on every run
+			const float4 t = *reinterpret_cast<const float4*>(a.grads[p] + i);
+			g4.x += t.x; g4.y += t.y; g4.z += t.z; g4.w += t.w;
+		}
+		float4 p4 = *reinterpret_cast<float4*>(param + i);
+		float4 m4 = *reinterpret_cast<float4*>(m + i);
+		float4 v4 = *reinterpret_cast<float4*>(v + i);
+		p4.x = adam_update(p4.x, g4.x * grad_scale, m4.x, v4.x, beta1, beta2, eps, lr_over_bc1, inv_sqrt_bc2);
+		p4.y = adam_update(p4.y, g4.y * grad_scale, m4.y, v4.y, beta1, beta2, eps, lr_over_bc1, inv_sqrt_bc2);
+		p4.z = adam_update(p4.z, g4.z * grad_scale, m4.z, v4.z, beta1, beta2, eps, lr_over_bc1, inv_sqrt_bc2);
+		p4.w = adam_update(p4.w, g4.w * grad_scale, m4.w, v4.w, beta1, beta2, eps, lr_over_bc1, inv_sqrt_bc2);
+		*reinterpret_cast<float4*>(param + i) = p4;
+		*reinterpret_cast<float4*>(m + i) = m4;
+		*reinterpret_cast<float4*>(v + i) = v4;
+		__half2 lo = __floats2half2_rn(p4.x, p4.y), hi = __floats2half2_rn(p4.z, p4.w);
+		uint2 o;
+		o.x = *reinterpret_cast<uint32_t*>(&lo);
+		o.y = *reinterpret_cast<uint32_t*>(&hi);
+		for (int p = 0; p < a.world; p++) *reinterpret_cast<uint2*>(a.shadow[p] + i) = o;   // all-gather of the fp16 shadow
+	}
+	// scalars of the sharded region that do not fill a quad (n_sharded % 4) and the replicated tail: every rank, same order
+	for (int64_t i = quads * 4 + tid; i < n_total; i += nthreads) {
+		float g = 0.f;
+		for (int p = 0; p < a.world; p++) g += a.grads[p][i];
+		float mm = m[i], vv = v[i];
+		const float pn = adam_update(param[i], g * grad_scale, mm, vv, beta1, beta2, eps, lr_over_bc1, inv_sqrt_bc2);
+		param[i] = pn; m[i] = mm; v[i] = vv;
+		a.shadow[a.rank][i] = __float2half_rn(pn);
+	}
+
+	peer_barrier(a, 1, epoch, done_counter);
+
+	// every peer has consumed this rank's gradient: clear it for the next step
+	const int64_t nq = n_total / 4;
+	for (int64_t q = tid; q < nq; q += nthreads) *reinterpret_cast<float4*>(grad_local + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+	for (int64_t i = nq * 4 + tid; i < n_total; i += nthreads) grad_local[i] = 0.f;
+	if (tid == 0) mine[2 * a.world] = epoch;
+}
+
+}  // namespace nrf
+
+using namespace nrf;
+
+extern "C" {
+
+int64_t nrf_peer_flags_bytes(int32_t world) { return world >= 1 && world <= NRF_MAX_PEERS ? (2 * world + 4) * 4 : -1; }
+
+int nrf_adam_step_sharded(const nrf_peer_group* pg, float* param, float* exp_avg, float* exp_avg_sq, int64_t n_sharded, int64_t n_total,
+	const void* sched_state, float beta1, float beta2, float eps, float grad_scale, nrf_stream stream)
+{
+	NRF_REQUIRE(pg != nullptr && pg->world >= 1 && pg->world <= NRF_MAX_PEERS && pg->rank >= 0 && pg->rank < pg->world, "bad peer group");
+	NRF_REQUIRE(n_sharded >= 0 && n_total >= n_sharded, "bad sizes");
+	if (n_total == 0) return NRF_OK;
+	NRF_REQUIRE(param && exp_avg && exp_avg_sq && sched_state, "null pointer");
+	PeerArgs a;
+	a.world = pg->world; a.rank = pg->rank;
+	for (int p = 0; p < pg->world; p++) {
+		NRF_REQUIRE(pg->grads[p] && pg->shadow_f16[p] && pg->flags[p], "null peer pointer");
+		NRF_REQUIRE(((reinterpret_cast<uintptr_t>(pg->grads[p]) & 15) | (reinterpret_cast<uintptr_t>(pg->shadow_f16[p]) & 7)) == 0, "peer buffers must be 16-byte aligned");
+		a.grads[p] = pg->grads[p];
+		a.shadow[p] = reinterpret_cast<__half*>(pg->shadow_f16[p]);
+		a.flags[p] = pg->flags[p];
+	}
+	NRF_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0,
+		"buffers must be 16-byte aligned");
+	// one CTA per SM, all co-resident: the in-kernel barriers need every CTA of the grid running
+	int sms = kNumSMs;
+	int dev = 0;
+	if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	adam_sharded_kernel<<<sms, 512, 0, as_stream(stream)>>>(a, param, exp_avg, exp_avg_sq, const_cast<float*>(a.grads[a.rank]), n_sharded, n_total,
+		reinterpret_cast<const AdamSchedState*>(sched_state), beta1, beta2, eps, grad_scale);
+	NRF_CHECK_LAUNCH("adam_sharded_kernel");
+	return NRF_OK;
+}
+
+}

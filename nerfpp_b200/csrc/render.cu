@@ -1,0 +1,95 @@
+// nrf_render_rays_fwd: RenderRays for inference (reference src/NeRFRenderer.h:366-459 with the Render prologue :549-583) as
+// ONE C-ABI call for the <CuHashEmbedder, CuSHEncoder, NeRFSmall> instantiation.
+//
+// Host-side sequencing only: it enqueues the kernels of this library on the caller's stream in the reference's order —
+//   ray prologue (viewdirs, IntersectWithAABB) -> SH per ray -> z = near(1-t)+far t -> [hash encode (points generated in-kernel)
+//   -> fused MLP (keep mask in the epilogue)] -> RawToOutputs -> SamplePDF + merge -> second network pass -> RawToOutputs
+// — into a caller-owned workspace (nrf_render_rays_workspace_bytes), with no allocation and no host synchronisation, so a tile
+// renderer needs one call per chunk of rays and the call is CUDA-graph capturable.
+#include "common.cuh"
+
+namespace nrf {
+
+static inline int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
+
+struct RenderWs {
+	int64_t ray_batch, ray_sh, z, z_fine, w_coarse, enc, keep, raw, total;
+};
+
+static RenderWs render_layout(const nrf_render_config* c, const nrf_hash_grid* g, int64_t R)
+{
+	RenderWs w;
+	const int64_t S = c->n_samples, T = c->n_samples + c->n_importance, D = static_cast<int64_t>(g->n_levels) * g->n_features;
+	const int64_t sh = static_cast<int64_t>(c->sh_degree) * c->sh_degree;
+	int64_t off = 0;
+	w.ray_batch = off; off = align256(off + R * 11 * 4);
+	w.ray_sh = off;    off = align256(off + R * sh * 4);
+	w.z = off;         off = align256(off + R * S * 4);
+	w.z_fine = off;    off = align256(off + R * T * 4);
+	w.w_coarse = off;  off = align256(off + R * S * 4);
+	w.enc = off;       off = align256(off + R * T * D * 2);
+	w.keep = off;      off = align256(off + R * T);
+	w.raw = off;       off = align256(off + R * T * 16);
+	w.total = off;
+	return w;
+}
+
+static int check_render_args(const nrf_render_config* c, const nrf_hash_grid* g)
+{
+	NRF_REQUIRE(c != nullptr && g != nullptr, "null config / grid");
+	NRF_REQUIRE(c->n_samples >= 3 && c->n_importance >= 1, "n_samples must be >= 3 and n_importance >= 1 (SURVEY §9-Q2)");
+	NRF_REQUIRE(c->sh_degree >= 1 && c->sh_degree <= 8, "sh_degree out of range");
+	return NRF_OK;
+}
+
+}  // namespace nrf
+
+using namespace nrf;
+
+extern "C" {
+
+int64_t nrf_render_rays_workspace_bytes(const nrf_render_config* cfg, const nrf_hash_grid* grid, int64_t n_rays)
+{
+	if (check_render_args(cfg, grid) != NRF_OK || n_rays < 0) return -1;
+	return render_layout(cfg, grid, n_rays).total;
+}
+
+int nrf_render_rays_fwd(const nrf_render_config* cfg, const nrf_hash_grid* grid, const void* table_f16, const nrf_mlp_small_shape* shape,
+	const void* packed, const float* rays_o, const float* rays_d, int64_t n_rays, const float* t_vals, const float* u, void* workspace,
+	int64_t workspace_bytes, float* rgb, float* depth, float* disp, float* acc, float* weights, float* z_out, nrf_stream stream)
+{
+	if (int rc = check_render_args(cfg, grid)) return rc;
+	NRF_REQUIRE(n_rays >= 0, "negative n_rays");
+	if (n_rays == 0) return NRF_OK;
+	NRF_REQUIRE(table_f16 && shape && packed && rays_o && rays_d && t_vals && u && workspace, "null pointer");
+	NRF_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+	const RenderWs w = render_layout(cfg, grid, n_rays);
+	NRF_REQUIRE(workspace_bytes >= w.total, "workspace too small (nrf_render_rays_workspace_bytes)");
+	const int S = cfg->n_samples, N = cfg->n_importance, T = S + N;
+	char* base = static_cast<char*>(workspace);
+	float* ray_batch = reinterpret_cast<float*>(base + w.ray_batch);
+	float* ray_sh = reinterpret_cast<float*>(base + w.ray_sh);
+	float* z = reinterpret_cast<float*>(base + w.z);
+	float* z_fine = z_out ? z_out : reinterpret_cast<float*>(base + w.z_fine);
+	float* w_coarse = reinterpret_cast<float*>(base + w.w_coarse);
+	void* enc = base + w.enc;
+	uint8_t* keep = reinterpret_cast<uint8_t*>(base + w.keep);
+	float* raw = reinterpret_cast<float*>(base + w.raw);
+
+	int rc;
+	if ((rc = nrf_rays_prepare(rays_o, rays_d, n_rays, cfg->bbox, cfg->near_plane, 1, ray_batch, stream))) return rc;
+	if ((rc = nrf_sh_encode_fwd(ray_batch + 8, 11, n_rays, cfg->sh_degree, ray_sh, stream))) return rc;
+	if ((rc = nrf_z_sample(ray_batch, 11, t_vals, n_rays, S, cfg->lin_disp, z, stream))) return rc;
+	// coarse pass
+	if ((rc = nrf_hash_encode_rays_fwd(grid, table_f16, ray_batch, 11, z, n_rays, S, 1, keep, enc, NRF_ENC_F16, nullptr, nullptr, nullptr, 0, stream))) return rc;
+	if ((rc = nrf_mlp_small_fwd(shape, packed, NRF_MLP_IN_ENC16_RAYDIRS, enc, ray_sh, S, keep, n_rays * S, raw, stream))) return rc;
+	if ((rc = nrf_composite_fwd(raw, 4, z, rays_d, nullptr, 0.f, cfg->white_bkgr, n_rays, S, nullptr, nullptr, nullptr, nullptr, w_coarse, stream))) return rc;
+	// importance sampling + merge, fine pass
+	if ((rc = nrf_sample_pdf_merge(z, w_coarse, u, 0, n_rays, S, N, nullptr, z_fine, stream))) return rc;
+	if ((rc = nrf_hash_encode_rays_fwd(grid, table_f16, ray_batch, 11, z_fine, n_rays, T, 1, keep, enc, NRF_ENC_F16, nullptr, nullptr, nullptr, 0, stream))) return rc;
+	if ((rc = nrf_mlp_small_fwd(shape, packed, NRF_MLP_IN_ENC16_RAYDIRS, enc, ray_sh, T, keep, n_rays * T, raw, stream))) return rc;
+	if ((rc = nrf_composite_fwd(raw, 4, z_fine, rays_d, nullptr, 0.f, cfg->white_bkgr, n_rays, T, rgb, depth, disp, acc, weights, stream))) return rc;
+	return NRF_OK;
+}
+
+}

@@ -319,3 +319,28 @@ def adam_step_scheduled(param, grad, exp_avg, exp_avg_sq, sched_state: torch.Ten
                         zero_grad=True, shadow_f16: torch.Tensor | None = None) -> None:
     _run("adam_step", lambda: lib().nrf_adam_step_scheduled(ptr(param, f32), ptr(grad, f32), ptr(exp_avg, f32), ptr(exp_avg_sq, f32), param.numel(),
                               ptr(sched_state), beta1, beta2, eps, grad_scale, int(zero_grad), ptr(shadow_f16), stream()))
+
+
+def render_rays_fwd(grid: HashGridSpec, table_f16, packed, rays_o, rays_d, t_vals, u, bbox, white_bkgr=False, sh_degree=4, near_plane=0.0,
+                    lin_disp=False, want_weights=False, want_z=False, workspace: torch.Tensor | None = None, shape=None):
+    """RenderRays (inference) as ONE C-ABI call; returns (maps, workspace) — pass the workspace back in to reuse it."""
+    shape = shape or mlp_shape()
+    r, s, n = rays_o.shape[0], t_vals.shape[0], u.shape[0]
+    cfg = cabi.RenderConfig(s, n, int(white_bkgr), int(lin_disp), sh_degree, float(near_plane))
+    for k in range(6):
+        cfg.bbox[k] = float(bbox[k])
+    g = grid.c_struct()
+    need = lib().nrf_render_rays_workspace_bytes(C.byref(cfg), C.byref(g), r)
+    if need < 0:
+        check(-1)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(max(need, 256), dtype=u8, device=rays_o.device)
+    dev = rays_o.device
+    rgb = torch.empty((r, 3), dtype=f32, device=dev)
+    depth, disp, acc = (torch.empty(r, dtype=f32, device=dev) for _ in range(3))
+    weights = torch.empty((r, s + n), dtype=f32, device=dev) if want_weights else None
+    z = torch.empty((r, s + n), dtype=f32, device=dev) if want_z else None
+    _run("render_rays_fwd", lambda: lib().nrf_render_rays_fwd(C.byref(cfg), C.byref(g), ptr(table_f16, f16), C.byref(shape), ptr(packed), ptr(rays_o, f32),
+                                    ptr(rays_d, f32), r, ptr(t_vals, f32), ptr(u, f32), ptr(workspace), workspace.numel(), ptr(rgb), ptr(depth),
+                                    ptr(disp), ptr(acc), ptr(weights), ptr(z), stream()))
+    return {"rgb": rgb, "depth": depth, "disp": disp, "acc": acc, "weights": weights, "z": z}, workspace

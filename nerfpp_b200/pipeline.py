@@ -104,6 +104,7 @@ class HashNeRF:
         # and the benchmark step then performs exactly the work the reference's step performs.
         self.reuse_coarse_rows = False
         self._u_cache = {}
+        self._render_ws = None
         self.refresh()
 
     # -- views into the flat buffers
@@ -135,17 +136,28 @@ class HashNeRF:
         raw = ops.mlp_small_fwd(self.packed, enc, ray_sh, s, keep)
         return enc, keep, raw.view(-1, s, 4)
 
+    def _u(self, n_importance):
+        if n_importance is None or n_importance == self.N:
+            return self.u
+        u = self._u_cache.get(n_importance)
+        if u is None:
+            u = self._u_cache[n_importance] = torch.linspace(0.0, 1.0, n_importance, dtype=f32).to(self.device)
+        return u
+
+    def render_rays_fused(self, rays_o, rays_d, white_bkgr=False, n_importance=None, want_weights=False, want_z=False):
+        """Inference RenderRays as ONE C-ABI call (nrf_render_rays_fwd) into a cached workspace."""
+        out, self._render_ws = ops.render_rays_fwd(self.grid, self.table_f16, self.packed, rays_o, rays_d, self.t_vals, self._u(n_importance),
+                                                   self.bbox, white_bkgr, self.sh_degree, want_weights=want_weights, want_z=want_z,
+                                                   workspace=self._render_ws)
+        return out
+
     def render_rays(self, rays_o, rays_d, white_bkgr=False, keep_for_backward=False, n_importance=None):
         ray_batch = ops.rays_prepare(rays_o, rays_d, self.bbox, 0.0, True)
         ray_sh = ops.sh_encode(ray_batch[:, 8:11], self.sh_degree)
         z = ops.z_sample(ray_batch, self.t_vals)
         enc_c, keep_c, raw = self._network(ray_batch, z, ray_sh)
         coarse = ops.composite_fwd(raw, z, rays_d, white_bkgr)
-        u = self.u
-        if n_importance is not None and n_importance != self.N:
-            u = self._u_cache.get(n_importance)
-            if u is None:
-                u = self._u_cache[n_importance] = torch.linspace(0.0, 1.0, n_importance, dtype=f32).to(self.device)
+        u = self._u(n_importance)
         # the merged list contains the coarse samples bit for bit: optionally their encoding rows are copied, not gathered again
         if self.reuse_coarse_rows:
             z_fine, perm = ops.sample_pdf_merge(z, coarse["weights"], u, want_perm=True)
@@ -162,7 +174,7 @@ class HashNeRF:
     def render_image(self, h, w, K, c2w, chunk=1 << 18, row_begin=0, row_end=None, white_bkgr=False, n_importance=None):
         """Render(h,w,K,c2w) for image rows [row_begin,row_end) (src/NeRFRenderer.h:540-547, RenderPath :684)."""
         rays_o, rays_d = ops.get_rays(h, w, K, c2w, row_begin, row_end, self.device)
-        outs = [self.render_rays(rays_o[i:i + chunk], rays_d[i:i + chunk], white_bkgr, n_importance=n_importance)
+        outs = [self.render_rays_fused(rays_o[i:i + chunk], rays_d[i:i + chunk], white_bkgr, n_importance=n_importance)
                 for i in range(0, rays_o.shape[0], chunk)]
         return {k: torch.cat([o[k] for o in outs], 0) for k in ("rgb", "depth", "disp", "acc")}
 
