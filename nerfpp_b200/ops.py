@@ -344,3 +344,9 @@ def render_rays_fwd(grid: HashGridSpec, table_f16, packed, rays_o, rays_d, t_val
                                     ptr(rays_d, f32), r, ptr(t_vals, f32), ptr(u, f32), ptr(workspace), workspace.numel(), ptr(rgb), ptr(depth),
                                     ptr(disp), ptr(acc), ptr(weights), ptr(z), stream()))
     return {"rgb": rgb, "depth": depth, "disp": disp, "acc": acc, "weights": weights, "z": z}, workspace
+
+
+def adam_step_sharded(peer_group, param, exp_avg, exp_avg_sq, n_sharded: int, sched_state, beta1=0.9, beta2=0.99, eps=1e-15, grad_scale=1.0) -> None:
+    """reduce-scatter + Adam + fp16 shadow all-gather over peer memory (nrf_adam_step_sharded); peer_group: cabi.PeerGroup."""
+    _run("adam_step", lambda: lib().nrf_adam_step_sharded(C.byref(peer_group), ptr(param, f32), ptr(exp_avg, f32), ptr(exp_avg_sq, f32), n_sharded,
+                              param.numel(), ptr(sched_state), beta1, beta2, eps, grad_scale, stream()))

@@ -72,3 +72,48 @@ def max_over_ranks(value: float, world: int, device) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+class PeerShardedOptimizer:
+    """Plumbing for nrf_adam_step_sharded: allocates the model's flat gradient, its fp16 shadow and a flag block in
+    torch.distributed symmetric memory (peer-mapped over NVLink), exchanges the peer addresses, and re-points the model at
+    those buffers.  After this, one kernel per rank performs reduce-scatter(grad) + Adam(owned shard) + all-gather(fp16 shadow);
+    NCCL is not on the training path any more (it still does the one-off parameter broadcast and the final render gather)."""
+
+    def __init__(self, model, rank: int, world: int, group=None):
+        import torch.distributed._symmetric_memory as symm
+        from . import cabi
+        group = group or dist.group.WORLD
+        dev = model.device
+        n = model.params.numel()
+        try:                                   # older torch releases need the group enabled explicitly
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:                      # noqa: BLE001
+            pass
+        self.grads = symm.empty(n, dtype=torch.float32, device=dev)
+        self.shadow = symm.empty(n, dtype=torch.float16, device=dev)
+        n_flags = max(int(cabi.lib().nrf_peer_flags_bytes(world)) // 4, 64)
+        self.flags = symm.empty(n_flags, dtype=torch.int32, device=dev)
+        self.grads.zero_()
+        self.flags.zero_()
+        self.shadow.copy_(model.shadow)
+        handles = [symm.rendezvous(t, group.group_name) for t in (self.grads, self.shadow, self.flags)]
+        pg = cabi.PeerGroup()
+        pg.world, pg.rank = world, rank
+        for field, h, t in zip(("grads", "shadow_f16", "flags"), handles, (self.grads, self.shadow, self.flags)):
+            ptrs = list(h.buffer_ptrs)
+            off = t.data_ptr() - ptrs[rank]    # offset of the tensor inside this rank's symmetric block (same on every rank)
+            assert 0 <= off < (1 << 40), "symmetric-memory tensor is not inside its own block"
+            for p in range(world):
+                getattr(pg, field)[p] = ptrs[p] + off
+        self.pg, self.handles, self.rank, self.world = pg, handles, rank, world
+        self.multicast = bool(getattr(handles[0], "has_multicast_support", False))
+        model.grads, model.shadow = self.grads, self.shadow
+        model.peer = self
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)
+
+    def shard_bounds(self, n_sharded: int) -> tuple[int, int]:
+        """[begin, end) scalars of the table this rank owns (same split as the kernel: quads, first ranks one extra)."""
+        b, e = shard_bounds(n_sharded // 4, self.rank, self.world)
+        return 4 * b, 4 * e

@@ -105,6 +105,8 @@ class HashNeRF:
         self.reuse_coarse_rows = False
         self._u_cache = {}
         self._render_ws = None
+        self.peer = None          # parallel.PeerShardedOptimizer when the fused data-parallel optimiser is in use
+        self.sched = None
         self.refresh()
 
     # -- views into the flat buffers
@@ -214,8 +216,7 @@ class HashNeRF:
         self._g_in = (torch.tensor([[0.0, 0.0, 4.0]], device=dev).repeat(n_rays, 1), torch.tensor([[0.0, 0.0, -1.0]], device=dev).repeat(n_rays, 1),
                       torch.full((n_rays, 3), 0.5, dtype=f32, device=dev))
         self._g_world, self._g_allreduce = world, allreduce
-        self.sched = torch.zeros(4, dtype=i32, device=dev)
-        self._sched_step = -1
+        self._init_sched()
         # warm-up outside the capture (one-time function attributes, level scales, allocator pools); its gradient is discarded
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -231,13 +232,44 @@ class HashNeRF:
             self._g_out = self.forward_backward(*self._g_in)
             if world == 1:
                 self._optimizer_step_scheduled(1.0)
+            elif self.peer is not None:
+                self._optimizer_step_sharded()
         self._g_opt = None
-        if world > 1:
+        if world > 1 and self.peer is None:
             self._g_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._g_opt):
                 self._optimizer_step_scheduled(1.0 / world)
         self.graph_kernels_per_step = cabi.launch_count() - l0 + 1   # + the loss memset
         return self
+
+    def _init_sched(self):
+        if self.sched is None:
+            self.sched = torch.zeros(4, dtype=i32, device=self.device)
+            self._sched_step = -1
+
+    def _sync_sched(self):
+        if self._sched_step != self.step:          # eager steps ran in between: re-seed the device-side step counter
+            self.sched[0:1].copy_(torch.tensor([self.step], dtype=i32), non_blocking=False)
+            self._sched_step = self.step
+
+    def _optimizer_step_sharded(self):
+        """Data-parallel step without NCCL: one kernel per rank over NVLink peer memory (parallel.PeerShardedOptimizer)."""
+        ops.adam_schedule_advance(self.sched, self.lr0, 0.1, float(self.lrate_decay * 1000))
+        ops.adam_step_sharded(self.peer.pg, self.params, self.exp_avg, self.exp_avg_sq, self.n_table, self.sched, 0.9, 0.99, 1e-15,
+                              1.0 / self.peer.world)
+        self.packed = ops.mlp_small_pack(self.mlp_params, out=self.packed)
+
+    def flags_timeout(self) -> int:
+        """1 if a peer barrier of the fused optimiser ever gave up waiting (a rank missed a step), else 0."""
+        return int(self.peer.flags[2 * self.peer.world + 2]) if self.peer is not None else 0
+
+    def optimizer_step_sharded(self):
+        """Eager (non-graph) entry of the fused data-parallel optimiser step."""
+        self._init_sched()
+        self._sync_sched()
+        self._optimizer_step_sharded()
+        self.step += 1
+        self._sched_step = self.step
 
     def _optimizer_step_scheduled(self, grad_scale):
         ops.adam_schedule_advance(self.sched, self.lr0, 0.1, float(self.lrate_decay * 1000))
@@ -246,8 +278,7 @@ class HashNeRF:
 
     def train_step_graph(self, rays_o, rays_d, target):
         """Replay of the captured step.  Inputs may be device tensors or pinned host tensors (copied on the current stream)."""
-        if self._sched_step != self.step:          # eager steps ran in between: re-seed the device-side step counter
-            self.sched[0:1].copy_(torch.tensor([self.step], dtype=i32), non_blocking=False)
+        self._sync_sched()
         for dst, src in zip(self._g_in, (rays_o, rays_d, target)):
             dst.copy_(src, non_blocking=True)
         self._g_fb.replay()
