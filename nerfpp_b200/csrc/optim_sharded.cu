@@ -86,54 +86,72 @@ __device__ __forceinline__ float adam_update(float p, float g, float& m, float& 
 
 // n_sharded: leading scalars partitioned over the ranks in contiguous shards (multiple of 4 per shard boundary);
 // [n_sharded, n_total): replicated tail (every rank reduces and updates it identically).
+// WORLD is a template parameter so that the peer loop unrolls and all W x U remote 16-byte loads of an iteration are in flight
+// together (NVLink round trips are ~2 us: the kernel lives on memory-level parallelism).
+template <int WORLD, int U>
 __global__ void __launch_bounds__(512, 1) adam_sharded_kernel(PeerArgs a, float* __restrict__ param, float* __restrict__ m, float* __restrict__ v,
 	float* __restrict__ grad_local, int64_t n_sharded, int64_t n_total, const AdamSchedState* __restrict__ sched, float beta1, float beta2, float eps,
 	float grad_scale)
 {
 	uint32_t* mine = a.flags[a.rank];
 	__shared__ uint32_t s_epoch;
-	if (threadIdx.x == 0) s_epoch = mine[2 * a.world] + 1u;   // every CTA reads the epoch before anyone bumps it (bumped after barrier 1)
+	if (threadIdx.x == 0) s_epoch = mine[2 * WORLD] + 1u;   // every CTA reads the epoch before anyone bumps it (bumped after barrier 1)
 	__syncthreads();
 	const uint32_t epoch = s_epoch;
-	uint32_t* done_counter = mine + 2 * a.world + 3;
+	uint32_t* done_counter = mine + 2 * WORLD + 3;
 
 	peer_barrier(a, 0, epoch, done_counter);
 
 	const float lr_over_bc1 = sched->lr_over_bc1, inv_sqrt_bc2 = sched->inv_sqrt_bc2;
 	// shard bounds in units of 4 scalars
 	const int64_t quads = n_sharded / 4;
-	const int64_t base = quads / a.world, extra = quads % a.world;
+	const int64_t base = quads / WORLD, extra = quads % WORLD;
 	const int64_t q_lo = a.rank * base + (a.rank < extra ? a.rank : extra);
 	const int64_t q_hi = q_lo + base + (a.rank < extra ? 1 : 0);
 	const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
 	const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
-	for (int64_t q = q_lo + tid; q < q_hi; q += nthreads) {
-		const int64_t i = q * 4;
-		float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-		for (int p = 0; p < a.world; p++) {   // fixed order: the sum is the same on every run
-			const float4 t = *reinterpret_cast<const float4*>(a.grads[p] + i);
-			g4.x += t.x; g4.y += t.y; g4.z += t.z; g4.w += t.w;
+	for (int64_t q0 = q_lo + tid; q0 < q_hi; q0 += nthreads * U) {
+		float4 g4[U][WORLD], p4[U], m4[U], v4[U];
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			const int64_t q = q0 + u * nthreads;
+			if (q < q_hi) {
+#pragma unroll
+				for (int p = 0; p < WORLD; p++) g4[u][p] = *reinterpret_cast<const float4*>(a.grads[p] + q * 4);
+				p4[u] = *reinterpret_cast<float4*>(param + q * 4);
+				m4[u] = *reinterpret_cast<float4*>(m + q * 4);
+				v4[u] = *reinterpret_cast<float4*>(v + q * 4);
+			}
 		}
-		float4 p4 = *reinterpret_cast<float4*>(param + i);
-		float4 m4 = *reinterpret_cast<float4*>(m + i);
-		float4 v4 = *reinterpret_cast<float4*>(v + i);
-		p4.x = adam_update(p4.x, g4.x * grad_scale, m4.x, v4.x, beta1, beta2, eps, lr_over_bc1, inv_sqrt_bc2);
-		p4.y = adam_update(p4.y, g4.y * grad_scale, m4.y, v4.y, beta1, beta2, eps, lr_over_bc1, inv_sqrt_bc2);
-		p4.z = adam_update(p4.z, g4.z * grad_scale, m4.z, v4.z, beta1, beta2, eps, lr_over_bc1, inv_sqrt_bc2);
-		p4.w = adam_update(p4.w, g4.w * grad_scale, m4.w, v4.w, beta1, beta2, eps, lr_over_bc1, inv_sqrt_bc2);
-		*reinterpret_cast<float4*>(param + i) = p4;
-		*reinterpret_cast<float4*>(m + i) = m4;
-		*reinterpret_cast<float4*>(v + i) = v4;
-		__half2 lo = __floats2half2_rn(p4.x, p4.y), hi = __floats2half2_rn(p4.z, p4.w);
-		uint2 o;
-		o.x = *reinterpret_cast<uint32_t*>(&lo);
-		o.y = *reinterpret_cast<uint32_t*>(&hi);
-		for (int p = 0; p < a.world; p++) *reinterpret_cast<uint2*>(a.shadow[p] + i) = o;   // all-gather of the fp16 shadow
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			const int64_t q = q0 + u * nthreads;
+			if (q >= q_hi) continue;
+			const int64_t i = q * 4;
+			float4 g = g4[u][0];
+#pragma unroll
+			for (int p = 1; p < WORLD; p++) { g.x += g4[u][p].x; g.y += g4[u][p].y; g.z += g4[u][p].z; g.w += g4[u][p].w; }   // fixed rank order
+			float4 pp = p4[u], mm = m4[u], vv = v4[u];
+			pp.x = adam_update(pp.x, g.x * grad_scale, mm.x, vv.x, beta1, beta2, eps, lr_over_bc1, inv_sqrt_bc2);
+			pp.y = adam_update(pp.y, g.y * grad_scale, mm.y, vv.y, beta1, beta2, eps, lr_over_bc1, inv_sqrt_bc2);
+			pp.z = adam_update(pp.z, g.z * grad_scale, mm.z, vv.z, beta1, beta2, eps, lr_over_bc1, inv_sqrt_bc2);
+			pp.w = adam_update(pp.w, g.w * grad_scale, mm.w, vv.w, beta1, beta2, eps, lr_over_bc1, inv_sqrt_bc2);
+			*reinterpret_cast<float4*>(param + i) = pp;
+			*reinterpret_cast<float4*>(m + i) = mm;
+			*reinterpret_cast<float4*>(v + i) = vv;
+			__half2 lo = __floats2half2_rn(pp.x, pp.y), hi = __floats2half2_rn(pp.z, pp.w);
+			uint2 o;
+			o.x = *reinterpret_cast<uint32_t*>(&lo);
+			o.y = *reinterpret_cast<uint32_t*>(&hi);
+#pragma unroll
+			for (int p = 0; p < WORLD; p++) *reinterpret_cast<uint2*>(a.shadow[p] + i) = o;   // all-gather of the fp16 shadow
+		}
 	}
 	// scalars of the sharded region that do not fill a quad (n_sharded % 4) and the replicated tail: every rank, same order
 	for (int64_t i = quads * 4 + tid; i < n_total; i += nthreads) {
 		float g = 0.f;
-		for (int p = 0; p < a.world; p++) g += a.grads[p][i];
+#pragma unroll
+		for (int p = 0; p < WORLD; p++) g += a.grads[p][i];
 		float mm = m[i], vv = v[i];
 		const float pn = adam_update(param[i], g * grad_scale, mm, vv, beta1, beta2, eps, lr_over_bc1, inv_sqrt_bc2);
 		param[i] = pn; m[i] = mm; v[i] = vv;
@@ -146,7 +164,7 @@ __global__ void __launch_bounds__(512, 1) adam_sharded_kernel(PeerArgs a, float*
 	const int64_t nq = n_total / 4;
 	for (int64_t q = tid; q < nq; q += nthreads) *reinterpret_cast<float4*>(grad_local + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
 	for (int64_t i = nq * 4 + tid; i < n_total; i += nthreads) grad_local[i] = 0.f;
-	if (tid == 0) mine[2 * a.world] = epoch;
+	if (tid == 0) mine[2 * WORLD] = epoch;
 }
 
 }  // namespace nrf
@@ -179,8 +197,20 @@ int nrf_adam_step_sharded(const nrf_peer_group* pg, float* param, float* exp_avg
 	int sms = kNumSMs;
 	int dev = 0;
 	if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	adam_sharded_kernel<<<sms, 512, 0, as_stream(stream)>>>(a, param, exp_avg, exp_avg_sq, const_cast<float*>(a.grads[a.rank]), n_sharded, n_total,
-		reinterpret_cast<const AdamSchedState*>(sched_state), beta1, beta2, eps, grad_scale);
+#define NRF_LAUNCH_SHARDED(W, U)                                                                                                   \
+	adam_sharded_kernel<W, U><<<sms, 512, 0, as_stream(stream)>>>(a, param, exp_avg, exp_avg_sq, const_cast<float*>(a.grads[a.rank]), \
+		n_sharded, n_total, reinterpret_cast<const AdamSchedState*>(sched_state), beta1, beta2, eps, grad_scale)
+	switch (pg->world) {
+		case 1: NRF_LAUNCH_SHARDED(1, 4); break;
+		case 2: NRF_LAUNCH_SHARDED(2, 4); break;
+		case 3: NRF_LAUNCH_SHARDED(3, 2); break;
+		case 4: NRF_LAUNCH_SHARDED(4, 2); break;
+		case 5: NRF_LAUNCH_SHARDED(5, 2); break;
+		case 6: NRF_LAUNCH_SHARDED(6, 2); break;
+		case 7: NRF_LAUNCH_SHARDED(7, 2); break;
+		default: NRF_LAUNCH_SHARDED(8, 2); break;
+	}
+#undef NRF_LAUNCH_SHARDED
 	NRF_CHECK_LAUNCH("adam_sharded_kernel");
 	return NRF_OK;
 }
