@@ -75,6 +75,16 @@ __device__ __forceinline__ void peer_barrier(const PeerArgs& a, int which, uint3
 	__syncthreads();
 }
 
+__device__ __forceinline__ uint32_t globaltimer_lo()
+{
+	uint32_t t;
+	asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(t));
+	return t;
+}
+// phase timestamps (ns, low word) of CTA 0 in words [kStampBase, kStampBase + 5) of the local flag block: kernel entry, after the
+// entry barrier, after the shard loop, after the exit barrier, after the gradient clear — read back by scripts/exp/dp_step.py
+constexpr int kStampBase = 2 * NRF_MAX_PEERS + 8;
+
 __device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, float beta1, float beta2, float eps, float lr_over_bc1,
 	float inv_sqrt_bc2)
 {
@@ -99,8 +109,11 @@ __global__ void __launch_bounds__(512, 1) adam_sharded_kernel(PeerArgs a, float*
 	__syncthreads();
 	const uint32_t epoch = s_epoch;
 	uint32_t* done_counter = mine + 2 * WORLD + 3;
+	const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
+	if (stamp) mine[kStampBase + 0] = globaltimer_lo();
 
 	peer_barrier(a, 0, epoch, done_counter);
+	if (stamp) mine[kStampBase + 1] = globaltimer_lo();
 
 	const float lr_over_bc1 = sched->lr_over_bc1, inv_sqrt_bc2 = sched->inv_sqrt_bc2;
 	// shard bounds in units of 4 scalars
@@ -158,13 +171,16 @@ __global__ void __launch_bounds__(512, 1) adam_sharded_kernel(PeerArgs a, float*
 		a.shadow[a.rank][i] = __float2half_rn(pn);
 	}
 
+	if (stamp) mine[kStampBase + 2] = globaltimer_lo();
 	peer_barrier(a, 1, epoch, done_counter);
+	if (stamp) mine[kStampBase + 3] = globaltimer_lo();
 
 	// every peer has consumed this rank's gradient: clear it for the next step
 	const int64_t nq = n_total / 4;
 	for (int64_t q = tid; q < nq; q += nthreads) *reinterpret_cast<float4*>(grad_local + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
 	for (int64_t i = nq * 4 + tid; i < n_total; i += nthreads) grad_local[i] = 0.f;
 	if (tid == 0) mine[2 * WORLD] = epoch;
+	if (stamp) mine[kStampBase + 4] = globaltimer_lo();
 }
 
 }  // namespace nrf
@@ -173,7 +189,7 @@ using namespace nrf;
 
 extern "C" {
 
-int64_t nrf_peer_flags_bytes(int32_t world) { return world >= 1 && world <= NRF_MAX_PEERS ? (2 * world + 4) * 4 : -1; }
+int64_t nrf_peer_flags_bytes(int32_t world) { return world >= 1 && world <= NRF_MAX_PEERS ? (kStampBase + 8) * 4 : -1; }
 
 int nrf_adam_step_sharded(const nrf_peer_group* pg, float* param, float* exp_avg, float* exp_avg_sq, int64_t n_sharded, int64_t n_total,
 	const void* sched_state, float beta1, float beta2, float eps, float grad_scale, nrf_stream stream)

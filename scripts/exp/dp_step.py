@@ -23,6 +23,9 @@ def nccl_step():
 def nccl_only():
     parallel.allreduce_gradients(a.grads, world)
 t_f = timeit(b.optimizer_step_sharded); t_n = timeit(nccl_step); t_ar = timeit(nccl_only)
+st = b.peer.flags[24:29].cpu().tolist()
+ph = [(st[i + 1] - st[i]) % (1 << 32) / 1e3 for i in range(4)]
+print(f"rank {rank} last fused kernel phases us: entry barrier {ph[0]:.1f} | shard loop (CTA 0) {ph[1]:.1f} | exit barrier {ph[2]:.1f} | grad clear {ph[3]:.1f}", flush=True)
 if rank == 0:
     print(f"world {world}: fused step {t_f:.1f} us | nccl all-reduce + adam + pack {t_n:.1f} us | all-reduce alone {t_ar:.1f} us | timeout flag {b.flags_timeout()}")
 dist.barrier(); dist.destroy_process_group()
