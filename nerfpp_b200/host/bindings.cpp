@@ -6,6 +6,7 @@
 #include <chrono>
 
 #include "renderer.h"
+#include "fused_adam.h"
 
 namespace py = pybind11;
 using torch::Tensor;
@@ -97,6 +98,8 @@ struct Pipeline {
 		d["near"] = r.Near; d["far"] = r.Far;
 		return d;
 	}
+	bool fused_adam = false;   ///< FusedAdam (one sm_100a kernel per parameter) instead of torch::optim::Adam; chosen before the first step
+	void UseFusedAdam(bool on) { TORCH_CHECK(!opt, "choose the optimiser before the first training step"); fused_adam = on; }
 	std::pair<std::vector<double>, std::vector<float>> TrainSteps(Tensor rays_o, Tensor rays_d, Tensor target, int n_steps, int n_samples,
 		int n_importance, int chunk, bool use_viewdirs, float lr, int lrate_decay)
 	{
@@ -104,7 +107,9 @@ struct Pipeline {
 			std::vector<Tensor> gv;
 			for (auto& p : embed->parameters()) gv.push_back(p);
 			for (auto& p : model->parameters()) gv.push_back(p);
-			opt = std::make_unique<torch::optim::Adam>(gv, torch::optim::AdamOptions(lr).eps(1e-15).betas(std::make_tuple(0.9, 0.99)));
+			const auto options = torch::optim::AdamOptions(lr).eps(1e-15).betas(std::make_tuple(0.9, 0.99));
+			if (fused_adam) opt = std::make_unique<FusedAdam>(gv, options);
+			else opt = std::make_unique<torch::optim::Adam>(gv, options);
 			global_step = 0;
 		}
 		std::vector<double> secs; std::vector<float> losses;
@@ -140,6 +145,7 @@ static void Bind(py::module_& m, const char* name)
 		.def("embed", &P::Embed).def("embed_dirs", &P::EmbedDirs).def("model", &P::Model)
 		.def("run_network", &P::RunNetwork).def("raw_to_outputs", &P::RawToOutputs)
 		.def("render_rays", &P::RenderRays).def("render", &P::Render).def("render_shipped", &P::RenderShipped).def("render_image", &P::RenderImage)
+		.def("use_fused_adam", &P::UseFusedAdam)
 		.def("train_steps", &P::TrainSteps, py::call_guard<py::gil_scoped_release>());
 }
 

@@ -195,3 +195,22 @@ def test_classic_pipeline_matches_reference(host, ref_cuda):
     r2 = ref.render(o, d, 64, 128, 4096, False, True)
     for k in ("rgb", "acc", "depth"):
         assert torch.allclose(r1[k], r2[k], rtol=2e-3, atol=2e-3), k
+
+
+def test_fused_adam_tracks_torch_adam(host):
+    """FusedAdam (nrf_adam_step per parameter, same state objects) in the reference's training loop vs torch::optim::Adam."""
+    pipes = []
+    for fused in (False, True):
+        host.manual_seed(7)
+        torch.manual_seed(7)
+        p = host.make_cuhash(torch.tensor(BBOX).cuda(), *ARGS)
+        p.init_model()
+        p.use_fused_adam(fused)
+        pipes.append(p)
+    o, d = _rays(512, seed=3)
+    tgt = torch.rand(512, 3, generator=torch.Generator().manual_seed(1)).cuda()
+    losses = [p.train_steps(o, d, tgt, 5, 64, 128, 512, True, 1e-2, 250)[1] for p in pipes]
+    np.testing.assert_allclose(losses[1], losses[0], rtol=5e-3)
+    for a, b in zip(pipes[0].model_params() + pipes[0].embed_params(), pipes[1].model_params() + pipes[1].embed_params()):
+        diff = (a - b).abs()
+        assert (diff > 1e-4).float().mean().item() < 2e-2 and diff.median().item() < 1e-6   # sign-like Adam: see test_gpu_pipeline
