@@ -156,11 +156,18 @@ def main() -> None:
     if world > 1:
         dp_mode = "nccl all-reduce of the flat gradient + dense Adam on every rank"
         if args.dp == "fused":
+            why = ""
             try:
-                parallel.PeerShardedOptimizer(model, rank, world)
+                peer = parallel.PeerShardedOptimizer(model, rank, world)
+            except Exception as e:  # noqa: BLE001 - symmetric memory unavailable on this rank
+                peer, why = None, f"{type(e).__name__}: {e}"
+            have = torch.tensor([int(peer is not None)], dtype=torch.int32, device=dev)
+            torch.distributed.all_reduce(have, op=torch.distributed.ReduceOp.MIN)      # all ranks or none
+            if bool(have.item()) and peer.self_test(model):
                 dp_mode = "fused peer-memory kernel per rank: reduce-scatter(grad) + Adam(1/N shard) + all-gather(fp16 shadow) over NVLink, no NCCL in the step"
-            except Exception as e:  # noqa: BLE001 - symmetric memory unavailable: stay on the NCCL path and say so
-                dp_mode += f" (fused path unavailable: {type(e).__name__}: {e})"
+            else:
+                model.peer = None        # stay on the NCCL path (the symmetric buffers remain ordinary device memory) and say so
+                dp_mode += f" (fused path unavailable: {why or 'peer self-test failed on some rank'})"
 
     pool = 8  # distinct pre-generated ray batches per rank, cycled
     dev_batches = [synthetic_rays(R, device=dev, seed=1000 * rank + i) for i in range(pool)]

@@ -113,6 +113,25 @@ class PeerShardedOptimizer:
         torch.cuda.synchronize(dev)
         dist.barrier(group)
 
+    def self_test(self, model) -> bool:
+        """One fused optimiser step on the all-zero gradient before training starts: with zero moments it leaves every parameter
+        unchanged but exercises the peer mappings and both barriers.  Returns True when every rank came through (collective)."""
+        ok = 1
+        try:
+            assert model.step == 0 and float(model.grads.abs().max()) == 0.0, "self_test must run before the first step"
+            before = model.shadow.clone()
+            model.optimizer_step_sharded()
+            torch.cuda.synchronize(model.device)
+            if model.flags_timeout() or not torch.equal(before, model.shadow):
+                ok = 0
+        except Exception:  # noqa: BLE001
+            ok = 0
+        model.step = 0
+        model._sched_step = -1          # the dry step advanced the device-side counter: re-seed it on the next step
+        flag = torch.tensor([ok], dtype=torch.int32, device=model.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return bool(flag.item())
+
     def shard_bounds(self, n_sharded: int) -> tuple[int, int]:
         """[begin, end) scalars of the table this rank owns (same split as the kernel: quads, first ranks one extra)."""
         b, e = shard_bounds(n_sharded // 4, self.rank, self.world)

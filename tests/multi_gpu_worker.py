@@ -31,7 +31,8 @@ def main():
     parallel.PeerShardedOptimizer(b, rank, world)
     c = HashNeRF(BBOX, log2_hashmap_size=15, seed=3, device=dev, lrate_decay=1)
     parallel.broadcast_parameters(c.params, world); c.refresh()
-    parallel.PeerShardedOptimizer(c, rank, world)
+    assert parallel.PeerShardedOptimizer(c, rank, world).self_test(c)     # dry step on the zero gradient: parameters untouched
+    assert c.step == 0
     c.capture_train_step(R, world)
 
     la, lb, lc = [], [], []
