@@ -15,7 +15,8 @@
 // src/CuHashEmbedder.cu:253), all other layers bf16 x bf16; accumulation is fp32 throughout.
 //
 // Backward: activations are recomputed (nothing saved by the forward).  The dX chain runs in registers like the
-// forward.  For dW = dY^T X, each warp drops its X_l / dY_l slabs into padded shared-memory tiles; after one CTA
+// forward; ReLU gates are kept as one 0xFFFF-per-active-half word per activation word (HSET2) and applied to the packed
+// bf16 gradient pairs with a single AND; the next tile's inputs are prefetched behind the dW phase.  For dW = dY^T X, each warp drops its X_l / dY_l slabs into padded shared-memory tiles; after one CTA
 // barrier the 8 warps split the 80 output 16x8 tiles between them, read the tiles with ldmatrix.trans (both
 // operands are "K = rows"-major) and keep their share of dW in registers across the whole persistent loop; one
 // fp32 atomicAdd per weight per CTA at the end.
@@ -284,21 +285,24 @@ __device__ __forceinline__ void store_frag(__nv_bfloat16* tile, int pitch, int r
 	}
 }
 
-// dD = dA where the stored activation (bf16 pair words in `tile`) is > 0
-template <int NT>
-__device__ __forceinline__ void relu_mask(float (&acc)[NT][4], const __nv_bfloat16* tile, int pitch, int row_g, int t)
+// per-element ReLU gates of an activation fragment: 0xFFFF where the fp16 activation is > 0 (one HSET2 per word); the gradient
+// fragment of the same layer has the same (k-step, element) layout, so gating is one AND per packed bf16 pair
+template <int KS>
+__device__ __forceinline__ void relu_gates(const uint32_t (&a)[KS][4], uint32_t (&m)[KS][4])
 {
-	const uint32_t* lo = reinterpret_cast<const uint32_t*>(tile + row_g * pitch);
-	const uint32_t* hi = reinterpret_cast<const uint32_t*>(tile + (row_g + 8) * pitch);
+	const __half2 zero = __float2half2_rn(0.f);
 #pragma unroll
-	for (int nt = 0; nt < NT; nt++) {
-		const uint32_t wl = lo[nt * 4 + t], wh = hi[nt * 4 + t];
-		// bf16 > 0  <=>  sign clear and magnitude non-zero
-		if (!((wl & 0x7fffu) != 0u && (wl & 0x8000u) == 0u)) acc[nt][0] = 0.f;
-		if (!((wl & 0x7fff0000u) != 0u && (wl & 0x80000000u) == 0u)) acc[nt][1] = 0.f;
-		if (!((wh & 0x7fffu) != 0u && (wh & 0x8000u) == 0u)) acc[nt][2] = 0.f;
-		if (!((wh & 0x7fff0000u) != 0u && (wh & 0x80000000u) == 0u)) acc[nt][3] = 0.f;
-	}
+	for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+		for (int e = 0; e < 4; e++) m[ks][e] = __hgt2_mask(*reinterpret_cast<const __half2*>(&a[ks][e]), zero);
+}
+template <int KS>
+__device__ __forceinline__ void apply_gates(uint32_t (&d)[KS][4], const uint32_t (&m)[KS][4])
+{
+#pragma unroll
+	for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+		for (int e = 0; e < 4; e++) d[ks][e] &= m[ks][e];
 }
 
 __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p)
@@ -363,12 +367,34 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 	for (int i = 0; i < 10; i++) dw[i][0] = dw[i][1] = dw[i][2] = dw[i][3] = 0.f;
 
 	const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
+	// inputs of the tile in flight (prefetched one tile ahead: the loads complete behind the dW phase)
+	uint32_t in_a0[2][4], in_v[4];
+	float4 in_g_lo, in_g_hi;
+	auto load_tile = [&](int64_t tile) {
+		const int64_t r_lo = tile * kTileRows + row_g, r_hi = r_lo + 8;
+		load_enc<IN_KIND>(enc, r_lo, r_hi, n, t, in_a0);
+		load_views<IN_KIND>(enc, ray_sh, S, r_lo, r_hi, n, t, in_v);
+		in_g_lo = make_float4(0.f, 0.f, 0.f, 0.f);
+		in_g_hi = in_g_lo;
+		if (r_lo < n) in_g_lo = __ldg(reinterpret_cast<const float4*>(grad_raw + r_lo * 4));
+		if (r_hi < n) in_g_hi = __ldg(reinterpret_cast<const float4*>(grad_raw + r_hi * 4));
+		if (keep) {
+			if (r_lo < n && !keep[r_lo]) in_g_lo.w = 0.f;
+			if (r_hi < n && !keep[r_hi]) in_g_hi.w = 0.f;
+		}
+	};
+	if (static_cast<int64_t>(blockIdx.x) < n_tiles) load_tile(blockIdx.x);
 	for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 		const int64_t r_lo = tile * kTileRows + row_g, r_hi = r_lo + 8;
-		// ---- forward recompute; every layer input is dropped into its X tile
+		const float4 g_lo = in_g_lo, g_hi = in_g_hi;
+		uint32_t m1[4][4], m3[4][4], m4[4][4];   // ReLU gates of X1, X3, X4
+		// ---- forward recompute; every layer input is dropped into its X tile (bf16, packed straight from the fp32 accumulators)
 		{
 			uint32_t a0[2][4];
-			load_enc<IN_KIND>(enc, r_lo, r_hi, n, t, a0);
+#pragma unroll
+			for (int ks = 0; ks < 2; ks++)
+#pragma unroll
+				for (int e = 0; e < 4; e++) a0[ks][e] = in_a0[ks][e];
 			float acc[8][4];
 			layer_mma<2, 8, true>(a0, wf + kF0, lane, acc);
 			uint32_t xb2[2][4], xb4[4][4];                               // bf16 copies for the dW products
@@ -376,12 +402,14 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			store_frag<2>(tiles + kTX0, kP32, row_g, t, xb2);
 			uint32_t a1[4][4];
 			repack<4, true, true>(acc, a1);
-			to_bf16<4>(a1, xb4);
+			relu_gates<4>(a1, m1);
+			repack<4, true, false>(acc, xb4);
 			store_frag<4>(tiles + kTX1, kP64, row_g, t, xb4);
 			float d1[2][4];
 			layer_mma<4, 2, true>(a1, wf + kF1, lane, d1);
 			uint32_t a2[2][4];
-			load_views<IN_KIND>(enc, ray_sh, S, r_lo, r_hi, n, t, a2[0]);
+#pragma unroll
+			for (int e = 0; e < 4; e++) a2[0][e] = in_v[e];
 			if (t == 0) { d1[0][0] = 0.f; d1[0][2] = 0.f; }
 			repack<1, false, true>(d1, reinterpret_cast<uint32_t(&)[1][4]>(a2[1]));
 			to_bf16<2>(a2, xb2);
@@ -389,23 +417,17 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			layer_mma<2, 8, true>(a2, wf + kF2, lane, acc);
 			uint32_t a3[4][4];
 			repack<4, true, true>(acc, a3);
-			to_bf16<4>(a3, xb4);
+			relu_gates<4>(a3, m3);
+			repack<4, true, false>(acc, xb4);
 			store_frag<4>(tiles + kTX3, kP64, row_g, t, xb4);
 			layer_mma<4, 8, true>(a3, wf + kF3, lane, acc);
 			repack<4, true, true>(acc, a3);
-			to_bf16<4>(a3, xb4);
+			relu_gates<4>(a3, m4);
+			repack<4, true, false>(acc, xb4);
 			store_frag<4>(tiles + kTX4, kP64, row_g, t, xb4);
 		}
-		__syncwarp();
 		// ---- backward chain
 		{
-			float4 g_lo = make_float4(0.f, 0.f, 0.f, 0.f), g_hi = g_lo;
-			if (r_lo < n) g_lo = __ldg(reinterpret_cast<const float4*>(grad_raw + r_lo * 4));
-			if (r_hi < n) g_hi = __ldg(reinterpret_cast<const float4*>(grad_raw + r_hi * 4));
-			if (keep) {
-				if (r_lo < n && !keep[r_lo]) g_lo.w = 0.f;
-				if (r_hi < n && !keep[r_hi]) g_hi.w = 0.f;
-			}
 			uint32_t d4[1][4];
 			d4[0][0] = t == 0 ? pack_bf16(g_lo.x, g_lo.y) : (t == 1 ? pack_bf16(g_lo.z, 0.f) : 0u);
 			d4[0][1] = t == 0 ? pack_bf16(g_hi.x, g_hi.y) : (t == 1 ? pack_bf16(g_hi.z, 0.f) : 0u);
@@ -414,13 +436,13 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			store_frag<1>(tiles + kTD4, kP8, row_g, t, d4);   // 8 real + 8 zero columns
 			float acc[8][4];
 			layer_mma<1, 8, false>(d4, wf + kB4, lane, acc);                 // dA4 = dD4 · W4
-			relu_mask<8>(acc, tiles + kTX4, kP64, row_g, t);
 			uint32_t d3[4][4];
 			repack<4, false, false>(acc, d3);
+			apply_gates<4>(d3, m4);
 			store_frag<4>(tiles + kTD3, kP64, row_g, t, d3);
 			layer_mma<4, 8, false>(d3, wf + kB3, lane, acc);                 // dA3 = dD3 · W3
-			relu_mask<8>(acc, tiles + kTX3, kP64, row_g, t);
 			repack<4, false, false>(acc, d3);
+			apply_gates<4>(d3, m3);
 			store_frag<4>(tiles + kTD2, kP64, row_g, t, d3);
 			float da2[4][4];
 			layer_mma<4, 4, false>(d3, wf + kB2, lane, da2);                 // dA2 = dD2 · W2p  (cols 0..15 views, 16..31 d1)
@@ -432,8 +454,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			dd1[0][3] = pack_bf16(da2[3][2], da2[3][3]);
 			store_frag<1>(tiles + kTD1, kP16, row_g, t, dd1);
 			layer_mma<1, 8, false>(dd1, wf + kB1, lane, acc);                // dA1 = dD1 · W1
-			relu_mask<8>(acc, tiles + kTX1, kP64, row_g, t);
 			repack<4, false, false>(acc, d3);
+			apply_gates<4>(d3, m1);
 			store_frag<4>(tiles + kTD0, kP64, row_g, t, d3);
 			if (grad_in) {
 				float de[4][4];
@@ -460,6 +482,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 				}
 			}
 		}
+		if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x);   // next tile's inputs travel while the dW phase runs
 		__syncthreads();
 		// ---- dW: 80 output tiles split over the 8 warps, 10 each
 		if (warp < 4) {

@@ -2,7 +2,8 @@
 
 The reference MLP (src/NeRF.cpp:363-412) is fp32 SGEMM.  The sm_100a kernels run the forward chain (and its recompute in
 the backward) in fp16 x fp16 and the gradient chain in bf16 x bf16, all with fp32 accumulation, re-quantising each
-activation / gradient where it becomes a tensor-core operand (activations are re-quantised to bf16 for the dW products).
+activation / gradient where it becomes a tensor-core operand (for the dW products the activations are packed to bf16 straight
+from the fp32 accumulators; encodings and view channels, which arrive as fp16 values, are re-quantised).
 Against the fp32 reference such a chain is only comparable in a norm sense: a pre-activation within rounding error of zero
 takes the other ReLU branch and changes that row's gradient by a whole term, which a max-norm bound cannot absorb.  So
 parity is established in four steps (tests/test_gpu_mlp.py):
@@ -36,6 +37,7 @@ def forward_backward(ws, x, g, keep=None):
     views = hf(x[:, 32:])
     acc0 = x0 @ hf(w0).t()
     a1 = hf(torch.relu(acc0))
+    x1b = bf(torch.relu(acc0))       # the dW copy of an activation is packed to bf16 straight from the fp32 accumulator
     d1 = a1 @ hf(w1).t()
     sigma = d1[:, 0].clone()
     d1z = d1.clone()
@@ -43,8 +45,10 @@ def forward_backward(ws, x, g, keep=None):
     a2 = torch.cat([views, hf(d1z)], -1)
     acc2 = a2 @ hf(w2p).t()
     a3 = hf(torch.relu(acc2))
+    x3b = bf(torch.relu(acc2))
     acc3 = a3 @ hf(w3).t()
     a4 = hf(torch.relu(acc3))
+    x4b = bf(torch.relu(acc3))
     c = a4 @ hf(w4).t()
     if keep is not None:
         sigma = sigma * keep.float()
@@ -68,11 +72,11 @@ def forward_backward(ws, x, g, keep=None):
     denc = dD0 @ bf(w0)
     gx = torch.cat([denc, dviews], -1)
     dW0 = dD0.t() @ bf(x0)
-    dW1 = dd1.t() @ bf(a1)
+    dW1 = dd1.t() @ x1b
     dW2p = dD2.t() @ bf(a2)
     dW2 = torch.cat([dW2p[:, :16], dW2p[:, 17:]], -1)
-    dW3 = dD3.t() @ bf(a3)
-    dW4 = d4.t() @ bf(a4)
+    dW3 = dD3.t() @ x3b
+    dW4 = d4.t() @ x4b
     return out, gx, [dW0, dW1, dW2, dW3, dW4], (a1 > 0, a3 > 0, a4 > 0)
 
 
