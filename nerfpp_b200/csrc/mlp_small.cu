@@ -194,6 +194,27 @@ __device__ __forceinline__ void load_views(const void* __restrict__ enc, const f
 	v = __ldg(reinterpret_cast<const float2*>(hi + 8 + 2 * t));  a[3] = pack_f16(v.x, v.y);
 }
 
+// the same four 8-byte loads, left un-converted (prefetch: a convert right after the load would stall on it)
+template <int IN_KIND>
+__device__ __forceinline__ void load_views_raw(const void* __restrict__ enc, const float* __restrict__ ray_sh, int S, int64_t r_lo, int64_t r_hi,
+	int64_t n, int t, float2 (&v)[4])
+{
+	const float* lo;
+	const float* hi;
+	if (IN_KIND == NRF_MLP_IN_ENC16_RAYDIRS) {
+		lo = ray_sh + (r_lo < n ? r_lo / S : 0) * 16;
+		hi = ray_sh + (r_hi < n ? r_hi / S : 0) * 16;
+	} else {
+		const float* x = reinterpret_cast<const float*>(enc);
+		lo = x + (r_lo < n ? r_lo : 0) * 48 + 32;
+		hi = x + (r_hi < n ? r_hi : 0) * 48 + 32;
+	}
+	v[0] = __ldg(reinterpret_cast<const float2*>(lo + 2 * t));
+	v[1] = __ldg(reinterpret_cast<const float2*>(hi + 2 * t));
+	v[2] = __ldg(reinterpret_cast<const float2*>(lo + 8 + 2 * t));
+	v[3] = __ldg(reinterpret_cast<const float2*>(hi + 8 + 2 * t));
+}
+
 __device__ __forceinline__ void copy_blob(uint32_t* dst, const uint32_t* __restrict__ src, int words)
 {
 	const uint4* s = reinterpret_cast<const uint4*>(src);
@@ -368,25 +389,27 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 
 	const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
 	// inputs of the tile in flight (prefetched one tile ahead: the loads complete behind the dW phase)
-	uint32_t in_a0[2][4], in_v[4];
+	uint32_t in_a0[2][4];
+	float2 in_v[4];
 	float4 in_g_lo, in_g_hi;
-	auto load_tile = [&](int64_t tile) {
+	uint8_t in_k_lo = 1, in_k_hi = 1;
+	auto load_tile = [&](int64_t tile) {   // loads only: every consumer of the loaded values sits in the next iteration
 		const int64_t r_lo = tile * kTileRows + row_g, r_hi = r_lo + 8;
 		load_enc<IN_KIND>(enc, r_lo, r_hi, n, t, in_a0);
-		load_views<IN_KIND>(enc, ray_sh, S, r_lo, r_hi, n, t, in_v);
+		load_views_raw<IN_KIND>(enc, ray_sh, S, r_lo, r_hi, n, t, in_v);
 		in_g_lo = make_float4(0.f, 0.f, 0.f, 0.f);
 		in_g_hi = in_g_lo;
 		if (r_lo < n) in_g_lo = __ldg(reinterpret_cast<const float4*>(grad_raw + r_lo * 4));
 		if (r_hi < n) in_g_hi = __ldg(reinterpret_cast<const float4*>(grad_raw + r_hi * 4));
-		if (keep) {
-			if (r_lo < n && !keep[r_lo]) in_g_lo.w = 0.f;
-			if (r_hi < n && !keep[r_hi]) in_g_hi.w = 0.f;
-		}
+		in_k_lo = (keep && r_lo < n) ? __ldg(keep + r_lo) : uint8_t(1);
+		in_k_hi = (keep && r_hi < n) ? __ldg(keep + r_hi) : uint8_t(1);
 	};
 	if (static_cast<int64_t>(blockIdx.x) < n_tiles) load_tile(blockIdx.x);
 	for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 		const int64_t r_lo = tile * kTileRows + row_g, r_hi = r_lo + 8;
-		const float4 g_lo = in_g_lo, g_hi = in_g_hi;
+		float4 g_lo = in_g_lo, g_hi = in_g_hi;
+		if (!in_k_lo) g_lo.w = 0.f;               // d(sigma) is dropped outside the box (src/NeRFRenderer.h:188)
+		if (!in_k_hi) g_hi.w = 0.f;
 		uint32_t m1[4][4], m3[4][4], m4[4][4];   // ReLU gates of X1, X3, X4
 		// ---- forward recompute; every layer input is dropped into its X tile (bf16, packed straight from the fp32 accumulators)
 		{
@@ -409,7 +432,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			layer_mma<4, 2, true>(a1, wf + kF1, lane, d1);
 			uint32_t a2[2][4];
 #pragma unroll
-			for (int e = 0; e < 4; e++) a2[0][e] = in_v[e];
+			for (int e = 0; e < 4; e++) a2[0][e] = pack_f16(in_v[e].x, in_v[e].y);
 			if (t == 0) { d1[0][0] = 0.f; d1[0][2] = 0.f; }
 			repack<1, false, true>(d1, reinterpret_cast<uint32_t(&)[1][4]>(a2[1]));
 			to_bf16<2>(a2, xb2);
