@@ -16,7 +16,6 @@ import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 from pathlib import Path
 
@@ -42,36 +41,38 @@ BYTES_PER_POINT = {
 }
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md recipe): one `nvidia-smi -lms` process
+    streaming a sample every 20 ms, started before the first timed region and stopped after the last."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.proc, self.rows = index, None, []
 
-    def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:  # noqa: BLE001 - sampling must never break the bench
-                pass
-            self._stop_evt.wait(0.1)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:  # noqa: BLE001 - sampling must never break the bench
+            self.proc = None
 
     def stop(self) -> dict:
-        self._stop_evt.set()
-        self.join(timeout=10)
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                out, _ = self.proc.communicate(timeout=10)
+                self.rows = [[c.strip() for c in line.split(",")] for line in out.splitlines() if line.count(",") >= 6]
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows if len(r) > 3 + i)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]), "samples": len(self.rows),
-                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons}
+                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons,
+                "window": "resident + roofline + e2e timed regions"}
 
 
 def reference_cpu_rays_per_s(steps: int, warmup: int, rays: int = CPU_SAMPLE_RAYS):
@@ -221,7 +222,6 @@ def main() -> None:
         step(dev_batches[i % pool])
     e1.record()
     sync_all()
-    clocks = sampler.stop()
     ms_total = parallel.max_over_ranks(e0.elapsed_time(e1), world, dev)
     loss_resident = float(model.loss)
 
@@ -258,6 +258,7 @@ def main() -> None:
         loss_host = float(model.loss)   # device -> host read of the step's result
     e3.record()
     sync_all()
+    clocks = sampler.stop()
     ms_e2e = parallel.max_over_ranks(e2.elapsed_time(e3), world, dev)
     launches = launches_per_step * args.steps   # kernels inside timed region A (graph: kernel nodes per replay x replays)
 

@@ -242,3 +242,58 @@ def test_huber_and_adam():
     close(pc, p64, rtol=1e-5, atol=1e-6)
     assert torch.equal(shadow, pc.half())
     assert torch.equal(pc[::7].cpu(), prm[::7])
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE-size properties
+def test_full_size_composite_and_sampler_properties():
+    """BASELINE C2 sizes (4096 rays, 64 coarse / 192 merged samples): size-independent properties of the rendering kernels —
+    weights in [0,1] with sum == acc <= 1, rgb linear in sigmoid(rgb logits) for fixed weights, depth inside [z_min, z_max],
+    the backward equals a finite difference of the forward along a random direction, merged z sorted and a superset of the
+    coarse z, importance samples inside the coarse span."""
+    from nerfpp_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(12)
+    R, S, N = 4096, 64, 128
+    raw = torch.randn(R, S, 4, generator=g, device="cuda")
+    z = 2 + torch.sort(torch.rand(R, S, generator=g, device="cuda") * 4, -1).values
+    d = torch.randn(R, 3, generator=g, device="cuda")
+    out = ops.composite_fwd(raw, z, d)
+    w = out["weights"]
+    assert float(w.min()) >= 0.0 and float(w.max()) <= 1.0
+    np.testing.assert_allclose(w.sum(-1).cpu().numpy(), out["acc"].cpu().numpy(), rtol=1e-5, atol=1e-6)
+    assert float(out["acc"].max()) <= 1.0 + 1e-5
+    np.testing.assert_allclose(out["rgb"].cpu().numpy(), (w[..., None] * torch.sigmoid(raw[..., :3])).sum(1).cpu().numpy(), rtol=1e-4, atol=1e-6)
+    hit = out["acc"] > 1e-3
+    assert bool(((out["depth"] >= z[:, 0] - 1e-4) & (out["depth"] <= z[:, -1] + 1e-4))[hit].all())
+    # directional derivative: <d_raw, v> == d/deps sum(rgb * G)(raw + eps v) (central difference in fp32: 1e-2 agreement)
+    G = torch.randn(R, 3, generator=g, device="cuda")
+    v = torch.randn(R, S, 4, generator=g, device="cuda")
+    d_raw = ops.composite_bwd(raw, z, d, g_rgb=G)
+    eps = 1e-2
+    fp = (ops.composite_fwd(raw + eps * v, z, d)["rgb"].double() * G).sum()
+    fm = (ops.composite_fwd(raw - eps * v, z, d)["rgb"].double() * G).sum()
+    lhs, rhs = float((d_raw.double() * v).sum()), float((fp - fm) / (2 * eps))
+    assert abs(lhs - rhs) <= 1e-2 * abs(rhs) + 1e-3, (lhs, rhs)
+    # sampler + merge at full size
+    zf, zs = ops.sample_pdf_merge(z, w, torch.linspace(0, 1, N).cuda(), want_samples=True)
+    assert zf.shape == (R, S + N) and bool((zf[:, 1:] >= zf[:, :-1]).all())
+    assert torch.equal(torch.sort(torch.cat([z, zs], -1), -1).values, zf)           # exactly the reference's sort(cat(...))
+    assert bool((zs >= z[:, :1]).all() and (zs <= z[:, -1:]).all())
+
+
+def test_new_entries_empty_and_ragged():
+    """n = 0 and ragged sizes through the fused-point, permutation and one-call render entries."""
+    from nerfpp_b200 import ops
+    from nerfpp_b200.pipeline import HashNeRF, synthetic_rays
+    m = HashNeRF((-1.5, -1.5, -1.5, 1.5, 1.5, 1.5), log2_hashmap_size=14, seed=1)
+    empty = torch.empty(0, 3, device="cuda")
+    rb0 = ops.rays_prepare(empty, empty, m.bbox, 0.0, True)
+    z0 = ops.z_sample(rb0, m.t_vals)
+    enc, keep = ops.hash_encode_rays_fwd(m.grid, m.table_f16, rb0, z0)
+    assert enc.shape == (0, 32) and keep.shape == (0,)
+    ops.hash_encode_rays_bwd(m.grid, rb0, z0, torch.empty(0, 32, device="cuda", dtype=torch.bfloat16), m.grads[:m.n_table])
+    out = m.render_rays_fused(empty, empty)
+    assert out["rgb"].shape == (0, 3)
+    for n in (1, 33, 129):
+        o, d, _ = synthetic_rays(n, seed=n)
+        a, b = m.render_rays(o, d), m.render_rays_fused(o, d)
+        assert torch.equal(a["rgb"], b["rgb"]) and torch.isfinite(a["rgb"]).all()
