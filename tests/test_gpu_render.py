@@ -267,12 +267,13 @@ def test_full_size_composite_and_sampler_properties():
     # directional derivative: <d_raw, v> == d/deps sum(rgb * G)(raw + eps v) (central difference in fp32: 1e-2 agreement)
     G = torch.randn(R, 3, generator=g, device="cuda")
     v = torch.randn(R, S, 4, generator=g, device="cuda")
+    v[:, -1, 3] = 0.0     # the last interval is 1e10 |d| (NeRFRenderer.h:240): alpha_last jumps 0 -> 1 at sigma = 0, not differentiable there
     d_raw = ops.composite_bwd(raw, z, d, g_rgb=G)
-    eps = 1e-2
+    eps = 2e-3
     fp = (ops.composite_fwd(raw + eps * v, z, d)["rgb"].double() * G).sum()
     fm = (ops.composite_fwd(raw - eps * v, z, d)["rgb"].double() * G).sum()
     lhs, rhs = float((d_raw.double() * v).sum()), float((fp - fm) / (2 * eps))
-    assert abs(lhs - rhs) <= 1e-2 * abs(rhs) + 1e-3, (lhs, rhs)
+    assert abs(lhs - rhs) <= 2e-2 * abs(rhs) + 1e-2, (lhs, rhs)     # relu(sigma) kinks inside +-eps|v| add O(eps) noise
     # sampler + merge at full size
     zf, zs = ops.sample_pdf_merge(z, w, torch.linspace(0, 1, N).cuda(), want_samples=True)
     assert zf.shape == (R, S + N) and bool((zf[:, 1:] >= zf[:, :-1]).all())
