@@ -308,8 +308,9 @@ def main() -> None:
                 "ms_per_launch": ms_kernel / n_launch, "share_of_step": (ms_kernel / roof_steps) / ms_eager,
                 "timing": f"CUDA-event pair around every launch over {roof_steps} eagerly launched steps run right after the timed region "
                           f"({ms_eager:.3f} ms/step eager)",
-                "l2_note": "the table shadow (17 MiB) is L2-resident: the kernel is bound by L2 sector throughput (one 32 B sector per 4 B gather / 8 B "
-                           "RED), not by HBM; see DESIGN.md"}
+                "l2_note": "the table shadow (17 MiB) is L2-resident: the kernel is bound by L1 tag lookups (forward) / L2 RED operations (backward), "
+                           "not by HBM. Ceilings measured on B200 with scripts/exp/{gather,red}_bench.cu: 280 G random 4 B gathers/s, 209 G REDs/s "
+                           "(any operand width); hash_fwd issues 301 G sector lookups/s, hash_bwd 206 G REDs/s (DESIGN.md §4)"}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
