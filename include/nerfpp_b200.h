@@ -162,6 +162,36 @@ int nrf_mlp_small_bwd(const nrf_mlp_small_shape* shape, const void* packed, nrf_
                       const float* grad_raw, void* grad_in, float* grad_params_flat, nrf_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Classic NeRF MLP, forward (inference) — NeRFImpl::forward (src/NeRF.cpp:92-126) fused on tcgen05 tensor cores: 8 x 256 ReLU
+ * layers with the skip concat [x | h] after layer 4 (:103-104), alpha head (:110), feature layer (:111), view branch
+ * [feature | dirs] -> 128 -> ReLU -> rgb (:112-119), biases included, out = [rgb(3), alpha] (:120).  Built for the BASELINE
+ * shape (NeRFExecutor.h:478: D=8, W=256, input_ch=63, input_ch_views=27, skips={4}, use_viewdirs); other shapes return
+ * NRF_ERR_UNSUPPORTED.  x [N, 90] fp32 = cat(embedded points, embedded dirs) (src/NeRFRenderer.h:182), out [N,4] fp32.
+ * Training of this model still goes through LibTorch autograd in the C++ layer (the backward is not built).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct nrf_mlp_nerf_shape {
+	int32_t depth;           /* 8   */
+	int32_t width;           /* 256 */
+	int32_t input_ch;        /* 63  */
+	int32_t input_ch_views;  /* 27  */
+	int32_t skip_layer;      /* 4   */
+	int32_t use_viewdirs;    /* 1   */
+} nrf_mlp_nerf_shape;
+
+typedef struct nrf_mlp_nerf_weights {   /* device pointers, torch Linear layout [out, in] row-major fp32 (src/NeRF.cpp:52-75) */
+	const float* pts_w[8];
+	const float* pts_b[8];
+	const float* feature_w; const float* feature_b;
+	const float* alpha_w;   const float* alpha_b;
+	const float* views_w;   const float* views_b;
+	const float* rgb_w;     const float* rgb_b;
+} nrf_mlp_nerf_weights;
+
+int64_t nrf_mlp_nerf_packed_bytes(const nrf_mlp_nerf_shape* shape);
+int nrf_mlp_nerf_pack(const nrf_mlp_nerf_shape* shape, const nrf_mlp_nerf_weights* weights, void* packed, nrf_stream stream);
+int nrf_mlp_nerf_fwd(const nrf_mlp_nerf_shape* shape, const void* packed, const float* x, int64_t n, float* out, nrf_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Volume rendering — NeRFRenderer::RawToOutputs (src/NeRFRenderer.h:199-282) with TruncExp
  * (src/CustomOps.cpp:5-16) folded in, and its backward.
  * raw [R,S,raw_stride] (channels 0..2 rgb logits, 3 density), z [R,S], rays_d [R,3],

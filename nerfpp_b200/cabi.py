@@ -43,6 +43,18 @@ class MlpSmallShape(Structure):
     ]
 
 
+class MlpNerfShape(Structure):
+    """struct nrf_mlp_nerf_shape"""
+    _fields_ = [("depth", c_int32), ("width", c_int32), ("input_ch", c_int32), ("input_ch_views", c_int32), ("skip_layer", c_int32),
+                ("use_viewdirs", c_int32)]
+
+
+class MlpNerfWeights(Structure):
+    """struct nrf_mlp_nerf_weights"""
+    _fields_ = [("pts_w", c_void_p * 8), ("pts_b", c_void_p * 8), ("feature_w", c_void_p), ("feature_b", c_void_p), ("alpha_w", c_void_p),
+                ("alpha_b", c_void_p), ("views_w", c_void_p), ("views_b", c_void_p), ("rgb_w", c_void_p), ("rgb_b", c_void_p)]
+
+
 class RenderConfig(Structure):
     """struct nrf_render_config"""
     _fields_ = [("n_samples", c_int32), ("n_importance", c_int32), ("white_bkgr", c_int32), ("lin_disp", c_int32), ("sh_degree", c_int32),
@@ -89,6 +101,9 @@ SIGNATURES = {
     "nrf_tangent_scatter": (c_int32, [_P, _P, _P, c_int32, _P, c_int32, _P, _P, POINTER(c_float), c_int64, c_int32, _P]),
     "nrf_huber_fwd_bwd": (c_int32, [_P, _P, c_int64, c_float, c_float, _P, _P, _P]),
     "nrf_adam_step": (c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int32, c_float, c_int32, _P, _P]),
+    "nrf_mlp_nerf_packed_bytes": (c_int64, [POINTER(MlpNerfShape)]),
+    "nrf_mlp_nerf_pack": (c_int32, [POINTER(MlpNerfShape), POINTER(MlpNerfWeights), _P, _P]),
+    "nrf_mlp_nerf_fwd": (c_int32, [POINTER(MlpNerfShape), _P, _P, c_int64, _P, _P]),
     "nrf_render_rays_workspace_bytes": (c_int64, [POINTER(RenderConfig), POINTER(HashGrid), c_int64]),
     "nrf_render_rays_fwd": (c_int32, [POINTER(RenderConfig), POINTER(HashGrid), _P, POINTER(MlpSmallShape), _P, _P, _P, c_int64, _P, _P, _P, c_int64,
                                       _P, _P, _P, _P, _P, _P, _P]),

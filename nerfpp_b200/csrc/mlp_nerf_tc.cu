@@ -1,0 +1,393 @@
+// Fused classic NeRF MLP forward (8 x 256, skip at layer 4, view branch) on tcgen05 / TMEM / TMA for sm_100a.
+//
+// Replaces NeRFImpl::forward (reference src/NeRF.cpp:92-126: 11 cuBLAS SGEMMs + bias/ReLU/cat kernels, every [N,256] fp32
+// activation round-tripping HBM) for inference: x [N, 63+27] fp32 (the positional embeddings of points and view
+// directions, src/NeRFRenderer.h:182) -> [N,4] = [rgb logits, alpha] (src/NeRF.cpp:120).
+//
+// Mapping (one persistent CTA per SM, one 128-point tile in flight):
+//   * activations never leave the SM: the A operand of every layer lives in TENSOR MEMORY as fp16 (TMEM columns 272..447:
+//     [pts 64 | h 256 | views 32] so that the skip layer reads [pts | h] and the view layer [feature | views] as ONE contiguous
+//     K range), accumulators D are fp32 in TMEM columns 0..255 (+16 for the 1- and 3-wide heads);
+//   * weights stream from L2 through a 4-deep ring of 32 KB shared-memory stages (one 64-wide K slab of a layer per stage,
+//     pre-packed by nrf_mlp_nerf_pack as UMMA K-major core matrices, so a stage is ONE contiguous TMA bulk copy);
+//     41 stages = 1.2 MB per tile, the same sequence for every tile;
+//   * warp 0 / lane 0 produces stages (mbarrier expect_tx + cp.async.bulk), warp 1 / lane 0 issues tcgen05.mma M=128, N<=256,
+//     K=16 per instruction and releases each stage with tcgen05.commit, warps 2..5 are the epilogue: one thread per row reads its
+//     accumulator row with tcgen05.ld, adds the bias (shared memory), applies ReLU, packs to fp16 and writes the next layer's A
+//     operand back to TMEM with tcgen05.st.
+// fp16 operands, fp32 accumulation: <= 1e-2 relative to the fp32 reference (tests/test_gpu_mlp_nerf.py).
+#include "tcgen05.cuh"
+#include "mlp_small_layout.cuh"
+
+namespace nrf {
+namespace nerf_tc {
+
+using namespace tc;
+
+constexpr int kW = 256, kInPts = 63, kInViews = 27, kInCh = kInPts + kInViews;
+constexpr int kRing = 4;
+constexpr int kStageBytes = 256 * 64 * 2;       // largest stage: N = 256, K = 64
+constexpr int kThreads = 32 * 6;
+// TMEM columns
+constexpr uint32_t kColD = 0, kColD16 = 256, kColPts = 272, kColH = 304, kColViews = 432;
+
+// ---- layer table ----------------------------------------------------------------------------------------------------
+// id: 0..7 pts_linears, 8 feature_linear, 9 alpha_linear, 10 views_linears[0], 11 rgb_linear
+constexpr int kLayers = 12;
+struct LayerInfo {
+	int N, K;            // padded
+	uint32_t a_col, d_col;
+};
+__host__ __device__ constexpr LayerInfo layer_info(int l)
+{
+	return l == 0 ? LayerInfo{256, 64, kColPts, kColD}
+	     : l == 5 ? LayerInfo{256, 320, kColPts, kColD}
+	     : l <= 8 ? LayerInfo{256, 256, kColH, kColD}
+	     : l == 9 ? LayerInfo{16, 256, kColH, kColD16}
+	     : l == 10 ? LayerInfo{128, 288, kColH, kColD}
+	     : LayerInfo{16, 128, kColH, kColD16};
+}
+// the narrow heads (N = 16) travel as ONE stage holding their whole K; everything else in 64-wide K slabs (last one may be 32)
+__host__ __device__ constexpr int layer_stages(int l) { return layer_info(l).N == 16 ? 1 : (layer_info(l).K + 63) / 64; }
+__host__ __device__ constexpr int stage_k(int l, int s)
+{
+	return layer_info(l).N == 16 ? layer_info(l).K : (layer_info(l).K - 64 * s >= 64 ? 64 : layer_info(l).K - 64 * s);
+}
+__host__ __device__ constexpr int stage_bytes(int l, int s) { return layer_info(l).N * stage_k(l, s) * 2; }
+__host__ __device__ constexpr int layer_bytes(int l)
+{
+	int b = 0;
+	for (int s = 0; s < layer_stages(l); s++) b += stage_bytes(l, s);
+	return b;
+}
+__host__ __device__ constexpr int layer_offset(int l)
+{
+	int b = 0;
+	for (int i = 0; i < l; i++) b += layer_bytes(i);
+	return b;
+}
+constexpr int kWeightBytes = layer_offset(kLayers);
+// biases (fp32) follow the weights: [layer][N padded]
+__host__ __device__ constexpr int bias_offset(int l)
+{
+	int b = 0;
+	for (int i = 0; i < l; i++) b += layer_info(i).N;
+	return b;
+}
+constexpr int kBiasFloats = bias_offset(kLayers);
+constexpr int kPackedBytes = kWeightBytes + kBiasFloats * 4;
+
+struct Weights {   // device pointers, torch Linear layout [out, in] row-major fp32
+	const float* w[kLayers];
+	const float* b[kLayers];
+};
+
+// padded logical weight Wp_l(n, k) in the kernel's A-operand order
+__device__ __forceinline__ float wp(const Weights& p, int l, int n, int k)
+{
+	switch (l) {
+		case 0: return k < kInPts ? p.w[0][n * kInPts + k] : 0.f;
+		case 5: return k < kInPts ? p.w[5][n * (kW + kInPts) + k] : (k < 64 ? 0.f : p.w[5][n * (kW + kInPts) + kInPts + (k - 64)]);   // [pts | h]
+		case 9: return n < 1 ? p.w[9][k] : 0.f;
+		case 10: return k < kW + kInViews ? p.w[10][n * (kW + kInViews) + k] : 0.f;                                                   // [feature | views]
+		case 11: return n < 3 ? p.w[11][n * (kW / 2) + k] : 0.f;
+		default: return p.w[l][n * kW + k];
+	}
+}
+
+__global__ void __launch_bounds__(256) nerf_pack_kernel(Weights p, uint32_t* __restrict__ blob)
+{
+	const int w = blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= kPackedBytes / 4) return;
+	if (w >= kWeightBytes / 4) {
+		const int i = w - kWeightBytes / 4;
+		int l = 0;
+		while (l + 1 < kLayers && i >= bias_offset(l + 1)) l++;
+		const int n = i - bias_offset(l);
+		const int real = l == 9 ? 1 : (l == 11 ? 3 : layer_info(l).N);
+		reinterpret_cast<float*>(blob)[w] = n < real ? p.b[l][n] : 0.f;
+		return;
+	}
+	int l = 0;
+	while (l + 1 < kLayers && w * 4 >= layer_offset(l + 1)) l++;
+	int q = w - layer_offset(l) / 4, s = 0, k_off = 0;
+	while (q >= stage_bytes(l, s) / 4) { q -= stage_bytes(l, s) / 4; k_off += stage_k(l, s); s++; }
+	// UMMA K-major core-matrix layout: word q of a stage holds (n, k) and (n, k+1); byte = (k/8)*(N*16) + n*16 + (k%8)*2
+	const int N = layer_info(l).N;
+	const int kc = q / (4 * N), n = (q >> 2) % N, k = k_off + 8 * kc + 2 * (q & 3);
+	blob[w] = pack_f16(wp(p, l, n, k), wp(p, l, n, k + 1));
+}
+
+struct __align__(128) Smem {
+	uint8_t ring[kRing][kStageBytes];
+	float bias[kBiasFloats];
+	uint64_t full[kRing], empty[kRing];
+	uint64_t a_ready, d_ready;
+	uint32_t tmem_base;
+};
+
+// epilogue of a 32-column accumulator chunk: + bias, optional ReLU, pack to 16 fp16 pairs
+template <bool RELU>
+__device__ __forceinline__ void bias_act_pack(const uint32_t (&acc)[32], const float* __restrict__ bias, uint32_t (&out)[16])
+{
+#pragma unroll
+	for (int i = 0; i < 8; i++) {
+		const float4 b = *reinterpret_cast<const float4*>(bias + 4 * i);
+		const float v0 = __uint_as_float(acc[4 * i]) + b.x, v1 = __uint_as_float(acc[4 * i + 1]) + b.y;
+		const float v2 = __uint_as_float(acc[4 * i + 2]) + b.z, v3 = __uint_as_float(acc[4 * i + 3]) + b.w;
+		out[2 * i] = RELU ? pack_f16_relu(v0, v1) : pack_f16(v0, v1);
+		out[2 * i + 1] = RELU ? pack_f16_relu(v2, v3) : pack_f16(v2, v3);
+	}
+}
+
+__device__ __forceinline__ void publish(uint64_t* bar, int lane)
+{
+	tmem_st_wait();
+	fence_before();
+	__syncwarp();
+	if (lane == 0) mbar_arrive(bar);
+}
+
+// groups of layers that share one A operand and one epilogue: {0} {1} {2} {3} {4} {5} {6} {7} {8,9} {10} {11}
+constexpr int kGroups = 11;
+__host__ __device__ constexpr int group_first(int g) { return g <= 8 ? g : g + 1; }
+__host__ __device__ constexpr int group_count(int g) { return g == 8 ? 2 : 1; }
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint8_t* __restrict__ blob, const float* __restrict__ x, int64_t n,
+	float* __restrict__ out)
+{
+	extern __shared__ __align__(128) uint8_t smem_raw[];
+	Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int64_t n_tiles = (n + 127) / 128;
+	const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+	if (warp == 1) {
+		if (lane == 0) {
+			for (int s = 0; s < kRing; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+			mbar_init(&sm.a_ready, 4);
+			mbar_init(&sm.d_ready, 1);
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncwarp();
+		tmem_alloc_all(&sm.tmem_base);
+	}
+	for (int i = threadIdx.x; i < kBiasFloats; i += kThreads) sm.bias[i] = reinterpret_cast<const float*>(blob + kWeightBytes)[i];
+	fence_before();
+	__syncthreads();
+	fence_after();
+	const uint32_t tmem = sm.tmem_base;
+
+	if (warp == 0) {
+		// ===== producer: the same 41-stage weight stream for every tile =====
+		if (lane == 0) {
+			uint32_t g = 0;
+			for (int64_t t = 0; t < my_tiles; t++) {
+#pragma unroll 1
+				for (int l = 0; l < kLayers; l++) {
+					int off = layer_offset(l);
+					for (int s = 0; s < layer_stages(l); s++, g++) {
+						const uint32_t slot = g % kRing, round = g / kRing;
+						mbar_wait(&sm.empty[slot], (round & 1u) ^ 1u);          // first round passes immediately
+						const uint32_t bytes = stage_bytes(l, s);
+						mbar_expect_tx(&sm.full[slot], bytes);
+						tma_bulk_g2s(sm.ring[slot], blob + off, bytes, &sm.full[slot]);
+						off += bytes;
+					}
+				}
+			}
+		}
+	} else if (warp == 1) {
+		// ===== MMA issuer =====
+		if (lane == 0) {
+			uint32_t g = 0, pa = 0;
+			for (int64_t t = 0; t < my_tiles; t++) {
+#pragma unroll 1
+				for (int grp = 0; grp < kGroups; grp++) {
+					mbar_wait(&sm.a_ready, pa);
+					pa ^= 1u;
+					fence_after();
+					for (int l = group_first(grp); l < group_first(grp) + group_count(grp); l++) {
+						const LayerInfo L = layer_info(l);
+						const uint32_t idesc = idesc_f16(128, L.N);
+						const uint32_t lbo = L.N * 16;
+						uint32_t a_col = tmem + L.a_col;
+						bool first = true;
+						for (int s = 0; s < layer_stages(l); s++, g++) {
+							const uint32_t slot = g % kRing, round = g / kRing;
+							mbar_wait(&sm.full[slot], round & 1u);
+							fence_after();
+							const uint32_t saddr = smem_u32(sm.ring[slot]);
+							const int ks = stage_k(l, s) / 16;
+							for (int j = 0; j < ks; j++) {
+								umma_ts(tmem + L.d_col, a_col, smem_desc(saddr + j * 2 * lbo, lbo, 128), idesc, first ? 0u : 1u);
+								first = false;
+								a_col += 8;
+							}
+							umma_commit(&sm.empty[slot]);   // the stage is free again once these MMAs have read it
+						}
+					}
+					umma_commit(&sm.d_ready);
+				}
+			}
+		}
+	} else {
+		// ===== epilogue warps: one thread per row of the tile =====
+		const int q = warp & 3;                                           // TMEM lane quarter this warp may access
+		const int row = (q << 5) | lane;
+		const uint32_t t_lane = tmem + (static_cast<uint32_t>(q << 5) << 16);
+		uint32_t pd = 0;
+		for (int64_t t = 0; t < my_tiles; t++) {
+			const int64_t tile = blockIdx.x + t * gridDim.x;
+			const int64_t r = tile * 128 + row;
+			const bool ok = r < n;
+			// ---- inputs: 63 point channels (+1 zero) and 27 view channels (+5 zero) as fp16 pairs into their TMEM columns
+			{
+				const float2* xr = reinterpret_cast<const float2*>(x + (ok ? r : 0) * kInCh);   // rows are 360 B: 8-byte aligned
+				uint32_t a16[16];
+#pragma unroll
+				for (int h = 0; h < 2; h++) {
+#pragma unroll
+					for (int i = 0; i < 16; i++) {
+						const int k = 32 * h + 2 * i;
+						float2 v = make_float2(0.f, 0.f);
+						if (ok) {
+							if (k + 1 < kInPts) v = __ldg(xr + k / 2);
+							else if (k < kInPts) v = make_float2(__ldg(x + r * kInCh + k), 0.f);
+						}
+						a16[i] = pack_f16(v.x, v.y);
+					}
+					tmem_st16(t_lane + kColPts + 16 * h, a16);
+				}
+#pragma unroll
+				for (int i = 0; i < 16; i++) {
+					const int k = 2 * i;
+					float v0 = 0.f, v1 = 0.f;
+					if (ok && k < kInViews) v0 = __ldg(x + r * kInCh + kInPts + k);
+					if (ok && k + 1 < kInViews) v1 = __ldg(x + r * kInCh + kInPts + k + 1);
+					a16[i] = pack_f16(v0, v1);
+				}
+				tmem_st16(t_lane + kColViews, a16);
+			}
+			publish(&sm.a_ready, lane);
+
+			float alpha = 0.f;
+#pragma unroll 1
+			for (int grp = 0; grp < kGroups; grp++) {
+				mbar_wait(&sm.d_ready, pd);
+				pd ^= 1u;
+				fence_after();
+				if (grp < 8) {
+					// pts_linears: relu(D + b) -> h (the next layer's A operand)
+					const float* bias = sm.bias + bias_offset(0) + grp * kW;
+#pragma unroll 1
+					for (int c = 0; c < 8; c++) {
+						uint32_t acc[32], a16[16];
+						tmem_ld32(t_lane + kColD + 32 * c, acc);
+						tmem_ld_wait();
+						bias_act_pack<true>(acc, bias + 32 * c, a16);
+						tmem_st16(t_lane + kColH + 16 * c, a16);
+					}
+					publish(&sm.a_ready, lane);
+				} else if (grp == 8) {
+					// feature_linear (no activation) -> h ; alpha_linear -> register
+					uint32_t d16[16];
+					tmem_ld16(t_lane + kColD16, d16);
+					tmem_ld_wait();
+					alpha = __uint_as_float(d16[0]) + sm.bias[bias_offset(9)];
+#pragma unroll 1
+					for (int c = 0; c < 8; c++) {
+						uint32_t acc[32], a16[16];
+						tmem_ld32(t_lane + kColD + 32 * c, acc);
+						tmem_ld_wait();
+						bias_act_pack<false>(acc, sm.bias + bias_offset(8) + 32 * c, a16);
+						tmem_st16(t_lane + kColH + 16 * c, a16);
+					}
+					publish(&sm.a_ready, lane);
+				} else if (grp == 9) {
+					// views_linears[0]: relu -> first 128 channels of h
+#pragma unroll 1
+					for (int c = 0; c < 4; c++) {
+						uint32_t acc[32], a16[16];
+						tmem_ld32(t_lane + kColD + 32 * c, acc);
+						tmem_ld_wait();
+						bias_act_pack<true>(acc, sm.bias + bias_offset(10) + 32 * c, a16);
+						tmem_st16(t_lane + kColH + 16 * c, a16);
+					}
+					publish(&sm.a_ready, lane);
+				} else {
+					// rgb_linear -> out = [rgb, alpha] (src/NeRF.cpp:119-120)
+					uint32_t c4[4];
+					tmem_ld4(t_lane + kColD16, c4);
+					tmem_ld_wait();
+					const float* b = sm.bias + bias_offset(11);
+					if (ok) *reinterpret_cast<float4*>(out + r * 4) = make_float4(__uint_as_float(c4[0]) + b[0], __uint_as_float(c4[1]) + b[1],
+						__uint_as_float(c4[2]) + b[2], alpha);
+				}
+			}
+		}
+	}
+
+	fence_before();
+	__syncthreads();
+	if (warp == 1) {
+		fence_after();
+		tmem_free_all(tmem);
+	}
+}
+
+static int check_shape(const nrf_mlp_nerf_shape* s)
+{
+	NRF_REQUIRE(s != nullptr, "shape is null");
+	if (!(s->depth == 8 && s->width == kW && s->input_ch == kInPts && s->input_ch_views == kInViews && s->skip_layer == 4 && s->use_viewdirs == 1)) {
+		set_error("nrf_mlp_nerf: only the BASELINE shape D=8 W=256 in=63+27 skip={4} use_viewdirs is built");
+		return NRF_ERR_UNSUPPORTED;
+	}
+	return NRF_OK;
+}
+
+}  // namespace nerf_tc
+}  // namespace nrf
+
+using namespace nrf;
+using namespace nrf::nerf_tc;
+
+extern "C" {
+
+int64_t nrf_mlp_nerf_packed_bytes(const nrf_mlp_nerf_shape* shape) { return nerf_tc::check_shape(shape) ? -1 : static_cast<int64_t>(kPackedBytes); }
+
+int nrf_mlp_nerf_pack(const nrf_mlp_nerf_shape* shape, const nrf_mlp_nerf_weights* w, void* packed, nrf_stream stream)
+{
+	if (int rc = nerf_tc::check_shape(shape)) return rc;
+	NRF_REQUIRE(w != nullptr && packed != nullptr, "null pointer");
+	NRF_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0, "packed blob must be 128-byte aligned");
+	Weights p;
+	for (int i = 0; i < 8; i++) { p.w[i] = w->pts_w[i]; p.b[i] = w->pts_b[i]; }
+	p.w[8] = w->feature_w; p.b[8] = w->feature_b;
+	p.w[9] = w->alpha_w; p.b[9] = w->alpha_b;
+	p.w[10] = w->views_w; p.b[10] = w->views_b;
+	p.w[11] = w->rgb_w; p.b[11] = w->rgb_b;
+	for (int i = 0; i < kLayers; i++) NRF_REQUIRE(p.w[i] && p.b[i], "null weight / bias pointer");
+	nerf_pack_kernel<<<(kPackedBytes / 4 + 255) / 256, 256, 0, as_stream(stream)>>>(p, reinterpret_cast<uint32_t*>(packed));
+	NRF_CHECK_LAUNCH("nerf_pack_kernel");
+	return NRF_OK;
+}
+
+int nrf_mlp_nerf_fwd(const nrf_mlp_nerf_shape* shape, const void* packed, const float* x, int64_t n, float* out, nrf_stream stream)
+{
+	if (int rc = nerf_tc::check_shape(shape)) return rc;
+	NRF_REQUIRE(n >= 0, "negative n");
+	if (n == 0) return NRF_OK;
+	NRF_REQUIRE(packed && x && out, "null pointer");
+	NRF_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+		"packed must be 128-byte, x 8-byte, out 16-byte aligned");
+	const int64_t tiles = (n + 127) / 128;
+	const int blocks = static_cast<int>(std::min<int64_t>(tiles, kNumSMs));
+	const int smem = static_cast<int>(sizeof(Smem)) + 128;
+	NRF_CUDA(cudaFuncSetAttribute(mlp_nerf_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+	mlp_nerf_fwd_tc_kernel<<<blocks, kThreads, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed), x, n, out);
+	NRF_CHECK_LAUNCH("mlp_nerf_fwd_tc_kernel");
+	return NRF_OK;
+}
+
+}

@@ -350,3 +350,38 @@ def adam_step_sharded(peer_group, param, exp_avg, exp_avg_sq, n_sharded: int, sc
     """reduce-scatter + Adam + fp16 shadow all-gather over peer memory (nrf_adam_step_sharded); peer_group: cabi.PeerGroup."""
     _run("adam_step", lambda: lib().nrf_adam_step_sharded(C.byref(peer_group), ptr(param, f32), ptr(exp_avg, f32), ptr(exp_avg_sq, f32), n_sharded,
                               param.numel(), ptr(sched_state), beta1, beta2, eps, grad_scale, stream()))
+
+
+def mlp_nerf_shape(depth=8, width=256, input_ch=63, input_ch_views=27, skip_layer=4, use_viewdirs=True):
+    return cabi.MlpNerfShape(depth, width, input_ch, input_ch_views, skip_layer, int(use_viewdirs))
+
+
+def mlp_nerf_pack(p: dict, shape=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """p: the reference's registered names ('model_pts_linears_<i>.weight' ... 'model_rgb_linear.bias', src/NeRF.cpp:76-89) ->
+    contiguous fp32 CUDA tensors.  Returns the packed fp16 UMMA-operand blob (+ fp32 biases) of nrf_mlp_nerf_fwd."""
+    shape = shape or mlp_nerf_shape()
+    nbytes = lib().nrf_mlp_nerf_packed_bytes(C.byref(shape))
+    if nbytes < 0:
+        check(-3)
+    w = cabi.MlpNerfWeights()
+    for i in range(8):
+        w.pts_w[i] = ptr(p[f"model_pts_linears_{i}.weight"], f32)
+        w.pts_b[i] = ptr(p[f"model_pts_linears_{i}.bias"], f32)
+    for name in ("feature", "alpha", "rgb"):
+        setattr(w, f"{name}_w", ptr(p[f"model_{name}_linear.weight"], f32))
+        setattr(w, f"{name}_b", ptr(p[f"model_{name}_linear.bias"], f32))
+    w.views_w, w.views_b = ptr(p["model_views_linears_0.weight"], f32), ptr(p["model_views_linears_0.bias"], f32)
+    if out is None:
+        out = torch.empty(nbytes, dtype=u8, device=p["model_rgb_linear.bias"].device)
+    _run("mlp_nerf_pack", lambda: lib().nrf_mlp_nerf_pack(C.byref(shape), C.byref(w), ptr(out), stream()))
+    return out
+
+
+def mlp_nerf_fwd(packed: torch.Tensor, x: torch.Tensor, shape=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """NeRFImpl::forward (inference): x [N, 90] fp32 -> [N, 4] = [rgb logits, alpha]."""
+    shape = shape or mlp_nerf_shape()
+    n = x.shape[0]
+    if out is None:
+        out = torch.empty((n, 4), dtype=f32, device=x.device)
+    _run("mlp_nerf_fwd", lambda: lib().nrf_mlp_nerf_fwd(C.byref(shape), ptr(packed), ptr(x, f32), n, ptr(out, f32), stream()))
+    return out
