@@ -140,6 +140,28 @@ __device__ __forceinline__ void bias_act_pack(const uint32_t (&acc)[32], const f
 	}
 }
 
+// D[:, 0 .. 32*CHUNKS) + bias -> (ReLU) -> fp16 -> the h columns, one thread per row.  The tcgen05.ld of chunk c+1 is in flight while
+// chunk c is converted and stored (two register buffers), so the TMEM read latency is paid once, not once per chunk.
+template <int CHUNKS, bool RELU>
+__device__ __forceinline__ void epilogue_to_h(uint32_t t_lane, const float* __restrict__ bias)
+{
+	uint32_t acc0[32], acc1[32], a16[16];
+	tmem_ld32(t_lane + kColD, acc0);
+#pragma unroll
+	for (int c = 0; c < CHUNKS; c += 2) {
+		tmem_ld_wait_for(acc0);
+		if (c + 1 < CHUNKS) tmem_ld32(t_lane + kColD + 32 * (c + 1), acc1);
+		bias_act_pack<RELU>(acc0, bias + 32 * c, a16);
+		tmem_st16(t_lane + kColH + 16 * c, a16);
+		if (c + 1 < CHUNKS) {
+			tmem_ld_wait_for(acc1);
+			if (c + 2 < CHUNKS) tmem_ld32(t_lane + kColD + 32 * (c + 2), acc0);
+			bias_act_pack<RELU>(acc1, bias + 32 * (c + 1), a16);
+			tmem_st16(t_lane + kColH + 16 * (c + 1), a16);
+		}
+	}
+}
+
 __device__ __forceinline__ void publish(uint64_t* bar, int lane)
 {
 	tmem_st_wait();
@@ -279,15 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint
 				fence_after();
 				if (grp < 8) {
 					// pts_linears: relu(D + b) -> h (the next layer's A operand)
-					const float* bias = sm.bias + bias_offset(0) + grp * kW;
-#pragma unroll 1
-					for (int c = 0; c < 8; c++) {
-						uint32_t acc[32], a16[16];
-						tmem_ld32(t_lane + kColD + 32 * c, acc);
-						tmem_ld_wait();
-						bias_act_pack<true>(acc, bias + 32 * c, a16);
-						tmem_st16(t_lane + kColH + 16 * c, a16);
-					}
+					epilogue_to_h<8, true>(t_lane, sm.bias + bias_offset(0) + grp * kW);
 					publish(&sm.a_ready, lane);
 				} else if (grp == 8) {
 					// feature_linear (no activation) -> h ; alpha_linear -> register
@@ -295,25 +309,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint
 					tmem_ld16(t_lane + kColD16, d16);
 					tmem_ld_wait();
 					alpha = __uint_as_float(d16[0]) + sm.bias[bias_offset(9)];
-#pragma unroll 1
-					for (int c = 0; c < 8; c++) {
-						uint32_t acc[32], a16[16];
-						tmem_ld32(t_lane + kColD + 32 * c, acc);
-						tmem_ld_wait();
-						bias_act_pack<false>(acc, sm.bias + bias_offset(8) + 32 * c, a16);
-						tmem_st16(t_lane + kColH + 16 * c, a16);
-					}
+					epilogue_to_h<8, false>(t_lane, sm.bias + bias_offset(8));
 					publish(&sm.a_ready, lane);
 				} else if (grp == 9) {
 					// views_linears[0]: relu -> first 128 channels of h
-#pragma unroll 1
-					for (int c = 0; c < 4; c++) {
-						uint32_t acc[32], a16[16];
-						tmem_ld32(t_lane + kColD + 32 * c, acc);
-						tmem_ld_wait();
-						bias_act_pack<true>(acc, sm.bias + bias_offset(10) + 32 * c, a16);
-						tmem_st16(t_lane + kColH + 16 * c, a16);
-					}
+					epilogue_to_h<4, true>(t_lane, sm.bias + bias_offset(10));
 					publish(&sm.a_ready, lane);
 				} else {
 					// rgb_linear -> out = [rgb, alpha] (src/NeRF.cpp:119-120)

@@ -86,6 +86,17 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4])
 	asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the same wait, tied to the destination registers of an earlier tcgen05.ld so that no use of them can be scheduled above it
+// (needed when another tcgen05.ld is issued between the load and its wait)
+__device__ __forceinline__ void tmem_ld_wait_for(uint32_t (&r)[32])
+{
+	asm volatile("tcgen05.wait::ld.sync.aligned;"
+		: "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
+		  "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]),
+		  "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]),
+		  "+r"(r[31])
+		:: "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16])
 {

@@ -37,8 +37,53 @@ NeRFImpl::NeRFImpl(const int d, const int w, const int input_ch, const int input
 	}
 }
 
+bool NeRFImpl::FusedShape() const
+{
+	const nrf_mlp_nerf_shape s{D, W, InputCh, InputChViews, Skips.size() == 1 ? *Skips.begin() : -1, UseViewDirs ? 1 : 0};
+	return nrf_mlp_nerf_packed_bytes(&s) > 0;   // the library answers -1 for shapes it was not built for
+}
+
+Tensor NeRFImpl::ForwardFused(const Tensor& x)
+{
+	torch::NoGradGuard no_grad;
+	const nrf_mlp_nerf_shape s{D, W, InputCh, InputChViews, *Skips.begin(), 1};
+	// re-pack only when a parameter changed (data pointer or version counter)
+	std::vector<Tensor> params;
+	for (size_t i = 0; i < PtsLinears->size(); i++) {
+		params.push_back(PtsLinears[i]->as<nn::Linear>()->weight);
+		params.push_back(PtsLinears[i]->as<nn::Linear>()->bias);
+	}
+	nn::LinearImpl* tail[4] = {FeatureLinear.get(), AlphaLinear.get(), ViewsLinears[0]->as<nn::Linear>(), RGBLinear.get()};
+	for (nn::LinearImpl* l : tail) {
+		params.push_back(l->weight);
+		params.push_back(l->bias);
+	}
+	std::vector<std::pair<const void*, uint32_t>> key;
+	for (const Tensor& t : params) key.emplace_back(t.data_ptr(), t._version());
+	if (!PackedBlob.defined() || key != PackedKey) {
+		std::vector<Tensor> dense;
+		for (const Tensor& t : params) dense.push_back(nrfhost::Dense(t, torch::kFloat32, "NeRF parameter"));
+		nrf_mlp_nerf_weights w{};
+		for (int i = 0; i < 8; i++) { w.pts_w[i] = dense[2 * i].data_ptr<float>(); w.pts_b[i] = dense[2 * i + 1].data_ptr<float>(); }
+		w.feature_w = dense[16].data_ptr<float>(); w.feature_b = dense[17].data_ptr<float>();
+		w.alpha_w = dense[18].data_ptr<float>();   w.alpha_b = dense[19].data_ptr<float>();
+		w.views_w = dense[20].data_ptr<float>();   w.views_b = dense[21].data_ptr<float>();
+		w.rgb_w = dense[22].data_ptr<float>();     w.rgb_b = dense[23].data_ptr<float>();
+		PackedBlob = torch::empty({nrf_mlp_nerf_packed_bytes(&s)}, torch::TensorOptions().dtype(torch::kUInt8).device(dense[0].device()));
+		nrfhost::Check(nrf_mlp_nerf_pack(&s, &w, PackedBlob.data_ptr(), nrfhost::Stream()), "nrf_mlp_nerf_pack");
+		PackedKey = key;
+	}
+	std::vector<int64_t> shape = x.sizes().vec();
+	Tensor flat = nrfhost::Dense(x, torch::kFloat32, "NeRF input").reshape({-1, int64_t(InputCh + InputChViews)});
+	Tensor out = torch::empty({flat.size(0), 4}, nrfhost::F32Like(flat));
+	nrfhost::Check(nrf_mlp_nerf_fwd(&s, PackedBlob.data_ptr(), flat.data_ptr<float>(), flat.size(0), out.data_ptr<float>(), nrfhost::Stream()), "nrf_mlp_nerf_fwd");
+	shape.back() = 4;
+	return out.view(shape);
+}
+
 Tensor NeRFImpl::forward(Tensor x)
 {
+	if (!torch::GradMode::is_enabled() && x.is_cuda() && x.size(-1) == InputCh + InputChViews && FusedShape()) return ForwardFused(x);
 	Tensor pts = x.narrow(-1, 0, InputCh), views = x.narrow(-1, InputCh, InputChViews);
 	Tensor h = pts;
 	for (size_t i = 0; i < PtsLinears->size(); i++) {

@@ -48,8 +48,10 @@ public:
 };
 TORCH_MODULE(BaseNeRF);
 
-/// Classic NeRF MLP (src/NeRF.h:44-77, src/NeRF.cpp:41-126).  Dense 256-wide GEMM chain: runs on cuBLAS through
-/// torch::linear (a plain library GEMM); the hand-written kernels of this repo target the HashNeRF path.
+/// Classic NeRF MLP (src/NeRF.h:44-77, src/NeRF.cpp:41-126).  Inference (no autograd graph, CUDA input) at the BASELINE shape
+/// D=8, W=256, 63+27 inputs, skips={4}, view branch runs as ONE fused tcgen05 kernel (nrf_mlp_nerf_fwd: activations stay in
+/// tensor memory, weights stream through a TMA ring); training and other shapes run the same maths through torch::linear
+/// (cuBLAS, a plain library GEMM chain) so that LibTorch autograd provides the backward.
 struct NeRFImpl : public BaseNeRFImpl {
 	int D, W, InputCh, InputChViews, OutputCh;
 	std::set<int> Skips;
@@ -61,6 +63,13 @@ struct NeRFImpl : public BaseNeRFImpl {
 		const std::set<int>& skips = std::set<int>{4}, const bool use_viewdirs = false, const std::string module_name = "nerf");
 	~NeRFImpl() override = default;
 	torch::Tensor forward(torch::Tensor x) override;
+
+	// ---- B200 additions
+	bool FusedShape() const;                   ///< true when nrf_mlp_nerf_fwd covers this configuration
+	torch::Tensor ForwardFused(const torch::Tensor& x);   ///< [.., 90] -> [.., 4] on the fused kernel (no autograd)
+private:
+	torch::Tensor PackedBlob;
+	std::vector<std::pair<const void*, uint32_t>> PackedKey;
 };
 TORCH_MODULE(NeRF);
 

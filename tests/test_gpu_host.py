@@ -42,6 +42,17 @@ def _rays(n, seed=0):
     return o.cuda(), d.cuda()
 
 
+def _positive_density(*pipes, value=0.3):
+    """Random-init classic NeRF has sigma = 0 +- 1e-4, and RawToOutputs is DISCONTINUOUS in the sign of the last sample's sigma
+    (the 1e10 interval, NeRFRenderer.h:240: acc jumps 0 -> 1), so fp16-operand vs fp32 GEMMs would be compared on a coin flip.
+    Shift the density bias away from zero in every pipeline (also exercises the re-pack on a parameter change)."""
+    with torch.no_grad():
+        for p in pipes:
+            for name, t in zip(p.model_param_names(), p.model_params()):
+                if name.endswith("alpha_linear.bias"):
+                    t.fill_(value)
+
+
 def _need(ref_cuda):
     if ref_cuda is None:
         pytest.skip("oracle/_ref/nerfpp_ref_cuda.so not loadable")
@@ -190,11 +201,44 @@ def test_classic_pipeline_matches_reference(host, ref_cuda):
     for a, b in zip(ours.model_params(), ref.model_params()):
         assert torch.equal(a, b)
     assert ours.model_param_names() == ref.model_param_names()
+    _positive_density(ours, ref)
     o, d = _rays(32)
     r1 = ours.render(o, d, 64, 128, 4096, False, True)
     r2 = ref.render(o, d, 64, 128, 4096, False, True)
     for k in ("rgb", "acc", "depth"):
-        assert torch.allclose(r1[k], r2[k], rtol=2e-3, atol=2e-3), k
+        # the coarse pass (never differentiated) runs on the fused fp16-operand forward: importance samples move by O(1e-3)
+        assert torch.allclose(r1[k], r2[k], rtol=1e-2, atol=1e-2), k
+
+
+def test_classic_inference_runs_on_the_fused_tcgen05_forward(host, ref_cuda):
+    """Under NoGradGuard (render_image) the drop-in NeRF::forward is ONE nrf_mlp_nerf_fwd launch; the reference renders the same
+    image through 11 cuBLAS SGEMMs.  fp16 operands vs fp32: maps agree to 1e-2; and the drop-in's own autograd path (torch::linear)
+    agrees with its fused path."""
+    _need(ref_cuda)
+    from nerfpp_b200 import cabi
+    pipes = []
+    for mod, extra in ((host, ()), (ref_cuda, (True,))):
+        mod.manual_seed(9)
+        torch.manual_seed(9)
+        p = mod.make_classic(torch.tensor(BBOX).cuda(), 10, 4, 8, 256, True, *extra)
+        p.init_model()
+        pipes.append(p)
+    ours, ref = pipes
+    _positive_density(ours, ref)
+    K = torch.tensor([[30.0, 0, 12.0], [0, 30.0, 10.0], [0, 0, 1]])
+    c2w = torch.eye(4)
+    c2w[2, 3] = 4.0
+    n0 = cabi.launch_count()
+    a = ours.render_image(20, 24, K.cuda(), c2w.cuda(), 64, 128, 4096, False, True)
+    assert cabi.launch_count() > n0
+    b = ref.render_image(20, 24, K.cuda(), c2w.cuda(), 64, 128, 4096, False, True)
+    for k in ("rgb", "acc", "depth"):
+        assert torch.allclose(a[k], b[k], rtol=1e-2, atol=1e-2), k
+    x = torch.rand(300, 90).cuda()
+    with torch.no_grad():
+        fused = ours.model(x)
+    plain = ours.model(x.requires_grad_(True))      # grad mode on: torch::linear path
+    assert float((fused - plain.detach()).abs().max()) <= 1e-2 * float(plain.abs().max()) + 1e-4
 
 
 def test_fused_adam_tracks_torch_adam(host):
