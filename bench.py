@@ -31,7 +31,7 @@ CPU_SAMPLE_RAYS = 256   # bounded sample of the 4096-ray step for the CPU arms
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/), largest launch
 NCU_TRAFFIC_BYTES = {
-    "hash_encode_fwd": 25.85e6 + 6.95e6,    # profiles/r1_hash_fwd_ncu.txt, 786 432-point launch
+    "hash_encode_fwd": 19.59e6 + 3.89e6,    # profiles/r1_hash_fwd_v3_ncu.txt, 786 432-point launch
     "hash_encode_bwd": 89.12e6 + 2.39e6,    # profiles/r1_hash_bwd_v2_ncu.txt
 }
 # algorithmic bytes per unit (SURVEY §8d with this repo's fp16 encoding output)
@@ -228,7 +228,7 @@ def main() -> None:
     # ---- roofline leg: the same steps launched eagerly so the dominant kernel can carry a CUDA-event pair on its stream
     # (a graph replay cannot); same buffers, same sizes, run back to back with the timed region
     roof_steps = min(args.steps, 50)
-    timer = ops.KernelTimer(only=[dominant])
+    timer = ops.KernelTimer(only=[dominant, "mlp_small_fwd", "mlp_small_bwd"])
     ops.set_timer(timer)
     sync_all()
     e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -240,6 +240,8 @@ def main() -> None:
     ops.set_timer(None)
     ms_eager = e4.elapsed_time(e5) / roof_steps
     n_launch, ms_kernel = timer.summary()[dominant]
+    _, ms_mlp_fwd = timer.summary()["mlp_small_fwd"]
+    _, ms_mlp_bwd = timer.summary()["mlp_small_bwd"]
 
     # ---- timed region B (e2e): the public API with HOST buffers — pinned H2D of the step's rays/targets and a D2H read
     # of the loss inside the timed region, every step
@@ -312,6 +314,20 @@ def main() -> None:
                            "not by HBM. Ceilings measured on B200 with scripts/exp/{gather,red}_bench.cu: 280 G random 4 B gathers/s, 209 G REDs/s "
                            "(any operand width); hash_fwd issues 301 G sector lookups/s, hash_bwd 206 G REDs/s (DESIGN.md §4)"}
 
+    # the tensor-core side of the step: fused NeRFSmall forward (tcgen05) and backward (mma.sync), useful FLOPs only
+    # (18 688 FLOP/point forward over coarse + fine points, 37 376 FLOP/point backward over the fine points; the backward also
+    # recomputes the forward, which is not counted)
+    peaks = json.loads(peaks_path.read_text()) if peaks_path.exists() else {}
+    tf_peak = peaks.get("bf16_tflops", 1590.0)
+    pts_fwd, pts_bwd = R * (2 * N_SAMPLES + N_IMPORTANCE), R * (N_SAMPLES + N_IMPORTANCE)
+    tf_fwd = pts_fwd * 18688 * roof_steps / (ms_mlp_fwd * 1e-3) / 1e12
+    tf_bwd = pts_bwd * 37376 * roof_steps / (ms_mlp_bwd * 1e-3) / 1e12
+    roofline_tensor = {"bound": "tensor", "unit": "TFLOP/s", "peak": tf_peak,
+                       "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS burst)" if peaks else "fallback B200_PROFILING.md",
+                       "mlp_small_fwd": {"achieved": tf_fwd, "frac": tf_fwd / tf_peak, "ms_per_step": ms_mlp_fwd / roof_steps, "pipe": "tcgen05"},
+                       "mlp_small_bwd": {"achieved": tf_bwd, "frac": tf_bwd / tf_peak, "ms_per_step": ms_mlp_bwd / roof_steps, "pipe": "mma.sync (HMMA)"},
+                       "note": "event pairs include both launches of the forward (coarse + fine) and their launch gaps; ncu per-launch figures in profiles/"}
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -334,7 +350,7 @@ def main() -> None:
                    "precision": "fp16 hash table reads / encodings, bf16 tensor-core MLP with fp32 accumulate, fp32 everything else"},
         "e2e": {"value": rays_total / (ms_e2e / 1e3), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches * world, "graph_replay": use_graph, "kernels_per_step": launches_per_step, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "gpu_launches": launches * world, "graph_replay": use_graph, "kernels_per_step": launches_per_step, "roofline": roofline, "roofline_tensor": roofline_tensor, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms_per_step"])},
         "final_loss": {"resident": loss_resident, "e2e": loss_host}, "render": render,
     }))
