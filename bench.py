@@ -121,6 +121,53 @@ def run_reference(args) -> None:
     }))
 
 
+def classic_nerf_leg(tf_peak: float, rows: int = 1024 * 192, reps: int = 10) -> dict:
+    """BASELINE C1's network (NeRFImpl 8x256, src/NeRF.cpp:92-126) at one 1024-ray training batch of 64+128 samples (196 608 rows):
+    inference forward, training forward (stores the layer inputs) and backward (gradient chain + weight gradients), each timed with
+    a CUDA-event pair over `reps` launches.  1.187 MFLOP/row forward, 2x that backward (no input gradient: layer 0 has dW only)."""
+    import ctypes
+    import math
+
+    import torch
+    from nerfpp_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    shapes = {f"model_pts_linears_{i}": (256, 63 if i == 0 else (319 if i == 5 else 256)) for i in range(8)}
+    shapes.update({"model_feature_linear": (256, 256), "model_alpha_linear": (1, 256), "model_views_linears_0": (128, 283), "model_rgb_linear": (3, 128)})
+    p = {}
+    for name, (o, i) in shapes.items():
+        p[name + ".weight"] = (torch.randn(o, i, generator=g) * math.sqrt(2.0 / i)).cuda()
+        p[name + ".bias"] = (torch.randn(o, generator=g) * 0.1).cuda()
+    x = (torch.rand(rows, 90, generator=g) * 2 - 1).cuda()
+    gout = (torch.randn(rows, 4, generator=g) * 1e-3).cuda()
+    packed, packed_t = ops.mlp_nerf_pack(p), ops.mlp_nerf_pack(p, train=True)
+    grads = {k: torch.zeros_like(v) for k, v in p.items()}
+    out, saved = ops.mlp_nerf_fwd_train(packed_t, x)
+    ws = torch.empty(ops.lib().nrf_mlp_nerf_bwd_workspace_bytes(ctypes.byref(ops.mlp_nerf_shape()), rows), dtype=torch.uint8, device="cuda")
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms_inf = timed(lambda: ops.mlp_nerf_fwd(packed, x, out=out))
+    ms_fwd = timed(lambda: ops.mlp_nerf_fwd_train(packed_t, x))
+    ms_bwd = timed(lambda: ops.mlp_nerf_bwd(packed_t, saved, gout, grads, workspace=ws))
+    fl = rows * 1.186816e6
+    bwd_flop = 2 * fl - rows * 2 * (63 * 256 + 63 * 256 + 27 * 128)      # no dX for the embedded inputs
+    return {"rows": rows, "config": "C1 network: 8x256 + skip + view branch, one 1024-ray batch x (64+128) samples",
+            "fwd_inference": {"ms": ms_inf, "achieved": fl / ms_inf / 1e9, "frac": fl / ms_inf / 1e9 / tf_peak, "dtype": "fp16"},
+            "fwd_train": {"ms": ms_fwd, "achieved": fl / ms_fwd / 1e9, "frac": fl / ms_fwd / 1e9 / tf_peak, "dtype": "bf16",
+                          "saved_bytes": int(saved.numel())},
+            "bwd": {"ms": ms_bwd, "achieved": bwd_flop / ms_bwd / 1e9, "frac": bwd_flop / ms_bwd / 1e9 / tf_peak, "dtype": "bf16",
+                    "kernels": "mlp_nerf_bwd_chain_kernel + mlp_nerf_bwd_dw_kernel"}}
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -327,6 +374,9 @@ def main() -> None:
                        "mlp_small_fwd": {"achieved": tf_fwd, "frac": tf_fwd / tf_peak, "ms_per_step": ms_mlp_fwd / roof_steps, "pipe": "tcgen05"},
                        "mlp_small_bwd": {"achieved": tf_bwd, "frac": tf_bwd / tf_peak, "ms_per_step": ms_mlp_bwd / roof_steps, "pipe": "mma.sync (HMMA)"},
                        "note": "event pairs include both launches of the forward (coarse + fine) and their launch gaps; ncu per-launch figures in profiles/"}
+
+    if rank == 0:
+        roofline_tensor["mlp_nerf"] = classic_nerf_leg(tf_peak)
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:

@@ -167,7 +167,16 @@ int nrf_mlp_small_bwd(const nrf_mlp_small_shape* shape, const void* packed, nrf_
  * [feature | dirs] -> 128 -> ReLU -> rgb (:112-119), biases included, out = [rgb(3), alpha] (:120).  Built for the BASELINE
  * shape (NeRFExecutor.h:478: D=8, W=256, input_ch=63, input_ch_views=27, skips={4}, use_viewdirs); other shapes return
  * NRF_ERR_UNSUPPORTED.  x [N, 90] fp32 = cat(embedded points, embedded dirs) (src/NeRFRenderer.h:182), out [N,4] fp32.
- * Training of this model still goes through LibTorch autograd in the C++ layer (the backward is not built).
+ *
+ * Training (the autograd backward of the same forward, src/NeRFExecutor.h:883-890 -> loss.backward()):
+ *   nrf_mlp_nerf_pack_train   bf16 copy of the weights in the same blob layout (bf16 keeps fp32's exponent range: with the
+ *                             reference's Xavier(0.1) initialisation, Trainable.h:43, fp16 activations of the deep layers are 0)
+ *   nrf_mlp_nerf_fwd_train    the forward on that blob; additionally stores every layer's input, bf16, into `saved`
+ *                             (nrf_mlp_nerf_saved_bytes(n) bytes, 128-byte aligned)
+ *   nrf_mlp_nerf_bwd          grad_out [N,4] fp32 (d loss / d [rgb, alpha]) -> gradients of the 12 weight matrices and biases,
+ *                             ADDED (+=, fp32 atomics) to the caller's tensors in torch Linear layout; `workspace` needs
+ *                             nrf_mlp_nerf_bwd_workspace_bytes(n) bytes.  No gradient with respect to x is produced: the
+ *                             positional embedder feeding x has no parameters (src/NeRF.cpp:4-39).
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct nrf_mlp_nerf_shape {
 	int32_t depth;           /* 8   */
@@ -190,6 +199,23 @@ typedef struct nrf_mlp_nerf_weights {   /* device pointers, torch Linear layout 
 int64_t nrf_mlp_nerf_packed_bytes(const nrf_mlp_nerf_shape* shape);
 int nrf_mlp_nerf_pack(const nrf_mlp_nerf_shape* shape, const nrf_mlp_nerf_weights* weights, void* packed, nrf_stream stream);
 int nrf_mlp_nerf_fwd(const nrf_mlp_nerf_shape* shape, const void* packed, const float* x, int64_t n, float* out, nrf_stream stream);
+
+typedef struct nrf_mlp_nerf_grads {     /* device pointers, same shapes as nrf_mlp_nerf_weights; accumulated into */
+	float* pts_w[8];
+	float* pts_b[8];
+	float* feature_w; float* feature_b;
+	float* alpha_w;   float* alpha_b;
+	float* views_w;   float* views_b;
+	float* rgb_w;     float* rgb_b;
+} nrf_mlp_nerf_grads;
+
+int nrf_mlp_nerf_pack_train(const nrf_mlp_nerf_shape* shape, const nrf_mlp_nerf_weights* weights, void* packed_train, nrf_stream stream);
+int64_t nrf_mlp_nerf_saved_bytes(const nrf_mlp_nerf_shape* shape, int64_t n);
+int64_t nrf_mlp_nerf_bwd_workspace_bytes(const nrf_mlp_nerf_shape* shape, int64_t n);
+int nrf_mlp_nerf_fwd_train(const nrf_mlp_nerf_shape* shape, const void* packed_train, const float* x, int64_t n, float* out, void* saved,
+                           nrf_stream stream);
+int nrf_mlp_nerf_bwd(const nrf_mlp_nerf_shape* shape, const void* packed_train, const void* saved, const float* grad_out, int64_t n,
+                     void* workspace, const nrf_mlp_nerf_grads* grads, nrf_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Volume rendering — NeRFRenderer::RawToOutputs (src/NeRFRenderer.h:199-282) with TruncExp

@@ -1,0 +1,536 @@
+// Backward of the classic NeRF MLP (NeRFImpl::forward, reference src/NeRF.cpp:92-126, differentiated by LibTorch autograd in the
+// reference: 11 cuBLAS SGEMM pairs + ReLU-mask / bias-sum kernels) on tcgen05 / TMEM / TMA for sm_100a.
+//
+// Two kernels over the scratch records of mlp_nerf_layout.cuh (written by nrf_mlp_nerf_fwd_train):
+//
+//  1. mlp_nerf_bwd_chain_kernel — the gradient chain  dY_{l-1} = (dY_l W_l) * relu'(h_l), one persistent CTA per SM, one 128-row tile
+//     in flight.  Same roles as the forward: warp 0 streams the FORWARD weight blob through a 4 x 32 KB TMA ring (38 of its 41
+//     stages, in reverse layer order; the stage bytes are read as an MN-major B operand, so no transposed copy of the weights
+//     exists), warp 1 issues tcgen05.mma M=128 N=64 K=16 with the bf16 gradient rows as A operand in TMEM and fp32 accumulators in
+//     TMEM, warps 2..5 (one thread per row) read the accumulator, apply the ReLU mask taken from the saved activation
+//     (bits != 0 after ReLU), pack to bf16, write the next A operand to TMEM and the gradient record to HBM.
+//     Gradients with respect to the inputs (embedded points / directions) are not produced: the positional embedder has no
+//     parameters (src/NeRF.cpp:4-39).
+//
+//  2. mlp_nerf_bwd_dw_kernel — dW_l = dY_l^T X_l and db_l = column sums of dY_l as ONE flat list of (unit, 64-row slab) work items
+//     split evenly over the SMs.  A unit is a 128-wide output block of one weight matrix; both MMA operands are the record
+//     regions as they lie in HBM (MN-major A and B, one bulk copy each per stage), accumulators stay in TMEM over a CTA's whole
+//     range of a unit and leave as fp32 REDs into the caller's gradient tensors.  The 4 epilogue warps sum the columns of the
+//     dY slabs from shared memory (bias gradients) while the tensor core works.
+//
+// bf16 operands, fp32 accumulation; parity tests/test_gpu_mlp_nerf.py (rel 1e-2 against the fp64 autograd of the oracle).
+#include "mlp_nerf_layout.cuh"
+#include <algorithm>
+
+namespace nrf {
+namespace nerf_tc {
+
+using namespace tc;
+
+constexpr int kBwdThreads = 32 * 6;
+// TMEM columns of the chain kernel: D fp32 [128 x 256], A bf16 [128 x 256] (128 columns), the two 16-wide head operands
+constexpr uint32_t kBD = 0, kBA = 256, kBRgb = 384, kBAlpha = 392;
+constexpr int kSteps = 10;
+// chain step -> the layer whose weights it multiplies: rgb, views, feature(+alpha), pts_linears 7..1
+__host__ __device__ constexpr int step_layer(int st) { return st == 0 ? 11 : (st == 1 ? 10 : (st == 2 ? 8 : 10 - st)); }
+__host__ __device__ constexpr int step_first_stage(int l) { return l == 5 ? 1 : 0; }        // stage 0 of layer 5 is the [pts] slab
+__host__ __device__ constexpr int step_stages(int l) { return l == 11 ? 1 : 4; }
+
+struct __align__(128) ChainSmem {
+	uint8_t ring[kRing][kStageBytes];
+	uint64_t full[kRing], empty[kRing];
+	uint64_t a_ready, d_ready;
+	uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void publish_bwd(uint64_t* bar, int lane)
+{
+	tmem_st_wait();
+	fence_before();
+	__syncwarp();
+	if (lane == 0) mbar_arrive(bar);
+}
+
+__device__ __forceinline__ void load_mask4(const uint8_t* __restrict__ region_row, int first_chunk, uint32_t (&h)[16])
+{
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		const uint4 v = __ldg(reinterpret_cast<const uint4*>(region_row + (first_chunk + i) * 1024));
+		h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
+	}
+}
+
+__device__ __forceinline__ void store_chunks4(uint8_t* __restrict__ region_row, int first_chunk, const uint32_t (&a16)[16])
+{
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+		*reinterpret_cast<uint4*>(region_row + (first_chunk + i) * 1024) = make_uint4(a16[4 * i], a16[4 * i + 1], a16[4 * i + 2], a16[4 * i + 3]);
+}
+
+// D[:, 0 .. 32*CHUNKS) -> (* relu mask of the saved activation) -> bf16 -> next A operand (TMEM) and the gradient record (HBM)
+template <int CHUNKS, bool MASK>
+__device__ __forceinline__ void epilogue_grad(uint32_t t_lane, const uint8_t* __restrict__ mask_row, uint8_t* __restrict__ out_row, bool to_tmem,
+	uint32_t (&hm)[16])
+{
+	uint32_t acc[32], a16[16];
+	const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll 1
+	for (int c = 0; c < CHUNKS; c++) {
+		tmem_ld32(t_lane + kBD + 32 * c, acc);
+		tmem_ld_wait_for(acc);
+#pragma unroll
+		for (int i = 0; i < 16; i++) {
+			uint32_t w = pack_bf16(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+			if (MASK) w &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&hm[i]), zero);
+			a16[i] = w;
+		}
+		if (MASK && c + 1 < CHUNKS) load_mask4(mask_row, 4 * (c + 1), hm);       // in flight behind the stores and the next TMEM read
+		if (to_tmem) tmem_st16(t_lane + kBA + 16 * c, a16);
+		store_chunks4(out_row, 4 * c, a16);
+	}
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_chain_kernel(const uint8_t* __restrict__ blob, const uint8_t* __restrict__ saved,
+	const float* __restrict__ grad_out, int64_t n, uint8_t* __restrict__ grads)
+{
+	extern __shared__ __align__(128) uint8_t smem_raw[];
+	ChainSmem& sm = *reinterpret_cast<ChainSmem*>(smem_raw);
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int64_t n_tiles = (n + 127) / 128;
+	const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+	if (warp == 1) {
+		if (lane == 0) {
+			for (int s = 0; s < kRing; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+			mbar_init(&sm.a_ready, 4);
+			mbar_init(&sm.d_ready, 1);
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncwarp();
+		tmem_alloc_all(&sm.tmem_base);
+	}
+	fence_before();
+	__syncthreads();
+	fence_after();
+	const uint32_t tmem = sm.tmem_base;
+
+	if (warp == 0) {
+		// ===== producer: 38 stages of the forward blob per tile, reverse layer order =====
+		if (lane == 0) {
+			uint32_t g = 0;
+			auto push = [&](int off, uint32_t bytes) {
+				const uint32_t slot = g % kRing, round = g / kRing;
+				mbar_wait(&sm.empty[slot], (round & 1u) ^ 1u);
+				mbar_expect_tx(&sm.full[slot], bytes);
+				tma_bulk_g2s(sm.ring[slot], blob + off, bytes, &sm.full[slot]);
+				g++;
+			};
+			for (int64_t t = 0; t < my_tiles; t++) {
+#pragma unroll 1
+				for (int st = 0; st < kSteps; st++) {
+					const int l = step_layer(st);
+					for (int s = step_first_stage(l); s < step_first_stage(l) + step_stages(l); s++) push(stage_offset(l, s), stage_bytes(l, s));
+					if (st == 2) push(stage_offset(9, 0), stage_bytes(9, 0));
+				}
+			}
+		}
+	} else if (warp == 1) {
+		// ===== MMA issuer =====
+		if (lane == 0) {
+			uint32_t g = 0, pa = 0;
+			for (int64_t t = 0; t < my_tiles; t++) {
+#pragma unroll 1
+				for (int st = 0; st < kSteps; st++) {
+					mbar_wait(&sm.a_ready, pa);
+					pa ^= 1u;
+					fence_after();
+					const int l = step_layer(st);
+					if (l == 11) {
+						// d_hv = d_rgb * W_rgb: K = 16 (3 real), N = 128
+						const uint32_t slot = g % kRing, round = g / kRing;
+						mbar_wait(&sm.full[slot], round & 1u);
+						fence_after();
+						umma_ts(tmem + kBD, tmem + kBRgb, smem_desc(smem_u32(sm.ring[slot]), 128, 16 * 16), idesc_16(128, 128, true, 0, 1), 0u);
+						umma_commit(&sm.empty[slot]);
+						g++;
+					} else {
+						const int n_out = layer_info(l).N;               // K of this product
+						const uint32_t idesc = idesc_16(128, 64, true, 0, 1);
+						for (int s = 0; s < 4; s++, g++) {
+							const uint32_t slot = g % kRing, round = g / kRing;
+							mbar_wait(&sm.full[slot], round & 1u);
+							fence_after();
+							const uint32_t saddr = smem_u32(sm.ring[slot]);
+							for (int j = 0; j < n_out / 16; j++)
+								umma_ts(tmem + kBD + 64 * s, tmem + kBA + 8 * j, smem_desc(saddr + j * 256, 128, n_out * 16), idesc, j ? 1u : 0u);
+							umma_commit(&sm.empty[slot]);
+						}
+						if (st == 2) {
+							// + d_alpha * W_alpha over all 256 columns: K = 16 (1 real)
+							const uint32_t slot = g % kRing, round = g / kRing;
+							mbar_wait(&sm.full[slot], round & 1u);
+							fence_after();
+							umma_ts(tmem + kBD, tmem + kBAlpha, smem_desc(smem_u32(sm.ring[slot]), 128, 16 * 16), idesc_16(128, 256, true, 0, 1), 1u);
+							umma_commit(&sm.empty[slot]);
+							g++;
+						}
+					}
+					umma_commit(&sm.d_ready);
+				}
+			}
+		}
+	} else {
+		// ===== epilogue warps: one thread per row =====
+		const int q = warp & 3;
+		const int row = (q << 5) | lane;
+		const uint32_t t_lane = tmem + (static_cast<uint32_t>(q << 5) << 16);
+		uint32_t pd = 0;
+		for (int64_t t = 0; t < my_tiles; t++) {
+			const int64_t tile = blockIdx.x + t * gridDim.x;
+			const int64_t r = tile * 128 + row;
+			const uint8_t* const rec_s = saved + tile * kSaveTile;
+			uint8_t* const rec_g = grads + tile * kGradTile;
+			uint32_t hm[16];
+			{
+				float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+				if (r < n) g4 = __ldg(reinterpret_cast<const float4*>(grad_out) + r);
+				uint32_t a16[16];
+#pragma unroll
+				for (int i = 0; i < 16; i++) a16[i] = 0u;
+				a16[0] = pack_bf16(g4.x, g4.y);
+				a16[1] = pack_bf16(g4.z, 0.f);
+				a16[8] = pack_bf16(g4.w, 0.f);
+				tmem_st16(t_lane + kBRgb, a16);          // columns kBRgb..+7 = [r g b 0..], kBAlpha..+7 = [alpha 0..]
+				uint8_t* o = rec_g + kGradOut + chunk_offset(16, row, 0);
+				*reinterpret_cast<uint4*>(o) = make_uint4(a16[0], pack_bf16(g4.z, g4.w), 0u, 0u);
+				*reinterpret_cast<uint4*>(o + 1024) = make_uint4(0u, 0u, 0u, 0u);
+			}
+			load_mask4(rec_s + kSaveHv + chunk_offset(128, row, 0), 0, hm);
+			publish_bwd(&sm.a_ready, lane);
+
+#pragma unroll 1
+			for (int st = 0; st < kSteps; st++) {
+				mbar_wait(&sm.d_ready, pd);
+				pd ^= 1u;
+				fence_after();
+				if (st == 0) {
+					epilogue_grad<4, true>(t_lane, rec_s + kSaveHv + chunk_offset(128, row, 0), rec_g + kGradHv + chunk_offset(128, row, 0), true, hm);
+				} else if (st == 1) {
+					epilogue_grad<8, false>(t_lane, nullptr, rec_g + kGradFeat + chunk_offset(256, row, 0), true, hm);
+				} else {
+					const int l = st == 2 ? 8 : 10 - st;         // the activation h_l whose ReLU is undone; the result is dY_{l-1}
+					epilogue_grad<8, true>(t_lane, rec_s + save_h(l) + chunk_offset(256, row, 0), rec_g + grad_y(l - 1) + chunk_offset(256, row, 0),
+						st + 1 < kSteps, hm);
+				}
+				if (st + 1 < kSteps) {
+					// mask of the next step, requested before the MMAs of that step are waited for
+					if (st == 0) { /* feature: no activation */ }
+					else if (st == 1) load_mask4(rec_s + save_h(8) + chunk_offset(256, row, 0), 0, hm);
+					else load_mask4(rec_s + save_h((st == 2 ? 8 : 10 - st) - 1) + chunk_offset(256, row, 0), 0, hm);
+					publish_bwd(&sm.a_ready, lane);
+				}
+			}
+		}
+	}
+
+	fence_before();
+	__syncthreads();
+	if (warp == 1) {
+		fence_after();
+		tmem_free_all(tmem);
+	}
+}
+
+// ---- weight gradients --------------------------------------------------------------------------------------------------
+constexpr int kMaxUnits = 28;
+constexpr int kDwStageBytes = 128 * 64 * 2 + 256 * 64 * 2;         // A: 128 columns x 64 rows, B: up to 256 columns x 64 rows
+struct Unit {
+	int32_t a_src, a_off, a_half;       // record kind (0 gradient, 1 saved), byte offset of the A slab of row half 0, stride to row half 1
+	int32_t b_src, b_off, b_half;
+	int32_t n;                          // MMA N (columns of B)
+	int32_t m_valid, n_lo, n_hi;        // D(m, n) is written for m < m_valid, n_lo <= n < n_hi ...
+	int32_t stride_m, stride_n;         // ... to out[m * stride_m + (n - n_lo) * stride_n]
+	int32_t bias_mode;                  // 0 none; 1 column sums of A -> bias[m]; 2 column sums of B -> bias[0..2] (rgb), bias2[0] (alpha)
+	int32_t pad_;
+	float* out;
+	float* bias;
+	float* bias2;
+};
+struct UnitTable {
+	Unit u[kMaxUnits];
+	int32_t count;
+};
+
+struct __align__(128) DwSmem {
+	uint8_t ring[kRing][kDwStageBytes];
+	uint64_t full[kRing], empty[kRing];
+	uint64_t d_ready[2], d_free[2];
+	uint32_t tmem_base;
+};
+
+__device__ __forceinline__ int64_t clamp_items(int64_t x, int64_t h) { return x < 0 ? 0 : (x > h ? h : x); }
+
+__global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_dw_kernel(const __grid_constant__ UnitTable T, const uint8_t* __restrict__ saved,
+	const uint8_t* __restrict__ grads, int64_t n_tiles)
+{
+	extern __shared__ __align__(128) uint8_t smem_raw[];
+	DwSmem& sm = *reinterpret_cast<DwSmem*>(smem_raw);
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int64_t H = 2 * n_tiles;                                   // 64-row slabs per unit
+	int64_t total = 0;
+	for (int u = 0; u < T.count; u++) total += H * (128 + T.u[u].n);
+	const int64_t lo_cost = total / gridDim.x * blockIdx.x + (total % gridDim.x) * blockIdx.x / gridDim.x;
+	const int64_t hi_cost = total / gridDim.x * (blockIdx.x + 1) + (total % gridDim.x) * (blockIdx.x + 1) / gridDim.x;
+
+	if (warp == 1) {
+		if (lane == 0) {
+			for (int s = 0; s < kRing; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 5); }
+			mbar_init(&sm.d_ready[0], 1);
+			mbar_init(&sm.d_ready[1], 1);
+			mbar_init(&sm.d_free[0], 4);
+			mbar_init(&sm.d_free[1], 4);
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncwarp();
+		tmem_alloc_all(&sm.tmem_base);
+	}
+	fence_before();
+	__syncthreads();
+	fence_after();
+	const uint32_t tmem = sm.tmem_base;
+
+	if (warp == 0) {
+		// ===== producer =====
+		if (lane == 0) {
+			uint32_t g = 0;
+			int64_t cum = 0;
+			for (int u = 0; u < T.count; u++) {
+				const Unit& U = T.u[u];
+				const int64_t c = 128 + U.n;
+				const int64_t lo = clamp_items((lo_cost - cum) / c, H), hi = clamp_items((hi_cost - cum) / c, H);
+				cum += H * c;
+				const uint8_t* a_base = (U.a_src ? saved : grads) + U.a_off;
+				const uint8_t* b_base = (U.b_src ? saved : grads) + U.b_off;
+				const int64_t a_tile = U.a_src ? kSaveTile : kGradTile, b_tile = U.b_src ? kSaveTile : kGradTile;
+				const uint32_t b_bytes = U.n * 128;
+				for (int64_t i = lo; i < hi; i++, g++) {
+					const uint32_t slot = g % kRing, round = g / kRing;
+					mbar_wait(&sm.empty[slot], (round & 1u) ^ 1u);
+					mbar_expect_tx(&sm.full[slot], 16384 + b_bytes);
+					tma_bulk_g2s(sm.ring[slot], a_base + (i >> 1) * a_tile + (i & 1) * U.a_half, 16384, &sm.full[slot]);
+					tma_bulk_g2s(sm.ring[slot] + 16384, b_base + (i >> 1) * b_tile + (i & 1) * U.b_half, b_bytes, &sm.full[slot]);
+				}
+			}
+		}
+	} else if (warp == 1) {
+		// ===== MMA issuer: D[128 columns of A, N] += A^T B over the 64 rows of a slab, 4 K steps =====
+		if (lane == 0) {
+			uint32_t g = 0, seg = 0;
+			int64_t cum = 0;
+			for (int u = 0; u < T.count; u++) {
+				const Unit& U = T.u[u];
+				const int64_t c = 128 + U.n;
+				const int64_t lo = clamp_items((lo_cost - cum) / c, H), hi = clamp_items((hi_cost - cum) / c, H);
+				cum += H * c;
+				if (hi <= lo) continue;
+				const uint32_t buf = seg & 1u;
+				mbar_wait(&sm.d_free[buf], ((seg >> 1) & 1u) ^ 1u);          // first use of each buffer passes immediately
+				fence_after();
+				const uint32_t idesc = idesc_16(128, U.n, true, 1, 1);
+				for (int64_t i = lo; i < hi; i++, g++) {
+					const uint32_t slot = g % kRing, round = g / kRing;
+					mbar_wait(&sm.full[slot], round & 1u);
+					fence_after();
+					const uint32_t saddr = smem_u32(sm.ring[slot]);
+#pragma unroll
+					for (int j = 0; j < 4; j++)
+						umma_ss(tmem + 256 * buf, smem_desc(saddr + j * 256, 128, 1024), smem_desc(saddr + 16384 + j * 256, 128, 1024), idesc,
+							(i > lo || j) ? 1u : 0u);
+					umma_commit(&sm.empty[slot]);
+				}
+				umma_commit(&sm.d_ready[buf]);
+				seg++;
+			}
+		}
+	} else {
+		// ===== epilogue warps: bias column sums while the slabs stream, then the accumulator flush =====
+		const int q = warp & 3;
+		const uint32_t t_lane = tmem + (static_cast<uint32_t>(q << 5) << 16);
+		uint32_t g = 0, seg = 0;
+		int64_t cum = 0;
+		for (int u = 0; u < T.count; u++) {
+			const Unit& U = T.u[u];
+			const int64_t c = 128 + U.n;
+			const int64_t lo = clamp_items((lo_cost - cum) / c, H), hi = clamp_items((hi_cost - cum) / c, H);
+			cum += H * c;
+			if (hi <= lo) continue;
+			float bs[4][8];
+#pragma unroll
+			for (int a = 0; a < 4; a++)
+#pragma unroll
+				for (int e = 0; e < 8; e++) bs[a][e] = 0.f;
+			const bool sum_a = U.bias_mode == 1, sum_b = U.bias_mode == 2 && q == 0;
+			for (int64_t i = lo; i < hi; i++, g++) {
+				const uint32_t slot = g % kRing, round = g / kRing;
+				mbar_wait(&sm.full[slot], round & 1u);
+				if (sum_a || sum_b) {
+					// warp q owns column chunks 4q..4q+3 of the A slab (or chunk 0 of the B slab); lanes take rows lane, lane + 32
+					const uint8_t* base = sm.ring[slot] + (sum_a ? (4 * q) * 1024 : 16384);
+					const int chunks = sum_a ? 4 : 1;
+					for (int a = 0; a < chunks; a++) {
+#pragma unroll
+						for (int h = 0; h < 2; h++) {
+							const uint4 v = *reinterpret_cast<const uint4*>(base + a * 1024 + (lane + 32 * h) * 16);
+							const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+							for (int e = 0; e < 4; e++) {
+								bs[a][2 * e] += __uint_as_float(w[e] << 16);
+								bs[a][2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+							}
+						}
+					}
+				}
+				__syncwarp();
+				if (lane == 0) mbar_arrive(&sm.empty[slot]);
+			}
+			// ---- flush ----
+			if (sum_a || sum_b) {
+#pragma unroll
+				for (int a = 0; a < 4; a++)
+#pragma unroll
+					for (int e = 0; e < 8; e++) {
+						const float s = warp_sum(bs[a][e]);
+						if (lane == 0) {
+							if (sum_a) { if (32 * q + 8 * a + e < U.m_valid) atomicAdd(U.bias + 32 * q + 8 * a + e, s); }
+							else if (a == 0 && e < 3) atomicAdd(U.bias + e, s);
+							else if (a == 0 && e == 3) atomicAdd(U.bias2, s);
+						}
+					}
+			}
+			const uint32_t buf = seg & 1u;
+			mbar_wait(&sm.d_ready[buf], (seg >> 1) & 1u);      // one barrier per accumulator buffer: the issuer can be a whole segment ahead
+			fence_after();
+			const int m = 32 * q + lane;
+			for (int c0 = 0; c0 < U.n; c0 += 16) {
+				uint32_t d16[16];
+				tmem_ld16(t_lane + 256 * buf + c0, d16);
+				tmem_ld_wait();
+				if (m < U.m_valid) {
+#pragma unroll
+					for (int j = 0; j < 16; j++) {
+						const int nn = c0 + j;
+						if (nn >= U.n_lo && nn < U.n_hi) atomicAdd(U.out + static_cast<int64_t>(m) * U.stride_m + static_cast<int64_t>(nn - U.n_lo) * U.stride_n, __uint_as_float(d16[j]));
+					}
+				}
+			}
+			fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&sm.d_free[buf]);
+			seg++;
+		}
+	}
+
+	fence_before();
+	__syncthreads();
+	if (warp == 1) {
+		fence_after();
+		tmem_free_all(tmem);
+	}
+}
+
+static Unit make_unit(int a_src, int a_region, int a_cols, int a_chunk0, int b_src, int b_region, int b_cols, int n, int m_valid, int n_lo, int n_hi,
+	int stride_m, int stride_n, float* out, int bias_mode = 0, float* bias = nullptr, float* bias2 = nullptr)
+{
+	Unit u{};
+	u.a_src = a_src; u.a_off = a_region + a_chunk0 * 1024; u.a_half = a_cols * 128;
+	u.b_src = b_src; u.b_off = b_region; u.b_half = b_cols * 128;
+	u.n = n; u.m_valid = m_valid; u.n_lo = n_lo; u.n_hi = n_hi; u.stride_m = stride_m; u.stride_n = stride_n;
+	u.bias_mode = bias_mode; u.out = out; u.bias = bias; u.bias2 = bias2;
+	return u;
+}
+
+static void build_units(const Grads& g, UnitTable& T)
+{
+	int c = 0;
+	for (int l = 0; l < 8; l++) {
+		const int ld = l == 0 ? kInPts : (l == 5 ? kW + kInPts : kW);
+		for (int mh = 0; mh < 2; mh++) {
+			float* w = g.w[l] + static_cast<int64_t>(128 * mh) * ld;
+			float* b = g.b[l] + 128 * mh;
+			if (l == 0) {
+				T.u[c++] = make_unit(0, grad_y(0), 256, 16 * mh, 1, kSavePts, 64, 64, 128, 0, kInPts, ld, 1, w, 1, b);
+			} else if (l == 5) {
+				T.u[c++] = make_unit(0, grad_y(5), 256, 16 * mh, 1, kSavePts, 64, 64, 128, 0, kInPts, ld, 1, w);
+				T.u[c++] = make_unit(0, grad_y(5), 256, 16 * mh, 1, save_h(5), 256, 256, 128, 0, 256, ld, 1, w + kInPts, 1, b);
+			} else {
+				T.u[c++] = make_unit(0, grad_y(l), 256, 16 * mh, 1, save_h(l), 256, 256, 128, 0, 256, ld, 1, w, 1, b);
+			}
+		}
+	}
+	for (int mh = 0; mh < 2; mh++)   // feature_linear
+		T.u[c++] = make_unit(0, kGradFeat, 256, 16 * mh, 1, save_h(8), 256, 256, 128, 0, 256, kW, 1, g.w[8] + 128 * mh * kW, 1, g.b[8] + 128 * mh);
+	// views_linears[0]: [feature | views]
+	T.u[c++] = make_unit(0, kGradHv, 128, 0, 1, kSaveFeat, 256, 256, 128, 0, 256, kW + kInViews, 1, g.w[10], 1, g.b[10]);
+	T.u[c++] = make_unit(0, kGradHv, 128, 0, 1, kSaveViews, 32, 32, 128, 0, kInViews, kW + kInViews, 1, g.w[10] + kW);
+	// heads, roles swapped (M = input index): rgb_linear [3,128] from hv, alpha_linear [1,256] from h8; their biases from dOut
+	T.u[c++] = make_unit(1, kSaveHv, 128, 0, 0, kGradOut, 16, 16, 128, 0, 3, 1, kW / 2, g.w[11], 2, g.b[11], g.b[9]);
+	for (int mh = 0; mh < 2; mh++)
+		T.u[c++] = make_unit(1, save_h(8), 256, 16 * mh, 0, kGradOut, 16, 16, 128, 3, 4, 1, kW, g.w[9] + 128 * mh);
+	T.count = c;
+}
+
+}  // namespace nerf_tc
+}  // namespace nrf
+
+using namespace nrf;
+using namespace nrf::nerf_tc;
+
+extern "C" {
+
+int64_t nrf_mlp_nerf_bwd_workspace_bytes(const nrf_mlp_nerf_shape* shape, int64_t n)
+{
+	if (nerf_tc::check_shape(shape) || n < 0) return -1;
+	return ((n + 127) / 128) * static_cast<int64_t>(kGradTile);
+}
+
+int nrf_mlp_nerf_bwd(const nrf_mlp_nerf_shape* shape, const void* packed_train, const void* saved, const float* grad_out, int64_t n, void* workspace,
+                     const nrf_mlp_nerf_grads* grads, nrf_stream stream)
+{
+	if (int rc = nerf_tc::check_shape(shape)) return rc;
+	NRF_REQUIRE(n >= 0, "negative n");
+	if (n == 0) return NRF_OK;
+	NRF_REQUIRE(packed_train && saved && grad_out && workspace && grads, "null pointer");
+	NRF_REQUIRE((reinterpret_cast<uintptr_t>(packed_train) & 127) == 0 && (reinterpret_cast<uintptr_t>(saved) & 127) == 0 &&
+		(reinterpret_cast<uintptr_t>(workspace) & 127) == 0 && (reinterpret_cast<uintptr_t>(grad_out) & 15) == 0,
+		"packed / saved / workspace must be 128-byte, grad_out 16-byte aligned");
+	Grads g;
+	for (int i = 0; i < 8; i++) { g.w[i] = grads->pts_w[i]; g.b[i] = grads->pts_b[i]; }
+	g.w[8] = grads->feature_w; g.b[8] = grads->feature_b;
+	g.w[9] = grads->alpha_w; g.b[9] = grads->alpha_b;
+	g.w[10] = grads->views_w; g.b[10] = grads->views_b;
+	g.w[11] = grads->rgb_w; g.b[11] = grads->rgb_b;
+	for (int i = 0; i < kLayers; i++) NRF_REQUIRE(g.w[i] && g.b[i], "null gradient pointer");
+	const int64_t tiles = (n + 127) / 128;
+	{
+		const int blocks = static_cast<int>(std::min<int64_t>(tiles, kNumSMs));
+		const int smem = static_cast<int>(sizeof(ChainSmem)) + 128;
+		NRF_CUDA(cudaFuncSetAttribute(mlp_nerf_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		mlp_nerf_bwd_chain_kernel<<<blocks, kBwdThreads, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed_train),
+			reinterpret_cast<const uint8_t*>(saved), grad_out, n, reinterpret_cast<uint8_t*>(workspace));
+		NRF_CHECK_LAUNCH("mlp_nerf_bwd_chain_kernel");
+	}
+	{
+		UnitTable T{};
+		build_units(g, T);
+		const int64_t items = 2 * tiles * T.count;
+		const int blocks = static_cast<int>(std::min<int64_t>(items, kNumSMs));
+		const int smem = static_cast<int>(sizeof(DwSmem)) + 128;
+		NRF_CUDA(cudaFuncSetAttribute(mlp_nerf_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		mlp_nerf_bwd_dw_kernel<<<blocks, kBwdThreads, smem, as_stream(stream)>>>(T, reinterpret_cast<const uint8_t*>(saved),
+			reinterpret_cast<const uint8_t*>(workspace), tiles);
+		NRF_CHECK_LAUNCH("mlp_nerf_bwd_dw_kernel");
+	}
+	return NRF_OK;
+}
+
+}

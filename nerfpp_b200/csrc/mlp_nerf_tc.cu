@@ -16,71 +16,14 @@
 //     accumulator row with tcgen05.ld, adds the bias (shared memory), applies ReLU, packs to fp16 and writes the next layer's A
 //     operand back to TMEM with tcgen05.st.
 // fp16 operands, fp32 accumulation: <= 1e-2 relative to the fp32 reference (tests/test_gpu_mlp_nerf.py).
-#include "tcgen05.cuh"
-#include "mlp_small_layout.cuh"
+#include "mlp_nerf_layout.cuh"
 
 namespace nrf {
 namespace nerf_tc {
 
 using namespace tc;
 
-constexpr int kW = 256, kInPts = 63, kInViews = 27, kInCh = kInPts + kInViews;
-constexpr int kRing = 4;
-constexpr int kStageBytes = 256 * 64 * 2;       // largest stage: N = 256, K = 64
 constexpr int kThreads = 32 * 6;
-// TMEM columns
-constexpr uint32_t kColD = 0, kColD16 = 256, kColPts = 272, kColH = 304, kColViews = 432;
-
-// ---- layer table ----------------------------------------------------------------------------------------------------
-// id: 0..7 pts_linears, 8 feature_linear, 9 alpha_linear, 10 views_linears[0], 11 rgb_linear
-constexpr int kLayers = 12;
-struct LayerInfo {
-	int N, K;            // padded
-	uint32_t a_col, d_col;
-};
-__host__ __device__ constexpr LayerInfo layer_info(int l)
-{
-	return l == 0 ? LayerInfo{256, 64, kColPts, kColD}
-	     : l == 5 ? LayerInfo{256, 320, kColPts, kColD}
-	     : l <= 8 ? LayerInfo{256, 256, kColH, kColD}
-	     : l == 9 ? LayerInfo{16, 256, kColH, kColD16}
-	     : l == 10 ? LayerInfo{128, 288, kColH, kColD}
-	     : LayerInfo{16, 128, kColH, kColD16};
-}
-// the narrow heads (N = 16) travel as ONE stage holding their whole K; everything else in 64-wide K slabs (last one may be 32)
-__host__ __device__ constexpr int layer_stages(int l) { return layer_info(l).N == 16 ? 1 : (layer_info(l).K + 63) / 64; }
-__host__ __device__ constexpr int stage_k(int l, int s)
-{
-	return layer_info(l).N == 16 ? layer_info(l).K : (layer_info(l).K - 64 * s >= 64 ? 64 : layer_info(l).K - 64 * s);
-}
-__host__ __device__ constexpr int stage_bytes(int l, int s) { return layer_info(l).N * stage_k(l, s) * 2; }
-__host__ __device__ constexpr int layer_bytes(int l)
-{
-	int b = 0;
-	for (int s = 0; s < layer_stages(l); s++) b += stage_bytes(l, s);
-	return b;
-}
-__host__ __device__ constexpr int layer_offset(int l)
-{
-	int b = 0;
-	for (int i = 0; i < l; i++) b += layer_bytes(i);
-	return b;
-}
-constexpr int kWeightBytes = layer_offset(kLayers);
-// biases (fp32) follow the weights: [layer][N padded]
-__host__ __device__ constexpr int bias_offset(int l)
-{
-	int b = 0;
-	for (int i = 0; i < l; i++) b += layer_info(i).N;
-	return b;
-}
-constexpr int kBiasFloats = bias_offset(kLayers);
-constexpr int kPackedBytes = kWeightBytes + kBiasFloats * 4;
-
-struct Weights {   // device pointers, torch Linear layout [out, in] row-major fp32
-	const float* w[kLayers];
-	const float* b[kLayers];
-};
 
 // padded logical weight Wp_l(n, k) in the kernel's A-operand order
 __device__ __forceinline__ float wp(const Weights& p, int l, int n, int k)
@@ -95,7 +38,7 @@ __device__ __forceinline__ float wp(const Weights& p, int l, int n, int k)
 	}
 }
 
-__global__ void __launch_bounds__(256) nerf_pack_kernel(Weights p, uint32_t* __restrict__ blob)
+__global__ void __launch_bounds__(256) nerf_pack_kernel(Weights p, uint32_t* __restrict__ blob, bool bf16)
 {
 	const int w = blockIdx.x * blockDim.x + threadIdx.x;
 	if (w >= kPackedBytes / 4) return;
@@ -115,7 +58,7 @@ __global__ void __launch_bounds__(256) nerf_pack_kernel(Weights p, uint32_t* __r
 	// UMMA K-major core-matrix layout: word q of a stage holds (n, k) and (n, k+1); byte = (k/8)*(N*16) + n*16 + (k%8)*2
 	const int N = layer_info(l).N;
 	const int kc = q / (4 * N), n = (q >> 2) % N, k = k_off + 8 * kc + 2 * (q & 3);
-	blob[w] = pack_f16(wp(p, l, n, k), wp(p, l, n, k + 1));
+	blob[w] = bf16 ? pack_bf16(wp(p, l, n, k), wp(p, l, n, k + 1)) : pack_f16(wp(p, l, n, k), wp(p, l, n, k + 1));
 }
 
 struct __align__(128) Smem {
@@ -127,7 +70,7 @@ struct __align__(128) Smem {
 };
 
 // epilogue of a 32-column accumulator chunk: + bias, optional ReLU, pack to 16 fp16 pairs
-template <bool RELU>
+template <bool RELU, bool BF16>
 __device__ __forceinline__ void bias_act_pack(const uint32_t (&acc)[32], const float* __restrict__ bias, uint32_t (&out)[16])
 {
 #pragma unroll
@@ -135,15 +78,28 @@ __device__ __forceinline__ void bias_act_pack(const uint32_t (&acc)[32], const f
 		const float4 b = *reinterpret_cast<const float4*>(bias + 4 * i);
 		const float v0 = __uint_as_float(acc[4 * i]) + b.x, v1 = __uint_as_float(acc[4 * i + 1]) + b.y;
 		const float v2 = __uint_as_float(acc[4 * i + 2]) + b.z, v3 = __uint_as_float(acc[4 * i + 3]) + b.w;
-		out[2 * i] = RELU ? pack_f16_relu(v0, v1) : pack_f16(v0, v1);
-		out[2 * i + 1] = RELU ? pack_f16_relu(v2, v3) : pack_f16(v2, v3);
+		if (BF16) {
+			out[2 * i] = RELU ? pack_bf16_relu(v0, v1) : pack_bf16(v0, v1);
+			out[2 * i + 1] = RELU ? pack_bf16_relu(v2, v3) : pack_bf16(v2, v3);
+		} else {
+			out[2 * i] = RELU ? pack_f16_relu(v0, v1) : pack_f16(v0, v1);
+			out[2 * i + 1] = RELU ? pack_f16_relu(v2, v3) : pack_f16(v2, v3);
+		}
 	}
 }
 
 // D[:, 0 .. 32*CHUNKS) + bias -> (ReLU) -> fp16 -> the h columns, one thread per row.  The tcgen05.ld of chunk c+1 is in flight while
 // chunk c is converted and stored (two register buffers), so the TMEM read latency is paid once, not once per chunk.
-template <int CHUNKS, bool RELU>
-__device__ __forceinline__ void epilogue_to_h(uint32_t t_lane, const float* __restrict__ bias)
+// 32 packed columns (16 words) of this thread's row -> 4 chunks of a scratch region (TRAIN only)
+__device__ __forceinline__ void save_chunks(uint8_t* __restrict__ region_row, int first_chunk, const uint32_t (&a16)[16])
+{
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+		*reinterpret_cast<uint4*>(region_row + (first_chunk + i) * 1024) = make_uint4(a16[4 * i], a16[4 * i + 1], a16[4 * i + 2], a16[4 * i + 3]);
+}
+
+template <int CHUNKS, bool RELU, bool TRAIN>
+__device__ __forceinline__ void epilogue_to_h(uint32_t t_lane, const float* __restrict__ bias, uint8_t* __restrict__ save_row)
 {
 	uint32_t acc0[32], acc1[32], a16[16];
 	tmem_ld32(t_lane + kColD, acc0);
@@ -151,13 +107,15 @@ __device__ __forceinline__ void epilogue_to_h(uint32_t t_lane, const float* __re
 	for (int c = 0; c < CHUNKS; c += 2) {
 		tmem_ld_wait_for(acc0);
 		if (c + 1 < CHUNKS) tmem_ld32(t_lane + kColD + 32 * (c + 1), acc1);
-		bias_act_pack<RELU>(acc0, bias + 32 * c, a16);
+		bias_act_pack<RELU, TRAIN>(acc0, bias + 32 * c, a16);
 		tmem_st16(t_lane + kColH + 16 * c, a16);
+		if (TRAIN) save_chunks(save_row, 4 * c, a16);
 		if (c + 1 < CHUNKS) {
 			tmem_ld_wait_for(acc1);
 			if (c + 2 < CHUNKS) tmem_ld32(t_lane + kColD + 32 * (c + 2), acc0);
-			bias_act_pack<RELU>(acc1, bias + 32 * (c + 1), a16);
+			bias_act_pack<RELU, TRAIN>(acc1, bias + 32 * (c + 1), a16);
 			tmem_st16(t_lane + kColH + 16 * (c + 1), a16);
+			if (TRAIN) save_chunks(save_row, 4 * (c + 1), a16);
 		}
 	}
 }
@@ -175,8 +133,11 @@ constexpr int kGroups = 11;
 __host__ __device__ constexpr int group_first(int g) { return g <= 8 ? g : g + 1; }
 __host__ __device__ constexpr int group_count(int g) { return g == 8 ? 2 : 1; }
 
+// TRAIN: bf16 operands (the exponent range survives Xavier(0.1) initialisation, src/LibTorchTraining/Trainable.h:43, where fp16
+// activations of the deep layers flush to zero) and every layer's input is stored to the scratch records of mlp_nerf_layout.cuh
+template <bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint8_t* __restrict__ blob, const float* __restrict__ x, int64_t n,
-	float* __restrict__ out)
+	float* __restrict__ out, uint8_t* __restrict__ saved)
 {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -231,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint
 					fence_after();
 					for (int l = group_first(grp); l < group_first(grp) + group_count(grp); l++) {
 						const LayerInfo L = layer_info(l);
-						const uint32_t idesc = idesc_f16(128, L.N);
+						const uint32_t idesc = idesc_16(128, L.N, TRAIN, 0, 0);
 						const uint32_t lbo = L.N * 16;
 						uint32_t a_col = tmem + L.a_col;
 						bool first = true;
@@ -263,6 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint
 			const int64_t tile = blockIdx.x + t * gridDim.x;
 			const int64_t r = tile * 128 + row;
 			const bool ok = r < n;
+			uint8_t* const rec = TRAIN ? saved + tile * kSaveTile : nullptr;    // rows past n are stored too (finite; their gradients are zero)
 			// ---- inputs: 63 point channels (+1 zero) and 27 view channels (+5 zero) as fp16 pairs into their TMEM columns
 			{
 				const float2* xr = reinterpret_cast<const float2*>(x + (ok ? r : 0) * kInCh);   // rows are 360 B: 8-byte aligned
@@ -277,9 +239,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint
 							if (k + 1 < kInPts) v = __ldg(xr + k / 2);
 							else if (k < kInPts) v = make_float2(__ldg(x + r * kInCh + k), 0.f);
 						}
-						a16[i] = pack_f16(v.x, v.y);
+						a16[i] = TRAIN ? pack_bf16(v.x, v.y) : pack_f16(v.x, v.y);
 					}
 					tmem_st16(t_lane + kColPts + 16 * h, a16);
+					if (TRAIN) save_chunks(rec + kSavePts + chunk_offset(64, row, 0), 4 * h, a16);
 				}
 #pragma unroll
 				for (int i = 0; i < 16; i++) {
@@ -287,9 +250,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint
 					float v0 = 0.f, v1 = 0.f;
 					if (ok && k < kInViews) v0 = __ldg(x + r * kInCh + kInPts + k);
 					if (ok && k + 1 < kInViews) v1 = __ldg(x + r * kInCh + kInPts + k + 1);
-					a16[i] = pack_f16(v0, v1);
+					a16[i] = TRAIN ? pack_bf16(v0, v1) : pack_f16(v0, v1);
 				}
 				tmem_st16(t_lane + kColViews, a16);
+				if (TRAIN) save_chunks(rec + kSaveViews + chunk_offset(32, row, 0), 0, a16);
 			}
 			publish(&sm.a_ready, lane);
 
@@ -301,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint
 				fence_after();
 				if (grp < 8) {
 					// pts_linears: relu(D + b) -> h (the next layer's A operand)
-					epilogue_to_h<8, true>(t_lane, sm.bias + bias_offset(0) + grp * kW);
+					epilogue_to_h<8, true, TRAIN>(t_lane, sm.bias + bias_offset(0) + grp * kW, rec + save_h(grp + 1) + chunk_offset(256, row, 0));
 					publish(&sm.a_ready, lane);
 				} else if (grp == 8) {
 					// feature_linear (no activation) -> h ; alpha_linear -> register
@@ -309,11 +273,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint
 					tmem_ld16(t_lane + kColD16, d16);
 					tmem_ld_wait();
 					alpha = __uint_as_float(d16[0]) + sm.bias[bias_offset(9)];
-					epilogue_to_h<8, false>(t_lane, sm.bias + bias_offset(8));
+					epilogue_to_h<8, false, TRAIN>(t_lane, sm.bias + bias_offset(8), rec + kSaveFeat + chunk_offset(256, row, 0));
 					publish(&sm.a_ready, lane);
 				} else if (grp == 9) {
 					// views_linears[0]: relu -> first 128 channels of h
-					epilogue_to_h<4, true>(t_lane, sm.bias + bias_offset(10));
+					epilogue_to_h<4, true, TRAIN>(t_lane, sm.bias + bias_offset(10), rec + kSaveHv + chunk_offset(128, row, 0));
 					publish(&sm.a_ready, lane);
 				} else {
 					// rgb_linear -> out = [rgb, alpha] (src/NeRF.cpp:119-120)
@@ -336,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint
 	}
 }
 
-static int check_shape(const nrf_mlp_nerf_shape* s)
+int check_shape(const nrf_mlp_nerf_shape* s)
 {
 	NRF_REQUIRE(s != nullptr, "shape is null");
 	if (!(s->depth == 8 && s->width == kW && s->input_ch == kInPts && s->input_ch_views == kInViews && s->skip_layer == 4 && s->use_viewdirs == 1)) {
@@ -352,11 +316,30 @@ static int check_shape(const nrf_mlp_nerf_shape* s)
 using namespace nrf;
 using namespace nrf::nerf_tc;
 
+template <bool TRAIN>
+static int fwd_common(const nrf_mlp_nerf_shape* shape, const void* packed, const float* x, int64_t n, float* out, void* saved, nrf_stream stream)
+{
+	if (int rc = nerf_tc::check_shape(shape)) return rc;
+	NRF_REQUIRE(n >= 0, "negative n");
+	if (n == 0) return NRF_OK;
+	NRF_REQUIRE(packed && x && out && (!TRAIN || saved), "null pointer");
+	NRF_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+		(reinterpret_cast<uintptr_t>(saved) & 127) == 0, "packed / saved must be 128-byte, x 8-byte, out 16-byte aligned");
+	const int64_t tiles = (n + 127) / 128;
+	const int blocks = static_cast<int>(std::min<int64_t>(tiles, kNumSMs));
+	const int smem = static_cast<int>(sizeof(Smem)) + 128;
+	NRF_CUDA(cudaFuncSetAttribute(mlp_nerf_fwd_tc_kernel<TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+	mlp_nerf_fwd_tc_kernel<TRAIN><<<blocks, kThreads, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed), x, n, out,
+		reinterpret_cast<uint8_t*>(saved));
+	NRF_CHECK_LAUNCH("mlp_nerf_fwd_tc_kernel");
+	return NRF_OK;
+}
+
 extern "C" {
 
 int64_t nrf_mlp_nerf_packed_bytes(const nrf_mlp_nerf_shape* shape) { return nerf_tc::check_shape(shape) ? -1 : static_cast<int64_t>(kPackedBytes); }
 
-int nrf_mlp_nerf_pack(const nrf_mlp_nerf_shape* shape, const nrf_mlp_nerf_weights* w, void* packed, nrf_stream stream)
+static int pack_common(const nrf_mlp_nerf_shape* shape, const nrf_mlp_nerf_weights* w, void* packed, bool bf16, nrf_stream stream)
 {
 	if (int rc = nerf_tc::check_shape(shape)) return rc;
 	NRF_REQUIRE(w != nullptr && packed != nullptr, "null pointer");
@@ -368,26 +351,36 @@ int nrf_mlp_nerf_pack(const nrf_mlp_nerf_shape* shape, const nrf_mlp_nerf_weight
 	p.w[10] = w->views_w; p.b[10] = w->views_b;
 	p.w[11] = w->rgb_w; p.b[11] = w->rgb_b;
 	for (int i = 0; i < kLayers; i++) NRF_REQUIRE(p.w[i] && p.b[i], "null weight / bias pointer");
-	nerf_pack_kernel<<<(kPackedBytes / 4 + 255) / 256, 256, 0, as_stream(stream)>>>(p, reinterpret_cast<uint32_t*>(packed));
+	nerf_pack_kernel<<<(kPackedBytes / 4 + 255) / 256, 256, 0, as_stream(stream)>>>(p, reinterpret_cast<uint32_t*>(packed), bf16);
 	NRF_CHECK_LAUNCH("nerf_pack_kernel");
 	return NRF_OK;
 }
 
+int nrf_mlp_nerf_pack(const nrf_mlp_nerf_shape* shape, const nrf_mlp_nerf_weights* w, void* packed, nrf_stream stream)
+{
+	return pack_common(shape, w, packed, false, stream);
+}
+
+int nrf_mlp_nerf_pack_train(const nrf_mlp_nerf_shape* shape, const nrf_mlp_nerf_weights* w, void* packed, nrf_stream stream)
+{
+	return pack_common(shape, w, packed, true, stream);
+}
+
+int64_t nrf_mlp_nerf_saved_bytes(const nrf_mlp_nerf_shape* shape, int64_t n)
+{
+	if (nerf_tc::check_shape(shape) || n < 0) return -1;
+	return ((n + 127) / 128) * static_cast<int64_t>(kSaveTile);
+}
+
 int nrf_mlp_nerf_fwd(const nrf_mlp_nerf_shape* shape, const void* packed, const float* x, int64_t n, float* out, nrf_stream stream)
 {
-	if (int rc = nerf_tc::check_shape(shape)) return rc;
-	NRF_REQUIRE(n >= 0, "negative n");
-	if (n == 0) return NRF_OK;
-	NRF_REQUIRE(packed && x && out, "null pointer");
-	NRF_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
-		"packed must be 128-byte, x 8-byte, out 16-byte aligned");
-	const int64_t tiles = (n + 127) / 128;
-	const int blocks = static_cast<int>(std::min<int64_t>(tiles, kNumSMs));
-	const int smem = static_cast<int>(sizeof(Smem)) + 128;
-	NRF_CUDA(cudaFuncSetAttribute(mlp_nerf_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-	mlp_nerf_fwd_tc_kernel<<<blocks, kThreads, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed), x, n, out);
-	NRF_CHECK_LAUNCH("mlp_nerf_fwd_tc_kernel");
-	return NRF_OK;
+	return fwd_common<false>(shape, packed, x, n, out, nullptr, stream);
+}
+
+int nrf_mlp_nerf_fwd_train(const nrf_mlp_nerf_shape* shape, const void* packed_train, const float* x, int64_t n, float* out, void* saved,
+                           nrf_stream stream)
+{
+	return fwd_common<true>(shape, packed_train, x, n, out, saved, stream);
 }
 
 }

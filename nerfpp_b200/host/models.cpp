@@ -43,11 +43,8 @@ bool NeRFImpl::FusedShape() const
 	return nrf_mlp_nerf_packed_bytes(&s) > 0;   // the library answers -1 for shapes it was not built for
 }
 
-Tensor NeRFImpl::ForwardFused(const Tensor& x)
+std::vector<Tensor> NeRFImpl::FusedParams()
 {
-	torch::NoGradGuard no_grad;
-	const nrf_mlp_nerf_shape s{D, W, InputCh, InputChViews, *Skips.begin(), 1};
-	// re-pack only when a parameter changed (data pointer or version counter)
 	std::vector<Tensor> params;
 	for (size_t i = 0; i < PtsLinears->size(); i++) {
 		params.push_back(PtsLinears[i]->as<nn::Linear>()->weight);
@@ -58,19 +55,87 @@ Tensor NeRFImpl::ForwardFused(const Tensor& x)
 		params.push_back(l->weight);
 		params.push_back(l->bias);
 	}
+	return params;
+}
+
+namespace {
+// 24 tensors in FusedParams() order -> the C ABI's pointer structs (weights and gradients share the field layout)
+template <typename S, typename P>
+S NerfPointers(const std::vector<Tensor>& t)
+{
+	S w{};
+	for (int i = 0; i < 8; i++) { w.pts_w[i] = (P)t[2 * i].data_ptr<float>(); w.pts_b[i] = (P)t[2 * i + 1].data_ptr<float>(); }
+	w.feature_w = (P)t[16].data_ptr<float>(); w.feature_b = (P)t[17].data_ptr<float>();
+	w.alpha_w = (P)t[18].data_ptr<float>();   w.alpha_b = (P)t[19].data_ptr<float>();
+	w.views_w = (P)t[20].data_ptr<float>();   w.views_b = (P)t[21].data_ptr<float>();
+	w.rgb_w = (P)t[22].data_ptr<float>();     w.rgb_b = (P)t[23].data_ptr<float>();
+	return w;
+}
+
+Tensor NerfPack(const nrf_mlp_nerf_shape& s, const std::vector<Tensor>& params, bool train)
+{
+	std::vector<Tensor> dense;
+	for (const Tensor& t : params) dense.push_back(nrfhost::Dense(t.detach(), torch::kFloat32, "NeRF parameter"));
+	const nrf_mlp_nerf_weights w = NerfPointers<nrf_mlp_nerf_weights, const float*>(dense);
+	Tensor blob = torch::empty({nrf_mlp_nerf_packed_bytes(&s)}, torch::TensorOptions().dtype(torch::kUInt8).device(dense[0].device()));
+	nrfhost::Check((train ? nrf_mlp_nerf_pack_train : nrf_mlp_nerf_pack)(&s, &w, blob.data_ptr(), nrfhost::Stream()), "nrf_mlp_nerf_pack");
+	return blob;
+}
+
+// NeRFImpl::forward with the backward LibTorch autograd would derive (src/NeRF.cpp:92-126), as three tcgen05 kernels:
+// nrf_mlp_nerf_fwd_train (stores every layer's input, bf16) and nrf_mlp_nerf_bwd (gradient chain + weight gradients).
+struct NerfTrainFunction : public torch::autograd::Function<NerfTrainFunction> {
+	static variable_list forward(AutogradContext* ctx, variable_list in)
+	{
+		// in = 24 parameters (FusedParams order), x [N, 90]
+		const nrf_mlp_nerf_shape s{8, 256, 63, 27, 4, 1};
+		std::vector<Tensor> params(in.begin(), in.begin() + 24);
+		const Tensor flat = nrfhost::Dense(in[24].detach(), torch::kFloat32, "NeRF input");
+		const int64_t n = flat.size(0);
+		Tensor blob = NerfPack(s, params, true);
+		Tensor out = torch::empty({n, 4}, nrfhost::F32Like(flat));
+		Tensor saved = torch::empty({std::max<int64_t>(nrf_mlp_nerf_saved_bytes(&s, n), 0)}, blob.options());
+		nrfhost::Check(nrf_mlp_nerf_fwd_train(&s, blob.data_ptr(), flat.data_ptr<float>(), n, out.data_ptr<float>(), saved.data_ptr(), nrfhost::Stream()),
+			"nrf_mlp_nerf_fwd_train");
+		ctx->save_for_backward({blob, saved});
+		std::vector<std::vector<int64_t>> shapes;
+		for (const Tensor& t : params) shapes.push_back(t.sizes().vec());
+		ctx->saved_data["n"] = n;
+		ctx->saved_data["shapes"] = shapes;
+		return {out};
+	}
+	static variable_list backward(AutogradContext* ctx, variable_list grad_out)
+	{
+		const nrf_mlp_nerf_shape s{8, 256, 63, 27, 4, 1};
+		const auto saved = ctx->get_saved_variables();
+		const int64_t n = ctx->saved_data["n"].toInt();
+		const auto shapes = ctx->saved_data["shapes"].toListRef();
+		const Tensor g = nrfhost::Dense(grad_out[0], torch::kFloat32, "NeRF output gradient");
+		std::vector<Tensor> grads;
+		for (const auto& sh : shapes) grads.push_back(torch::zeros(sh.toIntVector(), nrfhost::F32Like(g)));
+		if (n > 0) {
+			Tensor ws = torch::empty({nrf_mlp_nerf_bwd_workspace_bytes(&s, n)}, saved[0].options());
+			const nrf_mlp_nerf_grads gp = NerfPointers<nrf_mlp_nerf_grads, float*>(grads);
+			nrfhost::Check(nrf_mlp_nerf_bwd(&s, saved[0].data_ptr(), saved[1].data_ptr(), g.data_ptr<float>(), n, ws.data_ptr(), &gp, nrfhost::Stream()),
+				"nrf_mlp_nerf_bwd");
+		}
+		variable_list ret(grads.begin(), grads.end());
+		ret.push_back(Tensor());        // x: the positional embedder has no parameters (src/NeRF.cpp:4-39), no gradient is produced
+		return ret;
+	}
+};
+}  // namespace
+
+Tensor NeRFImpl::ForwardFused(const Tensor& x)
+{
+	torch::NoGradGuard no_grad;
+	const nrf_mlp_nerf_shape s{D, W, InputCh, InputChViews, *Skips.begin(), 1};
+	// re-pack only when a parameter changed (data pointer or version counter)
+	const std::vector<Tensor> params = FusedParams();
 	std::vector<std::pair<const void*, uint32_t>> key;
 	for (const Tensor& t : params) key.emplace_back(t.data_ptr(), t._version());
 	if (!PackedBlob.defined() || key != PackedKey) {
-		std::vector<Tensor> dense;
-		for (const Tensor& t : params) dense.push_back(nrfhost::Dense(t, torch::kFloat32, "NeRF parameter"));
-		nrf_mlp_nerf_weights w{};
-		for (int i = 0; i < 8; i++) { w.pts_w[i] = dense[2 * i].data_ptr<float>(); w.pts_b[i] = dense[2 * i + 1].data_ptr<float>(); }
-		w.feature_w = dense[16].data_ptr<float>(); w.feature_b = dense[17].data_ptr<float>();
-		w.alpha_w = dense[18].data_ptr<float>();   w.alpha_b = dense[19].data_ptr<float>();
-		w.views_w = dense[20].data_ptr<float>();   w.views_b = dense[21].data_ptr<float>();
-		w.rgb_w = dense[22].data_ptr<float>();     w.rgb_b = dense[23].data_ptr<float>();
-		PackedBlob = torch::empty({nrf_mlp_nerf_packed_bytes(&s)}, torch::TensorOptions().dtype(torch::kUInt8).device(dense[0].device()));
-		nrfhost::Check(nrf_mlp_nerf_pack(&s, &w, PackedBlob.data_ptr(), nrfhost::Stream()), "nrf_mlp_nerf_pack");
+		PackedBlob = NerfPack(s, params, false);
 		PackedKey = key;
 	}
 	std::vector<int64_t> shape = x.sizes().vec();
@@ -81,9 +146,21 @@ Tensor NeRFImpl::ForwardFused(const Tensor& x)
 	return out.view(shape);
 }
 
+Tensor NeRFImpl::ForwardFusedTrain(const Tensor& x)
+{
+	variable_list in = FusedParams();
+	std::vector<int64_t> shape = x.sizes().vec();
+	in.push_back(x.reshape({-1, int64_t(InputCh + InputChViews)}));
+	shape.back() = 4;
+	return NerfTrainFunction::apply(in)[0].view(shape);
+}
+
 Tensor NeRFImpl::forward(Tensor x)
 {
-	if (!torch::GradMode::is_enabled() && x.is_cuda() && x.size(-1) == InputCh + InputChViews && FusedShape()) return ForwardFused(x);
+	const bool fusable = x.is_cuda() && x.size(-1) == InputCh + InputChViews && FusedShape();
+	if (fusable && !torch::GradMode::is_enabled()) return ForwardFused(x);
+	// training: the fused backward yields parameter gradients only — an input that itself requires a gradient keeps the ATen path
+	if (fusable && FusedTraining && !x.requires_grad()) return ForwardFusedTrain(x);
 	Tensor pts = x.narrow(-1, 0, InputCh), views = x.narrow(-1, InputCh, InputChViews);
 	Tensor h = pts;
 	for (size_t i = 0; i < PtsLinears->size(); i++) {

@@ -50,8 +50,10 @@ TORCH_MODULE(BaseNeRF);
 
 /// Classic NeRF MLP (src/NeRF.h:44-77, src/NeRF.cpp:41-126).  Inference (no autograd graph, CUDA input) at the BASELINE shape
 /// D=8, W=256, 63+27 inputs, skips={4}, view branch runs as ONE fused tcgen05 kernel (nrf_mlp_nerf_fwd: activations stay in
-/// tensor memory, weights stream through a TMA ring); training and other shapes run the same maths through torch::linear
-/// (cuBLAS, a plain library GEMM chain) so that LibTorch autograd provides the backward.
+/// tensor memory, weights stream through a TMA ring).  Training at that shape (autograd recording, input without a gradient of
+/// its own — the positional embedder has no parameters) runs nrf_mlp_nerf_fwd_train / nrf_mlp_nerf_bwd behind one
+/// torch::autograd::Function: bf16 tcgen05 forward that stores every layer's input, gradient chain and weight gradients on the
+/// tensor cores.  Other shapes run the same maths through torch::linear (cuBLAS) with LibTorch autograd.
 struct NeRFImpl : public BaseNeRFImpl {
 	int D, W, InputCh, InputChViews, OutputCh;
 	std::set<int> Skips;
@@ -67,6 +69,9 @@ struct NeRFImpl : public BaseNeRFImpl {
 	// ---- B200 additions
 	bool FusedShape() const;                   ///< true when nrf_mlp_nerf_fwd covers this configuration
 	torch::Tensor ForwardFused(const torch::Tensor& x);   ///< [.., 90] -> [.., 4] on the fused kernel (no autograd)
+	torch::Tensor ForwardFusedTrain(const torch::Tensor& x);   ///< the same with the fused backward attached (parameter gradients)
+	std::vector<torch::Tensor> FusedParams();  ///< pts_linears w,b x8, feature w,b, alpha w,b, views w,b, rgb w,b
+	bool FusedTraining = true;                 ///< false: training goes through torch::linear + LibTorch autograd (fp32 cuBLAS)
 private:
 	torch::Tensor PackedBlob;
 	std::vector<std::pair<const void*, uint32_t>> PackedKey;

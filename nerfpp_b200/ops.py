@@ -356,13 +356,8 @@ def mlp_nerf_shape(depth=8, width=256, input_ch=63, input_ch_views=27, skip_laye
     return cabi.MlpNerfShape(depth, width, input_ch, input_ch_views, skip_layer, int(use_viewdirs))
 
 
-def mlp_nerf_pack(p: dict, shape=None, out: torch.Tensor | None = None) -> torch.Tensor:
-    """p: the reference's registered names ('model_pts_linears_<i>.weight' ... 'model_rgb_linear.bias', src/NeRF.cpp:76-89) ->
-    contiguous fp32 CUDA tensors.  Returns the packed fp16 UMMA-operand blob (+ fp32 biases) of nrf_mlp_nerf_fwd."""
-    shape = shape or mlp_nerf_shape()
-    nbytes = lib().nrf_mlp_nerf_packed_bytes(C.byref(shape))
-    if nbytes < 0:
-        check(-3)
+def _mlp_nerf_ptrs(p: dict) -> "cabi.MlpNerfWeights":
+    """nrf_mlp_nerf_weights / nrf_mlp_nerf_grads (same field layout) from the reference's registered names."""
     w = cabi.MlpNerfWeights()
     for i in range(8):
         w.pts_w[i] = ptr(p[f"model_pts_linears_{i}.weight"], f32)
@@ -371,10 +366,46 @@ def mlp_nerf_pack(p: dict, shape=None, out: torch.Tensor | None = None) -> torch
         setattr(w, f"{name}_w", ptr(p[f"model_{name}_linear.weight"], f32))
         setattr(w, f"{name}_b", ptr(p[f"model_{name}_linear.bias"], f32))
     w.views_w, w.views_b = ptr(p["model_views_linears_0.weight"], f32), ptr(p["model_views_linears_0.bias"], f32)
+    return w
+
+
+def mlp_nerf_pack(p: dict, shape=None, out: torch.Tensor | None = None, train: bool = False) -> torch.Tensor:
+    """p: the reference's registered names ('model_pts_linears_<i>.weight' ... 'model_rgb_linear.bias', src/NeRF.cpp:76-89) ->
+    contiguous fp32 CUDA tensors.  Returns the packed UMMA-operand blob (+ fp32 biases): fp16 for nrf_mlp_nerf_fwd, bf16
+    (train=True) for nrf_mlp_nerf_fwd_train / nrf_mlp_nerf_bwd."""
+    shape = shape or mlp_nerf_shape()
+    nbytes = lib().nrf_mlp_nerf_packed_bytes(C.byref(shape))
+    if nbytes < 0:
+        check(-3)
+    w = _mlp_nerf_ptrs(p)
     if out is None:
         out = torch.empty(nbytes, dtype=u8, device=p["model_rgb_linear.bias"].device)
-    _run("mlp_nerf_pack", lambda: lib().nrf_mlp_nerf_pack(C.byref(shape), C.byref(w), ptr(out), stream()))
+    fn = lib().nrf_mlp_nerf_pack_train if train else lib().nrf_mlp_nerf_pack
+    _run("mlp_nerf_pack", lambda: fn(C.byref(shape), C.byref(w), ptr(out), stream()))
     return out
+
+
+def mlp_nerf_fwd_train(packed_train: torch.Tensor, x: torch.Tensor, shape=None):
+    """Training forward: (out [N,4], saved) — saved holds every layer's input (bf16 records) for mlp_nerf_bwd."""
+    shape = shape or mlp_nerf_shape()
+    n = x.shape[0]
+    out = torch.empty((n, 4), dtype=f32, device=x.device)
+    saved = torch.empty(max(lib().nrf_mlp_nerf_saved_bytes(C.byref(shape), n), 0), dtype=u8, device=x.device)
+    _run("mlp_nerf_fwd_train", lambda: lib().nrf_mlp_nerf_fwd_train(C.byref(shape), ptr(packed_train), ptr(x, f32), n, ptr(out, f32), ptr(saved), stream()))
+    return out, saved
+
+
+def mlp_nerf_bwd(packed_train: torch.Tensor, saved: torch.Tensor, grad_out: torch.Tensor, grads: dict, shape=None, workspace: torch.Tensor | None = None):
+    """Backward of NeRFImpl::forward: grad_out [N,4] fp32 -> grads (dict with the parameter names of `mlp_nerf_pack`, fp32 CUDA
+    tensors of the parameters' shapes) += d loss / d parameter."""
+    shape = shape or mlp_nerf_shape()
+    n = grad_out.shape[0]
+    if workspace is None:
+        workspace = torch.empty(max(lib().nrf_mlp_nerf_bwd_workspace_bytes(C.byref(shape), n), 0), dtype=u8, device=grad_out.device)
+    g = _mlp_nerf_ptrs(grads)
+    _run("mlp_nerf_bwd", lambda: lib().nrf_mlp_nerf_bwd(C.byref(shape), ptr(packed_train), ptr(saved), ptr(grad_out, f32), n, ptr(workspace), C.byref(g),
+                                                        stream()))
+    return grads
 
 
 def mlp_nerf_fwd(packed: torch.Tensor, x: torch.Tensor, shape=None, out: torch.Tensor | None = None) -> torch.Tensor:

@@ -86,3 +86,140 @@ def test_full_size_render_batch_is_row_independent():
     assert torch.isfinite(full).all()
     for lo, hi in ((0, 5000), (777 * 128 + 3, 777 * 128 + 3 + 4099), (n - 130, n)):
         assert torch.equal(full[lo:hi], ops.mlp_nerf_fwd(packed, x[lo:hi].contiguous()))
+
+
+# ---------------------------------------------------------------------------------------------------------------- training
+# nrf_mlp_nerf_fwd_train / nrf_mlp_nerf_bwd against fp64 autograd of NeRFImpl::forward (the same graph as the pinned restatement
+# oracle/restate.py:nerf_forward, with the intermediate tensors kept).  bf16 operands, fp32 accumulation.  Two references:
+#   * emulate=True  — weights, inputs and every stored activation rounded to bf16 (straight-through), i.e. the kernels' rounding points,
+#     so the ReLU masks are the kernels' masks: tolerance 1e-2 of sum|terms| of each gradient (north star: "1e-2 bf16");
+#   * emulate=False — exact fp64.  A bf16 forward flips the ReLU mask of the ~0.3 % of units whose pre-activation is within bf16
+#     rounding of zero; with a random upstream gradient those flips are incoherent noise of order sqrt(flipped / n) in every weight
+#     gradient (5-15 % at n = 1000), so this comparison is made on direction (cosine), not element-wise.
+
+
+def _train_reference(x, p, gout, emulate):
+    rb = (lambda t: t + (t.bfloat16().double() - t).detach()) if emulate else (lambda t: t)
+    pd = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    q = {k: (rb(v) if k.endswith("weight") else v) for k, v in pd.items()}
+    xd = rb(x.double())
+    pts, views = xd[:, :63], xd[:, 63:]
+    h, hs, pre, xin = pts, {}, {}, {}
+    for i in range(8):
+        xin[f"model_pts_linears_{i}"] = h
+        pre[i] = h @ q[f"model_pts_linears_{i}.weight"].t() + q[f"model_pts_linears_{i}.bias"]          # src/NeRF.cpp:100
+        pre[i].retain_grad()
+        h = rb(torch.relu(pre[i]))
+        hs[i + 1] = h
+        if i == 4:
+            h = torch.cat([pts, h], -1)                                                               # :103-104
+    xin["model_alpha_linear"] = xin["model_feature_linear"] = h
+    alpha = h @ q["model_alpha_linear.weight"].t() + q["model_alpha_linear.bias"]                       # :110
+    alpha.retain_grad()
+    feat = rb(h @ q["model_feature_linear.weight"].t() + q["model_feature_linear.bias"])                # :111
+    feat.retain_grad()
+    xin["model_views_linears_0"] = torch.cat([feat, views], -1)
+    prev = xin["model_views_linears_0"] @ q["model_views_linears_0.weight"].t() + q["model_views_linears_0.bias"]   # :112-116
+    prev.retain_grad()
+    hv = rb(torch.relu(prev))
+    xin["model_rgb_linear"] = hv
+    rgb = hv @ q["model_rgb_linear.weight"].t() + q["model_rgb_linear.bias"]                            # :119
+    rgb.retain_grad()
+    out = torch.cat([rgb, alpha], -1)                                                                   # :120
+    (out * gout.double()).sum().backward()
+    dy = {f"model_pts_linears_{i}": pre[i].grad for i in range(8)}
+    dy.update({"model_alpha_linear": alpha.grad, "model_feature_linear": feat.grad, "model_views_linears_0": prev.grad, "model_rgb_linear": rgb.grad})
+    # sum |terms| of every gradient entry: the scale its rounding error is relative to
+    bound = {}
+    for name, d in dy.items():
+        bound[name + ".weight"] = float((d.abs().t() @ xin[name].detach().abs()).max())
+        bound[name + ".bias"] = float(d.abs().sum(0).max())
+    return dict(out=out.detach(), grads={k: v.grad for k, v in pd.items()}, bound=bound, pts=pts, views=views, hs=hs, pre=pre, feat=feat, prev=prev, hv=hv,
+                pd=pd)
+
+
+def _xavier_params(seed=0, gain=0.1, w=256):
+    """Trainable::Initialize (src/LibTorchTraining/Trainable.h:32-57): xavier_normal_(gain 0.1) weights, zero biases."""
+    g = torch.Generator().manual_seed(seed)
+    p = _params(seed, w)
+    for k, v in p.items():
+        if k.endswith(".weight"):
+            o, i = v.shape
+            p[k] = (torch.randn(o, i, generator=g) * gain * math.sqrt(2.0 / (i + o))).cuda()
+        else:
+            p[k] = torch.zeros_like(v)
+    return p
+
+
+def _check_grads(grads, ref, times=1.0, tol=1e-2):
+    for k, g in grads.items():
+        err = float((g.double() - times * ref["grads"][k]).abs().max())
+        assert err <= tol * times * ref["bound"][k], (k, err, ref["bound"][k])
+
+
+def _cosines(grads, ref):
+    return {k: float((g.double() * ref["grads"][k]).sum() / (g.double().norm() * ref["grads"][k].norm()).clamp_min(1e-300)) for k, g in grads.items()}
+
+
+@pytest.mark.parametrize("n", [1, 127, 129, 1000, 20011])
+def test_train_forward_and_backward_match_fp64_autograd(n):
+    from nerfpp_b200 import ops
+    p = _params(seed=n + 7)
+    x = _inputs(n, seed=n + 8)
+    gout = (torch.randn(n, 4, generator=torch.Generator().manual_seed(n)) * 1e-3).cuda()
+    emu, exact = _train_reference(x, p, gout, True), _train_reference(x, p, gout, False)
+    packed = ops.mlp_nerf_pack(p, train=True)
+    out, saved = ops.mlp_nerf_fwd_train(packed, x)
+    scale = float(exact["out"].abs().max())
+    assert float((out.double() - exact["out"]).abs().max()) <= 1e-2 * scale
+    assert float((out.double() - emu["out"]).abs().max()) <= 2e-3 * scale
+    grads = ops.mlp_nerf_bwd(packed, saved, gout, {k: torch.zeros_like(v) for k, v in p.items()})
+    _check_grads(grads, emu)
+    if n >= 1000:
+        cos = _cosines(grads, exact)
+        assert min(cos.values()) >= 0.97, cos
+    # += semantics: a second call doubles the result (fp32 atomics: order-dependent rounding only)
+    ops.mlp_nerf_bwd(packed, saved, gout, grads)
+    _check_grads(grads, emu, times=2.0)
+
+
+def test_backward_survives_reference_initialisation():
+    """Xavier(0.1): activations shrink ~14x per layer and the gradients of the first layers are ~1e-8 of the last layer's — below
+    fp16's range, inside bf16's.  Every gradient must match relative to ITS OWN scale."""
+    from nerfpp_b200 import ops
+    n = 4096
+    p = _xavier_params(seed=2)
+    x = _inputs(n, seed=3)
+    gout = torch.randn(n, 4, generator=torch.Generator().manual_seed(4)).cuda() / n
+    emu, exact = _train_reference(x, p, gout, True), _train_reference(x, p, gout, False)
+    packed = ops.mlp_nerf_pack(p, train=True)
+    out, saved = ops.mlp_nerf_fwd_train(packed, x)
+    assert float((out.double() - exact["out"]).abs().max()) <= 1e-2 * float(exact["out"].abs().max())
+    grads = ops.mlp_nerf_bwd(packed, saved, gout, {k: torch.zeros_like(v) for k, v in p.items()})
+    assert all(float(g.abs().max()) > 0 for g in grads.values())
+    _check_grads(grads, emu)
+    cos = _cosines(grads, exact)
+    assert min(cos.values()) >= 0.97, cos
+
+
+def test_training_empty_and_masked_rows():
+    from nerfpp_b200 import ops
+    p = _params(seed=1)
+    packed = ops.mlp_nerf_pack(p, train=True)
+    out, saved = ops.mlp_nerf_fwd_train(packed, torch.empty(0, 90, device="cuda"))
+    assert out.shape == (0, 4) and saved.numel() == 0
+    g0 = {k: torch.zeros_like(v) for k, v in p.items()}
+    ops.mlp_nerf_bwd(packed, saved, torch.empty(0, 4, device="cuda"), g0)
+    assert all(float(v.abs().max()) == 0 for v in g0.values())
+    # rows with zero upstream gradient contribute nothing: gradient of the full batch == gradient of the rows that have one
+    n = 700
+    x = _inputs(n, seed=9)
+    gout = torch.randn(n, 4, generator=torch.Generator().manual_seed(5)).cuda() * 1e-3
+    gout[300:] = 0
+    out, saved = ops.mlp_nerf_fwd_train(packed, x)
+    full = ops.mlp_nerf_bwd(packed, saved, gout, {k: torch.zeros_like(v) for k, v in p.items()})
+    out2, saved2 = ops.mlp_nerf_fwd_train(packed, x[:300].contiguous())
+    part = ops.mlp_nerf_bwd(packed, saved2, gout[:300].contiguous(), {k: torch.zeros_like(v) for k, v in p.items()})
+    for k in full:
+        s = float(part[k].abs().max())
+        assert float((full[k] - part[k]).abs().max()) <= 1e-5 * s + 1e-12, k
