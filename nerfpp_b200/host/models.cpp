@@ -85,9 +85,9 @@ Tensor NerfPack(const nrf_mlp_nerf_shape& s, const std::vector<Tensor>& params, 
 // NeRFImpl::forward with the backward LibTorch autograd would derive (src/NeRF.cpp:92-126), as three tcgen05 kernels:
 // nrf_mlp_nerf_fwd_train (stores every layer's input, bf16) and nrf_mlp_nerf_bwd (gradient chain + weight gradients).
 struct NerfTrainFunction : public torch::autograd::Function<NerfTrainFunction> {
-	static variable_list forward(AutogradContext* ctx, variable_list in)
+	static variable_list forward(AutogradContext* ctx, at::TensorList in)
 	{
-		// in = 24 parameters (FusedParams order), x [N, 90]
+		// in = 24 parameters (FusedParams order), x [N, 90]; passed as ONE TensorList so that every entry is an autograd input
 		const nrf_mlp_nerf_shape s{8, 256, 63, 27, 4, 1};
 		std::vector<Tensor> params(in.begin(), in.begin() + 24);
 		const Tensor flat = nrfhost::Dense(in[24].detach(), torch::kFloat32, "NeRF input");
@@ -152,7 +152,7 @@ Tensor NeRFImpl::ForwardFusedTrain(const Tensor& x)
 	std::vector<int64_t> shape = x.sizes().vec();
 	in.push_back(x.reshape({-1, int64_t(InputCh + InputChViews)}));
 	shape.back() = 4;
-	return NerfTrainFunction::apply(in)[0].view(shape);
+	return NerfTrainFunction::apply(at::TensorList(in))[0].view(shape);
 }
 
 Tensor NeRFImpl::forward(Tensor x)
