@@ -28,8 +28,12 @@ namespace nerf_tc {
 using namespace tc;
 
 constexpr int kBwdThreads = 32 * 6;
-// TMEM columns of the chain kernel: D fp32 [128 x 256], A bf16 [128 x 256] (128 columns), the two 16-wide head operands
-constexpr uint32_t kBD = 0, kBA = 256, kBRgb = 384, kBAlpha = 392;
+// TMEM columns of the chain kernel: D fp32 [128 x 256] and TWO A buffers of bf16 [128 x 256] (128 columns each): step st reads
+// A[st & 1] and its epilogue writes A[(st + 1) & 1] slab by slab while the MMAs of the later slabs still read the old operand.
+// The 16-wide head operands live in columns no other operand needs at that time: [r g b 0..] at the start of A[0] (read by step
+// 0, overwritten by step 1's output), [alpha 0..] at column 64 of A[1] (step 1's operand d_hv ends at 63; read by step 2).
+constexpr uint32_t kBD = 0, kBA0 = 256, kBA1 = 384, kBRgb = kBA0, kBAlpha = kBA1 + 64;
+__host__ __device__ constexpr uint32_t a_buf(int st) { return (st & 1) ? kBA1 : kBA0; }
 constexpr int kSteps = 10;
 // chain step -> the layer whose weights it multiplies: rgb, views, feature(+alpha), pts_linears 7..1
 __host__ __device__ constexpr int step_layer(int st) { return st == 0 ? 11 : (st == 1 ? 10 : (st == 2 ? 8 : 10 - st)); }
@@ -39,7 +43,7 @@ __host__ __device__ constexpr int step_stages(int l) { return l == 11 ? 1 : 4; }
 struct __align__(128) ChainSmem {
 	uint8_t ring[kRing][kStageBytes];
 	uint64_t full[kRing], empty[kRing];
-	uint64_t a_ready, d_ready;
+	uint64_t a_ready, slab_ready[4];
 	uint32_t tmem_base;
 };
 
@@ -51,15 +55,6 @@ __device__ __forceinline__ void publish_bwd(uint64_t* bar, int lane)
 	if (lane == 0) mbar_arrive(bar);
 }
 
-__device__ __forceinline__ void load_mask4(const uint8_t* __restrict__ region_row, int first_chunk, uint32_t (&h)[16])
-{
-#pragma unroll
-	for (int i = 0; i < 4; i++) {
-		const uint4 v = __ldg(reinterpret_cast<const uint4*>(region_row + (first_chunk + i) * 1024));
-		h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
-	}
-}
-
 __device__ __forceinline__ void store_chunks4(uint8_t* __restrict__ region_row, int first_chunk, const uint32_t (&a16)[16])
 {
 #pragma unroll
@@ -67,26 +62,54 @@ __device__ __forceinline__ void store_chunks4(uint8_t* __restrict__ region_row, 
 		*reinterpret_cast<uint4*>(region_row + (first_chunk + i) * 1024) = make_uint4(a16[4 * i], a16[4 * i + 1], a16[4 * i + 2], a16[4 * i + 3]);
 }
 
-// D[:, 0 .. 32*CHUNKS) -> (* relu mask of the saved activation) -> bf16 -> next A operand (TMEM) and the gradient record (HBM)
-template <int CHUNKS, bool MASK>
-__device__ __forceinline__ void epilogue_grad(uint32_t t_lane, const uint8_t* __restrict__ mask_row, uint8_t* __restrict__ out_row, bool to_tmem,
-	uint32_t (&hm)[16])
+// one 32-column accumulator chunk -> (* ReLU mask of the saved activation: bits != 0 after ReLU) -> bf16 pairs
+template <bool MASK>
+__device__ __forceinline__ void grad_pack(const uint32_t (&acc)[32], const uint32_t* __restrict__ hm, uint32_t (&a16)[16])
 {
-	uint32_t acc[32], a16[16];
 	const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
-#pragma unroll 1
-	for (int c = 0; c < CHUNKS; c++) {
-		tmem_ld32(t_lane + kBD + 32 * c, acc);
-		tmem_ld_wait_for(acc);
 #pragma unroll
-		for (int i = 0; i < 16; i++) {
-			uint32_t w = pack_bf16(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
-			if (MASK) w &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&hm[i]), zero);
-			a16[i] = w;
-		}
-		if (MASK && c + 1 < CHUNKS) load_mask4(mask_row, 4 * (c + 1), hm);       // in flight behind the stores and the next TMEM read
-		if (to_tmem) tmem_st16(t_lane + kBA + 16 * c, a16);
-		store_chunks4(out_row, 4 * c, a16);
+	for (int i = 0; i < 16; i++) {
+		uint32_t w = pack_bf16(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+		if (MASK) w &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&hm[i]), zero);
+		a16[i] = w;
+	}
+}
+
+// mask words of one 64-column slab (8 chunks of 16 bytes) of this thread's row
+__device__ __forceinline__ void load_mask_slab(const uint8_t* __restrict__ region_row, int slab, uint32_t (&h)[32])
+{
+#pragma unroll
+	for (int i = 0; i < 8; i++) {
+		const uint4 v = __ldg(reinterpret_cast<const uint4*>(region_row + (8 * slab + i) * 1024));
+		h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
+	}
+}
+
+// One chain step, slab by slab: the accumulator arrives as 64-column slabs (one per weight stage, each complete over K), so the
+// epilogue of slab s runs while the tensor core still works on slabs s+1.. .  SLABS of the 4 slabs carry data (all 4 barriers are
+// consumed to keep their phases in step).  hm0 / hm1 hold the mask words of slabs s (even / odd), requested two slabs ahead.
+template <int SLABS, bool MASK>
+__device__ __forceinline__ void epilogue_grad(uint32_t t_lane, uint64_t* slab_ready, uint32_t parity, const uint8_t* __restrict__ mask_row,
+	uint8_t* __restrict__ out_row, bool to_tmem, uint32_t a_next, uint32_t (&hm0)[32], uint32_t (&hm1)[32])
+{
+	uint32_t acc0[32], acc1[32], a16[16];
+#pragma unroll
+	for (int sl = 0; sl < 4; sl++) {
+		mbar_wait(&slab_ready[sl], parity);
+		if (sl >= SLABS) continue;
+		fence_after();
+		uint32_t (&hm)[32] = (sl & 1) ? hm1 : hm0;
+		tmem_ld32(t_lane + kBD + 64 * sl, acc0);
+		tmem_ld_wait_for(acc0);
+		tmem_ld32(t_lane + kBD + 64 * sl + 32, acc1);
+		grad_pack<MASK>(acc0, hm, a16);
+		if (to_tmem) tmem_st16(t_lane + a_next + 32 * sl, a16);
+		store_chunks4(out_row, 8 * sl, a16);
+		tmem_ld_wait_for(acc1);
+		grad_pack<MASK>(acc1, hm + 16, a16);
+		if (to_tmem) tmem_st16(t_lane + a_next + 32 * sl + 16, a16);
+		store_chunks4(out_row, 8 * sl + 4, a16);
+		if (MASK && sl + 2 < SLABS) load_mask_slab(mask_row, sl + 2, hm);
 	}
 }
 
@@ -103,7 +126,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_chain_kernel(cons
 		if (lane == 0) {
 			for (int s = 0; s < kRing; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
 			mbar_init(&sm.a_ready, 4);
-			mbar_init(&sm.d_ready, 1);
+			for (int s = 0; s < 4; s++) mbar_init(&sm.slab_ready[s], 1);
 			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		}
 		__syncwarp();
@@ -153,6 +176,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_chain_kernel(cons
 						umma_ts(tmem + kBD, tmem + kBRgb, smem_desc(smem_u32(sm.ring[slot]), 128, 16 * 16), idesc_16(128, 128, true, 0, 1), 0u);
 						umma_commit(&sm.empty[slot]);
 						g++;
+						for (int s = 0; s < 4; s++) umma_commit(&sm.slab_ready[s]);
 					} else {
 						const int n_out = layer_info(l).N;               // K of this product
 						const uint32_t idesc = idesc_16(128, 64, true, 0, 1);
@@ -162,8 +186,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_chain_kernel(cons
 							fence_after();
 							const uint32_t saddr = smem_u32(sm.ring[slot]);
 							for (int j = 0; j < n_out / 16; j++)
-								umma_ts(tmem + kBD + 64 * s, tmem + kBA + 8 * j, smem_desc(saddr + j * 256, 128, n_out * 16), idesc, j ? 1u : 0u);
+								umma_ts(tmem + kBD + 64 * s, tmem + a_buf(st) + 8 * j, smem_desc(saddr + j * 256, 128, n_out * 16), idesc, j ? 1u : 0u);
 							umma_commit(&sm.empty[slot]);
+							if (st != 2) umma_commit(&sm.slab_ready[s]);     // this 64-column slab of D is complete
 						}
 						if (st == 2) {
 							// + d_alpha * W_alpha over all 256 columns: K = 16 (1 real)
@@ -173,9 +198,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_chain_kernel(cons
 							umma_ts(tmem + kBD, tmem + kBAlpha, smem_desc(smem_u32(sm.ring[slot]), 128, 16 * 16), idesc_16(128, 256, true, 0, 1), 1u);
 							umma_commit(&sm.empty[slot]);
 							g++;
+							for (int s = 0; s < 4; s++) umma_commit(&sm.slab_ready[s]);
 						}
 					}
-					umma_commit(&sm.d_ready);
 				}
 			}
 		}
@@ -190,7 +215,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_chain_kernel(cons
 			const int64_t r = tile * 128 + row;
 			const uint8_t* const rec_s = saved + tile * kSaveTile;
 			uint8_t* const rec_g = grads + tile * kGradTile;
-			uint32_t hm[16];
+			uint32_t hm0[32], hm1[32];
 			{
 				float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
 				if (r < n) g4 = __ldg(reinterpret_cast<const float4*>(grad_out) + r);
@@ -199,34 +224,41 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_chain_kernel(cons
 				for (int i = 0; i < 16; i++) a16[i] = 0u;
 				a16[0] = pack_bf16(g4.x, g4.y);
 				a16[1] = pack_bf16(g4.z, 0.f);
-				a16[8] = pack_bf16(g4.w, 0.f);
-				tmem_st16(t_lane + kBRgb, a16);          // columns kBRgb..+7 = [r g b 0..], kBAlpha..+7 = [alpha 0..]
+				tmem_st16(t_lane + kBRgb, a16);          // K = 16 operand [r g b 0..]
 				uint8_t* o = rec_g + kGradOut + chunk_offset(16, row, 0);
 				*reinterpret_cast<uint4*>(o) = make_uint4(a16[0], pack_bf16(g4.z, g4.w), 0u, 0u);
+				a16[0] = pack_bf16(g4.w, 0.f);
+				a16[1] = 0u;
+				tmem_st16(t_lane + kBAlpha, a16);        // K = 16 operand [alpha 0..]
 				*reinterpret_cast<uint4*>(o + 1024) = make_uint4(0u, 0u, 0u, 0u);
 			}
-			load_mask4(rec_s + kSaveHv + chunk_offset(128, row, 0), 0, hm);
+			{
+				const uint8_t* m = rec_s + kSaveHv + chunk_offset(128, row, 0);
+				load_mask_slab(m, 0, hm0);
+				load_mask_slab(m, 1, hm1);
+			}
 			publish_bwd(&sm.a_ready, lane);
 
 #pragma unroll 1
 			for (int st = 0; st < kSteps; st++) {
-				mbar_wait(&sm.d_ready, pd);
-				pd ^= 1u;
-				fence_after();
 				if (st == 0) {
-					epilogue_grad<4, true>(t_lane, rec_s + kSaveHv + chunk_offset(128, row, 0), rec_g + kGradHv + chunk_offset(128, row, 0), true, hm);
+					epilogue_grad<2, true>(t_lane, sm.slab_ready, pd, rec_s + kSaveHv + chunk_offset(128, row, 0), rec_g + kGradHv + chunk_offset(128, row, 0),
+						true, a_buf(1), hm0, hm1);
 				} else if (st == 1) {
-					epilogue_grad<8, false>(t_lane, nullptr, rec_g + kGradFeat + chunk_offset(256, row, 0), true, hm);
+					epilogue_grad<4, false>(t_lane, sm.slab_ready, pd, nullptr, rec_g + kGradFeat + chunk_offset(256, row, 0), true, a_buf(2), hm0, hm1);
 				} else {
 					const int l = st == 2 ? 8 : 10 - st;         // the activation h_l whose ReLU is undone; the result is dY_{l-1}
-					epilogue_grad<8, true>(t_lane, rec_s + save_h(l) + chunk_offset(256, row, 0), rec_g + grad_y(l - 1) + chunk_offset(256, row, 0),
-						st + 1 < kSteps, hm);
+					epilogue_grad<4, true>(t_lane, sm.slab_ready, pd, rec_s + save_h(l) + chunk_offset(256, row, 0),
+						rec_g + grad_y(l - 1) + chunk_offset(256, row, 0), st + 1 < kSteps, a_buf(st + 1), hm0, hm1);
 				}
+				pd ^= 1u;
 				if (st + 1 < kSteps) {
-					// mask of the next step, requested before the MMAs of that step are waited for
-					if (st == 0) { /* feature: no activation */ }
-					else if (st == 1) load_mask4(rec_s + save_h(8) + chunk_offset(256, row, 0), 0, hm);
-					else load_mask4(rec_s + save_h((st == 2 ? 8 : 10 - st) - 1) + chunk_offset(256, row, 0), 0, hm);
+					// the first two mask slabs of the next step, requested before that step's MMAs are even issued
+					if (st >= 1) {
+						const uint8_t* m = rec_s + save_h(st == 1 ? 8 : (st == 2 ? 8 : 10 - st) - 1) + chunk_offset(256, row, 0);
+						load_mask_slab(m, 0, hm0);
+						load_mask_slab(m, 1, hm1);
+					}
 					publish_bwd(&sm.a_ready, lane);
 				}
 			}
