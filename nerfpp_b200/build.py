@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     for src in sources():
         obj = obj_dir / (src.stem + ".o")
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("NRF_NVCC_EXTRA", "").split(), "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     failed = False

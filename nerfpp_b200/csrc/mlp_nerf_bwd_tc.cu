@@ -113,6 +113,14 @@ __device__ __forceinline__ void epilogue_grad(uint32_t t_lane, uint64_t* slab_re
 	}
 }
 
+// KSTEPS K = 16 steps of one accumulator slab: A advances 8 TMEM columns, the MN-major B descriptor 256 bytes (16 output rows) per step
+template <int KSTEPS>
+__device__ __forceinline__ void issue_k(uint32_t d, uint32_t a0, uint64_t b0, uint32_t idesc)
+{
+#pragma unroll
+	for (int j = 0; j < KSTEPS; j++) umma_ts(d, a0 + 8 * j, b0 + static_cast<uint64_t>(16 * j), idesc, j ? 1u : 0u);
+}
+
 __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_chain_kernel(const uint8_t* __restrict__ blob, const uint8_t* __restrict__ saved,
 	const float* __restrict__ grad_out, int64_t n, uint8_t* __restrict__ grads)
 {
@@ -148,9 +156,20 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_chain_kernel(cons
 				tma_bulk_g2s(sm.ring[slot], blob + off, bytes, &sm.full[slot]);
 				g++;
 			};
+			// The ReLU masks are read from the saved activations by the epilogue threads one step after the producer passes here
+			// (it runs up to a ring ahead of the MMAs): pull each step's 64 KB mask tile into L2 now, so those loads are L2 hits.
+			auto prefetch_mask = [&](int64_t tile, int st) {
+				const uint8_t* rec = saved + tile * kSaveTile;
+				if (st == 0) tma_prefetch_l2(rec + kSaveHv, region_bytes(128));
+				else if (st >= 2) tma_prefetch_l2(rec + save_h(st == 2 ? 8 : 10 - st), region_bytes(256));
+			};
+			if (my_tiles > 0) { prefetch_mask(blockIdx.x, 0); prefetch_mask(blockIdx.x, 2); }
 			for (int64_t t = 0; t < my_tiles; t++) {
+				const int64_t tile = blockIdx.x + t * gridDim.x;
 #pragma unroll 1
 				for (int st = 0; st < kSteps; st++) {
+					if (st + 2 < kSteps) prefetch_mask(tile, st + 2);
+					else if (t + 1 < my_tiles) prefetch_mask(tile + gridDim.x, st + 2 - kSteps);      // steps 0 and (1: none) of the next tile
 					const int l = step_layer(st);
 					for (int s = step_first_stage(l); s < step_first_stage(l) + step_stages(l); s++) push(stage_offset(l, s), stage_bytes(l, s));
 					if (st == 2) push(stage_offset(9, 0), stage_bytes(9, 0));
@@ -184,9 +203,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_chain_kernel(cons
 							const uint32_t slot = g % kRing, round = g / kRing;
 							mbar_wait(&sm.full[slot], round & 1u);
 							fence_after();
-							const uint32_t saddr = smem_u32(sm.ring[slot]);
-							for (int j = 0; j < n_out / 16; j++)
-								umma_ts(tmem + kBD + 64 * s, tmem + a_buf(st) + 8 * j, smem_desc(saddr + j * 256, 128, n_out * 16), idesc, j ? 1u : 0u);
+							// one descriptor per stage, then 16 (8) back-to-back MMAs whose operands differ by constants: the issuing thread
+							// must not spend more than the 32 cycles an N = 64 MMA takes on each of them
+							const uint64_t b0 = smem_desc(smem_u32(sm.ring[slot]), 128, n_out * 16);
+							const uint32_t d = tmem + kBD + 64 * s, a0 = tmem + a_buf(st);
+							if (n_out == 256) issue_k<16>(d, a0, b0, idesc);
+							else issue_k<8>(d, a0, b0, idesc);
 							umma_commit(&sm.empty[slot]);
 							if (st != 2) umma_commit(&sm.slab_ready[s]);     // this 64-column slab of D is complete
 						}
@@ -274,13 +296,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_chain_kernel(cons
 }
 
 // ---- weight gradients --------------------------------------------------------------------------------------------------
-constexpr int kMaxUnits = 28;
-constexpr int kDwStageBytes = 128 * 64 * 2 + 256 * 64 * 2;         // A: 128 columns x 64 rows, B: up to 256 columns x 64 rows
+// A unit is one weight matrix (or one column block of it): D[M = columns of the A region (128 or 256), N] = A^T B summed over rows.
+// M = 256 runs as two M = 128 MMAs on the same B slab, so a dY slab and an activation slab are each read from HBM once per unit.
+constexpr int kMaxUnits = 16;
+constexpr int kDwRing = 3;
+constexpr int kDwStageBytes = 256 * 64 * 2 + 256 * 64 * 2;         // A: up to 256 columns x 64 rows, B: up to 256 columns x 64 rows
+constexpr int kDwAOff = 0, kDwBOff = 256 * 64 * 2;
 struct Unit {
-	int32_t a_src, a_off, a_half;       // record kind (0 gradient, 1 saved), byte offset of the A slab of row half 0, stride to row half 1
-	int32_t b_src, b_off, b_half;
-	int32_t n;                          // MMA N (columns of B)
-	int32_t m_valid, n_lo, n_hi;        // D(m, n) is written for m < m_valid, n_lo <= n < n_hi ...
+	int32_t a_src, a_off, a_cols;       // record kind (0 gradient, 1 saved), byte offset of the region in the record, region width (128 / 256)
+	int32_t b_src, b_off, b_cols;       // b_cols: region width = MMA N
+	int32_t n_lo, n_hi;                 // D(m, n) is written for n_lo <= n < n_hi ...
 	int32_t stride_m, stride_n;         // ... to out[m * stride_m + (n - n_lo) * stride_n]
 	int32_t bias_mode;                  // 0 none; 1 column sums of A -> bias[m]; 2 column sums of B -> bias[0..2] (rgb), bias2[0] (alpha)
 	int32_t pad_;
@@ -294,13 +319,32 @@ struct UnitTable {
 };
 
 struct __align__(128) DwSmem {
-	uint8_t ring[kRing][kDwStageBytes];
-	uint64_t full[kRing], empty[kRing];
-	uint64_t d_ready[2], d_free[2];
+	uint8_t ring[kDwRing][kDwStageBytes];
+	uint64_t full[kDwRing], empty[kDwRing];
+	uint64_t d_ready, d_free;
 	uint32_t tmem_base;
 };
 
+#ifdef NRF_PROFILE_DW
+// debug build only (NRF_NVCC_EXTRA=-DNRF_PROFILE_DW): per-CTA cycle counters of the dW kernel, read back by nrf_debug_dw_profile
+__device__ unsigned long long g_dw_prof[kNumSMs][8];
+#define DW_T0() const long long t0__ = clock64()
+#define DW_ADD(slot) g_dw_prof[blockIdx.x][slot] += static_cast<unsigned long long>(clock64() - t0__)
+__device__ __forceinline__ void g_prof_items(long long n) { g_dw_prof[blockIdx.x][7] += static_cast<unsigned long long>(n); }
+#else
+__device__ __forceinline__ void g_prof_items(long long) {}
+#define DW_T0()
+#define DW_ADD(slot)
+#endif
+
 __device__ __forceinline__ int64_t clamp_items(int64_t x, int64_t h) { return x < 0 ? 0 : (x > h ? h : x); }
+// relative time of one 64-row slab of a unit (measured per CTA with clock64, profiles/r1_mlp_nerf_bwd_dw_balance.txt): bytes moved for
+// the wide products, a latency floor (three slabs in flight) for the narrow ones
+__host__ __device__ __forceinline__ int64_t unit_cost(int a_cols, int b_cols)
+{
+	const int c = b_cols >= 64 ? a_cols + (b_cols > 160 ? b_cols : 160) : a_cols + b_cols;
+	return c > 272 ? c : 272;
+}
 
 __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_dw_kernel(const __grid_constant__ UnitTable T, const uint8_t* __restrict__ saved,
 	const uint8_t* __restrict__ grads, int64_t n_tiles)
@@ -310,17 +354,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_dw_kernel(const _
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int64_t H = 2 * n_tiles;                                   // 64-row slabs per unit
 	int64_t total = 0;
-	for (int u = 0; u < T.count; u++) total += H * (128 + T.u[u].n);
+	for (int u = 0; u < T.count; u++) total += H * unit_cost(T.u[u].a_cols, T.u[u].b_cols);
 	const int64_t lo_cost = total / gridDim.x * blockIdx.x + (total % gridDim.x) * blockIdx.x / gridDim.x;
 	const int64_t hi_cost = total / gridDim.x * (blockIdx.x + 1) + (total % gridDim.x) * (blockIdx.x + 1) / gridDim.x;
 
 	if (warp == 1) {
 		if (lane == 0) {
-			for (int s = 0; s < kRing; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 5); }
-			mbar_init(&sm.d_ready[0], 1);
-			mbar_init(&sm.d_ready[1], 1);
-			mbar_init(&sm.d_free[0], 4);
-			mbar_init(&sm.d_free[1], 4);
+			for (int s = 0; s < kDwRing; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 5); }
+			mbar_init(&sm.d_ready, 1);
+			mbar_init(&sm.d_free, 4);
 			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		}
 		__syncwarp();
@@ -332,55 +374,63 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_dw_kernel(const _
 	const uint32_t tmem = sm.tmem_base;
 
 	if (warp == 0) {
-		// ===== producer =====
+		// ===== producer: one bulk copy per operand and slab =====
 		if (lane == 0) {
 			uint32_t g = 0;
 			int64_t cum = 0;
 			for (int u = 0; u < T.count; u++) {
 				const Unit& U = T.u[u];
-				const int64_t c = 128 + U.n;
+				const int64_t c = unit_cost(U.a_cols, U.b_cols);
 				const int64_t lo = clamp_items((lo_cost - cum) / c, H), hi = clamp_items((hi_cost - cum) / c, H);
 				cum += H * c;
 				const uint8_t* a_base = (U.a_src ? saved : grads) + U.a_off;
 				const uint8_t* b_base = (U.b_src ? saved : grads) + U.b_off;
 				const int64_t a_tile = U.a_src ? kSaveTile : kGradTile, b_tile = U.b_src ? kSaveTile : kGradTile;
-				const uint32_t b_bytes = U.n * 128;
+				const uint32_t a_bytes = U.a_cols * 128, b_bytes = U.b_cols * 128;      // one 64-row half of the region
 				for (int64_t i = lo; i < hi; i++, g++) {
-					const uint32_t slot = g % kRing, round = g / kRing;
-					mbar_wait(&sm.empty[slot], (round & 1u) ^ 1u);
-					mbar_expect_tx(&sm.full[slot], 16384 + b_bytes);
-					tma_bulk_g2s(sm.ring[slot], a_base + (i >> 1) * a_tile + (i & 1) * U.a_half, 16384, &sm.full[slot]);
-					tma_bulk_g2s(sm.ring[slot] + 16384, b_base + (i >> 1) * b_tile + (i & 1) * U.b_half, b_bytes, &sm.full[slot]);
+					const uint32_t slot = g % kDwRing, round = g / kDwRing;
+					{ DW_T0(); mbar_wait(&sm.empty[slot], (round & 1u) ^ 1u); DW_ADD(2); }
+					mbar_expect_tx(&sm.full[slot], a_bytes + b_bytes);
+					tma_bulk_g2s(sm.ring[slot] + kDwAOff, a_base + (i >> 1) * a_tile + (i & 1) * a_bytes, a_bytes, &sm.full[slot]);
+					tma_bulk_g2s(sm.ring[slot] + kDwBOff, b_base + (i >> 1) * b_tile + (i & 1) * b_bytes, b_bytes, &sm.full[slot]);
 				}
 			}
 		}
 	} else if (warp == 1) {
-		// ===== MMA issuer: D[128 columns of A, N] += A^T B over the 64 rows of a slab, 4 K steps =====
+		// ===== MMA issuer: D[m block][128, N] += A^T B over the 64 rows of a slab: 4 K steps x (1 or 2) M blocks =====
 		if (lane == 0) {
 			uint32_t g = 0, seg = 0;
 			int64_t cum = 0;
 			for (int u = 0; u < T.count; u++) {
 				const Unit& U = T.u[u];
-				const int64_t c = 128 + U.n;
+				const int64_t c = unit_cost(U.a_cols, U.b_cols);
 				const int64_t lo = clamp_items((lo_cost - cum) / c, H), hi = clamp_items((hi_cost - cum) / c, H);
 				cum += H * c;
 				if (hi <= lo) continue;
-				const uint32_t buf = seg & 1u;
-				mbar_wait(&sm.d_free[buf], ((seg >> 1) & 1u) ^ 1u);          // first use of each buffer passes immediately
+				{ DW_T0(); mbar_wait(&sm.d_free, (seg & 1u) ^ 1u); DW_ADD(1); }         // the accumulators of the previous segment have been read out
 				fence_after();
-				const uint32_t idesc = idesc_16(128, U.n, true, 1, 1);
+				const uint32_t idesc = idesc_16(128, U.b_cols, true, 1, 1);
+				const int mblocks = U.a_cols / 128;
 				for (int64_t i = lo; i < hi; i++, g++) {
-					const uint32_t slot = g % kRing, round = g / kRing;
-					mbar_wait(&sm.full[slot], round & 1u);
+					const uint32_t slot = g % kDwRing, round = g / kDwRing;
+					{ DW_T0(); mbar_wait(&sm.full[slot], round & 1u); DW_ADD(0); }
 					fence_after();
 					const uint32_t saddr = smem_u32(sm.ring[slot]);
+					const uint64_t a0 = smem_desc(saddr + kDwAOff, 128, 1024), b0 = smem_desc(saddr + kDwBOff, 128, 1024);
+					const uint32_t acc = i > lo ? 1u : 0u;
+					if (mblocks == 2) {
 #pragma unroll
-					for (int j = 0; j < 4; j++)
-						umma_ss(tmem + 256 * buf, smem_desc(saddr + j * 256, 128, 1024), smem_desc(saddr + 16384 + j * 256, 128, 1024), idesc,
-							(i > lo || j) ? 1u : 0u);
+						for (int j = 0; j < 4; j++) {
+							umma_ss(tmem, a0 + static_cast<uint64_t>(16 * j), b0 + static_cast<uint64_t>(16 * j), idesc, j ? 1u : acc);
+							umma_ss(tmem + 256, a0 + static_cast<uint64_t>(1024 + 16 * j), b0 + static_cast<uint64_t>(16 * j), idesc, j ? 1u : acc);
+						}
+					} else {
+#pragma unroll
+						for (int j = 0; j < 4; j++) umma_ss(tmem, a0 + static_cast<uint64_t>(16 * j), b0 + static_cast<uint64_t>(16 * j), idesc, j ? 1u : acc);
+					}
 					umma_commit(&sm.empty[slot]);
 				}
-				umma_commit(&sm.d_ready[buf]);
+				umma_commit(&sm.d_ready);
 				seg++;
 			}
 		}
@@ -390,34 +440,46 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_dw_kernel(const _
 		const uint32_t t_lane = tmem + (static_cast<uint32_t>(q << 5) << 16);
 		uint32_t g = 0, seg = 0;
 		int64_t cum = 0;
+#ifdef NRF_PROFILE_DW
+		const long long t_start = clock64();
+		unsigned long long g_start;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_start));
+#endif
 		for (int u = 0; u < T.count; u++) {
 			const Unit& U = T.u[u];
-			const int64_t c = 128 + U.n;
+			const int64_t c = unit_cost(U.a_cols, U.b_cols);
 			const int64_t lo = clamp_items((lo_cost - cum) / c, H), hi = clamp_items((hi_cost - cum) / c, H);
 			cum += H * c;
 			if (hi <= lo) continue;
-			float bs[4][8];
+			float bs[8][8];
 #pragma unroll
-			for (int a = 0; a < 4; a++)
+			for (int a = 0; a < 8; a++)
 #pragma unroll
 				for (int e = 0; e < 8; e++) bs[a][e] = 0.f;
+#ifdef NRF_DW_NOSUM
+			const bool sum_a = false, sum_b = false;
+#else
 			const bool sum_a = U.bias_mode == 1, sum_b = U.bias_mode == 2 && q == 0;
+#endif
+			const int per_warp = U.a_cols / 32;          // column chunks of the A slab per warp: 8 (256 columns) or 4
 			for (int64_t i = lo; i < hi; i++, g++) {
-				const uint32_t slot = g % kRing, round = g / kRing;
+				const uint32_t slot = g % kDwRing, round = g / kDwRing;
 				mbar_wait(&sm.full[slot], round & 1u);
 				if (sum_a || sum_b) {
-					// warp q owns column chunks 4q..4q+3 of the A slab (or chunk 0 of the B slab); lanes take rows lane, lane + 32
-					const uint8_t* base = sm.ring[slot] + (sum_a ? (4 * q) * 1024 : 16384);
-					const int chunks = sum_a ? 4 : 1;
-					for (int a = 0; a < chunks; a++) {
+					// warp q owns column chunks per_warp*q .. of the A slab (or chunk 0 of the B slab); lanes take rows lane, lane + 32
+					const uint8_t* base = sm.ring[slot] + (sum_a ? kDwAOff + (per_warp * q) * 1024 : kDwBOff);
 #pragma unroll
-						for (int h = 0; h < 2; h++) {
-							const uint4 v = *reinterpret_cast<const uint4*>(base + a * 1024 + (lane + 32 * h) * 16);
-							const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+					for (int a = 0; a < 8; a++) {
+						if (a < (sum_a ? per_warp : 1)) {
 #pragma unroll
-							for (int e = 0; e < 4; e++) {
-								bs[a][2 * e] += __uint_as_float(w[e] << 16);
-								bs[a][2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+							for (int h = 0; h < 2; h++) {
+								const uint4 v = *reinterpret_cast<const uint4*>(base + a * 1024 + (lane + 32 * h) * 16);
+								const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+								for (int e = 0; e < 4; e++) {
+									bs[a][2 * e] += __uint_as_float(w[e] << 16);
+									bs[a][2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+								}
 							}
 						}
 					}
@@ -426,40 +488,59 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_dw_kernel(const _
 				if (lane == 0) mbar_arrive(&sm.empty[slot]);
 			}
 			// ---- flush ----
+			DW_T0();
 			if (sum_a || sum_b) {
 #pragma unroll
-				for (int a = 0; a < 4; a++)
+				for (int a = 0; a < 8; a++)
 #pragma unroll
 					for (int e = 0; e < 8; e++) {
 						const float s = warp_sum(bs[a][e]);
 						if (lane == 0) {
-							if (sum_a) { if (32 * q + 8 * a + e < U.m_valid) atomicAdd(U.bias + 32 * q + 8 * a + e, s); }
+							if (sum_a) { if (a < per_warp) atomicAdd(U.bias + 8 * (per_warp * q + a) + e, s); }
 							else if (a == 0 && e < 3) atomicAdd(U.bias + e, s);
 							else if (a == 0 && e == 3) atomicAdd(U.bias2, s);
 						}
 					}
 			}
-			const uint32_t buf = seg & 1u;
-			mbar_wait(&sm.d_ready[buf], (seg >> 1) & 1u);      // one barrier per accumulator buffer: the issuer can be a whole segment ahead
+			mbar_wait(&sm.d_ready, seg & 1u);
 			fence_after();
-			const int m = 32 * q + lane;
-			for (int c0 = 0; c0 < U.n; c0 += 16) {
-				uint32_t d16[16];
-				tmem_ld16(t_lane + 256 * buf + c0, d16);
-				tmem_ld_wait();
-				if (m < U.m_valid) {
+			if (warp == 2 && lane == 0) DW_ADD(5);
+			for (int mb = 0; mb < U.a_cols / 128; mb++) {
+				const int m = 128 * mb + 32 * q + lane;
+				for (int c0 = 0; c0 < U.b_cols; c0 += 16) {
+					uint32_t d16[16];
+					tmem_ld16(t_lane + 256 * mb + c0, d16);
+					tmem_ld_wait();
+					float* row = U.out + static_cast<int64_t>(m) * U.stride_m;
+					if (U.stride_n == 1 && c0 >= U.n_lo && c0 + 16 <= U.n_hi && ((reinterpret_cast<uintptr_t>(row + (c0 - U.n_lo))) & 15) == 0) {
+						// 16-byte vector REDs: the L2 atomic units are bound per operation, not per byte
 #pragma unroll
-					for (int j = 0; j < 16; j++) {
-						const int nn = c0 + j;
-						if (nn >= U.n_lo && nn < U.n_hi) atomicAdd(U.out + static_cast<int64_t>(m) * U.stride_m + static_cast<int64_t>(nn - U.n_lo) * U.stride_n, __uint_as_float(d16[j]));
+						for (int j = 0; j < 16; j += 4)
+							asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + (c0 - U.n_lo) + j), "f"(__uint_as_float(d16[j])),
+								"f"(__uint_as_float(d16[j + 1])), "f"(__uint_as_float(d16[j + 2])), "f"(__uint_as_float(d16[j + 3])) : "memory");
+					} else {
+#pragma unroll
+						for (int j = 0; j < 16; j++) {
+							const int nn = c0 + j;
+							if (nn >= U.n_lo && nn < U.n_hi) atomicAdd(row + static_cast<int64_t>(nn - U.n_lo) * U.stride_n, __uint_as_float(d16[j]));
+						}
 					}
 				}
 			}
 			fence_before();
 			__syncwarp();
-			if (lane == 0) mbar_arrive(&sm.d_free[buf]);
+			if (lane == 0) mbar_arrive(&sm.d_free);
+			if (warp == 2 && lane == 0) { DW_ADD(6); g_prof_items(hi - lo); }
 			seg++;
 		}
+#ifdef NRF_PROFILE_DW
+		if (warp == 2 && lane == 0) {
+			unsigned long long g_end;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
+			g_dw_prof[blockIdx.x][3] += static_cast<unsigned long long>(clock64() - t_start);       // whole kernel, cycles
+			g_dw_prof[blockIdx.x][4] += g_end - g_start;                                          // whole kernel, ns
+		}
+#endif
 	}
 
 	fence_before();
@@ -470,13 +551,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_dw_kernel(const _
 	}
 }
 
-static Unit make_unit(int a_src, int a_region, int a_cols, int a_chunk0, int b_src, int b_region, int b_cols, int n, int m_valid, int n_lo, int n_hi,
-	int stride_m, int stride_n, float* out, int bias_mode = 0, float* bias = nullptr, float* bias2 = nullptr)
+static Unit make_unit(int a_src, int a_region, int a_cols, int b_src, int b_region, int b_cols, int n_lo, int n_hi, int stride_m, int stride_n, float* out,
+	int bias_mode = 0, float* bias = nullptr, float* bias2 = nullptr)
 {
 	Unit u{};
-	u.a_src = a_src; u.a_off = a_region + a_chunk0 * 1024; u.a_half = a_cols * 128;
-	u.b_src = b_src; u.b_off = b_region; u.b_half = b_cols * 128;
-	u.n = n; u.m_valid = m_valid; u.n_lo = n_lo; u.n_hi = n_hi; u.stride_m = stride_m; u.stride_n = stride_n;
+	u.a_src = a_src; u.a_off = a_region; u.a_cols = a_cols;
+	u.b_src = b_src; u.b_off = b_region; u.b_cols = b_cols;
+	u.n_lo = n_lo; u.n_hi = n_hi; u.stride_m = stride_m; u.stride_n = stride_n;
 	u.bias_mode = bias_mode; u.out = out; u.bias = bias; u.bias2 = bias2;
 	return u;
 }
@@ -486,28 +567,21 @@ static void build_units(const Grads& g, UnitTable& T)
 	int c = 0;
 	for (int l = 0; l < 8; l++) {
 		const int ld = l == 0 ? kInPts : (l == 5 ? kW + kInPts : kW);
-		for (int mh = 0; mh < 2; mh++) {
-			float* w = g.w[l] + static_cast<int64_t>(128 * mh) * ld;
-			float* b = g.b[l] + 128 * mh;
-			if (l == 0) {
-				T.u[c++] = make_unit(0, grad_y(0), 256, 16 * mh, 1, kSavePts, 64, 64, 128, 0, kInPts, ld, 1, w, 1, b);
-			} else if (l == 5) {
-				T.u[c++] = make_unit(0, grad_y(5), 256, 16 * mh, 1, kSavePts, 64, 64, 128, 0, kInPts, ld, 1, w);
-				T.u[c++] = make_unit(0, grad_y(5), 256, 16 * mh, 1, save_h(5), 256, 256, 128, 0, 256, ld, 1, w + kInPts, 1, b);
-			} else {
-				T.u[c++] = make_unit(0, grad_y(l), 256, 16 * mh, 1, save_h(l), 256, 256, 128, 0, 256, ld, 1, w, 1, b);
-			}
+		if (l == 0) {
+			T.u[c++] = make_unit(0, grad_y(0), 256, 1, kSavePts, 64, 0, kInPts, ld, 1, g.w[0], 1, g.b[0]);
+		} else if (l == 5) {                                                      // [pts | h5]
+			T.u[c++] = make_unit(0, grad_y(5), 256, 1, kSavePts, 64, 0, kInPts, ld, 1, g.w[5]);
+			T.u[c++] = make_unit(0, grad_y(5), 256, 1, save_h(5), 256, 0, 256, ld, 1, g.w[5] + kInPts, 1, g.b[5]);
+		} else {
+			T.u[c++] = make_unit(0, grad_y(l), 256, 1, save_h(l), 256, 0, 256, ld, 1, g.w[l], 1, g.b[l]);
 		}
 	}
-	for (int mh = 0; mh < 2; mh++)   // feature_linear
-		T.u[c++] = make_unit(0, kGradFeat, 256, 16 * mh, 1, save_h(8), 256, 256, 128, 0, 256, kW, 1, g.w[8] + 128 * mh * kW, 1, g.b[8] + 128 * mh);
-	// views_linears[0]: [feature | views]
-	T.u[c++] = make_unit(0, kGradHv, 128, 0, 1, kSaveFeat, 256, 256, 128, 0, 256, kW + kInViews, 1, g.w[10], 1, g.b[10]);
-	T.u[c++] = make_unit(0, kGradHv, 128, 0, 1, kSaveViews, 32, 32, 128, 0, kInViews, kW + kInViews, 1, g.w[10] + kW);
+	T.u[c++] = make_unit(0, kGradFeat, 256, 1, save_h(8), 256, 0, 256, kW, 1, g.w[8], 1, g.b[8]);                          // feature_linear
+	T.u[c++] = make_unit(0, kGradHv, 128, 1, kSaveFeat, 256, 0, 256, kW + kInViews, 1, g.w[10], 1, g.b[10]);               // views_linears[0]: [feature |
+	T.u[c++] = make_unit(0, kGradHv, 128, 1, kSaveViews, 32, 0, kInViews, kW + kInViews, 1, g.w[10] + kW);                 //                     views]
 	// heads, roles swapped (M = input index): rgb_linear [3,128] from hv, alpha_linear [1,256] from h8; their biases from dOut
-	T.u[c++] = make_unit(1, kSaveHv, 128, 0, 0, kGradOut, 16, 16, 128, 0, 3, 1, kW / 2, g.w[11], 2, g.b[11], g.b[9]);
-	for (int mh = 0; mh < 2; mh++)
-		T.u[c++] = make_unit(1, save_h(8), 256, 16 * mh, 0, kGradOut, 16, 16, 128, 3, 4, 1, kW, g.w[9] + 128 * mh);
+	T.u[c++] = make_unit(1, kSaveHv, 128, 0, kGradOut, 16, 0, 3, 1, kW / 2, g.w[11], 2, g.b[11], g.b[9]);
+	T.u[c++] = make_unit(1, save_h(8), 256, 0, kGradOut, 16, 3, 4, 1, kW, g.w[9]);
 	T.count = c;
 }
 
@@ -564,5 +638,18 @@ int nrf_mlp_nerf_bwd(const nrf_mlp_nerf_shape* shape, const void* packed_train, 
 	}
 	return NRF_OK;
 }
+
+#ifdef NRF_PROFILE_DW
+/* debug builds only: [148][8] cycle counters {issuer waits full, issuer waits d_free, producer waits empty, epilogue waits full, epilogue sums,
+ * epilogue waits d_ready (incl. bias flush), flush incl. d_ready wait, items}; clears them */
+int nrf_debug_dw_profile(unsigned long long* host_out)
+{
+	NRF_CUDA(cudaDeviceSynchronize());
+	NRF_CUDA(cudaMemcpyFromSymbol(host_out, g_dw_prof, sizeof(unsigned long long) * kNumSMs * 8));
+	static unsigned long long zeros[kNumSMs * 8] = {};
+	NRF_CUDA(cudaMemcpyToSymbol(g_dw_prof, zeros, sizeof(zeros)));
+	return NRF_OK;
+}
+#endif
 
 }

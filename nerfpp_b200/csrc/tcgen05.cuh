@@ -38,6 +38,11 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 	             ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// asynchronous L2 prefetch of a contiguous global range (bytes: multiple of 16)
+__device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
+{
+	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
