@@ -146,7 +146,16 @@ static void Bind(py::module_& m, const char* name)
 		.def("run_network", &P::RunNetwork).def("raw_to_outputs", &P::RawToOutputs)
 		.def("render_rays", &P::RenderRays).def("render", &P::Render).def("render_shipped", &P::RenderShipped).def("render_image", &P::RenderImage)
 		.def("use_fused_adam", &P::UseFusedAdam)
-		.def("train_steps", &P::TrainSteps, py::call_guard<py::gil_scoped_release>());
+		.def("train_steps", &P::TrainSteps, py::call_guard<py::gil_scoped_release>())
+		// NeRFExecutor::SaveCheckpoint / the restore branch of Initialize (src/NeRFExecutor.h:1054-1068, 546-553): same file names
+		.def("save_checkpoint", [](P& p, const std::string& dir) {
+			torch::save(p.embed, dir + "/embedder_checkpoint.pt");
+			torch::save(p.model, dir + "/model_checkpoint.pt");
+		})
+		.def("load_checkpoint", [](P& p, const std::string& dir) {
+			torch::load(p.embed, dir + "/embedder_checkpoint.pt");
+			torch::load(p.model, dir + "/model_checkpoint.pt");
+		});
 }
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)

@@ -174,7 +174,16 @@ static void BindPipe(py::module_& m, const char* name)
 		.def("embed", &P::Embed).def("embed_dirs", &P::EmbedDirs).def("model", &P::Model)
 		.def("run_network", &P::RunNetwork).def("raw_to_outputs", &P::RawToOutputs)
 		.def("render_rays", &P::RenderRays).def("render", &P::Render).def("render_image", &P::RenderImage)
-		.def("train_steps", &P::TrainSteps, py::call_guard<py::gil_scoped_release>());
+		.def("train_steps", &P::TrainSteps, py::call_guard<py::gil_scoped_release>())
+		// NeRFExecutor::SaveCheckpoint / the restore branch of Initialize (src/NeRFExecutor.h:1054-1068, 546-553): same file names
+		.def("save_checkpoint", [](P& p, const std::string& dir) {
+			torch::save(p.embed, dir + "/embedder_checkpoint.pt");
+			torch::save(p.model, dir + "/model_checkpoint.pt");
+		})
+		.def("load_checkpoint", [](P& p, const std::string& dir) {
+			torch::load(p.embed, dir + "/embedder_checkpoint.pt");
+			torch::load(p.model, dir + "/model_checkpoint.pt");
+		});
 }
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)

@@ -289,3 +289,45 @@ def test_classic_training_runs_on_the_fused_tcgen05_kernels(host):
     losses = [p.train_steps(o, d, tgt, 20, 64, 128, 4096, True, 5e-4, 250)[1] for p in pipes]
     assert losses[0][-1] < losses[0][0] and losses[1][-1] < losses[1][0]
     np.testing.assert_allclose(losses[0], losses[1], rtol=5e-2)
+
+
+@pytest.mark.parametrize("kind", ["cuhash", "classic"])
+def test_checkpoints_are_interchangeable_with_the_reference(host, ref_cuda, kind, tmp_path):
+    """SURVEY §8f-4: torch::save archives written by NeRFExecutor::SaveCheckpoint (src/NeRFExecutor.h:1054-1068: embedder_checkpoint.pt,
+    model_checkpoint.pt) load into the drop-in modules and vice versa — same registered parameter / buffer names and shapes — and the
+    loaded model renders the same image as the one that wrote the archive."""
+    _need(ref_cuda)
+    make = (lambda mod, *extra: mod.make_cuhash(torch.tensor(BBOX).cuda(), *ARGS)) if kind == "cuhash" else \
+        (lambda mod, *extra: mod.make_classic(torch.tensor(BBOX).cuda(), 10, 4, 8, 256, True, *extra))
+    extra = () if kind == "cuhash" else (True,)
+    o, d = _rays(300, seed=8)
+    for writer, reader, w_extra, r_extra in ((ref_cuda, host, extra, ()), (host, ref_cuda, (), extra)):
+        writer.manual_seed(21)
+        torch.manual_seed(21)
+        a = make(writer, *w_extra)
+        a.init_model()
+        with torch.no_grad():                # trained-looking values: the initialisation renders an all-background image on both sides
+            for t in a.model_params():
+                if t.dim() == 2:
+                    t.mul_(12.0)
+            for t in a.embed_params():
+                t.copy_((torch.rand(t.shape, generator=torch.Generator().manual_seed(3)) * 2 - 1).to(t.device))
+        if kind == "classic":
+            _positive_density(a)
+        reader.manual_seed(5)
+        torch.manual_seed(5)
+        b = make(reader, *r_extra)
+        b.init_model()
+        ckpt = tmp_path / f"{kind}_{writer.__name__}"
+        ckpt.mkdir()
+        a.save_checkpoint(str(ckpt))
+        b.load_checkpoint(str(ckpt))
+        for x, y in zip(a.model_params() + a.embed_params() + a.embed_buffers(), b.model_params() + b.embed_params() + b.embed_buffers()):
+            assert torch.equal(x, y)
+        with torch.no_grad():
+            ra = a.render(o, d, 64, 128, 4096, False, True)
+            rb = b.render(o, d, 64, 128, 4096, False, True)
+        for k in ("rgb", "acc", "depth"):                                   # same criterion as the render parity test above
+            scale = max(1.0, rb[k].abs().max().item())
+            err = (ra[k] - rb[k]).abs() / scale
+            assert err.median().item() < 2e-3 and err.max().item() < 3e-2, (kind, k, err.median().item(), err.max().item())
