@@ -121,6 +121,72 @@ def run_reference(args) -> None:
     }))
 
 
+def _graph_timed(fn, reps: int) -> float:
+    """ms per launch of `fn` (C-ABI launches on torch's current stream): `reps` launches captured in ONE CUDA graph and replayed, so
+    the figure is device time of back-to-back launches, not ctypes / allocator time on the host (these kernels take 5-400 us)."""
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(reps):
+                fn()
+    torch.cuda.current_stream().wait_stream(side)
+    graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def render_ops_leg(hbm_peak: float, reps: int = 20) -> dict:
+    """HBM roofline of the CustomOps / RayUtils rendering kernels (compositing forward / backward, sample_pdf + merge), each timed alone
+    with a CUDA-event pair over `reps` launches at two sizes: the fine pass of one 4096-ray training step (64+128 samples) and a
+    262 144-ray render tile (BASELINE C4: one GPU's share of a 1080p frame, 64+64 samples).  Algorithmic bytes per SURVEY §8(d):
+    forward 24 B/sample + 44 B/ray, backward 40 B/sample + 12 B/ray of map gradients, sampler 4 B x (2S + N + S+N) per ray.
+    The same buffers are re-read by every launch: the small size (19 MB) is L2-resident, as it is inside the training step; the
+    large size (0.8-1.3 GB per launch) cannot be."""
+    import torch
+    from nerfpp_b200 import ops
+
+    def timed(fn):
+        return _graph_timed(fn, reps)
+
+    out = {"unit": "GB/s", "peak": hbm_peak, "sizes": {}}
+    g = torch.Generator().manual_seed(0)
+    for tag, rays, s_c, n_imp in (("train_fine_4096x192", 4096, 64, 128), ("render_tile_262144x128", 262144, 64, 64)):
+        s = s_c + n_imp
+        raw = torch.randn(rays, s, 4, generator=g).cuda()
+        z = (2 + torch.sort(torch.rand(rays, s, generator=g) * 4, -1).values).cuda()
+        d = torch.randn(rays, 3, generator=g).cuda()
+        g_rgb = torch.randn(rays, 3, generator=g).cuda()
+        d_raw = torch.empty_like(raw)
+        zc = z[:, :s_c].contiguous()
+        w = torch.rand(rays, s_c, generator=g).cuda()
+        u = torch.linspace(0, 1, n_imp).cuda()
+        from nerfpp_b200.cabi import lib, ptr, stream
+        maps = [torch.empty(rays, 3, device="cuda")] + [torch.empty(rays, device="cuda") for _ in range(3)] + [torch.empty(rays, s, device="cuda")]
+        merged = torch.empty(rays, s, device="cuda")
+        ms_f = timed(lambda: lib().nrf_composite_fwd(ptr(raw), 4, ptr(z), ptr(d), None, 0.0, 0, rays, s, *[ptr(m) for m in maps], stream()))
+        ms_b = timed(lambda: lib().nrf_composite_bwd(ptr(raw), 4, ptr(z), ptr(d), None, 0.0, 0, rays, s, ptr(g_rgb), None, None, None, None, ptr(d_raw),
+                                                       stream()))
+        ms_s = timed(lambda: lib().nrf_sample_pdf_merge(ptr(zc), ptr(w), ptr(u), 0, rays, s_c, n_imp, None, ptr(merged), stream()))
+        by_f, by_b, by_s = rays * (s * 24 + 44), rays * (s * 40 + 24), rays * 4 * (2 * s_c + n_imp + s)
+        out["sizes"][tag] = {
+            "composite_fwd": {"ms": ms_f, "achieved": by_f / ms_f / 1e6, "frac": by_f / ms_f / 1e6 / hbm_peak, "bytes": by_f},
+            "composite_bwd": {"ms": ms_b, "achieved": by_b / ms_b / 1e6, "frac": by_b / ms_b / 1e6 / hbm_peak, "bytes": by_b},
+            "sample_pdf_merge": {"ms": ms_s, "achieved": by_s / ms_s / 1e6, "frac": by_s / ms_s / 1e6 / hbm_peak, "bytes": by_s}}
+        del raw, z, d_raw
+    return out
+
+
 def classic_nerf_leg(tf_peak: float, rows: int = 1024 * 192, reps: int = 10) -> dict:
     """BASELINE C1's network (NeRFImpl 8x256, src/NeRF.cpp:92-126) at one 1024-ray training batch of 64+128 samples (196 608 rows):
     inference forward, training forward (stores the layer inputs) and backward (gradient chain + weight gradients), each timed with
@@ -354,7 +420,7 @@ def main() -> None:
     achieved = (bytes_per_step * roof_steps / 1e9) / (ms_kernel / 1e3)
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "traffic": NCU_TRAFFIC_BYTES.get(dominant), "peak_source": peak_src, "bytes_per_launch": bytes_per_step / kl_per_step,
-                "ms_per_launch": ms_kernel / n_launch, "share_of_step": (ms_kernel / roof_steps) / ms_eager,
+                "ms_per_launch": ms_kernel / n_launch, "share_of_step": (ms_kernel / roof_steps) / (ms_total / args.steps),
                 "timing": f"CUDA-event pair around every launch over {roof_steps} eagerly launched steps run right after the timed region "
                           f"({ms_eager:.3f} ms/step eager)",
                 "l2_note": "the table shadow (17 MiB) is L2-resident: the kernel is bound by L1 tag lookups (forward) / L2 RED operations (backward), "
@@ -375,8 +441,10 @@ def main() -> None:
                        "mlp_small_bwd": {"achieved": tf_bwd, "frac": tf_bwd / tf_peak, "ms_per_step": ms_mlp_bwd / roof_steps, "pipe": "mma.sync (HMMA)"},
                        "note": "event pairs include both launches of the forward (coarse + fine) and their launch gaps; ncu per-launch figures in profiles/"}
 
+    roofline_render_ops = None
     if rank == 0:
         roofline_tensor["mlp_nerf"] = classic_nerf_leg(tf_peak)
+        roofline_render_ops = render_ops_leg(roofline["peak"])
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -400,7 +468,7 @@ def main() -> None:
                    "precision": "fp16 hash table reads / encodings, bf16 tensor-core MLP with fp32 accumulate, fp32 everything else"},
         "e2e": {"value": rays_total / (ms_e2e / 1e3), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches * world, "graph_replay": use_graph, "kernels_per_step": launches_per_step, "roofline": roofline, "roofline_tensor": roofline_tensor, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "gpu_launches": launches * world, "graph_replay": use_graph, "kernels_per_step": launches_per_step, "roofline": roofline, "roofline_tensor": roofline_tensor, "roofline_render_ops": roofline_render_ops, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms_per_step"])},
         "final_loss": {"resident": loss_resident, "e2e": loss_host}, "render": render,
     }))

@@ -31,25 +31,41 @@ __device__ __forceinline__ float ray_norm(const float* __restrict__ rays_d, int6
 	return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
 }
 
-// src/NeRFRenderer.h:239-256 for one sample
-__device__ __forceinline__ SampleEval eval_sample(const float* __restrict__ raw, int raw_stride, const float* __restrict__ zrow,
-	const float* __restrict__ noise_row, float noise_std, float dnorm, int i, int S)
+// the global-memory operands of one sample: loaded for every block of a ray BEFORE any arithmetic (composite_fwd_nb_kernel,
+// composite_bwd_kernel), so a warp has all its sectors in flight at once instead of one 32-sample block per memory round trip
+struct SampleIn {
+	float4 v;          // raw[..., 0:4]
+	float zi, zn;      // z[i], z[i+1]
+	float noise;
+};
+
+__device__ __forceinline__ SampleIn load_sample(const float* __restrict__ raw, int raw_stride, const float* __restrict__ zrow,
+	const float* __restrict__ noise_row, int i, int S)
 {
-	SampleEval e;
-	float4 v;
-	if (raw_stride == 4) v = *reinterpret_cast<const float4*>(raw + static_cast<int64_t>(i) * 4);
+	SampleIn in;
+	if (raw_stride == 4) in.v = *reinterpret_cast<const float4*>(raw + static_cast<int64_t>(i) * 4);
 	else {
 		const float* p = raw + static_cast<int64_t>(i) * raw_stride;
-		v = make_float4(p[0], p[1], p[2], p[3]);
+		in.v = make_float4(p[0], p[1], p[2], p[3]);
 	}
+	in.zi = zrow[i];
+	in.zn = (i + 1 < S) ? zrow[i + 1] : 0.f;
+	in.noise = noise_row ? noise_row[i] : 0.f;
+	return in;
+}
+
+// src/NeRFRenderer.h:239-256 for one sample
+__device__ __forceinline__ SampleEval eval_loaded(const SampleIn& in, bool has_noise, float noise_std, float dnorm, int i, int S)
+{
+	SampleEval e;
+	const float4 v = in.v;
 	e.r = sigmoidf_(v.x);
 	e.g = sigmoidf_(v.y);
 	e.b = sigmoidf_(v.z);
-	const float zi = zrow[i];
-	const float d = (i + 1 < S) ? __fsub_rn(zrow[i + 1], zi) : 1e10f;
+	const float d = (i + 1 < S) ? __fsub_rn(in.zn, in.zi) : 1e10f;
 	e.dist = __fmul_rn(d, dnorm);
 	float sig = v.w;
-	if (noise_row) sig = __fadd_rn(sig, __fmul_rn(noise_row[i], noise_std));
+	if (has_noise) sig = __fadd_rn(sig, __fmul_rn(in.noise, noise_std));
 	e.sig = sig;
 	e.x = -__fmul_rn(fmaxf(sig, 0.f), e.dist);
 	// S == 1 reproduces a reference quirk: `dists` is built from z[...,1:]-z[...,:-1] ([R,0]) and the 1e10 tail is
@@ -57,6 +73,12 @@ __device__ __forceinline__ SampleEval eval_sample(const float* __restrict__ raw,
 	e.alpha = (S == 1) ? 0.f : 1.f - expf(e.x);
 	e.ell = logf(fmaxf(1.f - e.alpha, 1e-10f));
 	return e;
+}
+
+__device__ __forceinline__ SampleEval eval_sample(const float* __restrict__ raw, int raw_stride, const float* __restrict__ zrow,
+	const float* __restrict__ noise_row, float noise_std, float dnorm, int i, int S)
+{
+	return eval_loaded(load_sample(raw, raw_stride, zrow, noise_row, i, S), noise_row != nullptr, noise_std, dnorm, i, S);
 }
 
 __global__ void __launch_bounds__(kRaysPerCta * 32) composite_fwd_kernel(const float* __restrict__ raw, int raw_stride,
@@ -108,6 +130,64 @@ __global__ void __launch_bounds__(kRaysPerCta * 32) composite_fwd_kernel(const f
 	}
 }
 
+// S <= 32 * NB: the same arithmetic with every load of the ray issued up front
+template <int NB>
+__global__ void __launch_bounds__(kRaysPerCta * 32) composite_fwd_nb_kernel(const float* __restrict__ raw, int raw_stride,
+	const float* __restrict__ z, const float* __restrict__ rays_d, const float* __restrict__ noise, float noise_std, int white,
+	int64_t R, int S, float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ disp, float* __restrict__ acc,
+	float* __restrict__ weights)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t ray = static_cast<int64_t>(blockIdx.x) * kRaysPerCta + (threadIdx.x >> 5);
+	if (ray >= R) return;
+	const float* raw_row = raw + ray * S * raw_stride;
+	const float* zrow = z + ray * S;
+	const float* nrow = (noise && noise_std > 0.f) ? noise + ray * S : nullptr;
+	SampleIn in[NB];
+#pragma unroll
+	for (int b = 0; b < NB; b++) {
+		const int i = b * 32 + lane;
+		if (i < S) in[b] = load_sample(raw_row, raw_stride, zrow, nrow, i, S);
+	}
+	const float dnorm = ray_norm(rays_d, ray);
+
+	float carry = 0.f, sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f, sd = 0.f;
+#pragma unroll
+	for (int b = 0; b < NB; b++) {
+		const int i = b * 32 + lane;
+		float ell = 0.f, w = 0.f;
+		SampleEval e;
+		if (i < S) {
+			e = eval_loaded(in[b], nrow != nullptr, noise_std, dnorm, i, S);
+			ell = e.ell;
+		}
+		const float incl = warp_scan_incl(ell, lane);
+		const float T = expf(carry + (incl - ell));  // TruncExp forward is a plain exp (src/CustomOps.cpp:8)
+		if (i < S) {
+			w = e.alpha * T;
+			sr += w * e.r;
+			sg += w * e.g;
+			sb += w * e.b;
+			sa += w;
+			sd += w * in[b].zi;
+			if (weights) weights[ray * S + i] = w;
+		}
+		carry += __shfl_sync(0xffffffffu, incl, 31);
+	}
+	sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sa = warp_sum(sa); sd = warp_sum(sd);
+	if (lane == 0) {
+		if (white) {
+			const float bg = 1.f - sa;
+			sr += bg; sg += bg; sb += bg;
+		}
+		if (rgb) { rgb[ray * 3] = sr; rgb[ray * 3 + 1] = sg; rgb[ray * 3 + 2] = sb; }
+		const float dep = sd / fmaxf(sa, 1e-10f);
+		if (depth) depth[ray] = dep;
+		if (disp) disp[ray] = 1.f / fmaxf(1e-10f, dep);
+		if (acc) acc[ray] = sa;
+	}
+}
+
 template <int NB>
 __global__ void __launch_bounds__(kRaysPerCta * 32) composite_bwd_kernel(const float* __restrict__ raw, int raw_stride,
 	const float* __restrict__ z, const float* __restrict__ rays_d, const float* __restrict__ noise, float noise_std, int white,
@@ -124,23 +204,35 @@ __global__ void __launch_bounds__(kRaysPerCta * 32) composite_bwd_kernel(const f
 
 	SampleEval e[NB];
 	float Lx[NB];  // exclusive log-transmittance
+	float zi[NB];
 	float carry = 0.f, sa = 0.f, sd = 0.f;
+	{
+		SampleIn in[NB];
+#pragma unroll
+		for (int b = 0; b < NB; b++) {
+			const int i = b * 32 + lane;
+			if (i < S) in[b] = load_sample(raw_row, raw_stride, zrow, nrow, i, S);
+		}
+#pragma unroll
+		for (int b = 0; b < NB; b++) {
+			const int i = b * 32 + lane;
+			zi[b] = i < S ? in[b].zi : 0.f;
+			e[b] = i < S ? eval_loaded(in[b], nrow != nullptr, noise_std, dnorm, i, S) : SampleEval{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+		}
+	}
 #pragma unroll
 	for (int b = 0; b < NB; b++) {
 		const int i = b * 32 + lane;
 		float ell = 0.f;
 		if (i < S) {
-			e[b] = eval_sample(raw_row, raw_stride, zrow, nrow, noise_std, dnorm, i, S);
 			ell = e[b].ell;
-		} else {
-			e[b] = SampleEval{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 		}
 		const float incl = warp_scan_incl(ell, lane);
 		Lx[b] = carry + (incl - ell);
 		if (i < S) {
 			const float w = e[b].alpha * expf(Lx[b]);
 			sa += w;
-			sd += w * zrow[i];
+			sd += w * zi[b];
 		}
 		carry += __shfl_sync(0xffffffffu, incl, 31);
 	}
@@ -165,7 +257,7 @@ __global__ void __launch_bounds__(kRaysPerCta * 32) composite_bwd_kernel(const f
 		float G = 0.f, T = 0.f, dL = 0.f;
 		if (ok) {
 			T = expf(Lx[b]);
-			G = gr * e[b].r + gg * e[b].g + gb * e[b].b + gacc + gz * zrow[i];
+			G = gr * e[b].r + gg * e[b].g + gb * e[b].b + gacc + gz * zi[b];
 			if (g_weights) G += g_weights[ray * S + i];
 			dL = G * e[b].alpha * expf(fminf(fmaxf(Lx[b], -100.f), 5.f));  // TruncExp backward (src/CustomOps.cpp:14)
 		}
@@ -204,8 +296,20 @@ int nrf_composite_fwd(const float* raw, int32_t raw_stride, const float* z, cons
 	if (n_rays == 0) return NRF_OK;
 	NRF_REQUIRE(raw && z && rays_d, "null input");
 	const unsigned blocks = static_cast<unsigned>((n_rays + kRaysPerCta - 1) / kRaysPerCta);
-	composite_fwd_kernel<<<blocks, kRaysPerCta * 32, 0, as_stream(stream)>>>(raw, raw_stride, z, rays_d, noise, raw_noise_std,
-		white_bkgr, n_rays, n_samples, rgb, depth, disp, acc, weights);
+	cudaStream_t s = as_stream(stream);
+	const int nb = (n_samples + 31) / 32;
+#define NRF_CF(NBV)                                                                                                     \
+	case NBV:                                                                                                           \
+		composite_fwd_nb_kernel<NBV><<<blocks, kRaysPerCta * 32, 0, s>>>(raw, raw_stride, z, rays_d, noise, raw_noise_std, \
+			white_bkgr, n_rays, n_samples, rgb, depth, disp, acc, weights);                                              \
+		break
+	switch (nb) {
+		NRF_CF(1); NRF_CF(2); NRF_CF(3); NRF_CF(4); NRF_CF(5); NRF_CF(6); NRF_CF(7); NRF_CF(8);
+		default:
+			composite_fwd_kernel<<<blocks, kRaysPerCta * 32, 0, s>>>(raw, raw_stride, z, rays_d, noise, raw_noise_std, white_bkgr, n_rays,
+				n_samples, rgb, depth, disp, acc, weights);
+	}
+#undef NRF_CF
 	NRF_CHECK_LAUNCH("composite_fwd_kernel");
 	return NRF_OK;
 }

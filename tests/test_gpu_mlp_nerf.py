@@ -230,3 +230,33 @@ def test_training_empty_and_masked_rows():
     for k in full:
         s = float(part[k].abs().max())
         assert float((full[k] - part[k]).abs().max()) <= 1e-5 * s + 1e-12, k
+
+
+def test_full_size_training_batch_backward_properties():
+    """BASELINE C1 training batch (1024 rays x 192 samples = 196 608 rows), size-independent properties of the backward:
+    (a) linear in the upstream gradient for fixed saved activations: grads(a*g1 + g2) = a*grads(g1) + grads(g2);
+    (b) a sum over rows: the gradient of the full batch equals the sum of the gradients of its two halves (each half run as its own
+        forward + backward: different tiles, different work split over the SMs, different accumulation order)."""
+    from nerfpp_b200 import ops
+    n = 1024 * 192
+    p = _params(seed=11)
+    x = _inputs(n, seed=12)
+    gen = torch.Generator().manual_seed(13)
+    g1, g2 = (torch.randn(n, 4, generator=gen) * 1e-3).cuda(), (torch.randn(n, 4, generator=gen) * 1e-3).cuda()
+    packed = ops.mlp_nerf_pack(p, train=True)
+    out, saved = ops.mlp_nerf_fwd_train(packed, x)
+    assert torch.isfinite(out).all()
+    zeros = lambda: {k: torch.zeros_like(v) for k, v in p.items()}  # noqa: E731
+    ga, gb = ops.mlp_nerf_bwd(packed, saved, g1, zeros()), ops.mlp_nerf_bwd(packed, saved, g2, zeros())
+    gc = ops.mlp_nerf_bwd(packed, saved, (2.0 * g1 + g2).contiguous(), zeros())
+    for k in p:
+        ref = 2.0 * ga[k].double() + gb[k].double()
+        assert float((gc[k].double() - ref).abs().max()) <= 1e-2 * float(ref.abs().max()) + 1e-12, k    # bf16 rounding of the gradient rows
+    h = n // 2 + 64          # not a multiple of the 128-row tile on purpose
+    parts = zeros()
+    for lo, hi in ((0, h), (h, n)):
+        o2, s2 = ops.mlp_nerf_fwd_train(packed, x[lo:hi].contiguous())
+        assert torch.equal(o2, out[lo:hi])                                 # rows are independent, bit for bit
+        ops.mlp_nerf_bwd(packed, s2, g1[lo:hi].contiguous(), parts)      # += into the same tensors
+    for k in p:
+        assert float((parts[k] - ga[k]).abs().max()) <= 1e-4 * float(ga[k].abs().max()) + 1e-12, k   # fp32 summation order only
