@@ -7,8 +7,8 @@
 //     in flight.  Same roles as the forward: warp 0 streams the FORWARD weight blob through a 4 x 32 KB TMA ring (38 of its 41
 //     stages, in reverse layer order; the stage bytes are read as an MN-major B operand, so no transposed copy of the weights
 //     exists), warp 1 issues tcgen05.mma M=128 N=64 K=16 with the bf16 gradient rows as A operand in TMEM and fp32 accumulators in
-//     TMEM, warps 2..5 (one thread per row) read the accumulator, apply the ReLU mask taken from the saved activation
-//     (bits != 0 after ReLU), pack to bf16, write the next A operand to TMEM and the gradient record to HBM.
+//     TMEM, warps 2..5 (one thread per row) read the accumulator, apply the ReLU mask (one bit per unit, written by the forward:
+//     32 bytes per row and layer), pack to bf16, write the next A operand to TMEM and the gradient record to HBM.
 //     Gradients with respect to the inputs (embedded points / directions) are not produced: the positional embedder has no
 //     parameters (src/NeRF.cpp:4-39).
 //
@@ -40,9 +40,32 @@ __host__ __device__ constexpr int step_layer(int st) { return st == 0 ? 11 : (st
 __host__ __device__ constexpr int step_first_stage(int l) { return l == 5 ? 1 : 0; }        // stage 0 of layer 5 is the [pts] slab
 __host__ __device__ constexpr int step_stages(int l) { return l == 11 ? 1 : 4; }
 
+// The 38 weight stages of one tile in the order the chain consumes them, as (byte offset in the blob, bytes): a compile-time table in
+// constant memory.  (Evaluating stage_offset(l, s) — nested loops over the layer table — per stage cost the producer thread ~2 000
+// cycles per stage and was what the MMAs were waiting for: profiles/r1_mlp_nerf_bwd_chain_cycles.txt.)
+constexpr int kChainStages = 38;
+struct StageTable {
+	int off[kChainStages], bytes[kChainStages];
+};
+constexpr StageTable make_chain_table()
+{
+	StageTable t{};
+	int i = 0;
+	for (int st = 0; st < kSteps; st++) {
+		const int l = step_layer(st);
+		for (int s = step_first_stage(l); s < step_first_stage(l) + step_stages(l); s++, i++) { t.off[i] = stage_offset(l, s); t.bytes[i] = stage_bytes(l, s); }
+		if (st == 2) { t.off[i] = stage_offset(9, 0); t.bytes[i] = stage_bytes(9, 0); i++; }
+	}
+	return t;
+}
+__constant__ StageTable c_chain_table = make_chain_table();
+
+// 6 x 32 KB: one and a half chain steps of weights in flight, so the stream keeps running through the epilogue tail of a step (with
+// one step's worth the issuer waited ~500 cycles per stage for weights, profiles/r1_mlp_nerf_bwd_chain_cycles.txt)
+constexpr int kChainRing = 6;
 struct __align__(128) ChainSmem {
-	uint8_t ring[kRing][kStageBytes];
-	uint64_t full[kRing], empty[kRing];
+	uint8_t ring[kChainRing][kStageBytes];
+	uint64_t full[kChainRing], empty[kChainRing];
 	uint64_t a_ready, slab_ready[4];
 	uint32_t tmem_base;
 };
@@ -62,54 +85,63 @@ __device__ __forceinline__ void store_chunks4(uint8_t* __restrict__ region_row, 
 		*reinterpret_cast<uint4*>(region_row + (first_chunk + i) * 1024) = make_uint4(a16[4 * i], a16[4 * i + 1], a16[4 * i + 2], a16[4 * i + 3]);
 }
 
-// one 32-column accumulator chunk -> (* ReLU mask of the saved activation: bits != 0 after ReLU) -> bf16 pairs
+#ifdef NRF_PROFILE_CHAIN
+// debug build only (NRF_NVCC_EXTRA=-DNRF_PROFILE_CHAIN): per-CTA cycle counters of the chain kernel, read back by nrf_debug_chain_profile
+__device__ unsigned long long g_chain_prof[kNumSMs][8];
+#define CH_T0() const long long t0__ = clock64()
+#define CH_ADD(slot) g_chain_prof[blockIdx.x][slot] += static_cast<unsigned long long>(clock64() - t0__)
+#else
+#define CH_T0()
+#define CH_ADD(slot)
+#endif
+
+// one 32-column accumulator chunk -> (* ReLU mask word of the forward: bit i / 16+i = low / high half of pair i) -> bf16 pairs
 template <bool MASK>
-__device__ __forceinline__ void grad_pack(const uint32_t (&acc)[32], const uint32_t* __restrict__ hm, uint32_t (&a16)[16])
+__device__ __forceinline__ void grad_pack(const uint32_t (&acc)[32], uint32_t bits, uint32_t (&a16)[16])
 {
-	const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
 	for (int i = 0; i < 16; i++) {
 		uint32_t w = pack_bf16(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
-		if (MASK) w &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&hm[i]), zero);
+		if (MASK) w &= ((bits >> i) & 0x00010001u) * 0xFFFFu;
 		a16[i] = w;
-	}
-}
-
-// mask words of one 64-column slab (8 chunks of 16 bytes) of this thread's row
-__device__ __forceinline__ void load_mask_slab(const uint8_t* __restrict__ region_row, int slab, uint32_t (&h)[32])
-{
-#pragma unroll
-	for (int i = 0; i < 8; i++) {
-		const uint4 v = __ldg(reinterpret_cast<const uint4*>(region_row + (8 * slab + i) * 1024));
-		h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
 	}
 }
 
 // One chain step, slab by slab: the accumulator arrives as 64-column slabs (one per weight stage, each complete over K), so the
 // epilogue of slab s runs while the tensor core still works on slabs s+1.. .  SLABS of the 4 slabs carry data (all 4 barriers are
-// consumed to keep their phases in step).  hm0 / hm1 hold the mask words of slabs s (even / odd), requested two slabs ahead.
+// consumed to keep their phases in step).  bits: this row's 8 mask words of the step (32 bytes, fetched one step ahead).
 template <int SLABS, bool MASK>
-__device__ __forceinline__ void epilogue_grad(uint32_t t_lane, uint64_t* slab_ready, uint32_t parity, const uint8_t* __restrict__ mask_row,
-	uint8_t* __restrict__ out_row, bool to_tmem, uint32_t a_next, uint32_t (&hm0)[32], uint32_t (&hm1)[32])
+__device__ __forceinline__ void epilogue_grad(uint32_t t_lane, uint64_t* slab_ready, uint32_t parity, uint8_t* __restrict__ out_row, bool to_tmem,
+	uint32_t a_next, const uint32_t (&bits)[8])
 {
 	uint32_t acc0[32], acc1[32], a16[16];
 #pragma unroll
 	for (int sl = 0; sl < 4; sl++) {
-		mbar_wait(&slab_ready[sl], parity);
+		{ CH_T0(); mbar_wait(&slab_ready[sl], parity); if (threadIdx.x == 64) CH_ADD(3); }
 		if (sl >= SLABS) continue;
+		CH_T0();
 		fence_after();
-		uint32_t (&hm)[32] = (sl & 1) ? hm1 : hm0;
 		tmem_ld32(t_lane + kBD + 64 * sl, acc0);
 		tmem_ld_wait_for(acc0);
 		tmem_ld32(t_lane + kBD + 64 * sl + 32, acc1);
-		grad_pack<MASK>(acc0, hm, a16);
+		grad_pack<MASK>(acc0, bits[2 * sl], a16);
 		if (to_tmem) tmem_st16(t_lane + a_next + 32 * sl, a16);
 		store_chunks4(out_row, 8 * sl, a16);
 		tmem_ld_wait_for(acc1);
-		grad_pack<MASK>(acc1, hm + 16, a16);
+		grad_pack<MASK>(acc1, bits[2 * sl + 1], a16);
 		if (to_tmem) tmem_st16(t_lane + a_next + 32 * sl + 16, a16);
 		store_chunks4(out_row, 8 * sl + 4, a16);
-		if (MASK && sl + 2 < SLABS) load_mask_slab(mask_row, sl + 2, hm);
+		if (threadIdx.x == 64) CH_ADD(4);
+	}
+}
+
+__device__ __forceinline__ void load_bits(const uint8_t* __restrict__ bits_row, bool wide, uint32_t (&b)[8])
+{
+	const uint4 lo = __ldg(reinterpret_cast<const uint4*>(bits_row));
+	b[0] = lo.x; b[1] = lo.y; b[2] = lo.z; b[3] = lo.w;
+	if (wide) {
+		const uint4 hi = __ldg(reinterpret_cast<const uint4*>(bits_row) + 1);
+		b[4] = hi.x; b[5] = hi.y; b[6] = hi.z; b[7] = hi.w;
 	}
 }
 
@@ -126,13 +158,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_chain_kernel(cons
 {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	ChainSmem& sm = *reinterpret_cast<ChainSmem*>(smem_raw);
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;      // warp index the compiler can see is uniform
 	const int64_t n_tiles = (n + 127) / 128;
 	const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
 	if (warp == 1) {
 		if (lane == 0) {
-			for (int s = 0; s < kRing; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+			for (int s = 0; s < kChainRing; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
 			mbar_init(&sm.a_ready, 4);
 			for (int s = 0; s < 4; s++) mbar_init(&sm.slab_ready[s], 1);
 			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -150,78 +182,77 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_chain_kernel(cons
 		if (lane == 0) {
 			uint32_t g = 0;
 			auto push = [&](int off, uint32_t bytes) {
-				const uint32_t slot = g % kRing, round = g / kRing;
-				mbar_wait(&sm.empty[slot], (round & 1u) ^ 1u);
-				mbar_expect_tx(&sm.full[slot], bytes);
-				tma_bulk_g2s(sm.ring[slot], blob + off, bytes, &sm.full[slot]);
+				const uint32_t slot = g % kChainRing, round = g / kChainRing;
+				{ CH_T0(); mbar_wait(&sm.empty[slot], (round & 1u) ^ 1u); CH_ADD(7); }
+				{
+					CH_T0();
+					mbar_expect_tx(&sm.full[slot], bytes);
+					tma_bulk_g2s(sm.ring[slot], blob + off, bytes, &sm.full[slot]);
+					CH_ADD(5);
+				}
 				g++;
 			};
-			// The ReLU masks are read from the saved activations by the epilogue threads one step after the producer passes here
-			// (it runs up to a ring ahead of the MMAs): pull each step's 64 KB mask tile into L2 now, so those loads are L2 hits.
-			auto prefetch_mask = [&](int64_t tile, int st) {
-				const uint8_t* rec = saved + tile * kSaveTile;
-				if (st == 0) tma_prefetch_l2(rec + kSaveHv, region_bytes(128));
-				else if (st >= 2) tma_prefetch_l2(rec + save_h(st == 2 ? 8 : 10 - st), region_bytes(256));
-			};
-			if (my_tiles > 0) { prefetch_mask(blockIdx.x, 0); prefetch_mask(blockIdx.x, 2); }
 			for (int64_t t = 0; t < my_tiles; t++) {
-				const int64_t tile = blockIdx.x + t * gridDim.x;
 #pragma unroll 1
-				for (int st = 0; st < kSteps; st++) {
-					if (st + 2 < kSteps) prefetch_mask(tile, st + 2);
-					else if (t + 1 < my_tiles) prefetch_mask(tile + gridDim.x, st + 2 - kSteps);      // steps 0 and (1: none) of the next tile
-					const int l = step_layer(st);
-					for (int s = step_first_stage(l); s < step_first_stage(l) + step_stages(l); s++) push(stage_offset(l, s), stage_bytes(l, s));
-					if (st == 2) push(stage_offset(9, 0), stage_bytes(9, 0));
-				}
+				for (int i = 0; i < kChainStages; i++) push(c_chain_table.off[i], c_chain_table.bytes[i]);
 			}
 		}
 	} else if (warp == 1) {
-		// ===== MMA issuer =====
-		if (lane == 0) {
-			uint32_t g = 0, pa = 0;
-			for (int64_t t = 0; t < my_tiles; t++) {
+		// ===== MMA issuer: the whole warp runs the (warp-uniform) control flow, one elected lane issues =====
+		const bool leader = elect_one();
+		uint32_t g = 0, pa = 0;
+		for (int64_t t = 0; t < my_tiles; t++) {
 #pragma unroll 1
-				for (int st = 0; st < kSteps; st++) {
-					mbar_wait(&sm.a_ready, pa);
-					pa ^= 1u;
+			for (int st = 0; st < kSteps; st++) {
+				{ CH_T0(); mbar_wait(&sm.a_ready, pa); if (leader) CH_ADD(0); }
+				pa ^= 1u;
+				fence_after();
+				const int l = step_layer(st);
+				if (l == 11) {
+					// d_hv = d_rgb * W_rgb: K = 16 (3 real), N = 128
+					const uint32_t slot = g % kChainRing, round = g / kChainRing;
+					mbar_wait(&sm.full[slot], round & 1u);
 					fence_after();
-					const int l = step_layer(st);
-					if (l == 11) {
-						// d_hv = d_rgb * W_rgb: K = 16 (3 real), N = 128
-						const uint32_t slot = g % kRing, round = g / kRing;
-						mbar_wait(&sm.full[slot], round & 1u);
-						fence_after();
+					if (leader) {
 						umma_ts(tmem + kBD, tmem + kBRgb, smem_desc(smem_u32(sm.ring[slot]), 128, 16 * 16), idesc_16(128, 128, true, 0, 1), 0u);
 						umma_commit(&sm.empty[slot]);
-						g++;
 						for (int s = 0; s < 4; s++) umma_commit(&sm.slab_ready[s]);
-					} else {
-						const int n_out = layer_info(l).N;               // K of this product
-						const uint32_t idesc = idesc_16(128, 64, true, 0, 1);
-						for (int s = 0; s < 4; s++, g++) {
-							const uint32_t slot = g % kRing, round = g / kRing;
-							mbar_wait(&sm.full[slot], round & 1u);
-							fence_after();
-							// one descriptor per stage, then 16 (8) back-to-back MMAs whose operands differ by constants: the issuing thread
-							// must not spend more than the 32 cycles an N = 64 MMA takes on each of them
-							const uint64_t b0 = smem_desc(smem_u32(sm.ring[slot]), 128, n_out * 16);
-							const uint32_t d = tmem + kBD + 64 * s, a0 = tmem + a_buf(st);
+					}
+					__syncwarp();
+					g++;
+				} else {
+					const int n_out = layer_info(l).N;               // K of this product
+					const uint32_t idesc = idesc_16(128, 64, true, 0, 1);
+					for (int s = 0; s < 4; s++, g++) {
+						const uint32_t slot = g % kChainRing, round = g / kChainRing;
+						{ CH_T0(); mbar_wait(&sm.full[slot], round & 1u); if (leader) CH_ADD(1); }
+						fence_after();
+						CH_T0();
+						// one descriptor per stage, then 16 (8) back-to-back MMAs whose operands differ by constants: the issuing thread
+						// must not spend more than the 32 cycles an N = 64 MMA takes on each of them
+						const uint64_t b0 = smem_desc(smem_u32(sm.ring[slot]), 128, n_out * 16);
+						const uint32_t d = tmem + kBD + 64 * s, a0 = tmem + a_buf(st);
+						if (leader) {
 							if (n_out == 256) issue_k<16>(d, a0, b0, idesc);
 							else issue_k<8>(d, a0, b0, idesc);
 							umma_commit(&sm.empty[slot]);
 							if (st != 2) umma_commit(&sm.slab_ready[s]);     // this 64-column slab of D is complete
+							CH_ADD(2);
 						}
-						if (st == 2) {
-							// + d_alpha * W_alpha over all 256 columns: K = 16 (1 real)
-							const uint32_t slot = g % kRing, round = g / kRing;
-							mbar_wait(&sm.full[slot], round & 1u);
-							fence_after();
+						__syncwarp();
+					}
+					if (st == 2) {
+						// + d_alpha * W_alpha over all 256 columns: K = 16 (1 real)
+						const uint32_t slot = g % kChainRing, round = g / kChainRing;
+						mbar_wait(&sm.full[slot], round & 1u);
+						fence_after();
+						if (leader) {
 							umma_ts(tmem + kBD, tmem + kBAlpha, smem_desc(smem_u32(sm.ring[slot]), 128, 16 * 16), idesc_16(128, 256, true, 0, 1), 1u);
 							umma_commit(&sm.empty[slot]);
-							g++;
 							for (int s = 0; s < 4; s++) umma_commit(&sm.slab_ready[s]);
 						}
+						__syncwarp();
+						g++;
 					}
 				}
 			}
@@ -232,12 +263,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_chain_kernel(cons
 		const int row = (q << 5) | lane;
 		const uint32_t t_lane = tmem + (static_cast<uint32_t>(q << 5) << 16);
 		uint32_t pd = 0;
+#ifdef NRF_PROFILE_CHAIN
+		const long long t_start = clock64();
+#endif
 		for (int64_t t = 0; t < my_tiles; t++) {
 			const int64_t tile = blockIdx.x + t * gridDim.x;
 			const int64_t r = tile * 128 + row;
 			const uint8_t* const rec_s = saved + tile * kSaveTile;
 			uint8_t* const rec_g = grads + tile * kGradTile;
-			uint32_t hm0[32], hm1[32];
+			uint32_t bits[8];
 			{
 				float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
 				if (r < n) g4 = __ldg(reinterpret_cast<const float4*>(grad_out) + r);
@@ -254,37 +288,31 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_chain_kernel(cons
 				tmem_st16(t_lane + kBAlpha, a16);        // K = 16 operand [alpha 0..]
 				*reinterpret_cast<uint4*>(o + 1024) = make_uint4(0u, 0u, 0u, 0u);
 			}
-			{
-				const uint8_t* m = rec_s + kSaveHv + chunk_offset(128, row, 0);
-				load_mask_slab(m, 0, hm0);
-				load_mask_slab(m, 1, hm1);
-			}
+			load_bits(rec_s + bits_offset(0, row), false, bits);
 			publish_bwd(&sm.a_ready, lane);
 
 #pragma unroll 1
 			for (int st = 0; st < kSteps; st++) {
 				if (st == 0) {
-					epilogue_grad<2, true>(t_lane, sm.slab_ready, pd, rec_s + kSaveHv + chunk_offset(128, row, 0), rec_g + kGradHv + chunk_offset(128, row, 0),
-						true, a_buf(1), hm0, hm1);
+					epilogue_grad<2, true>(t_lane, sm.slab_ready, pd, rec_g + kGradHv + chunk_offset(128, row, 0), true, a_buf(1), bits);
 				} else if (st == 1) {
-					epilogue_grad<4, false>(t_lane, sm.slab_ready, pd, nullptr, rec_g + kGradFeat + chunk_offset(256, row, 0), true, a_buf(2), hm0, hm1);
+					epilogue_grad<4, false>(t_lane, sm.slab_ready, pd, rec_g + kGradFeat + chunk_offset(256, row, 0), true, a_buf(2), bits);
 				} else {
 					const int l = st == 2 ? 8 : 10 - st;         // the activation h_l whose ReLU is undone; the result is dY_{l-1}
-					epilogue_grad<4, true>(t_lane, sm.slab_ready, pd, rec_s + save_h(l) + chunk_offset(256, row, 0),
-						rec_g + grad_y(l - 1) + chunk_offset(256, row, 0), st + 1 < kSteps, a_buf(st + 1), hm0, hm1);
+					epilogue_grad<4, true>(t_lane, sm.slab_ready, pd, rec_g + grad_y(l - 1) + chunk_offset(256, row, 0), st + 1 < kSteps, a_buf(st + 1), bits);
 				}
 				pd ^= 1u;
 				if (st + 1 < kSteps) {
-					// the first two mask slabs of the next step, requested before that step's MMAs are even issued
-					if (st >= 1) {
-						const uint8_t* m = rec_s + save_h(st == 1 ? 8 : (st == 2 ? 8 : 10 - st) - 1) + chunk_offset(256, row, 0);
-						load_mask_slab(m, 0, hm0);
-						load_mask_slab(m, 1, hm1);
-					}
+					// the 32 mask bytes of the next step (h_8 after step 1, then h_7 .. h_1), requested before that step's MMAs are even issued
+					CH_T0();
+					if (st >= 1) load_bits(rec_s + bits_offset(st == 1 ? 8 : (st == 2 ? 8 : 10 - st) - 1, row), true, bits);
 					publish_bwd(&sm.a_ready, lane);
 				}
 			}
 		}
+#ifdef NRF_PROFILE_CHAIN
+		if (threadIdx.x == 64) g_chain_prof[blockIdx.x][6] += static_cast<unsigned long long>(clock64() - t_start);
+#endif
 	}
 
 	fence_before();
@@ -638,6 +666,19 @@ int nrf_mlp_nerf_bwd(const nrf_mlp_nerf_shape* shape, const void* packed_train, 
 	}
 	return NRF_OK;
 }
+
+#ifdef NRF_PROFILE_CHAIN
+/* debug builds only: [148][8] cycle counters {issuer waits a_ready, issuer waits full, issuer issue+commit, epilogue waits slab_ready,
+ * epilogue work, mask fetch + publish, epilogue warp total, producer waits empty}; clears them */
+int nrf_debug_chain_profile(unsigned long long* host_out)
+{
+	NRF_CUDA(cudaDeviceSynchronize());
+	NRF_CUDA(cudaMemcpyFromSymbol(host_out, g_chain_prof, sizeof(unsigned long long) * kNumSMs * 8));
+	static unsigned long long zeros[kNumSMs * 8] = {};
+	NRF_CUDA(cudaMemcpyToSymbol(g_chain_prof, zeros, sizeof(zeros)));
+	return NRF_OK;
+}
+#endif
 
 #ifdef NRF_PROFILE_DW
 /* debug builds only: [148][8] cycle counters {issuer waits full, issuer waits d_free, producer waits empty, epilogue waits full, epilogue sums,

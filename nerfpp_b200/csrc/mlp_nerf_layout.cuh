@@ -84,13 +84,18 @@ __host__ __device__ constexpr uint32_t chunk_offset(int cols, int r, int chunk)
 {
 	return static_cast<uint32_t>((r >> 6) * (cols * 128) + chunk * 1024 + (r & 63) * 16);
 }
-// saved activations: pts(64) views(32) h1..h8 (256 each: h_l = input of pts_linears[l]; h8 feeds feature / alpha) feature(256) hv(128)
+// saved activations (operands of the weight-gradient products): pts(64) views(32) h1..h8 (256 each: h_l = input of pts_linears[l]; h8 feeds feature / alpha) feature(256) hv(128)
 constexpr int kSavePts = 0;
 constexpr int kSaveViews = kSavePts + region_bytes(64);
 __host__ __device__ constexpr int save_h(int l) { return kSaveViews + region_bytes(32) + (l - 1) * region_bytes(256); }
 constexpr int kSaveFeat = save_h(9);
 constexpr int kSaveHv = kSaveFeat + region_bytes(256);
-constexpr int kSaveTile = kSaveHv + region_bytes(128);          // 647 168 B per 128 rows
+// ReLU masks, one bit per unit, for the gradient chain (which then never reads the activations themselves): 9 sets per tile
+// (0: hv, l = 1..8: h_l), each [128 rows][8 words]; word c of a row covers columns 32c .. 32c+31, bit i = column 32c + 2i,
+// bit 16 + i = column 32c + 2i + 1 (the low / high halves of the i-th packed bf16 pair: two instructions per pair to build)
+constexpr int kSaveBits = kSaveHv + region_bytes(128);
+__host__ __device__ constexpr int bits_offset(int set, int row) { return kSaveBits + set * 4096 + row * 32; }
+constexpr int kSaveTile = kSaveBits + 9 * 4096;                 // 684 032 B per 128 rows
 // gradients of the pre-activations: dOut(16: [r,g,b,alpha,0..]) d_hv(128) d_feature(256) dY_0..dY_7 (256 each)
 constexpr int kGradOut = 0;
 constexpr int kGradHv = kGradOut + region_bytes(16);

@@ -61,6 +61,23 @@ __global__ void __launch_bounds__(256) nerf_pack_kernel(Weights p, uint32_t* __r
 	blob[w] = bf16 ? pack_bf16(wp(p, l, n, k), wp(p, l, n, k + 1)) : pack_f16(wp(p, l, n, k), wp(p, l, n, k + 1));
 }
 
+// the 41 weight stages of one tile as (byte offset, bytes): compile-time table in constant memory, so that the producer thread does not
+// walk the layer table (nested constexpr loops evaluated at run time) for every stage
+constexpr int kFwdStages = 41;
+struct FwdStageTable {
+	int off[kFwdStages], bytes[kFwdStages];
+};
+constexpr FwdStageTable make_fwd_table()
+{
+	FwdStageTable t{};
+	int i = 0;
+	for (int l = 0; l < kLayers; l++)
+		for (int s = 0; s < layer_stages(l); s++, i++) { t.off[i] = stage_offset(l, s); t.bytes[i] = stage_bytes(l, s); }
+	return t;
+}
+static_assert(make_fwd_table().off[kFwdStages - 1] + make_fwd_table().bytes[kFwdStages - 1] == kWeightBytes, "stage table does not cover the blob");
+__constant__ FwdStageTable c_fwd_table = make_fwd_table();
+
 struct __align__(128) Smem {
 	uint8_t ring[kRing][kStageBytes];
 	float bias[kBiasFloats];
@@ -98,10 +115,20 @@ __device__ __forceinline__ void save_chunks(uint8_t* __restrict__ region_row, in
 		*reinterpret_cast<uint4*>(region_row + (first_chunk + i) * 1024) = make_uint4(a16[4 * i], a16[4 * i + 1], a16[4 * i + 2], a16[4 * i + 3]);
 }
 
+// ReLU mask word of 32 packed columns: bit i / 16+i = low / high half of pair i is non-zero (values are >= 0 after ReLU)
+__device__ __forceinline__ uint32_t relu_bits(const uint32_t (&a16)[16])
+{
+	uint32_t bits = 0;
+#pragma unroll
+	for (int i = 0; i < 16; i++) bits += __vminu2(a16[i], 0x00010001u) << i;
+	return bits;
+}
+
 template <int CHUNKS, bool RELU, bool TRAIN>
-__device__ __forceinline__ void epilogue_to_h(uint32_t t_lane, const float* __restrict__ bias, uint8_t* __restrict__ save_row)
+__device__ __forceinline__ void epilogue_to_h(uint32_t t_lane, const float* __restrict__ bias, uint8_t* __restrict__ save_row, uint8_t* __restrict__ bits_row)
 {
 	uint32_t acc0[32], acc1[32], a16[16];
+	uint32_t bw[CHUNKS];
 	tmem_ld32(t_lane + kColD, acc0);
 #pragma unroll
 	for (int c = 0; c < CHUNKS; c += 2) {
@@ -110,13 +137,19 @@ __device__ __forceinline__ void epilogue_to_h(uint32_t t_lane, const float* __re
 		bias_act_pack<RELU, TRAIN>(acc0, bias + 32 * c, a16);
 		tmem_st16(t_lane + kColH + 16 * c, a16);
 		if (TRAIN) save_chunks(save_row, 4 * c, a16);
+		if (TRAIN && RELU) bw[c] = relu_bits(a16);
 		if (c + 1 < CHUNKS) {
 			tmem_ld_wait_for(acc1);
 			if (c + 2 < CHUNKS) tmem_ld32(t_lane + kColD + 32 * (c + 2), acc0);
 			bias_act_pack<RELU, TRAIN>(acc1, bias + 32 * (c + 1), a16);
 			tmem_st16(t_lane + kColH + 16 * (c + 1), a16);
 			if (TRAIN) save_chunks(save_row, 4 * (c + 1), a16);
+			if (TRAIN && RELU) bw[c + 1] = relu_bits(a16);
 		}
+	}
+	if (TRAIN && RELU) {
+#pragma unroll
+		for (int c = 0; c < CHUNKS; c += 4) *reinterpret_cast<uint4*>(bits_row + 4 * c) = make_uint4(bw[c], bw[c + 1], bw[c + 2], bw[c + 3]);
 	}
 }
 
@@ -135,19 +168,25 @@ __host__ __device__ constexpr int group_count(int g) { return g == 8 ? 2 : 1; }
 
 // TRAIN: bf16 operands (the exponent range survives Xavier(0.1) initialisation, src/LibTorchTraining/Trainable.h:43, where fp16
 // activations of the deep layers flush to zero) and every layer's input is stored to the scratch records of mlp_nerf_layout.cuh
-template <bool TRAIN>
-__global__ void __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint8_t* __restrict__ blob, const float* __restrict__ x, int64_t n,
-	float* __restrict__ out, uint8_t* __restrict__ saved)
+// CL = 2: the CTAs of a 2-CTA cluster walk their tiles in lockstep and share ONE weight stream: each loads half of every stage and
+// multicasts it into both shared memories, so a stage costs one L2 read per cluster instead of one per SM.  (All 148 SMs pulling
+// the whole 1.2 MB blob per tile is 5.7 TB/s of L2 -> SM traffic — the measured pace of the CL = 1 kernel, not its tensor pipe.)
+template <bool TRAIN, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint8_t* __restrict__ blob,
+	const float* __restrict__ x, int64_t n, float* __restrict__ out, uint8_t* __restrict__ saved)
 {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int64_t n_tiles = (n + 127) / 128;
-	const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+	// every CTA runs the same number of rounds (the cluster shares the weight stream); a round past the last tile is a tile of no rows
+	const int64_t my_tiles = (n_tiles + gridDim.x - 1) / gridDim.x;
+	const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
+	constexpr uint16_t kAll = static_cast<uint16_t>((1u << CL) - 1u);
 
 	if (warp == 1) {
 		if (lane == 0) {
-			for (int s = 0; s < kRing; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+			for (int s = 0; s < kRing; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], CL); }
 			mbar_init(&sm.a_ready, 4);
 			mbar_init(&sm.d_ready, 1);
 			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -158,6 +197,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint
 	for (int i = threadIdx.x; i < kBiasFloats; i += kThreads) sm.bias[i] = reinterpret_cast<const float*>(blob + kWeightBytes)[i];
 	fence_before();
 	__syncthreads();
+	if (CL > 1) cluster_sync();          // the peers' barriers exist before anything is multicast to them
 	fence_after();
 	const uint32_t tmem = sm.tmem_base;
 
@@ -167,15 +207,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint
 			uint32_t g = 0;
 			for (int64_t t = 0; t < my_tiles; t++) {
 #pragma unroll 1
-				for (int l = 0; l < kLayers; l++) {
-					int off = layer_offset(l);
-					for (int s = 0; s < layer_stages(l); s++, g++) {
-						const uint32_t slot = g % kRing, round = g / kRing;
-						mbar_wait(&sm.empty[slot], (round & 1u) ^ 1u);          // first round passes immediately
-						const uint32_t bytes = stage_bytes(l, s);
-						mbar_expect_tx(&sm.full[slot], bytes);
+				for (int i = 0; i < kFwdStages; i++, g++) {
+					const uint32_t slot = g % kRing, round = g / kRing;
+					mbar_wait(&sm.empty[slot], (round & 1u) ^ 1u);          // first round passes immediately
+					const uint32_t bytes = c_fwd_table.bytes[i];
+					const int off = c_fwd_table.off[i];
+					mbar_expect_tx(&sm.full[slot], bytes);
+					if (CL > 1) {
+						const uint32_t part = bytes / CL;       // this CTA's share, delivered to every CTA of the cluster
+						tma_bulk_g2s_mc(sm.ring[slot] + cta_rank * part, blob + off + cta_rank * part, part, &sm.full[slot], kAll);
+					} else {
 						tma_bulk_g2s(sm.ring[slot], blob + off, bytes, &sm.full[slot]);
-						off += bytes;
 					}
 				}
 			}
@@ -207,7 +249,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint
 								first = false;
 								a_col += 8;
 							}
-							umma_commit(&sm.empty[slot]);   // the stage is free again once these MMAs have read it
+							if (CL > 1) umma_commit_mc(&sm.empty[slot], kAll);   // free in a peer's ring only when every CTA has read it
+							else umma_commit(&sm.empty[slot]);                  // the stage is free again once these MMAs have read it
 						}
 					}
 					umma_commit(&sm.d_ready);
@@ -224,7 +267,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint
 			const int64_t tile = blockIdx.x + t * gridDim.x;
 			const int64_t r = tile * 128 + row;
 			const bool ok = r < n;
-			uint8_t* const rec = TRAIN ? saved + tile * kSaveTile : nullptr;    // rows past n are stored too (finite; their gradients are zero)
+			// rows past n of the last tile are stored too (finite; their gradients are zero); a round past the last tile stores into the
+			// spare record that nrf_mlp_nerf_saved_bytes appends for this purpose
+			uint8_t* const rec = TRAIN ? saved + (tile < n_tiles ? tile : n_tiles) * kSaveTile : nullptr;
 			// ---- inputs: 63 point channels (+1 zero) and 27 view channels (+5 zero) as fp16 pairs into their TMEM columns
 			{
 				const float2* xr = reinterpret_cast<const float2*>(x + (ok ? r : 0) * kInCh);   // rows are 360 B: 8-byte aligned
@@ -265,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint
 				fence_after();
 				if (grp < 8) {
 					// pts_linears: relu(D + b) -> h (the next layer's A operand)
-					epilogue_to_h<8, true, TRAIN>(t_lane, sm.bias + bias_offset(0) + grp * kW, rec + save_h(grp + 1) + chunk_offset(256, row, 0));
+					epilogue_to_h<8, true, TRAIN>(t_lane, sm.bias + bias_offset(0) + grp * kW, rec + save_h(grp + 1) + chunk_offset(256, row, 0), rec + bits_offset(grp + 1, row));
 					publish(&sm.a_ready, lane);
 				} else if (grp == 8) {
 					// feature_linear (no activation) -> h ; alpha_linear -> register
@@ -273,11 +318,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint
 					tmem_ld16(t_lane + kColD16, d16);
 					tmem_ld_wait();
 					alpha = __uint_as_float(d16[0]) + sm.bias[bias_offset(9)];
-					epilogue_to_h<8, false, TRAIN>(t_lane, sm.bias + bias_offset(8), rec + kSaveFeat + chunk_offset(256, row, 0));
+					epilogue_to_h<8, false, TRAIN>(t_lane, sm.bias + bias_offset(8), rec + kSaveFeat + chunk_offset(256, row, 0), nullptr);
 					publish(&sm.a_ready, lane);
 				} else if (grp == 9) {
 					// views_linears[0]: relu -> first 128 channels of h
-					epilogue_to_h<4, true, TRAIN>(t_lane, sm.bias + bias_offset(10), rec + kSaveHv + chunk_offset(128, row, 0));
+					epilogue_to_h<4, true, TRAIN>(t_lane, sm.bias + bias_offset(10), rec + kSaveHv + chunk_offset(128, row, 0), rec + bits_offset(0, row));
 					publish(&sm.a_ready, lane);
 				} else {
 					// rgb_linear -> out = [rgb, alpha] (src/NeRF.cpp:119-120)
@@ -294,6 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint
 
 	fence_before();
 	__syncthreads();
+	if (CL > 1) cluster_sync();          // no CTA leaves while a peer can still multicast into its shared memory
 	if (warp == 1) {
 		fence_after();
 		tmem_free_all(tmem);
@@ -326,11 +372,20 @@ static int fwd_common(const nrf_mlp_nerf_shape* shape, const void* packed, const
 	NRF_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
 		(reinterpret_cast<uintptr_t>(saved) & 127) == 0, "packed / saved must be 128-byte, x 8-byte, out 16-byte aligned");
 	const int64_t tiles = (n + 127) / 128;
-	const int blocks = static_cast<int>(std::min<int64_t>(tiles, kNumSMs));
 	const int smem = static_cast<int>(sizeof(Smem)) + 128;
-	NRF_CUDA(cudaFuncSetAttribute(mlp_nerf_fwd_tc_kernel<TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-	mlp_nerf_fwd_tc_kernel<TRAIN><<<blocks, kThreads, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed), x, n, out,
-		reinterpret_cast<uint8_t*>(saved));
+	// NRF_NERF_CLUSTER=1 selects the one-CTA-per-stream kernel (A/B baseline); default: 2-CTA clusters sharing the weight stream
+	static const int cluster = [] { const char* e = getenv("NRF_NERF_CLUSTER"); return e && e[0] == '1' ? 1 : 2; }();
+	if (cluster == 2) {
+		const int blocks = static_cast<int>(std::min<int64_t>((tiles + 1) / 2 * 2, kNumSMs));
+		NRF_CUDA(cudaFuncSetAttribute(mlp_nerf_fwd_tc_kernel<TRAIN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		mlp_nerf_fwd_tc_kernel<TRAIN, 2><<<blocks, kThreads, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed), x, n, out,
+			reinterpret_cast<uint8_t*>(saved));
+	} else {
+		const int blocks = static_cast<int>(std::min<int64_t>(tiles, kNumSMs));
+		NRF_CUDA(cudaFuncSetAttribute(mlp_nerf_fwd_tc_kernel<TRAIN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		mlp_nerf_fwd_tc_kernel<TRAIN, 1><<<blocks, kThreads, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed), x, n, out,
+			reinterpret_cast<uint8_t*>(saved));
+	}
 	NRF_CHECK_LAUNCH("mlp_nerf_fwd_tc_kernel");
 	return NRF_OK;
 }
@@ -369,7 +424,7 @@ int nrf_mlp_nerf_pack_train(const nrf_mlp_nerf_shape* shape, const nrf_mlp_nerf_
 int64_t nrf_mlp_nerf_saved_bytes(const nrf_mlp_nerf_shape* shape, int64_t n)
 {
 	if (nerf_tc::check_shape(shape) || n < 0) return -1;
-	return ((n + 127) / 128) * static_cast<int64_t>(kSaveTile);
+	return ((n + 127) / 128 + 1) * static_cast<int64_t>(kSaveTile);      // + one spare record (idle rounds of a cluster write there)
 }
 
 int nrf_mlp_nerf_fwd(const nrf_mlp_nerf_shape* shape, const void* packed, const float* x, int64_t n, float* out, nrf_stream stream)

@@ -38,10 +38,34 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 	             ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// The same copy delivered to the SAME shared-memory offset of every CTA of the cluster named in cta_mask (one L2 read), each
+// destination CTA's mbarrier (same offset) receiving the complete_tx
+__device__ __forceinline__ void tma_bulk_g2s_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+	             ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+	uint32_t r;
+	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+	return r;
+}
+__device__ __forceinline__ void cluster_sync()
+{
+	asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // asynchronous L2 prefetch of a contiguous global range (bytes: multiple of 16)
 __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
 {
 	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+// true in exactly one lane of a converged warp (the pattern the compiler recognises for single-thread tcgen05 issue)
+__device__ __forceinline__ bool elect_one()
+{
+	uint32_t pred;
+	asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+	return pred != 0;
 }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -70,6 +94,13 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
 __device__ __forceinline__ void umma_commit(uint64_t* bar)
 {
 	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// the same arrival on the mbarrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask)
+{
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+	             ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 
 // tcgen05.ld / st, shape 32x32b: thread i of the warp owns TMEM lane (32*(warp%4) + i) and gets / gives consecutive columns

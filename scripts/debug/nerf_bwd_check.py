@@ -12,7 +12,7 @@ sys.path[:0] = [str(ROOT), str(ROOT / "oracle"), str(ROOT / "tests")]
 import restate as O  # noqa: E402
 from nerfpp_b200 import ops  # noqa: E402
 
-SAVE_TILE, GRAD_TILE = 647168, 626688
+SAVE_TILE, GRAD_TILE = 684032, 626688
 
 
 def region(buf, tile_bytes, off, cols, n):
