@@ -373,8 +373,11 @@ static int fwd_common(const nrf_mlp_nerf_shape* shape, const void* packed, const
 		(reinterpret_cast<uintptr_t>(saved) & 127) == 0, "packed / saved must be 128-byte, x 8-byte, out 16-byte aligned");
 	const int64_t tiles = (n + 127) / 128;
 	const int smem = static_cast<int>(sizeof(Smem)) + 128;
-	// NRF_NERF_CLUSTER=1 selects the one-CTA-per-stream kernel (A/B baseline); default: 2-CTA clusters sharing the weight stream
-	static const int cluster = [] { const char* e = getenv("NRF_NERF_CLUSTER"); return e && e[0] == '1' ? 1 : 2; }();
+	// NRF_NERF_CLUSTER=2 selects 2-CTA clusters that share one multicast weight stream.  Measured equal to the default (0.332 vs 0.330 ms
+	// at 196 608 rows): halving the L2 -> SM weight traffic changes nothing, i.e. the weight stream does not pace this kernel.  What does:
+	// one tile in flight, so a layer is its MMAs (16 x 128 cycles) THEN its epilogue, and the epilogue reads 128 KB of fp32 accumulators
+	// out of TMEM at 64 B/clk (2 048 cycles) — splitting it over 8 warps instead of 4 gained 5 % (inference) / lost 7 % (training).
+	static const int cluster = [] { const char* e = getenv("NRF_NERF_CLUSTER"); return e && e[0] == '2' ? 2 : 1; }();
 	if (cluster == 2) {
 		const int blocks = static_cast<int>(std::min<int64_t>((tiles + 1) / 2 * 2, kNumSMs));
 		NRF_CUDA(cudaFuncSetAttribute(mlp_nerf_fwd_tc_kernel<TRAIN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
