@@ -127,26 +127,32 @@ struct FreqBands {
 __global__ void __launch_bounds__(kEncThreads) posenc_kernel(const float* __restrict__ x, int64_t n, int in_dims, int num_freqs,
 	FreqBands fb, int include_input, float* __restrict__ out)
 {
-	extern __shared__ float xs[];  // [128 * in_dims]
+	extern __shared__ float xs[];  // [128 * in_dims] then [num_freqs] frequency bands
 	const int64_t base = static_cast<int64_t>(blockIdx.x) * kEncThreads;
-	const int64_t rows = min(static_cast<int64_t>(kEncThreads), n - base);
-	for (int64_t e = threadIdx.x; e < rows * in_dims; e += kEncThreads) xs[e] = x[base * in_dims + e];
+	const int rows = static_cast<int>(min(static_cast<int64_t>(kEncThreads), n - base));
+	float* fs = xs + kEncThreads * in_dims;
+	for (int e = threadIdx.x; e < rows * in_dims; e += kEncThreads) xs[e] = x[base * in_dims + e];
+	for (int e = threadIdx.x; e < num_freqs; e += kEncThreads) fs[e] = fb.f[e];
 	__syncthreads();
+	// 32-bit index arithmetic throughout (a CTA's block has at most 128 x out_dims elements): the 64-bit divisions of the first
+	// version cost more than the sinf/cosf they addressed (50 -> see profiles: 196 608 x 63 outputs)
 	const int out_dims = in_dims * (include_input ? 1 : 0) + 2 * num_freqs * in_dims;
-	const int64_t total = rows * out_dims;
+	const int total = rows * out_dims;
+	const int first = include_input ? in_dims : 0, two_in = 2 * in_dims;
 	float* dst = out + base * out_dims;
-	for (int64_t e = threadIdx.x; e < total; e += kEncThreads) {
-		const int r = static_cast<int>(e / out_dims);
-		int c = static_cast<int>(e % out_dims);
+	for (int e = threadIdx.x; e < total; e += kEncThreads) {
+		const int r = e / out_dims;
+		const int c = e - r * out_dims;
 		float v;
-		if (include_input && c < in_dims) {
+		if (c < first) {
 			v = xs[r * in_dims + c];
 		} else {
-			if (include_input) c -= in_dims;
-			const int band = c / (2 * in_dims);
-			const int rem = c % (2 * in_dims);
-			const float arg = __fmul_rn(xs[r * in_dims + (rem % in_dims)], fb.f[band]);
-			v = rem < in_dims ? sinf(arg) : cosf(arg);
+			const int cc = c - first;
+			const int band = cc / two_in;
+			const int rem = cc - band * two_in;
+			const bool is_sin = rem < in_dims;
+			const float arg = __fmul_rn(xs[r * in_dims + (is_sin ? rem : rem - in_dims)], fs[band]);
+			v = is_sin ? sinf(arg) : cosf(arg);
 		}
 		dst[e] = v;
 	}
@@ -192,7 +198,7 @@ int nrf_posenc_fwd(const float* x, int64_t n, int32_t input_dims, int32_t num_fr
 	FreqBands fb;
 	for (int i = 0; i < num_freqs; i++) fb.f[i] = freq_bands_host[i];
 	const unsigned blocks = static_cast<unsigned>((n + kEncThreads - 1) / kEncThreads);
-	posenc_kernel<<<blocks, kEncThreads, kEncThreads * input_dims * sizeof(float), as_stream(stream)>>>(x, n, input_dims, num_freqs, fb, include_input, out);
+	posenc_kernel<<<blocks, kEncThreads, (kEncThreads * input_dims + num_freqs) * sizeof(float), as_stream(stream)>>>(x, n, input_dims, num_freqs, fb, include_input, out);
 	NRF_CHECK_LAUNCH("posenc_kernel");
 	return NRF_OK;
 }
