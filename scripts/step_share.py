@@ -10,11 +10,11 @@ r = csv.reader(lines)
 hdr = next(r)
 ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
 rows = [(row[ki], float(row[vi].replace(",", "")) / 1000) for row in r]
-adam = [i for i, (k, _) in enumerate(rows) if k.startswith("adam_kernel")]
+adam = [i for i, (k, _) in enumerate(rows) if "adam_kernel(" in k]
 lo, hi = adam[-2] + 1, adam[-1] + 1
 agg = collections.OrderedDict()
 for k, us in rows[lo:hi]:
-    agg.setdefault(k.split("(")[0][-44:], []).append(us)
+    agg.setdefault(k.split("(")[0].replace("nrf::", "").replace("void ", "")[-44:], []).append(us)
 tot = sum(sum(v) for v in agg.values())
 print(f"# One training step (graph replay) out of {sys.argv[1]}: the launches between the last two adam_kernel launches.")
 print("# ncu per-launch times are cold-cache and serialised: compare SHARES." + (f"  bench.py (same command, no profiler): {sys.argv[2]} ms/step;" if len(sys.argv) > 2 else "")
