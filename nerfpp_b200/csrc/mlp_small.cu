@@ -16,14 +16,16 @@
 //
 // Backward: activations are recomputed (nothing saved by the forward).  The dX chain runs in registers like the
 // forward; ReLU gates are kept as one 0xFFFF-per-active-half word per activation word (HSET2) and applied to the packed
-// bf16 gradient pairs with a single AND; the next tile's inputs are prefetched behind the dW phase.  For dW = dY^T X, each warp drops its X_l / dY_l slabs into padded shared-memory tiles; after one CTA
-// barrier the 8 warps split the 80 output 16x8 tiles between them, read the tiles with ldmatrix.trans (both
-// operands are "K = rows"-major) and keep their share of dW in registers across the whole persistent loop; one
-// fp32 atomicAdd per weight per CTA at the end.
+// bf16 gradient pairs with a single AND; the next tile's inputs are prefetched behind the dW phase.  For dW = dY^T X, each warp drops
+// its X_l / dY_l slabs into shared-memory tiles laid out as UMMA canonical MN-major regions; after one CTA barrier ONE thread issues
+// 24 tcgen05.mma (SS form, both operands "K = rows"-major straight from those bytes) whose accumulators live in TMEM across the whole
+// persistent loop, while the warps already work on the next tile; one fp32 atomicAdd per weight per CTA at the end.
+// (NRF_MLP_BWD_DW=mma: the first version — 8 warps split 80 output 16x8 tiles, ldmatrix.trans + mma.sync, dW in registers.)
 //
 // The A2 operand is laid out [sh(16) | d1(16)] instead of [sh(16) | geo(15) | pad]: column 16 is the sigma slot,
 // whose weight column is zero (and whose value is zeroed), which avoids a cross-lane shift of the accumulators.
 #include "mlp_small_layout.cuh"
+#include "tcgen05.cuh"
 
 namespace nrf {
 
@@ -291,6 +293,42 @@ constexpr int kTD4 = kTX4 + kTileRows * kP64;
 constexpr int kTileElems = kTD4 + kTileRows * kP8;
 constexpr size_t kBwdSmem = static_cast<size_t>(kBlobWords) * 4 + static_cast<size_t>(kTileElems) * 2;
 
+// ---- tcgen05 weight-gradient path (TCDW): the X_l / dY_l tiles are stored as UMMA canonical MN-major regions
+// [column chunk of 8][128 rows][8] bf16 (chunk stride 2048 B, 8-row group stride 128 B), so that dW = dY^T X is a handful of
+// tcgen05.mma SS instructions per tile straight from these bytes (A and B both "rows = K"), accumulated in TMEM over the whole
+// persistent loop.  Regions that share an MMA are adjacent: A operands are 128 columns wide (M = 128):
+//   MMA1: A = [dY0 | dY2]  B = [X0 | X2] (N = 64)   -> rows 0..63 x cols 0..31 = dW0,  rows 64..127 x cols 32..63 = dW2
+//   MMA2: A = [dY3 | X1 ]  B = [X3 | dY1] (N = 80)  -> rows 0..63 x cols 0..63 = dW3,  rows 64..127 x cols 64..79 = dW1^T
+//   MMA3: A = [X4  | X3 ]  B = dY4 (N = 16)         -> rows 0..63 x cols 0..2  = dW4^T
+// (the other quadrants are finite garbage that is never read back)
+constexpr int kCRA = 0;                              // [dY0 | dY2]
+constexpr int kCRB = kCRA + 128 * 128 * 2;           // [dY3 | X1]
+constexpr int kCX4 = kCRB + 128 * 128 * 2;
+constexpr int kCX3 = kCX4 + 128 * 64 * 2;
+constexpr int kCD1 = kCX3 + 128 * 64 * 2;
+constexpr int kCX0 = kCD1 + 128 * 16 * 2;
+constexpr int kCX2 = kCX0 + 128 * 32 * 2;
+constexpr int kCD4 = kCX2 + 128 * 32 * 2;
+constexpr int kCTileBytes = kCD4 + 128 * 16 * 2;     // 122 880
+constexpr uint32_t kDwT0 = 0, kDwT1 = 64, kDwT2 = 144;        // TMEM columns of the three accumulators
+constexpr size_t kBwdSmemTc = static_cast<size_t>(kBlobWords) * 4 + kCTileBytes + 64;
+
+// instruction descriptor: kind::f16, bf16 x bf16 -> fp32, A and B MN-major, M = 128
+__host__ __device__ constexpr uint32_t idesc_mn(int N) { return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (uint32_t(N >> 3) << 17) | (8u << 24); }
+
+template <int KS>
+__device__ __forceinline__ void store_frag_c(uint8_t* region, int chunk0, int row_g, int t, const uint32_t (&a)[KS][4])
+{
+	uint8_t* p = region + chunk0 * 2048 + row_g * 16 + t * 4;
+#pragma unroll
+	for (int ks = 0; ks < KS; ks++) {
+		*reinterpret_cast<uint32_t*>(p + (2 * ks) * 2048) = a[ks][0];
+		*reinterpret_cast<uint32_t*>(p + (2 * ks) * 2048 + 128) = a[ks][1];          // row + 8
+		*reinterpret_cast<uint32_t*>(p + (2 * ks + 1) * 2048) = a[ks][2];
+		*reinterpret_cast<uint32_t*>(p + (2 * ks + 1) * 2048 + 128) = a[ks][3];
+	}
+}
+
 // store an A-fragment-shaped register set (KS k-steps) for rows (g, g+8) of this warp's slab
 template <int KS>
 __device__ __forceinline__ void store_frag(__nv_bfloat16* tile, int pitch, int row_g, int t, const uint32_t (&a)[KS][4])
@@ -370,7 +408,19 @@ __device__ __forceinline__ void dw_flush(float* __restrict__ gp, int layer, int 
 	}
 }
 
-template <int IN_KIND>
+// flush index of (layer, out m, padded in k) in the flat gradient, -1 for padding
+__device__ __forceinline__ int dw_index(int layer, int m, int k)
+{
+	switch (layer) {
+		case 0: return kW0 + m * 32 + k;
+		case 1: return kW1 + m * 64 + k;
+		case 2: return k < 16 ? kW2 + m * 31 + k : (k == 16 ? -1 : kW2 + m * 31 + k - 1);
+		case 3: return kW3 + m * 64 + k;
+		default: return m < 3 ? kW4 + m * 64 + k : -1;
+	}
+}
+
+template <int IN_KIND, bool TCDW>
 __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const uint32_t* __restrict__ blob, const void* __restrict__ enc,
 	const float* __restrict__ ray_sh, int S, const uint8_t* __restrict__ keep, int64_t n, const float* __restrict__ grad_raw,
 	void* __restrict__ grad_in, float* __restrict__ grad_params)
@@ -378,14 +428,29 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	uint32_t* wf = reinterpret_cast<uint32_t*>(smem_raw);
 	__nv_bfloat16* tiles = reinterpret_cast<__nv_bfloat16*>(smem_raw + static_cast<size_t>(kBlobWords) * 4);
+	uint8_t* ctiles = smem_raw + static_cast<size_t>(kBlobWords) * 4;                       // TCDW: canonical regions
+	uint64_t* dw_done = reinterpret_cast<uint64_t*>(ctiles + kCTileBytes);                  // TCDW: the tile's MMAs have read the regions
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctiles + kCTileBytes + 8);
+	const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), g = lane >> 2, t = lane & 3;
+	if (TCDW && warp == 0) {
+		if (lane == 0) {
+			tc::mbar_init(dw_done, 1);
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncwarp();
+		tc::tmem_alloc_all(tmem_slot);
+	}
 	copy_blob(wf, blob, kBlobWords);
+	if (TCDW) tc::fence_before();
 	__syncthreads();
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+	if (TCDW) tc::fence_after();
+	const uint32_t tmem = TCDW ? *tmem_slot : 0u;
 	const int row_g = warp * 16 + g;  // row inside the CTA tile
 
-	float dw[10][4];
+	float dw[TCDW ? 1 : 10][4];
 #pragma unroll
-	for (int i = 0; i < 10; i++) dw[i][0] = dw[i][1] = dw[i][2] = dw[i][3] = 0.f;
+	for (int i = 0; i < (TCDW ? 1 : 10); i++) dw[i][0] = dw[i][1] = dw[i][2] = dw[i][3] = 0.f;
+	uint32_t it = 0;                  // tiles done by this CTA
 
 	const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
 	// inputs of the tile in flight (prefetched one tile ahead: the loads complete behind the dW phase)
@@ -410,6 +475,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 		float4 g_lo = in_g_lo, g_hi = in_g_hi;
 		if (!in_k_lo) g_lo.w = 0.f;               // d(sigma) is dropped outside the box (src/NeRFRenderer.h:188)
 		if (!in_k_hi) g_hi.w = 0.f;
+		if (TCDW && it > 0) tc::mbar_wait(dw_done, (it - 1) & 1u);   // the previous tile's MMAs are done with the regions
 		uint32_t m1[4][4], m3[4][4], m4[4][4];   // ReLU gates of X1, X3, X4
 		// ---- forward recompute; every layer input is dropped into its X tile (bf16, packed straight from the fp32 accumulators)
 		{
@@ -422,12 +488,12 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			layer_mma<2, 8, true>(a0, wf + kF0, lane, acc);
 			uint32_t xb2[2][4], xb4[4][4];                               // bf16 copies for the dW products
 			to_bf16<2>(a0, xb2);
-			store_frag<2>(tiles + kTX0, kP32, row_g, t, xb2);
+			if (TCDW) store_frag_c<2>(ctiles + kCX0, 0, row_g, t, xb2); else store_frag<2>(tiles + kTX0, kP32, row_g, t, xb2);
 			uint32_t a1[4][4];
 			repack<4, true, true>(acc, a1);
 			relu_gates<4>(a1, m1);
 			repack<4, true, false>(acc, xb4);
-			store_frag<4>(tiles + kTX1, kP64, row_g, t, xb4);
+			if (TCDW) store_frag_c<4>(ctiles + kCRB, 8, row_g, t, xb4); else store_frag<4>(tiles + kTX1, kP64, row_g, t, xb4);
 			float d1[2][4];
 			layer_mma<4, 2, true>(a1, wf + kF1, lane, d1);
 			uint32_t a2[2][4];
@@ -436,18 +502,18 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			if (t == 0) { d1[0][0] = 0.f; d1[0][2] = 0.f; }
 			repack<1, false, true>(d1, reinterpret_cast<uint32_t(&)[1][4]>(a2[1]));
 			to_bf16<2>(a2, xb2);
-			store_frag<2>(tiles + kTX2, kP32, row_g, t, xb2);
+			if (TCDW) store_frag_c<2>(ctiles + kCX2, 0, row_g, t, xb2); else store_frag<2>(tiles + kTX2, kP32, row_g, t, xb2);
 			layer_mma<2, 8, true>(a2, wf + kF2, lane, acc);
 			uint32_t a3[4][4];
 			repack<4, true, true>(acc, a3);
 			relu_gates<4>(a3, m3);
 			repack<4, true, false>(acc, xb4);
-			store_frag<4>(tiles + kTX3, kP64, row_g, t, xb4);
+			if (TCDW) store_frag_c<4>(ctiles + kCX3, 0, row_g, t, xb4); else store_frag<4>(tiles + kTX3, kP64, row_g, t, xb4);
 			layer_mma<4, 8, true>(a3, wf + kF3, lane, acc);
 			repack<4, true, true>(acc, a3);
 			relu_gates<4>(a3, m4);
 			repack<4, true, false>(acc, xb4);
-			store_frag<4>(tiles + kTX4, kP64, row_g, t, xb4);
+			if (TCDW) store_frag_c<4>(ctiles + kCX4, 0, row_g, t, xb4); else store_frag<4>(tiles + kTX4, kP64, row_g, t, xb4);
 		}
 		// ---- backward chain
 		{
@@ -456,17 +522,17 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			d4[0][1] = t == 0 ? pack_bf16(g_hi.x, g_hi.y) : (t == 1 ? pack_bf16(g_hi.z, 0.f) : 0u);
 			d4[0][2] = 0u;
 			d4[0][3] = 0u;
-			store_frag<1>(tiles + kTD4, kP8, row_g, t, d4);   // 8 real + 8 zero columns
+			if (TCDW) store_frag_c<1>(ctiles + kCD4, 0, row_g, t, d4); else store_frag<1>(tiles + kTD4, kP8, row_g, t, d4);   // 8 real + 8 zero columns
 			float acc[8][4];
 			layer_mma<1, 8, false>(d4, wf + kB4, lane, acc);                 // dA4 = dD4 · W4
 			uint32_t d3[4][4];
 			repack<4, false, false>(acc, d3);
 			apply_gates<4>(d3, m4);
-			store_frag<4>(tiles + kTD3, kP64, row_g, t, d3);
+			if (TCDW) store_frag_c<4>(ctiles + kCRB, 0, row_g, t, d3); else store_frag<4>(tiles + kTD3, kP64, row_g, t, d3);
 			layer_mma<4, 8, false>(d3, wf + kB3, lane, acc);                 // dA3 = dD3 · W3
 			repack<4, false, false>(acc, d3);
 			apply_gates<4>(d3, m3);
-			store_frag<4>(tiles + kTD2, kP64, row_g, t, d3);
+			if (TCDW) store_frag_c<4>(ctiles + kCRA, 8, row_g, t, d3); else store_frag<4>(tiles + kTD2, kP64, row_g, t, d3);
 			float da2[4][4];
 			layer_mma<4, 4, false>(d3, wf + kB2, lane, da2);                 // dA2 = dD2 · W2p  (cols 0..15 views, 16..31 d1)
 			if (t == 0) { da2[2][0] += g_lo.w; da2[2][2] += g_hi.w; }        // + d(sigma)
@@ -475,11 +541,11 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			dd1[0][1] = pack_bf16(da2[2][2], da2[2][3]);
 			dd1[0][2] = pack_bf16(da2[3][0], da2[3][1]);
 			dd1[0][3] = pack_bf16(da2[3][2], da2[3][3]);
-			store_frag<1>(tiles + kTD1, kP16, row_g, t, dd1);
+			if (TCDW) store_frag_c<1>(ctiles + kCD1, 0, row_g, t, dd1); else store_frag<1>(tiles + kTD1, kP16, row_g, t, dd1);
 			layer_mma<1, 8, false>(dd1, wf + kB1, lane, acc);                // dA1 = dD1 · W1
 			repack<4, false, false>(acc, d3);
 			apply_gates<4>(d3, m1);
-			store_frag<4>(tiles + kTD0, kP64, row_g, t, d3);
+			if (TCDW) store_frag_c<4>(ctiles + kCRA, 0, row_g, t, d3); else store_frag<4>(tiles + kTD0, kP64, row_g, t, d3);
 			if (grad_in) {
 				float de[4][4];
 				layer_mma<4, 4, false>(d3, wf + kB0, lane, de);             // dEnc = dD0 · W0
@@ -506,6 +572,32 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			}
 		}
 		if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x);   // next tile's inputs travel while the dW phase runs
+		if (TCDW) {
+			// ---- dW on tcgen05: 3 MMAs per 16-row K step straight from the regions, accumulators stay in TMEM
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // the st.shared above -> visible to the MMA's async reads
+			__syncthreads();
+			if (warp == 0) {
+				const uint32_t base = tc::smem_u32(ctiles);
+				const uint64_t a1 = tc::smem_desc(base + kCRA, 128, 2048), b1 = tc::smem_desc(base + kCX0, 128, 2048);
+				const uint64_t a2 = tc::smem_desc(base + kCRB, 128, 2048), b2 = tc::smem_desc(base + kCX3, 128, 2048);
+				const uint64_t a3 = tc::smem_desc(base + kCX4, 128, 2048), b3 = tc::smem_desc(base + kCD4, 128, 2048);
+				const uint32_t first = it ? 1u : 0u;
+				if (tc::elect_one()) {
+					tc::fence_after();
+#pragma unroll
+					for (int j = 0; j < 8; j++) {                                    // K = 16 rows per step: +256 B on both descriptors
+						const uint64_t o = static_cast<uint64_t>(16 * j);
+						tc::umma_ss(tmem + kDwT0, a1 + o, b1 + o, idesc_mn(64), j ? 1u : first);
+						tc::umma_ss(tmem + kDwT1, a2 + o, b2 + o, idesc_mn(80), j ? 1u : first);
+						tc::umma_ss(tmem + kDwT2, a3 + o, b3 + o, idesc_mn(16), j ? 1u : first);
+					}
+					tc::umma_commit(dw_done);
+				}
+				__syncwarp();
+			}
+			it++;
+			continue;
+		}
 		__syncthreads();
 		// ---- dW: 80 output tiles split over the 8 warps, 10 each
 		if (warp < 4) {
@@ -522,6 +614,37 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 		__syncthreads();
 	}
 
+	if (TCDW) {
+		// ---- flush: one thread per accumulator row (TMEM lane), fp32 atomics into the flat gradient
+		if (it > 0) tc::mbar_wait(dw_done, (it - 1) & 1u);
+		tc::fence_after();
+		if (warp < 4 && it > 0) {
+			const int m = warp * 32 + lane;
+			const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+			for (int c0 = 0; c0 < 160; c0 += 16) {
+				uint32_t d16[16];
+				tc::tmem_ld16(t_lane + c0, d16);
+				tc::tmem_ld_wait();
+#pragma unroll
+				for (int j = 0; j < 16; j++) {
+					const int c = c0 + j;
+					int idx = -1;
+					if (c < 64) idx = (m < 64) ? (c < 32 ? dw_index(0, m, c) : -1) : (c >= 32 ? dw_index(2, m - 64, c - 32) : -1);
+					else if (c < 144) idx = (m < 64) ? (c < 128 ? dw_index(3, m, c - 64) : -1) : (c >= 128 ? dw_index(1, c - 128, m - 64) : -1);
+					else idx = (m < 64) ? dw_index(4, c - 144, m) : -1;
+					const float v = __uint_as_float(d16[j]);
+					if (idx >= 0 && v != 0.f) atomicAdd(grad_params + idx, v);
+				}
+			}
+		}
+		tc::fence_before();
+		__syncthreads();
+		if (warp == 0) {
+			tc::fence_after();
+			tc::tmem_free_all(tmem);
+		}
+		return;
+	}
 	// ---- flush dW
 	if (warp < 4) {
 #pragma unroll
@@ -620,13 +743,19 @@ int nrf_mlp_small_bwd(const nrf_mlp_small_shape* shape, const void* packed, nrf_
 	const int blocks = static_cast<int>(std::min<int64_t>(tiles, kNumSMs));
 	const uint32_t* blob = reinterpret_cast<const uint32_t*>(packed);
 	cudaStream_t s = as_stream(stream);
+	// NRF_MLP_BWD_DW=mma keeps the weight-gradient products on mma.sync + ldmatrix.trans (the A/B baseline); default: tcgen05 from the tiles
+	static const bool tcdw = [] { const char* e = getenv("NRF_MLP_BWD_DW"); return !(e && e[0] == 'm'); }();
+#define NRF_BWD_LAUNCH(KIND, TC, SMEM)                                                                                                   \
+	do {                                                                                                                                 \
+		NRF_CUDA(cudaFuncSetAttribute(mlp_small_bwd_kernel<KIND, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM))); \
+		mlp_small_bwd_kernel<KIND, TC><<<blocks, kBwdWarps * 32, SMEM, s>>>(blob, enc, ray_sh, samples_per_ray, keep, n, grad_raw, grad_in, grad_params_flat); \
+	} while (0)
 	if (in_kind == NRF_MLP_IN_ENC16_RAYDIRS) {
-		NRF_CUDA(cudaFuncSetAttribute(mlp_small_bwd_kernel<NRF_MLP_IN_ENC16_RAYDIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBwdSmem)));
-		mlp_small_bwd_kernel<NRF_MLP_IN_ENC16_RAYDIRS><<<blocks, kBwdWarps * 32, kBwdSmem, s>>>(blob, enc, ray_sh, samples_per_ray, keep, n, grad_raw, grad_in, grad_params_flat);
+		if (tcdw) NRF_BWD_LAUNCH(NRF_MLP_IN_ENC16_RAYDIRS, true, kBwdSmemTc); else NRF_BWD_LAUNCH(NRF_MLP_IN_ENC16_RAYDIRS, false, kBwdSmem);
 	} else {
-		NRF_CUDA(cudaFuncSetAttribute(mlp_small_bwd_kernel<NRF_MLP_IN_F32_CAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBwdSmem)));
-		mlp_small_bwd_kernel<NRF_MLP_IN_F32_CAT><<<blocks, kBwdWarps * 32, kBwdSmem, s>>>(blob, enc, ray_sh, samples_per_ray, keep, n, grad_raw, grad_in, grad_params_flat);
+		if (tcdw) NRF_BWD_LAUNCH(NRF_MLP_IN_F32_CAT, true, kBwdSmemTc); else NRF_BWD_LAUNCH(NRF_MLP_IN_F32_CAT, false, kBwdSmem);
 	}
+#undef NRF_BWD_LAUNCH
 	NRF_CHECK_LAUNCH("mlp_small_bwd_kernel");
 	return NRF_OK;
 }
