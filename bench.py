@@ -246,6 +246,12 @@ def main() -> None:
     ap.add_argument("--dp", default="fused", choices=["fused", "nccl"],
                     help="N>1 optimiser step: one peer-memory kernel (reduce-scatter + Adam + shadow all-gather) or NCCL all-reduce + dense Adam")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything native libraries print on file descriptor 1 while the job runs (NCCL's version
+    # banner, for one) is sent to stderr; the line itself goes to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference(args)
         return

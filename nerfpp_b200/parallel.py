@@ -12,6 +12,8 @@ from __future__ import annotations
 
 import os
 
+import sys
+
 import torch
 import torch.distributed as dist
 
@@ -123,8 +125,11 @@ class PeerShardedOptimizer:
             model.optimizer_step_sharded()
             torch.cuda.synchronize(model.device)
             if model.flags_timeout() or not torch.equal(before, model.shadow):
+                print(f"[nerfpp_b200] rank {self.rank}: fused optimiser self-test failed (flags_timeout={model.flags_timeout()}, "
+                      f"shadow changed={not torch.equal(before, model.shadow)})", file=sys.stderr, flush=True)
                 ok = 0
-        except Exception:  # noqa: BLE001
+        except Exception as e:  # noqa: BLE001
+            print(f"[nerfpp_b200] rank {self.rank}: fused optimiser self-test raised {type(e).__name__}: {e}", file=sys.stderr, flush=True)
             ok = 0
         model.step = 0
         model._sched_step = -1          # the dry step advanced the device-side counter: re-seed it on the next step
