@@ -127,6 +127,7 @@ class HashNeRF:
     def refresh(self):
         """Re-derive the fp16 table shadow and the packed MLP weights from the fp32 masters."""
         ops.table_to_half(self.table, self.table_f16)
+        self.shadow[self.n_table:].copy_(self.params[self.n_table:])      # the MLP tail of the shadow: what the Adam kernels will keep writing
         self.packed = ops.mlp_small_pack(self.mlp_params, out=self.packed)
 
     # -- RenderRays (src/NeRFRenderer.h:366-459)
