@@ -47,6 +47,27 @@ def test_argument_validation_without_gpu():
     assert lib.nrf_composite_fwd(None, 3, None, None, None, 0.0, 0, 4, 8, None, None, None, None, None, None) == -1
 
 
+def test_classic_nerf_training_sizes_and_validation_without_gpu():
+    """Host-side entries of the classic-NeRF training ABI: scratch sizes (one record per 128-row tile, + one spare forward record)
+    and loud refusal of shapes the kernels were not built for, null pointers and negative counts — no kernel is launched."""
+    from nerfpp_b200 import cabi, ops
+    lib = cabi.lib()
+    shape, bad = ops.mlp_nerf_shape(), ops.mlp_nerf_shape(width=128)
+    save_tile, grad_tile = 684032, 626688                                   # mlp_nerf_layout.cuh: kSaveTile, kGradTile
+    for n, tiles in ((0, 0), (1, 1), (128, 1), (129, 2), (196608, 1536)):
+        assert lib.nrf_mlp_nerf_saved_bytes(ctypes.byref(shape), n) == (tiles + 1) * save_tile
+        assert lib.nrf_mlp_nerf_bwd_workspace_bytes(ctypes.byref(shape), n) == tiles * grad_tile
+    assert lib.nrf_mlp_nerf_saved_bytes(ctypes.byref(bad), 128) == -1 and lib.nrf_mlp_nerf_bwd_workspace_bytes(ctypes.byref(bad), 128) == -1
+    assert lib.nrf_mlp_nerf_saved_bytes(ctypes.byref(shape), -1) == -1
+    assert lib.nrf_mlp_nerf_packed_bytes(ctypes.byref(shape)) > 1_200_000
+    assert lib.nrf_mlp_nerf_fwd_train(ctypes.byref(bad), None, None, 4, None, None, None) == -3          # NRF_ERR_UNSUPPORTED
+    assert lib.nrf_mlp_nerf_fwd_train(ctypes.byref(shape), None, None, 0, None, None, None) == 0         # empty batch: no-op
+    assert lib.nrf_mlp_nerf_fwd_train(ctypes.byref(shape), None, None, 4, None, None, None) == -1        # null pointers
+    assert lib.nrf_mlp_nerf_bwd(ctypes.byref(shape), None, None, None, 4, None, None, None) == -1
+    assert lib.nrf_mlp_nerf_bwd(ctypes.byref(shape), None, None, None, -2, None, None, None) == -1
+    assert b"negative" in lib.nrf_last_error()
+
+
 def test_product_path_refuses_cpu_tensors():
     import torch
     from nerfpp_b200 import cabi, ops

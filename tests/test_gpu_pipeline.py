@@ -234,3 +234,15 @@ def test_fused_render_entry_equals_the_composed_path():
             assert torch.equal(a[k], b[k]), k
     c = m.render_rays_fused(o, d, n_importance=64)
     assert c["rgb"].shape == (1, 3)
+
+
+def test_fp16_shadow_is_fully_initialised():
+    """The Adam kernels keep the WHOLE fp16 shadow (table + MLP tail) equal to the rounded fp32 masters; refresh() must start it that
+    way — the fused multi-GPU optimiser's dry self-test compares the full buffer (it once saw uninitialised memory in the tail and
+    fell back to NCCL)."""
+    m = HashNeRF(BBOX, log2_hashmap_size=12, seed=5)
+    assert torch.equal(m.shadow, m.params.half())
+    o, d, tgt = synthetic_rays(128, seed=2)
+    for _ in range(3):
+        m.train_step(o, d, tgt)
+    assert torch.equal(m.shadow, m.params.half())
