@@ -240,6 +240,7 @@ def test_fp16_shadow_is_fully_initialised():
     """The Adam kernels keep the WHOLE fp16 shadow (table + MLP tail) equal to the rounded fp32 masters; refresh() must start it that
     way — the fused multi-GPU optimiser's dry self-test compares the full buffer (it once saw uninitialised memory in the tail and
     fell back to NCCL)."""
+    from nerfpp_b200.pipeline import HashNeRF, synthetic_rays
     m = HashNeRF(BBOX, log2_hashmap_size=12, seed=5)
     assert torch.equal(m.shadow, m.params.half())
     o, d, tgt = synthetic_rays(128, seed=2)
