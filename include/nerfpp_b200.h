@@ -217,6 +217,19 @@ int nrf_mlp_nerf_fwd_train(const nrf_mlp_nerf_shape* shape, const void* packed_t
 int nrf_mlp_nerf_bwd(const nrf_mlp_nerf_shape* shape, const void* packed_train, const void* saved, const float* grad_out, int64_t n,
                      void* workspace, const nrf_mlp_nerf_grads* grads, nrf_stream stream);
 
+/* The same two forwards fed with what NeRFRenderer::RunNetwork (src/NeRFRenderer.h:164-194) starts from: sample positions
+ * points [N,3] and ray directions dirs [R,3] (row n belongs to ray n / samples_per_ray; the reference expands the directions per
+ * sample, :179-181).  The positional embeddings of both (EmbedderImpl::forward, src/NeRF.cpp:22-39, frequency bands passed from the
+ * host: 10 for points, 4 for directions — the BASELINE multires) are evaluated inside the kernel's input stage with the arithmetic of
+ * nrf_posenc_fwd, so the result is bit-identical to nrf_posenc_fwd x 2 + concatenation (:182) + nrf_mlp_nerf_fwd[_train] without the
+ * [N,63], [N,27] and [N,90] arrays.  nrf_mlp_nerf_bwd is unchanged (it never reads x). */
+int nrf_mlp_nerf_fwd_points(const nrf_mlp_nerf_shape* shape, const void* packed, const float* points, const float* dirs, int32_t samples_per_ray,
+                            const float* freqs_pts_host, int32_t n_freqs_pts, const float* freqs_views_host, int32_t n_freqs_views, int64_t n,
+                            float* out, nrf_stream stream);
+int nrf_mlp_nerf_fwd_train_points(const nrf_mlp_nerf_shape* shape, const void* packed_train, const float* points, const float* dirs,
+                                  int32_t samples_per_ray, const float* freqs_pts_host, int32_t n_freqs_pts, const float* freqs_views_host,
+                                  int32_t n_freqs_views, int64_t n, float* out, void* saved, nrf_stream stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Volume rendering — NeRFRenderer::RawToOutputs (src/NeRFRenderer.h:199-282) with TruncExp
  * (src/CustomOps.cpp:5-16) folded in, and its backward.

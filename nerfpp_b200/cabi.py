@@ -109,6 +109,9 @@ SIGNATURES = {
     "nrf_mlp_nerf_bwd_workspace_bytes": (c_int64, [POINTER(MlpNerfShape), c_int64]),
     "nrf_mlp_nerf_fwd_train": (c_int32, [POINTER(MlpNerfShape), _P, _P, c_int64, _P, _P, _P]),
     "nrf_mlp_nerf_bwd": (c_int32, [POINTER(MlpNerfShape), _P, _P, _P, c_int64, _P, POINTER(MlpNerfWeights), _P]),
+    "nrf_mlp_nerf_fwd_points": (c_int32, [POINTER(MlpNerfShape), _P, _P, _P, c_int32, POINTER(c_float), c_int32, POINTER(c_float), c_int32, c_int64, _P, _P]),
+    "nrf_mlp_nerf_fwd_train_points": (c_int32, [POINTER(MlpNerfShape), _P, _P, _P, c_int32, POINTER(c_float), c_int32, POINTER(c_float), c_int32, c_int64,
+                                                _P, _P, _P]),
     "nrf_render_rays_workspace_bytes": (c_int64, [POINTER(RenderConfig), POINTER(HashGrid), c_int64]),
     "nrf_render_rays_fwd": (c_int32, [POINTER(RenderConfig), POINTER(HashGrid), _P, POINTER(MlpSmallShape), _P, _P, _P, c_int64, _P, _P, _P, c_int64,
                                       _P, _P, _P, _P, _P, _P, _P]),

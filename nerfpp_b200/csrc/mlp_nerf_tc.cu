@@ -17,6 +17,7 @@
 //     operand back to TMEM with tcgen05.st.
 // fp16 operands, fp32 accumulation: <= 1e-2 relative to the fp32 reference (tests/test_gpu_mlp_nerf.py).
 #include "mlp_nerf_layout.cuh"
+#include <utility>
 
 namespace nrf {
 namespace nerf_tc {
@@ -171,9 +172,40 @@ __host__ __device__ constexpr int group_count(int g) { return g == 8 ? 2 : 1; }
 // CL = 2: the CTAs of a 2-CTA cluster walk their tiles in lockstep and share ONE weight stream: each loads half of every stage and
 // multicasts it into both shared memories, so a stage costs one L2 read per cluster instead of one per SM.  (All 148 SMs pulling
 // the whole 1.2 MB blob per tile is 5.7 TB/s of L2 -> SM traffic — the measured pace of the CL = 1 kernel, not its tensor pipe.)
-template <bool TRAIN, int CL>
+// RAW: x is the sample positions [N,3] and the positional embedding (EmbedderImpl::forward, src/NeRF.cpp:22-39: [x, sin(f0 x), cos(f0 x), ..],
+// same fp32 product and libdevice sinf / cosf as nrf_posenc_fwd, hence bit-identical operands) is evaluated by the thread that owns the row,
+// directions are read per RAY (row / samples_per_ray; the reference expands them per sample, src/NeRFRenderer.h:179-181): the [N,63] / [N,27]
+// embeddings and their [N,90] concatenation (src/NeRFRenderer.h:182) never exist in memory.
+struct RawInput {
+	const float* dirs;       // [R,3]
+	int samples_per_ray;
+	float fp[10], fv[4];     // frequency bands of the two embedders
+};
+
+// embedding channel k (compile-time) of a 3-vector: x(3), then per band sin(3), cos(3); zero past `dims`
+template <int K, int NB>
+__device__ __forceinline__ float posenc_channel(const float (&p)[3], const float (&f)[NB])
+{
+	if constexpr (K < 3) {
+		return p[K];
+	} else if constexpr (K >= 3 + 6 * NB) {
+		return 0.f;
+	} else {
+		constexpr int c = K - 3, band = c / 6, rem = c % 6;
+		const float arg = __fmul_rn(p[rem % 3], f[band]);
+		return rem < 3 ? sinf(arg) : cosf(arg);
+	}
+}
+template <int K0, int NB, bool BF16, int... I>
+__device__ __forceinline__ void posenc_pack16(const float (&p)[3], const float (&f)[NB], uint32_t (&a16)[16], std::integer_sequence<int, I...>)
+{
+	((a16[I] = BF16 ? pack_bf16(posenc_channel<K0 + 2 * I, NB>(p, f), posenc_channel<K0 + 2 * I + 1, NB>(p, f))
+	                : pack_f16(posenc_channel<K0 + 2 * I, NB>(p, f), posenc_channel<K0 + 2 * I + 1, NB>(p, f))), ...);
+}
+
+template <bool TRAIN, int CL, bool RAW>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kThreads, 1) mlp_nerf_fwd_tc_kernel(const uint8_t* __restrict__ blob,
-	const float* __restrict__ x, int64_t n, float* __restrict__ out, uint8_t* __restrict__ saved)
+	const float* __restrict__ x, int64_t n, float* __restrict__ out, uint8_t* __restrict__ saved, const RawInput raw)
 {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -271,7 +303,36 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kThreads, 1) mlp_ne
 			// spare record that nrf_mlp_nerf_saved_bytes appends for this purpose
 			uint8_t* const rec = TRAIN ? saved + (tile < n_tiles ? tile : n_tiles) * kSaveTile : nullptr;
 			// ---- inputs: 63 point channels (+1 zero) and 27 view channels (+5 zero) as fp16 pairs into their TMEM columns
-			{
+			if (RAW) {
+				float p[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f};
+				if (ok) {
+					const int64_t ray = r / raw.samples_per_ray;
+#pragma unroll
+					for (int c = 0; c < 3; c++) { p[c] = __ldg(x + r * 3 + c); d[c] = __ldg(raw.dirs + ray * 3 + c); }
+				}
+				uint32_t a16[16];
+				posenc_pack16<0, 10, TRAIN>(p, raw.fp, a16, std::make_integer_sequence<int, 16>{});
+				if (!ok) {
+#pragma unroll
+					for (int i = 0; i < 16; i++) a16[i] = 0u;          // cos(0) = 1 would otherwise leak into the padding rows
+				}
+				tmem_st16(t_lane + kColPts, a16);
+				if (TRAIN) save_chunks(rec + kSavePts + chunk_offset(64, row, 0), 0, a16);
+				posenc_pack16<32, 10, TRAIN>(p, raw.fp, a16, std::make_integer_sequence<int, 16>{});
+				if (!ok) {
+#pragma unroll
+					for (int i = 0; i < 16; i++) a16[i] = 0u;
+				}
+				tmem_st16(t_lane + kColPts + 16, a16);
+				if (TRAIN) save_chunks(rec + kSavePts + chunk_offset(64, row, 0), 4, a16);
+				posenc_pack16<0, 4, TRAIN>(d, raw.fv, a16, std::make_integer_sequence<int, 16>{});
+				if (!ok) {
+#pragma unroll
+					for (int i = 0; i < 16; i++) a16[i] = 0u;
+				}
+				tmem_st16(t_lane + kColViews, a16);
+				if (TRAIN) save_chunks(rec + kSaveViews + chunk_offset(32, row, 0), 0, a16);
+			} else {
 				const float2* xr = reinterpret_cast<const float2*>(x + (ok ? r : 0) * kInCh);   // rows are 360 B: 8-byte aligned
 				uint32_t a16[16];
 #pragma unroll
@@ -362,14 +423,15 @@ int check_shape(const nrf_mlp_nerf_shape* s)
 using namespace nrf;
 using namespace nrf::nerf_tc;
 
-template <bool TRAIN>
-static int fwd_common(const nrf_mlp_nerf_shape* shape, const void* packed, const float* x, int64_t n, float* out, void* saved, nrf_stream stream)
+template <bool TRAIN, bool RAW>
+static int fwd_common(const nrf_mlp_nerf_shape* shape, const void* packed, const float* x, int64_t n, float* out, void* saved, const RawInput& raw,
+	nrf_stream stream)
 {
 	if (int rc = nerf_tc::check_shape(shape)) return rc;
 	NRF_REQUIRE(n >= 0, "negative n");
 	if (n == 0) return NRF_OK;
-	NRF_REQUIRE(packed && x && out && (!TRAIN || saved), "null pointer");
-	NRF_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+	NRF_REQUIRE(packed && x && out && (!TRAIN || saved) && (!RAW || (raw.dirs && raw.samples_per_ray >= 1)), "null pointer");
+	NRF_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0 && (RAW || (reinterpret_cast<uintptr_t>(x) & 7) == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
 		(reinterpret_cast<uintptr_t>(saved) & 127) == 0, "packed / saved must be 128-byte, x 8-byte, out 16-byte aligned");
 	const int64_t tiles = (n + 127) / 128;
 	const int smem = static_cast<int>(sizeof(Smem)) + 128;
@@ -380,16 +442,27 @@ static int fwd_common(const nrf_mlp_nerf_shape* shape, const void* packed, const
 	static const int cluster = [] { const char* e = getenv("NRF_NERF_CLUSTER"); return e && e[0] == '2' ? 2 : 1; }();
 	if (cluster == 2) {
 		const int blocks = static_cast<int>(std::min<int64_t>((tiles + 1) / 2 * 2, kNumSMs));
-		NRF_CUDA(cudaFuncSetAttribute(mlp_nerf_fwd_tc_kernel<TRAIN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-		mlp_nerf_fwd_tc_kernel<TRAIN, 2><<<blocks, kThreads, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed), x, n, out,
-			reinterpret_cast<uint8_t*>(saved));
+		NRF_CUDA(cudaFuncSetAttribute(mlp_nerf_fwd_tc_kernel<TRAIN, 2, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		mlp_nerf_fwd_tc_kernel<TRAIN, 2, RAW><<<blocks, kThreads, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed), x, n, out,
+			reinterpret_cast<uint8_t*>(saved), raw);
 	} else {
 		const int blocks = static_cast<int>(std::min<int64_t>(tiles, kNumSMs));
-		NRF_CUDA(cudaFuncSetAttribute(mlp_nerf_fwd_tc_kernel<TRAIN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-		mlp_nerf_fwd_tc_kernel<TRAIN, 1><<<blocks, kThreads, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed), x, n, out,
-			reinterpret_cast<uint8_t*>(saved));
+		NRF_CUDA(cudaFuncSetAttribute(mlp_nerf_fwd_tc_kernel<TRAIN, 1, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		mlp_nerf_fwd_tc_kernel<TRAIN, 1, RAW><<<blocks, kThreads, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed), x, n, out,
+			reinterpret_cast<uint8_t*>(saved), raw);
 	}
 	NRF_CHECK_LAUNCH("mlp_nerf_fwd_tc_kernel");
+	return NRF_OK;
+}
+
+static int make_raw(const float* dirs, int32_t samples_per_ray, const float* freqs_pts, int32_t n_freqs_pts, const float* freqs_views, int32_t n_freqs_views,
+	RawInput& raw)
+{
+	NRF_REQUIRE(freqs_pts && freqs_views && n_freqs_pts == 10 && n_freqs_views == 4, "the fused embedding is built for multires 10 (points) and 4 (directions)");
+	raw.dirs = dirs;
+	raw.samples_per_ray = samples_per_ray;
+	for (int i = 0; i < 10; i++) raw.fp[i] = freqs_pts[i];
+	for (int i = 0; i < 4; i++) raw.fv[i] = freqs_views[i];
 	return NRF_OK;
 }
 
@@ -432,13 +505,31 @@ int64_t nrf_mlp_nerf_saved_bytes(const nrf_mlp_nerf_shape* shape, int64_t n)
 
 int nrf_mlp_nerf_fwd(const nrf_mlp_nerf_shape* shape, const void* packed, const float* x, int64_t n, float* out, nrf_stream stream)
 {
-	return fwd_common<false>(shape, packed, x, n, out, nullptr, stream);
+	return fwd_common<false, false>(shape, packed, x, n, out, nullptr, RawInput{}, stream);
 }
 
 int nrf_mlp_nerf_fwd_train(const nrf_mlp_nerf_shape* shape, const void* packed_train, const float* x, int64_t n, float* out, void* saved,
                            nrf_stream stream)
 {
-	return fwd_common<true>(shape, packed_train, x, n, out, saved, stream);
+	return fwd_common<true, false>(shape, packed_train, x, n, out, saved, RawInput{}, stream);
+}
+
+int nrf_mlp_nerf_fwd_points(const nrf_mlp_nerf_shape* shape, const void* packed, const float* points, const float* dirs, int32_t samples_per_ray,
+                            const float* freqs_pts_host, int32_t n_freqs_pts, const float* freqs_views_host, int32_t n_freqs_views, int64_t n, float* out,
+                            nrf_stream stream)
+{
+	RawInput raw{};
+	if (int rc = make_raw(dirs, samples_per_ray, freqs_pts_host, n_freqs_pts, freqs_views_host, n_freqs_views, raw)) return rc;
+	return fwd_common<false, true>(shape, packed, points, n, out, nullptr, raw, stream);
+}
+
+int nrf_mlp_nerf_fwd_train_points(const nrf_mlp_nerf_shape* shape, const void* packed_train, const float* points, const float* dirs,
+                                  int32_t samples_per_ray, const float* freqs_pts_host, int32_t n_freqs_pts, const float* freqs_views_host,
+                                  int32_t n_freqs_views, int64_t n, float* out, void* saved, nrf_stream stream)
+{
+	RawInput raw{};
+	if (int rc = make_raw(dirs, samples_per_ray, freqs_pts_host, n_freqs_pts, freqs_views_host, n_freqs_views, raw)) return rc;
+	return fwd_common<true, true>(shape, packed_train, points, n, out, saved, raw, stream);
 }
 
 }

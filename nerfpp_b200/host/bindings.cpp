@@ -173,6 +173,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 	m.def("total_variation_loss", [](CuHashPipe& p) { return TotalVariationLoss(p.embed); });
 
 	m.def("classic_set_fused_training", [](ClassicPipe& p, bool on) { p.model->FusedTraining = on; });
+	m.def("classic_set_fused_embedding", [](ClassicPipe& p, bool on) { p.model->FusedEmbedding = on; });
 	Bind<CuHashPipe>(m, "CuHashPipe");
 	Bind<ClassicPipe>(m, "ClassicPipe");
 	m.def("make_cuhash", [](Tensor bbox, int n_levels, int n_feat, int log2_t, int base_res, int finest_res, int sh_degree, int num_layers,

@@ -95,5 +95,9 @@ public:
 	~EmbedderImpl() override = default;
 	int GetOutputDims() override { return OutputDims; }
 	std::pair<torch::Tensor, torch::Tensor> forward(torch::Tensor x) override;
+	// ---- B200 additions: what a kernel that evaluates the embedding itself needs to know
+	const std::vector<float>& GetFreqBands() const { return FreqBands; }
+	bool GetIncludeInput() const { return IncludeInput; }
+	int GetInputDims() const { return InputDims; }
 };
 TORCH_MODULE(Embedder);

@@ -85,9 +85,11 @@ Tensor NerfPack(const nrf_mlp_nerf_shape& s, const std::vector<Tensor>& params, 
 // NeRFImpl::forward with the backward LibTorch autograd would derive (src/NeRF.cpp:92-126), as three tcgen05 kernels:
 // nrf_mlp_nerf_fwd_train (stores every layer's input, bf16) and nrf_mlp_nerf_bwd (gradient chain + weight gradients).
 struct NerfTrainFunction : public torch::autograd::Function<NerfTrainFunction> {
-	static variable_list forward(AutogradContext* ctx, at::TensorList in)
+	static variable_list forward(AutogradContext* ctx, at::TensorList in, int64_t samples_per_ray, std::vector<double> freqs_pts,
+		std::vector<double> freqs_views)
 	{
-		// in = 24 parameters (FusedParams order), x [N, 90]; passed as ONE TensorList so that every entry is an autograd input
+		// in = 24 parameters (FusedParams order) + x [N, 90], or + points [N,3], dirs [R,3] when samples_per_ray > 0;
+		// passed as ONE TensorList so that every entry is an autograd input
 		const nrf_mlp_nerf_shape s{8, 256, 63, 27, 4, 1};
 		std::vector<Tensor> params(in.begin(), in.begin() + 24);
 		const Tensor flat = nrfhost::Dense(in[24].detach(), torch::kFloat32, "NeRF input");
@@ -95,6 +97,13 @@ struct NerfTrainFunction : public torch::autograd::Function<NerfTrainFunction> {
 		Tensor blob = NerfPack(s, params, true);
 		Tensor out = torch::empty({n, 4}, nrfhost::F32Like(flat));
 		Tensor saved = torch::empty({std::max<int64_t>(nrf_mlp_nerf_saved_bytes(&s, n), 0)}, blob.options());
+		if (samples_per_ray > 0) {
+			const Tensor dirs = nrfhost::Dense(in[25].detach(), torch::kFloat32, "NeRF view directions");
+			const std::vector<float> fp(freqs_pts.begin(), freqs_pts.end()), fv(freqs_views.begin(), freqs_views.end());
+			nrfhost::Check(nrf_mlp_nerf_fwd_train_points(&s, blob.data_ptr(), flat.data_ptr<float>(), dirs.data_ptr<float>(), int32_t(samples_per_ray),
+				fp.data(), int32_t(fp.size()), fv.data(), int32_t(fv.size()), n, out.data_ptr<float>(), saved.data_ptr(), nrfhost::Stream()),
+				"nrf_mlp_nerf_fwd_train_points");
+		} else
 		nrfhost::Check(nrf_mlp_nerf_fwd_train(&s, blob.data_ptr(), flat.data_ptr<float>(), n, out.data_ptr<float>(), saved.data_ptr(), nrfhost::Stream()),
 			"nrf_mlp_nerf_fwd_train");
 		ctx->save_for_backward({blob, saved});
@@ -102,6 +111,7 @@ struct NerfTrainFunction : public torch::autograd::Function<NerfTrainFunction> {
 		for (const Tensor& t : params) shapes.push_back(t.sizes().vec());
 		ctx->saved_data["n"] = n;
 		ctx->saved_data["shapes"] = shapes;
+		ctx->saved_data["extra_inputs"] = int64_t(in.size()) - 24;
 		return {out};
 	}
 	static variable_list backward(AutogradContext* ctx, variable_list grad_out)
@@ -120,7 +130,8 @@ struct NerfTrainFunction : public torch::autograd::Function<NerfTrainFunction> {
 				"nrf_mlp_nerf_bwd");
 		}
 		variable_list ret(grads.begin(), grads.end());
-		ret.push_back(Tensor());        // x: the positional embedder has no parameters (src/NeRF.cpp:4-39), no gradient is produced
+		// x (or points, dirs): the positional embedder has no parameters (src/NeRF.cpp:4-39), no gradient is produced; then the 3 plain arguments
+		for (int64_t i = 0; i < ctx->saved_data["extra_inputs"].toInt() + 3; i++) ret.push_back(Tensor());
 		return ret;
 	}
 };
@@ -152,7 +163,41 @@ Tensor NeRFImpl::ForwardFusedTrain(const Tensor& x)
 	std::vector<int64_t> shape = x.sizes().vec();
 	in.push_back(x.reshape({-1, int64_t(InputCh + InputChViews)}));
 	shape.back() = 4;
-	return NerfTrainFunction::apply(at::TensorList(in))[0].view(shape);
+	return NerfTrainFunction::apply(at::TensorList(in), int64_t(0), std::vector<double>{}, std::vector<double>{})[0].view(shape);
+}
+
+bool NeRFImpl::FusedEmbeddingShape(EmbedderImpl& e_pts, EmbedderImpl& e_dirs) const
+{
+	return FusedEmbedding && FusedShape() && e_pts.GetIncludeInput() && e_dirs.GetIncludeInput() && e_pts.GetInputDims() == 3 && e_dirs.GetInputDims() == 3 &&
+	       e_pts.GetFreqBands().size() == 10 && e_dirs.GetFreqBands().size() == 4 && e_pts.GetOutputDims() == InputCh && e_dirs.GetOutputDims() == InputChViews;
+}
+
+Tensor NeRFImpl::ForwardPoints(const Tensor& points, const Tensor& view_dirs, int samples_per_ray, const std::vector<float>& freqs_pts,
+	const std::vector<float>& freqs_views)
+{
+	const Tensor pts = nrfhost::Dense(points.detach(), torch::kFloat32, "NeRF sample positions"), dirs = nrfhost::Dense(view_dirs.detach(), torch::kFloat32, "NeRF view directions");
+	TORCH_CHECK(pts.dim() == 2 && pts.size(1) == 3 && dirs.dim() == 2 && dirs.size(1) == 3 && pts.size(0) == dirs.size(0) * samples_per_ray,
+		"NeRF::ForwardPoints: points [R*S,3], view_dirs [R,3]");
+	if (torch::GradMode::is_enabled() && FusedTraining) {
+		variable_list in = FusedParams();
+		in.push_back(pts);
+		in.push_back(dirs);
+		return NerfTrainFunction::apply(at::TensorList(in), int64_t(samples_per_ray), std::vector<double>(freqs_pts.begin(), freqs_pts.end()),
+			std::vector<double>(freqs_views.begin(), freqs_views.end()))[0];
+	}
+	torch::NoGradGuard no_grad;
+	const nrf_mlp_nerf_shape s{D, W, InputCh, InputChViews, *Skips.begin(), 1};
+	const std::vector<Tensor> params = FusedParams();
+	std::vector<std::pair<const void*, uint32_t>> key;
+	for (const Tensor& t : params) key.emplace_back(t.data_ptr(), t._version());
+	if (!PackedBlob.defined() || key != PackedKey) {
+		PackedBlob = NerfPack(s, params, false);
+		PackedKey = key;
+	}
+	Tensor out = torch::empty({pts.size(0), 4}, nrfhost::F32Like(pts));
+	nrfhost::Check(nrf_mlp_nerf_fwd_points(&s, PackedBlob.data_ptr(), pts.data_ptr<float>(), dirs.data_ptr<float>(), samples_per_ray, freqs_pts.data(),
+		int32_t(freqs_pts.size()), freqs_views.data(), int32_t(freqs_views.size()), pts.size(0), out.data_ptr<float>(), nrfhost::Stream()), "nrf_mlp_nerf_fwd_points");
+	return out;
 }
 
 Tensor NeRFImpl::forward(Tensor x)

@@ -72,6 +72,13 @@ struct NeRFImpl : public BaseNeRFImpl {
 	torch::Tensor ForwardFusedTrain(const torch::Tensor& x);   ///< the same with the fused backward attached (parameter gradients)
 	std::vector<torch::Tensor> FusedParams();  ///< pts_linears w,b x8, feature w,b, alpha w,b, views w,b, rgb w,b
 	bool FusedTraining = true;                 ///< false: training goes through torch::linear + LibTorch autograd (fp32 cuBLAS)
+	bool FusedEmbedding = true;                ///< false: RunNetwork embeds and concatenates with separate kernels (the A/B baseline)
+	/// RunNetwork with the positional embeddings evaluated inside the MLP kernel (nrf_mlp_nerf_fwd[_train]_points): points [N,3],
+	/// view_dirs [R,3], N = R * samples_per_ray -> [N,4].  Differentiable w.r.t. the parameters when autograd is recording.
+	torch::Tensor ForwardPoints(const torch::Tensor& points, const torch::Tensor& view_dirs, int samples_per_ray,
+		const std::vector<float>& freqs_pts, const std::vector<float>& freqs_views);
+	/// true when ForwardPoints covers this model with these two embedders
+	bool FusedEmbeddingShape(class EmbedderImpl& e_pts, class EmbedderImpl& e_dirs) const;
 private:
 	torch::Tensor PackedBlob;
 	std::vector<std::pair<const void*, uint32_t>> PackedKey;

@@ -6,7 +6,9 @@
 //   * SamplePDF + sort(cat) is ONE kernel;
 //   * for <CuHashEmbedder, CuSHEncoder, NeRFSmall> RunNetwork is hash-encode -> fused MLP with the SH basis evaluated once
 //     per ray and the keep mask applied in the MLP epilogue; the coarse pass, which never receives a gradient
-//     (SURVEY §9-Q3), runs without an autograd graph.
+//     (SURVEY §9-Q3), runs without an autograd graph;
+//   * for <Embedder, Embedder, NeRF> at the BASELINE shape RunNetwork is ONE kernel: the positional embeddings of points and
+//     directions are evaluated in the fused MLP's input stage (directions per ray), in inference and in training.
 // Everything else (generic embedders / models, NDC, perturb > 0) follows the reference's ATen formulation.
 #pragma once
 #include <type_traits>
@@ -57,6 +59,9 @@ protected:
 	static constexpr bool kFusedHashPath =
 		std::is_same_v<TEmbedder, CuHashEmbedder> && std::is_same_v<TEmbedDirs, CuSHEncoder> && std::is_same_v<TNeRF, NeRFSmall>;
 
+	static constexpr bool kFusedClassicPath =
+		std::is_same_v<TEmbedder, ::Embedder> && std::is_same_v<TEmbedDirs, ::Embedder> && std::is_same_v<TNeRF, ::NeRF>;
+
 	/// embed -> (dir embed, cat) -> model -> sigma := 0 outside the box (src/NeRFRenderer.h:164-194)
 	virtual torch::Tensor RunNetwork(torch::Tensor inputs, torch::Tensor view_dirs, TNeRF fn, TEmbedder embed_fn, TEmbedDirs embeddirs_fn)
 	{
@@ -70,6 +75,16 @@ protected:
 				// SH once per RAY (the reference expands the directions per sample, :179-181)
 				torch::Tensor ray_sh = embeddirs_fn->forward(view_dirs.detach()).first;
 				out = nrfhost::HashNeRFNetwork(*embed_fn, *fn, flat, ray_sh, int(shape[1]));
+				shape.back() = out.size(-1);
+				return out.view(shape);
+			}
+		}
+		if constexpr (kFusedClassicPath) {
+			// positional embeddings evaluated inside the MLP kernel's input stage, directions per RAY: no [N,63] / [N,27] / [N,90] arrays.
+			// When autograd records and the fused training kernels are switched off, or the shape is not the built one, fall through.
+			if (dirs && inputs.dim() == 3 && flat.is_cuda() && fn->FusedEmbeddingShape(*embed_fn, *embeddirs_fn) &&
+				(!torch::GradMode::is_enabled() || fn->FusedTraining)) {
+				out = fn->ForwardPoints(flat, view_dirs, int(shape[1]), embed_fn->GetFreqBands(), embeddirs_fn->GetFreqBands());
 				shape.back() = out.size(-1);
 				return out.view(shape);
 			}

@@ -395,6 +395,24 @@ def mlp_nerf_fwd_train(packed_train: torch.Tensor, x: torch.Tensor, shape=None):
     return out, saved
 
 
+def mlp_nerf_fwd_points(packed: torch.Tensor, points: torch.Tensor, dirs: torch.Tensor, samples_per_ray: int, freqs_pts, freqs_views, train: bool = False,
+                        shape=None):
+    """RunNetwork for the classic model with the positional embeddings evaluated inside the MLP kernel: points [N,3], dirs [R,3]
+    (N = R * samples_per_ray) -> out [N,4] (train=True: (out, saved) as mlp_nerf_fwd_train)."""
+    shape = shape or mlp_nerf_shape()
+    n = points.shape[0]
+    out = torch.empty((n, 4), dtype=f32, device=points.device)
+    fp, fv = cabi.host_floats(freqs_pts), cabi.host_floats(freqs_views)
+    if not train:
+        _run("mlp_nerf_fwd", lambda: lib().nrf_mlp_nerf_fwd_points(C.byref(shape), ptr(packed), ptr(points, f32), ptr(dirs, f32), samples_per_ray, fp, len(fp), fv,
+                                                                   len(fv), n, ptr(out, f32), stream()))
+        return out
+    saved = torch.empty(max(lib().nrf_mlp_nerf_saved_bytes(C.byref(shape), n), 0), dtype=u8, device=points.device)
+    _run("mlp_nerf_fwd_train", lambda: lib().nrf_mlp_nerf_fwd_train_points(C.byref(shape), ptr(packed), ptr(points, f32), ptr(dirs, f32), samples_per_ray, fp,
+                                                                           len(fp), fv, len(fv), n, ptr(out, f32), ptr(saved), stream()))
+    return out, saved
+
+
 def mlp_nerf_bwd(packed_train: torch.Tensor, saved: torch.Tensor, grad_out: torch.Tensor, grads: dict, shape=None, workspace: torch.Tensor | None = None):
     """Backward of NeRFImpl::forward: grad_out [N,4] fp32 -> grads (dict with the parameter names of `mlp_nerf_pack`, fp32 CUDA
     tensors of the parameters' shapes) += d loss / d parameter."""

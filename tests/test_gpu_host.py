@@ -334,3 +334,40 @@ def test_checkpoints_are_interchangeable_with_the_reference(host, ref_cuda, kind
             if k == "depth":
                 err = err[solid]
             assert err.median().item() < 2e-3 and err.max().item() < 3e-2, (kind, k, err.median().item(), err.max().item())
+
+
+def test_classic_run_network_fuses_the_embeddings(host):
+    """RunNetwork for <Embedder, Embedder, NeRF> (src/NeRFRenderer.h:164-194): with the positional embeddings evaluated inside the MLP
+    kernel (default) the raw outputs, rendered maps and parameter gradients equal those of embed + expand + cat + forward with separate
+    kernels (FusedEmbedding = false): same operands, so inference is bit-identical; gradients differ by fp32 atomic order only."""
+    pipes = []
+    for fused in (True, False):
+        host.manual_seed(13)
+        torch.manual_seed(13)
+        p = host.make_classic(torch.tensor(BBOX).cuda(), 10, 4, 8, 256, True)
+        p.init_model()
+        host.classic_set_fused_embedding(p, fused)
+        pipes.append(p)
+    a, b = pipes
+    _positive_density(a, b)
+    with torch.no_grad():
+        for x, y in zip(a.model_params(), b.model_params()):
+            if x.dim() == 2:
+                x.mul_(12.0)
+                y.mul_(12.0)
+    g = torch.Generator().manual_seed(6)
+    pts = (torch.rand(37, 50, 3, generator=g) * 3 - 1.5).cuda()
+    dirs = torch.nn.functional.normalize(torch.randn(37, 3, generator=g), dim=-1).cuda()
+    with torch.no_grad():
+        ra, rb = a.run_network(pts, dirs), b.run_network(pts, dirs)
+        assert ra.shape == (37, 50, 4) and torch.equal(ra, rb)
+        o, d = _rays(300, seed=4)
+        ia, ib = a.render(o, d, 64, 128, 4096, False, True), b.render(o, d, 64, 128, 4096, False, True)
+        for k in ("rgb", "acc", "depth"):
+            assert torch.equal(ia[k], ib[k]), k
+    tgt = torch.rand(300, 3, generator=g).cuda()
+    a.train_steps(o, d, tgt, 1, 64, 128, 4096, True, 0.0, 250)
+    b.train_steps(o, d, tgt, 1, 64, 128, 4096, True, 0.0, 250)
+    for name, x, y in zip(a.model_param_names(), a.model_params(), b.model_params()):
+        assert float(y.grad.abs().max()) > 0, name
+        assert torch.allclose(x.grad, y.grad, rtol=1e-3, atol=1e-6 * float(y.grad.abs().max())), name

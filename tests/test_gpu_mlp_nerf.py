@@ -260,3 +260,30 @@ def test_full_size_training_batch_backward_properties():
         ops.mlp_nerf_bwd(packed, s2, g1[lo:hi].contiguous(), parts)      # += into the same tensors
     for k in p:
         assert float((parts[k] - ga[k]).abs().max()) <= 1e-4 * float(ga[k].abs().max()) + 1e-12, k   # fp32 summation order only
+
+
+# ---------------------------------------------------------------------------------------------------------------- fused embedding
+@pytest.mark.parametrize("n_rays,s", [(1, 1), (3, 43), (100, 192), (257, 64)])
+def test_points_entry_equals_embed_concat_forward_bit_for_bit(n_rays, s):
+    """nrf_mlp_nerf_fwd_points / _fwd_train_points == nrf_posenc_fwd (points) + nrf_posenc_fwd (directions expanded per sample,
+    src/NeRFRenderer.h:179-181) + cat (:182) + nrf_mlp_nerf_fwd / _fwd_train: the same operands, so the same bits; and the training
+    records they leave give the same gradients."""
+    from nerfpp_b200 import ops
+    g = torch.Generator().manual_seed(n_rays * 1000 + s)
+    n = n_rays * s
+    pts = (torch.rand(n, 3, generator=g) * 3 - 1.5).cuda()
+    dirs = torch.nn.functional.normalize(torch.randn(n_rays, 3, generator=g), dim=-1).cuda()
+    fp, fv = O.posenc_freqs(10), O.posenc_freqs(4)
+    x = torch.cat([ops.posenc(pts, fp), ops.posenc(dirs.repeat_interleave(s, 0).contiguous(), fv)], -1).contiguous()
+    p = _params(seed=s)
+    packed, packed_t = ops.mlp_nerf_pack(p), ops.mlp_nerf_pack(p, train=True)
+    assert torch.equal(ops.mlp_nerf_fwd_points(packed, pts, dirs, s, fp, fv), ops.mlp_nerf_fwd(packed, x))
+    out_a, saved_a = ops.mlp_nerf_fwd_train(packed_t, x)
+    out_b, saved_b = ops.mlp_nerf_fwd_points(packed_t, pts, dirs, s, fp, fv, train=True)
+    assert torch.equal(out_a, out_b)
+    tiles = (n + 127) // 128
+    assert torch.equal(saved_a[:tiles * 684032], saved_b[:tiles * 684032])          # every record, bit for bit (the spare record is scratch)
+    # fused embedding vs the oracle's embedding (restatement of EmbedderImpl::forward): same values up to sinf/cosf rounding
+    ref = O.nerf_forward(torch.cat([O.posenc(pts.cpu(), 10), O.posenc(dirs.cpu().repeat_interleave(s, 0), 4)], -1).double().cuda(),
+                         {k: v.double() for k, v in p.items()})
+    assert float((ops.mlp_nerf_fwd_points(packed, pts, dirs, s, fp, fv).double() - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
