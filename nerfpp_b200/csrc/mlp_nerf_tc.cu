@@ -25,6 +25,7 @@ namespace nerf_tc {
 using namespace tc;
 
 constexpr int kThreads = 32 * 6;
+constexpr int kStagePitch = 98;      // 16-bit elements per staged row (96 used): 49 words, odd, so the per-row accesses are conflict-free
 
 // padded logical weight Wp_l(n, k) in the kernel's A-operand order
 __device__ __forceinline__ float wp(const Weights& p, int l, int n, int k)
@@ -82,6 +83,7 @@ __constant__ FwdStageTable c_fwd_table = make_fwd_table();
 struct __align__(128) Smem {
 	uint8_t ring[kRing][kStageBytes];
 	float bias[kBiasFloats];
+	uint16_t stage[128 * kStagePitch];      // RAW input mode: one row of 64 + 32 embedding channels per thread (25 KB)
 	uint64_t full[kRing], empty[kRing];
 	uint64_t a_ready, d_ready;
 	uint32_t tmem_base;
@@ -182,25 +184,29 @@ struct RawInput {
 	float fp[10], fv[4];     // frequency bands of the two embedders
 };
 
-// embedding channel k (compile-time) of a 3-vector: x(3), then per band sin(3), cos(3); zero past `dims`
-template <int K, int NB>
-__device__ __forceinline__ float posenc_channel(const float (&p)[3], const float (&f)[NB])
+
+// x(3), then per band sin(3), cos(3) of one 3-vector, rounded to the operand type and written to this thread's staging row.  The band loop
+// is NOT unrolled on purpose: 84 inlined sinf / cosf bodies per thread (~5 000 SASS instructions) pushed the kernel out of the instruction
+// cache and cost more than the whole MLP tile.
+template <bool BF16>
+__device__ __forceinline__ void posenc_stage(const float (&p)[3], const float* __restrict__ f, int nb, uint16_t* __restrict__ row)
 {
-	if constexpr (K < 3) {
-		return p[K];
-	} else if constexpr (K >= 3 + 6 * NB) {
-		return 0.f;
-	} else {
-		constexpr int c = K - 3, band = c / 6, rem = c % 6;
-		const float arg = __fmul_rn(p[rem % 3], f[band]);
-		return rem < 3 ? sinf(arg) : cosf(arg);
+	auto put = [&](int k, float v) {
+		if (BF16) { const __nv_bfloat16 h = __float2bfloat16_rn(v); row[k] = *reinterpret_cast<const uint16_t*>(&h); }
+		else { const __half h = __float2half_rn(v); row[k] = *reinterpret_cast<const uint16_t*>(&h); }
+	};
+#pragma unroll
+	for (int c = 0; c < 3; c++) put(c, p[c]);
+#pragma unroll 1
+	for (int b = 0; b < nb; b++) {
+		const float fb = f[b];
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			const float arg = __fmul_rn(p[c], fb);
+			put(3 + 6 * b + c, sinf(arg));
+			put(3 + 6 * b + 3 + c, cosf(arg));
+		}
 	}
-}
-template <int K0, int NB, bool BF16, int... I>
-__device__ __forceinline__ void posenc_pack16(const float (&p)[3], const float (&f)[NB], uint32_t (&a16)[16], std::integer_sequence<int, I...>)
-{
-	((a16[I] = BF16 ? pack_bf16(posenc_channel<K0 + 2 * I, NB>(p, f), posenc_channel<K0 + 2 * I + 1, NB>(p, f))
-	                : pack_f16(posenc_channel<K0 + 2 * I, NB>(p, f), posenc_channel<K0 + 2 * I + 1, NB>(p, f))), ...);
 }
 
 template <bool TRAIN, int CL, bool RAW>
@@ -304,32 +310,32 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kThreads, 1) mlp_ne
 			uint8_t* const rec = TRAIN ? saved + (tile < n_tiles ? tile : n_tiles) * kSaveTile : nullptr;
 			// ---- inputs: 63 point channels (+1 zero) and 27 view channels (+5 zero) as fp16 pairs into their TMEM columns
 			if (RAW) {
-				float p[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f};
+				uint16_t* srow = sm.stage + row * kStagePitch;
+				uint32_t* srow32 = reinterpret_cast<uint32_t*>(srow);
 				if (ok) {
+					float p[3], d[3];
 					const int64_t ray = r / raw.samples_per_ray;
 #pragma unroll
 					for (int c = 0; c < 3; c++) { p[c] = __ldg(x + r * 3 + c); d[c] = __ldg(raw.dirs + ray * 3 + c); }
+					posenc_stage<TRAIN>(p, raw.fp, 10, srow);
+					srow[63] = 0;
+					posenc_stage<TRAIN>(d, raw.fv, 4, srow + 64);
+#pragma unroll
+					for (int k = 27; k < 32; k++) srow[64 + k] = 0;
+				} else {
+#pragma unroll
+					for (int i = 0; i < 48; i++) srow32[i] = 0u;
 				}
 				uint32_t a16[16];
-				posenc_pack16<0, 10, TRAIN>(p, raw.fp, a16, std::make_integer_sequence<int, 16>{});
-				if (!ok) {
 #pragma unroll
-					for (int i = 0; i < 16; i++) a16[i] = 0u;          // cos(0) = 1 would otherwise leak into the padding rows
-				}
-				tmem_st16(t_lane + kColPts, a16);
-				if (TRAIN) save_chunks(rec + kSavePts + chunk_offset(64, row, 0), 0, a16);
-				posenc_pack16<32, 10, TRAIN>(p, raw.fp, a16, std::make_integer_sequence<int, 16>{});
-				if (!ok) {
+				for (int h = 0; h < 2; h++) {
 #pragma unroll
-					for (int i = 0; i < 16; i++) a16[i] = 0u;
+					for (int i = 0; i < 16; i++) a16[i] = srow32[16 * h + i];
+					tmem_st16(t_lane + kColPts + 16 * h, a16);
+					if (TRAIN) save_chunks(rec + kSavePts + chunk_offset(64, row, 0), 4 * h, a16);
 				}
-				tmem_st16(t_lane + kColPts + 16, a16);
-				if (TRAIN) save_chunks(rec + kSavePts + chunk_offset(64, row, 0), 4, a16);
-				posenc_pack16<0, 4, TRAIN>(d, raw.fv, a16, std::make_integer_sequence<int, 16>{});
-				if (!ok) {
 #pragma unroll
-					for (int i = 0; i < 16; i++) a16[i] = 0u;
-				}
+				for (int i = 0; i < 16; i++) a16[i] = srow32[32 + i];
 				tmem_st16(t_lane + kColViews, a16);
 				if (TRAIN) save_chunks(rec + kSaveViews + chunk_offset(32, row, 0), 0, a16);
 			} else {

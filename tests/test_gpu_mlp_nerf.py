@@ -282,7 +282,14 @@ def test_points_entry_equals_embed_concat_forward_bit_for_bit(n_rays, s):
     out_b, saved_b = ops.mlp_nerf_fwd_points(packed_t, pts, dirs, s, fp, fv, train=True)
     assert torch.equal(out_a, out_b)
     tiles = (n + 127) // 128
-    assert torch.equal(saved_a[:tiles * 684032], saved_b[:tiles * 684032])          # every record, bit for bit (the spare record is scratch)
+    act = 647168                     # activation regions of a record (kSaveBits); the mask slots behind them are only partly written (hv: 16 of 32 B)
+    ra, rb = saved_a[:tiles * 684032].view(tiles, 684032), saved_b[:tiles * 684032].view(tiles, 684032)
+    assert torch.equal(ra[:, :act], rb[:, :act])                                       # every stored layer input, bit for bit
+    gout = (torch.randn(n, 4, generator=g) * 1e-3).cuda()
+    ga = ops.mlp_nerf_bwd(packed_t, saved_a, gout, {k: torch.zeros_like(v) for k, v in p.items()})
+    gb = ops.mlp_nerf_bwd(packed_t, saved_b, gout, {k: torch.zeros_like(v) for k, v in p.items()})
+    for k in p:
+        assert torch.allclose(ga[k], gb[k], rtol=1e-4, atol=1e-6 * float(ga[k].abs().max()) + 1e-12), k      # fp32 atomic order only
     # fused embedding vs the oracle's embedding (restatement of EmbedderImpl::forward): same values up to sinf/cosf rounding
     ref = O.nerf_forward(torch.cat([O.posenc(pts.cpu(), 10), O.posenc(dirs.cpu().repeat_interleave(s, 0), 4)], -1).double().cuda(),
                          {k: v.double() for k, v in p.items()})
