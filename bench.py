@@ -395,7 +395,7 @@ def main() -> None:
     frames = 3
 
     def render_frame():
-        maps = model.render_image(H, W, K, c2w, chunk=32768, row_begin=r0, row_end=r1, n_importance=64)
+        maps = model.render_image(H, W, K, c2w, chunk=131072, row_begin=r0, row_end=r1, n_importance=64)
         return parallel.gather_rows(maps["rgb"], H * W, rank, world, unit=W) if world > 1 else maps["rgb"]
 
     render_frame()
@@ -410,7 +410,7 @@ def main() -> None:
     render = {"metric": "render_msamples_per_s", "value": H * W * (N_SAMPLES + N_SAMPLES + 64) / (ms_render * 1e3), "unit": "Msamples/s",
               "frames_per_s": 1e3 / ms_render, "ms_per_frame": ms_render, "frames": frames,
               "config": "1920x1080 frame, image rows sharded over the GPUs, 64 coarse + 64 importance samples (192 network evaluations/ray), "
-                        "32768-ray chunks, rgb gathered on rank 0; untrained (random-init) model"}
+                        "131072-ray chunks, rgb gathered on rank 0; untrained (random-init) model"}
 
     if rank != 0:
         return
