@@ -282,6 +282,13 @@ int nrf_get_rays(int32_t h, int32_t w, const float* K_host, const float* c2w_hos
 int nrf_rays_prepare(const float* rays_o, const float* rays_d, int64_t n_rays, const float* bbox_host /*[6]*/,
                      float near_plane, int32_t use_viewdirs, float* ray_batch, nrf_stream stream);
 
+/* nrf_rays_prepare (with viewdirs) + nrf_z_sample + nrf_sh_encode_fwd(viewdirs) in ONE launch — the head of every RenderRays call
+ * (src/NeRFRenderer.h:549-583, :393-402, CuSHEncoder per ray) — bit-identical to the three separate entries.  ray_batch [R,11],
+ * z [R,S], ray_sh [R, sh_degree^2] (nullable), zero_scalar (nullable): one float set to 0 (the training step's loss accumulator). */
+int nrf_ray_setup(const float* rays_o, const float* rays_d, int64_t n_rays, const float* bbox_host /*[6]*/, float near_plane,
+                  const float* t_vals, int32_t n_samples, int32_t lin_disp, int32_t sh_degree, float* ray_batch, float* z, float* ray_sh,
+                  float* zero_scalar, nrf_stream stream);
+
 /* z = near*(1-t)+far*t (or the lin_disp variant), src/NeRFRenderer.h:393-402.  t_vals [S] device. */
 int nrf_z_sample(const float* ray_batch, int32_t ray_stride, const float* t_vals, int64_t n_rays, int32_t n_samples,
                  int32_t lin_disp, float* z, nrf_stream stream);

@@ -5,6 +5,7 @@
 // Arithmetic keeps ATen's un-fused order (__fmul_rn / __fadd_rn, no FMA contraction) so that z values, and through
 // them the sample points and hash cells, are the same floats the reference produces.
 #include "common.cuh"
+#include "sh_basis.cuh"
 
 namespace nrf {
 
@@ -35,16 +36,12 @@ struct Box {
 	float lo[3], hi[3];
 };
 
-__global__ void __launch_bounds__(256) rays_prepare_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-	int64_t n, Box box, float near_plane, int use_viewdirs, float* __restrict__ ray_batch)
+// IntersectWithAABB (src/RayUtils.h:87-126) and viewdirs = rays_d / norm(rays_d) (src/NeRFRenderer.h:559) for one ray
+__device__ __forceinline__ void prepare_ray(const float (&o)[3], const float (&d)[3], const Box& box, float near_plane, float& tnear, float& tfar,
+	float (&vd)[3])
 {
-	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	float o[3], d[3];
-#pragma unroll
-	for (int k = 0; k < 3; k++) { o[k] = rays_o[i * 3 + k]; d[k] = rays_d[i * 3 + k]; }
-	// IntersectWithAABB (src/RayUtils.h:87-126)
-	float tnear = -INFINITY, tfar = INFINITY;
+	tnear = -INFINITY;
+	tfar = INFINITY;
 #pragma unroll
 	for (int k = 0; k < 3; k++) {
 		const float frac = __fdiv_rn(1.0f, __fadd_rn(d[k], 1e-6f));
@@ -55,6 +52,20 @@ __global__ void __launch_bounds__(256) rays_prepare_kernel(const float* __restri
 	}
 	tnear = fmaxf(tnear, near_plane);
 	tfar = fmaxf(tfar, __fadd_rn(tnear, 1e-6f));
+	const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+#pragma unroll
+	for (int k = 0; k < 3; k++) vd[k] = __fdiv_rn(d[k], nrm);
+}
+
+__global__ void __launch_bounds__(256) rays_prepare_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+	int64_t n, Box box, float near_plane, int use_viewdirs, float* __restrict__ ray_batch)
+{
+	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float o[3], d[3], vd[3], tnear, tfar;
+#pragma unroll
+	for (int k = 0; k < 3; k++) { o[k] = rays_o[i * 3 + k]; d[k] = rays_d[i * 3 + k]; }
+	prepare_ray(o, d, box, near_plane, tnear, tfar, vd);
 	const int stride = use_viewdirs ? 11 : 8;
 	float* out = ray_batch + i * stride;
 #pragma unroll
@@ -62,14 +73,20 @@ __global__ void __launch_bounds__(256) rays_prepare_kernel(const float* __restri
 	out[6] = tnear;
 	out[7] = tfar;
 	if (use_viewdirs) {
-		// viewdirs = rays_d / norm(rays_d) (src/NeRFRenderer.h:559)
-		const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
 #pragma unroll
-		for (int k = 0; k < 3; k++) out[8 + k] = __fdiv_rn(d[k], nrm);
+		for (int k = 0; k < 3; k++) out[8 + k] = vd[k];
 	}
 }
 
 __device__ __forceinline__ float safe_inv(float x) { return fabsf(x) < 1e-8f ? __fdiv_rn(1.0f, 1e-8f) : __fdiv_rn(1.0f, x); }
+
+// z = near (1 - t) + far t, or its lin_disp form (src/NeRFRenderer.h:397, :400-401)
+__device__ __forceinline__ float z_value(float nr, float fr, float t, int lin_disp)
+{
+	const float omt = __fsub_rn(1.f, t);
+	if (!lin_disp) return __fadd_rn(__fmul_rn(nr, omt), __fmul_rn(fr, t));
+	return safe_inv(__fadd_rn(__fmul_rn(safe_inv(nr), omt), __fmul_rn(safe_inv(fr), t)));
+}
 
 __global__ void __launch_bounds__(256) z_sample_kernel(const float* __restrict__ ray_batch, int ray_stride, const float* __restrict__ t_vals,
 	int64_t R, int S, int lin_disp, float* __restrict__ z)
@@ -78,13 +95,41 @@ __global__ void __launch_bounds__(256) z_sample_kernel(const float* __restrict__
 	if (e >= R * S) return;
 	const int64_t ray = e / S;
 	const int s = static_cast<int>(e % S);
-	const float nr = ray_batch[ray * ray_stride + 6], fr = ray_batch[ray * ray_stride + 7];
-	const float t = t_vals[s];
-	const float omt = __fsub_rn(1.f, t);
-	float v;
-	if (!lin_disp) v = __fadd_rn(__fmul_rn(nr, omt), __fmul_rn(fr, t));                                   // src/NeRFRenderer.h:397
-	else v = safe_inv(__fadd_rn(__fmul_rn(safe_inv(nr), omt), __fmul_rn(safe_inv(fr), t)));              // :400-401
-	z[e] = v;
+	z[e] = z_value(ray_batch[ray * ray_stride + 6], ray_batch[ray * ray_stride + 7], t_vals[s], lin_disp);
+}
+
+// Render prologue + coarse depths + per-ray SH table in ONE launch (the head of every RenderRays call: three kernels and, in a training
+// step, the memset of the loss accumulator).  One thread per (ray, sample): each recomputes its ray's slab test (a dozen flops, the same
+// operations in the same order, hence the same near / far) and writes its z; the thread of sample 0 also writes the ray's [o, d, near,
+// far, viewdirs] row and its SH basis.  Bit-identical to nrf_rays_prepare + nrf_z_sample + nrf_sh_encode_fwd.
+template <int DEG>
+__global__ void __launch_bounds__(256) ray_setup_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, int64_t R, Box box,
+	float near_plane, const float* __restrict__ t_vals, int S, int lin_disp, float* __restrict__ ray_batch, float* __restrict__ z,
+	float* __restrict__ ray_sh, float* __restrict__ zero_scalar)
+{
+	const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (e == 0 && zero_scalar) *zero_scalar = 0.f;
+	if (e >= R * S) return;
+	const int64_t ray = e / S;
+	const int s = static_cast<int>(e % S);
+	float o[3], d[3], vd[3], tnear, tfar;
+#pragma unroll
+	for (int k = 0; k < 3; k++) { o[k] = rays_o[ray * 3 + k]; d[k] = rays_d[ray * 3 + k]; }
+	prepare_ray(o, d, box, near_plane, tnear, tfar, vd);
+	z[e] = z_value(tnear, tfar, t_vals[s], lin_disp);
+	if (s == 0) {
+		float* out = ray_batch + ray * 11;
+#pragma unroll
+		for (int k = 0; k < 3; k++) { out[k] = o[k]; out[3 + k] = d[k]; out[8 + k] = vd[k]; }
+		out[6] = tnear;
+		out[7] = tfar;
+		if (ray_sh) {
+			float b[DEG * DEG];
+			sh_basis<DEG>(vd[0], vd[1], vd[2], b);
+#pragma unroll
+			for (int k = 0; k < DEG * DEG; k++) ray_sh[ray * (DEG * DEG) + k] = b[k];
+		}
+	}
 }
 
 __global__ void __launch_bounds__(256) sample_points_kernel(const float* __restrict__ ray_batch, int ray_stride, const float* __restrict__ z,
@@ -184,6 +229,27 @@ int nrf_rays_prepare(const float* rays_o, const float* rays_d, int64_t n_rays, c
 	for (int k = 0; k < 3; k++) { b.lo[k] = bbox_host[k]; b.hi[k] = bbox_host[3 + k]; }
 	rays_prepare_kernel<<<static_cast<unsigned>((n_rays + 255) / 256), 256, 0, as_stream(stream)>>>(rays_o, rays_d, n_rays, b, near_plane, use_viewdirs, ray_batch);
 	NRF_CHECK_LAUNCH("rays_prepare_kernel");
+	return NRF_OK;
+}
+
+int nrf_ray_setup(const float* rays_o, const float* rays_d, int64_t n_rays, const float* bbox_host, float near_plane, const float* t_vals,
+	int32_t n_samples, int32_t lin_disp, int32_t sh_degree, float* ray_batch, float* z, float* ray_sh, float* zero_scalar, nrf_stream stream)
+{
+	NRF_REQUIRE(n_rays >= 0 && n_samples >= 1, "bad sizes");
+	NRF_REQUIRE(!ray_sh || (sh_degree >= 1 && sh_degree <= 8), "degree must be 1..8");
+	if (n_rays == 0) return NRF_OK;
+	NRF_REQUIRE(rays_o && rays_d && bbox_host && t_vals && ray_batch && z, "null pointer");
+	Box b;
+	for (int k = 0; k < 3; k++) { b.lo[k] = bbox_host[k]; b.hi[k] = bbox_host[3 + k]; }
+	const int64_t n = n_rays * n_samples;
+	const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+	cudaStream_t s = as_stream(stream);
+#define NRF_RS(D) case D: ray_setup_kernel<D><<<blocks, 256, 0, s>>>(rays_o, rays_d, n_rays, b, near_plane, t_vals, n_samples, lin_disp, ray_batch, z, ray_sh, zero_scalar); break
+	switch (ray_sh ? sh_degree : 1) {
+		NRF_RS(1); NRF_RS(2); NRF_RS(3); NRF_RS(4); NRF_RS(5); NRF_RS(6); NRF_RS(7); NRF_RS(8);
+	}
+#undef NRF_RS
+	NRF_CHECK_LAUNCH("ray_setup_kernel");
 	return NRF_OK;
 }
 

@@ -77,9 +77,9 @@ int nrf_render_rays_fwd(const nrf_render_config* cfg, const nrf_hash_grid* grid,
 	float* raw = reinterpret_cast<float*>(base + w.raw);
 
 	int rc;
-	if ((rc = nrf_rays_prepare(rays_o, rays_d, n_rays, cfg->bbox, cfg->near_plane, 1, ray_batch, stream))) return rc;
-	if ((rc = nrf_sh_encode_fwd(ray_batch + 8, 11, n_rays, cfg->sh_degree, ray_sh, stream))) return rc;
-	if ((rc = nrf_z_sample(ray_batch, 11, t_vals, n_rays, S, cfg->lin_disp, z, stream))) return rc;
+	// Render prologue + coarse depths + per-ray SH table: one launch (bit-identical to nrf_rays_prepare + nrf_sh_encode_fwd + nrf_z_sample)
+	if ((rc = nrf_ray_setup(rays_o, rays_d, n_rays, cfg->bbox, cfg->near_plane, t_vals, S, cfg->lin_disp, cfg->sh_degree, ray_batch, z, ray_sh, nullptr,
+	                        stream))) return rc;
 	// coarse pass
 	if ((rc = nrf_hash_encode_rays_fwd(grid, table_f16, ray_batch, 11, z, n_rays, S, 1, keep, enc, NRF_ENC_F16, nullptr, nullptr, nullptr, 0, stream))) return rc;
 	if ((rc = nrf_mlp_small_fwd(shape, packed, NRF_MLP_IN_ENC16_RAYDIRS, enc, ray_sh, S, keep, n_rays * S, raw, stream))) return rc;

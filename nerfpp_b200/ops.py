@@ -281,6 +281,19 @@ def rays_prepare(rays_o: torch.Tensor, rays_d: torch.Tensor, bbox, near_plane: f
     return out
 
 
+def ray_setup(rays_o: torch.Tensor, rays_d: torch.Tensor, bbox, near_plane: float, t_vals: torch.Tensor, sh_degree: int | None, lin_disp: bool = False,
+              zero_scalar: torch.Tensor | None = None):
+    """rays_prepare + z_sample + sh_encode(viewdirs) as one launch: (ray_batch [R,11], z [R,S], ray_sh [R,deg^2] or None)."""
+    r, s = rays_o.shape[0], t_vals.shape[0]
+    dev = rays_o.device
+    ray_batch = torch.empty((r, 11), dtype=f32, device=dev)
+    z = torch.empty((r, s), dtype=f32, device=dev)
+    ray_sh = torch.empty((r, sh_degree * sh_degree), dtype=f32, device=dev) if sh_degree else None
+    _run("ray_setup", lambda: lib().nrf_ray_setup(ptr(rays_o, f32), ptr(rays_d, f32), r, cabi.host_floats(bbox), near_plane, ptr(t_vals, f32), s, int(lin_disp),
+                                                  sh_degree or 0, ptr(ray_batch), ptr(z), ptr(ray_sh), ptr(zero_scalar), stream()))
+    return ray_batch, z, ray_sh
+
+
 def z_sample(ray_batch: torch.Tensor, t_vals: torch.Tensor, lin_disp: bool = False) -> torch.Tensor:
     r, stride = ray_batch.shape
     s = t_vals.shape[0]

@@ -154,10 +154,9 @@ class HashNeRF:
                                                    workspace=self._render_ws)
         return out
 
-    def render_rays(self, rays_o, rays_d, white_bkgr=False, keep_for_backward=False, n_importance=None):
-        ray_batch = ops.rays_prepare(rays_o, rays_d, self.bbox, 0.0, True)
-        ray_sh = ops.sh_encode(ray_batch[:, 8:11], self.sh_degree)
-        z = ops.z_sample(ray_batch, self.t_vals)
+    def render_rays(self, rays_o, rays_d, white_bkgr=False, keep_for_backward=False, n_importance=None, zero_scalar=None):
+        # Render prologue + coarse depths + per-ray SH (+ the caller's loss accumulator reset) in one launch
+        ray_batch, z, ray_sh = ops.ray_setup(rays_o, rays_d, self.bbox, 0.0, self.t_vals, self.sh_degree, zero_scalar=zero_scalar)
         enc_c, keep_c, raw = self._network(ray_batch, z, ray_sh)
         coarse = ops.composite_fwd(raw, z, rays_d, white_bkgr)
         u = self._u(n_importance)
@@ -184,9 +183,8 @@ class HashNeRF:
     # -- one optimisation step (src/NeRFExecutor.h:868-890, 923, 986-996)
     def forward_backward(self, rays_o, rays_d, target, grad_scale=1.0):
         """Render + huber + backward into self.grads (accumulating).  self.loss holds the mean huber loss."""
-        out = self.render_rays(rays_o, rays_d, keep_for_backward=True)
+        out = self.render_rays(rays_o, rays_d, keep_for_backward=True, zero_scalar=self.loss)
         ray_batch, enc, keep, raw, ray_sh = out.pop("_saved")
-        self.loss.zero_()
         g_rgb = torch.empty_like(out["rgb"])
         ops.huber_fwd_bwd(out["rgb"], target, self.loss, g_rgb, 1.0, grad_scale)
         d_raw = ops.composite_bwd(raw, out["z"], rays_d, g_rgb=g_rgb)
@@ -240,7 +238,7 @@ class HashNeRF:
             self._g_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._g_opt):
                 self._optimizer_step_scheduled(1.0 / world)
-        self.graph_kernels_per_step = cabi.launch_count() - l0 + 1   # + the loss memset
+        self.graph_kernels_per_step = cabi.launch_count() - l0
         return self
 
     def _init_sched(self):

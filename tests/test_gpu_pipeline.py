@@ -92,6 +92,7 @@ def test_render_against_reference_cuda_fixture(golden):
 
 def test_train_step_gradients_match_autograd_oracle():
     m = _model(seed=5, T=12)
+    torch.manual_seed(20261017)          # the parameters below come from the CUDA generator: do not depend on which tests ran before
     with torch.no_grad():
         m.params[:m.n_table] = torch.rand(m.n_table, device="cuda") * 2 - 1
         off = m.n_table

@@ -298,3 +298,22 @@ def test_new_entries_empty_and_ragged():
         o, d, _ = synthetic_rays(n, seed=n)
         a, b = m.render_rays(o, d), m.render_rays_fused(o, d)
         assert torch.equal(a["rgb"], b["rgb"]) and torch.isfinite(a["rgb"]).all()
+
+
+@pytest.mark.parametrize("r,s,deg,lin", [(1, 1, 4, False), (37, 64, 4, False), (4096, 64, 4, False), (300, 17, 8, True), (129, 33, 1, False)])
+def test_ray_setup_equals_the_three_kernels_bit_for_bit(r, s, deg, lin):
+    """nrf_ray_setup == nrf_rays_prepare (viewdirs) + nrf_z_sample + nrf_sh_encode_fwd(viewdirs), and resets the scalar it is given."""
+    from nerfpp_b200 import ops
+    g = torch.Generator().manual_seed(r * 100 + s)
+    o = (torch.randn(r, 3, generator=g) * 2.5).cuda()
+    d = torch.randn(r, 3, generator=g).cuda()
+    bbox = (-1.5, -1.2, -1.0, 1.5, 1.3, 1.1)
+    t = torch.linspace(0, 1, s).cuda()
+    rb = ops.rays_prepare(o, d, bbox, 0.05, True)
+    z = ops.z_sample(rb, t, lin)
+    sh = ops.sh_encode(rb[:, 8:11], deg)
+    acc = torch.full((1,), 7.0, device="cuda")
+    rb2, z2, sh2 = ops.ray_setup(o, d, bbox, 0.05, t, deg, lin_disp=lin, zero_scalar=acc)
+    assert torch.equal(rb, rb2) and torch.equal(z, z2) and torch.equal(sh, sh2) and float(acc) == 0.0
+    rb3, z3, sh3 = ops.ray_setup(o, d, bbox, 0.05, t, None, lin_disp=lin)
+    assert sh3 is None and torch.equal(rb, rb3) and torch.equal(z, z3)
