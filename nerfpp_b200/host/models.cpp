@@ -202,7 +202,9 @@ Tensor NeRFImpl::ForwardPoints(const Tensor& points, const Tensor& view_dirs, in
 
 Tensor NeRFImpl::forward(Tensor x)
 {
-	const bool fusable = x.is_cuda() && x.size(-1) == InputCh + InputChViews && FusedShape();
+	const bool built = x.size(-1) == InputCh + InputChViews && FusedShape();
+	TORCH_CHECK(!built || x.is_cuda(), "NeRF: the input must be a CUDA tensor (the sm_100a path has no CPU fallback)");
+	const bool fusable = built;
 	if (fusable && !torch::GradMode::is_enabled()) return ForwardFused(x);
 	// training: the fused backward yields parameter gradients only — an input that itself requires a gradient keeps the ATen path
 	if (fusable && FusedTraining && !x.requires_grad()) return ForwardFusedTrain(x);

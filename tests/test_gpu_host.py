@@ -234,6 +234,8 @@ def test_classic_inference_runs_on_the_fused_tcgen05_forward(host, ref_cuda):
     b = ref.render_image(20, 24, K.cuda(), c2w.cuda(), 64, 128, 4096, False, True)
     for k in ("rgb", "acc", "depth"):
         assert torch.allclose(a[k], b[k], rtol=1e-2, atol=1e-2), k
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ours.model(torch.rand(4, 90))                             # a CPU tensor at the built shape is refused, not routed through ATen
     x = torch.rand(300, 90).cuda()
     with torch.no_grad():
         fused = ours.model(x)
