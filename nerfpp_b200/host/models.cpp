@@ -178,7 +178,9 @@ Tensor NeRFImpl::ForwardPoints(const Tensor& points, const Tensor& view_dirs, in
 	const Tensor pts = nrfhost::Dense(points.detach(), torch::kFloat32, "NeRF sample positions"), dirs = nrfhost::Dense(view_dirs.detach(), torch::kFloat32, "NeRF view directions");
 	TORCH_CHECK(pts.dim() == 2 && pts.size(1) == 3 && dirs.dim() == 2 && dirs.size(1) == 3 && pts.size(0) == dirs.size(0) * samples_per_ray,
 		"NeRF::ForwardPoints: points [R*S,3], view_dirs [R,3]");
-	if (torch::GradMode::is_enabled() && FusedTraining) {
+	TORCH_CHECK(!torch::GradMode::is_enabled() || FusedTraining,
+		"NeRF::ForwardPoints: autograd is recording but FusedTraining is off - embed and call forward() instead (RunNetwork does)");
+	if (torch::GradMode::is_enabled()) {
 		variable_list in = FusedParams();
 		in.push_back(pts);
 		in.push_back(dirs);
