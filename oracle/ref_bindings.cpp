@@ -14,6 +14,8 @@
 #include "Sampler.h"       // SamplePDF                                            (src/Sampler.h:6)
 #include "RayUtils.h"      // GetRays, IntersectWithAABB                           (src/RayUtils.h:23,87)
 #include "NeRFRenderer.h"  // NeRFRenderer<>                                       (src/NeRFRenderer.h:88)
+#include "LeRF.h"          // LeRF                                                 (src/LeRF.h:6)
+#include "LeRFRenderer.h"  // RenderCLIPEmbedding, LeRFRenderer                    (src/LeRFRenderer.h:45,58)
 #ifdef NRF_REF_CUDA
 #include "CuHashEmbedder.h"  // src/CuHashEmbedder.h
 #include "CuSHEncoder.h"     // src/CuSHEncoder.h
@@ -186,6 +188,12 @@ static void BindPipe(py::module_& m, const char* name)
 		});
 }
 
+// Exposes the protected virtual RawToLEOutputs of the reference LeRF renderer (src/LeRFRenderer.h:68).
+struct OpenLeRFRenderer : public LeRFRenderer {
+	using LeRFRenderer::LeRFRenderer;
+	using LeRFRenderer::RawToLEOutputs;
+};
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 {
 	m.doc() = "reference (DeliriumV01D/NeRFpp) hot-path symbols, unmodified — test oracle only";
@@ -204,6 +212,29 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 	m.def("embedder", [](Tensor x, int multires) { Embedder e("embedder", multires); return e->forward(x).first; });   // src/NeRF.cpp:22
 	m.def("sh_encoder", [](Tensor x, int degree) { SHEncoder e("embeddirs", 3, degree); return e->forward(x).first; }); // src/NeRF.cpp:131
 	m.def("sort_merge", [](Tensor z, Tensor zs) { return std::get<0>(torch::sort(torch::cat({z, zs}, -1), -1)); });      // src/NeRFRenderer.h:431
+
+	// src/LeRF.cpp:3-26 (constructor as src/NeRFExecutor.h:507-514), :28-111 (forward).  The weights are copied into the module's own
+	// registered parameters ("<name>_sigma_le_net_<i>.weight", "<name>_le_net_<i>.weight"); the names are returned for the checkpoint test.
+	m.def("lerf_forward", [](Tensor x, std::vector<Tensor> sigma_w, std::vector<Tensor> le_w, int geo_feat, int hidden, int lang_dim) {
+		LeRF mod(geo_feat, static_cast<int>(sigma_w.size()), hidden, lang_dim, static_cast<int>(x.size(-1)), "lang_model");
+		torch::NoGradGuard ng;
+		auto np = mod->named_parameters();
+		std::vector<std::string> names;
+		for (size_t i = 0; i < sigma_w.size(); i++) np["lang_model_sigma_le_net_" + std::to_string(i) + ".weight"].copy_(sigma_w[i]);
+		for (size_t i = 0; i < le_w.size(); i++) np["lang_model_le_net_" + std::to_string(i) + ".weight"].copy_(le_w[i]);
+		for (auto& kv : np) names.push_back(kv.key());
+		mod->to(x.device());
+		return std::make_pair(mod->forward(x), names);
+	});
+	m.def("render_clip_embedding", [](Tensor e, Tensor w) { return RenderCLIPEmbedding(e, w); });   // src/LeRFRenderer.h:45-54
+	// src/LeRFRenderer.cpp:27-82.  Relevancy (RuCLIP, absent) comes from the stub header and stays undefined.
+	m.def("lerf_raw_to_outputs", [](Tensor raw_le, Tensor z, Tensor rays_d, int lang_dim) {
+		OpenLeRFRenderer r(nullptr, nullptr, torch::zeros({1, lang_dim}), torch::zeros({1, lang_dim}));
+		auto o = r.RawToLEOutputs(raw_le, z, rays_d, lang_dim, 0.f);
+		py::dict d;
+		d["rendered"] = o.RenderedLangEmbedding; d["weights"] = o.WeightsLE; d["depth"] = o.DepthMapLE; d["disp"] = o.DispMapLE; d["acc"] = o.AccMapLE;
+		return d;
+	});
 
 	BindPipe<HashCpuPipe>(m, "HashCpuPipe");
 	BindPipe<ClassicPipe>(m, "ClassicPipe");

@@ -260,6 +260,55 @@ def raw_to_outputs(raw: torch.Tensor, z: torch.Tensor, rays_d: torch.Tensor, raw
     return {"rgb": rgb_map, "depth": depth, "disp": disp, "acc": acc, "weights": weights}
 
 
+def lerf_forward(x: torch.Tensor, sigma_w, le_w) -> torch.Tensor:
+    """src/LeRF.cpp:78-110 (the live branch: an independent density net for the language field, then the language net on
+    cat(geo_feat_le, inputs_le)).  sigma_w / le_w: lists of torch Linear weights [out, in]; every layer is bias-free
+    (src/LeRF.cpp:12,15).  Returns [N, lang_embed_dim + 1] = [normalised embedding, sigma_le]."""
+    h = x
+    for i, w in enumerate(sigma_w):                                                         # :86-91
+        h = h @ w.t()
+        if i != len(sigma_w) - 1:
+            h = torch.relu(h)
+    sigma_le = h[..., 0]                                                                    # :92
+    geo = h[..., 1:]                                                                        # :93
+    h = torch.cat([geo, x], -1)                                                             # :96
+    for i, w in enumerate(le_w):                                                            # :97-102
+        h = h @ w.t()
+        if i != len(le_w) - 1:
+            h = torch.relu(h)
+    le = torch.nn.functional.normalize(h, dim=-1, eps=1e-8)                                 # :105
+    return torch.cat([le, sigma_le[..., None]], -1)                                         # :107-110
+
+
+def lerf_apply_keep(raw_le: torch.Tensor, keep: torch.Tensor) -> torch.Tensor:
+    """src/LeRFRenderer.cpp:18-20: sigma_le (last channel) := 0 where the point was outside the box."""
+    out = raw_le.clone()
+    out[~keep, -1] = 0
+    return out
+
+
+def render_clip_embedding(embeds: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+    """src/LeRFRenderer.h:45-54.  embeds [R,S,D], weights [R,S,1]."""
+    return torch.nn.functional.normalize(torch.sum(weights * embeds, -2), dim=-1, eps=1e-8)
+
+
+def raw_to_le_outputs(raw_le: torch.Tensor, z: torch.Tensor, rays_d: torch.Tensor, lang_embed_dim: int) -> dict:
+    """src/LeRFRenderer.cpp:27-82 with raw_noise_std = 0 (Relevancy, :79, is RuCLIP's and not restated)."""
+    dists = z[..., 1:] - z[..., :-1]                                                        # :39
+    dists = torch.cat([dists, torch.full_like(dists[..., :1], 1e10)], -1)                   # :40
+    dists = dists * torch.norm(rays_d[..., None, :], 2, -1)                                 # :41
+    emb = raw_le[..., :lang_embed_dim]                                                      # :46
+    dens = raw_le[..., lang_embed_dim]                                                      # :49
+    alpha = -TruncExp.apply(-torch.relu(dens) * dists) + 1.0                                # :37,53
+    logt = torch.cat([torch.zeros_like(alpha[:, :1]), torch.cumsum(torch.log(torch.clamp_min(1.0 - alpha, 1e-10)), -1)], -1)[:, :-1]   # :62-65
+    weights = alpha * TruncExp.apply(logt)                                                  # :66
+    depth = torch.sum(weights * z, -1) / torch.clamp_min(torch.sum(weights, -1), 1e-10)     # :70
+    disp = 1.0 / torch.max(1e-10 * torch.ones_like(depth), depth)                           # :71
+    acc = torch.sum(weights, -1)                                                            # :72
+    rendered = render_clip_embedding(emb, weights[..., None])                               # :75
+    return {"rendered": rendered, "weights": weights, "depth": depth, "disp": disp, "acc": acc}
+
+
 def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, det: bool = True, u: torch.Tensor | None = None,
                sums: str = "torch"):
     """src/Sampler.h:6-43.  Returns (samples, inds) — inds are the searchsorted indices (int64) for exactness checks.

@@ -158,7 +158,30 @@ def trunc_exp():
     npz("trunc_exp.npz", x=x.detach(), y=y, gx=x.grad)
 
 
+def lerf():
+    """LeRF head at the BASELINE C5 shape (src/main.cpp:210-213 with the 512-d language dimension of C5): LeRF(32, 2, 256, 512, 128),
+    and RawToLEOutputs on a small ray set, with the autograd gradients of the four weights and of the input."""
+    n, d_in, hid, geo, dim = 96, 128, 256, 32, 512
+    sw = [torch.randn(hid, d_in) * (2.0 / d_in) ** 0.5, torch.randn(1 + geo, hid) * (2.0 / hid) ** 0.5]
+    lw = [torch.randn(hid, geo + d_in) * (2.0 / (geo + d_in)) ** 0.5, torch.randn(dim, hid) * (2.0 / hid) ** 0.5]
+    x = torch.randn(n, d_in).half().float()
+    out, names = R.lerf_forward(x, sw, lw, geo, hid, dim)
+    r, s = 4, 24
+    raw = out.reshape(r, s, dim + 1).clone()
+    raw[..., -1] = raw[..., -1] * 4
+    raw[0, :, -1] = -1.0            # empty ray: the rendered embedding is normalize(0) = 0
+    raw[1, 5, -1] = 1e4             # opaque wall
+    z = 2 + torch.sort(torch.rand(r, s) * 4, -1).values
+    o, d = rays(r)
+    res = R.lerf_raw_to_outputs(raw, z, d, dim)
+    kw = {f"le_{k}": v for k, v in res.items()}
+    npz("lerf.npz", x=x, sw0=sw[0], sw1=sw[1], lw0=lw[0], lw1=lw[1], out=out, names=np.array(names), raw=raw, z=z, rays_d=d, **kw)
+
+
 if __name__ == "__main__":
+    if "--lerf-only" in sys.argv:      # leaves the other fixtures (and the RNG stream they were drawn from) untouched
+        lerf()
+        sys.exit(0)
     sample_pdf()
     raw_to_outputs()
     nerf_small()
@@ -167,3 +190,4 @@ if __name__ == "__main__":
     ray_utils()
     render_rays_classic()
     trunc_exp()
+    lerf()

@@ -46,6 +46,27 @@ def test_raw_to_outputs(golden, white):
     close(raw.grad, g[f"{tag}_d_raw"], rtol=1e-4, atol=1e-5)
 
 
+def test_lerf_head_and_outputs(golden, ref_cpu):
+    """LeRF::forward (src/LeRF.cpp:28-111) and RawToLEOutputs (src/LeRFRenderer.cpp:27-82) against the fixture generated from the
+    compiled reference, and live against oracle/_ref when present."""
+    g = golden("lerf.npz")
+    sw, lw = [T(g["sw0"]), T(g["sw1"])], [T(g["lw0"]), T(g["lw1"])]
+    out = O.lerf_forward(T(g["x"]), sw, lw)
+    close(out, g["out"], rtol=1e-5, atol=1e-6)
+    close(out[:, :512].norm(dim=-1), np.ones(out.shape[0]), rtol=1e-5)
+    res = O.raw_to_le_outputs(T(g["raw"]), T(g["z"]), T(g["rays_d"]), 512)
+    for k in ("rendered", "weights", "depth", "disp", "acc"):
+        close(res[k], g[f"le_{k}"], rtol=1e-5, atol=1e-6)
+    assert float(res["rendered"][0].abs().max()) == 0.0          # empty ray: normalize(0, eps) = 0
+    keep = torch.arange(out.shape[0]) % 3 != 0
+    masked = O.lerf_apply_keep(out, keep)
+    assert float(masked[~keep, -1].abs().max()) == 0.0 and torch.equal(masked[:, :-1], out[:, :-1])
+    if ref_cpu is not None:
+        live, names = ref_cpu.lerf_forward(T(g["x"]), sw, lw, 32, 256, 512)
+        close(out, live, rtol=1e-5, atol=1e-6)
+        assert list(names) == list(g["names"])
+
+
 def test_nerf_small(golden):
     g = golden("nerf_small.npz")
     for xk, ok, gxk, wk, gwk in (("x", "out", "gx", "w", "gw"), ("x2", "out2", "gx2", "v", "gv")):
