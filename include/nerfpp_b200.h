@@ -380,6 +380,52 @@ int nrf_adam_step_sharded(const nrf_peer_group* pg, float* param, float* exp_avg
                           int64_t n_total, const void* sched_state, float beta1, float beta2, float eps, float grad_scale,
                           nrf_stream stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * LeRF language head (BASELINE C5) — LeRFImpl::forward (src/LeRF.cpp:28-111), the keep mask of
+ * LeRFRenderer::RunLENetwork (src/LeRFRenderer.cpp:18-20) and RenderCLIPEmbedding (src/LeRFRenderer.h:45-54), fused on tcgen05
+ * tensor cores.  Built for the shape the reference trains (src/main.cpp:203-213, src/NeRFExecutor.h:507-514):
+ * LeRF(geo_feat_dim_le 32, num_layers_le 2, hidden_dim_le 256, lang_embed_dim 512, input_ch_le 16 levels x 8 features = 128), every
+ * layer bias-free (src/LeRF.cpp:12,15); other shapes return NRF_ERR_UNSUPPORTED.  enc_f16 [N,128] fp16 is the output of
+ * nrf_hash_encode_fwd on the language grid (n_features 8); keep u8 [N] (nullable) its keep mask.  Inference only in this round.
+ *
+ *   nrf_lerf_pack              weights (torch Linear layout [out,in] fp32) -> operand blob (nrf_lerf_packed_bytes, 128-byte aligned)
+ *   nrf_lerf_fwd               raw_le [N, 513] fp32 = [normalize(e, eps 1e-8) (512) | sigma_le], sigma_le := 0 where keep == 0
+ *                              (what LeRF::forward + RunLENetwork return; the compatibility entry)
+ *   nrf_lerf_sigma_fwd         raw4 [N,4] fp32 = [0,0,0,sigma_le]: the coarse pass of LeRFRenderer::RenderRays only needs the density
+ *                              (src/LeRFRenderer.cpp:133-139); raw4 is what nrf_composite_fwd (raw_stride 4) consumes
+ *   nrf_lerf_hidden_fwd        the fine pass without the [N,512] embedding: raw4 as above, `hidden` = the last hidden layer h2 as fp16
+ *                              tile records (nrf_lerf_hidden_bytes(n) bytes, 128-byte aligned), q [N] fp32 = |W_e1 h2|^2
+ *   nrf_lerf_render_embedding  weights [R,S] fp32 (WeightsLE from nrf_composite_fwd on raw4) + hidden + q ->
+ *                              rendered [R,512] = normalize(sum_s w_s e_s / max(|e_s|, 1e-8), eps 1e-8), evaluated as
+ *                              normalize(W_e1 sum_s (w_s / |e_s|) h2_s); hsum [R,256] fp32 is caller-owned workspace
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct nrf_lerf_shape {
+	int32_t geo_feat_dim;     /* 32  */
+	int32_t num_layers;       /* 2   */
+	int32_t hidden_dim;       /* 256 */
+	int32_t lang_embed_dim;   /* 512 */
+	int32_t input_ch;         /* 128 */
+} nrf_lerf_shape;
+
+typedef struct nrf_lerf_weights {   /* device pointers, fp32 row-major [out, in]; names as registered by src/LeRF.cpp:17-25 */
+	const float* sigma_w0;    /* <name>_sigma_le_net_0.weight [256, 128] */
+	const float* sigma_w1;    /* <name>_sigma_le_net_1.weight [33, 256]: row 0 sigma_le, rows 1..32 geo_feat_le */
+	const float* le_w0;       /* <name>_le_net_0.weight [256, 160]: columns [geo_feat_le 32 | inputs_le 128] */
+	const float* le_w1;       /* <name>_le_net_1.weight [512, 256] */
+} nrf_lerf_weights;
+
+int64_t nrf_lerf_packed_bytes(const nrf_lerf_shape* shape);
+int64_t nrf_lerf_hidden_bytes(const nrf_lerf_shape* shape, int64_t n);
+int nrf_lerf_pack(const nrf_lerf_shape* shape, const nrf_lerf_weights* weights, void* packed, nrf_stream stream);
+int nrf_lerf_fwd(const nrf_lerf_shape* shape, const void* packed, const void* enc_f16, const uint8_t* keep, int64_t n, float* raw_le,
+                 nrf_stream stream);
+int nrf_lerf_sigma_fwd(const nrf_lerf_shape* shape, const void* packed, const void* enc_f16, const uint8_t* keep, int64_t n, float* raw4,
+                       nrf_stream stream);
+int nrf_lerf_hidden_fwd(const nrf_lerf_shape* shape, const void* packed, const void* enc_f16, const uint8_t* keep, int64_t n, float* raw4,
+                        void* hidden, float* q, nrf_stream stream);
+int nrf_lerf_render_embedding(const nrf_lerf_shape* shape, const void* packed, const float* weights, const void* hidden, const float* q,
+                              int64_t n_rays, int32_t n_samples, float* hsum, float* rendered, nrf_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

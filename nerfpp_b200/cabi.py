@@ -55,6 +55,16 @@ class MlpNerfWeights(Structure):
                 ("alpha_b", c_void_p), ("views_w", c_void_p), ("views_b", c_void_p), ("rgb_w", c_void_p), ("rgb_b", c_void_p)]
 
 
+class LerfShape(Structure):
+    """struct nrf_lerf_shape"""
+    _fields_ = [("geo_feat_dim", c_int32), ("num_layers", c_int32), ("hidden_dim", c_int32), ("lang_embed_dim", c_int32), ("input_ch", c_int32)]
+
+
+class LerfWeights(Structure):
+    """struct nrf_lerf_weights"""
+    _fields_ = [("sigma_w0", c_void_p), ("sigma_w1", c_void_p), ("le_w0", c_void_p), ("le_w1", c_void_p)]
+
+
 class RenderConfig(Structure):
     """struct nrf_render_config"""
     _fields_ = [("n_samples", c_int32), ("n_importance", c_int32), ("white_bkgr", c_int32), ("lin_disp", c_int32), ("sh_degree", c_int32),
@@ -116,6 +126,13 @@ SIGNATURES = {
     "nrf_render_rays_workspace_bytes": (c_int64, [POINTER(RenderConfig), POINTER(HashGrid), c_int64]),
     "nrf_render_rays_fwd": (c_int32, [POINTER(RenderConfig), POINTER(HashGrid), _P, POINTER(MlpSmallShape), _P, _P, _P, c_int64, _P, _P, _P, c_int64,
                                       _P, _P, _P, _P, _P, _P, _P]),
+    "nrf_lerf_packed_bytes": (c_int64, [POINTER(LerfShape)]),
+    "nrf_lerf_hidden_bytes": (c_int64, [POINTER(LerfShape), c_int64]),
+    "nrf_lerf_pack": (c_int32, [POINTER(LerfShape), POINTER(LerfWeights), _P, _P]),
+    "nrf_lerf_fwd": (c_int32, [POINTER(LerfShape), _P, _P, _P, c_int64, _P, _P]),
+    "nrf_lerf_sigma_fwd": (c_int32, [POINTER(LerfShape), _P, _P, _P, c_int64, _P, _P]),
+    "nrf_lerf_hidden_fwd": (c_int32, [POINTER(LerfShape), _P, _P, _P, c_int64, _P, _P, _P, _P]),
+    "nrf_lerf_render_embedding": (c_int32, [POINTER(LerfShape), _P, _P, _P, _P, c_int64, c_int32, _P, _P, _P]),
     "nrf_peer_flags_bytes": (c_int64, [c_int32]),
     "nrf_adam_step_sharded": (c_int32, [POINTER(PeerGroup), _P, _P, _P, c_int64, c_int64, _P, c_float, c_float, c_float, c_float, _P]),
     "nrf_adam_schedule_advance": (c_int32, [_P, c_float, c_float, c_float, c_float, c_float, _P]),

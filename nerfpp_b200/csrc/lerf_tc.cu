@@ -1,0 +1,635 @@
+// Fused LeRF language head on tcgen05 / TMEM / TMA for sm_100a (BASELINE C5).
+//
+// Replaces LeRFImpl::forward (reference src/LeRF.cpp:28-111: 4 bias-free cuBLAS SGEMMs + relu / index / cat / normalize kernels), the keep
+// mask of LeRFRenderer::RunLENetwork (src/LeRFRenderer.cpp:18-20) and, with the two per-ray kernels at the end of this file, RenderCLIPEmbedding (src/LeRFRenderer.h:45-54) at
+// the shape the reference trains (src/main.cpp:203-213 with the 512-d language dimension of C5): LeRF(geo 32, 2 layers, hidden 256, D 512) on
+// the 16 x 8 = 128 channels of the language hash grid.
+//
+//   sigma net   h1 = relu(W_s0 enc)  [256]      s = W_s1 h1  [33] = [sigma_le | geo_feat 32]
+//   language    h2 = relu(W_e0 [geo | enc])  [256]      e = W_e1 h2  [512]      out = [e / max(|e|, 1e-8) | sigma_le]
+//
+// Same mapping as mlp_nerf_tc.cu (one persistent CTA per SM, one 128-point tile in flight, A operands fp16 in TENSOR MEMORY, fp32 accumulators
+// in TMEM, weights streamed through a 4 x 32 KB TMA ring as pre-packed UMMA K-major core matrices, warp 0 produces, warp 1 issues tcgen05.mma,
+// warps 2..5 are one epilogue thread per row).  TMEM columns: D 0..255 | D2 (sigma head, N = 48) 256..303 | [geo 16 | enc 64] 304..383 (so the
+// language net reads cat(geo, enc) as ONE contiguous K = 160 range, src/LeRF.cpp:96) | h 384..511.
+//
+// Three programs over the same kernel:
+//   SIGMA   {S0, S1}: sigma_le only — the coarse pass of LeRFRenderer::RenderRays needs nothing else (its embedding is discarded,
+//           src/LeRFRenderer.cpp:133-139).  Writes raw4 [N,4] = [0,0,0,sigma_le], the layout nrf_composite_fwd / nrf_sample_pdf_merge consume.
+//   HIDDEN  {S0, S1, E0, G}: the fine pass.  The [N, 512] embedding is never formed: the rendered embedding is
+//               normalize( sum_s w_s e_s / |e_s| ) = normalize( W_e1 * sum_s (w_s / |e_s|) h2_s )        (the last layer is linear),
+//           and |e_s|^2 = h2_s^T G h2_s with G = W_e1^T W_e1 [256 x 256] built once by the pack kernel — a 256-wide layer instead of the
+//           512-wide one.  Writes raw4, h2 (fp16 tile records, 512 B per row) and q = |e|^2 [N]; lerf_hsum_kernel + lerf_project_kernel finish per RAY.
+//           (The reference materialises raw_le [R,S,513] fp32 = 2 KB per sample.)
+//   RAW     {S0, S1, E0, E1 lower, E1 upper, E1 lower, E1 upper}: LeRF::forward itself, raw_le [N, 513] fp32.  The 512 outputs go through
+//           the 256 accumulator columns in two halves, twice: the first pass only accumulates |e|^2, the second scales and stores
+//           (through a per-warp shared-memory transpose, so a store instruction writes 128 contiguous bytes of one row).
+// fp16 operands, fp32 accumulation: <= 1e-2 relative to the fp32 reference (tests/test_gpu_lerf.py).
+#include "tcgen05.cuh"
+#include "mlp_small_layout.cuh"   // pack_f16 / pack_f16_relu
+#include <algorithm>
+
+namespace nrf {
+namespace lerf_tc {
+
+using namespace tc;
+
+constexpr int kIn = 128, kHid = 256, kGeo = 32, kDim = 512, kSigN = 48;   // kSigN: the 33 outputs of the sigma head padded to a UMMA N
+constexpr uint32_t kColD = 0, kColD2 = 256, kColGeo = 304, kColEnc = 320, kColH = 384;
+constexpr int kThreads = 32 * 6;
+constexpr int kRing = 4;
+constexpr int kStageBytes = 256 * 64 * 2;
+
+// layers: 0 S0 (128 -> 256), 1 S1 (256 -> [geo 32 | sigma | 0..]), 2 E0 (160 -> 256), 3 G (256 -> 256), 4 / 5 E1 outputs 0..255 / 256..511
+constexpr int kLayers = 6;
+struct LayerInfo {
+	int N, K;
+	uint32_t a_col, d_col;
+};
+__host__ __device__ constexpr LayerInfo layer_info(int l)
+{
+	return l == 0 ? LayerInfo{kHid, kIn, kColEnc, kColD}
+	     : l == 1 ? LayerInfo{kSigN, kHid, kColH, kColD2}
+	     : l == 2 ? LayerInfo{kHid, kGeo + kIn, kColGeo, kColD}
+	              : LayerInfo{kHid, kHid, kColH, kColD};
+}
+// the narrow sigma head travels as ONE stage holding its whole K (24 KB); everything else in 64-wide K slabs (E0's last one is 32)
+__host__ __device__ constexpr int layer_stages(int l) { return l == 1 ? 1 : (layer_info(l).K + 63) / 64; }
+__host__ __device__ constexpr int stage_k(int l, int s) { return l == 1 ? layer_info(l).K : (layer_info(l).K - 64 * s >= 64 ? 64 : layer_info(l).K - 64 * s); }
+__host__ __device__ constexpr int stage_bytes(int l, int s) { return layer_info(l).N * stage_k(l, s) * 2; }
+__host__ __device__ constexpr int layer_bytes(int l) { return layer_info(l).N * layer_info(l).K * 2; }
+__host__ __device__ constexpr int layer_offset(int l)
+{
+	int b = 0;
+	for (int i = 0; i < l; i++) b += layer_bytes(i);
+	return b;
+}
+constexpr int kWeightBytes = layer_offset(kLayers);             // 565 248
+// W_e1 transposed, fp32 [256 k][512 n], follows the operand blob (lerf_project_kernel reads it)
+constexpr int kProjBytes = kHid * kDim * 4;
+constexpr int kPackedBytes = kWeightBytes + kProjBytes;
+static_assert(kWeightBytes % 128 == 0, "blob alignment");
+
+enum Mode { kSigma = 0, kHidden = 1, kRaw = 2 };
+struct ModeTable {
+	int n_groups, group_layer[8];
+	int n_stages, off[24], bytes[24];
+};
+constexpr ModeTable make_mode(int mode)
+{
+	ModeTable t{};
+	const int seq_sigma[2] = {0, 1}, seq_hidden[4] = {0, 1, 2, 3}, seq_raw[7] = {0, 1, 2, 4, 5, 4, 5};
+	t.n_groups = mode == kSigma ? 2 : (mode == kHidden ? 4 : 7);
+	for (int g = 0; g < t.n_groups; g++) t.group_layer[g] = mode == kSigma ? seq_sigma[g] : (mode == kHidden ? seq_hidden[g] : seq_raw[g]);
+	int i = 0;
+	for (int g = 0; g < t.n_groups; g++) {
+		const int l = t.group_layer[g];
+		int off = layer_offset(l);
+		for (int s = 0; s < layer_stages(l); s++, i++) {
+			t.off[i] = off;
+			t.bytes[i] = stage_bytes(l, s);
+			off += stage_bytes(l, s);
+		}
+	}
+	t.n_stages = i;
+	return t;
+}
+static_assert(make_mode(kSigma).n_stages == 3 && make_mode(kHidden).n_stages == 10 && make_mode(kRaw).n_stages == 22, "stage programs");
+__constant__ ModeTable c_modes[3] = {make_mode(kSigma), make_mode(kHidden), make_mode(kRaw)};
+
+// h2 tile records of the HIDDEN program: [32 column chunks][128 rows][8 fp16] = 64 KB per 128-row tile; a warp store covers 512 contiguous bytes
+constexpr int kHiddenTile = 128 * kHid * 2;
+
+struct Weights {   // device pointers, torch Linear layout [out, in] row-major fp32, no biases (src/LeRF.cpp:12,15)
+	const float* s0;   // [256, 128]
+	const float* s1;   // [33, 256]   row 0 = sigma_le, rows 1..32 = geo_feat_le (src/LeRF.cpp:92-93)
+	const float* e0;   // [256, 160]  columns [geo 32 | enc 128] (src/LeRF.cpp:96)
+	const float* e1;   // [512, 256]
+};
+
+// padded logical weight Wp_l(n, k) in the kernel's operand order
+__device__ __forceinline__ float wp(const Weights& p, int l, int n, int k)
+{
+	switch (l) {
+		case 0: return p.s0[n * kIn + k];
+		case 1: return n < kGeo ? p.s1[(n + 1) * kHid + k] : (n == kGeo ? p.s1[k] : 0.f);     // [geo 0..31 | sigma | zeros]
+		case 2: return p.e0[n * (kGeo + kIn) + k];
+		case 3: {                                                                            // G = W_e1^T W_e1
+			float acc = 0.f;
+			for (int m = 0; m < kDim; m++) acc = fmaf(p.e1[m * kHid + n], p.e1[m * kHid + k], acc);
+			return acc;
+		}
+		case 4: return p.e1[n * kHid + k];
+		default: return p.e1[(n + 256) * kHid + k];
+	}
+}
+
+__global__ void __launch_bounds__(256) lerf_pack_kernel(Weights p, uint32_t* __restrict__ blob)
+{
+	const int w = blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= kPackedBytes / 4) return;
+	if (w >= kWeightBytes / 4) {
+		const int i = w - kWeightBytes / 4, k = i / kDim, n = i % kDim;
+		reinterpret_cast<float*>(blob)[w] = p.e1[n * kHid + k];
+		return;
+	}
+	int l = 0;
+	while (l + 1 < kLayers && w * 4 >= layer_offset(l + 1)) l++;
+	int q = w - layer_offset(l) / 4, s = 0, k_off = 0;
+	while (q >= stage_bytes(l, s) / 4) { q -= stage_bytes(l, s) / 4; k_off += stage_k(l, s); s++; }
+	// UMMA K-major core-matrix layout: word q of a stage holds (n, k) and (n, k+1); byte = (k/8)*(N*16) + n*16 + (k%8)*2
+	const int N = layer_info(l).N;
+	const int kc = q / (4 * N), n = (q >> 2) % N, k = k_off + 8 * kc + 2 * (q & 3);
+	blob[w] = pack_f16(wp(p, l, n, k), wp(p, l, n, k + 1));
+}
+
+struct __align__(128) Smem {
+	uint8_t ring[kRing][kStageBytes];
+	float tbuf[4][32][33];               // RAW: per-warp transpose of a 32 x 32 output block
+	uint64_t full[kRing], empty[kRing];
+	uint64_t a_ready, d_ready;
+	uint32_t tmem_base;
+};
+
+// tcgen05.wait::ld tied to the destination registers of a narrower load (see tmem_ld_wait_for in tcgen05.cuh)
+__device__ __forceinline__ void tmem_ld_wait_for4(uint32_t (&r)[4])
+{
+	asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) :: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_for16(uint32_t (&r)[16])
+{
+	asm volatile("tcgen05.wait::ld.sync.aligned;"
+		: "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
+		  "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+		:: "memory");
+}
+
+__device__ __forceinline__ void publish(uint64_t* bar, int lane)
+{
+	tmem_st_wait();
+	fence_before();
+	__syncwarp();
+	if (lane == 0) mbar_arrive(bar);
+}
+
+// relu(D[:, 0..255]) -> fp16 -> the h columns (the next layer's A operand), one thread per row; the tcgen05.ld of chunk c+1 is in flight while
+// chunk c is converted and stored.  SAVE: the packed row also goes to the h2 tile record.
+template <bool SAVE>
+__device__ __forceinline__ void relu_to_h(uint32_t t_lane, uint8_t* __restrict__ rec_row)
+{
+	uint32_t acc0[32], acc1[32], a16[16];
+	tmem_ld32(t_lane + kColD, acc0);
+#pragma unroll
+	for (int c = 0; c < 8; c += 2) {
+		tmem_ld_wait_for(acc0);
+		tmem_ld32(t_lane + kColD + 32 * (c + 1), acc1);
+#pragma unroll
+		for (int i = 0; i < 16; i++) a16[i] = pack_f16_relu(__uint_as_float(acc0[2 * i]), __uint_as_float(acc0[2 * i + 1]));
+		tmem_st16(t_lane + kColH + 16 * c, a16);
+		if (SAVE) {
+#pragma unroll
+			for (int i = 0; i < 4; i++)
+				*reinterpret_cast<uint4*>(rec_row + (4 * c + i) * 2048) = make_uint4(a16[4 * i], a16[4 * i + 1], a16[4 * i + 2], a16[4 * i + 3]);
+		}
+		tmem_ld_wait_for(acc1);
+		if (c + 2 < 8) tmem_ld32(t_lane + kColD + 32 * (c + 2), acc0);
+#pragma unroll
+		for (int i = 0; i < 16; i++) a16[i] = pack_f16_relu(__uint_as_float(acc1[2 * i]), __uint_as_float(acc1[2 * i + 1]));
+		tmem_st16(t_lane + kColH + 16 * (c + 1), a16);
+		if (SAVE) {
+#pragma unroll
+			for (int i = 0; i < 4; i++)
+				*reinterpret_cast<uint4*>(rec_row + (4 * (c + 1) + i) * 2048) = make_uint4(a16[4 * i], a16[4 * i + 1], a16[4 * i + 2], a16[4 * i + 3]);
+		}
+	}
+}
+
+// sum over the 256 accumulator columns of D^2 (this thread's row)
+__device__ __forceinline__ float sumsq_d(uint32_t t_lane)
+{
+	uint32_t acc0[32], acc1[32];
+	float s = 0.f;
+	tmem_ld32(t_lane + kColD, acc0);
+#pragma unroll
+	for (int c = 0; c < 8; c += 2) {
+		tmem_ld_wait_for(acc0);
+		tmem_ld32(t_lane + kColD + 32 * (c + 1), acc1);
+#pragma unroll
+		for (int i = 0; i < 32; i++) s = fmaf(__uint_as_float(acc0[i]), __uint_as_float(acc0[i]), s);
+		tmem_ld_wait_for(acc1);
+		if (c + 2 < 8) tmem_ld32(t_lane + kColD + 32 * (c + 2), acc0);
+#pragma unroll
+		for (int i = 0; i < 32; i++) s = fmaf(__uint_as_float(acc1[i]), __uint_as_float(acc1[i]), s);
+	}
+	return s;
+}
+
+// q = h^T (G h): D holds G h (fp32), the h columns hold h (fp16 pairs)
+__device__ __forceinline__ float dot_d_h(uint32_t t_lane)
+{
+	uint32_t acc[32], hh[16];
+	float s = 0.f;
+#pragma unroll 1
+	for (int c = 0; c < 8; c++) {
+		tmem_ld32(t_lane + kColD + 32 * c, acc);
+		tmem_ld16(t_lane + kColH + 16 * c, hh);
+		tmem_ld_wait_for(acc);
+		tmem_ld_wait_for16(hh);
+#pragma unroll
+		for (int i = 0; i < 16; i++) {
+			const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&hh[i]));
+			s = fmaf(h2.x, __uint_as_float(acc[2 * i]), s);
+			s = fmaf(h2.y, __uint_as_float(acc[2 * i + 1]), s);
+		}
+	}
+	return s;
+}
+
+// D[:, 0..255] * inv -> out[row, col0 .. col0 + 255] (row stride 513 floats) through the warp's transpose buffer
+__device__ __forceinline__ void scaled_store(uint32_t t_lane, float inv, float (*tb)[33], int lane, int64_t warp_row0, int64_t n, float* __restrict__ out, int col0)
+{
+	uint32_t acc[32];
+#pragma unroll 1
+	for (int c = 0; c < 8; c++) {
+		tmem_ld32(t_lane + kColD + 32 * c, acc);
+		tmem_ld_wait_for(acc);
+#pragma unroll
+		for (int i = 0; i < 32; i++) tb[lane][i] = __uint_as_float(acc[i]) * inv;
+		__syncwarp();
+#pragma unroll 4
+		for (int rr = 0; rr < 32; rr++) {
+			const int64_t gr = warp_row0 + rr;
+			if (gr < n) out[gr * (kDim + 1) + col0 + 32 * c + lane] = tb[rr][lane];
+		}
+		__syncwarp();
+	}
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) lerf_fwd_tc_kernel(const uint8_t* __restrict__ blob, const uint4* __restrict__ enc,
+	const uint8_t* __restrict__ keep, int64_t n, float* __restrict__ raw4, uint8_t* __restrict__ hidden, float* __restrict__ q_out, float* __restrict__ raw_le)
+{
+	extern __shared__ __align__(128) uint8_t smem_raw[];
+	Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int64_t n_tiles = (n + 127) / 128;
+	const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+	const ModeTable& mt = c_modes[MODE];
+
+	if (warp == 1) {
+		if (lane == 0) {
+			for (int s = 0; s < kRing; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+			mbar_init(&sm.a_ready, 4);
+			mbar_init(&sm.d_ready, 1);
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncwarp();
+		tmem_alloc_all(&sm.tmem_base);
+	}
+	fence_before();
+	__syncthreads();
+	fence_after();
+	const uint32_t tmem = sm.tmem_base;
+
+	if (warp == 0) {
+		// ===== producer: the same weight-stage sequence for every tile =====
+		if (lane == 0) {
+			uint32_t g = 0;
+			const int n_stages = mt.n_stages;
+			for (int64_t t = 0; t < my_tiles; t++) {
+#pragma unroll 1
+				for (int i = 0; i < n_stages; i++, g++) {
+					const uint32_t slot = g % kRing, round = g / kRing;
+					mbar_wait(&sm.empty[slot], (round & 1u) ^ 1u);          // first round passes immediately
+					const uint32_t bytes = mt.bytes[i];
+					mbar_expect_tx(&sm.full[slot], bytes);
+					tma_bulk_g2s(sm.ring[slot], blob + mt.off[i], bytes, &sm.full[slot]);
+				}
+			}
+		}
+	} else if (warp == 1) {
+		// ===== MMA issuer =====
+		if (lane == 0) {
+			uint32_t g = 0, pa = 0;
+			const int n_groups = mt.n_groups;
+			for (int64_t t = 0; t < my_tiles; t++) {
+#pragma unroll 1
+				for (int grp = 0; grp < n_groups; grp++) {
+					mbar_wait(&sm.a_ready, pa);
+					pa ^= 1u;
+					fence_after();
+					const int l = mt.group_layer[grp];
+					const LayerInfo L = layer_info(l);
+					const uint32_t idesc = idesc_f16(128, L.N);
+					const uint32_t lbo = L.N * 16;
+					uint32_t a_col = tmem + L.a_col;
+					bool first = true;
+					const int ns = layer_stages(l);
+					for (int s = 0; s < ns; s++, g++) {
+						const uint32_t slot = g % kRing, round = g / kRing;
+						mbar_wait(&sm.full[slot], round & 1u);
+						fence_after();
+						const uint32_t saddr = smem_u32(sm.ring[slot]);
+						const int ks = stage_k(l, s) / 16;
+						for (int j = 0; j < ks; j++) {
+							umma_ts(tmem + L.d_col, a_col, smem_desc(saddr + j * 2 * lbo, lbo, 128), idesc, first ? 0u : 1u);
+							first = false;
+							a_col += 8;
+						}
+						umma_commit(&sm.empty[slot]);                      // the stage is free again once these MMAs have read it
+					}
+					umma_commit(&sm.d_ready);
+				}
+			}
+		}
+	} else {
+		// ===== epilogue warps: one thread per row of the tile =====
+		const int qd = warp & 3;                                          // TMEM lane quarter this warp may access
+		const int row = (qd << 5) | lane;
+		const uint32_t t_lane = tmem + (static_cast<uint32_t>(qd << 5) << 16);
+		uint32_t pd = 0;
+		for (int64_t t = 0; t < my_tiles; t++) {
+			const int64_t tile = blockIdx.x + t * gridDim.x;
+			const int64_t r = tile * 128 + row;
+			const bool ok = r < n;
+			// ---- input: the 128 fp16 channels of the language hash grid, as they leave nrf_hash_encode_fwd
+			{
+				const uint4* er = enc + (ok ? r : 0) * (kIn / 8);
+				uint32_t a16[16];
+#pragma unroll
+				for (int h = 0; h < 4; h++) {
+#pragma unroll
+					for (int i = 0; i < 4; i++) {
+						const uint4 v = ok ? __ldg(er + 4 * h + i) : make_uint4(0u, 0u, 0u, 0u);
+						a16[4 * i] = v.x; a16[4 * i + 1] = v.y; a16[4 * i + 2] = v.z; a16[4 * i + 3] = v.w;
+					}
+					tmem_st16(t_lane + kColEnc + 16 * h, a16);
+				}
+			}
+			publish(&sm.a_ready, lane);
+
+			// ---- S0: h1 = relu(D)
+			mbar_wait(&sm.d_ready, pd);
+			pd ^= 1u;
+			fence_after();
+			relu_to_h<false>(t_lane, nullptr);
+			publish(&sm.a_ready, lane);
+
+			// ---- S1: [geo 32 | sigma]
+			mbar_wait(&sm.d_ready, pd);
+			pd ^= 1u;
+			fence_after();
+			float sigma;
+			{
+				uint32_t c4[4];
+				tmem_ld4(t_lane + kColD2 + kGeo, c4);
+				if (MODE != kSigma) {
+					uint32_t acc[32], a16[16];
+					tmem_ld32(t_lane + kColD2, acc);
+					tmem_ld_wait_for(acc);
+#pragma unroll
+					for (int i = 0; i < 16; i++) a16[i] = pack_f16(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+					tmem_st16(t_lane + kColGeo, a16);
+				}
+				tmem_ld_wait_for4(c4);
+				sigma = __uint_as_float(c4[0]);
+				if (keep != nullptr && ok && keep[r] == 0) sigma = 0.f;               // src/LeRFRenderer.cpp:18-20
+			}
+			if (MODE != kRaw) {
+				if (ok) *reinterpret_cast<float4*>(raw4 + r * 4) = make_float4(0.f, 0.f, 0.f, sigma);
+			}
+			if (MODE == kSigma) continue;       // the next tile's input stage is the next publish
+			publish(&sm.a_ready, lane);
+
+			// ---- E0: h2 = relu(D)
+			mbar_wait(&sm.d_ready, pd);
+			pd ^= 1u;
+			fence_after();
+			if (MODE == kHidden) relu_to_h<true>(t_lane, hidden + tile * kHiddenTile + row * 16);
+			else relu_to_h<false>(t_lane, nullptr);
+			publish(&sm.a_ready, lane);
+
+			if (MODE == kHidden) {
+				// ---- G: |e|^2 = h2 . (G h2)
+				mbar_wait(&sm.d_ready, pd);
+				pd ^= 1u;
+				fence_after();
+				const float qv = dot_d_h(t_lane);
+				if (ok) q_out[r] = qv;
+			} else {
+				// ---- E1, first pass: |e|^2 over both halves
+				float ss = 0.f;
+#pragma unroll 1
+				for (int half = 0; half < 2; half++) {
+					mbar_wait(&sm.d_ready, pd);
+					pd ^= 1u;
+					fence_after();
+					ss += sumsq_d(t_lane);
+					publish(&sm.a_ready, lane);
+				}
+				const float inv = 1.f / fmaxf(sqrtf(ss), 1e-8f);                      // F::normalize(eps 1e-8), src/LeRF.cpp:105
+				// ---- E1, second pass: scale and store
+#pragma unroll 1
+				for (int half = 0; half < 2; half++) {
+					mbar_wait(&sm.d_ready, pd);
+					pd ^= 1u;
+					fence_after();
+					scaled_store(t_lane, inv, sm.tbuf[qd], lane, tile * 128 + (qd << 5), n, raw_le, 256 * half);
+					if (half == 0) publish(&sm.a_ready, lane);
+				}
+				if (ok) raw_le[r * (kDim + 1) + kDim] = sigma;                        // src/LeRF.cpp:107-110
+			}
+		}
+	}
+
+	fence_before();
+	__syncthreads();
+	if (warp == 1) {
+		fence_after();
+		tmem_free_all(tmem);
+	}
+}
+
+static int check_shape(const nrf_lerf_shape* s)
+{
+	NRF_REQUIRE(s != nullptr, "shape is null");
+	if (!(s->input_ch == kIn && s->hidden_dim == kHid && s->geo_feat_dim == kGeo && s->lang_embed_dim == kDim && s->num_layers == 2)) {
+		set_error("nrf_lerf: only the BASELINE C5 shape LeRF(geo 32, 2 layers, hidden 256, D 512, in 128) is built");
+		return NRF_ERR_UNSUPPORTED;
+	}
+	return NRF_OK;
+}
+
+template <int MODE>
+static int launch(const nrf_lerf_shape* shape, const void* packed, const void* enc, const uint8_t* keep, int64_t n, float* raw4, void* hidden, float* q,
+	float* raw_le, nrf_stream stream)
+{
+	if (int rc = check_shape(shape)) return rc;
+	NRF_REQUIRE(n >= 0, "negative n");
+	if (n == 0) return NRF_OK;
+	NRF_REQUIRE(packed && enc, "null pointer");
+	NRF_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0 && (reinterpret_cast<uintptr_t>(enc) & 15) == 0 && (reinterpret_cast<uintptr_t>(raw4) & 15) == 0 &&
+		(reinterpret_cast<uintptr_t>(hidden) & 127) == 0, "packed / hidden must be 128-byte, enc / raw4 16-byte aligned");
+	const int64_t tiles = (n + 127) / 128;
+	const int smem = static_cast<int>(sizeof(Smem)) + 256;
+	const int blocks = static_cast<int>(std::min<int64_t>(tiles, kNumSMs));
+	NRF_CUDA(cudaFuncSetAttribute(lerf_fwd_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+	lerf_fwd_tc_kernel<MODE><<<blocks, kThreads, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed), reinterpret_cast<const uint4*>(enc), keep, n,
+		raw4, reinterpret_cast<uint8_t*>(hidden), q, raw_le);
+	NRF_CHECK_LAUNCH("lerf_fwd_tc_kernel");
+	return NRF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// Per-ray finish of the HIDDEN program: Hs[ray] = sum_s (w_s / max(|e_s|, 1e-8)) h2_s, then rendered = normalize(W_e1 Hs, eps 1e-8)
+// (src/LeRFRenderer.h:45-54 applied to the normalised embeddings of src/LeRF.cpp:105).
+
+// one block per ray, 8 warps; warp v owns column chunks v, v+8, v+16, v+24 of the h2 records; lane = sample within a group of 32
+__global__ void __launch_bounds__(256) lerf_hsum_kernel(const float* __restrict__ weights, const uint4* __restrict__ hidden, const float* __restrict__ q,
+	int32_t n_samples, float* __restrict__ hsum)
+{
+	extern __shared__ float cs[];
+	const int64_t ray = blockIdx.x;
+	for (int s = threadIdx.x; s < n_samples; s += blockDim.x) {
+		const int64_t row = ray * n_samples + s;
+		cs[s] = weights[row] / fmaxf(sqrtf(fmaxf(q[row], 0.f)), 1e-8f);
+	}
+	__syncthreads();
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	for (int j = warp; j < kHid / 8; j += 8) {
+		float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+		for (int s = lane; s < n_samples; s += 32) {
+			const int64_t row = ray * n_samples + s;
+			const uint4 v = __ldg(hidden + (row >> 7) * (kHiddenTile / 16) + j * 128 + (row & 127));
+			const float c = cs[s];
+			const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[i]));
+				acc[2 * i] = fmaf(c, f.x, acc[2 * i]);
+				acc[2 * i + 1] = fmaf(c, f.y, acc[2 * i + 1]);
+			}
+		}
+#pragma unroll
+		for (int i = 0; i < 8; i++) acc[i] = warp_sum(acc[i]);
+		if (lane == 0) {
+			float4* o = reinterpret_cast<float4*>(hsum + ray * kHid + j * 8);
+			o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+			o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+		}
+	}
+}
+
+// 8 rays per block, 256 threads; thread j computes outputs j and j + 256 of every ray from W_e1^T (fp32 [256][512], coalesced over j)
+constexpr int kProjRays = 8;
+__global__ void __launch_bounds__(256) lerf_project_kernel(const float* __restrict__ w_t, const float* __restrict__ hsum, int64_t n_rays, float* __restrict__ rendered)
+{
+	__shared__ float hs[kProjRays][kHid];
+	__shared__ float part[8][kProjRays];
+	const int64_t ray0 = static_cast<int64_t>(blockIdx.x) * kProjRays;
+	for (int i = threadIdx.x; i < kProjRays * kHid; i += 256) {
+		const int64_t ray = ray0 + i / kHid;
+		hs[i / kHid][i % kHid] = ray < n_rays ? hsum[ray * kHid + i % kHid] : 0.f;
+	}
+	__syncthreads();
+	float lo[kProjRays], hi[kProjRays];
+#pragma unroll
+	for (int i = 0; i < kProjRays; i++) lo[i] = hi[i] = 0.f;
+	const int j = threadIdx.x;
+#pragma unroll 4
+	for (int k = 0; k < kHid; k++) {
+		const float w0 = __ldg(w_t + k * kDim + j), w1 = __ldg(w_t + k * kDim + 256 + j);
+#pragma unroll
+		for (int i = 0; i < kProjRays; i++) {
+			lo[i] = fmaf(hs[i][k], w0, lo[i]);
+			hi[i] = fmaf(hs[i][k], w1, hi[i]);
+		}
+	}
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+	for (int i = 0; i < kProjRays; i++) {
+		const float s = warp_sum(lo[i] * lo[i] + hi[i] * hi[i]);
+		if (lane == 0) part[warp][i] = s;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int i = 0; i < kProjRays; i++) {
+		const int64_t ray = ray0 + i;
+		if (ray >= n_rays) break;
+		float ss = 0.f;
+#pragma unroll
+		for (int w = 0; w < 8; w++) ss += part[w][i];
+		const float inv = 1.f / fmaxf(sqrtf(ss), 1e-8f);
+		rendered[ray * kDim + j] = lo[i] * inv;
+		rendered[ray * kDim + 256 + j] = hi[i] * inv;
+	}
+}
+
+}  // namespace lerf_tc
+}  // namespace nrf
+
+using namespace nrf;
+using namespace nrf::lerf_tc;
+
+extern "C" {
+
+int64_t nrf_lerf_packed_bytes(const nrf_lerf_shape* shape) { return lerf_tc::check_shape(shape) ? -1 : static_cast<int64_t>(kPackedBytes); }
+
+int64_t nrf_lerf_hidden_bytes(const nrf_lerf_shape* shape, int64_t n)
+{
+	if (lerf_tc::check_shape(shape) || n < 0) return -1;
+	return ((n + 127) / 128) * static_cast<int64_t>(kHiddenTile);
+}
+
+int nrf_lerf_pack(const nrf_lerf_shape* shape, const nrf_lerf_weights* w, void* packed, nrf_stream stream)
+{
+	if (int rc = lerf_tc::check_shape(shape)) return rc;
+	NRF_REQUIRE(w != nullptr && packed != nullptr, "null pointer");
+	NRF_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0, "packed blob must be 128-byte aligned");
+	NRF_REQUIRE(w->sigma_w0 && w->sigma_w1 && w->le_w0 && w->le_w1, "null weight pointer");
+	Weights p{w->sigma_w0, w->sigma_w1, w->le_w0, w->le_w1};
+	lerf_pack_kernel<<<(kPackedBytes / 4 + 255) / 256, 256, 0, as_stream(stream)>>>(p, reinterpret_cast<uint32_t*>(packed));
+	NRF_CHECK_LAUNCH("lerf_pack_kernel");
+	return NRF_OK;
+}
+
+int nrf_lerf_fwd(const nrf_lerf_shape* shape, const void* packed, const void* enc_f16, const uint8_t* keep, int64_t n, float* raw_le, nrf_stream stream)
+{
+	if (int rc = lerf_tc::check_shape(shape)) return rc;
+	NRF_REQUIRE(n <= 0 || raw_le != nullptr, "null output");
+	return launch<kRaw>(shape, packed, enc_f16, keep, n, nullptr, nullptr, nullptr, raw_le, stream);
+}
+
+int nrf_lerf_sigma_fwd(const nrf_lerf_shape* shape, const void* packed, const void* enc_f16, const uint8_t* keep, int64_t n, float* raw4, nrf_stream stream)
+{
+	if (int rc = lerf_tc::check_shape(shape)) return rc;
+	NRF_REQUIRE(n <= 0 || raw4 != nullptr, "null output");
+	return launch<kSigma>(shape, packed, enc_f16, keep, n, raw4, nullptr, nullptr, nullptr, stream);
+}
+
+int nrf_lerf_hidden_fwd(const nrf_lerf_shape* shape, const void* packed, const void* enc_f16, const uint8_t* keep, int64_t n, float* raw4, void* hidden,
+                        float* q, nrf_stream stream)
+{
+	if (int rc = lerf_tc::check_shape(shape)) return rc;
+	NRF_REQUIRE(n <= 0 || (raw4 && hidden && q), "null output");
+	return launch<kHidden>(shape, packed, enc_f16, keep, n, raw4, hidden, q, nullptr, stream);
+}
+
+int nrf_lerf_render_embedding(const nrf_lerf_shape* shape, const void* packed, const float* weights, const void* hidden, const float* q, int64_t n_rays,
+                              int32_t n_samples, float* hsum, float* rendered, nrf_stream stream)
+{
+	if (int rc = lerf_tc::check_shape(shape)) return rc;
+	NRF_REQUIRE(n_rays >= 0 && n_samples >= 1 && n_samples <= 8192, "n_rays >= 0 and 1 <= n_samples <= 8192");
+	if (n_rays == 0) return NRF_OK;
+	NRF_REQUIRE(packed && weights && hidden && q && hsum && rendered, "null pointer");
+	NRF_REQUIRE((reinterpret_cast<uintptr_t>(hidden) & 15) == 0 && (reinterpret_cast<uintptr_t>(hsum) & 15) == 0, "hidden / hsum must be 16-byte aligned");
+	lerf_hsum_kernel<<<static_cast<unsigned>(n_rays), 256, n_samples * sizeof(float), as_stream(stream)>>>(weights, reinterpret_cast<const uint4*>(hidden), q,
+		n_samples, hsum);
+	NRF_CHECK_LAUNCH("lerf_hsum_kernel");
+	const float* w_t = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(packed) + kWeightBytes);
+	lerf_project_kernel<<<static_cast<unsigned>((n_rays + kProjRays - 1) / kProjRays), 256, 0, as_stream(stream)>>>(w_t, hsum, n_rays, rendered);
+	NRF_CHECK_LAUNCH("lerf_project_kernel");
+	return NRF_OK;
+}
+
+}

@@ -447,3 +447,69 @@ def mlp_nerf_fwd(packed: torch.Tensor, x: torch.Tensor, shape=None, out: torch.T
         out = torch.empty((n, 4), dtype=f32, device=x.device)
     _run("mlp_nerf_fwd", lambda: lib().nrf_mlp_nerf_fwd(C.byref(shape), ptr(packed), ptr(x, f32), n, ptr(out, f32), stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ LeRF language head
+
+LERF_WEIGHT_NAMES = ("sigma_le_net_0", "sigma_le_net_1", "le_net_0", "le_net_1")
+
+
+def lerf_shape(geo_feat_dim=32, num_layers=2, hidden_dim=256, lang_embed_dim=512, input_ch=128):
+    return cabi.LerfShape(geo_feat_dim, num_layers, hidden_dim, lang_embed_dim, input_ch)
+
+
+def lerf_pack(p: dict, shape=None, out: torch.Tensor | None = None, prefix: str = "lang_model") -> torch.Tensor:
+    """p: the reference's registered names ('<prefix>_sigma_le_net_<i>.weight', '<prefix>_le_net_<i>.weight', src/LeRF.cpp:17-25) ->
+    contiguous fp32 CUDA tensors.  Returns the operand blob of the fused head (fp16 UMMA core matrices of the four layers and of
+    G = W_e1^T W_e1, then W_e1^T in fp32)."""
+    shape = shape or lerf_shape()
+    nbytes = lib().nrf_lerf_packed_bytes(C.byref(shape))
+    if nbytes < 0:
+        check(-3)
+    w = cabi.LerfWeights(*[ptr(p[f"{prefix}_{n}.weight"], f32) for n in LERF_WEIGHT_NAMES])
+    if out is None:
+        out = torch.empty(nbytes, dtype=u8, device=p[f"{prefix}_le_net_1.weight"].device)
+    _run("lerf_pack", lambda: lib().nrf_lerf_pack(C.byref(shape), C.byref(w), ptr(out), stream()))
+    return out
+
+
+def lerf_fwd(packed: torch.Tensor, enc: torch.Tensor, keep: torch.Tensor | None = None, shape=None) -> torch.Tensor:
+    """LeRF::forward + the keep mask of RunLENetwork: enc [N,128] fp16 -> raw_le [N,513] fp32."""
+    shape = shape or lerf_shape()
+    n = enc.shape[0]
+    out = torch.empty((n, shape.lang_embed_dim + 1), dtype=f32, device=enc.device)
+    _run("lerf_fwd", lambda: lib().nrf_lerf_fwd(C.byref(shape), ptr(packed), ptr(enc, f16), ptr(keep, u8) if keep is not None else None, n, ptr(out), stream()))
+    return out
+
+
+def lerf_sigma_fwd(packed: torch.Tensor, enc: torch.Tensor, keep: torch.Tensor | None = None, shape=None) -> torch.Tensor:
+    """Density of the language field only: raw4 [N,4] = [0,0,0,sigma_le]."""
+    shape = shape or lerf_shape()
+    n = enc.shape[0]
+    raw4 = torch.empty((n, 4), dtype=f32, device=enc.device)
+    _run("lerf_sigma_fwd", lambda: lib().nrf_lerf_sigma_fwd(C.byref(shape), ptr(packed), ptr(enc, f16), ptr(keep, u8) if keep is not None else None, n,
+                                                             ptr(raw4), stream()))
+    return raw4
+
+
+def lerf_hidden_fwd(packed: torch.Tensor, enc: torch.Tensor, keep: torch.Tensor | None = None, shape=None):
+    """Fine pass without the [N,512] embedding: (raw4 [N,4], hidden (fp16 tile records of h2), q [N] = |e|^2)."""
+    shape = shape or lerf_shape()
+    n = enc.shape[0]
+    raw4 = torch.empty((n, 4), dtype=f32, device=enc.device)
+    hidden = torch.empty(max(lib().nrf_lerf_hidden_bytes(C.byref(shape), n), 0), dtype=u8, device=enc.device)
+    q = torch.empty(n, dtype=f32, device=enc.device)
+    _run("lerf_hidden_fwd", lambda: lib().nrf_lerf_hidden_fwd(C.byref(shape), ptr(packed), ptr(enc, f16), ptr(keep, u8) if keep is not None else None, n,
+                                                               ptr(raw4), ptr(hidden), ptr(q), stream()))
+    return raw4, hidden, q
+
+
+def lerf_render_embedding(packed: torch.Tensor, weights: torch.Tensor, hidden: torch.Tensor, q: torch.Tensor, shape=None) -> torch.Tensor:
+    """RenderCLIPEmbedding on the (never materialised) normalised embeddings: weights [R,S] -> rendered [R,512]."""
+    shape = shape or lerf_shape()
+    r, s = weights.shape
+    hsum = torch.empty((r, shape.hidden_dim), dtype=f32, device=weights.device)
+    out = torch.empty((r, shape.lang_embed_dim), dtype=f32, device=weights.device)
+    _run("lerf_render_embedding", lambda: lib().nrf_lerf_render_embedding(C.byref(shape), ptr(packed), ptr(weights, f32), ptr(hidden), ptr(q, f32), r, s,
+                                                                           ptr(hsum), ptr(out), stream()))
+    return out

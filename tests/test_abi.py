@@ -68,6 +68,30 @@ def test_classic_nerf_training_sizes_and_validation_without_gpu():
     assert b"negative" in lib.nrf_last_error()
 
 
+def test_lerf_head_sizes_and_validation_without_gpu():
+    """Host-side entries of the LeRF head ABI: blob / scratch sizes and loud refusal of shapes that are not built
+    (the reference's default 768-d language dimension, src/NeRFExecutor.h:63, included) — no kernel is launched."""
+    from nerfpp_b200 import cabi, ops
+    lib = cabi.lib()
+    shape = ops.lerf_shape()
+    operand = 2 * (256 * 128 + 48 * 256 + 256 * 160 + 3 * 256 * 256)          # S0, S1 (33 -> 48), E0, G, E1 lower / upper halves, fp16
+    assert lib.nrf_lerf_packed_bytes(ctypes.byref(shape)) == operand + 4 * 256 * 512
+    for n, tiles in ((0, 0), (1, 1), (128, 1), (129, 2), (196608, 1536)):
+        assert lib.nrf_lerf_hidden_bytes(ctypes.byref(shape), n) == tiles * 128 * 256 * 2
+    for bad in (ops.lerf_shape(lang_embed_dim=768), ops.lerf_shape(num_layers=3, hidden_dim=64), ops.lerf_shape(input_ch=32)):
+        assert lib.nrf_lerf_packed_bytes(ctypes.byref(bad)) == -1 and lib.nrf_lerf_hidden_bytes(ctypes.byref(bad), 128) == -1
+        assert lib.nrf_lerf_fwd(ctypes.byref(bad), None, None, None, 4, None, None) == -3                 # NRF_ERR_UNSUPPORTED
+    assert lib.nrf_lerf_hidden_bytes(ctypes.byref(shape), -1) == -1
+    assert lib.nrf_lerf_sigma_fwd(ctypes.byref(shape), None, None, None, 0, None, None) == 0             # empty batch: no-op
+    assert lib.nrf_lerf_fwd(ctypes.byref(shape), None, None, None, 4, None, None) == -1                  # null pointers
+    assert lib.nrf_lerf_hidden_fwd(ctypes.byref(shape), None, None, None, 4, None, None, None, None) == -1
+    assert lib.nrf_lerf_render_embedding(ctypes.byref(shape), None, None, None, None, 4, 0, None, None, None) == -1
+    assert lib.nrf_lerf_render_embedding(ctypes.byref(shape), None, None, None, None, 0, 8, None, None, None) == 0
+    with pytest.raises(cabi.NrfError):
+        import torch
+        ops.lerf_fwd(torch.zeros(8, dtype=torch.uint8), torch.zeros(4, 128, dtype=torch.float16))        # CPU tensors: no CPU path
+
+
 def test_product_path_refuses_cpu_tensors():
     import torch
     from nerfpp_b200 import cabi, ops
