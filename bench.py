@@ -234,6 +234,57 @@ def classic_nerf_leg(tf_peak: float, rows: int = 1024 * 192, reps: int = 10) -> 
                     "kernels": "mlp_nerf_bwd_chain_kernel + mlp_nerf_bwd_dw_kernel"}}
 
 
+def lerf_leg(tf_peak: float, rays: int = 1024, reps: int = 10) -> dict:
+    """BASELINE C5's language head (LeRF(32, 2, 256, 512, 128), src/LeRF.cpp:28-111) at one 1024-ray batch of 64 + 128 samples: the three
+    stage programs of the fused tcgen05 kernel and the per-ray finish, each timed with a CUDA-event pair over `reps` launches, and the whole
+    LeRFRenderer::RenderRays (inference).  FLOP counts are the REFERENCE's (the full 512-wide last layer), not the issued ones."""
+    import torch
+    from nerfpp_b200 import ops
+    from nerfpp_b200.lerf import LeRFField
+    f = LeRFField(seed=0)
+    g = torch.Generator().manual_seed(0)
+    for v in f.weights.values():
+        v.copy_((torch.randn(v.shape, generator=g) * (2.0 / v.shape[1]) ** 0.5).cuda())
+    f.table.copy_((torch.rand(f.n_table, generator=g) * 2 - 1).cuda())
+    f.refresh()
+    n_c, n_f = rays * 64, rays * 192
+    enc_c, enc_f = torch.randn(n_c, 128, generator=g).half().cuda(), torch.randn(n_f, 128, generator=g).half().cuda()
+    w = torch.rand(rays, 192, generator=g).cuda()
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms_sigma = timed(lambda: ops.lerf_sigma_fwd(f.packed, enc_c))
+    ms_hidden = timed(lambda: ops.lerf_hidden_fwd(f.packed, enc_f))
+    _, hidden, q = ops.lerf_hidden_fwd(f.packed, enc_f)
+    ms_finish = timed(lambda: ops.lerf_render_embedding(f.packed, w, hidden, q))
+    ms_raw = timed(lambda: ops.lerf_fwd(f.packed, enc_f))
+    from nerfpp_b200.pipeline import synthetic_rays
+    o, d, _ = synthetic_rays(rays, seed=3)
+    ms_render = timed(lambda: f.render_rays(o, d, return_weights=False))
+    fl_sigma, fl_full = 2 * (128 * 256 + 256 * 33), 2 * (128 * 256 + 256 * 33 + 160 * 256 + 256 * 512)
+
+    def tf(rows, flop, ms):
+        return rows * flop / ms / 1e9
+
+    return {"rays": rays, "config": "C5 language head: LeRF(32,2,256,512,128) on a 16x8 hash grid, 1024 rays x (64 coarse + 192 fine) samples, inference",
+            "sigma_program": {"rows": n_c, "ms": ms_sigma, "achieved": tf(n_c, fl_sigma, ms_sigma), "frac": tf(n_c, fl_sigma, ms_sigma) / tf_peak},
+            "hidden_program_plus_finish": {"rows": n_f, "ms": ms_hidden + ms_finish, "ms_tc_kernel": ms_hidden, "ms_per_ray_finish": ms_finish,
+                                           "achieved": tf(n_f, fl_full, ms_hidden + ms_finish), "frac": tf(n_f, fl_full, ms_hidden + ms_finish) / tf_peak,
+                                           "note": "reference-equivalent FLOPs (512-wide last layer); issued: 303 kFLOP/row (G = W^T W norm layer)"},
+            "raw_program": {"rows": n_f, "ms": ms_raw, "achieved": tf(n_f, fl_full, ms_raw), "frac": tf(n_f, fl_full, ms_raw) / tf_peak,
+                            "hbm_gbs": n_f * (513 * 4 + 256) / ms_raw / 1e6, "note": "writes raw_le [N,513] fp32 (the reference's layout)"},
+            "render_rays": {"ms": ms_render, "rays_per_s": rays / ms_render * 1e3, "dtype": "fp16 operands, fp32 accumulate"}}
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -456,6 +507,10 @@ def main() -> None:
     roofline_render_ops = None
     if rank == 0:
         roofline_tensor["mlp_nerf"] = classic_nerf_leg(tf_peak)
+        try:
+            roofline_tensor["lerf_head"] = lerf_leg(tf_peak)
+        except Exception as e:  # noqa: BLE001 - a secondary leg must not take the headline line down
+            roofline_tensor["lerf_head"] = {"error": f"{type(e).__name__}: {e}"}
         roofline_render_ops = render_ops_leg(roofline["peak"])
 
     cpu_baseline = None

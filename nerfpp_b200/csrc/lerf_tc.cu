@@ -520,11 +520,15 @@ __global__ void __launch_bounds__(256) lerf_hsum_kernel(const float* __restrict_
 	}
 }
 
-// 8 rays per block, 256 threads; thread j computes outputs j and j + 256 of every ray from W_e1^T (fp32 [256][512], coalesced over j)
-constexpr int kProjRays = 8;
+// 4 rays per block, 256 threads: thread = (output quad oq = tid & 127, k half kh = tid >> 7) accumulates 4 rays x 4 outputs over its 128 k from
+// W_e1^T (fp32 [256][512]: one 16-byte load per k, 512 contiguous bytes per warp, 8 in flight), the halves meet in shared memory, then each
+// thread owns outputs tid and tid + 256 of every ray for the norm and the store.  (The first version — 8 rays per block, two scalar loads per k —
+// was latency-bound on its 128 blocks: 60 us for 0.27 GFLOP.)
+constexpr int kProjRays = 4;
 __global__ void __launch_bounds__(256) lerf_project_kernel(const float* __restrict__ w_t, const float* __restrict__ hsum, int64_t n_rays, float* __restrict__ rendered)
 {
 	__shared__ float hs[kProjRays][kHid];
+	__shared__ __align__(16) float red[2][kProjRays][kDim];
 	__shared__ float part[8][kProjRays];
 	const int64_t ray0 = static_cast<int64_t>(blockIdx.x) * kProjRays;
 	for (int i = threadIdx.x; i < kProjRays * kHid; i += 256) {
@@ -532,22 +536,32 @@ __global__ void __launch_bounds__(256) lerf_project_kernel(const float* __restri
 		hs[i / kHid][i % kHid] = ray < n_rays ? hsum[ray * kHid + i % kHid] : 0.f;
 	}
 	__syncthreads();
-	float lo[kProjRays], hi[kProjRays];
+	const int oq = threadIdx.x & 127, kh = threadIdx.x >> 7;
+	float4 acc[kProjRays];
 #pragma unroll
-	for (int i = 0; i < kProjRays; i++) lo[i] = hi[i] = 0.f;
-	const int j = threadIdx.x;
-#pragma unroll 4
-	for (int k = 0; k < kHid; k++) {
-		const float w0 = __ldg(w_t + k * kDim + j), w1 = __ldg(w_t + k * kDim + 256 + j);
+	for (int i = 0; i < kProjRays; i++) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+	const float4* wq = reinterpret_cast<const float4*>(w_t) + oq;
+#pragma unroll 8
+	for (int k = kh * 128; k < kh * 128 + 128; k++) {
+		const float4 w = __ldg(wq + k * (kDim / 4));
 #pragma unroll
 		for (int i = 0; i < kProjRays; i++) {
-			lo[i] = fmaf(hs[i][k], w0, lo[i]);
-			hi[i] = fmaf(hs[i][k], w1, hi[i]);
+			const float h = hs[i][k];
+			acc[i].x = fmaf(h, w.x, acc[i].x);
+			acc[i].y = fmaf(h, w.y, acc[i].y);
+			acc[i].z = fmaf(h, w.z, acc[i].z);
+			acc[i].w = fmaf(h, w.w, acc[i].w);
 		}
 	}
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+	for (int i = 0; i < kProjRays; i++) *reinterpret_cast<float4*>(&red[kh][i][4 * oq]) = acc[i];
+	__syncthreads();
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, j = threadIdx.x;
+	float lo[kProjRays], hi[kProjRays];
 #pragma unroll
 	for (int i = 0; i < kProjRays; i++) {
+		lo[i] = red[0][i][j] + red[1][i][j];
+		hi[i] = red[0][i][256 + j] + red[1][i][256 + j];
 		const float s = warp_sum(lo[i] * lo[i] + hi[i] * hi[i]);
 		if (lane == 0) part[warp][i] = s;
 	}

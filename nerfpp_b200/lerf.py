@@ -1,0 +1,83 @@
+"""LeRF language field on the C ABI: LeRFRenderer::RenderRays / Render for inference (BASELINE C5).
+
+Host-side mirror, in Python, of src/LeRFRenderer.cpp:85-162 (RenderRays) and :266-331 (Render) for the instantiation the
+reference trains: CuHashEmbedder("lang_embedder", bbox, 16, 8, 19, 16, 512) (src/main.cpp:203-207, src/NeRFExecutor.h:461) and
+LeRF(32, 2, 256, D, 128, "lang_model") (src/NeRFExecutor.h:507-514) with D = 512 (BASELINE C5).  Every arithmetic step is one call
+into libnerfpp_b200.so; torch only owns the buffers and the stream.
+
+What is not computed, because the reference discards it: the coarse pass evaluates the language density only (its embedding,
+src/LeRFRenderer.cpp:133-134, is never used), and the fine pass never forms LangEmbedding [R,S,D] — RenderedLangEmbedding comes from
+the last hidden layer (nrf_lerf_hidden_fwd + nrf_lerf_render_embedding).  `return_embedding=True` evaluates the compatibility entry
+(nrf_lerf_fwd) as well and returns the reference's LangEmbedding / Raw tensors.
+Configuration is the parity one: ThinRay, Perturb 0, no raw noise, no stochastic preconditioning.  Relevancy (RuCLIP) is out of scope.
+Training of the language field (src/NeRFExecutor.h:957-983) is not built yet.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+from .ops import f16, f32
+from .pipeline import make_grid
+
+LERF_LAYERS = (("sigma_le_net_0", 256, 128), ("sigma_le_net_1", 33, 256), ("le_net_0", 256, 160), ("le_net_1", 512, 256))
+
+
+class LeRFField:
+    """Language hash grid + LeRF head of one replica, and the LeRFRenderer stages on them."""
+
+    def __init__(self, bbox=(-1.5, -1.5, -1.5, 1.5, 1.5, 1.5), n_levels=16, n_features=8, log2_hashmap_size=19, base_resolution=16,
+                 finest_resolution=512, n_samples=64, n_importance=128, device="cuda", seed=42, primes=None, prefix="lang_model"):
+        assert n_levels * n_features == 128, "the fused head is built for 128 input channels (16 levels x 8 features)"
+        self.device = torch.device(device)
+        self.bbox = tuple(float(v) for v in bbox)
+        self.prefix = prefix
+        self.grid = make_grid(bbox, n_levels, n_features, log2_hashmap_size, base_resolution, finest_resolution, device, seed, primes)
+        self.S, self.N = n_samples, n_importance
+        self.n_table = self.grid.used_scalars()
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        self.table = (torch.rand(self.n_table, generator=g) * 1e-4).to(device)                    # src/CuHashEmbedder.cpp:24
+        self.weights = {}
+        for name, fo, fi in LERF_LAYERS:                                                          # Trainable.h:43 Xavier normal, gain 0.1
+            self.weights[f"{prefix}_{name}.weight"] = (torch.randn(fo, fi, generator=g) * 0.1 * math.sqrt(2.0 / (fi + fo))).to(device)
+        self.t_vals = torch.linspace(0.0, 1.0, n_samples, dtype=f32).to(device)                   # src/LeRFRenderer.cpp:112
+        self.u = torch.linspace(0.0, 1.0, n_importance, dtype=f32).to(device)                     # src/Sampler.h:20
+        self.table_f16 = torch.empty(self.n_table, dtype=f16, device=device)
+        self.packed = None
+        self.refresh()
+
+    def refresh(self):
+        """Re-derive the fp16 table shadow and the operand blob from the fp32 masters (after loading a checkpoint)."""
+        ops.table_to_half(self.table, self.table_f16)
+        self.packed = ops.lerf_pack(self.weights, out=self.packed, prefix=self.prefix)
+
+    def render_rays(self, rays_o, rays_d, return_embedding=False, return_weights=True):
+        """LeRFRenderer::RenderRays after Render's prologue (IntersectWithAABB, src/LeRFRenderer.cpp:296-302): LeRFRendererOutputs as a dict."""
+        r = rays_o.shape[0]
+        ray_batch, z, _ = ops.ray_setup(rays_o, rays_d, self.bbox, 0.0, self.t_vals, None)
+        # coarse pass: density only (RunLENetwork + the weights of RawToLEOutputs)
+        enc, keep = ops.hash_encode_rays_fwd(self.grid, self.table_f16, ray_batch, z, clamp=True, out_f16=True)
+        raw4 = ops.lerf_sigma_fwd(self.packed, enc, keep)
+        coarse = ops.composite_fwd(raw4.view(r, self.S, 4), z, rays_d)
+        z_fine = ops.sample_pdf_merge(z, coarse["weights"], self.u)                               # :143-147
+        s = z_fine.shape[1]
+        # fine pass
+        enc, keep = ops.hash_encode_rays_fwd(self.grid, self.table_f16, ray_batch, z_fine, clamp=True, out_f16=True)
+        raw4, hidden, q = ops.lerf_hidden_fwd(self.packed, enc, keep)
+        comp = ops.composite_fwd(raw4.view(r, s, 4), z_fine, rays_d)
+        out = {"rendered": ops.lerf_render_embedding(self.packed, comp["weights"], hidden, q), "depth": comp["depth"], "disp": comp["disp"],
+               "acc": comp["acc"], "z": z_fine}
+        if return_weights:
+            out["weights"] = comp["weights"]
+        if return_embedding:
+            out["raw"] = ops.lerf_fwd(self.packed, enc, keep).view(r, s, -1)                      # LeRFRenderResult::Raw
+            out["embedding"] = out["raw"][..., :-1]                                               # LeRFRendererOutputs::LangEmbedding
+        return out
+
+    def render_image(self, h, w, K, c2w, chunk=1 << 15, row_begin=0, row_end=None):
+        """Render(h, w, K, c2w) for image rows [row_begin, row_end) (src/LeRFRenderer.cpp:266-331; chunking as BatchifyRays :165-263)."""
+        rays_o, rays_d = ops.get_rays(h, w, K, c2w, row_begin, row_end, self.device)
+        outs = [self.render_rays(rays_o[i:i + chunk], rays_d[i:i + chunk], return_weights=False) for i in range(0, rays_o.shape[0], chunk)]
+        return {k: torch.cat([o[k] for o in outs], 0) for k in ("rendered", "depth", "disp", "acc")}

@@ -396,6 +396,21 @@ def render_rays(ray_batch_: torch.Tensor, n_samples: int, n_importance: int, run
     return out2, out1, z_all
 
 
+def lerf_render_rays(ray_batch_: torch.Tensor, n_samples: int, n_importance: int, run_le_network, lang_embed_dim: int):
+    """src/LeRFRenderer.cpp:85-162 in the parity configuration (ThinRay, perturb 0, no noise, no preconditioning):
+    run_le_network(pts [R,S,3]) -> raw_le [R,S,D+1].  Returns (fine outputs, coarse outputs, z_fine)."""
+    o, d = ray_batch_[:, 0:3], ray_batch_[:, 3:6]
+    z = z_coarse(ray_batch_, n_samples)                                                     # :112-118
+    pts = o[:, None, :] + d[:, None, :] * z[:, :, None]                                     # :137
+    out1 = raw_to_le_outputs(run_le_network(pts), z, d, lang_embed_dim)                     # :140-141
+    z_mid = 0.5 * (z[:, 1:] + z[:, :-1])                                                    # :145
+    z_s, _ = sample_pdf(z_mid, out1["weights"][:, 1:-1], n_importance, True)                # :146
+    z_all, _ = torch.sort(torch.cat([z, z_s.detach()], -1), -1)                             # :147-149
+    pts = o[:, None, :] + d[:, None, :] * z_all[:, :, None]                                 # :150
+    out2 = raw_to_le_outputs(run_le_network(pts), z_all, d, lang_embed_dim)                 # :166-167
+    return out2, out1, z_all
+
+
 # ------------------------------------------------------------------------------------------------ training glue
 
 
