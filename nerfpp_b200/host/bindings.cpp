@@ -6,6 +6,7 @@
 #include <chrono>
 
 #include "renderer.h"
+#include "lerf.h"
 #include "fused_adam.h"
 
 namespace py = pybind11;
@@ -132,6 +133,74 @@ struct Pipeline {
 	}
 };
 
+// The language branch of NeRFExecutor (src/NeRFExecutor.h:458-470, 504-523, 531-535, 640-650, 957-983): second CuHashEmbedder + LeRF + LeRFRenderer
+struct OpenLeRFRenderer : public LeRFRenderer {
+	using LeRFRenderer::LeRFRenderer;
+	using LeRFRenderer::RunLENetwork;
+	using LeRFRenderer::RawToLEOutputs;
+};
+
+static py::dict ToDict(const LeRFRendererOutputs& o)
+{
+	py::dict d;
+	d["rendered"] = o.RenderedLangEmbedding; d["embedding"] = o.LangEmbedding; d["weights"] = o.WeightsLE; d["depth"] = o.DepthMapLE;
+	d["disp"] = o.DispMapLE; d["acc"] = o.AccMapLE; d["relevancy"] = o.Relevancy;
+	return d;
+}
+
+struct LerfPipe {
+	CuHashEmbedder embed{nullptr};
+	LeRF model{nullptr};
+	std::unique_ptr<OpenLeRFRenderer> renderer;
+	std::unique_ptr<torch::optim::Adam> opt;
+	Tensor bbox;
+
+	void Finish()
+	{
+		embed->to(torch::kCUDA); model->to(torch::kCUDA);
+		renderer = std::make_unique<OpenLeRFRenderer>(embed, model);
+	}
+	std::vector<Tensor> EmbedParams() { return embed->parameters(); }
+	std::vector<Tensor> ModelParams() { return model->parameters(); }
+	std::vector<std::string> ModelParamNames() { std::vector<std::string> r; for (auto& p : model->named_parameters()) r.push_back(p.key()); return r; }
+	void InitModel() { Trainable::Initialize(model); }
+	Tensor Model(Tensor x) { return model->forward(x); }
+	Tensor RunLENetwork(Tensor pts) { return renderer->RunLENetwork(pts, model, embed); }
+	py::dict RawToLEOutputs(Tensor raw_le, Tensor z, Tensor rays_d) { return ToDict(renderer->RawToLEOutputs(raw_le, z, rays_d, model->GetLangEmbedDim(), 0.f)); }
+	py::dict Render(Tensor rays_o, Tensor rays_d, int n_samples, int n_importance, int chunk, bool materialize, bool return_raw)
+	{
+		auto p = Params(n_samples, n_importance, chunk, false, false, bbox, true, 0.f, 0.f);
+		p.ReturnRaw = return_raw;
+		renderer->MaterializeLangEmbedding = materialize;
+		auto r = renderer->Render(0, 0, Tensor(), p, {rays_o, rays_d, Tensor()}, Tensor(), Tensor());
+		py::dict d = ToDict(r.Outputs);
+		d["near"] = r.Near; d["far"] = r.Far; d["raw"] = r.Raw;
+		return d;
+	}
+	/// the language lines of NeRFExecutor::Train (src/NeRFExecutor.h:957-983, 986): Render, huber(delta 1.25).sum(-1).nanmean(), backward, Adam
+	std::vector<float> TrainSteps(Tensor rays_o, Tensor rays_d, Tensor target, int n_steps, int n_samples, int n_importance, int chunk, float lr)
+	{
+		if (!opt) {
+			std::vector<Tensor> gv;
+			for (auto& p : embed->parameters()) gv.push_back(p);
+			for (auto& p : model->parameters()) gv.push_back(p);
+			opt = std::make_unique<torch::optim::Adam>(gv, torch::optim::AdamOptions(lr).eps(1e-15).betas(std::make_tuple(0.9, 0.99)));
+		}
+		std::vector<float> losses;
+		auto p = Params(n_samples, n_importance, chunk, false, false, bbox, true, 0.f, 0.f);
+		for (int i = 0; i < n_steps; i++) {
+			opt->zero_grad();
+			auto r = renderer->Render(0, 0, Tensor(), p, {rays_o, rays_d, Tensor()}, Tensor(), Tensor());
+			auto loss = torch::nn::functional::huber_loss(r.Outputs.RenderedLangEmbedding, target.detach(),
+				torch::nn::functional::HuberLossFuncOptions().reduction(torch::kNone).delta(1.25)).sum(-1).nanmean();
+			loss.backward();
+			opt->step();
+			losses.push_back(loss.item<float>());
+		}
+		return losses;
+	}
+};
+
 using CuHashPipe = Pipeline<CuHashEmbedder, CuSHEncoder, NeRFSmall>;
 using ClassicPipe = Pipeline<Embedder, Embedder, NeRF>;
 
@@ -184,6 +253,30 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 		p->embeddirs = CuSHEncoder("embeddirs", 3, sh_degree);
 		p->model = NeRFSmall(num_layers, hidden, geo_feat, num_layers_color, hidden_color, false, 3, 64, p->embed->GetOutputDims(),
 			p->embeddirs->GetOutputDims(), "model");
+		p->Finish();
+		return p;
+	});
+	py::class_<LerfPipe>(m, "LerfPipe")
+		.def("embed_params", &LerfPipe::EmbedParams).def("model_params", &LerfPipe::ModelParams).def("model_param_names", &LerfPipe::ModelParamNames)
+		.def("init_model", &LerfPipe::InitModel).def("model", &LerfPipe::Model).def("run_le_network", &LerfPipe::RunLENetwork)
+		.def("raw_to_le_outputs", &LerfPipe::RawToLEOutputs).def("render", &LerfPipe::Render)
+		.def("train_steps", &LerfPipe::TrainSteps, py::call_guard<py::gil_scoped_release>())
+		// NeRFExecutor::SaveCheckpoint / restore for the language branch (src/NeRFExecutor.h:556-560, 574-578, 1062-1066): same file names
+		.def("save_checkpoint", [](LerfPipe& p, const std::string& dir) {
+			torch::save(p.embed, dir + "/lang_embedder_checkpoint.pt");
+			torch::save(p.model, dir + "/lang_model_checkpoint.pt");
+		})
+		.def("load_checkpoint", [](LerfPipe& p, const std::string& dir) {
+			torch::load(p.embed, dir + "/lang_embedder_checkpoint.pt");
+			torch::load(p.model, dir + "/lang_model_checkpoint.pt");
+		});
+	// src/NeRFExecutor.h:461 and :507-514
+	m.def("make_lerf", [](Tensor bbox, int n_levels, int n_feat, int log2_t, int base_res, int finest_res, int geo_feat, int num_layers, int hidden,
+		int lang_dim) {
+		auto p = std::make_unique<LerfPipe>();
+		p->bbox = bbox;
+		p->embed = CuHashEmbedder("lang_embedder", bbox, n_levels, n_feat, log2_t, base_res, finest_res);
+		p->model = LeRF(geo_feat, num_layers, hidden, lang_dim, p->embed->GetOutputDims(), "lang_model");
 		p->Finish();
 		return p;
 	});

@@ -168,7 +168,7 @@ using CuHashPipe = RefPipeline<CuHashEmbedder, CuSHEncoder, NeRFSmall>;
 template <class P>
 static void BindPipe(py::module_& m, const char* name)
 {
-	py::class_<P>(m, name)
+	py::class_<P>(m, name, py::module_local())
 		.def("embed_params", &P::EmbedParams).def("model_params", &P::ModelParams)
 		.def("model_param_names", &P::ModelParamNames)
 		.def("embed_buffers", &P::EmbedBuffers).def("embed_buffer_names", &P::EmbedBufferNames)
@@ -192,7 +192,73 @@ static void BindPipe(py::module_& m, const char* name)
 struct OpenLeRFRenderer : public LeRFRenderer {
 	using LeRFRenderer::LeRFRenderer;
 	using LeRFRenderer::RawToLEOutputs;
+	using LeRFRenderer::RunLENetwork;
 };
+
+#ifdef NRF_REF_CUDA
+// The language branch of NeRFExecutor (src/NeRFExecutor.h:458-470, 504-523, 531-535, 957-983) on the reference's own classes:
+// CuHashEmbedder("lang_embedder", ...) + LeRF(..., "lang_model") + LeRFRenderer.  Same call surface as LerfPipe in
+// nerfpp_b200/host/bindings.cpp.  Relevancy comes from stub/RuCLIPProcessor.h (undefined): prompts are dummies.
+static py::dict LeOutputsToDict(const LeRFRendererOutputs& o)
+{
+	py::dict d;
+	d["rendered"] = o.RenderedLangEmbedding; d["embedding"] = o.LangEmbedding; d["weights"] = o.WeightsLE; d["depth"] = o.DepthMapLE;
+	d["disp"] = o.DispMapLE; d["acc"] = o.AccMapLE; d["relevancy"] = o.Relevancy;
+	return d;
+}
+
+struct LerfRefPipe {
+	CuHashEmbedder embed{nullptr};
+	LeRF model{nullptr};
+	std::unique_ptr<OpenLeRFRenderer> renderer;
+	std::unique_ptr<torch::optim::Adam> opt;
+	Tensor bbox;
+
+	void Finish()
+	{
+		embed->to(torch::kCUDA); model->to(torch::kCUDA);
+		const int d = model->GetLangEmbedDim();
+		renderer = std::make_unique<OpenLeRFRenderer>(embed, model, torch::zeros({1, d}), torch::zeros({1, d}));
+	}
+	std::vector<Tensor> EmbedParams() { return embed->parameters(); }
+	std::vector<Tensor> ModelParams() { return model->parameters(); }
+	std::vector<std::string> ModelParamNames() { std::vector<std::string> r; for (auto& p : model->named_parameters()) r.push_back(p.key()); return r; }
+	void InitModel() { Trainable::Initialize(model); }
+	Tensor Model(Tensor x) { return model->forward(x); }
+	Tensor RunLENetwork(Tensor pts) { return renderer->RunLENetwork(pts, model, embed); }                         // src/LeRFRenderer.cpp:5
+	py::dict RawToLEOutputs(Tensor raw_le, Tensor z, Tensor rays_d) { return LeOutputsToDict(renderer->RawToLEOutputs(raw_le, z, rays_d, model->GetLangEmbedDim(), 0.f)); }
+	py::dict Render(Tensor rays_o, Tensor rays_d, int n_samples, int n_importance, int chunk, bool /*materialize*/, bool return_raw)   // src/LeRFRenderer.cpp:266
+	{
+		auto p = MakeParams(n_samples, n_importance, chunk, false, false, bbox, return_raw, false);
+		auto r = renderer->Render(0, 0, Tensor(), p, {rays_o, rays_d, Tensor()}, Tensor(), Tensor());
+		py::dict d = LeOutputsToDict(r.Outputs);
+		d["near"] = r.Near; d["far"] = r.Far; d["raw"] = r.Raw;
+		return d;
+	}
+	// src/NeRFExecutor.h:957-983, 986 (the language loss is back-propagated on its own)
+	std::vector<float> TrainSteps(Tensor rays_o, Tensor rays_d, Tensor target, int n_steps, int n_samples, int n_importance, int chunk, float lr)
+	{
+		if (!opt) {
+			std::vector<Tensor> gv;
+			for (auto& p : embed->parameters()) gv.push_back(p);
+			for (auto& p : model->parameters()) gv.push_back(p);
+			opt = std::make_unique<torch::optim::Adam>(gv, torch::optim::AdamOptions(lr).eps(1e-15).betas(std::make_tuple(0.9, 0.99)));
+		}
+		std::vector<float> losses;
+		auto p = MakeParams(n_samples, n_importance, chunk, false, false, bbox, false, false);
+		for (int i = 0; i < n_steps; i++) {
+			opt->zero_grad();
+			auto r = renderer->Render(0, 0, Tensor(), p, {rays_o, rays_d, Tensor()}, Tensor(), Tensor());
+			auto loss = torch::nn::functional::huber_loss(r.Outputs.RenderedLangEmbedding, target.detach(),
+				torch::nn::functional::HuberLossFuncOptions().reduction(torch::kNone).delta(1.25)).sum(-1).nanmean();
+			loss.backward();
+			opt->step();
+			losses.push_back(loss.item<float>());
+		}
+		return losses;
+	}
+};
+#endif
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 {
@@ -275,5 +341,29 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 		return p;
 	});
 	m.def("cu_sh_encoder", [](Tensor x, int degree) { CuSHEncoder e("embeddirs", 3, degree); return e->forward(x).first; });   // src/CuSHEncoder.cu:109
+	py::class_<LerfRefPipe>(m, "LerfPipe", py::module_local())
+		.def("embed_params", &LerfRefPipe::EmbedParams).def("model_params", &LerfRefPipe::ModelParams).def("model_param_names", &LerfRefPipe::ModelParamNames)
+		.def("init_model", &LerfRefPipe::InitModel).def("model", &LerfRefPipe::Model).def("run_le_network", &LerfRefPipe::RunLENetwork)
+		.def("raw_to_le_outputs", &LerfRefPipe::RawToLEOutputs).def("render", &LerfRefPipe::Render)
+		.def("train_steps", &LerfRefPipe::TrainSteps, py::call_guard<py::gil_scoped_release>())
+		// src/NeRFExecutor.h:556-560, 1062-1066
+		.def("save_checkpoint", [](LerfRefPipe& p, const std::string& dir) {
+			torch::save(p.embed, dir + "/lang_embedder_checkpoint.pt");
+			torch::save(p.model, dir + "/lang_model_checkpoint.pt");
+		})
+		.def("load_checkpoint", [](LerfRefPipe& p, const std::string& dir) {
+			torch::load(p.embed, dir + "/lang_embedder_checkpoint.pt");
+			torch::load(p.model, dir + "/lang_model_checkpoint.pt");
+		});
+	// src/NeRFExecutor.h:461 and :507-514
+	m.def("make_lerf", [](Tensor bbox, int n_levels, int n_feat, int log2_t, int base_res, int finest_res, int geo_feat, int num_layers, int hidden,
+		int lang_dim) {
+		auto p = std::make_unique<LerfRefPipe>();
+		p->bbox = bbox;
+		p->embed = CuHashEmbedder("lang_embedder", bbox, n_levels, n_feat, log2_t, base_res, finest_res);
+		p->model = LeRF(geo_feat, num_layers, hidden, lang_dim, p->embed->GetOutputDims(), "lang_model");
+		p->Finish();
+		return p;
+	});
 #endif
 }
