@@ -348,19 +348,29 @@ __global__ void __launch_bounds__(kThreads, 1) lerf_fwd_tc_kernel(const uint8_t*
 		const int row = (qd << 5) | lane;
 		const uint32_t t_lane = tmem + (static_cast<uint32_t>(qd << 5) << 16);
 		uint32_t pd = 0;
+		// The input row of the NEXT tile is requested while the last MMAs of the current tile run (16 x 16 B per thread, held in registers):
+		// at the top of a tile its global-load latency (the tensor pipe idle meanwhile) is already paid.
+		uint4 pre[16];
+		auto load_row = [&](int64_t tile_idx) {
+			const int64_t rr = tile_idx * 128 + row;
+			const bool in = tile_idx < n_tiles && rr < n;
+			const uint4* er = enc + (in ? rr : 0) * (kIn / 8);
+#pragma unroll
+			for (int i = 0; i < 16; i++) pre[i] = in ? __ldg(er + i) : make_uint4(0u, 0u, 0u, 0u);
+		};
+		if (my_tiles > 0) load_row(blockIdx.x);
 		for (int64_t t = 0; t < my_tiles; t++) {
 			const int64_t tile = blockIdx.x + t * gridDim.x;
 			const int64_t r = tile * 128 + row;
 			const bool ok = r < n;
-			// ---- input: the 128 fp16 channels of the language hash grid, as they leave nrf_hash_encode_fwd
+			// ---- input: the 128 fp16 channels of the language hash grid, as they leave nrf_hash_encode_fwd (already in registers, see load_row)
 			{
-				const uint4* er = enc + (ok ? r : 0) * (kIn / 8);
 				uint32_t a16[16];
 #pragma unroll
 				for (int h = 0; h < 4; h++) {
 #pragma unroll
 					for (int i = 0; i < 4; i++) {
-						const uint4 v = ok ? __ldg(er + 4 * h + i) : make_uint4(0u, 0u, 0u, 0u);
+						const uint4 v = pre[4 * h + i];
 						a16[4 * i] = v.x; a16[4 * i + 1] = v.y; a16[4 * i + 2] = v.z; a16[4 * i + 3] = v.w;
 					}
 					tmem_st16(t_lane + kColEnc + 16 * h, a16);
@@ -374,6 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) lerf_fwd_tc_kernel(const uint8_t*
 			fence_after();
 			relu_to_h<false>(t_lane, nullptr);
 			publish(&sm.a_ready, lane);
+			if (MODE == kSigma) load_row(tile + gridDim.x);
 
 			// ---- S1: [geo 32 | sigma]
 			mbar_wait(&sm.d_ready, pd);
@@ -408,6 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) lerf_fwd_tc_kernel(const uint8_t*
 			if (MODE == kHidden) relu_to_h<true>(t_lane, hidden + tile * kHiddenTile + row * 16);
 			else relu_to_h<false>(t_lane, nullptr);
 			publish(&sm.a_ready, lane);
+			if (MODE == kHidden) load_row(tile + gridDim.x);
 
 			if (MODE == kHidden) {
 				// ---- G: |e|^2 = h2 . (G h2)
@@ -428,6 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) lerf_fwd_tc_kernel(const uint8_t*
 					publish(&sm.a_ready, lane);
 				}
 				const float inv = 1.f / fmaxf(sqrtf(ss), 1e-8f);                      // F::normalize(eps 1e-8), src/LeRF.cpp:105
+				load_row(tile + gridDim.x);
 				// ---- E1, second pass: scale and store
 #pragma unroll 1
 				for (int half = 0; half < 2; half++) {

@@ -76,6 +76,28 @@ class LeRFField:
             out["embedding"] = out["raw"][..., :-1]                                               # LeRFRendererOutputs::LangEmbedding
         return out
 
+    # -- the same chunk as ONE CUDA-graph replay (11 kernels of 3..110 us behind 11 ctypes calls are launch-bound otherwise)
+    def capture_render(self, n_rays: int):
+        dev = self.device
+        self._g_in = (torch.tensor([[0.0, 0.0, 4.0]], device=dev).repeat(n_rays, 1), torch.tensor([[0.0, 0.0, -1.0]], device=dev).repeat(n_rays, 1))
+        side = torch.cuda.Stream(device=dev)                      # warm-up outside the capture (function attributes, level scales, allocator pools)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self.render_rays(*self._g_in, return_weights=False)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self._g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g):
+            self._g_out = self.render_rays(*self._g_in, return_weights=False)
+        return self
+
+    def render_rays_graph(self, rays_o, rays_d):
+        """Replay of the captured chunk; inputs may be device tensors or pinned host tensors.  The returned tensors are overwritten by the next replay."""
+        self._g_in[0].copy_(rays_o, non_blocking=True)
+        self._g_in[1].copy_(rays_d, non_blocking=True)
+        self._g.replay()
+        return self._g_out
+
     def render_image(self, h, w, K, c2w, chunk=1 << 15, row_begin=0, row_end=None):
         """Render(h, w, K, c2w) for image rows [row_begin, row_end) (src/LeRFRenderer.cpp:266-331; chunking as BatchifyRays :165-263)."""
         rays_o, rays_d = ops.get_rays(h, w, K, c2w, row_begin, row_end, self.device)

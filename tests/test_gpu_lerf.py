@@ -233,6 +233,17 @@ def test_render_rays_matches_composed_oracle():
     assert float((out["rendered"].cpu() - via).abs().max()) <= 1e-2 * float(via.abs().max())
 
 
+def test_graph_replay_equals_eager():
+    f = _field(seed=7)
+    o, d = _rays(96, seed=2)
+    eager = f.render_rays(o.cuda(), d.cuda(), return_weights=False)
+    f.capture_render(96)
+    out = f.render_rays_graph(o.pin_memory(), d.pin_memory())
+    torch.cuda.synchronize()
+    for k in ("rendered", "depth", "acc", "z"):
+        assert torch.equal(out[k], eager[k]), k
+
+
 def test_render_image_tiles_agree():
     """Image rows sharded across ranks (BASELINE C4/C5 rendering): two half-frames equal the whole frame bit for bit."""
     f = _field(seed=5)
