@@ -36,7 +36,6 @@ using namespace tc;
 
 constexpr int kIn = 128, kHid = 256, kGeo = 32, kDim = 512, kSigN = 48;   // kSigN: the 33 outputs of the sigma head padded to a UMMA N
 constexpr uint32_t kColD = 0, kColD2 = 256, kColGeo = 304, kColEnc = 320, kColH = 384;
-constexpr int kThreads = 32 * 6;
 constexpr int kRing = 4;
 constexpr int kStageBytes = 256 * 64 * 2;
 
@@ -65,10 +64,22 @@ __host__ __device__ constexpr int layer_offset(int l)
 	return b;
 }
 constexpr int kWeightBytes = layer_offset(kLayers);             // 565 248
-// W_e1 transposed, fp32 [256 k][512 n], follows the operand blob (lerf_project_kernel reads it)
+// The same four layers S0, S1, E0, G once more, packed as N-SLABS for lerf_fwd_slab_kernel: a slab = 128 outputs (48 for S1) x the whole K,
+// so an accumulator slab is complete on its own and its epilogue runs under the MMAs of the next slab.  Same per-layer sizes / offsets.
+constexpr int kSlabBase = kWeightBytes;
+constexpr int kSlabBytes = layer_offset(4);                     // 303 104
+__host__ __device__ constexpr int slab_n(int l) { return l == 1 ? kSigN : 128; }
+__host__ __device__ constexpr int slab_count(int l) { return l == 1 ? 1 : 2; }
+__host__ __device__ constexpr int slab_bytes(int l) { return slab_n(l) * layer_info(l).K * 2; }
+// a slab travels as 1 or 2 K-stages of at most 32 KB: S0 128 x 128, S1 48 x 256, E0 2 x (128 x 80), G 2 x (128 x 128)
+__host__ __device__ constexpr int slab_kstages(int l) { return l >= 2 ? 2 : 1; }
+__host__ __device__ constexpr int slab_stage_k(int l) { return layer_info(l).K / slab_kstages(l); }
+__host__ __device__ constexpr int slab_stage_bytes(int l) { return slab_n(l) * slab_stage_k(l) * 2; }
+// W_e1 transposed, fp32 [256 k][512 n], follows the operand blobs (lerf_project_kernel reads it)
+constexpr int kProjBase = kSlabBase + kSlabBytes;
 constexpr int kProjBytes = kHid * kDim * 4;
-constexpr int kPackedBytes = kWeightBytes + kProjBytes;
-static_assert(kWeightBytes % 128 == 0, "blob alignment");
+constexpr int kPackedBytes = kProjBase + kProjBytes;
+static_assert(kWeightBytes % 128 == 0 && kSlabBytes % 128 == 0, "blob alignment");
 
 enum Mode { kSigma = 0, kHidden = 1, kRaw = 2 };
 struct ModeTable {
@@ -96,6 +107,28 @@ constexpr ModeTable make_mode(int mode)
 }
 static_assert(make_mode(kSigma).n_stages == 3 && make_mode(kHidden).n_stages == 10 && make_mode(kRaw).n_stages == 22, "stage programs");
 __constant__ ModeTable c_modes[3] = {make_mode(kSigma), make_mode(kHidden), make_mode(kRaw)};
+
+struct SlabTable {
+	int n_groups, group_layer[4];
+	int n_stages, off[16], bytes[16];
+};
+constexpr SlabTable make_slab_table(int mode)
+{
+	SlabTable t{};
+	t.n_groups = mode == kSigma ? 2 : 4;
+	int i = 0;
+	for (int g = 0; g < t.n_groups; g++) {
+		t.group_layer[g] = g;
+		for (int sl = 0; sl < slab_count(g) * slab_kstages(g); sl++, i++) {
+			t.off[i] = kSlabBase + layer_offset(g) + sl * slab_stage_bytes(g);
+			t.bytes[i] = slab_stage_bytes(g);
+		}
+	}
+	t.n_stages = i;
+	return t;
+}
+static_assert(make_slab_table(kSigma).n_stages == 3 && make_slab_table(kHidden).n_stages == 11, "slab programs");
+__constant__ SlabTable c_slab[2] = {make_slab_table(kSigma), make_slab_table(kHidden)};
 
 // h2 tile records of the HIDDEN program: [32 column chunks][128 rows][8 fp16] = 64 KB per 128-row tile; a warp store covers 512 contiguous bytes
 constexpr int kHiddenTile = 128 * kHid * 2;
@@ -128,9 +161,21 @@ __global__ void __launch_bounds__(256) lerf_pack_kernel(Weights p, uint32_t* __r
 {
 	const int w = blockIdx.x * blockDim.x + threadIdx.x;
 	if (w >= kPackedBytes / 4) return;
-	if (w >= kWeightBytes / 4) {
-		const int i = w - kWeightBytes / 4, k = i / kDim, n = i % kDim;
+	if (w >= kProjBase / 4) {
+		const int i = w - kProjBase / 4, k = i / kDim, n = i % kDim;
 		reinterpret_cast<float*>(blob)[w] = p.e1[n * kHid + k];
+		return;
+	}
+	if (w >= kSlabBase / 4) {
+		// N-slab stages: word q of a stage of Ns outputs holds (n, k) and (n, k+1) at byte (k_local/8)*(Ns*16) + n_local*16 + (k%8)*2
+		const int ws = w - kSlabBase / 4;
+		int l = 0;
+		while (l + 1 < 4 && ws * 4 >= layer_offset(l + 1)) l++;
+		// stages of a layer in (slab, K-stage) order
+		const int q0 = ws - layer_offset(l) / 4, words = slab_stage_bytes(l) / 4, stg = q0 / words, q = q0 % words, Ns = slab_n(l);
+		const int sl = stg / slab_kstages(l), ks = stg % slab_kstages(l);
+		const int kc = q / (4 * Ns), n = 128 * sl + (q >> 2) % Ns, k = slab_stage_k(l) * ks + 8 * kc + 2 * (q & 3);
+		blob[w] = pack_f16(wp(p, l, n, k), wp(p, l, n, k + 1));
 		return;
 	}
 	int l = 0;
@@ -145,9 +190,11 @@ __global__ void __launch_bounds__(256) lerf_pack_kernel(Weights p, uint32_t* __r
 
 struct __align__(128) Smem {
 	uint8_t ring[kRing][kStageBytes];
-	float tbuf[4][32][33];               // RAW: per-warp transpose of a 32 x 32 output block
+	float tbuf[8][32][33];               // RAW: per-warp transpose of a 32 x 32 output block
+	float xpart[2][128];                 // HV == 2: partial row sums exchanged between the two warps of a lane quarter
 	uint64_t full[kRing], empty[kRing];
 	uint64_t a_ready, d_ready;
+	uint64_t d_full[5], d_empty[5];       // slab kernel: accumulator slabs 0..3 of D, 4 = the sigma head's own columns
 	uint32_t tmem_base;
 };
 
@@ -172,15 +219,19 @@ __device__ __forceinline__ void publish(uint64_t* bar, int lane)
 	if (lane == 0) mbar_arrive(bar);
 }
 
-// relu(D[:, 0..255]) -> fp16 -> the h columns (the next layer's A operand), one thread per row; the tcgen05.ld of chunk c+1 is in flight while
-// chunk c is converted and stored.  SAVE: the packed row also goes to the h2 tile record.
-template <bool SAVE>
-__device__ __forceinline__ void relu_to_h(uint32_t t_lane, uint8_t* __restrict__ rec_row)
+// Epilogue helpers.  HV = warps per TMEM lane quarter (1: four epilogue warps, one thread per row does all 256 accumulator columns;
+// 2: eight warps, warps w and w + 4 share a quarter and each takes 128 columns).  c0 = first 32-column chunk of this warp, CH = 8 / HV chunks.
+
+// relu(D) -> fp16 -> the h columns (the next layer's A operand); the tcgen05.ld of chunk c+1 is in flight while chunk c is converted and
+// stored.  SAVE: the packed row also goes to the h2 tile record.
+template <bool SAVE, int CH>
+__device__ __forceinline__ void relu_to_h(uint32_t t_lane, uint8_t* __restrict__ rec_row, int c0)
 {
 	uint32_t acc0[32], acc1[32], a16[16];
-	tmem_ld32(t_lane + kColD, acc0);
+	tmem_ld32(t_lane + kColD + 32 * c0, acc0);
 #pragma unroll
-	for (int c = 0; c < 8; c += 2) {
+	for (int cc = 0; cc < CH; cc += 2) {
+		const int c = c0 + cc;
 		tmem_ld_wait_for(acc0);
 		tmem_ld32(t_lane + kColD + 32 * (c + 1), acc1);
 #pragma unroll
@@ -192,7 +243,7 @@ __device__ __forceinline__ void relu_to_h(uint32_t t_lane, uint8_t* __restrict__
 				*reinterpret_cast<uint4*>(rec_row + (4 * c + i) * 2048) = make_uint4(a16[4 * i], a16[4 * i + 1], a16[4 * i + 2], a16[4 * i + 3]);
 		}
 		tmem_ld_wait_for(acc1);
-		if (c + 2 < 8) tmem_ld32(t_lane + kColD + 32 * (c + 2), acc0);
+		if (cc + 2 < CH) tmem_ld32(t_lane + kColD + 32 * (c + 2), acc0);
 #pragma unroll
 		for (int i = 0; i < 16; i++) a16[i] = pack_f16_relu(__uint_as_float(acc1[2 * i]), __uint_as_float(acc1[2 * i + 1]));
 		tmem_st16(t_lane + kColH + 16 * (c + 1), a16);
@@ -204,33 +255,36 @@ __device__ __forceinline__ void relu_to_h(uint32_t t_lane, uint8_t* __restrict__
 	}
 }
 
-// sum over the 256 accumulator columns of D^2 (this thread's row)
-__device__ __forceinline__ float sumsq_d(uint32_t t_lane)
+// sum of D^2 over this warp's accumulator columns (this thread's row)
+template <int CH>
+__device__ __forceinline__ float sumsq_d(uint32_t t_lane, int c0)
 {
 	uint32_t acc0[32], acc1[32];
 	float s = 0.f;
-	tmem_ld32(t_lane + kColD, acc0);
+	tmem_ld32(t_lane + kColD + 32 * c0, acc0);
 #pragma unroll
-	for (int c = 0; c < 8; c += 2) {
+	for (int cc = 0; cc < CH; cc += 2) {
+		const int c = c0 + cc;
 		tmem_ld_wait_for(acc0);
 		tmem_ld32(t_lane + kColD + 32 * (c + 1), acc1);
 #pragma unroll
 		for (int i = 0; i < 32; i++) s = fmaf(__uint_as_float(acc0[i]), __uint_as_float(acc0[i]), s);
 		tmem_ld_wait_for(acc1);
-		if (c + 2 < 8) tmem_ld32(t_lane + kColD + 32 * (c + 2), acc0);
+		if (cc + 2 < CH) tmem_ld32(t_lane + kColD + 32 * (c + 2), acc0);
 #pragma unroll
 		for (int i = 0; i < 32; i++) s = fmaf(__uint_as_float(acc1[i]), __uint_as_float(acc1[i]), s);
 	}
 	return s;
 }
 
-// q = h^T (G h): D holds G h (fp32), the h columns hold h (fp16 pairs)
-__device__ __forceinline__ float dot_d_h(uint32_t t_lane)
+// this warp's part of q = h^T (G h): D holds G h (fp32), the h columns hold h (fp16 pairs)
+template <int CH>
+__device__ __forceinline__ float dot_d_h(uint32_t t_lane, int c0)
 {
 	uint32_t acc[32], hh[16];
 	float s = 0.f;
 #pragma unroll 1
-	for (int c = 0; c < 8; c++) {
+	for (int c = c0; c < c0 + CH; c++) {
 		tmem_ld32(t_lane + kColD + 32 * c, acc);
 		tmem_ld16(t_lane + kColH + 16 * c, hh);
 		tmem_ld_wait_for(acc);
@@ -245,12 +299,14 @@ __device__ __forceinline__ float dot_d_h(uint32_t t_lane)
 	return s;
 }
 
-// D[:, 0..255] * inv -> out[row, col0 .. col0 + 255] (row stride 513 floats) through the warp's transpose buffer
-__device__ __forceinline__ void scaled_store(uint32_t t_lane, float inv, float (*tb)[33], int lane, int64_t warp_row0, int64_t n, float* __restrict__ out, int col0)
+// this warp's D columns * inv -> out[row, col0 + 32 c ..] (row stride 513 floats) through the warp's transpose buffer
+template <int CH>
+__device__ __forceinline__ void scaled_store(uint32_t t_lane, float inv, float (*tb)[33], int lane, int64_t warp_row0, int64_t n, float* __restrict__ out, int col0,
+	int c0)
 {
 	uint32_t acc[32];
 #pragma unroll 1
-	for (int c = 0; c < 8; c++) {
+	for (int c = c0; c < c0 + CH; c++) {
 		tmem_ld32(t_lane + kColD + 32 * c, acc);
 		tmem_ld_wait_for(acc);
 #pragma unroll
@@ -265,8 +321,15 @@ __device__ __forceinline__ void scaled_store(uint32_t t_lane, float inv, float (
 	}
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1) lerf_fwd_tc_kernel(const uint8_t* __restrict__ blob, const uint4* __restrict__ enc,
+// all epilogue threads (named barrier 1; warps 0 and 1 never take part)
+template <int HV>
+__device__ __forceinline__ void epilogue_sync()
+{
+	asm volatile("bar.sync 1, %0;" ::"n"(128 * HV) : "memory");
+}
+
+template <int MODE, int HV>
+__global__ void __launch_bounds__(32 * (2 + 4 * HV), 1) lerf_fwd_tc_kernel(const uint8_t* __restrict__ blob, const uint4* __restrict__ enc,
 	const uint8_t* __restrict__ keep, int64_t n, float* __restrict__ raw4, uint8_t* __restrict__ hidden, float* __restrict__ q_out, float* __restrict__ raw_le)
 {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -275,11 +338,13 @@ __global__ void __launch_bounds__(kThreads, 1) lerf_fwd_tc_kernel(const uint8_t*
 	const int64_t n_tiles = (n + 127) / 128;
 	const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 	const ModeTable& mt = c_modes[MODE];
+	constexpr int CH = 8 / HV;               // 32-column accumulator chunks per epilogue warp
+	constexpr int PRE = 16 / HV;             // 16-byte pieces of the input row per epilogue thread
 
 	if (warp == 1) {
 		if (lane == 0) {
 			for (int s = 0; s < kRing; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-			mbar_init(&sm.a_ready, 4);
+			mbar_init(&sm.a_ready, 4 * HV);
 			mbar_init(&sm.d_ready, 1);
 			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		}
@@ -343,13 +408,245 @@ __global__ void __launch_bounds__(kThreads, 1) lerf_fwd_tc_kernel(const uint8_t*
 			}
 		}
 	} else {
-		// ===== epilogue warps: one thread per row of the tile =====
+		// ===== epilogue warps: HV threads per row of the tile =====
+		const int ew = warp - 2;
 		const int qd = warp & 3;                                          // TMEM lane quarter this warp may access
+		const int half = ew >> 2;                                         // which share of the columns (always 0 when HV == 1)
+		const int c0 = half * CH;
 		const int row = (qd << 5) | lane;
 		const uint32_t t_lane = tmem + (static_cast<uint32_t>(qd << 5) << 16);
 		uint32_t pd = 0;
-		// The input row of the NEXT tile is requested while the last MMAs of the current tile run (16 x 16 B per thread, held in registers):
+		// The input row of the NEXT tile is requested while the last MMAs of the current tile run (PRE x 16 B per thread, held in registers):
 		// at the top of a tile its global-load latency (the tensor pipe idle meanwhile) is already paid.
+		uint4 pre[PRE];
+		auto load_row = [&](int64_t tile_idx) {
+			const int64_t rr = tile_idx * 128 + row;
+			const bool in = tile_idx < n_tiles && rr < n;
+			const uint4* er = enc + (in ? rr : 0) * (kIn / 8) + half * PRE;
+#pragma unroll
+			for (int i = 0; i < PRE; i++) pre[i] = in ? __ldg(er + i) : make_uint4(0u, 0u, 0u, 0u);
+		};
+		if (my_tiles > 0) load_row(blockIdx.x);
+		for (int64_t t = 0; t < my_tiles; t++) {
+			const int64_t tile = blockIdx.x + t * gridDim.x;
+			const int64_t r = tile * 128 + row;
+			const bool ok = r < n;
+			// ---- input: the 128 fp16 channels of the language hash grid, as they leave nrf_hash_encode_fwd (already in registers, see load_row)
+			{
+				uint32_t a16[16];
+#pragma unroll
+				for (int h = 0; h < PRE / 4; h++) {
+#pragma unroll
+					for (int i = 0; i < 4; i++) {
+						const uint4 v = pre[4 * h + i];
+						a16[4 * i] = v.x; a16[4 * i + 1] = v.y; a16[4 * i + 2] = v.z; a16[4 * i + 3] = v.w;
+					}
+					tmem_st16(t_lane + kColEnc + 4 * PRE * half + 16 * h, a16);
+				}
+			}
+			publish(&sm.a_ready, lane);
+
+			// ---- S0: h1 = relu(D)
+			mbar_wait(&sm.d_ready, pd);
+			pd ^= 1u;
+			fence_after();
+			relu_to_h<false, CH>(t_lane, nullptr, c0);
+			publish(&sm.a_ready, lane);
+			if (MODE == kSigma) load_row(tile + gridDim.x);
+
+			// ---- S1: [geo 32 | sigma] (48 columns: the first warp of each quarter)
+			mbar_wait(&sm.d_ready, pd);
+			pd ^= 1u;
+			fence_after();
+			float sigma = 0.f;
+			if (half == 0) {
+				uint32_t c4[4];
+				tmem_ld4(t_lane + kColD2 + kGeo, c4);
+				if (MODE != kSigma) {
+					uint32_t acc[32], a16[16];
+					tmem_ld32(t_lane + kColD2, acc);
+					tmem_ld_wait_for(acc);
+#pragma unroll
+					for (int i = 0; i < 16; i++) a16[i] = pack_f16(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+					tmem_st16(t_lane + kColGeo, a16);
+				}
+				tmem_ld_wait_for4(c4);
+				sigma = __uint_as_float(c4[0]);
+				if (keep != nullptr && ok && keep[r] == 0) sigma = 0.f;               // src/LeRFRenderer.cpp:18-20
+				if (MODE != kRaw) {
+					if (ok) *reinterpret_cast<float4*>(raw4 + r * 4) = make_float4(0.f, 0.f, 0.f, sigma);
+				}
+			}
+			if (MODE == kSigma) continue;       // the next tile's input stage is the next publish
+			publish(&sm.a_ready, lane);
+
+			// ---- E0: h2 = relu(D)
+			mbar_wait(&sm.d_ready, pd);
+			pd ^= 1u;
+			fence_after();
+			if (MODE == kHidden) relu_to_h<true, CH>(t_lane, hidden + tile * kHiddenTile + row * 16, c0);
+			else relu_to_h<false, CH>(t_lane, nullptr, c0);
+			publish(&sm.a_ready, lane);
+			if (MODE == kHidden) load_row(tile + gridDim.x);
+
+			if (MODE == kHidden) {
+				// ---- G: |e|^2 = h2 . (G h2)
+				mbar_wait(&sm.d_ready, pd);
+				pd ^= 1u;
+				fence_after();
+				float qv = dot_d_h<CH>(t_lane, c0);
+				if (HV > 1) {
+					if (half != 0) sm.xpart[0][row] = qv;
+					epilogue_sync<HV>();
+					if (half == 0) qv += sm.xpart[0][row];
+				}
+				if (ok && half == 0) q_out[r] = qv;
+			} else {
+				// ---- E1, first pass: |e|^2 over both halves of the outputs
+				float ss = 0.f;
+#pragma unroll 1
+				for (int pass = 0; pass < 2; pass++) {
+					mbar_wait(&sm.d_ready, pd);
+					pd ^= 1u;
+					fence_after();
+					ss += sumsq_d<CH>(t_lane, c0);
+					publish(&sm.a_ready, lane);
+				}
+				if (HV > 1) {
+					sm.xpart[half][row] = ss;
+					epilogue_sync<HV>();
+					ss = sm.xpart[0][row] + sm.xpart[1][row];
+				}
+				const float inv = 1.f / fmaxf(sqrtf(ss), 1e-8f);                      // F::normalize(eps 1e-8), src/LeRF.cpp:105
+				load_row(tile + gridDim.x);
+				// ---- E1, second pass: scale and store
+#pragma unroll 1
+				for (int pass = 0; pass < 2; pass++) {
+					mbar_wait(&sm.d_ready, pd);
+					pd ^= 1u;
+					fence_after();
+					scaled_store<CH>(t_lane, inv, sm.tbuf[ew], lane, tile * 128 + (qd << 5), n, raw_le, 256 * pass, c0);
+					if (pass == 0) publish(&sm.a_ready, lane);
+				}
+				if (ok && half == 0) raw_le[r * (kDim + 1) + kDim] = sigma;           // src/LeRF.cpp:107-110
+			}
+		}
+	}
+
+	fence_before();
+	__syncthreads();
+	if (warp == 1) {
+		fence_after();
+		tmem_free_all(tmem);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// Slab-granular variant of the SIGMA / HIDDEN programs.  Same roles, TMEM columns and arithmetic as lerf_fwd_tc_kernel, but a layer is issued
+// as two N-slabs of 128 outputs (one or two weight stages each, complete over K), and every slab of the accumulator has its own full / empty barrier pair:
+// the epilogue of slab 0 (TMEM read of 128 fp32 columns, ReLU, fp16 pack, tcgen05.st) runs under the MMAs of slab 1, instead of after the
+// whole layer.  No layer of this network reads and writes the h columns at the same time (S0: enc -> h, S1: h -> geo, E0: [geo|enc] -> h,
+// G: h -> q), so one h buffer is enough.  The results are bit-identical to the K-slab kernel's (same products, same K order per output).
+// A/B variant, off by default (see launch()).
+__device__ __forceinline__ void slab_release(uint64_t* bar, int lane)
+{
+	fence_before();
+	__syncwarp();
+	if (lane == 0) mbar_arrive(bar);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(32 * 6, 1) lerf_fwd_slab_kernel(const uint8_t* __restrict__ blob, const uint4* __restrict__ enc,
+	const uint8_t* __restrict__ keep, int64_t n, float* __restrict__ raw4, uint8_t* __restrict__ hidden, float* __restrict__ q_out)
+{
+	extern __shared__ __align__(128) uint8_t smem_raw[];
+	Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int64_t n_tiles = (n + 127) / 128;
+	const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+	const SlabTable& st = c_slab[MODE];
+
+	if (warp == 1) {
+		if (lane == 0) {
+			for (int s = 0; s < kRing; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+			for (int b = 0; b < 5; b++) { mbar_init(&sm.d_full[b], 1); mbar_init(&sm.d_empty[b], 4); }
+			mbar_init(&sm.a_ready, 4);
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncwarp();
+		tmem_alloc_all(&sm.tmem_base);
+	}
+	fence_before();
+	__syncthreads();
+	fence_after();
+	const uint32_t tmem = sm.tmem_base;
+
+	if (warp == 0) {
+		// ===== producer =====
+		if (lane == 0) {
+			uint32_t g = 0;
+			const int n_stages = st.n_stages;
+			for (int64_t t = 0; t < my_tiles; t++) {
+#pragma unroll 1
+				for (int i = 0; i < n_stages; i++, g++) {
+					const uint32_t slot = g % kRing, round = g / kRing;
+					mbar_wait(&sm.empty[slot], (round & 1u) ^ 1u);
+					const uint32_t bytes = st.bytes[i];
+					mbar_expect_tx(&sm.full[slot], bytes);
+					tma_bulk_g2s(sm.ring[slot], blob + st.off[i], bytes, &sm.full[slot]);
+				}
+			}
+		}
+	} else if (warp == 1) {
+		// ===== MMA issuer: per layer, slab by slab =====
+		if (lane == 0) {
+			uint32_t g = 0, pa = 0, ph = 0;
+			const int n_groups = st.n_groups;
+			for (int64_t t = 0; t < my_tiles; t++) {
+#pragma unroll 1
+				for (int l = 0; l < n_groups; l++) {
+					mbar_wait(&sm.a_ready, pa);                        // the whole A operand of this layer is in TMEM
+					pa ^= 1u;
+					fence_after();
+					const LayerInfo L = layer_info(l);
+					const int ns = slab_n(l), cnt = slab_count(l), kst = slab_kstages(l), ksteps = slab_stage_k(l) / 16;
+					const uint32_t idesc = idesc_f16(128, ns);
+					const uint32_t lbo = ns * 16;
+					const uint32_t d_base = tmem + (l == 1 ? kColD2 : kColD);
+					const int b0 = l == 1 ? 4 : 0;
+#pragma unroll 1
+					for (int sl = 0; sl < cnt; sl++) {
+						const int b = b0 + sl;
+						mbar_wait(&sm.d_empty[b], ((ph >> b) & 1u) ^ 1u);  // the previous user's epilogue has this slab in registers
+						ph ^= 1u << b;
+						uint32_t a_col = tmem + L.a_col;
+						for (int ks = 0; ks < kst; ks++, g++) {
+							const uint32_t slot = g % kRing, round = g / kRing;
+							mbar_wait(&sm.full[slot], round & 1u);
+							fence_after();
+							const uint32_t saddr = smem_u32(sm.ring[slot]);
+							for (int j = 0; j < ksteps; j++) {
+								umma_ts(d_base + 128 * sl, a_col, smem_desc(saddr + j * 2 * lbo, lbo, 128), idesc, (ks | j) ? 1u : 0u);
+								a_col += 8;
+							}
+							umma_commit(&sm.empty[slot]);
+						}
+						umma_commit(&sm.d_full[b]);
+					}
+				}
+			}
+		}
+	} else {
+		// ===== epilogue warps: one thread per row =====
+		const int qd = warp & 3;
+		const int row = (qd << 5) | lane;
+		const uint32_t t_lane = tmem + (static_cast<uint32_t>(qd << 5) << 16);
+		uint32_t ph = 0;
+		auto wait_full = [&](int b) {
+			mbar_wait(&sm.d_full[b], (ph >> b) & 1u);
+			ph ^= 1u << b;
+			fence_after();
+		};
 		uint4 pre[16];
 		auto load_row = [&](int64_t tile_idx) {
 			const int64_t rr = tile_idx * 128 + row;
@@ -363,7 +660,6 @@ __global__ void __launch_bounds__(kThreads, 1) lerf_fwd_tc_kernel(const uint8_t*
 			const int64_t tile = blockIdx.x + t * gridDim.x;
 			const int64_t r = tile * 128 + row;
 			const bool ok = r < n;
-			// ---- input: the 128 fp16 channels of the language hash grid, as they leave nrf_hash_encode_fwd (already in registers, see load_row)
 			{
 				uint32_t a16[16];
 #pragma unroll
@@ -378,18 +674,18 @@ __global__ void __launch_bounds__(kThreads, 1) lerf_fwd_tc_kernel(const uint8_t*
 			}
 			publish(&sm.a_ready, lane);
 
-			// ---- S0: h1 = relu(D)
-			mbar_wait(&sm.d_ready, pd);
-			pd ^= 1u;
-			fence_after();
-			relu_to_h<false>(t_lane, nullptr);
+			// ---- S0: h1 = relu(D), slab by slab
+#pragma unroll 1
+			for (int sl = 0; sl < 2; sl++) {
+				wait_full(sl);
+				relu_to_h<false, 4>(t_lane, nullptr, 4 * sl);
+				slab_release(&sm.d_empty[sl], lane);             // every tcgen05.ld of the slab has completed inside relu_to_h
+			}
 			publish(&sm.a_ready, lane);
 			if (MODE == kSigma) load_row(tile + gridDim.x);
 
 			// ---- S1: [geo 32 | sigma]
-			mbar_wait(&sm.d_ready, pd);
-			pd ^= 1u;
-			fence_after();
+			wait_full(4);
 			float sigma;
 			{
 				uint32_t c4[4];
@@ -398,60 +694,42 @@ __global__ void __launch_bounds__(kThreads, 1) lerf_fwd_tc_kernel(const uint8_t*
 					uint32_t acc[32], a16[16];
 					tmem_ld32(t_lane + kColD2, acc);
 					tmem_ld_wait_for(acc);
+					tmem_ld_wait_for4(c4);
+					slab_release(&sm.d_empty[4], lane);
 #pragma unroll
 					for (int i = 0; i < 16; i++) a16[i] = pack_f16(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
 					tmem_st16(t_lane + kColGeo, a16);
+				} else {
+					tmem_ld_wait_for4(c4);
+					slab_release(&sm.d_empty[4], lane);
 				}
-				tmem_ld_wait_for4(c4);
 				sigma = __uint_as_float(c4[0]);
 				if (keep != nullptr && ok && keep[r] == 0) sigma = 0.f;               // src/LeRFRenderer.cpp:18-20
 			}
-			if (MODE != kRaw) {
-				if (ok) *reinterpret_cast<float4*>(raw4 + r * 4) = make_float4(0.f, 0.f, 0.f, sigma);
-			}
-			if (MODE == kSigma) continue;       // the next tile's input stage is the next publish
+			if (ok) *reinterpret_cast<float4*>(raw4 + r * 4) = make_float4(0.f, 0.f, 0.f, sigma);
+			if (MODE == kSigma) continue;
 			publish(&sm.a_ready, lane);
 
-			// ---- E0: h2 = relu(D)
-			mbar_wait(&sm.d_ready, pd);
-			pd ^= 1u;
-			fence_after();
-			if (MODE == kHidden) relu_to_h<true>(t_lane, hidden + tile * kHiddenTile + row * 16);
-			else relu_to_h<false>(t_lane, nullptr);
-			publish(&sm.a_ready, lane);
-			if (MODE == kHidden) load_row(tile + gridDim.x);
-
-			if (MODE == kHidden) {
-				// ---- G: |e|^2 = h2 . (G h2)
-				mbar_wait(&sm.d_ready, pd);
-				pd ^= 1u;
-				fence_after();
-				const float qv = dot_d_h(t_lane);
-				if (ok) q_out[r] = qv;
-			} else {
-				// ---- E1, first pass: |e|^2 over both halves
-				float ss = 0.f;
+			// ---- E0: h2 = relu(D) (+ the h2 tile record)
+			uint8_t* const rec_row = hidden + tile * kHiddenTile + row * 16;
 #pragma unroll 1
-				for (int half = 0; half < 2; half++) {
-					mbar_wait(&sm.d_ready, pd);
-					pd ^= 1u;
-					fence_after();
-					ss += sumsq_d(t_lane);
-					publish(&sm.a_ready, lane);
-				}
-				const float inv = 1.f / fmaxf(sqrtf(ss), 1e-8f);                      // F::normalize(eps 1e-8), src/LeRF.cpp:105
-				load_row(tile + gridDim.x);
-				// ---- E1, second pass: scale and store
-#pragma unroll 1
-				for (int half = 0; half < 2; half++) {
-					mbar_wait(&sm.d_ready, pd);
-					pd ^= 1u;
-					fence_after();
-					scaled_store(t_lane, inv, sm.tbuf[qd], lane, tile * 128 + (qd << 5), n, raw_le, 256 * half);
-					if (half == 0) publish(&sm.a_ready, lane);
-				}
-				if (ok) raw_le[r * (kDim + 1) + kDim] = sigma;                        // src/LeRF.cpp:107-110
+			for (int sl = 0; sl < 2; sl++) {
+				wait_full(sl);
+				relu_to_h<true, 4>(t_lane, rec_row, 4 * sl);
+				slab_release(&sm.d_empty[sl], lane);
 			}
+			publish(&sm.a_ready, lane);
+			load_row(tile + gridDim.x);
+
+			// ---- G: |e|^2 = h2 . (G h2)
+			float qv = 0.f;
+#pragma unroll 1
+			for (int sl = 0; sl < 2; sl++) {
+				wait_full(sl);
+				qv += dot_d_h<4>(t_lane, 4 * sl);
+				slab_release(&sm.d_empty[sl], lane);
+			}
+			if (ok) q_out[r] = qv;
 		}
 	}
 
@@ -486,9 +764,31 @@ static int launch(const nrf_lerf_shape* shape, const void* packed, const void* e
 	const int64_t tiles = (n + 127) / 128;
 	const int smem = static_cast<int>(sizeof(Smem)) + 256;
 	const int blocks = static_cast<int>(std::min<int64_t>(tiles, kNumSMs));
-	NRF_CUDA(cudaFuncSetAttribute(lerf_fwd_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-	lerf_fwd_tc_kernel<MODE><<<blocks, kThreads, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed), reinterpret_cast<const uint4*>(enc), keep, n,
-		raw4, reinterpret_cast<uint8_t*>(hidden), q, raw_le);
+	// NRF_LERF_SLAB=1 selects the slab-granular kernel for SIGMA / HIDDEN.  Measured and NOT the default: the epilogue of slab 0 does run under
+	// the MMAs of slab 1, but a tcgen05.mma with its A operand in TMEM costs about the same whatever N <= 256 is (fine pass, 196 608 rows:
+	// 4 slabs of N = 64: 126.5 us, 2 slabs of N = 128: 101.5 us, one N = 256 accumulator: 98.4 us), so splitting N multiplies the MMA time
+	// by the slab count and the overlap only wins that back.
+	static const bool slab = [] { const char* e = getenv("NRF_LERF_SLAB"); return e && e[0] == '1'; }();
+	if (MODE != kRaw && slab) {
+		constexpr int SM = MODE == kRaw ? kHidden : MODE;
+		NRF_CUDA(cudaFuncSetAttribute(lerf_fwd_slab_kernel<SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		lerf_fwd_slab_kernel<SM><<<blocks, 32 * 6, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed), reinterpret_cast<const uint4*>(enc), keep, n,
+			raw4, reinterpret_cast<uint8_t*>(hidden), q);
+		NRF_CHECK_LAUNCH("lerf_fwd_slab_kernel");
+		return NRF_OK;
+	}
+	// epilogue warps per TMEM lane quarter: two for RAW (its 403 MB of 4-byte stores are instruction-bound: 331 -> 251 us), one otherwise
+	// (the TMEM read bandwidth, not the per-thread work, bounds those epilogues: 98.4 us with four warps, 102.0 us with eight); NRF_LERF_EPI_WARPS=4|8 overrides
+	static const int hv = [] { const char* e = getenv("NRF_LERF_EPI_WARPS"); return e && e[0] == '4' ? 1 : (e && e[0] == '8' ? 2 : (MODE == kRaw ? 2 : 1)); }();
+	if (hv == 2) {
+		NRF_CUDA(cudaFuncSetAttribute(lerf_fwd_tc_kernel<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		lerf_fwd_tc_kernel<MODE, 2><<<blocks, 32 * 10, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed), reinterpret_cast<const uint4*>(enc), keep, n,
+			raw4, reinterpret_cast<uint8_t*>(hidden), q, raw_le);
+	} else {
+		NRF_CUDA(cudaFuncSetAttribute(lerf_fwd_tc_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		lerf_fwd_tc_kernel<MODE, 1><<<blocks, 32 * 6, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed), reinterpret_cast<const uint4*>(enc), keep, n,
+			raw4, reinterpret_cast<uint8_t*>(hidden), q, raw_le);
+	}
 	NRF_CHECK_LAUNCH("lerf_fwd_tc_kernel");
 	return NRF_OK;
 }
@@ -653,7 +953,7 @@ int nrf_lerf_render_embedding(const nrf_lerf_shape* shape, const void* packed, c
 	lerf_hsum_kernel<<<static_cast<unsigned>(n_rays), 256, n_samples * sizeof(float), as_stream(stream)>>>(weights, reinterpret_cast<const uint4*>(hidden), q,
 		n_samples, hsum);
 	NRF_CHECK_LAUNCH("lerf_hsum_kernel");
-	const float* w_t = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(packed) + kWeightBytes);
+	const float* w_t = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(packed) + kProjBase);
 	lerf_project_kernel<<<static_cast<unsigned>((n_rays + kProjRays - 1) / kProjRays), 256, 0, as_stream(stream)>>>(w_t, hsum, n_rays, rendered);
 	NRF_CHECK_LAUNCH("lerf_project_kernel");
 	return NRF_OK;
