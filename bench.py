@@ -466,6 +466,41 @@ def main() -> None:
               "config": "1920x1080 frame, image rows sharded over the GPUs, 64 coarse + 64 importance samples (192 network evaluations/ray), "
                         "131072-ray chunks, rgb gathered on rank 0; untrained (random-init) model"}
 
+    # ---- LeRF render leg (BASELINE C5's field, the C4 frame): RenderedLangEmbedding of one 1920x1080 frame, image rows sharded over the ranks,
+    # 64 coarse + 128 importance samples (256 head evaluations per ray), no communication until the final gather of the [rows, 512] map
+    render_lerf = None
+    try:
+        from nerfpp_b200.lerf import LeRFField
+        field = LeRFField(BBOX, seed=0)                    # same seed on every rank: identical table, primes and weights without a broadcast
+        g = torch.Generator().manual_seed(0)
+        for v in field.weights.values():
+            v.copy_((torch.randn(v.shape, generator=g) * (2.0 / v.shape[1]) ** 0.5).to(dev))
+        field.table.copy_((torch.rand(field.n_table, generator=g) * 2 - 1).to(dev))
+        field.refresh()
+        field.render_image(H, W, K, c2w, chunk=8192, row_begin=r0, row_end=min(r0 + 8, r1))      # warm-up on a few rows
+        torch.cuda.synchronize(dev)
+        ready = 1.0
+    except Exception as e:  # noqa: BLE001 - a secondary leg must not take the headline line down
+        ready, render_lerf = 0.0, {"error": f"{type(e).__name__}: {e}"}
+    if -parallel.max_over_ranks(-ready, world, dev) > 0.5:             # every rank is ready (min over ranks), else all skip together
+
+        def lerf_frame():
+            maps = field.render_image(H, W, K, c2w, chunk=8192, row_begin=r0, row_end=r1)
+            return parallel.gather_rows(maps["rendered"], H * W, rank, world, unit=W) if world > 1 else maps["rendered"]
+
+        sync_all()
+        e8, e9 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e8.record()
+        emb = lerf_frame()
+        e9.record()
+        sync_all()
+        ms_lerf = parallel.max_over_ranks(e8.elapsed_time(e9), world, dev)
+        render_lerf = {"metric": "lerf_render_rays_per_s", "value": H * W / (ms_lerf * 1e-3), "unit": "rays/s", "ms_per_frame": ms_lerf, "frames": 1,
+                       "msamples_per_s": H * W * (N_SAMPLES + N_SAMPLES + N_IMPORTANCE) / (ms_lerf * 1e3),
+                       "config": "1920x1080 frame of RenderedLangEmbedding [H,W,512] fp32, LeRF(32,2,256,512,128) on a 16x8 T2^19 language grid, image rows sharded "
+                                 "over the GPUs, 64 coarse (density-only head) + 192 fine samples per ray, 8192-ray chunks, map gathered on rank 0; random-init field"}
+        del emb
+
     if rank != 0:
         return
 
@@ -540,7 +575,7 @@ def main() -> None:
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches * world, "graph_replay": use_graph, "kernels_per_step": launches_per_step, "roofline": roofline, "roofline_tensor": roofline_tensor, "roofline_render_ops": roofline_render_ops, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms_per_step"])},
-        "final_loss": {"resident": loss_resident, "e2e": loss_host}, "render": render,
+        "final_loss": {"resident": loss_resident, "e2e": loss_host}, "render": render, "render_lerf": render_lerf,
     }))
 
 
