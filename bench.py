@@ -270,6 +270,14 @@ def lerf_leg(tf_peak: float, rays: int = 1024, reps: int = 10) -> dict:
     from nerfpp_b200.pipeline import synthetic_rays
     o, d, _ = synthetic_rays(rays, seed=3)
     ms_render = timed(lambda: f.render_rays(o, d, return_weights=False))
+    # per-kernel shares of the chunk: one CUDA-event pair around every C-ABI call over `reps` eager chunks
+    kt = ops.KernelTimer()
+    ops.set_timer(kt)
+    for _ in range(reps):
+        f.render_rays(o, d, return_weights=False)
+    torch.cuda.synchronize()
+    ops.set_timer(None)
+    kernels_ms = {k: round(ms / reps, 4) for k, (_, ms) in sorted(kt.summary().items(), key=lambda kv: -kv[1][1])}
     f.capture_render(rays)
     ms_render_graph = timed(lambda: f.render_rays_graph(o, d))
     fl_sigma, fl_full = 2 * (128 * 256 + 256 * 33), 2 * (128 * 256 + 256 * 33 + 160 * 256 + 256 * 512)
@@ -284,7 +292,7 @@ def lerf_leg(tf_peak: float, rays: int = 1024, reps: int = 10) -> dict:
                                            "note": "reference-equivalent FLOPs (512-wide last layer); issued: 303 kFLOP/row (G = W^T W norm layer)"},
             "raw_program": {"rows": n_f, "ms": ms_raw, "achieved": tf(n_f, fl_full, ms_raw), "frac": tf(n_f, fl_full, ms_raw) / tf_peak,
                             "hbm_gbs": n_f * (513 * 4 + 256) / ms_raw / 1e6, "note": "writes raw_le [N,513] fp32 (the reference's layout)"},
-            "render_rays": {"ms": ms_render_graph, "rays_per_s": rays / ms_render_graph * 1e3, "ms_eager": ms_render, "dtype": "fp16 operands, fp32 accumulate",
+            "render_rays": {"ms": ms_render_graph, "rays_per_s": rays / ms_render_graph * 1e3, "ms_eager": ms_render, "kernels_ms_per_chunk": kernels_ms, "dtype": "fp16 operands, fp32 accumulate",
                             "note": "LeRFRenderer::RenderRays of one 1024-ray chunk (11 kernels) replayed as one CUDA graph; ms_eager = the same through 11 ctypes calls"}}
 
 

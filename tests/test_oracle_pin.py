@@ -67,6 +67,29 @@ def test_lerf_head_and_outputs(golden, ref_cpu):
         assert list(names) == list(g["names"])
 
 
+def test_lerf_render_identity_the_fused_path_relies_on(golden):
+    """The fused fine pass never forms the [N,512] embedding (nerfpp_b200/csrc/lerf_tc.cu): with e_s = W h_s (no bias, no activation after the
+    last layer, src/LeRF.cpp:97-105), RenderCLIPEmbedding(normalize(e), w) = normalize(W sum_s (w_s / |e_s|) h_s) and |e_s|^2 = h_s^T (W^T W) h_s.
+    Checked in fp64 on the fixture's weights with the oracle's own functions."""
+    g = golden("lerf.npz")
+    w = [T(g[k]).double() for k in ("sw0", "sw1", "lw0", "lw1")]
+    x = T(g["x"]).double()
+    r, s = 4, 24
+    h1 = torch.relu(x @ w[0].t())
+    sg = h1 @ w[1].t()
+    h2 = torch.relu(torch.cat([sg[:, 1:], x], -1) @ w[2].t())
+    e = h2 @ w[3].t()
+    raw = O.lerf_forward(x, w[:2], w[2:])
+    close(raw[:, :512], torch.nn.functional.normalize(e, dim=-1, eps=1e-8), rtol=1e-12, atol=1e-14)
+    q = ((h2 @ (w[3].t() @ w[3])) * h2).sum(-1)
+    close(q, (e * e).sum(-1), rtol=1e-10)
+    wts = torch.rand(r, s, generator=torch.Generator().manual_seed(0)).double()
+    ref = O.render_clip_embedding(raw[:, :512].reshape(r, s, 512), wts[..., None])
+    c = wts / q.sqrt().clamp_min(1e-8).reshape(r, s)
+    hsum = (c[..., None] * h2.reshape(r, s, 256)).sum(1)
+    close(torch.nn.functional.normalize(hsum @ w[3].t(), dim=-1, eps=1e-8), ref, rtol=1e-9, atol=1e-12)
+
+
 def test_nerf_small(golden):
     g = golden("nerf_small.npz")
     for xk, ok, gxk, wk, gwk in (("x", "out", "gx", "w", "gw"), ("x2", "out2", "gx2", "v", "gv")):
