@@ -78,7 +78,9 @@ __host__ __device__ constexpr int slab_stage_bytes(int l) { return slab_n(l) * s
 // W_e1 transposed, fp32 [256 k][512 n], follows the operand blobs (lerf_project_kernel reads it)
 constexpr int kProjBase = kSlabBase + kSlabBytes;
 constexpr int kProjBytes = kHid * kDim * 4;
-constexpr int kPackedBytes = kProjBase + kProjBytes;
+// one fp32 after it: the power-of-two scale the fp16 copy of G was divided by (lerf_gscale_kernel), so that a trained W_e1 cannot overflow it
+constexpr int kScaleBase = kProjBase + kProjBytes;
+constexpr int kPackedBytes = kScaleBase + 128;
 static_assert(kWeightBytes % 128 == 0 && kSlabBytes % 128 == 0, "blob alignment");
 
 enum Mode { kSigma = 0, kHidden = 1, kRaw = 2 };
@@ -133,6 +135,9 @@ __constant__ SlabTable c_slab[2] = {make_slab_table(kSigma), make_slab_table(kHi
 // h2 tile records of the HIDDEN program: [32 column chunks][128 rows][8 fp16] = 64 KB per 128-row tile; a warp store covers 512 contiguous bytes
 constexpr int kHiddenTile = 128 * kHid * 2;
 
+struct Weights;
+__device__ __forceinline__ float wp(const Weights& p, int l, int n, int k, float g_inv);
+
 struct Weights {   // device pointers, torch Linear layout [out, in] row-major fp32, no biases (src/LeRF.cpp:12,15)
 	const float* s0;   // [256, 128]
 	const float* s1;   // [33, 256]   row 0 = sigma_le, rows 1..32 = geo_feat_le (src/LeRF.cpp:92-93)
@@ -141,7 +146,7 @@ struct Weights {   // device pointers, torch Linear layout [out, in] row-major f
 };
 
 // padded logical weight Wp_l(n, k) in the kernel's operand order
-__device__ __forceinline__ float wp(const Weights& p, int l, int n, int k)
+__device__ __forceinline__ float wp(const Weights& p, int l, int n, int k, float g_inv)
 {
 	switch (l) {
 		case 0: return p.s0[n * kIn + k];
@@ -150,17 +155,39 @@ __device__ __forceinline__ float wp(const Weights& p, int l, int n, int k)
 		case 3: {                                                                            // G = W_e1^T W_e1
 			float acc = 0.f;
 			for (int m = 0; m < kDim; m++) acc = fmaf(p.e1[m * kHid + n], p.e1[m * kHid + k], acc);
-			return acc;
+			return acc * g_inv;                                                              // |G_nk| <= max diagonal <= 256 after scaling
 		}
 		case 4: return p.e1[n * kHid + k];
 		default: return p.e1[(n + 256) * kHid + k];
 	}
 }
 
+// scale of G: the smallest power of two s >= 1 with max_k (W_e1^T W_e1)_kk / s <= 256 (|G_nk| <= sqrt(G_nn G_kk), so every entry fits fp16
+// with 8 bits of headroom); thread k sums column k of W_e1
+__global__ void __launch_bounds__(kHid) lerf_gscale_kernel(Weights p, float* __restrict__ scale_out)
+{
+	__shared__ float red[kHid / 32];
+	const int k = threadIdx.x;
+	float d = 0.f;
+	for (int m = 0; m < kDim; m++) d = fmaf(p.e1[m * kHid + k], p.e1[m * kHid + k], d);
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
+	if ((k & 31) == 0) red[k >> 5] = d;
+	__syncthreads();
+	if (k == 0) {
+		float mx = 0.f;
+		for (int i = 0; i < kHid / 32; i++) mx = fmaxf(mx, red[i]);
+		float sc = 1.f;
+		while (mx > 256.f * sc && sc < 1e30f) sc *= 2.f;
+		scale_out[0] = sc;
+	}
+}
+
 __global__ void __launch_bounds__(256) lerf_pack_kernel(Weights p, uint32_t* __restrict__ blob)
 {
 	const int w = blockIdx.x * blockDim.x + threadIdx.x;
-	if (w >= kPackedBytes / 4) return;
+	if (w >= kScaleBase / 4) return;                       // the scale word is lerf_gscale_kernel's
+	const float g_inv = 1.f / reinterpret_cast<const float*>(blob)[kScaleBase / 4];
 	if (w >= kProjBase / 4) {
 		const int i = w - kProjBase / 4, k = i / kDim, n = i % kDim;
 		reinterpret_cast<float*>(blob)[w] = p.e1[n * kHid + k];
@@ -175,7 +202,7 @@ __global__ void __launch_bounds__(256) lerf_pack_kernel(Weights p, uint32_t* __r
 		const int q0 = ws - layer_offset(l) / 4, words = slab_stage_bytes(l) / 4, stg = q0 / words, q = q0 % words, Ns = slab_n(l);
 		const int sl = stg / slab_kstages(l), ks = stg % slab_kstages(l);
 		const int kc = q / (4 * Ns), n = 128 * sl + (q >> 2) % Ns, k = slab_stage_k(l) * ks + 8 * kc + 2 * (q & 3);
-		blob[w] = pack_f16(wp(p, l, n, k), wp(p, l, n, k + 1));
+		blob[w] = pack_f16(wp(p, l, n, k, g_inv), wp(p, l, n, k + 1, g_inv));
 		return;
 	}
 	int l = 0;
@@ -185,7 +212,7 @@ __global__ void __launch_bounds__(256) lerf_pack_kernel(Weights p, uint32_t* __r
 	// UMMA K-major core-matrix layout: word q of a stage holds (n, k) and (n, k+1); byte = (k/8)*(N*16) + n*16 + (k%8)*2
 	const int N = layer_info(l).N;
 	const int kc = q / (4 * N), n = (q >> 2) % N, k = k_off + 8 * kc + 2 * (q & 3);
-	blob[w] = pack_f16(wp(p, l, n, k), wp(p, l, n, k + 1));
+	blob[w] = pack_f16(wp(p, l, n, k, g_inv), wp(p, l, n, k + 1, g_inv));
 }
 
 struct __align__(128) Smem {
@@ -494,7 +521,7 @@ __global__ void __launch_bounds__(32 * (2 + 4 * HV), 1) lerf_fwd_tc_kernel(const
 				mbar_wait(&sm.d_ready, pd);
 				pd ^= 1u;
 				fence_after();
-				float qv = dot_d_h<CH>(t_lane, c0);
+				float qv = dot_d_h<CH>(t_lane, c0) * __ldg(reinterpret_cast<const float*>(blob + kScaleBase));     // G travels divided by this power of two
 				if (HV > 1) {
 					if (half != 0) sm.xpart[0][row] = qv;
 					epilogue_sync<HV>();
@@ -729,7 +756,7 @@ __global__ void __launch_bounds__(32 * 6, 1) lerf_fwd_slab_kernel(const uint8_t*
 				qv += dot_d_h<4>(t_lane, 4 * sl);
 				slab_release(&sm.d_empty[sl], lane);
 			}
-			if (ok) q_out[r] = qv;
+			if (ok) q_out[r] = qv * __ldg(reinterpret_cast<const float*>(blob + kScaleBase));
 		}
 	}
 
@@ -915,7 +942,9 @@ int nrf_lerf_pack(const nrf_lerf_shape* shape, const nrf_lerf_weights* w, void* 
 	NRF_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0, "packed blob must be 128-byte aligned");
 	NRF_REQUIRE(w->sigma_w0 && w->sigma_w1 && w->le_w0 && w->le_w1, "null weight pointer");
 	Weights p{w->sigma_w0, w->sigma_w1, w->le_w0, w->le_w1};
-	lerf_pack_kernel<<<(kPackedBytes / 4 + 255) / 256, 256, 0, as_stream(stream)>>>(p, reinterpret_cast<uint32_t*>(packed));
+	lerf_gscale_kernel<<<1, kHid, 0, as_stream(stream)>>>(p, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + kScaleBase));
+	NRF_CHECK_LAUNCH("lerf_gscale_kernel");
+	lerf_pack_kernel<<<(kScaleBase / 4 + 255) / 256, 256, 0, as_stream(stream)>>>(p, reinterpret_cast<uint32_t*>(packed));
 	NRF_CHECK_LAUNCH("lerf_pack_kernel");
 	return NRF_OK;
 }

@@ -76,7 +76,7 @@ def test_lerf_head_sizes_and_validation_without_gpu():
     shape = ops.lerf_shape()
     operand = 2 * (256 * 128 + 48 * 256 + 256 * 160 + 3 * 256 * 256)          # S0, S1 (33 -> 48), E0, G, E1 lower / upper halves, fp16
     slabs = 2 * (256 * 128 + 48 * 256 + 256 * 160 + 256 * 256)                  # S0, S1, E0, G once more as N-slab stages (the A/B kernel)
-    assert lib.nrf_lerf_packed_bytes(ctypes.byref(shape)) == operand + slabs + 4 * 256 * 512
+    assert lib.nrf_lerf_packed_bytes(ctypes.byref(shape)) == operand + slabs + 4 * 256 * 512 + 128      # + W_e1^T fp32 + the scale of G
     for n, tiles in ((0, 0), (1, 1), (128, 1), (129, 2), (196608, 1536)):
         assert lib.nrf_lerf_hidden_bytes(ctypes.byref(shape), n) == tiles * 128 * 256 * 2
     for bad in (ops.lerf_shape(lang_embed_dim=768), ops.lerf_shape(num_layers=3, hidden_dim=64), ops.lerf_shape(input_ch=32)):

@@ -109,6 +109,40 @@ def test_sigma_and_hidden_programs_equal_the_raw_program():
     assert float((rec - h2).abs().max()) <= TOL * float(h2.abs().max())
 
 
+def test_large_last_layer_does_not_overflow_the_norm_matrix():
+    """G = W_e1^T W_e1 travels in fp16 divided by a power of two chosen by nrf_lerf_pack: with |W_e1| ~ 18 its diagonal (~1.6e5) would overflow
+    fp16 unscaled; the norms, the rendered embedding and the raw program stay within tolerance."""
+    from nerfpp_b200 import ops
+    r, s = 16, 96
+    n = r * s
+    p = _params(seed=21)
+    p[NAMES[3]] = p[NAMES[3]] * 200.0
+    p[NAMES[1]] = p[NAMES[1]].clone()
+    p[NAMES[1]][0] *= 6.0
+    enc = _enc(n, seed=22)
+    packed = ops.lerf_pack(p)
+    raw4, hidden, q = ops.lerf_hidden_fwd(packed, enc)
+    w = [p[k].cpu().double() for k in NAMES]
+    x = enc.cpu().double()
+    h1 = torch.relu(x @ w[0].t())
+    sg = h1 @ w[1].t()
+    h2 = torch.relu(torch.cat([sg[:, 1:], x], -1) @ w[2].t())
+    e = h2 @ w[3].t()
+    qref = (e * e).sum(-1)
+    assert float(qref.max()) > 1e6 and bool(torch.isfinite(q).all())
+    assert float(((q.cpu().double() - qref).abs() / qref.clamp_min(1e-6)).max()) <= 2 * TOL
+    g = torch.Generator().manual_seed(5)
+    z = (2 + torch.sort(torch.rand(r, s, generator=g) * 4, -1).values).cuda()
+    d = torch.randn(r, 3, generator=g).cuda()
+    comp = ops.composite_fwd(raw4.view(r, s, 4), z, d)
+    rendered = ops.lerf_render_embedding(packed, comp["weights"], hidden, q)
+    ref_raw = _oracle(enc, p, None, torch.float32).view(r, s, 513)
+    ref_raw[..., 512] = raw4.view(r, s, 4)[..., 3].cpu()
+    ref = O.raw_to_le_outputs(ref_raw, z.cpu(), d.cpu(), 512)["rendered"].double()
+    assert float((rendered.cpu().double() - ref).abs().max()) <= TOL * float(ref.abs().max())
+    _check_raw(ops.lerf_fwd(packed, enc), _oracle(enc, p))
+
+
 @pytest.mark.parametrize("r,s", [(64, 192), (7, 64), (3, 200)])
 def test_fused_render_matches_raw_to_le_outputs(r, s):
     """Fine pass without the [N,512] embedding: composite(sigma) -> weights, then normalize(W_e1 sum_s (w_s / |e_s|) h2_s) against
