@@ -487,10 +487,10 @@ def main() -> None:
         field.refresh()
         field.render_image(H, W, K, c2w, chunk=8192, row_begin=r0, row_end=min(r0 + 8, r1))      # warm-up on a few rows
         torch.cuda.synchronize(dev)
-        ready = 1.0
+        ready = True
     except Exception as e:  # noqa: BLE001 - a secondary leg must not take the headline line down
-        ready, render_lerf = 0.0, {"error": f"{type(e).__name__}: {e}"}
-    if -parallel.max_over_ranks(-ready, world, dev) > 0.5:             # every rank is ready (min over ranks), else all skip together
+        ready, render_lerf = False, {"error": f"{type(e).__name__}: {e}"}
+    if parallel.all_ranks_ready(ready, world, dev):                    # else all ranks skip the leg together
 
         def lerf_frame():
             maps = field.render_image(H, W, K, c2w, chunk=8192, row_begin=r0, row_end=r1)

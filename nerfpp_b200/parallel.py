@@ -60,11 +60,16 @@ def gather_rows(local: torch.Tensor, n_total: int, rank: int, world: int, dst: i
     if world == 1:
         return local
     shapes = [tuple(unit * v for v in shard_bounds(n_total // unit, r, world)) for r in range(world)]
+    # equal-size exchange (gloo's gather refuses ragged shards; shard sizes differ by at most one unit): pad to the largest shard, trim on dst
+    biggest = max(e - b for b, e in shapes)
+    local = local.contiguous()
+    if local.shape[0] < biggest:
+        local = torch.cat([local, local.new_zeros((biggest - local.shape[0],) + tuple(local.shape[1:]))], 0)
     if rank == dst:
-        parts = [torch.empty((e - b,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) for b, e in shapes]
-        dist.gather(local.contiguous(), parts, dst=dst)
-        return torch.cat(parts, 0)
-    dist.gather(local.contiguous(), None, dst=dst)
+        parts = [torch.empty_like(local) for _ in shapes]
+        dist.gather(local, parts, dst=dst)
+        return torch.cat([p[:e - b] for p, (b, e) in zip(parts, shapes)], 0)
+    dist.gather(local, None, dst=dst)
     return None
 
 
@@ -74,6 +79,12 @@ def max_over_ranks(value: float, world: int, device) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def all_ranks_ready(ok: bool, world: int, device) -> bool:
+    """True only if EVERY rank passed ok = True (min over ranks).  Called before the first collective of an optional leg, so that a rank
+    whose set-up failed makes all ranks skip it together instead of leaving the others waiting in a gather."""
+    return -max_over_ranks(-(1.0 if ok else 0.0), world, device) > 0.5
 
 
 class PeerShardedOptimizer:

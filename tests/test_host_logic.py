@@ -66,8 +66,15 @@ def _worker(rank, world, port, out):
     parallel.broadcast_parameters(params, w)
     rows = parallel.gather_rows(per_ray[b:e], n_rays, r, w)
     tmax = parallel.max_over_ranks(float(r + 1), w, "cpu")
+    # image rows as the sharded unit (the render / render_lerf legs): 5 rows of width 4, [rows * 4, 3] map
+    img = torch.arange(5 * 4 * 3, dtype=torch.float32).reshape(20, 3)
+    rb, re = parallel.shard_bounds(5, r, w)
+    tiles = parallel.gather_rows(img[rb * 4:re * 4], 20, r, w, unit=4)
+    ready_all = parallel.all_ranks_ready(True, w, "cpu")
+    ready_one = parallel.all_ranks_ready(r == 0, w, "cpu")       # rank 1 failed its set-up: every rank must see False
+    assert ready_all and not ready_one
     if r == 0:
-        torch.save({"flat": flat, "scale": scale, "params": params, "rows": rows, "tmax": tmax}, out)
+        torch.save({"flat": flat, "scale": scale, "params": params, "rows": rows, "tmax": tmax, "tiles": tiles}, out)
     else:
         assert torch.equal(params, torch.zeros(6)) and rows is None
     dist.destroy_process_group()
@@ -81,3 +88,4 @@ def test_world_size_2_exchange_on_gloo(tmp_path):
     assert torch.equal(got["flat"], per_ray.sum(0))            # all-reduce(sum) over ray shards == single-process sum
     assert got["scale"] == 0.5 and got["tmax"] == 2.0
     assert torch.equal(got["rows"], per_ray)                   # tile gather restores row order
+    assert torch.equal(got["tiles"], torch.arange(60, dtype=torch.float32).reshape(20, 3))   # image-row shards (3 + 2 rows of width 4)
