@@ -396,6 +396,61 @@ def render_rays(ray_batch_: torch.Tensor, n_samples: int, n_importance: int, run
     return out2, out1, z_all
 
 
+def lerf_language_loss(rendered: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """src/NeRFExecutor.h:964-968: huber(delta 1.25, no reduction).sum(-1).nanmean()."""
+    return torch.nn.functional.huber_loss(rendered, target, reduction="none", delta=1.25).sum(-1).nanmean()
+
+
+def lerf_backward_fused_form(x: torch.Tensor, sigma_w, le_w, z: torch.Tensor, rays_d: torch.Tensor, target: torch.Tensor) -> dict:
+    """The gradients of the language loss written the way the fused kernels will evaluate them: the [N,512] embedding is
+    never formed; everything per sample is 256-wide.  x [R,S,C] (the hash encoding of the fine pass), 2-layer nets (BASELINE C5).
+    Explicit formulas, no autograd except for the compositing weights (an existing kernel, nrf_composite_bwd).  Returns d loss / d
+    {sigma_w0, sigma_w1, le_w0, le_w1, x}; tests compare it with autograd through lerf_forward + raw_to_le_outputs."""
+    r_, s_, c_ = x.shape
+    xf = x.reshape(-1, c_)
+    w_s0, w_s1 = sigma_w
+    w_e0, w_e1 = le_w
+    a1 = xf @ w_s0.t()
+    h1 = torch.relu(a1)
+    sg = h1 @ w_s1.t()                                            # [sigma | geo]
+    gx = torch.cat([sg[:, 1:], xf], -1)
+    a2 = gx @ w_e0.t()
+    h2 = torch.relu(a2)
+    gram = w_e1.t() @ w_e1                                        # G
+    t = h2 @ gram                                                 # G h2 (symmetric)
+    n2 = (t * h2).sum(-1)                                         # |e|^2 = h2^T G h2
+    n = n2.sqrt().clamp_min(1e-8)
+    sigma = sg[:, 0].reshape(r_, s_).detach().requires_grad_(True)
+    raw4 = torch.cat([torch.zeros(r_, s_, 3, dtype=x.dtype), sigma[..., None]], -1)
+    w = raw_to_outputs(raw4, z, rays_d)["weights"]                # the compositing weights of the density column
+    c = (w.detach() / n.reshape(r_, s_))
+    hs = (c[..., None] * h2.reshape(r_, s_, -1)).sum(1)           # [R,256]
+    e_ray = hs @ w_e1.t()                                         # E = W_e1 Hs
+    e_norm = e_ray.norm(dim=-1, keepdim=True).clamp_min(1e-8)
+    rendered = e_ray / e_norm
+    # loss -> d rendered (huber, delta 1.25, summed over channels, mean over rays)
+    diff = rendered - target
+    d_r = torch.where(diff.abs() <= 1.25, diff, 1.25 * torch.sign(diff)) / r_
+    d_e = (d_r - rendered * (rendered * d_r).sum(-1, keepdim=True)) / e_norm                        # normalize backward, per ray
+    u = d_e @ w_e1                                                                                  # W_e1^T dE   [R,256]
+    u_rows = u[:, None, :].expand(r_, s_, -1).reshape(-1, u.shape[-1])
+    d_w = ((h2 * u_rows).sum(-1) / n).reshape(r_, s_)                                               # d loss / d w_s
+    (d_sigma,) = torch.autograd.grad(w, sigma, d_w)                                                 # compositing backward (existing kernel)
+    cf, dwf = c.reshape(-1), d_w.reshape(-1)
+    beta = cf * dwf / n                                                                              # W_e1^T e_hat = G h2 / n
+    d_h2 = cf[:, None] * u_rows - beta[:, None] * t
+    d_we1 = d_e.t() @ hs - w_e1 @ ((beta[:, None] * h2).t() @ h2)                                   # outer term - W_e1 * weighted Gram
+    d_a2 = d_h2 * (a2 > 0)
+    d_we0 = d_a2.t() @ gx
+    d_gx = d_a2 @ w_e0
+    d_s = torch.cat([d_sigma.reshape(-1, 1), d_gx[:, :sg.shape[1] - 1]], -1)
+    d_ws1 = d_s.t() @ h1
+    d_a1 = (d_s @ w_s1) * (a1 > 0)
+    d_ws0 = d_a1.t() @ xf
+    d_x = d_a1 @ w_s0 + d_gx[:, sg.shape[1] - 1:]
+    return {"sigma_w0": d_ws0, "sigma_w1": d_ws1, "le_w0": d_we0, "le_w1": d_we1, "x": d_x.reshape(r_, s_, c_), "rendered": rendered}
+
+
 def lerf_render_rays(ray_batch_: torch.Tensor, n_samples: int, n_importance: int, run_le_network, lang_embed_dim: int):
     """src/LeRFRenderer.cpp:85-162 in the parity configuration (ThinRay, perturb 0, no noise, no preconditioning):
     run_le_network(pts [R,S,3]) -> raw_le [R,S,D+1].  Returns (fine outputs, coarse outputs, z_fine)."""

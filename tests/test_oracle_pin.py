@@ -90,6 +90,30 @@ def test_lerf_render_identity_the_fused_path_relies_on(golden):
     close(torch.nn.functional.normalize(hsum @ w[3].t(), dim=-1, eps=1e-8), ref, rtol=1e-9, atol=1e-12)
 
 
+def test_lerf_backward_in_fused_form_equals_autograd(golden):
+    """The backward the fused LeRF kernels are planned around (256-wide per sample, G h2 recomputed, weighted Gram matrix for the
+    norm term of the last layer) against torch.autograd through the oracle's LeRF::forward + RawToLEOutputs + the language loss, fp64."""
+    g = golden("lerf.npz")
+    sw, lw = [T(g["sw0"]).double(), T(g["sw1"]).double()], [T(g["lw0"]).double(), T(g["lw1"]).double()]
+    sw[1] = sw[1].clone()
+    sw[1][0] *= 4.0                                                           # densities of O(1): rays terminate inside the interval
+    r, s = 4, 24
+    x = T(g["x"]).double().reshape(r, s, 128)
+    z, d = T(g["z"]).double(), T(g["rays_d"]).double()
+    target = torch.nn.functional.normalize(torch.randn(r, 512, generator=torch.Generator().manual_seed(1), dtype=torch.float64), dim=-1)
+    leaves = [t.clone().requires_grad_(True) for t in (*sw, *lw, x)]
+    raw = O.lerf_forward(leaves[4].reshape(-1, 128), leaves[:2], leaves[2:4]).reshape(r, s, 513)
+    out = O.raw_to_le_outputs(raw, z, d, 512)
+    loss = O.lerf_language_loss(out["rendered"], target)
+    grads = torch.autograd.grad(loss, leaves)
+    mine = O.lerf_backward_fused_form(x, sw, lw, z, d, target)
+    close(mine["rendered"], out["rendered"], rtol=1e-9, atol=1e-12)
+    for key, ref in zip(("sigma_w0", "sigma_w1", "le_w0", "le_w1", "x"), grads):
+        scale = float(ref.abs().max())
+        assert scale > 0
+        assert float((mine[key] - ref).abs().max()) <= 1e-9 * scale, key
+
+
 def test_nerf_small(golden):
     g = golden("nerf_small.npz")
     for xk, ok, gxk, wk, gwk in (("x", "out", "gx", "w", "gw"), ("x2", "out2", "gx2", "v", "gv")):
