@@ -109,6 +109,23 @@ def test_product_never_imports_the_oracle():
             assert not re.search(r"(import|from)\s+(oracle|restate)\b|oracle/_ref|nerfpp_ref|#include\s+\"[^\"]*oracle", text), p
 
 
+def test_reference_call_sites_compile_against_the_compat_headers():
+    """The statements of the reference's NeRFExecutor / main.cpp that touch the hot-path classes (tests/compat_call_sites.cpp, each citing its
+    line), written against the reference's own header names, compile with nerfpp_b200/host/compat first on the include path — HashNeRF + LeRF
+    and classic NeRF instantiations (syntax + template instantiation only: nothing is linked or run)."""
+    import subprocess
+    import sysconfig
+    import torch
+    tdir = Path(torch.__file__).resolve().parent
+    inc = []
+    for d in (ROOT / "nerfpp_b200/host/compat", ROOT / "nerfpp_b200/host", ROOT / "include", tdir / "include", tdir / "include/torch/csrc/api/include",
+              Path("/usr/local/cuda/include"), Path(sysconfig.get_paths()["include"])):
+        inc += ["-I", str(d)]
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-w", "-D_GLIBCXX_USE_CXX11_ABI=1", *inc, str(ROOT / "tests/compat_call_sites.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+
+
 def test_cpp_host_layer_loads_and_refuses_cpu_tensors():
     """nerfpp_b200_torch.so (the torch::Tensor drop-in layer) builds, imports and exposes the reference's class surface; like
     the C ABI it has no CPU path."""
