@@ -24,6 +24,18 @@ def test_grid_buffers_mirror_reference_constructor():
     assert g8.used_scalars() == (15 + 8) * (1 << 19)
 
 
+def test_lerf_parameter_names_and_shapes_are_the_reference_modules(golden):
+    """The Python mirror's parameter table (nerfpp_b200/lerf.py, ops.lerf_pack) against the names the reference's LeRF registers
+    (fixture tests/golden/lerf.npz, written from oracle/_ref: src/LeRF.cpp:17-25) and the shapes of its weights."""
+    from nerfpp_b200 import lerf, ops
+    g = golden("lerf.npz")
+    names = [f"lang_model_{n}.weight" for n, _, _ in lerf.LERF_LAYERS]
+    assert names == list(g["names"]) == [f"lang_model_{n}.weight" for n in ops.LERF_WEIGHT_NAMES]
+    assert [(o, i) for _, o, i in lerf.LERF_LAYERS] == [tuple(g[k].shape) for k in ("sw0", "sw1", "lw0", "lw1")]
+    s = ops.lerf_shape()
+    assert (s.geo_feat_dim, s.num_layers, s.hidden_dim, s.lang_embed_dim, s.input_ch) == (32, 2, 256, 512, 128)      # src/main.cpp:203-213, C5: D = 512
+
+
 def test_shard_bounds_partition():
     for n, world in ((4096, 8), (1080, 8), (7, 3), (5, 8), (32768, 4)):
         spans = [parallel.shard_bounds(n, r, world) for r in range(world)]
