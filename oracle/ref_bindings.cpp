@@ -293,6 +293,32 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 		return std::make_pair(mod->forward(x), names);
 	});
 	m.def("render_clip_embedding", [](Tensor e, Tensor w) { return RenderCLIPEmbedding(e, w); });   // src/LeRFRenderer.h:45-54
+	// The language branch of one training iteration on already-encoded samples, through the reference's own modules and LibTorch autograd:
+	// LeRF::forward (src/LeRF.cpp:28) -> RawToLEOutputs (src/LeRFRenderer.cpp:27) -> huber(delta 1.25).sum(-1).nanmean() (src/NeRFExecutor.h:964-968)
+	// -> backward (:981).  x [R,S,C]; returns (loss, rendered, d loss / d {sigma_le_net_0, sigma_le_net_1, le_net_0, le_net_1, x}).
+	m.def("lerf_language_grads", [](Tensor x, std::vector<Tensor> sigma_w, std::vector<Tensor> le_w, Tensor z, Tensor rays_d, Tensor target,
+		int geo_feat, int hidden, int lang_dim) {
+		LeRF mod(geo_feat, static_cast<int>(sigma_w.size()), hidden, lang_dim, static_cast<int>(x.size(-1)), "lang_model");
+		mod->to(x.scalar_type());
+		auto np = mod->named_parameters();
+		{
+			torch::NoGradGuard ng;
+			for (size_t i = 0; i < sigma_w.size(); i++) np["lang_model_sigma_le_net_" + std::to_string(i) + ".weight"].copy_(sigma_w[i]);
+			for (size_t i = 0; i < le_w.size(); i++) np["lang_model_le_net_" + std::to_string(i) + ".weight"].copy_(le_w[i]);
+		}
+		Tensor xin = x.detach().clone().set_requires_grad(true);
+		Tensor raw = mod->forward(xin.reshape({-1, x.size(-1)})).reshape({x.size(0), x.size(1), lang_dim + 1});
+		OpenLeRFRenderer r(nullptr, nullptr, torch::zeros({1, lang_dim}), torch::zeros({1, lang_dim}));
+		auto o = r.RawToLEOutputs(raw, z, rays_d, lang_dim, 0.f);
+		Tensor loss = torch::nn::functional::huber_loss(o.RenderedLangEmbedding, target.detach(),
+			torch::nn::functional::HuberLossFuncOptions().reduction(torch::kNone).delta(1.25)).sum(-1).nanmean();
+		loss.backward();
+		std::vector<Tensor> grads;
+		for (size_t i = 0; i < sigma_w.size(); i++) grads.push_back(np["lang_model_sigma_le_net_" + std::to_string(i) + ".weight"].grad());
+		for (size_t i = 0; i < le_w.size(); i++) grads.push_back(np["lang_model_le_net_" + std::to_string(i) + ".weight"].grad());
+		grads.push_back(xin.grad());
+		return std::make_tuple(loss.detach(), o.RenderedLangEmbedding.detach(), grads);
+	}, py::call_guard<py::gil_scoped_release>());
 	// src/LeRFRenderer.cpp:27-82.  Relevancy (RuCLIP, absent) comes from the stub header and stays undefined.
 	m.def("lerf_raw_to_outputs", [](Tensor raw_le, Tensor z, Tensor rays_d, int lang_dim) {
 		OpenLeRFRenderer r(nullptr, nullptr, torch::zeros({1, lang_dim}), torch::zeros({1, lang_dim}));

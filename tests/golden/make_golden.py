@@ -178,7 +178,29 @@ def lerf():
     npz("lerf.npz", x=x, sw0=sw[0], sw1=sw[1], lw0=lw[0], lw1=lw[1], out=out, names=np.array(names), raw=raw, z=z, rays_d=d, **kw)
 
 
+def lerf_grads():
+    """The language branch of one training iteration on already-encoded samples through the reference's own LeRF + RawToLEOutputs + LibTorch
+    autograd (fp64): loss, rendered embedding, d loss / d x in full, and for each weight gradient its first 8 rows + Frobenius norm (size)."""
+    g = np.load(HERE / "lerf.npz")
+    sw = [torch.from_numpy(g["sw0"]).double(), torch.from_numpy(g["sw1"]).double()]
+    lw = [torch.from_numpy(g["lw0"]).double(), torch.from_numpy(g["lw1"]).double()]
+    sw[1] = sw[1].clone()
+    sw[1][0] *= 4.0
+    r, s = 4, 24
+    x = torch.from_numpy(g["x"]).double().reshape(r, s, 128)
+    z, d = torch.from_numpy(g["z"]).double(), torch.from_numpy(g["rays_d"]).double()
+    target = torch.nn.functional.normalize(torch.randn(r, 512, generator=torch.Generator().manual_seed(1), dtype=torch.float64), dim=-1)
+    loss, rendered, grads = R.lerf_language_grads(x, sw, lw, z, d, target, 32, 256, 512)
+    kw = {}
+    for k, gr in zip(("sigma_w0", "sigma_w1", "le_w0", "le_w1"), grads[:4]):
+        kw[f"g_{k}_rows"], kw[f"g_{k}_norm"] = gr[:8].clone(), gr.norm()
+    npz("lerf_grads.npz", loss=loss, rendered=rendered, target=target, g_x=grads[4], **kw)
+
+
 if __name__ == "__main__":
+    if "--lerf-grads-only" in sys.argv:
+        lerf_grads()
+        sys.exit(0)
     if "--lerf-only" in sys.argv:      # leaves the other fixtures (and the RNG stream they were drawn from) untouched
         lerf()
         sys.exit(0)
@@ -191,3 +213,4 @@ if __name__ == "__main__":
     render_rays_classic()
     trunc_exp()
     lerf()
+    lerf_grads()

@@ -90,7 +90,7 @@ def test_lerf_render_identity_the_fused_path_relies_on(golden):
     close(torch.nn.functional.normalize(hsum @ w[3].t(), dim=-1, eps=1e-8), ref, rtol=1e-9, atol=1e-12)
 
 
-def test_lerf_backward_in_fused_form_equals_autograd(golden):
+def test_lerf_backward_in_fused_form_equals_autograd(golden, ref_cpu):
     """The backward the fused LeRF kernels are planned around (256-wide per sample, G h2 recomputed, weighted Gram matrix for the
     norm term of the last layer) against torch.autograd through the oracle's LeRF::forward + RawToLEOutputs + the language loss, fp64."""
     g = golden("lerf.npz")
@@ -112,6 +112,18 @@ def test_lerf_backward_in_fused_form_equals_autograd(golden):
         scale = float(ref.abs().max())
         assert scale > 0
         assert float((mine[key] - ref).abs().max()) <= 1e-9 * scale, key
+    # the same against the REFERENCE's own modules and LibTorch autograd: fixture (tests/golden/make_golden.py:lerf_grads), and live when built
+    f = golden("lerf_grads.npz")
+    assert torch.equal(T(f["target"]), target)
+    close(loss, f["loss"], rtol=1e-12)
+    close(mine["x"], f["g_x"], rtol=1e-9, atol=1e-9 * float(np.abs(f["g_x"]).max()))
+    for key in ("sigma_w0", "sigma_w1", "le_w0", "le_w1"):
+        close(mine[key][:8], f[f"g_{key}_rows"], rtol=1e-9, atol=1e-9 * float(np.abs(f[f"g_{key}_rows"]).max()))
+        close(mine[key].norm(), f[f"g_{key}_norm"], rtol=1e-9)
+    if ref_cpu is not None and hasattr(ref_cpu, "lerf_language_grads"):
+        _, _, live = ref_cpu.lerf_language_grads(x, sw, lw, z, d, target, 32, 256, 512)
+        for key, ref in zip(("sigma_w0", "sigma_w1", "le_w0", "le_w1", "x"), live):
+            assert float((mine[key] - ref).abs().max()) <= 1e-9 * float(ref.abs().max()), key
 
 
 def test_nerf_small(golden):
