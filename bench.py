@@ -28,12 +28,9 @@ RAYS_PER_GPU = 4096
 N_SAMPLES, N_IMPORTANCE = 64, 128
 BBOX = (-1.5, -1.5, -1.5, 1.5, 1.5, 1.5)
 CPU_SAMPLE_RAYS = 256   # bounded sample of the 4096-ray step for the CPU arms
+CPU_STEPS, CPU_WARMUP = 10, 2   # cpu_baseline inside the GPU line (the reference arm uses the driver's --steps / --warmup on the same sample)
+MLP_BWD_PIPE = "mma.sync (HMMA) chain + tcgen05 dW"
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/), largest launch
-NCU_TRAFFIC_BYTES = {
-    "hash_encode_fwd": 19.59e6 + 3.89e6,    # profiles/r1_hash_fwd_v3_ncu.txt, 786 432-point launch
-    "hash_encode_bwd": 89.12e6 + 2.39e6,    # profiles/r1_hash_bwd_v2_ncu.txt
-}
 # algorithmic bytes per unit (SURVEY §8d with this repo's fp16 encoding output)
 BYTES_PER_POINT = {
     "hash_encode_fwd": 12 + 512 + 64 + 1,   # xyz in, 16 lvl x 8 corners x 2 feat x fp16 gathered, fp16 [32] out, keep byte
@@ -296,15 +293,103 @@ def lerf_leg(tf_peak: float, rays: int = 1024, reps: int = 10) -> dict:
                             "note": "LeRFRenderer::RenderRays of one 1024-ray chunk (11 kernels) replayed as one CUDA graph; ms_eager = the same through 11 ctypes calls"}}
 
 
+def graph_breakdown(model, batch, world: int, reps: int = 20) -> dict:
+    """Per-launch device times INSIDE the step: the same step captured a second time with an external CUDA-event pair around every
+    C-ABI call (event-record nodes in the graph), replayed `reps` times.  No host launch gaps, the L2 state each kernel sees is the
+    step's own.  Returns {entry name: [ms per launch, in launch order]} (hash_encode_fwd: [coarse, fine])."""
+    import torch
+    from nerfpp_b200 import ops
+    timer = ops.KernelTimer(external=True)
+    model._sync_sched()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            ops.set_timer(timer)
+            try:
+                model.forward_backward(*batch)
+                if model.peer is not None:
+                    model._optimizer_step_sharded()
+                elif world == 1:
+                    model._optimizer_step_scheduled(1.0)
+                else:
+                    model.grads.zero_()      # NCCL path: the all-reduce + Adam are not part of this breakdown (replicas must stay identical)
+            finally:
+                ops.set_timer(None)
+    torch.cuda.current_stream().wait_stream(side)
+    acc = {k: [0.0] * len(v) for k, v in timer.records.items()}
+    for _ in range(reps):
+        graph.replay()
+        torch.cuda.synchronize()
+        for k, v in timer.records.items():
+            for j, (e0, e1) in enumerate(v):
+                acc[k][j] += e0.elapsed_time(e1)
+        model.step += 1
+        model._sched_step = model.step
+    return {k: [t / reps for t in v] for k, v in acc.items()}
+
+
+def gpu_loop_leg(which: str, rays: int, steps: int) -> dict:
+    """NeRFExecutor::Train's loop (Render + huber + backward + Adam, reference src/NeRFExecutor.h:868-996) in C++ on one GPU at the C2 shape:
+    `reference_cuda` = the reference's own CUDA instantiation NeRFRenderer<CuHashEmbedder,CuSHEncoder,NeRFSmall> (oracle/_ref/nerfpp_ref_cuda.so,
+    unmodified sources, nvcc -arch=sm_100) — the same-box GPU comparison of SURVEY §8(d); `dropin_cpp` = the SAME loop on this repo's C++
+    drop-in classes (nerfpp_b200/lib/nerfpp_b200_torch.so).  Timed with CUDA events around `steps` steps after 5 warm-up steps."""
+    import torch
+    from nerfpp_b200.pipeline import synthetic_rays
+    if which == "reference_cuda":
+        import nerfpp_ref_cuda as R
+    else:
+        from nerfpp_b200 import build
+        sys.path.insert(0, str(build.build_host().parent))
+        import nerfpp_b200_torch as R
+    R.manual_seed(42)
+    devnull = os.open(os.devnull, os.O_WRONLY)   # the reference prints parameter names from Trainable::Initialize
+    saved = os.dup(1)
+    os.dup2(devnull, 1)
+    try:
+        pipe = R.make_cuhash(torch.tensor(BBOX).cuda(), 16, 2, 19, 16, 512, 4, 2, 64, 15, 3, 64)
+        pipe.init_model()
+    finally:
+        os.dup2(saved, 1)
+        os.close(devnull)
+    fast = which == "dropin_cpp" and hasattr(pipe, "use_train_graph")
+    if which == "dropin_cpp":
+        pipe.use_fused_adam(True)
+        if fast:
+            pipe.use_train_graph(True)
+    o, d, tgt = synthetic_rays(rays, device="cuda", seed=0)
+    pipe.train_steps(o, d, tgt, 5, N_SAMPLES, N_IMPORTANCE, rays, True, 1e-2, 250)   # warm-up; single chunk (SURVEY §9-Q1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    secs, losses = pipe.train_steps(o, d, tgt, steps, N_SAMPLES, N_IMPORTANCE, rays, True, 1e-2, 250)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"ms_per_step": ms, "value": rays / ms * 1e3, "unit": "rays/s", "rays": rays, "steps": steps, "loss_last": losses[-1],
+            "loop": "C++: Render + huber_loss + backward + Adam per step, loss.item() every step (the reference's own loop)",
+            "impl": ("reference CUDA path (CuHashEmbedder/CuSHEncoder kernels + LibTorch), unmodified, on this B200" if which == "reference_cuda" else
+                     "nerfpp_b200 C++ drop-in classes (torch::Tensor boundary, FusedAdam" + (", captured train graph)" if fast else ")"))}
+
+
+def lerf_train_leg(rank: int, world: int, dev) -> dict | None:
+    """BASELINE C5: training of the language field, 1024 rays per GPU (filled in by the fused LeRF backward)."""
+    return None
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU per step")
+    ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU per step (weak scaling, the headline)")
+    ap.add_argument("--global-rays", type=int, default=8 * RAYS_PER_GPU,
+                    help="global batch of the strong-scaling sub-record (BASELINE C3: 8 x 4096 rays split over the GPUs); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the captured step")
+    ap.add_argument("--quick", action="store_true", help="headline + roofline only: skip the render / LeRF / classic / C++-loop legs")
     ap.add_argument("--dp", default="fused", choices=["fused", "nccl"],
                     help="N>1 optimiser step: one peer-memory kernel (reduce-scatter + Adam + shadow all-gather) or NCCL all-reduce + dense Adam")
     args = ap.parse_args()
@@ -334,7 +419,7 @@ def main() -> None:
     parallel.broadcast_parameters(model.params, world)
     model.refresh()
 
-    dp_mode = "single"
+    dp_mode, dp_check = "single", None
     if world > 1:
         dp_mode = "nccl all-reduce of the flat gradient + dense Adam on every rank"
         if args.dp == "fused":
@@ -345,16 +430,21 @@ def main() -> None:
                 peer, why = None, f"{type(e).__name__}: {e}"
             have = torch.tensor([int(peer is not None)], dtype=torch.int32, device=dev)
             torch.distributed.all_reduce(have, op=torch.distributed.ReduceOp.MIN)      # all ranks or none
-            if bool(have.item()) and peer.self_test(model):
+            if bool(have.item()):
+                # one step on a RANDOM gradient through the fused kernel and through NCCL all-reduce + dense Adam, compared (collective)
+                dp_check = peer.dp_check(model)
+            if dp_check is not None and dp_check["ok"]:
                 dp_mode = "fused peer-memory kernel per rank: reduce-scatter(grad) + Adam(1/N shard) + all-gather(fp16 shadow) over NVLink, no NCCL in the step"
             else:
                 model.peer = None        # stay on the NCCL path (the symmetric buffers remain ordinary device memory) and say so
-                dp_mode += f" (fused path unavailable: {why or 'peer self-test failed on some rank'})"
+                dp_mode += f" (fused path unavailable: {why or 'dp_check failed: ' + json.dumps(dp_check)})"
 
     pool = 8  # distinct pre-generated ray batches per rank, cycled
-    dev_batches = [synthetic_rays(R, device=dev, seed=1000 * rank + i) for i in range(pool)]
-    host_batches = [tuple(t.cpu().pin_memory() for t in b) for b in dev_batches]
-    stage = tuple(torch.empty_like(t) for t in dev_batches[0])
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
 
     def eager_step(batch):
         model.forward_backward(*batch)
@@ -364,87 +454,89 @@ def main() -> None:
             scale = parallel.allreduce_gradients(model.grads, world)
             model.optimizer_step(grad_scale=scale)
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            torch.distributed.barrier()
-
-    # ---- warm-up, instrumented: every kernel gets an event pair so the dominant one can be named
-    timer = ops.KernelTimer()
-    ops.set_timer(timer)
-    for i in range(warmup):
-        eager_step(dev_batches[i % pool])
-    torch.cuda.synchronize()
-    ops.set_timer(None)
-    breakdown = {k: {"launches_per_step": n / warmup, "ms_per_step": ms / warmup} for k, (n, ms) in timer.summary().items()}
-    dominant = max(("hash_encode_fwd", "hash_encode_bwd"), key=lambda k: breakdown.get(k, {"ms_per_step": 0})["ms_per_step"])
-
-    # ---- the step as the public API runs it: one CUDA-graph replay (two around the all-reduce when world > 1)
-    use_graph = not args.no_graph
-    if use_graph:
-        model.capture_train_step(R, world, lambda g: parallel.allreduce_gradients(g, world))
-        step = lambda batch: model.train_step_graph(*batch)   # noqa: E731
-        for i in range(3):
-            step(dev_batches[i % pool])
-        launches_per_step = model.graph_kernels_per_step
-    else:
-        step = eager_step
-        l0 = cabi.launch_count()
-        step(dev_batches[0])
-        launches_per_step = cabi.launch_count() - l0 + 1
-
-    # ---- timed region A: K steps, inputs resident in HBM
-    sampler = ClockSampler(local_rank)
-    sync_all()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        step(dev_batches[i % pool])
-    e1.record()
-    sync_all()
-    ms_total = parallel.max_over_ranks(e0.elapsed_time(e1), world, dev)
-    loss_resident = float(model.loss)
-
-    # ---- roofline leg: the same steps launched eagerly so the dominant kernel can carry a CUDA-event pair on its stream
-    # (a graph replay cannot); same buffers, same sizes, run back to back with the timed region
-    roof_steps = min(args.steps, 50)
-    timer = ops.KernelTimer(only=[dominant, "mlp_small_fwd", "mlp_small_bwd"])
-    ops.set_timer(timer)
-    sync_all()
-    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e4.record()
-    for i in range(roof_steps):
-        eager_step(dev_batches[i % pool])
-    e5.record()
-    sync_all()
-    ops.set_timer(None)
-    ms_eager = e4.elapsed_time(e5) / roof_steps
-    n_launch, ms_kernel = timer.summary()[dominant]
-    _, ms_mlp_fwd = timer.summary()["mlp_small_fwd"]
-    _, ms_mlp_bwd = timer.summary()["mlp_small_bwd"]
-
-    # ---- timed region B (e2e): the public API with HOST buffers — pinned H2D of the step's rays/targets and a D2H read
-    # of the loss inside the timed region, every step
-    sync_all()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    loss_host = 0.0
-    for i in range(args.steps):
-        hb = host_batches[i % pool]
+    def train_leg(rays_per_gpu: int, steps: int, n_warm: int, seed0: int, with_e2e: bool):
+        """Timed regions of one configuration: `steps` replays of the captured step with resident inputs (value), then the same
+        through the public call with pinned HOST buffers and a loss read per step (e2e).  CUDA events, max over ranks."""
+        dev_batches = [synthetic_rays(rays_per_gpu, device=dev, seed=seed0 + 1000 * rank + i) for i in range(pool)]
+        for i in range(n_warm):
+            eager_step(dev_batches[i % pool])
+        use_graph = not args.no_graph
         if use_graph:
-            step(hb)                    # train_step_graph copies the pinned host rays/targets into its static inputs
+            model.capture_train_step(rays_per_gpu, world, lambda g: parallel.allreduce_gradients(g, world))
+            step = lambda batch: model.train_step_graph(*batch)   # noqa: E731
+            for i in range(3):
+                step(dev_batches[i % pool])
+            launches_per_step = model.graph_kernels_per_step
         else:
-            for dst, src in zip(stage, hb):
-                dst.copy_(src, non_blocking=True)
-            step(stage)
-        loss_host = float(model.loss)   # device -> host read of the step's result
-    e3.record()
-    sync_all()
-    clocks = sampler.stop()
-    ms_e2e = parallel.max_over_ranks(e2.elapsed_time(e3), world, dev)
-    launches = launches_per_step * args.steps   # kernels inside timed region A (graph: kernel nodes per replay x replays)
+            step = eager_step
+            l0 = cabi.launch_count()
+            step(dev_batches[0])
+            launches_per_step = cabi.launch_count() - l0 + 1
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(dev_batches[i % pool])
+        e1.record()
+        sync_all()
+        out = {"ms_total": parallel.max_over_ranks(e0.elapsed_time(e1), world, dev), "loss": float(model.loss), "launches_per_step": launches_per_step,
+               "dev_batches": dev_batches, "use_graph": use_graph}
+        if with_e2e:
+            host_batches = [tuple(t.cpu().pin_memory() for t in b) for b in dev_batches]
+            stage = tuple(torch.empty_like(t) for t in dev_batches[0])
+            sync_all()
+            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e2.record()
+            loss_host = 0.0
+            for i in range(steps):
+                hb = host_batches[i % pool]
+                if use_graph:
+                    step(hb)                    # train_step_graph copies the pinned host rays/targets into its static inputs
+                else:
+                    for dst, src in zip(stage, hb):
+                        dst.copy_(src, non_blocking=True)
+                    step(stage)
+                loss_host = float(model.loss)   # device -> host read of the step's result
+            e3.record()
+            sync_all()
+            out.update(ms_e2e=parallel.max_over_ranks(e2.elapsed_time(e3), world, dev), loss_e2e=loss_host,
+                       h2d=sum(t.numel() * t.element_size() for t in host_batches[0]))
+        return out
 
+    # ---- headline: weak scaling, R rays per GPU (BASELINE C2 at N=1; C3's per-GPU share at N=8)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    head = train_leg(R, args.steps, warmup, 0, with_e2e=True)
+    clocks = sampler.stop()
+    ms_total, ms_e2e, use_graph, launches_per_step = head["ms_total"], head["ms_e2e"], head["use_graph"], head["launches_per_step"]
+    dev_batches = head["dev_batches"]
+    launches = launches_per_step * args.steps   # kernels inside the resident timed region (graph: kernel nodes per replay x replays)
+
+    # ---- per-launch device times inside the step (second capture with external event pairs), for the roofline and the breakdown
+    per_launch = graph_breakdown(model, dev_batches[0], world)
+    if model.peer is not None:
+        model.peer.check()
+    timeout_after = model.flags_timeout() if model.peer is not None else 0
+    if world > 1:
+        timeout_after = int(parallel.max_over_ranks(float(timeout_after), world, dev))
+
+    # ---- BASELINE C3 as written: a FIXED global batch of 8 x 4096 rays split over the ranks (strong scaling)
+    strong = None
+    if args.global_rays and args.global_rays % world == 0 and not args.no_graph:
+        rs = args.global_rays // world
+        if rs == R:
+            strong = {"global_rays": args.global_rays, "rays_per_gpu": rs, "ms_per_step": ms_total / args.steps,
+                      "value": args.global_rays * args.steps / (ms_total / 1e3), "steps": args.steps, "note": "same configuration as the headline at this N"}
+        else:
+            s_steps = max(10, min(args.steps, 50))
+            leg = train_leg(rs, s_steps, 3, 7000, with_e2e=False)
+            strong = {"global_rays": args.global_rays, "rays_per_gpu": rs, "ms_per_step": leg["ms_total"] / s_steps,
+                      "value": args.global_rays * s_steps / (leg["ms_total"] / 1e3), "steps": s_steps}
+        strong.update(unit="rays/s", scaling="strong",
+                      config="BASELINE C3: fixed global batch of 8 x 4096 rays per step, ray-sharded over the GPUs (32768 / 16384 / 8192 / 4096 rays per GPU at "
+                             "N = 1 / 2 / 4 / 8); efficiency(N) = value(N) / (N x value(1)) from the per-N records")
+
+    quick = args.quick
     # ---- render leg (BASELINE C4): one 1920x1080 frame, image rows sharded over the ranks, 64 coarse + 64 importance samples
     # (the fine pass evaluates 128 samples/ray), no communication until the final gather of the maps to rank 0
     import math
@@ -455,42 +547,46 @@ def main() -> None:
     c2w[2, 3] = 4.0
     r0, r1 = parallel.shard_bounds(H, rank, world)
     frames = 3
+    render = None
+    if not quick:
+        def render_frame():
+            maps = model.render_image(H, W, K, c2w, chunk=131072, row_begin=r0, row_end=r1, n_importance=64)
+            return parallel.gather_rows(maps["rgb"], H * W, rank, world, unit=W) if world > 1 else maps["rgb"]
 
-    def render_frame():
-        maps = model.render_image(H, W, K, c2w, chunk=131072, row_begin=r0, row_end=r1, n_importance=64)
-        return parallel.gather_rows(maps["rgb"], H * W, rank, world, unit=W) if world > 1 else maps["rgb"]
-
-    render_frame()
-    sync_all()
-    e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e6.record()
-    for _ in range(frames):
-        img = render_frame()
-    e7.record()
-    sync_all()
-    ms_render = parallel.max_over_ranks(e6.elapsed_time(e7), world, dev) / frames
-    render = {"metric": "render_msamples_per_s", "value": H * W * (N_SAMPLES + N_SAMPLES + 64) / (ms_render * 1e3), "unit": "Msamples/s",
-              "frames_per_s": 1e3 / ms_render, "ms_per_frame": ms_render, "frames": frames,
-              "config": "1920x1080 frame, image rows sharded over the GPUs, 64 coarse + 64 importance samples (192 network evaluations/ray), "
-                        "131072-ray chunks, rgb gathered on rank 0; untrained (random-init) model"}
+        render_frame()
+        sync_all()
+        e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e6.record()
+        for _ in range(frames):
+            img = render_frame()
+        e7.record()
+        sync_all()
+        ms_render = parallel.max_over_ranks(e6.elapsed_time(e7), world, dev) / frames
+        render = {"metric": "render_msamples_per_s", "value": H * W * (N_SAMPLES + N_SAMPLES + 64) / (ms_render * 1e3), "unit": "Msamples/s",
+                  "frames_per_s": 1e3 / ms_render, "ms_per_frame": ms_render, "frames": frames,
+                  "config": "1920x1080 frame, image rows sharded over the GPUs, 64 coarse + 64 importance samples (192 network evaluations/ray), "
+                            "131072-ray chunks, rgb gathered on rank 0; untrained (random-init) model"}
+        del img
 
     # ---- LeRF render leg (BASELINE C5's field, the C4 frame): RenderedLangEmbedding of one 1920x1080 frame, image rows sharded over the ranks,
     # 64 coarse + 128 importance samples (256 head evaluations per ray), no communication until the final gather of the [rows, 512] map
     render_lerf = None
-    try:
-        from nerfpp_b200.lerf import LeRFField
-        field = LeRFField(BBOX, seed=0)                    # same seed on every rank: identical table, primes and weights without a broadcast
-        g = torch.Generator().manual_seed(0)
-        for v in field.weights.values():
-            v.copy_((torch.randn(v.shape, generator=g) * (2.0 / v.shape[1]) ** 0.5).to(dev))
-        field.table.copy_((torch.rand(field.n_table, generator=g) * 2 - 1).to(dev))
-        field.refresh()
-        field.render_image(H, W, K, c2w, chunk=8192, row_begin=r0, row_end=min(r0 + 8, r1))      # warm-up on a few rows
-        torch.cuda.synchronize(dev)
-        ready = True
-    except Exception as e:  # noqa: BLE001 - a secondary leg must not take the headline line down
-        ready, render_lerf = False, {"error": f"{type(e).__name__}: {e}"}
-    if parallel.all_ranks_ready(ready, world, dev):                    # else all ranks skip the leg together
+    ready = False
+    if not quick:
+        try:
+            from nerfpp_b200.lerf import LeRFField
+            field = LeRFField(BBOX, seed=0)                    # same seed on every rank: identical table, primes and weights without a broadcast
+            g = torch.Generator().manual_seed(0)
+            for v in field.weights.values():
+                v.copy_((torch.randn(v.shape, generator=g) * (2.0 / v.shape[1]) ** 0.5).to(dev))
+            field.table.copy_((torch.rand(field.n_table, generator=g) * 2 - 1).to(dev))
+            field.refresh()
+            field.render_image(H, W, K, c2w, chunk=8192, row_begin=r0, row_end=min(r0 + 8, r1))      # warm-up on a few rows
+            torch.cuda.synchronize(dev)
+            ready = True
+        except Exception as e:  # noqa: BLE001 - a secondary leg must not take the headline line down
+            ready, render_lerf = False, {"error": f"{type(e).__name__}: {e}"}
+    if not quick and parallel.all_ranks_ready(ready, world, dev):                    # else all ranks skip the leg together
 
         def lerf_frame():
             maps = field.render_image(H, W, K, c2w, chunk=8192, row_begin=r0, row_end=r1)
@@ -509,49 +605,71 @@ def main() -> None:
                                  "over the GPUs, 64 coarse (density-only head) + 192 fine samples per ray, 8192-ray chunks, map gathered on rank 0; random-init field"}
         del emb
 
+    # ---- LeRF training leg (BASELINE C5): 1024 rays per GPU, language field trained through the fused head backward
+    train_lerf = lerf_train_leg(rank, world, dev) if not quick else None
+
     if rank != 0:
         return
 
     peaks_path = ROOT / "MEASURED_PEAKS.json"
-    if peaks_path.exists():
-        peak_gbs, peak_src = json.loads(peaks_path.read_text())["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (sustained copy)"
+    peaks = json.loads(peaks_path.read_text()) if peaks_path.exists() else {}
+    if peaks:
+        peak_gbs, peak_src = peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (sustained copy)"
     else:
         peak_gbs, peak_src = 6650.0, "fallback B200_PROFILING.md"
-    pts_per_step = R * (N_SAMPLES + N_SAMPLES + N_IMPORTANCE) if dominant == "hash_encode_fwd" else R * (N_SAMPLES + N_IMPORTANCE)
-    bytes_per_step = BYTES_PER_POINT[dominant] * pts_per_step
-    kl_per_step = n_launch / roof_steps
-    achieved = (bytes_per_step * roof_steps / 1e9) / (ms_kernel / 1e3)
-    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": NCU_TRAFFIC_BYTES.get(dominant), "peak_source": peak_src, "bytes_per_launch": bytes_per_step / kl_per_step,
-                "ms_per_launch": ms_kernel / n_launch, "share_of_step": (ms_kernel / roof_steps) / (ms_total / args.steps),
-                "timing": f"CUDA-event pair around every launch over {roof_steps} eagerly launched steps run right after the timed region "
-                          f"({ms_eager:.3f} ms/step eager)",
-                "l2_note": "the table shadow (17 MiB) is L2-resident: the kernel is bound by L1 tag lookups (forward) / L2 RED operations (backward), "
-                           "not by HBM. Ceilings measured on B200 with scripts/exp/{gather,red}_bench.cu: 280 G random 4 B gathers/s, 209 G REDs/s "
-                           "(any operand width); hash_fwd issues 301 G sector lookups/s, hash_bwd 206 G REDs/s (DESIGN.md §4)"}
+    ms_step = ms_total / args.steps
+    n_c, n_f = R * N_SAMPLES, R * (N_SAMPLES + N_IMPORTANCE)
+    traffic_path = ROOT / "profiles" / "r2_ncu_traffic.json"        # dram bytes per launch out of the committed ncu --set full captures
+    traffic = json.loads(traffic_path.read_text()) if traffic_path.exists() else {}
 
-    # the tensor-core side of the step: fused NeRFSmall forward (tcgen05) and backward (mma.sync), useful FLOPs only
-    # (18 688 FLOP/point forward over coarse + fine points, 37 376 FLOP/point backward over the fine points; the backward also
-    # recomputes the forward, which is not counted)
-    peaks = json.loads(peaks_path.read_text()) if peaks_path.exists() else {}
+    def hbm_row(name, ms, units, bytes_per_unit, traffic_key=None, extra=None):
+        by = units * bytes_per_unit
+        row = {"kernel": name, "ms_per_launch": ms, "bytes_per_launch": by, "achieved": by / ms / 1e6, "frac": by / ms / 1e6 / peak_gbs,
+               "share_of_step": ms / ms_step, "traffic": traffic.get(traffic_key or name)}
+        if extra:
+            row.update(extra)
+        return row
+
+    fwd_ms = per_launch.get("hash_encode_fwd", [0.0, 0.0])
+    bwd_ms = per_launch.get("hash_encode_bwd", [0.0])
+    reused = n_c if model.reuse_coarse_rows else 0
+    launches_hbm = {
+        "hash_encode_fwd_coarse": hbm_row("hash_fwd_kernel (coarse pass)", fwd_ms[0], n_c, BYTES_PER_POINT["hash_encode_fwd"], "hash_encode_fwd_coarse"),
+        "hash_encode_fwd_fine": hbm_row("hash_fwd_kernel (fine pass)", fwd_ms[-1], n_f, BYTES_PER_POINT["hash_encode_fwd"], "hash_encode_fwd_fine",
+                                        {"rows_copied_from_the_coarse_pass": reused,
+                                         "achieved_counting_copied_rows_as_128B": ((n_f - reused) * BYTES_PER_POINT["hash_encode_fwd"] + reused * 129) / fwd_ms[-1] / 1e6}),
+        "hash_encode_bwd": hbm_row("hash_bwd_kernel", bwd_ms[0], n_f, BYTES_PER_POINT["hash_encode_bwd"], "hash_encode_bwd"),
+    }
+    dom_key = max(launches_hbm, key=lambda k: launches_hbm[k]["ms_per_launch"])
+    dom = launches_hbm[dom_key]
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak_gbs, "unit": "GB/s", "frac": dom["frac"],
+                "traffic": dom["traffic"], "peak_source": peak_src, "bytes_per_launch": dom["bytes_per_launch"], "ms_per_launch": dom["ms_per_launch"],
+                "share_of_step": dom["share_of_step"], "launches": launches_hbm,
+                "timing": "external CUDA-event pair around the launch INSIDE a second capture of the step graph, mean of 20 replays run right after the timed "
+                          "regions (device time in situ: no host launch gaps, the step's own L2 state)",
+                "traffic_source": "profiles/r2_ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full)" if traffic else None,
+                "l2_note": "the table shadow (17 MiB) is L2-resident: the kernel is bound by L1 miss sectors (forward) / L2 RED operations (backward), "
+                           "not by HBM. Ceilings measured on B200 with scripts/exp/{gather,red}_bench.cu: 280 G random 4 B gathers/s, 209 G REDs/s "
+                           "(any operand width) (DESIGN.md §4)"}
+
+    # the tensor-core side of the step: fused NeRFSmall forward and backward, useful FLOPs only (18 688 FLOP/point forward over coarse +
+    # fine points, 37 376 FLOP/point backward over the fine points; the backward also recomputes the forward, which is not counted)
     tf_peak = peaks.get("bf16_tflops", 1590.0)
-    pts_fwd, pts_bwd = R * (2 * N_SAMPLES + N_IMPORTANCE), R * (N_SAMPLES + N_IMPORTANCE)
-    tf_fwd = pts_fwd * 18688 * roof_steps / (ms_mlp_fwd * 1e-3) / 1e12
-    tf_bwd = pts_bwd * 37376 * roof_steps / (ms_mlp_bwd * 1e-3) / 1e12
+    mf, mb = per_launch.get("mlp_small_fwd", [0.0, 0.0]), per_launch.get("mlp_small_bwd", [0.0])
+    tf_fwd = (n_c + n_f) * 18688 / (sum(mf) * 1e-3) / 1e12
+    tf_bwd = n_f * 37376 / (mb[0] * 1e-3) / 1e12
     roofline_tensor = {"bound": "tensor", "unit": "TFLOP/s", "peak": tf_peak,
                        "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS burst)" if peaks else "fallback B200_PROFILING.md",
-                       "mlp_small_fwd": {"achieved": tf_fwd, "frac": tf_fwd / tf_peak, "ms_per_step": ms_mlp_fwd / roof_steps, "pipe": "tcgen05"},
-                       "mlp_small_bwd": {"achieved": tf_bwd, "frac": tf_bwd / tf_peak, "ms_per_step": ms_mlp_bwd / roof_steps, "pipe": "mma.sync (HMMA)"},
-                       "note": "event pairs include both launches of the forward (coarse + fine) and their launch gaps; ncu per-launch figures in profiles/"}
-    # what actually bounds the tcgen05 forward: its epilogues read every layer's fp32 accumulators out of TMEM at 64 B/clk/SM
-    # (B300_MICROARCH.md, LDTM throughput): 224 accumulator columns x 4 B per point
+                       "mlp_small_fwd": {"achieved": tf_fwd, "frac": tf_fwd / tf_peak, "ms_per_step": sum(mf), "ms_per_launch": mf, "pipe": "tcgen05"},
+                       "mlp_small_bwd": {"achieved": tf_bwd, "frac": tf_bwd / tf_peak, "ms_per_step": mb[0], "pipe": MLP_BWD_PIPE},
+                       "note": "in-graph event pairs per launch (coarse, fine); ncu per-launch figures in profiles/"}
     sm_mhz = peaks.get("sm_max_mhz", 1965.0)
-    tmem_floor_ms = pts_fwd * 224 * 4 / (148 * 64 * sm_mhz * 1e6) * 1e3
+    tmem_floor_ms = (n_c + n_f) * 224 * 4 / (148 * 64 * sm_mhz * 1e6) * 1e3
     roofline_tensor["mlp_small_fwd"]["tmem_read_roofline"] = {"bytes_per_point": 896, "peak": "64 B/clk/SM x 148 SMs", "floor_ms_per_step": tmem_floor_ms,
-                                                               "frac": tmem_floor_ms / (ms_mlp_fwd / roof_steps)}
+                                                               "frac": tmem_floor_ms / max(sum(mf), 1e-9)}
 
     roofline_render_ops = None
-    if rank == 0:
+    if not quick:
         roofline_tensor["mlp_nerf"] = classic_nerf_leg(tf_peak)
         try:
             roofline_tensor["lerf_head"] = lerf_leg(tf_peak)
@@ -559,31 +677,51 @@ def main() -> None:
             roofline_tensor["lerf_head"] = {"error": f"{type(e).__name__}: {e}"}
         roofline_render_ops = render_ops_leg(roofline["peak"])
 
+    # ---- the same step through the C++ surfaces, on this GPU (N = 1 only): the reference's own CUDA path and the C++ drop-in classes
+    dropin_cpp = reference_cuda = None
+    if world == 1 and not quick:
+        for which in ("reference_cuda", "dropin_cpp"):
+            try:
+                leg = gpu_loop_leg(which, R, 30)
+            except Exception as e:  # noqa: BLE001
+                leg = {"error": f"{type(e).__name__}: {e}"}
+            if which == "reference_cuda":
+                reference_cuda = leg
+            else:
+                dropin_cpp = leg
+        if reference_cuda and dropin_cpp and "value" in reference_cuda and "value" in dropin_cpp:
+            dropin_cpp["vs_reference_cuda"] = dropin_cpp["value"] / reference_cuda["value"]
+            reference_cuda["ours_vs_reference_cuda"] = (R * args.steps / (ms_total / 1e3)) / reference_cuda["value"]
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            v, sps, threads = reference_cpu_rays_per_s(steps=6, warmup=1)
+            v, sps, threads = reference_cpu_rays_per_s(steps=CPU_STEPS, warmup=CPU_WARMUP)
             cpu_baseline = {"value": v, "unit": "rays/s", "cores": threads, "kind": "reference",
-                            "sample": f"{CPU_SAMPLE_RAYS}-ray sample of the {RAYS_PER_GPU}-ray step, 6 steps after 1 warm-up ({sps:.2f} s/step)"}
+                            "sample": f"{CPU_SAMPLE_RAYS}-ray sample of the {RAYS_PER_GPU}-ray step, {CPU_STEPS} steps after {CPU_WARMUP} warm-up ({sps:.2f} s/step)"}
         except ImportError as e:
             cpu_baseline = {"value": None, "unit": "rays/s", "cores": 0, "kind": "reference", "sample": f"oracle/_ref not importable: {e}"}
 
     rays_total = R * world * args.steps
-    h2d = sum(t.numel() * t.element_size() for t in host_batches[0])
     print(json.dumps({
         "metric": "train_rays_per_s", "value": rays_total / (ms_total / 1e3), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-        "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "C2/C3 HashNeRF training: L16 F2 T2^19 hash grid 16->512 + SH deg 4 + NeRFSmall 32->64->16 | 31->64->64->3, "
                                f"{R} rays/GPU/step of an 800x800 view, 64 coarse + 128 importance samples, huber + Adam(0.9,0.99,1e-15)",
                    "rays_per_gpu": R, "global_rays": R * world, "parallelism": f"ray-sharded dp{world}: {dp_mode}",
                    "l2": "not flushed explicitly: each step streams ~300 MB (Adam pass over 8.9M params + moments + gradient) through the 126 MB L2",
-                   "precision": "fp16 hash table reads / encodings, bf16 tensor-core MLP with fp32 accumulate, fp32 everything else"},
-        "e2e": {"value": rays_total / (ms_e2e / 1e3), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                   "precision": "fp16 hash table reads / encodings, bf16 tensor-core MLP with fp32 accumulate, fp32 everything else",
+                   "reuse_coarse_rows": bool(model.reuse_coarse_rows)},
+        "e2e": {"value": rays_total / (ms_e2e / 1e3), "unit": "rays/s", "h2d_bytes_per_step": head["h2d"], "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches * world, "graph_replay": use_graph, "kernels_per_step": launches_per_step, "roofline": roofline, "roofline_tensor": roofline_tensor, "roofline_render_ops": roofline_render_ops, "cpu_baseline": cpu_baseline, "clocks": clocks,
-        "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms_per_step"])},
-        "final_loss": {"resident": loss_resident, "e2e": loss_host}, "render": render, "render_lerf": render_lerf,
+        "gpu_launches": launches * world, "graph_replay": use_graph, "kernels_per_step": launches_per_step, "roofline": roofline,
+        "roofline_tensor": roofline_tensor, "roofline_render_ops": roofline_render_ops, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "kernels_ms_per_step": {k: [round(t, 4) for t in v] for k, v in sorted(per_launch.items(), key=lambda kv: -sum(kv[1]))},
+        "kernels_ms_per_step_sum": round(sum(sum(v) for v in per_launch.values()), 4),
+        "dp_check": dp_check, "flags_timeout_after_timed_regions": timeout_after, "strong": strong,
+        "reference_cuda": reference_cuda, "dropin_cpp": dropin_cpp,
+        "final_loss": {"resident": head["loss"], "e2e": head["loss_e2e"]}, "render": render, "render_lerf": render_lerf, "train_lerf": train_lerf,
     }))
 
 

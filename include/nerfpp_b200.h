@@ -72,6 +72,12 @@ typedef struct nrf_hash_grid {
 int nrf_hash_level_scales(int32_t base_resolution, int32_t finest_resolution, int32_t n_levels,
                           float* level_scale, nrf_stream stream);
 
+/* Inspection entry for parity tests: for every (point, level, corner) the SCALAR address into the table (feat_local_idx[level] +
+ * hashed position * n_features, src/CuHashEmbedder.cu:55,70-77,150) and the trilinear weight (:83-90), computed by the same device
+ * code the encode kernels use; corner order 000,001,...,111 (z fastest).  addr int64 [N, L, 8], weights fp32 [N, L, 8]. */
+int nrf_hash_cells(const nrf_hash_grid* grid, const float* points, int64_t n_points, int clamp_points, int64_t* addr,
+                   float* weights, nrf_stream stream);
+
 /* fp32 master table -> fp16 shadow, round-to-nearest-even (src/CuHashEmbedder.cu:257). */
 int nrf_table_to_half(const float* table_f32, void* table_f16, int64_t n_scalars, nrf_stream stream);
 

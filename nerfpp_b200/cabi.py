@@ -88,6 +88,7 @@ SIGNATURES = {
     "nrf_launch_count": (c_int64, []),
     "nrf_hash_level_scales": (c_int32, [c_int32, c_int32, c_int32, _P, _P]),
     "nrf_table_to_half": (c_int32, [_P, _P, c_int64, _P]),
+    "nrf_hash_cells": (c_int32, [POINTER(HashGrid), _P, c_int64, c_int32, _P, _P, _P]),
     "nrf_hash_encode_fwd": (c_int32, [POINTER(HashGrid), _P, _P, c_int64, c_int32, _P, _P, c_int32, _P]),
     "nrf_hash_encode_bwd": (c_int32, [POINTER(HashGrid), _P, c_int64, c_int32, _P, c_int32, _P, _P]),
     "nrf_hash_encode_rays_fwd": (c_int32, [POINTER(HashGrid), _P, _P, c_int32, _P, c_int64, c_int32, c_int32, _P, _P, c_int32, _P, _P, _P, c_int32, _P]),

@@ -17,6 +17,9 @@
 //   * level metadata (scale, primes, offsets) is staged once per CTA in shared memory;
 //   * the backward accumulates in fp32 with vector RED (red.global.add.v2.f32), no x128 loss scale.
 #include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
+#include <limits.h>
 
 namespace nrf {
 
@@ -182,100 +185,117 @@ __device__ __forceinline__ void unpack(const typename FeatVec<F>::type& v, float
 }
 
 // F features per level; CH = levels handled per 16-byte output chunk (8 halves).
-template <int F, bool OUT_F32>
-__global__ void __launch_bounds__(256) hash_fwd_kernel(HashArgs a, const __half* __restrict__ table,
-	PointSrc ps, Reuse ru, int64_t n_points, int clamp_points, uint8_t* __restrict__ keep, void* __restrict__ out)
+//
+// Work item = (point, part).  SPLIT == 1: one thread walks all levels of its point.  SPLIT == number of chunks (4 at L16 F2): SPLIT
+// neighbouring lanes share a point and each handles ONE chunk of CH levels, so a warp writes 32 / SPLIT complete rows as one contiguous
+// block and an item is 1 / SPLIT of the dependent-latency chain.  Every thread handles `iters` items at a stride of the whole grid: the
+// host sizes the grid as ONE wave of co-resident CTAs in which every SM gets the same number of items (launch_plan) — the 1-CTA-per-256-
+// points launch left a 15 %-full second wave on the coarse pass (1 024 CTAs on 888 slots: 105 us for a third of the fine pass's points).
+template <int F, bool OUT_F32, int SPLIT>
+__global__ void __launch_bounds__(128) hash_fwd_kernel(HashArgs a, const __half* __restrict__ table,
+	PointSrc ps, Reuse ru, int64_t n_items, int64_t stride, int iters, int clamp_points, uint8_t* __restrict__ keep, void* __restrict__ out)
 {
 	constexpr int CH = 8 / F;
 	using V = typename FeatVec<F>::type;
 	__shared__ HashMeta m;
 	stage_meta(m, a);
-
-	int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-	if (i >= n_points) return;
-
-	if (ru.perm) {
-		const uint32_t ray = static_cast<uint32_t>(i) / static_cast<uint32_t>(ps.S);
-		const int t = static_cast<int>(static_cast<uint32_t>(i) - ray * static_cast<uint32_t>(ps.S));
-		const int p = ru.perm[i];
-		const int64_t row0 = static_cast<int64_t>(ray) * ps.S;
-		if (p >= 0 && t >= ps.S - ru.S_prev) {
-			// copy the row the coarse pass produced for this very point (16-byte vectors; rows are 16-byte aligned, host-checked)
-			const int64_t from = static_cast<int64_t>(ray) * ru.S_prev + (t - (ps.S - ru.S_prev));
-			const int row_bytes = a.n_levels * F * (OUT_F32 ? 4 : 2);
-			const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(ru.enc) + from * row_bytes);
-			uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + (row0 + p) * row_bytes);
-			for (int q = 0; q < row_bytes / 16; q++) d4[q] = __ldg(s4 + q);
-			if (keep) keep[row0 + p] = ru.keep ? ru.keep[from] : 1;
-			return;
-		}
-		i = row0 + (p >= 0 ? p : -(p + 1));   // the merged position this thread encodes
-	}
-
-	float x, y, z;
-	load_point(ps, i, x, y, z);
-	if (clamp_points) {
-		const bool k = clamp_point(a, x, y, z);
-		if (keep) keep[i] = k ? 1 : 0;
-	}
-	const float qx = (x - a.min_x) / (a.max_x - a.min_x);
-	const float qy = (y - a.min_y) / (a.max_y - a.min_y);
-	const float qz = (z - a.min_z) / (a.max_z - a.min_z);
-
 	const int L = a.n_levels;
-	const int64_t row = i * (static_cast<int64_t>(L) * F);
-	for (int l0 = 0; l0 < L; l0 += CH) {
-		__half2 acc[4];
+	const int row_bytes = L * F * (OUT_F32 ? 4 : 2);
+
+	int64_t item = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	for (int it = 0; it < iters; it++, item += stride) {
+		if (item >= n_items) break;
+		int64_t i = SPLIT == 1 ? item : item / SPLIT;
+		const int part = SPLIT == 1 ? 0 : static_cast<int>(item & (SPLIT - 1));
+
+		if (ru.perm) {
+			const uint32_t ray = static_cast<uint32_t>(i) / static_cast<uint32_t>(ps.S);
+			const int t = static_cast<int>(static_cast<uint32_t>(i) - ray * static_cast<uint32_t>(ps.S));
+			const int p = ru.perm[i];
+			const int64_t row0 = static_cast<int64_t>(ray) * ps.S;
+			if (p >= 0 && t >= ps.S - ru.S_prev) {
+				// copy the row the coarse pass produced for this very point (16-byte vectors; rows are 16-byte aligned, host-checked)
+				const int64_t from = static_cast<int64_t>(ray) * ru.S_prev + (t - (ps.S - ru.S_prev));
+				const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(ru.enc) + from * row_bytes);
+				uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + (row0 + p) * row_bytes);
+				const int nq = row_bytes / 16;
+				if (SPLIT == 1) {
+					for (int q = 0; q < nq; q++) d4[q] = __ldg(s4 + q);
+				} else {
+					for (int q = part; q < nq; q += SPLIT) d4[q] = __ldg(s4 + q);
+				}
+				if (keep && part == 0) keep[row0 + p] = ru.keep ? ru.keep[from] : 1;
+				continue;
+			}
+			i = row0 + (p >= 0 ? p : -(p + 1));   // the merged position this thread encodes
+		}
+
+		float x, y, z;
+		load_point(ps, i, x, y, z);
+		if (clamp_points) {
+			const bool k = clamp_point(a, x, y, z);
+			if (keep && part == 0) keep[i] = k ? 1 : 0;
+		}
+		const float qx = (x - a.min_x) / (a.max_x - a.min_x);
+		const float qy = (y - a.min_y) / (a.max_y - a.min_y);
+		const float qz = (z - a.min_z) / (a.max_z - a.min_z);
+
+		const int64_t row = i * (static_cast<int64_t>(L) * F);
+		const int l_begin = SPLIT == 1 ? 0 : part * CH;
+		const int l_end = SPLIT == 1 ? L : min(L, l_begin + CH);
+		for (int l0 = l_begin; l0 < l_end; l0 += CH) {
+			__half2 acc[4];
 #pragma unroll
-		for (int j = 0; j < CH; j++) {
-			const int l = l0 + j;
-			if (l < L) {
-				Cell c;
-				locate(m, l, qx, qy, qz, c);
-				const __half* base = table + m.offset[l];
-				V v[8];
+			for (int j = 0; j < CH; j++) {
+				const int l = l0 + j;
+				if (l < L) {
+					Cell c;
+					locate(m, l, qx, qy, qz, c);
+					const __half* base = table + m.offset[l];
+					V v[8];
 #pragma unroll
-				for (int d = 0; d < 8; d++) v[d] = __ldg(reinterpret_cast<const V*>(base + static_cast<size_t>(c.pos[d]) * F));
-				float f[8][F];
+					for (int d = 0; d < 8; d++) v[d] = __ldg(reinterpret_cast<const V*>(base + static_cast<size_t>(c.pos[d]) * F));
+					float f[8][F];
 #pragma unroll
-				for (int d = 0; d < 8; d++) unpack<F>(v[d], f[d]);
+					for (int d = 0; d < 8; d++) unpack<F>(v[d], f[d]);
 #pragma unroll
-				for (int k = 0; k < F; k += 2) {
-					// same summation order as src/CuHashEmbedder.cu:96-100
-					const float r0 = c.w[0] * f[0][k] + c.w[1] * f[1][k] + c.w[2] * f[2][k] + c.w[3] * f[3][k] +
-					                 c.w[4] * f[4][k] + c.w[5] * f[5][k] + c.w[6] * f[6][k] + c.w[7] * f[7][k];
-					const float r1 = c.w[0] * f[0][k + 1] + c.w[1] * f[1][k + 1] + c.w[2] * f[2][k + 1] + c.w[3] * f[3][k + 1] +
-					                 c.w[4] * f[4][k + 1] + c.w[5] * f[5][k + 1] + c.w[6] * f[6][k + 1] + c.w[7] * f[7][k + 1];
-					acc[(j * F + k) / 2] = __halves2half2(__float2half_rn(r0), __float2half_rn(r1));
+					for (int k = 0; k < F; k += 2) {
+						// same summation order as src/CuHashEmbedder.cu:96-100
+						const float r0 = c.w[0] * f[0][k] + c.w[1] * f[1][k] + c.w[2] * f[2][k] + c.w[3] * f[3][k] +
+						                 c.w[4] * f[4][k] + c.w[5] * f[5][k] + c.w[6] * f[6][k] + c.w[7] * f[7][k];
+						const float r1 = c.w[0] * f[0][k + 1] + c.w[1] * f[1][k + 1] + c.w[2] * f[2][k + 1] + c.w[3] * f[3][k + 1] +
+						                 c.w[4] * f[4][k + 1] + c.w[5] * f[5][k + 1] + c.w[6] * f[6][k + 1] + c.w[7] * f[7][k + 1];
+						acc[(j * F + k) / 2] = __halves2half2(__float2half_rn(r0), __float2half_rn(r1));
+					}
+				} else {
+#pragma unroll
+					for (int k = 0; k < F; k += 2) acc[(j * F + k) / 2] = __halves2half2(__half(0), __half(0));
+				}
+			}
+			const int n_valid = min(CH, L - l0) * F;  // scalars of this chunk that exist
+			if (OUT_F32) {
+				float* o = reinterpret_cast<float*>(out) + row + static_cast<int64_t>(l0) * F;
+				float v8[8];
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					const float2 t = __half22float2(acc[k]);
+					v8[2 * k] = t.x;
+					v8[2 * k + 1] = t.y;
+				}
+				if (n_valid == 8 && ((L * F) % 4 == 0)) {
+					reinterpret_cast<float4*>(o)[0] = make_float4(v8[0], v8[1], v8[2], v8[3]);
+					reinterpret_cast<float4*>(o)[1] = make_float4(v8[4], v8[5], v8[6], v8[7]);
+				} else {
+					for (int k = 0; k < n_valid; k++) o[k] = v8[k];
 				}
 			} else {
-#pragma unroll
-				for (int k = 0; k < F; k += 2) acc[(j * F + k) / 2] = __halves2half2(__half(0), __half(0));
-			}
-		}
-		const int n_valid = min(CH, L - l0) * F;  // scalars of this chunk that exist
-		if (OUT_F32) {
-			float* o = reinterpret_cast<float*>(out) + row + static_cast<int64_t>(l0) * F;
-			float v8[8];
-#pragma unroll
-			for (int k = 0; k < 4; k++) {
-				const float2 t = __half22float2(acc[k]);
-				v8[2 * k] = t.x;
-				v8[2 * k + 1] = t.y;
-			}
-			if (n_valid == 8 && ((L * F) % 4 == 0)) {
-				reinterpret_cast<float4*>(o)[0] = make_float4(v8[0], v8[1], v8[2], v8[3]);
-				reinterpret_cast<float4*>(o)[1] = make_float4(v8[4], v8[5], v8[6], v8[7]);
-			} else {
-				for (int k = 0; k < n_valid; k++) o[k] = v8[k];
-			}
-		} else {
-			__half* o = reinterpret_cast<__half*>(out) + row + static_cast<int64_t>(l0) * F;
-			if (n_valid == 8 && ((L * F) % 8 == 0)) {
-				*reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(acc);
-			} else {
-				const __half* hs = reinterpret_cast<const __half*>(acc);
-				for (int k = 0; k < n_valid; k++) o[k] = hs[k];
+				__half* o = reinterpret_cast<__half*>(out) + row + static_cast<int64_t>(l0) * F;
+				if (n_valid == 8 && ((L * F) % 8 == 0)) {
+					*reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(acc);
+				} else {
+					const __half* hs = reinterpret_cast<const __half*>(acc);
+					for (int k = 0; k < n_valid; k++) o[k] = hs[k];
+				}
 			}
 		}
 	}
@@ -296,8 +316,9 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b)
 //   3. lets only the first lane of a run issue the vector REDs.
 // Any point order is handled correctly (a run is defined by adjacency, not by key equality); ray-major order is what
 // makes it pay.  The reference issues N*L*8 half2 atomics regardless.
+// Like the forward, the grid is one balanced wave (launch_plan): thread t handles points t, t + stride, ... (`iters` of them, warp-uniform).
 template <int F, bool GRAD_BF16>
-__global__ void __launch_bounds__(256) hash_bwd_kernel(HashArgs a, PointSrc ps, int64_t n_points,
+__global__ void __launch_bounds__(128) hash_bwd_kernel(HashArgs a, PointSrc ps, int64_t n_points, int64_t stride, int iters,
 	int clamp_points, const void* __restrict__ grad_enc, float* __restrict__ grad_table)
 {
 	constexpr int CH = 8 / F;   // levels per 8-value gradient chunk (16 B of bf16 / 32 B of fp32)
@@ -306,7 +327,8 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(HashArgs a, PointSrc ps, 
 	stage_meta(m, a);
 
 	const int lane = threadIdx.x & 31;
-	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	for (int it = 0; it < iters; it++, i += stride) {
 	const bool valid = i < n_points;   // no early return: the whole warp takes part in the shuffles
 
 	float x = 0.f, y = 0.f, z = 0.f;
@@ -409,6 +431,31 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(HashArgs a, PointSrc ps, 
 			}
 		}
 	}
+	}   // items of this thread
+}
+
+// Inspection entry (tests): the scalar addresses and trilinear weights the encode kernels use, from the SAME clamp_point / locate code.
+__global__ void __launch_bounds__(128) hash_cells_kernel(HashArgs a, const float* __restrict__ points, int64_t n_points, int clamp_points,
+	int n_features, int64_t* __restrict__ addr, float* __restrict__ weights)
+{
+	__shared__ HashMeta m;
+	stage_meta(m, a);
+	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= n_points) return;
+	float x = points[i * 3 + 0], y = points[i * 3 + 1], z = points[i * 3 + 2];
+	if (clamp_points) clamp_point(a, x, y, z);
+	const float qx = (x - a.min_x) / (a.max_x - a.min_x);
+	const float qy = (y - a.min_y) / (a.max_y - a.min_y);
+	const float qz = (z - a.min_z) / (a.max_z - a.min_z);
+	for (int l = 0; l < a.n_levels; l++) {
+		Cell c;
+		locate(m, l, qx, qy, qz, c);
+		for (int d = 0; d < 8; d++) {
+			const int64_t o = (i * a.n_levels + l) * 8 + d;
+			addr[o] = static_cast<int64_t>(m.offset[l]) + static_cast<int64_t>(c.pos[d]) * n_features;
+			weights[o] = c.w[d];
+		}
+	}
 }
 
 __global__ void __launch_bounds__(256) table_to_half_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n)
@@ -446,6 +493,41 @@ static int fill_args(const nrf_hash_grid* g, HashArgs& a)
 	return NRF_OK;
 }
 
+// One balanced wave: `items` work items on CTAs of `block` threads, at most `occ` co-resident per SM.  Every thread takes k items
+// (grid-stride); k is chosen to minimise k x ceil(CTAs / SMs) — the number of item-rounds the fullest SM runs — over the k that keep
+// the grid within one wave; ties go to the smaller k (more threads in flight).  NRF_HASH_PLAN=legacy restores one item per thread.
+struct LaunchPlan { unsigned grid; int64_t stride; int iters; };
+
+static LaunchPlan launch_plan(int64_t items, int block, int occ)
+{
+	static const bool legacy = [] { const char* e = getenv("NRF_HASH_PLAN"); return e && strcmp(e, "legacy") == 0; }();
+	int sms = kNumSMs;
+	int dev = 0;
+	if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	const int64_t ctas1 = (items + block - 1) / block;
+	if (legacy || ctas1 <= static_cast<int64_t>(sms) * occ) return {static_cast<unsigned>(ctas1), ctas1 * block, 1};
+	const int64_t wave = static_cast<int64_t>(sms) * occ * block;
+	const int64_t kmin = (items + wave - 1) / wave;
+	int64_t best_k = kmin, best_cost = INT64_MAX;
+	for (int64_t k = kmin; k <= 2 * kmin + 2; k++) {
+		const int64_t ctas = (items + k * block - 1) / (k * block);
+		const int64_t per_sm = (ctas + sms - 1) / sms;
+		if (per_sm > occ) continue;
+		const int64_t cost = k * per_sm;
+		if (cost < best_cost) { best_cost = cost; best_k = k; }
+	}
+	const int64_t ctas = (items + best_k * block - 1) / (best_k * block);
+	return {static_cast<unsigned>(ctas), ctas * block, static_cast<int>(best_k)};
+}
+
+template <typename K>
+static int occupancy_of(K kernel, int block)
+{
+	int occ = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 8; }
+	return occ;
+}
+
 }  // namespace nrf
 
 using namespace nrf;
@@ -458,6 +540,20 @@ int nrf_hash_level_scales(int32_t base_resolution, int32_t finest_resolution, in
 	NRF_REQUIRE(n_levels >= 1 && n_levels <= NRF_MAX_LEVELS, "n_levels out of range");
 	level_scale_kernel<<<1, NRF_MAX_LEVELS, 0, as_stream(stream)>>>(base_resolution, finest_resolution, n_levels, level_scale);
 	NRF_CHECK_LAUNCH("level_scale_kernel");
+	return NRF_OK;
+}
+
+int nrf_hash_cells(const nrf_hash_grid* grid, const float* points, int64_t n_points, int clamp_points, int64_t* addr, float* weights,
+	nrf_stream stream)
+{
+	HashArgs a;
+	if (int rc = fill_args(grid, a)) return rc;
+	NRF_REQUIRE(n_points >= 0, "negative n_points");
+	if (n_points == 0) return NRF_OK;
+	NRF_REQUIRE(points && addr && weights, "null pointer");
+	hash_cells_kernel<<<static_cast<unsigned>((n_points + 127) / 128), 128, 0, as_stream(stream)>>>(a, points, n_points, clamp_points, grid->n_features,
+		addr, weights);
+	NRF_CHECK_LAUNCH("hash_cells_kernel");
 	return NRF_OK;
 }
 
@@ -481,17 +577,36 @@ static int launch_hash_fwd(const nrf_hash_grid* grid, const void* table_f16, con
 	NRF_REQUIRE(table_f16 && enc_out, "null table / output");
 	NRF_REQUIRE(layout == NRF_ENC_F32 || layout == NRF_ENC_F16, "bad layout");
 	const int F = grid->n_features;
-	const unsigned blocks = static_cast<unsigned>((n_points + 255) / 256);
 	const __half* t = reinterpret_cast<const __half*>(table_f16);
 	cudaStream_t s = as_stream(stream);
-#define NRF_LAUNCH_FWD(FF)                                                                                               \
-	if (layout == NRF_ENC_F32) hash_fwd_kernel<FF, true><<<blocks, 256, 0, s>>>(a, t, ps, ru, n_points, clamp_points, keep, enc_out); \
-	else hash_fwd_kernel<FF, false><<<blocks, 256, 0, s>>>(a, t, ps, ru, n_points, clamp_points, keep, enc_out)
-	if (F == 2) { NRF_LAUNCH_FWD(2); }
-	else if (F == 4) { NRF_LAUNCH_FWD(4); }
-	else if (F == 8) { NRF_LAUNCH_FWD(8); }
+	// lanes per point: one per 16-byte chunk of the row when the chunks of a row are a power of two (4 at L16 F2, 16 at L16 F8)
+	static const int split_env = [] { const char* e = getenv("NRF_HASH_SPLIT"); return e ? atoi(e) : -1; }();
+	const int chunks = (grid->n_levels * F + 7) / 8;
+	const bool can_split = (grid->n_levels * F) % 8 == 0 && (chunks & (chunks - 1)) == 0 && chunks <= 32 && chunks > 1;
+	const bool split = can_split && split_env != 0;
+#define NRF_LAUNCH_FWD2(FF, O32, SP)                                                                                              \
+	do {                                                                                                                          \
+		static const int occ = occupancy_of(hash_fwd_kernel<FF, O32, SP>, 128);                                                   \
+		const int64_t items = n_points * (SP);                                                                                   \
+		const LaunchPlan lp = launch_plan(items, 128, occ);                                                                      \
+		hash_fwd_kernel<FF, O32, SP><<<lp.grid, 128, 0, s>>>(a, t, ps, ru, items, lp.stride, lp.iters, clamp_points, keep, enc_out); \
+	} while (0)
+#define NRF_LAUNCH_FWD(FF, SP)                                                     \
+	do {                                                                           \
+		if (split) {                                                               \
+			if (layout == NRF_ENC_F32) NRF_LAUNCH_FWD2(FF, true, SP);              \
+			else NRF_LAUNCH_FWD2(FF, false, SP);                                   \
+		} else {                                                                   \
+			if (layout == NRF_ENC_F32) NRF_LAUNCH_FWD2(FF, true, 1);               \
+			else NRF_LAUNCH_FWD2(FF, false, 1);                                    \
+		}                                                                          \
+	} while (0)
+	if (F == 2) { if (chunks == 4) NRF_LAUNCH_FWD(2, 4); else NRF_LAUNCH_FWD(2, 1); }
+	else if (F == 4) { if (chunks == 8) NRF_LAUNCH_FWD(4, 8); else NRF_LAUNCH_FWD(4, 1); }
+	else if (F == 8) { if (chunks == 16) NRF_LAUNCH_FWD(8, 16); else NRF_LAUNCH_FWD(8, 1); }
 	else { set_error("nrf_hash_encode_fwd: n_features must be 2, 4 or 8"); return NRF_ERR_UNSUPPORTED; }
 #undef NRF_LAUNCH_FWD
+#undef NRF_LAUNCH_FWD2
 	NRF_CHECK_LAUNCH("hash_fwd_kernel");
 	return NRF_OK;
 }
@@ -504,16 +619,24 @@ static int launch_hash_bwd(const nrf_hash_grid* grid, const PointSrc& ps, int64_
 	NRF_REQUIRE(grad_table != nullptr && grad_enc != nullptr, "null grad_table / grad");
 	NRF_REQUIRE(layout == NRF_GRAD_F32 || layout == NRF_GRAD_BF16, "bad layout");
 	const int F = grid->n_features;
-	const unsigned blocks = static_cast<unsigned>((n_points + 255) / 256);
 	cudaStream_t s = as_stream(stream);
-#define NRF_LAUNCH_BWD(FF)                                                                                          \
-	if (layout == NRF_GRAD_BF16) hash_bwd_kernel<FF, true><<<blocks, 256, 0, s>>>(a, ps, n_points, clamp_points, grad_enc, grad_table); \
-	else hash_bwd_kernel<FF, false><<<blocks, 256, 0, s>>>(a, ps, n_points, clamp_points, grad_enc, grad_table)
+#define NRF_LAUNCH_BWD2(FF, BF)                                                                                                   \
+	do {                                                                                                                          \
+		static const int occ = occupancy_of(hash_bwd_kernel<FF, BF>, 128);                                                        \
+		const LaunchPlan lp = launch_plan(n_points, 128, occ);                                                                   \
+		hash_bwd_kernel<FF, BF><<<lp.grid, 128, 0, s>>>(a, ps, n_points, lp.stride, lp.iters, clamp_points, grad_enc, grad_table); \
+	} while (0)
+#define NRF_LAUNCH_BWD(FF)                                             \
+	do {                                                               \
+		if (layout == NRF_GRAD_BF16) NRF_LAUNCH_BWD2(FF, true);        \
+		else NRF_LAUNCH_BWD2(FF, false);                               \
+	} while (0)
 	if (F == 2) { NRF_LAUNCH_BWD(2); }
 	else if (F == 4) { NRF_LAUNCH_BWD(4); }
 	else if (F == 8) { NRF_LAUNCH_BWD(8); }
 	else { set_error("nrf_hash_encode_bwd: n_features must be 2, 4 or 8"); return NRF_ERR_UNSUPPORTED; }
 #undef NRF_LAUNCH_BWD
+#undef NRF_LAUNCH_BWD2
 	NRF_CHECK_LAUNCH("hash_bwd_kernel");
 	return NRF_OK;
 }

@@ -45,34 +45,43 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p)
 }
 
 // All CTAs of all ranks meet here.  CTA 0 / thread 0 raises this rank's slot in every peer's flag block to `epoch` and waits for
-// every peer's slot in the local block; the other CTAs wait for the local release word.  Needs all CTAs co-resident (grid <= SMs).
-// A rank that never arrives (crashed peer) releases the others after ~2 s with the timeout marker set instead of hanging the box.
-__device__ __forceinline__ void peer_barrier(const PeerArgs& a, int which, uint32_t epoch, uint32_t* done_counter)
+// every peer's slot in the local block; the other CTAs wait for the local release word.  Needs all CTAs co-resident (cooperative launch,
+// grid <= SMs).  A rank that never arrives (crashed peer) releases the others after ~2 s: EVERY path that gives up sets the sticky
+// timeout marker, and the barrier then returns false to the whole CTA — the caller must not write parameters, shadows or gradients after
+// a failed barrier (the host reads the marker and raises: PeerShardedOptimizer.check).
+__device__ __forceinline__ bool peer_barrier(const PeerArgs& a, int which, uint32_t epoch, uint32_t* done_counter)
 {
 	uint32_t* mine = a.flags[a.rank];
+	uint32_t* marker = mine + 2 * a.world + 2;
+	__shared__ int s_ok;
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		__threadfence_system();   // this CTA's peer stores / loads are ordered before its arrival
+		const uint32_t target = 2u * (epoch - 1u) + which + 1u;
 		const uint32_t arrived = atomicAdd(done_counter, 1u) + 1u;
-		if (arrived == gridDim.x * (2u * (epoch - 1u) + which + 1u)) {
+		if (arrived == gridDim.x * target) {
 			// last CTA of this rank to arrive: tell the peers, wait for them, release the local CTAs
 			for (int p = 0; p < a.world; p++) st_release_sys(a.flags[p] + which * a.world + a.rank, epoch);
 			const long long t0 = clock64();
-			for (int p = 0; p < a.world; p++) {
+			bool late = false;
+			for (int p = 0; p < a.world && !late; p++) {
 				while (ld_acquire_sys(mine + which * a.world + p) < epoch) {
-					if (clock64() - t0 > 4000000000LL) { mine[2 * a.world + 2] = 1u; break; }
+					if (clock64() - t0 > 4000000000LL) { late = true; break; }
 				}
 			}
-			st_release_sys(mine + 2 * a.world + 1, 2u * (epoch - 1u) + which + 1u);
+			if (late) atomicExch(marker, 1u);
+			st_release_sys(mine + 2 * a.world + 1, target);
 		} else {
 			const long long t0 = clock64();
-			while (ld_acquire_gpu(mine + 2 * a.world + 1) < 2u * (epoch - 1u) + which + 1u) {
-				if (clock64() - t0 > 6000000000LL) break;
+			while (ld_acquire_gpu(mine + 2 * a.world + 1) < target) {
+				if (clock64() - t0 > 6000000000LL) { atomicExch(marker, 1u); break; }
 			}
 		}
 		__threadfence_system();
+		s_ok = ld_acquire_gpu(marker) == 0u;
 	}
 	__syncthreads();
+	return s_ok != 0;
 }
 
 __device__ __forceinline__ uint32_t globaltimer_lo()
@@ -100,19 +109,23 @@ __device__ __forceinline__ float adam_update(float p, float g, float& m, float& 
 // together (NVLink round trips are ~2 us: the kernel lives on memory-level parallelism).
 template <int WORLD, int U>
 __global__ void __launch_bounds__(512, 1) adam_sharded_kernel(PeerArgs a, float* __restrict__ param, float* __restrict__ m, float* __restrict__ v,
-	float* __restrict__ grad_local, int64_t n_sharded, int64_t n_total, const AdamSchedState* __restrict__ sched, float beta1, float beta2, float eps,
+	float* grad_local, int64_t n_sharded, int64_t n_total, const AdamSchedState* __restrict__ sched, float beta1, float beta2, float eps,
 	float grad_scale)
 {
 	uint32_t* mine = a.flags[a.rank];
-	__shared__ uint32_t s_epoch;
-	if (threadIdx.x == 0) s_epoch = mine[2 * WORLD] + 1u;   // every CTA reads the epoch before anyone bumps it (bumped after barrier 1)
+	__shared__ uint32_t s_epoch, s_dead;
+	if (threadIdx.x == 0) {
+		s_epoch = mine[2 * WORLD] + 1u;   // every CTA reads the epoch before anyone bumps it (bumped after barrier 1)
+		s_dead = mine[2 * WORLD + 2];     // sticky: an earlier step lost a peer -> this and every later step write nothing
+	}
 	__syncthreads();
+	if (s_dead) return;
 	const uint32_t epoch = s_epoch;
 	uint32_t* done_counter = mine + 2 * WORLD + 3;
 	const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
 	if (stamp) mine[kStampBase + 0] = globaltimer_lo();
 
-	peer_barrier(a, 0, epoch, done_counter);
+	if (!peer_barrier(a, 0, epoch, done_counter)) return;   // some peer's gradient may be incomplete: touch nothing
 	if (stamp) mine[kStampBase + 1] = globaltimer_lo();
 
 	const float lr_over_bc1 = sched->lr_over_bc1, inv_sqrt_bc2 = sched->inv_sqrt_bc2;
@@ -172,7 +185,7 @@ __global__ void __launch_bounds__(512, 1) adam_sharded_kernel(PeerArgs a, float*
 	}
 
 	if (stamp) mine[kStampBase + 2] = globaltimer_lo();
-	peer_barrier(a, 1, epoch, done_counter);
+	if (!peer_barrier(a, 1, epoch, done_counter)) return;   // a peer may still be reading this rank's gradient: do not clear it
 	if (stamp) mine[kStampBase + 3] = globaltimer_lo();
 
 	// every peer has consumed this rank's gradient: clear it for the next step
@@ -213,9 +226,23 @@ int nrf_adam_step_sharded(const nrf_peer_group* pg, float* param, float* exp_avg
 	int sms = kNumSMs;
 	int dev = 0;
 	if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-#define NRF_LAUNCH_SHARDED(W, U)                                                                                                   \
-	adam_sharded_kernel<W, U><<<sms, 512, 0, as_stream(stream)>>>(a, param, exp_avg, exp_avg_sq, const_cast<float*>(a.grads[a.rank]), \
-		n_sharded, n_total, reinterpret_cast<const AdamSchedState*>(sched_state), beta1, beta2, eps, grad_scale)
+	// cooperative launch: the driver guarantees that all CTAs are co-resident (or refuses the launch) — the in-kernel barriers spin
+	float* grad_local = const_cast<float*>(a.grads[a.rank]);
+	const AdamSchedState* sched = reinterpret_cast<const AdamSchedState*>(sched_state);
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(sms);
+	cfg.blockDim = dim3(512);
+	cfg.dynamicSmemBytes = 0;
+	cfg.stream = as_stream(stream);
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeCooperative;
+	attr[0].val.cooperative = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	cudaError_t launch_err = cudaSuccess;
+#define NRF_LAUNCH_SHARDED(W, U)                                                                                                     \
+	launch_err = cudaLaunchKernelEx(&cfg, adam_sharded_kernel<W, U>, a, param, exp_avg, exp_avg_sq, grad_local, n_sharded, n_total, sched, \
+		beta1, beta2, eps, grad_scale)
 	switch (pg->world) {
 		case 1: NRF_LAUNCH_SHARDED(1, 4); break;
 		case 2: NRF_LAUNCH_SHARDED(2, 4); break;
@@ -227,6 +254,7 @@ int nrf_adam_step_sharded(const nrf_peer_group* pg, float* param, float* exp_avg
 		default: NRF_LAUNCH_SHARDED(8, 2); break;
 	}
 #undef NRF_LAUNCH_SHARDED
+	if (launch_err != cudaSuccess) { set_error("adam_sharded_kernel: %s", cudaGetErrorString(launch_err)); cudaGetLastError(); return NRF_ERR_CUDA; }
 	NRF_CHECK_LAUNCH("adam_sharded_kernel");
 	return NRF_OK;
 }

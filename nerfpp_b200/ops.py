@@ -20,8 +20,9 @@ class KernelTimer:
     """Optional per-kernel CUDA-event timing on the launching stream (bench.py roofline / breakdown).
     `only`: restrict to these entry names (without the nrf_ prefix) so the timed region carries two events per step."""
 
-    def __init__(self, only=None):
+    def __init__(self, only=None, external=False):
         self.only = set(only) if only else None
+        self.external = external      # events that may be recorded inside a CUDA-graph capture and read after a replay
         self.records: dict[str, list] = {}
 
     def summary(self) -> dict:
@@ -40,7 +41,7 @@ def set_timer(t: KernelTimer | None) -> None:
 def _run(name: str, call) -> None:
     t = _timer
     if t is not None and (t.only is None or name in t.only):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True, external=t.external), torch.cuda.Event(enable_timing=True, external=t.external)
         e0.record()
         status = call()
         e1.record()
@@ -97,6 +98,16 @@ def hash_level_scales(base_res: int, finest_res: int, n_levels: int, device) -> 
     out = torch.empty(n_levels, dtype=f32, device=device)
     _run("hash_level_scales", lambda: lib().nrf_hash_level_scales(base_res, finest_res, n_levels, ptr(out), stream()))
     return out
+
+
+def hash_cells(grid: HashGridSpec, points: torch.Tensor, clamp: bool = True):
+    """(addr int64 [N,L,8], weights f32 [N,L,8]): the scalar addresses / trilinear weights the encode kernels use (inspection entry)."""
+    n = points.shape[0]
+    addr = torch.empty((n, grid.n_levels, 8), dtype=torch.int64, device=points.device)
+    w = torch.empty((n, grid.n_levels, 8), dtype=f32, device=points.device)
+    g = grid.c_struct()
+    _run("hash_cells", lambda: lib().nrf_hash_cells(C.byref(g), ptr(points, f32), n, int(clamp), ptr(addr), ptr(w), stream()))
+    return addr, w
 
 
 def table_to_half(table: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:

@@ -123,30 +123,100 @@ class PeerShardedOptimizer:
         self.multicast = bool(getattr(handles[0], "has_multicast_support", False))
         model.grads, model.shadow = self.grads, self.shadow
         model.peer = self
+        self._flag_host = None
         torch.cuda.synchronize(dev)
         dist.barrier(group)
 
-    def self_test(self, model) -> bool:
-        """One fused optimiser step on the all-zero gradient before training starts: with zero moments it leaves every parameter
-        unchanged but exercises the peer mappings and both barriers.  Returns True when every rank came through (collective)."""
-        ok = 1
-        try:
-            assert model.step == 0 and float(model.grads.abs().max()) == 0.0, "self_test must run before the first step"
-            before = model.shadow.clone()
-            model.optimizer_step_sharded()
-            torch.cuda.synchronize(model.device)
-            if model.flags_timeout() or not torch.equal(before, model.shadow):
-                print(f"[nerfpp_b200] rank {self.rank}: fused optimiser self-test failed (flags_timeout={model.flags_timeout()}, "
-                      f"shadow changed={not torch.equal(before, model.shadow)})", file=sys.stderr, flush=True)
-                ok = 0
-        except Exception as e:  # noqa: BLE001
-            print(f"[nerfpp_b200] rank {self.rank}: fused optimiser self-test raised {type(e).__name__}: {e}", file=sys.stderr, flush=True)
-            ok = 0
+    def dp_check(self, model, seed: int = 1234) -> dict:
+        """ONE optimiser step on a random per-rank gradient through BOTH data-parallel paths, on the model's own buffers, then everything
+        is put back: (A) NCCL all-reduce(sum) + dense Adam on clones (parallel.allreduce_gradients + nrf_adam_step), (B) the fused
+        peer-memory kernel.  Collective; call before training starts (model.step == 0).  Returns
+          max_abs_shadow_diff               max |shadow_B - shadow_A| over the whole flat vector, max over ranks (A and B differ only in the
+                                            order of the cross-rank sum: NCCL's ring vs fixed rank order), and the number of entries where
+                                            it exceeds 5 % of lr (a summed gradient within rounding of zero flips the sign of the step)
+          shadows_bit_identical_across_ranks   every rank holds rank 0's fp16 shadow bit for bit after (B)
+          owner_master_matches_shadow       on every rank the owned fp32 shard rounds to the shadow it published
+          flags_timeout                     max over ranks of the sticky barrier-timeout marker
+        The first Adam step moves every parameter by ~lr * sign(g), so a wrong reduction (a missing rank, a wrong shard) shows up at
+        the 1e-2 level against lr-sized differences of 0 for a correct one."""
+        from . import ops
+        dev, world, rank = model.device, self.world, self.rank
+        assert model.step == 0, "dp_check must run before the first step"
+        saved = {k: getattr(model, k).clone() for k in ("params", "exp_avg", "exp_avg_sq", "shadow")}
+        g = torch.Generator(device=dev).manual_seed(seed + rank)
+        grad = torch.randn(model.params.numel(), generator=g, device=dev, dtype=torch.float32) * 1e-3
+        # (A) reference path on clones
+        g_sum = grad.clone()
+        dist.all_reduce(g_sum, op=dist.ReduceOp.SUM)
+        pa, ma, va = saved["params"].clone(), saved["exp_avg"].clone(), saved["exp_avg_sq"].clone()
+        shadow_a = torch.empty_like(saved["shadow"])
+        ops.adam_step(pa, g_sum, ma, va, model.lr0, 1, 0.9, 0.99, 1e-15, 1.0 / world, True, shadow_a)
+        # (B) fused path on the live buffers
+        model.grads.copy_(grad)
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        model.optimizer_step_sharded()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        d = (model.shadow.float() - shadow_a.float()).abs()
+        diff = d.max()
+        n_diff = (d > 0.05 * model.lr0).sum()          # sign flips of a ~zero summed gradient (the step is ~lr * sign(g)): expect 0, allow a handful
+        ref = model.shadow.clone()
+        dist.broadcast(ref, src=0)
+        same = torch.equal(ref, model.shadow)
+        lo, hi = self.shard_bounds(model.n_table)
+        owner_ok = torch.equal(model.params[lo:hi].half(), model.shadow[lo:hi])
+        master_diff = (model.params[lo:hi] - pa[lo:hi]).abs().max() if hi > lo else torch.zeros((), device=dev)
+        cleared = float(model.grads.abs().max()) == 0.0
+        stats = torch.tensor([float(diff), float(master_diff), float(not same), float(not owner_ok), float(not cleared), float(self.timeout()), float(n_diff)],
+                             dtype=torch.float64, device=dev)
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        # put everything back (every rank restores its own buffers; the peers' writes into this rank's shadow are overwritten)
+        dist.barrier()
+        for k, v in saved.items():
+            getattr(model, k).copy_(v)
+        model.grads.zero_()
         model.step = 0
-        model._sched_step = -1          # the dry step advanced the device-side counter: re-seed it on the next step
-        flag = torch.tensor([ok], dtype=torch.int32, device=model.device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        return bool(flag.item())
+        model._sched_step = -1          # the check advanced the device-side counter: re-seed it on the next step
+        model.packed = ops.mlp_small_pack(model.mlp_params, out=model.packed)
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        out = {"max_abs_shadow_diff": stats[0].item(), "max_abs_owned_master_diff": stats[1].item(),
+               "shadows_bit_identical_across_ranks": stats[2].item() == 0.0, "owner_master_matches_shadow": stats[3].item() == 0.0,
+               "gradient_cleared": stats[4].item() == 0.0, "flags_timeout": int(stats[5].item()), "entries_differing_by_more_than_5pct_of_lr": int(stats[6].item()),
+               "entries": int(model.params.numel()), "lr": model.lr0,
+               "what": "one step on a random per-rank gradient: fused peer-memory kernel vs NCCL all-reduce + dense Adam"}
+        out["ok"] = bool(out["shadows_bit_identical_across_ranks"] and out["owner_master_matches_shadow"] and out["gradient_cleared"]
+                         and out["flags_timeout"] == 0 and out["entries_differing_by_more_than_5pct_of_lr"] <= 8)
+        return out
+
+    def timeout(self) -> int:
+        """The sticky barrier-timeout marker of this rank's flag block (synchronises the device)."""
+        return int(self.flags[2 * self.world + 2])
+
+    def check(self) -> None:
+        """Raises if a peer barrier of the fused optimiser ever gave up waiting.  Reads a pinned-host mirror of the marker that
+        `mirror_flag` refreshes asynchronously after every step: no device synchronisation, at most a few steps late."""
+        if self._flag_host is not None and int(self._flag_host[0]) != 0:
+            raise RuntimeError(f"nerfpp_b200: rank {self.rank}: a peer barrier of the fused data-parallel optimiser timed out — a rank missed a "
+                               "step; parameters were left untouched from that step on (nrf_adam_step_sharded)")
+
+    def mirror_flag(self) -> None:
+        if self._flag_host is None:
+            self._flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._flag_host.copy_(self.flags[2 * self.world + 2: 2 * self.world + 3], non_blocking=True)
+
+    def allgather_master(self, model) -> None:
+        """Re-assemble the fp32 master and the Adam moments on every rank: under the fused optimiser a rank only updates the shard it
+        owns (the forward reads the fp16 shadow), so before a checkpoint (the reference's embedder_checkpoint.pt,
+        src/NeRFExecutor.h:1055-1069), HashNeRF.refresh() or a switch back to the NCCL path the owners publish their shards.
+        Collective (one broadcast per rank and buffer: 3 x 35 MB in total, off the hot path)."""
+        torch.cuda.synchronize(model.device)
+        for r in range(self.world):
+            b, e = shard_bounds(model.n_table // 4, r, self.world)
+            for buf in (model.params, model.exp_avg, model.exp_avg_sq):
+                dist.broadcast(buf[4 * b:4 * e], src=r)
+        model.masters_synced = True
 
     def shard_bounds(self, n_sharded: int) -> tuple[int, int]:
         """[begin, end) scalars of the table this rank owns (same split as the kernel: quads, first ranks one extra)."""

@@ -99,19 +99,21 @@ class HashNeRF:
         self.t_vals = torch.linspace(0.0, 1.0, n_samples, dtype=f32).to(device)                  # src/NeRFRenderer.h:393
         self.u = torch.linspace(0.0, 1.0, n_importance, dtype=f32).to(device)                    # src/Sampler.h:20
         self.loss = torch.zeros(1, dtype=f32, device=device)
-        # Copy the coarse samples' encoding rows into the fine pass instead of gathering them again (bit-identical, tested).
-        # Off by default: measured gain is only ~10 % of the fine-pass encode (the rows it skips are the L1-friendly ones),
-        # and the benchmark step then performs exactly the work the reference's step performs.
-        self.reuse_coarse_rows = False
+        # Copy the coarse samples' encoding rows into the fine pass instead of gathering them again: the merged z list contains the
+        # coarse samples bit for bit, so the rows are bit-identical (tests/test_gpu_hash.py::test_row_reuse...); ~10 % of the fine-pass encode.
+        self.reuse_coarse_rows = True
         self._u_cache = {}
         self._render_ws = None
         self.peer = None          # parallel.PeerShardedOptimizer when the fused data-parallel optimiser is in use
+        self.masters_synced = True  # False while the fused optimiser has stepped and the non-owned fp32 shards are stale
         self.sched = None
         self.refresh()
 
     # -- views into the flat buffers
     @property
-    def table(self): return self.params[:self.n_table]
+    def table(self):
+        self._require_synced("table")
+        return self.params[:self.n_table]
     @property
     def mlp_params(self): return self.params[self.n_table:]
     @property
@@ -123,6 +125,17 @@ class HashNeRF:
             out.append(self.mlp_params[off:off + fo * fi].view(fo, fi))
             off += fo * fi
         return out
+
+    def _require_synced(self, what):
+        if not self.masters_synced:
+            raise RuntimeError(f"HashNeRF.{what}: the fp32 master is sharded over the ranks (fused data-parallel optimiser) and this rank's "
+                               "non-owned shards are stale — call model.peer.allgather_master(model) first (collective)")
+
+    def state_dict(self):
+        """fp32 master + Adam moments + step, valid on every rank (gathers the owners' shards first under the fused optimiser)."""
+        if self.peer is not None and not self.masters_synced:
+            self.peer.allgather_master(self)
+        return {"params": self.params.clone(), "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": self.step}
 
     def refresh(self):
         """Re-derive the fp16 table shadow and the packed MLP weights from the fp32 masters."""
@@ -253,20 +266,23 @@ class HashNeRF:
 
     def _optimizer_step_sharded(self):
         """Data-parallel step without NCCL: one kernel per rank over NVLink peer memory (parallel.PeerShardedOptimizer)."""
+        self.masters_synced = False
         ops.adam_schedule_advance(self.sched, self.lr0, 0.1, float(self.lrate_decay * 1000))
         ops.adam_step_sharded(self.peer.pg, self.params, self.exp_avg, self.exp_avg_sq, self.n_table, self.sched, 0.9, 0.99, 1e-15,
                               1.0 / self.peer.world)
         self.packed = ops.mlp_small_pack(self.mlp_params, out=self.packed)
 
     def flags_timeout(self) -> int:
-        """1 if a peer barrier of the fused optimiser ever gave up waiting (a rank missed a step), else 0."""
-        return int(self.peer.flags[2 * self.peer.world + 2]) if self.peer is not None else 0
+        """1 if a peer barrier of the fused optimiser ever gave up waiting (a rank missed a step), else 0.  Synchronises."""
+        return self.peer.timeout() if self.peer is not None else 0
 
     def optimizer_step_sharded(self):
         """Eager (non-graph) entry of the fused data-parallel optimiser step."""
+        self.peer.check()
         self._init_sched()
         self._sync_sched()
         self._optimizer_step_sharded()
+        self.peer.mirror_flag()
         self.step += 1
         self._sched_step = self.step
 
@@ -277,6 +293,8 @@ class HashNeRF:
 
     def train_step_graph(self, rays_o, rays_d, target):
         """Replay of the captured step.  Inputs may be device tensors or pinned host tensors (copied on the current stream)."""
+        if self.peer is not None:
+            self.peer.check()             # a lost peer fails loudly (pinned-host mirror of the timeout marker, no synchronisation)
         self._sync_sched()
         for dst, src in zip(self._g_in, (rays_o, rays_d, target)):
             dst.copy_(src, non_blocking=True)
@@ -284,6 +302,9 @@ class HashNeRF:
         if self._g_opt is not None:
             self._g_allreduce(self.grads)
             self._g_opt.replay()
+        elif self.peer is not None:
+            self.masters_synced = False
+            self.peer.mirror_flag()
         self.step += 1
         self._sched_step = self.step
         return self.loss

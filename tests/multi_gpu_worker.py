@@ -1,6 +1,8 @@
 """Worker for tests/test_gpu_multi.py (one process per GPU, launched by torch.distributed.run).
-Checks the fused data-parallel optimiser (nrf_adam_step_sharded over NVLink peer memory) against the NCCL all-reduce +
-dense-Adam path, and the row-sharded render gather."""
+Checks (1) that an N-rank step produces the 1-GPU gradient of the same global batch ("DP training" row), (2) the fused
+data-parallel optimiser (nrf_adam_step_sharded over NVLink peer memory) against the NCCL all-reduce + dense-Adam path — on a random
+gradient (dp_check) and over a training trajectory, eager and graph-replayed —, (3) the fp32 master gather for checkpoints, and (4) the
+row-sharded render gather."""
 import os
 import sys
 
@@ -20,19 +22,40 @@ def main():
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     R = 512
-    batches = [synthetic_rays(R, device=dev, seed=100 * rank + i) for i in range(3)]
 
+    # ---- (1) gradients of an N-rank step == gradients of the 1-GPU step on the same global batch, up to reduction order
+    g_model = HashNeRF(BBOX, log2_hashmap_size=15, seed=5, device=dev)
+    parallel.broadcast_parameters(g_model.params, world); g_model.refresh()
+    go, gd, gt = synthetic_rays(R * world, device=dev, seed=77)              # the same global batch on every rank
+    b, e = parallel.shard_bounds(R * world, rank, world)
+    g_model.grads.zero_()
+    g_model.forward_backward(go[b:e].contiguous(), gd[b:e].contiguous(), gt[b:e].contiguous(), grad_scale=1.0 / world)   # loss = mean over the GLOBAL batch
+    sharded = g_model.grads.clone()
+    dist.all_reduce(sharded, op=dist.ReduceOp.SUM)
+    g_model.grads.zero_()
+    g_model.forward_backward(go, gd, gt)
+    whole = g_model.grads.clone()
+    g_model.grads.zero_()
+    rel = float((sharded.double() - whole.double()).norm() / whole.double().norm())
+    rel_mlp = float((sharded[g_model.n_table:].double() - whole[g_model.n_table:].double()).norm() / whole[g_model.n_table:].double().norm())
+    assert float(whole.abs().max()) > 0
+    assert rel <= 1e-5 and rel_mlp <= 1e-5, ("DP gradient differs from the 1-GPU gradient", rel, rel_mlp)
+
+    batches = [synthetic_rays(R, device=dev, seed=100 * rank + i) for i in range(3)]
     # A: NCCL all-reduce + dense Adam on every rank (eager)
     a = HashNeRF(BBOX, log2_hashmap_size=15, seed=3, device=dev, lrate_decay=1)
     parallel.broadcast_parameters(a.params, world); a.refresh()
     # B: fused peer-memory optimiser (eager), C: the same inside the captured graph
-    b = HashNeRF(BBOX, log2_hashmap_size=15, seed=3, device=dev, lrate_decay=1)
-    parallel.broadcast_parameters(b.params, world); b.refresh()
-    parallel.PeerShardedOptimizer(b, rank, world)
+    b_ = HashNeRF(BBOX, log2_hashmap_size=15, seed=3, device=dev, lrate_decay=1)
+    parallel.broadcast_parameters(b_.params, world); b_.refresh()
+    parallel.PeerShardedOptimizer(b_, rank, world)
     c = HashNeRF(BBOX, log2_hashmap_size=15, seed=3, device=dev, lrate_decay=1)
     parallel.broadcast_parameters(c.params, world); c.refresh()
-    assert parallel.PeerShardedOptimizer(c, rank, world).self_test(c)     # dry step on the zero gradient: parameters untouched
-    assert c.step == 0
+    # ---- (2a) one step on a random gradient through both paths; everything is restored afterwards
+    before = c.params.clone()
+    chk = parallel.PeerShardedOptimizer(c, rank, world).dp_check(c)
+    assert chk["ok"], chk
+    assert c.step == 0 and torch.equal(before, c.params) and float(c.grads.abs().max()) == 0.0
     c.capture_train_step(R, world)
 
     la, lb, lc = [], [], []
@@ -41,13 +64,14 @@ def main():
         a.forward_backward(*batch)
         a.optimizer_step(grad_scale=parallel.allreduce_gradients(a.grads, world))
         la.append(float(a.loss))
-        b.forward_backward(*batch)
-        b.optimizer_step_sharded()
-        lb.append(float(b.loss))
+        b_.forward_backward(*batch)
+        b_.optimizer_step_sharded()
+        lb.append(float(b_.loss))
         lc.append(float(c.train_step_graph(*batch)))
     torch.cuda.synchronize()
-    for name, m, losses in (("eager", b, lb), ("graph", c, lc)):
+    for name, m, losses in (("eager", b_, lb), ("graph", c, lc)):
         assert int(m.flags_timeout()) == 0, f"{name}: peer barrier timed out"
+        m.peer.check()
         # every rank holds the SAME fp16 shadow, bit for bit
         ref = m.shadow.clone()
         dist.broadcast(ref, src=0)
@@ -68,6 +92,29 @@ def main():
         assert frac < 3e-2 and d.median().item() < 1e-6, (name, frac)
         assert m.step == 6 and int(m.sched[0]) == 6
 
+        # ---- (3) the fp32 master is sharded: refresh / table refuse to run on stale shards, allgather_master re-assembles them
+        assert not m.masters_synced
+        try:
+            m.refresh()
+            raise AssertionError("refresh() must refuse stale fp32 shards")
+        except RuntimeError:
+            pass
+        sd = m.state_dict()                       # gathers (collective)
+        assert m.masters_synced
+        assert torch.equal(sd["params"][:m.n_table].half(), m.shadow[:m.n_table]), f"{name}: gathered master != shadow"
+        full = sd["params"].clone()
+        dist.broadcast(full, src=0)
+        assert torch.equal(full, sd["params"]), f"{name}: gathered masters differ between ranks"
+        for k in ("exp_avg", "exp_avg_sq"):
+            t = sd[k].clone()
+            dist.broadcast(t, src=0)
+            assert torch.equal(t, sd[k]), f"{name}: gathered {k} differs between ranks"
+        d_master = (a.params - sd["params"]).abs()
+        assert (d_master > 1e-4).float().mean().item() < 3e-2 and d_master.median().item() < 1e-6
+        shadow_before = m.shadow.clone()
+        m.refresh()                               # now allowed, and a no-op on the shadow
+        assert torch.equal(shadow_before, m.shadow)
+
     # row-sharded render + final gather
     H, W = 24, 32
     K = [[40.0, 0, 16.0], [0, 40.0, 12.0], [0, 0, 1]]
@@ -78,7 +125,7 @@ def main():
     if rank == 0:
         whole = c.render_image(H, W, K, c2w)["rgb"]
         assert torch.equal(full, whole)
-        print("MULTI_GPU_WORKER_OK", world, la[-1], lb[-1], lc[-1])
+        print("MULTI_GPU_WORKER_OK", world, la[-1], lb[-1], lc[-1], "dp_grad_rel", rel, rel_mlp, "dp_check", chk)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -71,6 +71,40 @@ def test_indices_bit_exact_at_vertices():
         assert expect.max() < n_sc
 
 
+@pytest.mark.parametrize("F,T", [(2, 19), (8, 19), (2, 14)])
+def test_every_point_level_corner_address_is_bit_exact(F, T):
+    """for EVERY (point, level, corner) — all 16 levels, the ten non-power-of-two ones included, all 8 corners — the
+    table address and the trilinear weight the kernels use (nrf_hash_cells runs the encode kernels' own clamp / locate code) equal the
+    oracle's restatement of src/CuHashEmbedder.cu:44-90 bit for bit.  Points: uniform in the box, exact box corners, cell boundaries,
+    outside points (clamped), and points within a few ulp of cell boundaries of the non-power-of-two levels."""
+    from nerfpp_b200 import ops
+    grid = _grid(F=F, T=T)
+    meta = _np(grid)
+    pts = _points(20000, seed=21).cpu().numpy()
+    # points straddling cell boundaries of every level: vertex coordinate +- {0, 1, 2} ulp
+    rng = np.random.default_rng(4)
+    near = []
+    for l, sc in enumerate(meta["scales"]):
+        v = rng.integers(0, int(np.ceil(sc)) + 1, size=(400, 3)).astype(np.float64)
+        p = (v / float(sc) * 3.0 - 1.5).astype(np.float32)
+        for k in (-2, -1, 0, 1, 2):
+            q = p.copy()
+            for _ in range(abs(k)):
+                q = np.nextafter(q, np.float32(np.inf if k > 0 else -np.inf), dtype=np.float32)
+            near.append(q)
+    pts = np.concatenate([pts] + near, 0).astype(np.float32)
+    addr, w = ops.hash_cells(grid, torch.from_numpy(pts).cuda(), clamp=True)
+    cl, _ = O.clamp_keep(pts, BBOX[:3], BBOX[3:])
+    pos, w_ref = O.hash_cells(cl, scales=meta["scales"], box_min=meta["box_min"], box_max=meta["box_max"], primes=meta["primes"],
+                              biases=meta["biases"], sizes=meta["sizes"])
+    expect = meta["offsets"].astype(np.int64)[None, :, None] + pos.astype(np.int64) * F
+    got = addr.cpu().numpy()
+    bad = np.argwhere(got != expect)
+    assert bad.size == 0, f"{len(bad)} of {got.size} (point, level, corner) addresses differ; first: {bad[:5].tolist()}"
+    assert np.array_equal(w.cpu().numpy(), w_ref), "trilinear weights differ"
+    assert got.max() + F <= grid.used_scalars()
+
+
 @pytest.mark.parametrize("table_kind", ["init", "unit"])
 def test_forward_matches_oracle(table_kind):
     from nerfpp_b200 import ops

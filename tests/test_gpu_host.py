@@ -152,6 +152,35 @@ def test_model_and_render_stages_match_reference(host, ref_cuda):
     assert torch.allclose(r3["rgb"], r1["rgb"], rtol=1e-5, atol=1e-6)
 
 
+def test_c2_size_render_matches_reference(host, ref_cuda):
+    """SURVEY App. B "full RenderRays" row at the BASELINE C2 batch: 4096 rays, T = 2^19, 64 + 128 samples, ThinRay, no noise, single
+    chunk, through both Render()s on the same B200 — sample count exact, maps within the bf16 class."""
+    _need(ref_cuda)
+    from nerfpp_b200.pipeline import synthetic_rays
+    ours, ref = _pair(host, ref_cuda, seed=11, args=(16, 2, 19, 16, 512, 4, 2, 64, 15, 3, 64))
+    with torch.no_grad():                                                   # O(1) signal instead of the 1e-4 / 0.1-gain init
+        t = (torch.rand_like(ref.embed_params()[0]) * 2 - 1).half().float()
+        ours.embed_params()[0].copy_(t)
+        ref.embed_params()[0].copy_(t)
+        for a, b in zip(ours.model_params(), ref.model_params()):
+            w = torch.randn_like(b) * (2.0 / b.shape[1]) ** 0.5
+            a.copy_(w)
+            b.copy_(w)
+    o, d, _ = synthetic_rays(4096, seed=12)
+    r1 = ours.render(o, d, 64, 128, 4096, False, True)
+    r2 = ref.render(o, d, 64, 128, 4096, False, True)
+    assert r1["weights"].shape == r2["weights"].shape == (4096, 192)        # sample count = S + N_imp, exact
+    assert abs(r1["near"] - r2["near"]) < 1e-6 and abs(r1["far"] - r2["far"]) < 1e-6
+    hit = r2["acc"] > 0.5
+    assert int(hit.sum()) > 1000
+    for k in ("rgb", "acc", "depth"):
+        scale = max(1.0, r2[k].abs().max().item())
+        err = (r1[k] - r2[k]).abs() / scale
+        print(k, "median", err.median().item(), "p99", err.flatten().kthvalue(int(0.99 * err.numel())).values.item(), "max", err.max().item())
+        assert err.median().item() < 2e-3 and err.flatten().kthvalue(int(0.99 * err.numel())).values.item() < 1e-2, k
+        assert err.max().item() < 1e-1, k     # a coarse-pass weight within rounding of a CDF step moves one importance sample
+
+
 def test_train_steps_track_reference(host, ref_cuda):
     _need(ref_cuda)
     from nerfpp_b200.pipeline import synthetic_rays
@@ -287,10 +316,45 @@ def test_classic_training_runs_on_the_fused_tcgen05_kernels(host):
         ga, gb = a.grad.double(), b.grad.double()
         assert float(gb.norm()) > 0, name
         cos = float((ga * gb).sum() / (ga.norm() * gb.norm()))
+        # Xavier(0.1): activations shrink ~14x per layer, a large share of the units sit within bf16 rounding of the ReLU kink, and the
+        # bf16 forward flips them — direction check here; the element-wise 1e-2 check on the same active sets is
+        # tests/test_gpu_mlp_nerf.py::test_train_forward_and_backward_match_fp64_autograd, and the O(1)-weights case follows
         assert cos >= 0.97 and 0.8 <= float(ga.norm() / gb.norm()) <= 1.25, (name, cos, float(ga.norm() / gb.norm()))
     losses = [p.train_steps(o, d, tgt, 20, 64, 128, 4096, True, 5e-4, 250)[1] for p in pipes]
     assert losses[0][-1] < losses[0][0] and losses[1][-1] < losses[1][0]
     np.testing.assert_allclose(losses[0], losses[1], rtol=5e-2)
+
+
+def test_classic_training_gradients_with_order_one_weights(host):
+    """The same comparison with He-initialised weights (activations O(1): few units within bf16 rounding of the ReLU kink): the fused bf16
+    training path against torch::linear + LibTorch autograd in fp32, through the whole Render + huber + backward — norm-wise rel 2e-2."""
+    import math
+    pipes = []
+    for fused in (True, False):
+        host.manual_seed(13)
+        torch.manual_seed(13)
+        p = host.make_classic(torch.tensor(BBOX).cuda(), 10, 4, 8, 256, True)
+        p.init_model()
+        host.classic_set_fused_training(p, fused)
+        pipes.append(p)
+    g = torch.Generator().manual_seed(14)
+    with torch.no_grad():
+        for a, b in zip(pipes[0].model_params(), pipes[1].model_params()):
+            w = torch.randn(a.shape, generator=g) * (math.sqrt(2.0 / a.shape[1]) if a.dim() == 2 else 0.1)
+            a.copy_(w.cuda())
+            b.copy_(w.cuda())
+    _positive_density(*pipes)
+    o, d = _rays(256, seed=6)
+    tgt = torch.rand(256, 3, generator=torch.Generator().manual_seed(3)).cuda()
+    for p in pipes:
+        p.train_steps(o, d, tgt, 1, 64, 128, 4096, True, 0.0, 250)
+    worst = 0.0
+    for name, a, b in zip(pipes[0].model_param_names(), pipes[0].model_params(), pipes[1].model_params()):
+        ga, gb = a.grad.double(), b.grad.double()
+        rel = float((ga - gb).norm() / gb.norm().clamp_min(1e-300))
+        worst = max(worst, rel)
+        print(name, "rel", rel)
+        assert rel <= 2e-2, (name, rel)
 
 
 @pytest.mark.parametrize("kind", ["cuhash", "classic"])

@@ -99,43 +99,7 @@ def test_full_size_render_batch_is_row_independent():
 
 
 def _train_reference(x, p, gout, emulate):
-    rb = (lambda t: t + (t.bfloat16().double() - t).detach()) if emulate else (lambda t: t)
-    pd = {k: v.double().requires_grad_(True) for k, v in p.items()}
-    q = {k: (rb(v) if k.endswith("weight") else v) for k, v in pd.items()}
-    xd = rb(x.double())
-    pts, views = xd[:, :63], xd[:, 63:]
-    h, hs, pre, xin = pts, {}, {}, {}
-    for i in range(8):
-        xin[f"model_pts_linears_{i}"] = h
-        pre[i] = h @ q[f"model_pts_linears_{i}.weight"].t() + q[f"model_pts_linears_{i}.bias"]          # src/NeRF.cpp:100
-        pre[i].retain_grad()
-        h = rb(torch.relu(pre[i]))
-        hs[i + 1] = h
-        if i == 4:
-            h = torch.cat([pts, h], -1)                                                               # :103-104
-    xin["model_alpha_linear"] = xin["model_feature_linear"] = h
-    alpha = h @ q["model_alpha_linear.weight"].t() + q["model_alpha_linear.bias"]                       # :110
-    alpha.retain_grad()
-    feat = rb(h @ q["model_feature_linear.weight"].t() + q["model_feature_linear.bias"])                # :111
-    feat.retain_grad()
-    xin["model_views_linears_0"] = torch.cat([feat, views], -1)
-    prev = xin["model_views_linears_0"] @ q["model_views_linears_0.weight"].t() + q["model_views_linears_0.bias"]   # :112-116
-    prev.retain_grad()
-    hv = rb(torch.relu(prev))
-    xin["model_rgb_linear"] = hv
-    rgb = hv @ q["model_rgb_linear.weight"].t() + q["model_rgb_linear.bias"]                            # :119
-    rgb.retain_grad()
-    out = torch.cat([rgb, alpha], -1)                                                                   # :120
-    (out * gout.double()).sum().backward()
-    dy = {f"model_pts_linears_{i}": pre[i].grad for i in range(8)}
-    dy.update({"model_alpha_linear": alpha.grad, "model_feature_linear": feat.grad, "model_views_linears_0": prev.grad, "model_rgb_linear": rgb.grad})
-    # sum |terms| of every gradient entry: the scale its rounding error is relative to
-    bound = {}
-    for name, d in dy.items():
-        bound[name + ".weight"] = float((d.abs().t() @ xin[name].detach().abs()).max())
-        bound[name + ".bias"] = float(d.abs().sum(0).max())
-    return dict(out=out.detach(), grads={k: v.grad for k, v in pd.items()}, bound=bound, pts=pts, views=views, hs=hs, pre=pre, feat=feat, prev=prev, hv=hv,
-                pd=pd)
+    return O.nerf_train_reference(x, p, gout, emulate)
 
 
 def _xavier_params(seed=0, gain=0.1, w=256):
