@@ -392,7 +392,7 @@ int nrf_adam_step_sharded(const nrf_peer_group* pg, float* param, float* exp_avg
  * tensor cores.  Built for the shape the reference trains (src/main.cpp:203-213, src/NeRFExecutor.h:507-514):
  * LeRF(geo_feat_dim_le 32, num_layers_le 2, hidden_dim_le 256, lang_embed_dim 512, input_ch_le 16 levels x 8 features = 128), every
  * layer bias-free (src/LeRF.cpp:12,15); other shapes return NRF_ERR_UNSUPPORTED.  enc_f16 [N,128] fp16 is the output of
- * nrf_hash_encode_fwd on the language grid (n_features 8); keep u8 [N] (nullable) its keep mask.  Inference only in this round.
+ * nrf_hash_encode_fwd on the language grid (n_features 8); keep u8 [N] (nullable) its keep mask.
  *
  *   nrf_lerf_pack              weights (torch Linear layout [out,in] fp32) -> operand blob (nrf_lerf_packed_bytes, 128-byte aligned)
  *   nrf_lerf_fwd               raw_le [N, 513] fp32 = [normalize(e, eps 1e-8) (512) | sigma_le], sigma_le := 0 where keep == 0
@@ -431,6 +431,38 @@ int nrf_lerf_hidden_fwd(const nrf_lerf_shape* shape, const void* packed, const v
                         void* hidden, float* q, nrf_stream stream);
 int nrf_lerf_render_embedding(const nrf_lerf_shape* shape, const void* packed, const float* weights, const void* hidden, const float* q,
                               int64_t n_rays, int32_t n_samples, float* hsum, float* rendered, nrf_stream stream);
+
+/* Training of the language field — replaces LibTorch autograd behind LeRFImpl::forward (src/LeRF.cpp:78-110), RenderCLIPEmbedding
+ * (src/LeRFRenderer.h:45-54) inside RawToLEOutputs (src/LeRFRenderer.cpp:27-82) and the language loss (src/NeRFExecutor.h:957-983).
+ * bf16 operands, fp32 accumulation; the [N,512] embedding is formed neither forward nor backward.  One fine-pass batch of n = n_rays *
+ * n_samples rows (the coarse pass is never differentiated) goes through, in order:
+ *   nrf_lerf_fwd_train               enc -> raw4 [N,4] = [0,0,0,sigma_le], q [N] = |W_e1 h2|^2, `saved` (nrf_lerf_train_saved_bytes(n) bytes,
+ *                                    128-byte aligned): per 128-row tile the bf16 records [x | geo], h1, h2 and the ReLU mask of h1
+ *   nrf_composite_fwd                (existing) raw4 -> comp_weights [R,S]
+ *   nrf_lerf_render_embedding_train  -> hsum [R,256], rendered [R,512], enorm [R] = |W_e1 hsum|
+ *   nrf_lerf_bwd_rays                d loss / d rendered — either grad_rendered [R,512] (any loss; target NULL) or the reference's loss
+ *                                    formed here from target [R,512] (huber delta 1.25 summed over channels, mean over rays; loss_out[0] +=
+ *                                    loss, grad_rendered NULL) — times grad_scale -> grad_le_w1 [512,256] += dE Hs^T, dw_out [R,S] =
+ *                                    d loss / d comp_weights; per-ray / per-row coefficients stay in `workspace`
+ *                                    (nrf_lerf_bwd_workspace_bytes(n, n_rays) bytes, 256-byte aligned, caller-owned, reused by the next entry)
+ *   nrf_composite_bwd                (existing) g_weights = dw_out -> d_raw4 [N,4]
+ *   nrf_lerf_bwd_rows                gradient chain + weight gradients: grads->{sigma_w0, sigma_w1, le_w0, le_w1} += (fp32, the shapes
+ *                                    of `weights`; the struct's pointers are written through), d_enc_bf16 [N,128] bf16 = d loss / d enc, the
+ *                                    layout nrf_hash_encode_bwd (NRF_GRAD_BF16) reads.  `packed` must be the blob of the same `weights`. */
+int64_t nrf_lerf_train_saved_bytes(const nrf_lerf_shape* shape, int64_t n);
+int64_t nrf_lerf_bwd_workspace_bytes(const nrf_lerf_shape* shape, int64_t n, int64_t n_rays);
+int nrf_lerf_fwd_train(const nrf_lerf_shape* shape, const void* packed, const void* enc_f16, const uint8_t* keep, int64_t n, float* raw4,
+                       void* saved, float* q, nrf_stream stream);
+int nrf_lerf_render_embedding_train(const nrf_lerf_shape* shape, const void* packed, const float* weights, const void* saved,
+                                    const float* q, int64_t n_rays, int32_t n_samples, float* hsum, float* rendered, float* enorm,
+                                    nrf_stream stream);
+int nrf_lerf_bwd_rays(const nrf_lerf_shape* shape, const nrf_lerf_weights* weights, const void* saved, const float* q,
+                      const float* comp_weights, const float* hsum, const float* rendered, const float* enorm, const float* target,
+                      const float* grad_rendered, int64_t n_rays, int32_t n_samples, float grad_scale, float* loss_out,
+                      float* grad_le_w1, void* workspace, float* dw_out, nrf_stream stream);
+int nrf_lerf_bwd_rows(const nrf_lerf_shape* shape, const void* packed, const nrf_lerf_weights* weights, const void* saved,
+                      const uint8_t* keep, const float* d_raw4, int64_t n, int32_t n_samples, void* workspace,
+                      const nrf_lerf_weights* grads, void* d_enc_bf16, nrf_stream stream);
 
 #ifdef __cplusplus
 }

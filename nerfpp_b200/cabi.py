@@ -134,6 +134,12 @@ SIGNATURES = {
     "nrf_lerf_sigma_fwd": (c_int32, [POINTER(LerfShape), _P, _P, _P, c_int64, _P, _P]),
     "nrf_lerf_hidden_fwd": (c_int32, [POINTER(LerfShape), _P, _P, _P, c_int64, _P, _P, _P, _P]),
     "nrf_lerf_render_embedding": (c_int32, [POINTER(LerfShape), _P, _P, _P, _P, c_int64, c_int32, _P, _P, _P]),
+    "nrf_lerf_train_saved_bytes": (c_int64, [POINTER(LerfShape), c_int64]),
+    "nrf_lerf_bwd_workspace_bytes": (c_int64, [POINTER(LerfShape), c_int64, c_int64]),
+    "nrf_lerf_fwd_train": (c_int32, [POINTER(LerfShape), _P, _P, _P, c_int64, _P, _P, _P, _P]),
+    "nrf_lerf_render_embedding_train": (c_int32, [POINTER(LerfShape), _P, _P, _P, _P, c_int64, c_int32, _P, _P, _P, _P]),
+    "nrf_lerf_bwd_rays": (c_int32, [POINTER(LerfShape), POINTER(LerfWeights), _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_float, _P, _P, _P, _P, _P]),
+    "nrf_lerf_bwd_rows": (c_int32, [POINTER(LerfShape), _P, POINTER(LerfWeights), _P, _P, _P, c_int64, c_int32, _P, POINTER(LerfWeights), _P, _P]),
     "nrf_peer_flags_bytes": (c_int64, [c_int32]),
     "nrf_adam_step_sharded": (c_int32, [POINTER(PeerGroup), _P, _P, _P, c_int64, c_int64, _P, c_float, c_float, c_float, c_float, _P]),
     "nrf_adam_schedule_advance": (c_int32, [_P, c_float, c_float, c_float, c_float, c_float, _P]),

@@ -19,7 +19,6 @@
 #include "common.cuh"
 #include <stdlib.h>
 #include <string.h>
-#include <limits.h>
 
 namespace nrf {
 
@@ -189,8 +188,7 @@ __device__ __forceinline__ void unpack(const typename FeatVec<F>::type& v, float
 // Work item = (point, part).  SPLIT == 1: one thread walks all levels of its point.  SPLIT == number of chunks (4 at L16 F2): SPLIT
 // neighbouring lanes share a point and each handles ONE chunk of CH levels, so a warp writes 32 / SPLIT complete rows as one contiguous
 // block and an item is 1 / SPLIT of the dependent-latency chain.  Every thread handles `iters` items at a stride of the whole grid: the
-// host sizes the grid as ONE wave of co-resident CTAs in which every SM gets the same number of items (launch_plan) — the 1-CTA-per-256-
-// points launch left a 15 %-full second wave on the coarse pass (1 024 CTAs on 888 slots: 105 us for a third of the fine pass's points).
+// launch passes iters = 1 (one item per thread; see launch_plan for the persistent-grid experiment that was not kept).
 template <int F, bool OUT_F32, int SPLIT>
 __global__ void __launch_bounds__(128) hash_fwd_kernel(HashArgs a, const __half* __restrict__ table,
 	PointSrc ps, Reuse ru, int64_t n_items, int64_t stride, int iters, int clamp_points, uint8_t* __restrict__ keep, void* __restrict__ out)
@@ -316,7 +314,7 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b)
 //   3. lets only the first lane of a run issue the vector REDs.
 // Any point order is handled correctly (a run is defined by adjacency, not by key equality); ray-major order is what
 // makes it pay.  The reference issues N*L*8 half2 atomics regardless.
-// Like the forward, the grid is one balanced wave (launch_plan): thread t handles points t, t + stride, ... (`iters` of them, warp-uniform).
+// Thread t handles points t, t + stride, ... (`iters` of them, warp-uniform; the launch passes iters = 1).
 template <int F, bool GRAD_BF16>
 __global__ void __launch_bounds__(128) hash_bwd_kernel(HashArgs a, PointSrc ps, int64_t n_points, int64_t stride, int iters,
 	int clamp_points, const void* __restrict__ grad_enc, float* __restrict__ grad_table)
@@ -493,39 +491,19 @@ static int fill_args(const nrf_hash_grid* g, HashArgs& a)
 	return NRF_OK;
 }
 
-// One balanced wave: `items` work items on CTAs of `block` threads, at most `occ` co-resident per SM.  Every thread takes k items
-// (grid-stride); k is chosen to minimise k x ceil(CTAs / SMs) — the number of item-rounds the fullest SM runs — over the k that keep
-// the grid within one wave; ties go to the smaller k (more threads in flight).  NRF_HASH_PLAN=legacy restores one item per thread.
+// One work item per thread, 128-thread CTAs.  MEASURED AND NOT KEPT (gpurun_out/r2a/hash_plan_ab.jsonl -> profiles/r2_hash_plan_ab.jsonl): a
+// one-wave persistent grid in which every SM gets the same number of items (k items per thread at a stride of the grid).  The coarse
+// pass costs 1.75x the fine pass per point (95 us / 262 144 points vs 167 us / 786 432) and round 1 suspected the 15 %-full second
+// wave of its launch; the balanced grid did not move it (97.6 us) and made the other launches slower (fine 166.6 -> 183.8 us, backward
+// 264 -> 293 us).  The coarse pass is slower per point because its samples are 3x further apart along the ray: neighbouring lanes share
+// a cell on fewer levels, so the warp's gathers coalesce into more distinct 32-byte sectors per point — the same L1-miss sector
+// ceiling as the fine pass (1 sector / clk / SM), not a launch-shape effect.
 struct LaunchPlan { unsigned grid; int64_t stride; int iters; };
 
-static LaunchPlan launch_plan(int64_t items, int block, int occ)
+static LaunchPlan launch_plan(int64_t items, int block)
 {
-	static const bool legacy = [] { const char* e = getenv("NRF_HASH_PLAN"); return e && strcmp(e, "legacy") == 0; }();
-	int sms = kNumSMs;
-	int dev = 0;
-	if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	const int64_t ctas1 = (items + block - 1) / block;
-	if (legacy || ctas1 <= static_cast<int64_t>(sms) * occ) return {static_cast<unsigned>(ctas1), ctas1 * block, 1};
-	const int64_t wave = static_cast<int64_t>(sms) * occ * block;
-	const int64_t kmin = (items + wave - 1) / wave;
-	int64_t best_k = kmin, best_cost = INT64_MAX;
-	for (int64_t k = kmin; k <= 2 * kmin + 2; k++) {
-		const int64_t ctas = (items + k * block - 1) / (k * block);
-		const int64_t per_sm = (ctas + sms - 1) / sms;
-		if (per_sm > occ) continue;
-		const int64_t cost = k * per_sm;
-		if (cost < best_cost) { best_cost = cost; best_k = k; }
-	}
-	const int64_t ctas = (items + best_k * block - 1) / (best_k * block);
-	return {static_cast<unsigned>(ctas), ctas * block, static_cast<int>(best_k)};
-}
-
-template <typename K>
-static int occupancy_of(K kernel, int block)
-{
-	int occ = 0;
-	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 8; }
-	return occ;
+	const int64_t ctas = (items + block - 1) / block;
+	return {static_cast<unsigned>(ctas), ctas * block, 1};
 }
 
 }  // namespace nrf
@@ -586,9 +564,8 @@ static int launch_hash_fwd(const nrf_hash_grid* grid, const void* table_f16, con
 	const bool split = can_split && split_env != 0;
 #define NRF_LAUNCH_FWD2(FF, O32, SP)                                                                                              \
 	do {                                                                                                                          \
-		static const int occ = occupancy_of(hash_fwd_kernel<FF, O32, SP>, 128);                                                   \
 		const int64_t items = n_points * (SP);                                                                                   \
-		const LaunchPlan lp = launch_plan(items, 128, occ);                                                                      \
+		const LaunchPlan lp = launch_plan(items, 128);                                                                           \
 		hash_fwd_kernel<FF, O32, SP><<<lp.grid, 128, 0, s>>>(a, t, ps, ru, items, lp.stride, lp.iters, clamp_points, keep, enc_out); \
 	} while (0)
 #define NRF_LAUNCH_FWD(FF, SP)                                                     \
@@ -622,8 +599,7 @@ static int launch_hash_bwd(const nrf_hash_grid* grid, const PointSrc& ps, int64_
 	cudaStream_t s = as_stream(stream);
 #define NRF_LAUNCH_BWD2(FF, BF)                                                                                                   \
 	do {                                                                                                                          \
-		static const int occ = occupancy_of(hash_bwd_kernel<FF, BF>, 128);                                                        \
-		const LaunchPlan lp = launch_plan(n_points, 128, occ);                                                                   \
+		const LaunchPlan lp = launch_plan(n_points, 128);                                                                        \
 		hash_bwd_kernel<FF, BF><<<lp.grid, 128, 0, s>>>(a, ps, n_points, lp.stride, lp.iters, clamp_points, grad_enc, grad_table); \
 	} while (0)
 #define NRF_LAUNCH_BWD(FF)                                             \

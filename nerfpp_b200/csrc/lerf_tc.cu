@@ -25,126 +25,13 @@
 //           the 256 accumulator columns in two halves, twice: the first pass only accumulates |e|^2, the second scales and stores
 //           (through a per-warp shared-memory transpose, so a store instruction writes 128 contiguous bytes of one row).
 // fp16 operands, fp32 accumulation: <= 1e-2 relative to the fp32 reference (tests/test_gpu_lerf.py).
-#include "tcgen05.cuh"
-#include "mlp_small_layout.cuh"   // pack_f16 / pack_f16_relu
+#include "lerf_layout.cuh"
 #include <algorithm>
 
 namespace nrf {
 namespace lerf_tc {
 
-using namespace tc;
-
-constexpr int kIn = 128, kHid = 256, kGeo = 32, kDim = 512, kSigN = 48;   // kSigN: the 33 outputs of the sigma head padded to a UMMA N
-constexpr uint32_t kColD = 0, kColD2 = 256, kColGeo = 304, kColEnc = 320, kColH = 384;
-constexpr int kRing = 4;
-constexpr int kStageBytes = 256 * 64 * 2;
-
-// layers: 0 S0 (128 -> 256), 1 S1 (256 -> [geo 32 | sigma | 0..]), 2 E0 (160 -> 256), 3 G (256 -> 256), 4 / 5 E1 outputs 0..255 / 256..511
-constexpr int kLayers = 6;
-struct LayerInfo {
-	int N, K;
-	uint32_t a_col, d_col;
-};
-__host__ __device__ constexpr LayerInfo layer_info(int l)
-{
-	return l == 0 ? LayerInfo{kHid, kIn, kColEnc, kColD}
-	     : l == 1 ? LayerInfo{kSigN, kHid, kColH, kColD2}
-	     : l == 2 ? LayerInfo{kHid, kGeo + kIn, kColGeo, kColD}
-	              : LayerInfo{kHid, kHid, kColH, kColD};
-}
-// the narrow sigma head travels as ONE stage holding its whole K (24 KB); everything else in 64-wide K slabs (E0's last one is 32)
-__host__ __device__ constexpr int layer_stages(int l) { return l == 1 ? 1 : (layer_info(l).K + 63) / 64; }
-__host__ __device__ constexpr int stage_k(int l, int s) { return l == 1 ? layer_info(l).K : (layer_info(l).K - 64 * s >= 64 ? 64 : layer_info(l).K - 64 * s); }
-__host__ __device__ constexpr int stage_bytes(int l, int s) { return layer_info(l).N * stage_k(l, s) * 2; }
-__host__ __device__ constexpr int layer_bytes(int l) { return layer_info(l).N * layer_info(l).K * 2; }
-__host__ __device__ constexpr int layer_offset(int l)
-{
-	int b = 0;
-	for (int i = 0; i < l; i++) b += layer_bytes(i);
-	return b;
-}
-constexpr int kWeightBytes = layer_offset(kLayers);             // 565 248
-// The same four layers S0, S1, E0, G once more, packed as N-SLABS for lerf_fwd_slab_kernel: a slab = 128 outputs (48 for S1) x the whole K,
-// so an accumulator slab is complete on its own and its epilogue runs under the MMAs of the next slab.  Same per-layer sizes / offsets.
-constexpr int kSlabBase = kWeightBytes;
-constexpr int kSlabBytes = layer_offset(4);                     // 303 104
-__host__ __device__ constexpr int slab_n(int l) { return l == 1 ? kSigN : 128; }
-__host__ __device__ constexpr int slab_count(int l) { return l == 1 ? 1 : 2; }
-__host__ __device__ constexpr int slab_bytes(int l) { return slab_n(l) * layer_info(l).K * 2; }
-// a slab travels as 1 or 2 K-stages of at most 32 KB: S0 128 x 128, S1 48 x 256, E0 2 x (128 x 80), G 2 x (128 x 128)
-__host__ __device__ constexpr int slab_kstages(int l) { return l >= 2 ? 2 : 1; }
-__host__ __device__ constexpr int slab_stage_k(int l) { return layer_info(l).K / slab_kstages(l); }
-__host__ __device__ constexpr int slab_stage_bytes(int l) { return slab_n(l) * slab_stage_k(l) * 2; }
-// W_e1 transposed, fp32 [256 k][512 n], follows the operand blobs (lerf_project_kernel reads it)
-constexpr int kProjBase = kSlabBase + kSlabBytes;
-constexpr int kProjBytes = kHid * kDim * 4;
-// one fp32 after it: the power-of-two scale the fp16 copy of G was divided by (lerf_gscale_kernel), so that a trained W_e1 cannot overflow it
-constexpr int kScaleBase = kProjBase + kProjBytes;
-constexpr int kPackedBytes = kScaleBase + 128;
-static_assert(kWeightBytes % 128 == 0 && kSlabBytes % 128 == 0, "blob alignment");
-
-enum Mode { kSigma = 0, kHidden = 1, kRaw = 2 };
-struct ModeTable {
-	int n_groups, group_layer[8];
-	int n_stages, off[24], bytes[24];
-};
-constexpr ModeTable make_mode(int mode)
-{
-	ModeTable t{};
-	const int seq_sigma[2] = {0, 1}, seq_hidden[4] = {0, 1, 2, 3}, seq_raw[7] = {0, 1, 2, 4, 5, 4, 5};
-	t.n_groups = mode == kSigma ? 2 : (mode == kHidden ? 4 : 7);
-	for (int g = 0; g < t.n_groups; g++) t.group_layer[g] = mode == kSigma ? seq_sigma[g] : (mode == kHidden ? seq_hidden[g] : seq_raw[g]);
-	int i = 0;
-	for (int g = 0; g < t.n_groups; g++) {
-		const int l = t.group_layer[g];
-		int off = layer_offset(l);
-		for (int s = 0; s < layer_stages(l); s++, i++) {
-			t.off[i] = off;
-			t.bytes[i] = stage_bytes(l, s);
-			off += stage_bytes(l, s);
-		}
-	}
-	t.n_stages = i;
-	return t;
-}
-static_assert(make_mode(kSigma).n_stages == 3 && make_mode(kHidden).n_stages == 10 && make_mode(kRaw).n_stages == 22, "stage programs");
-__constant__ ModeTable c_modes[3] = {make_mode(kSigma), make_mode(kHidden), make_mode(kRaw)};
-
-struct SlabTable {
-	int n_groups, group_layer[4];
-	int n_stages, off[16], bytes[16];
-};
-constexpr SlabTable make_slab_table(int mode)
-{
-	SlabTable t{};
-	t.n_groups = mode == kSigma ? 2 : 4;
-	int i = 0;
-	for (int g = 0; g < t.n_groups; g++) {
-		t.group_layer[g] = g;
-		for (int sl = 0; sl < slab_count(g) * slab_kstages(g); sl++, i++) {
-			t.off[i] = kSlabBase + layer_offset(g) + sl * slab_stage_bytes(g);
-			t.bytes[i] = slab_stage_bytes(g);
-		}
-	}
-	t.n_stages = i;
-	return t;
-}
-static_assert(make_slab_table(kSigma).n_stages == 3 && make_slab_table(kHidden).n_stages == 11, "slab programs");
-__constant__ SlabTable c_slab[2] = {make_slab_table(kSigma), make_slab_table(kHidden)};
-
-// h2 tile records of the HIDDEN program: [32 column chunks][128 rows][8 fp16] = 64 KB per 128-row tile; a warp store covers 512 contiguous bytes
-constexpr int kHiddenTile = 128 * kHid * 2;
-
-struct Weights;
-__device__ __forceinline__ float wp(const Weights& p, int l, int n, int k, float g_inv);
-
-struct Weights {   // device pointers, torch Linear layout [out, in] row-major fp32, no biases (src/LeRF.cpp:12,15)
-	const float* s0;   // [256, 128]
-	const float* s1;   // [33, 256]   row 0 = sigma_le, rows 1..32 = geo_feat_le (src/LeRF.cpp:92-93)
-	const float* e0;   // [256, 160]  columns [geo 32 | enc 128] (src/LeRF.cpp:96)
-	const float* e1;   // [512, 256]
-};
-
+__constant__ ModeTable c_modes[kModes] = {make_mode(kSigma), make_mode(kHidden), make_mode(kRaw), make_mode(kTrain), make_mode(kChain)};
 // padded logical weight Wp_l(n, k) in the kernel's operand order
 __device__ __forceinline__ float wp(const Weights& p, int l, int n, int k, float g_inv)
 {
@@ -193,16 +80,19 @@ __global__ void __launch_bounds__(256) lerf_pack_kernel(Weights p, uint32_t* __r
 		reinterpret_cast<float*>(blob)[w] = p.e1[n * kHid + k];
 		return;
 	}
-	if (w >= kSlabBase / 4) {
-		// N-slab stages: word q of a stage of Ns outputs holds (n, k) and (n, k+1) at byte (k_local/8)*(Ns*16) + n_local*16 + (k%8)*2
-		const int ws = w - kSlabBase / 4;
+	if (w >= kTrainBase / 4) {
+		// the bf16 copy of S0, S1, E0, G: same stage layout as the fp16 copy below
+		const int wt = w - kTrainBase / 4;
 		int l = 0;
-		while (l + 1 < 4 && ws * 4 >= layer_offset(l + 1)) l++;
-		// stages of a layer in (slab, K-stage) order
-		const int q0 = ws - layer_offset(l) / 4, words = slab_stage_bytes(l) / 4, stg = q0 / words, q = q0 % words, Ns = slab_n(l);
-		const int sl = stg / slab_kstages(l), ks = stg % slab_kstages(l);
-		const int kc = q / (4 * Ns), n = 128 * sl + (q >> 2) % Ns, k = slab_stage_k(l) * ks + 8 * kc + 2 * (q & 3);
-		blob[w] = pack_f16(wp(p, l, n, k, g_inv), wp(p, l, n, k + 1, g_inv));
+		while (l + 1 < 4 && wt * 4 >= layer_offset(l + 1)) l++;
+		int q = wt - layer_offset(l) / 4, st = 0, k_off = 0;
+		while (q >= stage_bytes(l, st) / 4) { q -= stage_bytes(l, st) / 4; k_off += stage_k(l, st); st++; }
+		const int N = layer_info(l).N;
+		const int kc = q / (4 * N), n = (q >> 2) % N, k = k_off + 8 * kc + 2 * (q & 3);
+		// W_e0 travels with its input columns as [x 128 | geo 32] in the training copy (lerf_bwd_tc.cu: the two products that meet in d x then
+		// write the same accumulator blocks); pairs (k, k + 1) never straddle the boundary
+		const int ks = l == 2 ? (k < kIn ? k + kGeo : k - kIn) : k;
+		blob[w] = pack_bf16(wp(p, l, n, ks, g_inv), wp(p, l, n, ks + 1, g_inv));
 		return;
 	}
 	int l = 0;
@@ -221,7 +111,6 @@ struct __align__(128) Smem {
 	float xpart[2][128];                 // HV == 2: partial row sums exchanged between the two warps of a lane quarter
 	uint64_t full[kRing], empty[kRing];
 	uint64_t a_ready, d_ready;
-	uint64_t d_full[5], d_empty[5];       // slab kernel: accumulator slabs 0..3 of D, 4 = the sigma head's own columns
 	uint32_t tmem_base;
 };
 
@@ -304,8 +193,45 @@ __device__ __forceinline__ float sumsq_d(uint32_t t_lane, int c0)
 	return s;
 }
 
+// TRAIN: relu(D) -> bf16 -> the h columns and the 256-column record region (region_row = the row's first chunk of the region, chunks 1 KB apart);
+// BITS: also the ReLU mask words of the row (8 x 32 bits, see lerf_layout.cuh)
+template <bool BITS>
+__device__ __forceinline__ void relu_to_h_train(uint32_t t_lane, uint8_t* __restrict__ region_row, uint32_t* __restrict__ bits_row)
+{
+	uint32_t acc0[32], acc1[32], a16[16], words[8];
+	tmem_ld32(t_lane + kColD, acc0);
+#pragma unroll
+	for (int c = 0; c < 8; c += 2) {
+		tmem_ld_wait_for(acc0);
+		tmem_ld32(t_lane + kColD + 32 * (c + 1), acc1);
+#pragma unroll
+		for (int half = 0; half < 2; half++) {
+			uint32_t (&acc)[32] = half ? acc1 : acc0;
+			if (half) {
+				tmem_ld_wait_for(acc1);
+				if (c + 2 < 8) tmem_ld32(t_lane + kColD + 32 * (c + 2), acc0);
+			}
+			uint32_t m = 0u;
+#pragma unroll
+			for (int i = 0; i < 16; i++) {
+				a16[i] = pack_bf16_relu(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+				if (BITS) m |= ((a16[i] & 0xFFFFu) ? (1u << i) : 0u) | ((a16[i] >> 16) ? (1u << (16 + i)) : 0u);
+			}
+			words[c + half] = m;
+			tmem_st16(t_lane + kColH + 16 * (c + half), a16);
+#pragma unroll
+			for (int i = 0; i < 4; i++)
+				*reinterpret_cast<uint4*>(region_row + (4 * (c + half) + i) * 1024) = make_uint4(a16[4 * i], a16[4 * i + 1], a16[4 * i + 2], a16[4 * i + 3]);
+		}
+	}
+	if (BITS) {
+		reinterpret_cast<uint4*>(bits_row)[0] = make_uint4(words[0], words[1], words[2], words[3]);
+		reinterpret_cast<uint4*>(bits_row)[1] = make_uint4(words[4], words[5], words[6], words[7]);
+	}
+}
+
 // this warp's part of q = h^T (G h): D holds G h (fp32), the h columns hold h (fp16 pairs)
-template <int CH>
+template <int CH, bool BF16 = false>
 __device__ __forceinline__ float dot_d_h(uint32_t t_lane, int c0)
 {
 	uint32_t acc[32], hh[16];
@@ -318,7 +244,8 @@ __device__ __forceinline__ float dot_d_h(uint32_t t_lane, int c0)
 		tmem_ld_wait_for16(hh);
 #pragma unroll
 		for (int i = 0; i < 16; i++) {
-			const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&hh[i]));
+			const float2 h2 = BF16 ? make_float2(__uint_as_float(hh[i] << 16), __uint_as_float(hh[i] & 0xFFFF0000u))
+			                       : __half22float2(*reinterpret_cast<const __half2*>(&hh[i]));
 			s = fmaf(h2.x, __uint_as_float(acc[2 * i]), s);
 			s = fmaf(h2.y, __uint_as_float(acc[2 * i + 1]), s);
 		}
@@ -367,6 +294,8 @@ __global__ void __launch_bounds__(32 * (2 + 4 * HV), 1) lerf_fwd_tc_kernel(const
 	const ModeTable& mt = c_modes[MODE];
 	constexpr int CH = 8 / HV;               // 32-column accumulator chunks per epilogue warp
 	constexpr int PRE = 16 / HV;             // 16-byte pieces of the input row per epilogue thread
+	// TRAIN keeps the language net's input as [x 64 columns | geo 16 columns] (the order of the training blob's W_e0), inference as [geo | x]
+	constexpr uint32_t colEnc = MODE == kTrain ? 304u : kColEnc, colGeo = MODE == kTrain ? 368u : kColGeo;
 
 	if (warp == 1) {
 		if (lane == 0) {
@@ -412,9 +341,9 @@ __global__ void __launch_bounds__(32 * (2 + 4 * HV), 1) lerf_fwd_tc_kernel(const
 					fence_after();
 					const int l = mt.group_layer[grp];
 					const LayerInfo L = layer_info(l);
-					const uint32_t idesc = idesc_f16(128, L.N);
+					const uint32_t idesc = idesc16(128, L.N, MODE == kTrain, 0, 0);
 					const uint32_t lbo = L.N * 16;
-					uint32_t a_col = tmem + L.a_col;
+					uint32_t a_col = tmem + (l == 0 ? colEnc : (l == 2 ? (MODE == kTrain ? colEnc : colGeo) : L.a_col));
 					bool first = true;
 					const int ns = layer_stages(l);
 					for (int s = 0; s < ns; s++, g++) {
@@ -459,6 +388,8 @@ __global__ void __launch_bounds__(32 * (2 + 4 * HV), 1) lerf_fwd_tc_kernel(const
 			const int64_t r = tile * 128 + row;
 			const bool ok = r < n;
 			// ---- input: the 128 fp16 channels of the language hash grid, as they leave nrf_hash_encode_fwd (already in registers, see load_row)
+			// TRAIN: bf16 operands; every layer input also goes to the tile's record (hidden = the record base, lerf_layout.cuh)
+			uint8_t* const rec = MODE == kTrain ? hidden + tile * static_cast<int64_t>(kSaveTile) : nullptr;
 			{
 				uint32_t a16[16];
 #pragma unroll
@@ -468,7 +399,18 @@ __global__ void __launch_bounds__(32 * (2 + 4 * HV), 1) lerf_fwd_tc_kernel(const
 						const uint4 v = pre[4 * h + i];
 						a16[4 * i] = v.x; a16[4 * i + 1] = v.y; a16[4 * i + 2] = v.z; a16[4 * i + 3] = v.w;
 					}
-					tmem_st16(t_lane + kColEnc + 4 * PRE * half + 16 * h, a16);
+					if (MODE == kTrain) {
+#pragma unroll
+						for (int i = 0; i < 16; i++) {
+							const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&a16[i]));
+							a16[i] = pack_bf16(f.x, f.y);
+						}
+#pragma unroll
+						for (int i = 0; i < 4; i++)      // x = columns 0..127 of the [x | geo] region: chunks 4h + i
+							*reinterpret_cast<uint4*>(rec + kSaveGX + chunk_offset(kGeo + kIn, row, 4 * h + i)) =
+								make_uint4(a16[4 * i], a16[4 * i + 1], a16[4 * i + 2], a16[4 * i + 3]);
+					}
+					tmem_st16(t_lane + colEnc + 4 * PRE * half + 16 * h, a16);
 				}
 			}
 			publish(&sm.a_ready, lane);
@@ -477,7 +419,8 @@ __global__ void __launch_bounds__(32 * (2 + 4 * HV), 1) lerf_fwd_tc_kernel(const
 			mbar_wait(&sm.d_ready, pd);
 			pd ^= 1u;
 			fence_after();
-			relu_to_h<false, CH>(t_lane, nullptr, c0);
+			if (MODE == kTrain) relu_to_h_train<true>(t_lane, rec + kSaveH1 + chunk_offset(kHid, row, 0), reinterpret_cast<uint32_t*>(rec + kSaveBits1 + row * 32));
+			else relu_to_h<false, CH>(t_lane, nullptr, c0);
 			publish(&sm.a_ready, lane);
 			if (MODE == kSigma) load_row(tile + gridDim.x);
 
@@ -494,8 +437,15 @@ __global__ void __launch_bounds__(32 * (2 + 4 * HV), 1) lerf_fwd_tc_kernel(const
 					tmem_ld32(t_lane + kColD2, acc);
 					tmem_ld_wait_for(acc);
 #pragma unroll
-					for (int i = 0; i < 16; i++) a16[i] = pack_f16(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
-					tmem_st16(t_lane + kColGeo, a16);
+					for (int i = 0; i < 16; i++)
+						a16[i] = MODE == kTrain ? pack_bf16(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]))
+						                        : pack_f16(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+					tmem_st16(t_lane + colGeo, a16);
+					if (MODE == kTrain) {
+#pragma unroll
+						for (int i = 0; i < 4; i++)      // geo = columns 128..159 of the [x | geo] region
+							*reinterpret_cast<uint4*>(rec + kSaveGX + chunk_offset(kGeo + kIn, row, 16 + i)) = make_uint4(a16[4 * i], a16[4 * i + 1], a16[4 * i + 2], a16[4 * i + 3]);
+					}
 				}
 				tmem_ld_wait_for4(c4);
 				sigma = __uint_as_float(c4[0]);
@@ -512,16 +462,17 @@ __global__ void __launch_bounds__(32 * (2 + 4 * HV), 1) lerf_fwd_tc_kernel(const
 			pd ^= 1u;
 			fence_after();
 			if (MODE == kHidden) relu_to_h<true, CH>(t_lane, hidden + tile * kHiddenTile + row * 16, c0);
+			else if (MODE == kTrain) relu_to_h_train<false>(t_lane, rec + kSaveH2 + chunk_offset(kHid, row, 0), nullptr);
 			else relu_to_h<false, CH>(t_lane, nullptr, c0);
 			publish(&sm.a_ready, lane);
-			if (MODE == kHidden) load_row(tile + gridDim.x);
+			if (MODE == kHidden || MODE == kTrain) load_row(tile + gridDim.x);
 
-			if (MODE == kHidden) {
+			if (MODE == kHidden || MODE == kTrain) {
 				// ---- G: |e|^2 = h2 . (G h2)
 				mbar_wait(&sm.d_ready, pd);
 				pd ^= 1u;
 				fence_after();
-				float qv = dot_d_h<CH>(t_lane, c0) * __ldg(reinterpret_cast<const float*>(blob + kScaleBase));     // G travels divided by this power of two
+				float qv = dot_d_h<CH, MODE == kTrain>(t_lane, c0) * __ldg(reinterpret_cast<const float*>(blob + kScaleBase));     // G travels divided by this power of two
 				if (HV > 1) {
 					if (half != 0) sm.xpart[0][row] = qv;
 					epilogue_sync<HV>();
@@ -568,207 +519,7 @@ __global__ void __launch_bounds__(32 * (2 + 4 * HV), 1) lerf_fwd_tc_kernel(const
 	}
 }
 
-// ---------------------------------------------------------------------------------------------------------------------------------------
-// Slab-granular variant of the SIGMA / HIDDEN programs.  Same roles, TMEM columns and arithmetic as lerf_fwd_tc_kernel, but a layer is issued
-// as two N-slabs of 128 outputs (one or two weight stages each, complete over K), and every slab of the accumulator has its own full / empty barrier pair:
-// the epilogue of slab 0 (TMEM read of 128 fp32 columns, ReLU, fp16 pack, tcgen05.st) runs under the MMAs of slab 1, instead of after the
-// whole layer.  No layer of this network reads and writes the h columns at the same time (S0: enc -> h, S1: h -> geo, E0: [geo|enc] -> h,
-// G: h -> q), so one h buffer is enough.  The results are bit-identical to the K-slab kernel's (same products, same K order per output).
-// A/B variant, off by default (see launch()).
-__device__ __forceinline__ void slab_release(uint64_t* bar, int lane)
-{
-	fence_before();
-	__syncwarp();
-	if (lane == 0) mbar_arrive(bar);
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(32 * 6, 1) lerf_fwd_slab_kernel(const uint8_t* __restrict__ blob, const uint4* __restrict__ enc,
-	const uint8_t* __restrict__ keep, int64_t n, float* __restrict__ raw4, uint8_t* __restrict__ hidden, float* __restrict__ q_out)
-{
-	extern __shared__ __align__(128) uint8_t smem_raw[];
-	Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int64_t n_tiles = (n + 127) / 128;
-	const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-	const SlabTable& st = c_slab[MODE];
-
-	if (warp == 1) {
-		if (lane == 0) {
-			for (int s = 0; s < kRing; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-			for (int b = 0; b < 5; b++) { mbar_init(&sm.d_full[b], 1); mbar_init(&sm.d_empty[b], 4); }
-			mbar_init(&sm.a_ready, 4);
-			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-		}
-		__syncwarp();
-		tmem_alloc_all(&sm.tmem_base);
-	}
-	fence_before();
-	__syncthreads();
-	fence_after();
-	const uint32_t tmem = sm.tmem_base;
-
-	if (warp == 0) {
-		// ===== producer =====
-		if (lane == 0) {
-			uint32_t g = 0;
-			const int n_stages = st.n_stages;
-			for (int64_t t = 0; t < my_tiles; t++) {
-#pragma unroll 1
-				for (int i = 0; i < n_stages; i++, g++) {
-					const uint32_t slot = g % kRing, round = g / kRing;
-					mbar_wait(&sm.empty[slot], (round & 1u) ^ 1u);
-					const uint32_t bytes = st.bytes[i];
-					mbar_expect_tx(&sm.full[slot], bytes);
-					tma_bulk_g2s(sm.ring[slot], blob + st.off[i], bytes, &sm.full[slot]);
-				}
-			}
-		}
-	} else if (warp == 1) {
-		// ===== MMA issuer: per layer, slab by slab =====
-		if (lane == 0) {
-			uint32_t g = 0, pa = 0, ph = 0;
-			const int n_groups = st.n_groups;
-			for (int64_t t = 0; t < my_tiles; t++) {
-#pragma unroll 1
-				for (int l = 0; l < n_groups; l++) {
-					mbar_wait(&sm.a_ready, pa);                        // the whole A operand of this layer is in TMEM
-					pa ^= 1u;
-					fence_after();
-					const LayerInfo L = layer_info(l);
-					const int ns = slab_n(l), cnt = slab_count(l), kst = slab_kstages(l), ksteps = slab_stage_k(l) / 16;
-					const uint32_t idesc = idesc_f16(128, ns);
-					const uint32_t lbo = ns * 16;
-					const uint32_t d_base = tmem + (l == 1 ? kColD2 : kColD);
-					const int b0 = l == 1 ? 4 : 0;
-#pragma unroll 1
-					for (int sl = 0; sl < cnt; sl++) {
-						const int b = b0 + sl;
-						mbar_wait(&sm.d_empty[b], ((ph >> b) & 1u) ^ 1u);  // the previous user's epilogue has this slab in registers
-						ph ^= 1u << b;
-						uint32_t a_col = tmem + L.a_col;
-						for (int ks = 0; ks < kst; ks++, g++) {
-							const uint32_t slot = g % kRing, round = g / kRing;
-							mbar_wait(&sm.full[slot], round & 1u);
-							fence_after();
-							const uint32_t saddr = smem_u32(sm.ring[slot]);
-							for (int j = 0; j < ksteps; j++) {
-								umma_ts(d_base + 128 * sl, a_col, smem_desc(saddr + j * 2 * lbo, lbo, 128), idesc, (ks | j) ? 1u : 0u);
-								a_col += 8;
-							}
-							umma_commit(&sm.empty[slot]);
-						}
-						umma_commit(&sm.d_full[b]);
-					}
-				}
-			}
-		}
-	} else {
-		// ===== epilogue warps: one thread per row =====
-		const int qd = warp & 3;
-		const int row = (qd << 5) | lane;
-		const uint32_t t_lane = tmem + (static_cast<uint32_t>(qd << 5) << 16);
-		uint32_t ph = 0;
-		auto wait_full = [&](int b) {
-			mbar_wait(&sm.d_full[b], (ph >> b) & 1u);
-			ph ^= 1u << b;
-			fence_after();
-		};
-		uint4 pre[16];
-		auto load_row = [&](int64_t tile_idx) {
-			const int64_t rr = tile_idx * 128 + row;
-			const bool in = tile_idx < n_tiles && rr < n;
-			const uint4* er = enc + (in ? rr : 0) * (kIn / 8);
-#pragma unroll
-			for (int i = 0; i < 16; i++) pre[i] = in ? __ldg(er + i) : make_uint4(0u, 0u, 0u, 0u);
-		};
-		if (my_tiles > 0) load_row(blockIdx.x);
-		for (int64_t t = 0; t < my_tiles; t++) {
-			const int64_t tile = blockIdx.x + t * gridDim.x;
-			const int64_t r = tile * 128 + row;
-			const bool ok = r < n;
-			{
-				uint32_t a16[16];
-#pragma unroll
-				for (int h = 0; h < 4; h++) {
-#pragma unroll
-					for (int i = 0; i < 4; i++) {
-						const uint4 v = pre[4 * h + i];
-						a16[4 * i] = v.x; a16[4 * i + 1] = v.y; a16[4 * i + 2] = v.z; a16[4 * i + 3] = v.w;
-					}
-					tmem_st16(t_lane + kColEnc + 16 * h, a16);
-				}
-			}
-			publish(&sm.a_ready, lane);
-
-			// ---- S0: h1 = relu(D), slab by slab
-#pragma unroll 1
-			for (int sl = 0; sl < 2; sl++) {
-				wait_full(sl);
-				relu_to_h<false, 4>(t_lane, nullptr, 4 * sl);
-				slab_release(&sm.d_empty[sl], lane);             // every tcgen05.ld of the slab has completed inside relu_to_h
-			}
-			publish(&sm.a_ready, lane);
-			if (MODE == kSigma) load_row(tile + gridDim.x);
-
-			// ---- S1: [geo 32 | sigma]
-			wait_full(4);
-			float sigma;
-			{
-				uint32_t c4[4];
-				tmem_ld4(t_lane + kColD2 + kGeo, c4);
-				if (MODE != kSigma) {
-					uint32_t acc[32], a16[16];
-					tmem_ld32(t_lane + kColD2, acc);
-					tmem_ld_wait_for(acc);
-					tmem_ld_wait_for4(c4);
-					slab_release(&sm.d_empty[4], lane);
-#pragma unroll
-					for (int i = 0; i < 16; i++) a16[i] = pack_f16(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
-					tmem_st16(t_lane + kColGeo, a16);
-				} else {
-					tmem_ld_wait_for4(c4);
-					slab_release(&sm.d_empty[4], lane);
-				}
-				sigma = __uint_as_float(c4[0]);
-				if (keep != nullptr && ok && keep[r] == 0) sigma = 0.f;               // src/LeRFRenderer.cpp:18-20
-			}
-			if (ok) *reinterpret_cast<float4*>(raw4 + r * 4) = make_float4(0.f, 0.f, 0.f, sigma);
-			if (MODE == kSigma) continue;
-			publish(&sm.a_ready, lane);
-
-			// ---- E0: h2 = relu(D) (+ the h2 tile record)
-			uint8_t* const rec_row = hidden + tile * kHiddenTile + row * 16;
-#pragma unroll 1
-			for (int sl = 0; sl < 2; sl++) {
-				wait_full(sl);
-				relu_to_h<true, 4>(t_lane, rec_row, 4 * sl);
-				slab_release(&sm.d_empty[sl], lane);
-			}
-			publish(&sm.a_ready, lane);
-			load_row(tile + gridDim.x);
-
-			// ---- G: |e|^2 = h2 . (G h2)
-			float qv = 0.f;
-#pragma unroll 1
-			for (int sl = 0; sl < 2; sl++) {
-				wait_full(sl);
-				qv += dot_d_h<4>(t_lane, 4 * sl);
-				slab_release(&sm.d_empty[sl], lane);
-			}
-			if (ok) q_out[r] = qv * __ldg(reinterpret_cast<const float*>(blob + kScaleBase));
-		}
-	}
-
-	fence_before();
-	__syncthreads();
-	if (warp == 1) {
-		fence_after();
-		tmem_free_all(tmem);
-	}
-}
-
-static int check_shape(const nrf_lerf_shape* s)
+int check_shape(const nrf_lerf_shape* s)
 {
 	NRF_REQUIRE(s != nullptr, "shape is null");
 	if (!(s->input_ch == kIn && s->hidden_dim == kHid && s->geo_feat_dim == kGeo && s->lang_embed_dim == kDim && s->num_layers == 2)) {
@@ -791,22 +542,9 @@ static int launch(const nrf_lerf_shape* shape, const void* packed, const void* e
 	const int64_t tiles = (n + 127) / 128;
 	const int smem = static_cast<int>(sizeof(Smem)) + 256;
 	const int blocks = static_cast<int>(std::min<int64_t>(tiles, kNumSMs));
-	// NRF_LERF_SLAB=1 selects the slab-granular kernel for SIGMA / HIDDEN.  Measured and NOT the default: the epilogue of slab 0 does run under
-	// the MMAs of slab 1, but a tcgen05.mma with its A operand in TMEM costs about the same whatever N <= 256 is (fine pass, 196 608 rows:
-	// 4 slabs of N = 64: 126.5 us, 2 slabs of N = 128: 101.5 us, one N = 256 accumulator: 98.4 us), so splitting N multiplies the MMA time
-	// by the slab count and the overlap only wins that back.
-	static const bool slab = [] { const char* e = getenv("NRF_LERF_SLAB"); return e && e[0] == '1'; }();
-	if (MODE != kRaw && slab) {
-		constexpr int SM = MODE == kRaw ? kHidden : MODE;
-		NRF_CUDA(cudaFuncSetAttribute(lerf_fwd_slab_kernel<SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-		lerf_fwd_slab_kernel<SM><<<blocks, 32 * 6, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed), reinterpret_cast<const uint4*>(enc), keep, n,
-			raw4, reinterpret_cast<uint8_t*>(hidden), q);
-		NRF_CHECK_LAUNCH("lerf_fwd_slab_kernel");
-		return NRF_OK;
-	}
 	// epilogue warps per TMEM lane quarter: two for RAW (its 403 MB of 4-byte stores are instruction-bound: 331 -> 251 us), one otherwise
 	// (the TMEM read bandwidth, not the per-thread work, bounds those epilogues: 98.4 us with four warps, 102.0 us with eight); NRF_LERF_EPI_WARPS=4|8 overrides
-	static const int hv = [] { const char* e = getenv("NRF_LERF_EPI_WARPS"); return e && e[0] == '4' ? 1 : (e && e[0] == '8' ? 2 : (MODE == kRaw ? 2 : 1)); }();
+	static const int hv = MODE == kTrain ? 1 : [] { const char* e = getenv("NRF_LERF_EPI_WARPS"); return e && e[0] == '4' ? 1 : (e && e[0] == '8' ? 2 : (MODE == kRaw ? 2 : 1)); }();
 	if (hv == 2) {
 		NRF_CUDA(cudaFuncSetAttribute(lerf_fwd_tc_kernel<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 		lerf_fwd_tc_kernel<MODE, 2><<<blocks, 32 * 10, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(packed), reinterpret_cast<const uint4*>(enc), keep, n,
@@ -825,6 +563,8 @@ static int launch(const nrf_lerf_shape* shape, const void* packed, const void* e
 // (src/LeRFRenderer.h:45-54 applied to the normalised embeddings of src/LeRF.cpp:105).
 
 // one block per ray, 8 warps; warp v owns column chunks v, v+8, v+16, v+24 of the h2 records; lane = sample within a group of 32
+// TRAIN: h2 comes from the bf16 training records (region layout, lerf_layout.cuh) instead of the fp16 inference records
+template <bool TRAIN>
 __global__ void __launch_bounds__(256) lerf_hsum_kernel(const float* __restrict__ weights, const uint4* __restrict__ hidden, const float* __restrict__ q,
 	int32_t n_samples, float* __restrict__ hsum)
 {
@@ -840,12 +580,14 @@ __global__ void __launch_bounds__(256) lerf_hsum_kernel(const float* __restrict_
 		float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 		for (int s = lane; s < n_samples; s += 32) {
 			const int64_t row = ray * n_samples + s;
-			const uint4 v = __ldg(hidden + (row >> 7) * (kHiddenTile / 16) + j * 128 + (row & 127));
+			const uint4 v = TRAIN ? __ldg(hidden + ((row >> 7) * static_cast<int64_t>(kSaveTile) + kSaveH2 + chunk_offset(kHid, static_cast<int>(row & 127), j)) / 16)
+			                      : __ldg(hidden + (row >> 7) * (kHiddenTile / 16) + j * 128 + (row & 127));
 			const float c = cs[s];
 			const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
 			for (int i = 0; i < 4; i++) {
-				const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[i]));
+				const float2 f = TRAIN ? make_float2(__uint_as_float(w4[i] << 16), __uint_as_float(w4[i] & 0xFFFF0000u))
+				                       : __half22float2(*reinterpret_cast<const __half2*>(&w4[i]));
 				acc[2 * i] = fmaf(c, f.x, acc[2 * i]);
 				acc[2 * i + 1] = fmaf(c, f.y, acc[2 * i + 1]);
 			}
@@ -865,7 +607,8 @@ __global__ void __launch_bounds__(256) lerf_hsum_kernel(const float* __restrict_
 // thread owns outputs tid and tid + 256 of every ray for the norm and the store.  (The first version — 8 rays per block, two scalar loads per k —
 // was latency-bound on its 128 blocks: 60 us for 0.27 GFLOP.)
 constexpr int kProjRays = 4;
-__global__ void __launch_bounds__(256) lerf_project_kernel(const float* __restrict__ w_t, const float* __restrict__ hsum, int64_t n_rays, float* __restrict__ rendered)
+__global__ void __launch_bounds__(256) lerf_project_kernel(const float* __restrict__ w_t, const float* __restrict__ hsum, int64_t n_rays, float* __restrict__ rendered,
+	float* __restrict__ enorm)
 {
 	__shared__ float hs[kProjRays][kHid];
 	__shared__ __align__(16) float red[2][kProjRays][kDim];
@@ -913,7 +656,9 @@ __global__ void __launch_bounds__(256) lerf_project_kernel(const float* __restri
 		float ss = 0.f;
 #pragma unroll
 		for (int w = 0; w < 8; w++) ss += part[w][i];
-		const float inv = 1.f / fmaxf(sqrtf(ss), 1e-8f);
+		const float nrm = fmaxf(sqrtf(ss), 1e-8f);
+		const float inv = 1.f / nrm;
+		if (enorm != nullptr && j == 0) enorm[ray] = nrm;       // |W_e1 Hs|: the backward of the normalisation divides by it
 		rendered[ray * kDim + j] = lo[i] * inv;
 		rendered[ray * kDim + 256 + j] = hi[i] * inv;
 	}
@@ -971,21 +716,52 @@ int nrf_lerf_hidden_fwd(const nrf_lerf_shape* shape, const void* packed, const v
 	return launch<kHidden>(shape, packed, enc_f16, keep, n, raw4, hidden, q, nullptr, stream);
 }
 
-int nrf_lerf_render_embedding(const nrf_lerf_shape* shape, const void* packed, const float* weights, const void* hidden, const float* q, int64_t n_rays,
-                              int32_t n_samples, float* hsum, float* rendered, nrf_stream stream)
+static int render_embedding_impl(bool train, const nrf_lerf_shape* shape, const void* packed, const float* weights, const void* hidden, const float* q, int64_t n_rays,
+	int32_t n_samples, float* hsum, float* rendered, float* enorm, nrf_stream stream)
 {
 	if (int rc = lerf_tc::check_shape(shape)) return rc;
 	NRF_REQUIRE(n_rays >= 0 && n_samples >= 1 && n_samples <= 8192, "n_rays >= 0 and 1 <= n_samples <= 8192");
 	if (n_rays == 0) return NRF_OK;
 	NRF_REQUIRE(packed && weights && hidden && q && hsum && rendered, "null pointer");
 	NRF_REQUIRE((reinterpret_cast<uintptr_t>(hidden) & 15) == 0 && (reinterpret_cast<uintptr_t>(hsum) & 15) == 0, "hidden / hsum must be 16-byte aligned");
-	lerf_hsum_kernel<<<static_cast<unsigned>(n_rays), 256, n_samples * sizeof(float), as_stream(stream)>>>(weights, reinterpret_cast<const uint4*>(hidden), q,
-		n_samples, hsum);
+	if (train)
+		lerf_hsum_kernel<true><<<static_cast<unsigned>(n_rays), 256, n_samples * sizeof(float), as_stream(stream)>>>(weights, reinterpret_cast<const uint4*>(hidden), q,
+			n_samples, hsum);
+	else
+		lerf_hsum_kernel<false><<<static_cast<unsigned>(n_rays), 256, n_samples * sizeof(float), as_stream(stream)>>>(weights, reinterpret_cast<const uint4*>(hidden), q,
+			n_samples, hsum);
 	NRF_CHECK_LAUNCH("lerf_hsum_kernel");
 	const float* w_t = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(packed) + kProjBase);
-	lerf_project_kernel<<<static_cast<unsigned>((n_rays + kProjRays - 1) / kProjRays), 256, 0, as_stream(stream)>>>(w_t, hsum, n_rays, rendered);
+	lerf_project_kernel<<<static_cast<unsigned>((n_rays + kProjRays - 1) / kProjRays), 256, 0, as_stream(stream)>>>(w_t, hsum, n_rays, rendered, enorm);
 	NRF_CHECK_LAUNCH("lerf_project_kernel");
 	return NRF_OK;
+}
+
+int nrf_lerf_render_embedding(const nrf_lerf_shape* shape, const void* packed, const float* weights, const void* hidden, const float* q, int64_t n_rays,
+                              int32_t n_samples, float* hsum, float* rendered, nrf_stream stream)
+{
+	return render_embedding_impl(false, shape, packed, weights, hidden, q, n_rays, n_samples, hsum, rendered, nullptr, stream);
+}
+
+int64_t nrf_lerf_train_saved_bytes(const nrf_lerf_shape* shape, int64_t n)
+{
+	if (lerf_tc::check_shape(shape) || n < 0) return -1;
+	return ((n + 127) / 128) * static_cast<int64_t>(kSaveTile);
+}
+
+int nrf_lerf_fwd_train(const nrf_lerf_shape* shape, const void* packed, const void* enc_f16, const uint8_t* keep, int64_t n, float* raw4, void* saved,
+                       float* q, nrf_stream stream)
+{
+	if (int rc = lerf_tc::check_shape(shape)) return rc;
+	NRF_REQUIRE(n <= 0 || (raw4 && saved && q), "null output");
+	return launch<kTrain>(shape, packed, enc_f16, keep, n, raw4, saved, q, nullptr, stream);
+}
+
+int nrf_lerf_render_embedding_train(const nrf_lerf_shape* shape, const void* packed, const float* weights, const void* saved, const float* q, int64_t n_rays,
+                                    int32_t n_samples, float* hsum, float* rendered, float* enorm, nrf_stream stream)
+{
+	NRF_REQUIRE(n_rays <= 0 || enorm != nullptr, "null enorm");
+	return render_embedding_impl(true, shape, packed, weights, saved, q, n_rays, n_samples, hsum, rendered, enorm, stream);
 }
 
 }

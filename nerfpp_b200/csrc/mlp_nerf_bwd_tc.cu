@@ -20,6 +20,7 @@
 //
 // bf16 operands, fp32 accumulation; parity tests/test_gpu_mlp_nerf.py (rel 1e-2 against the fp64 autograd of the oracle).
 #include "mlp_nerf_layout.cuh"
+#include "dw_units.cuh"
 #include <algorithm>
 
 namespace nrf {
@@ -326,25 +327,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_chain_kernel(cons
 // ---- weight gradients --------------------------------------------------------------------------------------------------
 // A unit is one weight matrix (or one column block of it): D[M = columns of the A region (128 or 256), N] = A^T B summed over rows.
 // M = 256 runs as two M = 128 MMAs on the same B slab, so a dY slab and an activation slab are each read from HBM once per unit.
-constexpr int kMaxUnits = 16;
 constexpr int kDwRing = 3;
 constexpr int kDwStageBytes = 256 * 64 * 2 + 256 * 64 * 2;         // A: up to 256 columns x 64 rows, B: up to 256 columns x 64 rows
 constexpr int kDwAOff = 0, kDwBOff = 256 * 64 * 2;
-struct Unit {
-	int32_t a_src, a_off, a_cols;       // record kind (0 gradient, 1 saved), byte offset of the region in the record, region width (128 / 256)
-	int32_t b_src, b_off, b_cols;       // b_cols: region width = MMA N
-	int32_t n_lo, n_hi;                 // D(m, n) is written for n_lo <= n < n_hi ...
-	int32_t stride_m, stride_n;         // ... to out[m * stride_m + (n - n_lo) * stride_n]
-	int32_t bias_mode;                  // 0 none; 1 column sums of A -> bias[m]; 2 column sums of B -> bias[0..2] (rgb), bias2[0] (alpha)
-	int32_t pad_;
-	float* out;
-	float* bias;
-	float* bias2;
-};
-struct UnitTable {
-	Unit u[kMaxUnits];
-	int32_t count;
-};
+using dw::Unit;
+using dw::UnitTable;
+using dw::kMaxUnits;
 
 struct __align__(128) DwSmem {
 	uint8_t ring[kDwRing][kDwStageBytes];
@@ -413,14 +401,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_dw_kernel(const _
 				cum += H * c;
 				const uint8_t* a_base = (U.a_src ? saved : grads) + U.a_off;
 				const uint8_t* b_base = (U.b_src ? saved : grads) + U.b_off;
-				const int64_t a_tile = U.a_src ? kSaveTile : kGradTile, b_tile = U.b_src ? kSaveTile : kGradTile;
-				const uint32_t a_bytes = U.a_cols * 128, b_bytes = U.b_cols * 128;      // one 64-row half of the region
+				const int64_t a_tile = U.a_src ? T.save_tile : T.grad_tile, b_tile = U.b_src ? T.save_tile : T.grad_tile;
+				const uint32_t a_bytes = U.a_cols * 128, b_bytes = U.b_cols * 128;      // one 64-row half of the operand's columns
+				const uint32_t a_half = U.a_half ? U.a_half : a_bytes, b_half = U.b_half ? U.b_half : b_bytes;   // distance between the halves (region width x 128)
 				for (int64_t i = lo; i < hi; i++, g++) {
 					const uint32_t slot = g % kDwRing, round = g / kDwRing;
 					{ DW_T0(); mbar_wait(&sm.empty[slot], (round & 1u) ^ 1u); DW_ADD(2); }
 					mbar_expect_tx(&sm.full[slot], a_bytes + b_bytes);
-					tma_bulk_g2s(sm.ring[slot] + kDwAOff, a_base + (i >> 1) * a_tile + (i & 1) * a_bytes, a_bytes, &sm.full[slot]);
-					tma_bulk_g2s(sm.ring[slot] + kDwBOff, b_base + (i >> 1) * b_tile + (i & 1) * b_bytes, b_bytes, &sm.full[slot]);
+					tma_bulk_g2s(sm.ring[slot] + kDwAOff, a_base + (i >> 1) * a_tile + (i & 1) * a_half, a_bytes, &sm.full[slot]);
+					tma_bulk_g2s(sm.ring[slot] + kDwBOff, b_base + (i >> 1) * b_tile + (i & 1) * b_half, b_bytes, &sm.full[slot]);
 				}
 			}
 		}
@@ -551,6 +540,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_dw_kernel(const _
 						for (int j = 0; j < 16; j++) {
 							const int nn = c0 + j;
 							if (nn >= U.n_lo && nn < U.n_hi) atomicAdd(row + static_cast<int64_t>(nn - U.n_lo) * U.stride_n, __uint_as_float(d16[j]));
+							else if (U.out2 != nullptr && nn >= U.n2_lo && nn < U.n2_hi)
+								atomicAdd(U.out2 + static_cast<int64_t>(m) * U.stride_m + static_cast<int64_t>(nn - U.n2_lo) * U.stride_n, __uint_as_float(d16[j]));
 						}
 					}
 				}
@@ -614,6 +605,20 @@ static void build_units(const Grads& g, UnitTable& T)
 }
 
 }  // namespace nerf_tc
+
+namespace dw {
+int launch_dw_units(const UnitTable& T, const void* saved, const void* grads, int64_t n_tiles, nrf_stream stream)
+{
+	using namespace nerf_tc;
+	const int64_t items = 2 * n_tiles * T.count;
+	const int blocks = static_cast<int>(std::min<int64_t>(items, kNumSMs));
+	const int smem = static_cast<int>(sizeof(DwSmem)) + 128;
+	NRF_CUDA(cudaFuncSetAttribute(mlp_nerf_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+	mlp_nerf_bwd_dw_kernel<<<blocks, kBwdThreads, smem, as_stream(stream)>>>(T, reinterpret_cast<const uint8_t*>(saved), reinterpret_cast<const uint8_t*>(grads), n_tiles);
+	NRF_CHECK_LAUNCH("mlp_nerf_bwd_dw_kernel");
+	return NRF_OK;
+}
+}  // namespace dw
 }  // namespace nrf
 
 using namespace nrf;
@@ -656,13 +661,9 @@ int nrf_mlp_nerf_bwd(const nrf_mlp_nerf_shape* shape, const void* packed_train, 
 	{
 		UnitTable T{};
 		build_units(g, T);
-		const int64_t items = 2 * tiles * T.count;
-		const int blocks = static_cast<int>(std::min<int64_t>(items, kNumSMs));
-		const int smem = static_cast<int>(sizeof(DwSmem)) + 128;
-		NRF_CUDA(cudaFuncSetAttribute(mlp_nerf_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-		mlp_nerf_bwd_dw_kernel<<<blocks, kBwdThreads, smem, as_stream(stream)>>>(T, reinterpret_cast<const uint8_t*>(saved),
-			reinterpret_cast<const uint8_t*>(workspace), tiles);
-		NRF_CHECK_LAUNCH("mlp_nerf_bwd_dw_kernel");
+		T.save_tile = kSaveTile;
+		T.grad_tile = kGradTile;
+		if (int rc = dw::launch_dw_units(T, saved, workspace, tiles, stream)) return rc;
 	}
 	return NRF_OK;
 }

@@ -10,7 +10,11 @@ src/LeRFRenderer.cpp:133-134, is never used), and the fine pass never forms Lang
 the last hidden layer (nrf_lerf_hidden_fwd + nrf_lerf_render_embedding).  `return_embedding=True` evaluates the compatibility entry
 (nrf_lerf_fwd) as well and returns the reference's LangEmbedding / Raw tensors.
 Configuration is the parity one: ThinRay, Perturb 0, no raw noise, no stochastic preconditioning.  Relevancy (RuCLIP) is out of scope.
-Training of the language field (src/NeRFExecutor.h:957-983) is not built yet.
+
+Training of the language field (src/NeRFExecutor.h:957-983: RenderRays on the language renderer, huber(delta 1.25).sum(-1).nanmean() against the
+CLIP target, backward, Adam over {lang_embedder, lang_model}): `LeRFField.train_step` — the fine pass through nrf_lerf_fwd_train, the fused backward
+(nrf_lerf_bwd_rays / nrf_composite_bwd / nrf_lerf_bwd_rows), nrf_hash_encode_bwd at F = 8 and ONE Adam launch over the flat vector
+[language table | the four weight matrices].
 """
 from __future__ import annotations
 
@@ -23,6 +27,25 @@ from .ops import f16, f32
 from .pipeline import make_grid
 
 LERF_LAYERS = (("sigma_le_net_0", 256, 128), ("sigma_le_net_1", 33, 256), ("le_net_0", 256, 160), ("le_net_1", 512, 256))
+
+
+def head_forward_backward(packed, weights: dict, enc, keep, z, rays_d, target, grads: dict, loss_out=None, grad_scale=1.0, prefix="lang_model",
+                          workspace=None):
+    """The differentiated part of LeRFRenderer::RenderRays' fine pass + the language loss, forward and backward, on the fused kernels:
+    enc [R*S,128] fp16 (hash encoding of the fine samples), keep [R*S] u8 | None, z [R,S], rays_d [R,3], target [R,512].
+    grads[<prefix>_<layer>.weight] += d loss / d weight (fp32).  Returns (out dict with rendered / weights / depth / acc, d_enc [R*S,128] bf16)."""
+    r, s = z.shape
+    raw4, saved, q = ops.lerf_fwd_train(packed, enc, keep)
+    comp = ops.composite_fwd(raw4.view(r, s, 4), z, rays_d)
+    rendered, hsum, enorm = ops.lerf_render_embedding_train(packed, comp["weights"], saved, q)
+    if workspace is None:
+        workspace = ops.lerf_bwd_workspace(r * s, r, enc.device)
+    dw = ops.lerf_bwd_rays(weights, saved, q, comp["weights"], hsum, rendered, enorm, grads[f"{prefix}_le_net_1.weight"], workspace, target=target,
+                           grad_scale=grad_scale, loss_out=loss_out, prefix=prefix)
+    d_raw4 = ops.composite_bwd(raw4.view(r, s, 4), z, rays_d, g_weights=dw)
+    d_enc = ops.lerf_bwd_rows(packed, weights, saved, keep, d_raw4, s, workspace, grads, prefix=prefix)
+    return {"rendered": rendered, "weights": comp["weights"], "depth": comp["depth"], "disp": comp["disp"], "acc": comp["acc"], "raw4": raw4, "q": q,
+            "dw": dw, "d_raw4": d_raw4}, d_enc
 
 
 class LeRFField:

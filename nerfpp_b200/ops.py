@@ -524,3 +524,65 @@ def lerf_render_embedding(packed: torch.Tensor, weights: torch.Tensor, hidden: t
     _run("lerf_render_embedding", lambda: lib().nrf_lerf_render_embedding(C.byref(shape), ptr(packed), ptr(weights, f32), ptr(hidden), ptr(q, f32), r, s,
                                                                            ptr(hsum), ptr(out), stream()))
     return out
+
+
+# ---- training of the language head (nrf_lerf_fwd_train ... nrf_lerf_bwd_rows)
+
+
+def _lerf_ptrs(p: dict, prefix: str) -> "cabi.LerfWeights":
+    return cabi.LerfWeights(*[ptr(p[f"{prefix}_{n}.weight"], f32) for n in LERF_WEIGHT_NAMES])
+
+
+def lerf_fwd_train(packed: torch.Tensor, enc: torch.Tensor, keep: torch.Tensor | None = None, shape=None):
+    """Training forward of the fine pass: (raw4 [N,4], saved (bf16 tile records of [x | geo], h1, h2 + the ReLU mask of h1), q [N] = |e|^2)."""
+    shape = shape or lerf_shape()
+    n = enc.shape[0]
+    raw4 = torch.empty((n, 4), dtype=f32, device=enc.device)
+    saved = torch.empty(max(lib().nrf_lerf_train_saved_bytes(C.byref(shape), n), 0), dtype=u8, device=enc.device)
+    q = torch.empty(n, dtype=f32, device=enc.device)
+    _run("lerf_fwd_train", lambda: lib().nrf_lerf_fwd_train(C.byref(shape), ptr(packed), ptr(enc, f16), ptr(keep, u8) if keep is not None else None, n,
+                                                             ptr(raw4), ptr(saved), ptr(q), stream()))
+    return raw4, saved, q
+
+
+def lerf_render_embedding_train(packed: torch.Tensor, weights: torch.Tensor, saved: torch.Tensor, q: torch.Tensor, shape=None):
+    """(rendered [R,512], hsum [R,256], enorm [R]) from the training records."""
+    shape = shape or lerf_shape()
+    r, s = weights.shape
+    hsum = torch.empty((r, shape.hidden_dim), dtype=f32, device=weights.device)
+    out = torch.empty((r, shape.lang_embed_dim), dtype=f32, device=weights.device)
+    enorm = torch.empty(r, dtype=f32, device=weights.device)
+    _run("lerf_render_embedding", lambda: lib().nrf_lerf_render_embedding_train(C.byref(shape), ptr(packed), ptr(weights, f32), ptr(saved), ptr(q, f32), r, s,
+                                                                                 ptr(hsum), ptr(out), ptr(enorm), stream()))
+    return out, hsum, enorm
+
+
+def lerf_bwd_workspace(n: int, n_rays: int, device, shape=None) -> torch.Tensor:
+    shape = shape or lerf_shape()
+    return torch.empty(max(lib().nrf_lerf_bwd_workspace_bytes(C.byref(shape), n, n_rays), 256), dtype=u8, device=device)
+
+
+def lerf_bwd_rays(weights: dict, saved, q, comp_weights, hsum, rendered, enorm, grad_le_w1, workspace, target=None, grad_rendered=None, grad_scale=1.0,
+                  loss_out=None, prefix="lang_model", shape=None) -> torch.Tensor:
+    """Per-ray half of the backward; returns dw [R,S] = d loss / d compositing weights (feed it to composite_bwd as g_weights)."""
+    shape = shape or lerf_shape()
+    r, s = comp_weights.shape
+    dw = torch.empty((r, s), dtype=f32, device=comp_weights.device)
+    w = _lerf_ptrs(weights, prefix)
+    _run("lerf_bwd_rays", lambda: lib().nrf_lerf_bwd_rays(C.byref(shape), C.byref(w), ptr(saved), ptr(q, f32), ptr(comp_weights, f32), ptr(hsum, f32),
+                                                           ptr(rendered, f32), ptr(enorm, f32), ptr(target), ptr(grad_rendered), r, s, grad_scale, ptr(loss_out),
+                                                           ptr(grad_le_w1, f32), ptr(workspace), ptr(dw), stream()))
+    return dw
+
+
+def lerf_bwd_rows(packed, weights: dict, saved, keep, d_raw4, n_samples: int, workspace, grads: dict, prefix="lang_model", shape=None,
+                  d_enc: torch.Tensor | None = None) -> torch.Tensor:
+    """Per-row half: grads[<prefix>_<layer>.weight] += (fp32), returns d_enc [N,128] bf16."""
+    shape = shape or lerf_shape()
+    n = d_raw4.numel() // 4
+    if d_enc is None:
+        d_enc = torch.empty((n, shape.input_ch), dtype=bf16, device=d_raw4.device)
+    w, g = _lerf_ptrs(weights, prefix), _lerf_ptrs(grads, prefix)
+    _run("lerf_bwd_rows", lambda: lib().nrf_lerf_bwd_rows(C.byref(shape), ptr(packed), C.byref(w), ptr(saved), ptr(keep, u8) if keep is not None else None,
+                                                           ptr(d_raw4, f32), n, n_samples, ptr(workspace), C.byref(g), ptr(d_enc), stream()))
+    return d_enc
