@@ -373,9 +373,93 @@ def gpu_loop_leg(which: str, rays: int, steps: int) -> dict:
                      "nerfpp_b200 C++ drop-in classes (torch::Tensor boundary, FusedAdam" + (", captured train graph)" if fast else ")"))}
 
 
-def lerf_train_leg(rank: int, world: int, dev) -> dict | None:
-    """BASELINE C5: training of the language field, 1024 rays per GPU (filled in by the fused LeRF backward)."""
-    return None
+def lerf_train_leg(rank: int, world: int, dev, hash_model, tf_peak: float, rays: int = 1024, steps: int = 50) -> dict | None:
+    """BASELINE C5: LeRF training, 1024 rays per GPU.  One iteration of NeRFExecutor::Train with use_lerf (src/NeRFExecutor.h:868-996) = the HashNeRF
+    step (render + huber + backward) AND the language step (LeRFRenderer::Render + huber(1.25).sum(-1).nanmean() + backward, :957-983), then Adam
+    over both parameter sets.  Timed: the language step alone and the joint iteration (both captured graphs replayed back to back), CUDA events,
+    max over ranks.  Collective: every rank calls it."""
+    import torch
+    from nerfpp_b200 import ops, parallel
+    from nerfpp_b200.lerf import LeRFField
+    from nerfpp_b200.pipeline import synthetic_rays
+    out, ready, field = {}, True, None
+    try:
+        field = LeRFField(BBOX, seed=0, device=dev)            # same seed on every rank: identical replicas without a broadcast
+        g = torch.Generator().manual_seed(0)
+        for v in field.weights.values():                       # O(1) signals (He-scaled weights, table U(-1,1)): every ReLU / density regime is exercised
+            v.copy_((torch.randn(v.shape, generator=g) * (2.0 / v.shape[1]) ** 0.5).to(dev))
+        field.params[:field.n_table].copy_((torch.rand(field.n_table, generator=g) * 2 - 1).to(dev))
+        field.refresh()
+    except Exception as e:  # noqa: BLE001 - a secondary leg must not take the headline line down
+        ready, out = False, {"error": f"{type(e).__name__}: {e}"}
+    if not parallel.all_ranks_ready(ready, world, dev):
+        return out or {"error": "set-up failed on another rank"}
+    dp_mode, dp_check = "single", None
+    if world > 1:
+        dp_mode = "nccl all-reduce of the flat gradient + dense Adam"
+        try:
+            peer = parallel.PeerShardedOptimizer(field, rank, world)
+        except Exception as e:  # noqa: BLE001
+            peer, dp_mode = None, dp_mode + f" (fused path unavailable: {type(e).__name__}: {e})"
+        have = torch.tensor([int(peer is not None)], dtype=torch.int32, device=dev)
+        torch.distributed.all_reduce(have, op=torch.distributed.ReduceOp.MIN)
+        if bool(have.item()):
+            dp_check = peer.dp_check(field)
+        if dp_check is not None and dp_check["ok"]:
+            dp_mode = "fused peer-memory kernel (reduce-scatter + Adam + fp16 shadow all-gather over NVLink)"
+        else:
+            field.peer = None
+    pool = 4
+    batches = []
+    for i in range(pool):
+        o, d, _ = synthetic_rays(rays, device=dev, seed=5000 + 1000 * rank + i)
+        tgt = torch.nn.functional.normalize(torch.randn(rays, 512, generator=torch.Generator().manual_seed(9000 + 1000 * rank + i)), dim=-1).to(dev)
+        batches.append((o, d, tgt))
+    nerf_batches = [synthetic_rays(rays, device=dev, seed=6000 + 1000 * rank + i) for i in range(pool)]
+    field.capture_train_step(rays, world, lambda gr: parallel.allreduce_gradients(gr, world))
+    hash_model.capture_train_step(rays, world, lambda gr: parallel.allreduce_gradients(gr, world))
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+
+    def timed(fn):
+        for i in range(3):
+            fn(i)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        sync_all()
+        return parallel.max_over_ranks(e0.elapsed_time(e1), world, dev) / steps
+
+    losses = []
+    ms_lang = timed(lambda i: losses.append(field.train_step_graph(*batches[i % pool])) if i % 10 == 0 else field.train_step_graph(*batches[i % pool]))
+    loss_first, loss_last = float(field.loss), None
+    ms_joint = timed(lambda i: (hash_model.train_step_graph(*nerf_batches[i % pool]), field.train_step_graph(*batches[i % pool])))
+    loss_last = float(field.loss)
+    per_launch = graph_breakdown(field, batches[0], world, reps=10)
+    if field.peer is not None:
+        field.peer.check()
+    rows = rays * (N_SAMPLES + N_IMPORTANCE)
+    fwd_ms, bwd_ms = per_launch.get("lerf_fwd_train", [0.0])[0], per_launch.get("lerf_bwd_rows", [0.0])[0]
+    fl_fwd, fl_bwd = rows * 303104, rows * 606208
+    return {"metric": "lerf_train_rays_per_s", "value": rays * world / (ms_joint * 1e-3), "unit": "rays/s", "ms_per_step": ms_joint, "steps": steps,
+            "rays_per_gpu": rays, "n_gpus": world, "scaling": "weak",
+            "language_step_only": {"ms_per_step": ms_lang, "value": rays * world / (ms_lang * 1e-3), "kernels_per_step": field.graph_kernels_per_step},
+            "loss": {"after_language_only_leg": loss_first, "after_joint_leg": loss_last},
+            "kernels_ms_per_step": {k: [round(t, 4) for t in v] for k, v in sorted(per_launch.items(), key=lambda kv: -sum(kv[1]))},
+            "roofline_tensor": {"peak": tf_peak, "unit": "TFLOP/s", "rows": rows,
+                                "lerf_head_fwd_train": {"ms": fwd_ms, "achieved": fl_fwd / max(fwd_ms, 1e-9) / 1e9, "frac": fl_fwd / max(fwd_ms, 1e-9) / 1e9 / tf_peak,
+                                                        "flop_per_row": 303104},
+                                "lerf_head_bwd": {"ms": bwd_ms, "achieved": fl_bwd / max(bwd_ms, 1e-9) / 1e9, "frac": fl_bwd / max(bwd_ms, 1e-9) / 1e9 / tf_peak,
+                                                  "flop_per_row": 606208, "kernels": "lerf_bwd_chain_kernel + mlp_nerf_bwd_dw_kernel (4 units) + lerf_gram_apply_kernel"}},
+            "dp_check": dp_check, "parallelism": f"ray-sharded dp{world}: {dp_mode}",
+            "config": "BASELINE C5: HashNeRF (L16 F2 T2^19 + SH4 + NeRFSmall) and the language field (L16 F8 T2^19 grid + LeRF(32,2,256,512,128)) trained jointly, "
+                      f"{rays} rays/GPU/step, 64 + 128 samples, random unit 512-d targets; random-init O(1) language weights"}
 
 
 def main() -> None:
@@ -606,7 +690,11 @@ def main() -> None:
         del emb
 
     # ---- LeRF training leg (BASELINE C5): 1024 rays per GPU, language field trained through the fused head backward
-    train_lerf = lerf_train_leg(rank, world, dev) if not quick else None
+    peaks_early = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    try:
+        train_lerf = lerf_train_leg(rank, world, dev, model, peaks_early.get("bf16_tflops", 1590.0)) if not quick else None
+    except Exception as e:  # noqa: BLE001 - after the readiness agreement a failure here is local: report it, do not hang the line
+        train_lerf = {"error": f"{type(e).__name__}: {e}"}
 
     if rank != 0:
         return

@@ -24,7 +24,7 @@ import torch
 
 from . import ops
 from .ops import f16, f32
-from .pipeline import make_grid
+from .pipeline import FlatAdamModel, make_grid
 
 LERF_LAYERS = (("sigma_le_net_0", 256, 128), ("sigma_le_net_1", 33, 256), ("le_net_0", 256, 160), ("le_net_1", 512, 256))
 
@@ -48,11 +48,14 @@ def head_forward_backward(packed, weights: dict, enc, keep, z, rays_d, target, g
             "dw": dw, "d_raw4": d_raw4}, d_enc
 
 
-class LeRFField:
-    """Language hash grid + LeRF head of one replica, and the LeRFRenderer stages on them."""
+class LeRFField(FlatAdamModel):
+    """Language hash grid + LeRF head of one replica, and the LeRFRenderer stages on them.  Parameters live in ONE flat fp32 vector
+    [reachable table scalars | sigma_le_net_0 | sigma_le_net_1 | le_net_0 | le_net_1] (`table` / `weights` are views), so that training is one
+    gradient exchange and one Adam launch, as for HashNeRF."""
 
     def __init__(self, bbox=(-1.5, -1.5, -1.5, 1.5, 1.5, 1.5), n_levels=16, n_features=8, log2_hashmap_size=19, base_resolution=16,
-                 finest_resolution=512, n_samples=64, n_importance=128, device="cuda", seed=42, primes=None, prefix="lang_model"):
+                 finest_resolution=512, n_samples=64, n_importance=128, device="cuda", seed=42, primes=None, prefix="lang_model", lr=1e-2,
+                 lrate_decay=250):
         assert n_levels * n_features == 128, "the fused head is built for 128 input channels (16 levels x 8 features)"
         self.device = torch.device(device)
         self.bbox = tuple(float(v) for v in bbox)
@@ -61,33 +64,79 @@ class LeRFField:
         self.S, self.N = n_samples, n_importance
         self.n_table = self.grid.used_scalars()
         g = torch.Generator(device="cpu").manual_seed(seed)
-        self.table = (torch.rand(self.n_table, generator=g) * 1e-4).to(device)                    # src/CuHashEmbedder.cpp:24
-        self.weights = {}
+        self._init_flat(self.n_table + sum(fo * fi for _, fo, fi in LERF_LAYERS), device, lr, lrate_decay)
+        self.params[:self.n_table] = (torch.rand(self.n_table, generator=g) * 1e-4).to(device)    # src/CuHashEmbedder.cpp:24
+        self.weights, self.weight_grads = {}, {}
+        off = self.n_table
         for name, fo, fi in LERF_LAYERS:                                                          # Trainable.h:43 Xavier normal, gain 0.1
-            self.weights[f"{prefix}_{name}.weight"] = (torch.randn(fo, fi, generator=g) * 0.1 * math.sqrt(2.0 / (fi + fo))).to(device)
+            view = self.params[off:off + fo * fi].view(fo, fi)
+            view.copy_((torch.randn(fo, fi, generator=g) * 0.1 * math.sqrt(2.0 / (fi + fo))).to(device))
+            self.weights[f"{prefix}_{name}.weight"] = view
+            self.weight_grads[f"{prefix}_{name}.weight"] = self.grads[off:off + fo * fi].view(fo, fi)
+            off += fo * fi
         self.t_vals = torch.linspace(0.0, 1.0, n_samples, dtype=f32).to(device)                   # src/LeRFRenderer.cpp:112
         self.u = torch.linspace(0.0, 1.0, n_importance, dtype=f32).to(device)                     # src/Sampler.h:20
-        self.table_f16 = torch.empty(self.n_table, dtype=f16, device=device)
         self.packed = None
+        self.reuse_coarse_rows = True        # the fine pass copies the coarse samples' encoding rows instead of gathering them again (bit-identical)
+        self._bwd_ws = None
         self.refresh()
 
-    def refresh(self):
-        """Re-derive the fp16 table shadow and the operand blob from the fp32 masters (after loading a checkpoint)."""
-        ops.table_to_half(self.table, self.table_f16)
+    def repack(self):
         self.packed = ops.lerf_pack(self.weights, out=self.packed, prefix=self.prefix)
+
+    def bind_peer_buffers(self):
+        """After parallel.PeerShardedOptimizer re-pointed self.grads at symmetric memory: the per-layer gradient views follow."""
+        off = self.n_table
+        for name, fo, fi in LERF_LAYERS:
+            self.weight_grads[f"{self.prefix}_{name}.weight"] = self.grads[off:off + fo * fi].view(fo, fi)
+            off += fo * fi
+
+    def _static_inputs(self, n_rays):
+        dev = self.device
+        tgt = torch.zeros((n_rays, 512), dtype=f32, device=dev)
+        tgt[:, 0] = 1.0
+        return (torch.tensor([[0.0, 0.0, 4.0]], device=dev).repeat(n_rays, 1), torch.tensor([[0.0, 0.0, -1.0]], device=dev).repeat(n_rays, 1), tgt)
+
+    # -- one optimisation step of the language field (src/NeRFExecutor.h:957-983, 986-996)
+    def forward_backward(self, rays_o, rays_d, target, grad_scale=1.0):
+        """LeRFRenderer::RenderRays + the language loss + backward into self.grads (accumulating).  self.loss holds the loss.  The coarse pass is
+        inference (it never receives a gradient); the fine pass runs the bf16 training program of the fused head."""
+        r = rays_o.shape[0]
+        ray_batch, z, _ = ops.ray_setup(rays_o, rays_d, self.bbox, 0.0, self.t_vals, None, zero_scalar=self.loss)
+        enc_c, keep_c = ops.hash_encode_rays_fwd(self.grid, self.table_f16, ray_batch, z, clamp=True, out_f16=True)
+        raw4 = ops.lerf_sigma_fwd(self.packed, enc_c, keep_c)
+        coarse = ops.composite_fwd(raw4.view(r, self.S, 4), z, rays_d)
+        if self.reuse_coarse_rows:
+            z_fine, perm = ops.sample_pdf_merge(z, coarse["weights"], self.u, want_perm=True)
+            reuse = (perm, enc_c, keep_c, z.shape[1])
+        else:
+            z_fine, reuse = ops.sample_pdf_merge(z, coarse["weights"], self.u), None
+        s = z_fine.shape[1]
+        enc, keep = ops.hash_encode_rays_fwd(self.grid, self.table_f16, ray_batch, z_fine, clamp=True, out_f16=True, reuse=reuse)
+        if self._bwd_ws is None or self._bwd_ws[0] != (r, s):
+            self._bwd_ws = ((r, s), ops.lerf_bwd_workspace(r * s, r, self.device))
+        out, d_enc = head_forward_backward(self.packed, self.weights, enc, keep, z_fine, rays_d, target, self.weight_grads, loss_out=self.loss,
+                                           grad_scale=grad_scale, prefix=self.prefix, workspace=self._bwd_ws[1])
+        ops.hash_encode_rays_bwd(self.grid, ray_batch, z_fine, d_enc, self.grads[:self.n_table], clamp=True)
+        out["z"] = z_fine
+        return out
 
     def render_rays(self, rays_o, rays_d, return_embedding=False, return_weights=True):
         """LeRFRenderer::RenderRays after Render's prologue (IntersectWithAABB, src/LeRFRenderer.cpp:296-302): LeRFRendererOutputs as a dict."""
         r = rays_o.shape[0]
         ray_batch, z, _ = ops.ray_setup(rays_o, rays_d, self.bbox, 0.0, self.t_vals, None)
         # coarse pass: density only (RunLENetwork + the weights of RawToLEOutputs)
-        enc, keep = ops.hash_encode_rays_fwd(self.grid, self.table_f16, ray_batch, z, clamp=True, out_f16=True)
-        raw4 = ops.lerf_sigma_fwd(self.packed, enc, keep)
+        enc_c, keep_c = ops.hash_encode_rays_fwd(self.grid, self.table_f16, ray_batch, z, clamp=True, out_f16=True)
+        raw4 = ops.lerf_sigma_fwd(self.packed, enc_c, keep_c)
         coarse = ops.composite_fwd(raw4.view(r, self.S, 4), z, rays_d)
-        z_fine = ops.sample_pdf_merge(z, coarse["weights"], self.u)                               # :143-147
+        if self.reuse_coarse_rows:                                                                # :143-147; the merged list holds the coarse z bit for bit
+            z_fine, perm = ops.sample_pdf_merge(z, coarse["weights"], self.u, want_perm=True)
+            reuse = (perm, enc_c, keep_c, z.shape[1])
+        else:
+            z_fine, reuse = ops.sample_pdf_merge(z, coarse["weights"], self.u), None
         s = z_fine.shape[1]
         # fine pass
-        enc, keep = ops.hash_encode_rays_fwd(self.grid, self.table_f16, ray_batch, z_fine, clamp=True, out_f16=True)
+        enc, keep = ops.hash_encode_rays_fwd(self.grid, self.table_f16, ray_batch, z_fine, clamp=True, out_f16=True, reuse=reuse)
         raw4, hidden, q = ops.lerf_hidden_fwd(self.packed, enc, keep)
         comp = ops.composite_fwd(raw4.view(r, s, 4), z_fine, rays_d)
         out = {"rendered": ops.lerf_render_embedding(self.packed, comp["weights"], hidden, q), "depth": comp["depth"], "disp": comp["disp"],

@@ -123,6 +123,8 @@ class PeerShardedOptimizer:
         self.multicast = bool(getattr(handles[0], "has_multicast_support", False))
         model.grads, model.shadow = self.grads, self.shadow
         model.peer = self
+        if hasattr(model, "bind_peer_buffers"):
+            model.bind_peer_buffers()          # views into the flat gradient follow it into symmetric memory
         self._flag_host = None
         torch.cuda.synchronize(dev)
         dist.barrier(group)
@@ -178,7 +180,7 @@ class PeerShardedOptimizer:
         model.grads.zero_()
         model.step = 0
         model._sched_step = -1          # the check advanced the device-side counter: re-seed it on the next step
-        model.packed = ops.mlp_small_pack(model.mlp_params, out=model.packed)
+        model.repack()
         torch.cuda.synchronize(dev)
         dist.barrier()
         out = {"max_abs_shadow_diff": stats[0].item(), "max_abs_owned_master_diff": stats[1].item(),

@@ -64,7 +64,154 @@ def make_grid(bbox, n_levels=16, n_features=2, log2_hashmap_size=19, base_resolu
         base_resolution=base_resolution, finest_resolution=finest_resolution)
 
 
-class HashNeRF:
+class FlatAdamModel:
+    """One flat fp32 parameter vector [hash-table scalars (n_table) | network weights] with its gradient, Adam moments and fp16 shadow, and the
+    optimiser step on it (src/NeRFExecutor.h:539 Adam(0.9, 0.99, eps 1e-15); :986-996 step + learning-rate decay) as ONE kernel launch:
+    dense (nrf_adam_step[_scheduled]) or, data-parallel, the fused peer-memory kernel (parallel.PeerShardedOptimizer).  Subclasses provide
+    `repack()` (operand blob of the network from the fp32 weights) and fill `params`."""
+
+    def _init_flat(self, n_params: int, device, lr: float, lrate_decay: int):
+        self.params = torch.empty(n_params, dtype=f32, device=device)
+        self.grads = torch.zeros_like(self.params)
+        self.exp_avg = torch.zeros_like(self.params)
+        self.exp_avg_sq = torch.zeros_like(self.params)
+        self.shadow = torch.empty(self.params.shape, dtype=f16, device=device)                   # fp16 copy; table part is what the gathers read
+        self.lr0, self.lrate_decay, self.step = lr, lrate_decay, 0
+        self.loss = torch.zeros(1, dtype=f32, device=device)
+        self.peer = None          # parallel.PeerShardedOptimizer when the fused data-parallel optimiser is in use
+        self.masters_synced = True  # False while the fused optimiser has stepped and the non-owned fp32 shards are stale
+        self.sched = None
+
+    @property
+    def table(self):
+        self._require_synced("table")
+        return self.params[:self.n_table]
+
+    @property
+    def table_f16(self): return self.shadow[:self.n_table]
+
+    def _require_synced(self, what):
+        if not self.masters_synced:
+            raise RuntimeError(f"{type(self).__name__}.{what}: the fp32 master is sharded over the ranks (fused data-parallel optimiser) and this rank's "
+                               "non-owned shards are stale — call model.peer.allgather_master(model) first (collective)")
+
+    def state_dict(self):
+        """fp32 master + Adam moments + step, valid on every rank (gathers the owners' shards first under the fused optimiser)."""
+        if self.peer is not None and not self.masters_synced:
+            self.peer.allgather_master(self)
+        return {"params": self.params.clone(), "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": self.step}
+
+    def refresh(self):
+        """Re-derive the fp16 table shadow and the packed network weights from the fp32 masters."""
+        ops.table_to_half(self.table, self.table_f16)
+        self.shadow[self.n_table:].copy_(self.params[self.n_table:])      # the network tail of the shadow: what the Adam kernels will keep writing
+        self.repack()
+
+    def optimizer_step(self, grad_scale=1.0):
+        self.step += 1
+        # src/NeRFExecutor.h:986-996: step() runs with the rate set at the END of the previous iteration,
+        # lr0 * 0.1^(global_step / decay_steps) with global_step counted from 0 and incremented after the update
+        lr = self.lr0 * (0.1 ** (max(self.step - 2, 0) / (self.lrate_decay * 1000)))
+        ops.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, lr, self.step, 0.9, 0.99, 1e-15,
+                      grad_scale, True, self.shadow)
+        self.repack()
+
+    def _init_sched(self):
+        if self.sched is None:
+            self.sched = torch.zeros(4, dtype=i32, device=self.device)
+            self._sched_step = -1
+
+    def _sync_sched(self):
+        if self._sched_step != self.step:          # eager steps ran in between: re-seed the device-side step counter
+            self.sched[0:1].copy_(torch.tensor([self.step], dtype=i32), non_blocking=False)
+            self._sched_step = self.step
+
+    def _optimizer_step_sharded(self):
+        """Data-parallel step without NCCL: one kernel per rank over NVLink peer memory (parallel.PeerShardedOptimizer)."""
+        self.masters_synced = False
+        ops.adam_schedule_advance(self.sched, self.lr0, 0.1, float(self.lrate_decay * 1000))
+        ops.adam_step_sharded(self.peer.pg, self.params, self.exp_avg, self.exp_avg_sq, self.n_table, self.sched, 0.9, 0.99, 1e-15,
+                              1.0 / self.peer.world)
+        self.repack()
+
+    def flags_timeout(self) -> int:
+        """1 if a peer barrier of the fused optimiser ever gave up waiting (a rank missed a step), else 0.  Synchronises."""
+        return self.peer.timeout() if self.peer is not None else 0
+
+    def optimizer_step_sharded(self):
+        """Eager (non-graph) entry of the fused data-parallel optimiser step."""
+        self.peer.check()
+        self._init_sched()
+        self._sync_sched()
+        self._optimizer_step_sharded()
+        self.peer.mirror_flag()
+        self.step += 1
+        self._sched_step = self.step
+
+    def _optimizer_step_scheduled(self, grad_scale):
+        ops.adam_schedule_advance(self.sched, self.lr0, 0.1, float(self.lrate_decay * 1000))
+        ops.adam_step_scheduled(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.sched, 0.9, 0.99, 1e-15, grad_scale, True, self.shadow)
+        self.repack()
+
+    # -- the step as ONE CUDA-graph replay (launch-bound otherwise: ~20 kernels of 3..300 us behind ~20 ctypes calls)
+    def capture_train_step(self, n_rays: int, world: int = 1, allreduce=None):
+        """Captures forward_backward and the optimiser for a fixed ray count.  world == 1: one graph per step;
+        world > 1: graph(render + loss + backward) -> allreduce(self.grads) (eager NCCL call) -> graph(Adam + repack), or, with the fused
+        peer-memory optimiser, one graph.  The step count / bias corrections / decayed rate advance on the device (nrf_adam_schedule_advance)."""
+        dev = self.device
+        self._g_in = self._static_inputs(n_rays)
+        self._g_world, self._g_allreduce = world, allreduce
+        self._init_sched()
+        # warm-up outside the capture (one-time function attributes, level scales, allocator pools); its gradient is discarded
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self.forward_backward(*self._g_in)
+            self.grads.zero_()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from . import cabi
+        l0 = cabi.launch_count()
+        self._g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g_fb):
+            self._g_out = self.forward_backward(*self._g_in)
+            if world == 1:
+                self._optimizer_step_scheduled(1.0)
+            elif self.peer is not None:
+                self._optimizer_step_sharded()
+        self._g_opt = None
+        if world > 1 and self.peer is None:
+            self._g_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._g_opt):
+                self._optimizer_step_scheduled(1.0 / world)
+        self.graph_kernels_per_step = cabi.launch_count() - l0
+        return self
+
+    def train_step_graph(self, *inputs):
+        """Replay of the captured step.  Inputs may be device tensors or pinned host tensors (copied on the current stream)."""
+        if self.peer is not None:
+            self.peer.check()             # a lost peer fails loudly (pinned-host mirror of the timeout marker, no synchronisation)
+        self._sync_sched()
+        for dst, src in zip(self._g_in, inputs):
+            dst.copy_(src, non_blocking=True)
+        self._g_fb.replay()
+        if self._g_opt is not None:
+            self._g_allreduce(self.grads)
+            self._g_opt.replay()
+        elif self.peer is not None:
+            self.masters_synced = False
+            self.peer.mirror_flag()
+        self.step += 1
+        self._sched_step = self.step
+        return self.loss
+
+    def train_step(self, *inputs):
+        self.forward_backward(*inputs)
+        self.optimizer_step()
+        return self.loss
+
+
+class HashNeRF(FlatAdamModel):
     """Parameters + optimiser state of one HashNeRF replica, as flat device buffers.
 
     params = [table scalars the kernels can reach | NeRFSmall weights], one fp32 vector, so the data-parallel
@@ -83,41 +230,26 @@ class HashNeRF:
         self.sh_degree, self.S, self.N = sh_degree, n_samples, n_importance
         self.n_table = self.grid.used_scalars()
         g = torch.Generator(device="cpu").manual_seed(seed)
-        self.params = torch.empty(self.n_table + MLP_PARAMS, dtype=f32, device=device)
+        self._init_flat(self.n_table + MLP_PARAMS, device, lr, lrate_decay)
         self.params[:self.n_table] = (torch.rand(self.n_table, generator=g) * 1e-4).to(device)   # src/CuHashEmbedder.cpp:24
         off = self.n_table
         for fo, fi in MLP_LAYERS:                                                                 # Trainable.h:43 Xavier normal, gain 0.1
             std = 0.1 * math.sqrt(2.0 / (fi + fo))
             self.params[off:off + fo * fi] = (torch.randn(fo * fi, generator=g) * std).to(device)
             off += fo * fi
-        self.grads = torch.zeros_like(self.params)
-        self.exp_avg = torch.zeros_like(self.params)
-        self.exp_avg_sq = torch.zeros_like(self.params)
-        self.shadow = torch.empty(self.params.shape, dtype=f16, device=device)                   # fp16 copy; table part is what the gathers read
         self.packed = None
-        self.lr0, self.lrate_decay, self.step = lr, lrate_decay, 0
         self.t_vals = torch.linspace(0.0, 1.0, n_samples, dtype=f32).to(device)                  # src/NeRFRenderer.h:393
         self.u = torch.linspace(0.0, 1.0, n_importance, dtype=f32).to(device)                    # src/Sampler.h:20
-        self.loss = torch.zeros(1, dtype=f32, device=device)
         # Copy the coarse samples' encoding rows into the fine pass instead of gathering them again: the merged z list contains the
         # coarse samples bit for bit, so the rows are bit-identical (tests/test_gpu_hash.py::test_row_reuse...); ~10 % of the fine-pass encode.
         self.reuse_coarse_rows = True
         self._u_cache = {}
         self._render_ws = None
-        self.peer = None          # parallel.PeerShardedOptimizer when the fused data-parallel optimiser is in use
-        self.masters_synced = True  # False while the fused optimiser has stepped and the non-owned fp32 shards are stale
-        self.sched = None
         self.refresh()
 
     # -- views into the flat buffers
     @property
-    def table(self):
-        self._require_synced("table")
-        return self.params[:self.n_table]
-    @property
     def mlp_params(self): return self.params[self.n_table:]
-    @property
-    def table_f16(self): return self.shadow[:self.n_table]
 
     def mlp_weights(self):
         out, off = [], 0
@@ -126,22 +258,13 @@ class HashNeRF:
             off += fo * fi
         return out
 
-    def _require_synced(self, what):
-        if not self.masters_synced:
-            raise RuntimeError(f"HashNeRF.{what}: the fp32 master is sharded over the ranks (fused data-parallel optimiser) and this rank's "
-                               "non-owned shards are stale — call model.peer.allgather_master(model) first (collective)")
-
-    def state_dict(self):
-        """fp32 master + Adam moments + step, valid on every rank (gathers the owners' shards first under the fused optimiser)."""
-        if self.peer is not None and not self.masters_synced:
-            self.peer.allgather_master(self)
-        return {"params": self.params.clone(), "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": self.step}
-
-    def refresh(self):
-        """Re-derive the fp16 table shadow and the packed MLP weights from the fp32 masters."""
-        ops.table_to_half(self.table, self.table_f16)
-        self.shadow[self.n_table:].copy_(self.params[self.n_table:])      # the MLP tail of the shadow: what the Adam kernels will keep writing
+    def repack(self):
         self.packed = ops.mlp_small_pack(self.mlp_params, out=self.packed)
+
+    def _static_inputs(self, n_rays):
+        dev = self.device
+        return (torch.tensor([[0.0, 0.0, 4.0]], device=dev).repeat(n_rays, 1), torch.tensor([[0.0, 0.0, -1.0]], device=dev).repeat(n_rays, 1),
+                torch.full((n_rays, 3), 0.5, dtype=f32, device=dev))
 
     # -- RenderRays (src/NeRFRenderer.h:366-459)
     def _network(self, ray_batch, z, ray_sh, reuse=None):
@@ -204,110 +327,6 @@ class HashNeRF:
         g_enc = ops.mlp_small_bwd(self.packed, enc, ray_sh, raw.shape[1], keep, d_raw.view(-1, 4), self.grads[self.n_table:])
         ops.hash_encode_rays_bwd(self.grid, ray_batch, out["z"], g_enc, self.grads[:self.n_table], clamp=True)
         return out
-
-    def optimizer_step(self, grad_scale=1.0):
-        self.step += 1
-        # src/NeRFExecutor.h:986-996: step() runs with the rate set at the END of the previous iteration,
-        # lr0 * 0.1^(global_step / decay_steps) with global_step counted from 0 and incremented after the update
-        lr = self.lr0 * (0.1 ** (max(self.step - 2, 0) / (self.lrate_decay * 1000)))
-        ops.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, lr, self.step, 0.9, 0.99, 1e-15,
-                      grad_scale, True, self.shadow)
-        self.packed = ops.mlp_small_pack(self.mlp_params, out=self.packed)
-
-    def train_step(self, rays_o, rays_d, target):
-        self.forward_backward(rays_o, rays_d, target)
-        self.optimizer_step()
-        return self.loss
-
-    # -- the same step as ONE CUDA-graph replay (launch-bound otherwise: ~20 kernels of 3..300 us behind ~20 ctypes calls)
-    def capture_train_step(self, n_rays: int, world: int = 1, allreduce=None):
-        """Captures forward_backward and the optimiser for a fixed ray count.  world == 1: one graph per step;
-        world > 1: graph(render + loss + backward) -> allreduce(self.grads) (eager NCCL call) -> graph(Adam + repack).
-        The step count / bias corrections / decayed rate advance on the device (nrf_adam_schedule_advance)."""
-        dev = self.device
-        self._g_in = (torch.tensor([[0.0, 0.0, 4.0]], device=dev).repeat(n_rays, 1), torch.tensor([[0.0, 0.0, -1.0]], device=dev).repeat(n_rays, 1),
-                      torch.full((n_rays, 3), 0.5, dtype=f32, device=dev))
-        self._g_world, self._g_allreduce = world, allreduce
-        self._init_sched()
-        # warm-up outside the capture (one-time function attributes, level scales, allocator pools); its gradient is discarded
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            self.forward_backward(*self._g_in)
-            self.grads.zero_()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        from . import cabi
-        l0 = cabi.launch_count()
-        self._g_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._g_fb):
-            self._g_out = self.forward_backward(*self._g_in)
-            if world == 1:
-                self._optimizer_step_scheduled(1.0)
-            elif self.peer is not None:
-                self._optimizer_step_sharded()
-        self._g_opt = None
-        if world > 1 and self.peer is None:
-            self._g_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._g_opt):
-                self._optimizer_step_scheduled(1.0 / world)
-        self.graph_kernels_per_step = cabi.launch_count() - l0
-        return self
-
-    def _init_sched(self):
-        if self.sched is None:
-            self.sched = torch.zeros(4, dtype=i32, device=self.device)
-            self._sched_step = -1
-
-    def _sync_sched(self):
-        if self._sched_step != self.step:          # eager steps ran in between: re-seed the device-side step counter
-            self.sched[0:1].copy_(torch.tensor([self.step], dtype=i32), non_blocking=False)
-            self._sched_step = self.step
-
-    def _optimizer_step_sharded(self):
-        """Data-parallel step without NCCL: one kernel per rank over NVLink peer memory (parallel.PeerShardedOptimizer)."""
-        self.masters_synced = False
-        ops.adam_schedule_advance(self.sched, self.lr0, 0.1, float(self.lrate_decay * 1000))
-        ops.adam_step_sharded(self.peer.pg, self.params, self.exp_avg, self.exp_avg_sq, self.n_table, self.sched, 0.9, 0.99, 1e-15,
-                              1.0 / self.peer.world)
-        self.packed = ops.mlp_small_pack(self.mlp_params, out=self.packed)
-
-    def flags_timeout(self) -> int:
-        """1 if a peer barrier of the fused optimiser ever gave up waiting (a rank missed a step), else 0.  Synchronises."""
-        return self.peer.timeout() if self.peer is not None else 0
-
-    def optimizer_step_sharded(self):
-        """Eager (non-graph) entry of the fused data-parallel optimiser step."""
-        self.peer.check()
-        self._init_sched()
-        self._sync_sched()
-        self._optimizer_step_sharded()
-        self.peer.mirror_flag()
-        self.step += 1
-        self._sched_step = self.step
-
-    def _optimizer_step_scheduled(self, grad_scale):
-        ops.adam_schedule_advance(self.sched, self.lr0, 0.1, float(self.lrate_decay * 1000))
-        ops.adam_step_scheduled(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.sched, 0.9, 0.99, 1e-15, grad_scale, True, self.shadow)
-        self.packed = ops.mlp_small_pack(self.mlp_params, out=self.packed)
-
-    def train_step_graph(self, rays_o, rays_d, target):
-        """Replay of the captured step.  Inputs may be device tensors or pinned host tensors (copied on the current stream)."""
-        if self.peer is not None:
-            self.peer.check()             # a lost peer fails loudly (pinned-host mirror of the timeout marker, no synchronisation)
-        self._sync_sched()
-        for dst, src in zip(self._g_in, (rays_o, rays_d, target)):
-            dst.copy_(src, non_blocking=True)
-        self._g_fb.replay()
-        if self._g_opt is not None:
-            self._g_allreduce(self.grads)
-            self._g_opt.replay()
-        elif self.peer is not None:
-            self.masters_synced = False
-            self.peer.mirror_flag()
-        self.step += 1
-        self._sched_step = self.step
-        return self.loss
 
 
 def synthetic_rays(n, h=800, w=800, device="cuda", seed=0, radius=4.0):

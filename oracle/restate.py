@@ -401,25 +401,35 @@ def lerf_language_loss(rendered: torch.Tensor, target: torch.Tensor) -> torch.Te
     return torch.nn.functional.huber_loss(rendered, target, reduction="none", delta=1.25).sum(-1).nanmean()
 
 
-def lerf_backward_fused_form(x: torch.Tensor, sigma_w, le_w, z: torch.Tensor, rays_d: torch.Tensor, target: torch.Tensor) -> dict:
-    """The gradients of the language loss written the way the fused kernels will evaluate them: the [N,512] embedding is
+def lerf_backward_fused_form(x: torch.Tensor, sigma_w, le_w, z: torch.Tensor, rays_d: torch.Tensor, target: torch.Tensor, emulate: bool = False) -> dict:
+    """The gradients of the language loss written the way the fused kernels evaluate them: the [N,512] embedding is
     never formed; everything per sample is 256-wide.  x [R,S,C] (the hash encoding of the fine pass), 2-layer nets (BASELINE C5).
     Explicit formulas, no autograd except for the compositing weights (an existing kernel, nrf_composite_bwd).  Returns d loss / d
-    {sigma_w0, sigma_w1, le_w0, le_w1, x}; tests compare it with autograd through lerf_forward + raw_to_le_outputs."""
+    {sigma_w0, sigma_w1, le_w0, le_w1, x}; tests compare it with autograd through lerf_forward + raw_to_le_outputs.
+    emulate=True additionally rounds to bf16 what the sm_100a kernels store in bf16 (h1, geo, h2, the G operand, and the gradient rows
+    d a2, d s, d a1, beta h2, d x), so that the ReLU active sets are the kernels' own (csrc/lerf_tc.cu TRAIN program, csrc/lerf_bwd_tc.cu);
+    the caller rounds x and the three tensor-core weight matrices."""
+    rb = (lambda t: t.float().bfloat16().to(t.dtype)) if emulate else (lambda t: t)
     r_, s_, c_ = x.shape
     xf = x.reshape(-1, c_)
     w_s0, w_s1 = sigma_w
     w_e0, w_e1 = le_w
     a1 = xf @ w_s0.t()
-    h1 = torch.relu(a1)
+    h1 = rb(torch.relu(a1))
     sg = h1 @ w_s1.t()                                            # [sigma | geo]
-    gx = torch.cat([sg[:, 1:], xf], -1)
+    geo = rb(sg[:, 1:])
+    gx = torch.cat([geo, xf], -1)
     a2 = gx @ w_e0.t()
-    h2 = torch.relu(a2)
+    h2 = rb(torch.relu(a2))
     gram = w_e1.t() @ w_e1                                        # G
+    if emulate:                                                   # the operand travels as bf16(G / 2^k), 2^k >= max diag / 256 (lerf_gscale_kernel)
+        gs = 1.0
+        while float(gram.diagonal().max()) > 256.0 * gs:
+            gs *= 2.0
+        gram = rb(gram / gs) * gs
     t = h2 @ gram                                                 # G h2 (symmetric)
     n2 = (t * h2).sum(-1)                                         # |e|^2 = h2^T G h2
-    n = n2.sqrt().clamp_min(1e-8)
+    n = n2.clamp_min(0).sqrt().clamp_min(1e-8)
     sigma = sg[:, 0].reshape(r_, s_).detach().requires_grad_(True)
     raw4 = torch.cat([torch.zeros(r_, s_, 3, dtype=x.dtype), sigma[..., None]], -1)
     w = raw_to_outputs(raw4, z, rays_d)["weights"]                # the compositing weights of the density column
@@ -439,15 +449,15 @@ def lerf_backward_fused_form(x: torch.Tensor, sigma_w, le_w, z: torch.Tensor, ra
     cf, dwf = c.reshape(-1), d_w.reshape(-1)
     beta = cf * dwf / n                                                                              # W_e1^T e_hat = G h2 / n
     d_h2 = cf[:, None] * u_rows - beta[:, None] * t
-    d_we1 = d_e.t() @ hs - w_e1 @ ((beta[:, None] * h2).t() @ h2)                                   # outer term - W_e1 * weighted Gram
-    d_a2 = d_h2 * (a2 > 0)
+    d_we1 = d_e.t() @ hs - w_e1 @ (rb(beta[:, None] * h2).t() @ h2)                                 # outer term - W_e1 * weighted Gram
+    d_a2 = rb(d_h2 * ((h2 > 0) if emulate else (a2 > 0)))
     d_we0 = d_a2.t() @ gx
     d_gx = d_a2 @ w_e0
-    d_s = torch.cat([d_sigma.reshape(-1, 1), d_gx[:, :sg.shape[1] - 1]], -1)
+    d_s = rb(torch.cat([d_sigma.reshape(-1, 1), d_gx[:, :sg.shape[1] - 1]], -1))
     d_ws1 = d_s.t() @ h1
-    d_a1 = (d_s @ w_s1) * (a1 > 0)
+    d_a1 = rb((d_s @ w_s1) * ((h1 > 0) if emulate else (a1 > 0)))
     d_ws0 = d_a1.t() @ xf
-    d_x = d_a1 @ w_s0 + d_gx[:, sg.shape[1] - 1:]
+    d_x = rb(d_a1 @ w_s0 + d_gx[:, sg.shape[1] - 1:])
     return {"sigma_w0": d_ws0, "sigma_w1": d_ws1, "le_w0": d_we0, "le_w1": d_we1, "x": d_x.reshape(r_, s_, c_), "rendered": rendered}
 
 

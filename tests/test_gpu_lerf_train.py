@@ -51,22 +51,31 @@ def _bf16(t):
 
 @pytest.mark.parametrize("r,s,seed", [(64, 48, 0), (37, 192, 1), (5, 24, 2)])
 def test_fused_training_forward_and_backward_match_the_oracle(r, s, seed):
-    """Against the fp64 oracle evaluated on bf16-rounded operands (x, W_s0, W_s1, W_e0 — what the tensor cores read; W_e1 enters in fp32): what is left
-    is the bf16 rounding of the stored activations / gradient rows and the ReLU units they flip.  Ragged tile counts (rows % 128 != 0) included."""
+    """Two references, both the fp64 oracle on bf16-rounded operands (x, W_s0, W_s1, W_e0 — what the tensor cores read; W_e1 enters in fp32):
+      * emulate=True  — h1, geo, h2, the G operand and the gradient rows also rounded to bf16 where the kernels store them, so the ReLU active
+        sets are the kernels' own: rel 1e-2 norm-wise on every gradient (the north star's bf16 figure);
+      * emulate=False — exact.  The bf16 rounding of h1 / geo flips the ~0.1 % of h2 units whose pre-activation is within rounding of zero; each
+        flipped unit is an O(1) error of its own gradient, i.e. noise of order sqrt(flipped share) — a direction check (cosine), as for the
+        classic MLP (tests/test_gpu_mlp_nerf.py).
+    Ragged tile counts (rows % 128 != 0) included."""
     w, x, z, d, target = _case(r, s, seed)
     loss, out, grads, d_x = _run(x, w, z, d, target)
     wq = [_bf16(w[0]), _bf16(w[1]), _bf16(w[2]), w[3].double()]
     ref = O.lerf_backward_fused_form(_bf16(x), wq[:2], wq[2:], z.double(), d.double(), target.double())
+    emu = O.lerf_backward_fused_form(_bf16(x), wq[:2], wq[2:], z.double(), d.double(), target.double(), emulate=True)
     ref_loss = float(O.lerf_language_loss(ref["rendered"], target.double()))
     cos = torch.nn.functional.cosine_similarity(out["rendered"].double().cpu(), ref["rendered"], dim=-1)
-    print(f"R {r} S {s}: loss {loss:.6f} vs {ref_loss:.6f}; rendered cosine min {float(cos.min()):.6f}; "
-          + ", ".join(f"{k} {_rel(grads[k], ref[k]):.2e}" for k in KEYS) + f", x {_rel(d_x, ref['x']):.2e}")
+    print(f"R {r} S {s}: loss {loss:.6f} vs {ref_loss:.6f}; rendered cosine min {float(cos.min()):.6f}\n   vs exact fp64:   "
+          + ", ".join(f"{k} {_rel(grads[k], ref[k]):.2e}" for k in KEYS) + f", x {_rel(d_x, ref['x']):.2e}\n   vs bf16 points:  "
+          + ", ".join(f"{k} {_rel(grads[k], emu[k]):.2e}" for k in KEYS) + f", x {_rel(d_x, emu['x']):.2e}")
     assert abs(loss - ref_loss) <= 1e-2 * abs(ref_loss)
     assert float(cos.min()) > 1 - 1e-3
     assert float((out["rendered"].double().cpu() - ref["rendered"]).abs().max()) <= 1e-2 * float(ref["rendered"].abs().max())
     for k in KEYS:
-        assert _rel(grads[k], ref[k]) <= 2e-2, (k, _rel(grads[k], ref[k]))
-    assert _rel(d_x, ref["x"]) <= 2e-2
+        assert _rel(grads[k], emu[k]) <= 1e-2, (k, _rel(grads[k], emu[k]))
+        assert float((grads[k] * ref[k]).sum() / (grads[k].norm() * ref[k].norm())) >= 0.99, k
+    assert _rel(d_x, emu["x"]) <= 1e-2
+    assert float((d_x * ref["x"]).sum() / (d_x.norm() * ref["x"].norm())) >= 0.99
 
 
 def test_against_the_reference_autograd_fixture(golden):
@@ -95,7 +104,7 @@ def test_keep_mask_grad_rendered_entry_and_accumulation():
     keep = (torch.rand(16 * 40, generator=torch.Generator().manual_seed(4)) > 0.2).to(torch.uint8).cuda()
     loss, out, grads, d_x = _run(x, w, z, d, target, keep)
     assert bool((out["raw4"][keep == 0, 3] == 0).all())
-    assert bool((out["d_raw4"][keep == 0] == 0).all())
+    assert bool((out["d_raw4"].view(-1, 4)[keep == 0] == 0).all())
     assert bool(torch.isfinite(d_x).all()) and float(out["weights"].view(-1)[keep == 0].abs().max()) == 0.0      # no density, no weight
     # (b) + (c) through the raw entries
     weights = {n: t.float().cuda().contiguous() for n, t in zip(NAMES, w)}
@@ -145,3 +154,44 @@ def test_full_size_c5_batch_properties():
     l3 = torch.zeros(1, device="cuda")
     head_forward_backward(packed2, step, enc, None, zc, dc, tc, {n: torch.zeros_like(t) for n, t in weights.items()}, loss_out=l3)
     assert float(l3) < float(loss), (float(l3), float(loss))
+
+
+def _field(seed=5):
+    from nerfpp_b200.lerf import LeRFField
+    f = LeRFField(log2_hashmap_size=14, seed=seed, lrate_decay=1, lr=2e-3)
+    g = torch.Generator().manual_seed(seed)
+    for v in f.weights.values():                                  # O(1) signals: the reference's U[0,1e-4) table gives ONE density sign for all points
+        v.copy_((torch.randn(v.shape, generator=g) * (2.0 / v.shape[1]) ** 0.5).cuda())
+    f.params[:f.n_table].copy_((torch.rand(f.n_table, generator=g) * 2 - 1).cuda())
+    f.refresh()
+    return f
+
+
+def test_language_field_trains_eagerly_and_as_a_graph():
+    """LeRFField.train_step (render + language loss + fused backward + hash scatter at F = 8 + one Adam launch over [table | weights]): the loss goes
+    down, the captured graph follows the eager trajectory, the step touches table and weights, and the fine-pass row reuse changes nothing."""
+    from nerfpp_b200.pipeline import synthetic_rays
+    rays = 256
+    o, d, _ = synthetic_rays(rays, seed=2)
+    tgt = torch.nn.functional.normalize(torch.randn(rays, 512, generator=torch.Generator().manual_seed(3)), dim=-1).cuda()
+    a, b, c = _field(), _field(), _field()
+    c.reuse_coarse_rows = False
+    p0 = a.params.clone()
+    la = [float(a.train_step(o, d, tgt)) for _ in range(12)]
+    b.capture_train_step(rays)
+    lb = [float(b.train_step_graph(o, d, tgt)) for _ in range(12)]
+    lc = [float(c.train_step(o, d, tgt)) for _ in range(3)]
+    print("language loss eager", [round(v, 5) for v in la], "graph", [round(v, 5) for v in lb])
+    assert all(np.isfinite(la)) and la[-1] < 0.97 * la[0], la
+    np.testing.assert_allclose(lb, la, rtol=2e-2)
+    np.testing.assert_allclose(lc, la[:3], rtol=1e-3)
+    moved = (a.params - p0).abs()
+    assert float(moved[:a.n_table].max()) > 0 and float(moved[a.n_table:].max()) > 0
+    assert float(a.grads.abs().max()) == 0.0                      # cleared by the Adam kernel
+    # inference on the trained field agrees with the training forward's rendering (fp16 vs bf16 operands)
+    out_t = a.forward_backward(o, d, tgt)
+    a.grads.zero_()
+    out_i = a.render_rays(o, d)
+    cos = torch.nn.functional.cosine_similarity(out_t["rendered"], out_i["rendered"], dim=-1)
+    hit = out_i["acc"] > 0.5
+    assert float(cos[hit].min()) > 0.995, float(cos[hit].min())
