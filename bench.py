@@ -384,7 +384,9 @@ def lerf_train_leg(rank: int, world: int, dev, hash_model, tf_peak: float, rays:
     from nerfpp_b200.pipeline import synthetic_rays
     out, ready, field = {}, True, None
     try:
-        field = LeRFField(BBOX, seed=0, device=dev)            # same seed on every rank: identical replicas without a broadcast
+        # same seed on every rank: identical replicas without a broadcast.  lr 5e-4: with O(1) weights the reference's 1e-2 kills the density within ~50
+        # steps (relu on sigma: every weight -> 0, every gradient -> 0) and the scatter / chain kernels would be timed on the all-zero skip path
+        field = LeRFField(BBOX, seed=0, device=dev, lr=5e-4)
         g = torch.Generator().manual_seed(0)
         for v in field.weights.values():                       # O(1) signals (He-scaled weights, table U(-1,1)): every ReLU / density regime is exercised
             v.copy_((torch.randn(v.shape, generator=g) * (2.0 / v.shape[1]) ** 0.5).to(dev))

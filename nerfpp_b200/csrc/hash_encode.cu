@@ -304,6 +304,11 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b)
 	asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d)
+{
+	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // Backward: dTable[corner] += w_corner * dEnc, fp32 RED (src/CuHashEmbedder.cu:106-216).
 //
 // Warp-aggregated scatter.  Points arrive in ray-major order (samples of a ray are consecutive), so on the coarse levels
@@ -420,11 +425,18 @@ __global__ void __launch_bounds__(128) hash_bwd_kernel(HashArgs a, PointSrc ps, 
 			}
 			if (active && !cont) {   // first lane of a run owns the run's sum
 				float* base = grad_table + m.offset[l];
+				const bool vec4_ok = (reinterpret_cast<uintptr_t>(base) & 15) == 0;
 #pragma unroll
 				for (int d = 0; d < 8; d++) {
 					float* p = base + static_cast<size_t>(c.pos[d]) * F;
+					if (F % 4 == 0 && vec4_ok) {
+						// an entry of F >= 4 features is 16-byte aligned when the level offset is: half as many L2 atomic operations
 #pragma unroll
-					for (int k = 0; k < F; k += 2) red_add_v2(p + k, v[d][k], v[d][k + 1]);
+						for (int k = 0; k + 3 < F; k += 4) red_add_v4(p + k, v[d][k], v[d][k + 1], v[d][k + 2], v[d][k + 3]);
+					} else {
+#pragma unroll
+						for (int k = 0; k < F; k += 2) red_add_v2(p + k, v[d][k], v[d][k + 1]);
+					}
 				}
 			}
 		}

@@ -16,9 +16,9 @@
 //
 // The chain kernel is the mlp_nerf_bwd_chain_kernel design at 4 layers: one persistent CTA per SM, one 128-row tile in flight, warp 0 streams
 // the bf16 FORWARD blob (its stage bytes read as an MN-major B operand give dY W without a transposed copy), warp 1 issues tcgen05.mma with the
-// gradient rows as A operand in TMEM and fp32 accumulators in TMEM, warps 2..5 are one epilogue thread per row.  TMEM columns:
+// gradient rows as A operand in TMEM and fp32 accumulators in TMEM, warps 2..9 are two epilogue threads per row (half of the accumulator columns each).  TMEM columns:
 //   D 0..255  (t = G h2 | then d[x 128 | g 32] in 0..159, onto which d a1 W_s0 is ACCUMULATED in 0..127)   | d s operand 160..183
-//   A 256..383 (d a2, then d a1 compacted in place out of the d h1 accumulator)  | h2 operand 384..511  | d h1 accumulator 256..511
+//   A 256..383 (d a2, then d a1 written over the head of the d h1 accumulator once it has been read)  | h2 operand 384..511  | d h1 accumulator 256..511
 // The training blob packs W_e0 with its input columns as [x 128 | geo 32] so that the two products that meet in d x write the same 64-column
 // accumulator blocks.  bf16 operands, fp32 accumulation; parity tests/test_gpu_lerf_train.py (rel 1e-2 against fp64).
 #include "lerf_layout.cuh"
@@ -31,7 +31,7 @@ namespace lerf_tc {
 __constant__ ModeTable c_chain = make_mode(kChain);
 
 constexpr uint32_t kCD = 0, kCS = 160, kCA = 256, kCH2 = 384, kCD2 = 256;
-constexpr int kChainThreads = 32 * 6;
+constexpr int kChainThreads = 32 * 10;     // producer, issuer, 8 epilogue warps (two per TMEM lane quarter, half of the columns each)
 
 struct __align__(128) ChainSmem {
 	uint8_t ring[kRing][kStageBytes];
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) lerf_bwd_chain_kernel(const 
 	if (warp == 1) {
 		if (lane == 0) {
 			for (int s = 0; s < kRing; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-			mbar_init(&sm.a_ready, 4);
+			mbar_init(&sm.a_ready, 8);
 			mbar_init(&sm.d_ready, 1);
 			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		}
@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) lerf_bwd_chain_kernel(const 
 			__syncwarp();
 		}
 	} else {
-		// ===== epilogue warps: one thread per row =====
-		const int qd = warp & 3;
+		// ===== epilogue warps: two threads per row (warps w and w + 4 share a TMEM lane quarter; `half` takes column chunks 4 half .. 4 half + 3) =====
+		const int qd = warp & 3, half = (warp - 2) >> 2;
 		const int row = (qd << 5) | lane;
 		const uint32_t t_lane = tmem + (static_cast<uint32_t>(qd << 5) << 16);
 		const float gscale = __ldg(reinterpret_cast<const float*>(blob + kScaleBase));     // the G operand travels divided by this power of two
@@ -199,14 +199,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) lerf_bwd_chain_kernel(const 
 			const uint8_t* const rec_s = saved + tile * static_cast<int64_t>(kSaveTile);
 			uint8_t* const rec_g = grads + tile * static_cast<int64_t>(kGradTile);
 			const float2 cb = ok ? __ldg(coef + r) : make_float2(0.f, 0.f);          // (c_s, beta_s)
-			float d_sigma = ok ? __ldg(d_raw4 + r * 4 + 3) : 0.f;
-			if (ok && keep != nullptr && keep[r] == 0) d_sigma = 0.f;                 // sigma_le was overwritten with 0 there (src/LeRFRenderer.cpp:18-20)
 			const float* const u_row = u + (ok ? r / n_samples : 0) * kHid;
 			// ---- the h2 record row -> A operand of step 0
 			{
 				const uint8_t* h2_row = rec_s + kSaveH2 + chunk_offset(kHid, row, 0);
 #pragma unroll
-				for (int c = 0; c < 8; c++) {
+				for (int cc = 0; cc < 4; cc++) {
+					const int c = 4 * half + cc;
 					uint32_t a16[16];
 #pragma unroll
 					for (int i = 0; i < 4; i++) {
@@ -224,24 +223,28 @@ __global__ void __launch_bounds__(kChainThreads, 1) lerf_bwd_chain_kernel(const 
 				uint8_t* const da2_row = rec_g + kGradA2 + chunk_offset(kHid, row, 0);
 				uint8_t* const bh2_row = rec_g + kGradBH2 + chunk_offset(kHid, row, 0);
 				const float bt = cb.y * gscale;
-#pragma unroll 1
-				for (int c = 0; c < 8; c++) {
-					uint32_t acc[32], hh[16], a16[16], b16[16];
-					tmem_ld32(t_lane + kCD + 32 * c, acc);
-					tmem_ld16(t_lane + kCH2 + 16 * c, hh);
-					float uu[32];
+				uint32_t acc[2][32], hh[2][16];
+				float4 uu[2][8];
+				auto fetch = [&](int c, int b) {
+					tmem_ld32(t_lane + kCD + 32 * c, acc[b]);
+					tmem_ld16(t_lane + kCH2 + 16 * c, hh[b]);
 #pragma unroll
-					for (int i = 0; i < 8; i++) {
-						const float4 v = __ldg(reinterpret_cast<const float4*>(u_row + 32 * c) + i);
-						uu[4 * i] = v.x; uu[4 * i + 1] = v.y; uu[4 * i + 2] = v.z; uu[4 * i + 3] = v.w;
-					}
-					tmem_ld_wait_for(acc);
-					tmem_ld_wait_for16b(hh);
+					for (int i = 0; i < 8; i++) uu[b][i] = __ldg(reinterpret_cast<const float4*>(u_row + 32 * c) + i);
+				};
+				fetch(4 * half, 0);
+#pragma unroll
+				for (int cc = 0; cc < 4; cc++) {
+					const int c = 4 * half + cc, b = cc & 1;
+					tmem_ld_wait_for(acc[b]);
+					tmem_ld_wait_for16b(hh[b]);
+					if (cc + 1 < 4) fetch(c + 1, b ^ 1);         // the next chunk's TMEM / L1 reads fly under this chunk's arithmetic and stores
+					uint32_t a16[16], b16[16];
 #pragma unroll
 					for (int i = 0; i < 16; i++) {
-						const float h_lo = __uint_as_float(hh[i] << 16), h_hi = __uint_as_float(hh[i] & 0xFFFF0000u);
-						const float g_lo = h_lo > 0.f ? cb.x * uu[2 * i] - bt * __uint_as_float(acc[2 * i]) : 0.f;
-						const float g_hi = h_hi > 0.f ? cb.x * uu[2 * i + 1] - bt * __uint_as_float(acc[2 * i + 1]) : 0.f;
+						const float u_lo = (i & 1) ? uu[b][i >> 1].z : uu[b][i >> 1].x, u_hi = (i & 1) ? uu[b][i >> 1].w : uu[b][i >> 1].y;
+						const float h_lo = __uint_as_float(hh[b][i] << 16), h_hi = __uint_as_float(hh[b][i] & 0xFFFF0000u);
+						const float g_lo = h_lo > 0.f ? cb.x * u_lo - bt * __uint_as_float(acc[b][2 * i]) : 0.f;
+						const float g_hi = h_hi > 0.f ? cb.x * u_hi - bt * __uint_as_float(acc[b][2 * i + 1]) : 0.f;
 						a16[i] = pack_bf16(g_lo, g_hi);
 						b16[i] = pack_bf16(cb.y * h_lo, cb.y * h_hi);
 					}
@@ -254,7 +257,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) lerf_bwd_chain_kernel(const 
 
 			// ---- step 1: d g (accumulator columns 128..159) -> d s = [d g 32 | d sigma | 0..] (48 columns: A operand of step 2 + record)
 			mbar_wait(&sm.d_ready, pd); pd ^= 1u; fence_after();
-			{
+			if (half == 0) {
+				float d_sigma = ok ? __ldg(d_raw4 + r * 4 + 3) : 0.f;
+				if (ok && keep != nullptr && keep[r] == 0) d_sigma = 0.f;             // sigma_le was overwritten with 0 there (src/LeRFRenderer.cpp:18-20)
 				uint32_t acc[32], a16[16], tail[8];
 				tmem_ld32(t_lane + kCD + 128, acc);
 				tmem_ld_wait_for(acc);
@@ -272,43 +277,50 @@ __global__ void __launch_bounds__(kChainThreads, 1) lerf_bwd_chain_kernel(const 
 			}
 			publish_chain(&sm.a_ready, lane);
 
-			// ---- step 2: d a1 = d h1 * [h1 > 0], compacted in place (bf16 pairs of chunk c land in columns the chunk itself occupied) + record
+			// ---- step 2: d a1 = d h1 * [h1 > 0] + record.  The bf16 pairs of chunk c go to columns 256 + 16 c: inside the accumulator columns of chunk
+			// c / 2, which belong to the OTHER half for c >= 4 — so both halves first read all their chunks, meet, and only then overwrite.
 			mbar_wait(&sm.d_ready, pd); pd ^= 1u; fence_after();
 			{
-				uint32_t bits[8];
-				{
-					const uint4 lo = __ldg(reinterpret_cast<const uint4*>(rec_s + kSaveBits1 + row * 32));
-					const uint4 hi = __ldg(reinterpret_cast<const uint4*>(rec_s + kSaveBits1 + row * 32) + 1);
-					bits[0] = lo.x; bits[1] = lo.y; bits[2] = lo.z; bits[3] = lo.w; bits[4] = hi.x; bits[5] = hi.y; bits[6] = hi.z; bits[7] = hi.w;
-				}
+				const uint4 bw = __ldg(reinterpret_cast<const uint4*>(rec_s + kSaveBits1 + row * 32) + half);
+				const uint32_t bits[4] = {bw.x, bw.y, bw.z, bw.w};
 				uint8_t* const da1_row = rec_g + kGradA1 + chunk_offset(kHid, row, 0);
+				uint32_t packed[4][16];
+				uint32_t acc[2][32];
+				tmem_ld32(t_lane + kCD2 + 32 * (4 * half), acc[0]);
 #pragma unroll
-				for (int c = 0; c < 8; c++) {
-					uint32_t acc[32], a16[16];
-					tmem_ld32(t_lane + kCD2 + 32 * c, acc);
-					tmem_ld_wait_for(acc);
+				for (int cc = 0; cc < 4; cc++) {
+					const int c = 4 * half + cc, b = cc & 1;
+					tmem_ld_wait_for(acc[b]);
+					if (cc + 1 < 4) tmem_ld32(t_lane + kCD2 + 32 * (c + 1), acc[b ^ 1]);
 #pragma unroll
 					for (int i = 0; i < 16; i++) {
-						uint32_t w = pack_bf16(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
-						w &= ((bits[c] >> i) & 0x00010001u) * 0xFFFFu;
-						a16[i] = w;
+						uint32_t w = pack_bf16(__uint_as_float(acc[b][2 * i]), __uint_as_float(acc[b][2 * i + 1]));
+						w &= ((bits[cc] >> i) & 0x00010001u) * 0xFFFFu;
+						packed[cc][i] = w;
 					}
-					tmem_st16(t_lane + kCA + 16 * c, a16);
-					store_chunks4(da1_row, 4 * c, a16);
+					store_chunks4(da1_row, 4 * c, packed[cc]);
 				}
+				fence_before();
+				asm volatile("bar.sync 1, 256;" ::: "memory");       // all 8 epilogue warps: every tcgen05.ld of the d h1 accumulator has completed
+				fence_after();
+#pragma unroll
+				for (int cc = 0; cc < 4; cc++) tmem_st16(t_lane + kCA + 16 * (4 * half + cc), packed[cc]);
 			}
 			publish_chain(&sm.a_ready, lane);
 
 			// ---- step 3: d x (accumulator columns 0..127) -> bf16 [N, 128] row-major, the layout nrf_hash_encode_bwd reads
 			mbar_wait(&sm.d_ready, pd); pd ^= 1u; fence_after();
 			{
+				uint32_t acc[2][32];
+				tmem_ld32(t_lane + kCD + 32 * (2 * half), acc[0]);
+				tmem_ld32(t_lane + kCD + 32 * (2 * half + 1), acc[1]);
 #pragma unroll
-				for (int c = 0; c < 4; c++) {
-					uint32_t acc[32], a16[16];
-					tmem_ld32(t_lane + kCD + 32 * c, acc);
-					tmem_ld_wait_for(acc);
+				for (int cc = 0; cc < 2; cc++) {
+					const int c = 2 * half + cc;
+					uint32_t a16[16];
+					tmem_ld_wait_for(acc[cc]);
 #pragma unroll
-					for (int i = 0; i < 16; i++) a16[i] = pack_bf16(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+					for (int i = 0; i < 16; i++) a16[i] = pack_bf16(__uint_as_float(acc[cc][2 * i]), __uint_as_float(acc[cc][2 * i + 1]));
 					if (ok) {
 #pragma unroll
 						for (int i = 0; i < 4; i++) d_enc[r * (kIn / 8) + 4 * c + i] = make_uint4(a16[4 * i], a16[4 * i + 1], a16[4 * i + 2], a16[4 * i + 3]);
@@ -368,26 +380,29 @@ __global__ void __launch_bounds__(256) lerf_ray_grad_kernel(const float* __restr
 	for (int h = 0; h < 2; h++) d_e[ray * kDim + j + 256 * h] = (clamped ? dr[h] : dr[h] - rr[h] * d) / nrm;
 }
 
-// u[ray, k] = sum_n dE[ray, n] W_e1[n, k]: 8 rays per block, thread = k
+// u[ray, k] = sum_n dE[ray, n] W_e1[n, k]: 8 rays per block, thread = k.  dE sits transposed in shared memory ([n][ray]: a thread reads its 8
+// rays' values as two 16-byte broadcasts) and 16 weight loads are in flight per thread.  No atomics: u feeds d_enc, whose bits must not depend on
+// scheduling (chunked / whole-batch equality, tests/test_gpu_lerf_train.py).  (First version: [ray][n] tile, 8 scalar LDS per n: 73 us.)
 constexpr int kURays = 8;
 __global__ void __launch_bounds__(256) lerf_u_kernel(const float* __restrict__ w_e1, const float* __restrict__ d_e, int64_t n_rays, float* __restrict__ u)
 {
-	__shared__ float de[kURays][kDim];
+	__shared__ __align__(16) float de[kDim][kURays];
 	const int64_t ray0 = static_cast<int64_t>(blockIdx.x) * kURays;
 	for (int i = threadIdx.x; i < kURays * kDim; i += 256) {
-		const int64_t ray = ray0 + i / kDim;
-		de[i / kDim][i % kDim] = ray < n_rays ? d_e[ray * kDim + i % kDim] : 0.f;
+		const int rr = i / kDim, nn = i % kDim;
+		de[nn][rr] = ray0 + rr < n_rays ? d_e[(ray0 + rr) * kDim + nn] : 0.f;
 	}
 	__syncthreads();
 	float acc[kURays];
 #pragma unroll
 	for (int i = 0; i < kURays; i++) acc[i] = 0.f;
 	const int k = threadIdx.x;
-#pragma unroll 8
+#pragma unroll 16
 	for (int nn = 0; nn < kDim; nn++) {
 		const float w = __ldg(w_e1 + nn * kHid + k);
-#pragma unroll
-		for (int i = 0; i < kURays; i++) acc[i] = fmaf(de[i][nn], w, acc[i]);
+		const float4 a = *reinterpret_cast<const float4*>(&de[nn][0]), b = *reinterpret_cast<const float4*>(&de[nn][4]);
+		acc[0] = fmaf(a.x, w, acc[0]); acc[1] = fmaf(a.y, w, acc[1]); acc[2] = fmaf(a.z, w, acc[2]); acc[3] = fmaf(a.w, w, acc[3]);
+		acc[4] = fmaf(b.x, w, acc[4]); acc[5] = fmaf(b.y, w, acc[5]); acc[6] = fmaf(b.z, w, acc[6]); acc[7] = fmaf(b.w, w, acc[7]);
 	}
 #pragma unroll
 	for (int i = 0; i < kURays; i++)
@@ -404,6 +419,7 @@ __global__ void __launch_bounds__(256) lerf_outer_kernel(const float* __restrict
 	float acc[kOuterRows];
 #pragma unroll
 	for (int i = 0; i < kOuterRows; i++) acc[i] = 0.f;
+#pragma unroll 4
 	for (int64_t ray = lo; ray < hi; ray++) {
 		const float hs = __ldg(hsum + ray * kHid + k);
 		const float4 a = __ldg(reinterpret_cast<const float4*>(d_e + ray * kDim + n0)), b = __ldg(reinterpret_cast<const float4*>(d_e + ray * kDim + n0) + 1);

@@ -58,7 +58,9 @@ constexpr int kProjBase = kTrainBase + kTrainBytes;
 constexpr int kProjBytes = kHid * kDim * 4;
 // one fp32 after it: the power-of-two scale the 16-bit copies of G were divided by (lerf_gscale_kernel), so that a trained W_e1 cannot overflow fp16
 constexpr int kScaleBase = kProjBase + kProjBytes;
-constexpr int kPackedBytes = kScaleBase + 128;
+// and G = W_e1^T W_e1 itself in fp32 [256][256] (lerf_gram_kernel; the pack kernel rounds the 16-bit operand copies from it)
+constexpr int kGramBase = kScaleBase + 128;
+constexpr int kPackedBytes = kGramBase + kHid * kHid * 4;
 static_assert(kWeightBytes % 128 == 0 && kTrainBytes % 128 == 0, "blob alignment");
 
 // stage programs: the weight stages one 128-row tile consumes, in order, as (byte offset in the blob, bytes)

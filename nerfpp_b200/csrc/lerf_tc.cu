@@ -32,31 +32,46 @@ namespace nrf {
 namespace lerf_tc {
 
 __constant__ ModeTable c_modes[kModes] = {make_mode(kSigma), make_mode(kHidden), make_mode(kRaw), make_mode(kTrain), make_mode(kChain)};
-// padded logical weight Wp_l(n, k) in the kernel's operand order
-__device__ __forceinline__ float wp(const Weights& p, int l, int n, int k, float g_inv)
+// padded logical weight Wp_l(n, k) in the kernel's operand order; gram = G = W_e1^T W_e1 (fp32 [256][256], lerf_gram_kernel)
+__device__ __forceinline__ float wp(const Weights& p, const float* __restrict__ gram, int l, int n, int k, float g_inv)
 {
 	switch (l) {
 		case 0: return p.s0[n * kIn + k];
 		case 1: return n < kGeo ? p.s1[(n + 1) * kHid + k] : (n == kGeo ? p.s1[k] : 0.f);     // [geo 0..31 | sigma | zeros]
 		case 2: return p.e0[n * (kGeo + kIn) + k];
-		case 3: {                                                                            // G = W_e1^T W_e1
-			float acc = 0.f;
-			for (int m = 0; m < kDim; m++) acc = fmaf(p.e1[m * kHid + n], p.e1[m * kHid + k], acc);
-			return acc * g_inv;                                                              // |G_nk| <= max diagonal <= 256 after scaling
-		}
+		case 3: return gram[n * kHid + k] * g_inv;                                            // |G_nk| <= max diagonal <= 256 after scaling
 		case 4: return p.e1[n * kHid + k];
 		default: return p.e1[(n + 256) * kHid + k];
 	}
 }
 
-// scale of G: the smallest power of two s >= 1 with max_k (W_e1^T W_e1)_kk / s <= 256 (|G_nk| <= sqrt(G_nn G_kk), so every entry fits fp16
-// with 8 bits of headroom); thread k sums column k of W_e1
-__global__ void __launch_bounds__(kHid) lerf_gscale_kernel(Weights p, float* __restrict__ scale_out)
+// G[n][k] = sum_m W_e1[m][n] W_e1[m][k]: block = 4 rows n, thread = k; the four columns W_e1[.][n0..n0+3] are staged in shared memory, 16
+// coalesced loads of W_e1[m][k] in flight per thread; fixed summation order (no atomics: the same weights must pack to the same bits).
+// (The first pack kernel evaluated this 512-term sum once per packed word, twice: 108 us per optimiser step, profiles/r2_lerf_train_launches_v1.txt.)
+__global__ void __launch_bounds__(kHid) lerf_gram_kernel(Weights p, float* __restrict__ gram)
+{
+	__shared__ __align__(16) float col[kDim][4];
+	const int n0 = blockIdx.x * 4, k = threadIdx.x;
+	for (int i = threadIdx.x; i < kDim * 4; i += kHid) col[i >> 2][i & 3] = p.e1[(i >> 2) * kHid + n0 + (i & 3)];
+	__syncthreads();
+	float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 16
+	for (int m = 0; m < kDim; m++) {
+		const float w = __ldg(p.e1 + m * kHid + k);
+		const float4 c = *reinterpret_cast<const float4*>(&col[m][0]);
+		acc[0] = fmaf(c.x, w, acc[0]); acc[1] = fmaf(c.y, w, acc[1]); acc[2] = fmaf(c.z, w, acc[2]); acc[3] = fmaf(c.w, w, acc[3]);
+	}
+#pragma unroll
+	for (int i = 0; i < 4; i++) gram[(n0 + i) * kHid + k] = acc[i];
+}
+
+// scale of G: the smallest power of two s >= 1 with max_k G_kk / s <= 256 (|G_nk| <= sqrt(G_nn G_kk), so every entry fits fp16
+// with 8 bits of headroom)
+__global__ void __launch_bounds__(kHid) lerf_gscale_kernel(const float* __restrict__ gram, float* __restrict__ scale_out)
 {
 	__shared__ float red[kHid / 32];
 	const int k = threadIdx.x;
-	float d = 0.f;
-	for (int m = 0; m < kDim; m++) d = fmaf(p.e1[m * kHid + k], p.e1[m * kHid + k], d);
+	float d = gram[k * kHid + k];
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
 	if ((k & 31) == 0) red[k >> 5] = d;
@@ -75,6 +90,7 @@ __global__ void __launch_bounds__(256) lerf_pack_kernel(Weights p, uint32_t* __r
 	const int w = blockIdx.x * blockDim.x + threadIdx.x;
 	if (w >= kScaleBase / 4) return;                       // the scale word is lerf_gscale_kernel's
 	const float g_inv = 1.f / reinterpret_cast<const float*>(blob)[kScaleBase / 4];
+	const float* const gram = reinterpret_cast<const float*>(blob) + kGramBase / 4;
 	if (w >= kProjBase / 4) {
 		const int i = w - kProjBase / 4, k = i / kDim, n = i % kDim;
 		reinterpret_cast<float*>(blob)[w] = p.e1[n * kHid + k];
@@ -92,7 +108,7 @@ __global__ void __launch_bounds__(256) lerf_pack_kernel(Weights p, uint32_t* __r
 		// W_e0 travels with its input columns as [x 128 | geo 32] in the training copy (lerf_bwd_tc.cu: the two products that meet in d x then
 		// write the same accumulator blocks); pairs (k, k + 1) never straddle the boundary
 		const int ks = l == 2 ? (k < kIn ? k + kGeo : k - kIn) : k;
-		blob[w] = pack_bf16(wp(p, l, n, ks, g_inv), wp(p, l, n, ks + 1, g_inv));
+		blob[w] = pack_bf16(wp(p, gram, l, n, ks, g_inv), wp(p, gram, l, n, ks + 1, g_inv));
 		return;
 	}
 	int l = 0;
@@ -102,7 +118,7 @@ __global__ void __launch_bounds__(256) lerf_pack_kernel(Weights p, uint32_t* __r
 	// UMMA K-major core-matrix layout: word q of a stage holds (n, k) and (n, k+1); byte = (k/8)*(N*16) + n*16 + (k%8)*2
 	const int N = layer_info(l).N;
 	const int kc = q / (4 * N), n = (q >> 2) % N, k = k_off + 8 * kc + 2 * (q & 3);
-	blob[w] = pack_f16(wp(p, l, n, k, g_inv), wp(p, l, n, k + 1, g_inv));
+	blob[w] = pack_f16(wp(p, gram, l, n, k, g_inv), wp(p, gram, l, n, k + 1, g_inv));
 }
 
 struct __align__(128) Smem {
@@ -687,7 +703,10 @@ int nrf_lerf_pack(const nrf_lerf_shape* shape, const nrf_lerf_weights* w, void* 
 	NRF_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0, "packed blob must be 128-byte aligned");
 	NRF_REQUIRE(w->sigma_w0 && w->sigma_w1 && w->le_w0 && w->le_w1, "null weight pointer");
 	Weights p{w->sigma_w0, w->sigma_w1, w->le_w0, w->le_w1};
-	lerf_gscale_kernel<<<1, kHid, 0, as_stream(stream)>>>(p, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + kScaleBase));
+	float* const gram = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + kGramBase);
+	lerf_gram_kernel<<<kHid / 4, kHid, 0, as_stream(stream)>>>(p, gram);
+	NRF_CHECK_LAUNCH("lerf_gram_kernel");
+	lerf_gscale_kernel<<<1, kHid, 0, as_stream(stream)>>>(gram, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + kScaleBase));
 	NRF_CHECK_LAUNCH("lerf_gscale_kernel");
 	lerf_pack_kernel<<<(kScaleBase / 4 + 255) / 256, 256, 0, as_stream(stream)>>>(p, reinterpret_cast<uint32_t*>(packed));
 	NRF_CHECK_LAUNCH("lerf_pack_kernel");

@@ -261,6 +261,22 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 		.def("init_model", &LerfPipe::InitModel).def("model", &LerfPipe::Model).def("run_le_network", &LerfPipe::RunLENetwork)
 		.def("raw_to_le_outputs", &LerfPipe::RawToLEOutputs).def("render", &LerfPipe::Render)
 		.def("train_steps", &LerfPipe::TrainSteps, py::call_guard<py::gil_scoped_release>())
+		// A/B: false routes training through the reference's formulation (torch::linear + LibTorch autograd) instead of the fused backward
+		.def("use_fused_training", [](LerfPipe& p, bool on) { p.renderer->UseFusedTraining = on; })
+		.def("language_grads", [](LerfPipe& p, Tensor rays_o, Tensor rays_d, Tensor target, int n_samples, int n_importance) {
+			// one backward of the language loss (src/NeRFExecutor.h:957-983) without an optimiser step: (loss, d embeddings, d weights...)
+			for (auto& t : p.embed->parameters()) if (t.grad().defined()) t.mutable_grad().zero_();
+			for (auto& t : p.model->parameters()) if (t.grad().defined()) t.mutable_grad().zero_();
+			auto prm = Params(n_samples, n_importance, 1 << 20, false, false, p.bbox, true, 0.f, 0.f);
+			auto r = p.renderer->Render(0, 0, Tensor(), prm, {rays_o, rays_d, Tensor()}, Tensor(), Tensor());
+			auto loss = torch::nn::functional::huber_loss(r.Outputs.RenderedLangEmbedding, target.detach(),
+				torch::nn::functional::HuberLossFuncOptions().reduction(torch::kNone).delta(1.25)).sum(-1).nanmean();
+			loss.backward();
+			std::vector<Tensor> g;
+			for (auto& t : p.embed->parameters()) g.push_back(t.grad().clone());
+			for (auto& t : p.model->parameters()) g.push_back(t.grad().clone());
+			return std::make_pair(loss.item<float>(), g);
+		})
 		// NeRFExecutor::SaveCheckpoint / restore for the language branch (src/NeRFExecutor.h:556-560, 574-578, 1062-1066): same file names
 		.def("save_checkpoint", [](LerfPipe& p, const std::string& dir) {
 			torch::save(p.embed, dir + "/lang_embedder_checkpoint.pt");

@@ -91,7 +91,9 @@ Tensor LeRFImpl::forward(Tensor x)
 	if (!Fused()) return ForwardAten(x);
 	TORCH_CHECK(x.is_cuda(), "nerfpp_b200: LeRF::forward needs a CUDA tensor at the fused shape (the sm_100a path has no CPU fallback)");
 	const bool recording = torch::GradMode::is_enabled() && (x.requires_grad() || AnyRequiresGrad(Weights()));
-	if (recording) return ForwardAten(x);          // training: LibTorch autograd over torch::linear (fused backward not built yet)
+	// a bare LeRF::forward under autograd returns the [N, 513] tensor the reference returns, through torch::linear; the TRAINING path of the
+	// drop-in is LeRFRenderer::RenderRays, whose fine pass is one fused autograd node (LerfFineFn) that never forms this tensor
+	if (recording) return ForwardAten(x);
 	std::vector<int64_t> shape = x.sizes().vec();
 	Tensor enc = nrfhost::Dense(x.detach().reshape({-1, shape.back()}), torch::kFloat16, "LeRF input");
 	Tensor packed = Packed();
@@ -100,6 +102,93 @@ Tensor LeRFImpl::forward(Tensor x)
 	nrfhost::Check(nrf_lerf_fwd(&s, packed.data_ptr(), enc.data_ptr(), nullptr, enc.size(0), nrfhost::Ptr<float>(out), nrfhost::Stream()), "nrf_lerf_fwd");
 	shape.back() = LangEmbedDim + 1;
 	return out.view(shape);
+}
+
+// ------------------------------------------------------------------------------------------------ fused training of the fine pass
+namespace {
+
+using torch::autograd::AutogradContext;
+using torch::autograd::variable_list;
+
+// RunLENetwork + RawToLEOutputs of the FINE pass under autograd as ONE node (src/LeRFRenderer.cpp:150,165-166 with src/LeRF.cpp:78-110 and
+// src/LeRFRenderer.h:45-54 inside): hash encode (F = 8) -> bf16 tcgen05 head (nrf_lerf_fwd_train) -> compositing -> per-ray projection.  The
+// backward is the fused chain of csrc/lerf_bwd_tc.cu; the [N, 512] embedding is formed in neither direction.  Inputs 0..4 are the leaves that
+// receive gradients (lang_embedder Embeddings, the four Linear weights); points / z / rays_d are detached upstream (:147).
+struct LerfFineFn : public torch::autograd::Function<LerfFineFn> {
+	static variable_list forward(AutogradContext* ctx, Tensor embeddings, Tensor w_s0, Tensor w_s1, Tensor w_e0, Tensor w_e1, Tensor points, Tensor z,
+		Tensor rays_d, int64_t lerf_module, int64_t embed_module)
+	{
+		auto* lerf = reinterpret_cast<LeRFImpl*>(lerf_module);
+		auto* embed = reinterpret_cast<CuHashEmbedderImpl*>(embed_module);
+		const int64_t r = z.size(0), ns = z.size(1), n = r * ns;
+		const nrf_lerf_shape s = lerf->Shape();
+		auto [enc, keep] = embed->EncodeF16(points);
+		Tensor packed = lerf->Packed();
+		const auto f32 = nrfhost::F32Like(z);
+		const auto u8 = torch::TensorOptions().dtype(torch::kUInt8).device(z.device());
+		Tensor raw4 = torch::empty({r, ns, 4}, f32), q = torch::empty({n}, f32);
+		Tensor saved = torch::empty({nrf_lerf_train_saved_bytes(&s, n)}, u8);
+		nrfhost::Check(nrf_lerf_fwd_train(&s, packed.data_ptr(), enc.data_ptr(), reinterpret_cast<const uint8_t*>(keep.data_ptr()), n, nrfhost::Ptr<float>(raw4),
+			saved.data_ptr(), nrfhost::Ptr<float>(q), nrfhost::Stream()), "nrf_lerf_fwd_train");
+		Tensor depth = torch::empty({r}, f32), disp = torch::empty({r}, f32), acc = torch::empty({r}, f32), weights = torch::empty({r, ns}, f32);
+		Tensor rgb = torch::empty({r, 3}, f32);
+		nrfhost::Check(nrf_composite_fwd(nrfhost::CPtr<float>(raw4), 4, nrfhost::CPtr<float>(z), nrfhost::CPtr<float>(rays_d), nullptr, 0.f, 0, r, int32_t(ns),
+			nrfhost::Ptr<float>(rgb), nrfhost::Ptr<float>(depth), nrfhost::Ptr<float>(disp), nrfhost::Ptr<float>(acc), nrfhost::Ptr<float>(weights), nrfhost::Stream()),
+			"nrf_composite_fwd");
+		Tensor hsum = torch::empty({r, s.hidden_dim}, f32), rendered = torch::empty({r, s.lang_embed_dim}, f32), enorm = torch::empty({r}, f32);
+		nrfhost::Check(nrf_lerf_render_embedding_train(&s, packed.data_ptr(), nrfhost::CPtr<float>(weights), saved.data_ptr(), nrfhost::CPtr<float>(q), r, int32_t(ns),
+			nrfhost::Ptr<float>(hsum), nrfhost::Ptr<float>(rendered), nrfhost::Ptr<float>(enorm), nrfhost::Stream()), "nrf_lerf_render_embedding_train");
+		ctx->save_for_backward({w_s0, w_s1, w_e0, w_e1, points, z, rays_d, keep, raw4, q, saved, weights, hsum, rendered, enorm, packed});
+		ctx->saved_data["lerf"] = lerf_module;
+		ctx->saved_data["embed"] = embed_module;
+		ctx->saved_data["embed_numel"] = embeddings.numel();
+		ctx->mark_non_differentiable({weights, depth, disp, acc});
+		return {rendered, weights, depth, disp, acc};
+	}
+
+	static variable_list backward(AutogradContext* ctx, variable_list g)
+	{
+		auto sv = ctx->get_saved_variables();
+		Tensor w_s0 = sv[0], w_s1 = sv[1], w_e0 = sv[2], w_e1 = sv[3], points = sv[4], z = sv[5], rays_d = sv[6], keep = sv[7], raw4 = sv[8], q = sv[9],
+		       saved = sv[10], weights = sv[11], hsum = sv[12], rendered = sv[13], enorm = sv[14], packed = sv[15];
+		auto* lerf = reinterpret_cast<LeRFImpl*>(ctx->saved_data["lerf"].toInt());
+		auto* embed = reinterpret_cast<CuHashEmbedderImpl*>(ctx->saved_data["embed"].toInt());
+		const int64_t r = z.size(0), ns = z.size(1), n = r * ns;
+		const nrf_lerf_shape s = lerf->Shape();
+		const auto f32 = nrfhost::F32Like(z);
+		Tensor grad_table = torch::zeros({ctx->saved_data["embed_numel"].toInt()}, f32).view(embed->Embeddings.sizes());
+		Tensor g0 = torch::zeros_like(w_s0), g1 = torch::zeros_like(w_s1), g2 = torch::zeros_like(w_e0), g3 = torch::zeros_like(w_e1);
+		if (!g[0].defined()) return {grad_table, g0, g1, g2, g3, Tensor(), Tensor(), Tensor(), Tensor(), Tensor()};
+		Tensor g_r = nrfhost::Dense(g[0], torch::kFloat32, "d loss / d RenderedLangEmbedding");
+		// dense fp32 views of the weights as they were at forward time (the blob `packed` was built from them)
+		Tensor d0 = nrfhost::Dense(w_s0.detach(), torch::kFloat32, "w"), d1 = nrfhost::Dense(w_s1.detach(), torch::kFloat32, "w"),
+		       d2 = nrfhost::Dense(w_e0.detach(), torch::kFloat32, "w"), d3 = nrfhost::Dense(w_e1.detach(), torch::kFloat32, "w");
+		const nrf_lerf_weights wp{d0.data_ptr<float>(), d1.data_ptr<float>(), d2.data_ptr<float>(), d3.data_ptr<float>()};
+		const nrf_lerf_weights gp{g0.data_ptr<float>(), g1.data_ptr<float>(), g2.data_ptr<float>(), g3.data_ptr<float>()};
+		Tensor ws = torch::empty({nrf_lerf_bwd_workspace_bytes(&s, n, r)}, torch::TensorOptions().dtype(torch::kUInt8).device(z.device()));
+		Tensor dw = torch::empty({r, ns}, f32), d_raw4 = torch::empty({r, ns, 4}, f32);
+		nrfhost::Check(nrf_lerf_bwd_rays(&s, &wp, saved.data_ptr(), nrfhost::CPtr<float>(q), nrfhost::CPtr<float>(weights), nrfhost::CPtr<float>(hsum),
+			nrfhost::CPtr<float>(rendered), nrfhost::CPtr<float>(enorm), nullptr, nrfhost::CPtr<float>(g_r), r, int32_t(ns), 1.f, nullptr, g3.data_ptr<float>(),
+			ws.data_ptr(), nrfhost::Ptr<float>(dw), nrfhost::Stream()), "nrf_lerf_bwd_rays");
+		nrfhost::Check(nrf_composite_bwd(nrfhost::CPtr<float>(raw4), 4, nrfhost::CPtr<float>(z), nrfhost::CPtr<float>(rays_d), nullptr, 0.f, 0, r, int32_t(ns),
+			nullptr, nullptr, nullptr, nullptr, nrfhost::CPtr<float>(dw), nrfhost::Ptr<float>(d_raw4), nrfhost::Stream()), "nrf_composite_bwd");
+		Tensor d_enc = torch::empty({n, s.input_ch}, torch::TensorOptions().dtype(torch::kBFloat16).device(z.device()));
+		nrfhost::Check(nrf_lerf_bwd_rows(&s, packed.data_ptr(), &wp, saved.data_ptr(), reinterpret_cast<const uint8_t*>(keep.data_ptr()), nrfhost::CPtr<float>(d_raw4),
+			n, int32_t(ns), ws.data_ptr(), &gp, d_enc.data_ptr(), nrfhost::Stream()), "nrf_lerf_bwd_rows");
+		embed->Backward(points, d_enc, grad_table);
+		return {grad_table, g0, g1, g2, g3, Tensor(), Tensor(), Tensor(), Tensor(), Tensor()};
+	}
+};
+
+}  // namespace
+
+bool LeRFRenderer::FusedTraining(const Tensor& ray_batch, const Tensor& cone_angle, float perturb, int n_importance, float raw_noise_std,
+	float stochastic_preconditioning_alpha)
+{
+	const bool recording = torch::GradMode::is_enabled() && (AnyRequiresGrad(Lerf->Weights()) || LangEmbedFn->Embeddings.requires_grad());
+	const bool thin = !(cone_angle.defined() && cone_angle.numel() != 0);
+	return UseFusedTraining && recording && ray_batch.is_cuda() && Lerf->Fused() && LangEmbedFn->GetOutputDims() == Lerf->Shape().input_ch && thin &&
+		perturb == 0.f && n_importance > 0 && raw_noise_std == 0.f && stochastic_preconditioning_alpha == 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------ LeRFRenderer (src/LeRFRenderer.cpp)
@@ -199,6 +288,41 @@ LeRFRenderResult LeRFRenderer::RenderRays(Tensor ray_batch, Tensor cone_angle, c
 		}
 		if (RelevancyFn && LerfPositives.defined() && LerfNegatives.defined())
 			result.Outputs.Relevancy = RelevancyFn(rendered, LerfPositives.to(device), LerfNegatives.to(device));
+	} else if (FusedTraining(rb, cone_angle, perturb, n_importance, raw_noise_std, stochastic_preconditioning_alpha)) {
+		// training at the built shape: the coarse pass only feeds SamplePDF, whose output is detached (:147) — density-only head, no graph;
+		// the fine pass is ONE autograd node on the fused forward / backward kernels (LerfFineFn)
+		const int64_t r = rb.size(0);
+		const nrf_lerf_shape s = Lerf->Shape();
+		Tensor z_vals;
+		{
+			torch::NoGradGuard no_grad;
+			Tensor packed = Lerf->Packed();
+			z_vals = nrfhost::ZSample(rb, n_samples, lin_disp);
+			auto [enc_c, keep_c] = LangEmbedFn->EncodeF16(nrfhost::SamplePoints(rb, z_vals).reshape({-1, 3}));
+			Tensor raw4 = torch::empty({r, n_samples, 4}, nrfhost::F32Like(rb));
+			nrfhost::Check(nrf_lerf_sigma_fwd(&s, packed.data_ptr(), enc_c.data_ptr(), reinterpret_cast<const uint8_t*>(keep_c.data_ptr()), r * n_samples,
+				nrfhost::Ptr<float>(raw4), nrfhost::Stream()), "nrf_lerf_sigma_fwd");
+			nrfhost::CompositeResult coarse = nrfhost::Composite(raw4, z_vals, rays_d, 0.f, false);
+			z_vals = nrfhost::SamplePdfMerge(z_vals, coarse.weights, n_importance);
+		}
+		Tensor pts = nrfhost::SamplePoints(rb, z_vals).reshape({-1, 3});
+		std::vector<Tensor> w = Lerf->Weights();
+		variable_list out = LerfFineFn::apply(LangEmbedFn->Embeddings, w[0], w[1], w[2], w[3], pts, z_vals, rays_d, reinterpret_cast<int64_t>(Lerf.get()),
+			reinterpret_cast<int64_t>(LangEmbedFn.get()));
+		result.Outputs.RenderedLangEmbedding = out[0]; result.Outputs.WeightsLE = out[1]; result.Outputs.DepthMapLE = out[2];
+		result.Outputs.DispMapLE = out[3]; result.Outputs.AccMapLE = out[4];
+		if (return_raw || MaterializeLangEmbedding) {
+			torch::NoGradGuard no_grad;       // the reference's Raw / LangEmbedding tensors, values only (nothing downstream of them is differentiated)
+			auto [enc, keep] = LangEmbedFn->EncodeF16(pts);
+			Tensor packed = Lerf->Packed();
+			Tensor raw = torch::empty({r, z_vals.size(1), dim + 1}, nrfhost::F32Like(rb));
+			nrfhost::Check(nrf_lerf_fwd(&s, packed.data_ptr(), enc.data_ptr(), reinterpret_cast<const uint8_t*>(keep.data_ptr()), r * z_vals.size(1),
+				nrfhost::Ptr<float>(raw), nrfhost::Stream()), "nrf_lerf_fwd");
+			if (return_raw) result.Raw = raw;
+			if (MaterializeLangEmbedding) result.Outputs.LangEmbedding = raw.narrow(-1, 0, dim);
+		}
+		if (RelevancyFn && LerfPositives.defined() && LerfNegatives.defined())
+			result.Outputs.Relevancy = RelevancyFn(result.Outputs.RenderedLangEmbedding, LerfPositives.to(device), LerfNegatives.to(device));
 	} else {
 		// the reference's sequence (:112-172) on the drop-in pieces
 		Tensor z_vals = nrfhost::ZSample(rb, n_samples, lin_disp);

@@ -10,9 +10,12 @@
 //     LeRFRenderer::RenderRays runs hash encode -> density-only head (coarse) -> compositing -> SamplePDF+merge -> hash encode ->
 //     fused head without the [N,512] embedding -> compositing -> per-ray projection (nrf_lerf_sigma_fwd / _hidden_fwd /
 //     _render_embedding), every step a C-ABI call;
-//   * training (autograd recording) and other shapes: the reference's formulation on the drop-in pieces — hash encode forward /
-//     backward on the sm_100a kernels (CuHashEmbedder::forward, F = 8), compositing as one differentiable op, the four bias-free
-//     Linear layers through torch::linear.  A fused backward of the head is not built in this round.
+//   * training (autograd recording) at the built shape, parity configuration (thin rays, no jitter / noise / preconditioning):
+//     LeRFRenderer::RenderRays runs the coarse pass as inference and the fine pass as ONE autograd node on the fused kernels
+//     (nrf_lerf_fwd_train -> nrf_composite_fwd -> nrf_lerf_render_embedding_train; backward nrf_lerf_bwd_rays -> nrf_composite_bwd ->
+//     nrf_lerf_bwd_rows -> nrf_hash_encode_bwd at F = 8): gradients arrive at lang_embedder's Embeddings and the four Linear weights;
+//   * other shapes / the jittered configurations: the reference's formulation on the drop-in pieces — hash encode forward / backward on the
+//     sm_100a kernels (CuHashEmbedder::forward), compositing as one differentiable op, the Linear layers through torch::linear;
 //   * Relevancy (src/LeRFRenderer.cpp:79) belongs to RuCLIP, which the reference does not vendor: LeRFRenderer::RelevancyFn is the
 //     hook a build that has RuCLIP assigns; unset, LeRFRendererOutputs::Relevancy stays undefined.
 #pragma once
@@ -108,6 +111,11 @@ public:
 	/// The fused inference path never forms LangEmbedding [R,S,D] (2 KB per sample that no caller of the reference reads:
 	/// src/NeRFExecutor.h:642-650,706-720,957-983 use RenderedLangEmbedding / Relevancy only).  true: evaluate it as well (nrf_lerf_fwd).
 	bool MaterializeLangEmbedding = false;
+	/// false: training goes through the reference's formulation on torch::linear (A/B and tests); true (default): the fused backward
+	bool UseFusedTraining = true;
+	/// true when RenderRays can take the fused training path for these arguments
+	bool FusedTraining(const torch::Tensor& ray_batch, const torch::Tensor& cone_angle, float perturb, int n_importance, float raw_noise_std,
+		float stochastic_preconditioning_alpha);
 	/// true when RenderRays can take the fused inference path for these arguments
 	bool FusedInference(const torch::Tensor& ray_batch, const torch::Tensor& cone_angle, float perturb, int n_importance, float raw_noise_std,
 		float stochastic_preconditioning_alpha);

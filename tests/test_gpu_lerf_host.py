@@ -108,9 +108,43 @@ def test_render_matches_the_reference_renderer(host, ref_cuda):
     assert torch.equal(rm["rendered"], ra["rendered"])            # chunking does not change a ray's result
 
 
+def test_fused_training_node_matches_libtorch_autograd(host):
+    """LeRFRenderer::Render under autograd: the fused fine-pass node (nrf_lerf_fwd_train / nrf_lerf_bwd_rays / nrf_lerf_bwd_rows behind ONE
+    torch::autograd::Function) against the SAME drop-in classes routed through torch::linear + LibTorch autograd (fp32 cuBLAS — the
+    reference's arithmetic): loss, the gradient of every Linear weight and of the language table."""
+    from nerfpp_b200 import cabi
+    pipes = []
+    for fused in (True, False):
+        host.manual_seed(21)
+        torch.manual_seed(21)
+        p = host.make_lerf(torch.tensor(BBOX).cuda(), *ARGS)
+        p.init_model()
+        _trained_looking(p)
+        p.use_fused_training(fused)
+        pipes.append(p)
+    o, d = _rays(256, seed=22)
+    tgt = torch.nn.functional.normalize(torch.randn(256, 512, generator=torch.Generator().manual_seed(23)), dim=-1).cuda()
+    n0 = cabi.launch_count()
+    la, ga = pipes[0].language_grads(o, d, tgt, 64, 128)
+    n1 = cabi.launch_count()
+    lb, gb = pipes[1].language_grads(o, d, tgt, 64, 128)
+    assert n1 - n0 >= 12                     # the fused path is made of C-ABI launches (chain, dW, per-ray kernels ...)
+    assert abs(la - lb) <= 1e-2 * abs(lb)
+    names = ["embeddings"] + pipes[0].model_param_names()
+    stats = {}
+    for name, a, b in zip(names, ga, gb):
+        a, b = a.double(), b.double()
+        assert float(b.norm()) > 0, name
+        stats[name] = (float((a - b).norm() / b.norm()), float((a * b).sum() / (a.norm() * b.norm())))
+    print("fused vs LibTorch autograd (rel, cos):", {k: (round(r, 4), round(c, 5)) for k, (r, c) in stats.items()})
+    for name, (rel, cos) in stats.items():
+        # bf16 operands against fp32 SGEMMs, different ReLU active sets near zero (see tests/test_gpu_lerf_train.py): direction + scale
+        assert cos >= 0.99 and rel <= 1.5e-1, (name, rel, cos)
+
+
 def test_training_steps_track_the_reference(host, ref_cuda):
     """The language lines of NeRFExecutor::Train (src/NeRFExecutor.h:957-986): Render -> huber(delta 1.25).sum(-1).nanmean() -> backward -> Adam.
-    The drop-in trains through CuHashEmbedder's sm_100a forward / backward (F = 8), the differentiable compositing op and torch::linear."""
+    The drop-in trains through the fused fine-pass node (bf16 tcgen05 forward / backward of the head, CuHashEmbedder's sm_100a kernels at F = 8)."""
     _need(ref_cuda)
     a, b = _pair(host, ref_cuda, seed=11)
     o, d = _rays(256, seed=12)
