@@ -8,6 +8,7 @@
 #include "renderer.h"
 #include "lerf.h"
 #include "fused_adam.h"
+#include "train_graph.h"
 
 namespace py = pybind11;
 using torch::Tensor;
@@ -101,9 +102,26 @@ struct Pipeline {
 	}
 	bool fused_adam = false;   ///< FusedAdam (one sm_100a kernel per parameter) instead of torch::optim::Adam; chosen before the first step
 	void UseFusedAdam(bool on) { TORCH_CHECK(!opt, "choose the optimiser before the first training step"); fused_adam = on; }
+	bool train_graph = false;  ///< HashNeRFTrainGraph: the whole iteration as one CUDA-graph replay (HashNeRF instantiation only)
+	std::unique_ptr<HashNeRFTrainGraph> graph;
+	void UseTrainGraph(bool on) { TORCH_CHECK(!opt && !graph, "choose the training path before the first training step"); train_graph = on; }
 	std::pair<std::vector<double>, std::vector<float>> TrainSteps(Tensor rays_o, Tensor rays_d, Tensor target, int n_steps, int n_samples,
 		int n_importance, int chunk, bool use_viewdirs, float lr, int lrate_decay)
 	{
+		if constexpr (std::is_same_v<N, NeRFSmall>) {
+			if (train_graph) {
+				// NeRFExecutor::Train's iteration as one graph replay; loss.item() every step like the reference's loop
+				if (!graph) graph = std::make_unique<HashNeRFTrainGraph>(embed, embeddirs, model, bbox, n_samples, n_importance, lr, lrate_decay, rays_o.size(0));
+				std::vector<double> secs; std::vector<float> losses;
+				for (int i = 0; i < n_steps; i++) {
+					auto t0 = std::chrono::steady_clock::now();
+					const float lv = graph->Step(rays_o, rays_d, target).template item<float>();
+					secs.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+					losses.push_back(lv);
+				}
+				return {secs, losses};
+			}
+		}
 		if (!opt) {
 			std::vector<Tensor> gv;
 			for (auto& p : embed->parameters()) gv.push_back(p);
@@ -214,7 +232,7 @@ static void Bind(py::module_& m, const char* name)
 		.def("embed", &P::Embed).def("embed_dirs", &P::EmbedDirs).def("model", &P::Model)
 		.def("run_network", &P::RunNetwork).def("raw_to_outputs", &P::RawToOutputs)
 		.def("render_rays", &P::RenderRays).def("render", &P::Render).def("render_shipped", &P::RenderShipped).def("render_image", &P::RenderImage)
-		.def("use_fused_adam", &P::UseFusedAdam)
+		.def("use_fused_adam", &P::UseFusedAdam).def("use_train_graph", &P::UseTrainGraph)
 		.def("train_steps", &P::TrainSteps, py::call_guard<py::gil_scoped_release>())
 		// NeRFExecutor::SaveCheckpoint / the restore branch of Initialize (src/NeRFExecutor.h:1054-1068, 546-553): same file names
 		.def("save_checkpoint", [](P& p, const std::string& dir) {
@@ -276,7 +294,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 			for (auto& t : p.embed->parameters()) g.push_back(t.grad().clone());
 			for (auto& t : p.model->parameters()) g.push_back(t.grad().clone());
 			return std::make_pair(loss.item<float>(), g);
-		})
+		}, py::call_guard<py::gil_scoped_release>())
 		// NeRFExecutor::SaveCheckpoint / restore for the language branch (src/NeRFExecutor.h:556-560, 574-578, 1062-1066): same file names
 		.def("save_checkpoint", [](LerfPipe& p, const std::string& dir) {
 			torch::save(p.embed, dir + "/lang_embedder_checkpoint.pt");

@@ -194,6 +194,52 @@ def test_train_steps_track_reference(host, ref_cuda):
     assert l1[-1] < 0.8 * l1[0]
 
 
+def test_train_graph_tracks_the_autograd_loop(host, tmp_path):
+    """HashNeRFTrainGraph (host/train_graph.h): NeRFExecutor::Train's iteration as ONE CUDA-graph replay on the C++ surface — the same kernels in
+    the same order as the autograd loop issues them, on parameters that stay owned by the modules (re-pointed at one flat vector).  Same seed, same
+    batch: the two loops follow the same loss trajectory, the modules end up holding the trained parameters, and checkpoints still round-trip."""
+    from nerfpp_b200.pipeline import synthetic_rays
+    pipes = []
+    for graph in (True, False):
+        host.manual_seed(3)
+        torch.manual_seed(3)
+        p = host.make_cuhash(torch.tensor(BBOX).cuda(), 16, 2, 15, 16, 512, 4, 2, 64, 15, 3, 64)
+        p.init_model()
+        p.use_fused_adam(True)
+        p.use_train_graph(graph)
+        pipes.append(p)
+    o, d, tgt = synthetic_rays(1024, seed=4)
+    before = [t.detach().clone() for t in pipes[0].model_params() + pipes[0].embed_params()]
+    _, la = pipes[0].train_steps(o, d, tgt, 25, 64, 128, 4096, True, 1e-2, 250)
+    _, lb = pipes[1].train_steps(o, d, tgt, 25, 64, 128, 4096, True, 1e-2, 250)
+    la, lb = np.asarray(la), np.asarray(lb)
+    print("graph   ", la[[0, 5, 12, 24]], "autograd", lb[[0, 5, 12, 24]])
+    assert abs(la[0] - lb[0]) < 1e-5 * lb[0] + 1e-7
+    assert np.all(np.abs(la - lb) < 2e-2 * lb + 1e-5)
+    assert la[-1] < 0.8 * la[0]
+    after = pipes[0].model_params() + pipes[0].embed_params()
+    assert all(float((a - b).abs().max()) > 0 for a, b in zip(after, before))          # the MODULES' parameters moved
+    assert pipes[0].model_param_names() == pipes[1].model_param_names()
+    for a, b in zip(after, pipes[1].model_params() + pipes[1].embed_params()):
+        diff = (a - b).abs()
+        assert (diff > 1e-3).float().mean().item() < 3e-2, float((diff > 1e-3).float().mean())   # sign-like Adam: compare the bulk
+    # the trained modules render (autograd-free path: fp16 shadow / packed weights re-derived from the re-pointed parameters)
+    r1 = pipes[0].render(o[:96], d[:96], 64, 128, 4096, False, True)
+    r2 = pipes[1].render(o[:96], d[:96], 64, 128, 4096, False, True)
+    assert float((r1["rgb"] - r2["rgb"]).abs().mean()) < 2e-2
+    # checkpoint round trip through torch::save / torch::load on the re-pointed parameters
+    pipes[0].save_checkpoint(str(tmp_path))
+    host.manual_seed(9)
+    q = host.make_cuhash(torch.tensor(BBOX).cuda(), 16, 2, 15, 16, 512, 4, 2, 64, 15, 3, 64)
+    q.init_model()
+    q.load_checkpoint(str(tmp_path))
+    r3 = q.render(o[:96], d[:96], 64, 128, 4096, False, True)
+    assert torch.equal(r3["rgb"], r1["rgb"])
+    # and training continues from the graph state
+    _, lc = pipes[0].train_steps(o, d, tgt, 5, 64, 128, 4096, True, 1e-2, 250)
+    assert lc[-1] <= la[-1] * 1.05
+
+
 def test_shipped_configuration_runs(host):
     """thin_ray = false, raw noise and stochastic preconditioning on (src/main.cpp:187): the RNG-gated stages."""
     host.manual_seed(1)
