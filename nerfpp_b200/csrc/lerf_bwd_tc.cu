@@ -19,8 +19,10 @@
 // gradient rows as A operand in TMEM and fp32 accumulators in TMEM, warps 2..9 are two epilogue threads per row (half of the accumulator columns each).  TMEM columns:
 //   D 0..255  (t = G h2 | then d[x 128 | g 32] in 0..159, onto which d a1 W_s0 is ACCUMULATED in 0..127)   | d s operand 160..183
 //   A 256..383 (d a2, then d a1 written over the head of the d h1 accumulator once it has been read)  | h2 operand 384..511  | d h1 accumulator 256..511
-// The training blob packs W_e0 with its input columns as [x 128 | geo 32] so that the two products that meet in d x write the same 64-column
-// accumulator blocks.  bf16 operands, fp32 accumulation; parity tests/test_gpu_lerf_train.py (rel 1e-2 against fp64).
+// The bf16 blob packs W_e0 with its input columns as [x 128 | geo 32] so that the two products that meet in d x write the same 64-column
+// accumulator blocks.  The forward and the G h2 product run on fp16 operands, gradient rows are bf16 (range), accumulation fp32; the weight-
+// gradient products read bf16 copies of the activations (one tcgen05.mma cannot mix the formats).  Parity tests/test_gpu_lerf_train.py (rel 1e-2
+// against fp64 at the kernels' rounding points).
 #include "lerf_layout.cuh"
 #include "dw_units.cuh"
 #include <algorithm>
@@ -127,10 +129,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) lerf_bwd_chain_kernel(const 
 			return slot;
 		};
 		for (int64_t t = 0; t < my_tiles; t++) {
-			// ---- step 0: t = h2 G (K-major B, as in the forward): 4 stages x 4 K steps, N = 256
+			// ---- step 0: t = h2 G (fp16 operands, K-major B, as in the forward): 4 stages x 4 K steps, N = 256
 			mbar_wait(&sm.a_ready, pa); pa ^= 1u; fence_after();
 			{
-				const uint32_t idesc = idesc16(128, kHid, true, 0, 0), lbo = kHid * 16;
+				const uint32_t idesc = idesc16(128, kHid, false, 0, 0), lbo = kHid * 16;
 				uint32_t a_col = tmem + kCH2;
 				for (int s = 0; s < 4; s++) {
 					const uint32_t slot = next_stage();
@@ -242,7 +244,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) lerf_bwd_chain_kernel(const 
 #pragma unroll
 					for (int i = 0; i < 16; i++) {
 						const float u_lo = (i & 1) ? uu[b][i >> 1].z : uu[b][i >> 1].x, u_hi = (i & 1) ? uu[b][i >> 1].w : uu[b][i >> 1].y;
-						const float h_lo = __uint_as_float(hh[b][i] << 16), h_hi = __uint_as_float(hh[b][i] & 0xFFFF0000u);
+						const float2 hf = half2_bits_to_float2(hh[b][i]);        // h2 is stored / multiplied as fp16
+						const float h_lo = hf.x, h_hi = hf.y;
 						const float g_lo = h_lo > 0.f ? cb.x * u_lo - bt * __uint_as_float(acc[b][2 * i]) : 0.f;
 						const float g_hi = h_hi > 0.f ? cb.x * u_hi - bt * __uint_as_float(acc[b][2 * i + 1]) : 0.f;
 						a16[i] = pack_bf16(g_lo, g_hi);
@@ -452,8 +455,9 @@ __global__ void __launch_bounds__(256) lerf_row_coef_kernel(const float* __restr
 			const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
 			for (int i = 0; i < 4; i++) {
-				acc = fmaf(__uint_as_float(w4[i] << 16), us[8 * j + 2 * i], acc);
-				acc = fmaf(__uint_as_float(w4[i] & 0xFFFF0000u), us[8 * j + 2 * i + 1], acc);
+				const float2 hf = half2_bits_to_float2(w4[i]);
+				acc = fmaf(hf.x, us[8 * j + 2 * i], acc);
+				acc = fmaf(hf.y, us[8 * j + 2 * i + 1], acc);
 			}
 		}
 		part[warp * n_samples + s] = acc;
@@ -583,20 +587,18 @@ int nrf_lerf_bwd_rows(const nrf_lerf_shape* shape, const void* packed, const nrf
 			U.n_lo = n_lo; U.n_hi = n_hi; U.stride_m = stride_m; U.stride_n = stride_n; U.out = out;
 			return U;
 		};
-		// dW_e0 [256, 160] = d a2^T [x 128 | g 32]: record columns 0..127 are W_e0's input columns 32..159, 128..159 its columns 0..31
-		{
-			dw::Unit& U = unit(0, kGradA2, kHid, 1, kSaveGX, kGeo + kIn, 0, 0, kIn, kGeo + kIn, 1, ge0 + kGeo);
-			U.n2_lo = kIn; U.n2_hi = kIn + kGeo; U.out2 = ge0;
-		}
-		// dW_s0 [256, 128] = d a1^T x: x = the first 128 columns of the [x | g] region
-		unit(0, kGradA1, kHid, 1, kSaveGX, kIn, (kGeo + kIn) * 128, 0, kIn, kIn, 1, gs0);
+		// all operands bf16: the gradient rows written by the chain, and the bf16 copies of the activations saved by the forward
+		// dW_e0 [256, 160] = d a2^T [geo 32 | x 128]
+		unit(0, kGradA2, kHid, 1, kSaveGX, kGeo + kIn, 0, 0, kGeo + kIn, kGeo + kIn, 1, ge0);
+		// dW_s0 [256, 128] = d a1^T x: x = columns 32..159 of the [geo | x] region
+		unit(0, kGradA1, kHid, 1, kSaveGX + (kGeo / 8) * 1024, kIn, (kGeo + kIn) * 128, 0, kIn, kIn, 1, gs0);
 		// dW_s1 [33, 256], roles swapped (M = input index): D[m, n] = sum h1[., m] d s[., n]; n < 32 -> row n + 1 (geo), n = 32 -> row 0 (sigma)
 		{
 			dw::Unit& U = unit(1, kSaveH1, kHid, 0, kGradS, kSigN, 0, 0, kGeo, 1, kHid, gs1 + kHid);
 			U.n2_lo = kGeo; U.n2_hi = kGeo + 1; U.out2 = gs1;
 		}
 		// P [256, 256] = (beta h2)^T h2
-		unit(0, kGradBH2, kHid, 1, kSaveH2, kHid, 0, 0, kHid, kHid, 1, w.gram);
+		unit(0, kGradBH2, kHid, 1, kSaveH2B, kHid, 0, 0, kHid, kHid, 1, w.gram);
 		T.count = c;
 		T.save_tile = kSaveTile;
 		T.grad_tile = kGradTile;

@@ -9,8 +9,9 @@
 //   * a K-major   B operand with MN = outputs, K = inputs  (forward:  D[rows, out] = A[rows, in]  * W^T), SBO 128, LBO N*16
 //   * an MN-major B operand with MN = inputs,  K = outputs (backward: D[rows, in]  = dY[rows, out] * W ), SBO N*16, LBO 128
 // so the gradient chain streams the forward blob and only the descriptors change (the mlp_nerf_layout.cuh scheme).
-// Two copies: fp16 (inference programs SIGMA / HIDDEN / RAW) and bf16 (training forward + gradient chain: gradients need fp32's exponent
-// range, and both operands of a tcgen05.mma kind::f16 weight-gradient product are kept in ONE 16-bit format).
+// Two copies: fp16 (the forward programs SIGMA / HIDDEN / RAW / TRAIN and the chain's G h2 product: activations are O(1) and keep 11 bits)
+// and bf16 (the gradient products of the chain: gradient rows need fp32's exponent range).  A and B of one tcgen05.mma kind::f16 must share
+// their 16-bit format (a mixed descriptor faults on B200), so the weight-gradient products dW = dY^T X read BF16 copies of the activations.
 #pragma once
 #include "tcgen05.cuh"
 #include "mlp_small_layout.cuh"   // pack_f16 / pack_bf16 (+ relu variants)
@@ -50,7 +51,7 @@ __host__ __device__ constexpr int layer_offset(int l)
 	return b;
 }
 constexpr int kWeightBytes = layer_offset(kLayers);             // 565 248: the fp16 copy of all six layers
-// the bf16 copy of S0, S1, E0, G (training forward, gradient chain), same per-layer sizes / offsets
+// the bf16 copy of S0, S1, E0 (+ G, unused) for the gradient chain, same per-layer sizes / offsets; W_e0's input columns reordered [x | geo]
 constexpr int kTrainBase = kWeightBytes;
 constexpr int kTrainBytes = layer_offset(4);                    // 303 104
 // W_e1 transposed, fp32 [256 k][512 n], follows the operand blobs (lerf_project_kernel reads it)
@@ -75,13 +76,13 @@ constexpr ModeTable make_mode(int mode)
 	ModeTable t{};
 	const int seq_sigma[2] = {0, 1}, seq_hidden[4] = {0, 1, 2, 3}, seq_raw[7] = {0, 1, 2, 4, 5, 4, 5}, seq_chain[4] = {3, 2, 1, 0};
 	t.n_groups = mode == kSigma ? 2 : (mode == kRaw ? 7 : 4);
-	const int base = (mode == kTrain || mode == kChain) ? kTrainBase : 0;
 	for (int g = 0; g < t.n_groups; g++)
 		t.group_layer[g] = mode == kSigma ? seq_sigma[g] : (mode == kRaw ? seq_raw[g] : (mode == kChain ? seq_chain[g] : seq_hidden[g]));
 	int i = 0;
 	for (int g = 0; g < t.n_groups; g++) {
 		const int l = t.group_layer[g];
-		int off = base + layer_offset(l);
+		// the chain reads G from the fp16 copy (its A operand h2 is fp16) and W_e0, W_s1, W_s0 from the bf16 copy (A operand = bf16 gradient rows)
+		int off = ((mode == kChain && l != 3) ? kTrainBase : 0) + layer_offset(l);
 		for (int s = 0; s < layer_stages(l); s++, i++) {
 			t.off[i] = off;
 			t.bytes[i] = stage_bytes(l, s);
@@ -97,7 +98,7 @@ static_assert(make_mode(kSigma).n_stages == 3 && make_mode(kHidden).n_stages == 
 // h2 tile records of the HIDDEN program (inference): [32 column chunks][128 rows][8 fp16] = 64 KB per 128-row tile; a warp store covers 512 contiguous bytes
 constexpr int kHiddenTile = 128 * kHid * 2;
 
-// ---- training records (bf16), one per 128-row tile, made of regions of C columns stored as [row half (2)][C/8 column chunks][64 rows][8 elements]:
+// ---- training records, one per 128-row tile, made of regions of C columns stored as [row half (2)][C/8 column chunks][64 rows][8 elements]:
 // a 64-row half of a region is contiguous and is at the same time the MN-major A operand (M = columns, K = rows) and the MN-major B operand
 // (N = columns, K = rows) of a weight-gradient product dW = dY^T X (SBO 1024, LBO 128) — the classic-NeRF record layout (mlp_nerf_layout.cuh).
 __host__ __device__ constexpr int region_bytes(int cols) { return 128 * cols * 2; }
@@ -105,14 +106,18 @@ __host__ __device__ constexpr uint32_t chunk_offset(int cols, int r, int chunk)
 {
 	return static_cast<uint32_t>((r >> 6) * (cols * 128) + chunk * 1024 + (r & 63) * 16);
 }
-// saved by the training forward: [x 128 | geo 32] (the input of le_net[0] in the training blob's column order), h1, h2, and the ReLU mask of h1 (one bit per unit: word c of a row
-// covers columns 32c .. 32c+31, bit i = column 32c + 2i, bit 16 + i = column 32c + 2i + 1 — the low / high halves of the i-th packed pair)
+// saved by the training forward: bf16 copies of [geo 32 | x 128] (the input of le_net[0]), h1 and h2 (B / A operands of the weight-gradient
+// products), h2 once more in fp16 (what the forward itself multiplied: the A operand of the chain's G h2 product and the source of the per-ray
+// sums, whose rounding the density gradient — a cancellation-prone residual of the compositing backward — amplifies), and the ReLU mask of h1
+// (one bit per unit: word c of a row covers columns 32c .. 32c+31, bit i = column 32c + 2i, bit 16 + i = column 32c + 2i + 1 — the low / high
+// halves of the i-th packed pair)
 constexpr int kSaveGX = 0;
 constexpr int kSaveH1 = kSaveGX + region_bytes(kGeo + kIn);
-constexpr int kSaveH2 = kSaveH1 + region_bytes(kHid);
-constexpr int kSaveBits1 = kSaveH2 + region_bytes(kHid);
-constexpr int kSaveTile = kSaveBits1 + 128 * 32;                 // 176 128 B per 128 rows
-// written by the gradient chain: d a2 (256), d s = [d geo 32 | d sigma | 0..] (48), d a1 (256), beta * h2 (256: A operand of the weighted Gram matrix)
+constexpr int kSaveH2 = kSaveH1 + region_bytes(kHid);             // fp16
+constexpr int kSaveH2B = kSaveH2 + region_bytes(kHid);            // bf16
+constexpr int kSaveBits1 = kSaveH2B + region_bytes(kHid);
+constexpr int kSaveTile = kSaveBits1 + 128 * 32;                 // 241 664 B per 128 rows
+// written by the gradient chain (bf16): d a2 (256), d s = [d geo 32 | d sigma | 0..] (48), d a1 (256), beta * h2 (256: A operand of the weighted Gram matrix)
 constexpr int kGradA2 = 0;
 constexpr int kGradS = kGradA2 + region_bytes(kHid);
 constexpr int kGradA1 = kGradS + region_bytes(kSigN);
@@ -124,6 +129,12 @@ __host__ __device__ constexpr uint32_t idesc16(int M, int N, bool bf16, int a_mn
 {
 	return (1u << 4) | (bf16 ? (1u << 7) | (1u << 10) : 0u) | (uint32_t(a_mn) << 15) | (uint32_t(b_mn) << 16) | (uint32_t(N >> 3) << 17) |
 	       (uint32_t(M >> 4) << 24);
+}
+__device__ __forceinline__ float2 half2_bits_to_float2(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+__device__ __forceinline__ uint32_t half2_bits_to_bf16x2(uint32_t w)
+{
+	const float2 f = half2_bits_to_float2(w);
+	return pack_bf16(f.x, f.y);
 }
 
 struct Weights {   // device pointers, torch Linear layout [out, in] row-major fp32, no biases (src/LeRF.cpp:12,15)

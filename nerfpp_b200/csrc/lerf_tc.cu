@@ -209,12 +209,13 @@ __device__ __forceinline__ float sumsq_d(uint32_t t_lane, int c0)
 	return s;
 }
 
-// TRAIN: relu(D) -> bf16 -> the h columns and the 256-column record region (region_row = the row's first chunk of the region, chunks 1 KB apart);
-// BITS: also the ReLU mask words of the row (8 x 32 bits, see lerf_layout.cuh)
-template <bool BITS>
-__device__ __forceinline__ void relu_to_h_train(uint32_t t_lane, uint8_t* __restrict__ region_row, uint32_t* __restrict__ bits_row)
+// TRAIN: relu(D) -> fp16 -> the h columns (the next layer's A operand); the row also goes to the bf16 record region (region_row = the row's first
+// chunk of the region, chunks 1 KB apart: operand of the weight-gradient products) and, H16, to the fp16 region as well; BITS: the ReLU mask words
+// of the row (8 x 32 bits, see lerf_layout.cuh)
+template <bool BITS, bool H16>
+__device__ __forceinline__ void relu_to_h_train(uint32_t t_lane, uint8_t* __restrict__ region_row, uint8_t* __restrict__ region16_row, uint32_t* __restrict__ bits_row)
 {
-	uint32_t acc0[32], acc1[32], a16[16], words[8];
+	uint32_t acc0[32], acc1[32], a16[16], r16[16], words[8];
 	tmem_ld32(t_lane + kColD, acc0);
 #pragma unroll
 	for (int c = 0; c < 8; c += 2) {
@@ -230,14 +231,17 @@ __device__ __forceinline__ void relu_to_h_train(uint32_t t_lane, uint8_t* __rest
 			uint32_t m = 0u;
 #pragma unroll
 			for (int i = 0; i < 16; i++) {
-				a16[i] = pack_bf16_relu(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+				a16[i] = pack_f16_relu(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+				r16[i] = pack_bf16_relu(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
 				if (BITS) m |= ((a16[i] & 0xFFFFu) ? (1u << i) : 0u) | ((a16[i] >> 16) ? (1u << (16 + i)) : 0u);
 			}
 			words[c + half] = m;
 			tmem_st16(t_lane + kColH + 16 * (c + half), a16);
 #pragma unroll
-			for (int i = 0; i < 4; i++)
-				*reinterpret_cast<uint4*>(region_row + (4 * (c + half) + i) * 1024) = make_uint4(a16[4 * i], a16[4 * i + 1], a16[4 * i + 2], a16[4 * i + 3]);
+			for (int i = 0; i < 4; i++) {
+				*reinterpret_cast<uint4*>(region_row + (4 * (c + half) + i) * 1024) = make_uint4(r16[4 * i], r16[4 * i + 1], r16[4 * i + 2], r16[4 * i + 3]);
+				if (H16) *reinterpret_cast<uint4*>(region16_row + (4 * (c + half) + i) * 1024) = make_uint4(a16[4 * i], a16[4 * i + 1], a16[4 * i + 2], a16[4 * i + 3]);
+			}
 		}
 	}
 	if (BITS) {
@@ -310,8 +314,7 @@ __global__ void __launch_bounds__(32 * (2 + 4 * HV), 1) lerf_fwd_tc_kernel(const
 	const ModeTable& mt = c_modes[MODE];
 	constexpr int CH = 8 / HV;               // 32-column accumulator chunks per epilogue warp
 	constexpr int PRE = 16 / HV;             // 16-byte pieces of the input row per epilogue thread
-	// TRAIN keeps the language net's input as [x 64 columns | geo 16 columns] (the order of the training blob's W_e0), inference as [geo | x]
-	constexpr uint32_t colEnc = MODE == kTrain ? 304u : kColEnc, colGeo = MODE == kTrain ? 368u : kColGeo;
+	constexpr uint32_t colEnc = kColEnc, colGeo = kColGeo;
 
 	if (warp == 1) {
 		if (lane == 0) {
@@ -357,9 +360,9 @@ __global__ void __launch_bounds__(32 * (2 + 4 * HV), 1) lerf_fwd_tc_kernel(const
 					fence_after();
 					const int l = mt.group_layer[grp];
 					const LayerInfo L = layer_info(l);
-					const uint32_t idesc = idesc16(128, L.N, MODE == kTrain, 0, 0);
+					const uint32_t idesc = idesc16(128, L.N, false, 0, 0);
 					const uint32_t lbo = L.N * 16;
-					uint32_t a_col = tmem + (l == 0 ? colEnc : (l == 2 ? (MODE == kTrain ? colEnc : colGeo) : L.a_col));
+					uint32_t a_col = tmem + L.a_col;
 					bool first = true;
 					const int ns = layer_stages(l);
 					for (int s = 0; s < ns; s++, g++) {
@@ -404,7 +407,7 @@ __global__ void __launch_bounds__(32 * (2 + 4 * HV), 1) lerf_fwd_tc_kernel(const
 			const int64_t r = tile * 128 + row;
 			const bool ok = r < n;
 			// ---- input: the 128 fp16 channels of the language hash grid, as they leave nrf_hash_encode_fwd (already in registers, see load_row)
-			// TRAIN: bf16 operands; every layer input also goes to the tile's record (hidden = the record base, lerf_layout.cuh)
+			// TRAIN: the HIDDEN program + every layer input also goes to the tile's record (hidden = the record base, lerf_layout.cuh)
 			uint8_t* const rec = MODE == kTrain ? hidden + tile * static_cast<int64_t>(kSaveTile) : nullptr;
 			{
 				uint32_t a16[16];
@@ -417,14 +420,10 @@ __global__ void __launch_bounds__(32 * (2 + 4 * HV), 1) lerf_fwd_tc_kernel(const
 					}
 					if (MODE == kTrain) {
 #pragma unroll
-						for (int i = 0; i < 16; i++) {
-							const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&a16[i]));
-							a16[i] = pack_bf16(f.x, f.y);
-						}
-#pragma unroll
-						for (int i = 0; i < 4; i++)      // x = columns 0..127 of the [x | geo] region: chunks 4h + i
-							*reinterpret_cast<uint4*>(rec + kSaveGX + chunk_offset(kGeo + kIn, row, 4 * h + i)) =
-								make_uint4(a16[4 * i], a16[4 * i + 1], a16[4 * i + 2], a16[4 * i + 3]);
+						for (int i = 0; i < 4; i++)      // x = columns 32..159 of the [geo | x] region (bf16 copy): chunks 4 + 4h + i
+							*reinterpret_cast<uint4*>(rec + kSaveGX + chunk_offset(kGeo + kIn, row, 4 + 4 * h + i)) =
+								make_uint4(half2_bits_to_bf16x2(a16[4 * i]), half2_bits_to_bf16x2(a16[4 * i + 1]), half2_bits_to_bf16x2(a16[4 * i + 2]),
+									half2_bits_to_bf16x2(a16[4 * i + 3]));
 					}
 					tmem_st16(t_lane + colEnc + 4 * PRE * half + 16 * h, a16);
 				}
@@ -435,7 +434,7 @@ __global__ void __launch_bounds__(32 * (2 + 4 * HV), 1) lerf_fwd_tc_kernel(const
 			mbar_wait(&sm.d_ready, pd);
 			pd ^= 1u;
 			fence_after();
-			if (MODE == kTrain) relu_to_h_train<true>(t_lane, rec + kSaveH1 + chunk_offset(kHid, row, 0), reinterpret_cast<uint32_t*>(rec + kSaveBits1 + row * 32));
+			if (MODE == kTrain) relu_to_h_train<true, false>(t_lane, rec + kSaveH1 + chunk_offset(kHid, row, 0), nullptr, reinterpret_cast<uint32_t*>(rec + kSaveBits1 + row * 32));
 			else relu_to_h<false, CH>(t_lane, nullptr, c0);
 			publish(&sm.a_ready, lane);
 			if (MODE == kSigma) load_row(tile + gridDim.x);
@@ -453,14 +452,14 @@ __global__ void __launch_bounds__(32 * (2 + 4 * HV), 1) lerf_fwd_tc_kernel(const
 					tmem_ld32(t_lane + kColD2, acc);
 					tmem_ld_wait_for(acc);
 #pragma unroll
-					for (int i = 0; i < 16; i++)
-						a16[i] = MODE == kTrain ? pack_bf16(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]))
-						                        : pack_f16(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+					for (int i = 0; i < 16; i++) a16[i] = pack_f16(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
 					tmem_st16(t_lane + colGeo, a16);
 					if (MODE == kTrain) {
 #pragma unroll
-						for (int i = 0; i < 4; i++)      // geo = columns 128..159 of the [x | geo] region
-							*reinterpret_cast<uint4*>(rec + kSaveGX + chunk_offset(kGeo + kIn, row, 16 + i)) = make_uint4(a16[4 * i], a16[4 * i + 1], a16[4 * i + 2], a16[4 * i + 3]);
+						for (int i = 0; i < 4; i++)      // geo = columns 0..31 of the [geo | x] region (bf16 copy)
+							*reinterpret_cast<uint4*>(rec + kSaveGX + chunk_offset(kGeo + kIn, row, i)) =
+								make_uint4(pack_bf16(__uint_as_float(acc[8 * i]), __uint_as_float(acc[8 * i + 1])), pack_bf16(__uint_as_float(acc[8 * i + 2]), __uint_as_float(acc[8 * i + 3])),
+									pack_bf16(__uint_as_float(acc[8 * i + 4]), __uint_as_float(acc[8 * i + 5])), pack_bf16(__uint_as_float(acc[8 * i + 6]), __uint_as_float(acc[8 * i + 7])));
 					}
 				}
 				tmem_ld_wait_for4(c4);
@@ -478,7 +477,7 @@ __global__ void __launch_bounds__(32 * (2 + 4 * HV), 1) lerf_fwd_tc_kernel(const
 			pd ^= 1u;
 			fence_after();
 			if (MODE == kHidden) relu_to_h<true, CH>(t_lane, hidden + tile * kHiddenTile + row * 16, c0);
-			else if (MODE == kTrain) relu_to_h_train<false>(t_lane, rec + kSaveH2 + chunk_offset(kHid, row, 0), nullptr);
+			else if (MODE == kTrain) relu_to_h_train<false, true>(t_lane, rec + kSaveH2B + chunk_offset(kHid, row, 0), rec + kSaveH2 + chunk_offset(kHid, row, 0), nullptr);
 			else relu_to_h<false, CH>(t_lane, nullptr, c0);
 			publish(&sm.a_ready, lane);
 			if (MODE == kHidden || MODE == kTrain) load_row(tile + gridDim.x);
@@ -488,7 +487,7 @@ __global__ void __launch_bounds__(32 * (2 + 4 * HV), 1) lerf_fwd_tc_kernel(const
 				mbar_wait(&sm.d_ready, pd);
 				pd ^= 1u;
 				fence_after();
-				float qv = dot_d_h<CH, MODE == kTrain>(t_lane, c0) * __ldg(reinterpret_cast<const float*>(blob + kScaleBase));     // G travels divided by this power of two
+				float qv = dot_d_h<CH>(t_lane, c0) * __ldg(reinterpret_cast<const float*>(blob + kScaleBase));     // G travels divided by this power of two
 				if (HV > 1) {
 					if (half != 0) sm.xpart[0][row] = qv;
 					epilogue_sync<HV>();
@@ -579,7 +578,7 @@ static int launch(const nrf_lerf_shape* shape, const void* packed, const void* e
 // (src/LeRFRenderer.h:45-54 applied to the normalised embeddings of src/LeRF.cpp:105).
 
 // one block per ray, 8 warps; warp v owns column chunks v, v+8, v+16, v+24 of the h2 records; lane = sample within a group of 32
-// TRAIN: h2 comes from the bf16 training records (region layout, lerf_layout.cuh) instead of the fp16 inference records
+// TRAIN: h2 comes from the training records (region layout, lerf_layout.cuh) instead of the inference records
 template <bool TRAIN>
 __global__ void __launch_bounds__(256) lerf_hsum_kernel(const float* __restrict__ weights, const uint4* __restrict__ hidden, const float* __restrict__ q,
 	int32_t n_samples, float* __restrict__ hsum)
@@ -602,8 +601,7 @@ __global__ void __launch_bounds__(256) lerf_hsum_kernel(const float* __restrict_
 			const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
 			for (int i = 0; i < 4; i++) {
-				const float2 f = TRAIN ? make_float2(__uint_as_float(w4[i] << 16), __uint_as_float(w4[i] & 0xFFFF0000u))
-				                       : __half22float2(*reinterpret_cast<const __half2*>(&w4[i]));
+				const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[i]));
 				acc[2 * i] = fmaf(c, f.x, acc[2 * i]);
 				acc[2 * i + 1] = fmaf(c, f.y, acc[2 * i + 1]);
 			}

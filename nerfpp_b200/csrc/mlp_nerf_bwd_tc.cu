@@ -426,6 +426,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_nerf_bwd_dw_kernel(const _
 				if (hi <= lo) continue;
 				{ DW_T0(); mbar_wait(&sm.d_free, (seg & 1u) ^ 1u); DW_ADD(1); }         // the accumulators of the previous segment have been read out
 				fence_after();
+				// both operands bf16, MN-major.  (A and B of a tcgen05.mma kind::f16 must carry the SAME 16-bit format: an instruction descriptor that
+				// mixes bf16 gradient rows with fp16 activation rows raises an illegal-instruction fault on B200, gpurun_out/r2i.)
 				const uint32_t idesc = idesc_16(128, U.b_cols, true, 1, 1);
 				const int mblocks = U.a_cols / 128;
 				for (int64_t i = lo; i < hi; i++, g++) {

@@ -406,27 +406,32 @@ def lerf_backward_fused_form(x: torch.Tensor, sigma_w, le_w, z: torch.Tensor, ra
     never formed; everything per sample is 256-wide.  x [R,S,C] (the hash encoding of the fine pass), 2-layer nets (BASELINE C5).
     Explicit formulas, no autograd except for the compositing weights (an existing kernel, nrf_composite_bwd).  Returns d loss / d
     {sigma_w0, sigma_w1, le_w0, le_w1, x}; tests compare it with autograd through lerf_forward + raw_to_le_outputs.
-    emulate=True additionally rounds to bf16 what the sm_100a kernels store in bf16 (h1, geo, h2, the G operand, and the gradient rows
-    d a2, d s, d a1, beta h2, d x), so that the ReLU active sets are the kernels' own (csrc/lerf_tc.cu TRAIN program, csrc/lerf_bwd_tc.cu);
-    the caller rounds x and the three tensor-core weight matrices."""
+    emulate=True additionally applies the rounding points of the sm_100a kernels (csrc/lerf_tc.cu TRAIN program, csrc/lerf_bwd_tc.cu), so that the
+    ReLU active sets are the kernels' own: the forward runs on fp16 operands (W_s0, W_s1, W_e0, G / 2^k and h1, geo, h2), the gradient chain
+    on bf16 operands (W_e0, W_s1, W_s0 and the gradient rows d a2, d s, d a1, beta h2, d x), the weight-gradient products on bf16 copies of the
+    activations ([geo | x], h1, h2 rounded from the fp32 accumulators); W_e1 enters in fp32.  Pass the UNROUNDED weights; x must hold
+    fp16-representable values (it is the fp16 output of the hash encoder)."""
+    rh = (lambda t: t.float().half().to(t.dtype)) if emulate else (lambda t: t)
     rb = (lambda t: t.float().bfloat16().to(t.dtype)) if emulate else (lambda t: t)
     r_, s_, c_ = x.shape
     xf = x.reshape(-1, c_)
     w_s0, w_s1 = sigma_w
     w_e0, w_e1 = le_w
-    a1 = xf @ w_s0.t()
-    h1 = rb(torch.relu(a1))
-    sg = h1 @ w_s1.t()                                            # [sigma | geo]
-    geo = rb(sg[:, 1:])
+    a1 = xf @ rh(w_s0).t()
+    h1 = rh(torch.relu(a1))
+    sg = h1 @ rh(w_s1).t()                                        # [sigma | geo]
+    geo = rh(sg[:, 1:])
     gx = torch.cat([geo, xf], -1)
-    a2 = gx @ w_e0.t()
-    h2 = rb(torch.relu(a2))
+    a2 = gx @ rh(w_e0).t()
+    h2 = rh(torch.relu(a2))
+    # bf16 copies for the weight-gradient products (identical to the values above when not emulating)
+    h1_b, gx_b, h2_b = rb(torch.relu(a1)), torch.cat([rb(sg[:, 1:]), rb(xf)], -1), rb(torch.relu(a2))
     gram = w_e1.t() @ w_e1                                        # G
-    if emulate:                                                   # the operand travels as bf16(G / 2^k), 2^k >= max diag / 256 (lerf_gscale_kernel)
+    if emulate:                                                   # the operand travels as fp16(G / 2^k), 2^k >= max diag / 256 (lerf_gscale_kernel)
         gs = 1.0
         while float(gram.diagonal().max()) > 256.0 * gs:
             gs *= 2.0
-        gram = rb(gram / gs) * gs
+        gram = rh(gram / gs) * gs
     t = h2 @ gram                                                 # G h2 (symmetric)
     n2 = (t * h2).sum(-1)                                         # |e|^2 = h2^T G h2
     n = n2.clamp_min(0).sqrt().clamp_min(1e-8)
@@ -449,15 +454,15 @@ def lerf_backward_fused_form(x: torch.Tensor, sigma_w, le_w, z: torch.Tensor, ra
     cf, dwf = c.reshape(-1), d_w.reshape(-1)
     beta = cf * dwf / n                                                                              # W_e1^T e_hat = G h2 / n
     d_h2 = cf[:, None] * u_rows - beta[:, None] * t
-    d_we1 = d_e.t() @ hs - w_e1 @ (rb(beta[:, None] * h2).t() @ h2)                                 # outer term - W_e1 * weighted Gram
+    d_we1 = d_e.t() @ hs - w_e1 @ (rb(beta[:, None] * h2).t() @ h2_b)                               # outer term - W_e1 * weighted Gram
     d_a2 = rb(d_h2 * ((h2 > 0) if emulate else (a2 > 0)))
-    d_we0 = d_a2.t() @ gx
-    d_gx = d_a2 @ w_e0
+    d_we0 = d_a2.t() @ gx_b
+    d_gx = d_a2 @ rb(w_e0)
     d_s = rb(torch.cat([d_sigma.reshape(-1, 1), d_gx[:, :sg.shape[1] - 1]], -1))
-    d_ws1 = d_s.t() @ h1
-    d_a1 = rb((d_s @ w_s1) * ((h1 > 0) if emulate else (a1 > 0)))
-    d_ws0 = d_a1.t() @ xf
-    d_x = rb(d_a1 @ w_s0 + d_gx[:, sg.shape[1] - 1:])
+    d_ws1 = d_s.t() @ h1_b
+    d_a1 = rb((d_s @ rb(w_s1)) * ((h1 > 0) if emulate else (a1 > 0)))
+    d_ws0 = d_a1.t() @ gx_b[:, sg.shape[1] - 1:]
+    d_x = rb(d_a1 @ rb(w_s0) + d_gx[:, sg.shape[1] - 1:])
     return {"sigma_w0": d_ws0, "sigma_w1": d_ws1, "le_w0": d_we0, "le_w1": d_we1, "x": d_x.reshape(r_, s_, c_), "rendered": rendered}
 
 

@@ -139,7 +139,7 @@ def test_fused_training_node_matches_libtorch_autograd(host):
     print("fused vs LibTorch autograd (rel, cos):", {k: (round(r, 4), round(c, 5)) for k, (r, c) in stats.items()})
     for name, (rel, cos) in stats.items():
         # bf16 operands against fp32 SGEMMs, different ReLU active sets near zero (see tests/test_gpu_lerf_train.py): direction + scale
-        assert cos >= 0.99 and rel <= 1.5e-1, (name, rel, cos)
+        assert cos >= 0.995 and rel <= 8e-2, (name, rel, cos)
 
 
 def test_training_steps_track_the_reference(host, ref_cuda):

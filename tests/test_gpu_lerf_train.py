@@ -1,7 +1,7 @@
 """GPU parity of the fused LeRF training path (nrf_lerf_fwd_train, nrf_lerf_render_embedding_train, nrf_lerf_bwd_rays, nrf_lerf_bwd_rows) through the
 C ABI against the oracle: oracle/restate.py:lerf_backward_fused_form — pinned in fp64 against autograd through the reference's own LeRF +
 LeRFRenderer::RawToLEOutputs + the language loss (tests/test_oracle_pin.py, tests/golden/lerf_grads.npz).  bf16 tensor-core arithmetic: the
-tolerance is the north star's bf16 figure (rel 1e-2) on the forward and 2e-2 norm-wise on the gradients."""
+tolerance is the north star's bf16 figure (rel 1e-2) on the forward and on every gradient at the kernels' rounding points."""
 import math
 
 import numpy as np
@@ -45,37 +45,33 @@ def _case(r, s, seed, sigma_gain=4.0):
     return w, x, z, d, target
 
 
-def _bf16(t):
-    return t.float().bfloat16().double()
-
-
 @pytest.mark.parametrize("r,s,seed", [(64, 48, 0), (37, 192, 1), (5, 24, 2)])
 def test_fused_training_forward_and_backward_match_the_oracle(r, s, seed):
-    """Two references, both the fp64 oracle on bf16-rounded operands (x, W_s0, W_s1, W_e0 — what the tensor cores read; W_e1 enters in fp32):
-      * emulate=True  — h1, geo, h2, the G operand and the gradient rows also rounded to bf16 where the kernels store them, so the ReLU active
-        sets are the kernels' own: rel 1e-2 norm-wise on every gradient (the north star's bf16 figure);
-      * emulate=False — exact.  The bf16 rounding of h1 / geo flips the ~0.1 % of h2 units whose pre-activation is within rounding of zero; each
-        flipped unit is an O(1) error of its own gradient, i.e. noise of order sqrt(flipped share) — a direction check (cosine), as for the
-        classic MLP (tests/test_gpu_mlp_nerf.py).
+    """Two references, both the fp64 oracle (oracle/restate.py:lerf_backward_fused_form) on the same fp16 encodings:
+      * emulate=True  — with the kernels' rounding points (fp16 operands and stored activations in the forward, bf16 operands and gradient rows in
+        the chain), so the ReLU active sets are the kernels' own: rel 1e-2 norm-wise on every gradient (the north star's bf16 figure);
+      * emulate=False — exact.  Rounding h1 / geo flips the h2 units whose pre-activation is within rounding of zero; each flipped unit is an O(1)
+        error of its own gradient, i.e. noise of order sqrt(flipped share), and the density gradient is a cancellation-prone residual of the
+        compositing backward — a direction + scale check (cosine / norm-wise 1e-1), as for the classic MLP (tests/test_gpu_mlp_nerf.py).
     Ragged tile counts (rows % 128 != 0) included."""
     w, x, z, d, target = _case(r, s, seed)
     loss, out, grads, d_x = _run(x, w, z, d, target)
-    wq = [_bf16(w[0]), _bf16(w[1]), _bf16(w[2]), w[3].double()]
-    ref = O.lerf_backward_fused_form(_bf16(x), wq[:2], wq[2:], z.double(), d.double(), target.double())
-    emu = O.lerf_backward_fused_form(_bf16(x), wq[:2], wq[2:], z.double(), d.double(), target.double(), emulate=True)
+    wd = [t.double() for t in w]
+    ref = O.lerf_backward_fused_form(x.double(), wd[:2], wd[2:], z.double(), d.double(), target.double())
+    emu = O.lerf_backward_fused_form(x.double(), wd[:2], wd[2:], z.double(), d.double(), target.double(), emulate=True)
     ref_loss = float(O.lerf_language_loss(ref["rendered"], target.double()))
     cos = torch.nn.functional.cosine_similarity(out["rendered"].double().cpu(), ref["rendered"], dim=-1)
-    print(f"R {r} S {s}: loss {loss:.6f} vs {ref_loss:.6f}; rendered cosine min {float(cos.min()):.6f}\n   vs exact fp64:   "
-          + ", ".join(f"{k} {_rel(grads[k], ref[k]):.2e}" for k in KEYS) + f", x {_rel(d_x, ref['x']):.2e}\n   vs bf16 points:  "
+    print(f"R {r} S {s}: loss {loss:.6f} vs {ref_loss:.6f}; rendered cosine min {float(cos.min()):.6f}\n   vs exact fp64:      "
+          + ", ".join(f"{k} {_rel(grads[k], ref[k]):.2e}" for k in KEYS) + f", x {_rel(d_x, ref['x']):.2e}\n   vs rounding points: "
           + ", ".join(f"{k} {_rel(grads[k], emu[k]):.2e}" for k in KEYS) + f", x {_rel(d_x, emu['x']):.2e}")
     assert abs(loss - ref_loss) <= 1e-2 * abs(ref_loss)
     assert float(cos.min()) > 1 - 1e-3
     assert float((out["rendered"].double().cpu() - ref["rendered"]).abs().max()) <= 1e-2 * float(ref["rendered"].abs().max())
     for k in KEYS:
         assert _rel(grads[k], emu[k]) <= 1e-2, (k, _rel(grads[k], emu[k]))
-        assert float((grads[k] * ref[k]).sum() / (grads[k].norm() * ref[k].norm())) >= 0.99, k
+        assert float((grads[k] * ref[k]).sum() / (grads[k].norm() * ref[k].norm())) >= 0.995 and _rel(grads[k], ref[k]) <= 1e-1, k
     assert _rel(d_x, emu["x"]) <= 1e-2
-    assert float((d_x * ref["x"]).sum() / (d_x.norm() * ref["x"].norm())) >= 0.99
+    assert float((d_x * ref["x"]).sum() / (d_x.norm() * ref["x"].norm())) >= 0.995 and _rel(d_x, ref["x"]) <= 1e-1
 
 
 def test_against_the_reference_autograd_fixture(golden):
