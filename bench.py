@@ -568,25 +568,40 @@ def main() -> None:
         out = {"ms_total": parallel.max_over_ranks(e0.elapsed_time(e1), world, dev), "loss": float(model.loss), "launches_per_step": launches_per_step,
                "dev_batches": dev_batches, "use_graph": use_graph}
         if with_e2e:
-            host_batches = [tuple(t.cpu().pin_memory() for t in b) for b in dev_batches]
-            stage = tuple(torch.empty_like(t) for t in dev_batches[0])
+            # the public call with HOST inputs: what the host owns per step is the list of sampled pixels (NeRFDataset::get_batch draws them,
+            # src/NeRFDataset.cpp:154-155); rays (GetRayBatch, :109-144) and targets (the image gather, :156) are formed on the device inside the
+            # step's first kernel from the resident training view (HashNeRF.set_camera).  Pinned int32 [R,2] H2D + a D2H read of the loss, every step.
+            from nerfpp_b200.pipeline import synthetic_pixels, synthetic_view
+            K_view, c2w_view = synthetic_view(800, 800)
+            image = torch.rand(800, 800, 3, generator=torch.Generator().manual_seed(77)).to(dev)
+            model.set_camera(image, K_view, c2w_view)
+            host_pix = [synthetic_pixels(rays_per_gpu, 800, 800, seed=seed0 + 3000 + 1000 * rank + i).pin_memory() for i in range(pool)]
+            if use_graph:
+                model.capture_train_step(rays_per_gpu, world, lambda g: parallel.allreduce_gradients(g, world), pixels=True)
+                pstep = lambda hb: model.train_step_graph(hb)   # noqa: E731 - copies the pinned pixel list into its static input
+            else:
+                stage_pix = torch.empty((rays_per_gpu, 2), dtype=torch.int32, device=dev)
+
+                def pstep(hb):
+                    stage_pix.copy_(hb, non_blocking=True)
+                    model.forward_backward(stage_pix)
+                    if model.peer is not None:
+                        model.optimizer_step_sharded()
+                    else:
+                        model.optimizer_step(grad_scale=parallel.allreduce_gradients(model.grads, world))
+            for i in range(3):
+                pstep(host_pix[i % pool])
             sync_all()
             e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e2.record()
             loss_host = 0.0
             for i in range(steps):
-                hb = host_batches[i % pool]
-                if use_graph:
-                    step(hb)                    # train_step_graph copies the pinned host rays/targets into its static inputs
-                else:
-                    for dst, src in zip(stage, hb):
-                        dst.copy_(src, non_blocking=True)
-                    step(stage)
+                pstep(host_pix[i % pool])
                 loss_host = float(model.loss)   # device -> host read of the step's result
             e3.record()
             sync_all()
             out.update(ms_e2e=parallel.max_over_ranks(e2.elapsed_time(e3), world, dev), loss_e2e=loss_host,
-                       h2d=sum(t.numel() * t.element_size() for t in host_batches[0]))
+                       h2d=host_pix[0].numel() * host_pix[0].element_size())
         return out
 
     # ---- headline: weak scaling, R rays per GPU (BASELINE C2 at N=1; C3's per-GPU share at N=8)
@@ -804,7 +819,9 @@ def main() -> None:
                    "precision": "fp16 hash table reads / encodings, bf16 tensor-core MLP with fp32 accumulate, fp32 everything else",
                    "reuse_coarse_rows": bool(model.reuse_coarse_rows)},
         "e2e": {"value": rays_total / (ms_e2e / 1e3), "unit": "rays/s", "h2d_bytes_per_step": head["h2d"], "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "input": "pinned-host int32 [R,2] pixel coordinates of the step's batch; rays (GetRayBatch) and targets (image gather) are formed on the "
+                         "device by the step's first kernel from the resident 800x800 training view"},
         "gpu_launches": launches * world, "graph_replay": use_graph, "kernels_per_step": launches_per_step, "roofline": roofline,
         "roofline_tensor": roofline_tensor, "roofline_render_ops": roofline_render_ops, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "kernels_ms_per_step": {k: [round(t, 4) for t in v] for k, v in sorted(per_launch.items(), key=lambda kv: -sum(kv[1]))},

@@ -295,6 +295,20 @@ int nrf_ray_setup(const float* rays_o, const float* rays_d, int64_t n_rays, cons
                   const float* t_vals, int32_t n_samples, int32_t lin_disp, int32_t sh_degree, float* ray_batch, float* z, float* ray_sh,
                   float* zero_scalar, nrf_stream stream);
 
+/* NeRFDataset::GetRayBatch (src/NeRFDataset.cpp:109-144) and the target gather of NeRFDataset::get_batch (:156) on the device: pix_hw int32
+ * [R,2] = (row, column) of every sampled pixel (the reference draws them with torch::randint, :154-155) -> rays_o, rays_d [R,3] (the
+ * GetRays arithmetic at that pixel, bit for bit) and, when image fp32 [img_h, img_w, img_c] is given, target [R, img_c] = image[row, col].
+ * cone_angle_host (nullable): the scalar the reference returns, (1/fx + 1/fy) / 2 (:136-141). */
+int nrf_ray_batch(const int32_t* pix_hw, int64_t n_rays, const float* K_host, const float* c2w_host, const float* image, int32_t img_h,
+                  int32_t img_w, int32_t img_c, float* rays_o, float* rays_d, float* target, float* cone_angle_host, nrf_stream stream);
+
+/* nrf_ray_batch + nrf_ray_setup in ONE launch: a training step then needs (pixel indices, K, c2w) instead of host-generated rays and
+ * targets.  rays_o / rays_d / target are OUTPUTS (the compositing and loss kernels read them). */
+int nrf_ray_setup_pixels(const int32_t* pix_hw, int64_t n_rays, const float* K_host, const float* c2w_host, const float* image, int32_t img_h,
+                         int32_t img_w, int32_t img_c, const float* bbox_host, float near_plane, const float* t_vals, int32_t n_samples,
+                         int32_t lin_disp, int32_t sh_degree, float* rays_o, float* rays_d, float* target, float* ray_batch, float* z,
+                         float* ray_sh, float* zero_scalar, nrf_stream stream);
+
 /* z = near*(1-t)+far*t (or the lin_disp variant), src/NeRFRenderer.h:393-402.  t_vals [S] device. */
 int nrf_z_sample(const float* ray_batch, int32_t ray_stride, const float* t_vals, int64_t n_rays, int32_t n_samples,
                  int32_t lin_disp, float* z, nrf_stream stream);

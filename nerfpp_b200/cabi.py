@@ -108,6 +108,9 @@ SIGNATURES = {
     "nrf_get_rays": (c_int32, [c_int32, c_int32, POINTER(c_float), POINTER(c_float), c_int32, c_int32, _P, _P, _P]),
     "nrf_rays_prepare": (c_int32, [_P, _P, c_int64, POINTER(c_float), c_float, c_int32, _P, _P]),
     "nrf_ray_setup": (c_int32, [_P, _P, c_int64, POINTER(c_float), c_float, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P]),
+    "nrf_ray_batch": (c_int32, [_P, c_int64, POINTER(c_float), POINTER(c_float), _P, c_int32, c_int32, c_int32, _P, _P, _P, POINTER(c_float), _P]),
+    "nrf_ray_setup_pixels": (c_int32, [_P, c_int64, POINTER(c_float), POINTER(c_float), _P, c_int32, c_int32, c_int32, POINTER(c_float), c_float, _P, c_int32,
+                                       c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nrf_z_sample": (c_int32, [_P, c_int32, _P, c_int64, c_int32, c_int32, _P, _P]),
     "nrf_sample_points": (c_int32, [_P, c_int32, _P, c_int64, c_int32, _P, _P]),
     "nrf_tangent_scatter": (c_int32, [_P, _P, _P, c_int32, _P, c_int32, _P, _P, POINTER(c_float), c_int64, c_int32, _P]),

@@ -14,21 +14,46 @@ struct Cam {
 	float m[12];  // c2w[:3,:4] row-major
 };
 
+// GetDirections + the rotation into the world frame for ONE pixel (src/RayUtils.h:5-32; NeRFDataset::GetRayBatch, src/NeRFDataset.cpp:117-131,
+// is the same expression on a list of pixel coordinates)
+__device__ __forceinline__ void pixel_ray(const Cam& c, int py, int px, float (&o)[3], float (&d)[3])
+{
+	const float dx = __fdiv_rn(__fsub_rn(static_cast<float>(px), c.cx), c.fx);
+	const float dy = -__fdiv_rn(__fsub_rn(static_cast<float>(py), c.cy), c.fy);
+	const float dz = -1.f;
+#pragma unroll
+	for (int r = 0; r < 3; r++) {
+		d[r] = __fadd_rn(__fadd_rn(__fmul_rn(dx, c.m[r * 4 + 0]), __fmul_rn(dy, c.m[r * 4 + 1])), __fmul_rn(dz, c.m[r * 4 + 2]));
+		o[r] = c.m[r * 4 + 3];
+	}
+}
+
 __global__ void __launch_bounds__(256) get_rays_kernel(Cam c, int w, int row_begin, int64_t n, float* __restrict__ rays_o, float* __restrict__ rays_d)
 {
 	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const int py = row_begin + static_cast<int>(i / w), px = static_cast<int>(i % w);
-	// GetDirections (src/RayUtils.h:5-21)
-	const float dx = __fdiv_rn(__fsub_rn(static_cast<float>(px), c.cx), c.fx);
-	const float dy = -__fdiv_rn(__fsub_rn(static_cast<float>(py), c.cy), c.fy);
-	const float dz = -1.f;
-	// rays_d = sum(dirs[..., None, :] * c2w[:3,:3], -1) (src/RayUtils.h:28-32)
+	// GetDirections (src/RayUtils.h:5-21), rays_d = sum(dirs[..., None, :] * c2w[:3,:3], -1) (:28-32)
+	float o[3], d[3];
+	pixel_ray(c, py, px, o, d);
 #pragma unroll
-	for (int r = 0; r < 3; r++) {
-		const float v = __fadd_rn(__fadd_rn(__fmul_rn(dx, c.m[r * 4 + 0]), __fmul_rn(dy, c.m[r * 4 + 1])), __fmul_rn(dz, c.m[r * 4 + 2]));
-		rays_d[i * 3 + r] = v;
-		rays_o[i * 3 + r] = c.m[r * 4 + 3];
+	for (int r = 0; r < 3; r++) { rays_d[i * 3 + r] = d[r]; rays_o[i * 3 + r] = o[r]; }
+}
+
+// NeRFDataset::GetRayBatch (src/NeRFDataset.cpp:109-144) and the target gather of get_batch (:156: CurrentImage.index({rand_h, rand_w}))
+__global__ void __launch_bounds__(256) ray_batch_kernel(Cam c, const int32_t* __restrict__ pix_hw, int64_t n, const float* __restrict__ image, int img_w, int img_c,
+	float* __restrict__ rays_o, float* __restrict__ rays_d, float* __restrict__ target)
+{
+	const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const int py = pix_hw[2 * i], px = pix_hw[2 * i + 1];
+	float o[3], d[3];
+	pixel_ray(c, py, px, o, d);
+#pragma unroll
+	for (int r = 0; r < 3; r++) { rays_o[i * 3 + r] = o[r]; rays_d[i * 3 + r] = d[r]; }
+	if (image && target) {
+		const float* src = image + (static_cast<int64_t>(py) * img_w + px) * img_c;
+		for (int k = 0; k < img_c; k++) target[i * img_c + k] = __ldg(src + k);
 	}
 }
 
@@ -102,8 +127,20 @@ __global__ void __launch_bounds__(256) z_sample_kernel(const float* __restrict__
 // step, the memset of the loss accumulator).  One thread per (ray, sample): each recomputes its ray's slab test (a dozen flops, the same
 // operations in the same order, hence the same near / far) and writes its z; the thread of sample 0 also writes the ray's [o, d, near,
 // far, viewdirs] row and its SH basis.  Bit-identical to nrf_rays_prepare + nrf_z_sample + nrf_sh_encode_fwd.
-template <int DEG>
-__global__ void __launch_bounds__(256) ray_setup_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, int64_t R, Box box,
+// PIXELS: the rays come from pixel coordinates + the camera (ray_batch_kernel's arithmetic) instead of rays_o / rays_d arrays, which are then
+// OUTPUTS (the compositing kernels read rays_d), as is the gathered target.
+struct PixelSrc {
+	Cam cam;
+	const int32_t* pix_hw;
+	const float* image;
+	int img_w, img_c;
+	float* rays_o_out;
+	float* rays_d_out;
+	float* target_out;
+};
+
+template <int DEG, bool PIXELS>
+__global__ void __launch_bounds__(256) ray_setup_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, PixelSrc ps, int64_t R, Box box,
 	float near_plane, const float* __restrict__ t_vals, int S, int lin_disp, float* __restrict__ ray_batch, float* __restrict__ z,
 	float* __restrict__ ray_sh, float* __restrict__ zero_scalar)
 {
@@ -113,8 +150,21 @@ __global__ void __launch_bounds__(256) ray_setup_kernel(const float* __restrict_
 	const int64_t ray = e / S;
 	const int s = static_cast<int>(e % S);
 	float o[3], d[3], vd[3], tnear, tfar;
+	if (PIXELS) {
+		const int py = ps.pix_hw[2 * ray], px = ps.pix_hw[2 * ray + 1];
+		pixel_ray(ps.cam, py, px, o, d);
+		if (s == 0) {
 #pragma unroll
-	for (int k = 0; k < 3; k++) { o[k] = rays_o[ray * 3 + k]; d[k] = rays_d[ray * 3 + k]; }
+			for (int k = 0; k < 3; k++) { ps.rays_o_out[ray * 3 + k] = o[k]; ps.rays_d_out[ray * 3 + k] = d[k]; }
+			if (ps.image && ps.target_out) {
+				const float* src = ps.image + (static_cast<int64_t>(py) * ps.img_w + px) * ps.img_c;
+				for (int k = 0; k < ps.img_c; k++) ps.target_out[ray * ps.img_c + k] = __ldg(src + k);
+			}
+		}
+	} else {
+#pragma unroll
+		for (int k = 0; k < 3; k++) { o[k] = rays_o[ray * 3 + k]; d[k] = rays_d[ray * 3 + k]; }
+	}
 	prepare_ray(o, d, box, near_plane, tnear, tfar, vd);
 	z[e] = z_value(tnear, tfar, t_vals[s], lin_disp);
 	if (s == 0) {
@@ -200,6 +250,12 @@ __global__ void __launch_bounds__(256) tangent_scatter_kernel(float* __restrict_
 
 using namespace nrf;
 
+static void fill_cam(Cam& c, const float* K_host, const float* c2w_host)
+{
+	c.fx = K_host[0]; c.cx = K_host[2]; c.fy = K_host[4]; c.cy = K_host[5];
+	for (int i = 0; i < 12; i++) c.m[i] = c2w_host[i];
+}
+
 extern "C" {
 
 int nrf_get_rays(int32_t h, int32_t w, const float* K_host, const float* c2w_host, int32_t row_begin, int32_t row_end,
@@ -211,8 +267,7 @@ int nrf_get_rays(int32_t h, int32_t w, const float* K_host, const float* c2w_hos
 	if (n == 0) return NRF_OK;
 	NRF_REQUIRE(rays_o && rays_d, "null output");
 	Cam c;
-	c.fx = K_host[0]; c.cx = K_host[2]; c.fy = K_host[4]; c.cy = K_host[5];
-	for (int i = 0; i < 12; i++) c.m[i] = c2w_host[i];
+	fill_cam(c, K_host, c2w_host);
 	get_rays_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(c, w, row_begin, n, rays_o, rays_d);
 	NRF_CHECK_LAUNCH("get_rays_kernel");
 	return NRF_OK;
@@ -232,25 +287,65 @@ int nrf_rays_prepare(const float* rays_o, const float* rays_d, int64_t n_rays, c
 	return NRF_OK;
 }
 
-int nrf_ray_setup(const float* rays_o, const float* rays_d, int64_t n_rays, const float* bbox_host, float near_plane, const float* t_vals,
-	int32_t n_samples, int32_t lin_disp, int32_t sh_degree, float* ray_batch, float* z, float* ray_sh, float* zero_scalar, nrf_stream stream)
+int nrf_ray_batch(const int32_t* pix_hw, int64_t n_rays, const float* K_host, const float* c2w_host, const float* image, int32_t img_h, int32_t img_w,
+	int32_t img_c, float* rays_o, float* rays_d, float* target, float* cone_angle_host, nrf_stream stream)
+{
+	NRF_REQUIRE(n_rays >= 0, "bad sizes");
+	NRF_REQUIRE(K_host && c2w_host, "null camera");
+	if (cone_angle_host) *cone_angle_host = (1.0f / K_host[0] + 1.0f / K_host[4]) / 2.0f;      // src/NeRFDataset.cpp:136-141
+	if (n_rays == 0) return NRF_OK;
+	NRF_REQUIRE(pix_hw && rays_o && rays_d, "null pointer");
+	NRF_REQUIRE((image == nullptr) == (target == nullptr) && (!image || (img_h > 0 && img_w > 0 && img_c > 0)), "image and target go together");
+	Cam c;
+	fill_cam(c, K_host, c2w_host);
+	ray_batch_kernel<<<static_cast<unsigned>((n_rays + 255) / 256), 256, 0, as_stream(stream)>>>(c, pix_hw, n_rays, image, img_w, img_c, rays_o, rays_d, target);
+	NRF_CHECK_LAUNCH("ray_batch_kernel");
+	return NRF_OK;
+}
+
+static int launch_ray_setup(bool pixels, const float* rays_o, const float* rays_d, const PixelSrc& ps, int64_t n_rays, const float* bbox_host, float near_plane,
+	const float* t_vals, int32_t n_samples, int32_t lin_disp, int32_t sh_degree, float* ray_batch, float* z, float* ray_sh, float* zero_scalar, nrf_stream stream)
 {
 	NRF_REQUIRE(n_rays >= 0 && n_samples >= 1, "bad sizes");
 	NRF_REQUIRE(!ray_sh || (sh_degree >= 1 && sh_degree <= 8), "degree must be 1..8");
 	if (n_rays == 0) return NRF_OK;
-	NRF_REQUIRE(rays_o && rays_d && bbox_host && t_vals && ray_batch && z, "null pointer");
+	NRF_REQUIRE(bbox_host && t_vals && ray_batch && z, "null pointer");
 	Box b;
 	for (int k = 0; k < 3; k++) { b.lo[k] = bbox_host[k]; b.hi[k] = bbox_host[3 + k]; }
 	const int64_t n = n_rays * n_samples;
 	const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
 	cudaStream_t s = as_stream(stream);
-#define NRF_RS(D) case D: ray_setup_kernel<D><<<blocks, 256, 0, s>>>(rays_o, rays_d, n_rays, b, near_plane, t_vals, n_samples, lin_disp, ray_batch, z, ray_sh, zero_scalar); break
+#define NRF_RS(D) case D:                                                                                                                                     \
+		if (pixels) ray_setup_kernel<D, true><<<blocks, 256, 0, s>>>(rays_o, rays_d, ps, n_rays, b, near_plane, t_vals, n_samples, lin_disp, ray_batch, z, ray_sh, zero_scalar); \
+		else ray_setup_kernel<D, false><<<blocks, 256, 0, s>>>(rays_o, rays_d, ps, n_rays, b, near_plane, t_vals, n_samples, lin_disp, ray_batch, z, ray_sh, zero_scalar);   \
+		break
 	switch (ray_sh ? sh_degree : 1) {
 		NRF_RS(1); NRF_RS(2); NRF_RS(3); NRF_RS(4); NRF_RS(5); NRF_RS(6); NRF_RS(7); NRF_RS(8);
 	}
 #undef NRF_RS
 	NRF_CHECK_LAUNCH("ray_setup_kernel");
 	return NRF_OK;
+}
+
+int nrf_ray_setup(const float* rays_o, const float* rays_d, int64_t n_rays, const float* bbox_host, float near_plane, const float* t_vals,
+	int32_t n_samples, int32_t lin_disp, int32_t sh_degree, float* ray_batch, float* z, float* ray_sh, float* zero_scalar, nrf_stream stream)
+{
+	NRF_REQUIRE(n_rays <= 0 || (rays_o && rays_d), "null pointer");
+	const PixelSrc ps{};
+	return launch_ray_setup(false, rays_o, rays_d, ps, n_rays, bbox_host, near_plane, t_vals, n_samples, lin_disp, sh_degree, ray_batch, z, ray_sh, zero_scalar, stream);
+}
+
+int nrf_ray_setup_pixels(const int32_t* pix_hw, int64_t n_rays, const float* K_host, const float* c2w_host, const float* image, int32_t img_h, int32_t img_w,
+	int32_t img_c, const float* bbox_host, float near_plane, const float* t_vals, int32_t n_samples, int32_t lin_disp, int32_t sh_degree, float* rays_o,
+	float* rays_d, float* target, float* ray_batch, float* z, float* ray_sh, float* zero_scalar, nrf_stream stream)
+{
+	NRF_REQUIRE(K_host && c2w_host, "null camera");
+	NRF_REQUIRE(n_rays <= 0 || (pix_hw && rays_o && rays_d), "null pointer");
+	NRF_REQUIRE((image == nullptr) == (target == nullptr) && (!image || (img_h > 0 && img_w > 0 && img_c > 0)), "image and target go together");
+	PixelSrc ps{};
+	fill_cam(ps.cam, K_host, c2w_host);
+	ps.pix_hw = pix_hw; ps.image = image; ps.img_w = img_w; ps.img_c = img_c; ps.rays_o_out = rays_o; ps.rays_d_out = rays_d; ps.target_out = target;
+	return launch_ray_setup(true, nullptr, nullptr, ps, n_rays, bbox_host, near_plane, t_vals, n_samples, lin_disp, sh_degree, ray_batch, z, ray_sh, zero_scalar, stream);
 }
 
 int nrf_z_sample(const float* ray_batch, int32_t ray_stride, const float* t_vals, int64_t n_rays, int32_t n_samples,

@@ -305,6 +305,42 @@ def ray_setup(rays_o: torch.Tensor, rays_d: torch.Tensor, bbox, near_plane: floa
     return ray_batch, z, ray_sh
 
 
+def _cam(K, c2w):
+    return (cabi.host_floats(torch.as_tensor(K, dtype=f32).reshape(-1).tolist()), cabi.host_floats(torch.as_tensor(c2w, dtype=f32)[:3, :4].reshape(-1).tolist()))
+
+
+def ray_batch(pix_hw: torch.Tensor, K, c2w, image: torch.Tensor | None = None):
+    """NeRFDataset::GetRayBatch on the device: pix_hw int32 [R,2] (row, col) -> (rays_o, rays_d, target | None, cone_angle)."""
+    r = pix_hw.shape[0]
+    rays_o = torch.empty((r, 3), dtype=f32, device=pix_hw.device)
+    rays_d = torch.empty((r, 3), dtype=f32, device=pix_hw.device)
+    target = torch.empty((r, image.shape[2]), dtype=f32, device=pix_hw.device) if image is not None else None
+    kh, ch = _cam(K, c2w)
+    cone = C.c_float(0.0)
+    h, w, c = image.shape if image is not None else (0, 0, 0)
+    _run("ray_batch", lambda: lib().nrf_ray_batch(ptr(pix_hw, i32), r, kh, ch, ptr(image), h, w, c, ptr(rays_o), ptr(rays_d), ptr(target), C.byref(cone), stream()))
+    return rays_o, rays_d, target, float(cone.value)
+
+
+def ray_setup_pixels(pix_hw: torch.Tensor, K, c2w, image: torch.Tensor | None, bbox, near_plane: float, t_vals: torch.Tensor, sh_degree: int | None,
+                     lin_disp: bool = False, zero_scalar: torch.Tensor | None = None, cam=None):
+    """ray_batch + ray_setup as one launch: (rays_o, rays_d, target | None, ray_batch [R,11], z [R,S], ray_sh | None)."""
+    r, s = pix_hw.shape[0], t_vals.shape[0]
+    dev = pix_hw.device
+    rays_o = torch.empty((r, 3), dtype=f32, device=dev)
+    rays_d = torch.empty((r, 3), dtype=f32, device=dev)
+    target = torch.empty((r, image.shape[2]), dtype=f32, device=dev) if image is not None else None
+    rb = torch.empty((r, 11), dtype=f32, device=dev)
+    z = torch.empty((r, s), dtype=f32, device=dev)
+    ray_sh = torch.empty((r, sh_degree * sh_degree), dtype=f32, device=dev) if sh_degree else None
+    kh, ch = cam if cam is not None else _cam(K, c2w)
+    h, w, c = image.shape if image is not None else (0, 0, 0)
+    _run("ray_setup", lambda: lib().nrf_ray_setup_pixels(ptr(pix_hw, i32), r, kh, ch, ptr(image), h, w, c, cabi.host_floats(bbox), near_plane, ptr(t_vals, f32), s,
+                                                         int(lin_disp), sh_degree or 0, ptr(rays_o), ptr(rays_d), ptr(target), ptr(rb), ptr(z), ptr(ray_sh),
+                                                         ptr(zero_scalar), stream()))
+    return rays_o, rays_d, target, rb, z, ray_sh
+
+
 def z_sample(ray_batch: torch.Tensor, t_vals: torch.Tensor, lin_disp: bool = False) -> torch.Tensor:
     r, stride = ray_batch.shape
     s = t_vals.shape[0]

@@ -154,12 +154,13 @@ class FlatAdamModel:
         self.repack()
 
     # -- the step as ONE CUDA-graph replay (launch-bound otherwise: ~20 kernels of 3..300 us behind ~20 ctypes calls)
-    def capture_train_step(self, n_rays: int, world: int = 1, allreduce=None):
-        """Captures forward_backward and the optimiser for a fixed ray count.  world == 1: one graph per step;
+    def capture_train_step(self, n_rays: int, world: int = 1, allreduce=None, pixels: bool = False):
+        """Captures forward_backward and the optimiser for a fixed ray count.  pixels: the step's input is the int32 [n_rays,2] pixel list of the
+        current training view (HashNeRF.set_camera) instead of rays + targets.  world == 1: one graph per step;
         world > 1: graph(render + loss + backward) -> allreduce(self.grads) (eager NCCL call) -> graph(Adam + repack), or, with the fused
         peer-memory optimiser, one graph.  The step count / bias corrections / decayed rate advance on the device (nrf_adam_schedule_advance)."""
         dev = self.device
-        self._g_in = self._static_inputs(n_rays)
+        self._g_in = self._static_inputs(n_rays, pixels) if pixels else self._static_inputs(n_rays)
         self._g_world, self._g_allreduce = world, allreduce
         self._init_sched()
         # warm-up outside the capture (one-time function attributes, level scales, allocator pools); its gradient is discarded
@@ -245,6 +246,7 @@ class HashNeRF(FlatAdamModel):
         self.reuse_coarse_rows = True
         self._u_cache = {}
         self._render_ws = None
+        self._cam = None
         self.refresh()
 
     # -- views into the flat buffers
@@ -261,10 +263,19 @@ class HashNeRF(FlatAdamModel):
     def repack(self):
         self.packed = ops.mlp_small_pack(self.mlp_params, out=self.packed)
 
-    def _static_inputs(self, n_rays):
+    def _static_inputs(self, n_rays, pixels=False):
         dev = self.device
+        if pixels:
+            assert self._cam is not None, "set_camera(image, K, c2w) first"
+            return (torch.zeros((n_rays, 2), dtype=i32, device=dev),)
         return (torch.tensor([[0.0, 0.0, 4.0]], device=dev).repeat(n_rays, 1), torch.tensor([[0.0, 0.0, -1.0]], device=dev).repeat(n_rays, 1),
                 torch.full((n_rays, 3), 0.5, dtype=f32, device=dev))
+
+    def set_camera(self, image: torch.Tensor, K, c2w):
+        """The current training view (NeRFDataset's CurrentImage / K / pose, src/NeRFDataset.cpp:149-157): image fp32 [H,W,3] on the device.  A step
+        can then be fed with pixel coordinates only: GetRayBatch (:109-144) and the target gather (:156) run inside the step's first kernel."""
+        assert image.is_cuda and image.dtype == f32 and image.dim() == 3 and image.is_contiguous()
+        self._cam = (image, ops._cam(K, c2w))
 
     # -- RenderRays (src/NeRFRenderer.h:366-459)
     def _network(self, ray_batch, z, ray_sh, reuse=None):
@@ -290,9 +301,9 @@ class HashNeRF(FlatAdamModel):
                                                    workspace=self._render_ws)
         return out
 
-    def render_rays(self, rays_o, rays_d, white_bkgr=False, keep_for_backward=False, n_importance=None, zero_scalar=None):
-        # Render prologue + coarse depths + per-ray SH (+ the caller's loss accumulator reset) in one launch
-        ray_batch, z, ray_sh = ops.ray_setup(rays_o, rays_d, self.bbox, 0.0, self.t_vals, self.sh_degree, zero_scalar=zero_scalar)
+    def render_rays(self, rays_o, rays_d, white_bkgr=False, keep_for_backward=False, n_importance=None, zero_scalar=None, setup=None):
+        # Render prologue + coarse depths + per-ray SH (+ the caller's loss accumulator reset) in one launch (setup: already done by the caller)
+        ray_batch, z, ray_sh = setup if setup is not None else ops.ray_setup(rays_o, rays_d, self.bbox, 0.0, self.t_vals, self.sh_degree, zero_scalar=zero_scalar)
         enc_c, keep_c, raw = self._network(ray_batch, z, ray_sh)
         coarse = ops.composite_fwd(raw, z, rays_d, white_bkgr)
         u = self._u(n_importance)
@@ -317,9 +328,17 @@ class HashNeRF(FlatAdamModel):
         return {k: torch.cat([o[k] for o in outs], 0) for k in ("rgb", "depth", "disp", "acc")}
 
     # -- one optimisation step (src/NeRFExecutor.h:868-890, 923, 986-996)
-    def forward_backward(self, rays_o, rays_d, target, grad_scale=1.0):
-        """Render + huber + backward into self.grads (accumulating).  self.loss holds the mean huber loss."""
-        out = self.render_rays(rays_o, rays_d, keep_for_backward=True, zero_scalar=self.loss)
+    def forward_backward(self, *inputs, grad_scale=1.0):
+        """Render + huber + backward into self.grads (accumulating).  self.loss holds the mean huber loss.  inputs: (rays_o, rays_d, target), or
+        (pix_hw,) — int32 [R,2] pixel coordinates of the view given to set_camera: rays and targets are then formed on the device."""
+        if len(inputs) == 1:
+            image, cam = self._cam
+            rays_o, rays_d, target, rb, z, sh = ops.ray_setup_pixels(inputs[0], None, None, image, self.bbox, 0.0, self.t_vals, self.sh_degree,
+                                                                     zero_scalar=self.loss, cam=cam)
+            out = self.render_rays(rays_o, rays_d, keep_for_backward=True, setup=(rb, z, sh))
+        else:
+            rays_o, rays_d, target = inputs
+            out = self.render_rays(rays_o, rays_d, keep_for_backward=True, zero_scalar=self.loss)
         ray_batch, enc, keep, raw, ray_sh = out.pop("_saved")
         g_rgb = torch.empty_like(out["rgb"])
         ops.huber_fwd_bwd(out["rgb"], target, self.loss, g_rgb, 1.0, grad_scale)
@@ -327,6 +346,27 @@ class HashNeRF(FlatAdamModel):
         g_enc = ops.mlp_small_bwd(self.packed, enc, ray_sh, raw.shape[1], keep, d_raw.view(-1, 4), self.grads[self.n_table:])
         ops.hash_encode_rays_bwd(self.grid, ray_batch, out["z"], g_enc, self.grads[:self.n_table], clamp=True)
         return out
+
+
+def synthetic_view(h=800, w=800, radius=4.0):
+    """(K [3,3], c2w [4,4]) of the synthetic training view of BASELINE C2: pinhole with camera_angle_x = 0.6911 (src/load_blender.h:144-185) on a
+    radius-4 sphere pose (pose_spherical(30, -30, 4), :43-57)."""
+    focal = 0.5 * w / math.tan(0.5 * 0.6911)
+    K = torch.tensor([[focal, 0, 0.5 * w], [0, focal, 0.5 * h], [0, 0, 1]], dtype=f32)
+    th, ph = math.radians(30.0), math.radians(-30.0)
+    rot_phi = torch.tensor([[1, 0, 0], [0, math.cos(ph), -math.sin(ph)], [0, math.sin(ph), math.cos(ph)]], dtype=f32)
+    rot_th = torch.tensor([[math.cos(th), 0, -math.sin(th)], [0, 1, 0], [math.sin(th), 0, math.cos(th)]], dtype=f32)
+    R = rot_th @ rot_phi
+    c2w = torch.eye(4, dtype=f32)
+    c2w[:3, :3] = R
+    c2w[:3, 3] = R @ torch.tensor([0.0, 0.0, radius])
+    return K, c2w
+
+
+def synthetic_pixels(n, h=800, w=800, seed=0):
+    """Pixel sampling of NeRFDataset::get_batch (src/NeRFDataset.cpp:154-155): int32 [n,2] = (row, col), host tensor."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.stack([torch.randint(0, h, (n,), generator=g), torch.randint(0, w, (n,), generator=g)], -1).to(torch.int32)
 
 
 def synthetic_rays(n, h=800, w=800, device="cuda", seed=0, radius=4.0):

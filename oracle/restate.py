@@ -352,6 +352,19 @@ def get_rays(h: int, w: int, K: torch.Tensor, c2w: torch.Tensor):
     return rays_o, rays_d
 
 
+def get_ray_batch(rand_h: torch.Tensor, rand_w: torch.Tensor, K: torch.Tensor, c2w: torch.Tensor):
+    """src/NeRFDataset.cpp:109-144 (NeRFDataset::GetRayBatch): rays of a list of pixel coordinates, and the scalar cone angle."""
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    dirsx = (rand_w.to(torch.float32) - cx) / fx                                             # :122
+    dirsy = -(rand_h.to(torch.float32) - cy) / fy                                            # :123
+    dirsz = -torch.ones_like(dirsx)                                                          # :124
+    dirs = torch.stack([dirsx, dirsy, dirsz], -1)                                            # :126
+    rays_d = torch.sum(dirs[..., None, :] * c2w[:3, :3], -1)                                 # :128-131
+    rays_o = c2w[:3, -1].expand(rays_d.shape)                                                # :133
+    cone_angle = (1.0 / fx + 1.0 / fy) / 2.0                                                 # :137-141
+    return rays_o, rays_d, cone_angle
+
+
 def intersect_aabb(rays_o: torch.Tensor, rays_d: torch.Tensor, bbox: torch.Tensor, near_plane: float = 0.0):
     """src/RayUtils.h:87-126."""
     aabb = bbox.reshape(2, 3)

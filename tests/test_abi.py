@@ -75,10 +75,14 @@ def test_lerf_head_sizes_and_validation_without_gpu():
     lib = cabi.lib()
     shape = ops.lerf_shape()
     operand = 2 * (256 * 128 + 48 * 256 + 256 * 160 + 3 * 256 * 256)          # S0, S1 (33 -> 48), E0, G, E1 lower / upper halves, fp16
-    slabs = 2 * (256 * 128 + 48 * 256 + 256 * 160 + 256 * 256)                  # S0, S1, E0, G once more as N-slab stages (the A/B kernel)
-    assert lib.nrf_lerf_packed_bytes(ctypes.byref(shape)) == operand + slabs + 4 * 256 * 512 + 128      # + W_e1^T fp32 + the scale of G
+    train = 2 * (256 * 128 + 48 * 256 + 256 * 160 + 256 * 256)                  # S0, S1, E0, G once more in bf16 (the gradient chain's copy)
+    # + W_e1^T fp32 + the scale of G + G itself in fp32
+    assert lib.nrf_lerf_packed_bytes(ctypes.byref(shape)) == operand + train + 4 * 256 * 512 + 128 + 4 * 256 * 256
     for n, tiles in ((0, 0), (1, 1), (128, 1), (129, 2), (196608, 1536)):
         assert lib.nrf_lerf_hidden_bytes(ctypes.byref(shape), n) == tiles * 128 * 256 * 2
+        # training records per 128-row tile: bf16 [geo | x] (160), h1, h2 (256 each), fp16 h2 (256), 32 mask bytes per row
+        assert lib.nrf_lerf_train_saved_bytes(ctypes.byref(shape), n) == tiles * (128 * 2 * (160 + 3 * 256) + 128 * 32)
+        assert lib.nrf_lerf_bwd_workspace_bytes(ctypes.byref(shape), n, max(n // 192, 0)) >= tiles * 128 * 2 * (3 * 256 + 48)
     for bad in (ops.lerf_shape(lang_embed_dim=768), ops.lerf_shape(num_layers=3, hidden_dim=64), ops.lerf_shape(input_ch=32)):
         assert lib.nrf_lerf_packed_bytes(ctypes.byref(bad)) == -1 and lib.nrf_lerf_hidden_bytes(ctypes.byref(bad), 128) == -1
         assert lib.nrf_lerf_fwd(ctypes.byref(bad), None, None, None, 4, None, None) == -3                 # NRF_ERR_UNSUPPORTED

@@ -248,3 +248,42 @@ def test_fp16_shadow_is_fully_initialised():
     for _ in range(3):
         m.train_step(o, d, tgt)
     assert torch.equal(m.shadow, m.params.half())
+
+
+def test_device_side_ray_batch_equals_get_rays_and_the_ray_path():
+    """SURVEY §8f-3: NeRFDataset::GetRayBatch + the target gather on the device (nrf_ray_batch, nrf_ray_setup_pixels).  (a) the rays of a pixel
+    list are the rows of nrf_get_rays at those pixels, bit for bit (that kernel is pinned to the reference's GetRays fixture); (b) against the
+    oracle's restatement of GetRayBatch (src/NeRFDataset.cpp:109-144); (c) the fused set-up equals ray_batch + ray_setup bit for bit; (d) a
+    training step fed with pixel coordinates follows the step fed with the same rays and targets."""
+    import restate as O
+    from nerfpp_b200 import ops
+    from nerfpp_b200.pipeline import HashNeRF, synthetic_pixels, synthetic_view
+    h, w = 60, 80
+    K, c2w = synthetic_view(h, w)
+    pix = synthetic_pixels(500, h, w, seed=3)
+    pix[0] = torch.tensor([0, 0]); pix[1] = torch.tensor([h - 1, w - 1])
+    image = torch.rand(h, w, 3, generator=torch.Generator().manual_seed(4)).cuda()
+    rays_o, rays_d, target, cone = ops.ray_batch(pix.cuda(), K, c2w, image)
+    full_o, full_d = ops.get_rays(h, w, K, c2w)
+    idx = (pix[:, 0].long() * w + pix[:, 1].long()).cuda()
+    assert torch.equal(rays_d, full_d[idx]) and torch.equal(rays_o, full_o[idx])
+    assert torch.equal(target, image[pix[:, 0].long().cuda(), pix[:, 1].long().cuda()])
+    ro, rd, ca = O.get_ray_batch(pix[:, 0], pix[:, 1], K, c2w)
+    assert torch.allclose(rays_d.cpu(), rd, rtol=1e-6, atol=1e-7) and torch.equal(rays_o.cpu(), ro.expand_as(rd).contiguous())
+    assert abs(cone - float(ca)) <= 1e-9
+    m = HashNeRF(BBOX, log2_hashmap_size=14, seed=42)
+    a = ops.ray_setup(rays_o, rays_d, m.bbox, 0.0, m.t_vals, 4)
+    b = ops.ray_setup_pixels(pix.cuda(), K, c2w, image, m.bbox, 0.0, m.t_vals, 4)
+    assert torch.equal(b[0], rays_o) and torch.equal(b[1], rays_d) and torch.equal(b[2], target)
+    for x, y in zip(a, b[3:]):
+        assert torch.equal(x, y)
+    # (d) two replicas, same seed: one stepped on (rays, targets), one on pixel coordinates (eagerly and as a captured graph)
+    m1, m2, m3 = (HashNeRF(BBOX, log2_hashmap_size=14, seed=42) for _ in range(3))
+    for mm in (m2, m3):
+        mm.set_camera(image, K, c2w)
+    m3.capture_train_step(pix.shape[0], pixels=True)
+    l1 = [float(m1.train_step(rays_o, rays_d, target)) for _ in range(4)]
+    l2 = [float(m2.train_step(pix.cuda())) for _ in range(4)]
+    l3 = [float(m3.train_step_graph(pix.pin_memory())) for _ in range(4)]
+    np.testing.assert_allclose(l2, l1, rtol=1e-4)
+    np.testing.assert_allclose(l3, l1, rtol=1e-4)
