@@ -393,6 +393,11 @@ typedef struct nrf_peer_group {
 	const float* grads[NRF_MAX_PEERS];
 	void* shadow_f16[NRF_MAX_PEERS];
 	uint32_t* flags[NRF_MAX_PEERS];
+	/* optional NVSwitch multicast mappings of the SAME two buffers (NULL: peer loads / stores on the pointers above): one address that
+	 * reads the sum over all ranks (multimem.ld_reduce: the reduction happens in the switch, each element crosses this GPU's link once
+	 * instead of world - 1 times) / writes every rank's copy (multimem.st) */
+	const float* grads_mc;
+	void* shadow_f16_mc;
 } nrf_peer_group;
 
 int64_t nrf_peer_flags_bytes(int32_t world);

@@ -77,7 +77,7 @@ NRF_MAX_PEERS = 8
 class PeerGroup(Structure):
     """struct nrf_peer_group"""
     _fields_ = [("world", c_int32), ("rank", c_int32), ("grads", c_void_p * NRF_MAX_PEERS), ("shadow_f16", c_void_p * NRF_MAX_PEERS),
-                ("flags", c_void_p * NRF_MAX_PEERS)]
+                ("flags", c_void_p * NRF_MAX_PEERS), ("grads_mc", c_void_p), ("shadow_f16_mc", c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol include/nerfpp_b200.h declares (tests/test_abi.py checks)

@@ -120,7 +120,15 @@ class PeerShardedOptimizer:
             for p in range(world):
                 getattr(pg, field)[p] = ptrs[p] + off
         self.pg, self.handles, self.rank, self.world = pg, handles, rank, world
-        self.multicast = bool(getattr(handles[0], "has_multicast_support", False))
+        # NVSwitch multicast mappings of the gradient and the shadow (multimem.ld_reduce / multimem.st): the reduction happens in the switch.
+        # NRF_DP_MULTICAST=0 keeps the peer-load kernel (A/B).
+        self.multicast = False
+        if bool(getattr(handles[0], "has_multicast_support", False)) and os.environ.get("NRF_DP_MULTICAST", "1") != "0":
+            mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in handles[:2]]
+            if all(mc):
+                pg.grads_mc = mc[0] + (self.grads.data_ptr() - list(handles[0].buffer_ptrs)[rank])
+                pg.shadow_f16_mc = mc[1] + (self.shadow.data_ptr() - list(handles[1].buffer_ptrs)[rank])
+                self.multicast = True
         model.grads, model.shadow = self.grads, self.shadow
         model.peer = self
         if hasattr(model, "bind_peer_buffers"):
@@ -187,6 +195,7 @@ class PeerShardedOptimizer:
                "shadows_bit_identical_across_ranks": stats[2].item() == 0.0, "owner_master_matches_shadow": stats[3].item() == 0.0,
                "gradient_cleared": stats[4].item() == 0.0, "flags_timeout": int(stats[5].item()), "entries_differing_by_more_than_5pct_of_lr": int(stats[6].item()),
                "entries": int(model.params.numel()), "lr": model.lr0,
+               "multicast": bool(self.multicast),
                "what": "one step on a random per-rank gradient: fused peer-memory kernel vs NCCL all-reduce + dense Adam"}
         out["ok"] = bool(out["shadows_bit_identical_across_ranks"] and out["owner_master_matches_shadow"] and out["gradient_cleared"]
                          and out["flags_timeout"] == 0 and out["entries_differing_by_more_than_5pct_of_lr"] <= 8)

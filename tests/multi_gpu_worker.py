@@ -51,9 +51,14 @@ def main():
     parallel.PeerShardedOptimizer(b_, rank, world)
     c = HashNeRF(BBOX, log2_hashmap_size=15, seed=3, device=dev, lrate_decay=1)
     parallel.broadcast_parameters(c.params, world); c.refresh()
-    # ---- (2a) one step on a random gradient through both paths; everything is restored afterwards
+    # ---- (2a) one step on a random gradient through both paths; everything is restored afterwards.  b_ uses the NVSwitch multicast mappings when
+    # the box has them (multimem.ld_reduce / multimem.st), c the plain peer loads / stores: both forms of the kernel are checked
+    os.environ["NRF_DP_MULTICAST"] = "0"
     before = c.params.clone()
-    chk = parallel.PeerShardedOptimizer(c, rank, world).dp_check(c)
+    peer_c = parallel.PeerShardedOptimizer(c, rank, world)
+    os.environ.pop("NRF_DP_MULTICAST")
+    assert not peer_c.multicast
+    chk = peer_c.dp_check(c)
     assert chk["ok"], chk
     assert c.step == 0 and torch.equal(before, c.params) and float(c.grads.abs().max()) == 0.0
     c.capture_train_step(R, world)
@@ -125,7 +130,7 @@ def main():
     if rank == 0:
         whole = c.render_image(H, W, K, c2w)["rgb"]
         assert torch.equal(full, whole)
-        print("MULTI_GPU_WORKER_OK", world, la[-1], lb[-1], lc[-1], "dp_grad_rel", rel, rel_mlp, "dp_check", chk)
+        print("MULTI_GPU_WORKER_OK", world, la[-1], lb[-1], lc[-1], "dp_grad_rel", rel, rel_mlp, "multicast(b)", b_.peer.multicast, "dp_check", chk)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -16,3 +16,4 @@ def test_fused_data_parallel_optimizer_two_gpus():
            "--master-port", "29533", os.path.join(here, "multi_gpu_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "MULTI_GPU_WORKER_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    print([line for line in out.stdout.splitlines() if "MULTI_GPU_WORKER_OK" in line][0])
