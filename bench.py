@@ -373,6 +373,44 @@ def gpu_loop_leg(which: str, rays: int, steps: int) -> dict:
                      "nerfpp_b200 C++ drop-in classes (torch::Tensor boundary, FusedAdam" + (", captured train graph)" if fast else ")"))}
 
 
+def shipped_leg(dev, rays: int, steps: int = 50) -> dict:
+    """BASELINE C2, second run: the step with the RNG-gated stages of the reference's shipped configuration ON — thin_ray = false
+    (in-cone jitter of both passes, src/NeRFRenderer.h:307-362), raw_noise_std 0.5 and stochastic preconditioning alpha = 0.01 x bbox diagonal
+    (mid-schedule values of src/NeRFExecutor.h:411-412) — at the BASELINE shape, captured as one CUDA graph (torch's Philox generator is
+    graph-safe: the offset advances per replay).  The jittered sample points are explicit arrays here, so both passes gather from a point list."""
+    import torch
+    from nerfpp_b200.pipeline import HashNeRF, synthetic_rays
+    m = HashNeRF(BBOX, n_samples=N_SAMPLES, n_importance=N_IMPORTANCE, device=dev, seed=42)
+    batch = synthetic_rays(rays, device=dev, seed=31)
+    cone, noise_std, alpha = (1.0 / 1111.1 + 1.0 / 1111.1) / 2.0, 0.5, 0.01 * (3 * 3.0 ** 2) ** 0.5
+    m._init_sched()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        m.forward_backward_shipped(*batch, cone, noise_std, alpha)
+        m.grads.zero_()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        m.forward_backward_shipped(*batch, cone, noise_std, alpha)
+        m._optimizer_step_scheduled(1.0)
+    for _ in range(5):
+        g.replay()
+    torch.cuda.synchronize(dev)
+    first = float(m.loss)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    return {"ms_per_step": ms, "value": rays / ms * 1e3, "unit": "rays/s", "steps": steps, "loss": {"first": first, "last": float(m.loss)},
+            "config": f"C2 shape, {rays} rays, thin_ray = false (cone jitter both passes), raw_noise_std {noise_std}, stochastic preconditioning alpha "
+                      f"{alpha:.4f} + ReflectBoundary; torch Philox draws (the reference's own rand / randn calls), everything else C ABI; one CUDA graph"}
+
+
 def lerf_train_leg(rank: int, world: int, dev, hash_model, tf_peak: float, rays: int = 1024, steps: int = 50) -> dict | None:
     """BASELINE C5: LeRF training, 1024 rays per GPU.  One iteration of NeRFExecutor::Train with use_lerf (src/NeRFExecutor.h:868-996) = the HashNeRF
     step (render + huber + backward) AND the language step (LeRFRenderer::Render + huber(1.25).sum(-1).nanmean() + backward, :957-983), then Adam
@@ -782,6 +820,13 @@ def main() -> None:
             roofline_tensor["lerf_head"] = {"error": f"{type(e).__name__}: {e}"}
         roofline_render_ops = render_ops_leg(roofline["peak"])
 
+    as_shipped = None
+    if world == 1 and not quick:
+        try:
+            as_shipped = shipped_leg(dev, R)
+        except Exception as e:  # noqa: BLE001
+            as_shipped = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- the same step through the C++ surfaces, on this GPU (N = 1 only): the reference's own CUDA path and the C++ drop-in classes
     dropin_cpp = reference_cuda = None
     if world == 1 and not quick:
@@ -827,7 +872,7 @@ def main() -> None:
         "kernels_ms_per_step": {k: [round(t, 4) for t in v] for k, v in sorted(per_launch.items(), key=lambda kv: -sum(kv[1]))},
         "kernels_ms_per_step_sum": round(sum(sum(v) for v in per_launch.values()), 4),
         "dp_check": dp_check, "flags_timeout_after_timed_regions": timeout_after, "strong": strong,
-        "reference_cuda": reference_cuda, "dropin_cpp": dropin_cpp,
+        "reference_cuda": reference_cuda, "dropin_cpp": dropin_cpp, "train_as_shipped": as_shipped,
         "final_loss": {"resident": head["loss"], "e2e": head["loss_e2e"]}, "render": render, "render_lerf": render_lerf, "train_lerf": train_lerf,
     }))
 

@@ -317,6 +317,10 @@ int nrf_z_sample(const float* ray_batch, int32_t ray_stride, const float* t_vals
 int nrf_sample_points(const float* ray_batch, int32_t ray_stride, const float* z, int64_t n_rays, int32_t n_samples,
                       float* pts, nrf_stream stream);
 
+/* Stochastic preconditioning (src/NeRFRenderer.h:435-443) + ReflectBoundary (:285-304), in place: pts [N,3] += noise [N,3] * alpha, folded back
+ * into bbox_host[6] by reflection.  noise: the reference's torch::randn_like(pts) draw, supplied by the caller. */
+int nrf_precondition_points(float* pts, const float* noise, float alpha, const float* bbox_host, int64_t n_points, nrf_stream stream);
+
 /* TangentScatter (src/NeRFRenderer.h:307-362): pts [R,S,3] += (tangent*r*cos(theta) + bitangent*r*sin(theta)) * cone_angle*z,
  * then clamp into bbox_host[6] (nullable = no clamp).  rand_r / rand_theta [R,S] are the two torch::rand draws of :342-343
  * (drawn by the host so the RNG stream matches the reference's).  cone_angle: one scalar (cone_stride 0) or one per ray

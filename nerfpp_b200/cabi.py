@@ -113,6 +113,7 @@ SIGNATURES = {
                                        c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nrf_z_sample": (c_int32, [_P, c_int32, _P, c_int64, c_int32, c_int32, _P, _P]),
     "nrf_sample_points": (c_int32, [_P, c_int32, _P, c_int64, c_int32, _P, _P]),
+    "nrf_precondition_points": (c_int32, [_P, _P, c_float, POINTER(c_float), c_int64, _P]),
     "nrf_tangent_scatter": (c_int32, [_P, _P, _P, c_int32, _P, c_int32, _P, _P, POINTER(c_float), c_int64, c_int32, _P]),
     "nrf_huber_fwd_bwd": (c_int32, [_P, _P, c_int64, c_float, c_float, _P, _P, _P]),
     "nrf_adam_step": (c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int32, c_float, c_int32, _P, _P]),

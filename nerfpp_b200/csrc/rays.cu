@@ -246,6 +246,21 @@ __global__ void __launch_bounds__(256) tangent_scatter_kernel(float* __restrict_
 	p[0] = px; p[1] = py; p[2] = pz;
 }
 
+// Stochastic preconditioning of the fine-pass sample positions (src/NeRFRenderer.h:435-443): pts += noise * alpha, then ReflectBoundary
+// (:285-304): normalise to the box, fold with period 2 (fmod; q -> 2 - q above 1), map back.  noise [R,S,3] standard normal (the reference's
+// torch::randn_like draw, supplied by the host so that the Philox stream is the caller's).
+__global__ void __launch_bounds__(256) precondition_kernel(float* __restrict__ pts, const float* __restrict__ noise, float alpha, Box box, int64_t n3)
+{
+	const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (e >= n3) return;
+	const int k = static_cast<int>(e % 3);
+	const float lo = box.lo[k], ext = __fsub_rn(box.hi[k], box.lo[k]);
+	const float p = __fadd_rn(pts[e], __fmul_rn(noise[e], alpha));
+	float q = fmodf(__fdiv_rn(__fsub_rn(p, lo), ext), 2.0f);
+	q = q > 1.0f ? __fsub_rn(2.0f, q) : q;
+	pts[e] = __fadd_rn(__fmul_rn(q, ext), lo);
+}
+
 }  // namespace nrf
 
 using namespace nrf;
@@ -369,6 +384,19 @@ int nrf_sample_points(const float* ray_batch, int32_t ray_stride, const float* z
 	const int64_t n = n_rays * n_samples * 3;
 	sample_points_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(ray_batch, ray_stride, z, n_rays, n_samples, pts);
 	NRF_CHECK_LAUNCH("sample_points_kernel");
+	return NRF_OK;
+}
+
+int nrf_precondition_points(float* pts, const float* noise, float alpha, const float* bbox_host, int64_t n_points, nrf_stream stream)
+{
+	NRF_REQUIRE(n_points >= 0 && bbox_host != nullptr, "bad arguments");
+	if (n_points == 0) return NRF_OK;
+	NRF_REQUIRE(pts && noise, "null pointer");
+	Box b;
+	for (int k = 0; k < 3; k++) { b.lo[k] = bbox_host[k]; b.hi[k] = bbox_host[3 + k]; }
+	const int64_t n3 = n_points * 3;
+	precondition_kernel<<<static_cast<unsigned>((n3 + 255) / 256), 256, 0, as_stream(stream)>>>(pts, noise, alpha, b, n3);
+	NRF_CHECK_LAUNCH("precondition_kernel");
 	return NRF_OK;
 }
 

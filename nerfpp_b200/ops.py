@@ -357,6 +357,22 @@ def sample_points(ray_batch: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
     return pts
 
 
+def tangent_scatter(pts: torch.Tensor, z: torch.Tensor, cone_angle: torch.Tensor, rays_d: torch.Tensor, rand_r: torch.Tensor, rand_theta: torch.Tensor,
+                    bbox=None) -> torch.Tensor:
+    """TangentScatter in place on pts [R,S,3]; cone_angle: one-element tensor (shared) or [R]; rand_* [R,S] uniform variates."""
+    r, s = z.shape
+    stride = 0 if cone_angle.numel() == 1 else 1
+    _run("tangent_scatter", lambda: lib().nrf_tangent_scatter(ptr(pts, f32), ptr(z, f32), ptr(cone_angle, f32), stride, ptr(rays_d, f32), rays_d.shape[1],
+                                                              ptr(rand_r, f32), ptr(rand_theta, f32), cabi.host_floats(bbox) if bbox is not None else None, r, s, stream()))
+    return pts
+
+
+def precondition_points(pts: torch.Tensor, noise: torch.Tensor, alpha: float, bbox) -> torch.Tensor:
+    """Stochastic preconditioning + ReflectBoundary in place on pts [..., 3]."""
+    _run("precondition_points", lambda: lib().nrf_precondition_points(ptr(pts, f32), ptr(noise, f32), alpha, cabi.host_floats(bbox), pts.numel() // 3, stream()))
+    return pts
+
+
 def huber_fwd_bwd(pred: torch.Tensor, target: torch.Tensor, loss_out: torch.Tensor, grad: torch.Tensor | None,
                   delta: float = 1.0, grad_scale: float = 1.0) -> None:
     _run("huber_fwd_bwd", lambda: lib().nrf_huber_fwd_bwd(ptr(pred, f32), ptr(target, f32), pred.numel(), delta, grad_scale, ptr(loss_out, f32),

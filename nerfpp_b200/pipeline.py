@@ -320,6 +320,41 @@ class HashNeRF(FlatAdamModel):
             out["_saved"] = (ray_batch, enc, keep, raw, ray_sh)
         return out
 
+    def forward_backward_shipped(self, rays_o, rays_d, target, cone_angle: float, raw_noise_std: float, sp_alpha: float):
+        """The step with the RNG-gated stages of the reference's shipped configuration ON (src/main.cpp:187 thin_ray = false; src/NeRFExecutor.h:
+        411-412 raw_noise_std and StochasticPreconditioningAlpha > 0): in-cone jitter of both passes' sample points (TangentScatter,
+        src/NeRFRenderer.h:307-362), stochastic preconditioning + ReflectBoundary of the fine pass (:435-443), density noise in both RawToOutputs
+        (:253-254).  The variates are torch.rand / torch.randn draws — the reference's own calls — so results are statistically, not bitwise, equal
+        (SURVEY §9-Q4); everything else is the C ABI.  The jittered points are explicit [R,S,3] arrays here (the parity path never forms them)."""
+        dev = self.device
+        r = rays_o.shape[0]
+        cone = torch.tensor([cone_angle], dtype=f32, device=dev)
+        ray_batch, z, ray_sh = ops.ray_setup(rays_o, rays_d, self.bbox, 0.0, self.t_vals, self.sh_degree, zero_scalar=self.loss)
+
+        def network(zz, precondition):
+            s = zz.shape[1]
+            pts = ops.sample_points(ray_batch, zz)
+            if precondition and sp_alpha > 0:
+                ops.precondition_points(pts, torch.randn_like(pts), sp_alpha, self.bbox)
+            ops.tangent_scatter(pts, zz, cone, rays_d, torch.rand((r, s), device=dev), torch.rand((r, s), device=dev), self.bbox)
+            pts = pts.view(-1, 3)
+            enc, keep = ops.hash_encode_fwd(self.grid, self.table_f16, pts, clamp=True, out_f16=True)
+            raw = ops.mlp_small_fwd(self.packed, enc, ray_sh, s, keep).view(r, s, 4)
+            noise = torch.randn((r, s), device=dev) if raw_noise_std > 0 else None
+            return pts, enc, keep, raw, noise
+
+        _, _, _, raw_c, noise_c = network(z, False)
+        coarse = ops.composite_fwd(raw_c, z, rays_d, noise=noise_c, raw_noise_std=raw_noise_std)
+        z_fine = ops.sample_pdf_merge(z, coarse["weights"], self.u)
+        pts, enc, keep, raw, noise = network(z_fine, True)
+        out = ops.composite_fwd(raw, z_fine, rays_d, noise=noise, raw_noise_std=raw_noise_std)
+        g_rgb = torch.empty_like(out["rgb"])
+        ops.huber_fwd_bwd(out["rgb"], target, self.loss, g_rgb, 1.0, 1.0)
+        d_raw = ops.composite_bwd(raw, z_fine, rays_d, noise=noise, raw_noise_std=raw_noise_std, g_rgb=g_rgb)
+        g_enc = ops.mlp_small_bwd(self.packed, enc, ray_sh, raw.shape[1], keep, d_raw.view(-1, 4), self.grads[self.n_table:])
+        ops.hash_encode_bwd(self.grid, pts, g_enc, self.grads[:self.n_table], clamp=True)
+        return out
+
     def render_image(self, h, w, K, c2w, chunk=1 << 18, row_begin=0, row_end=None, white_bkgr=False, n_importance=None):
         """Render(h,w,K,c2w) for image rows [row_begin,row_end) (src/NeRFRenderer.h:540-547, RenderPath :684)."""
         rays_o, rays_d = ops.get_rays(h, w, K, c2w, row_begin, row_end, self.device)

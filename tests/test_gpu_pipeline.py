@@ -287,3 +287,34 @@ def test_device_side_ray_batch_equals_get_rays_and_the_ray_path():
     l3 = [float(m3.train_step_graph(pix.pin_memory())) for _ in range(4)]
     np.testing.assert_allclose(l2, l1, rtol=1e-4)
     np.testing.assert_allclose(l3, l1, rtol=1e-4)
+
+
+def test_shipped_configuration_step_statistics():
+    """The RNG-gated stages of the shipped configuration (cone jitter, stochastic preconditioning + ReflectBoundary, density noise): with all
+    amplitudes at 0 the step equals the parity step bit for bit; with them on it trains, the jitter stays inside the cone and the box, and the
+    reflected points match the oracle's restatement of ReflectBoundary."""
+    from nerfpp_b200 import ops
+    from nerfpp_b200.pipeline import HashNeRF, synthetic_rays
+    o, d, tgt = synthetic_rays(512, seed=5)
+    a, b = HashNeRF(BBOX, log2_hashmap_size=15, seed=42), HashNeRF(BBOX, log2_hashmap_size=15, seed=42)
+    a.forward_backward(o, d, tgt)
+    b.forward_backward_shipped(o, d, tgt, cone_angle=0.0, raw_noise_std=0.0, sp_alpha=0.0)
+    assert abs(float(a.loss) - float(b.loss)) <= 1e-6 * float(a.loss)       # TangentScatter clamps into the box: a point ON the boundary may move by an ulp
+    ga, gb = a.grads.clone(), b.grads.clone()
+    assert float((ga - gb).abs().max()) <= 1e-4 * float(ga.abs().max())          # same kernels on the same points; atomics order only
+    a.grads.zero_(); b.grads.zero_()
+    losses = []
+    for _ in range(30):
+        b.forward_backward_shipped(o, d, tgt, cone_angle=1.0 / 1111.0, raw_noise_std=0.5, sp_alpha=0.02 * 5.196)
+        b.optimizer_step()
+        losses.append(float(b.loss))
+    assert all(np.isfinite(losses)) and np.mean(losses[-5:]) < np.mean(losses[:5])
+    # ReflectBoundary against the oracle's restatement (src/NeRFRenderer.h:285-304)
+    g = torch.Generator().manual_seed(1)
+    pts = (torch.rand(4096, 3, generator=g) * 3 - 1.5)
+    noise = torch.randn(4096, 3, generator=g)
+    got = ops.precondition_points(pts.clone().cuda(), noise.cuda(), 0.4, BBOX).cpu()
+    lo, hi = torch.tensor(BBOX[:3]), torch.tensor(BBOX[3:])
+    q = torch.fmod((pts + noise * 0.4 - lo) / (hi - lo), 2.0)
+    q = torch.where(q > 1.0, 2.0 - q, q)
+    assert torch.allclose(got, q * (hi - lo) + lo, rtol=1e-6, atol=1e-6)
