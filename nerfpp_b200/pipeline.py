@@ -320,15 +320,19 @@ class HashNeRF(FlatAdamModel):
             out["_saved"] = (ray_batch, enc, keep, raw, ray_sh)
         return out
 
-    def forward_backward_shipped(self, rays_o, rays_d, target, cone_angle: float, raw_noise_std: float, sp_alpha: float):
+    def forward_backward_shipped(self, rays_o, rays_d, target, cone_angle: float, raw_noise_std: float, sp_alpha: float, clamp_to_box: bool = True):
         """The step with the RNG-gated stages of the reference's shipped configuration ON (src/main.cpp:187 thin_ray = false; src/NeRFExecutor.h:
         411-412 raw_noise_std and StochasticPreconditioningAlpha > 0): in-cone jitter of both passes' sample points (TangentScatter,
         src/NeRFRenderer.h:307-362), stochastic preconditioning + ReflectBoundary of the fine pass (:435-443), density noise in both RawToOutputs
         (:253-254).  The variates are torch.rand / torch.randn draws — the reference's own calls — so results are statistically, not bitwise, equal
-        (SURVEY §9-Q4); everything else is the C ABI.  The jittered points are explicit [R,S,3] arrays here (the parity path never forms them)."""
+        (SURVEY §9-Q4); everything else is the C ABI.  The jittered points are explicit [R,S,3] arrays here (the parity path never forms them).
+        clamp_to_box: TangentScatter clamps the jittered points into the box (:356-360) — which also pulls the samples of rays that MISS the box
+        onto its surface, where they pass the embedder's keep test; False (tests) leaves them outside."""
         dev = self.device
         r = rays_o.shape[0]
-        cone = torch.tensor([cone_angle], dtype=f32, device=dev)
+        if getattr(self, "_cone", None) is None or self._cone[0] != cone_angle:
+            self._cone = (cone_angle, torch.full((1,), cone_angle, dtype=f32, device=dev))
+        cone = self._cone[1]
         ray_batch, z, ray_sh = ops.ray_setup(rays_o, rays_d, self.bbox, 0.0, self.t_vals, self.sh_degree, zero_scalar=self.loss)
 
         def network(zz, precondition):
@@ -336,7 +340,7 @@ class HashNeRF(FlatAdamModel):
             pts = ops.sample_points(ray_batch, zz)
             if precondition and sp_alpha > 0:
                 ops.precondition_points(pts, torch.randn_like(pts), sp_alpha, self.bbox)
-            ops.tangent_scatter(pts, zz, cone, rays_d, torch.rand((r, s), device=dev), torch.rand((r, s), device=dev), self.bbox)
+            ops.tangent_scatter(pts, zz, cone, rays_d, torch.rand((r, s), device=dev), torch.rand((r, s), device=dev), self.bbox if clamp_to_box else None)
             pts = pts.view(-1, 3)
             enc, keep = ops.hash_encode_fwd(self.grid, self.table_f16, pts, clamp=True, out_f16=True)
             raw = ops.mlp_small_fwd(self.packed, enc, ray_sh, s, keep).view(r, s, 4)
