@@ -253,6 +253,13 @@ int nrf_composite_bwd(const float* raw, int32_t raw_stride, const float* z, cons
                       const float* g_rgb, const float* g_depth, const float* g_disp, const float* g_acc,
                       const float* g_weights, float* d_raw, nrf_stream stream);
 
+/* The training tail of the colour pass in ONE launch: RawToOutputs forward of every ray, huber_loss(RGBMap, target, delta) with mean reduction
+ * over the R*3 values (src/NeRFExecutor.h:883-886) and the backward of both — equal to nrf_composite_fwd -> nrf_huber_fwd_bwd ->
+ * nrf_composite_bwd(g_rgb).  loss_out[0] += loss (caller zeroes), rgb_out [R,3] (nullable) the RGBMap, d_raw [R,S,4] = d (loss * grad_scale) / d raw. */
+int nrf_composite_huber_bwd(const float* raw, int32_t raw_stride, const float* z, const float* rays_d, const float* noise,
+                            float raw_noise_std, int32_t white_bkgr, int64_t n_rays, int32_t n_samples, const float* target, float delta,
+                            float grad_scale, float* loss_out, float* rgb_out, float* d_raw, nrf_stream stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Hierarchical resampling — SamplePDF (src/Sampler.h:6-43).
  * bins [R,B], weights [R,B-1], u: [n_samples] shared (det: linspace(0,1,n), src/Sampler.h:20) when u_per_ray==0,

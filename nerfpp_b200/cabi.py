@@ -103,6 +103,7 @@ SIGNATURES = {
     "nrf_mlp_small_bwd": (c_int32, [POINTER(MlpSmallShape), _P, c_int32, _P, _P, c_int32, _P, c_int64, _P, _P, _P, _P]),
     "nrf_composite_fwd": (c_int32, [_P, c_int32, _P, _P, _P, c_float, c_int32, c_int64, c_int32, _P, _P, _P, _P, _P, _P]),
     "nrf_composite_bwd": (c_int32, [_P, c_int32, _P, _P, _P, c_float, c_int32, c_int64, c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    "nrf_composite_huber_bwd": (c_int32, [_P, c_int32, _P, _P, _P, c_float, c_int32, c_int64, c_int32, _P, c_float, c_float, _P, _P, _P, _P]),
     "nrf_sample_pdf": (c_int32, [_P, _P, c_int32, _P, c_int32, c_int64, c_int32, _P, _P]),
     "nrf_sample_pdf_merge": (c_int32, [_P, _P, _P, c_int32, c_int64, c_int32, c_int32, _P, _P, _P]),
     "nrf_get_rays": (c_int32, [c_int32, c_int32, POINTER(c_float), POINTER(c_float), c_int32, c_int32, _P, _P, _P]),

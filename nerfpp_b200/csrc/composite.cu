@@ -188,11 +188,22 @@ __global__ void __launch_bounds__(kRaysPerCta * 32) composite_fwd_nb_kernel(cons
 	}
 }
 
-template <int NB>
+// The training tail of the colour pass as ONE kernel (HUBER): RawToOutputs forward of the ray (recomputed here anyway), the huber loss of its
+// RGB against the target (src/NeRFExecutor.h:883-886: mean over all R*3 values, delta 1) and the backward — instead of composite forward ->
+// huber -> composite backward with an [R,3] gradient round trip and two more launches.
+struct HuberArgs {
+	const float* target;     // [R,3]
+	float delta, grad_scale;
+	float inv_n;             // 1 / (R * 3)
+	float* loss_out;         // += mean loss
+	float* rgb_out;          // [R,3] nullable
+};
+
+template <int NB, bool HUBER>
 __global__ void __launch_bounds__(kRaysPerCta * 32) composite_bwd_kernel(const float* __restrict__ raw, int raw_stride,
 	const float* __restrict__ z, const float* __restrict__ rays_d, const float* __restrict__ noise, float noise_std, int white,
 	int64_t R, int S, const float* __restrict__ g_rgb, const float* __restrict__ g_depth, const float* __restrict__ g_disp,
-	const float* __restrict__ g_acc, const float* __restrict__ g_weights, float* __restrict__ d_raw)
+	const float* __restrict__ g_acc, const float* __restrict__ g_weights, float* __restrict__ d_raw, HuberArgs hub)
 {
 	const int lane = threadIdx.x & 31;
 	const int64_t ray = static_cast<int64_t>(blockIdx.x) * kRaysPerCta + (threadIdx.x >> 5);
@@ -205,7 +216,7 @@ __global__ void __launch_bounds__(kRaysPerCta * 32) composite_bwd_kernel(const f
 	SampleEval e[NB];
 	float Lx[NB];  // exclusive log-transmittance
 	float zi[NB];
-	float carry = 0.f, sa = 0.f, sd = 0.f;
+	float carry = 0.f, sa = 0.f, sd = 0.f, sr = 0.f, sg = 0.f, sb = 0.f;
 	{
 		SampleIn in[NB];
 #pragma unroll
@@ -233,13 +244,32 @@ __global__ void __launch_bounds__(kRaysPerCta * 32) composite_bwd_kernel(const f
 			const float w = e[b].alpha * expf(Lx[b]);
 			sa += w;
 			sd += w * zi[b];
+			if (HUBER) { sr += w * e[b].r; sg += w * e[b].g; sb += w * e[b].b; }
 		}
 		carry += __shfl_sync(0xffffffffu, incl, 31);
 	}
 	sa = warp_sum(sa);
 	sd = warp_sum(sd);
 
-	const float gr = g_rgb ? g_rgb[ray * 3] : 0.f, gg = g_rgb ? g_rgb[ray * 3 + 1] : 0.f, gb = g_rgb ? g_rgb[ray * 3 + 2] : 0.f;
+	float gr, gg, gb;
+	if (HUBER) {
+		// the forward's RGB of this ray (same sums as composite_fwd_nb_kernel), then d huber / d rgb
+		sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb);
+		if (white) { const float bg = 1.f - sa; sr += bg; sg += bg; sb += bg; }
+		const float er = sr - hub.target[ray * 3], eg = sg - hub.target[ray * 3 + 1], eb = sb - hub.target[ray * 3 + 2];
+		const float d = hub.delta;
+		gr = (fabsf(er) < d ? er : (er > 0.f ? d : -d)) * hub.inv_n * hub.grad_scale;      // the expression of huber_kernel (optim.cu)
+		gg = (fabsf(eg) < d ? eg : (eg > 0.f ? d : -d)) * hub.inv_n * hub.grad_scale;
+		gb = (fabsf(eb) < d ? eb : (eb > 0.f ? d : -d)) * hub.inv_n * hub.grad_scale;
+		if (lane == 0) {
+			const float l = (fabsf(er) < d ? 0.5f * er * er : d * (fabsf(er) - 0.5f * d)) + (fabsf(eg) < d ? 0.5f * eg * eg : d * (fabsf(eg) - 0.5f * d)) +
+			                (fabsf(eb) < d ? 0.5f * eb * eb : d * (fabsf(eb) - 0.5f * d));
+			if (hub.loss_out) atomicAdd(hub.loss_out, l * hub.inv_n);
+			if (hub.rgb_out) { hub.rgb_out[ray * 3] = sr; hub.rgb_out[ray * 3 + 1] = sg; hub.rgb_out[ray * 3 + 2] = sb; }
+		}
+	} else {
+		gr = g_rgb ? g_rgb[ray * 3] : 0.f; gg = g_rgb ? g_rgb[ray * 3 + 1] : 0.f; gb = g_rgb ? g_rgb[ray * 3 + 2] : 0.f;
+	}
 	const float den = fmaxf(sa, 1e-10f);
 	const float dep = sd / den;
 	float gdep = g_depth ? g_depth[ray] : 0.f;
@@ -326,15 +356,44 @@ int nrf_composite_bwd(const float* raw, int32_t raw_stride, const float* z, cons
 	const unsigned blocks = static_cast<unsigned>((n_rays + kRaysPerCta - 1) / kRaysPerCta);
 	cudaStream_t s = as_stream(stream);
 	const int nb = (n_samples + 31) / 32;
+	const HuberArgs none{};
 #define NRF_CB(NBV)                                                                                                  \
 	case NBV:                                                                                                        \
-		composite_bwd_kernel<NBV><<<blocks, kRaysPerCta * 32, 0, s>>>(raw, raw_stride, z, rays_d, noise, raw_noise_std, \
-			white_bkgr, n_rays, n_samples, g_rgb, g_depth, g_disp, g_acc, g_weights, d_raw);                          \
+		composite_bwd_kernel<NBV, false><<<blocks, kRaysPerCta * 32, 0, s>>>(raw, raw_stride, z, rays_d, noise, raw_noise_std, \
+			white_bkgr, n_rays, n_samples, g_rgb, g_depth, g_disp, g_acc, g_weights, d_raw, none);                    \
 		break
 	switch (nb) {
 		NRF_CB(1); NRF_CB(2); NRF_CB(3); NRF_CB(4); NRF_CB(5); NRF_CB(6); NRF_CB(7); NRF_CB(8);
 	}
 #undef NRF_CB
+	NRF_CHECK_LAUNCH("composite_bwd_kernel");
+	return NRF_OK;
+}
+
+int nrf_composite_huber_bwd(const float* raw, int32_t raw_stride, const float* z, const float* rays_d, const float* noise, float raw_noise_std,
+	int32_t white_bkgr, int64_t n_rays, int32_t n_samples, const float* target, float delta, float grad_scale, float* loss_out, float* rgb_out,
+	float* d_raw, nrf_stream stream)
+{
+	NRF_REQUIRE(n_rays >= 0 && n_samples >= 1, "bad sizes");
+	NRF_REQUIRE(raw_stride >= 4, "raw_stride must be >= 4");
+	NRF_REQUIRE(n_samples <= 32 * kMaxBlocks, "n_samples > 256 is not supported by the backward");
+	if (n_rays == 0) return NRF_OK;
+	NRF_REQUIRE(raw && z && rays_d && d_raw && target, "null input");
+	const unsigned blocks = static_cast<unsigned>((n_rays + kRaysPerCta - 1) / kRaysPerCta);
+	cudaStream_t s = as_stream(stream);
+	const int nb = (n_samples + 31) / 32;
+	HuberArgs hub;
+	hub.target = target; hub.delta = delta; hub.inv_n = 1.f / static_cast<float>(n_rays * 3); hub.grad_scale = grad_scale;
+	hub.loss_out = loss_out; hub.rgb_out = rgb_out;
+#define NRF_CH(NBV)                                                                                                  \
+	case NBV:                                                                                                        \
+		composite_bwd_kernel<NBV, true><<<blocks, kRaysPerCta * 32, 0, s>>>(raw, raw_stride, z, rays_d, noise, raw_noise_std, \
+			white_bkgr, n_rays, n_samples, nullptr, nullptr, nullptr, nullptr, nullptr, d_raw, hub);                  \
+		break
+	switch (nb) {
+		NRF_CH(1); NRF_CH(2); NRF_CH(3); NRF_CH(4); NRF_CH(5); NRF_CH(6); NRF_CH(7); NRF_CH(8);
+	}
+#undef NRF_CH
 	NRF_CHECK_LAUNCH("composite_bwd_kernel");
 	return NRF_OK;
 }

@@ -512,6 +512,18 @@ static int fill_args(const nrf_hash_grid* g, HashArgs& a)
 // ceiling as the fine pass (1 sector / clk / SM), not a launch-shape effect.
 struct LaunchPlan { unsigned grid; int64_t stride; int iters; };
 
+// experiment hook (scripts/exp/hash_occupancy.py): NRF_HASH_OCC=k pads every CTA with dynamic shared memory so that only k CTAs of 128 threads are
+// resident per SM — how much of the machine the gather / scatter kernels need before the L1-miss path saturates (can a tensor-core kernel co-run?)
+static int occ_pad_bytes()
+{
+	static const int pad = [] {
+		const char* e = getenv("NRF_HASH_OCC");
+		const int k = e ? atoi(e) : 0;
+		return k > 0 ? (227 * 1024) / k - 2048 : 0;
+	}();
+	return pad;
+}
+
 static LaunchPlan launch_plan(int64_t items, int block)
 {
 	const int64_t ctas = (items + block - 1) / block;
@@ -578,7 +590,8 @@ static int launch_hash_fwd(const nrf_hash_grid* grid, const void* table_f16, con
 	do {                                                                                                                          \
 		const int64_t items = n_points * (SP);                                                                                   \
 		const LaunchPlan lp = launch_plan(items, 128);                                                                           \
-		hash_fwd_kernel<FF, O32, SP><<<lp.grid, 128, 0, s>>>(a, t, ps, ru, items, lp.stride, lp.iters, clamp_points, keep, enc_out); \
+		if (occ_pad_bytes() > 48 * 1024) cudaFuncSetAttribute(hash_fwd_kernel<FF, O32, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, occ_pad_bytes()); \
+		hash_fwd_kernel<FF, O32, SP><<<lp.grid, 128, occ_pad_bytes(), s>>>(a, t, ps, ru, items, lp.stride, lp.iters, clamp_points, keep, enc_out); \
 	} while (0)
 #define NRF_LAUNCH_FWD(FF, SP)                                                     \
 	do {                                                                           \
@@ -612,7 +625,8 @@ static int launch_hash_bwd(const nrf_hash_grid* grid, const PointSrc& ps, int64_
 #define NRF_LAUNCH_BWD2(FF, BF)                                                                                                   \
 	do {                                                                                                                          \
 		const LaunchPlan lp = launch_plan(n_points, 128);                                                                        \
-		hash_bwd_kernel<FF, BF><<<lp.grid, 128, 0, s>>>(a, ps, n_points, lp.stride, lp.iters, clamp_points, grad_enc, grad_table); \
+		if (occ_pad_bytes() > 48 * 1024) cudaFuncSetAttribute(hash_bwd_kernel<FF, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, occ_pad_bytes()); \
+		hash_bwd_kernel<FF, BF><<<lp.grid, 128, occ_pad_bytes(), s>>>(a, ps, n_points, lp.stride, lp.iters, clamp_points, grad_enc, grad_table); \
 	} while (0)
 #define NRF_LAUNCH_BWD(FF)                                             \
 	do {                                                               \

@@ -114,21 +114,17 @@ void HashNeRFTrainGraph::Enqueue(bool with_optimizer)
 		NRF_ENC_F16, perm.data_ptr<int16_t>(), enc_c.data_ptr(), keep_c.data_ptr<uint8_t>(), S, st), "nrf_hash_encode_rays_fwd");
 	nrfhost::Check(nrf_mlp_small_fwd(&shape, Packed.data_ptr(), NRF_MLP_IN_ENC16_RAYDIRS, enc.data_ptr(), ray_sh.data_ptr<float>(), sf, keep.data_ptr<uint8_t>(), nf,
 		raw.data_ptr<float>(), st), "nrf_mlp_small_fwd");
+	// RawToOutputs of the fine pass + huber_loss + their backward (src/NeRFRenderer.h:447-448, src/NeRFExecutor.h:883-890, 923): one launch
 	Rgb = F32({R, 3}, dev);
-	Tensor w_f = F32({R, sf}, dev);
-	nrfhost::Check(nrf_composite_fwd(raw.data_ptr<float>(), 4, z_f.data_ptr<float>(), InD.data_ptr<float>(), nullptr, 0.f, 0, R, sf, Rgb.data_ptr<float>(),
-		depth.data_ptr<float>(), disp.data_ptr<float>(), acc.data_ptr<float>(), w_f.data_ptr<float>(), st), "nrf_composite_fwd");
-	// loss and backward (src/NeRFExecutor.h:883-890, 923)
-	Tensor g_rgb = F32({R, 3}, dev), d_raw = F32({R, sf, 4}, dev);
-	nrfhost::Check(nrf_huber_fwd_bwd(Rgb.data_ptr<float>(), InT.data_ptr<float>(), R * 3, 1.f, 1.f, Loss.data_ptr<float>(), g_rgb.data_ptr<float>(), st), "nrf_huber_fwd_bwd");
-	nrfhost::Check(nrf_composite_bwd(raw.data_ptr<float>(), 4, z_f.data_ptr<float>(), InD.data_ptr<float>(), nullptr, 0.f, 0, R, sf, g_rgb.data_ptr<float>(), nullptr,
-		nullptr, nullptr, nullptr, d_raw.data_ptr<float>(), st), "nrf_composite_bwd");
+	Tensor d_raw = F32({R, sf, 4}, dev);
+	nrfhost::Check(nrf_composite_huber_bwd(raw.data_ptr<float>(), 4, z_f.data_ptr<float>(), InD.data_ptr<float>(), nullptr, 0.f, 0, R, sf, InT.data_ptr<float>(), 1.f, 1.f,
+		Loss.data_ptr<float>(), Rgb.data_ptr<float>(), d_raw.data_ptr<float>(), st), "nrf_composite_huber_bwd");
 	Tensor g_enc = torch::empty({nf, 32}, torch::TensorOptions().dtype(torch::kBFloat16).device(dev));
 	nrfhost::Check(nrf_mlp_small_bwd(&shape, Packed.data_ptr(), NRF_MLP_IN_ENC16_RAYDIRS, enc.data_ptr(), ray_sh.data_ptr<float>(), sf, keep.data_ptr<uint8_t>(), nf,
 		d_raw.data_ptr<float>(), g_enc.data_ptr(), g_mlp, st), "nrf_mlp_small_bwd");
 	nrfhost::Check(nrf_hash_encode_rays_bwd(&grid, ray_batch.data_ptr<float>(), 11, z_f.data_ptr<float>(), R, sf, 1, g_enc.data_ptr(), NRF_GRAD_BF16, g_table, st),
 		"nrf_hash_encode_rays_bwd");
-	Keep = {ray_batch, z, ray_sh, enc_c, keep_c, raw_c, rgb_c, depth, disp, acc, w_c, z_f, perm, enc, keep, raw, w_f, g_rgb, d_raw, g_enc};
+	Keep = {ray_batch, z, ray_sh, enc_c, keep_c, raw_c, rgb_c, depth, disp, acc, w_c, z_f, perm, enc, keep, raw, d_raw, g_enc};
 	if (!with_optimizer) return;
 	// Optimizer->step() + the decayed rate (src/NeRFExecutor.h:539, 986-996): schedule record advanced on the device, Adam over the reachable table
 	// prefix (+ fp16 shadow + gradient clear) and over the weights, re-pack

@@ -4,10 +4,10 @@
 //     Optimizer->zero_grad(); Render(rays) -> huber_loss(RGBMap, target) -> loss.backward(); Optimizer->step(); set_lr(decayed)
 // which, on the drop-in classes, is ~60 kernel launches behind ATen / autograd bookkeeping (1.2 ms per 4096-ray step, of which 0.8 ms is kernel
 // time).  HashNeRFTrainGraph runs the SAME step — the same C-ABI kernels in the same order as the autograd path issues them — as one captured
-// graph of 16 kernel nodes:
-//     ray setup -> [hash encode -> NeRFSmall] coarse -> RawToOutputs -> SamplePDF + merge -> [hash encode -> NeRFSmall] fine -> RawToOutputs
-//     -> huber (loss + d rgb) -> RawToOutputs backward -> NeRFSmall backward -> hash scatter -> Adam (+ fp16 shadow, gradient clear, LR schedule
-//     on the device) -> weight re-pack
+// graph of 14 kernel nodes:
+//     ray setup -> [hash encode -> NeRFSmall] coarse -> RawToOutputs -> SamplePDF + merge -> [hash encode -> NeRFSmall] fine ->
+//     RawToOutputs + huber + RawToOutputs backward (one kernel) -> NeRFSmall backward -> hash scatter -> Adam (+ fp16 shadow, gradient clear,
+//     LR schedule on the device) -> weight re-pack
 // Parity configuration of the benchmark (ThinRay, Perturb 0, no raw noise, no stochastic preconditioning, one chunk, coarse pass not
 // differentiated — SURVEY §9-Q3/Q4); anything else stays on the autograd path of renderer.h.
 //

@@ -251,6 +251,16 @@ def composite_bwd(raw, z, rays_d, white_bkgr=False, noise=None, raw_noise_std=0.
     return out
 
 
+def composite_huber_bwd(raw, z, rays_d, target, loss_out, white_bkgr=False, noise=None, raw_noise_std=0.0, delta=1.0, grad_scale=1.0, want_rgb=True):
+    """composite_fwd + huber_fwd_bwd + composite_bwd(g_rgb) of a training step as ONE launch: returns (d_raw [R,S,4], rgb [R,3] | None)."""
+    r, s, c = raw.shape
+    d_raw = torch.empty((r, s, 4), dtype=f32, device=raw.device)
+    rgb = torch.empty((r, 3), dtype=f32, device=raw.device) if want_rgb else None
+    _run("composite_huber_bwd", lambda: lib().nrf_composite_huber_bwd(ptr(raw, f32), c, ptr(z, f32), ptr(rays_d, f32), ptr(noise), raw_noise_std, int(white_bkgr),
+                                                                      r, s, ptr(target, f32), delta, grad_scale, ptr(loss_out, f32), ptr(rgb), ptr(d_raw), stream()))
+    return d_raw, rgb
+
+
 def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
     r, b = bins.shape
     per_ray = u.dim() == 2

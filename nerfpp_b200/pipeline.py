@@ -301,7 +301,7 @@ class HashNeRF(FlatAdamModel):
                                                    workspace=self._render_ws)
         return out
 
-    def render_rays(self, rays_o, rays_d, white_bkgr=False, keep_for_backward=False, n_importance=None, zero_scalar=None, setup=None):
+    def render_rays(self, rays_o, rays_d, white_bkgr=False, keep_for_backward=False, n_importance=None, zero_scalar=None, setup=None, fine_composite=True):
         # Render prologue + coarse depths + per-ray SH (+ the caller's loss accumulator reset) in one launch (setup: already done by the caller)
         ray_batch, z, ray_sh = setup if setup is not None else ops.ray_setup(rays_o, rays_d, self.bbox, 0.0, self.t_vals, self.sh_degree, zero_scalar=zero_scalar)
         enc_c, keep_c, raw = self._network(ray_batch, z, ray_sh)
@@ -314,7 +314,8 @@ class HashNeRF(FlatAdamModel):
         else:
             z_fine, reuse = ops.sample_pdf_merge(z, coarse["weights"], u), None
         enc, keep, raw = self._network(ray_batch, z_fine, ray_sh, reuse)
-        out = ops.composite_fwd(raw, z_fine, rays_d, white_bkgr)
+        # fine_composite False (training): the caller composites, takes the loss and back-propagates in one launch (ops.composite_huber_bwd)
+        out = ops.composite_fwd(raw, z_fine, rays_d, white_bkgr) if fine_composite else {}
         out["z"] = z_fine
         if keep_for_backward:
             out["_saved"] = (ray_batch, enc, keep, raw, ray_sh)
@@ -374,14 +375,13 @@ class HashNeRF(FlatAdamModel):
             image, cam = self._cam
             rays_o, rays_d, target, rb, z, sh = ops.ray_setup_pixels(inputs[0], None, None, image, self.bbox, 0.0, self.t_vals, self.sh_degree,
                                                                      zero_scalar=self.loss, cam=cam)
-            out = self.render_rays(rays_o, rays_d, keep_for_backward=True, setup=(rb, z, sh))
+            out = self.render_rays(rays_o, rays_d, keep_for_backward=True, setup=(rb, z, sh), fine_composite=False)
         else:
             rays_o, rays_d, target = inputs
-            out = self.render_rays(rays_o, rays_d, keep_for_backward=True, zero_scalar=self.loss)
+            out = self.render_rays(rays_o, rays_d, keep_for_backward=True, zero_scalar=self.loss, fine_composite=False)
         ray_batch, enc, keep, raw, ray_sh = out.pop("_saved")
-        g_rgb = torch.empty_like(out["rgb"])
-        ops.huber_fwd_bwd(out["rgb"], target, self.loss, g_rgb, 1.0, grad_scale)
-        d_raw = ops.composite_bwd(raw, out["z"], rays_d, g_rgb=g_rgb)
+        # RawToOutputs of the fine pass + huber + their backward: one launch
+        d_raw, out["rgb"] = ops.composite_huber_bwd(raw, out["z"], rays_d, target, self.loss, grad_scale=grad_scale)
         g_enc = ops.mlp_small_bwd(self.packed, enc, ray_sh, raw.shape[1], keep, d_raw.view(-1, 4), self.grads[self.n_table:])
         ops.hash_encode_rays_bwd(self.grid, ray_batch, out["z"], g_enc, self.grads[:self.n_table], clamp=True)
         return out

@@ -317,3 +317,25 @@ def test_ray_setup_equals_the_three_kernels_bit_for_bit(r, s, deg, lin):
     assert torch.equal(rb, rb2) and torch.equal(z, z2) and torch.equal(sh, sh2) and float(acc) == 0.0
     rb3, z3, sh3 = ops.ray_setup(o, d, bbox, 0.05, t, None, lin_disp=lin)
     assert sh3 is None and torch.equal(rb, rb3) and torch.equal(z, z3)
+
+
+@pytest.mark.parametrize("S,white", [(192, False), (64, True), (33, False)])
+def test_fused_composite_huber_backward_equals_the_three_entries(S, white):
+    """nrf_composite_huber_bwd (the training tail of the colour pass in one launch) against nrf_composite_fwd -> nrf_huber_fwd_bwd ->
+    nrf_composite_bwd: same RGB and d_raw bit for bit (the same expressions in the same order), same loss up to the order of the atomic sum."""
+    from nerfpp_b200 import ops
+    g = torch.Generator().manual_seed(S)
+    R = 300
+    raw = (torch.randn(R, S, 4, generator=g) * 2).cuda()
+    z = (2 + torch.sort(torch.rand(R, S, generator=g) * 4, -1).values).cuda()
+    d = torch.randn(R, 3, generator=g).cuda()
+    tgt = (torch.rand(R, 3, generator=g) * 3 - 1).cuda()                      # errors beyond delta = 1 included
+    out = ops.composite_fwd(raw, z, d, white)
+    loss_a, g_rgb = torch.zeros(1, device="cuda"), torch.empty(R, 3, device="cuda")
+    ops.huber_fwd_bwd(out["rgb"], tgt, loss_a, g_rgb, 1.0, 0.5)
+    d_a = ops.composite_bwd(raw, z, d, white, g_rgb=g_rgb)
+    loss_b = torch.zeros(1, device="cuda")
+    d_b, rgb_b = ops.composite_huber_bwd(raw, z, d, tgt, loss_b, white_bkgr=white, grad_scale=0.5)
+    assert torch.equal(rgb_b, out["rgb"])
+    assert torch.equal(d_b, d_a)
+    assert abs(float(loss_a) - float(loss_b)) <= 1e-6 * abs(float(loss_a))
