@@ -703,8 +703,12 @@ def main() -> None:
         ms_render = parallel.max_over_ranks(e6.elapsed_time(e7), world, dev) / frames
         render = {"metric": "render_msamples_per_s", "value": H * W * (N_SAMPLES + N_SAMPLES + 64) / (ms_render * 1e3), "unit": "Msamples/s",
                   "frames_per_s": 1e3 / ms_render, "ms_per_frame": ms_render, "frames": frames,
-                  "config": "1920x1080 frame, image rows sharded over the GPUs, 64 coarse + 64 importance samples (192 network evaluations/ray), "
-                            "131072-ray chunks, rgb gathered on rank 0; untrained (random-init) model"}
+                  "config": "1920x1080 frame, image rows sharded over the GPUs, 64 coarse + 64 importance samples (192 network evaluations/ray in the "
+                            "reference, which is what Msamples/s counts), 131072-ray chunks, rgb gathered on rank 0; untrained (random-init) model",
+                  "evaluations_per_ray": {"reference": 192, "computed": 128 if os.environ.get("NRF_RENDER_REUSE", "1") != "0" else 192,
+                                          "note": "one network for both passes (src/NeRFRenderer.h:422,447): the 64 coarse samples inside the merged fine "
+                                                  "pass keep the raw rows of the coarse pass; maps bit-identical to evaluating all 128 "
+                                                  "(tests/test_gpu_variants.py NRF_RENDER_REUSE=0)"}}
         del img
 
     # ---- LeRF render leg (BASELINE C5's field, the C4 frame): RenderedLangEmbedding of one 1920x1080 frame, image rows sharded over the ranks,
@@ -799,11 +803,14 @@ def main() -> None:
     # fine points, 37 376 FLOP/point backward over the fine points; the backward also recomputes the forward, which is not counted)
     tf_peak = peaks.get("bf16_tflops", 1590.0)
     mf, mb = per_launch.get("mlp_small_fwd", [0.0, 0.0]), per_launch.get("mlp_small_bwd", [0.0])
-    tf_fwd = (n_c + n_f) * 18688 / (sum(mf) * 1e-3) / 1e12
+    # reuse_coarse_raw: the fine forward evaluates the importance samples only (the coarse samples' raw rows are the coarse pass's own)
+    n_eval = n_c + (n_f - n_c if getattr(model, "reuse_coarse_raw", False) and model.reuse_coarse_rows else n_f)
+    tf_fwd = n_eval * 18688 / (sum(mf) * 1e-3) / 1e12
     tf_bwd = n_f * 37376 / (mb[0] * 1e-3) / 1e12
     roofline_tensor = {"bound": "tensor", "unit": "TFLOP/s", "peak": tf_peak,
                        "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS burst)" if peaks else "fallback B200_PROFILING.md",
-                       "mlp_small_fwd": {"achieved": tf_fwd, "frac": tf_fwd / tf_peak, "ms_per_step": sum(mf), "ms_per_launch": mf, "pipe": "tcgen05"},
+                       "mlp_small_fwd": {"achieved": tf_fwd, "frac": tf_fwd / tf_peak, "ms_per_step": sum(mf), "ms_per_launch": mf, "pipe": "tcgen05",
+                                         "rows_evaluated_per_step": n_eval, "rows_the_reference_evaluates": n_c + n_f},
                        "mlp_small_bwd": {"achieved": tf_bwd, "frac": tf_bwd / tf_peak, "ms_per_step": mb[0], "pipe": MLP_BWD_PIPE},
                        "note": "in-graph event pairs per launch (coarse, fine); ncu per-launch figures in profiles/"}
     # TMEM -> register read rate, measured with scripts/exp/tmem_ld_bench.cu (profiles/r2_tmem_ld_bench.jsonl): 61 B/clk per WARP (a warp owns one
@@ -811,7 +818,7 @@ def main() -> None:
     # called this kernel TMEM-read-bound; it has 16 epilogue warps, so its read floor is 8x lower than its time: the kernel is bound by the latency of
     # five dependent MMA -> tcgen05.ld -> convert -> tcgen05.st round trips per tile (4 tile pipelines per SM share the 512 columns), not by bandwidth
     sm_mhz = peaks.get("sm_max_mhz", 1965.0)
-    tmem_floor_ms = (n_c + n_f) * 224 * 4 / (148 * 480 * sm_mhz * 1e6) * 1e3
+    tmem_floor_ms = n_eval * 224 * 4 / (148 * 480 * sm_mhz * 1e6) * 1e3
     roofline_tensor["mlp_small_fwd"]["tmem_read"] = {"bytes_per_point": 896, "measured_peak": "480 B/clk/SM with 16 reading warps (61 B/clk per warp)",
                                                       "floor_ms_per_step": tmem_floor_ms, "frac": tmem_floor_ms / max(sum(mf), 1e-9),
                                                       "source": "profiles/r2_tmem_ld_bench.jsonl"}
@@ -867,7 +874,12 @@ def main() -> None:
                    "rays_per_gpu": R, "global_rays": R * world, "parallelism": f"ray-sharded dp{world}: {dp_mode}",
                    "l2": "not flushed explicitly: each step streams ~300 MB (Adam pass over 8.9M params + moments + gradient) through the 126 MB L2",
                    "precision": "fp16 hash table reads / encodings, bf16 tensor-core MLP with fp32 accumulate, fp32 everything else",
-                   "reuse_coarse_rows": bool(model.reuse_coarse_rows)},
+                   "reuse_coarse_rows": bool(model.reuse_coarse_rows),
+                   "reuse_coarse_raw": bool(getattr(model, "reuse_coarse_raw", False)),
+                   "reuse_note": "the merged fine pass holds the 64 coarse samples bit for bit and the reference uses ONE network for both passes "
+                                 "(src/NeRFRenderer.h:422,447): their encoding rows are copied and their raw rows taken from the coarse pass, the fine "
+                                 "forward gathers / evaluates the 128 importance samples only; outputs and gradients are bit-identical to evaluating all "
+                                 "192 (tests/test_gpu_pipeline.py::test_coarse_reuse_leaves_the_render_unchanged); the backward covers all 192"},
         "e2e": {"value": rays_total / (ms_e2e / 1e3), "unit": "rays/s", "h2d_bytes_per_step": head["h2d"], "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps,
                 "input": "pinned-host int32 [R,2] pixel coordinates of the step's batch; rays (GetRayBatch) and targets (image gather) are formed on the "

@@ -108,7 +108,8 @@ int nrf_hash_encode_bwd(const nrf_hash_grid* grid, const float* points, int64_t 
  * Row reuse (forward only; reuse_perm NULL to disable): reuse_perm [R, S] int16 is nrf_sample_pdf_merge_perm's output for this
  * merged z (S = n_importance + reuse_samples).  The reuse_samples coarse samples whose z it reports as bit-identical are not
  * gathered again: their rows (and keep flags) are copied from the coarse call's output reuse_enc [R, reuse_samples, L*F] (same
- * layout) / reuse_keep [R, reuse_samples] — same point, same table, same bits; all other samples are encoded as usual. */
+ * layout) / reuse_keep [R, reuse_samples] — same point, same table, same bits; all other samples are encoded as usual.
+ * reuse_enc NULL: those rows of enc_out are left unwritten (inference through nrf_mlp_small_fwd_importance, which never reads them). */
 int nrf_hash_encode_rays_fwd(const nrf_hash_grid* grid, const void* table_f16, const float* ray_batch, int32_t ray_stride,
                              const float* z, int64_t n_rays, int32_t n_samples, int clamp_points, uint8_t* keep, void* enc_out,
                              nrf_enc_layout layout, const int16_t* reuse_perm, const void* reuse_enc, const uint8_t* reuse_keep,
@@ -160,6 +161,17 @@ typedef enum nrf_mlp_input {
 int nrf_mlp_small_fwd(const nrf_mlp_small_shape* shape, const void* packed, nrf_mlp_input in_kind, const void* enc,
                       const float* ray_sh, int32_t samples_per_ray, const uint8_t* keep, int64_t n,
                       float* raw_out, nrf_stream stream);
+
+/* The fine pass of RenderRays when coarse and fine share one network (src/NeRFRenderer.h:422,447; src/NeRFExecutor.h:882-890):
+ * only the n_importance NEW samples of each ray are evaluated.  Work row (ray, j < n_importance) reads its fp16 encoding at row
+ * perm[ray, j] of enc_merged [R, n_merged, 32] (keep_merged [R, n_merged], nullable, likewise; views: ray_sh [R,16]) and writes
+ * raw_merged [R, n_merged, 4] at the same row.  perm [R, n_merged] int16 = nrf_sample_pdf_merge_perm's output; the coarse
+ * samples' rows of raw_merged are the coarse pass's own rows, moved there by nrf_sample_pdf_merge_rows — the same bits a full
+ * nrf_mlp_small_fwd over the merged rows produces (rows are independent), at n_importance / n_merged of its work.
+ * NRF_ERR_UNSUPPORTED when the tcgen05 forward is switched off (NRF_MLP_FWD=mma): callers then evaluate all merged rows. */
+int nrf_mlp_small_fwd_importance(const nrf_mlp_small_shape* shape, const void* packed, const void* enc_merged, const float* ray_sh,
+                                 const uint8_t* keep_merged, const int16_t* perm, int64_t n_rays, int32_t n_importance,
+                                 int32_t n_merged, float* raw_merged, nrf_stream stream);
 
 /* grad_raw [N,4].  grad_in: bf16 [N,32] (NRF_MLP_IN_ENC16_RAYDIRS) or fp32 [N,48] (NRF_MLP_IN_F32_CAT), may be NULL.
  * grad_params_flat[param_count] fp32 is ACCUMULATED into.  Activations are recomputed, nothing was saved. */
@@ -276,11 +288,21 @@ int nrf_sample_pdf_merge(const float* z_coarse, const float* weights, const floa
                          float* z_merged, nrf_stream stream);
 
 /* Same, and perm_out [R, n_importance + S] int16 (nullable): entry j < n_importance is the merged position of the j-th
- * importance sample; entry n_importance + k is the merged position p of coarse sample k if z_merged[r,p] is bit-identical to
- * z_coarse[r,k], else -(p+1) (only on degenerate rays, e.g. ones that miss the box, where fp32 z is not monotone). */
+ * importance sample (in sorted order); entry n_importance + k is the merged position p of coarse sample k, with z_merged[r,p]
+ * bit-identical to z_coarse[r,k] (on rays whose fp32 z is not monotone — ones that miss the box — the sample goes to the sorted
+ * rank of its value).  u_per_ray != 0 re-sorts everything and reports -(p+1) for every coarse sample: nothing is reusable. */
 int nrf_sample_pdf_merge_perm(const float* z_coarse, const float* weights, const float* u, int32_t u_per_ray,
                               int64_t n_rays, int32_t n_samples, int32_t n_importance, float* z_samples,
                               float* z_merged, int16_t* perm_out, nrf_stream stream);
+
+/* Same, and (u shared by the rays only) the coarse pass's raw rows travel with their samples: rows_coarse [R,S,4] f32 ->
+ * rows_merged [R,S+n_importance,4] at the merged positions of the coarse samples.  The reference uses ONE network for the coarse
+ * and the fine pass (src/NeRFRenderer.h:422,447; src/NeRFExecutor.h:882-890), so these are the fine pass's raw rows for those
+ * samples bit for bit; nrf_mlp_small_fwd_importance fills in the importance samples.  Both pointers NULL: as _perm. */
+int nrf_sample_pdf_merge_rows(const float* z_coarse, const float* weights, const float* u, int32_t u_per_ray,
+                              int64_t n_rays, int32_t n_samples, int32_t n_importance, float* z_samples,
+                              float* z_merged, int16_t* perm_out, const float* rows_coarse, float* rows_merged,
+                              nrf_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Rays — RayUtils / Render prologue

@@ -94,12 +94,14 @@ SIGNATURES = {
     "nrf_hash_encode_rays_fwd": (c_int32, [POINTER(HashGrid), _P, _P, c_int32, _P, c_int64, c_int32, c_int32, _P, _P, c_int32, _P, _P, _P, c_int32, _P]),
     "nrf_hash_encode_rays_bwd": (c_int32, [POINTER(HashGrid), _P, c_int32, _P, c_int64, c_int32, c_int32, _P, c_int32, _P, _P]),
     "nrf_sample_pdf_merge_perm": (c_int32, [_P, _P, _P, c_int32, c_int64, c_int32, c_int32, _P, _P, _P, _P]),
+    "nrf_sample_pdf_merge_rows": (c_int32, [_P, _P, _P, c_int32, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P, _P]),
     "nrf_sh_encode_fwd": (c_int32, [_P, c_int32, c_int64, c_int32, _P, _P]),
     "nrf_posenc_fwd": (c_int32, [_P, c_int64, c_int32, c_int32, POINTER(c_float), c_int32, _P, _P]),
     "nrf_mlp_small_packed_bytes": (c_int64, [POINTER(MlpSmallShape)]),
     "nrf_mlp_small_param_count": (c_int64, [POINTER(MlpSmallShape)]),
     "nrf_mlp_small_pack": (c_int32, [POINTER(MlpSmallShape), _P, _P, _P]),
     "nrf_mlp_small_fwd": (c_int32, [POINTER(MlpSmallShape), _P, c_int32, _P, _P, c_int32, _P, c_int64, _P, _P]),
+    "nrf_mlp_small_fwd_importance": (c_int32, [POINTER(MlpSmallShape), _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
     "nrf_mlp_small_bwd": (c_int32, [POINTER(MlpSmallShape), _P, c_int32, _P, _P, c_int32, _P, c_int64, _P, _P, _P, _P]),
     "nrf_composite_fwd": (c_int32, [_P, c_int32, _P, _P, _P, c_float, c_int32, c_int64, c_int32, _P, _P, _P, _P, _P, _P]),
     "nrf_composite_bwd": (c_int32, [_P, c_int32, _P, _P, _P, c_float, c_int32, c_int64, c_int32, _P, _P, _P, _P, _P, _P, _P]),

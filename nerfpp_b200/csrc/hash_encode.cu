@@ -94,11 +94,12 @@ __device__ __forceinline__ void load_point(const PointSrc& ps, int64_t i, float&
 // cells, same table).  perm [R, N+S_prev] is nrf_sample_pdf_merge_perm's output: thread t of a ray handles
 //   t <  N          the t-th importance sample: encode it, write row perm[t]
 //   t >= N, p >= 0  coarse sample t-N, found unchanged at merged position p: COPY its row (and keep flag) from the coarse pass
+//                   (enc == nullptr: leave the row alone — inference, where nrf_mlp_small_fwd_importance never reads it)
 //   t >= N, p <  0  coarse sample whose z moved: encode the merged position -(p+1) like any other
 // so that warps are homogeneous (all-encode or all-copy) instead of one lane in three idling through every gather.
 struct Reuse {
 	const int16_t* perm;      // [R, S] (S = N + S_prev) or nullptr
-	const void* enc;          // [R, S_prev, L*F] in the output layout
+	const void* enc;          // [R, S_prev, L*F] in the output layout, or nullptr = do not copy
 	const uint8_t* keep;      // [R, S_prev] or nullptr
 	int S_prev;
 };
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(128) hash_fwd_kernel(HashArgs a, const __half*
 				const int64_t from = static_cast<int64_t>(ray) * ru.S_prev + (t - (ps.S - ru.S_prev));
 				const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(ru.enc) + from * row_bytes);
 				uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + (row0 + p) * row_bytes);
-				const int nq = row_bytes / 16;
+				const int nq = ru.enc ? row_bytes / 16 : 0;   // enc == nullptr: the caller reads these rows nowhere (inference), skip the copy
 				if (SPLIT == 1) {
 					for (int q = 0; q < nq; q++) d4[q] = __ldg(s4 + q);
 				} else {
@@ -675,7 +676,7 @@ int nrf_hash_encode_rays_fwd(const nrf_hash_grid* grid, const void* table_f16, c
 	NRF_REQUIRE(n_points < (int64_t(1) << 31), "n_rays * n_samples must be < 2^31 per call");
 	Reuse ru{nullptr, nullptr, nullptr, 0};
 	if (reuse_perm) {
-		NRF_REQUIRE(grid != nullptr && reuse_enc && reuse_samples >= 1 && reuse_samples <= n_samples && n_samples < 32768, "bad reuse arguments");
+		NRF_REQUIRE(grid != nullptr && reuse_samples >= 1 && reuse_samples <= n_samples && n_samples < 32768, "bad reuse arguments");
 		const int row_bytes = grid->n_levels * grid->n_features * (layout == NRF_ENC_F32 ? 4 : 2);
 		NRF_REQUIRE(row_bytes % 16 == 0 && ((reinterpret_cast<uintptr_t>(reuse_enc) | reinterpret_cast<uintptr_t>(enc_out)) & 15) == 0,
 			"row reuse needs 16-byte aligned rows");

@@ -666,6 +666,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 // mlp_small_tc.cu
 cudaError_t launch_mlp_small_fwd_tc(const uint32_t* blob, int in_kind, const void* enc, const float* ray_sh, int S, const uint8_t* keep, int64_t n,
 	float* raw_out, cudaStream_t stream);
+cudaError_t launch_mlp_small_fwd_tc_importance(const uint32_t* blob, const void* enc, const float* ray_sh, const uint8_t* keep, const int16_t* perm,
+	int64_t n_rays, int n_importance, int n_merged, float* raw_out, cudaStream_t stream);
 
 // NRF_MLP_FWD=mma selects the mma.sync forward (kept as the A/B baseline of the tcgen05 kernel); read once
 static bool use_tcgen05_fwd()
@@ -727,6 +729,26 @@ int nrf_mlp_small_fwd(const nrf_mlp_small_shape* shape, const void* packed, nrf_
 	else
 		mlp_small_fwd_kernel<NRF_MLP_IN_F32_CAT><<<blocks, kFwdWarps * 32, 0, as_stream(stream)>>>(blob, enc, ray_sh, samples_per_ray, keep, n, raw_out);
 	NRF_CHECK_LAUNCH("mlp_small_fwd_kernel");
+	return NRF_OK;
+}
+
+int nrf_mlp_small_fwd_importance(const nrf_mlp_small_shape* shape, const void* packed, const void* enc_merged, const float* ray_sh,
+	const uint8_t* keep_merged, const int16_t* perm, int64_t n_rays, int32_t n_importance, int32_t n_merged, float* raw_merged, nrf_stream stream)
+{
+	if (int rc = check_shape(shape)) return rc;
+	NRF_REQUIRE(n_rays >= 0 && n_importance >= 1 && n_merged > n_importance && n_merged < 32768, "bad sizes");
+	NRF_REQUIRE(n_rays * n_merged < (int64_t(1) << 31), "n_rays * n_merged must be < 2^31 per call");
+	if (n_rays == 0) return NRF_OK;
+	NRF_REQUIRE(packed && enc_merged && ray_sh && perm && raw_merged, "null pointer");
+	if (!use_tcgen05_fwd()) {
+		set_error("nrf_mlp_small_fwd_importance: runs on the tcgen05 forward only (NRF_MLP_FWD=mma is set)");
+		return NRF_ERR_UNSUPPORTED;
+	}
+	NRF_REQUIRE(((reinterpret_cast<uintptr_t>(packed) | reinterpret_cast<uintptr_t>(enc_merged) | reinterpret_cast<uintptr_t>(raw_merged)) & 15) == 0,
+		"packed / enc_merged / raw_merged must be 16-byte aligned");
+	NRF_CUDA(launch_mlp_small_fwd_tc_importance(reinterpret_cast<const uint32_t*>(packed), enc_merged, ray_sh, keep_merged, perm, n_rays, n_importance,
+		n_merged, raw_merged, as_stream(stream)));
+	count_launch();
 	return NRF_OK;
 }
 

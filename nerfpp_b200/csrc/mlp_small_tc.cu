@@ -78,10 +78,26 @@ struct RowInputs {
 	bool kept;
 };
 
-template <int IN_KIND>
-__device__ __forceinline__ void load_enc_row(RowInputs& in, const void* __restrict__ enc, int64_t r, int64_t n)
+// Importance-only evaluation (nrf_mlp_small_fwd_importance): work row r = (ray, j < N) lives at row ray * T + perm[ray, j] of the
+// merged fine-pass arrays (perm: nrf_sample_pdf_merge_perm); perm == nullptr: rows are their own positions.
+struct RowMap {
+	const int16_t* perm;
+	int N, T;
+};
+
+__device__ __forceinline__ int64_t merged_row(const RowMap& m, int64_t r, int64_t n)
 {
-	const bool ok = r < n;
+	if (r >= n) return 0;
+	const uint32_t ray = static_cast<uint32_t>(r) / static_cast<uint32_t>(m.N);
+	const uint32_t j = static_cast<uint32_t>(r) - ray * static_cast<uint32_t>(m.N);
+	const int64_t row0 = static_cast<int64_t>(ray) * m.T;
+	return row0 + m.perm[row0 + j];
+}
+
+// r: the row's position in enc / keep / raw_out; ok: the work row exists
+template <int IN_KIND>
+__device__ __forceinline__ void load_enc_row(RowInputs& in, const void* __restrict__ enc, int64_t r, bool ok)
+{
 	if (IN_KIND == NRF_MLP_IN_ENC16_RAYDIRS) {
 		const uint4* e = reinterpret_cast<const uint4*>(enc) + r * 4;
 #pragma unroll
@@ -100,12 +116,12 @@ __device__ __forceinline__ void load_enc_row(RowInputs& in, const void* __restri
 	}
 }
 
+// w: the work row (ray = w / S); r: its position in enc / keep
 template <int IN_KIND>
 __device__ __forceinline__ void load_view_row(RowInputs& in, const void* __restrict__ enc, const float* __restrict__ ray_sh, int S,
-	const uint8_t* __restrict__ keep, int64_t r, int64_t n)
+	const uint8_t* __restrict__ keep, int64_t w, int64_t r, bool ok)
 {
-	const bool ok = r < n;
-	const float4* vp = IN_KIND == NRF_MLP_IN_ENC16_RAYDIRS ? reinterpret_cast<const float4*>(ray_sh + (ok ? r / S : 0) * 16)
+	const float4* vp = IN_KIND == NRF_MLP_IN_ENC16_RAYDIRS ? reinterpret_cast<const float4*>(ray_sh + (ok ? w / S : 0) * 16)
 	                                                       : reinterpret_cast<const float4*>(reinterpret_cast<const float*>(enc) + (ok ? r : 0) * 48 + 32);
 #pragma unroll
 	for (int q = 0; q < 4; q++) {
@@ -125,9 +141,9 @@ __device__ __forceinline__ void publish_a(uint64_t* a_ready, int lane)
 	if (lane == 0) mbar_arrive(a_ready);
 }
 
-template <int IN_KIND>
+template <int IN_KIND, bool MAPPED>
 __global__ void __launch_bounds__(kThreads, 1) mlp_small_fwd_tc_kernel(const uint32_t* __restrict__ blob, const void* __restrict__ enc,
-	const float* __restrict__ ray_sh, int S, const uint8_t* __restrict__ keep, int64_t n, float* __restrict__ raw_out)
+	const float* __restrict__ ray_sh, int S, const uint8_t* __restrict__ keep, int64_t n, RowMap map, float* __restrict__ raw_out)
 {
 	__shared__ Smem sm;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -164,11 +180,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_small_fwd_tc_kernel(const uin
 	int64_t tile = blockIdx.x + static_cast<int64_t>(gridDim.x) * s;
 
 	RowInputs in;
-	if (tile < n_tiles) load_enc_row<IN_KIND>(in, enc, tile * 128 + row, n);
+	int64_t r_next = 0;                                             // position of the prefetched row in enc / keep / raw_out
+	if (tile < n_tiles) {
+		const int64_t w = tile * 128 + row;
+		r_next = MAPPED ? merged_row(map, w, n) : w;
+		load_enc_row<IN_KIND>(in, enc, r_next, w < n);
+	}
 	if (issuer) mbar_wait(&sm.w_ready, 0);
 
 	for (; tile < n_tiles; tile += stride) {
-		const int64_t r = tile * 128 + row;
+		const int64_t w = tile * 128 + row;                         // work row
+		const int64_t r = r_next;
+		const bool ok = w < n;
 		// ---- layer 0 operand
 		tmem_st16(t_lane + kColA, in.e);
 		publish_a(a_ready, lane);
@@ -188,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_small_fwd_tc_kernel(const uin
 		publish_a(a_ready, lane);
 		if (issuer) issue_layer<1>(a_ready, d_ready, pa, col, w_saddr);
 		// this row's view channels (per-ray SH table: cache hits) arrive while layer 1 runs
-		load_view_row<IN_KIND>(in, enc, ray_sh, S, keep, r, n);
+		load_view_row<IN_KIND>(in, enc, ray_sh, S, keep, w, r, ok);
 
 		// ---- layer 1 -> [sigma | geo(15)]; colour input = [views(16) | 0 | geo(15)]
 		mbar_wait(d_ready, pd); pd ^= 1u;
@@ -223,7 +246,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_small_fwd_tc_kernel(const uin
 				else issue_layer<4>(a_ready, d_ready, pa, col, w_saddr);
 			}
 			// next tile's encodings: in flight while this tile finishes its last two layers
-			if (l == 2 && tile + stride < n_tiles) load_enc_row<IN_KIND>(in, enc, (tile + stride) * 128 + row, n);
+			if (l == 2 && tile + stride < n_tiles) {
+				const int64_t wn = (tile + stride) * 128 + row;
+				r_next = MAPPED ? merged_row(map, wn, n) : wn;
+				load_enc_row<IN_KIND>(in, enc, r_next, wn < n);
+			}
 		}
 
 		// ---- layer 4 -> rgb; out = [r, g, b, sigma (0 outside the box, src/NeRFRenderer.h:188)]
@@ -232,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_small_fwd_tc_kernel(const uin
 		uint32_t c[4];
 		tmem_ld4(t_lane + kColD16, c);
 		tmem_ld_wait();
-		if (r < n) *reinterpret_cast<float4*>(raw_out + r * 4) = make_float4(__uint_as_float(c[0]), __uint_as_float(c[1]), __uint_as_float(c[2]), kept ? sigma : 0.f);
+		if (ok) *reinterpret_cast<float4*>(raw_out + r * 4) = make_float4(__uint_as_float(c[0]), __uint_as_float(c[1]), __uint_as_float(c[2]), kept ? sigma : 0.f);
 	}
 
 	fence_before();
@@ -251,10 +278,22 @@ cudaError_t launch_mlp_small_fwd_tc(const uint32_t* blob, int in_kind, const voi
 {
 	const int64_t tiles = (n + 127) / 128;
 	const int blocks = static_cast<int>(std::min<int64_t>((tiles + tc::kSlots - 1) / tc::kSlots, kNumSMs));
+	const tc::RowMap none{nullptr, 1, 1};
 	if (in_kind == NRF_MLP_IN_ENC16_RAYDIRS)
-		tc::mlp_small_fwd_tc_kernel<NRF_MLP_IN_ENC16_RAYDIRS><<<blocks, tc::kThreads, 0, stream>>>(blob, enc, ray_sh, S, keep, n, raw_out);
+		tc::mlp_small_fwd_tc_kernel<NRF_MLP_IN_ENC16_RAYDIRS, false><<<blocks, tc::kThreads, 0, stream>>>(blob, enc, ray_sh, S, keep, n, none, raw_out);
 	else
-		tc::mlp_small_fwd_tc_kernel<NRF_MLP_IN_F32_CAT><<<blocks, tc::kThreads, 0, stream>>>(blob, enc, ray_sh, S, keep, n, raw_out);
+		tc::mlp_small_fwd_tc_kernel<NRF_MLP_IN_F32_CAT, false><<<blocks, tc::kThreads, 0, stream>>>(blob, enc, ray_sh, S, keep, n, none, raw_out);
+	return cudaGetLastError();
+}
+
+// called by nrf_mlp_small_fwd_importance (mlp_small.cu): n = n_rays * n_importance work rows scattered over the merged arrays
+cudaError_t launch_mlp_small_fwd_tc_importance(const uint32_t* blob, const void* enc, const float* ray_sh, const uint8_t* keep, const int16_t* perm,
+	int64_t n_rays, int n_importance, int n_merged, float* raw_out, cudaStream_t stream)
+{
+	const int64_t n = n_rays * n_importance, tiles = (n + 127) / 128;
+	const int blocks = static_cast<int>(std::min<int64_t>((tiles + tc::kSlots - 1) / tc::kSlots, kNumSMs));
+	const tc::RowMap map{perm, n_importance, n_merged};
+	tc::mlp_small_fwd_tc_kernel<NRF_MLP_IN_ENC16_RAYDIRS, true><<<blocks, tc::kThreads, 0, stream>>>(blob, enc, ray_sh, n_importance, keep, n, map, raw_out);
 	return cudaGetLastError();
 }
 

@@ -13,7 +13,7 @@ namespace nrf {
 static inline int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
 
 struct RenderWs {
-	int64_t ray_batch, ray_sh, z, z_fine, w_coarse, enc, keep, raw, total;
+	int64_t ray_batch, ray_sh, z, z_fine, w_coarse, enc, keep, raw, raw_coarse, perm, total;
 };
 
 static RenderWs render_layout(const nrf_render_config* c, const nrf_hash_grid* g, int64_t R)
@@ -30,6 +30,8 @@ static RenderWs render_layout(const nrf_render_config* c, const nrf_hash_grid* g
 	w.enc = off;       off = align256(off + R * T * D * 2);
 	w.keep = off;      off = align256(off + R * T);
 	w.raw = off;       off = align256(off + R * T * 16);
+	w.raw_coarse = off; off = align256(off + R * S * 16);
+	w.perm = off;      off = align256(off + R * T * 2);
 	w.total = off;
 	return w;
 }
@@ -75,6 +77,12 @@ int nrf_render_rays_fwd(const nrf_render_config* cfg, const nrf_hash_grid* grid,
 	void* enc = base + w.enc;
 	uint8_t* keep = reinterpret_cast<uint8_t*>(base + w.keep);
 	float* raw = reinterpret_cast<float*>(base + w.raw);
+	float* raw_coarse = reinterpret_cast<float*>(base + w.raw_coarse);
+	int16_t* perm = reinterpret_cast<int16_t*>(base + w.perm);
+	// One network for both passes (src/NeRFRenderer.h:422,447): the merged fine pass re-uses the coarse pass's raw rows for the coarse
+	// samples and gathers / evaluates the importance samples only — the same bits as evaluating all S + N rows (tests/test_gpu_render.py).
+	// NRF_RENDER_REUSE=0 evaluates every merged row (the A/B baseline).
+	static const bool reuse = [] { const char* e = getenv("NRF_RENDER_REUSE"); return !(e && e[0] == '0'); }();
 
 	int rc;
 	// Render prologue + coarse depths + per-ray SH table: one launch (bit-identical to nrf_rays_prepare + nrf_sh_encode_fwd + nrf_z_sample)
@@ -82,12 +90,24 @@ int nrf_render_rays_fwd(const nrf_render_config* cfg, const nrf_hash_grid* grid,
 	                        stream))) return rc;
 	// coarse pass
 	if ((rc = nrf_hash_encode_rays_fwd(grid, table_f16, ray_batch, 11, z, n_rays, S, 1, keep, enc, NRF_ENC_F16, nullptr, nullptr, nullptr, 0, stream))) return rc;
-	if ((rc = nrf_mlp_small_fwd(shape, packed, NRF_MLP_IN_ENC16_RAYDIRS, enc, ray_sh, S, keep, n_rays * S, raw, stream))) return rc;
-	if ((rc = nrf_composite_fwd(raw, 4, z, rays_d, nullptr, 0.f, cfg->white_bkgr, n_rays, S, nullptr, nullptr, nullptr, nullptr, w_coarse, stream))) return rc;
+	if ((rc = nrf_mlp_small_fwd(shape, packed, NRF_MLP_IN_ENC16_RAYDIRS, enc, ray_sh, S, keep, n_rays * S, reuse ? raw_coarse : raw, stream))) return rc;
+	if ((rc = nrf_composite_fwd(reuse ? raw_coarse : raw, 4, z, rays_d, nullptr, 0.f, cfg->white_bkgr, n_rays, S, nullptr, nullptr, nullptr, nullptr, w_coarse,
+	                            stream))) return rc;
 	// importance sampling + merge, fine pass
-	if ((rc = nrf_sample_pdf_merge(z, w_coarse, u, 0, n_rays, S, N, nullptr, z_fine, stream))) return rc;
-	if ((rc = nrf_hash_encode_rays_fwd(grid, table_f16, ray_batch, 11, z_fine, n_rays, T, 1, keep, enc, NRF_ENC_F16, nullptr, nullptr, nullptr, 0, stream))) return rc;
-	if ((rc = nrf_mlp_small_fwd(shape, packed, NRF_MLP_IN_ENC16_RAYDIRS, enc, ray_sh, T, keep, n_rays * T, raw, stream))) return rc;
+	bool fine_done = false;
+	if (reuse) {
+		if ((rc = nrf_sample_pdf_merge_rows(z, w_coarse, u, 0, n_rays, S, N, nullptr, z_fine, perm, raw_coarse, raw, stream))) return rc;
+		if ((rc = nrf_hash_encode_rays_fwd(grid, table_f16, ray_batch, 11, z_fine, n_rays, T, 1, keep, enc, NRF_ENC_F16, perm, nullptr, nullptr, S, stream))) return rc;
+		rc = nrf_mlp_small_fwd_importance(shape, packed, enc, ray_sh, keep, perm, n_rays, N, T, raw, stream);
+		if (rc != NRF_OK && rc != NRF_ERR_UNSUPPORTED) return rc;
+		fine_done = rc == NRF_OK;
+	} else {
+		if ((rc = nrf_sample_pdf_merge(z, w_coarse, u, 0, n_rays, S, N, nullptr, z_fine, stream))) return rc;
+	}
+	if (!fine_done) {
+		if ((rc = nrf_hash_encode_rays_fwd(grid, table_f16, ray_batch, 11, z_fine, n_rays, T, 1, keep, enc, NRF_ENC_F16, nullptr, nullptr, nullptr, 0, stream))) return rc;
+		if ((rc = nrf_mlp_small_fwd(shape, packed, NRF_MLP_IN_ENC16_RAYDIRS, enc, ray_sh, T, keep, n_rays * T, raw, stream))) return rc;
+	}
 	if ((rc = nrf_composite_fwd(raw, 4, z_fine, rays_d, nullptr, 0.f, cfg->white_bkgr, n_rays, T, rgb, depth, disp, acc, weights, stream))) return rc;
 	return NRF_OK;
 }

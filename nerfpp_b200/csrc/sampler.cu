@@ -137,7 +137,8 @@ __device__ __forceinline__ void restore_order(float* a, int n, int lane)
 // shared memory per warp: cdf[B] bins[B] zs[N] zc[S] (+ sort scratch when u is per-ray)
 __global__ void __launch_bounds__(kSamplerWarps * 32) sample_pdf_merge_kernel(const float* __restrict__ z_coarse,
 	const float* __restrict__ weights, const float* __restrict__ u, int u_per_ray, int64_t R, int S, int N,
-	float* __restrict__ z_samples, float* __restrict__ z_merged, int16_t* __restrict__ perm_out, int per_warp_floats, int sort_pow2)
+	float* __restrict__ z_samples, float* __restrict__ z_merged, int16_t* __restrict__ perm_out, const float4* __restrict__ rows_coarse,
+	float4* __restrict__ rows_merged, int per_warp_floats, int sort_pow2)
 {
 	extern __shared__ float smem[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -168,15 +169,34 @@ __global__ void __launch_bounds__(kSamplerWarps * 32) sample_pdf_merge_kernel(co
 		restore_order(zs, N, lane);
 		restore_order(zc, S, lane);
 		// rank merge; ties: coarse samples first
-		// perm_out (optional) [R, N+S]: entry j < N is the merged position of the j-th importance sample; entry N+k is the merged
-		// position p of coarse sample k when its z is still bit-identical to z_coarse[r,k] (restore_order did not move another
-		// value there), else -(p+1).  "perm >= 0 at N+k" therefore always means "same z, hence same point" — the contract the
-		// row reuse of nrf_hash_encode_rays_fwd relies on.
+		// perm_out (optional) [R, N+S]: entry j < N is the merged position of the j-th importance sample (in sorted order); entry N+k
+		// is the merged position of coarse sample k, i.e. z_merged[perm[N+k]] is bit-identical to z_coarse[r,k] — "same z, hence
+		// same point": the contract the row reuse of nrf_hash_encode_rays_fwd and nrf_mlp_small_fwd_importance rely on.  With u shared
+		// by the rays every entry is >= 0; the per-ray-u path below reports -(p+1) (nothing reusable).
+		// rows_coarse / rows_merged (optional): the coarse pass's 16-byte raw rows [R,S,4] travel to their merged positions [R,S+N,4].
 		int16_t* po = perm_out ? perm_out + ray * (S + N) : nullptr;
-		for (int k = lane; k < S; k += 32) {
-			const int pos = k + lower_bound(zs, N, zc[k]);
-			out[pos] = zc[k];
-			if (po) po[N + k] = static_cast<int16_t>(zc[k] == zrow[k] ? pos : -(pos + 1));
+		bool moved = false;
+		for (int k = lane; k < S; k += 32) moved |= zc[k] != zrow[k];
+		if (!__any_sync(0xffffffffu, moved)) {
+			for (int k = lane; k < S; k += 32) {
+				const int pos = k + lower_bound(zs, N, zc[k]);
+				out[pos] = zc[k];
+				if (po) po[N + k] = static_cast<int16_t>(pos);
+				if (rows_merged) rows_merged[ray * (S + N) + pos] = __ldg(rows_coarse + ray * S + k);
+			}
+		} else {
+			// restore_order permuted the coarse list (a ray that misses the box): coarse sample k goes to the sorted rank of its value,
+			// equal values in index order — the same merged array, and every sample keeps a position that holds its own z
+			for (int k = lane; k < S; k += 32) {
+				const float v = zrow[k];
+				int rank = lower_bound(zc, S, v);
+				for (int i = 0; i < k; i++) rank += zrow[i] == v ? 1 : 0;
+				rank = min(rank, S - 1);   // only a NaN depth could get here out of range
+				const int pos = rank + lower_bound(zs, N, v);
+				out[pos] = v;
+				if (po) po[N + k] = static_cast<int16_t>(pos);
+				if (rows_merged) rows_merged[ray * (S + N) + pos] = __ldg(rows_coarse + ray * S + k);
+			}
 		}
 		for (int j = lane; j < N; j += 32) {
 			const int pos = j + upper_bound(zc, S, zs[j]);
@@ -238,12 +258,23 @@ int nrf_sample_pdf_merge(const float* z_coarse, const float* weights, const floa
 int nrf_sample_pdf_merge_perm(const float* z_coarse, const float* weights, const float* u, int32_t u_per_ray, int64_t n_rays,
 	int32_t n_samples, int32_t n_importance, float* z_samples, float* z_merged, int16_t* perm_out, nrf_stream stream)
 {
+	return nrf_sample_pdf_merge_rows(z_coarse, weights, u, u_per_ray, n_rays, n_samples, n_importance, z_samples, z_merged, perm_out, nullptr, nullptr,
+		stream);
+}
+
+int nrf_sample_pdf_merge_rows(const float* z_coarse, const float* weights, const float* u, int32_t u_per_ray, int64_t n_rays,
+	int32_t n_samples, int32_t n_importance, float* z_samples, float* z_merged, int16_t* perm_out, const float* rows_coarse, float* rows_merged,
+	nrf_stream stream)
+{
 	NRF_REQUIRE(n_samples >= 3, "n_samples must be >= 3");
 	NRF_REQUIRE(n_importance >= 1, "n_importance must be >= 1");
 	NRF_REQUIRE(n_samples + n_importance <= 1024, "n_samples + n_importance > 1024");
 	NRF_REQUIRE(n_rays >= 0, "bad sizes");
 	if (n_rays == 0) return NRF_OK;
 	NRF_REQUIRE(z_coarse && weights && u && z_merged, "null pointer");
+	NRF_REQUIRE((rows_coarse == nullptr) == (rows_merged == nullptr), "rows_coarse and rows_merged go together");
+	NRF_REQUIRE(!rows_merged || !u_per_ray, "the raw-row scatter needs u shared by the rays (per-ray u re-sorts: nothing is reusable)");
+	NRF_REQUIRE(((reinterpret_cast<uintptr_t>(rows_coarse) | reinterpret_cast<uintptr_t>(rows_merged)) & 15) == 0, "raw rows must be 16-byte aligned");
 	int pow2 = 1;
 	while (pow2 < n_samples + n_importance) pow2 <<= 1;
 	const int per_warp = 2 * (n_samples - 1) + n_importance + n_samples + (u_per_ray ? pow2 : 0);
@@ -251,7 +282,8 @@ int nrf_sample_pdf_merge_perm(const float* z_coarse, const float* weights, const
 	NRF_REQUIRE(smem <= 48 * 1024, "shared memory budget exceeded");
 	const unsigned blocks = static_cast<unsigned>((n_rays + kSamplerWarps - 1) / kSamplerWarps);
 	sample_pdf_merge_kernel<<<blocks, kSamplerWarps * 32, smem, as_stream(stream)>>>(z_coarse, weights, u, u_per_ray, n_rays,
-		n_samples, n_importance, z_samples, z_merged, perm_out, per_warp, pow2);
+		n_samples, n_importance, z_samples, z_merged, perm_out, reinterpret_cast<const float4*>(rows_coarse), reinterpret_cast<float4*>(rows_merged),
+		per_warp, pow2);
 	NRF_CHECK_LAUNCH("sample_pdf_merge_kernel");
 	return NRF_OK;
 }

@@ -105,15 +105,18 @@ void HashNeRFTrainGraph::Enqueue(bool with_optimizer)
 	Tensor rgb_c = F32({R, 3}, dev), depth = F32({R}, dev), disp = F32({R}, dev), acc = F32({R}, dev), w_c = F32({R, S}, dev);
 	nrfhost::Check(nrf_composite_fwd(raw_c.data_ptr<float>(), 4, z.data_ptr<float>(), InD.data_ptr<float>(), nullptr, 0.f, 0, R, S, rgb_c.data_ptr<float>(),
 		depth.data_ptr<float>(), disp.data_ptr<float>(), acc.data_ptr<float>(), w_c.data_ptr<float>(), st), "nrf_composite_fwd");
-	// importance samples; the merged list contains the coarse samples bit for bit, so their encoding rows are copied, not gathered again
+	// importance samples; the merged list contains the coarse samples bit for bit, so their encoding rows are copied, not gathered again, and
+	// (one network for both passes, src/NeRFRenderer.h:422,447) their raw rows are the coarse pass's: the fine forward evaluates the N new samples
 	Tensor z_f = F32({R, sf}, dev), perm = torch::empty({R, sf}, torch::TensorOptions().dtype(torch::kInt16).device(dev));
-	nrfhost::Check(nrf_sample_pdf_merge_perm(z.data_ptr<float>(), w_c.data_ptr<float>(), U.data_ptr<float>(), 0, R, S, N, nullptr, z_f.data_ptr<float>(),
-		perm.data_ptr<int16_t>(), st), "nrf_sample_pdf_merge_perm");
 	Tensor enc = torch::empty({nf, 32}, torch::TensorOptions().dtype(torch::kFloat16).device(dev)), keep = torch::empty({nf}, u8), raw = F32({R, sf, 4}, dev);
+	nrfhost::Check(nrf_sample_pdf_merge_rows(z.data_ptr<float>(), w_c.data_ptr<float>(), U.data_ptr<float>(), 0, R, S, N, nullptr, z_f.data_ptr<float>(),
+		perm.data_ptr<int16_t>(), raw_c.data_ptr<float>(), raw.data_ptr<float>(), st), "nrf_sample_pdf_merge_rows");
 	nrfhost::Check(nrf_hash_encode_rays_fwd(&grid, table16, ray_batch.data_ptr<float>(), 11, z_f.data_ptr<float>(), R, sf, 1, keep.data_ptr<uint8_t>(), enc.data_ptr(),
 		NRF_ENC_F16, perm.data_ptr<int16_t>(), enc_c.data_ptr(), keep_c.data_ptr<uint8_t>(), S, st), "nrf_hash_encode_rays_fwd");
-	nrfhost::Check(nrf_mlp_small_fwd(&shape, Packed.data_ptr(), NRF_MLP_IN_ENC16_RAYDIRS, enc.data_ptr(), ray_sh.data_ptr<float>(), sf, keep.data_ptr<uint8_t>(), nf,
-		raw.data_ptr<float>(), st), "nrf_mlp_small_fwd");
+	if (nrf_mlp_small_fwd_importance(&shape, Packed.data_ptr(), enc.data_ptr(), ray_sh.data_ptr<float>(), keep.data_ptr<uint8_t>(), perm.data_ptr<int16_t>(), R, N, sf,
+		raw.data_ptr<float>(), st) != NRF_OK)      // NRF_MLP_FWD=mma: every merged row
+		nrfhost::Check(nrf_mlp_small_fwd(&shape, Packed.data_ptr(), NRF_MLP_IN_ENC16_RAYDIRS, enc.data_ptr(), ray_sh.data_ptr<float>(), sf, keep.data_ptr<uint8_t>(), nf,
+			raw.data_ptr<float>(), st), "nrf_mlp_small_fwd");
 	// RawToOutputs of the fine pass + huber_loss + their backward (src/NeRFRenderer.h:447-448, src/NeRFExecutor.h:883-890, 923): one launch
 	Rgb = F32({R, 3}, dev);
 	Tensor d_raw = F32({R, sf, 4}, dev);

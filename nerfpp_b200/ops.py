@@ -209,6 +209,18 @@ def mlp_small_fwd(packed: torch.Tensor, enc: torch.Tensor, ray_sh: torch.Tensor 
     return out
 
 
+def mlp_small_fwd_importance(packed: torch.Tensor, enc_merged: torch.Tensor, ray_sh: torch.Tensor, keep_merged: torch.Tensor | None,
+                             perm: torch.Tensor, n_importance: int, raw_merged: torch.Tensor, shape=None) -> torch.Tensor:
+    """Evaluate the importance samples only (rows perm[:, :n_importance] of the merged arrays) into raw_merged, whose coarse-sample
+    rows sample_pdf_merge(raw_coarse=...) already holds.  Same bits as mlp_small_fwd over all merged rows."""
+    shape = shape or mlp_shape()
+    r, t = perm.shape
+    assert enc_merged.dtype == f16 and enc_merged.shape[0] == r * t and raw_merged.shape[0] == r * t
+    _run("mlp_small_fwd", lambda: lib().nrf_mlp_small_fwd_importance(C.byref(shape), ptr(packed), ptr(enc_merged, f16), ptr(ray_sh, f32), ptr(keep_merged),
+                                  ptr(perm, torch.int16), r, n_importance, t, ptr(raw_merged, f32), stream()))
+    return raw_merged
+
+
 def mlp_small_bwd(packed: torch.Tensor, enc: torch.Tensor, ray_sh: torch.Tensor | None, samples_per_ray: int,
                   keep: torch.Tensor | None, grad_raw: torch.Tensor, grad_params: torch.Tensor, want_grad_in: bool = True,
                   shape=None, grad_in: torch.Tensor | None = None):
@@ -270,16 +282,20 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, u: torch.Tensor) -> to
     return out
 
 
-def sample_pdf_merge(z_coarse: torch.Tensor, weights: torch.Tensor, u: torch.Tensor, want_samples: bool = False, want_perm: bool = False):
+def sample_pdf_merge(z_coarse: torch.Tensor, weights: torch.Tensor, u: torch.Tensor, want_samples: bool = False, want_perm: bool = False,
+                     raw_coarse: torch.Tensor | None = None):
+    """z_merged [, z_samples] [, perm] [, raw_merged].  raw_coarse [R*S, 4] (u shared by the rays): the coarse pass's raw rows are
+    moved to their merged positions in raw_merged [R*(S+N), 4]; the other rows are left for mlp_small_fwd_importance."""
     r, s = z_coarse.shape
     per_ray = u.dim() == 2
     n = u.shape[-1]
     merged = torch.empty((r, s + n), dtype=f32, device=z_coarse.device)
     samples = torch.empty((r, n), dtype=f32, device=z_coarse.device) if want_samples else None
     src = torch.empty((r, s + n), dtype=torch.int16, device=z_coarse.device) if want_perm else None
-    _run("sample_pdf_merge", lambda: lib().nrf_sample_pdf_merge_perm(ptr(z_coarse, f32), ptr(weights, f32), ptr(u, f32), int(per_ray), r, s, n, ptr(samples),
-                                     ptr(merged), ptr(src), stream()))
-    out = (merged,) + ((samples,) if want_samples else ()) + ((src,) if want_perm else ())
+    raw = torch.empty((r * (s + n), 4), dtype=f32, device=z_coarse.device) if raw_coarse is not None else None
+    _run("sample_pdf_merge", lambda: lib().nrf_sample_pdf_merge_rows(ptr(z_coarse, f32), ptr(weights, f32), ptr(u, f32), int(per_ray), r, s, n, ptr(samples),
+                                     ptr(merged), ptr(src), ptr(raw_coarse, f32), ptr(raw), stream()))
+    out = (merged,) + ((samples,) if want_samples else ()) + ((src,) if want_perm else ()) + ((raw,) if raw is not None else ())
     return out if len(out) > 1 else merged
 
 

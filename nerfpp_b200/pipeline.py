@@ -16,6 +16,7 @@ Configuration is the parity one: ThinRay, Perturb 0, no raw noise, no stochastic
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -244,6 +245,7 @@ class HashNeRF(FlatAdamModel):
         # Copy the coarse samples' encoding rows into the fine pass instead of gathering them again: the merged z list contains the
         # coarse samples bit for bit, so the rows are bit-identical (tests/test_gpu_hash.py::test_row_reuse...); ~10 % of the fine-pass encode.
         self.reuse_coarse_rows = True
+        self.reuse_coarse_raw = os.environ.get("NRF_MLP_FWD", "")[:1] != "m"   # the importance-only forward exists on the tcgen05 kernel only
         self._u_cache = {}
         self._render_ws = None
         self._cam = None
@@ -307,13 +309,21 @@ class HashNeRF(FlatAdamModel):
         enc_c, keep_c, raw = self._network(ray_batch, z, ray_sh)
         coarse = ops.composite_fwd(raw, z, rays_d, white_bkgr)
         u = self._u(n_importance)
-        # the merged list contains the coarse samples bit for bit: optionally their encoding rows are copied, not gathered again
-        if self.reuse_coarse_rows:
-            z_fine, perm = ops.sample_pdf_merge(z, coarse["weights"], u, want_perm=True)
-            reuse = (perm, enc_c, keep_c, z.shape[1])
+        # the merged list contains the coarse samples bit for bit: their encoding rows are copied, not gathered again (reuse_coarse_rows), and —
+        # one network for both passes (src/NeRFRenderer.h:422,447) — their raw rows are the coarse pass's own (reuse_coarse_raw): the fine
+        # forward evaluates the importance samples only.  Same bits either way (tests/test_gpu_pipeline.py).
+        if self.reuse_coarse_rows and self.reuse_coarse_raw:
+            z_fine, perm, raw_m = ops.sample_pdf_merge(z, coarse["weights"], u, want_perm=True, raw_coarse=raw.view(-1, 4))
+            enc, keep = ops.hash_encode_rays_fwd(self.grid, self.table_f16, ray_batch, z_fine, clamp=True, out_f16=True,
+                                                 reuse=(perm, enc_c, keep_c, z.shape[1]))
+            raw = ops.mlp_small_fwd_importance(self.packed, enc, ray_sh, keep, perm, u.shape[-1], raw_m).view(-1, z_fine.shape[1], 4)
         else:
-            z_fine, reuse = ops.sample_pdf_merge(z, coarse["weights"], u), None
-        enc, keep, raw = self._network(ray_batch, z_fine, ray_sh, reuse)
+            if self.reuse_coarse_rows:
+                z_fine, perm = ops.sample_pdf_merge(z, coarse["weights"], u, want_perm=True)
+                reuse = (perm, enc_c, keep_c, z.shape[1])
+            else:
+                z_fine, reuse = ops.sample_pdf_merge(z, coarse["weights"], u), None
+            enc, keep, raw = self._network(ray_batch, z_fine, ray_sh, reuse)
         # fine_composite False (training): the caller composites, takes the loss and back-propagates in one launch (ops.composite_huber_bwd)
         out = ops.composite_fwd(raw, z_fine, rays_d, white_bkgr) if fine_composite else {}
         out["z"] = z_fine

@@ -297,7 +297,8 @@ def test_fused_point_generation_is_bit_identical():
 
 def test_coarse_row_reuse_is_bit_identical():
     """The fine pass copies the encoding rows of the coarse samples it contains (same z => same point): the result must
-    equal a full re-encode bit for bit, src must name only bit-identical z, and every coarse sample must be found."""
+    equal a full re-encode bit for bit, perm must name only bit-identical z, and EVERY coarse sample must be found — also on the
+    ray that misses the box, whose coarse depths the merge re-orders.  The raw-row scatter follows the same positions."""
     from nerfpp_b200 import ops
     grid = _grid()
     g = torch.Generator(device="cuda").manual_seed(6)
@@ -320,7 +321,11 @@ def test_coarse_row_reuse_is_bit_identical():
     assert torch.equal(z_at[claimed], z[claimed])                      # a claimed position holds the coarse z bit for bit
     assert bool((pl[:, :N] >= 0).all())
     regular = (z[:, 1:] > z[:, :-1]).all(dim=1)                        # strictly increasing coarse z (rays that really cross the box)
-    assert int(regular.sum()) > R // 2 and bool(claimed[regular].all()) and not bool(claimed.all())
+    assert int(regular.sum()) > R // 2 and not bool(regular.all()) and bool(claimed.all())
+    rows = torch.randn(R * S, 4, generator=g, device="cuda")
+    zf2, perm2, merged_rows = ops.sample_pdf_merge(z, w, torch.linspace(0, 1, N).cuda(), want_perm=True, raw_coarse=rows)
+    assert torch.equal(zf2, zf) and torch.equal(perm2, perm)
+    assert torch.equal(torch.gather(merged_rows.view(R, S + N, 4), 1, pos[:, N:, None].expand(-1, -1, 4)), rows.view(R, S, 4))
     src = perm
     enc_c, keep_c = ops.hash_encode_rays_fwd(grid, t16, rb2, z)
     full, keep_full = ops.hash_encode_rays_fwd(grid, t16, rb2, zf)

@@ -4,7 +4,10 @@ process through the parity tests of the default path.
   NRF_MLP_BWD_DW=mma    weight gradients of NeRFSmall on mma.sync + ldmatrix.trans instead of tcgen05 (csrc/mlp_small.cu)
   NRF_NERF_CLUSTER=2    classic-NeRF forward with 2-CTA clusters sharing one multicast weight stream (csrc/mlp_nerf_tc.cu)
   NRF_LERF_EPI_WARPS=8  eight epilogue warps in the LeRF SIGMA / HIDDEN programs (csrc/lerf_tc.cu)
-  NRF_ADAM_L2HINT=0     Adam without the L2 eviction-priority hints (csrc/optim.cu)"""
+  NRF_ADAM_L2HINT=0     Adam without the L2 eviction-priority hints (csrc/optim.cu)
+  NRF_RENDER_REUSE=0    nrf_render_rays_fwd evaluating every merged row of the fine pass instead of the importance samples only (csrc/render.cu):
+                        the test compares it with the composed path, which reuses — bit for bit
+  NRF_HASH_SPLIT=0      hash forward with one thread per point instead of four lanes per point (csrc/hash_encode.cu)"""
 import os
 import subprocess
 import sys
@@ -20,6 +23,9 @@ VARIANTS = [
     ({"NRF_NERF_CLUSTER": "2"}, ["test_gpu_mlp_nerf.py"], "forward_matches_oracle or repeatable"),
     ({"NRF_LERF_EPI_WARPS": "8"}, ["test_gpu_lerf.py"], "fixture or oracle"),
     ({"NRF_ADAM_L2HINT": "0"}, ["test_gpu_render.py"], "adam"),
+    ({"NRF_RENDER_REUSE": "0"}, ["test_gpu_pipeline.py"], "fused_render_entry"),
+    ({"NRF_MLP_FWD": "mma"}, ["test_gpu_pipeline.py"], "fused_render_entry or coarse_reuse"),
+    ({"NRF_HASH_SPLIT": "0"}, ["test_gpu_hash.py"], "fixture or reuse or rays"),
 ]
 
 
