@@ -114,6 +114,14 @@ int nrf_hash_encode_rays_fwd(const nrf_hash_grid* grid, const void* table_f16, c
                              const float* z, int64_t n_rays, int32_t n_samples, int clamp_points, uint8_t* keep, void* enc_out,
                              nrf_enc_layout layout, const int16_t* reuse_perm, const void* reuse_enc, const uint8_t* reuse_keep,
                              int32_t reuse_samples, nrf_stream stream);
+/* Same call, same results; ray_group > 1 only changes the order in which the kernel walks the points: neighbouring lanes take the
+ * SAME sample of ray_group neighbouring rays instead of consecutive samples of one ray.  For the rays of a rendered frame
+ * (GetRays order: adjacent pixels, src/RayUtils.h:23-46) those points lie a fraction of a fine cell apart and share most corner
+ * fetches; for a training batch of random pixels (src/NeRFDataset.cpp:109-144) there is nothing to share: use 1. */
+int nrf_hash_encode_rays_fwd_grouped(const nrf_hash_grid* grid, const void* table_f16, const float* ray_batch, int32_t ray_stride,
+                                     const float* z, int64_t n_rays, int32_t n_samples, int clamp_points, uint8_t* keep,
+                                     void* enc_out, nrf_enc_layout layout, const int16_t* reuse_perm, const void* reuse_enc,
+                                     const uint8_t* reuse_keep, int32_t reuse_samples, int32_t ray_group, nrf_stream stream);
 int nrf_hash_encode_rays_bwd(const nrf_hash_grid* grid, const float* ray_batch, int32_t ray_stride, const float* z,
                              int64_t n_rays, int32_t n_samples, int clamp_points, const void* grad_enc, nrf_grad_layout layout,
                              float* grad_table, nrf_stream stream);

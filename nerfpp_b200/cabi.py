@@ -92,6 +92,8 @@ SIGNATURES = {
     "nrf_hash_encode_fwd": (c_int32, [POINTER(HashGrid), _P, _P, c_int64, c_int32, _P, _P, c_int32, _P]),
     "nrf_hash_encode_bwd": (c_int32, [POINTER(HashGrid), _P, c_int64, c_int32, _P, c_int32, _P, _P]),
     "nrf_hash_encode_rays_fwd": (c_int32, [POINTER(HashGrid), _P, _P, c_int32, _P, c_int64, c_int32, c_int32, _P, _P, c_int32, _P, _P, _P, c_int32, _P]),
+    "nrf_hash_encode_rays_fwd_grouped": (c_int32, [POINTER(HashGrid), _P, _P, c_int32, _P, c_int64, c_int32, c_int32, _P, _P, c_int32, _P, _P, _P, c_int32,
+                                                   c_int32, _P]),
     "nrf_hash_encode_rays_bwd": (c_int32, [POINTER(HashGrid), _P, c_int32, _P, c_int64, c_int32, c_int32, _P, c_int32, _P, _P]),
     "nrf_sample_pdf_merge_perm": (c_int32, [_P, _P, _P, c_int32, c_int64, c_int32, c_int32, _P, _P, _P, _P]),
     "nrf_sample_pdf_merge_rows": (c_int32, [_P, _P, _P, c_int32, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P, _P]),

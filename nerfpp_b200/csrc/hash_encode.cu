@@ -74,6 +74,10 @@ struct PointSrc {
 	const float* ray_batch;   // [R, ray_stride]: o at 0..2, d at 3..5
 	const float* z;           // [R,S]
 	int ray_stride, S;
+	// forward only: work items run (ray tile, sample, ray in tile) instead of (ray, sample) when group > 1, so that neighbouring lanes hold
+	// the SAME sample of `group` neighbouring rays — for the rays of a rendered frame (adjacent pixels) these points lie a fraction of a
+	// fine cell apart and share most of their corner fetches, while consecutive samples of one ray are cells apart.  Results do not change.
+	int group, R;
 };
 
 __device__ __forceinline__ void load_point(const PointSrc& ps, int64_t i, float& x, float& y, float& z)
@@ -206,6 +210,13 @@ __global__ void __launch_bounds__(128) hash_fwd_kernel(HashArgs a, const __half*
 		if (item >= n_items) break;
 		int64_t i = SPLIT == 1 ? item : item / SPLIT;
 		const int part = SPLIT == 1 ? 0 : static_cast<int>(item & (SPLIT - 1));
+		if (ps.group > 1) {
+			const uint32_t per = static_cast<uint32_t>(ps.group) * static_cast<uint32_t>(ps.S);
+			const uint32_t tile = static_cast<uint32_t>(i) / per, rem = static_cast<uint32_t>(i) - tile * per;
+			const uint32_t smp = rem / static_cast<uint32_t>(ps.group), ray = tile * ps.group + (rem - smp * ps.group);
+			if (ray >= static_cast<uint32_t>(ps.R)) continue;
+			i = static_cast<int64_t>(ray) * ps.S + smp;
+		}
 
 		if (ru.perm) {
 			const uint32_t ray = static_cast<uint32_t>(i) / static_cast<uint32_t>(ps.S);
@@ -589,7 +600,7 @@ static int launch_hash_fwd(const nrf_hash_grid* grid, const void* table_f16, con
 	const bool split = can_split && split_env != 0;
 #define NRF_LAUNCH_FWD2(FF, O32, SP)                                                                                              \
 	do {                                                                                                                          \
-		const int64_t items = n_points * (SP);                                                                                   \
+		const int64_t items = (ps.group > 1 ? (static_cast<int64_t>(ps.R) + ps.group - 1) / ps.group * ps.group * ps.S : n_points) * (SP); \
 		const LaunchPlan lp = launch_plan(items, 128);                                                                           \
 		if (occ_pad_bytes() > 48 * 1024) cudaFuncSetAttribute(hash_fwd_kernel<FF, O32, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, occ_pad_bytes()); \
 		hash_fwd_kernel<FF, O32, SP><<<lp.grid, 128, occ_pad_bytes(), s>>>(a, t, ps, ru, items, lp.stride, lp.iters, clamp_points, keep, enc_out); \
@@ -669,6 +680,15 @@ int nrf_hash_encode_rays_fwd(const nrf_hash_grid* grid, const void* table_f16, c
 	int64_t n_rays, int32_t n_samples, int clamp_points, uint8_t* keep, void* enc_out, nrf_enc_layout layout, const int16_t* reuse_perm,
 	const void* reuse_enc, const uint8_t* reuse_keep, int32_t reuse_samples, nrf_stream stream)
 {
+	return nrf_hash_encode_rays_fwd_grouped(grid, table_f16, ray_batch, ray_stride, z, n_rays, n_samples, clamp_points, keep, enc_out, layout, reuse_perm,
+		reuse_enc, reuse_keep, reuse_samples, 1, stream);
+}
+
+int nrf_hash_encode_rays_fwd_grouped(const nrf_hash_grid* grid, const void* table_f16, const float* ray_batch, int32_t ray_stride, const float* z,
+	int64_t n_rays, int32_t n_samples, int clamp_points, uint8_t* keep, void* enc_out, nrf_enc_layout layout, const int16_t* reuse_perm,
+	const void* reuse_enc, const uint8_t* reuse_keep, int32_t reuse_samples, int32_t ray_group, nrf_stream stream)
+{
+	NRF_REQUIRE(ray_group >= 1 && ray_group <= 1024, "ray_group out of range");
 	NRF_REQUIRE(n_rays >= 0 && n_samples >= 1 && ray_stride >= 6, "bad sizes");
 	if (n_rays == 0) { HashArgs a; return fill_args(grid, a); }
 	NRF_REQUIRE(ray_batch && z, "null ray_batch / z");
@@ -682,7 +702,8 @@ int nrf_hash_encode_rays_fwd(const nrf_hash_grid* grid, const void* table_f16, c
 			"row reuse needs 16-byte aligned rows");
 		ru = Reuse{reuse_perm, reuse_enc, reuse_keep, reuse_samples};
 	}
-	const PointSrc ps{nullptr, ray_batch, z, ray_stride, n_samples};
+	NRF_REQUIRE((n_rays + ray_group) * n_samples < (int64_t(1) << 31), "(n_rays + ray_group) * n_samples must be < 2^31 per call");
+	const PointSrc ps{nullptr, ray_batch, z, ray_stride, n_samples, ray_group, static_cast<int>(n_rays)};
 	return launch_hash_fwd(grid, table_f16, ps, ru, n_points, clamp_points, keep, enc_out, layout, stream);
 }
 

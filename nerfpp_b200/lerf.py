@@ -19,6 +19,7 @@ CLIP target, backward, Adam over {lang_embedder, lang_model}): `LeRFField.train_
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -77,6 +78,7 @@ class LeRFField(FlatAdamModel):
         self.t_vals = torch.linspace(0.0, 1.0, n_samples, dtype=f32).to(device)                   # src/LeRFRenderer.cpp:112
         self.u = torch.linspace(0.0, 1.0, n_importance, dtype=f32).to(device)                     # src/Sampler.h:20
         self.packed = None
+        self.render_ray_group = int(os.environ.get("NRF_RENDER_RAY_GROUP", "32"))   # render_image: GetRays order = adjacent pixels
         self.reuse_coarse_rows = True        # the fine pass copies the coarse samples' encoding rows instead of gathering them again (bit-identical)
         self._bwd_ws = None
         self.refresh()
@@ -121,12 +123,13 @@ class LeRFField(FlatAdamModel):
         out["z"] = z_fine
         return out
 
-    def render_rays(self, rays_o, rays_d, return_embedding=False, return_weights=True):
-        """LeRFRenderer::RenderRays after Render's prologue (IntersectWithAABB, src/LeRFRenderer.cpp:296-302): LeRFRendererOutputs as a dict."""
+    def render_rays(self, rays_o, rays_d, return_embedding=False, return_weights=True, ray_group=1):
+        """LeRFRenderer::RenderRays after Render's prologue (IntersectWithAABB, src/LeRFRenderer.cpp:296-302): LeRFRendererOutputs as a dict.
+        ray_group > 1: the rays are neighbouring pixels of a frame — the encode kernels walk ray_group of them together (same results)."""
         r = rays_o.shape[0]
         ray_batch, z, _ = ops.ray_setup(rays_o, rays_d, self.bbox, 0.0, self.t_vals, None)
         # coarse pass: density only (RunLENetwork + the weights of RawToLEOutputs)
-        enc_c, keep_c = ops.hash_encode_rays_fwd(self.grid, self.table_f16, ray_batch, z, clamp=True, out_f16=True)
+        enc_c, keep_c = ops.hash_encode_rays_fwd(self.grid, self.table_f16, ray_batch, z, clamp=True, out_f16=True, ray_group=ray_group)
         raw4 = ops.lerf_sigma_fwd(self.packed, enc_c, keep_c)
         coarse = ops.composite_fwd(raw4.view(r, self.S, 4), z, rays_d)
         if self.reuse_coarse_rows:                                                                # :143-147; the merged list holds the coarse z bit for bit
@@ -136,7 +139,7 @@ class LeRFField(FlatAdamModel):
             z_fine, reuse = ops.sample_pdf_merge(z, coarse["weights"], self.u), None
         s = z_fine.shape[1]
         # fine pass
-        enc, keep = ops.hash_encode_rays_fwd(self.grid, self.table_f16, ray_batch, z_fine, clamp=True, out_f16=True, reuse=reuse)
+        enc, keep = ops.hash_encode_rays_fwd(self.grid, self.table_f16, ray_batch, z_fine, clamp=True, out_f16=True, reuse=reuse, ray_group=ray_group)
         raw4, hidden, q = ops.lerf_hidden_fwd(self.packed, enc, keep)
         comp = ops.composite_fwd(raw4.view(r, s, 4), z_fine, rays_d)
         out = {"rendered": ops.lerf_render_embedding(self.packed, comp["weights"], hidden, q), "depth": comp["depth"], "disp": comp["disp"],
@@ -173,5 +176,6 @@ class LeRFField(FlatAdamModel):
     def render_image(self, h, w, K, c2w, chunk=1 << 15, row_begin=0, row_end=None):
         """Render(h, w, K, c2w) for image rows [row_begin, row_end) (src/LeRFRenderer.cpp:266-331; chunking as BatchifyRays :165-263)."""
         rays_o, rays_d = ops.get_rays(h, w, K, c2w, row_begin, row_end, self.device)
-        outs = [self.render_rays(rays_o[i:i + chunk], rays_d[i:i + chunk], return_weights=False) for i in range(0, rays_o.shape[0], chunk)]
+        outs = [self.render_rays(rays_o[i:i + chunk], rays_d[i:i + chunk], return_weights=False, ray_group=self.render_ray_group)
+                for i in range(0, rays_o.shape[0], chunk)]
         return {k: torch.cat([o[k] for o in outs], 0) for k in ("rendered", "depth", "disp", "acc")}

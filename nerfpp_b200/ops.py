@@ -140,17 +140,18 @@ def hash_encode_bwd(grid: HashGridSpec, points: torch.Tensor, grad_enc: torch.Te
 
 
 def hash_encode_rays_fwd(grid: HashGridSpec, table_f16: torch.Tensor, ray_batch: torch.Tensor, z: torch.Tensor, clamp: bool = True,
-                         out_f16: bool = True, reuse=None):
-    """Fused point generation + encode.  reuse = (perm [R,S] int16, enc_prev [R*S_prev, D], keep_prev [R*S_prev] | None, S_prev)."""
+                         out_f16: bool = True, reuse=None, ray_group: int = 1):
+    """Fused point generation + encode.  reuse = (perm [R,S] int16, enc_prev [R*S_prev, D] | None, keep_prev [R*S_prev] | None, S_prev).
+    ray_group > 1: the kernel walks the same sample of ray_group neighbouring rays together (rays of a rendered frame); same results."""
     r, s = z.shape
     d = grid.n_levels * grid.n_features
     out = torch.empty((r * s, d), dtype=f16 if out_f16 else f32, device=z.device)
     keep = torch.empty(r * s, dtype=u8, device=z.device) if clamp else None
     g = grid.c_struct()
     src, enc_prev, keep_prev, s_prev = reuse if reuse is not None else (None, None, None, 0)
-    _run("hash_encode_fwd", lambda: lib().nrf_hash_encode_rays_fwd(C.byref(g), ptr(table_f16, f16), ptr(ray_batch, f32), ray_batch.shape[1], ptr(z, f32),
+    _run("hash_encode_fwd", lambda: lib().nrf_hash_encode_rays_fwd_grouped(C.byref(g), ptr(table_f16, f16), ptr(ray_batch, f32), ray_batch.shape[1], ptr(z, f32),
                                     r, s, int(clamp), ptr(keep), ptr(out), cabi.ENC_F16 if out_f16 else cabi.ENC_F32, ptr(src, torch.int16) if src is not None else None,
-                                    ptr(enc_prev), ptr(keep_prev), s_prev, stream()))
+                                    ptr(enc_prev), ptr(keep_prev), s_prev, ray_group, stream()))
     return out, keep
 
 

@@ -333,6 +333,29 @@ def test_coarse_row_reuse_is_bit_identical():
     assert torch.equal(full, fast) and torch.equal(keep_full, keep_fast)
 
 
+@pytest.mark.parametrize("feat", [2, 8])
+def test_ray_grouped_order_changes_no_bit(feat):
+    """nrf_hash_encode_rays_fwd_grouped walks the same sample of ray_group neighbouring rays together: rows and keep flags are those of the
+    per-ray order, for a ragged ray count (not a multiple of the group), with and without row reuse, at F = 2 (4 lanes / point) and F = 8 (16)."""
+    from nerfpp_b200 import ops
+    grid = _grid(F=feat, T=16)
+    g = torch.Generator(device="cuda").manual_seed(16)
+    t16 = ops.table_to_half(torch.rand(grid.table_scalars(), generator=g, device="cuda") * 2 - 1)
+    R, S, N = 301, 64, 64
+    rb = _ray_batch(R, seed=9)
+    rb2 = ops.rays_prepare(rb[:, 0:3].contiguous(), rb[:, 3:6].contiguous(), BBOX, 0.0, True)
+    z = ops.z_sample(rb2, torch.linspace(0, 1, S).cuda())
+    base, keep = ops.hash_encode_rays_fwd(grid, t16, rb2, z)
+    w = torch.rand(R, S, generator=g, device="cuda")
+    zf, perm = ops.sample_pdf_merge(z, w, torch.linspace(0, 1, N).cuda(), want_perm=True)
+    fine, keep_f = ops.hash_encode_rays_fwd(grid, t16, rb2, zf)
+    for group in (8, 32, 1000):
+        a, k = ops.hash_encode_rays_fwd(grid, t16, rb2, z, ray_group=group)
+        assert torch.equal(a, base) and torch.equal(k, keep), group
+        b, kb = ops.hash_encode_rays_fwd(grid, t16, rb2, zf, reuse=(perm, base, keep, S), ray_group=group)
+        assert torch.equal(b, fine) and torch.equal(kb, keep_f), group
+
+
 def test_against_reference_cuda_kernels(ref_cuda):
     """Live: the reference's CuHashEmbedder forward/backward kernels on the same table, primes and points."""
     if ref_cuda is None:
