@@ -109,7 +109,8 @@ int nrf_hash_encode_bwd(const nrf_hash_grid* grid, const float* points, int64_t 
  * merged z (S = n_importance + reuse_samples).  The reuse_samples coarse samples whose z it reports as bit-identical are not
  * gathered again: their rows (and keep flags) are copied from the coarse call's output reuse_enc [R, reuse_samples, L*F] (same
  * layout) / reuse_keep [R, reuse_samples] — same point, same table, same bits; all other samples are encoded as usual.
- * reuse_enc NULL: those rows of enc_out are left unwritten (inference through nrf_mlp_small_fwd_importance, which never reads them). */
+ * reuse_enc NULL: those rows of enc_out (and their keep flags) are left as they are (inference through nrf_mlp_small_fwd_importance,
+ * which never reads them). */
 int nrf_hash_encode_rays_fwd(const nrf_hash_grid* grid, const void* table_f16, const float* ray_batch, int32_t ray_stride,
                              const float* z, int64_t n_rays, int32_t n_samples, int clamp_points, uint8_t* keep, void* enc_out,
                              nrf_enc_layout layout, const int16_t* reuse_perm, const void* reuse_enc, const uint8_t* reuse_keep,

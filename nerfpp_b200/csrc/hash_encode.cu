@@ -27,7 +27,11 @@ struct HashMeta {
 	float bx[NRF_MAX_LEVELS], by[NRF_MAX_LEVELS], bz[NRF_MAX_LEVELS];
 	uint32_t pa[NRF_MAX_LEVELS], pb[NRF_MAX_LEVELS], pc[NRF_MAX_LEVELS];
 	uint32_t offset[NRF_MAX_LEVELS], size[NRF_MAX_LEVELS], mask[NRF_MAX_LEVELS];
+	// x % size without a division (Granlund & Montgomery, unsigned division by an invariant): t = umulhi(x, magic),
+	// q = (t + ((x - t) >> 1)) >> shift, x - q * size.  shift == kPow2 marks a power-of-two size: x & mask instead.
+	uint32_t magic[NRF_MAX_LEVELS], shift[NRF_MAX_LEVELS];
 };
+constexpr uint32_t kPow2 = 32u;
 
 struct HashArgs {
 	int n_levels, n_volumes;
@@ -53,7 +57,14 @@ __device__ __forceinline__ void stage_meta(HashMeta& m, const HashArgs& a)
 		m.offset[l] = static_cast<uint32_t>(a.feat_local_idx[l]);
 		const uint32_t sz = static_cast<uint32_t>(a.feat_local_size[l]);
 		m.size[l] = sz;
-		m.mask[l] = (sz & (sz - 1u)) == 0u ? sz - 1u : 0u;  // power of two -> and-mask, else generic %
+		if ((sz & (sz - 1u)) == 0u) {
+			m.mask[l] = sz - 1u; m.magic[l] = 0u; m.shift[l] = kPow2;
+		} else {
+			const uint32_t lg = 32u - static_cast<uint32_t>(__clz(sz - 1u));                    // ceil(log2 size), size >= 3 here
+			m.mask[l] = 0u;
+			m.magic[l] = static_cast<uint32_t>((((1ull << lg) - sz) << 32) / sz + 1ull);
+			m.shift[l] = lg - 1u;
+		}
 	}
 	__syncthreads();
 }
@@ -78,6 +89,7 @@ struct PointSrc {
 	// the SAME sample of `group` neighbouring rays — for the rays of a rendered frame (adjacent pixels) these points lie a fraction of a
 	// fine cell apart and share most of their corner fetches, while consecutive samples of one ray are cells apart.  Results do not change.
 	int group, R;
+	int S_work;       // samples per ray the grouped order enumerates: S, or (row reuse without a copy) the importance samples only
 };
 
 __device__ __forceinline__ void load_point(const PointSrc& ps, int64_t i, float& x, float& y, float& z)
@@ -140,14 +152,18 @@ __device__ __forceinline__ void locate(const HashMeta& m, int l, float qx, float
 	c.pos[5] = x1 ^ y0 ^ z1;
 	c.pos[6] = x1 ^ y1 ^ z0;
 	c.pos[7] = x1 ^ y1 ^ z1;
-	const uint32_t mask = m.mask[l];
-	if (mask) {
+	const uint32_t sh = m.shift[l];
+	if (sh == kPow2) {
+		const uint32_t mask = m.mask[l];
 #pragma unroll
 		for (int d = 0; d < 8; d++) c.pos[d] &= mask;
 	} else {
-		const uint32_t sz = m.size[l];
+		const uint32_t sz = m.size[l], mg = m.magic[l];
 #pragma unroll
-		for (int d = 0; d < 8; d++) c.pos[d] %= sz;
+		for (int d = 0; d < 8; d++) {
+			const uint32_t x = c.pos[d], t = __umulhi(x, mg);
+			c.pos[d] = x - ((t + ((x - t) >> 1)) >> sh) * sz;                                     // == x % sz, every x
+		}
 	}
 	const float a = px - fx, b = py - fy, cc = pz - fz;
 	c.w[0] = (1.f - a) * (1.f - b) * (1.f - cc);
@@ -211,7 +227,10 @@ __global__ void __launch_bounds__(128) hash_fwd_kernel(HashArgs a, const __half*
 		int64_t i = SPLIT == 1 ? item : item / SPLIT;
 		const int part = SPLIT == 1 ? 0 : static_cast<int>(item & (SPLIT - 1));
 		if (ps.group > 1) {
-			const uint32_t per = static_cast<uint32_t>(ps.group) * static_cast<uint32_t>(ps.S);
+			// (ray tile, sample, ray in tile); only the first S_work samples of a ray are enumerated.  MEASURED AND NOT KEPT
+			// (profiles/r2_render_ray_group_sweep.jsonl): lanes = 32 neighbouring rays with the level chunk warp-uniform, so that one gather
+			// instruction covers 32 rays at ONE level — 54.9 ms / C4 frame against 50.6 ms with SPLIT lanes per point.
+			const uint32_t per = static_cast<uint32_t>(ps.group) * static_cast<uint32_t>(ps.S_work);
 			const uint32_t tile = static_cast<uint32_t>(i) / per, rem = static_cast<uint32_t>(i) - tile * per;
 			const uint32_t smp = rem / static_cast<uint32_t>(ps.group), ray = tile * ps.group + (rem - smp * ps.group);
 			if (ray >= static_cast<uint32_t>(ps.R)) continue;
@@ -600,7 +619,7 @@ static int launch_hash_fwd(const nrf_hash_grid* grid, const void* table_f16, con
 	const bool split = can_split && split_env != 0;
 #define NRF_LAUNCH_FWD2(FF, O32, SP)                                                                                              \
 	do {                                                                                                                          \
-		const int64_t items = (ps.group > 1 ? (static_cast<int64_t>(ps.R) + ps.group - 1) / ps.group * ps.group * ps.S : n_points) * (SP); \
+		const int64_t items = (ps.group > 1 ? (static_cast<int64_t>(ps.R) + ps.group - 1) / ps.group * ps.group * ps.S_work : n_points) * (SP); \
 		const LaunchPlan lp = launch_plan(items, 128);                                                                           \
 		if (occ_pad_bytes() > 48 * 1024) cudaFuncSetAttribute(hash_fwd_kernel<FF, O32, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, occ_pad_bytes()); \
 		hash_fwd_kernel<FF, O32, SP><<<lp.grid, 128, occ_pad_bytes(), s>>>(a, t, ps, ru, items, lp.stride, lp.iters, clamp_points, keep, enc_out); \
@@ -703,7 +722,8 @@ int nrf_hash_encode_rays_fwd_grouped(const nrf_hash_grid* grid, const void* tabl
 		ru = Reuse{reuse_perm, reuse_enc, reuse_keep, reuse_samples};
 	}
 	NRF_REQUIRE((n_rays + ray_group) * n_samples < (int64_t(1) << 31), "(n_rays + ray_group) * n_samples must be < 2^31 per call");
-	const PointSrc ps{nullptr, ray_batch, z, ray_stride, n_samples, ray_group, static_cast<int>(n_rays)};
+	const int s_work = reuse_perm && !reuse_enc && ray_group > 1 ? n_samples - reuse_samples : n_samples;   // nothing to copy: skip those items
+	const PointSrc ps{nullptr, ray_batch, z, ray_stride, n_samples, ray_group, static_cast<int>(n_rays), s_work};
 	return launch_hash_fwd(grid, table_f16, ps, ru, n_points, clamp_points, keep, enc_out, layout, stream);
 }
 

@@ -354,6 +354,13 @@ def test_ray_grouped_order_changes_no_bit(feat):
         assert torch.equal(a, base) and torch.equal(k, keep), group
         b, kb = ops.hash_encode_rays_fwd(grid, t16, rb2, zf, reuse=(perm, base, keep, S), ray_group=group)
         assert torch.equal(b, fine) and torch.equal(kb, keep_f), group
+        # inference: no copy of the coarse rows (reuse_enc NULL) — the importance samples' rows and keep flags are all that is written
+        c, kc = ops.hash_encode_rays_fwd(grid, t16, rb2, zf, reuse=(perm, None, None, S), ray_group=group)
+        new = perm[:, :N].long()
+        d = fine.shape[1]
+        assert torch.equal(torch.gather(c.view(R, S + N, d), 1, new[:, :, None].expand(-1, -1, d)),
+                           torch.gather(fine.view(R, S + N, d), 1, new[:, :, None].expand(-1, -1, d))), group
+        assert torch.equal(torch.gather(kc.view(R, S + N), 1, new), torch.gather(keep_f.view(R, S + N), 1, new)), group
 
 
 def test_against_reference_cuda_kernels(ref_cuda):
