@@ -347,6 +347,12 @@ int nrf_ray_setup_pixels(const int32_t* pix_hw, int64_t n_rays, const float* K_h
                          int32_t lin_disp, int32_t sh_degree, float* rays_o, float* rays_d, float* target, float* ray_batch, float* z,
                          float* ray_sh, float* zero_scalar, nrf_stream stream);
 
+/* The same prologue for a tile of a frame: ray r is pixel first_pixel + r in GetRays order (src/RayUtils.h:23-46) of an img_w wide view.
+ * rays_o (nullable) / rays_d [R,3] are outputs. */
+int nrf_ray_setup_tile(const float* K_host, const float* c2w_host, int32_t img_w, int64_t first_pixel, int64_t n_rays,
+                       const float* bbox_host, float near_plane, const float* t_vals, int32_t n_samples, int32_t lin_disp,
+                       int32_t sh_degree, float* rays_o, float* rays_d, float* ray_batch, float* z, float* ray_sh, nrf_stream stream);
+
 /* z = near*(1-t)+far*t (or the lin_disp variant), src/NeRFRenderer.h:393-402.  t_vals [S] device. */
 int nrf_z_sample(const float* ray_batch, int32_t ray_stride, const float* t_vals, int64_t n_rays, int32_t n_samples,
                  int32_t lin_disp, float* z, nrf_stream stream);
@@ -390,6 +396,16 @@ int nrf_render_rays_fwd(const nrf_render_config* cfg, const nrf_hash_grid* grid,
                         const nrf_mlp_small_shape* shape, const void* packed, const float* rays_o, const float* rays_d,
                         int64_t n_rays, const float* t_vals, const float* u, void* workspace, int64_t workspace_bytes,
                         float* rgb, float* depth, float* disp, float* acc, float* weights, float* z_out, nrf_stream stream);
+
+/* The same for a tile of a frame given only the camera (Render(h, w, K, c2w), src/NeRFRenderer.h:540-547 with GetRays,
+ * src/RayUtils.h:23-46, fused into the prologue kernel): ray r is pixel first_pixel + r in GetRays order (row-major, img_w wide) of the
+ * view (K_host[9] row-major 3x3, c2w_host[12] = c2w[:3,:4]).  No rays_o / rays_d arrays exist; same results as nrf_get_rays +
+ * nrf_render_rays_fwd bit for bit.  Workspace: nrf_render_rays_workspace_bytes(cfg, grid, n_rays). */
+int nrf_render_tile_fwd(const nrf_render_config* cfg, const nrf_hash_grid* grid, const void* table_f16,
+                        const nrf_mlp_small_shape* shape, const void* packed, const float* K_host, const float* c2w_host,
+                        int32_t img_w, int64_t first_pixel, int64_t n_rays, const float* t_vals, const float* u, void* workspace,
+                        int64_t workspace_bytes, float* rgb, float* depth, float* disp, float* acc, float* weights, float* z_out,
+                        nrf_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Training glue restated from NeRFExecutor::Train (src/NeRFExecutor.h:883-890, 539, 986)

@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(256) z_sample_kernel(const float* __restrict__
 // OUTPUTS (the compositing kernels read rays_d), as is the gathered target.
 struct PixelSrc {
 	Cam cam;
-	const int32_t* pix_hw;
+	const int32_t* pix_hw;     // [R,2] (row, column), or nullptr: ray r is pixel first_pixel + r of the image in GetRays order (row-major, img_w wide)
+	int64_t first_pixel;
 	const float* image;
 	int img_w, img_c;
 	float* rays_o_out;
@@ -151,11 +152,22 @@ __global__ void __launch_bounds__(256) ray_setup_kernel(const float* __restrict_
 	const int s = static_cast<int>(e % S);
 	float o[3], d[3], vd[3], tnear, tfar;
 	if (PIXELS) {
-		const int py = ps.pix_hw[2 * ray], px = ps.pix_hw[2 * ray + 1];
+		int py, px;
+		if (ps.pix_hw) {
+			py = ps.pix_hw[2 * ray];
+			px = ps.pix_hw[2 * ray + 1];
+		} else {
+			const int64_t lin = ps.first_pixel + ray;
+			py = static_cast<int>(lin / ps.img_w);
+			px = static_cast<int>(lin - static_cast<int64_t>(py) * ps.img_w);
+		}
 		pixel_ray(ps.cam, py, px, o, d);
 		if (s == 0) {
 #pragma unroll
-			for (int k = 0; k < 3; k++) { ps.rays_o_out[ray * 3 + k] = o[k]; ps.rays_d_out[ray * 3 + k] = d[k]; }
+			for (int k = 0; k < 3; k++) {
+				if (ps.rays_o_out) ps.rays_o_out[ray * 3 + k] = o[k];
+				ps.rays_d_out[ray * 3 + k] = d[k];
+			}
 			if (ps.image && ps.target_out) {
 				const float* src = ps.image + (static_cast<int64_t>(py) * ps.img_w + px) * ps.img_c;
 				for (int k = 0; k < ps.img_c; k++) ps.target_out[ray * ps.img_c + k] = __ldg(src + k);
@@ -361,6 +373,19 @@ int nrf_ray_setup_pixels(const int32_t* pix_hw, int64_t n_rays, const float* K_h
 	fill_cam(ps.cam, K_host, c2w_host);
 	ps.pix_hw = pix_hw; ps.image = image; ps.img_w = img_w; ps.img_c = img_c; ps.rays_o_out = rays_o; ps.rays_d_out = rays_d; ps.target_out = target;
 	return launch_ray_setup(true, nullptr, nullptr, ps, n_rays, bbox_host, near_plane, t_vals, n_samples, lin_disp, sh_degree, ray_batch, z, ray_sh, zero_scalar, stream);
+}
+
+int nrf_ray_setup_tile(const float* K_host, const float* c2w_host, int32_t img_w, int64_t first_pixel, int64_t n_rays, const float* bbox_host, float near_plane,
+	const float* t_vals, int32_t n_samples, int32_t lin_disp, int32_t sh_degree, float* rays_o, float* rays_d, float* ray_batch, float* z, float* ray_sh,
+	nrf_stream stream)
+{
+	NRF_REQUIRE(K_host && c2w_host, "null camera");
+	NRF_REQUIRE(img_w > 0 && first_pixel >= 0, "bad image width / first pixel");
+	NRF_REQUIRE(n_rays <= 0 || rays_d, "null rays_d");
+	PixelSrc ps{};
+	fill_cam(ps.cam, K_host, c2w_host);
+	ps.first_pixel = first_pixel; ps.img_w = img_w; ps.rays_o_out = rays_o; ps.rays_d_out = rays_d;
+	return launch_ray_setup(true, nullptr, nullptr, ps, n_rays, bbox_host, near_plane, t_vals, n_samples, lin_disp, sh_degree, ray_batch, z, ray_sh, nullptr, stream);
 }
 
 int nrf_z_sample(const float* ray_batch, int32_t ray_stride, const float* t_vals, int64_t n_rays, int32_t n_samples,

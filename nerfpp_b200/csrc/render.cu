@@ -13,7 +13,7 @@ namespace nrf {
 static inline int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
 
 struct RenderWs {
-	int64_t ray_batch, ray_sh, z, z_fine, w_coarse, enc, keep, raw, raw_coarse, perm, total;
+	int64_t ray_batch, ray_sh, z, z_fine, w_coarse, enc, keep, raw, raw_coarse, perm, rays_d, total;
 };
 
 static RenderWs render_layout(const nrf_render_config* c, const nrf_hash_grid* g, int64_t R)
@@ -32,6 +32,7 @@ static RenderWs render_layout(const nrf_render_config* c, const nrf_hash_grid* g
 	w.raw = off;       off = align256(off + R * T * 16);
 	w.raw_coarse = off; off = align256(off + R * S * 16);
 	w.perm = off;      off = align256(off + R * T * 2);
+	w.rays_d = off;    off = align256(off + R * 3 * 4);
 	w.total = off;
 	return w;
 }
@@ -56,14 +57,21 @@ int64_t nrf_render_rays_workspace_bytes(const nrf_render_config* cfg, const nrf_
 	return render_layout(cfg, grid, n_rays).total;
 }
 
-int nrf_render_rays_fwd(const nrf_render_config* cfg, const nrf_hash_grid* grid, const void* table_f16, const nrf_mlp_small_shape* shape,
-	const void* packed, const float* rays_o, const float* rays_d, int64_t n_rays, const float* t_vals, const float* u, void* workspace,
-	int64_t workspace_bytes, float* rgb, float* depth, float* disp, float* acc, float* weights, float* z_out, nrf_stream stream)
+}
+
+// rays_o / rays_d given: RenderRays on a ray list.  Else (tile): ray r is pixel first_pixel + r of an img_w wide image seen through (K, c2w) —
+// GetRays (src/RayUtils.h:23-46) happens inside the prologue kernel and rays_d lands in the workspace for the compositing kernels.
+static int render_impl(const nrf_render_config* cfg, const nrf_hash_grid* grid, const void* table_f16, const nrf_mlp_small_shape* shape,
+	const void* packed, const float* rays_o, const float* rays_d, const float* K_host, const float* c2w_host, int32_t img_w, int64_t first_pixel,
+	int64_t n_rays, const float* t_vals, const float* u, void* workspace, int64_t workspace_bytes, float* rgb, float* depth, float* disp, float* acc,
+	float* weights, float* z_out, nrf_stream stream)
 {
 	if (int rc = check_render_args(cfg, grid)) return rc;
 	NRF_REQUIRE(n_rays >= 0, "negative n_rays");
 	if (n_rays == 0) return NRF_OK;
-	NRF_REQUIRE(table_f16 && shape && packed && rays_o && rays_d && t_vals && u && workspace, "null pointer");
+	const bool tile = rays_d == nullptr;
+	NRF_REQUIRE(table_f16 && shape && packed && t_vals && u && workspace, "null pointer");
+	NRF_REQUIRE(tile ? (K_host && c2w_host && img_w > 0 && first_pixel >= 0) : (rays_o != nullptr), "rays or camera missing");
 	NRF_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
 	const RenderWs w = render_layout(cfg, grid, n_rays);
 	NRF_REQUIRE(workspace_bytes >= w.total, "workspace too small (nrf_render_rays_workspace_bytes)");
@@ -89,8 +97,13 @@ int nrf_render_rays_fwd(const nrf_render_config* cfg, const nrf_hash_grid* grid,
 
 	int rc;
 	// Render prologue + coarse depths + per-ray SH table: one launch (bit-identical to nrf_rays_prepare + nrf_sh_encode_fwd + nrf_z_sample)
-	if ((rc = nrf_ray_setup(rays_o, rays_d, n_rays, cfg->bbox, cfg->near_plane, t_vals, S, cfg->lin_disp, cfg->sh_degree, ray_batch, z, ray_sh, nullptr,
-	                        stream))) return rc;
+	if (tile) {
+		float* rd = reinterpret_cast<float*>(base + w.rays_d);
+		if ((rc = nrf_ray_setup_tile(K_host, c2w_host, img_w, first_pixel, n_rays, cfg->bbox, cfg->near_plane, t_vals, S, cfg->lin_disp, cfg->sh_degree, nullptr,
+		                             rd, ray_batch, z, ray_sh, stream))) return rc;
+		rays_d = rd;
+	} else if ((rc = nrf_ray_setup(rays_o, rays_d, n_rays, cfg->bbox, cfg->near_plane, t_vals, S, cfg->lin_disp, cfg->sh_degree, ray_batch, z, ray_sh,
+	                               nullptr, stream))) return rc;
 	// coarse pass
 	if ((rc = nrf_hash_encode_rays_fwd_grouped(grid, table_f16, ray_batch, 11, z, n_rays, S, 1, keep, enc, NRF_ENC_F16, nullptr, nullptr, nullptr, 0, group, stream)))
 		return rc;
@@ -116,6 +129,27 @@ int nrf_render_rays_fwd(const nrf_render_config* cfg, const nrf_hash_grid* grid,
 	}
 	if ((rc = nrf_composite_fwd(raw, 4, z_fine, rays_d, nullptr, 0.f, cfg->white_bkgr, n_rays, T, rgb, depth, disp, acc, weights, stream))) return rc;
 	return NRF_OK;
+}
+
+extern "C" {
+
+int nrf_render_rays_fwd(const nrf_render_config* cfg, const nrf_hash_grid* grid, const void* table_f16, const nrf_mlp_small_shape* shape,
+	const void* packed, const float* rays_o, const float* rays_d, int64_t n_rays, const float* t_vals, const float* u, void* workspace,
+	int64_t workspace_bytes, float* rgb, float* depth, float* disp, float* acc, float* weights, float* z_out, nrf_stream stream)
+{
+	NRF_REQUIRE(n_rays <= 0 || (rays_o && rays_d), "null rays");
+	return render_impl(cfg, grid, table_f16, shape, packed, rays_o, rays_d, nullptr, nullptr, 0, 0, n_rays, t_vals, u, workspace, workspace_bytes, rgb, depth,
+		disp, acc, weights, z_out, stream);
+}
+
+int nrf_render_tile_fwd(const nrf_render_config* cfg, const nrf_hash_grid* grid, const void* table_f16, const nrf_mlp_small_shape* shape,
+	const void* packed, const float* K_host, const float* c2w_host, int32_t img_w, int64_t first_pixel, int64_t n_rays, const float* t_vals,
+	const float* u, void* workspace, int64_t workspace_bytes, float* rgb, float* depth, float* disp, float* acc, float* weights, float* z_out,
+	nrf_stream stream)
+{
+	NRF_REQUIRE(K_host && c2w_host, "null camera");
+	return render_impl(cfg, grid, table_f16, shape, packed, nullptr, nullptr, K_host, c2w_host, img_w, first_pixel, n_rays, t_vals, u, workspace,
+		workspace_bytes, rgb, depth, disp, acc, weights, z_out, stream);
 }
 
 }

@@ -425,10 +425,13 @@ def adam_step_scheduled(param, grad, exp_avg, exp_avg_sq, sched_state: torch.Ten
 
 
 def render_rays_fwd(grid: HashGridSpec, table_f16, packed, rays_o, rays_d, t_vals, u, bbox, white_bkgr=False, sh_degree=4, near_plane=0.0,
-                    lin_disp=False, want_weights=False, want_z=False, workspace: torch.Tensor | None = None, shape=None):
-    """RenderRays (inference) as ONE C-ABI call; returns (maps, workspace) — pass the workspace back in to reuse it."""
+                    lin_disp=False, want_weights=False, want_z=False, workspace: torch.Tensor | None = None, shape=None, tile=None):
+    """RenderRays (inference) as ONE C-ABI call; returns (maps, workspace) — pass the workspace back in to reuse it.
+    tile = (K, c2w, img_w, first_pixel, n_rays): the rays are pixels first_pixel .. first_pixel + n_rays of that view in GetRays order and are
+    generated inside the call (nrf_render_tile_fwd); rays_o / rays_d are then ignored."""
     shape = shape or mlp_shape()
-    r, s, n = rays_o.shape[0], t_vals.shape[0], u.shape[0]
+    dev = table_f16.device
+    r, s, n = (tile[4] if tile is not None else rays_o.shape[0]), t_vals.shape[0], u.shape[0]
     cfg = cabi.RenderConfig(s, n, int(white_bkgr), int(lin_disp), sh_degree, float(near_plane))
     for k in range(6):
         cfg.bbox[k] = float(bbox[k])
@@ -437,15 +440,20 @@ def render_rays_fwd(grid: HashGridSpec, table_f16, packed, rays_o, rays_d, t_val
     if need < 0:
         check(-1)
     if workspace is None or workspace.numel() < need:
-        workspace = torch.empty(max(need, 256), dtype=u8, device=rays_o.device)
-    dev = rays_o.device
+        workspace = torch.empty(max(need, 256), dtype=u8, device=dev)
     rgb = torch.empty((r, 3), dtype=f32, device=dev)
     depth, disp, acc = (torch.empty(r, dtype=f32, device=dev) for _ in range(3))
     weights = torch.empty((r, s + n), dtype=f32, device=dev) if want_weights else None
     z = torch.empty((r, s + n), dtype=f32, device=dev) if want_z else None
-    _run("render_rays_fwd", lambda: lib().nrf_render_rays_fwd(C.byref(cfg), C.byref(g), ptr(table_f16, f16), C.byref(shape), ptr(packed), ptr(rays_o, f32),
-                                    ptr(rays_d, f32), r, ptr(t_vals, f32), ptr(u, f32), ptr(workspace), workspace.numel(), ptr(rgb), ptr(depth),
-                                    ptr(disp), ptr(acc), ptr(weights), ptr(z), stream()))
+    if tile is not None:
+        kh, ch = _cam(tile[0], tile[1])
+        _run("render_rays_fwd", lambda: lib().nrf_render_tile_fwd(C.byref(cfg), C.byref(g), ptr(table_f16, f16), C.byref(shape), ptr(packed), kh, ch, int(tile[2]),
+                                        int(tile[3]), r, ptr(t_vals, f32), ptr(u, f32), ptr(workspace), workspace.numel(), ptr(rgb), ptr(depth),
+                                        ptr(disp), ptr(acc), ptr(weights), ptr(z), stream()))
+    else:
+        _run("render_rays_fwd", lambda: lib().nrf_render_rays_fwd(C.byref(cfg), C.byref(g), ptr(table_f16, f16), C.byref(shape), ptr(packed), ptr(rays_o, f32),
+                                        ptr(rays_d, f32), r, ptr(t_vals, f32), ptr(u, f32), ptr(workspace), workspace.numel(), ptr(rgb), ptr(depth),
+                                        ptr(disp), ptr(acc), ptr(weights), ptr(z), stream()))
     return {"rgb": rgb, "depth": depth, "disp": disp, "acc": acc, "weights": weights, "z": z}, workspace
 
 

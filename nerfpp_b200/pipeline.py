@@ -370,11 +370,22 @@ class HashNeRF(FlatAdamModel):
         ops.hash_encode_bwd(self.grid, pts, g_enc, self.grads[:self.n_table], clamp=True)
         return out
 
-    def render_image(self, h, w, K, c2w, chunk=1 << 18, row_begin=0, row_end=None, white_bkgr=False, n_importance=None):
-        """Render(h,w,K,c2w) for image rows [row_begin,row_end) (src/NeRFRenderer.h:540-547, RenderPath :684)."""
-        rays_o, rays_d = ops.get_rays(h, w, K, c2w, row_begin, row_end, self.device)
-        outs = [self.render_rays_fused(rays_o[i:i + chunk], rays_d[i:i + chunk], white_bkgr, n_importance=n_importance)
-                for i in range(0, rays_o.shape[0], chunk)]
+    def render_image(self, h, w, K, c2w, chunk=1 << 18, row_begin=0, row_end=None, white_bkgr=False, n_importance=None, from_camera=True):
+        """Render(h,w,K,c2w) for image rows [row_begin,row_end) (src/NeRFRenderer.h:540-547, RenderPath :684).  from_camera (default): each chunk
+        is ONE C-ABI call that needs only (K, c2w, first pixel, count) — GetRays runs inside its prologue kernel (nrf_render_tile_fwd, SURVEY
+        §8f-3); False: nrf_get_rays + nrf_render_rays_fwd on the ray arrays.  Same bits either way."""
+        row_end = h if row_end is None else row_end
+        n, first = (row_end - row_begin) * w, row_begin * w
+        if from_camera:
+            outs = []
+            for i in range(0, n, chunk):
+                out, self._render_ws = ops.render_rays_fwd(self.grid, self.table_f16, self.packed, None, None, self.t_vals, self._u(n_importance), self.bbox,
+                                                           white_bkgr, self.sh_degree, workspace=self._render_ws,
+                                                           tile=(K, c2w, w, first + i, min(chunk, n - i)))
+                outs.append(out)
+        else:
+            rays_o, rays_d = ops.get_rays(h, w, K, c2w, row_begin, row_end, self.device)
+            outs = [self.render_rays_fused(rays_o[i:i + chunk], rays_d[i:i + chunk], white_bkgr, n_importance=n_importance) for i in range(0, n, chunk)]
         return {k: torch.cat([o[k] for o in outs], 0) for k in ("rgb", "depth", "disp", "acc")}
 
     # -- one optimisation step (src/NeRFExecutor.h:868-890, 923, 986-996)

@@ -164,6 +164,13 @@ def test_render_image_tiles_agree():
     bot = m.render_image(30, 40, K, c2w, row_begin=15, row_end=30)
     assert torch.equal(full["rgb"], torch.cat([top["rgb"], bot["rgb"]], 0))
     assert full["rgb"].shape == (1200, 3)
+    # from the camera alone (nrf_render_tile_fwd: GetRays inside the prologue kernel) == nrf_get_rays + nrf_render_rays_fwd, also when a
+    # chunk starts in the middle of an image row
+    for chunk in (1 << 18, 333):
+        rays = m.render_image(30, 40, K, c2w, chunk=chunk, row_begin=7, row_end=30, from_camera=False)
+        cam = m.render_image(30, 40, K, c2w, chunk=chunk, row_begin=7, row_end=30)
+        for k in ("rgb", "depth", "disp", "acc"):
+            assert torch.equal(rays[k], cam[k]), (k, chunk)
 
 
 def test_graph_replay_matches_eager_steps():
