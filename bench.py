@@ -373,6 +373,32 @@ def gpu_loop_leg(which: str, rays: int, steps: int) -> dict:
                      "nerfpp_b200 C++ drop-in classes (torch::Tensor boundary, FusedAdam" + (", captured train graph)" if fast else ")"))}
 
 
+def shipped_shape_leg(dev, rays: int, steps: int = 50) -> dict:
+    """The network shape src/main.cpp:176-191 ships: SH degree 8 (64 view channels into NeRFSmall), finest resolution 1024, 64 + 192 samples —
+    parity configuration (thin rays, no noise), one CUDA graph.  The 64 view channels enter the fused kernels as a per-ray bias of the colour
+    net's first layer (NRF_MLP_IN_ENC16_RAYBIAS): two small per-ray kernels on top of the C2 step's launches."""
+    import torch
+    from nerfpp_b200.pipeline import HashNeRF, synthetic_rays
+    m = HashNeRF(BBOX, finest_resolution=1024, sh_degree=8, n_samples=N_SAMPLES, n_importance=192, device=dev, seed=42)
+    batch = synthetic_rays(rays, device=dev, seed=31)
+    m.capture_train_step(rays)
+    for _ in range(5):
+        m.train_step_graph(*batch)
+    torch.cuda.synchronize(dev)
+    first = float(m.loss)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        m.train_step_graph(*batch)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    return {"ms_per_step": ms, "value": rays / ms * 1e3, "unit": "rays/s", "steps": steps, "kernels_per_step": m.graph_kernels_per_step,
+            "loss": {"first": first, "last": float(m.loss)},
+            "config": f"src/main.cpp:176-191 shape: L16 F2 T2^19 16->1024 grid, SH degree 8 (64 view channels), NeRFSmall 32->64->16 | 79->64->64->3, "
+                      f"{rays} rays x (64 coarse + 192 importance) samples, parity configuration, one CUDA graph"}
+
+
 def shipped_leg(dev, rays: int, steps: int = 50) -> dict:
     """BASELINE C2, second run: the step with the RNG-gated stages of the reference's shipped configuration ON — thin_ray = false
     (in-cone jitter of both passes, src/NeRFRenderer.h:307-362), raw_noise_std 0.5 and stochastic preconditioning alpha = 0.01 x bbox diagonal
@@ -832,6 +858,12 @@ def main() -> None:
             roofline_tensor["lerf_head"] = {"error": f"{type(e).__name__}: {e}"}
         roofline_render_ops = render_ops_leg(roofline["peak"])
 
+    shipped_shape = None
+    if world == 1 and not quick:
+        try:
+            shipped_shape = shipped_shape_leg(dev, R)
+        except Exception as e:  # noqa: BLE001 - a secondary leg must not take the headline line down
+            shipped_shape = {"error": f"{type(e).__name__}: {e}"}
     as_shipped = None
     if world == 1 and not quick:
         try:
@@ -889,7 +921,7 @@ def main() -> None:
         "kernels_ms_per_step": {k: [round(t, 4) for t in v] for k, v in sorted(per_launch.items(), key=lambda kv: -sum(kv[1]))},
         "kernels_ms_per_step_sum": round(sum(sum(v) for v in per_launch.values()), 4),
         "dp_check": dp_check, "flags_timeout_after_timed_regions": timeout_after, "strong": strong,
-        "reference_cuda": reference_cuda, "dropin_cpp": dropin_cpp, "train_as_shipped": as_shipped,
+        "reference_cuda": reference_cuda, "dropin_cpp": dropin_cpp, "train_as_shipped": as_shipped, "train_shipped_shape": shipped_shape,
         "final_loss": {"resident": head["loss"], "e2e": head["loss_e2e"]}, "render": render, "render_lerf": render_lerf, "train_lerf": train_lerf,
     }))
 

@@ -146,7 +146,7 @@ int nrf_posenc_fwd(const float* x, int64_t n, int32_t input_dims, int32_t num_fr
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct nrf_mlp_small_shape {
 	int32_t input_ch;          /* 32  (hash L*F)             */
-	int32_t input_ch_views;    /* 16  (SH degree 4)          */
+	int32_t input_ch_views;    /* 16  (SH degree 4); 1..64 via NRF_MLP_IN_ENC16_RAYBIAS */
 	int32_t hidden_dim;        /* 64                          */
 	int32_t geo_feat_dim;      /* 15                          */
 	int32_t hidden_dim_color;  /* 64                          */
@@ -163,7 +163,10 @@ int nrf_mlp_small_pack(const nrf_mlp_small_shape* shape, const float* params_fla
 
 typedef enum nrf_mlp_input {
 	NRF_MLP_IN_ENC16_RAYDIRS = 0, /* enc: fp16 [N,32]; views: per-ray SH table fp32 [R,16]; row n uses ray n / samples_per_ray */
-	NRF_MLP_IN_F32_CAT = 1        /* enc: fp32 [N, input_ch + input_ch_views] = cat(embedded, embedded_dirs) (src/NeRFRenderer.h:182) */
+	NRF_MLP_IN_F32_CAT = 1,       /* enc: fp32 [N, input_ch + input_ch_views] = cat(embedded, embedded_dirs) (src/NeRFRenderer.h:182) */
+	NRF_MLP_IN_ENC16_RAYBIAS = 2  /* enc: fp16 [N,32]; the view channels enter as a per-RAY bias of the colour net's first layer: the "ray_sh" argument is
+	                                 bias [R,64] fp32 = nrf_mlp_small_view_bias_fwd's output; row n uses ray n / samples_per_ray.  Any input_ch_views in
+	                                 1..64 (SH degree 1..8; 64 = the shipped degree 8, src/main.cpp:176); the other two kinds are built for 16 */
 } nrf_mlp_input;
 
 /* keep (nullable): sigma := 0 where keep==0 (src/NeRFRenderer.h:187-188).  raw_out [N,4] = [r,g,b,sigma]. */
@@ -178,15 +181,32 @@ int nrf_mlp_small_fwd(const nrf_mlp_small_shape* shape, const void* packed, nrf_
  * samples' rows of raw_merged are the coarse pass's own rows, moved there by nrf_sample_pdf_merge_rows — the same bits a full
  * nrf_mlp_small_fwd over the merged rows produces (rows are independent), at n_importance / n_merged of its work.
  * NRF_ERR_UNSUPPORTED when the tcgen05 forward is switched off (NRF_MLP_FWD=mma): callers then evaluate all merged rows. */
-int nrf_mlp_small_fwd_importance(const nrf_mlp_small_shape* shape, const void* packed, const void* enc_merged, const float* ray_sh,
-                                 const uint8_t* keep_merged, const int16_t* perm, int64_t n_rays, int32_t n_importance,
-                                 int32_t n_merged, float* raw_merged, nrf_stream stream);
+int nrf_mlp_small_fwd_importance(const nrf_mlp_small_shape* shape, const void* packed, nrf_mlp_input in_kind, const void* enc_merged,
+                                 const float* ray_sh, const uint8_t* keep_merged, const int16_t* perm, int64_t n_rays,
+                                 int32_t n_importance, int32_t n_merged, float* raw_merged, nrf_stream stream);
+
+/* The view term of the colour net's first layer (src/NeRF.cpp:383-392: h = cat([input_views, geo_feat]) -> Linear) depends on the ray only:
+ * bias_out[r, n] = sum_k ray_sh[r, k] W[n, k] over the input_ch_views columns of color_net_0's weight (the packed blob carries an fp32
+ * copy of that block), fp32.  Computed once per ray batch, shared by the coarse and the fine pass, and handed to the fused
+ * kernels as NRF_MLP_IN_ENC16_RAYBIAS.  grad_bias_zero (nullable) [R,64]: zeroed by the same launch (the accumulator of _bwd_raybias). */
+int nrf_mlp_small_view_bias_fwd(const nrf_mlp_small_shape* shape, const void* packed, const float* ray_sh, int64_t n_rays,
+                                float* bias_out, float* grad_bias_zero, nrf_stream stream);
+/* ... and its weight gradient: grad_params_flat[color_net_0 view columns] += grad_bias^T ray_sh, with grad_bias [R,64] accumulated by
+ * nrf_mlp_small_bwd_raybias (the per-ray sum of the gradient at that layer's pre-activation). */
+int nrf_mlp_small_view_bias_bwd(const nrf_mlp_small_shape* shape, const float* ray_sh, const float* grad_bias, int64_t n_rays,
+                                float* grad_params_flat, nrf_stream stream);
 
 /* grad_raw [N,4].  grad_in: bf16 [N,32] (NRF_MLP_IN_ENC16_RAYDIRS) or fp32 [N,48] (NRF_MLP_IN_F32_CAT), may be NULL.
  * grad_params_flat[param_count] fp32 is ACCUMULATED into.  Activations are recomputed, nothing was saved. */
 int nrf_mlp_small_bwd(const nrf_mlp_small_shape* shape, const void* packed, nrf_mlp_input in_kind, const void* enc,
                       const float* ray_sh, int32_t samples_per_ray, const uint8_t* keep, int64_t n,
                       const float* grad_raw, void* grad_in, float* grad_params_flat, nrf_stream stream);
+/* Same for every in_kind; NRF_MLP_IN_ENC16_RAYBIAS additionally needs grad_bias [R,64] fp32 (ACCUMULATED into: per-ray sums of the gradient
+ * at the colour net's first pre-activation; samples_per_ray % 16 == 0) — the view columns of color_net_0's gradient then come from
+ * nrf_mlp_small_view_bias_bwd.  grad_bias is ignored (may be NULL) for the other kinds. */
+int nrf_mlp_small_bwd_raybias(const nrf_mlp_small_shape* shape, const void* packed, nrf_mlp_input in_kind, const void* enc,
+                              const float* ray_sh, int32_t samples_per_ray, const uint8_t* keep, int64_t n,
+                              const float* grad_raw, void* grad_in, float* grad_params_flat, float* grad_bias, nrf_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Classic NeRF MLP, forward (inference) — NeRFImpl::forward (src/NeRF.cpp:92-126) fused on tcgen05 tensor cores: 8 x 256 ReLU

@@ -16,7 +16,7 @@ from . import build as _build
 NRF_MAX_LEVELS = 32
 ENC_F32, ENC_F16 = 0, 1
 GRAD_F32, GRAD_BF16 = 0, 1
-MLP_IN_ENC16_RAYDIRS, MLP_IN_F32_CAT = 0, 1
+MLP_IN_ENC16_RAYDIRS, MLP_IN_F32_CAT, MLP_IN_ENC16_RAYBIAS = 0, 1, 2
 
 
 class NrfError(RuntimeError):
@@ -103,7 +103,10 @@ SIGNATURES = {
     "nrf_mlp_small_param_count": (c_int64, [POINTER(MlpSmallShape)]),
     "nrf_mlp_small_pack": (c_int32, [POINTER(MlpSmallShape), _P, _P, _P]),
     "nrf_mlp_small_fwd": (c_int32, [POINTER(MlpSmallShape), _P, c_int32, _P, _P, c_int32, _P, c_int64, _P, _P]),
-    "nrf_mlp_small_fwd_importance": (c_int32, [POINTER(MlpSmallShape), _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
+    "nrf_mlp_small_fwd_importance": (c_int32, [POINTER(MlpSmallShape), _P, c_int32, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
+    "nrf_mlp_small_view_bias_fwd": (c_int32, [POINTER(MlpSmallShape), _P, _P, c_int64, _P, _P, _P]),
+    "nrf_mlp_small_view_bias_bwd": (c_int32, [POINTER(MlpSmallShape), _P, _P, c_int64, _P, _P]),
+    "nrf_mlp_small_bwd_raybias": (c_int32, [POINTER(MlpSmallShape), _P, c_int32, _P, _P, c_int32, _P, c_int64, _P, _P, _P, _P, _P]),
     "nrf_mlp_small_bwd": (c_int32, [POINTER(MlpSmallShape), _P, c_int32, _P, _P, c_int32, _P, c_int64, _P, _P, _P, _P]),
     "nrf_composite_fwd": (c_int32, [_P, c_int32, _P, _P, _P, c_float, c_int32, c_int64, c_int32, _P, _P, _P, _P, _P, _P]),
     "nrf_composite_bwd": (c_int32, [_P, c_int32, _P, _P, _P, c_float, c_int32, c_int64, c_int32, _P, _P, _P, _P, _P, _P, _P]),

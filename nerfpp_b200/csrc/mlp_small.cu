@@ -30,10 +30,15 @@
 namespace nrf {
 
 
-__global__ void __launch_bounds__(256) mlp_pack_kernel(const float* __restrict__ p, uint32_t* __restrict__ blob)
+__global__ void __launch_bounds__(256) mlp_pack_kernel(const float* __restrict__ p, int V, uint32_t* __restrict__ blob)
 {
 	const int w = blockIdx.x * blockDim.x + threadIdx.x;
-	if (w >= kTotalWords) return;
+	if (w >= kPackedWords) return;
+	if (w >= kViewBase) {
+		const int q = w - kViewBase, n = q >> 6, k = q & 63;
+		reinterpret_cast<float*>(blob)[w] = k < V ? p[kW2 + n * w2_stride(V) + k] : 0.f;
+		return;
+	}
 	if (w >= kUmmaBase) {
 		// UMMA K-major core-matrix layout (mlp_small_layout.cuh): word q of layer l holds (n, k) and (n, k+1)
 		int layer, base, N;
@@ -44,7 +49,7 @@ __global__ void __launch_bounds__(256) mlp_pack_kernel(const float* __restrict__
 		else { layer = 4; base = kU4; N = 16; }
 		const int q = w - base;
 		const int kc = q / (4 * N), n = (q >> 2) % N, k = 8 * kc + 2 * (q & 3);
-		blob[w] = pack_f16(wp(p, layer, n, k), wp(p, layer, n, k + 1));
+		blob[w] = pack_f16(wp(p, V, layer, n, k), wp(p, V, layer, n, k + 1));
 		return;
 	}
 	int layer, base, NT;
@@ -69,13 +74,13 @@ __global__ void __launch_bounds__(256) mlp_pack_kernel(const float* __restrict__
 	const int nn = nt * 8 + g, kk = ks * 16 + 2 * t + 8 * j;
 	float lo, hi;
 	if (!bwd) {
-		lo = wp(p, layer, nn, kk);
-		hi = wp(p, layer, nn, kk + 1);
+		lo = wp(p, V, layer, nn, kk);
+		hi = wp(p, V, layer, nn, kk + 1);
 	} else {
 		// B'[k'][n'] = Wp(k', n'): k' = output channel (padded with zero rows), n' = input channel
 		const int n_out = layer == 1 ? 16 : (layer == 4 ? 8 : 64);
-		lo = kk < n_out ? wp(p, layer, kk, nn) : 0.f;
-		hi = kk + 1 < n_out ? wp(p, layer, kk + 1, nn) : 0.f;
+		lo = kk < n_out ? wp(p, V, layer, kk, nn) : 0.f;
+		hi = kk + 1 < n_out ? wp(p, V, layer, kk + 1, nn) : 0.f;
 	}
 	// forward operands (activations AND weights) are fp16 on every layer: 10-bit mantissa, 8x fewer ReLU sign flips against
 	// the fp32 reference than bf16; the gradient chain stays bf16 (fp32 range, no loss scale)
@@ -148,7 +153,7 @@ __device__ __forceinline__ void to_bf16(const uint32_t (&a)[KS][4], uint32_t (&b
 template <int IN_KIND>
 __device__ __forceinline__ void load_enc(const void* __restrict__ enc, int64_t r_lo, int64_t r_hi, int64_t n, int t, uint32_t (&a)[2][4])
 {
-	if (IN_KIND == NRF_MLP_IN_ENC16_RAYDIRS) {
+	if (IN_KIND != NRF_MLP_IN_F32_CAT) {
 		const uint32_t* e = reinterpret_cast<const uint32_t*>(enc);  // 16 words per row
 #pragma unroll
 		for (int ks = 0; ks < 2; ks++) {
@@ -201,6 +206,11 @@ template <int IN_KIND>
 __device__ __forceinline__ void load_views_raw(const void* __restrict__ enc, const float* __restrict__ ray_sh, int S, int64_t r_lo, int64_t r_hi,
 	int64_t n, int t, float2 (&v)[4])
 {
+	if (IN_KIND == NRF_MLP_IN_ENC16_RAYBIAS) {   // the view term arrives as a bias of the layer: k-step 0 of the colour input carries zeros
+#pragma unroll
+		for (int i = 0; i < 4; i++) v[i] = make_float2(0.f, 0.f);
+		return;
+	}
 	const float* lo;
 	const float* hi;
 	if (IN_KIND == NRF_MLP_IN_ENC16_RAYDIRS) {
@@ -391,39 +401,62 @@ __device__ __forceinline__ void dw_accumulate(const __nv_bfloat16* D, int dp, in
 }
 
 // flush one 16x8 accumulator tile of layer `layer` (m = out channel, n = in channel, padded indexing) to the flat gradient
-__device__ __forceinline__ void dw_flush(float* __restrict__ gp, int layer, int m0, int n0, int g, int t, const float (&acc)[4])
+__device__ __forceinline__ void dw_flush(float* __restrict__ gp, int V, int layer, int m0, int n0, int g, int t, const float (&acc)[4])
 {
 #pragma unroll
 	for (int e = 0; e < 4; e++) {
 		const int m = m0 + g + (e >> 1) * 8, k = n0 + 2 * t + (e & 1);
-		int idx = -1;
-		switch (layer) {
-			case 0: idx = kW0 + m * 32 + k; break;
-			case 1: idx = kW1 + m * 64 + k; break;
-			case 2: idx = k < 16 ? kW2 + m * 31 + k : (k == 16 ? -1 : kW2 + m * 31 + k - 1); break;
-			case 3: idx = kW3 + m * 64 + k; break;
-			default: idx = m < 3 ? kW4 + m * 64 + k : -1; break;
-		}
+		const int idx = w_index(V, layer, m, k);
 		if (idx >= 0 && acc[e] != 0.f) atomicAdd(gp + idx, acc[e]);
 	}
 }
 
-// flush index of (layer, out m, padded in k) in the flat gradient, -1 for padding
-__device__ __forceinline__ int dw_index(int layer, int m, int k)
+// NRF_MLP_IN_ENC16_RAYBIAS: acc (colour layer 0 pre-activation, [8 n-tiles][4]) += bias[ray of the row][64]
+__device__ __forceinline__ void add_ray_bias(float (&acc)[8][4], const float* __restrict__ bias, int S, int64_t r_lo, int64_t r_hi, int64_t n, int t)
 {
-	switch (layer) {
-		case 0: return kW0 + m * 32 + k;
-		case 1: return kW1 + m * 64 + k;
-		case 2: return k < 16 ? kW2 + m * 31 + k : (k == 16 ? -1 : kW2 + m * 31 + k - 1);
-		case 3: return kW3 + m * 64 + k;
-		default: return m < 3 ? kW4 + m * 64 + k : -1;
+	const float* lo = bias + (r_lo < n ? r_lo / S : 0) * 64 + 2 * t;
+	const float* hi = bias + (r_hi < n ? r_hi / S : 0) * 64 + 2 * t;
+#pragma unroll
+	for (int nt = 0; nt < 8; nt++) {
+		const float2 a = __ldg(reinterpret_cast<const float2*>(lo + nt * 8)), b = __ldg(reinterpret_cast<const float2*>(hi + nt * 8));
+		acc[nt][0] += a.x; acc[nt][1] += a.y; acc[nt][2] += b.x; acc[nt][3] += b.y;
+	}
+}
+
+// NRF_MLP_IN_ENC16_RAYBIAS: grad_bias[ray][64] += column sums of the slab's gated bf16 gradient of that pre-activation (A-fragment layout).
+// The 16 rows of a slab belong to ONE ray (samples_per_ray is a multiple of 16, host-checked; rows past n carry zeros).
+__device__ __forceinline__ void reduce_ray_bias_grad(const uint32_t (&d)[4][4], float* __restrict__ grad_bias, int S, int64_t slab_row0, int64_t n, int g, int t)
+{
+	float2 s[8];
+#pragma unroll
+	for (int ks = 0; ks < 4; ks++)
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d[ks][2 * h]));
+			const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d[ks][2 * h + 1]));
+			s[2 * ks + h] = make_float2(a.x + b.x, a.y + b.y);
+		}
+#pragma unroll
+	for (int off = 4; off < 32; off <<= 1)
+#pragma unroll
+		for (int i = 0; i < 8; i++) {
+			s[i].x += __shfl_xor_sync(0xffffffffu, s[i].x, off);
+			s[i].y += __shfl_xor_sync(0xffffffffu, s[i].y, off);
+		}
+	if (g == 0 && slab_row0 < n) {
+		float* o = grad_bias + (slab_row0 / S) * 64 + 2 * t;
+#pragma unroll
+		for (int i = 0; i < 8; i++) {          // columns 8 i + 2 t, + 1
+			if (s[i].x != 0.f) atomicAdd(o + 8 * i, s[i].x);
+			if (s[i].y != 0.f) atomicAdd(o + 8 * i + 1, s[i].y);
+		}
 	}
 }
 
 template <int IN_KIND, bool TCDW>
 __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const uint32_t* __restrict__ blob, const void* __restrict__ enc,
 	const float* __restrict__ ray_sh, int S, const uint8_t* __restrict__ keep, int64_t n, const float* __restrict__ grad_raw,
-	void* __restrict__ grad_in, float* __restrict__ grad_params)
+	void* __restrict__ grad_in, float* __restrict__ grad_params, int V, float* __restrict__ grad_bias)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	uint32_t* wf = reinterpret_cast<uint32_t*>(smem_raw);
@@ -504,6 +537,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			to_bf16<2>(a2, xb2);
 			if (TCDW) store_frag_c<2>(ctiles + kCX2, 0, row_g, t, xb2); else store_frag<2>(tiles + kTX2, kP32, row_g, t, xb2);
 			layer_mma<2, 8, true>(a2, wf + kF2, lane, acc);
+			if (IN_KIND == NRF_MLP_IN_ENC16_RAYBIAS) add_ray_bias(acc, ray_sh, S, r_lo, r_hi, n, t);
 			uint32_t a3[4][4];
 			repack<4, true, true>(acc, a3);
 			relu_gates<4>(a3, m3);
@@ -532,6 +566,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			layer_mma<4, 8, false>(d3, wf + kB3, lane, acc);                 // dA3 = dD3 · W3
 			repack<4, false, false>(acc, d3);
 			apply_gates<4>(d3, m3);
+			if (IN_KIND == NRF_MLP_IN_ENC16_RAYBIAS) reduce_ray_bias_grad(d3, grad_bias, S, tile * kTileRows + warp * 16, n, g, t);
 			if (TCDW) store_frag_c<4>(ctiles + kCRA, 8, row_g, t, d3); else store_frag<4>(tiles + kTD2, kP64, row_g, t, d3);
 			float da2[4][4];
 			layer_mma<4, 4, false>(d3, wf + kB2, lane, da2);                 // dA2 = dD2 · W2p  (cols 0..15 views, 16..31 d1)
@@ -549,7 +584,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			if (grad_in) {
 				float de[4][4];
 				layer_mma<4, 4, false>(d3, wf + kB0, lane, de);             // dEnc = dD0 · W0
-				if (IN_KIND == NRF_MLP_IN_ENC16_RAYDIRS) {
+				if (IN_KIND != NRF_MLP_IN_F32_CAT) {
 					uint32_t* o = reinterpret_cast<uint32_t*>(grad_in);      // bf16 [N,32] = 16 words per row
 #pragma unroll
 					for (int nt = 0; nt < 4; nt++) {
@@ -629,9 +664,9 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 				for (int j = 0; j < 16; j++) {
 					const int c = c0 + j;
 					int idx = -1;
-					if (c < 64) idx = (m < 64) ? (c < 32 ? dw_index(0, m, c) : -1) : (c >= 32 ? dw_index(2, m - 64, c - 32) : -1);
-					else if (c < 144) idx = (m < 64) ? (c < 128 ? dw_index(3, m, c - 64) : -1) : (c >= 128 ? dw_index(1, c - 128, m - 64) : -1);
-					else idx = (m < 64) ? dw_index(4, c - 144, m) : -1;
+					if (c < 64) idx = (m < 64) ? (c < 32 ? w_index(V, 0, m, c) : -1) : (c >= 32 ? w_index(V, 2, m - 64, c - 32) : -1);
+					else if (c < 144) idx = (m < 64) ? (c < 128 ? w_index(V, 3, m, c - 64) : -1) : (c >= 128 ? w_index(V, 1, c - 128, m - 64) : -1);
+					else idx = (m < 64) ? w_index(V, 4, c - 144, m) : -1;
 					const float v = __uint_as_float(d16[j]);
 					if (idx >= 0 && v != 0.f) atomicAdd(grad_params + idx, v);
 				}
@@ -648,25 +683,88 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 	// ---- flush dW
 	if (warp < 4) {
 #pragma unroll
-		for (int nt = 0; nt < 8; nt++) dw_flush(grad_params, 3, warp * 16, nt * 8, g, t, dw[nt]);
+		for (int nt = 0; nt < 8; nt++) dw_flush(grad_params, V, 3, warp * 16, nt * 8, g, t, dw[nt]);
 #pragma unroll
-		for (int nt = 0; nt < 2; nt++) dw_flush(grad_params, 1, 0, warp * 16 + nt * 8, g, t, dw[8 + nt]);
+		for (int nt = 0; nt < 2; nt++) dw_flush(grad_params, V, 1, 0, warp * 16 + nt * 8, g, t, dw[8 + nt]);
 	} else {
 		const int h = (warp - 4) & 1;
 		const int layer = warp < 6 ? 0 : 2;
 #pragma unroll
-		for (int nt = 0; nt < 4; nt++) dw_flush(grad_params, layer, h * 32, nt * 8, g, t, dw[nt]);
+		for (int nt = 0; nt < 4; nt++) dw_flush(grad_params, V, layer, h * 32, nt * 8, g, t, dw[nt]);
 #pragma unroll
-		for (int nt = 0; nt < 4; nt++) dw_flush(grad_params, layer, h * 32 + 16, nt * 8, g, t, dw[4 + nt]);
+		for (int nt = 0; nt < 4; nt++) dw_flush(grad_params, V, layer, h * 32 + 16, nt * 8, g, t, dw[4 + nt]);
 #pragma unroll
-		for (int nt = 0; nt < 2; nt++) dw_flush(grad_params, 4, 0, (warp - 4) * 16 + nt * 8, g, t, dw[8 + nt]);
+		for (int nt = 0; nt < 2; nt++) dw_flush(grad_params, V, 4, 0, (warp - 4) * 16 + nt * 8, g, t, dw[8 + nt]);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------- per-ray view term (NRF_MLP_IN_ENC16_RAYBIAS)
+// bias[r][n] = sum_k ray_sh[r][k] W2[n][k], k < V, in fp32 (the one place the view channels meet their weights: once per RAY, not per sample).
+// One CTA stages the view block of W2 (64 x V floats) and walks kRaysPerBlock rays, 64 outputs each.  Optionally zeroes the grad_bias rows of its
+// rays (the accumulator reduce_ray_bias_grad adds into later in the step).
+constexpr int kViewBiasThreads = 256, kRaysPerBlock = 16;
+
+__global__ void __launch_bounds__(kViewBiasThreads) view_bias_fwd_kernel(const uint32_t* __restrict__ blob, int V, const float* __restrict__ ray_sh, int64_t R,
+	float* __restrict__ bias, float* __restrict__ grad_bias_zero)
+{
+	extern __shared__ float vb_smem[];
+	float* w = vb_smem;                              // [64][V + 1]
+	float* sh = vb_smem + 64 * (V + 1);              // [4][V]
+	for (int i = threadIdx.x; i < 64 * V; i += blockDim.x) {
+		const int n = i / V, k = i - n * V;
+		w[n * (V + 1) + k] = reinterpret_cast<const float*>(blob)[kViewBase + n * 64 + k];
+	}
+	const int n = threadIdx.x & 63, q = threadIdx.x >> 6;
+	const int64_t ray0 = static_cast<int64_t>(blockIdx.x) * kRaysPerBlock;
+	for (int pass = 0; pass < kRaysPerBlock / 4; pass++) {
+		__syncthreads();
+		const int64_t rbase = ray0 + pass * 4;
+		for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) {
+			const int64_t r = rbase + i / V;
+			sh[i] = r < R ? ray_sh[r * V + (i % V)] : 0.f;
+		}
+		__syncthreads();
+		const int64_t r = rbase + q;
+		if (r < R) {
+			float acc = 0.f;
+			for (int k = 0; k < V; k++) acc = fmaf(sh[q * V + k], w[n * (V + 1) + k], acc);
+			bias[r * 64 + n] = acc;
+			if (grad_bias_zero) grad_bias_zero[r * 64 + n] = 0.f;
+		}
+	}
+}
+
+// dW2[n][k] += sum_r grad_bias[r][n] ray_sh[r][k], k < V.  A CTA reduces kBiasBwdRays rays from shared memory; thread = (n, 16 consecutive k / 4).
+constexpr int kBiasBwdRays = 64;
+
+__global__ void __launch_bounds__(256) view_bias_bwd_kernel(const float* __restrict__ ray_sh, int V, const float* __restrict__ grad_bias, int64_t R,
+	float* __restrict__ grad_params)
+{
+	extern __shared__ float vb_smem[];
+	float* g = vb_smem;                              // [kBiasBwdRays][64]
+	float* sh = vb_smem + kBiasBwdRays * 64;         // [kBiasBwdRays][V]
+	const int64_t ray0 = static_cast<int64_t>(blockIdx.x) * kBiasBwdRays;
+	for (int i = threadIdx.x; i < kBiasBwdRays * 64; i += blockDim.x) {
+		const int64_t r = ray0 + i / 64;
+		g[i] = r < R ? grad_bias[r * 64 + (i & 63)] : 0.f;
+	}
+	for (int i = threadIdx.x; i < kBiasBwdRays * V; i += blockDim.x) {
+		const int64_t r = ray0 + i / V;
+		sh[i] = r < R ? ray_sh[r * V + (i % V)] : 0.f;
+	}
+	__syncthreads();
+	for (int o = threadIdx.x; o < 64 * V; o += blockDim.x) {
+		const int n = o / V, k = o - n * V;
+		float acc = 0.f;
+		for (int r = 0; r < kBiasBwdRays; r++) acc = fmaf(g[r * 64 + n], sh[r * V + k], acc);
+		if (acc != 0.f) atomicAdd(grad_params + kW2 + n * w2_stride(V) + k, acc);
 	}
 }
 
 // mlp_small_tc.cu
 cudaError_t launch_mlp_small_fwd_tc(const uint32_t* blob, int in_kind, const void* enc, const float* ray_sh, int S, const uint8_t* keep, int64_t n,
 	float* raw_out, cudaStream_t stream);
-cudaError_t launch_mlp_small_fwd_tc_importance(const uint32_t* blob, const void* enc, const float* ray_sh, const uint8_t* keep, const int16_t* perm,
+cudaError_t launch_mlp_small_fwd_tc_importance(const uint32_t* blob, int in_kind, const void* enc, const float* ray_sh, const uint8_t* keep, const int16_t* perm,
 	int64_t n_rays, int n_importance, int n_merged, float* raw_out, cudaStream_t stream);
 
 // NRF_MLP_FWD=mma selects the mma.sync forward (kept as the A/B baseline of the tcgen05 kernel); read once
@@ -679,9 +777,20 @@ static bool use_tcgen05_fwd()
 static int check_shape(const nrf_mlp_small_shape* s)
 {
 	NRF_REQUIRE(s != nullptr, "shape is null");
-	if (!(s->input_ch == 32 && s->input_ch_views == 16 && s->hidden_dim == 64 && s->geo_feat_dim == 15 &&
+	if (!(s->input_ch == 32 && s->input_ch_views >= 1 && s->input_ch_views <= 64 && s->hidden_dim == 64 && s->geo_feat_dim == 15 &&
 	      s->hidden_dim_color == 64 && s->num_layers == 2 && s->num_layers_color == 3)) {
-		set_error("nrf_mlp_small: only the BASELINE shape 32+16 -> 64 -> 16 | 31 -> 64 -> 64 -> 3 is built");
+		set_error("nrf_mlp_small: built for 32 + V -> 64 -> 16 | V + 15 -> 64 -> 64 -> 3 with 1 <= V <= 64 view channels (SH degree 1..8)");
+		return NRF_ERR_UNSUPPORTED;
+	}
+	return NRF_OK;
+}
+
+// the per-sample view input (k-step 0 of the colour net) exists for V = 16 only; other V go through the per-ray bias
+static int check_in_kind(const nrf_mlp_small_shape* s, nrf_mlp_input in_kind)
+{
+	NRF_REQUIRE(in_kind == NRF_MLP_IN_ENC16_RAYDIRS || in_kind == NRF_MLP_IN_F32_CAT || in_kind == NRF_MLP_IN_ENC16_RAYBIAS, "bad in_kind");
+	if (s->input_ch_views != 16 && in_kind != NRF_MLP_IN_ENC16_RAYBIAS) {
+		set_error("nrf_mlp_small: input_ch_views != 16 runs as NRF_MLP_IN_ENC16_RAYBIAS (nrf_mlp_small_view_bias_fwd / _bwd carry the view term)");
 		return NRF_ERR_UNSUPPORTED;
 	}
 	return NRF_OK;
@@ -693,16 +802,46 @@ using namespace nrf;
 
 extern "C" {
 
-int64_t nrf_mlp_small_packed_bytes(const nrf_mlp_small_shape* shape) { return check_shape(shape) ? -1 : static_cast<int64_t>(kTotalWords) * 4; }
-int64_t nrf_mlp_small_param_count(const nrf_mlp_small_shape* shape) { return check_shape(shape) ? -1 : kParamCount; }
+int64_t nrf_mlp_small_packed_bytes(const nrf_mlp_small_shape* shape) { return check_shape(shape) ? -1 : static_cast<int64_t>(kPackedWords) * 4; }
+int64_t nrf_mlp_small_param_count(const nrf_mlp_small_shape* shape) { return check_shape(shape) ? -1 : param_count(shape->input_ch_views); }
 
 int nrf_mlp_small_pack(const nrf_mlp_small_shape* shape, const float* params_flat, void* packed, nrf_stream stream)
 {
 	if (int rc = check_shape(shape)) return rc;
 	NRF_REQUIRE(params_flat && packed, "null pointer");
 	NRF_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "packed blob must be 16-byte aligned");
-	mlp_pack_kernel<<<(kTotalWords + 255) / 256, 256, 0, as_stream(stream)>>>(params_flat, reinterpret_cast<uint32_t*>(packed));
+	mlp_pack_kernel<<<(kPackedWords + 255) / 256, 256, 0, as_stream(stream)>>>(params_flat, shape->input_ch_views, reinterpret_cast<uint32_t*>(packed));
 	NRF_CHECK_LAUNCH("mlp_pack_kernel");
+	return NRF_OK;
+}
+
+int nrf_mlp_small_view_bias_fwd(const nrf_mlp_small_shape* shape, const void* packed, const float* ray_sh, int64_t n_rays, float* bias_out,
+	float* grad_bias_zero, nrf_stream stream)
+{
+	if (int rc = check_shape(shape)) return rc;
+	NRF_REQUIRE(n_rays >= 0, "negative n_rays");
+	if (n_rays == 0) return NRF_OK;
+	NRF_REQUIRE(packed && ray_sh && bias_out, "null pointer");
+	const int V = shape->input_ch_views;
+	const size_t smem = static_cast<size_t>(64 * (V + 1) + 4 * V) * sizeof(float);
+	const unsigned blocks = static_cast<unsigned>((n_rays + kRaysPerBlock - 1) / kRaysPerBlock);
+	view_bias_fwd_kernel<<<blocks, kViewBiasThreads, smem, as_stream(stream)>>>(reinterpret_cast<const uint32_t*>(packed), V, ray_sh, n_rays, bias_out, grad_bias_zero);
+	NRF_CHECK_LAUNCH("view_bias_fwd_kernel");
+	return NRF_OK;
+}
+
+int nrf_mlp_small_view_bias_bwd(const nrf_mlp_small_shape* shape, const float* ray_sh, const float* grad_bias, int64_t n_rays, float* grad_params_flat,
+	nrf_stream stream)
+{
+	if (int rc = check_shape(shape)) return rc;
+	NRF_REQUIRE(n_rays >= 0, "negative n_rays");
+	if (n_rays == 0) return NRF_OK;
+	NRF_REQUIRE(ray_sh && grad_bias && grad_params_flat, "null pointer");
+	const int V = shape->input_ch_views;
+	const size_t smem = static_cast<size_t>(kBiasBwdRays) * (64 + V) * sizeof(float);
+	const unsigned blocks = static_cast<unsigned>((n_rays + kBiasBwdRays - 1) / kBiasBwdRays);
+	view_bias_bwd_kernel<<<blocks, 256, smem, as_stream(stream)>>>(ray_sh, V, grad_bias, n_rays, grad_params_flat);
+	NRF_CHECK_LAUNCH("view_bias_bwd_kernel");
 	return NRF_OK;
 }
 
@@ -710,14 +849,19 @@ int nrf_mlp_small_fwd(const nrf_mlp_small_shape* shape, const void* packed, nrf_
 	const float* ray_sh, int32_t samples_per_ray, const uint8_t* keep, int64_t n, float* raw_out, nrf_stream stream)
 {
 	if (int rc = check_shape(shape)) return rc;
+	if (int rc = check_in_kind(shape, in_kind)) return rc;
 	NRF_REQUIRE(n >= 0, "negative n");
 	if (n == 0) return NRF_OK;
 	NRF_REQUIRE(packed && enc && raw_out, "null pointer");
 	NRF_REQUIRE(in_kind == NRF_MLP_IN_F32_CAT || (ray_sh && samples_per_ray >= 1), "ray_sh / samples_per_ray missing");
 	const uint32_t* blob = reinterpret_cast<const uint32_t*>(packed);
+	if (in_kind == NRF_MLP_IN_ENC16_RAYBIAS && !use_tcgen05_fwd()) {
+		set_error("nrf_mlp_small_fwd: NRF_MLP_IN_ENC16_RAYBIAS runs on the tcgen05 forward only (NRF_MLP_FWD=mma is set)");
+		return NRF_ERR_UNSUPPORTED;
+	}
 	if (use_tcgen05_fwd()) {
 		NRF_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "packed blob must be 16-byte aligned");
-		NRF_REQUIRE(in_kind != NRF_MLP_IN_ENC16_RAYDIRS || (reinterpret_cast<uintptr_t>(enc) & 15) == 0, "enc must be 16-byte aligned");
+		NRF_REQUIRE(in_kind == NRF_MLP_IN_F32_CAT || (reinterpret_cast<uintptr_t>(enc) & 15) == 0, "enc must be 16-byte aligned");
 		NRF_CUDA(launch_mlp_small_fwd_tc(blob, in_kind, enc, ray_sh, samples_per_ray, keep, n, raw_out, as_stream(stream)));
 		count_launch();
 		return NRF_OK;
@@ -732,10 +876,12 @@ int nrf_mlp_small_fwd(const nrf_mlp_small_shape* shape, const void* packed, nrf_
 	return NRF_OK;
 }
 
-int nrf_mlp_small_fwd_importance(const nrf_mlp_small_shape* shape, const void* packed, const void* enc_merged, const float* ray_sh,
+int nrf_mlp_small_fwd_importance(const nrf_mlp_small_shape* shape, const void* packed, nrf_mlp_input in_kind, const void* enc_merged, const float* ray_sh,
 	const uint8_t* keep_merged, const int16_t* perm, int64_t n_rays, int32_t n_importance, int32_t n_merged, float* raw_merged, nrf_stream stream)
 {
 	if (int rc = check_shape(shape)) return rc;
+	if (int rc = check_in_kind(shape, in_kind)) return rc;
+	NRF_REQUIRE(in_kind != NRF_MLP_IN_F32_CAT, "the importance-only forward reads fp16 encodings (RAYDIRS / RAYBIAS)");
 	NRF_REQUIRE(n_rays >= 0 && n_importance >= 1 && n_merged > n_importance && n_merged < 32768, "bad sizes");
 	NRF_REQUIRE(n_rays * n_merged < (int64_t(1) << 31), "n_rays * n_merged must be < 2^31 per call");
 	if (n_rays == 0) return NRF_OK;
@@ -746,7 +892,7 @@ int nrf_mlp_small_fwd_importance(const nrf_mlp_small_shape* shape, const void* p
 	}
 	NRF_REQUIRE(((reinterpret_cast<uintptr_t>(packed) | reinterpret_cast<uintptr_t>(enc_merged) | reinterpret_cast<uintptr_t>(raw_merged)) & 15) == 0,
 		"packed / enc_merged / raw_merged must be 16-byte aligned");
-	NRF_CUDA(launch_mlp_small_fwd_tc_importance(reinterpret_cast<const uint32_t*>(packed), enc_merged, ray_sh, keep_merged, perm, n_rays, n_importance,
+	NRF_CUDA(launch_mlp_small_fwd_tc_importance(reinterpret_cast<const uint32_t*>(packed), in_kind, enc_merged, ray_sh, keep_merged, perm, n_rays, n_importance,
 		n_merged, raw_merged, as_stream(stream)));
 	count_launch();
 	return NRF_OK;
@@ -756,11 +902,23 @@ int nrf_mlp_small_bwd(const nrf_mlp_small_shape* shape, const void* packed, nrf_
 	const float* ray_sh, int32_t samples_per_ray, const uint8_t* keep, int64_t n, const float* grad_raw, void* grad_in,
 	float* grad_params_flat, nrf_stream stream)
 {
+	NRF_REQUIRE(in_kind != NRF_MLP_IN_ENC16_RAYBIAS, "NRF_MLP_IN_ENC16_RAYBIAS: use nrf_mlp_small_bwd_raybias (it also returns the gradient of the bias)");
+	return nrf_mlp_small_bwd_raybias(shape, packed, in_kind, enc, ray_sh, samples_per_ray, keep, n, grad_raw, grad_in, grad_params_flat, nullptr, stream);
+}
+
+int nrf_mlp_small_bwd_raybias(const nrf_mlp_small_shape* shape, const void* packed, nrf_mlp_input in_kind, const void* enc,
+	const float* ray_sh, int32_t samples_per_ray, const uint8_t* keep, int64_t n, const float* grad_raw, void* grad_in,
+	float* grad_params_flat, float* grad_bias, nrf_stream stream)
+{
 	if (int rc = check_shape(shape)) return rc;
+	if (int rc = check_in_kind(shape, in_kind)) return rc;
 	NRF_REQUIRE(n >= 0, "negative n");
 	if (n == 0) return NRF_OK;
 	NRF_REQUIRE(packed && enc && grad_raw && grad_params_flat, "null pointer");
 	NRF_REQUIRE(in_kind == NRF_MLP_IN_F32_CAT || (ray_sh && samples_per_ray >= 1), "ray_sh / samples_per_ray missing");
+	NRF_REQUIRE(in_kind != NRF_MLP_IN_ENC16_RAYBIAS || (grad_bias && samples_per_ray % 16 == 0),
+		"NRF_MLP_IN_ENC16_RAYBIAS needs grad_bias and samples_per_ray % 16 == 0 (a 16-row slab must lie within one ray)");
+	const int V = shape->input_ch_views;
 	const int64_t tiles = (n + kTileRows - 1) / kTileRows;
 	const int blocks = static_cast<int>(std::min<int64_t>(tiles, kNumSMs));
 	const uint32_t* blob = reinterpret_cast<const uint32_t*>(packed);
@@ -770,10 +928,13 @@ int nrf_mlp_small_bwd(const nrf_mlp_small_shape* shape, const void* packed, nrf_
 #define NRF_BWD_LAUNCH(KIND, TC, SMEM)                                                                                                   \
 	do {                                                                                                                                 \
 		NRF_CUDA(cudaFuncSetAttribute(mlp_small_bwd_kernel<KIND, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM))); \
-		mlp_small_bwd_kernel<KIND, TC><<<blocks, kBwdWarps * 32, SMEM, s>>>(blob, enc, ray_sh, samples_per_ray, keep, n, grad_raw, grad_in, grad_params_flat); \
+		mlp_small_bwd_kernel<KIND, TC><<<blocks, kBwdWarps * 32, SMEM, s>>>(blob, enc, ray_sh, samples_per_ray, keep, n, grad_raw, grad_in, grad_params_flat, V, \
+			grad_bias);                                                                                                                  \
 	} while (0)
 	if (in_kind == NRF_MLP_IN_ENC16_RAYDIRS) {
 		if (tcdw) NRF_BWD_LAUNCH(NRF_MLP_IN_ENC16_RAYDIRS, true, kBwdSmemTc); else NRF_BWD_LAUNCH(NRF_MLP_IN_ENC16_RAYDIRS, false, kBwdSmem);
+	} else if (in_kind == NRF_MLP_IN_ENC16_RAYBIAS) {
+		if (tcdw) NRF_BWD_LAUNCH(NRF_MLP_IN_ENC16_RAYBIAS, true, kBwdSmemTc); else NRF_BWD_LAUNCH(NRF_MLP_IN_ENC16_RAYBIAS, false, kBwdSmem);
 	} else {
 		if (tcdw) NRF_BWD_LAUNCH(NRF_MLP_IN_F32_CAT, true, kBwdSmemTc); else NRF_BWD_LAUNCH(NRF_MLP_IN_F32_CAT, false, kBwdSmem);
 	}

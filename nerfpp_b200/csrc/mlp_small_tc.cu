@@ -98,7 +98,7 @@ __device__ __forceinline__ int64_t merged_row(const RowMap& m, int64_t r, int64_
 template <int IN_KIND>
 __device__ __forceinline__ void load_enc_row(RowInputs& in, const void* __restrict__ enc, int64_t r, bool ok)
 {
-	if (IN_KIND == NRF_MLP_IN_ENC16_RAYDIRS) {
+	if (IN_KIND != NRF_MLP_IN_F32_CAT) {
 		const uint4* e = reinterpret_cast<const uint4*>(enc) + r * 4;
 #pragma unroll
 		for (int q = 0; q < 4; q++) {
@@ -121,6 +121,12 @@ template <int IN_KIND>
 __device__ __forceinline__ void load_view_row(RowInputs& in, const void* __restrict__ enc, const float* __restrict__ ray_sh, int S,
 	const uint8_t* __restrict__ keep, int64_t w, int64_t r, bool ok)
 {
+	in.kept = !(keep && ok && !keep[r]);
+	if (IN_KIND == NRF_MLP_IN_ENC16_RAYBIAS) {   // the view term is a per-ray bias of the layer (add_ray_bias): K chunk 0 carries zeros
+#pragma unroll
+		for (int q = 0; q < 8; q++) in.v[q] = 0u;
+		return;
+	}
 	const float4* vp = IN_KIND == NRF_MLP_IN_ENC16_RAYDIRS ? reinterpret_cast<const float4*>(ray_sh + (ok ? w / S : 0) * 16)
 	                                                       : reinterpret_cast<const float4*>(reinterpret_cast<const float*>(enc) + (ok ? r : 0) * 48 + 32);
 #pragma unroll
@@ -129,7 +135,20 @@ __device__ __forceinline__ void load_view_row(RowInputs& in, const void* __restr
 		in.v[2 * q] = pack_f16(v.x, v.y);
 		in.v[2 * q + 1] = pack_f16(v.z, v.w);
 	}
-	in.kept = !(keep && ok && !keep[r]);
+}
+
+// NRF_MLP_IN_ENC16_RAYBIAS: acc (32 fp32 accumulator bit patterns, columns c0 .. c0 + 31 of colour layer 0) += bias[ray][c0 ..]
+__device__ __forceinline__ void add_ray_bias(uint32_t (&acc)[32], const float* __restrict__ bias_row, int c0)
+{
+	const float4* b = reinterpret_cast<const float4*>(bias_row + c0);
+#pragma unroll
+	for (int q = 0; q < 8; q++) {
+		const float4 v = __ldg(b + q);
+		acc[4 * q] = __float_as_uint(__uint_as_float(acc[4 * q]) + v.x);
+		acc[4 * q + 1] = __float_as_uint(__uint_as_float(acc[4 * q + 1]) + v.y);
+		acc[4 * q + 2] = __float_as_uint(__uint_as_float(acc[4 * q + 2]) + v.z);
+		acc[4 * q + 3] = __float_as_uint(__uint_as_float(acc[4 * q + 3]) + v.w);
+	}
 }
 
 // publish the A operand this warp just wrote to TMEM: one mbarrier arrival per warp
@@ -236,6 +255,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_small_fwd_tc_kernel(const uin
 			tmem_ld32(t_lane + kColD, acc0);
 			tmem_ld32(t_lane + kColD + 32, acc1);
 			tmem_ld_wait();
+			if (IN_KIND == NRF_MLP_IN_ENC16_RAYBIAS && l == 2) {
+				const float* brow = ray_sh + (ok ? w / S : 0) * 64;
+				add_ray_bias(acc0, brow, 0);
+				add_ray_bias(acc1, brow, 32);
+			}
 			relu_pack(acc0, a16);
 			tmem_st16(t_lane + kColA, a16);
 			relu_pack(acc1, a16);
@@ -281,19 +305,24 @@ cudaError_t launch_mlp_small_fwd_tc(const uint32_t* blob, int in_kind, const voi
 	const tc::RowMap none{nullptr, 1, 1};
 	if (in_kind == NRF_MLP_IN_ENC16_RAYDIRS)
 		tc::mlp_small_fwd_tc_kernel<NRF_MLP_IN_ENC16_RAYDIRS, false><<<blocks, tc::kThreads, 0, stream>>>(blob, enc, ray_sh, S, keep, n, none, raw_out);
+	else if (in_kind == NRF_MLP_IN_ENC16_RAYBIAS)
+		tc::mlp_small_fwd_tc_kernel<NRF_MLP_IN_ENC16_RAYBIAS, false><<<blocks, tc::kThreads, 0, stream>>>(blob, enc, ray_sh, S, keep, n, none, raw_out);
 	else
 		tc::mlp_small_fwd_tc_kernel<NRF_MLP_IN_F32_CAT, false><<<blocks, tc::kThreads, 0, stream>>>(blob, enc, ray_sh, S, keep, n, none, raw_out);
 	return cudaGetLastError();
 }
 
 // called by nrf_mlp_small_fwd_importance (mlp_small.cu): n = n_rays * n_importance work rows scattered over the merged arrays
-cudaError_t launch_mlp_small_fwd_tc_importance(const uint32_t* blob, const void* enc, const float* ray_sh, const uint8_t* keep, const int16_t* perm,
+cudaError_t launch_mlp_small_fwd_tc_importance(const uint32_t* blob, int in_kind, const void* enc, const float* ray_sh, const uint8_t* keep, const int16_t* perm,
 	int64_t n_rays, int n_importance, int n_merged, float* raw_out, cudaStream_t stream)
 {
 	const int64_t n = n_rays * n_importance, tiles = (n + 127) / 128;
 	const int blocks = static_cast<int>(std::min<int64_t>((tiles + tc::kSlots - 1) / tc::kSlots, kNumSMs));
 	const tc::RowMap map{perm, n_importance, n_merged};
-	tc::mlp_small_fwd_tc_kernel<NRF_MLP_IN_ENC16_RAYDIRS, true><<<blocks, tc::kThreads, 0, stream>>>(blob, enc, ray_sh, n_importance, keep, n, map, raw_out);
+	if (in_kind == NRF_MLP_IN_ENC16_RAYBIAS)
+		tc::mlp_small_fwd_tc_kernel<NRF_MLP_IN_ENC16_RAYBIAS, true><<<blocks, tc::kThreads, 0, stream>>>(blob, enc, ray_sh, n_importance, keep, n, map, raw_out);
+	else
+		tc::mlp_small_fwd_tc_kernel<NRF_MLP_IN_ENC16_RAYDIRS, true><<<blocks, tc::kThreads, 0, stream>>>(blob, enc, ray_sh, n_importance, keep, n, map, raw_out);
 	return cudaGetLastError();
 }
 

@@ -13,7 +13,7 @@ namespace nrf {
 static inline int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
 
 struct RenderWs {
-	int64_t ray_batch, ray_sh, z, z_fine, w_coarse, enc, keep, raw, raw_coarse, perm, rays_d, total;
+	int64_t ray_batch, ray_sh, z, z_fine, w_coarse, enc, keep, raw, raw_coarse, perm, rays_d, view_bias, total;
 };
 
 static RenderWs render_layout(const nrf_render_config* c, const nrf_hash_grid* g, int64_t R)
@@ -33,6 +33,7 @@ static RenderWs render_layout(const nrf_render_config* c, const nrf_hash_grid* g
 	w.raw_coarse = off; off = align256(off + R * S * 16);
 	w.perm = off;      off = align256(off + R * T * 2);
 	w.rays_d = off;    off = align256(off + R * 3 * 4);
+	w.view_bias = off; off = align256(off + (c->sh_degree != 4 ? R * 64 * 4 : 0));
 	w.total = off;
 	return w;
 }
@@ -104,10 +105,20 @@ static int render_impl(const nrf_render_config* cfg, const nrf_hash_grid* grid, 
 		rays_d = rd;
 	} else if ((rc = nrf_ray_setup(rays_o, rays_d, n_rays, cfg->bbox, cfg->near_plane, t_vals, S, cfg->lin_disp, cfg->sh_degree, ray_batch, z, ray_sh,
 	                               nullptr, stream))) return rc;
+	// SH degree != 4 (shape->input_ch_views != 16): the view channels enter the network as a per-ray bias, computed once for both passes
+	NRF_REQUIRE(shape->input_ch_views == cfg->sh_degree * cfg->sh_degree, "shape->input_ch_views must be sh_degree^2");
+	nrf_mlp_input kind = NRF_MLP_IN_ENC16_RAYDIRS;
+	const float* views = ray_sh;
+	if (shape->input_ch_views != 16) {
+		float* vb = reinterpret_cast<float*>(base + w.view_bias);
+		if ((rc = nrf_mlp_small_view_bias_fwd(shape, packed, ray_sh, n_rays, vb, nullptr, stream))) return rc;
+		kind = NRF_MLP_IN_ENC16_RAYBIAS;
+		views = vb;
+	}
 	// coarse pass
 	if ((rc = nrf_hash_encode_rays_fwd_grouped(grid, table_f16, ray_batch, 11, z, n_rays, S, 1, keep, enc, NRF_ENC_F16, nullptr, nullptr, nullptr, 0, group, stream)))
 		return rc;
-	if ((rc = nrf_mlp_small_fwd(shape, packed, NRF_MLP_IN_ENC16_RAYDIRS, enc, ray_sh, S, keep, n_rays * S, reuse ? raw_coarse : raw, stream))) return rc;
+	if ((rc = nrf_mlp_small_fwd(shape, packed, kind, enc, views, S, keep, n_rays * S, reuse ? raw_coarse : raw, stream))) return rc;
 	if ((rc = nrf_composite_fwd(reuse ? raw_coarse : raw, 4, z, rays_d, nullptr, 0.f, cfg->white_bkgr, n_rays, S, nullptr, nullptr, nullptr, nullptr, w_coarse,
 	                            stream))) return rc;
 	// importance sampling + merge, fine pass
@@ -116,7 +127,7 @@ static int render_impl(const nrf_render_config* cfg, const nrf_hash_grid* grid, 
 		if ((rc = nrf_sample_pdf_merge_rows(z, w_coarse, u, 0, n_rays, S, N, nullptr, z_fine, perm, raw_coarse, raw, stream))) return rc;
 		if ((rc = nrf_hash_encode_rays_fwd_grouped(grid, table_f16, ray_batch, 11, z_fine, n_rays, T, 1, keep, enc, NRF_ENC_F16, perm, nullptr, nullptr, S, group,
 		                                           stream))) return rc;
-		rc = nrf_mlp_small_fwd_importance(shape, packed, enc, ray_sh, keep, perm, n_rays, N, T, raw, stream);
+		rc = nrf_mlp_small_fwd_importance(shape, packed, kind, enc, views, keep, perm, n_rays, N, T, raw, stream);
 		if (rc != NRF_OK && rc != NRF_ERR_UNSUPPORTED) return rc;
 		fine_done = rc == NRF_OK;
 	} else {
@@ -125,7 +136,7 @@ static int render_impl(const nrf_render_config* cfg, const nrf_hash_grid* grid, 
 	if (!fine_done) {
 		if ((rc = nrf_hash_encode_rays_fwd_grouped(grid, table_f16, ray_batch, 11, z_fine, n_rays, T, 1, keep, enc, NRF_ENC_F16, nullptr, nullptr, nullptr, 0, group,
 		                                           stream))) return rc;
-		if ((rc = nrf_mlp_small_fwd(shape, packed, NRF_MLP_IN_ENC16_RAYDIRS, enc, ray_sh, T, keep, n_rays * T, raw, stream))) return rc;
+		if ((rc = nrf_mlp_small_fwd(shape, packed, kind, enc, views, T, keep, n_rays * T, raw, stream))) return rc;
 	}
 	if ((rc = nrf_composite_fwd(raw, 4, z_fine, rays_d, nullptr, 0.f, cfg->white_bkgr, n_rays, T, rgb, depth, disp, acc, weights, stream))) return rc;
 	return NRF_OK;

@@ -255,7 +255,9 @@ bool NeRFSmallImpl::Fused() const
 {
 	if (UsePredNormal) return false;
 	const nrf_mlp_small_shape s = Shape();
-	return nrf_mlp_small_param_count(&s) > 0;   // the library answers -1 for shapes it was not built for
+	// the library answers -1 for shapes it was not built for; other view widths exist there as NRF_MLP_IN_ENC16_RAYBIAS (a per-ray view term,
+	// nerfpp_b200.pipeline), which this per-point module interface ([N, input_ch + input_ch_views] rows) cannot express: ATen formulation
+	return s.input_ch_views == 16 && nrf_mlp_small_param_count(&s) > 0;
 }
 
 std::vector<Tensor> NeRFSmallImpl::Weights()

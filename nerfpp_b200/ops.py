@@ -199,10 +199,11 @@ def mlp_small_pack(params_flat: torch.Tensor, shape=None, out: torch.Tensor | No
 
 
 def mlp_small_fwd(packed: torch.Tensor, enc: torch.Tensor, ray_sh: torch.Tensor | None, samples_per_ray: int,
-                  keep: torch.Tensor | None, shape=None, out: torch.Tensor | None = None) -> torch.Tensor:
+                  keep: torch.Tensor | None, shape=None, out: torch.Tensor | None = None, ray_bias: bool = False) -> torch.Tensor:
+    """ray_bias: ray_sh is the per-ray view term [R,64] of mlp_small_view_bias_fwd (NRF_MLP_IN_ENC16_RAYBIAS: any view width 1..64)."""
     shape = shape or mlp_shape()
     n = enc.shape[0]
-    kind = cabi.MLP_IN_ENC16_RAYDIRS if enc.dtype == f16 else cabi.MLP_IN_F32_CAT
+    kind = (cabi.MLP_IN_ENC16_RAYBIAS if ray_bias else cabi.MLP_IN_ENC16_RAYDIRS) if enc.dtype == f16 else cabi.MLP_IN_F32_CAT
     if out is None:
         out = torch.empty((n, 4), dtype=f32, device=enc.device)
     _run("mlp_small_fwd", lambda: lib().nrf_mlp_small_fwd(C.byref(shape), ptr(packed), kind, ptr(enc), ptr(ray_sh), samples_per_ray, ptr(keep),
@@ -211,32 +212,55 @@ def mlp_small_fwd(packed: torch.Tensor, enc: torch.Tensor, ray_sh: torch.Tensor 
 
 
 def mlp_small_fwd_importance(packed: torch.Tensor, enc_merged: torch.Tensor, ray_sh: torch.Tensor, keep_merged: torch.Tensor | None,
-                             perm: torch.Tensor, n_importance: int, raw_merged: torch.Tensor, shape=None) -> torch.Tensor:
+                             perm: torch.Tensor, n_importance: int, raw_merged: torch.Tensor, shape=None, ray_bias: bool = False) -> torch.Tensor:
     """Evaluate the importance samples only (rows perm[:, :n_importance] of the merged arrays) into raw_merged, whose coarse-sample
     rows sample_pdf_merge(raw_coarse=...) already holds.  Same bits as mlp_small_fwd over all merged rows."""
     shape = shape or mlp_shape()
     r, t = perm.shape
     assert enc_merged.dtype == f16 and enc_merged.shape[0] == r * t and raw_merged.shape[0] == r * t
-    _run("mlp_small_fwd", lambda: lib().nrf_mlp_small_fwd_importance(C.byref(shape), ptr(packed), ptr(enc_merged, f16), ptr(ray_sh, f32), ptr(keep_merged),
-                                  ptr(perm, torch.int16), r, n_importance, t, ptr(raw_merged, f32), stream()))
+    kind = cabi.MLP_IN_ENC16_RAYBIAS if ray_bias else cabi.MLP_IN_ENC16_RAYDIRS
+    _run("mlp_small_fwd", lambda: lib().nrf_mlp_small_fwd_importance(C.byref(shape), ptr(packed), kind, ptr(enc_merged, f16), ptr(ray_sh, f32),
+                                  ptr(keep_merged), ptr(perm, torch.int16), r, n_importance, t, ptr(raw_merged, f32), stream()))
     return raw_merged
+
+
+def mlp_small_view_bias_fwd(packed: torch.Tensor, ray_sh: torch.Tensor, shape=None, out: torch.Tensor | None = None,
+                            grad_bias_zero: torch.Tensor | None = None) -> torch.Tensor:
+    """The view term of the colour net's first layer, once per ray: ray_sh [R,V] -> bias [R,64] fp32 (and grad_bias_zero [R,64] := 0)."""
+    shape = shape or mlp_shape()
+    r = ray_sh.shape[0]
+    assert ray_sh.shape[1] == shape.input_ch_views
+    if out is None:
+        out = torch.empty((r, 64), dtype=f32, device=ray_sh.device)
+    _run("mlp_small_view_bias", lambda: lib().nrf_mlp_small_view_bias_fwd(C.byref(shape), ptr(packed), ptr(ray_sh, f32), r, ptr(out, f32),
+                                        ptr(grad_bias_zero, f32) if grad_bias_zero is not None else None, stream()))
+    return out
+
+
+def mlp_small_view_bias_bwd(ray_sh: torch.Tensor, grad_bias: torch.Tensor, grad_params: torch.Tensor, shape=None) -> None:
+    """grad_params[view columns of color_net_0] += grad_bias^T ray_sh."""
+    shape = shape or mlp_shape()
+    _run("mlp_small_view_bias", lambda: lib().nrf_mlp_small_view_bias_bwd(C.byref(shape), ptr(ray_sh, f32), ptr(grad_bias, f32), ray_sh.shape[0],
+                                        ptr(grad_params, f32), stream()))
 
 
 def mlp_small_bwd(packed: torch.Tensor, enc: torch.Tensor, ray_sh: torch.Tensor | None, samples_per_ray: int,
                   keep: torch.Tensor | None, grad_raw: torch.Tensor, grad_params: torch.Tensor, want_grad_in: bool = True,
-                  shape=None, grad_in: torch.Tensor | None = None):
+                  shape=None, grad_in: torch.Tensor | None = None, grad_bias: torch.Tensor | None = None):
+    """grad_bias [R,64] (accumulated into) selects NRF_MLP_IN_ENC16_RAYBIAS: ray_sh is then the per-ray view term."""
     shape = shape or mlp_shape()
     n = enc.shape[0]
     if enc.dtype == f16:
-        kind = cabi.MLP_IN_ENC16_RAYDIRS
+        kind = cabi.MLP_IN_ENC16_RAYBIAS if grad_bias is not None else cabi.MLP_IN_ENC16_RAYDIRS
         if want_grad_in and grad_in is None:
             grad_in = torch.empty((n, 32), dtype=bf16, device=enc.device)
     else:
         kind = cabi.MLP_IN_F32_CAT
         if want_grad_in and grad_in is None:
             grad_in = torch.empty((n, 48), dtype=f32, device=enc.device)
-    _run("mlp_small_bwd", lambda: lib().nrf_mlp_small_bwd(C.byref(shape), ptr(packed), kind, ptr(enc), ptr(ray_sh), samples_per_ray, ptr(keep), n,
-                                  ptr(grad_raw, f32), ptr(grad_in) if want_grad_in else None, ptr(grad_params, f32), stream()))
+    _run("mlp_small_bwd", lambda: lib().nrf_mlp_small_bwd_raybias(C.byref(shape), ptr(packed), kind, ptr(enc), ptr(ray_sh), samples_per_ray, ptr(keep), n,
+                                  ptr(grad_raw, f32), ptr(grad_in) if want_grad_in else None, ptr(grad_params, f32),
+                                  ptr(grad_bias, f32) if grad_bias is not None else None, stream()))
     return grad_in
 
 

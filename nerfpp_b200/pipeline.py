@@ -28,6 +28,11 @@ MLP_PARAMS = 9344  # 64*32 + 16*64 + 64*31 + 64*64 + 3*64  (src/NeRF.cpp:338-342
 MLP_LAYERS = [(64, 32), (16, 64), (64, 31), (64, 64), (3, 64)]
 
 
+def mlp_layers(n_views: int = 16):
+    """[out, in] of sigma_net_0, sigma_net_1, color_net_0 (in = views + geo 15), color_net_1, color_net_2 (src/NeRF.cpp:338-342)."""
+    return [(64, 32), (16, 64), (64, n_views + 15), (64, 64), (3, 64)]
+
+
 def _is_prime(x: int) -> bool:
     i = 2
     while i * i <= x:
@@ -224,18 +229,27 @@ class HashNeRF(FlatAdamModel):
 
     def __init__(self, bbox=(-1.5, -1.5, -1.5, 1.5, 1.5, 1.5), n_levels=16, n_features=2, log2_hashmap_size=19,
                  base_resolution=16, finest_resolution=512, sh_degree=4, n_samples=64, n_importance=128,
-                 device="cuda", seed=42, lr=1e-2, lrate_decay=250, primes=None):
-        assert n_levels * n_features == 32 and sh_degree == 4, "the fused MLP is built for 32 + 16 inputs"
+                 device="cuda", seed=42, lr=1e-2, lrate_decay=250, primes=None, ray_bias=None):
+        """sh_degree 4 (16 view channels): the view channels are the first k-step of the fused colour net.  Any other degree 1..8 (8 = the
+        reference's shipped configuration, src/main.cpp:176): the view term of that layer is computed once per RAY and enters the fused kernels
+        as a bias (ops.mlp_small_view_bias_fwd / _bwd, NRF_MLP_IN_ENC16_RAYBIAS).  ray_bias=True forces that form at degree 4 (tests)."""
+        assert n_levels * n_features == 32 and 1 <= sh_degree <= 8, "the fused MLP is built for 32 encoding channels and SH degree 1..8"
+        self.n_views = sh_degree * sh_degree
+        self.ray_bias = (self.n_views != 16) if ray_bias is None else bool(ray_bias)
+        assert self.ray_bias or self.n_views == 16
+        self.mlp_shape = ops.mlp_shape(input_ch_views=self.n_views)
+        self.mlp_layers = mlp_layers(self.n_views)
+        self._grad_bias = None
         self.device = torch.device(device)
         self.bbox = tuple(float(v) for v in bbox)
         self.grid = make_grid(bbox, n_levels, n_features, log2_hashmap_size, base_resolution, finest_resolution, device, seed, primes)
         self.sh_degree, self.S, self.N = sh_degree, n_samples, n_importance
         self.n_table = self.grid.used_scalars()
         g = torch.Generator(device="cpu").manual_seed(seed)
-        self._init_flat(self.n_table + MLP_PARAMS, device, lr, lrate_decay)
+        self._init_flat(self.n_table + sum(fo * fi for fo, fi in self.mlp_layers), device, lr, lrate_decay)
         self.params[:self.n_table] = (torch.rand(self.n_table, generator=g) * 1e-4).to(device)   # src/CuHashEmbedder.cpp:24
         off = self.n_table
-        for fo, fi in MLP_LAYERS:                                                                 # Trainable.h:43 Xavier normal, gain 0.1
+        for fo, fi in self.mlp_layers:                                                            # Trainable.h:43 Xavier normal, gain 0.1
             std = 0.1 * math.sqrt(2.0 / (fi + fo))
             self.params[off:off + fo * fi] = (torch.randn(fo * fi, generator=g) * std).to(device)
             off += fo * fi
@@ -257,13 +271,26 @@ class HashNeRF(FlatAdamModel):
 
     def mlp_weights(self):
         out, off = [], 0
-        for fo, fi in MLP_LAYERS:
+        for fo, fi in self.mlp_layers:
             out.append(self.mlp_params[off:off + fo * fi].view(fo, fi))
             off += fo * fi
         return out
 
     def repack(self):
-        self.packed = ops.mlp_small_pack(self.mlp_params, out=self.packed)
+        self.packed = ops.mlp_small_pack(self.mlp_params, shape=self.mlp_shape, out=self.packed)
+
+    def _views(self, ray_sh, for_backward=False):
+        """What the fused MLP kernels take as the rays' view input: the SH table itself (16 channels), or — ray_bias — the view term of the
+        colour net's first layer, one [64] row per ray, shared by the coarse and the fine pass (for_backward: its gradient accumulator is
+        zeroed by the same launch)."""
+        if not self.ray_bias:
+            return ray_sh
+        gb = None
+        if for_backward:
+            if self._grad_bias is None or self._grad_bias.shape[0] != ray_sh.shape[0]:
+                self._grad_bias = torch.empty((ray_sh.shape[0], 64), dtype=f32, device=self.device)
+            gb = self._grad_bias
+        return ops.mlp_small_view_bias_fwd(self.packed, ray_sh, shape=self.mlp_shape, grad_bias_zero=gb)
 
     def _static_inputs(self, n_rays, pixels=False):
         dev = self.device
@@ -280,12 +307,12 @@ class HashNeRF(FlatAdamModel):
         self._cam = (image, ops._cam(K, c2w))
 
     # -- RenderRays (src/NeRFRenderer.h:366-459)
-    def _network(self, ray_batch, z, ray_sh, reuse=None):
+    def _network(self, ray_batch, z, views, reuse=None):
         """RunNetwork (src/NeRFRenderer.h:164-194): points are generated inside the encode kernel (o + d z), the SH basis comes
-        per ray, sigma is zeroed outside the box in the MLP epilogue.  reuse: see ops.hash_encode_rays_fwd."""
+        per ray (views: see _views), sigma is zeroed outside the box in the MLP epilogue.  reuse: see ops.hash_encode_rays_fwd."""
         s = z.shape[1]
         enc, keep = ops.hash_encode_rays_fwd(self.grid, self.table_f16, ray_batch, z, clamp=True, out_f16=True, reuse=reuse)
-        raw = ops.mlp_small_fwd(self.packed, enc, ray_sh, s, keep)
+        raw = ops.mlp_small_fwd(self.packed, enc, views, s, keep, shape=self.mlp_shape, ray_bias=self.ray_bias)
         return enc, keep, raw.view(-1, s, 4)
 
     def _u(self, n_importance):
@@ -300,13 +327,14 @@ class HashNeRF(FlatAdamModel):
         """Inference RenderRays as ONE C-ABI call (nrf_render_rays_fwd) into a cached workspace."""
         out, self._render_ws = ops.render_rays_fwd(self.grid, self.table_f16, self.packed, rays_o, rays_d, self.t_vals, self._u(n_importance),
                                                    self.bbox, white_bkgr, self.sh_degree, want_weights=want_weights, want_z=want_z,
-                                                   workspace=self._render_ws)
+                                                   workspace=self._render_ws, shape=self.mlp_shape)
         return out
 
     def render_rays(self, rays_o, rays_d, white_bkgr=False, keep_for_backward=False, n_importance=None, zero_scalar=None, setup=None, fine_composite=True):
         # Render prologue + coarse depths + per-ray SH (+ the caller's loss accumulator reset) in one launch (setup: already done by the caller)
         ray_batch, z, ray_sh = setup if setup is not None else ops.ray_setup(rays_o, rays_d, self.bbox, 0.0, self.t_vals, self.sh_degree, zero_scalar=zero_scalar)
-        enc_c, keep_c, raw = self._network(ray_batch, z, ray_sh)
+        views = self._views(ray_sh, for_backward=keep_for_backward)
+        enc_c, keep_c, raw = self._network(ray_batch, z, views)
         coarse = ops.composite_fwd(raw, z, rays_d, white_bkgr)
         u = self._u(n_importance)
         # the merged list contains the coarse samples bit for bit: their encoding rows are copied, not gathered again (reuse_coarse_rows), and —
@@ -316,19 +344,20 @@ class HashNeRF(FlatAdamModel):
             z_fine, perm, raw_m = ops.sample_pdf_merge(z, coarse["weights"], u, want_perm=True, raw_coarse=raw.view(-1, 4))
             enc, keep = ops.hash_encode_rays_fwd(self.grid, self.table_f16, ray_batch, z_fine, clamp=True, out_f16=True,
                                                  reuse=(perm, enc_c, keep_c, z.shape[1]))
-            raw = ops.mlp_small_fwd_importance(self.packed, enc, ray_sh, keep, perm, u.shape[-1], raw_m).view(-1, z_fine.shape[1], 4)
+            raw = ops.mlp_small_fwd_importance(self.packed, enc, views, keep, perm, u.shape[-1], raw_m, shape=self.mlp_shape,
+                                               ray_bias=self.ray_bias).view(-1, z_fine.shape[1], 4)
         else:
             if self.reuse_coarse_rows:
                 z_fine, perm = ops.sample_pdf_merge(z, coarse["weights"], u, want_perm=True)
                 reuse = (perm, enc_c, keep_c, z.shape[1])
             else:
                 z_fine, reuse = ops.sample_pdf_merge(z, coarse["weights"], u), None
-            enc, keep, raw = self._network(ray_batch, z_fine, ray_sh, reuse)
+            enc, keep, raw = self._network(ray_batch, z_fine, views, reuse)
         # fine_composite False (training): the caller composites, takes the loss and back-propagates in one launch (ops.composite_huber_bwd)
         out = ops.composite_fwd(raw, z_fine, rays_d, white_bkgr) if fine_composite else {}
         out["z"] = z_fine
         if keep_for_backward:
-            out["_saved"] = (ray_batch, enc, keep, raw, ray_sh)
+            out["_saved"] = (ray_batch, enc, keep, raw, views, ray_sh)
         return out
 
     def forward_backward_shipped(self, rays_o, rays_d, target, cone_angle: float, raw_noise_std: float, sp_alpha: float, clamp_to_box: bool = True):
@@ -345,6 +374,7 @@ class HashNeRF(FlatAdamModel):
             self._cone = (cone_angle, torch.full((1,), cone_angle, dtype=f32, device=dev))
         cone = self._cone[1]
         ray_batch, z, ray_sh = ops.ray_setup(rays_o, rays_d, self.bbox, 0.0, self.t_vals, self.sh_degree, zero_scalar=self.loss)
+        views = self._views(ray_sh, for_backward=True)
 
         def network(zz, precondition):
             s = zz.shape[1]
@@ -354,7 +384,7 @@ class HashNeRF(FlatAdamModel):
             ops.tangent_scatter(pts, zz, cone, rays_d, torch.rand((r, s), device=dev), torch.rand((r, s), device=dev), self.bbox if clamp_to_box else None)
             pts = pts.view(-1, 3)
             enc, keep = ops.hash_encode_fwd(self.grid, self.table_f16, pts, clamp=True, out_f16=True)
-            raw = ops.mlp_small_fwd(self.packed, enc, ray_sh, s, keep).view(r, s, 4)
+            raw = ops.mlp_small_fwd(self.packed, enc, views, s, keep, shape=self.mlp_shape, ray_bias=self.ray_bias).view(r, s, 4)
             noise = torch.randn((r, s), device=dev) if raw_noise_std > 0 else None
             return pts, enc, keep, raw, noise
 
@@ -366,7 +396,7 @@ class HashNeRF(FlatAdamModel):
         g_rgb = torch.empty_like(out["rgb"])
         ops.huber_fwd_bwd(out["rgb"], target, self.loss, g_rgb, 1.0, 1.0)
         d_raw = ops.composite_bwd(raw, z_fine, rays_d, noise=noise, raw_noise_std=raw_noise_std, g_rgb=g_rgb)
-        g_enc = ops.mlp_small_bwd(self.packed, enc, ray_sh, raw.shape[1], keep, d_raw.view(-1, 4), self.grads[self.n_table:])
+        g_enc = self._mlp_backward(enc, views, ray_sh, raw.shape[1], keep, d_raw)
         ops.hash_encode_bwd(self.grid, pts, g_enc, self.grads[:self.n_table], clamp=True)
         return out
 
@@ -380,13 +410,22 @@ class HashNeRF(FlatAdamModel):
             outs = []
             for i in range(0, n, chunk):
                 out, self._render_ws = ops.render_rays_fwd(self.grid, self.table_f16, self.packed, None, None, self.t_vals, self._u(n_importance), self.bbox,
-                                                           white_bkgr, self.sh_degree, workspace=self._render_ws,
+                                                           white_bkgr, self.sh_degree, workspace=self._render_ws, shape=self.mlp_shape,
                                                            tile=(K, c2w, w, first + i, min(chunk, n - i)))
                 outs.append(out)
         else:
             rays_o, rays_d = ops.get_rays(h, w, K, c2w, row_begin, row_end, self.device)
             outs = [self.render_rays_fused(rays_o[i:i + chunk], rays_d[i:i + chunk], white_bkgr, n_importance=n_importance) for i in range(0, n, chunk)]
         return {k: torch.cat([o[k] for o in outs], 0) for k in ("rgb", "depth", "disp", "acc")}
+
+    def _mlp_backward(self, enc, views, ray_sh, samples_per_ray, keep, d_raw):
+        """NeRFSmall backward into self.grads (weights) -> gradient of the encodings (bf16 [N,32])."""
+        g_mlp = self.grads[self.n_table:]
+        if not self.ray_bias:
+            return ops.mlp_small_bwd(self.packed, enc, views, samples_per_ray, keep, d_raw.view(-1, 4), g_mlp, shape=self.mlp_shape)
+        g_enc = ops.mlp_small_bwd(self.packed, enc, views, samples_per_ray, keep, d_raw.view(-1, 4), g_mlp, shape=self.mlp_shape, grad_bias=self._grad_bias)
+        ops.mlp_small_view_bias_bwd(ray_sh, self._grad_bias, g_mlp, shape=self.mlp_shape)          # the view columns of color_net_0
+        return g_enc
 
     # -- one optimisation step (src/NeRFExecutor.h:868-890, 923, 986-996)
     def forward_backward(self, *inputs, grad_scale=1.0):
@@ -400,10 +439,10 @@ class HashNeRF(FlatAdamModel):
         else:
             rays_o, rays_d, target = inputs
             out = self.render_rays(rays_o, rays_d, keep_for_backward=True, zero_scalar=self.loss, fine_composite=False)
-        ray_batch, enc, keep, raw, ray_sh = out.pop("_saved")
+        ray_batch, enc, keep, raw, views, ray_sh = out.pop("_saved")
         # RawToOutputs of the fine pass + huber + their backward: one launch
         d_raw, out["rgb"] = ops.composite_huber_bwd(raw, out["z"], rays_d, target, self.loss, grad_scale=grad_scale)
-        g_enc = ops.mlp_small_bwd(self.packed, enc, ray_sh, raw.shape[1], keep, d_raw.view(-1, 4), self.grads[self.n_table:])
+        g_enc = self._mlp_backward(enc, views, ray_sh, raw.shape[1], keep, d_raw)
         ops.hash_encode_rays_bwd(self.grid, ray_batch, out["z"], g_enc, self.grads[:self.n_table], clamp=True)
         return out
 

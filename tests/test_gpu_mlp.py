@@ -117,6 +117,74 @@ def test_fused_input_path_matches_cat_path():
     check_against_emulation_and_fp32(ws, x.cpu(), g.cpu(), out_b.cpu(), gx_b.cpu(), gp_b.cpu(), keep.cpu())
 
 
+@pytest.mark.parametrize("degree", [4, 8, 3])
+def test_per_ray_view_term_form(degree):
+    """NRF_MLP_IN_ENC16_RAYBIAS: the view channels (any SH degree; 8 = the reference's shipped 64-d input, src/main.cpp:176) enter as a per-ray
+    bias of the colour net's first layer.  Forward against the fp32 restatement of NeRFSmallImpl::forward at that width; gradients against
+    autograd of the same; at degree 4 also against the kernels' own per-sample view input (same weights, same blob)."""
+    from nerfpp_b200 import ops
+    torch.manual_seed(10 + degree)
+    V = degree * degree
+    rays, s = 23, 32                                           # 736 rows: ragged vs the 128-row tiles; a 16-row slab lies within one ray
+    n = rays * s
+    shape = ops.mlp_shape(input_ch_views=V)
+    ws = [torch.randn(o, i) * (2.0 / i) ** 0.5 for o, i in ((64, 32), (16, 64), (64, V + 15), (64, 64), (3, 64))]
+    params = flat(ws).cuda()
+    assert params.numel() == 9344 + 64 * (V - 16)
+    packed = ops.mlp_small_pack(params, shape=shape)
+    enc = torch.randn(n, 32).half().cuda()
+    ray_sh = ops.sh_encode(torch.nn.functional.normalize(torch.randn(rays, 3), dim=-1).cuda(), degree)
+    keep = (torch.rand(n) > 0.2).to(torch.uint8).cuda()
+    gb = torch.full((rays, 64), 7.0, device="cuda")
+    bias = ops.mlp_small_view_bias_fwd(packed, ray_sh, shape=shape, grad_bias_zero=gb)
+    assert float(gb.abs().max()) == 0.0                        # the accumulator is cleared by the same launch
+    assert rel_err(bias, ray_sh.cpu() @ ws[2][:, :V].t()) < 1e-5
+    out = ops.mlp_small_fwd(packed, enc, bias, s, keep, shape=shape, ray_bias=True)
+    # fp32 reference
+    x = torch.cat([enc.float().cpu(), ray_sh.cpu().repeat_interleave(s, 0)], -1)
+    wr = [w.clone().requires_grad_(True) for w in ws]
+    xr = x.clone().requires_grad_(True)
+    ref = O.nerf_small_forward(xr, (wr[:2], wr[2:]), input_ch_views=V)
+    ref = torch.cat([ref[:, :3], ref[:, 3:] * keep.cpu().float()[:, None]], -1)
+    assert rel_err(out, ref.detach()) < 1e-2
+    assert float(out[keep == 0, 3].abs().max()) == 0.0
+    g = torch.randn(n, 4)
+    ref.backward(g)
+    gp = torch.zeros_like(params)
+    gx = ops.mlp_small_bwd(packed, enc, bias, s, keep, g.cuda(), gp, shape=shape, grad_bias=gb)
+    ops.mlp_small_view_bias_bwd(ray_sh, gb, gp, shape=shape)
+
+    def cos(a, b):
+        a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+        return float(a @ b / (a.norm() * b.norm()).clamp_min(1e-300))
+
+    # bf16 gradient chain + a fraction of a percent of ReLU units on the other branch than fp32 (test_against_reference_fixture quantifies both)
+    assert cos(gx.float(), xr.grad[:, :32]) > 0.999 and rel_err(gx.float(), xr.grad[:, :32]) < 5e-2
+    for i, (a, b) in enumerate(zip(split(gp.cpu(), ws), [w.grad for w in wr])):
+        assert cos(a, b) > 0.999 and rel_err(a, b) < 5e-2, f"dW{i}"
+    # the view columns are exact up to the bf16 rounding of the per-ray gradient sums
+    assert rel_err(split(gp.cpu(), ws)[2][:, :V], wr[2].grad[:, :V]) < 2e-2
+    if degree == 4:
+        out_v = ops.mlp_small_fwd(packed, enc, ray_sh, s, keep)
+        assert rel_err(out, out_v) < 3e-3                      # fp32 view term vs fp16 view operands in the MMA
+        gp_v = torch.zeros_like(params)
+        gx_v = ops.mlp_small_bwd(packed, enc, ray_sh, s, keep, g.cuda(), gp_v)
+        assert rel_err(gx.float(), gx_v.float()) < 2e-2 and rel_err(gp, gp_v) < 2e-2
+    else:
+        with pytest.raises(Exception):                         # the per-sample view input is built for 16 channels only
+            ops.mlp_small_fwd(packed, enc, ray_sh, s, keep, shape=shape)
+    # importance-only forward on the same form: rows at perm positions
+    N, S = 16, 16
+    perm = torch.stack([torch.randperm(s)[:s] for _ in range(rays)]).to(torch.int16).cuda()      # [R, T = 32]: first N entries = new rows
+    raw_m = torch.zeros(n, 4, device="cuda")
+    ops.mlp_small_fwd_importance(packed, enc, bias, keep, perm, N, raw_m, shape=shape, ray_bias=True)
+    rows = (torch.arange(rays, device="cuda")[:, None] * s + perm[:, :N].long()).flatten()
+    assert torch.equal(raw_m[rows], out[rows])
+    untouched = torch.ones(n, dtype=torch.bool, device="cuda")
+    untouched[rows] = False
+    assert float(raw_m[untouched].abs().max()) == 0.0
+
+
 def test_sizes_and_accumulation():
     from nerfpp_b200 import ops
     torch.manual_seed(0)

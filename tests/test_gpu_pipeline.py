@@ -248,6 +248,47 @@ def test_coarse_reuse_leaves_the_render_unchanged():
             assert torch.equal(a["_saved"][i], b["_saved"][i]), name
 
 
+def test_per_ray_view_term_model_matches_the_view_input_model():
+    """HashNeRF(ray_bias=True) at SH degree 4 == the default model (same seed): loss, maps and gradients within the bf16 class."""
+    from nerfpp_b200.pipeline import HashNeRF, synthetic_rays
+    a = HashNeRF(BBOX, log2_hashmap_size=14, seed=42)
+    b = HashNeRF(BBOX, log2_hashmap_size=14, seed=42, ray_bias=True)
+    assert torch.equal(a.params, b.params)
+    o, d, tgt = synthetic_rays(256, seed=3)
+    oa, ob = a.forward_backward(o, d, tgt), b.forward_backward(o, d, tgt)
+    np.testing.assert_allclose(float(b.loss), float(a.loss), rtol=2e-3)
+    np.testing.assert_allclose(ob["rgb"].cpu().numpy(), oa["rgb"].cpu().numpy(), rtol=1e-2, atol=2e-3)
+    ga, gb = a.grads.double(), b.grads.double()
+    assert float(ga @ gb / (ga.norm() * gb.norm())) > 0.9995
+    w2 = slice(a.n_table + 3072, a.n_table + 3072 + 64 * 31)                 # color_net_0: the layer whose view columns take the other route
+    np.testing.assert_allclose(gb[w2].cpu().numpy(), ga[w2].cpu().numpy(), rtol=5e-2, atol=2e-2 * float(ga[w2].abs().max()))
+
+
+def test_shipped_shape_trains_and_renders():
+    """The reference's shipped network shape (src/main.cpp:176-191): SH degree 8 (64 view channels), finest resolution 1024, 64 + 192
+    samples.  Loss falls on the fused kernels; the one-call render entry equals the composed path bit for bit at this shape too."""
+    from nerfpp_b200.pipeline import HashNeRF, synthetic_rays
+    m = HashNeRF(BBOX, log2_hashmap_size=15, finest_resolution=1024, sh_degree=8, n_importance=192, seed=42)
+    assert m.ray_bias and m.params.numel() == m.n_table + 9344 + 64 * 48
+    o, d, tgt = synthetic_rays(512, seed=1)
+    losses = []
+    for _ in range(40):
+        m.train_step(o, d, tgt)
+        losses.append(float(m.loss))
+    assert np.isfinite(losses).all() and losses[-1] < 0.9 * losses[0], (losses[0], losses[-1])
+    assert float(m.grads[m.n_table + 3072: m.n_table + 3072 + 64 * 79].abs().max()) > 0      # color_net_0 incl. its 64 view columns is trained
+    o2, d2, _ = synthetic_rays(300, seed=6)
+    x = m.render_rays(o2, d2)
+    y = m.render_rays_fused(o2, d2, want_weights=True, want_z=True)
+    for k in ("rgb", "depth", "disp", "acc", "weights", "z"):
+        assert torch.equal(x[k], y[k]), k
+    g = m.capture_train_step(512)
+    l0 = float(m.loss)
+    for _ in range(5):
+        m.train_step_graph(o, d, tgt)
+    assert np.isfinite(float(m.loss)) and float(m.loss) <= l0 * 1.05
+
+
 def test_fused_render_entry_equals_the_composed_path():
     """nrf_render_rays_fwd (one C-ABI call) == the same kernels called one by one, bit for bit, incl. a ragged ray count."""
     from nerfpp_b200.pipeline import synthetic_rays
