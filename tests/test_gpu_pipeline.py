@@ -275,18 +275,20 @@ def test_shipped_shape_trains_and_renders():
     for _ in range(40):
         m.train_step(o, d, tgt)
         losses.append(float(m.loss))
+    w2_before = m.mlp_weights()[2].clone()
     assert np.isfinite(losses).all() and losses[-1] < 0.9 * losses[0], (losses[0], losses[-1])
-    assert float(m.grads[m.n_table + 3072: m.n_table + 3072 + 64 * 79].abs().max()) > 0      # color_net_0 incl. its 64 view columns is trained
+    m.train_step(o, d, tgt)
+    moved = (m.mlp_weights()[2] - w2_before).abs().amax(dim=0)               # color_net_0 [64, 64 view + 15 geo columns]
+    assert float(moved[:64].min()) > 0 and float(moved[64:].min()) > 0        # the view columns train through the per-ray route
     o2, d2, _ = synthetic_rays(300, seed=6)
     x = m.render_rays(o2, d2)
     y = m.render_rays_fused(o2, d2, want_weights=True, want_z=True)
     for k in ("rgb", "depth", "disp", "acc", "weights", "z"):
         assert torch.equal(x[k], y[k]), k
-    g = m.capture_train_step(512)
-    l0 = float(m.loss)
+    m.capture_train_step(512)                                                 # the same step as one CUDA graph keeps training
     for _ in range(5):
         m.train_step_graph(o, d, tgt)
-    assert np.isfinite(float(m.loss)) and float(m.loss) <= l0 * 1.05
+    assert np.isfinite(float(m.loss)) and float(m.loss) <= losses[-1] * 1.05, (float(m.loss), losses[-1])
 
 
 def test_fused_render_entry_equals_the_composed_path():
