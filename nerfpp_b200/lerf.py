@@ -78,6 +78,7 @@ class LeRFField(FlatAdamModel):
         self.t_vals = torch.linspace(0.0, 1.0, n_samples, dtype=f32).to(device)                   # src/LeRFRenderer.cpp:112
         self.u = torch.linspace(0.0, 1.0, n_importance, dtype=f32).to(device)                     # src/Sampler.h:20
         self.packed = None
+        self._render_graph = None
         self.render_ray_group = int(os.environ.get("NRF_RENDER_RAY_GROUP", "32"))   # render_image: GetRays order = adjacent pixels
         self.reuse_coarse_rows = True        # the fine pass copies the coarse samples' encoding rows instead of gathering them again (bit-identical)
         self._bwd_ws = None
@@ -173,9 +174,41 @@ class LeRFField(FlatAdamModel):
         self._g.replay()
         return self._g_out
 
-    def render_image(self, h, w, K, c2w, chunk=1 << 15, row_begin=0, row_end=None):
-        """Render(h, w, K, c2w) for image rows [row_begin, row_end) (src/LeRFRenderer.cpp:266-331; chunking as BatchifyRays :165-263)."""
+    def _chunk_graph(self, chunk):
+        """render_rays of one full chunk as a CUDA graph (11 launches + their allocations replayed as one): a frame is hundreds of chunks, and the
+        eager path is bound by the host (ctypes calls, allocator) rather than by the GPU.  Inputs / outputs are static buffers; weights and table are
+        read through the persistent packed / shadow buffers, so a re-packed or trained field renders correctly without a new capture."""
+        if self._render_graph is not None and self._render_graph[0] == (chunk, self.render_ray_group):
+            return self._render_graph
+        dev = self.device
+        o = torch.tensor([[0.0, 0.0, 4.0]], device=dev).repeat(chunk, 1)
+        d = torch.tensor([[0.0, 0.0, -1.0]], device=dev).repeat(chunk, 1)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self.render_rays(o, d, return_weights=False, ray_group=self.render_ray_group)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self.render_rays(o, d, return_weights=False, ray_group=self.render_ray_group)
+        self._render_graph = ((chunk, self.render_ray_group), g, o, d, out)
+        return self._render_graph
+
+    def render_image(self, h, w, K, c2w, chunk=1 << 15, row_begin=0, row_end=None, use_graph=True):
+        """Render(h, w, K, c2w) for image rows [row_begin, row_end) (src/LeRFRenderer.cpp:266-331; chunking as BatchifyRays :165-263).  Full chunks
+        replay one captured graph (use_graph), the ragged last chunk is launched eagerly; same kernels, same results."""
         rays_o, rays_d = ops.get_rays(h, w, K, c2w, row_begin, row_end, self.device)
-        outs = [self.render_rays(rays_o[i:i + chunk], rays_d[i:i + chunk], return_weights=False, ray_group=self.render_ray_group)
-                for i in range(0, rays_o.shape[0], chunk)]
-        return {k: torch.cat([o[k] for o in outs], 0) for k in ("rendered", "depth", "disp", "acc")}
+        keys = ("rendered", "depth", "disp", "acc")
+        n = rays_o.shape[0]
+        outs = []
+        for i in range(0, n, chunk):
+            if use_graph and i + chunk <= n and n >= 2 * chunk:
+                _, g, o, d, out = self._chunk_graph(chunk)
+                o.copy_(rays_o[i:i + chunk])
+                d.copy_(rays_d[i:i + chunk])
+                g.replay()
+                outs.append({k: out[k].clone() for k in keys})
+            else:
+                outs.append(self.render_rays(rays_o[i:i + chunk], rays_d[i:i + chunk], return_weights=False, ray_group=self.render_ray_group))
+        return {k: torch.cat([o[k] for o in outs], 0) for k in keys}
