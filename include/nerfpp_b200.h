@@ -288,7 +288,8 @@ int nrf_composite_fwd(const float* raw, int32_t raw_stride, const float* z, cons
                       float* rgb /*[R,3]*/, float* depth /*[R]*/, float* disp /*[R]*/, float* acc /*[R]*/,
                       float* weights /*[R,S] nullable*/, nrf_stream stream);
 
-/* g_* are the upstream gradients of the five outputs (each nullable = zero).  d_raw [R,S,4]. */
+/* g_* are the upstream gradients of the five outputs (each nullable = zero).  d_raw [R,S,4].  n_samples <= 2048 (register-resident
+ * kernels up to 256 samples per ray, a two-pass kernel beyond). */
 int nrf_composite_bwd(const float* raw, int32_t raw_stride, const float* z, const float* rays_d, const float* noise,
                       float raw_noise_std, int32_t white_bkgr, int64_t n_rays, int32_t n_samples,
                       const float* g_rgb, const float* g_depth, const float* g_disp, const float* g_acc,

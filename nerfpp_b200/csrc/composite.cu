@@ -311,6 +311,119 @@ __global__ void __launch_bounds__(kRaysPerCta * 32) composite_bwd_kernel(const f
 	}
 }
 
+// Any S (the kernels above keep a ray's S <= 256 samples in registers): two passes over the ray in 32-sample blocks.  Pass 1 re-evaluates the
+// forward (sums, and the log-transmittance carried into every block, kept in shared memory); pass 2 walks the blocks backwards, evaluating each
+// sample again, with the suffix sum of dL carried across blocks.  Same expressions, same order of the scans as composite_bwd_kernel.
+constexpr int kGenericMaxBlocks = 64;   // S <= 2048
+
+template <bool HUBER>
+__global__ void __launch_bounds__(kRaysPerCta * 32) composite_bwd_generic_kernel(const float* __restrict__ raw, int raw_stride,
+	const float* __restrict__ z, const float* __restrict__ rays_d, const float* __restrict__ noise, float noise_std, int white,
+	int64_t R, int S, const float* __restrict__ g_rgb, const float* __restrict__ g_depth, const float* __restrict__ g_disp,
+	const float* __restrict__ g_acc, const float* __restrict__ g_weights, float* __restrict__ d_raw, HuberArgs hub)
+{
+	__shared__ float block_carry[kRaysPerCta][kGenericMaxBlocks];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const int64_t ray = static_cast<int64_t>(blockIdx.x) * kRaysPerCta + wid;
+	if (ray >= R) return;
+	const float* raw_row = raw + ray * S * raw_stride;
+	const float* zrow = z + ray * S;
+	const float* nrow = (noise && noise_std > 0.f) ? noise + ray * S : nullptr;
+	const float dnorm = ray_norm(rays_d, ray);
+	const int nb = (S + 31) / 32;
+	const SampleEval none{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+
+	float carry = 0.f, sa = 0.f, sd = 0.f, sr = 0.f, sg = 0.f, sb = 0.f;
+	for (int b = 0; b < nb; b++) {
+		const int i = b * 32 + lane;
+		SampleEval e = none;
+		float zi = 0.f;
+		if (i < S) {
+			const SampleIn in = load_sample(raw_row, raw_stride, zrow, nrow, i, S);
+			zi = in.zi;
+			e = eval_loaded(in, nrow != nullptr, noise_std, dnorm, i, S);
+		}
+		const float ell = i < S ? e.ell : 0.f;
+		const float incl = warp_scan_incl(ell, lane);
+		if (lane == 0) block_carry[wid][b] = carry;
+		if (i < S) {
+			const float w = e.alpha * expf(carry + (incl - ell));
+			sa += w;
+			sd += w * zi;
+			if (HUBER) { sr += w * e.r; sg += w * e.g; sb += w * e.b; }
+		}
+		carry += __shfl_sync(0xffffffffu, incl, 31);
+	}
+	__syncwarp();
+	sa = warp_sum(sa);
+	sd = warp_sum(sd);
+	float gr, gg, gb;
+	if (HUBER) {
+		sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb);
+		if (white) { const float bg = 1.f - sa; sr += bg; sg += bg; sb += bg; }
+		const float er = sr - hub.target[ray * 3], eg = sg - hub.target[ray * 3 + 1], eb = sb - hub.target[ray * 3 + 2];
+		const float d = hub.delta;
+		gr = (fabsf(er) < d ? er : (er > 0.f ? d : -d)) * hub.inv_n * hub.grad_scale;
+		gg = (fabsf(eg) < d ? eg : (eg > 0.f ? d : -d)) * hub.inv_n * hub.grad_scale;
+		gb = (fabsf(eb) < d ? eb : (eb > 0.f ? d : -d)) * hub.inv_n * hub.grad_scale;
+		if (lane == 0) {
+			const float l = (fabsf(er) < d ? 0.5f * er * er : d * (fabsf(er) - 0.5f * d)) + (fabsf(eg) < d ? 0.5f * eg * eg : d * (fabsf(eg) - 0.5f * d)) +
+			                (fabsf(eb) < d ? 0.5f * eb * eb : d * (fabsf(eb) - 0.5f * d));
+			if (hub.loss_out) atomicAdd(hub.loss_out, l * hub.inv_n);
+			if (hub.rgb_out) { hub.rgb_out[ray * 3] = sr; hub.rgb_out[ray * 3 + 1] = sg; hub.rgb_out[ray * 3 + 2] = sb; }
+		}
+	} else {
+		gr = g_rgb ? g_rgb[ray * 3] : 0.f; gg = g_rgb ? g_rgb[ray * 3 + 1] : 0.f; gb = g_rgb ? g_rgb[ray * 3 + 2] : 0.f;
+	}
+	const float den = fmaxf(sa, 1e-10f);
+	const float dep = sd / den;
+	float gdep = g_depth ? g_depth[ray] : 0.f;
+	if (g_disp && dep > 1e-10f) gdep += g_disp[ray] * (-1.f / (dep * dep));
+	float gacc = g_acc ? g_acc[ray] : 0.f;
+	if (white) gacc -= (gr + gg + gb);
+	if (sa >= 1e-10f) gacc -= gdep * sd / (den * den);
+	const float gz = gdep / den;
+
+	float rcarry = 0.f;
+	for (int b = nb - 1; b >= 0; b--) {
+		const int i = b * 32 + lane;
+		const bool ok = i < S;
+		SampleEval e = none;
+		float zi = 0.f;
+		if (ok) {
+			const SampleIn in = load_sample(raw_row, raw_stride, zrow, nrow, i, S);
+			zi = in.zi;
+			e = eval_loaded(in, nrow != nullptr, noise_std, dnorm, i, S);
+		}
+		const float ell = ok ? e.ell : 0.f;
+		const float Lx = block_carry[wid][b] + (warp_scan_incl(ell, lane) - ell);
+		float G = 0.f, T = 0.f, dL = 0.f;
+		if (ok) {
+			T = expf(Lx);
+			G = gr * e.r + gg * e.g + gb * e.b + gacc + gz * zi;
+			if (g_weights) G += g_weights[ray * S + i];
+			dL = G * e.alpha * expf(fminf(fmaxf(Lx, -100.f), 5.f));
+		}
+		const float incl = warp_scan_incl_rev(dL, lane);
+		const float dell = rcarry + (incl - dL);
+		rcarry += __shfl_sync(0xffffffffu, incl, 0);
+		if (ok) {
+			float dalpha = G * T;
+			const float om = 1.f - e.alpha;
+			if (om >= 1e-10f) dalpha -= dell / om;
+			const float dx = -dalpha * expf(fminf(fmaxf(e.x, -100.f), 5.f));
+			const float dsig = (e.sig > 0.f && S > 1) ? -e.dist * dx : 0.f;
+			const float w = e.alpha * T;
+			float4 o;
+			o.x = w * gr * e.r * (1.f - e.r);
+			o.y = w * gg * e.g * (1.f - e.g);
+			o.z = w * gb * e.b * (1.f - e.b);
+			o.w = dsig;
+			*reinterpret_cast<float4*>(d_raw + (ray * S + i) * 4) = o;
+		}
+	}
+}
+
 }  // namespace nrf
 
 using namespace nrf;
@@ -350,7 +463,7 @@ int nrf_composite_bwd(const float* raw, int32_t raw_stride, const float* z, cons
 {
 	NRF_REQUIRE(n_rays >= 0 && n_samples >= 1, "bad sizes");
 	NRF_REQUIRE(raw_stride >= 4, "raw_stride must be >= 4");
-	NRF_REQUIRE(n_samples <= 32 * kMaxBlocks, "n_samples > 256 is not supported by the backward");
+	NRF_REQUIRE(n_samples <= 32 * kGenericMaxBlocks, "n_samples > 2048 is not supported by the backward");
 	if (n_rays == 0) return NRF_OK;
 	NRF_REQUIRE(raw && z && rays_d && d_raw, "null input");
 	const unsigned blocks = static_cast<unsigned>((n_rays + kRaysPerCta - 1) / kRaysPerCta);
@@ -364,6 +477,9 @@ int nrf_composite_bwd(const float* raw, int32_t raw_stride, const float* z, cons
 		break
 	switch (nb) {
 		NRF_CB(1); NRF_CB(2); NRF_CB(3); NRF_CB(4); NRF_CB(5); NRF_CB(6); NRF_CB(7); NRF_CB(8);
+		default:   // more samples than a warp keeps in registers: the two-pass kernel
+			composite_bwd_generic_kernel<false><<<blocks, kRaysPerCta * 32, 0, s>>>(raw, raw_stride, z, rays_d, noise, raw_noise_std, white_bkgr, n_rays,
+				n_samples, g_rgb, g_depth, g_disp, g_acc, g_weights, d_raw, none);
 	}
 #undef NRF_CB
 	NRF_CHECK_LAUNCH("composite_bwd_kernel");
@@ -376,7 +492,7 @@ int nrf_composite_huber_bwd(const float* raw, int32_t raw_stride, const float* z
 {
 	NRF_REQUIRE(n_rays >= 0 && n_samples >= 1, "bad sizes");
 	NRF_REQUIRE(raw_stride >= 4, "raw_stride must be >= 4");
-	NRF_REQUIRE(n_samples <= 32 * kMaxBlocks, "n_samples > 256 is not supported by the backward");
+	NRF_REQUIRE(n_samples <= 32 * kGenericMaxBlocks, "n_samples > 2048 is not supported by the backward");
 	if (n_rays == 0) return NRF_OK;
 	NRF_REQUIRE(raw && z && rays_d && d_raw && target, "null input");
 	const unsigned blocks = static_cast<unsigned>((n_rays + kRaysPerCta - 1) / kRaysPerCta);
@@ -392,6 +508,9 @@ int nrf_composite_huber_bwd(const float* raw, int32_t raw_stride, const float* z
 		break
 	switch (nb) {
 		NRF_CH(1); NRF_CH(2); NRF_CH(3); NRF_CH(4); NRF_CH(5); NRF_CH(6); NRF_CH(7); NRF_CH(8);
+		default:
+			composite_bwd_generic_kernel<true><<<blocks, kRaysPerCta * 32, 0, s>>>(raw, raw_stride, z, rays_d, noise, raw_noise_std, white_bkgr, n_rays,
+				n_samples, nullptr, nullptr, nullptr, nullptr, nullptr, d_raw, hub);
 	}
 #undef NRF_CH
 	NRF_CHECK_LAUNCH("composite_bwd_kernel");

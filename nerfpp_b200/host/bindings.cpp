@@ -259,6 +259,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 	m.def("reflect_boundary", &ReflectBoundary);
 	m.def("total_variation_loss", [](CuHashPipe& p) { return TotalVariationLoss(p.embed); });
 
+	m.def("invalidate_caches", [](CuHashPipe& p) { p.embed->InvalidateCaches(); p.model->InvalidateCaches(); });
+	m.def("classic_invalidate_caches", [](ClassicPipe& p) { p.model->InvalidateCaches(); });
+	m.def("lerf_invalidate_caches", [](LerfPipe& p) { p.embed->InvalidateCaches(); p.model->InvalidateCaches(); });
 	m.def("classic_set_fused_training", [](ClassicPipe& p, bool on) { p.model->FusedTraining = on; });
 	m.def("classic_set_fused_embedding", [](ClassicPipe& p, bool on) { p.model->FusedEmbedding = on; });
 	Bind<CuHashPipe>(m, "CuHashPipe");

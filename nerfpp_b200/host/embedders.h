@@ -52,6 +52,9 @@ public:
 	std::pair<torch::Tensor, torch::Tensor> EncodeF16(const torch::Tensor& x);
 	/// accumulates dL/dEmbeddings for bf16 / fp32 [N, L*F] encoding gradients into grad_table (fp32, same shape as Embeddings)
 	void Backward(const torch::Tensor& points, const torch::Tensor& grad_enc, torch::Tensor& grad_table);
+	/// The fp16 shadow is rebuilt when Embeddings' (data_ptr, Tensor::_version()) changes.  A write that bypasses the version counter —
+	/// Embeddings.data().copy_(), variable_data(), a raw kernel or an NCCL broadcast into the storage — must be followed by this call.
+	void InvalidateCaches() { ShadowSource = nullptr; }
 
 private:
 	torch::Tensor LevelScale, Shadow;

@@ -45,6 +45,8 @@ public:
 	std::vector<torch::Tensor> Weights();      ///< sigma_le_net_0, sigma_le_net_1, le_net_0, le_net_1 weights, each [out,in]
 	torch::Tensor Packed();                    ///< operand blob of the current weights (re-packed only when a weight changed)
 	torch::Tensor ForwardAten(const torch::Tensor& x);   ///< the reference's formulation (torch::linear), differentiable
+	/// after a write to a weight that bypasses Tensor::_version() (param.data().copy_(), raw kernel, NCCL broadcast): re-pack on next use
+	void InvalidateCaches() { PackedKey.clear(); PackedBlob = torch::Tensor(); }
 
 private:
 	torch::Tensor PackedBlob;

@@ -79,6 +79,9 @@ struct NeRFImpl : public BaseNeRFImpl {
 		const std::vector<float>& freqs_pts, const std::vector<float>& freqs_views);
 	/// true when ForwardPoints covers this model with these two embedders
 	bool FusedEmbeddingShape(class EmbedderImpl& e_pts, class EmbedderImpl& e_dirs) const;
+	/// The operand blobs are re-packed when a parameter's (data_ptr, Tensor::_version()) changes; after a write that bypasses the version
+	/// counter (param.data().copy_(), a raw kernel, an NCCL broadcast into the storage) call this.
+	void InvalidateCaches() { PackedKey.clear(); PackedBlob = torch::Tensor(); }
 private:
 	torch::Tensor PackedBlob;
 	std::vector<std::pair<const void*, uint32_t>> PackedKey;
@@ -110,6 +113,8 @@ public:
 	torch::Tensor Packed();
 	int GetInputCh() const { return InputCh; }
 	int GetInputChViews() const { return InputChViews; }
+	/// see NeRFImpl::InvalidateCaches
+	void InvalidateCaches() { PackedKey.clear(); PackedBlob = torch::Tensor(); }
 
 private:
 	torch::Tensor PackedBlob, FlatParams;

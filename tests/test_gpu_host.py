@@ -484,3 +484,25 @@ def test_classic_run_network_fuses_the_embeddings(host):
     for name, x, y in zip(a.model_param_names(), a.model_params(), b.model_params()):
         assert float(y.grad.abs().max()) > 0, name
         assert torch.allclose(x.grad, y.grad, rtol=1e-3, atol=1e-6 * float(y.grad.abs().max())), name
+
+
+def test_writes_behind_the_version_counter_need_invalidate_caches(host):
+    """The fp16 table shadow and the packed weight blobs are keyed on (data_ptr, Tensor::_version()).  A write through an alias with its own
+    version counter (`.data`, a raw kernel, an NCCL broadcast) is invisible to that key: InvalidateCaches() is the documented hand-shake."""
+    host.manual_seed(7)
+    pipe = host.make_cuhash(torch.tensor(BBOX).cuda(), *ARGS)
+    table = pipe.embed_params()[0]
+    with torch.no_grad():
+        table.copy_(torch.rand_like(table) * 2 - 1)
+    x = (torch.rand(257, 3, device="cuda") * 2 - 1)
+    with torch.no_grad():
+        a = pipe.embed(x)[0].clone()
+        table.mul_(2.0)                                   # through the parameter: version bumped, the shadow follows
+        b = pipe.embed(x)[0].clone()
+        np.testing.assert_allclose(b.cpu().numpy(), 2 * a.cpu().numpy(), rtol=2e-3, atol=1e-4)
+        table.data.mul_(0.5)                              # through .data: own version counter, the key does not move
+        stale = pipe.embed(x)[0].clone()
+        assert torch.equal(stale, b)
+        host.invalidate_caches(pipe)
+        c = pipe.embed(x)[0]
+        np.testing.assert_allclose(c.cpu().numpy(), a.cpu().numpy(), rtol=2e-3, atol=1e-4)

@@ -34,7 +34,7 @@ def test_composite_against_reference_fixture(golden, white):
     close(d_raw, ref, rtol=1e-3, atol=1e-3 * np.abs(ref).max() * 1e-2)
 
 
-@pytest.mark.parametrize("S", [1, 31, 64, 192, 256])
+@pytest.mark.parametrize("S", [1, 31, 64, 192, 256, 257, 448])      # > 256: the two-pass backward (the register-resident kernels stop at 256)
 def test_composite_random(S):
     from nerfpp_b200 import ops
     torch.manual_seed(S)
@@ -319,7 +319,7 @@ def test_ray_setup_equals_the_three_kernels_bit_for_bit(r, s, deg, lin):
     assert sh3 is None and torch.equal(rb, rb3) and torch.equal(z, z3)
 
 
-@pytest.mark.parametrize("S,white", [(192, False), (64, True), (33, False)])
+@pytest.mark.parametrize("S,white", [(192, False), (64, True), (33, False), (320, True)])
 def test_fused_composite_huber_backward_equals_the_three_entries(S, white):
     """nrf_composite_huber_bwd (the training tail of the colour pass in one launch) against nrf_composite_fwd -> nrf_huber_fwd_bwd ->
     nrf_composite_bwd: same RGB and d_raw bit for bit (the same expressions in the same order), same loss up to the order of the atomic sum."""
@@ -336,6 +336,10 @@ def test_fused_composite_huber_backward_equals_the_three_entries(S, white):
     d_a = ops.composite_bwd(raw, z, d, white, g_rgb=g_rgb)
     loss_b = torch.zeros(1, device="cuda")
     d_b, rgb_b = ops.composite_huber_bwd(raw, z, d, tgt, loss_b, white_bkgr=white, grad_scale=0.5)
-    assert torch.equal(rgb_b, out["rgb"])
-    assert torch.equal(d_b, d_a)
+    if S <= 256:
+        assert torch.equal(rgb_b, out["rgb"])
+        assert torch.equal(d_b, d_a)
+    else:       # beyond 256 samples the forward and the two-pass backward are separate looped kernels: same expressions, own summation order
+        close(rgb_b, out["rgb"], rtol=1e-5, atol=1e-6)
+        close(d_b, d_a, rtol=1e-4, atol=1e-6 * float(d_a.abs().max()))
     assert abs(float(loss_a) - float(loss_b)) <= 1e-6 * abs(float(loss_a))
