@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(128) hash_fwd_kernel(HashArgs a, const __half*
 	constexpr int CH = 8 / F;
 	using V = typename FeatVec<F>::type;
 	__shared__ HashMeta m;
+	pdl_prologue();
 	stage_meta(m, a);
 	const int L = a.n_levels;
 	const int row_bytes = L * F * (OUT_F32 ? 4 : 2);
@@ -358,6 +359,7 @@ __global__ void __launch_bounds__(128) hash_bwd_kernel(HashArgs a, PointSrc ps, 
 	constexpr int CH = 8 / F;   // levels per 8-value gradient chunk (16 B of bf16 / 32 B of fp32)
 	constexpr uint32_t FULL = 0xffffffffu;
 	__shared__ HashMeta m;
+	pdl_prologue();
 	stage_meta(m, a);
 
 	const int lane = threadIdx.x & 31;
@@ -622,7 +624,7 @@ static int launch_hash_fwd(const nrf_hash_grid* grid, const void* table_f16, con
 		const int64_t items = (ps.group > 1 ? (static_cast<int64_t>(ps.R) + ps.group - 1) / ps.group * ps.group * ps.S_work : n_points) * (SP); \
 		const LaunchPlan lp = launch_plan(items, 128);                                                                           \
 		if (occ_pad_bytes() > 48 * 1024) cudaFuncSetAttribute(hash_fwd_kernel<FF, O32, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, occ_pad_bytes()); \
-		hash_fwd_kernel<FF, O32, SP><<<lp.grid, 128, occ_pad_bytes(), s>>>(a, t, ps, ru, items, lp.stride, lp.iters, clamp_points, keep, enc_out); \
+		launch_kernel(hash_fwd_kernel<FF, O32, SP>, lp.grid, 128, occ_pad_bytes(), s, a, t, ps, ru, items, lp.stride, lp.iters, clamp_points, keep, enc_out); \
 	} while (0)
 #define NRF_LAUNCH_FWD(FF, SP)                                                     \
 	do {                                                                           \
@@ -657,7 +659,7 @@ static int launch_hash_bwd(const nrf_hash_grid* grid, const PointSrc& ps, int64_
 	do {                                                                                                                          \
 		const LaunchPlan lp = launch_plan(n_points, 128);                                                                        \
 		if (occ_pad_bytes() > 48 * 1024) cudaFuncSetAttribute(hash_bwd_kernel<FF, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, occ_pad_bytes()); \
-		hash_bwd_kernel<FF, BF><<<lp.grid, 128, occ_pad_bytes(), s>>>(a, ps, n_points, lp.stride, lp.iters, clamp_points, grad_enc, grad_table); \
+		launch_kernel(hash_bwd_kernel<FF, BF>, lp.grid, 128, occ_pad_bytes(), s, a, ps, n_points, lp.stride, lp.iters, clamp_points, grad_enc, grad_table); \
 	} while (0)
 #define NRF_LAUNCH_BWD(FF)                                             \
 	do {                                                               \

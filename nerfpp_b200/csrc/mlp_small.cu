@@ -32,6 +32,7 @@ namespace nrf {
 
 __global__ void __launch_bounds__(256) mlp_pack_kernel(const float* __restrict__ p, int V, uint32_t* __restrict__ blob)
 {
+	pdl_prologue();
 	const int w = blockIdx.x * blockDim.x + threadIdx.x;
 	if (w >= kPackedWords) return;
 	if (w >= kViewBase) {
@@ -459,6 +460,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 	void* __restrict__ grad_in, float* __restrict__ grad_params, int V, float* __restrict__ grad_bias)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
+	pdl_prologue();
 	uint32_t* wf = reinterpret_cast<uint32_t*>(smem_raw);
 	__nv_bfloat16* tiles = reinterpret_cast<__nv_bfloat16*>(smem_raw + static_cast<size_t>(kBlobWords) * 4);
 	uint8_t* ctiles = smem_raw + static_cast<size_t>(kBlobWords) * 4;                       // TCDW: canonical regions
@@ -708,6 +710,7 @@ __global__ void __launch_bounds__(kViewBiasThreads) view_bias_fwd_kernel(const u
 	float* __restrict__ bias, float* __restrict__ grad_bias_zero)
 {
 	extern __shared__ float vb_smem[];
+	pdl_prologue();
 	float* w = vb_smem;                              // [64][V + 1]
 	float* sh = vb_smem + 64 * (V + 1);              // [4][V]
 	for (int i = threadIdx.x; i < 64 * V; i += blockDim.x) {
@@ -741,6 +744,7 @@ __global__ void __launch_bounds__(256) view_bias_bwd_kernel(const float* __restr
 	float* __restrict__ grad_params)
 {
 	extern __shared__ float vb_smem[];
+	pdl_prologue();
 	float* g = vb_smem;                              // [kBiasBwdRays][64]
 	float* sh = vb_smem + kBiasBwdRays * 64;         // [kBiasBwdRays][V]
 	const int64_t ray0 = static_cast<int64_t>(blockIdx.x) * kBiasBwdRays;
@@ -810,7 +814,7 @@ int nrf_mlp_small_pack(const nrf_mlp_small_shape* shape, const float* params_fla
 	if (int rc = check_shape(shape)) return rc;
 	NRF_REQUIRE(params_flat && packed, "null pointer");
 	NRF_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "packed blob must be 16-byte aligned");
-	mlp_pack_kernel<<<(kPackedWords + 255) / 256, 256, 0, as_stream(stream)>>>(params_flat, shape->input_ch_views, reinterpret_cast<uint32_t*>(packed));
+	launch_kernel(mlp_pack_kernel, (kPackedWords + 255) / 256, 256, 0, as_stream(stream), params_flat, shape->input_ch_views, reinterpret_cast<uint32_t*>(packed));
 	NRF_CHECK_LAUNCH("mlp_pack_kernel");
 	return NRF_OK;
 }
@@ -825,7 +829,8 @@ int nrf_mlp_small_view_bias_fwd(const nrf_mlp_small_shape* shape, const void* pa
 	const int V = shape->input_ch_views;
 	const size_t smem = static_cast<size_t>(64 * (V + 1) + 4 * V) * sizeof(float);
 	const unsigned blocks = static_cast<unsigned>((n_rays + kRaysPerBlock - 1) / kRaysPerBlock);
-	view_bias_fwd_kernel<<<blocks, kViewBiasThreads, smem, as_stream(stream)>>>(reinterpret_cast<const uint32_t*>(packed), V, ray_sh, n_rays, bias_out, grad_bias_zero);
+	launch_kernel(view_bias_fwd_kernel, blocks, kViewBiasThreads, smem, as_stream(stream), reinterpret_cast<const uint32_t*>(packed), V, ray_sh, n_rays, bias_out,
+		grad_bias_zero);
 	NRF_CHECK_LAUNCH("view_bias_fwd_kernel");
 	return NRF_OK;
 }
@@ -840,7 +845,7 @@ int nrf_mlp_small_view_bias_bwd(const nrf_mlp_small_shape* shape, const float* r
 	const int V = shape->input_ch_views;
 	const size_t smem = static_cast<size_t>(kBiasBwdRays) * (64 + V) * sizeof(float);
 	const unsigned blocks = static_cast<unsigned>((n_rays + kBiasBwdRays - 1) / kBiasBwdRays);
-	view_bias_bwd_kernel<<<blocks, 256, smem, as_stream(stream)>>>(ray_sh, V, grad_bias, n_rays, grad_params_flat);
+	launch_kernel(view_bias_bwd_kernel, blocks, 256, smem, as_stream(stream), ray_sh, V, grad_bias, n_rays, grad_params_flat);
 	NRF_CHECK_LAUNCH("view_bias_bwd_kernel");
 	return NRF_OK;
 }
@@ -928,8 +933,8 @@ int nrf_mlp_small_bwd_raybias(const nrf_mlp_small_shape* shape, const void* pack
 #define NRF_BWD_LAUNCH(KIND, TC, SMEM)                                                                                                   \
 	do {                                                                                                                                 \
 		NRF_CUDA(cudaFuncSetAttribute(mlp_small_bwd_kernel<KIND, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM))); \
-		mlp_small_bwd_kernel<KIND, TC><<<blocks, kBwdWarps * 32, SMEM, s>>>(blob, enc, ray_sh, samples_per_ray, keep, n, grad_raw, grad_in, grad_params_flat, V, \
-			grad_bias);                                                                                                                  \
+		launch_kernel(mlp_small_bwd_kernel<KIND, TC>, blocks, kBwdWarps * 32, SMEM, s, blob, enc, ray_sh, samples_per_ray, keep, n, grad_raw, grad_in,      \
+			grad_params_flat, V, grad_bias);                                                                                             \
 	} while (0)
 	if (in_kind == NRF_MLP_IN_ENC16_RAYDIRS) {
 		if (tcdw) NRF_BWD_LAUNCH(NRF_MLP_IN_ENC16_RAYDIRS, true, kBwdSmemTc); else NRF_BWD_LAUNCH(NRF_MLP_IN_ENC16_RAYDIRS, false, kBwdSmem);

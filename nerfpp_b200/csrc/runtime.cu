@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 
 namespace nrf {
 
@@ -17,6 +18,12 @@ void set_error(const char* fmt, ...)
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled()
+{
+	static const bool v = [] { const char* e = getenv("NRF_PDL"); return e && e[0] == '1'; }();   // opt-in: measured gain 3 us of 812
+	return v;
+}
 
 }  // namespace nrf
 

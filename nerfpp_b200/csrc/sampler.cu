@@ -15,28 +15,28 @@ namespace nrf {
 
 constexpr int kSamplerWarps = 4;
 
-// number of entries of the ascending array a[0..n) that are <= v  (searchsorted right=true)
+// number of entries of the ascending array a[0..n) that are <= v  (searchsorted right=true).  Branch-free descent over power-of-two steps:
+// the trip count depends on n only (warp-uniform), each step is one predicated load and a select — about half the instructions of the
+// lo / hi loop, and the kernels here are bound by instruction issue.
 __device__ __forceinline__ int upper_bound(const float* a, int n, float v)
 {
-	int lo = 0, hi = n;
-	while (lo < hi) {
-		const int mid = (lo + hi) >> 1;
-		if (a[mid] <= v) lo = mid + 1;
-		else hi = mid;
+	int pos = 0;
+	for (int step = 1 << (31 - __clz(n | 1)); step > 0; step >>= 1) {
+		const int p = pos + step;
+		if (p <= n && a[p - 1] <= v) pos = p;
 	}
-	return lo;
+	return pos;
 }
 
 // number of entries that are < v
 __device__ __forceinline__ int lower_bound(const float* a, int n, float v)
 {
-	int lo = 0, hi = n;
-	while (lo < hi) {
-		const int mid = (lo + hi) >> 1;
-		if (a[mid] < v) lo = mid + 1;
-		else hi = mid;
+	int pos = 0;
+	for (int step = 1 << (31 - __clz(n | 1)); step > 0; step >>= 1) {
+		const int p = pos + step;
+		if (p <= n && a[p - 1] < v) pos = p;
 	}
-	return lo;
+	return pos;
 }
 
 // inclusive prefix sum / max across the warp
@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(kSamplerWarps * 32) sample_pdf_merge_kernel(co
 	float4* __restrict__ rows_merged, int per_warp_floats, int sort_pow2)
 {
 	extern __shared__ float smem[];
+	pdl_prologue();
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int64_t ray = static_cast<int64_t>(blockIdx.x) * kSamplerWarps + warp;
 	if (ray >= R) return;
@@ -213,6 +214,84 @@ __global__ void __launch_bounds__(kSamplerWarps * 32) sample_pdf_merge_kernel(co
 	}
 }
 
+// The same, one CTA per ray (u shared by the rays).  A training batch is a few thousand rays — less than one wave of warps — so the warp-per-ray
+// kernel above runs at the latency of ONE warp walking a ray's ~14 dependent binary searches per lane; here every thread owns one importance
+// sample (and one coarse sample in the merge), the chain is 3 searches long; warp 0 builds the cdf (the same code, the same bits) while the
+// others stage the depths.  Same arithmetic per element as
+// the warp kernel: bit-identical outputs (tests/test_gpu_render.py::test_sampler_block_kernel_equals_warp_kernel).
+constexpr int kSamplerBlock = 128;
+constexpr int64_t kBlockPerRayMaxRays = 16384;       // about two waves of the warp-per-ray kernel
+
+__global__ void __launch_bounds__(kSamplerBlock) sample_pdf_merge_block_kernel(const float* __restrict__ z_coarse, const float* __restrict__ weights,
+	const float* __restrict__ u, int64_t R, int S, int N, float* __restrict__ z_samples, float* __restrict__ z_merged, int16_t* __restrict__ perm_out,
+	const float4* __restrict__ rows_coarse, float4* __restrict__ rows_merged)
+{
+	extern __shared__ float smem[];
+	pdl_prologue();
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+	const int64_t ray = blockIdx.x;
+	const int B = S - 1;
+	float* cdf = smem;
+	float* bins = cdf + B;
+	float* zs = bins + B;
+	float* zc = zs + N;
+	const float* zrow = z_coarse + ray * S;
+	if (warp == 0) build_cdf(weights + ray * S + 1, S - 2, cdf, lane);                                   // Weights[:, 1:-1], src/NeRFRenderer.h:428
+	for (int k = tid; k < S; k += kSamplerBlock) zc[k] = zrow[k];
+	for (int k = tid; k < B; k += kSamplerBlock) bins[k] = 0.5f * __fadd_rn(zrow[k + 1], zrow[k]);      // z_vals_mid, :427
+	__syncthreads();
+	for (int j = tid; j < N; j += kSamplerBlock) {
+		const float s = invert_cdf(cdf, bins, B, u[j]);
+		zs[j] = s;
+		if (z_samples) z_samples[ray * N + j] = s;
+	}
+	__syncthreads();
+	// restore_order on both lists (see sample_pdf_merge_kernel), CTA-wide
+	for (;;) {
+		int swapped = 0;
+#pragma unroll
+		for (int phase = 0; phase < 2; phase++) {
+			for (int j = 2 * tid + phase; j + 1 < N; j += 2 * kSamplerBlock) {
+				const float x = zs[j], y = zs[j + 1];
+				if (x > y) { zs[j] = y; zs[j + 1] = x; swapped = 1; }
+			}
+			for (int j = 2 * tid + phase; j + 1 < S; j += 2 * kSamplerBlock) {
+				const float x = zc[j], y = zc[j + 1];
+				if (x > y) { zc[j] = y; zc[j + 1] = x; swapped = 1; }
+			}
+			__syncthreads();
+		}
+		if (!__syncthreads_or(swapped)) break;
+	}
+	float* out = z_merged + ray * (S + N);
+	int16_t* po = perm_out ? perm_out + ray * (S + N) : nullptr;
+	int moved = 0;
+	for (int k = tid; k < S; k += kSamplerBlock) moved |= zc[k] != zrow[k];
+	moved = __syncthreads_or(moved);
+	for (int k = tid; k < S; k += kSamplerBlock) {
+		float v;
+		int rank;
+		if (!moved) {
+			v = zc[k];
+			rank = k;
+		} else {
+			v = zrow[k];
+			rank = lower_bound(zc, S, v);
+			for (int i = 0; i < k; i++) rank += zrow[i] == v ? 1 : 0;
+			rank = min(rank, S - 1);
+		}
+		const int pos = rank + lower_bound(zs, N, v);
+		out[pos] = v;
+		if (po) po[N + k] = static_cast<int16_t>(pos);
+		if (rows_merged) rows_merged[ray * (S + N) + pos] = __ldg(rows_coarse + ray * S + k);
+	}
+	for (int j = tid; j < N; j += kSamplerBlock) {
+		const int pos = j + upper_bound(zc, S, zs[j]);
+		out[pos] = zs[j];
+		if (po) po[j] = static_cast<int16_t>(pos);
+	}
+}
+
 __global__ void __launch_bounds__(kSamplerWarps * 32) sample_pdf_kernel(const float* __restrict__ bins_g,
 	const float* __restrict__ weights, int B, const float* __restrict__ u, int u_per_ray, int64_t R, int N,
 	float* __restrict__ out)
@@ -280,8 +359,19 @@ int nrf_sample_pdf_merge_rows(const float* z_coarse, const float* weights, const
 	const int per_warp = 2 * (n_samples - 1) + n_importance + n_samples + (u_per_ray ? pow2 : 0);
 	const size_t smem = static_cast<size_t>(kSamplerWarps) * per_warp * sizeof(float);
 	NRF_REQUIRE(smem <= 48 * 1024, "shared memory budget exceeded");
+	// few rays (a training batch): one CTA per ray, latency of 3 searches instead of 14; many rays (a render chunk): one warp per ray, fewer
+	// instructions per ray.  NRF_SAMPLER_BLOCK=0 / 1 forces the warp / CTA kernel (tests, A/B).
+	static const int force = [] { const char* e = getenv("NRF_SAMPLER_BLOCK"); return e ? atoi(e) : -1; }();
+	const bool per_block = !u_per_ray && (force == 1 || (force != 0 && n_rays <= kBlockPerRayMaxRays));
+	if (per_block) {
+		const size_t smem_b = static_cast<size_t>(2 * (n_samples - 1) + n_importance + n_samples) * sizeof(float);
+		launch_kernel(sample_pdf_merge_block_kernel, static_cast<unsigned>(n_rays), kSamplerBlock, smem_b, as_stream(stream), z_coarse, weights, u, n_rays,
+			n_samples, n_importance, z_samples, z_merged, perm_out, reinterpret_cast<const float4*>(rows_coarse), reinterpret_cast<float4*>(rows_merged));
+		NRF_CHECK_LAUNCH("sample_pdf_merge_block_kernel");
+		return NRF_OK;
+	}
 	const unsigned blocks = static_cast<unsigned>((n_rays + kSamplerWarps - 1) / kSamplerWarps);
-	sample_pdf_merge_kernel<<<blocks, kSamplerWarps * 32, smem, as_stream(stream)>>>(z_coarse, weights, u, u_per_ray, n_rays,
+	launch_kernel(sample_pdf_merge_kernel, blocks, kSamplerWarps * 32, smem, as_stream(stream), z_coarse, weights, u, u_per_ray, n_rays,
 		n_samples, n_importance, z_samples, z_merged, perm_out, reinterpret_cast<const float4*>(rows_coarse), reinterpret_cast<float4*>(rows_merged),
 		per_warp, pow2);
 	NRF_CHECK_LAUNCH("sample_pdf_merge_kernel");

@@ -72,6 +72,39 @@ def test_composite_noise_and_stride():
 
 
 # ------------------------------------------------------------------------------------------------ sampler
+@pytest.mark.parametrize("S,N", [(64, 128), (64, 192), (33, 50)])
+def test_sampler_block_kernel_equals_warp_kernel(S, N):
+    """nrf_sample_pdf_merge_rows picks a CTA-per-ray kernel for small batches (<= 16384 rays: a training step) and a warp-per-ray kernel for
+    large ones (a render chunk).  Same arithmetic per element: every output must agree bit for bit — depths, samples, positions and the
+    travelling raw rows — including zero-weight rays and rays whose fp32 coarse depths are not monotone (they miss the box)."""
+    from nerfpp_b200 import ops
+    g = torch.Generator().manual_seed(S * 1000 + N)
+    R = 20000                                                                 # one call: warp kernel; two halves: CTA kernel
+    near = 2 + torch.rand(R, 1, generator=g)
+    far = near + 3 * torch.rand(R, 1, generator=g)
+    far[::97] = near[::97] + 1e-6                                             # IntersectWithAABB's far for a ray that misses the box
+    t = torch.linspace(0, 1, S)
+    z = (near * (1 - t) + far * t).cuda()
+    w = torch.rand(R, S, generator=g) ** 4
+    w[::53] = 0.0
+    w[1::211, 5:] = 0.0                                                       # all the mass in a few bins: long runs of equal samples
+    w = w.cuda()
+    u = torch.linspace(0, 1, N).cuda()
+    rows = torch.randn(R * S, 4, generator=g).cuda()
+    whole = ops.sample_pdf_merge(z, w, u, want_samples=True, want_perm=True, raw_coarse=rows)
+    h = R // 2
+    parts = [ops.sample_pdf_merge(z[a:b].contiguous(), w[a:b].contiguous(), u, want_samples=True, want_perm=True, raw_coarse=rows[a * S:b * S].contiguous())
+             for a, b in ((0, h), (h, R))]
+    pos = whole[2].long()[:, N:]                                              # merged positions of the coarse samples: the only rows written
+    for i, name in enumerate(("z_merged", "z_samples", "perm")):
+        assert torch.equal(whole[i], torch.cat([p[i] for p in parts], 0)), name
+    got = torch.cat([p[3].view(-1, S + N, 4) for p in parts], 0)
+    idx = pos[:, :, None].expand(-1, -1, 4)
+    assert torch.equal(torch.gather(whole[3].view(R, S + N, 4), 1, idx), torch.gather(got, 1, idx))
+    assert torch.equal(torch.gather(got, 1, idx), rows.view(R, S, 4))
+    assert torch.equal(torch.sort(whole[0], -1).values, whole[0])
+
+
 def assert_samples_match(got, bins, w, n, ref=None):
     """got == the restatement with correctly rounded sums (tight), and that restatement == the torch-summed reference
     except at ulp ties between u and a cdf knot (count reported and bounded; see oracle/restate.py sample_pdf)."""
