@@ -7,7 +7,9 @@ process through the parity tests of the default path.
   NRF_ADAM_L2HINT=0     Adam without the L2 eviction-priority hints (csrc/optim.cu)
   NRF_RENDER_REUSE=0    nrf_render_rays_fwd evaluating every merged row of the fine pass instead of the importance samples only (csrc/render.cu):
                         the test compares it with the composed path, which reuses — bit for bit
-  NRF_HASH_SPLIT=0      hash forward with one thread per point instead of four lanes per point (csrc/hash_encode.cu)"""
+  NRF_HASH_SPLIT=0      hash forward with one thread per point instead of four lanes per point (csrc/hash_encode.cu)
+  NRF_PDL=1             programmatic dependent launch along the step's kernel chain (csrc/common.cuh launch_kernel / pdl_prologue)
+  NRF_SAMPLER_BLOCK=0   warp-per-ray sampler also for training-sized batches (csrc/sampler.cu)"""
 import os
 import subprocess
 import sys
@@ -26,6 +28,8 @@ VARIANTS = [
     ({"NRF_RENDER_REUSE": "0"}, ["test_gpu_pipeline.py"], "fused_render_entry"),
     ({"NRF_MLP_FWD": "mma"}, ["test_gpu_pipeline.py"], "fused_render_entry or coarse_reuse"),
     ({"NRF_HASH_SPLIT": "0"}, ["test_gpu_hash.py"], "fixture or reuse or rays"),
+    ({"NRF_PDL": "1"}, ["test_gpu_pipeline.py"], "graph or gradients or trains or reuse or render"),
+    ({"NRF_SAMPLER_BLOCK": "0"}, ["test_gpu_render.py"], "sample_pdf or merge or sampler"),
 ]
 
 
