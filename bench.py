@@ -605,62 +605,58 @@ def main() -> None:
             model.optimizer_step(grad_scale=scale)
 
     def train_leg(rays_per_gpu: int, steps: int, n_warm: int, seed0: int, with_e2e: bool):
-        """Timed regions of one configuration: `steps` replays of the captured step with resident inputs (value), then the same
-        through the public call with pinned HOST buffers and a loss read per step (e2e).  CUDA events, max over ranks."""
+        """Timed regions of one configuration.  What a step consumes is the list of pixels sampled for it (NeRFDataset::get_batch draws them,
+        src/NeRFDataset.cpp:154-155): rays (GetRayBatch, :109-144) and targets (the image gather, :156) are formed on the device inside the step's
+        first kernel from the resident training view (HashNeRF.set_camera).  value: `steps` replays of the captured step with the pixel lists
+        resident in HBM; e2e: the same call with pinned HOST int32 [R,2] lists (H2D inside the timed region) and a D2H read of the loss every
+        step.  CUDA events, max over ranks."""
+        from nerfpp_b200.pipeline import synthetic_pixels, synthetic_view
         dev_batches = [synthetic_rays(rays_per_gpu, device=dev, seed=seed0 + 1000 * rank + i) for i in range(pool)]
         for i in range(n_warm):
             eager_step(dev_batches[i % pool])
+        K_view, c2w_view = synthetic_view(800, 800)
+        image = torch.rand(800, 800, 3, generator=torch.Generator().manual_seed(77)).to(dev)
+        model.set_camera(image, K_view, c2w_view)
+        host_pix = [synthetic_pixels(rays_per_gpu, 800, 800, seed=seed0 + 3000 + 1000 * rank + i).pin_memory() for i in range(pool)]
+        dev_pix = [p.to(dev) for p in host_pix]
         use_graph = not args.no_graph
         if use_graph:
-            model.capture_train_step(rays_per_gpu, world, lambda g: parallel.allreduce_gradients(g, world))
-            step = lambda batch: model.train_step_graph(*batch)   # noqa: E731
-            for i in range(3):
-                step(dev_batches[i % pool])
+            model.capture_train_step(rays_per_gpu, world, lambda g: parallel.allreduce_gradients(g, world), pixels=True)
+            step = lambda pix: model.train_step_graph(pix)   # noqa: E731 - copies the pixel list (device or pinned host) into its static input
             launches_per_step = model.graph_kernels_per_step
         else:
-            step = eager_step
+            stage_pix = torch.empty((rays_per_gpu, 2), dtype=torch.int32, device=dev)
+
+            def step(pix):
+                stage_pix.copy_(pix, non_blocking=True)
+                model.forward_backward(stage_pix)
+                if model.peer is not None:
+                    model.optimizer_step_sharded()
+                else:
+                    model.optimizer_step(grad_scale=parallel.allreduce_gradients(model.grads, world))
             l0 = cabi.launch_count()
-            step(dev_batches[0])
+            step(dev_pix[0])
             launches_per_step = cabi.launch_count() - l0 + 1
+        for i in range(3):
+            step(dev_pix[i % pool])
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
-            step(dev_batches[i % pool])
+            step(dev_pix[i % pool])
         e1.record()
         sync_all()
         out = {"ms_total": parallel.max_over_ranks(e0.elapsed_time(e1), world, dev), "loss": float(model.loss), "launches_per_step": launches_per_step,
                "dev_batches": dev_batches, "use_graph": use_graph}
         if with_e2e:
-            # the public call with HOST inputs: what the host owns per step is the list of sampled pixels (NeRFDataset::get_batch draws them,
-            # src/NeRFDataset.cpp:154-155); rays (GetRayBatch, :109-144) and targets (the image gather, :156) are formed on the device inside the
-            # step's first kernel from the resident training view (HashNeRF.set_camera).  Pinned int32 [R,2] H2D + a D2H read of the loss, every step.
-            from nerfpp_b200.pipeline import synthetic_pixels, synthetic_view
-            K_view, c2w_view = synthetic_view(800, 800)
-            image = torch.rand(800, 800, 3, generator=torch.Generator().manual_seed(77)).to(dev)
-            model.set_camera(image, K_view, c2w_view)
-            host_pix = [synthetic_pixels(rays_per_gpu, 800, 800, seed=seed0 + 3000 + 1000 * rank + i).pin_memory() for i in range(pool)]
-            if use_graph:
-                model.capture_train_step(rays_per_gpu, world, lambda g: parallel.allreduce_gradients(g, world), pixels=True)
-                pstep = lambda hb: model.train_step_graph(hb)   # noqa: E731 - copies the pinned pixel list into its static input
-            else:
-                stage_pix = torch.empty((rays_per_gpu, 2), dtype=torch.int32, device=dev)
-
-                def pstep(hb):
-                    stage_pix.copy_(hb, non_blocking=True)
-                    model.forward_backward(stage_pix)
-                    if model.peer is not None:
-                        model.optimizer_step_sharded()
-                    else:
-                        model.optimizer_step(grad_scale=parallel.allreduce_gradients(model.grads, world))
             for i in range(3):
-                pstep(host_pix[i % pool])
+                step(host_pix[i % pool])
             sync_all()
             e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e2.record()
             loss_host = 0.0
             for i in range(steps):
-                pstep(host_pix[i % pool])
+                step(host_pix[i % pool])
                 loss_host = float(model.loss)   # device -> host read of the step's result
             e3.record()
             sync_all()
@@ -906,6 +902,9 @@ def main() -> None:
                    "rays_per_gpu": R, "global_rays": R * world, "parallelism": f"ray-sharded dp{world}: {dp_mode}",
                    "l2": "not flushed explicitly: each step streams ~300 MB (Adam pass over 8.9M params + moments + gradient) through the 126 MB L2",
                    "precision": "fp16 hash table reads / encodings, bf16 tensor-core MLP with fp32 accumulate, fp32 everything else",
+                   "feed": "a step consumes the int32 [R,2] pixel list sampled for it (src/NeRFDataset.cpp:154-155); rays (GetRayBatch) and targets (the image "
+                           "gather) are formed by the step's first kernel from the resident 800x800 view.  value: lists resident in HBM (one 32 KB D2D copy "
+                           "into the graph's static input per step); e2e: the same lists in pinned host memory + a loss read per step",
                    "reuse_coarse_rows": bool(model.reuse_coarse_rows),
                    "reuse_coarse_raw": bool(getattr(model, "reuse_coarse_raw", False)),
                    "reuse_note": "the merged fine pass holds the 64 coarse samples bit for bit and the reference uses ONE network for both passes "
@@ -915,7 +914,10 @@ def main() -> None:
         "e2e": {"value": rays_total / (ms_e2e / 1e3), "unit": "rays/s", "h2d_bytes_per_step": head["h2d"], "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps,
                 "input": "pinned-host int32 [R,2] pixel coordinates of the step's batch; rays (GetRayBatch) and targets (image gather) are formed on the "
-                         "device by the step's first kernel from the resident 800x800 training view"},
+                         "device by the step's first kernel from the resident 800x800 training view",
+                "note": "same captured step as `value`, run right after it on the same model (K more optimisation steps): the hash gathers / scatter are "
+                        "data dependent — as the density concentrates, importance samples cluster and share cells (kernels_ms_per_step is taken after "
+                        "both regions) — so e2e can come out faster than value although it adds the H2D copy and the loss read"},
         "gpu_launches": launches * world, "graph_replay": use_graph, "kernels_per_step": launches_per_step, "roofline": roofline,
         "roofline_tensor": roofline_tensor, "roofline_render_ops": roofline_render_ops, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "kernels_ms_per_step": {k: [round(t, 4) for t in v] for k, v in sorted(per_launch.items(), key=lambda kv: -sum(kv[1]))},
