@@ -14,7 +14,6 @@
 namespace nrf {
 
 constexpr int kRaysPerCta = 8;       // warps
-constexpr int kMaxBlocks = 8;        // S <= 256
 
 struct SampleEval {
 	float r, g, b;     // sigmoid(rgb logits)

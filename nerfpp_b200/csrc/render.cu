@@ -91,7 +91,11 @@ static int render_impl(const nrf_render_config* cfg, const nrf_hash_grid* grid, 
 	// One network for both passes (src/NeRFRenderer.h:422,447): the merged fine pass re-uses the coarse pass's raw rows for the coarse
 	// samples and gathers / evaluates the importance samples only — the same bits as evaluating all S + N rows (tests/test_gpu_render.py).
 	// NRF_RENDER_REUSE=0 evaluates every merged row (the A/B baseline).
-	static const bool reuse = [] { const char* e = getenv("NRF_RENDER_REUSE"); return !(e && e[0] == '0'); }();
+	static const bool reuse = [] {
+		const char* e = getenv("NRF_RENDER_REUSE");
+		const char* f = getenv("NRF_MLP_FWD");             // the importance-only forward exists on the tcgen05 kernel only
+		return !(e && e[0] == '0') && !(f && f[0] == 'm');
+	}();
 	// The rays of a chunk are adjacent pixels of a frame (GetRays order): the encode kernel walks the same sample of kRayGroup neighbouring rays
 	// together (nrf_hash_encode_rays_fwd_grouped).  NRF_RENDER_RAY_GROUP=1 restores the per-ray order (the A/B baseline).
 	static const int group = [] { const char* e = getenv("NRF_RENDER_RAY_GROUP"); const int g = e ? atoi(e) : 32; return g >= 1 && g <= 1024 ? g : 32; }();
@@ -122,18 +126,13 @@ static int render_impl(const nrf_render_config* cfg, const nrf_hash_grid* grid, 
 	if ((rc = nrf_composite_fwd(reuse ? raw_coarse : raw, 4, z, rays_d, nullptr, 0.f, cfg->white_bkgr, n_rays, S, nullptr, nullptr, nullptr, nullptr, w_coarse,
 	                            stream))) return rc;
 	// importance sampling + merge, fine pass
-	bool fine_done = false;
 	if (reuse) {
 		if ((rc = nrf_sample_pdf_merge_rows(z, w_coarse, u, 0, n_rays, S, N, nullptr, z_fine, perm, raw_coarse, raw, stream))) return rc;
 		if ((rc = nrf_hash_encode_rays_fwd_grouped(grid, table_f16, ray_batch, 11, z_fine, n_rays, T, 1, keep, enc, NRF_ENC_F16, perm, nullptr, nullptr, S, group,
 		                                           stream))) return rc;
-		rc = nrf_mlp_small_fwd_importance(shape, packed, kind, enc, views, keep, perm, n_rays, N, T, raw, stream);
-		if (rc != NRF_OK && rc != NRF_ERR_UNSUPPORTED) return rc;
-		fine_done = rc == NRF_OK;
+		if ((rc = nrf_mlp_small_fwd_importance(shape, packed, kind, enc, views, keep, perm, n_rays, N, T, raw, stream))) return rc;
 	} else {
 		if ((rc = nrf_sample_pdf_merge(z, w_coarse, u, 0, n_rays, S, N, nullptr, z_fine, stream))) return rc;
-	}
-	if (!fine_done) {
 		if ((rc = nrf_hash_encode_rays_fwd_grouped(grid, table_f16, ray_batch, 11, z_fine, n_rays, T, 1, keep, enc, NRF_ENC_F16, nullptr, nullptr, nullptr, 0, group,
 		                                           stream))) return rc;
 		if ((rc = nrf_mlp_small_fwd(shape, packed, kind, enc, views, T, keep, n_rays * T, raw, stream))) return rc;

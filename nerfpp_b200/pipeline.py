@@ -24,10 +24,6 @@ import torch
 from . import ops
 from .ops import HashGridSpec, f16, f32, i32
 
-MLP_PARAMS = 9344  # 64*32 + 16*64 + 64*31 + 64*64 + 3*64  (src/NeRF.cpp:338-342 at the BASELINE shape)
-MLP_LAYERS = [(64, 32), (16, 64), (64, 31), (64, 64), (3, 64)]
-
-
 def mlp_layers(n_views: int = 16):
     """[out, in] of sigma_net_0, sigma_net_1, color_net_0 (in = views + geo 15), color_net_1, color_net_2 (src/NeRF.cpp:338-342)."""
     return [(64, 32), (16, 64), (64, n_views + 15), (64, 64), (3, 64)]
