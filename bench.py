@@ -373,6 +373,51 @@ def gpu_loop_leg(which: str, rays: int, steps: int) -> dict:
                      "nerfpp_b200 C++ drop-in classes (torch::Tensor boundary, FusedAdam" + (", captured train graph)" if fast else ")"))}
 
 
+def cpp_render_leg(which: str) -> dict:
+    """BASELINE C4 through the C++ surface: NeRFRenderer::Render(h, w, K, params, c2w) (src/NeRFRenderer.h:530-604) of one 1920x1080 frame, 64 + 64
+    samples, 131072-ray chunks, NoGradGuard — `dropin_cpp`: this repo's drop-in classes (RenderRays = one C-ABI call per chunk), `dropin_cpp_staged`:
+    the same classes with the one-call path switched off (stage by stage, the path training takes), `reference_cuda`: the reference's own classes
+    and CUDA kernels on this B200.  Random-init weights with O(1) table values.  Two frames after one warm-up frame, CUDA events."""
+    import math
+    import torch
+    if which == "reference_cuda":
+        import nerfpp_ref_cuda as R
+    else:
+        from nerfpp_b200 import build
+        sys.path.insert(0, str(build.build_host().parent))
+        import nerfpp_b200_torch as R
+    R.manual_seed(42)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)
+    try:
+        pipe = R.make_cuhash(torch.tensor(BBOX).cuda(), 16, 2, 19, 16, 512, 4, 2, 64, 15, 3, 64)
+        pipe.init_model()
+    finally:
+        os.dup2(saved, 1)
+        os.close(devnull)
+    if which != "reference_cuda":
+        pipe.use_fused_inference(which == "dropin_cpp")
+    H, W = 1080, 1920
+    focal = 0.5 * W / math.tan(0.5 * 0.6911)
+    K = torch.tensor([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]]).cuda()
+    c2w = torch.eye(4)
+    c2w[2, 3] = 4.0
+    c2w = c2w.cuda()
+    frames = 2 if which != "reference_cuda" else 1
+    pipe.render_image(H, W, K, c2w, N_SAMPLES, 64, 131072, False, True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(frames):
+        out = pipe.render_image(H, W, K, c2w, N_SAMPLES, 64, 131072, False, True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / frames
+    assert tuple(out["rgb"].shape[:2]) == (H, W)
+    return {"ms_per_frame": ms, "msamples_per_s": H * W * (N_SAMPLES + N_SAMPLES + 64) / (ms * 1e3), "frames": frames, "impl": which}
+
+
 def shipped_shape_leg(dev, rays: int, steps: int = 50) -> dict:
     """The network shape src/main.cpp:176-191 ships: SH degree 8 (64 view channels into NeRFSmall), finest resolution 1024, 64 + 192 samples —
     parity configuration (thin rays, no noise), one CUDA graph.  The 64 view channels enter the fused kernels as a per-ray bias of the colour
@@ -888,6 +933,17 @@ def main() -> None:
             dropin_cpp["vs_reference_cuda"] = dropin_cpp["value"] / reference_cuda["value"]
             reference_cuda["ours_vs_reference_cuda"] = (R * args.steps / (ms_total / 1e3)) / reference_cuda["value"]
 
+    # ---- BASELINE C4 through the same C++ surfaces (N = 1 only)
+    render_cpp = None
+    if world == 1 and not quick:
+        render_cpp = {}
+        for which in ("dropin_cpp", "dropin_cpp_staged", "reference_cuda"):
+            try:
+                render_cpp[which] = cpp_render_leg(which)
+            except Exception as e:  # noqa: BLE001
+                render_cpp[which] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -928,7 +984,7 @@ def main() -> None:
         "kernels_ms_per_step": {k: [round(t, 4) for t in v] for k, v in sorted(per_launch.items(), key=lambda kv: -sum(kv[1]))},
         "kernels_ms_per_step_sum": round(sum(sum(v) for v in per_launch.values()), 4),
         "dp_check": dp_check, "flags_timeout_after_timed_regions": timeout_after, "strong": strong,
-        "reference_cuda": reference_cuda, "dropin_cpp": dropin_cpp, "train_as_shipped": as_shipped, "train_shipped_shape": shipped_shape,
+        "reference_cuda": reference_cuda, "dropin_cpp": dropin_cpp, "train_as_shipped": as_shipped, "train_shipped_shape": shipped_shape, "render_cpp": render_cpp,
         "final_loss": {"resident": head["loss"], "e2e": head["loss_e2e"]}, "render": render, "render_lerf": render_lerf, "train_lerf": train_lerf,
     }))
 

@@ -374,6 +374,11 @@ int nrf_ray_setup_tile(const float* K_host, const float* c2w_host, int32_t img_w
                        const float* bbox_host, float near_plane, const float* t_vals, int32_t n_samples, int32_t lin_disp,
                        int32_t sh_degree, float* rays_o, float* rays_d, float* ray_batch, float* z, float* ray_sh, nrf_stream stream);
 
+/* The same prologue for an already prepared ray batch (rows [o d near far viewdirs], ray_stride >= 11): z from its near / far, the SH table
+ * from its viewdirs; rays_d [R,3] and the packed [R,11] ray_batch are outputs. */
+int nrf_ray_setup_prepared(const float* ray_batch_in, int32_t ray_stride, int64_t n_rays, const float* t_vals, int32_t n_samples,
+                           int32_t lin_disp, int32_t sh_degree, float* rays_d, float* ray_batch, float* z, float* ray_sh, nrf_stream stream);
+
 /* z = near*(1-t)+far*t (or the lin_disp variant), src/NeRFRenderer.h:393-402.  t_vals [S] device. */
 int nrf_z_sample(const float* ray_batch, int32_t ray_stride, const float* t_vals, int64_t n_rays, int32_t n_samples,
                  int32_t lin_disp, float* z, nrf_stream stream);
@@ -427,6 +432,14 @@ int nrf_render_tile_fwd(const nrf_render_config* cfg, const nrf_hash_grid* grid,
                         int32_t img_w, int64_t first_pixel, int64_t n_rays, const float* t_vals, const float* u, void* workspace,
                         int64_t workspace_bytes, float* rgb, float* depth, float* disp, float* acc, float* weights, float* z_out,
                         nrf_stream stream);
+
+/* The same for a prepared ray batch — rows [o(3) d(3) near far viewdirs(3) ...] of ray_stride >= 11 floats, what BatchifyRays hands to RenderRays
+ * (src/NeRFRenderer.h:483, built by Render :549-583): near / far / viewdirs are taken from the batch, cfg->bbox / near_plane are not used.
+ * This is the call the drop-in NeRFRenderer::RenderRays makes when no autograd graph is recorded (host/renderer.h). */
+int nrf_render_raybatch_fwd(const nrf_render_config* cfg, const nrf_hash_grid* grid, const void* table_f16,
+                            const nrf_mlp_small_shape* shape, const void* packed, const float* ray_batch, int32_t ray_stride,
+                            int64_t n_rays, const float* t_vals, const float* u, void* workspace, int64_t workspace_bytes,
+                            float* rgb, float* depth, float* disp, float* acc, float* weights, float* z_out, nrf_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Training glue restated from NeRFExecutor::Train (src/NeRFExecutor.h:883-890, 539, 986)

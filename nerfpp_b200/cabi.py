@@ -141,6 +141,9 @@ SIGNATURES = {
                                       _P, _P, _P, _P, _P, _P, _P]),
     "nrf_render_tile_fwd": (c_int32, [POINTER(RenderConfig), POINTER(HashGrid), _P, POINTER(MlpSmallShape), _P, POINTER(c_float), POINTER(c_float), c_int32,
                                       c_int64, c_int64, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    "nrf_render_raybatch_fwd": (c_int32, [POINTER(RenderConfig), POINTER(HashGrid), _P, POINTER(MlpSmallShape), _P, _P, c_int32, c_int64, _P, _P, _P, c_int64,
+                                          _P, _P, _P, _P, _P, _P, _P]),
+    "nrf_ray_setup_prepared": (c_int32, [_P, c_int32, c_int64, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P]),
     "nrf_ray_setup_tile": (c_int32, [POINTER(c_float), POINTER(c_float), c_int32, c_int64, c_int64, POINTER(c_float), c_float, _P, c_int32, c_int32, c_int32,
                                      _P, _P, _P, _P, _P, _P]),
     "nrf_lerf_packed_bytes": (c_int64, [POINTER(LerfShape)]),

@@ -138,6 +138,10 @@ struct PixelSrc {
 	float* rays_o_out;
 	float* rays_d_out;
 	float* target_out;
+	// or: the rays arrive as rows [o(3) d(3) near far viewdirs(3)] of an already prepared batch (what BatchifyRays hands to RenderRays,
+	// src/NeRFRenderer.h:483): near / far / viewdirs are TAKEN from it, not recomputed
+	const float* prepared;
+	int prepared_stride;
 };
 
 template <int DEG, bool PIXELS>
@@ -152,33 +156,43 @@ __global__ void __launch_bounds__(256) ray_setup_kernel(const float* __restrict_
 	const int64_t ray = e / S;
 	const int s = static_cast<int>(e % S);
 	float o[3], d[3], vd[3], tnear, tfar;
+	bool prepared = false;
 	if (PIXELS) {
-		int py, px;
-		if (ps.pix_hw) {
-			py = ps.pix_hw[2 * ray];
-			px = ps.pix_hw[2 * ray + 1];
+		if (ps.prepared) {
+			const float* rb = ps.prepared + ray * ps.prepared_stride;
+#pragma unroll
+			for (int k = 0; k < 3; k++) { o[k] = rb[k]; d[k] = rb[3 + k]; vd[k] = rb[8 + k]; }
+			tnear = rb[6];
+			tfar = rb[7];
+			prepared = true;
 		} else {
-			const int64_t lin = ps.first_pixel + ray;
-			py = static_cast<int>(lin / ps.img_w);
-			px = static_cast<int>(lin - static_cast<int64_t>(py) * ps.img_w);
+			int py, px;
+			if (ps.pix_hw) {
+				py = ps.pix_hw[2 * ray];
+				px = ps.pix_hw[2 * ray + 1];
+			} else {
+				const int64_t lin = ps.first_pixel + ray;
+				py = static_cast<int>(lin / ps.img_w);
+				px = static_cast<int>(lin - static_cast<int64_t>(py) * ps.img_w);
+			}
+			pixel_ray(ps.cam, py, px, o, d);
+			if (s == 0 && ps.image && ps.target_out) {
+				const float* src = ps.image + (static_cast<int64_t>(py) * ps.img_w + px) * ps.img_c;
+				for (int k = 0; k < ps.img_c; k++) ps.target_out[ray * ps.img_c + k] = __ldg(src + k);
+			}
 		}
-		pixel_ray(ps.cam, py, px, o, d);
 		if (s == 0) {
 #pragma unroll
 			for (int k = 0; k < 3; k++) {
 				if (ps.rays_o_out) ps.rays_o_out[ray * 3 + k] = o[k];
 				ps.rays_d_out[ray * 3 + k] = d[k];
 			}
-			if (ps.image && ps.target_out) {
-				const float* src = ps.image + (static_cast<int64_t>(py) * ps.img_w + px) * ps.img_c;
-				for (int k = 0; k < ps.img_c; k++) ps.target_out[ray * ps.img_c + k] = __ldg(src + k);
-			}
 		}
 	} else {
 #pragma unroll
 		for (int k = 0; k < 3; k++) { o[k] = rays_o[ray * 3 + k]; d[k] = rays_d[ray * 3 + k]; }
 	}
-	prepare_ray(o, d, box, near_plane, tnear, tfar, vd);
+	if (!prepared) prepare_ray(o, d, box, near_plane, tnear, tfar, vd);
 	z[e] = z_value(tnear, tfar, t_vals[s], lin_disp);
 	if (s == 0) {
 		float* out = ray_batch + ray * 11;
@@ -387,6 +401,17 @@ int nrf_ray_setup_tile(const float* K_host, const float* c2w_host, int32_t img_w
 	fill_cam(ps.cam, K_host, c2w_host);
 	ps.first_pixel = first_pixel; ps.img_w = img_w; ps.rays_o_out = rays_o; ps.rays_d_out = rays_d;
 	return launch_ray_setup(true, nullptr, nullptr, ps, n_rays, bbox_host, near_plane, t_vals, n_samples, lin_disp, sh_degree, ray_batch, z, ray_sh, nullptr, stream);
+}
+
+int nrf_ray_setup_prepared(const float* ray_batch_in, int32_t ray_stride, int64_t n_rays, const float* t_vals, int32_t n_samples, int32_t lin_disp,
+	int32_t sh_degree, float* rays_d, float* ray_batch, float* z, float* ray_sh, nrf_stream stream)
+{
+	NRF_REQUIRE(ray_stride >= 11, "a prepared ray batch has rows [o d near far viewdirs]: ray_stride >= 11");
+	NRF_REQUIRE(n_rays <= 0 || (ray_batch_in && rays_d), "null pointer");
+	PixelSrc ps{};
+	ps.prepared = ray_batch_in; ps.prepared_stride = ray_stride; ps.rays_d_out = rays_d;
+	const float no_box[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // never read: near / far come with the batch
+	return launch_ray_setup(true, nullptr, nullptr, ps, n_rays, no_box, 0.f, t_vals, n_samples, lin_disp, sh_degree, ray_batch, z, ray_sh, nullptr, stream);
 }
 
 int nrf_z_sample(const float* ray_batch, int32_t ray_stride, const float* t_vals, int64_t n_rays, int32_t n_samples,

@@ -60,19 +60,28 @@ int64_t nrf_render_rays_workspace_bytes(const nrf_render_config* cfg, const nrf_
 
 }
 
-// rays_o / rays_d given: RenderRays on a ray list.  Else (tile): ray r is pixel first_pixel + r of an img_w wide image seen through (K, c2w) —
-// GetRays (src/RayUtils.h:23-46) happens inside the prologue kernel and rays_d lands in the workspace for the compositing kernels.
+// Where the rays come from: rays_o / rays_d arrays (RenderRays on a ray list); a prepared batch [o d near far viewdirs] (what BatchifyRays hands
+// to RenderRays, src/NeRFRenderer.h:483: its near / far / viewdirs are taken as given); or the camera alone (tile: ray r is pixel first_pixel + r
+// of an img_w wide image seen through (K, c2w), GetRays, src/RayUtils.h:23-46, inside the prologue kernel).  In the last two cases rays_d lands
+// in the workspace for the compositing kernels.
+struct RaySrc {
+	const float* rays_o; const float* rays_d;                  // arrays
+	const float* prepared; int32_t prepared_stride;            // prepared batch
+	const float* K_host; const float* c2w_host; int32_t img_w; int64_t first_pixel;   // tile
+};
+
 static int render_impl(const nrf_render_config* cfg, const nrf_hash_grid* grid, const void* table_f16, const nrf_mlp_small_shape* shape,
-	const void* packed, const float* rays_o, const float* rays_d, const float* K_host, const float* c2w_host, int32_t img_w, int64_t first_pixel,
-	int64_t n_rays, const float* t_vals, const float* u, void* workspace, int64_t workspace_bytes, float* rgb, float* depth, float* disp, float* acc,
-	float* weights, float* z_out, nrf_stream stream)
+	const void* packed, const RaySrc& src, int64_t n_rays, const float* t_vals, const float* u, void* workspace, int64_t workspace_bytes, float* rgb,
+	float* depth, float* disp, float* acc, float* weights, float* z_out, nrf_stream stream)
 {
 	if (int rc = check_render_args(cfg, grid)) return rc;
 	NRF_REQUIRE(n_rays >= 0, "negative n_rays");
 	if (n_rays == 0) return NRF_OK;
-	const bool tile = rays_d == nullptr;
+	const bool tile = src.K_host != nullptr, prepared = src.prepared != nullptr;
+	const float* rays_d = src.rays_d;
 	NRF_REQUIRE(table_f16 && shape && packed && t_vals && u && workspace, "null pointer");
-	NRF_REQUIRE(tile ? (K_host && c2w_host && img_w > 0 && first_pixel >= 0) : (rays_o != nullptr), "rays or camera missing");
+	NRF_REQUIRE(prepared ? src.prepared_stride >= 11 : (tile ? (src.c2w_host && src.img_w > 0 && src.first_pixel >= 0) : (src.rays_o && src.rays_d)),
+		"rays, prepared batch or camera missing");
 	NRF_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
 	const RenderWs w = render_layout(cfg, grid, n_rays);
 	NRF_REQUIRE(workspace_bytes >= w.total, "workspace too small (nrf_render_rays_workspace_bytes)");
@@ -102,12 +111,17 @@ static int render_impl(const nrf_render_config* cfg, const nrf_hash_grid* grid, 
 
 	int rc;
 	// Render prologue + coarse depths + per-ray SH table: one launch (bit-identical to nrf_rays_prepare + nrf_sh_encode_fwd + nrf_z_sample)
-	if (tile) {
+	if (prepared) {
 		float* rd = reinterpret_cast<float*>(base + w.rays_d);
-		if ((rc = nrf_ray_setup_tile(K_host, c2w_host, img_w, first_pixel, n_rays, cfg->bbox, cfg->near_plane, t_vals, S, cfg->lin_disp, cfg->sh_degree, nullptr,
-		                             rd, ray_batch, z, ray_sh, stream))) return rc;
+		if ((rc = nrf_ray_setup_prepared(src.prepared, src.prepared_stride, n_rays, t_vals, S, cfg->lin_disp, cfg->sh_degree, rd, ray_batch, z, ray_sh, stream)))
+			return rc;
 		rays_d = rd;
-	} else if ((rc = nrf_ray_setup(rays_o, rays_d, n_rays, cfg->bbox, cfg->near_plane, t_vals, S, cfg->lin_disp, cfg->sh_degree, ray_batch, z, ray_sh,
+	} else if (tile) {
+		float* rd = reinterpret_cast<float*>(base + w.rays_d);
+		if ((rc = nrf_ray_setup_tile(src.K_host, src.c2w_host, src.img_w, src.first_pixel, n_rays, cfg->bbox, cfg->near_plane, t_vals, S, cfg->lin_disp,
+		                             cfg->sh_degree, nullptr, rd, ray_batch, z, ray_sh, stream))) return rc;
+		rays_d = rd;
+	} else if ((rc = nrf_ray_setup(src.rays_o, src.rays_d, n_rays, cfg->bbox, cfg->near_plane, t_vals, S, cfg->lin_disp, cfg->sh_degree, ray_batch, z, ray_sh,
 	                               nullptr, stream))) return rc;
 	// SH degree != 4 (shape->input_ch_views != 16): the view channels enter the network as a per-ray bias, computed once for both passes
 	NRF_REQUIRE(shape->input_ch_views == cfg->sh_degree * cfg->sh_degree, "shape->input_ch_views must be sh_degree^2");
@@ -148,8 +162,17 @@ int nrf_render_rays_fwd(const nrf_render_config* cfg, const nrf_hash_grid* grid,
 	int64_t workspace_bytes, float* rgb, float* depth, float* disp, float* acc, float* weights, float* z_out, nrf_stream stream)
 {
 	NRF_REQUIRE(n_rays <= 0 || (rays_o && rays_d), "null rays");
-	return render_impl(cfg, grid, table_f16, shape, packed, rays_o, rays_d, nullptr, nullptr, 0, 0, n_rays, t_vals, u, workspace, workspace_bytes, rgb, depth,
-		disp, acc, weights, z_out, stream);
+	const RaySrc src{rays_o, rays_d, nullptr, 0, nullptr, nullptr, 0, 0};
+	return render_impl(cfg, grid, table_f16, shape, packed, src, n_rays, t_vals, u, workspace, workspace_bytes, rgb, depth, disp, acc, weights, z_out, stream);
+}
+
+int nrf_render_raybatch_fwd(const nrf_render_config* cfg, const nrf_hash_grid* grid, const void* table_f16, const nrf_mlp_small_shape* shape,
+	const void* packed, const float* ray_batch, int32_t ray_stride, int64_t n_rays, const float* t_vals, const float* u, void* workspace,
+	int64_t workspace_bytes, float* rgb, float* depth, float* disp, float* acc, float* weights, float* z_out, nrf_stream stream)
+{
+	NRF_REQUIRE(n_rays <= 0 || ray_batch, "null ray batch");
+	const RaySrc src{nullptr, nullptr, ray_batch, ray_stride, nullptr, nullptr, 0, 0};
+	return render_impl(cfg, grid, table_f16, shape, packed, src, n_rays, t_vals, u, workspace, workspace_bytes, rgb, depth, disp, acc, weights, z_out, stream);
 }
 
 int nrf_render_tile_fwd(const nrf_render_config* cfg, const nrf_hash_grid* grid, const void* table_f16, const nrf_mlp_small_shape* shape,
@@ -158,8 +181,8 @@ int nrf_render_tile_fwd(const nrf_render_config* cfg, const nrf_hash_grid* grid,
 	nrf_stream stream)
 {
 	NRF_REQUIRE(K_host && c2w_host, "null camera");
-	return render_impl(cfg, grid, table_f16, shape, packed, nullptr, nullptr, K_host, c2w_host, img_w, first_pixel, n_rays, t_vals, u, workspace,
-		workspace_bytes, rgb, depth, disp, acc, weights, z_out, stream);
+	const RaySrc src{nullptr, nullptr, nullptr, 0, K_host, c2w_host, img_w, first_pixel};
+	return render_impl(cfg, grid, table_f16, shape, packed, src, n_rays, t_vals, u, workspace, workspace_bytes, rgb, depth, disp, acc, weights, z_out, stream);
 }
 
 }

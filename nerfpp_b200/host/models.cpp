@@ -260,6 +260,13 @@ bool NeRFSmallImpl::Fused() const
 	return s.input_ch_views == 16 && nrf_mlp_small_param_count(&s) > 0;
 }
 
+bool NeRFSmallImpl::FusedPerRay() const
+{
+	if (UsePredNormal) return false;
+	const nrf_mlp_small_shape s = Shape();
+	return nrf_mlp_small_param_count(&s) > 0;
+}
+
 std::vector<Tensor> NeRFSmallImpl::Weights()
 {
 	std::vector<Tensor> w;

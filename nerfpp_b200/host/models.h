@@ -106,7 +106,8 @@ public:
 	torch::Tensor forward(torch::Tensor x) override;
 
 	// ---- B200 additions
-	bool Fused() const;                        ///< true when the fused kernels cover this shape
+	bool Fused() const;                        ///< true when the fused kernels cover this shape through the per-point interface (16 view channels)
+	bool FusedPerRay() const;                  ///< true when they cover it with the view channels per RAY (any SH degree 1..8: nrf_render_raybatch_fwd)
 	nrf_mlp_small_shape Shape() const;
 	std::vector<torch::Tensor> Weights();      ///< sigma_net_0.., color_net_0.. weights, each [out,in]
 	/// tensor-core operand blob of the current weights (re-packed only when a weight changed)

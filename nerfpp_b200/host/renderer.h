@@ -7,6 +7,8 @@
 //   * for <CuHashEmbedder, CuSHEncoder, NeRFSmall> RunNetwork is hash-encode -> fused MLP with the SH basis evaluated once
 //     per ray and the keep mask applied in the MLP epilogue; the coarse pass, which never receives a gradient
 //     (SURVEY §9-Q3), runs without an autograd graph;
+//   * for the same trio, a chunk rendered without an autograd graph in the parity configuration is ONE C-ABI call (nrf_render_raybatch_fwd):
+//     the fine pass evaluates the importance samples only and the gathers walk neighbouring rays together;
 //   * for <Embedder, Embedder, NeRF> at the BASELINE shape RunNetwork is ONE kernel: the positional embeddings of points and
 //     directions are evaluated in the fused MLP's input stage (directions per ray), in inference and in training.
 // Everything else (generic embedders / models, NDC, perturb > 0) follows the reference's ATen formulation.
@@ -114,7 +116,62 @@ protected:
 		return o;
 	}
 
+	torch::Tensor RenderWs;   ///< scratch of the one-call inference path, grown on demand and reused by every chunk
+
+	/// true when RenderRays can run as ONE C-ABI call (nrf_render_raybatch_fwd): <CuHashEmbedder, CuSHEncoder, NeRFSmall> at a shape the fused
+	/// kernels cover, no autograd graph, parity configuration (thin rays, no jitter / noise / preconditioning), rows [o d near far viewdirs]
+	bool FusedInference(const torch::Tensor& ray_batch, const torch::Tensor& cone_angle, int n_samples, bool return_raw, float perturb, int n_importance,
+		float raw_noise_std, float sp_alpha)
+	{
+		if constexpr (!kFusedHashPath) return false;
+		else {
+			if (!UseFusedInference || torch::GradMode::is_enabled()) return false;
+			if (!ray_batch.is_cuda() || ray_batch.dim() != 2 || ray_batch.size(1) != 11) return false;
+			if ((cone_angle.defined() && cone_angle.numel() != 0) || perturb != 0.f || raw_noise_std != 0.f || sp_alpha != 0.f || return_raw) return false;
+			if (n_importance < 1 || n_samples < 3 || n_samples + n_importance > 1024) return false;
+			const int deg = EmbeddirsFn->GetDegree();
+			return NeRF->FusedPerRay() && EmbedFn->GetOutputDims() == NeRF->GetInputCh() && NeRF->GetInputChViews() == deg * deg && deg >= 1 && deg <= 8;
+		}
+	}
+
+	/// RenderRays as one call: ray prologue from the prepared batch, both passes (the fine one evaluates the importance samples only: one network
+	/// for both, src/NeRFRenderer.h:422,447), SamplePDF + merge, RawToOutputs.  Same kernels as the staged path below, hence the same bits.
+	NeRFRenderResult RenderRaysFused(const torch::Tensor& ray_batch, int n_samples, bool lin_disp, int n_importance, bool white_bkgr, bool return_weights)
+	{
+		NeRFRenderResult result;
+		if constexpr (kFusedHashPath) {
+			torch::NoGradGuard no_grad;
+			torch::Tensor rb = nrfhost::Dense(ray_batch.detach(), torch::kFloat32, "ray_batch");
+			const int64_t R = rb.size(0);
+			nrf_render_config cfg{};
+			cfg.n_samples = n_samples; cfg.n_importance = n_importance; cfg.white_bkgr = white_bkgr ? 1 : 0; cfg.lin_disp = lin_disp ? 1 : 0;
+			cfg.sh_degree = EmbeddirsFn->GetDegree(); cfg.near_plane = 0.f;                       // bbox / near_plane are not read for a prepared batch
+			const nrf_hash_grid grid = EmbedFn->Grid();
+			const nrf_mlp_small_shape shape = NeRF->Shape();
+			const int64_t need = nrf_render_rays_workspace_bytes(&cfg, &grid, R);
+			TORCH_CHECK(need >= 0, "nrf_render_rays_workspace_bytes: ", nrf_last_error());
+			if (!RenderWs.defined() || RenderWs.numel() < need || RenderWs.device() != rb.device())
+				RenderWs = torch::empty({std::max<int64_t>(need, 256)}, torch::TensorOptions().dtype(torch::kUInt8).device(rb.device()));
+			torch::Tensor t_vals = nrfhost::UnitLinspace(n_samples, rb.device()), u = nrfhost::UnitLinspace(n_importance, rb.device());
+			torch::Tensor table = EmbedFn->ShadowF16(), packed = NeRF->Packed();
+			NeRFRendererOutputs& o = result.Outputs;
+			o.RGBMap = torch::empty({R, 3}, nrfhost::F32Like(rb));
+			o.DepthMap = torch::empty({R}, nrfhost::F32Like(rb));
+			o.DispMap = torch::empty({R}, nrfhost::F32Like(rb));
+			o.AccMap = torch::empty({R}, nrfhost::F32Like(rb));
+			if (return_weights) o.Weights = torch::empty({R, n_samples + n_importance}, nrfhost::F32Like(rb));
+			nrfhost::Check(nrf_render_raybatch_fwd(&cfg, &grid, table.data_ptr(), &shape, packed.data_ptr(), rb.data_ptr<float>(), int32_t(rb.size(1)), R,
+				t_vals.data_ptr<float>(), u.data_ptr<float>(), RenderWs.data_ptr(), RenderWs.numel(), o.RGBMap.data_ptr<float>(), o.DepthMap.data_ptr<float>(),
+				o.DispMap.data_ptr<float>(), o.AccMap.data_ptr<float>(), return_weights ? o.Weights.data_ptr<float>() : nullptr, nullptr, nrfhost::Stream()),
+				"nrf_render_raybatch_fwd");
+		}
+		return result;
+	}
+
 public:
+	/// false: inference goes stage by stage like training (A/B and tests); true (default): one C-ABI call per chunk when FusedInference() holds
+	bool UseFusedInference = true;
+
 	NeRFRenderer(TEmbedder embed_fn, TEmbedDirs embeddirs_fn, TNeRF nerf) : EmbedFn(embed_fn), EmbeddirsFn(embeddirs_fn), NeRF(nerf) {}
 	virtual ~NeRFRenderer() {}
 
@@ -124,6 +181,8 @@ public:
 		const float raw_noise_std = 0.f, const float stochastic_preconditioning_alpha = 0.f, torch::Tensor bounding_box = torch::Tensor(),
 		const bool return_weights = true)
 	{
+		if (FusedInference(ray_batch, cone_angle, n_samples, return_raw, perturb, n_importance, raw_noise_std, stochastic_preconditioning_alpha))
+			return RenderRaysFused(ray_batch, n_samples, lin_disp, n_importance, white_bkgr, return_weights);
 		NeRFRenderResult result;
 		const torch::Device device = ray_batch.device();
 		torch::Tensor rb = nrfhost::Dense(ray_batch.detach(), torch::kFloat32, "ray_batch");

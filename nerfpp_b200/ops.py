@@ -449,13 +449,15 @@ def adam_step_scheduled(param, grad, exp_avg, exp_avg_sq, sched_state: torch.Ten
 
 
 def render_rays_fwd(grid: HashGridSpec, table_f16, packed, rays_o, rays_d, t_vals, u, bbox, white_bkgr=False, sh_degree=4, near_plane=0.0,
-                    lin_disp=False, want_weights=False, want_z=False, workspace: torch.Tensor | None = None, shape=None, tile=None):
+                    lin_disp=False, want_weights=False, want_z=False, workspace: torch.Tensor | None = None, shape=None, tile=None, ray_batch=None):
     """RenderRays (inference) as ONE C-ABI call; returns (maps, workspace) — pass the workspace back in to reuse it.
     tile = (K, c2w, img_w, first_pixel, n_rays): the rays are pixels first_pixel .. first_pixel + n_rays of that view in GetRays order and are
-    generated inside the call (nrf_render_tile_fwd); rays_o / rays_d are then ignored."""
+    generated inside the call (nrf_render_tile_fwd); ray_batch [R, >= 11]: a prepared batch [o d near far viewdirs] (nrf_render_raybatch_fwd).
+    rays_o / rays_d are ignored in both cases."""
     shape = shape or mlp_shape()
     dev = table_f16.device
-    r, s, n = (tile[4] if tile is not None else rays_o.shape[0]), t_vals.shape[0], u.shape[0]
+    r = tile[4] if tile is not None else (ray_batch.shape[0] if ray_batch is not None else rays_o.shape[0])
+    s, n = t_vals.shape[0], u.shape[0]
     cfg = cabi.RenderConfig(s, n, int(white_bkgr), int(lin_disp), sh_degree, float(near_plane))
     for k in range(6):
         cfg.bbox[k] = float(bbox[k])
@@ -469,7 +471,11 @@ def render_rays_fwd(grid: HashGridSpec, table_f16, packed, rays_o, rays_d, t_val
     depth, disp, acc = (torch.empty(r, dtype=f32, device=dev) for _ in range(3))
     weights = torch.empty((r, s + n), dtype=f32, device=dev) if want_weights else None
     z = torch.empty((r, s + n), dtype=f32, device=dev) if want_z else None
-    if tile is not None:
+    if ray_batch is not None:
+        _run("render_rays_fwd", lambda: lib().nrf_render_raybatch_fwd(C.byref(cfg), C.byref(g), ptr(table_f16, f16), C.byref(shape), ptr(packed), ptr(ray_batch, f32),
+                                        ray_batch.shape[1], r, ptr(t_vals, f32), ptr(u, f32), ptr(workspace), workspace.numel(), ptr(rgb), ptr(depth),
+                                        ptr(disp), ptr(acc), ptr(weights), ptr(z), stream()))
+    elif tile is not None:
         kh, ch = _cam(tile[0], tile[1])
         _run("render_rays_fwd", lambda: lib().nrf_render_tile_fwd(C.byref(cfg), C.byref(g), ptr(table_f16, f16), C.byref(shape), ptr(packed), kh, ch, int(tile[2]),
                                         int(tile[3]), r, ptr(t_vals, f32), ptr(u, f32), ptr(workspace), workspace.numel(), ptr(rgb), ptr(depth),

@@ -303,6 +303,20 @@ def test_fused_render_entry_equals_the_composed_path():
             assert torch.equal(a[k], b[k]), k
     c = m.render_rays_fused(o, d, n_importance=64)
     assert c["rgb"].shape == (1, 3)
+    # a prepared batch [o d near far viewdirs] (what BatchifyRays hands to RenderRays): same bits; its near / far are taken as given
+    from nerfpp_b200 import ops
+    o, d, _ = synthetic_rays(300, seed=8)
+    rb = ops.rays_prepare(o, d, m.bbox, 0.0, True)
+    a = m.render_rays_fused(o, d, want_weights=True, want_z=True)
+    b, _ = ops.render_rays_fwd(m.grid, m.table_f16, m.packed, None, None, m.t_vals, m.u, m.bbox, sh_degree=m.sh_degree, want_weights=True, want_z=True,
+                               shape=m.mlp_shape, ray_batch=rb)
+    for k in ("rgb", "depth", "disp", "acc", "weights", "z"):
+        assert torch.equal(a[k], b[k]), k
+    rb2 = rb.clone()
+    rb2[:, 6] += 0.25                                                           # a caller-chosen near plane
+    c, _ = ops.render_rays_fwd(m.grid, m.table_f16, m.packed, None, None, m.t_vals, m.u, m.bbox, sh_degree=m.sh_degree, want_z=True, shape=m.mlp_shape, ray_batch=rb2)
+    ok = rb2[:, 6] < rb2[:, 7]                                                  # (a ray whose shifted near passes its far has no ordered depths)
+    assert int(ok.sum()) > 100 and torch.equal(c["z"][ok, 0], rb2[ok, 6])
 
 
 def test_fp16_shadow_is_fully_initialised():
