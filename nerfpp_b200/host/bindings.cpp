@@ -234,6 +234,7 @@ static void Bind(py::module_& m, const char* name)
 		.def("render_rays", &P::RenderRays).def("render", &P::Render).def("render_shipped", &P::RenderShipped).def("render_image", &P::RenderImage)
 		.def("use_fused_adam", &P::UseFusedAdam).def("use_train_graph", &P::UseTrainGraph)
 		.def("use_fused_inference", [](P& p, bool on) { p.renderer->UseFusedInference = on; })
+		.def("reuse_coarse_rows", [](P& p, bool on) { p.renderer->ReuseCoarseRows = on; })
 		.def("train_steps", &P::TrainSteps, py::call_guard<py::gil_scoped_release>())
 		// NeRFExecutor::SaveCheckpoint / the restore branch of Initialize (src/NeRFExecutor.h:1054-1068, 546-553): same file names
 		.def("save_checkpoint", [](P& p, const std::string& dir) {

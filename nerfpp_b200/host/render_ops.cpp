@@ -59,6 +59,20 @@ Tensor nrfhost::SamplePdfMerge(const Tensor& z_vals, const Tensor& weights, int 
 	return merged;
 }
 
+std::tuple<Tensor, Tensor, Tensor> nrfhost::SamplePdfMergeRows(const Tensor& z_vals, const Tensor& weights, int n_importance, const Tensor& raw_coarse)
+{
+	Tensor z = Dense(z_vals.detach(), torch::kFloat32, "z_vals"), w = Dense(weights.detach(), torch::kFloat32, "weights");
+	Tensor rc = Dense(raw_coarse.detach(), torch::kFloat32, "raw");
+	TORCH_CHECK(rc.dim() == 3 && rc.size(0) == z.size(0) && rc.size(1) == z.size(1) && rc.size(2) == 4, "SamplePdfMergeRows: raw must be [R,S,4]");
+	Tensor u = UnitLinspace(n_importance, z.device());
+	const int64_t R = z.size(0), T = z.size(1) + n_importance;
+	Tensor merged = torch::empty({R, T}, F32Like(z)), raw = torch::empty({R, T, 4}, F32Like(z));
+	Tensor perm = torch::empty({R, T}, torch::TensorOptions().dtype(torch::kInt16).device(z.device()));
+	Check(nrf_sample_pdf_merge_rows(CPtr<float>(z), CPtr<float>(w), CPtr<float>(u), 0, R, int32_t(z.size(1)), n_importance, nullptr, Ptr<float>(merged),
+		perm.data_ptr<int16_t>(), CPtr<float>(rc), Ptr<float>(raw), Stream()), "nrf_sample_pdf_merge_rows");
+	return {merged, perm, raw};
+}
+
 // ------------------------------------------------------------------------------------------------ rays
 Tensor GetDirections(const int h, const int w, Tensor k)
 {

@@ -48,6 +48,10 @@ torch::Tensor ZSample(const torch::Tensor& ray_batch, int n_samples, bool lin_di
 torch::Tensor SamplePoints(const torch::Tensor& ray_batch, const torch::Tensor& z_vals);
 /// z_mid, SamplePDF(z_mid, w[:,1:-1]) and sort(cat(z, z_samples)) in one kernel (src/NeRFRenderer.h:427-431); det only
 torch::Tensor SamplePdfMerge(const torch::Tensor& z_vals, const torch::Tensor& weights, int n_importance);
+/// The same merge, and the coarse pass's raw rows [R,S,4] travel to their merged positions (nrf_sample_pdf_merge_rows): returns
+/// {z_merged [R,S+N], perm [R,S+N] int16 (entry j < N: merged position of importance sample j), raw_merged [R,S+N,4] with the coarse rows filled}
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> SamplePdfMergeRows(const torch::Tensor& z_vals, const torch::Tensor& weights, int n_importance,
+	const torch::Tensor& raw_coarse);
 /// linspace(0,1,n) on the device, built once per (n, device)
 torch::Tensor UnitLinspace(int n, const torch::Device& device);
 

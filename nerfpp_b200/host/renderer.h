@@ -171,6 +171,8 @@ protected:
 public:
 	/// false: inference goes stage by stage like training (A/B and tests); true (default): one C-ABI call per chunk when FusedInference() holds
 	bool UseFusedInference = true;
+	/// staged inference: the fine pass evaluates the importance samples only and takes the coarse samples' raw rows from the coarse pass
+	bool ReuseCoarseRows = true;
 
 	NeRFRenderer(TEmbedder embed_fn, TEmbedDirs embeddirs_fn, TNeRF nerf) : EmbedFn(embed_fn), EmbeddirsFn(embeddirs_fn), NeRF(nerf) {}
 	virtual ~NeRFRenderer() {}
@@ -208,7 +210,20 @@ public:
 			raw = RunNetwork(pts, viewdirs, NeRF, EmbedFn, EmbeddirsFn);                                    // :422
 			coarse = RawToOutputs(raw, cone_angle, z_vals, rays_d, raw_noise_std, white_bkgr);              // :423
 		}
-		if (n_importance > 0) {
+		// Inference in the parity configuration: the merged list holds the coarse samples bit for bit and ONE network serves both passes (:422,447),
+		// so their raw rows are the coarse pass's own — the fine pass evaluates the n_importance NEW samples only (any embedder / model with 4-channel
+		// rows; a model evaluated through cuBLAS may round a row differently in another batch shape, the fused models do not).
+		if (n_importance > 0 && ReuseCoarseRows && !torch::GradMode::is_enabled() && perturb == 0.f && stochastic_preconditioning_alpha == 0.f &&
+			!(cone_angle.defined() && cone_angle.numel() != 0) && raw.dim() == 3 && raw.size(-1) == 4) {
+			auto [z_merged, perm, raw_merged] = nrfhost::SamplePdfMergeRows(z_vals, coarse.Weights, n_importance, raw);
+			torch::Tensor at = perm.narrow(1, 0, n_importance).to(torch::kLong);                           // merged positions of the importance samples
+			torch::Tensor z_new = torch::gather(z_merged, 1, at).contiguous();
+			torch::Tensor raw_new = RunNetwork(nrfhost::SamplePoints(rb, z_new), viewdirs, NeRF, EmbedFn, EmbeddirsFn);   // [R, N, 4]
+			raw_merged.scatter_(1, at.unsqueeze(-1).expand({-1, -1, 4}), raw_new.to(torch::kFloat32));
+			z_vals = z_merged;
+			raw = raw_merged;
+			result.Outputs = RawToOutputs(raw, cone_angle, z_vals, rays_d, raw_noise_std, white_bkgr);      // :448
+		} else if (n_importance > 0) {
 			if (perturb == 0.f) {
 				z_vals = nrfhost::SamplePdfMerge(z_vals, coarse.Weights, n_importance);                     // :427-431 in one kernel
 			} else {

@@ -308,6 +308,15 @@ def test_classic_inference_runs_on_the_fused_tcgen05_forward(host, ref_cuda):
     b = ref.render_image(20, 24, K.cuda(), c2w.cuda(), 64, 128, 4096, False, True)
     for k in ("rgb", "acc", "depth"):
         assert torch.allclose(a[k], b[k], rtol=1e-2, atol=1e-2), k
+    # staged inference evaluates the importance samples only (one network for both passes): the coarse samples' rows come from the coarse pass.
+    # Same rows through the same row-independent kernel => the same maps bit for bit, with a third fewer network evaluations
+    ours.reuse_coarse_rows(False)
+    n1 = cabi.launch_count()
+    full = ours.render_image(20, 24, K.cuda(), c2w.cuda(), 64, 128, 4096, False, True)
+    ours.reuse_coarse_rows(True)
+    for k in ("rgb", "acc", "depth", "weights"):
+        assert torch.equal(a[k], full[k]), k
+    assert cabi.launch_count() > n1
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ours.model(torch.rand(4, 90))                             # a CPU tensor at the built shape is refused, not routed through ATen
     x = torch.rand(300, 90).cuda()
