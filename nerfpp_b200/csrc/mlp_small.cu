@@ -286,7 +286,8 @@ __global__ void __launch_bounds__(kFwdWarps * 32) mlp_small_fwd_kernel(const uin
 }
 
 // ---------------------------------------------------------------------------------------------- backward
-constexpr int kBwdWarps = 8;
+constexpr int kBwdWarps = 8;               // the mma.sync-dW variant (NRF_MLP_BWD_DW=mma)
+constexpr int kBwdWarpsTc = 12;            // the tcgen05-dW kernel
 constexpr int kTileRows = kBwdWarps * 16;  // 128
 // padded tile pitches (bf16 elements)
 constexpr int kP32 = 40, kP64 = 72, kP16 = 24, kP8 = 16;
@@ -312,31 +313,38 @@ constexpr size_t kBwdSmem = static_cast<size_t>(kBlobWords) * 4 + static_cast<si
 //   MMA2: A = [dY3 | X1 ]  B = [X3 | dY1] (N = 80)  -> rows 0..63 x cols 0..63 = dW3,  rows 64..127 x cols 64..79 = dW1^T
 //   MMA3: A = [X4  | X3 ]  B = dY4 (N = 16)         -> rows 0..63 x cols 0..2  = dW4^T
 // (the other quadrants are finite garbage that is never read back)
-constexpr int kCRA = 0;                              // [dY0 | dY2]
-constexpr int kCRB = kCRA + 128 * 128 * 2;           // [dY3 | X1]
-constexpr int kCX4 = kCRB + 128 * 128 * 2;
-constexpr int kCX3 = kCX4 + 128 * 64 * 2;
-constexpr int kCD1 = kCX3 + 128 * 64 * 2;
-constexpr int kCX0 = kCD1 + 128 * 16 * 2;
-constexpr int kCX2 = kCX0 + 128 * 32 * 2;
-constexpr int kCD4 = kCX2 + 128 * 32 * 2;
-constexpr int kCTileBytes = kCD4 + 128 * 16 * 2;     // 122 880
+// WARPS warps = WARPS * 16 rows per CTA tile (8: the register-chained kernel as first built; 12: a third more warps per scheduler to hide the
+// latency of the dependent chain, at <= 170 registers per thread)
+template <int WARPS>
+struct BwdTc {
+	static constexpr int kRows = WARPS * 16;
+	static constexpr int kChunk = kRows * 16;                        // bytes between 8-column chunks of a region
+	static constexpr int kCRA = 0;                                   // [dY0 | dY2]
+	static constexpr int kCRB = kCRA + kRows * 128 * 2;              // [dY3 | X1]
+	static constexpr int kCX4 = kCRB + kRows * 128 * 2;
+	static constexpr int kCX3 = kCX4 + kRows * 64 * 2;
+	static constexpr int kCD1 = kCX3 + kRows * 64 * 2;
+	static constexpr int kCX0 = kCD1 + kRows * 16 * 2;
+	static constexpr int kCX2 = kCX0 + kRows * 32 * 2;
+	static constexpr int kCD4 = kCX2 + kRows * 32 * 2;
+	static constexpr int kBytes = kCD4 + kRows * 16 * 2;             // 122 880 at 8 warps, 184 320 at 12
+	static constexpr size_t kSmem = static_cast<size_t>(kBlobWords) * 4 + kBytes + 64;
+};
 constexpr uint32_t kDwT0 = 0, kDwT1 = 64, kDwT2 = 144;        // TMEM columns of the three accumulators
-constexpr size_t kBwdSmemTc = static_cast<size_t>(kBlobWords) * 4 + kCTileBytes + 64;
 
 // instruction descriptor: kind::f16, bf16 x bf16 -> fp32, A and B MN-major, M = 128
 __host__ __device__ constexpr uint32_t idesc_mn(int N) { return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (uint32_t(N >> 3) << 17) | (8u << 24); }
 
-template <int KS>
+template <int KS, int CHUNK>
 __device__ __forceinline__ void store_frag_c(uint8_t* region, int chunk0, int row_g, int t, const uint32_t (&a)[KS][4])
 {
-	uint8_t* p = region + chunk0 * 2048 + row_g * 16 + t * 4;
+	uint8_t* p = region + chunk0 * CHUNK + row_g * 16 + t * 4;
 #pragma unroll
 	for (int ks = 0; ks < KS; ks++) {
-		*reinterpret_cast<uint32_t*>(p + (2 * ks) * 2048) = a[ks][0];
-		*reinterpret_cast<uint32_t*>(p + (2 * ks) * 2048 + 128) = a[ks][1];          // row + 8
-		*reinterpret_cast<uint32_t*>(p + (2 * ks + 1) * 2048) = a[ks][2];
-		*reinterpret_cast<uint32_t*>(p + (2 * ks + 1) * 2048 + 128) = a[ks][3];
+		*reinterpret_cast<uint32_t*>(p + (2 * ks) * CHUNK) = a[ks][0];
+		*reinterpret_cast<uint32_t*>(p + (2 * ks) * CHUNK + 128) = a[ks][1];          // row + 8
+		*reinterpret_cast<uint32_t*>(p + (2 * ks + 1) * CHUNK) = a[ks][2];
+		*reinterpret_cast<uint32_t*>(p + (2 * ks + 1) * CHUNK + 128) = a[ks][3];
 	}
 }
 
@@ -454,18 +462,21 @@ __device__ __forceinline__ void reduce_ray_bias_grad(const uint32_t (&d)[4][4], 
 	}
 }
 
-template <int IN_KIND, bool TCDW>
-__global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const uint32_t* __restrict__ blob, const void* __restrict__ enc,
+template <int IN_KIND, bool TCDW, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) mlp_small_bwd_kernel(const uint32_t* __restrict__ blob, const void* __restrict__ enc,
 	const float* __restrict__ ray_sh, int S, const uint8_t* __restrict__ keep, int64_t n, const float* __restrict__ grad_raw,
 	void* __restrict__ grad_in, float* __restrict__ grad_params, int V, float* __restrict__ grad_bias)
 {
+	static_assert(TCDW || WARPS == kBwdWarps, "the mma.sync weight-gradient split is written for 8 warps");
+	using C = BwdTc<WARPS>;
+	constexpr int kRowsT = WARPS * 16;                                                       // rows of a CTA tile
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	pdl_prologue();
 	uint32_t* wf = reinterpret_cast<uint32_t*>(smem_raw);
 	__nv_bfloat16* tiles = reinterpret_cast<__nv_bfloat16*>(smem_raw + static_cast<size_t>(kBlobWords) * 4);
 	uint8_t* ctiles = smem_raw + static_cast<size_t>(kBlobWords) * 4;                       // TCDW: canonical regions
-	uint64_t* dw_done = reinterpret_cast<uint64_t*>(ctiles + kCTileBytes);                  // TCDW: the tile's MMAs have read the regions
-	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctiles + kCTileBytes + 8);
+	uint64_t* dw_done = reinterpret_cast<uint64_t*>(ctiles + C::kBytes);                    // TCDW: the tile's MMAs have read the regions
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctiles + C::kBytes + 8);
 	const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), g = lane >> 2, t = lane & 3;
 	if (TCDW && warp == 0) {
 		if (lane == 0) {
@@ -487,14 +498,14 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 	for (int i = 0; i < (TCDW ? 1 : 10); i++) dw[i][0] = dw[i][1] = dw[i][2] = dw[i][3] = 0.f;
 	uint32_t it = 0;                  // tiles done by this CTA
 
-	const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
+	const int64_t n_tiles = (n + kRowsT - 1) / kRowsT;
 	// inputs of the tile in flight (prefetched one tile ahead: the loads complete behind the dW phase)
 	uint32_t in_a0[2][4];
 	float2 in_v[4];
 	float4 in_g_lo, in_g_hi;
 	uint8_t in_k_lo = 1, in_k_hi = 1;
 	auto load_tile = [&](int64_t tile) {   // loads only: every consumer of the loaded values sits in the next iteration
-		const int64_t r_lo = tile * kTileRows + row_g, r_hi = r_lo + 8;
+		const int64_t r_lo = tile * kRowsT + row_g, r_hi = r_lo + 8;
 		load_enc<IN_KIND>(enc, r_lo, r_hi, n, t, in_a0);
 		load_views_raw<IN_KIND>(enc, ray_sh, S, r_lo, r_hi, n, t, in_v);
 		in_g_lo = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -506,7 +517,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 	};
 	if (static_cast<int64_t>(blockIdx.x) < n_tiles) load_tile(blockIdx.x);
 	for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-		const int64_t r_lo = tile * kTileRows + row_g, r_hi = r_lo + 8;
+		const int64_t r_lo = tile * kRowsT + row_g, r_hi = r_lo + 8;
 		float4 g_lo = in_g_lo, g_hi = in_g_hi;
 		if (!in_k_lo) g_lo.w = 0.f;               // d(sigma) is dropped outside the box (src/NeRFRenderer.h:188)
 		if (!in_k_hi) g_hi.w = 0.f;
@@ -523,12 +534,12 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			layer_mma<2, 8, true>(a0, wf + kF0, lane, acc);
 			uint32_t xb2[2][4], xb4[4][4];                               // bf16 copies for the dW products
 			to_bf16<2>(a0, xb2);
-			if (TCDW) store_frag_c<2>(ctiles + kCX0, 0, row_g, t, xb2); else store_frag<2>(tiles + kTX0, kP32, row_g, t, xb2);
+			if (TCDW) store_frag_c<2, C::kChunk>(ctiles + C::kCX0, 0, row_g, t, xb2); else store_frag<2>(tiles + kTX0, kP32, row_g, t, xb2);
 			uint32_t a1[4][4];
 			repack<4, true, true>(acc, a1);
 			relu_gates<4>(a1, m1);
 			repack<4, true, false>(acc, xb4);
-			if (TCDW) store_frag_c<4>(ctiles + kCRB, 8, row_g, t, xb4); else store_frag<4>(tiles + kTX1, kP64, row_g, t, xb4);
+			if (TCDW) store_frag_c<4, C::kChunk>(ctiles + C::kCRB, 8, row_g, t, xb4); else store_frag<4>(tiles + kTX1, kP64, row_g, t, xb4);
 			float d1[2][4];
 			layer_mma<4, 2, true>(a1, wf + kF1, lane, d1);
 			uint32_t a2[2][4];
@@ -537,19 +548,19 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			if (t == 0) { d1[0][0] = 0.f; d1[0][2] = 0.f; }
 			repack<1, false, true>(d1, reinterpret_cast<uint32_t(&)[1][4]>(a2[1]));
 			to_bf16<2>(a2, xb2);
-			if (TCDW) store_frag_c<2>(ctiles + kCX2, 0, row_g, t, xb2); else store_frag<2>(tiles + kTX2, kP32, row_g, t, xb2);
+			if (TCDW) store_frag_c<2, C::kChunk>(ctiles + C::kCX2, 0, row_g, t, xb2); else store_frag<2>(tiles + kTX2, kP32, row_g, t, xb2);
 			layer_mma<2, 8, true>(a2, wf + kF2, lane, acc);
 			if (IN_KIND == NRF_MLP_IN_ENC16_RAYBIAS) add_ray_bias(acc, ray_sh, S, r_lo, r_hi, n, t);
 			uint32_t a3[4][4];
 			repack<4, true, true>(acc, a3);
 			relu_gates<4>(a3, m3);
 			repack<4, true, false>(acc, xb4);
-			if (TCDW) store_frag_c<4>(ctiles + kCX3, 0, row_g, t, xb4); else store_frag<4>(tiles + kTX3, kP64, row_g, t, xb4);
+			if (TCDW) store_frag_c<4, C::kChunk>(ctiles + C::kCX3, 0, row_g, t, xb4); else store_frag<4>(tiles + kTX3, kP64, row_g, t, xb4);
 			layer_mma<4, 8, true>(a3, wf + kF3, lane, acc);
 			repack<4, true, true>(acc, a3);
 			relu_gates<4>(a3, m4);
 			repack<4, true, false>(acc, xb4);
-			if (TCDW) store_frag_c<4>(ctiles + kCX4, 0, row_g, t, xb4); else store_frag<4>(tiles + kTX4, kP64, row_g, t, xb4);
+			if (TCDW) store_frag_c<4, C::kChunk>(ctiles + C::kCX4, 0, row_g, t, xb4); else store_frag<4>(tiles + kTX4, kP64, row_g, t, xb4);
 		}
 		// ---- backward chain
 		{
@@ -558,18 +569,18 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			d4[0][1] = t == 0 ? pack_bf16(g_hi.x, g_hi.y) : (t == 1 ? pack_bf16(g_hi.z, 0.f) : 0u);
 			d4[0][2] = 0u;
 			d4[0][3] = 0u;
-			if (TCDW) store_frag_c<1>(ctiles + kCD4, 0, row_g, t, d4); else store_frag<1>(tiles + kTD4, kP8, row_g, t, d4);   // 8 real + 8 zero columns
+			if (TCDW) store_frag_c<1, C::kChunk>(ctiles + C::kCD4, 0, row_g, t, d4); else store_frag<1>(tiles + kTD4, kP8, row_g, t, d4);   // 8 real + 8 zero columns
 			float acc[8][4];
 			layer_mma<1, 8, false>(d4, wf + kB4, lane, acc);                 // dA4 = dD4 · W4
 			uint32_t d3[4][4];
 			repack<4, false, false>(acc, d3);
 			apply_gates<4>(d3, m4);
-			if (TCDW) store_frag_c<4>(ctiles + kCRB, 0, row_g, t, d3); else store_frag<4>(tiles + kTD3, kP64, row_g, t, d3);
+			if (TCDW) store_frag_c<4, C::kChunk>(ctiles + C::kCRB, 0, row_g, t, d3); else store_frag<4>(tiles + kTD3, kP64, row_g, t, d3);
 			layer_mma<4, 8, false>(d3, wf + kB3, lane, acc);                 // dA3 = dD3 · W3
 			repack<4, false, false>(acc, d3);
 			apply_gates<4>(d3, m3);
-			if (IN_KIND == NRF_MLP_IN_ENC16_RAYBIAS) reduce_ray_bias_grad(d3, grad_bias, S, tile * kTileRows + warp * 16, n, g, t);
-			if (TCDW) store_frag_c<4>(ctiles + kCRA, 8, row_g, t, d3); else store_frag<4>(tiles + kTD2, kP64, row_g, t, d3);
+			if (IN_KIND == NRF_MLP_IN_ENC16_RAYBIAS) reduce_ray_bias_grad(d3, grad_bias, S, tile * kRowsT + warp * 16, n, g, t);
+			if (TCDW) store_frag_c<4, C::kChunk>(ctiles + C::kCRA, 8, row_g, t, d3); else store_frag<4>(tiles + kTD2, kP64, row_g, t, d3);
 			float da2[4][4];
 			layer_mma<4, 4, false>(d3, wf + kB2, lane, da2);                 // dA2 = dD2 · W2p  (cols 0..15 views, 16..31 d1)
 			if (t == 0) { da2[2][0] += g_lo.w; da2[2][2] += g_hi.w; }        // + d(sigma)
@@ -578,11 +589,11 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			dd1[0][1] = pack_bf16(da2[2][2], da2[2][3]);
 			dd1[0][2] = pack_bf16(da2[3][0], da2[3][1]);
 			dd1[0][3] = pack_bf16(da2[3][2], da2[3][3]);
-			if (TCDW) store_frag_c<1>(ctiles + kCD1, 0, row_g, t, dd1); else store_frag<1>(tiles + kTD1, kP16, row_g, t, dd1);
+			if (TCDW) store_frag_c<1, C::kChunk>(ctiles + C::kCD1, 0, row_g, t, dd1); else store_frag<1>(tiles + kTD1, kP16, row_g, t, dd1);
 			layer_mma<1, 8, false>(dd1, wf + kB1, lane, acc);                // dA1 = dD1 · W1
 			repack<4, false, false>(acc, d3);
 			apply_gates<4>(d3, m1);
-			if (TCDW) store_frag_c<4>(ctiles + kCRA, 0, row_g, t, d3); else store_frag<4>(tiles + kTD0, kP64, row_g, t, d3);
+			if (TCDW) store_frag_c<4, C::kChunk>(ctiles + C::kCRA, 0, row_g, t, d3); else store_frag<4>(tiles + kTD0, kP64, row_g, t, d3);
 			if (grad_in) {
 				float de[4][4];
 				layer_mma<4, 4, false>(d3, wf + kB0, lane, de);             // dEnc = dD0 · W0
@@ -615,14 +626,14 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_small_bwd_kernel(const 
 			__syncthreads();
 			if (warp == 0) {
 				const uint32_t base = tc::smem_u32(ctiles);
-				const uint64_t a1 = tc::smem_desc(base + kCRA, 128, 2048), b1 = tc::smem_desc(base + kCX0, 128, 2048);
-				const uint64_t a2 = tc::smem_desc(base + kCRB, 128, 2048), b2 = tc::smem_desc(base + kCX3, 128, 2048);
-				const uint64_t a3 = tc::smem_desc(base + kCX4, 128, 2048), b3 = tc::smem_desc(base + kCD4, 128, 2048);
+				const uint64_t a1 = tc::smem_desc(base + C::kCRA, 128, C::kChunk), b1 = tc::smem_desc(base + C::kCX0, 128, C::kChunk);
+				const uint64_t a2 = tc::smem_desc(base + C::kCRB, 128, C::kChunk), b2 = tc::smem_desc(base + C::kCX3, 128, C::kChunk);
+				const uint64_t a3 = tc::smem_desc(base + C::kCX4, 128, C::kChunk), b3 = tc::smem_desc(base + C::kCD4, 128, C::kChunk);
 				const uint32_t first = it ? 1u : 0u;
 				if (tc::elect_one()) {
 					tc::fence_after();
 #pragma unroll
-					for (int j = 0; j < 8; j++) {                                    // K = 16 rows per step: +256 B on both descriptors
+					for (int j = 0; j < WARPS; j++) {                                // K = 16 rows per step: +256 B on both descriptors
 						const uint64_t o = static_cast<uint64_t>(16 * j);
 						tc::umma_ss(tmem + kDwT0, a1 + o, b1 + o, idesc_mn(64), j ? 1u : first);
 						tc::umma_ss(tmem + kDwT1, a2 + o, b2 + o, idesc_mn(80), j ? 1u : first);
@@ -924,25 +935,30 @@ int nrf_mlp_small_bwd_raybias(const nrf_mlp_small_shape* shape, const void* pack
 	NRF_REQUIRE(in_kind != NRF_MLP_IN_ENC16_RAYBIAS || (grad_bias && samples_per_ray % 16 == 0),
 		"NRF_MLP_IN_ENC16_RAYBIAS needs grad_bias and samples_per_ray % 16 == 0 (a 16-row slab must lie within one ray)");
 	const int V = shape->input_ch_views;
-	const int64_t tiles = (n + kTileRows - 1) / kTileRows;
-	const int blocks = static_cast<int>(std::min<int64_t>(tiles, kNumSMs));
+	// NRF_MLP_BWD_WARPS=8 keeps the 8-warp (128-row) tiles of the tcgen05-dW kernel (the A/B baseline); default 12 warps (192 rows)
+	static const int tc_warps = [] { const char* e = getenv("NRF_MLP_BWD_WARPS"); return e && atoi(e) == 8 ? 8 : kBwdWarpsTc; }();
 	const uint32_t* blob = reinterpret_cast<const uint32_t*>(packed);
 	cudaStream_t s = as_stream(stream);
 	// NRF_MLP_BWD_DW=mma keeps the weight-gradient products on mma.sync + ldmatrix.trans (the A/B baseline); default: tcgen05 from the tiles
 	static const bool tcdw = [] { const char* e = getenv("NRF_MLP_BWD_DW"); return !(e && e[0] == 'm'); }();
-#define NRF_BWD_LAUNCH(KIND, TC, SMEM)                                                                                                   \
+#define NRF_BWD_LAUNCH(KIND, TC, W, SMEM)                                                                                                \
 	do {                                                                                                                                 \
-		NRF_CUDA(cudaFuncSetAttribute(mlp_small_bwd_kernel<KIND, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM))); \
-		launch_kernel(mlp_small_bwd_kernel<KIND, TC>, blocks, kBwdWarps * 32, SMEM, s, blob, enc, ray_sh, samples_per_ray, keep, n, grad_raw, grad_in,      \
+		const int64_t tiles = (n + (W) * 16 - 1) / ((W) * 16);                                                                            \
+		const int blocks = static_cast<int>(std::min<int64_t>(tiles, kNumSMs));                                                           \
+		NRF_CUDA(cudaFuncSetAttribute(mlp_small_bwd_kernel<KIND, TC, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM))); \
+		launch_kernel(mlp_small_bwd_kernel<KIND, TC, W>, blocks, (W) * 32, SMEM, s, blob, enc, ray_sh, samples_per_ray, keep, n, grad_raw, grad_in,         \
 			grad_params_flat, V, grad_bias);                                                                                             \
 	} while (0)
-	if (in_kind == NRF_MLP_IN_ENC16_RAYDIRS) {
-		if (tcdw) NRF_BWD_LAUNCH(NRF_MLP_IN_ENC16_RAYDIRS, true, kBwdSmemTc); else NRF_BWD_LAUNCH(NRF_MLP_IN_ENC16_RAYDIRS, false, kBwdSmem);
-	} else if (in_kind == NRF_MLP_IN_ENC16_RAYBIAS) {
-		if (tcdw) NRF_BWD_LAUNCH(NRF_MLP_IN_ENC16_RAYBIAS, true, kBwdSmemTc); else NRF_BWD_LAUNCH(NRF_MLP_IN_ENC16_RAYBIAS, false, kBwdSmem);
-	} else {
-		if (tcdw) NRF_BWD_LAUNCH(NRF_MLP_IN_F32_CAT, true, kBwdSmemTc); else NRF_BWD_LAUNCH(NRF_MLP_IN_F32_CAT, false, kBwdSmem);
-	}
+#define NRF_BWD_KIND(KIND)                                                                                   \
+	do {                                                                                                     \
+		if (!tcdw) NRF_BWD_LAUNCH(KIND, false, kBwdWarps, kBwdSmem);                                         \
+		else if (tc_warps == 8) NRF_BWD_LAUNCH(KIND, true, 8, BwdTc<8>::kSmem);                              \
+		else NRF_BWD_LAUNCH(KIND, true, kBwdWarpsTc, BwdTc<kBwdWarpsTc>::kSmem);                             \
+	} while (0)
+	if (in_kind == NRF_MLP_IN_ENC16_RAYDIRS) NRF_BWD_KIND(NRF_MLP_IN_ENC16_RAYDIRS);
+	else if (in_kind == NRF_MLP_IN_ENC16_RAYBIAS) NRF_BWD_KIND(NRF_MLP_IN_ENC16_RAYBIAS);
+	else NRF_BWD_KIND(NRF_MLP_IN_F32_CAT);
+#undef NRF_BWD_KIND
 #undef NRF_BWD_LAUNCH
 	NRF_CHECK_LAUNCH("mlp_small_bwd_kernel");
 	return NRF_OK;

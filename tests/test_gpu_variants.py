@@ -9,7 +9,8 @@ process through the parity tests of the default path.
                         the test compares it with the composed path, which reuses — bit for bit
   NRF_HASH_SPLIT=0      hash forward with one thread per point instead of four lanes per point (csrc/hash_encode.cu)
   NRF_PDL=1             programmatic dependent launch along the step's kernel chain (csrc/common.cuh launch_kernel / pdl_prologue)
-  NRF_SAMPLER_BLOCK=0   warp-per-ray sampler also for training-sized batches (csrc/sampler.cu)"""
+  NRF_SAMPLER_BLOCK=0   warp-per-ray sampler also for training-sized batches (csrc/sampler.cu)
+  NRF_MLP_BWD_WARPS=8   NeRFSmall backward with 8 warps / 128-row tiles instead of 12 / 192 (csrc/mlp_small.cu)"""
 import os
 import subprocess
 import sys
@@ -30,6 +31,7 @@ VARIANTS = [
     ({"NRF_HASH_SPLIT": "0"}, ["test_gpu_hash.py"], "fixture or reuse or rays"),
     ({"NRF_PDL": "1"}, ["test_gpu_pipeline.py"], "graph or gradients or trains or reuse or render"),
     ({"NRF_SAMPLER_BLOCK": "0"}, ["test_gpu_render.py"], "sample_pdf or merge or sampler"),
+    ({"NRF_MLP_BWD_WARPS": "8"}, ["test_gpu_mlp.py"], "fixture or fused_input or per_ray"),
 ]
 
 
