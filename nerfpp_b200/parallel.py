@@ -121,9 +121,12 @@ class PeerShardedOptimizer:
                 getattr(pg, field)[p] = ptrs[p] + off
         self.pg, self.handles, self.rank, self.world = pg, handles, rank, world
         # NVSwitch multicast mappings of the gradient and the shadow (multimem.ld_reduce / multimem.st): the reduction happens in the switch.
-        # NRF_DP_MULTICAST=0 keeps the peer-load kernel (A/B).
+        # NRF_DP_MULTICAST=0 keeps the peer-load kernel, =1 forces multicast (A/B).  Default: multicast from 4 ranks up — with two ranks every
+        # byte crosses the link once either way and multimem only adds latency (0.887 vs 0.862 ms per step at N = 2; 0.882 vs 0.901 ms at N = 8:
+        # profiles/r2_bench_{2,8}gpu_{multicast,peerloads}.json).
         self.multicast = False
-        if bool(getattr(handles[0], "has_multicast_support", False)) and os.environ.get("NRF_DP_MULTICAST", "1") != "0":
+        want = os.environ.get("NRF_DP_MULTICAST", "auto")
+        if bool(getattr(handles[0], "has_multicast_support", False)) and (want == "1" or (want != "0" and self.world >= 4)):
             mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in handles[:2]]
             if all(mc):
                 pg.grads_mc = mc[0] + (self.grads.data_ptr() - list(handles[0].buffer_ptrs)[rank])

@@ -16,6 +16,6 @@ t=d.get("train_lerf") or {}
 print("   train_lerf", {k:t.get(k) for k in ("value","ms_per_step","error")}, (t.get("dp_check") or {}).get("ok"))
 PY
 }
-run_bench "" NRF_DP_MULTICAST=1
-if [ -n "$AB" ]; then run_bench "_peerloads" NRF_DP_MULTICAST=0; fi
+run_bench "" NRF_DP_MULTICAST=auto
+if [ -n "$AB" ]; then run_bench "_multicast" NRF_DP_MULTICAST=1; run_bench "_peerloads" NRF_DP_MULTICAST=0; fi
 tail -3 $OUT/bench_${N}gpu.err

@@ -48,7 +48,9 @@ def main():
     # B: fused peer-memory optimiser (eager), C: the same inside the captured graph
     b_ = HashNeRF(BBOX, log2_hashmap_size=15, seed=3, device=dev, lrate_decay=1)
     parallel.broadcast_parameters(b_.params, world); b_.refresh()
+    os.environ["NRF_DP_MULTICAST"] = "1"          # forced: the default picks multicast from 4 ranks up, and both forms of the kernel are checked here
     parallel.PeerShardedOptimizer(b_, rank, world)
+    os.environ.pop("NRF_DP_MULTICAST")
     c = HashNeRF(BBOX, log2_hashmap_size=15, seed=3, device=dev, lrate_decay=1)
     parallel.broadcast_parameters(c.params, world); c.refresh()
     # ---- (2a) one step on a random gradient through both paths; everything is restored afterwards.  b_ uses the NVSwitch multicast mappings when
