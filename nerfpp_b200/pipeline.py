@@ -272,6 +272,12 @@ class HashNeRF(FlatAdamModel):
             off += fo * fi
         return out
 
+    def mlp_grads_view(self, layer: int):
+        """Gradient of NeRFSmall weight `layer` (0..4) as a [out, in] view into the flat gradient."""
+        off = self.n_table + sum(fo * fi for fo, fi in self.mlp_layers[:layer])
+        fo, fi = self.mlp_layers[layer]
+        return self.grads[off:off + fo * fi].view(fo, fi)
+
     def repack(self):
         self.packed = ops.mlp_small_pack(self.mlp_params, shape=self.mlp_shape, out=self.packed)
 
