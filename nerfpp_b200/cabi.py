@@ -95,6 +95,7 @@ SIGNATURES = {
     "nrf_hash_encode_rays_fwd_grouped": (c_int32, [POINTER(HashGrid), _P, _P, c_int32, _P, c_int64, c_int32, c_int32, _P, _P, c_int32, _P, _P, _P, c_int32,
                                                    c_int32, _P]),
     "nrf_hash_encode_rays_bwd": (c_int32, [POINTER(HashGrid), _P, c_int32, _P, c_int64, c_int32, c_int32, _P, c_int32, _P, _P]),
+    "nrf_hash_encode_rays_bwd_levels": (c_int32, [POINTER(HashGrid), _P, c_int32, _P, c_int64, c_int32, c_int32, _P, c_int32, _P, c_int32, c_int32, _P]),
     "nrf_sample_pdf_merge_perm": (c_int32, [_P, _P, _P, c_int32, c_int64, c_int32, c_int32, _P, _P, _P, _P]),
     "nrf_sample_pdf_merge_rows": (c_int32, [_P, _P, _P, c_int32, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P, _P]),
     "nrf_sh_encode_fwd": (c_int32, [_P, c_int32, c_int64, c_int32, _P, _P]),
@@ -161,6 +162,8 @@ SIGNATURES = {
     "nrf_lerf_bwd_rows": (c_int32, [POINTER(LerfShape), _P, POINTER(LerfWeights), _P, _P, _P, c_int64, c_int32, _P, POINTER(LerfWeights), _P, _P]),
     "nrf_peer_flags_bytes": (c_int64, [c_int32]),
     "nrf_adam_step_sharded": (c_int32, [POINTER(PeerGroup), _P, _P, _P, c_int64, c_int64, _P, c_float, c_float, c_float, c_float, _P]),
+    "nrf_adam_step_sharded_range": (c_int32, [POINTER(PeerGroup), _P, _P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_float, c_float, c_float, c_float,
+                                              c_int32, _P]),
     "nrf_adam_schedule_advance": (c_int32, [_P, c_float, c_float, c_float, c_float, c_float, _P]),
     "nrf_adam_step_scheduled": (c_int32, [_P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float, c_int32, _P, _P]),
 }

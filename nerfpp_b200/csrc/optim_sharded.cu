@@ -78,9 +78,9 @@ __device__ __forceinline__ bool peer_barrier(const PeerArgs& a, int which, uint3
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		__threadfence_system();   // this CTA's peer stores / loads are ordered before its arrival
-		const uint32_t target = 2u * (epoch - 1u) + which + 1u;
-		const uint32_t arrived = atomicAdd(done_counter, 1u) + 1u;
-		if (arrived == gridDim.x * target) {
+		const uint32_t target = 2u * (epoch - 1u) + which + 1u;       // value of the release word once this barrier has been passed (monotone over calls)
+		const uint32_t arrived = atomicAdd(done_counter, 1u) + 1u;    // counts the arrivals of THIS call: reset at its end, so calls may differ in grid size
+		if (arrived == gridDim.x * (which + 1u)) {
 			// last CTA of this rank to arrive: tell the peers, wait for them, release the local CTAs
 			for (int p = 0; p < a.world; p++) st_release_sys(a.flags[p] + which * a.world + a.rank, epoch);
 			const long long t0 = clock64();
@@ -130,10 +130,13 @@ __device__ __forceinline__ float adam_update(float p, float g, float& m, float& 
 // together (NVLink round trips are ~2 us: the kernel lives on memory-level parallelism).
 // MC: the gradient sum of a quad is ONE multimem.ld_reduce on the multicast mapping and the fp16 result ONE multimem.st, instead of WORLD peer
 // loads and WORLD peer stores: per GPU and step 1/W x 35.6 MB arrives reduced (4.5 MB at W = 8) instead of (W-1)/W x 35.6 MB.
+// One call may cover only part of the flat vector: the sharded scalars [range_lo, range_hi) (multiples of 4; partitioned over the ranks) and the
+// replicated scalars [tail_lo, tail_hi).  The default step is one call over everything; the overlapped step (parallel.py) exchanges the part of
+// the gradient that is already complete on a side stream, with a narrow grid and its own flag block, while the backward still scatters the rest.
 template <int WORLD, int U, bool MC>
 __global__ void __launch_bounds__(512, 1) adam_sharded_kernel(PeerArgs a, float* __restrict__ param, float* __restrict__ m, float* __restrict__ v,
-	float* grad_local, int64_t n_sharded, int64_t n_total, const AdamSchedState* __restrict__ sched, float beta1, float beta2, float eps,
-	float grad_scale)
+	float* grad_local, int64_t range_lo, int64_t range_hi, int64_t tail_lo, int64_t tail_hi, const AdamSchedState* __restrict__ sched, float beta1,
+	float beta2, float eps, float grad_scale)
 {
 	uint32_t* mine = a.flags[a.rank];
 	__shared__ uint32_t s_epoch, s_dead;
@@ -153,9 +156,9 @@ __global__ void __launch_bounds__(512, 1) adam_sharded_kernel(PeerArgs a, float*
 
 	const float lr_over_bc1 = sched->lr_over_bc1, inv_sqrt_bc2 = sched->inv_sqrt_bc2;
 	// shard bounds in units of 4 scalars
-	const int64_t quads = n_sharded / 4;
+	const int64_t quads = (range_hi - range_lo) / 4;
 	const int64_t base = quads / WORLD, extra = quads % WORLD;
-	const int64_t q_lo = a.rank * base + (a.rank < extra ? a.rank : extra);
+	const int64_t q_lo = range_lo / 4 + a.rank * base + (a.rank < extra ? a.rank : extra);
 	const int64_t q_hi = q_lo + base + (a.rank < extra ? 1 : 0);
 	const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
 	const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -206,8 +209,8 @@ __global__ void __launch_bounds__(512, 1) adam_sharded_kernel(PeerArgs a, float*
 			}
 		}
 	}
-	// scalars of the sharded region that do not fill a quad (n_sharded % 4) and the replicated tail: every rank, same order
-	for (int64_t i = quads * 4 + tid; i < n_total; i += nthreads) {
+	// the replicated scalars (the MLP weights, and what of the table does not fill a quad): every rank, same order
+	for (int64_t i = tail_lo + tid; i < tail_hi; i += nthreads) {
 		float g = 0.f;
 		if (MC) {
 			g = multimem_ld_reduce_add(a.grads_mc + i);       // every rank reads the same switch-reduced sum: the replicas of the tail stay identical
@@ -225,11 +228,13 @@ __global__ void __launch_bounds__(512, 1) adam_sharded_kernel(PeerArgs a, float*
 	if (!peer_barrier(a, 1, epoch, done_counter)) return;   // a peer may still be reading this rank's gradient: do not clear it
 	if (stamp) mine[kStampBase + 3] = globaltimer_lo();
 
-	// every peer has consumed this rank's gradient: clear it for the next step
-	const int64_t nq = n_total / 4;
-	for (int64_t q = tid; q < nq; q += nthreads) *reinterpret_cast<float4*>(grad_local + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-	for (int64_t i = nq * 4 + tid; i < n_total; i += nthreads) grad_local[i] = 0.f;
-	if (tid == 0) mine[2 * WORLD] = epoch;
+	// every peer has consumed this call's part of this rank's gradient: clear it for the next step
+	for (int64_t q = range_lo / 4 + tid; q < range_hi / 4; q += nthreads) *reinterpret_cast<float4*>(grad_local + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+	for (int64_t i = tail_lo + tid; i < tail_hi; i += nthreads) grad_local[i] = 0.f;
+	if (tid == 0) {
+		mine[2 * WORLD] = epoch;
+		*done_counter = 0u;   // every CTA of this call has arrived at both barriers (the exit barrier was released): the next call counts from zero
+	}
 	if (stamp) mine[kStampBase + 4] = globaltimer_lo();
 }
 
@@ -244,9 +249,20 @@ int64_t nrf_peer_flags_bytes(int32_t world) { return world >= 1 && world <= NRF_
 int nrf_adam_step_sharded(const nrf_peer_group* pg, float* param, float* exp_avg, float* exp_avg_sq, int64_t n_sharded, int64_t n_total,
 	const void* sched_state, float beta1, float beta2, float eps, float grad_scale, nrf_stream stream)
 {
-	NRF_REQUIRE(pg != nullptr && pg->world >= 1 && pg->world <= NRF_MAX_PEERS && pg->rank >= 0 && pg->rank < pg->world, "bad peer group");
 	NRF_REQUIRE(n_sharded >= 0 && n_total >= n_sharded, "bad sizes");
-	if (n_total == 0) return NRF_OK;
+	const int64_t q4 = n_sharded / 4 * 4;
+	return nrf_adam_step_sharded_range(pg, param, exp_avg, exp_avg_sq, 0, q4, q4, n_total, sched_state, beta1, beta2, eps, grad_scale, 0, stream);
+}
+
+int nrf_adam_step_sharded_range(const nrf_peer_group* pg, float* param, float* exp_avg, float* exp_avg_sq, int64_t range_begin, int64_t range_end,
+	int64_t tail_begin, int64_t tail_end, const void* sched_state, float beta1, float beta2, float eps, float grad_scale, int32_t n_ctas,
+	nrf_stream stream)
+{
+	NRF_REQUIRE(pg != nullptr && pg->world >= 1 && pg->world <= NRF_MAX_PEERS && pg->rank >= 0 && pg->rank < pg->world, "bad peer group");
+	NRF_REQUIRE(range_begin >= 0 && range_end >= range_begin && range_begin % 4 == 0 && range_end % 4 == 0, "sharded range must be made of whole quads");
+	NRF_REQUIRE(tail_begin >= 0 && tail_end >= tail_begin, "bad tail range");
+	NRF_REQUIRE(n_ctas >= 0, "bad n_ctas");
+	if (range_end == range_begin && tail_end == tail_begin) return NRF_OK;
 	NRF_REQUIRE(param && exp_avg && exp_avg_sq && sched_state, "null pointer");
 	PeerArgs a;
 	a.world = pg->world; a.rank = pg->rank;
@@ -259,15 +275,16 @@ int nrf_adam_step_sharded(const nrf_peer_group* pg, float* param, float* exp_avg
 	}
 	NRF_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0,
 		"buffers must be 16-byte aligned");
-	// one CTA per SM, all co-resident: the in-kernel barriers need every CTA of the grid running
+	// one CTA per SM (or n_ctas of them), all co-resident: the in-kernel barriers need every CTA of the grid running
 	int sms = kNumSMs;
 	int dev = 0;
 	if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	NRF_REQUIRE(n_ctas <= sms, "n_ctas exceeds the number of SMs");
 	// cooperative launch: the driver guarantees that all CTAs are co-resident (or refuses the launch) — the in-kernel barriers spin
 	float* grad_local = const_cast<float*>(a.grads[a.rank]);
 	const AdamSchedState* sched = reinterpret_cast<const AdamSchedState*>(sched_state);
 	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3(sms);
+	cfg.gridDim = dim3(n_ctas > 0 ? n_ctas : sms);
 	cfg.blockDim = dim3(512);
 	cfg.dynamicSmemBytes = 0;
 	cfg.stream = as_stream(stream);
@@ -282,10 +299,10 @@ int nrf_adam_step_sharded(const nrf_peer_group* pg, float* param, float* exp_avg
 	const bool mc = pg->grads_mc != nullptr && pg->shadow_f16_mc != nullptr && pg->world > 1;
 	NRF_REQUIRE(!mc || (((reinterpret_cast<uintptr_t>(pg->grads_mc) & 15) | (reinterpret_cast<uintptr_t>(pg->shadow_f16_mc) & 7)) == 0), "multicast mappings must be 16-byte aligned");
 #define NRF_LAUNCH_SHARDED(W, U)                                                                                                                 \
-	launch_err = mc ? cudaLaunchKernelEx(&cfg, adam_sharded_kernel<W, 4, true>, a, param, exp_avg, exp_avg_sq, grad_local, n_sharded, n_total, sched,  \
-	                      beta1, beta2, eps, grad_scale)                                                                                         \
-	                : cudaLaunchKernelEx(&cfg, adam_sharded_kernel<W, U, false>, a, param, exp_avg, exp_avg_sq, grad_local, n_sharded, n_total, sched, \
-	                      beta1, beta2, eps, grad_scale)
+	launch_err = mc ? cudaLaunchKernelEx(&cfg, adam_sharded_kernel<W, 4, true>, a, param, exp_avg, exp_avg_sq, grad_local, range_begin, range_end,     \
+	                      tail_begin, tail_end, sched, beta1, beta2, eps, grad_scale)                                                            \
+	                : cudaLaunchKernelEx(&cfg, adam_sharded_kernel<W, U, false>, a, param, exp_avg, exp_avg_sq, grad_local, range_begin, range_end,    \
+	                      tail_begin, tail_end, sched, beta1, beta2, eps, grad_scale)
 	switch (pg->world) {
 		case 1: NRF_LAUNCH_SHARDED(1, 4); break;
 		case 2: NRF_LAUNCH_SHARDED(2, 4); break;
