@@ -322,6 +322,14 @@ def test_coarse_row_reuse_is_bit_identical():
     assert bool((pl[:, :N] >= 0).all())
     regular = (z[:, 1:] > z[:, :-1]).all(dim=1)                        # strictly increasing coarse z (rays that really cross the box)
     assert int(regular.sum()) > R // 2 and not bool(regular.all()) and bool(claimed.all())
+    # the positions against an independent formulation (torch.searchsorted): importance sample j goes behind every coarse depth <= it
+    # ("coarse first on ties"), coarse sample k behind every importance depth < it — on the rays whose two lists are sorted as they stand
+    _, zs = ops.sample_pdf_merge(z, w, torch.linspace(0, 1, N).cuda(), want_samples=True)
+    tidy = regular & (zs[:, 1:] >= zs[:, :-1]).all(dim=1)
+    assert int(tidy.sum()) > R // 2
+    ar_n, ar_s = torch.arange(N, device="cuda"), torch.arange(S, device="cuda")
+    assert torch.equal(pl[tidy, :N], ar_n + torch.searchsorted(z[tidy].contiguous(), zs[tidy].contiguous(), right=True))
+    assert torch.equal(pl[tidy, N:], ar_s + torch.searchsorted(zs[tidy].contiguous(), z[tidy].contiguous(), right=False))
     rows = torch.randn(R * S, 4, generator=g, device="cuda")
     zf2, perm2, merged_rows = ops.sample_pdf_merge(z, w, torch.linspace(0, 1, N).cuda(), want_perm=True, raw_coarse=rows)
     assert torch.equal(zf2, zf) and torch.equal(perm2, perm)
