@@ -300,6 +300,7 @@ def graph_breakdown(model, batch, world: int, reps: int = 20) -> dict:
     import torch
     from nerfpp_b200 import ops
     timer = ops.KernelTimer(external=True)
+    model._init_sched()
     model._sync_sched()
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())

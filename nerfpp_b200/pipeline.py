@@ -83,6 +83,7 @@ class FlatAdamModel:
         self.peer = None          # parallel.PeerShardedOptimizer when the fused data-parallel optimiser is in use
         self.masters_synced = True  # False while the fused optimiser has stepped and the non-owned fp32 shards are stale
         self.sched = None
+        self._sched_step = -1
 
     @property
     def table(self):
