@@ -10,7 +10,7 @@ r = csv.reader(lines)
 hdr = next(r)
 ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
 rows = [(row[ki], float(row[vi].replace(",", "")) / 1000) for row in r]
-adam = [i for i, (k, _) in enumerate(rows) if "adam_kernel(" in k]
+adam = [i for i, (k, _) in enumerate(rows) if "adam_kernel" in k]
 lo, hi = adam[-2] + 1, adam[-1] + 1
 agg = collections.OrderedDict()
 for k, us in rows[lo:hi]:
