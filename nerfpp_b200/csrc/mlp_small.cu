@@ -521,7 +521,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mlp_small_bwd_kernel(const uint
 		float4 g_lo = in_g_lo, g_hi = in_g_hi;
 		if (!in_k_lo) g_lo.w = 0.f;               // d(sigma) is dropped outside the box (src/NeRFRenderer.h:188)
 		if (!in_k_hi) g_hi.w = 0.f;
-		if (TCDW && it > 0) tc::mbar_wait(dw_done, (it - 1) & 1u);   // the previous tile's MMAs are done with the regions
+		uint32_t cur_a0[2][4];
+		float2 cur_v[4];
+#pragma unroll
+		for (int ks = 0; ks < 2; ks++)
+#pragma unroll
+			for (int e = 0; e < 4; e++) cur_a0[ks][e] = in_a0[ks][e];
+#pragma unroll
+		for (int e = 0; e < 4; e++) cur_v[e] = in_v[e];
+		// tcgen05 dW: the weight-gradient MMAs are issued by one thread and the warps loop straight on, so the next tile's inputs are requested
+		// HERE, a whole recompute + gradient chain ahead of their first use (the mma.sync dW variant requests them behind its dW phase, below)
+		if (TCDW && tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x);
 		uint32_t m1[4][4], m3[4][4], m4[4][4];   // ReLU gates of X1, X3, X4
 		// ---- forward recompute; every layer input is dropped into its X tile (bf16, packed straight from the fp32 accumulators)
 		{
@@ -529,11 +539,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mlp_small_bwd_kernel(const uint
 #pragma unroll
 			for (int ks = 0; ks < 2; ks++)
 #pragma unroll
-				for (int e = 0; e < 4; e++) a0[ks][e] = in_a0[ks][e];
+				for (int e = 0; e < 4; e++) a0[ks][e] = cur_a0[ks][e];
 			float acc[8][4];
 			layer_mma<2, 8, true>(a0, wf + kF0, lane, acc);
 			uint32_t xb2[2][4], xb4[4][4];                               // bf16 copies for the dW products
 			to_bf16<2>(a0, xb2);
+			// the previous tile's weight-gradient MMAs must be done with the regions before the first store into them (they ran behind layer 0)
+			if (TCDW && it > 0) tc::mbar_wait(dw_done, (it - 1) & 1u);
 			if (TCDW) store_frag_c<2, C::kChunk>(ctiles + C::kCX0, 0, row_g, t, xb2); else store_frag<2>(tiles + kTX0, kP32, row_g, t, xb2);
 			uint32_t a1[4][4];
 			repack<4, true, true>(acc, a1);
@@ -544,7 +556,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mlp_small_bwd_kernel(const uint
 			layer_mma<4, 2, true>(a1, wf + kF1, lane, d1);
 			uint32_t a2[2][4];
 #pragma unroll
-			for (int e = 0; e < 4; e++) a2[0][e] = pack_f16(in_v[e].x, in_v[e].y);
+			for (int e = 0; e < 4; e++) a2[0][e] = pack_f16(cur_v[e].x, cur_v[e].y);
 			if (t == 0) { d1[0][0] = 0.f; d1[0][2] = 0.f; }
 			repack<1, false, true>(d1, reinterpret_cast<uint32_t(&)[1][4]>(a2[1]));
 			to_bf16<2>(a2, xb2);
@@ -619,7 +631,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mlp_small_bwd_kernel(const uint
 				}
 			}
 		}
-		if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x);   // next tile's inputs travel while the dW phase runs
+		if (!TCDW && tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x);   // next tile's inputs travel while the dW phase runs
 		if (TCDW) {
 			// ---- dW on tcgen05: 3 MMAs per 16-row K step straight from the regions, accumulators stay in TMEM
 			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // the st.shared above -> visible to the MMA's async reads
