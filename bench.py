@@ -406,7 +406,9 @@ def cpp_render_leg(which: str) -> dict:
     c2w[2, 3] = 4.0
     c2w = c2w.cuda()
     frames = 2 if which != "reference_cuda" else 1
-    pipe.render_image(H, W, K, c2w, N_SAMPLES, 64, 131072, False, True)
+    torch.cuda.empty_cache()                        # the legs before this one leave the caching allocator fragmented: start from a clean pool
+    for _ in range(2 if which != "reference_cuda" else 1):
+        pipe.render_image(H, W, K, c2w, N_SAMPLES, 64, 131072, False, True)      # untimed: workspace, output maps and the cat buffers reach their sizes
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
