@@ -762,6 +762,8 @@ def main() -> None:
             maps = model.render_image(H, W, K, c2w, chunk=131072, row_begin=r0, row_end=r1, n_importance=64)
             return parallel.gather_rows(maps["rgb"], H * W, rank, world, unit=W) if world > 1 else maps["rgb"]
 
+        torch.cuda.empty_cache()      # the training legs leave the caching allocator fragmented: the frame's chunk buffers start from a clean pool
+        render_frame()
         render_frame()
         sync_all()
         e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
